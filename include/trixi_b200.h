@@ -1,0 +1,231 @@
+/* libtrixi_b200 -- C ABI of the B200-native DGSEM right-hand side / 2N Runge-Kutta / CFL path.
+ *
+ * The reference (Trixi.jl v0.17.4-DEV) has no FFI for this path: it is selected by Julia multiple
+ * dispatch on the `backend` argument.  Each entry point below is what the Julia
+ * method named in its comment forwards to with `ccall` (see INTEGRATION.md / julia/TrixiB200.jl).
+ * Plain pointers and sizes only; all arrays use the reference's own layouts: column-major,
+ * variable index fastest, `u[v, i, j, (k,) element]` (src/solvers/dg.jl:1169-1212), index arrays are
+ * Julia `Int` = int64 and 1-based.
+ *
+ * Conventions: the caller owns every host array; `create` copies what it needs and
+ * the library owns all device memory.  No call aborts: every function returns 0 on success or a
+ * negative TRIXI_B200_E* code, and `trixi_b200_last_error` gives the message.  NaNs propagate like in
+ * the reference (math.jl:89-97,137-146).  One handle per GPU, calls from one thread at a time.
+ * There is NO CPU fallback: without a CUDA device `create` fails with TRIXI_B200_ENODEVICE.
+ */
+#ifndef TRIXI_B200_H
+#define TRIXI_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TRIXI_B200_ABI_VERSION 1
+
+/* status codes */
+#define TRIXI_B200_OK 0
+#define TRIXI_B200_EINVAL (-1)      /* bad descriptor / unsupported combination */
+#define TRIXI_B200_ENODEVICE (-2)   /* no usable CUDA device */
+#define TRIXI_B200_ECUDA (-3)       /* CUDA runtime error (message in last_error) */
+#define TRIXI_B200_ENOMEM (-4)
+#define TRIXI_B200_ECOMM (-5)       /* halo exchange / NCCL error */
+
+/* mesh kinds (dispatch of rhs_hyperbolic!: dgsem_tree/dg_2d.jl:113-120, dgsem_structured/dg.jl:41-94,
+ * dgsem_p4est/dg_3d_parallel.jl:8-13) */
+enum { TRIXI_B200_MESH_TREE = 0, TRIXI_B200_MESH_STRUCTURED = 1, TRIXI_B200_MESH_P4EST = 2 };
+
+/* equations (src/equations/) */
+enum {
+    TRIXI_B200_EQ_ADVECTION_2D = 1, /* linear_scalar_advection_2d.jl; params: a1, a2 */
+    TRIXI_B200_EQ_EULER_2D = 2,     /* compressible_euler_2d.jl; params: gamma, inv_gamma_minus_one */
+    TRIXI_B200_EQ_EULER_3D = 3,     /* compressible_euler_3d.jl:45-54; params: gamma, inv_gamma_minus_one */
+    TRIXI_B200_EQ_MHD_3D = 4,       /* ideal_glm_mhd_3d.jl:49-59; params: gamma, inv_gamma_minus_one, c_h */
+    TRIXI_B200_EQ_ADVECTION_3D = 5  /* linear_scalar_advection_3d.jl; params: a1, a2, a3 */
+};
+
+/* volume integral types (src/solvers/dg.jl:105,135-141) */
+enum { TRIXI_B200_VOLINT_WEAK_FORM = 0, TRIXI_B200_VOLINT_FLUX_DIFFERENCING = 1 };
+
+/* numerical fluxes (src/equations/numerical_fluxes.jl, compressible_euler_3d.jl) */
+enum {
+    TRIXI_B200_FLUX_CENTRAL = 0,            /* numerical_fluxes.jl:17-25 */
+    TRIXI_B200_FLUX_RANOCHA = 1,            /* compressible_euler_3d.jl:746-828 */
+    TRIXI_B200_FLUX_LLF = 2,                /* FluxLaxFriedrichs(max_abs_speed)  :229-253, euler :1156-1199 */
+    TRIXI_B200_FLUX_LLF_NAIVE = 3,          /* FluxLaxFriedrichs(max_abs_speed_naive) euler :1112-1153 */
+    TRIXI_B200_FLUX_HLL_DAVIS = 4,          /* FluxHLL(min_max_speed_davis) :422-449, euler :1240-1285 */
+    TRIXI_B200_FLUX_HLL_NAIVE = 5,          /* FluxHLL(min_max_speed_naive) */
+    TRIXI_B200_FLUX_SHIMA_ETAL = 6,         /* compressible_euler_3d.jl:473-547 */
+    TRIXI_B200_FLUX_KENNEDY_GRUBER = 7,     /* :560-627 */
+    TRIXI_B200_FLUX_CHANDRASHEKAR = 8,      /* :639-733 */
+    TRIXI_B200_FLUX_HINDENLANG_GASSNER = 9, /* ideal_glm_mhd_3d.jl:680-855 */
+    TRIXI_B200_FLUX_GODUNOV = 10,           /* linear_scalar_advection_2d.jl:248-275 */
+    TRIXI_B200_FLUX_RANOCHA_TURBO = 11,     /* dg_3d_compressible_euler.jl:265-617: hoisted logs */
+    TRIXI_B200_FLUX_LLF_MHD_POWELL = 12,
+    TRIXI_B200_FLUX_HINDENLANG_GASSNER_POWELL = 13
+};
+
+/* source terms (calc_sources! dg_3d.jl:1417-1437 calls an arbitrary closure; here: registry) */
+enum {
+    TRIXI_B200_SRC_NONE = 0,
+    TRIXI_B200_SRC_CONVERGENCE_TEST = 1,              /* compressible_euler_3d.jl:127-153 / _2d */
+    TRIXI_B200_SRC_EOC_TEST_EULER = 2,                /* compressible_euler_3d.jl:265-284 */
+    TRIXI_B200_SRC_EOC_TEST_COUPLED_EULER_GRAVITY = 3 /* :228-249 */
+};
+
+/* initial conditions usable as Dirichlet boundary value functions */
+enum {
+    TRIXI_B200_IC_NONE = 0,
+    TRIXI_B200_IC_CONSTANT = 1,         /* compressible_euler_3d.jl:78-86 */
+    TRIXI_B200_IC_CONVERGENCE_TEST = 2, /* :94-111 */
+    TRIXI_B200_IC_WEAK_BLAST_WAVE = 3,  /* :163-184 */
+    TRIXI_B200_IC_EOC_TEST_COUPLED_EULER_GRAVITY = 4
+};
+
+/* boundary conditions, per direction -x,+x,-y,+y,-z,+z (semidiscretization_hyperbolic.jl:158-164) */
+enum {
+    TRIXI_B200_BC_PERIODIC = 0, /* basic_types.jl:58-127: no boundary faces in that direction */
+    TRIXI_B200_BC_DIRICHLET = 1, /* BoundaryConditionDirichlet equations.jl:159-183 */
+    TRIXI_B200_BC_SLIP_WALL = 2  /* compressible_euler_3d.jl:315-417 */
+};
+
+/* Descriptor: everything `create_cache` (dgsem_tree/dg_2d.jl:14-37) and the DG/equation structs hold
+ * that the hot path reads.  All pointers are host pointers, read during `create` only. */
+typedef struct trixi_b200_desc {
+    int32_t abi_version; /* TRIXI_B200_ABI_VERSION */
+    int32_t device;      /* CUDA device ordinal, -1 = current */
+    int32_t ndims, nvars, nnodes, mesh_kind;
+    int64_t nelements;
+
+    int32_t equation;
+    int32_t volume_integral, volume_flux, surface_flux;
+    int32_t source_terms;
+    int32_t boundary_conditions[6]; /* TRIXI_B200_BC_* per direction */
+    int32_t boundary_ic[6];         /* TRIXI_B200_IC_* for Dirichlet directions */
+    int32_t reserved0;
+    double eq_params[8];
+
+    /* LobattoLegendreBasis (basis_lobatto_legendre.jl:17-31), column-major [n, n] */
+    const double *derivative_split;
+    const double *derivative_hat;
+    const double *inverse_weights; /* [n]; surface lifting uses inverse_weights[1] (dg_3d.jl:1349) */
+
+    /* element container (containers_3d.jl:9-18 / dgsem_structured/containers.jl:8-34) */
+    const double *inverse_jacobian;      /* Tree: [nelements]; curved: [n^d, nelements] */
+    const double *node_coordinates;      /* [ndims, n^d, nelements] */
+    const double *contravariant_vectors; /* curved only: [ndims, ndims, n^d, nelements], else NULL */
+
+    /* interface container (containers_3d.jl:136-144), conforming faces */
+    int64_t ninterfaces;
+    const int64_t *interface_neighbor_ids;  /* [2, ninterfaces] 1-based, 1 = left/-, 2 = right/+ */
+    const int64_t *interface_orientations;  /* [ninterfaces] in 1..ndims */
+    const int64_t *interface_node_indices;  /* P4est only: [2, ninterfaces, ndims] symbols 0..5, else NULL */
+
+    /* boundary container (containers_3d.jl:284-295), sorted by direction */
+    int64_t nboundaries;
+    const int64_t *boundary_neighbor_ids;     /* [nboundaries] */
+    const int64_t *boundary_orientations;     /* [nboundaries] */
+    const int64_t *boundary_neighbor_sides;   /* [nboundaries] 1: element on the - side */
+    const double *boundary_node_coordinates;  /* [ndims, n^(d-1), nboundaries] */
+    int64_t n_boundaries_per_direction[6];
+
+    /* L2 mortar container (containers_3d.jl:495-510); nmortars = 0 on conforming meshes */
+    int64_t nmortars;
+    const int64_t *mortar_neighbor_ids; /* [2^(d-1)+1, nmortars] */
+    const int64_t *mortar_large_sides;  /* [nmortars] */
+    const int64_t *mortar_orientations; /* [nmortars] */
+    const double *mortar_forward_upper, *mortar_forward_lower; /* [n, n] */
+    const double *mortar_reverse_upper, *mortar_reverse_lower; /* [n, n] */
+
+    /* StructuredMesh: left_neighbors [ndims, nelements], 0 = domain boundary (containers.jl:8-34) */
+    const int64_t *left_neighbors;
+
+    /* distributed run (replaces P4estMPICache dg_parallel.jl:8-20): faces shared with other ranks */
+    int32_t rank, world_size;
+    int64_t nmpiinterfaces;
+    const int64_t *mpi_local_neighbor_ids; /* [nmpiinterfaces] local element, 1-based */
+    const int64_t *mpi_local_sides;        /* [nmpiinterfaces] 1: local element is left/-, 2: right/+ */
+    const int64_t *mpi_orientations;       /* [nmpiinterfaces] */
+    const int64_t *mpi_neighbor_ranks;     /* [nmpiinterfaces] peer rank of each face; faces are sorted by
+                                              (peer rank, global interface id) on both sides */
+} trixi_b200_desc;
+
+typedef struct trixi_b200_handle trixi_b200_handle;
+
+/* ---- life cycle --------------------------------------------------------------------------------
+ * Called once after `create_cache(mesh, equations, dg, RealT, uEltype)` (dgsem_tree/dg_2d.jl:14-37);
+ * mirrors what `trixi_adapt`/`semidiscretize(...; storage_type)` does for the reference GPU path
+ * (semidiscretization.jl:115-126): all containers are uploaded once. */
+int trixi_b200_create(const trixi_b200_desc *desc, trixi_b200_handle **out);
+void trixi_b200_destroy(trixi_b200_handle *h);
+const char *trixi_b200_last_error(const trixi_b200_handle *h); /* h may be NULL: last create error */
+int trixi_b200_abi_version(void);
+
+/* Device-resident solution vectors owned by the handle: u, du, u_tmp (methods_2N.jl:95-111).
+ * `which`: 0 = u, 1 = du, 2 = u_tmp.  Host arrays have nvars*n^d*nelements doubles. */
+int trixi_b200_upload(trixi_b200_handle *h, int which, const double *host);
+int trixi_b200_download(trixi_b200_handle *h, int which, double *host); /* Array(u) analysis_dg3d.jl:172-177 */
+void *trixi_b200_device_ptr(trixi_b200_handle *h, int which);           /* raw device pointer (for DLPack/torch views) */
+int trixi_b200_synchronize(trixi_b200_handle *h);
+void *trixi_b200_stream(trixi_b200_handle *h); /* the library-owned cudaStream_t */
+
+/* ---- hot path -----------------------------------------------------------------------------------
+ * rhs_hyperbolic!(backend, du, u, t, mesh, equations, boundary_conditions, source_terms, dg, cache)
+ * (dgsem_tree/dg_2d.jl:113-186; structured dgsem_structured/dg.jl:41-94): du <- rhs(u, t), host
+ * buffers: copies u host->device, runs the kernels, copies du device->host, synchronises. */
+int trixi_b200_rhs_host(trixi_b200_handle *h, double *du_host, const double *u_host, double t);
+/* same on the device-resident vectors (asynchronous on the handle's stream) */
+int trixi_b200_rhs(trixi_b200_handle *h, double t);
+
+/* max_dt(u, t, mesh, constant_speed, equations, dg, cache) (stepsize_dg3d.jl:8-32, stepsize_dg2d.jl):
+ * returns 2 / (nnodes * max_e invJ_e * sum_d max_nodes lambda_d) over the device-resident u;
+ * the caller multiplies by cfl(t) (stepsize.jl:146-154).  With world_size > 1 the minimum over ranks
+ * is taken (stepsize_dg3d.jl:264-279).  Synchronises. */
+int trixi_b200_max_dt(trixi_b200_handle *h, double t, double *dt_out);
+
+/* step!(integrator::SimpleIntegrator2N) stage loop (methods_2N.jl:144-159): for every stage
+ * du <- rhs(u, t + c_s dt); u_tmp <- du - a_s u_tmp; u <- u + (b_s dt) u_tmp, with the stage update
+ * fused into the last RHS kernel.  u_tmp is zeroed first.  Asynchronous. */
+int trixi_b200_step_2n(trixi_b200_handle *h, double t, double dt, const double *a, const double *b,
+                       const double *c, int nstages);
+/* `nsteps` steps with the CFL step size recomputed on the device after every step
+ * (StepsizeCallback interval = 1, stepsize.jl:93-126) and the final step clipped to t_end
+ * (time_integration.jl:46-55); no host round trip inside.  Returns the number of steps taken, the
+ * final time and the last dt through the out-pointers.  Synchronises at the end. */
+int trixi_b200_solve_2n(trixi_b200_handle *h, double t0, double t_end, double cfl, int64_t max_steps,
+                        const double *a, const double *b, const double *c, int nstages,
+                        int64_t *steps_out, double *t_out, double *dt_out);
+
+/* GlmSpeedCallback (glm_speed.jl:85-105) mutates equations.c_h every step */
+int trixi_b200_set_eq_param(trixi_b200_handle *h, int index, double value);
+
+/* ---- stage-level entry points (parity tests against the reference's stage functions) ------------
+ * calc_volume_integral! (calc_volume_integral.jl:180-191): du <- volume terms only (set_zero! included) */
+int trixi_b200_calc_volume_integral(trixi_b200_handle *h);
+/* prolong2interfaces! + calc_interface_flux! + prolong2boundaries! + calc_boundary_flux!
+ * (dg_3d.jl:530-602,651-768) -> surface_flux_values[nvars, n^(d-1), 2*ndims, nelements] */
+int trixi_b200_calc_surface_fluxes(trixi_b200_handle *h, double t);
+int trixi_b200_download_surface_flux_values(trixi_b200_handle *h, double *host);
+
+/* ---- distributed halo exchange (replaces MPI Isend/Irecv of dg_parallel.jl:66-182) --------------
+ * The host process group (torch.distributed / MPI) moves the opaque ids; the data path is NCCL. */
+int trixi_b200_comm_unique_id(void *id_out_128_bytes);
+int trixi_b200_comm_init(trixi_b200_handle *h, const void *id_128_bytes);
+
+/* ---- measurement helpers --------------------------------------------------------------------- */
+/* number of kernel launches issued by this handle since creation */
+int64_t trixi_b200_launch_count(const trixi_b200_handle *h);
+/* elapsed device milliseconds of the most recent trixi_b200_rhs/step_2n call, measured with CUDA
+ * events on the handle's stream (feeds the PerformanceCounter, semidiscretization_hyperbolic.jl:586-594) */
+int trixi_b200_last_elapsed_ms(trixi_b200_handle *h, float *ms_out);
+/* per-kernel-class accumulated device time (ms) and launch counts since the last reset; classes:
+ * 0 = surface-flux kernel, 1 = element kernel (volume+surface+jacobian+source+RK), 2 = max_dt,
+ * 3 = halo pack/unpack.  Enabling costs two event records per launch. */
+int trixi_b200_profile_enable(trixi_b200_handle *h, int on);
+int trixi_b200_profile_read(trixi_b200_handle *h, int kernel_class, double *ms_out, int64_t *launches_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TRIXI_B200_H */

@@ -1,0 +1,138 @@
+"""TEST INFRASTRUCTURE -- NOT PART OF THE PRODUCT.
+
+ctypes wrapper of ``oracle/libtrixi_oracle.so`` (the C restatement of the reference's CPU hot path,
+``oracle/trixi_oracle.c``).  Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU
+baseline / ``--impl reference`` legs may import this module.  ``OracleBackend`` exposes the same
+methods as ``trixi_b200.lib.B200Backend`` so the host-side integrator/callbacks can be driven by
+either; the product never constructs it.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "libtrixi_oracle.so")
+_lib = None
+
+
+def build(force=False):
+    src = os.path.join(_HERE, "trixi_oracle.c")
+    hdr = os.path.join(_HERE, "..", "include", "trixi_b200.h")
+    if (not force and os.path.exists(_LIB)
+            and os.path.getmtime(_LIB) >= max(os.path.getmtime(src), os.path.getmtime(hdr))):
+        return _LIB
+    subprocess.run(["make", "-C", _HERE, "-B", "libtrixi_oracle.so"], check=True, capture_output=True)
+    return _LIB
+
+
+def load():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(_LIB)
+        _lib.oracle_max_dt.restype = C.c_double
+        _lib.oracle_num_threads.restype = C.c_int
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+class OracleBackend:
+    U, DU, U_TMP = 0, 1, 2
+
+    def __init__(self, semi, num_threads=None):
+        self.lib = load()
+        if num_threads is not None:
+            self.lib.oracle_set_num_threads(int(num_threads))
+        self.semi = semi
+        self.holder = semi.descriptor()
+        self.desc = self.holder.desc
+        n = semi.u_length()
+        self.u_length = n
+        self.vec = [np.zeros(n), np.zeros(n), np.zeros(n)]
+        d = self.desc
+        nf = d.nnodes ** (d.ndims - 1)
+        self.interfaces_u = np.zeros(2 * d.nvars * nf * max(d.ninterfaces, 1))
+        self.boundaries_u = np.zeros(2 * d.nvars * nf * max(d.nboundaries, 1))
+        self.sfv = np.zeros(d.nvars * nf * 2 * d.ndims * d.nelements)
+        self.nrhs = 0
+
+    def num_threads(self):
+        return self.lib.oracle_num_threads()
+
+    # same surface as B200Backend ------------------------------------------------------------------
+    def upload(self, which, host):
+        self.vec[which][:] = np.asarray(host).ravel(order="F")
+
+    def download(self, which, host=None):
+        if host is None:
+            return self.vec[which].copy()
+        host[:] = self.vec[which]
+        return host
+
+    def synchronize(self):
+        pass
+
+    def rhs_arrays(self, du, u, t):
+        self.lib.oracle_rhs(self.holder.byref(), _p(du), _p(u), C.c_double(t), _p(self.interfaces_u),
+                            _p(self.boundaries_u), _p(self.sfv))
+        self.nrhs += 1
+
+    def rhs_host(self, du_host, u_host, t):
+        u = np.ascontiguousarray(np.asarray(u_host).ravel(order="K"))
+        du = np.empty_like(u)
+        self.rhs_arrays(du, u, float(t))
+        flat = du_host.ravel(order="K")
+        if not np.shares_memory(flat, du_host):
+            raise ValueError("du_host must be contiguous")
+        flat[:] = du
+
+    def rhs(self, t):
+        self.rhs_arrays(self.vec[1], self.vec[0], float(t))
+
+    def max_dt(self, t=0.0):
+        return self.lib.oracle_max_dt(self.holder.byref(), _p(self.vec[0]))
+
+    def step_2n(self, t, dt, a, b, c):
+        a, b, c = (np.ascontiguousarray(x, dtype=np.float64) for x in (a, b, c))
+        self.lib.oracle_step_2n(self.holder.byref(), _p(self.vec[0]), _p(self.vec[1]), _p(self.vec[2]),
+                                C.c_double(t), C.c_double(dt), _p(a), _p(b), _p(c), C.c_int(len(c)),
+                                _p(self.interfaces_u), _p(self.boundaries_u), _p(self.sfv))
+        self.nrhs += len(c)
+
+    # stage-level ------------------------------------------------------------------------------------
+    def calc_volume_integral(self):
+        self.lib.oracle_set_zero(self.holder.byref(), _p(self.vec[1]))
+        self.lib.oracle_calc_volume_integral(self.holder.byref(), _p(self.vec[1]), _p(self.vec[0]))
+
+    def calc_surface_fluxes(self, t):
+        h = self.holder.byref()
+        self.sfv[:] = np.nan
+        self.lib.oracle_prolong2interfaces(h, _p(self.interfaces_u), _p(self.vec[0]))
+        self.lib.oracle_calc_interface_flux(h, _p(self.sfv), _p(self.interfaces_u))
+        if self.desc.nboundaries > 0:
+            self.lib.oracle_prolong2boundaries(h, _p(self.boundaries_u), _p(self.vec[0]))
+            self.lib.oracle_calc_boundary_flux(h, _p(self.sfv), _p(self.boundaries_u), C.c_double(t))
+
+    def download_surface_flux_values(self, host):
+        host[:] = self.sfv
+        return host
+
+    def numflux(self, flux_id, u_ll, u_rr, orientation):
+        u_ll = np.ascontiguousarray(u_ll, dtype=np.float64)
+        u_rr = np.ascontiguousarray(u_rr, dtype=np.float64)
+        f = np.empty_like(u_ll)
+        self.lib.oracle_numflux(self.holder.byref(), C.c_int(flux_id), _p(u_ll), _p(u_rr), C.c_int(orientation), _p(f))
+        return f
+
+    def flux(self, u, orientation):
+        u = np.ascontiguousarray(u, dtype=np.float64)
+        f = np.empty_like(u)
+        self.lib.oracle_flux(self.holder.byref(), _p(u), C.c_int(orientation), _p(f))
+        return f

@@ -1,0 +1,800 @@
+/* TEST INFRASTRUCTURE -- NOT PART OF THE PRODUCT.
+ *
+ * CPU restatement (plain C + OpenMP) of the reference's DGSEM hot path, stage by stage, used only
+ *   - by tests/ as the parity oracle for the CUDA kernels,
+ *   - by __graft_entry__.smoke() as the checker,
+ *   - by bench.py's cpu_baseline / `--impl reference` leg (kind = "port").
+ * Nothing under trixi.jl_b200/ may import, link or call this file.
+ *
+ * The reference (Trixi.jl, pure Julia) cannot run in the build container or on the GPU box (no
+ * julia).  Parity is pinned instead against the reference's own golden L2/Linf vectors
+ * (test/test_tree_3d_euler.jl, test/test_tree_2d_advection.jl, ...): tests/test_oracle_golden.py runs
+ * this oracle through the full elixir configurations and reproduces them.
+ *
+ * Every function cites the reference file:line it follows (paths relative to the reference root).
+ * Arrays use the reference's layouts (column-major, variable fastest, 1-based int64 indices).
+ * Compiled with -ffp-contract=fast to mirror `@muladd` (dg_3d.jl:5).
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <float.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#include "../include/trixi_b200.h"
+
+#define MAXV 9
+
+typedef struct {
+    int nd, nv, id;
+    double gamma, inv_gm1;
+    double a[3];
+    double c_h;
+} eqn_t;
+
+static eqn_t make_eqn(const trixi_b200_desc *d) {
+    eqn_t e;
+    memset(&e, 0, sizeof(e));
+    e.nd = d->ndims;
+    e.nv = d->nvars;
+    e.id = d->equation;
+    if (e.id == TRIXI_B200_EQ_ADVECTION_2D || e.id == TRIXI_B200_EQ_ADVECTION_3D) {
+        e.a[0] = d->eq_params[0];
+        e.a[1] = d->eq_params[1];
+        e.a[2] = d->eq_params[2];
+    } else {
+        e.gamma = d->eq_params[0];
+        e.inv_gm1 = d->eq_params[1];
+        e.c_h = d->eq_params[2];
+    }
+    return e;
+}
+
+static inline int ipow(int b, int e) {
+    int r = 1;
+    for (int i = 0; i < e; ++i) r *= b;
+    return r;
+}
+
+/* ---- src/auxiliary/math.jl --------------------------------------------------------------------- */
+/* ln_mean math.jl:198-210 */
+static inline double ln_mean(double x, double y) {
+    const double epsilon_f2 = 1.0e-4;
+    double f2 = (x * (x - 2 * y) + y * y) / (x * (x + 2 * y) + y * y);
+    if (f2 < epsilon_f2) {
+        /* @evalpoly(f2, 2, 2/3, 2/5, 2/7): Horner with muladd */
+        double p = fma(f2, fma(f2, fma(f2, 2.0 / 7.0, 2.0 / 5.0), 2.0 / 3.0), 2.0);
+        return (x + y) / p;
+    } else {
+        return (y - x) / log(y / x);
+    }
+}
+/* inv_ln_mean math.jl:238-250 */
+static inline double inv_ln_mean(double x, double y) {
+    const double epsilon_f2 = 1.0e-4;
+    double f2 = (x * (x - 2 * y) + y * y) / (x * (x + 2 * y) + y * y);
+    if (f2 < epsilon_f2) {
+        double p = fma(f2, fma(f2, fma(f2, 2.0 / 7.0, 2.0 / 5.0), 2.0 / 3.0), 2.0);
+        return p / (x + y);
+    } else {
+        return log(y / x) / (y - x);
+    }
+}
+
+/* ---- compressible Euler 2D/3D (compressible_euler_3d.jl, compressible_euler_2d.jl) -------------- */
+/* cons2prim compressible_euler_3d.jl:1783-1793 / compressible_euler_2d.jl:2038-2047;
+ * prim = (rho, v[0..nd-1], p) */
+static inline void euler_cons2prim(const eqn_t *eq, const double *u, double *rho, double *v, double *p) {
+    int nd = eq->nd;
+    *rho = u[0];
+    double kin = 0.0;
+    for (int d = 0; d < nd; ++d) {
+        v[d] = u[1 + d] / u[0];
+        kin += u[1 + d] * v[d];
+    }
+    *p = (eq->gamma - 1) * (u[nd + 1] - 0.5 * kin);
+}
+
+/* flux(u, orientation, eq) compressible_euler_3d.jl:420-447 */
+static inline void euler_flux(const eqn_t *eq, const double *u, int o, double *f) {
+    int nd = eq->nd;
+    double rho, v[3], p;
+    euler_cons2prim(eq, u, &rho, v, &p);
+    double rv = u[1 + o];
+    f[0] = rv;
+    for (int d = 0; d < nd; ++d) f[1 + d] = rv * v[d];
+    f[1 + o] += p;
+    f[nd + 1] = (u[nd + 1] + p) * v[o];
+}
+
+/* flux_ranocha compressible_euler_3d.jl:746-793 */
+static inline void euler_flux_ranocha(const eqn_t *eq, const double *ul, const double *ur, int o, double *f) {
+    int nd = eq->nd;
+    double rho_ll, v_ll[3], p_ll, rho_rr, v_rr[3], p_rr;
+    euler_cons2prim(eq, ul, &rho_ll, v_ll, &p_ll);
+    euler_cons2prim(eq, ur, &rho_rr, v_rr, &p_rr);
+    double rho_mean = ln_mean(rho_ll, rho_rr);
+    double inv_rho_p_mean = p_ll * p_rr * inv_ln_mean(rho_ll * p_rr, rho_rr * p_ll);
+    double v_avg[3], vsq = 0.0;
+    for (int d = 0; d < nd; ++d) {
+        v_avg[d] = 0.5 * (v_ll[d] + v_rr[d]);
+        vsq += v_ll[d] * v_rr[d];
+    }
+    double p_avg = 0.5 * (p_ll + p_rr);
+    double velocity_square_avg = 0.5 * vsq;
+    double f1 = rho_mean * v_avg[o];
+    f[0] = f1;
+    for (int d = 0; d < nd; ++d) f[1 + d] = f1 * v_avg[d];
+    f[1 + o] += p_avg;
+    f[nd + 1] = f1 * (velocity_square_avg + inv_rho_p_mean * eq->inv_gm1) +
+                0.5 * (p_ll * v_rr[o] + p_rr * v_ll[o]);
+}
+
+/* flux_shima_etal compressible_euler_3d.jl:473-510 */
+static inline void euler_flux_shima(const eqn_t *eq, const double *ul, const double *ur, int o, double *f) {
+    int nd = eq->nd;
+    double rho_ll, v_ll[3], p_ll, rho_rr, v_rr[3], p_rr;
+    euler_cons2prim(eq, ul, &rho_ll, v_ll, &p_ll);
+    euler_cons2prim(eq, ur, &rho_rr, v_rr, &p_rr);
+    double rho_avg = 0.5 * (rho_ll + rho_rr), p_avg = 0.5 * (p_ll + p_rr);
+    double v_avg[3], kin = 0.0;
+    for (int d = 0; d < nd; ++d) {
+        v_avg[d] = 0.5 * (v_ll[d] + v_rr[d]);
+        kin += v_ll[d] * v_rr[d];
+    }
+    double kin_avg = 0.5 * kin;
+    double pv_avg = 0.5 * (p_ll * v_rr[o] + p_rr * v_ll[o]);
+    double f1 = rho_avg * v_avg[o];
+    f[0] = f1;
+    for (int d = 0; d < nd; ++d) f[1 + d] = f1 * v_avg[d];
+    f[1 + o] += p_avg;
+    f[nd + 1] = p_avg * v_avg[o] * eq->inv_gm1 + f1 * kin_avg + pv_avg;
+}
+
+/* flux_kennedy_gruber compressible_euler_3d.jl:560-600 */
+static inline void euler_flux_kennedy_gruber(const eqn_t *eq, const double *ul, const double *ur, int o,
+                                             double *f) {
+    int nd = eq->nd;
+    double rho_ll, v_ll[3], p_ll, rho_rr, v_rr[3], p_rr;
+    euler_cons2prim(eq, ul, &rho_ll, v_ll, &p_ll);
+    euler_cons2prim(eq, ur, &rho_rr, v_rr, &p_rr);
+    double rho_avg = 0.5 * (rho_ll + rho_rr), p_avg = 0.5 * (p_ll + p_rr);
+    double v_avg[3];
+    for (int d = 0; d < nd; ++d) v_avg[d] = 0.5 * (v_ll[d] + v_rr[d]);
+    double e_avg = 0.5 * (ul[nd + 1] / rho_ll + ur[nd + 1] / rho_rr);
+    double f1 = rho_avg * v_avg[o];
+    f[0] = f1;
+    for (int d = 0; d < nd; ++d) f[1 + d] = f1 * v_avg[d];
+    f[1 + o] += p_avg;
+    f[nd + 1] = (rho_avg * e_avg + p_avg) * v_avg[o];
+}
+
+/* flux_chandrashekar compressible_euler_3d.jl:639-690 */
+static inline void euler_flux_chandrashekar(const eqn_t *eq, const double *ul, const double *ur, int o,
+                                            double *f) {
+    int nd = eq->nd;
+    double rho_ll, v_ll[3], p_ll, rho_rr, v_rr[3], p_rr;
+    euler_cons2prim(eq, ul, &rho_ll, v_ll, &p_ll);
+    euler_cons2prim(eq, ur, &rho_rr, v_rr, &p_rr);
+    double beta_ll = 0.5 * rho_ll / p_ll, beta_rr = 0.5 * rho_rr / p_rr;
+    double kl = 0.0, kr = 0.0, v_avg[3];
+    for (int d = 0; d < nd; ++d) {
+        kl += v_ll[d] * v_ll[d];
+        kr += v_rr[d] * v_rr[d];
+        v_avg[d] = 0.5 * (v_ll[d] + v_rr[d]);
+    }
+    double specific_kin_ll = 0.5 * kl, specific_kin_rr = 0.5 * kr;
+    double rho_avg = 0.5 * (rho_ll + rho_rr);
+    double rho_mean = ln_mean(rho_ll, rho_rr);
+    double beta_mean = ln_mean(beta_ll, beta_rr);
+    double beta_avg = 0.5 * (beta_ll + beta_rr);
+    double p_mean = 0.5 * rho_avg / beta_avg;
+    double velocity_square_avg = specific_kin_ll + specific_kin_rr;
+    double f1 = rho_mean * v_avg[o];
+    f[0] = f1;
+    for (int d = 0; d < nd; ++d) f[1 + d] = f1 * v_avg[d];
+    f[1 + o] += p_mean;
+    double s = f1 * 0.5 * (1 / (eq->gamma - 1) / beta_mean - velocity_square_avg);
+    for (int d = 0; d < nd; ++d) s += f[1 + d] * v_avg[d];
+    f[nd + 1] = s;
+}
+
+/* max_abs_speed_naive compressible_euler_3d.jl:1112-1133; max_abs_speed :1156-1177 */
+static inline double euler_max_abs_speed(const eqn_t *eq, const double *ul, const double *ur, int o, int naive) {
+    double rho_ll, v_ll[3], p_ll, rho_rr, v_rr[3], p_rr;
+    euler_cons2prim(eq, ul, &rho_ll, v_ll, &p_ll);
+    euler_cons2prim(eq, ur, &rho_rr, v_rr, &p_rr);
+    double c_ll = sqrt(eq->gamma * p_ll / rho_ll);
+    double c_rr = sqrt(eq->gamma * p_rr / rho_rr);
+    if (naive) return fmax(fabs(v_ll[o]), fabs(v_rr[o])) + fmax(c_ll, c_rr);
+    return fmax(fabs(v_ll[o]) + c_ll, fabs(v_rr[o]) + c_rr);
+}
+
+/* min_max_speed_davis compressible_euler_3d.jl:1240-1261; min_max_speed_naive :1202-1220 */
+static inline void euler_min_max_speed(const eqn_t *eq, const double *ul, const double *ur, int o, int naive,
+                                       double *lmin, double *lmax) {
+    double rho_ll, v_ll[3], p_ll, rho_rr, v_rr[3], p_rr;
+    euler_cons2prim(eq, ul, &rho_ll, v_ll, &p_ll);
+    euler_cons2prim(eq, ur, &rho_rr, v_rr, &p_rr);
+    double c_ll = sqrt(eq->gamma * p_ll / rho_ll);
+    double c_rr = sqrt(eq->gamma * p_rr / rho_rr);
+    if (naive) {
+        *lmin = v_ll[o] - c_ll;
+        *lmax = v_rr[o] + c_rr;
+    } else {
+        *lmin = fmin(v_ll[o] - c_ll, v_rr[o] - c_rr);
+        *lmax = fmax(v_ll[o] + c_ll, v_rr[o] + c_rr);
+    }
+}
+
+/* ---- linear scalar advection (linear_scalar_advection_2d.jl:221-246) ----------------------------- */
+static inline void adv_flux(const eqn_t *eq, const double *u, int o, double *f) { f[0] = eq->a[o] * u[0]; }
+
+/* ---- generic pointwise dispatch --------------------------------------------------------------------- */
+static inline int is_euler(const eqn_t *eq) {
+    return eq->id == TRIXI_B200_EQ_EULER_2D || eq->id == TRIXI_B200_EQ_EULER_3D;
+}
+
+static inline void phys_flux(const eqn_t *eq, const double *u, int o, double *f) {
+    if (is_euler(eq))
+        euler_flux(eq, u, o, f);
+    else
+        adv_flux(eq, u, o, f);
+}
+
+static inline double max_abs_speed_disp(const eqn_t *eq, const double *ul, const double *ur, int o, int naive) {
+    if (is_euler(eq)) return euler_max_abs_speed(eq, ul, ur, o, naive);
+    /* advection: max_abs_speed falls back to max_abs_speed_naive = |a| (numerical_fluxes.jl:219-225) */
+    return fabs(eq->a[o]);
+}
+
+/* two-point numerical flux with an integer orientation (o is 0-based here) */
+static void numflux(const eqn_t *eq, int flux_id, const double *ul, const double *ur, int o, double *f) {
+    int nv = eq->nv;
+    switch (flux_id) {
+    case TRIXI_B200_FLUX_CENTRAL: { /* numerical_fluxes.jl:17-25 */
+        double fl[MAXV], fr[MAXV];
+        phys_flux(eq, ul, o, fl);
+        phys_flux(eq, ur, o, fr);
+        for (int v = 0; v < nv; ++v) f[v] = 0.5 * (fl[v] + fr[v]);
+        return;
+    }
+    case TRIXI_B200_FLUX_LLF:
+    case TRIXI_B200_FLUX_LLF_NAIVE: { /* FluxPlusDissipation :37-45 + DissipationLocalLaxFriedrichs :172-178 */
+        double fl[MAXV], fr[MAXV];
+        phys_flux(eq, ul, o, fl);
+        phys_flux(eq, ur, o, fr);
+        double lam = max_abs_speed_disp(eq, ul, ur, o, flux_id == TRIXI_B200_FLUX_LLF_NAIVE);
+        for (int v = 0; v < nv; ++v) f[v] = 0.5 * (fl[v] + fr[v]) + (-0.5 * lam * (ur[v] - ul[v]));
+        return;
+    }
+    case TRIXI_B200_FLUX_HLL_DAVIS:
+    case TRIXI_B200_FLUX_HLL_NAIVE: { /* FluxHLL numerical_fluxes.jl:422-440 */
+        double lmin, lmax;
+        euler_min_max_speed(eq, ul, ur, o, flux_id == TRIXI_B200_FLUX_HLL_NAIVE, &lmin, &lmax);
+        if (lmin >= 0 && lmax >= 0) {
+            phys_flux(eq, ul, o, f);
+        } else if (lmax <= 0 && lmin <= 0) {
+            phys_flux(eq, ur, o, f);
+        } else {
+            double fl[MAXV], fr[MAXV];
+            phys_flux(eq, ul, o, fl);
+            phys_flux(eq, ur, o, fr);
+            double inv = 1.0 / (lmax - lmin);
+            double factor_ll = lmax * inv, factor_rr = lmin * inv, factor_diss = lmin * lmax * inv;
+            for (int v = 0; v < nv; ++v)
+                f[v] = factor_ll * fl[v] - factor_rr * fr[v] + factor_diss * (ur[v] - ul[v]);
+        }
+        return;
+    }
+    case TRIXI_B200_FLUX_RANOCHA:
+    case TRIXI_B200_FLUX_RANOCHA_TURBO: /* turbo computes the same flux with hoisted logs; oracle = generic */
+        euler_flux_ranocha(eq, ul, ur, o, f);
+        return;
+    case TRIXI_B200_FLUX_SHIMA_ETAL:
+        euler_flux_shima(eq, ul, ur, o, f);
+        return;
+    case TRIXI_B200_FLUX_KENNEDY_GRUBER:
+        euler_flux_kennedy_gruber(eq, ul, ur, o, f);
+        return;
+    case TRIXI_B200_FLUX_CHANDRASHEKAR:
+        euler_flux_chandrashekar(eq, ul, ur, o, f);
+        return;
+    case TRIXI_B200_FLUX_GODUNOV: /* linear_scalar_advection_2d.jl:248-260 */
+        f[0] = eq->a[o] >= 0 ? eq->a[o] * ul[0] : eq->a[o] * ur[0];
+        return;
+    default:
+        for (int v = 0; v < nv; ++v) f[v] = NAN;
+    }
+}
+
+/* ---- initial conditions used as Dirichlet data ----------------------------------------------------- */
+static void ic_eval(const eqn_t *eq, int ic, const double *x, double t, double *u) {
+    int nd = eq->nd;
+    if (is_euler(eq)) {
+        switch (ic) {
+        case TRIXI_B200_IC_CONSTANT: /* compressible_euler_3d.jl:78-86, _2d.jl:71-78 */
+            u[0] = 1.0;
+            u[1] = 0.1;
+            u[2] = -0.2;
+            if (nd == 3) u[3] = 0.7;
+            u[nd + 1] = 10.0;
+            return;
+        case TRIXI_B200_IC_CONVERGENCE_TEST: { /* compressible_euler_3d.jl:94-111 */
+            double s = 0.0;
+            for (int d = 0; d < nd; ++d) s += x[d];
+            double omega = 2 * M_PI * 0.5;
+            double ini = 2 + 0.1 * sin(omega * (s - t));
+            for (int v = 0; v <= nd; ++v) u[v] = ini;
+            u[nd + 1] = ini * ini;
+            return;
+        }
+        default:
+            break;
+        }
+    } else if (ic == TRIXI_B200_IC_CONVERGENCE_TEST) { /* linear_scalar_advection_2d.jl:67-80 */
+        double s = 0.0;
+        for (int d = 0; d < nd; ++d) s += x[d] - eq->a[d] * t;
+        u[0] = 1 + 0.5 * sin(2 * M_PI * 0.5 * s);
+        return;
+    } else if (ic == TRIXI_B200_IC_CONSTANT) {
+        u[0] = 2.0;
+        return;
+    }
+    for (int v = 0; v < eq->nv; ++v) u[v] = NAN;
+}
+
+/* boundary_condition_slip_wall compressible_euler_3d.jl:315-366 (normal version) specialised to the
+ * unit normal of `orientation` as done by :374-389, then :398-414 for the sign by direction */
+static void euler_slip_wall_normal(const eqn_t *eq, const double *u_inner, const double *nrm, double *f) {
+    int nd = eq->nd;
+    double norm_ = 0.0;
+    for (int d = 0; d < nd; ++d) norm_ += nrm[d] * nrm[d];
+    norm_ = sqrt(norm_);
+    double normal[3] = {0, 0, 0};
+    for (int d = 0; d < nd; ++d) normal[d] = nrm[d] / norm_;
+    /* rotate_to_x: only the normal velocity and rho, p are needed */
+    double rho = u_inner[0];
+    double rv_n = 0.0;
+    for (int d = 0; d < nd; ++d) rv_n += normal[d] * u_inner[1 + d];
+    /* u_local = (rho, rho v_n, rho v_t1, rho v_t2, E): kinetic energy is rotation invariant */
+    double kin = 0.0;
+    for (int d = 0; d < nd; ++d) kin += u_inner[1 + d] * (u_inner[1 + d] / rho);
+    double v_normal = rv_n / rho;
+    double p_local = (eq->gamma - 1) * (u_inner[nd + 1] - 0.5 * kin);
+    double p_star;
+    if (v_normal <= 0) {
+        double sound_speed = sqrt(eq->gamma * p_local / rho);
+        double base = 1 + 0.5 * (eq->gamma - 1) * v_normal / sound_speed;
+        if (base >= 0)
+            p_star = p_local * pow(base, 2 * eq->gamma * eq->inv_gm1);
+        else
+            p_star = 0.0;
+    } else {
+        double A = 2 / ((eq->gamma + 1) * rho);
+        double B = p_local * (eq->gamma - 1) / (eq->gamma + 1);
+        p_star = p_local + 0.5 * v_normal / A * (v_normal + sqrt(v_normal * v_normal + 4 * A * (p_local + B)));
+    }
+    f[0] = 0.0;
+    for (int d = 0; d < nd; ++d) f[1 + d] = p_star * normal[d] * norm_;
+    f[nd + 1] = 0.0;
+}
+
+/* boundary flux for TreeMesh: bc(u_inner, orientation, direction, x, t, surface_flux, eq)
+ * (dg_3d.jl:757); direction is 1-based like the reference, o 0-based */
+static void boundary_flux(const eqn_t *eq, int bc, int ic, int surface_flux, const double *u_inner, int o,
+                          int direction, const double *x, double t, double *f) {
+    if (bc == TRIXI_B200_BC_DIRICHLET) { /* equations.jl:164-183 */
+        double ub[MAXV];
+        ic_eval(eq, ic, x, t, ub);
+        if (direction % 2 == 0)
+            numflux(eq, surface_flux, u_inner, ub, o, f);
+        else
+            numflux(eq, surface_flux, ub, u_inner, o, f);
+    } else if (bc == TRIXI_B200_BC_SLIP_WALL) { /* compressible_euler_3d.jl:374-414 */
+        double nrm[3] = {0, 0, 0};
+        nrm[o] = 1.0;
+        if (direction % 2 == 1) {
+            double mn[3] = {-nrm[0], -nrm[1], -nrm[2]};
+            euler_slip_wall_normal(eq, u_inner, mn, f);
+            for (int v = 0; v < eq->nv; ++v) f[v] = -f[v];
+        } else {
+            euler_slip_wall_normal(eq, u_inner, nrm, f);
+        }
+    } else {
+        for (int v = 0; v < eq->nv; ++v) f[v] = NAN;
+    }
+}
+
+/* ---- source terms ---------------------------------------------------------------------------------- */
+static void source_terms(const eqn_t *eq, int src, const double *u, const double *x, double t, double *du) {
+    int nd = eq->nd;
+    (void)u;
+    double s = 0.0;
+    for (int d = 0; d < nd; ++d) s += x[d];
+    switch (src) {
+    case TRIXI_B200_SRC_CONVERGENCE_TEST: {
+        double omega = 2 * M_PI * 0.5, g = eq->gamma;
+        double si = sin(omega * (s - t)), co = cos(omega * (s - t));
+        double rho = 2 + 0.1 * si;
+        double rho_x = omega * 0.1 * co;
+        if (nd == 3) { /* compressible_euler_3d.jl:127-153 */
+            double tmp = (2 * rho - 1.5) * (g - 1);
+            du[0] = 2 * rho_x;
+            du[1] = du[2] = du[3] = rho_x * (2 + tmp);
+            du[4] = rho_x * (4 * rho + 3 * tmp);
+        } else { /* compressible_euler_2d.jl:120-145 */
+            double tmp = (2 * rho - 1) * (g - 1);
+            du[0] = rho_x;
+            du[1] = du[2] = rho_x * (1 + tmp);
+            du[3] = 2 * rho_x * (rho + tmp);
+        }
+        return;
+    }
+    case TRIXI_B200_SRC_EOC_TEST_EULER: {
+        /* sincospi(x) */
+        double r = fmod(s - t, 2.0);
+        double si = sin(M_PI * r), co = cos(M_PI * r);
+        double rhox = 0.1 * M_PI * co, rho = 2 + 0.1 * si;
+        if (nd == 3) { /* compressible_euler_3d.jl:265-284 */
+            double C_grav = -4.0 * 1 / (3 * M_PI);
+            du[0] = rhox * 2;
+            du[1] = du[2] = du[3] = rhox * (2 - C_grav * rho);
+            du[4] = rhox * (3 - 5 * C_grav * rho);
+        } else { /* compressible_euler_2d.jl:272-292 */
+            double C_grav = -2.0 * 1 / M_PI;
+            du[0] = rhox;
+            du[1] = du[2] = rhox * (1 - C_grav * rho);
+            du[3] = rhox * (1 - 3 * C_grav * rho);
+        }
+        return;
+    }
+    default:
+        for (int v = 0; v < eq->nv; ++v) du[v] = 0.0;
+    }
+}
+
+/* ---- index helpers ------------------------------------------------------------------------------------ */
+/* volume node (0-based linear) of face node (a, b) on the layer `s` normal to orientation o
+ * (face node order: x-faces (j,k), y-faces (i,k), z-faces (i,j), dg_3d.jl:540-563) */
+static inline int face_to_volume_node(int nd, int n, int o, int s, int a, int b) {
+    if (nd == 2) return o == 0 ? s + n * a : a + n * s;
+    if (o == 0) return s + n * (a + n * b);
+    if (o == 1) return a + n * (s + n * b);
+    return a + n * (b + n * s);
+}
+
+/* ---- stages: src/solvers/dgsem_tree/dg_3d.jl, dg_2d.jl --------------------------------------------- */
+/* set_zero! solvers.jl:8-25 */
+void oracle_set_zero(const trixi_b200_desc *d, double *du) {
+    int64_t len = (int64_t)d->nvars * ipow(d->nnodes, d->ndims) * d->nelements;
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < len; ++i) du[i] = 0.0;
+}
+
+/* weak_form_kernel! dg_3d.jl:133-164 / dg_2d.jl:195-221 */
+static void weak_form_kernel(const trixi_b200_desc *d, const eqn_t *eq, double *du, const double *u) {
+    int n = d->nnodes, nd = d->ndims, nv = d->nvars;
+    int n3 = nd == 3 ? n : 1;
+    const double *Dhat = d->derivative_hat;
+    for (int k = 0; k < n3; ++k)
+        for (int j = 0; j < n; ++j)
+            for (int i = 0; i < n; ++i) {
+                const double *un = u + (int64_t)nv * (i + n * (j + n * k));
+                double f[MAXV];
+                phys_flux(eq, un, 0, f);
+                for (int ii = 0; ii < n; ++ii) {
+                    double w = Dhat[ii + n * i];
+                    double *t = du + (int64_t)nv * (ii + n * (j + n * k));
+                    for (int v = 0; v < nv; ++v) t[v] = t[v] + w * f[v];
+                }
+                phys_flux(eq, un, 1, f);
+                for (int jj = 0; jj < n; ++jj) {
+                    double w = Dhat[jj + n * j];
+                    double *t = du + (int64_t)nv * (i + n * (jj + n * k));
+                    for (int v = 0; v < nv; ++v) t[v] = t[v] + w * f[v];
+                }
+                if (nd == 3) {
+                    phys_flux(eq, un, 2, f);
+                    for (int kk = 0; kk < n; ++kk) {
+                        double w = Dhat[kk + n * k];
+                        double *t = du + (int64_t)nv * (i + n * (j + n * kk));
+                        for (int v = 0; v < nv; ++v) t[v] = t[v] + w * f[v];
+                    }
+                }
+            }
+}
+
+/* flux_differencing_kernel! dg_3d.jl:166-214 / dg_2d.jl:223-259 */
+static void flux_differencing_kernel(const trixi_b200_desc *d, const eqn_t *eq, double *du, const double *u) {
+    int n = d->nnodes, nd = d->ndims, nv = d->nvars;
+    int n3 = nd == 3 ? n : 1;
+    const double *Ds = d->derivative_split;
+    int vf = d->volume_flux;
+    for (int k = 0; k < n3; ++k)
+        for (int j = 0; j < n; ++j)
+            for (int i = 0; i < n; ++i) {
+                int64_t node = i + n * (j + n * k);
+                const double *un = u + nv * node;
+                double f[MAXV];
+                for (int ii = i + 1; ii < n; ++ii) {
+                    int64_t node2 = ii + n * (j + n * k);
+                    numflux(eq, vf, un, u + nv * node2, 0, f);
+                    double w1 = Ds[i + n * ii], w2 = Ds[ii + n * i];
+                    for (int v = 0; v < nv; ++v) du[nv * node + v] = du[nv * node + v] + w1 * f[v];
+                    for (int v = 0; v < nv; ++v) du[nv * node2 + v] = du[nv * node2 + v] + w2 * f[v];
+                }
+                for (int jj = j + 1; jj < n; ++jj) {
+                    int64_t node2 = i + n * (jj + n * k);
+                    numflux(eq, vf, un, u + nv * node2, 1, f);
+                    double w1 = Ds[j + n * jj], w2 = Ds[jj + n * j];
+                    for (int v = 0; v < nv; ++v) du[nv * node + v] = du[nv * node + v] + w1 * f[v];
+                    for (int v = 0; v < nv; ++v) du[nv * node2 + v] = du[nv * node2 + v] + w2 * f[v];
+                }
+                if (nd == 3)
+                    for (int kk = k + 1; kk < n; ++kk) {
+                        int64_t node2 = i + n * (j + n * kk);
+                        numflux(eq, vf, un, u + nv * node2, 2, f);
+                        double w1 = Ds[k + n * kk], w2 = Ds[kk + n * k];
+                        for (int v = 0; v < nv; ++v) du[nv * node + v] = du[nv * node + v] + w1 * f[v];
+                        for (int v = 0; v < nv; ++v) du[nv * node2 + v] = du[nv * node2 + v] + w2 * f[v];
+                    }
+            }
+}
+
+/* calc_volume_integral! calc_volume_integral.jl:180-191 (+ dispatch :11-33) */
+void oracle_calc_volume_integral(const trixi_b200_desc *d, double *du, const double *u) {
+    eqn_t eq = make_eqn(d);
+    int64_t esz = (int64_t)d->nvars * ipow(d->nnodes, d->ndims);
+#pragma omp parallel for schedule(static)
+    for (int64_t e = 0; e < d->nelements; ++e) {
+        if (d->volume_integral == TRIXI_B200_VOLINT_WEAK_FORM)
+            weak_form_kernel(d, &eq, du + e * esz, u + e * esz);
+        else
+            flux_differencing_kernel(d, &eq, du + e * esz, u + e * esz);
+    }
+}
+
+/* prolong2interfaces! dg_3d.jl:530-567 / dg_2d.jl:515-541; interfaces_u[2, nv, nf, I] */
+void oracle_prolong2interfaces(const trixi_b200_desc *d, double *iu, const double *u) {
+    int n = d->nnodes, nd = d->ndims, nv = d->nvars;
+    int nf = ipow(n, nd - 1), nb = nd == 3 ? n : 1;
+    int64_t esz = (int64_t)nv * ipow(n, nd);
+#pragma omp parallel for schedule(static)
+    for (int64_t I = 0; I < d->ninterfaces; ++I) {
+        int64_t left = d->interface_neighbor_ids[2 * I] - 1, right = d->interface_neighbor_ids[2 * I + 1] - 1;
+        int o = (int)d->interface_orientations[I] - 1;
+        for (int b = 0; b < nb; ++b)
+            for (int a = 0; a < n; ++a) {
+                int fn = a + n * b;
+                int nl = face_to_volume_node(nd, n, o, n - 1, a, b);
+                int nr = face_to_volume_node(nd, n, o, 0, a, b);
+                for (int v = 0; v < nv; ++v) {
+                    iu[0 + 2 * (v + nv * (fn + (int64_t)nf * I))] = u[left * esz + nv * nl + v];
+                    iu[1 + 2 * (v + nv * (fn + (int64_t)nf * I))] = u[right * esz + nv * nr + v];
+                }
+            }
+    }
+}
+
+/* calc_interface_flux! dg_3d.jl:569-602 / dg_2d.jl:543-576; sfv[nv, nf, 2*nd, nelem] */
+void oracle_calc_interface_flux(const trixi_b200_desc *d, double *sfv, const double *iu) {
+    eqn_t eq = make_eqn(d);
+    int n = d->nnodes, nd = d->ndims, nv = d->nvars;
+    int nf = ipow(n, nd - 1);
+    int64_t fsz = (int64_t)nv * nf * 2 * nd;
+#pragma omp parallel for schedule(static)
+    for (int64_t I = 0; I < d->ninterfaces; ++I) {
+        int64_t left = d->interface_neighbor_ids[2 * I] - 1, right = d->interface_neighbor_ids[2 * I + 1] - 1;
+        int o = (int)d->interface_orientations[I] - 1;
+        int left_direction = 2 * (o + 1) - 1, right_direction = 2 * (o + 1) - 2; /* 0-based directions */
+        for (int fn = 0; fn < nf; ++fn) {
+            double ul[MAXV], ur[MAXV], f[MAXV];
+            for (int v = 0; v < nv; ++v) {
+                ul[v] = iu[0 + 2 * (v + nv * (fn + (int64_t)nf * I))];
+                ur[v] = iu[1 + 2 * (v + nv * (fn + (int64_t)nf * I))];
+            }
+            numflux(&eq, d->surface_flux, ul, ur, o, f);
+            for (int v = 0; v < nv; ++v) {
+                sfv[left * fsz + v + nv * (fn + nf * left_direction)] = f[v];
+                sfv[right * fsz + v + nv * (fn + nf * right_direction)] = f[v];
+            }
+        }
+    }
+}
+
+/* prolong2boundaries! dg_3d.jl:651-701; boundaries_u[2, nv, nf, B] */
+void oracle_prolong2boundaries(const trixi_b200_desc *d, double *bu, const double *u) {
+    int n = d->nnodes, nd = d->ndims, nv = d->nvars;
+    int nf = ipow(n, nd - 1), nb = nd == 3 ? n : 1;
+    int64_t esz = (int64_t)nv * ipow(n, nd);
+#pragma omp parallel for schedule(static)
+    for (int64_t B = 0; B < d->nboundaries; ++B) {
+        int64_t element = d->boundary_neighbor_ids[B] - 1;
+        int o = (int)d->boundary_orientations[B] - 1;
+        int side = (int)d->boundary_neighbor_sides[B];
+        for (int b = 0; b < nb; ++b)
+            for (int a = 0; a < n; ++a) {
+                int fn = a + n * b;
+                int vn = face_to_volume_node(nd, n, o, side == 1 ? n - 1 : 0, a, b);
+                for (int v = 0; v < nv; ++v)
+                    bu[(side == 1 ? 0 : 1) + 2 * (v + nv * (fn + (int64_t)nf * B))] = u[element * esz + nv * vn + v];
+            }
+    }
+}
+
+/* calc_boundary_flux! dg_3d.jl:703-768 */
+void oracle_calc_boundary_flux(const trixi_b200_desc *d, double *sfv, const double *bu, double t) {
+    eqn_t eq = make_eqn(d);
+    int n = d->nnodes, nd = d->ndims, nv = d->nvars;
+    int nf = ipow(n, nd - 1);
+    int64_t fsz = (int64_t)nv * nf * 2 * nd;
+    int64_t first = 0;
+    for (int direction = 1; direction <= 2 * nd; ++direction) {
+        int64_t cnt = d->n_boundaries_per_direction[direction - 1];
+        int bc = d->boundary_conditions[direction - 1], ic = d->boundary_ic[direction - 1];
+#pragma omp parallel for schedule(static)
+        for (int64_t B = first; B < first + cnt; ++B) {
+            int64_t neighbor = d->boundary_neighbor_ids[B] - 1;
+            int o = (int)d->boundary_orientations[B] - 1;
+            int side = (int)d->boundary_neighbor_sides[B];
+            for (int fn = 0; fn < nf; ++fn) {
+                double ui[MAXV], f[MAXV];
+                for (int v = 0; v < nv; ++v) ui[v] = bu[(side == 1 ? 0 : 1) + 2 * (v + nv * (fn + (int64_t)nf * B))];
+                const double *x = d->boundary_node_coordinates + (int64_t)nd * (fn + (int64_t)nf * B);
+                boundary_flux(&eq, bc, ic, d->surface_flux, ui, o, direction, x, t, f);
+                for (int v = 0; v < nv; ++v) sfv[neighbor * fsz + v + nv * (fn + nf * (direction - 1))] = f[v];
+            }
+        }
+        first += cnt;
+    }
+}
+
+/* calc_surface_integral! dg_3d.jl:1337-1394 / dg_2d.jl:1245-1300 */
+void oracle_calc_surface_integral(const trixi_b200_desc *d, double *du, const double *sfv) {
+    int n = d->nnodes, nd = d->ndims, nv = d->nvars;
+    int nf = ipow(n, nd - 1), nb = nd == 3 ? n : 1;
+    int64_t esz = (int64_t)nv * ipow(n, nd), fsz = (int64_t)nv * nf * 2 * nd;
+    double factor = d->inverse_weights[0];
+#pragma omp parallel for schedule(static)
+    for (int64_t e = 0; e < d->nelements; ++e) {
+        double *due = du + e * esz;
+        const double *s = sfv + e * fsz;
+        for (int m = 0; m < nb; ++m)
+            for (int l = 0; l < n; ++l) {
+                int fn = l + n * m;
+                for (int v = 0; v < nv; ++v) {
+                    for (int o = 0; o < nd; ++o) {
+                        int lo = face_to_volume_node(nd, n, o, 0, l, m);
+                        int hi = face_to_volume_node(nd, n, o, n - 1, l, m);
+                        due[nv * lo + v] = due[nv * lo + v] - s[v + nv * (fn + nf * (2 * o))] * factor;
+                        due[nv * hi + v] = due[nv * hi + v] + s[v + nv * (fn + nf * (2 * o + 1))] * factor;
+                    }
+                }
+            }
+    }
+}
+
+/* apply_jacobian! dg_3d.jl:1396-1414 */
+void oracle_apply_jacobian(const trixi_b200_desc *d, double *du) {
+    int64_t esz = (int64_t)d->nvars * ipow(d->nnodes, d->ndims);
+#pragma omp parallel for schedule(static)
+    for (int64_t e = 0; e < d->nelements; ++e) {
+        double factor = -d->inverse_jacobian[e];
+        for (int64_t i = 0; i < esz; ++i) du[e * esz + i] *= factor;
+    }
+}
+
+/* calc_sources! dg_3d.jl:1417-1437 */
+void oracle_calc_sources(const trixi_b200_desc *d, double *du, const double *u, double t) {
+    if (d->source_terms == TRIXI_B200_SRC_NONE) return;
+    eqn_t eq = make_eqn(d);
+    int nv = d->nvars, nd = d->ndims;
+    int64_t nn = ipow(d->nnodes, nd);
+#pragma omp parallel for schedule(static)
+    for (int64_t e = 0; e < d->nelements; ++e)
+        for (int64_t q = 0; q < nn; ++q) {
+            double s[MAXV];
+            source_terms(&eq, d->source_terms, u + nv * (q + nn * e), d->node_coordinates + nd * (q + nn * e), t, s);
+            for (int v = 0; v < nv; ++v) du[nv * (q + nn * e) + v] += s[v];
+        }
+}
+
+/* rhs_hyperbolic! dgsem_tree/dg_2d.jl:113-186.  Work arrays: interfaces_u [2,nv,nf,I],
+ * boundaries_u [2,nv,nf,B], sfv [nv,nf,2nd,nelem] (owned by the caller = the cache). */
+void oracle_rhs(const trixi_b200_desc *d, double *du, const double *u, double t, double *interfaces_u,
+                double *boundaries_u, double *sfv) {
+    oracle_set_zero(d, du);
+    oracle_calc_volume_integral(d, du, u);
+    oracle_prolong2interfaces(d, interfaces_u, u);
+    oracle_calc_interface_flux(d, sfv, interfaces_u);
+    if (d->nboundaries > 0) {
+        oracle_prolong2boundaries(d, boundaries_u, u);
+        oracle_calc_boundary_flux(d, sfv, boundaries_u, t);
+    }
+    /* mortars: none on conforming meshes (dg_3d.jl:770-1007 are no-ops for nmortars == 0) */
+    oracle_calc_surface_integral(d, du, sfv);
+    oracle_apply_jacobian(d, du);
+    oracle_calc_sources(d, du, u, t);
+}
+
+/* max_dt stepsize_dg3d.jl:8-32 (constant_speed False), stepsize_dg2d.jl:60-75 (True) */
+double oracle_max_dt(const trixi_b200_desc *d, const double *u) {
+    eqn_t eq = make_eqn(d);
+    int nv = d->nvars, nd = d->ndims;
+    int64_t nn = ipow(d->nnodes, nd);
+    double max_scaled_speed = DBL_TRUE_MIN; /* nextfloat(zero(t)) */
+    int nanflag = 0;
+#pragma omp parallel for schedule(static) reduction(max : max_scaled_speed) reduction(| : nanflag)
+    for (int64_t e = 0; e < d->nelements; ++e) {
+        double ml[3] = {0, 0, 0};
+        if (is_euler(&eq)) {
+            for (int64_t q = 0; q < nn; ++q) {
+                double rho, v[3], p;
+                euler_cons2prim(&eq, u + nv * (q + nn * e), &rho, v, &p);
+                double c = sqrt(eq.gamma * p / rho); /* max_abs_speeds compressible_euler_3d.jl:1770-1775 */
+                for (int dd = 0; dd < nd; ++dd) {
+                    double l = fabs(v[dd]) + c;
+                    if (isnan(l)) nanflag = 1;
+                    ml[dd] = fmax(ml[dd], l);
+                }
+            }
+        } else {
+            for (int dd = 0; dd < nd; ++dd) ml[dd] = fabs(eq.a[dd]);
+        }
+        double s = 0.0;
+        for (int dd = 0; dd < nd; ++dd) s += ml[dd];
+        double val = d->inverse_jacobian[e] * s;
+        if (val > max_scaled_speed) max_scaled_speed = val;
+    }
+    if (nanflag) return NAN; /* Base.max propagates NaN */
+    return 2 / (d->nnodes * max_scaled_speed);
+}
+
+/* stage loop of step!(::SimpleIntegrator2N) methods_2N.jl:144-159 */
+void oracle_step_2n(const trixi_b200_desc *d, double *u, double *du, double *u_tmp, double t, double dt,
+                    const double *a, const double *b, const double *c, int nstages, double *interfaces_u,
+                    double *boundaries_u, double *sfv) {
+    int64_t len = (int64_t)d->nvars * ipow(d->nnodes, d->ndims) * d->nelements;
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < len; ++i) u_tmp[i] = 0.0;
+    for (int s = 0; s < nstages; ++s) {
+        double t_stage = t + dt * c[s];
+        oracle_rhs(d, du, u, t_stage, interfaces_u, boundaries_u, sfv);
+        double a_stage = a[s], b_stage_dt = b[s] * dt;
+#pragma omp parallel for schedule(static)
+        for (int64_t i = 0; i < len; ++i) {
+            u_tmp[i] = du[i] - u_tmp[i] * a_stage;
+            u[i] += u_tmp[i] * b_stage_dt;
+        }
+    }
+}
+
+/* pointwise two-point flux for unit tests (flux consistency, test/test_unit.jl:1590-1641) */
+void oracle_numflux(const trixi_b200_desc *d, int flux_id, const double *ul, const double *ur, int orientation,
+                    double *f) {
+    eqn_t eq = make_eqn(d);
+    numflux(&eq, flux_id, ul, ur, orientation - 1, f);
+}
+void oracle_flux(const trixi_b200_desc *d, const double *u, int orientation, double *f) {
+    eqn_t eq = make_eqn(d);
+    phys_flux(&eq, u, orientation - 1, f);
+}
+
+int oracle_num_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+void oracle_set_num_threads(int n) {
+#ifdef _OPENMP
+    omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}

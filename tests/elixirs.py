@@ -1,0 +1,207 @@
+"""The reference's example elixirs restated with the trixi_b200 host API, each with the golden L2/Linf
+values the reference's own test-suite asserts (``@test_trixi_include``).  Used by the CPU oracle
+pinning tests and by the GPU end-to-end tests."""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import trixi_b200 as T
+
+
+def initial_condition_density_wave_2d(x, t, equations):
+    # compressible_euler_2d.jl:161-171
+    v1, v2 = 0.1, 0.2
+    s = 2 * (x[0] + x[1] - t * (v1 + v2))
+    r = np.mod(s, 2.0)
+    rho = 1 + 0.98 * np.sin(math.pi * np.where(r > 1.0, r - 2.0, r))
+    p = 20.0
+    e = p / (equations.gamma - 1) + 0.5 * rho * (v1**2 + v2**2)
+    return np.stack([rho, rho * v1, rho * v2, e])
+
+
+class Elixir:
+    def __init__(self, name, build, tspan, cfl, l2, linf, source, maxiters=None, rtol=1e-9, atol=2e-13):
+        self.name, self.build, self.tspan, self.cfl = name, build, tspan, cfl
+        self.l2, self.linf, self.source = np.array(l2), np.array(linf), source
+        self.maxiters, self.rtol, self.atol = maxiters, rtol, atol
+
+    def semi(self, **overrides):
+        return self.build(**overrides)
+
+    def run(self, semi):
+        ode = T.semidiscretize(semi, self.tspan)
+        analysis = T.AnalysisCallback(semi, interval=100)
+        callbacks = T.CallbackSet(T.SummaryCallback(), analysis, T.StepsizeCallback(cfl=self.cfl))
+        sol = T.solve(ode, T.CarpenterKennedy2N54(), dt=1.0, callback=callbacks, maxiters=self.maxiters)
+        l2, linf = analysis(sol)
+        return sol, l2, linf
+
+    def check(self, l2, linf):
+        np.testing.assert_allclose(l2, self.l2, rtol=self.rtol, atol=self.atol)
+        np.testing.assert_allclose(linf, self.linf, rtol=self.rtol, atol=self.atol)
+
+
+def _euler3d_ec(initial_condition=T.initial_condition_weak_blast_wave, flux=T.flux_ranocha, level=3):
+    # examples/tree_3d_dgsem/elixir_euler_ec.jl
+    eq = T.CompressibleEulerEquations3D(1.4)
+    solver = T.DGSEM(polydeg=3, surface_flux=flux, volume_integral=T.VolumeIntegralFluxDifferencing(flux))
+    mesh = T.TreeMesh((-2.0, -2.0, -2.0), (2.0, 2.0, 2.0), initial_refinement_level=level, periodicity=True)
+    return T.SemidiscretizationHyperbolic(mesh, eq, initial_condition, solver,
+                                          boundary_conditions=T.boundary_condition_periodic)
+
+
+def _euler3d_source_terms(volume_integral=None, level=2):
+    # examples/tree_3d_dgsem/elixir_euler_source_terms.jl
+    eq = T.CompressibleEulerEquations3D(1.4)
+    solver = T.DGSEM(polydeg=3, surface_flux=T.FluxLaxFriedrichs(T.max_abs_speed_naive),
+                     volume_integral=volume_integral or T.VolumeIntegralWeakForm())
+    mesh = T.TreeMesh((0.0, 0.0, 0.0), (2.0, 2.0, 2.0), initial_refinement_level=level, periodicity=True)
+    return T.SemidiscretizationHyperbolic(mesh, eq, T.initial_condition_convergence_test, solver,
+                                          source_terms=T.source_terms_convergence_test)
+
+
+def _euler3d_convergence():
+    # examples/tree_3d_dgsem/elixir_euler_convergence.jl
+    eq = T.CompressibleEulerEquations3D(2.0)
+    solver = T.DGSEM(polydeg=3, surface_flux=T.flux_hll, volume_integral=T.VolumeIntegralWeakForm())
+    mesh = T.TreeMesh((0.0, 0.0, 0.0), (2.0, 2.0, 2.0), initial_refinement_level=2, periodicity=True)
+    return T.SemidiscretizationHyperbolic(mesh, eq, T.initial_condition_eoc_test_coupled_euler_gravity, solver,
+                                          source_terms=T.source_terms_eoc_test_euler)
+
+
+def _euler3d_tgv(level=3):
+    # examples/tree_3d_dgsem/elixir_euler_taylor_green_vortex.jl
+    eq = T.CompressibleEulerEquations3D(1.4)
+    solver = T.DGSEM(polydeg=3, surface_flux=T.FluxLaxFriedrichs(T.max_abs_speed_naive),
+                     volume_integral=T.VolumeIntegralFluxDifferencing(T.flux_ranocha))
+    mesh = T.TreeMesh((-math.pi,) * 3, (math.pi,) * 3, initial_refinement_level=level, periodicity=True)
+    return T.SemidiscretizationHyperbolic(mesh, eq, T.initial_condition_taylor_green_vortex, solver)
+
+
+def _euler3d_density_pulse():
+    # examples/tree_3d_dgsem/elixir_euler_density_pulse.jl
+    eq = T.CompressibleEulerEquations3D(1.4)
+    solver = T.DGSEM(polydeg=3, surface_flux=T.flux_ranocha,
+                     volume_integral=T.VolumeIntegralFluxDifferencing(T.flux_ranocha))
+    mesh = T.TreeMesh((-2.0,) * 3, (2.0,) * 3, initial_refinement_level=3, periodicity=True)
+    return T.SemidiscretizationHyperbolic(mesh, eq, T.initial_condition_density_pulse, solver)
+
+
+def _advection2d_basic():
+    # examples/tree_2d_dgsem/elixir_advection_basic.jl
+    eq = T.LinearScalarAdvectionEquation2D((0.2, -0.7))
+    solver = T.DGSEM(polydeg=3, surface_flux=T.flux_lax_friedrichs)
+    mesh = T.TreeMesh((-1.0, -1.0), (1.0, 1.0), initial_refinement_level=4, periodicity=True)
+    return T.SemidiscretizationHyperbolic(mesh, eq, T.initial_condition_convergence_test, solver)
+
+
+def _euler2d_source_terms(periodic=True):
+    # examples/tree_2d_dgsem/elixir_euler_source_terms.jl and ..._nonperiodic.jl
+    eq = T.CompressibleEulerEquations2D(1.4)
+    solver = T.DGSEM(polydeg=3, surface_flux=T.FluxLaxFriedrichs(T.max_abs_speed_naive))
+    mesh = T.TreeMesh((0.0, 0.0), (2.0, 2.0), initial_refinement_level=4, periodicity=periodic)
+    bcs = (T.boundary_condition_periodic if periodic
+           else T.BoundaryConditionDirichlet(T.initial_condition_convergence_test))
+    return T.SemidiscretizationHyperbolic(mesh, eq, T.initial_condition_convergence_test, solver,
+                                          source_terms=T.source_terms_convergence_test, boundary_conditions=bcs)
+
+
+def _euler2d_ec(flux=T.flux_ranocha):
+    # examples/tree_2d_dgsem/elixir_euler_ec.jl
+    eq = T.CompressibleEulerEquations2D(1.4)
+    solver = T.DGSEM(polydeg=3, surface_flux=flux, volume_integral=T.VolumeIntegralFluxDifferencing(flux))
+    mesh = T.TreeMesh((-2.0, -2.0), (2.0, 2.0), initial_refinement_level=5, periodicity=True)
+    return T.SemidiscretizationHyperbolic(mesh, eq, T.initial_condition_weak_blast_wave, solver)
+
+
+def _euler2d_density_wave():
+    # examples/tree_2d_dgsem/elixir_euler_density_wave.jl
+    eq = T.CompressibleEulerEquations2D(1.4)
+    solver = T.DGSEM(polydeg=5, surface_flux=T.flux_central)
+    mesh = T.TreeMesh((-1.0, -1.0), (1.0, 1.0), initial_refinement_level=2, periodicity=True)
+    return T.SemidiscretizationHyperbolic(mesh, eq, initial_condition_density_wave_2d, solver)
+
+
+ELIXIRS = {e.name: e for e in [
+    Elixir("tree_3d_euler_ec", _euler3d_ec, (0.0, 0.4), 1.3,
+           [0.02526341317987378, 0.016632068583699623, 0.016632068583699623, 0.01662548715216875,
+            0.0913477018048886],
+           [0.4372549540810414, 0.28613118232798984, 0.28613118232799006, 0.28796686065271876,
+            1.5072828647309124], "test/test_tree_3d_euler.jl:272-291"),
+    Elixir("tree_3d_euler_ec_constant",
+           lambda: _euler3d_ec(initial_condition=T.initial_condition_constant), (0.0, 0.4), 1.3,
+           [4.183721551616214e-16, 6.059779958716338e-16, 4.916596221090319e-16, 9.739943366304456e-16,
+            3.7485908743251566e-15],
+           [2.4424906541753444e-15, 3.733124920302089e-15, 4.440892098500626e-15, 5.329070518200751e-15,
+            2.4868995751603507e-14], "test/test_tree_3d_euler.jl:293-316", rtol=0, atol=5e-13),
+    Elixir("tree_3d_euler_ec_chandrashekar", lambda: _euler3d_ec(flux=T.flux_chandrashekar), (0.0, 0.4), 1.3,
+           [0.025265721172813106, 0.016649800693500427, 0.01664980069350042, 0.01664379306708522,
+            0.09137248646784184],
+           [0.4373399329742198, 0.28434487167605427, 0.28434487167605427, 0.28522678968890774,
+            1.532471676033761], "test/test_tree_3d_euler.jl:318-341"),
+    Elixir("tree_3d_euler_ec_kennedy_gruber", lambda: _euler3d_ec(flux=T.flux_kennedy_gruber), (0.0, 0.4), 1.3,
+           [0.025280033869871984, 0.016675487948639846, 0.016675487948639853, 0.016668992714991282,
+            0.091455613470441],
+           [0.43348628145015766, 0.28853549062014217, 0.28853549062014217, 0.2903943042772536,
+            1.5236557526482426], "test/test_tree_3d_euler.jl:343-367"),
+    Elixir("tree_3d_euler_ec_shima_etal", lambda: _euler3d_ec(flux=T.flux_shima_etal), (0.0, 0.4), 1.3,
+           [0.025261716925811403, 0.016637655557848952, 0.01663765555784895, 0.01663105921013437,
+            0.09136239054024566],
+           [0.43692416928732536, 0.28622033209064734, 0.28622033209064746, 0.2881197143457632,
+            1.506534270303663], "test/test_tree_3d_euler.jl:369-392"),
+    Elixir("tree_3d_euler_source_terms", _euler3d_source_terms, (0.0, 5.0), 0.6,
+           [0.010385936842224346, 0.009776048833895767, 0.00977604883389591, 0.009776048833895733,
+            0.01506687097416608],
+           [0.03285848350791731, 0.0321792316408982, 0.032179231640894645, 0.032179231640895534,
+            0.0655408023333299], "test/test_tree_3d_euler.jl:5-24"),
+    Elixir("tree_3d_euler_source_terms_split_form",
+           lambda: _euler3d_source_terms(volume_integral=T.VolumeIntegralFluxDifferencing(T.flux_central)),
+           (0.0, 5.0), 0.6,
+           [0.010385936842223388, 0.009776048833894784, 0.009776048833894784, 0.009776048833894765,
+            0.015066870974164096],
+           [0.03285848350791687, 0.032179231640897754, 0.0321792316408942, 0.0321792316408982,
+            0.06554080233333615], "test/test_tree_3d_euler.jl:82-105"),
+    Elixir("tree_3d_euler_convergence", _euler3d_convergence, (0.0, 1.0), 1.1,
+           [0.0003637241020254673, 0.00039555708663848046, 0.00039555708663832644, 0.0003955570866385083,
+            0.0007811613481643962],
+           [0.0024000660244567484, 0.002963541002521053, 0.0029635410025201647, 0.002963541002522385,
+            0.007191437359379549], "test/test_tree_3d_euler.jl:107-122"),
+    Elixir("tree_3d_euler_taylor_green_vortex", _euler3d_tgv, (0.0, 0.5), 1.4,
+           [0.00034949871748737876, 0.03133384111621587, 0.03133384111621582, 0.04378599329988925,
+            0.015796137903453026],
+           [0.0013935237751798724, 0.0724080091006194, 0.07240800910061806, 0.12795921224174792,
+            0.07677156293692633], "test/test_tree_3d_euler.jl:167-200"),
+    Elixir("tree_3d_euler_density_pulse", _euler3d_density_pulse, (0.0, 0.4), 1.1,
+           [0.057196526814004715, 0.057196526814004715, 0.05719652681400473, 0.057196526814004736,
+            0.08579479022100575],
+           [0.27415246703018203, 0.2741524670301829, 0.2741524670301827, 0.27415246703018226,
+            0.41122870054527816], "test/test_tree_3d_euler.jl:251-270"),
+    Elixir("tree_2d_advection_basic", _advection2d_basic, (0.0, 1.0), 1.6,
+           [8.311947673061856e-6], [6.627000273229378e-5], "test/test_tree_2d_advection.jl:5-16"),
+    Elixir("tree_2d_euler_source_terms", _euler2d_source_terms, (0.0, 2.0), 1.0,
+           [9.321181253186009e-7, 1.4181210743438511e-6, 1.4181210743487851e-6, 4.824553091276693e-6],
+           [9.577246529612893e-6, 1.1707525976012434e-5, 1.1707525976456523e-5, 4.8869615580926506e-5],
+           "test/test_tree_2d_euler.jl:5-22"),
+    Elixir("tree_2d_euler_source_terms_nonperiodic", lambda: _euler2d_source_terms(periodic=False),
+           (0.0, 2.0), 1.0,
+           [2.259440511766445e-6, 2.318888155713922e-6, 2.3188881557894307e-6, 6.3327863238858925e-6],
+           [1.498738264560373e-5, 1.9182011928187137e-5, 1.918201192685487e-5, 6.0526717141407005e-5],
+           "test/test_tree_2d_euler.jl:241-262"),
+    Elixir("tree_2d_euler_ec", _euler2d_ec, (0.0, 0.4), 1.0,
+           [0.061751715597716854, 0.05018223615408711, 0.05018989446443463, 0.225871559730513],
+           [0.29347582879608825, 0.31081249232844693, 0.3107380389947736, 1.0540358049885143],
+           "test/test_tree_2d_euler.jl:290-307"),
+    Elixir("tree_2d_euler_ec_kennedy_gruber", lambda: _euler2d_ec(flux=T.flux_kennedy_gruber), (0.0, 0.4), 1.0,
+           [0.03481471610306124, 0.027694280613944234, 0.027697905866996532, 0.12932052501462554],
+           [0.31052098400669004, 0.3481295959664616, 0.34807152194137336, 1.1044947556170719],
+           "test/test_tree_2d_euler.jl:309-332", maxiters=10),
+    Elixir("tree_2d_euler_ec_chandrashekar", lambda: _euler2d_ec(flux=T.flux_chandrashekar), (0.0, 0.4), 1.0,
+           [0.03481122603050542, 0.027662840593087695, 0.027665658732350273, 0.12927455860656786],
+           [0.3110089578739834, 0.34888111987218107, 0.3488278669826813, 1.1056349046774305],
+           "test/test_tree_2d_euler.jl:334-357", maxiters=10),
+    Elixir("tree_2d_euler_density_wave", _euler2d_density_wave, (0.0, 0.5), 1.6,
+           [0.0010600778457964775, 0.00010600778457634275, 0.00021201556915872665, 2.650194614399671e-5],
+           [0.006614198043413566, 0.0006614198043973507, 0.001322839608837334, 0.000165354951256802],
+           "test/test_tree_2d_euler.jl:117-135"),
+]}

@@ -1,0 +1,17 @@
+"""trixi.jl_b200 -- B200-native drop-in for Trixi.jl's DGSEM hot path.
+
+Host-side mirror of the reference API (names as exported by ``src/Trixi.jl:204-396``) above the
+C ABI of ``libtrixi_b200.so`` (``include/trixi_b200.h``).  Import it as ``trixi_b200`` (the directory
+name contains a dot; ``trixi_b200.py`` at the repository root is the loader).
+"""
+from .basis import LobattoLegendreBasis, SolutionAnalyzer, gauss_lobatto_nodes_weights  # noqa: F401
+from .callbacks import (AliveCallback, AnalysisCallback, StepsizeCallback, SummaryCallback,  # noqa: F401
+                        calc_error_norms)
+from .equations import *  # noqa: F401,F403
+from .mesh import CartesianBoxMesh, TreeMesh  # noqa: F401
+from .semidiscretization import (ODEProblem, SemidiscretizationHyperbolic, compute_coefficients,  # noqa: F401
+                                 rhs_hyperbolic, semidiscretize)
+from .solver import (DGSEM, SurfaceIntegralWeakForm, VolumeIntegralFluxDifferencing,  # noqa: F401
+                     VolumeIntegralWeakForm)
+from .time_integration import (CallbackSet, CarpenterKennedy2N43, CarpenterKennedy2N54, init,  # noqa: F401
+                               solve, step)

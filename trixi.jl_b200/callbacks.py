@@ -1,0 +1,120 @@
+"""Step callbacks.
+
+* ``StepsizeCallback`` (``src/callbacks_step/stepsize.jl:93-154``): the ``max_dt`` reduction is the
+  hot-path part and runs on the device (``trixi_b200_max_dt``); the callback only multiplies by cfl.
+* ``AnalysisCallback`` (``src/callbacks_step/analysis.jl:227-376``, error norms
+  ``analysis_dg3d.jl:123-161`` / ``analysis_dg2d.jl``): stays on the host like in the reference GPU
+  path, which copies ``u`` back (``analysis_dg3d.jl:172-177``).  Out of the timed region.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .basis import SolutionAnalyzer
+
+
+class _Callback:
+    def initialize(self, integrator):
+        pass
+
+    def condition(self, integrator):
+        return False
+
+    def affect(self, integrator):
+        pass
+
+    def finalize(self, integrator):
+        pass
+
+
+class SummaryCallback(_Callback):
+    pass
+
+
+class AliveCallback(_Callback):
+    def __init__(self, analysis_interval=0, alive_interval=None):
+        pass
+
+
+class StepsizeCallback(_Callback):
+    """``StepsizeCallback(; cfl, interval=1)`` (stepsize.jl:67-68,93-126)."""
+
+    def __init__(self, cfl=1.0, interval=1):
+        self.cfl = cfl
+        self.interval = interval
+
+    def _cfl(self, t):
+        return self.cfl(t) if callable(self.cfl) else self.cfl
+
+    def initialize(self, integrator):
+        self.affect(integrator)
+
+    def condition(self, integrator):
+        return self.interval > 0 and integrator.stats.naccept % self.interval == 0
+
+    def affect(self, integrator):
+        # calculate_dt (stepsize.jl:146-154): cfl(t) * max_dt(u, t, mesh, ...)
+        dt = self._cfl(integrator.t) * integrator.backend.max_dt(integrator.t)
+        integrator.dt = dt
+        integrator.dtcache = dt
+
+    def __call__(self, ode):
+        """``stepsize_callback(ode)`` (stepsize.jl:128-143)."""
+        backend = ode.p.backend()
+        backend.upload(backend.U, ode.u0)
+        return self._cfl(ode.tspan[0]) * backend.max_dt(ode.tspan[0])
+
+
+def multiply_dimensionwise(matrix, data):
+    """``multiply_dimensionwise`` (basis_lobatto_legendre.jl / interpolation.jl): apply ``matrix`` along
+    every spatial axis of ``data[var, i, j, (k)]`` (leading axis untouched, trailing axes batch)."""
+    nd = data.ndim - 2  # [var, i, j, (k), element]
+    out = data
+    for d in range(nd):
+        out = np.moveaxis(np.tensordot(matrix, out, axes=([1], [1 + d])), 0, 1 + d)
+    return out
+
+
+def calc_error_norms(u, t, semi, analyzer=None):
+    """L2 / Linf errors against ``initial_condition(x, t)`` on the analysis grid
+    (analysis_dg3d.jl:123-161, analysis_dg2d.jl:133-168), conservative variables."""
+    mesh, eq, dg, cache = semi.mesh, semi.equations, semi.solver, semi.cache
+    if analyzer is None:
+        analyzer = SolutionAnalyzer(dg.basis)
+    nd = mesh.ndims
+    V, w = analyzer.vandermonde, analyzer.weights
+    u = np.asarray(u).reshape(semi.u_shape(), order="F")
+    u_local = multiply_dimensionwise(V, u)
+    x_local = multiply_dimensionwise(V, cache.elements.node_coordinates)
+    u_exact = semi.initial_condition(x_local, t, eq)
+    diff = u_exact - u_local
+    wprod = w
+    for _ in range(nd - 1):
+        wprod = np.multiply.outer(wprod, w)
+    volume_jacobian = (1.0 / cache.elements.inverse_jacobian) ** nd  # dgsem_tree/dg.jl:8-10
+    weight = wprod[..., None] * volume_jacobian  # [na.., nelem]
+    l2 = np.sqrt((diff**2 * weight[None]).reshape(eq.nvars, -1).sum(axis=1) / mesh.length_level_0**nd)
+    linf = np.abs(diff).reshape(eq.nvars, -1).max(axis=1)
+    return l2, linf
+
+
+class AnalysisCallback(_Callback):
+    """``AnalysisCallback(semi; interval)`` (analysis.jl:95-158): records L2/Linf errors; the final
+    values are what the reference's tests compare (``analysis_callback(sol)``, analysis.jl:640-668)."""
+
+    def __init__(self, semi, interval=0):
+        self.semi = semi
+        self.interval = interval
+        self.analyzer = SolutionAnalyzer(semi.solver.basis)
+        self.history = []
+
+    def condition(self, integrator):
+        return (self.interval > 0 and integrator.iter % self.interval == 0) or integrator.finalstep
+
+    def affect(self, integrator):
+        l2, linf = calc_error_norms(integrator.download_u(), integrator.t, self.semi, self.analyzer)
+        self.history.append((integrator.iter, integrator.t, l2, linf))
+
+    def __call__(self, sol):
+        l2, linf = calc_error_norms(sol.u[-1], sol.t[-1], self.semi, self.analyzer)
+        return l2, linf

@@ -1,0 +1,221 @@
+"""ctypes binding of ``libtrixi_b200.so`` (the C ABI of ``include/trixi_b200.h``).
+
+This is the Python twin of ``julia/TrixiB200.jl``: every call is a thin forward, no arithmetic
+happens on this side.  The library must be present and a CUDA device must be usable -- there is no
+CPU fallback (BASELINE.json north_star); failures raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libtrixi_b200.so")
+
+EXPORTS = [
+    "trixi_b200_create", "trixi_b200_destroy", "trixi_b200_last_error", "trixi_b200_abi_version",
+    "trixi_b200_upload", "trixi_b200_download", "trixi_b200_device_ptr", "trixi_b200_synchronize",
+    "trixi_b200_stream", "trixi_b200_rhs_host", "trixi_b200_rhs", "trixi_b200_max_dt",
+    "trixi_b200_step_2n", "trixi_b200_solve_2n", "trixi_b200_set_eq_param",
+    "trixi_b200_calc_volume_integral", "trixi_b200_calc_surface_fluxes",
+    "trixi_b200_download_surface_flux_values", "trixi_b200_comm_unique_id", "trixi_b200_comm_init",
+    "trixi_b200_launch_count", "trixi_b200_last_elapsed_ms", "trixi_b200_profile_enable",
+    "trixi_b200_profile_read",
+]
+
+_lib = None
+
+
+class TrixiB200Error(RuntimeError):
+    pass
+
+
+def load_library(path=None):
+    """dlopen the shared library and declare the prototypes.  Raises if it is missing: the CUDA
+    extension is the product, not an optional accelerator."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    path = path or LIB_PATH
+    if not os.path.exists(path):
+        raise TrixiB200Error(f"{path} not found -- build it with `python -m __graft_entry__` / "
+                             "trixi.jl_b200/build.py; there is no CPU fallback")
+    lib = C.CDLL(path)
+    vp, dp, i64p = C.c_void_p, _abi.c_double_p, _abi.c_int64_p
+    lib.trixi_b200_create.argtypes = [C.POINTER(_abi.Desc), C.POINTER(vp)]
+    lib.trixi_b200_create.restype = C.c_int
+    lib.trixi_b200_destroy.argtypes = [vp]
+    lib.trixi_b200_destroy.restype = None
+    lib.trixi_b200_last_error.argtypes = [vp]
+    lib.trixi_b200_last_error.restype = C.c_char_p
+    lib.trixi_b200_abi_version.argtypes = []
+    lib.trixi_b200_abi_version.restype = C.c_int
+    lib.trixi_b200_upload.argtypes = [vp, C.c_int, dp]
+    lib.trixi_b200_download.argtypes = [vp, C.c_int, dp]
+    lib.trixi_b200_device_ptr.argtypes = [vp, C.c_int]
+    lib.trixi_b200_device_ptr.restype = vp
+    lib.trixi_b200_synchronize.argtypes = [vp]
+    lib.trixi_b200_stream.argtypes = [vp]
+    lib.trixi_b200_stream.restype = vp
+    lib.trixi_b200_rhs_host.argtypes = [vp, dp, dp, C.c_double]
+    lib.trixi_b200_rhs.argtypes = [vp, C.c_double]
+    lib.trixi_b200_max_dt.argtypes = [vp, C.c_double, dp]
+    lib.trixi_b200_step_2n.argtypes = [vp, C.c_double, C.c_double, dp, dp, dp, C.c_int]
+    lib.trixi_b200_solve_2n.argtypes = [vp, C.c_double, C.c_double, C.c_double, C.c_int64, dp, dp, dp,
+                                        C.c_int, i64p, dp, dp]
+    lib.trixi_b200_set_eq_param.argtypes = [vp, C.c_int, C.c_double]
+    lib.trixi_b200_calc_volume_integral.argtypes = [vp]
+    lib.trixi_b200_calc_surface_fluxes.argtypes = [vp, C.c_double]
+    lib.trixi_b200_download_surface_flux_values.argtypes = [vp, dp]
+    lib.trixi_b200_comm_unique_id.argtypes = [vp]
+    lib.trixi_b200_comm_init.argtypes = [vp, vp]
+    lib.trixi_b200_launch_count.argtypes = [vp]
+    lib.trixi_b200_launch_count.restype = C.c_int64
+    lib.trixi_b200_last_elapsed_ms.argtypes = [vp, C.POINTER(C.c_float)]
+    lib.trixi_b200_profile_enable.argtypes = [vp, C.c_int]
+    lib.trixi_b200_profile_read.argtypes = [vp, C.c_int, dp, i64p]
+    for name in EXPORTS:
+        fn = getattr(lib, name)
+        if fn.restype is C.c_int and name not in ("trixi_b200_abi_version",):
+            pass
+    if lib.trixi_b200_abi_version() != _abi.ABI_VERSION:
+        raise TrixiB200Error("libtrixi_b200.so ABI version mismatch")
+    if path == LIB_PATH:
+        _lib = lib
+    return lib
+
+
+def _dptr(a):
+    return a.ctypes.data_as(_abi.c_double_p)
+
+
+def _check_host(a, length, writable=False):
+    if not isinstance(a, np.ndarray) or a.dtype != np.float64:
+        raise TypeError("expected a float64 NumPy array")
+    if a.size != length:
+        raise ValueError(f"array has {a.size} entries, expected {length}")
+    if not (a.flags.f_contiguous or a.flags.c_contiguous):
+        raise ValueError("array must be contiguous")
+    if writable and not a.flags.writeable:
+        raise ValueError("array must be writeable")
+    return a
+
+
+class B200Backend:
+    """One handle = one GPU's share of the semidiscretization (device-resident u, du, u_tmp and all
+    containers).  Method names follow the C exports."""
+
+    U, DU, U_TMP = 0, 1, 2
+
+    def __init__(self, desc_holder, u_length):
+        self.lib = load_library()
+        self._holder = desc_holder
+        self.u_length = int(u_length)
+        h = C.c_void_p()
+        rc = self.lib.trixi_b200_create(desc_holder.byref(), C.byref(h))
+        if rc != 0:
+            msg = self.lib.trixi_b200_last_error(None)
+            raise TrixiB200Error(f"trixi_b200_create failed ({rc}): {msg.decode() if msg else ''}")
+        self.h = h
+
+    def _ck(self, rc):
+        if rc != 0:
+            msg = self.lib.trixi_b200_last_error(self.h)
+            raise TrixiB200Error(f"libtrixi_b200 error {rc}: {msg.decode() if msg else ''}")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.trixi_b200_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # data movement
+    def upload(self, which, host):
+        self._ck(self.lib.trixi_b200_upload(self.h, which, _dptr(_check_host(host, self.u_length))))
+
+    def download(self, which, host=None):
+        if host is None:
+            host = np.empty(self.u_length)
+        self._ck(self.lib.trixi_b200_download(self.h, which, _dptr(_check_host(host, self.u_length, True))))
+        return host
+
+    def synchronize(self):
+        self._ck(self.lib.trixi_b200_synchronize(self.h))
+
+    def device_ptr(self, which):
+        return self.lib.trixi_b200_device_ptr(self.h, which)
+
+    # hot path
+    def rhs_host(self, du_host, u_host, t):
+        self._ck(self.lib.trixi_b200_rhs_host(self.h, _dptr(_check_host(du_host, self.u_length, True)),
+                                              _dptr(_check_host(u_host, self.u_length)), float(t)))
+
+    def rhs(self, t):
+        self._ck(self.lib.trixi_b200_rhs(self.h, float(t)))
+
+    def max_dt(self, t=0.0):
+        out = C.c_double()
+        self._ck(self.lib.trixi_b200_max_dt(self.h, float(t), C.byref(out)))
+        return out.value
+
+    def step_2n(self, t, dt, a, b, c):
+        a, b, c = (np.ascontiguousarray(x, dtype=np.float64) for x in (a, b, c))
+        self._ck(self.lib.trixi_b200_step_2n(self.h, float(t), float(dt), _dptr(a), _dptr(b), _dptr(c), len(c)))
+
+    def solve_2n(self, t0, t_end, cfl, max_steps, a, b, c):
+        a, b, c = (np.ascontiguousarray(x, dtype=np.float64) for x in (a, b, c))
+        steps, t_out, dt_out = C.c_int64(), C.c_double(), C.c_double()
+        self._ck(self.lib.trixi_b200_solve_2n(self.h, float(t0), float(t_end), float(cfl), int(max_steps),
+                                              _dptr(a), _dptr(b), _dptr(c), len(c), C.byref(steps),
+                                              C.byref(t_out), C.byref(dt_out)))
+        return steps.value, t_out.value, dt_out.value
+
+    def set_eq_param(self, index, value):
+        self._ck(self.lib.trixi_b200_set_eq_param(self.h, int(index), float(value)))
+
+    # stage-level
+    def calc_volume_integral(self):
+        self._ck(self.lib.trixi_b200_calc_volume_integral(self.h))
+
+    def calc_surface_fluxes(self, t):
+        self._ck(self.lib.trixi_b200_calc_surface_fluxes(self.h, float(t)))
+
+    def download_surface_flux_values(self, host):
+        self._ck(self.lib.trixi_b200_download_surface_flux_values(self.h, _dptr(host)))
+        return host
+
+    # measurement
+    def launch_count(self):
+        return int(self.lib.trixi_b200_launch_count(self.h))
+
+    def last_elapsed_ms(self):
+        out = C.c_float()
+        self._ck(self.lib.trixi_b200_last_elapsed_ms(self.h, C.byref(out)))
+        return out.value
+
+    def profile_enable(self, on=True):
+        self._ck(self.lib.trixi_b200_profile_enable(self.h, int(on)))
+
+    def profile_read(self, kernel_class):
+        ms, n = C.c_double(), C.c_int64()
+        self._ck(self.lib.trixi_b200_profile_read(self.h, kernel_class, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    # distributed
+    def comm_unique_id(self):
+        buf = C.create_string_buffer(128)
+        self._ck(self.lib.trixi_b200_comm_unique_id(buf))
+        return buf.raw
+
+    def comm_init(self, unique_id):
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        self._ck(self.lib.trixi_b200_comm_init(self.h, buf))

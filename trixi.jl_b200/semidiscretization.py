@@ -1,0 +1,216 @@
+"""``SemidiscretizationHyperbolic`` and the ``rhs_hyperbolic!`` wrapper.
+
+Mirrors ``src/semidiscretization/semidiscretization_hyperbolic.jl:14-30,50-76,578-597`` and
+``semidiscretization.jl:102-153,224-242``.  The constructor builds the containers on the host
+(``create_cache``) and the C-ABI descriptor; the device handle is created on first use -- the
+analogue of ``semidiscretize(...; storage_type=CuArray)`` adapting all containers once
+(``semidiscretization.jl:115-126``).  There is no CPU fallback: every RHS evaluation goes through
+``libtrixi_b200.so``.
+"""
+from __future__ import annotations
+
+import time
+
+import numpy as np
+
+from . import _abi
+from .containers import init_boundaries, init_elements, init_interfaces
+from .equations import (BC_DIRICHLET, BC_PERIODIC, BC_SLIP_WALL, IC_NONE, SRC_NONE,
+                        BoundaryConditionDirichlet, boundary_condition_periodic, resolve_flux)
+from .mesh import TreeMesh
+
+MESH_TREE, MESH_STRUCTURED, MESH_P4EST = 0, 1, 2
+
+_DIRECTION_NAMES = ("x_neg", "x_pos", "y_neg", "y_pos", "z_neg", "z_pos")
+
+
+class PerformanceCounter:
+    """``PerformanceCounter`` (auxiliary/auxiliary.jl:22-41): accumulates synchronised RHS run time."""
+
+    def __init__(self):
+        self.ncalls_since_readout = 0
+        self.runtime = 0.0
+
+    def put(self, runtime_ns):
+        self.ncalls_since_readout += 1
+        self.runtime += runtime_ns
+
+    def take(self):
+        r = self.runtime / max(self.ncalls_since_readout, 1)
+        self.ncalls_since_readout = 0
+        self.runtime = 0.0
+        return r
+
+
+class Cache:
+    pass
+
+
+def create_cache(mesh, equations, solver):
+    """``create_cache`` for TreeMesh (dgsem_tree/dg_2d.jl:14-37)."""
+    cache = Cache()
+    if isinstance(mesh, TreeMesh):
+        cache.elements = init_elements(mesh, solver.basis)
+        cache.interfaces = init_interfaces(mesh)
+        cache.boundaries = init_boundaries(mesh, cache.elements, solver.basis)
+    else:
+        raise TypeError(f"unsupported mesh type {type(mesh).__name__}")
+    return cache
+
+
+def _digest_boundary_conditions(boundary_conditions, mesh):
+    """semidiscretization_hyperbolic.jl:115-206: a single BC applies to all directions; a dict keyed
+    x_neg, x_pos, ... gives one per direction; periodic BCs must match the mesh periodicity."""
+    nd = mesh.ndims
+    if isinstance(boundary_conditions, dict):
+        names = _DIRECTION_NAMES[:2 * nd]
+        if set(boundary_conditions) != set(names):
+            raise ValueError(f"boundary_conditions must have exactly the keys {names}")
+        bcs = [boundary_conditions[k] for k in names]
+    elif isinstance(boundary_conditions, (tuple, list)):
+        if len(boundary_conditions) != 2 * nd:
+            raise ValueError("need one boundary condition per direction")
+        bcs = list(boundary_conditions)
+    else:
+        bcs = [boundary_conditions] * (2 * nd)
+    tags, ics = [0] * 6, [0] * 6
+    for i, bc in enumerate(bcs):
+        periodic_dim = mesh.periodicity[i // 2]
+        if bc is boundary_condition_periodic:
+            if not periodic_dim:
+                raise ValueError(f"boundary_condition_periodic in non-periodic direction {_DIRECTION_NAMES[i]}")
+            tags[i] = BC_PERIODIC
+        else:
+            if periodic_dim:
+                raise ValueError(f"non-periodic boundary condition in periodic direction {_DIRECTION_NAMES[i]}")
+            if isinstance(bc, BoundaryConditionDirichlet):
+                tags[i], ics[i] = BC_DIRICHLET, bc.ic_id
+            elif getattr(bc, "tag", None) == BC_SLIP_WALL:
+                tags[i] = BC_SLIP_WALL
+            else:
+                raise TypeError(f"boundary condition {bc!r} is not in the libtrixi_b200 registry")
+    return tags, ics
+
+
+class SemidiscretizationHyperbolic:
+    """``SemidiscretizationHyperbolic(mesh, equations, initial_condition, solver; source_terms,
+    boundary_conditions)`` (semidiscretization_hyperbolic.jl:50-76)."""
+
+    def __init__(self, mesh, equations, initial_condition, solver, source_terms=None,
+                 boundary_conditions=boundary_condition_periodic, device=-1):
+        if mesh.ndims != equations.ndims:
+            raise ValueError("mesh and equations must have the same number of dimensions")
+        self.mesh, self.equations, self.solver = mesh, equations, solver
+        self.initial_condition = initial_condition
+        self.source_terms = source_terms
+        self.boundary_conditions = boundary_conditions
+        self.cache = create_cache(mesh, equations, solver)
+        self.performance_counter = PerformanceCounter()
+        self.device = device
+        self._bc_tags, self._bc_ics = _digest_boundary_conditions(boundary_conditions, mesh)
+        self._desc = None
+        self._backend = None
+
+    # ---- sizes -----------------------------------------------------------------------------------
+    @property
+    def nelements(self):
+        return self.cache.elements.nelements
+
+    def ndofs(self):
+        """Number of DOFs = nodes (docs/src/performance.md:201-218, solvers/dg.jl:969-971)."""
+        return self.nelements * self.solver.nnodes ** self.mesh.ndims
+
+    def u_shape(self):
+        return (self.equations.nvars,) + (self.solver.nnodes,) * self.mesh.ndims + (self.nelements,)
+
+    def u_length(self):
+        return int(np.prod(self.u_shape()))
+
+    # ---- descriptor -------------------------------------------------------------------------------
+    def descriptor(self):
+        if self._desc is not None:
+            return self._desc
+        h = _abi.DescHolder()
+        d = h.desc
+        eq, dg, cache = self.equations, self.solver, self.cache
+        d.abi_version = _abi.ABI_VERSION
+        d.device = self.device
+        d.ndims, d.nvars, d.nnodes = self.mesh.ndims, eq.nvars, dg.nnodes
+        d.mesh_kind = MESH_TREE
+        d.nelements = self.nelements
+        d.equation = eq.eq_id
+        d.volume_integral = dg.volume_integral.kind
+        d.volume_flux = resolve_flux(dg.volume_integral.volume_flux)
+        d.surface_flux = resolve_flux(dg.surface_integral.surface_flux)
+        d.source_terms = SRC_NONE if self.source_terms is None else self.source_terms.tag
+        for i in range(6):
+            d.boundary_conditions[i] = self._bc_tags[i]
+            d.boundary_ic[i] = self._bc_ics[i]
+        for i, p in enumerate(eq.params()):
+            d.eq_params[i] = p
+        h.set_f64("derivative_split", dg.basis.derivative_split)
+        h.set_f64("derivative_hat", dg.basis.derivative_hat)
+        h.set_f64("inverse_weights", dg.basis.inverse_weights)
+        h.set_f64("inverse_jacobian", cache.elements.inverse_jacobian)
+        h.set_f64("node_coordinates", cache.elements.node_coordinates)
+        d.ninterfaces = cache.interfaces.ninterfaces
+        h.set_i64("interface_neighbor_ids", cache.interfaces.neighbor_ids)
+        h.set_i64("interface_orientations", cache.interfaces.orientations)
+        b = cache.boundaries
+        d.nboundaries = b.nboundaries
+        if b.nboundaries:
+            h.set_i64("boundary_neighbor_ids", b.neighbor_ids)
+            h.set_i64("boundary_orientations", b.orientations)
+            h.set_i64("boundary_neighbor_sides", b.neighbor_sides)
+            h.set_f64("boundary_node_coordinates", b.node_coordinates)
+        for i in range(6):
+            d.n_boundaries_per_direction[i] = int(b.n_boundaries_per_direction[i])
+        d.nmortars = 0
+        d.rank, d.world_size = 0, 1
+        d.nmpiinterfaces = 0
+        self._desc = h
+        return h
+
+    # ---- device backend ---------------------------------------------------------------------------
+    def backend(self):
+        """The B200 backend object (``trixi_backend(u)`` analogue, auxiliary/containers.jl:278-285)."""
+        if self._backend is None:
+            from .lib import B200Backend
+            self._backend = B200Backend(self.descriptor(), self.u_length())
+        return self._backend
+
+    def set_backend(self, backend):
+        """Tests inject the CPU oracle here; the product never does."""
+        self._backend = backend
+
+
+def mesh_equations_solver_cache(semi):
+    return semi.mesh, semi.equations, semi.solver, semi.cache
+
+
+def compute_coefficients(t, semi):
+    """``compute_coefficients(t, semi)`` (semidiscretization.jl:224-242): u0 = initial_condition(x, t)
+    at every node, shape [nvars, n, n, (n,) nelements] Fortran-ordered (solvers/dg.jl:1200-1210)."""
+    x = semi.cache.elements.node_coordinates
+    u = semi.initial_condition(x, t, semi.equations)
+    return np.asfortranarray(u, dtype=np.float64)
+
+
+class ODEProblem:
+    def __init__(self, f, u0, tspan, p):
+        self.f, self.u0, self.tspan, self.p = f, u0, tspan, p
+
+
+def semidiscretize(semi, tspan):
+    """``semidiscretize(semi, tspan)`` (semidiscretization.jl:102-153)."""
+    u0 = compute_coefficients(tspan[0], semi)
+    return ODEProblem(rhs_hyperbolic, u0, (float(tspan[0]), float(tspan[1])), semi)
+
+
+def rhs_hyperbolic(du_ode, u_ode, semi, t):
+    """``rhs_hyperbolic!(du_ode, u_ode, semi, t)`` (semidiscretization_hyperbolic.jl:578-597): host
+    buffers in and out; the run time (synchronised, copies included) feeds the PerformanceCounter."""
+    t0 = time.perf_counter_ns()
+    semi.backend().rhs_host(du_ode, u_ode, t)
+    semi.performance_counter.put(time.perf_counter_ns() - t0)
+    return None

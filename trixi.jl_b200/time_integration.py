@@ -1,0 +1,141 @@
+"""Trixi-native 2N low-storage Runge-Kutta integrators with the OrdinaryDiffEq-like facade.
+
+Mirrors ``src/time_integration/methods_2N.jl:24-48`` (CarpenterKennedy2N54), ``:50-76``
+(CarpenterKennedy2N43), ``:95-129`` (SimpleIntegrator2N, init), ``:131-168`` (step!) and
+``time_integration.jl:46-55,72-124`` (limit_dt!, callbacks, solve!).  The stage loop itself
+(RHS + fused ``u_tmp``/``u`` update, ``methods_2N.jl:144-159``) runs inside
+``trixi_b200_step_2n`` on device-resident vectors; the host only sequences steps and callbacks.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+
+class CarpenterKennedy2N54:
+    """Coefficients from methods_2N.jl:29-46."""
+
+    def __init__(self):
+        self.a = np.array([0.0,
+                           567301805773.0 / 1357537059087.0,
+                           2404267990393.0 / 2016746695238.0,
+                           3550918686646.0 / 2091501179385.0,
+                           1275806237668.0 / 842570457699.0])
+        self.b = np.array([1432997174477.0 / 9575080441755.0,
+                           5161836677717.0 / 13612068292357.0,
+                           1720146321549.0 / 2090206949498.0,
+                           3134564353537.0 / 4481467310338.0,
+                           2277821191437.0 / 14882151754819.0])
+        self.c = np.array([0.0,
+                           1432997174477.0 / 9575080441755.0,
+                           2526269341429.0 / 6820363962896.0,
+                           2006345519317.0 / 3224310063776.0,
+                           2802321613138.0 / 2924317926251.0])
+
+
+class CarpenterKennedy2N43:
+    """Coefficients from methods_2N.jl:60-74."""
+
+    def __init__(self):
+        self.a = np.array([0.0, 756391.0 / 934407.0, 36441873.0 / 15625000.0, 1953125.0 / 1085297.0])
+        self.b = np.array([8.0 / 141.0, 6627.0 / 2000.0, 609375.0 / 1085297.0, 198961.0 / 526383.0])
+        self.c = np.array([0.0, 8.0 / 141.0, 86.0 / 125.0, 1.0])
+
+
+class CallbackSet:
+    def __init__(self, *callbacks):
+        self.discrete_callbacks = [cb for cb in callbacks if cb is not None]
+
+
+class _Stats:
+    def __init__(self):
+        self.naccept = 0
+        self.nf = 0
+
+
+class SimpleIntegrator2N:
+    """methods_2N.jl:95-111.  ``u`` lives on the device (handle-owned); ``integrator.u`` downloads."""
+
+    def __init__(self, ode, alg, dt, callback, maxiters=None):
+        self.semi = self.p = ode.p
+        self.backend = ode.p.backend()
+        self.alg = alg
+        self.t = float(ode.tspan[0])
+        self.tspan = ode.tspan
+        self.dt = float(dt)
+        self.dtcache = float(dt)
+        self.iter = 0
+        self.stats = _Stats()
+        self.callback = callback
+        self.maxiters = maxiters if maxiters is not None else np.iinfo(np.int64).max
+        self.finalstep = False
+        self.backend.upload(self.backend.U, ode.u0)
+        self._u0 = ode.u0
+
+    @property
+    def u(self):
+        return self.download_u()
+
+    def download_u(self):
+        flat = np.empty(self.semi.u_length())
+        self.backend.download(self.backend.U, flat)
+        return flat.reshape(self.semi.u_shape(), order="F")
+
+    def terminate(self):
+        self.finalstep = True
+
+
+def limit_dt(integrator, t_end):
+    """time_integration.jl:46-55."""
+    if integrator.t + integrator.dt > t_end or math.isclose(integrator.t + integrator.dt, t_end,
+                                                             rel_tol=math.sqrt(np.finfo(float).eps), abs_tol=0.0):
+        integrator.dt = t_end - integrator.t
+        integrator.terminate()
+
+
+def step(integrator):
+    """``step!(integrator::SimpleIntegrator2N)`` (methods_2N.jl:131-168)."""
+    alg = integrator.alg
+    t_end = integrator.tspan[1]
+    assert not integrator.finalstep
+    if math.isnan(integrator.dt):
+        raise RuntimeError("time step size `dt` is NaN")
+    limit_dt(integrator, t_end)
+    integrator.backend.step_2n(integrator.t, integrator.dt, alg.a, alg.b, alg.c)
+    integrator.stats.nf += len(alg.c)
+    integrator.iter += 1
+    integrator.stats.naccept += 1
+    integrator.t += integrator.dt
+    if integrator.callback is not None:
+        for cb in integrator.callback.discrete_callbacks:
+            if cb.condition(integrator):
+                cb.affect(integrator)
+    if integrator.iter >= integrator.maxiters and not integrator.finalstep:
+        integrator.terminate()
+
+
+class TimeIntegratorSolution:
+    def __init__(self, t, u, prob, integrator):
+        self.t, self.u, self.prob, self.integrator = t, u, prob, integrator
+
+
+def init(ode, alg, dt, callback=None, maxiters=None):
+    """methods_2N.jl:113-129."""
+    integrator = SimpleIntegrator2N(ode, alg, dt, callback, maxiters)
+    if callback is not None:
+        for cb in callback.discrete_callbacks:
+            cb.initialize(integrator)
+    return integrator
+
+
+def solve(ode, alg, dt, callback=None, maxiters=None):
+    """``Trixi.solve(ode, alg; dt, callback)`` (time_integration.jl:103-124)."""
+    integrator = init(ode, alg, dt, callback, maxiters)
+    while not integrator.finalstep:
+        step(integrator)
+    if callback is not None:
+        for cb in callback.discrete_callbacks:
+            cb.finalize(integrator)
+    return TimeIntegratorSolution((ode.tspan[0], integrator.t), (ode.u0, integrator.download_u()), ode,
+                                  integrator)
