@@ -1,0 +1,320 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the hot path (BASELINE.json): 3D compressible Euler,
+entropy-conservative flux-differencing DGSEM (flux_ranocha volume + surface flux), polydeg 3, periodic
+TreeMesh; metric = DOF-updates/s (DOF x RHS evaluations per second; PID = ns per DOF per RHS is
+reported beside it).
+
+A "step" is one CarpenterKennedy2N54 time step = 5 RHS evaluations with the stage update fused in,
+plus the CFL max_dt reduction (StepsizeCallback interval 1).  One JSON line on stdout (rank 0).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--level L] [--impl b200|reference]
+
+`--impl reference` times the CPU restatement of the reference's rhs! (oracle/, OpenMP, all host
+cores) on a bounded sample of the same workload; Julia/Trixi itself cannot run here.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "dof_updates_per_s"
+UNIT = "DOF-updates/s"
+ALGO_FLOP_PER_DOF_VOLUME = 312.5  # 4.5 pairs x 67 + 11 (p = 3, Euler 3D, flux_ranocha)
+
+
+def make_semi(level, device=-1):
+    import trixi_b200 as T
+    # examples/tree_3d_dgsem/elixir_euler_ec.jl at a larger refinement level
+    eq = T.CompressibleEulerEquations3D(1.4)
+    solver = T.DGSEM(polydeg=3, surface_flux=T.flux_ranocha,
+                     volume_integral=T.VolumeIntegralFluxDifferencing(T.flux_ranocha))
+    mesh = T.TreeMesh((-2.0,) * 3, (2.0,) * 3, initial_refinement_level=level, periodicity=True)
+    return T.SemidiscretizationHyperbolic(mesh, eq, T.initial_condition_weak_blast_wave, solver, device=device)
+
+
+def workload_name(level):
+    n = 1 << level
+    return (f"tree_3d_dgsem/elixir_euler_ec.jl: 3D Euler EC flux differencing (flux_ranocha), polydeg=3, "
+            f"TreeMesh level {level} ({n}^3 elements, {64 * n**3 / 1e6:.1f} M DOF), periodic, weak blast wave IC")
+
+
+class ClockSampler:
+    """nvidia-smi sampling during the timed region (B200_PROFILING.md clocks line)."""
+
+    def __init__(self, index=0):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            pass
+        sm, smax, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                smax.append(float(parts[1]))
+                power.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(power) if power else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f), "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+def oracle_backend(semi, threads=None):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle
+    return oracle.OracleBackend(semi, num_threads=threads)
+
+
+def time_cpu_reference(level, steps, warmup):
+    """The reference's CPU path restated (oracle/trixi_oracle.c, OpenMP over all host cores):
+    CarpenterKennedy2N54 steps on a bounded sample (smaller TreeMesh level of the same workload)."""
+    import trixi_b200 as T
+    semi = make_semi(level)
+    ob = oracle_backend(semi)
+    u0 = T.compute_coefficients(0.0, semi)
+    ob.upload(0, u0)
+    alg = T.CarpenterKennedy2N54()
+    dt = 1.3 * ob.max_dt()
+    for _ in range(warmup):
+        ob.step_2n(0.0, dt, alg.a, alg.b, alg.c)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        ob.step_2n(0.0, dt, alg.a, alg.b, alg.c)
+        ob.max_dt()
+    dt_wall = time.perf_counter() - t0
+    ndofs = semi.ndofs()
+    value = ndofs * 5 * steps / dt_wall
+    return value, dt_wall, ob.num_threads(), ndofs
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    level = args.cpu_level
+    value, wall, threads, ndofs = time_cpu_reference(level, args.steps, args.warmup)
+    sample = (f"{workload_name(level)}; {args.steps} CK54 steps (5 rhs! + stage updates + max_dt each) "
+              f"after {args.warmup} warm-up, OpenMP C restatement of the reference's CPU rhs! "
+              f"(Julia/Trixi.jl not installable on this box)")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "pid_ns_per_dof_rhs": 1e9 / value * threads,
+        "config": {"workload": workload_name(args.level), "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_b200(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    import trixi_b200 as T
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    semi = make_semi(args.level, device=local_rank)
+    gpu = semi.backend()
+    ndofs = semi.ndofs()
+    u0 = T.compute_coefficients(0.0, semi)
+    gpu.upload(0, u0)
+    alg = T.CarpenterKennedy2N54()
+    cfl = 1.3
+    dt = cfl * gpu.max_dt()
+
+    def one_step(t):
+        gpu.step_2n(t, dt_holder[0], alg.a, alg.b, alg.c)
+        dt_holder[0] = cfl * gpu.max_dt()  # StepsizeCallback after every step (stepsize.jl:93-126)
+
+    dt_holder = [dt]
+    t = 0.0
+    for _ in range(args.warmup):
+        one_step(t)
+        t += dt_holder[0]
+
+    # ---- device-resident timed region --------------------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    gpu.profile_enable(True)
+    launches0 = gpu.launch_count()
+    barrier()
+    gpu.timer_start()
+    t_wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        one_step(t)
+        t += dt_holder[0]
+    ms = gpu.timer_stop()
+    barrier()
+    wall = time.perf_counter() - t_wall0
+    launches = gpu.launch_count() - launches0
+    elem_ms, elem_n = gpu.profile_read(1)
+    surf_ms, surf_n = gpu.profile_read(0)
+    cfl_ms, cfl_n = gpu.profile_read(2)
+    gpu.profile_enable(False)
+    clocks = sampler.stop() if rank == 0 else None
+
+    t_ms = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms_max = float(t_ms.item())
+    u_final = gpu.download(0)
+    finite = bool(np.isfinite(u_final).all())
+    total_dofs = ndofs * world  # weak scaling: every rank owns a level-L mesh partition
+    value = total_dofs * 5 * args.steps / (ms_max * 1e-3)
+
+    # ---- end-to-end through the public API with host buffers ---------------------------------------
+    n = semi.u_length()
+    u_pin = torch.empty(n, dtype=torch.float64).pin_memory()
+    du_pin = torch.empty(n, dtype=torch.float64).pin_memory()
+    u_host, du_host = u_pin.numpy(), du_pin.numpy()
+    u_host[:] = u0.ravel(order="F")
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    T.rhs_hyperbolic(du_host, u_host, semi, 0.0)  # warm-up
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        T.rhs_hyperbolic(du_host, u_host, semi, 0.0)  # H2D u, kernels, D2H du, synchronised
+    barrier()
+    e2e_wall = time.perf_counter() - t0
+    t_e2e = torch.tensor([e2e_wall], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    e2e_value = total_dofs * e2e_steps / float(t_e2e.item())
+    e2e_finite = bool(np.isfinite(du_host).all())
+
+    if rank == 0:
+        peaks, peak_kind = measured_peaks()
+        fp64_peak = gpu.measure_fp64_peak()
+        copy_gbs = gpu.measure_copy_bandwidth()
+        # dominant kernel: the fused element kernel (volume + surface + Jacobian + 2N stage).
+        # algorithmic bytes/DOF in RK mode: read u 40 + surface_flux_values 60 + u_tmp 40 (stages 2-5),
+        # write u_tmp 40 + u 40 -> 220 B (stage 1: 180 B); average over the 5 stages = 212 B
+        elem_avg_ms = elem_ms / max(elem_n, 1)
+        algo_bytes = ndofs * 212.0
+        achieved_gbs = algo_bytes / (elem_avg_ms * 1e-3) * 1e-9
+        algo_flops = ndofs * (ALGO_FLOP_PER_DOF_VOLUME + 5 * 9.0)
+        cpu = None
+        if not args.no_cpu_baseline:
+            cv, cwall, cthreads, cdofs = time_cpu_reference(args.cpu_level, 3, 1)
+            cpu = {"value": cv, "unit": UNIT, "cores": cthreads, "kind": "port",
+                   "sample": f"{workload_name(args.cpu_level)}; 3 CK54 steps (15 rhs!) after 1 warm-up; "
+                             "OpenMP C restatement of the reference's CPU rhs! (oracle/trixi_oracle.c)"}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "pid_ns_per_dof_rhs": 1e9 / value * world,
+            "config": {"workload": workload_name(args.level), "ndofs_per_gpu": ndofs,
+                       "rhs_per_step": 5, "time_integrator": "CarpenterKennedy2N54 (fused stage update)",
+                       "l2_hygiene": "inputs larger than L2 (u alone is %.1f GB)" % (n * 8 / 1e9),
+                       "parallelism": "1 rank per GPU" if world == 1 else f"{world} ranks, independent partitions"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * 8, "d2h_bytes_per_step": n * 8,
+                    "call": "rhs_hyperbolic(du_host, u_host, semi, t) -> trixi_b200_rhs_host, pinned host buffers",
+                    "steps": e2e_steps, "finite": e2e_finite},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "kernel": "k_element (volume+surface+jacobian+2N stage)",
+                         "achieved": achieved_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": achieved_gbs / peaks["hbm_gbs"], "peak_kind": peak_kind, "traffic": None,
+                         "avg_launch_ms": elem_avg_ms, "launches": elem_n,
+                         "algorithmic_bytes_per_dof": 212.0,
+                         "fp64": {"achieved_tflops": algo_flops / (elem_avg_ms * 1e-3) * 1e-12,
+                                  "peak_tflops_measured_dfma": fp64_peak,
+                                  "algorithmic_flop_per_dof": ALGO_FLOP_PER_DOF_VOLUME + 45.0},
+                         "copy_gbs_measured_here": copy_gbs},
+            "kernel_time_share": {"surface_flux_ms": surf_ms, "element_ms": elem_ms, "max_dt_ms": cfl_ms,
+                                  "timed_region_ms": ms_max},
+            "wall_s": wall, "finite": finite,
+        }
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--level", type=int, default=7, help="TreeMesh refinement level per GPU (7 = 134 M DOF)")
+    ap.add_argument("--cpu-level", type=int, default=5, help="refinement level of the bounded CPU sample")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    run_b200(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -24,6 +24,12 @@ extern "C" {
 
 #define TRIXI_B200_ABI_VERSION 1
 
+#if defined(__GNUC__)
+#define TRIXI_B200_API __attribute__((visibility("default")))
+#else
+#define TRIXI_B200_API
+#endif
+
 /* status codes */
 #define TRIXI_B200_OK 0
 #define TRIXI_B200_EINVAL (-1)      /* bad descriptor / unsupported combination */
@@ -157,73 +163,80 @@ typedef struct trixi_b200_handle trixi_b200_handle;
  * Called once after `create_cache(mesh, equations, dg, RealT, uEltype)` (dgsem_tree/dg_2d.jl:14-37);
  * mirrors what `trixi_adapt`/`semidiscretize(...; storage_type)` does for the reference GPU path
  * (semidiscretization.jl:115-126): all containers are uploaded once. */
-int trixi_b200_create(const trixi_b200_desc *desc, trixi_b200_handle **out);
-void trixi_b200_destroy(trixi_b200_handle *h);
-const char *trixi_b200_last_error(const trixi_b200_handle *h); /* h may be NULL: last create error */
-int trixi_b200_abi_version(void);
+TRIXI_B200_API int trixi_b200_create(const trixi_b200_desc *desc, trixi_b200_handle **out);
+TRIXI_B200_API void trixi_b200_destroy(trixi_b200_handle *h);
+TRIXI_B200_API const char *trixi_b200_last_error(const trixi_b200_handle *h); /* h may be NULL: last create error */
+TRIXI_B200_API int trixi_b200_abi_version(void);
 
 /* Device-resident solution vectors owned by the handle: u, du, u_tmp (methods_2N.jl:95-111).
  * `which`: 0 = u, 1 = du, 2 = u_tmp.  Host arrays have nvars*n^d*nelements doubles. */
-int trixi_b200_upload(trixi_b200_handle *h, int which, const double *host);
-int trixi_b200_download(trixi_b200_handle *h, int which, double *host); /* Array(u) analysis_dg3d.jl:172-177 */
-void *trixi_b200_device_ptr(trixi_b200_handle *h, int which);           /* raw device pointer (for DLPack/torch views) */
-int trixi_b200_synchronize(trixi_b200_handle *h);
-void *trixi_b200_stream(trixi_b200_handle *h); /* the library-owned cudaStream_t */
+TRIXI_B200_API int trixi_b200_upload(trixi_b200_handle *h, int which, const double *host);
+TRIXI_B200_API int trixi_b200_download(trixi_b200_handle *h, int which, double *host); /* Array(u) analysis_dg3d.jl:172-177 */
+TRIXI_B200_API void *trixi_b200_device_ptr(trixi_b200_handle *h, int which);           /* raw device pointer (for DLPack/torch views) */
+TRIXI_B200_API int trixi_b200_synchronize(trixi_b200_handle *h);
+TRIXI_B200_API void *trixi_b200_stream(trixi_b200_handle *h); /* the library-owned cudaStream_t */
 
 /* ---- hot path -----------------------------------------------------------------------------------
  * rhs_hyperbolic!(backend, du, u, t, mesh, equations, boundary_conditions, source_terms, dg, cache)
  * (dgsem_tree/dg_2d.jl:113-186; structured dgsem_structured/dg.jl:41-94): du <- rhs(u, t), host
  * buffers: copies u host->device, runs the kernels, copies du device->host, synchronises. */
-int trixi_b200_rhs_host(trixi_b200_handle *h, double *du_host, const double *u_host, double t);
+TRIXI_B200_API int trixi_b200_rhs_host(trixi_b200_handle *h, double *du_host, const double *u_host, double t);
 /* same on the device-resident vectors (asynchronous on the handle's stream) */
-int trixi_b200_rhs(trixi_b200_handle *h, double t);
+TRIXI_B200_API int trixi_b200_rhs(trixi_b200_handle *h, double t);
 
 /* max_dt(u, t, mesh, constant_speed, equations, dg, cache) (stepsize_dg3d.jl:8-32, stepsize_dg2d.jl):
  * returns 2 / (nnodes * max_e invJ_e * sum_d max_nodes lambda_d) over the device-resident u;
  * the caller multiplies by cfl(t) (stepsize.jl:146-154).  With world_size > 1 the minimum over ranks
  * is taken (stepsize_dg3d.jl:264-279).  Synchronises. */
-int trixi_b200_max_dt(trixi_b200_handle *h, double t, double *dt_out);
+TRIXI_B200_API int trixi_b200_max_dt(trixi_b200_handle *h, double t, double *dt_out);
 
 /* step!(integrator::SimpleIntegrator2N) stage loop (methods_2N.jl:144-159): for every stage
  * du <- rhs(u, t + c_s dt); u_tmp <- du - a_s u_tmp; u <- u + (b_s dt) u_tmp, with the stage update
  * fused into the last RHS kernel.  u_tmp is zeroed first.  Asynchronous. */
-int trixi_b200_step_2n(trixi_b200_handle *h, double t, double dt, const double *a, const double *b,
+TRIXI_B200_API int trixi_b200_step_2n(trixi_b200_handle *h, double t, double dt, const double *a, const double *b,
                        const double *c, int nstages);
 /* `nsteps` steps with the CFL step size recomputed on the device after every step
  * (StepsizeCallback interval = 1, stepsize.jl:93-126) and the final step clipped to t_end
  * (time_integration.jl:46-55); no host round trip inside.  Returns the number of steps taken, the
  * final time and the last dt through the out-pointers.  Synchronises at the end. */
-int trixi_b200_solve_2n(trixi_b200_handle *h, double t0, double t_end, double cfl, int64_t max_steps,
+TRIXI_B200_API int trixi_b200_solve_2n(trixi_b200_handle *h, double t0, double t_end, double cfl, int64_t max_steps,
                         const double *a, const double *b, const double *c, int nstages,
                         int64_t *steps_out, double *t_out, double *dt_out);
 
 /* GlmSpeedCallback (glm_speed.jl:85-105) mutates equations.c_h every step */
-int trixi_b200_set_eq_param(trixi_b200_handle *h, int index, double value);
+TRIXI_B200_API int trixi_b200_set_eq_param(trixi_b200_handle *h, int index, double value);
 
 /* ---- stage-level entry points (parity tests against the reference's stage functions) ------------
  * calc_volume_integral! (calc_volume_integral.jl:180-191): du <- volume terms only (set_zero! included) */
-int trixi_b200_calc_volume_integral(trixi_b200_handle *h);
+TRIXI_B200_API int trixi_b200_calc_volume_integral(trixi_b200_handle *h);
 /* prolong2interfaces! + calc_interface_flux! + prolong2boundaries! + calc_boundary_flux!
  * (dg_3d.jl:530-602,651-768) -> surface_flux_values[nvars, n^(d-1), 2*ndims, nelements] */
-int trixi_b200_calc_surface_fluxes(trixi_b200_handle *h, double t);
-int trixi_b200_download_surface_flux_values(trixi_b200_handle *h, double *host);
+TRIXI_B200_API int trixi_b200_calc_surface_fluxes(trixi_b200_handle *h, double t);
+TRIXI_B200_API int trixi_b200_download_surface_flux_values(trixi_b200_handle *h, double *host);
 
 /* ---- distributed halo exchange (replaces MPI Isend/Irecv of dg_parallel.jl:66-182) --------------
  * The host process group (torch.distributed / MPI) moves the opaque ids; the data path is NCCL. */
-int trixi_b200_comm_unique_id(void *id_out_128_bytes);
-int trixi_b200_comm_init(trixi_b200_handle *h, const void *id_128_bytes);
+TRIXI_B200_API int trixi_b200_comm_unique_id(void *id_out_128_bytes);
+TRIXI_B200_API int trixi_b200_comm_init(trixi_b200_handle *h, const void *id_128_bytes);
 
 /* ---- measurement helpers --------------------------------------------------------------------- */
 /* number of kernel launches issued by this handle since creation */
-int64_t trixi_b200_launch_count(const trixi_b200_handle *h);
+TRIXI_B200_API int64_t trixi_b200_launch_count(const trixi_b200_handle *h);
 /* elapsed device milliseconds of the most recent trixi_b200_rhs/step_2n call, measured with CUDA
  * events on the handle's stream (feeds the PerformanceCounter, semidiscretization_hyperbolic.jl:586-594) */
-int trixi_b200_last_elapsed_ms(trixi_b200_handle *h, float *ms_out);
+TRIXI_B200_API int trixi_b200_last_elapsed_ms(trixi_b200_handle *h, float *ms_out);
+/* CUDA-event stopwatch on the handle's stream (bench.py brackets its timed region with it) */
+TRIXI_B200_API int trixi_b200_timer_start(trixi_b200_handle *h);
+TRIXI_B200_API int trixi_b200_timer_stop(trixi_b200_handle *h, float *ms_out); /* synchronises */
+/* Dependency-free DFMA / streaming-copy microbenchmarks on the handle's device: the FP64 roofline
+ * denominator is not in MEASURED_PEAKS.json and must be measured on the box. */
+TRIXI_B200_API int trixi_b200_measure_fp64_peak(trixi_b200_handle *h, double *tflops_out);
+TRIXI_B200_API int trixi_b200_measure_copy_bandwidth(trixi_b200_handle *h, double *gbs_out);
 /* per-kernel-class accumulated device time (ms) and launch counts since the last reset; classes:
  * 0 = surface-flux kernel, 1 = element kernel (volume+surface+jacobian+source+RK), 2 = max_dt,
  * 3 = halo pack/unpack.  Enabling costs two event records per launch. */
-int trixi_b200_profile_enable(trixi_b200_handle *h, int on);
-int trixi_b200_profile_read(trixi_b200_handle *h, int kernel_class, double *ms_out, int64_t *launches_out);
+TRIXI_B200_API int trixi_b200_profile_enable(trixi_b200_handle *h, int on);
+TRIXI_B200_API int trixi_b200_profile_read(trixi_b200_handle *h, int kernel_class, double *ms_out, int64_t *launches_out);
 
 #ifdef __cplusplus
 }

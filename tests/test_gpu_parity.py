@@ -1,0 +1,184 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI of libtrixi_b200.so) against the CPU
+oracle on identical seeded inputs.  Tolerance for floating point is the one BASELINE.json states:
+per-RHS  max|du_gpu - du_ref| <= 1e-12 * max|du_ref|."""
+import numpy as np
+import pytest
+import trixi_b200 as T
+
+from elixirs import ELIXIRS
+
+pytestmark = pytest.mark.gpu
+
+RHS_TOL = 1e-12
+
+
+def _random_admissible_state(semi, seed=0, perturb=None):
+    """rho in U[0.5,2], v in U[-1,1]^d, p in U[0.5,2] (regular ln_mean branch), or a
+    1e-3 perturbation of a constant state (series branch f^2 < 1e-4, math.jl:199-206)."""
+    rng = np.random.default_rng(seed)
+    eq = semi.equations
+    shape = semi.u_shape()[1:]
+    if isinstance(eq, T.LinearScalarAdvectionEquation2D):
+        return np.asfortranarray(rng.uniform(0.5, 2.0, size=(1,) + shape))
+    nd = eq.ndims
+    if perturb is None:
+        rho = rng.uniform(0.5, 2.0, size=shape)
+        v = [rng.uniform(-1.0, 1.0, size=shape) for _ in range(nd)]
+        p = rng.uniform(0.5, 2.0, size=shape)
+    else:
+        rho = 1.0 + perturb * rng.uniform(-1.0, 1.0, size=shape)
+        v = [0.3 + perturb * rng.uniform(-1.0, 1.0, size=shape) for _ in range(nd)]
+        p = 1.0 + perturb * rng.uniform(-1.0, 1.0, size=shape)
+    return np.asfortranarray(eq.prim2cons((rho, *v, p)))
+
+
+def _rel_err(a, b):
+    return np.max(np.abs(a - b)) / np.max(np.abs(b))
+
+
+RHS_CASES = ["tree_3d_euler_ec", "tree_3d_euler_source_terms", "tree_3d_euler_source_terms_split_form",
+             "tree_3d_euler_convergence", "tree_3d_euler_taylor_green_vortex", "tree_3d_euler_ec_chandrashekar",
+             "tree_3d_euler_ec_kennedy_gruber", "tree_3d_euler_ec_shima_etal", "tree_2d_advection_basic",
+             "tree_2d_euler_source_terms", "tree_2d_euler_source_terms_nonperiodic", "tree_2d_euler_ec",
+             "tree_2d_euler_density_wave"]
+
+
+@pytest.mark.parametrize("name", RHS_CASES)
+@pytest.mark.parametrize("state", ["initial_condition", "random", "perturbed"])
+def test_rhs_matches_oracle(name, state, oracle_module):
+    semi = ELIXIRS[name].semi()
+    if state == "initial_condition":
+        u = T.compute_coefficients(0.0, semi)
+    elif state == "random":
+        u = _random_admissible_state(semi, seed=1)
+    else:
+        u = _random_admissible_state(semi, seed=2, perturb=1e-3)
+    t = 0.37
+    ref = oracle_module.OracleBackend(semi)
+    du_ref = np.empty_like(u)
+    ref.rhs_host(du_ref, u, t)
+    du_gpu = np.full_like(u, np.nan)
+    T.rhs_hyperbolic(du_gpu, u, semi, t)  # the public call: host buffers in and out through the C ABI
+    assert np.all(np.isfinite(du_gpu))
+    assert _rel_err(du_gpu, du_ref) <= RHS_TOL
+
+
+@pytest.mark.parametrize("name", ["tree_3d_euler_ec", "tree_3d_euler_source_terms", "tree_2d_euler_source_terms_nonperiodic"])
+def test_stage_level_parity(name, oracle_module):
+    """calc_volume_integral! and the surface flux stages separately, like the reference's kernel parity
+    tests (test/test_performance_specializations_3d.jl:49-89)."""
+    semi = ELIXIRS[name].semi()
+    u = _random_admissible_state(semi, seed=3)
+    ref = oracle_module.OracleBackend(semi)
+    gpu = semi.backend()
+    ref.upload(0, u)
+    gpu.upload(0, u.ravel(order="F"))
+    ref.calc_volume_integral()
+    gpu.calc_volume_integral()
+    vol_ref, vol_gpu = ref.download(1), gpu.download(1)
+    assert _rel_err(vol_gpu, vol_ref) <= RHS_TOL
+    ref.calc_surface_fluxes(0.2)
+    gpu.calc_surface_fluxes(0.2)
+    sfv_ref = ref.sfv.copy()
+    sfv_gpu = gpu.download_surface_flux_values(np.empty_like(sfv_ref))
+    # faces without a flux (none here: periodic or Dirichlet everywhere) would be NaN on both sides
+    assert np.array_equal(np.isnan(sfv_ref), np.isnan(sfv_gpu))
+    m = ~np.isnan(sfv_ref)
+    assert _rel_err(sfv_gpu[m], sfv_ref[m]) <= RHS_TOL
+
+
+@pytest.mark.parametrize("name", ["tree_3d_euler_ec", "tree_2d_advection_basic", "tree_2d_euler_density_wave"])
+def test_max_dt_matches_oracle(name, oracle_module):
+    semi = ELIXIRS[name].semi()
+    u = _random_admissible_state(semi, seed=4)
+    ref = oracle_module.OracleBackend(semi)
+    gpu = semi.backend()
+    ref.upload(0, u)
+    gpu.upload(0, u.ravel(order="F"))
+    assert gpu.max_dt() == pytest.approx(ref.max_dt(), rel=1e-14)
+
+
+def test_max_dt_propagates_nan(oracle_module):
+    semi = ELIXIRS["tree_3d_euler_ec"].semi()
+    u = _random_admissible_state(semi, seed=5)
+    u[4, 1, 2, 3, 7] = -100.0  # negative pressure -> sqrt(NaN) like the reference's NaN-returning sqrt
+    gpu = semi.backend()
+    gpu.upload(0, u.ravel(order="F"))
+    assert np.isnan(gpu.max_dt())
+
+
+@pytest.mark.parametrize("name", ["tree_3d_euler_ec", "tree_3d_euler_source_terms", "tree_2d_advection_basic"])
+def test_step_2n_matches_oracle(name, oracle_module):
+    """Three full CarpenterKennedy2N54 steps (5 RHS + fused stage updates each) against the oracle's
+    separate RHS / axpy sweeps (methods_2N.jl:144-159)."""
+    semi = ELIXIRS[name].semi()
+    u = T.compute_coefficients(0.0, semi)
+    alg = T.CarpenterKennedy2N54()
+    ref = oracle_module.OracleBackend(semi)
+    gpu = semi.backend()
+    ref.upload(0, u)
+    gpu.upload(0, u.ravel(order="F"))
+    dt = 0.5 * ref.max_dt()
+    for k in range(3):
+        ref.step_2n(0.1 + k * dt, dt, alg.a, alg.b, alg.c)
+        gpu.step_2n(0.1 + k * dt, dt, alg.a, alg.b, alg.c)
+    u_ref, u_gpu = ref.download(0), gpu.download(0)
+    assert _rel_err(u_gpu, u_ref) <= 1e-13
+    assert _rel_err(gpu.download(2), ref.download(2)) <= 1e-11  # u_tmp
+
+
+GOLDEN_GPU = ["tree_3d_euler_ec", "tree_3d_euler_ec_constant", "tree_3d_euler_source_terms",
+              "tree_3d_euler_convergence", "tree_3d_euler_taylor_green_vortex", "tree_3d_euler_density_pulse",
+              "tree_2d_advection_basic", "tree_2d_euler_source_terms", "tree_2d_euler_source_terms_nonperiodic",
+              "tree_2d_euler_ec", "tree_2d_euler_density_wave"]
+
+
+@pytest.mark.parametrize("name", GOLDEN_GPU)
+def test_full_run_reproduces_reference_golden(name):
+    """AnalysisCallback L2/Linf after the full run agree with the reference's golden values to 1e-9
+    relative (BASELINE.json north_star)."""
+    ex = ELIXIRS[name]
+    semi = ex.semi()
+    sol, l2, linf = ex.run(semi)
+    ex.check(l2, linf)
+    assert semi.backend().launch_count() > 0
+
+
+def test_solve_2n_device_loop_matches_host_loop():
+    ex = ELIXIRS["tree_3d_euler_ec"]
+    semi = ex.semi()
+    sol, l2, linf = ex.run(semi)
+    semi2 = ex.semi()
+    gpu = semi2.backend()
+    ode = T.semidiscretize(semi2, ex.tspan)
+    gpu.upload(0, ode.u0.ravel(order="F"))
+    alg = T.CarpenterKennedy2N54()
+    steps, t_end, _ = gpu.solve_2n(ex.tspan[0], ex.tspan[1], ex.cfl, 10**9, alg.a, alg.b, alg.c)
+    assert steps == sol.integrator.iter
+    assert t_end == pytest.approx(ex.tspan[1], abs=1e-15)
+    u = gpu.download(0).reshape(semi2.u_shape(), order="F")
+    np.testing.assert_allclose(u, sol.u[-1], rtol=0, atol=1e-13)
+
+
+# ---- size-independent properties at a large size (the oracle would take too long) ---------------------
+def test_free_stream_preservation_large():
+    """initial_condition_constant => du == 0 up to round-off on a 32^3-element mesh (2.1 M DOF)
+    (test/test_tree_3d_euler.jl:293-316 pins errors ~1e-15)."""
+    semi = ELIXIRS["tree_3d_euler_ec"].build(initial_condition=T.initial_condition_constant, level=5)
+    u = T.compute_coefficients(0.0, semi)
+    du = np.empty_like(u)
+    T.rhs_hyperbolic(du, u, semi, 0.0)
+    assert np.max(np.abs(du)) < 1e-11
+
+
+def test_conservation_large():
+    """Periodic domain, conservative fluxes: sum_e J_e sum_nodes w du = 0 for every variable."""
+    semi = ELIXIRS["tree_3d_euler_taylor_green_vortex"].build(level=5)
+    u = T.compute_coefficients(0.0, semi)
+    du = np.empty_like(u)
+    T.rhs_hyperbolic(du, u, semi, 0.0)
+    w = semi.solver.basis.weights
+    w3 = w[:, None, None] * w[None, :, None] * w[None, None, :]
+    total = np.einsum("vijke,ijk->v", du, w3) / semi.cache.elements.inverse_jacobian[0] ** 3
+    scale = np.einsum("vijke,ijk->v", np.abs(du), w3) / semi.cache.elements.inverse_jacobian[0] ** 3
+    assert np.all(np.abs(total) <= 1e-12 * np.maximum(scale, 1.0))

@@ -1,0 +1,332 @@
+// Generic DGSEM kernels for Cartesian (TreeMesh) elements, templated on <equation, nnodes>.
+//
+// Launch structure of one RHS evaluation:
+//   1. k_interface_flux   prolong2interfaces! + calc_interface_flux! fused (dg_3d.jl:530-602): gathers
+//                         both face states straight from u, writes surface_flux_values of both elements.
+//   2. k_boundary_flux    prolong2boundaries! + calc_boundary_flux! fused (dg_3d.jl:651-768).
+//   3. k_element          set_zero! + calc_volume_integral! + calc_surface_integral! + apply_jacobian!
+//                         + calc_sources! fused (dg_3d.jl:133-214,1337-1437), and optionally the 2N
+//                         Runge-Kutta stage update (methods_2N.jl:150-158) and the per-element CFL
+//                         maxima of max_dt (stepsize_dg3d.jl:8-32) in the same pass.
+// Because the surface fluxes only depend on u, they are computed first; the element kernel then
+// produces the finished du (or the updated u) in a single sweep: u and du are each touched once.
+#pragma once
+#include "physics.cuh"
+
+namespace tb {
+
+constexpr int kMaxNodes = 8;
+
+struct KParams {
+    // sizes
+    long long nelements, ninterfaces, nboundaries;
+    // solution vectors
+    const double *u;  // [nv, n^d, nelem]
+    double *du;
+    double *u_tmp;
+    double *u_out;  // RK mode: updated u (may alias u)
+    double *sfv;    // surface_flux_values [nv, n^(d-1), 2d, nelem]
+    // operators (column-major [n, n]) live in constant-like global memory, staged to smem per block
+    const double *dsplit, *dhat;
+    double inv_weight0;
+    // geometry
+    const double *inverse_jacobian;  // [nelem]
+    const double *node_coordinates;  // [nd, n^d, nelem]
+    // connectivity (1-based int64 as uploaded)
+    const long long *if_neighbors;  // [2, I]
+    const long long *if_orient;     // [I]
+    const long long *bd_neighbor, *bd_orient, *bd_side;
+    const double *bd_coords;  // [nd, n^(d-1), B]
+    const int *bd_direction;  // [B] 1-based direction of each boundary (from n_boundaries_per_direction)
+    int bc[6], bc_ic[6];
+    // physics
+    EqParams eq;
+    int volume_integral, volume_flux, surface_flux, source_terms;
+    double t;
+    // RK stage (mode 1): u_tmp = du - u_tmp * a; u = u + u_tmp * b_dt
+    int mode;  // 0: write du, 1: 2N stage update
+    double rk_a, rk_b_dt;
+    // CFL fused output: per-block max of invJ * sum_d max_nodes lambda_d, encoded as ordered uint64
+    unsigned long long *cfl_key;  // nullptr: skip
+};
+
+__host__ __device__ constexpr int ipow(int b, int e) { return e == 0 ? 1 : b * ipow(b, e - 1); }
+
+// volume node (0-based linear) of face node fn on layer s normal to orientation o
+// (face node order x:(j,k) y:(i,k) z:(i,j), dg_3d.jl:540-563)
+template <int ND, int N>
+TB_DEV int face_to_volume_node(int o, int s, int fn) {
+    if constexpr (ND == 2) {
+        return o == 0 ? s + N * fn : fn + N * s;
+    } else {
+        const int a = fn % N, b = fn / N;
+        return o == 0 ? s + N * (a + N * b) : (o == 1 ? a + N * (s + N * b) : a + N * (b + N * s));
+    }
+}
+
+TB_DEV unsigned long long cfl_encode(double v) {
+    // positive doubles order like their bit patterns; NaN must win the max (Base.max propagates NaN,
+    // stepsize_dg3d.jl:24-28)
+    if (isnan(v)) return 0x7ff8000000000000ull;
+    return (unsigned long long)__double_as_longlong(v);
+}
+
+// ---- 1. interfaces ------------------------------------------------------------------------------
+template <class EQ, int N>
+__global__ void __launch_bounds__(256) k_interface_flux(const KParams P) {
+    constexpr int ND = EQ::NDIMS, NV = EQ::NVARS, NF = ipow(N, ND - 1), NN = ipow(N, ND);
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long I = gid / NF;
+    const int fn = (int)(gid % NF);
+    if (I >= P.ninterfaces) return;
+    const EQ eq(P.eq);
+    const long long left = P.if_neighbors[2 * I] - 1, right = P.if_neighbors[2 * I + 1] - 1;
+    const int o = (int)P.if_orient[I] - 1;
+    const int nl = face_to_volume_node<ND, N>(o, N - 1, fn), nr = face_to_volume_node<ND, N>(o, 0, fn);
+    double ul[NV], ur[NV], f[NV];
+    const double *pl = P.u + (left * NN + nl) * NV, *pr = P.u + (right * NN + nr) * NV;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+        ul[v] = pl[v];
+        ur[v] = pr[v];
+    }
+    eq.numflux(P.surface_flux, ul, ur, o, f);
+    // left element: direction 2*orientation (1-based) = index 2o+1; right element: 2o (dg_3d.jl:581-597)
+    double *sl = P.sfv + ((left * (2 * ND) + (2 * o + 1)) * NF + fn) * NV;
+    double *sr = P.sfv + ((right * (2 * ND) + (2 * o)) * NF + fn) * NV;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+        sl[v] = f[v];
+        sr[v] = f[v];
+    }
+}
+
+// ---- 2. boundaries ------------------------------------------------------------------------------
+template <class EQ, int N>
+__global__ void __launch_bounds__(256) k_boundary_flux(const KParams P) {
+    constexpr int ND = EQ::NDIMS, NV = EQ::NVARS, NF = ipow(N, ND - 1), NN = ipow(N, ND);
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long B = gid / NF;
+    const int fn = (int)(gid % NF);
+    if (B >= P.nboundaries) return;
+    const EQ eq(P.eq);
+    const long long element = P.bd_neighbor[B] - 1;
+    const int o = (int)P.bd_orient[B] - 1;
+    const int side = (int)P.bd_side[B];
+    const int direction = P.bd_direction[B];  // 1-based
+    const int vn = face_to_volume_node<ND, N>(o, side == 1 ? N - 1 : 0, fn);
+    double ui[NV], f[NV], x[ND];
+    const double *pu = P.u + (element * NN + vn) * NV;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) ui[v] = pu[v];
+#pragma unroll
+    for (int d = 0; d < ND; ++d) x[d] = P.bd_coords[(B * NF + fn) * ND + d];
+    boundary_flux(eq, P.bc[direction - 1], P.bc_ic[direction - 1], P.surface_flux, ui, o, direction, x, P.t, f);
+    double *s = P.sfv + ((element * (2 * ND) + (direction - 1)) * NF + fn) * NV;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) s[v] = f[v];
+}
+
+// ---- 3. element kernel ----------------------------------------------------------------------------
+// One thread per node, EPB elements per block.  Shared memory: the block's u tile (coalesced flat copy
+// of EPB contiguous element records), the D matrix, and for the weak form the nodal fluxes.
+template <class EQ, int N>
+struct ElemCfg {
+    static constexpr int ND = EQ::NDIMS, NV = EQ::NVARS, NN = ipow(N, ND);
+    static constexpr int EPB = NN >= 128 ? 1 : 128 / NN;  // elements per block
+    static constexpr int THREADS = EPB * NN;
+    // node record stride in shared memory (odd number of doubles -> conflict-free 64-bit access)
+    static constexpr int US = (NV % 2 == 0) ? NV + 1 : NV;
+};
+
+template <class EQ, int N, int VOLINT, bool WITH_SURFACE>
+__global__ void __launch_bounds__(ElemCfg<EQ, N>::THREADS) k_element(const KParams P) {
+    using C = ElemCfg<EQ, N>;
+    constexpr int ND = C::ND, NV = C::NV, NN = C::NN, EPB = C::EPB, US = C::US, NF = ipow(N, ND - 1);
+    extern __shared__ double smem[];
+    double *s_u = smem;                     // [EPB*NN][US]
+    double *s_D = s_u + EPB * NN * US;      // [N*N] column-major
+    double *s_f = s_D + N * N;              // weak form: [ND][EPB*NN][US]
+    __shared__ double s_red[C::THREADS / 32 > 0 ? C::THREADS / 32 : 1];
+
+    const EQ eq(P.eq);
+    const int tid = threadIdx.x;
+    const long long e0 = (long long)blockIdx.x * EPB;
+    const int nel = (int)min((long long)EPB, P.nelements - e0);
+
+    // stage D and the u tile
+    const double *Dsrc = VOLINT == TRIXI_B200_VOLINT_WEAK_FORM ? P.dhat : P.dsplit;
+    for (int q = tid; q < N * N; q += C::THREADS) s_D[q] = Dsrc[q];
+    {
+        const double *src = P.u + e0 * NN * NV;
+        const int total = nel * NN * NV;
+        for (int q = tid; q < total; q += C::THREADS) {
+            const int node = q / NV, v = q - node * NV;
+            s_u[node * US + v] = src[q];
+        }
+    }
+    __syncthreads();
+
+    const int le = tid / NN;        // local element
+    const int node = tid - le * NN; // node within element
+    const bool active = le < nel;
+    const long long e = e0 + le;
+    int idx[3];
+    idx[0] = node % N;
+    idx[1] = (node / N) % N;
+    idx[2] = ND == 3 ? node / (N * N) : 0;
+    const int stride[3] = {1, N, N * N};
+    const double *ue = s_u + le * NN * US;
+
+    double un[NV], acc[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+        un[v] = active ? ue[node * US + v] : 0.0;
+        acc[v] = 0.0;
+    }
+
+    if constexpr (VOLINT == TRIXI_B200_VOLINT_WEAK_FORM) {
+        // weak_form_kernel! (dg_3d.jl:133-164): du[:, ii, j, k] += Dhat[ii, i] * flux1(u[i, j, k]) ...
+        if (active) {
+#pragma unroll
+            for (int d = 0; d < ND; ++d) {
+                double f[NV];
+                eq.flux(un, d, f);
+#pragma unroll
+                for (int v = 0; v < NV; ++v) s_f[(d * EPB * NN + le * NN + node) * US + v] = f[v];
+            }
+        }
+        __syncthreads();
+        if (active) {
+#pragma unroll
+            for (int d = 0; d < ND; ++d) {
+                const int base = node - idx[d] * stride[d];
+#pragma unroll
+                for (int l = 0; l < N; ++l) {
+                    const double w = s_D[idx[d] + N * l];  // Dhat[idx_d, l]
+                    const double *f = s_f + (d * EPB * NN + le * NN + base + l * stride[d]) * US;
+#pragma unroll
+                    for (int v = 0; v < NV; ++v) acc[v] = fma(w, f[v], acc[v]);
+                }
+            }
+        }
+    } else {
+        // flux_differencing_kernel! (dg_3d.jl:166-214): the reference evaluates each symmetric pair once
+        // as volume_flux(u_lower, u_upper); every node here evaluates its own partners with the same
+        // argument order, so both ends see the bit-identical flux.
+        if (active) {
+#pragma unroll
+            for (int d = 0; d < ND; ++d) {
+                const int base = node - idx[d] * stride[d];
+#pragma unroll 1
+                for (int l = 0; l < N; ++l) {
+                    if (l == idx[d]) continue;
+                    double up[NV], f[NV];
+                    const double *pu = ue + (base + l * stride[d]) * US;
+#pragma unroll
+                    for (int v = 0; v < NV; ++v) up[v] = pu[v];
+                    if (l > idx[d])
+                        eq.numflux(P.volume_flux, un, up, d, f);
+                    else
+                        eq.numflux(P.volume_flux, up, un, d, f);
+                    const double w = s_D[idx[d] + N * l];  // Dsplit[idx_d, l]
+#pragma unroll
+                    for (int v = 0; v < NV; ++v) acc[v] = fma(w, f[v], acc[v]);
+                }
+            }
+        }
+    }
+
+    if (!active) return;
+
+    if constexpr (WITH_SURFACE) {
+        // calc_surface_integral! (dg_3d.jl:1337-1394): - on the negative faces, + on the positive ones
+        const double *sf = P.sfv + e * (2 * ND) * NF * NV;
+#pragma unroll
+        for (int d = 0; d < ND; ++d) {
+            int fn;
+            if constexpr (ND == 2)
+                fn = d == 0 ? idx[1] : idx[0];
+            else
+                fn = d == 0 ? idx[1] + N * idx[2] : (d == 1 ? idx[0] + N * idx[2] : idx[0] + N * idx[1]);
+            if (idx[d] == 0) {
+                const double *s = sf + ((2 * d) * NF + fn) * NV;
+#pragma unroll
+                for (int v = 0; v < NV; ++v) acc[v] = acc[v] - s[v] * P.inv_weight0;
+            }
+            if (idx[d] == N - 1) {
+                const double *s = sf + ((2 * d + 1) * NF + fn) * NV;
+#pragma unroll
+                for (int v = 0; v < NV; ++v) acc[v] = acc[v] + s[v] * P.inv_weight0;
+            }
+        }
+        // apply_jacobian! (dg_3d.jl:1396-1414)
+        const double factor = -P.inverse_jacobian[e];
+#pragma unroll
+        for (int v = 0; v < NV; ++v) acc[v] *= factor;
+        // calc_sources! (dg_3d.jl:1417-1437)
+        if (P.source_terms != TRIXI_B200_SRC_NONE) {
+            double x[ND], s[NV];
+#pragma unroll
+            for (int d = 0; d < ND; ++d) x[d] = P.node_coordinates[(e * NN + node) * ND + d];
+            eq.source_terms(P.source_terms, un, x, P.t, s);
+#pragma unroll
+            for (int v = 0; v < NV; ++v) acc[v] += s[v];
+        }
+    }
+
+    const long long off = (e * NN + node) * NV;
+    if (P.mode == 0) {
+#pragma unroll
+        for (int v = 0; v < NV; ++v) P.du[off + v] = acc[v];
+    } else {
+        // 2N stage (methods_2N.jl:152-158): u_tmp = du - u_tmp * a; u += u_tmp * (b * dt)
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            // first stage: a = 0 and u_tmp = 0 (methods_2N.jl:144), so du - 0 * 0 == du exactly; skipping
+            // the read also removes the `u_tmp .= 0` sweep
+            const double tmp = P.rk_a == 0.0 ? acc[v] : acc[v] - P.u_tmp[off + v] * P.rk_a;
+            P.u_tmp[off + v] = tmp;
+            un[v] = un[v] + tmp * P.rk_b_dt;
+            P.u_out[off + v] = un[v];
+        }
+    }
+    (void)s_red;
+}
+
+// ---- max_dt ------------------------------------------------------------------------------------------
+// stepsize_dg3d.jl:8-32: per element, maxima over nodes of each directional speed separately, summed,
+// times inverse_jacobian; global max via atomicMax on the ordered bit pattern.
+template <class EQ, int N>
+__global__ void __launch_bounds__(ElemCfg<EQ, N>::THREADS) k_max_dt(const KParams P) {
+    using C = ElemCfg<EQ, N>;
+    constexpr int ND = C::ND, NV = C::NV, NN = C::NN, EPB = C::EPB;
+    __shared__ unsigned long long s_lam[ND][EPB];
+    const EQ eq(P.eq);
+    const int tid = threadIdx.x;
+    const long long e0 = (long long)blockIdx.x * EPB;
+    const int le = tid / NN, node = tid - le * NN;
+    const long long e = e0 + le;
+    if (tid < ND * EPB) (&s_lam[0][0])[tid] = 0ull;
+    __syncthreads();
+    if (e < P.nelements) {
+        double un[NV], lam[ND];
+        const double *pu = P.u + (e * NN + node) * NV;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) un[v] = pu[v];
+        eq.max_abs_speeds(un, lam);
+#pragma unroll
+        for (int d = 0; d < ND; ++d) atomicMax(&s_lam[d][le], cfl_encode(lam[d]));
+    }
+    __syncthreads();
+    if (tid < EPB && e0 + tid < P.nelements) {
+        double s = 0.0;
+#pragma unroll
+        for (int d = 0; d < ND; ++d) s += __longlong_as_double((long long)s_lam[d][tid]);
+        const double val = P.inverse_jacobian[e0 + tid] * s;
+        atomicMax(P.cfl_key, cfl_encode(val));
+    }
+}
+
+
+}  // namespace tb

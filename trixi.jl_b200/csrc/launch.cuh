@@ -1,0 +1,104 @@
+// Host-side launchers for the templated kernels and the per-equation dispatch tables.
+#pragma once
+#include "kernels.cuh"
+
+namespace tb {
+
+struct Launchers {
+    void (*interface_flux)(const KParams &, cudaStream_t);
+    void (*boundary_flux)(const KParams &, cudaStream_t);
+    // with_surface = false: volume terms only (stage-level parity entry point)
+    cudaError_t (*element)(const KParams &, bool with_surface, cudaStream_t);
+    void (*max_dt)(const KParams &, cudaStream_t);
+    int ndims, nvars, nnodes;
+};
+
+template <class EQ, int N>
+void launch_interface_flux(const KParams &P, cudaStream_t s) {
+    constexpr int NF = ipow(N, EQ::NDIMS - 1);
+    const long long total = P.ninterfaces * NF;
+    if (total == 0) return;
+    const int threads = 256;
+    const unsigned blocks = (unsigned)((total + threads - 1) / threads);
+    k_interface_flux<EQ, N><<<blocks, threads, 0, s>>>(P);
+}
+
+template <class EQ, int N>
+void launch_boundary_flux(const KParams &P, cudaStream_t s) {
+    constexpr int NF = ipow(N, EQ::NDIMS - 1);
+    const long long total = P.nboundaries * NF;
+    if (total == 0) return;
+    const int threads = 256;
+    const unsigned blocks = (unsigned)((total + threads - 1) / threads);
+    k_boundary_flux<EQ, N><<<blocks, threads, 0, s>>>(P);
+}
+
+template <class EQ, int N, int VOLINT, bool WS>
+cudaError_t launch_element_variant(const KParams &P, cudaStream_t s) {
+    using C = ElemCfg<EQ, N>;
+    const size_t smem = sizeof(double) * ((size_t)C::EPB * C::NN * C::US + N * N +
+                                          (VOLINT == TRIXI_B200_VOLINT_WEAK_FORM
+                                               ? (size_t)C::ND * C::EPB * C::NN * C::US
+                                               : 0));
+    auto kern = k_element<EQ, N, VOLINT, WS>;
+    if (smem > 48 * 1024) {
+        static bool configured = false;
+        if (!configured) {
+            cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (err != cudaSuccess) return err;
+            configured = true;
+        }
+    }
+    const unsigned blocks = (unsigned)((P.nelements + C::EPB - 1) / C::EPB);
+    kern<<<blocks, C::THREADS, smem, s>>>(P);
+    return cudaSuccess;
+}
+
+template <class EQ, int N>
+cudaError_t launch_element(const KParams &P, bool with_surface, cudaStream_t s) {
+    if (P.nelements == 0) return cudaSuccess;
+    if (P.volume_integral == TRIXI_B200_VOLINT_WEAK_FORM) {
+        return with_surface ? launch_element_variant<EQ, N, TRIXI_B200_VOLINT_WEAK_FORM, true>(P, s)
+                            : launch_element_variant<EQ, N, TRIXI_B200_VOLINT_WEAK_FORM, false>(P, s);
+    }
+    return with_surface ? launch_element_variant<EQ, N, TRIXI_B200_VOLINT_FLUX_DIFFERENCING, true>(P, s)
+                        : launch_element_variant<EQ, N, TRIXI_B200_VOLINT_FLUX_DIFFERENCING, false>(P, s);
+}
+
+template <class EQ, int N>
+void launch_max_dt(const KParams &P, cudaStream_t s) {
+    using C = ElemCfg<EQ, N>;
+    if (P.nelements == 0) return;
+    const unsigned blocks = (unsigned)((P.nelements + C::EPB - 1) / C::EPB);
+    k_max_dt<EQ, N><<<blocks, C::THREADS, 0, s>>>(P);
+}
+
+template <class EQ, int N>
+const Launchers *make_launchers() {
+    static const Launchers L = {&launch_interface_flux<EQ, N>, &launch_boundary_flux<EQ, N>,
+                                &launch_element<EQ, N>,        &launch_max_dt<EQ, N>,
+                                EQ::NDIMS,                     EQ::NVARS,
+                                N};
+    return &L;
+}
+
+template <class EQ>
+const Launchers *launchers_for_nnodes(int n) {
+    switch (n) {
+    case 2: return make_launchers<EQ, 2>();
+    case 3: return make_launchers<EQ, 3>();
+    case 4: return make_launchers<EQ, 4>();
+    case 5: return make_launchers<EQ, 5>();
+    case 6: return make_launchers<EQ, 6>();
+    case 7: return make_launchers<EQ, 7>();
+    case 8: return make_launchers<EQ, 8>();
+    default: return nullptr;
+    }
+}
+
+// one translation unit per equation (parallel nvcc)
+const Launchers *get_launchers_advection2d(int nnodes);
+const Launchers *get_launchers_euler2d(int nnodes);
+const Launchers *get_launchers_euler3d(int nnodes);
+
+}  // namespace tb

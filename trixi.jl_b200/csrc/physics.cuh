@@ -1,0 +1,430 @@
+// Pointwise physics as __device__ functions: the reference's L1 layer
+// (src/equations/*.jl, src/auxiliary/math.jl) re-expressed for sm_100a.  Orientation is a plain int
+// (0-based) consumed through selects only -- no dynamically indexed register arrays -- so the same
+// code folds to straight-line FP64 when the caller unrolls over directions (volume kernels) and
+// costs a few predicated moves when the orientation is per-face data (surface kernels).
+// nvcc's default -fmad=true contracts a*b+c into DFMA, mirroring the reference's @muladd.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+
+#include "../../include/trixi_b200.h"
+
+namespace tb {
+
+struct EqParams {
+    double p[8];
+};
+
+#define TB_DEV __device__ __forceinline__
+
+template <int ND>
+TB_DEV double pick(const double (&v)[ND], int o) {
+    if constexpr (ND == 1) return v[0];
+    if constexpr (ND == 2) return o == 0 ? v[0] : v[1];
+    if constexpr (ND == 3) return o == 0 ? v[0] : (o == 1 ? v[1] : v[2]);
+}
+
+// ---- src/auxiliary/math.jl ------------------------------------------------------------------------
+// ln_mean (math.jl:198-210): Ismail-Roe series for f^2 < 1e-4, else (y-x)/log(y/x)
+TB_DEV double ln_mean(double x, double y) {
+    const double f2 = (x * (x - 2 * y) + y * y) / (x * (x + 2 * y) + y * y);
+    if (f2 < 1.0e-4) {
+        const double p = fma(f2, fma(f2, fma(f2, 2.0 / 7.0, 2.0 / 5.0), 2.0 / 3.0), 2.0);
+        return (x + y) / p;
+    }
+    return (y - x) / log(y / x);
+}
+// inv_ln_mean (math.jl:238-250)
+TB_DEV double inv_ln_mean(double x, double y) {
+    const double f2 = (x * (x - 2 * y) + y * y) / (x * (x + 2 * y) + y * y);
+    if (f2 < 1.0e-4) {
+        const double p = fma(f2, fma(f2, fma(f2, 2.0 / 7.0, 2.0 / 5.0), 2.0 / 3.0), 2.0);
+        return p / (x + y);
+    }
+    return log(y / x) / (y - x);
+}
+
+// ---- linear scalar advection (linear_scalar_advection_2d.jl / _3d.jl) -------------------------------
+template <int ND>
+struct Advection {
+    static constexpr int NDIMS = ND, NVARS = 1;
+    static constexpr bool kConstantSpeed = true;  // have_constant_speed (linear_scalar_advection_2d.jl:290)
+    double a0, a1, a2;
+    __host__ __device__ explicit Advection(const EqParams &q) : a0(q.p[0]), a1(q.p[1]), a2(q.p[2]) {}
+    TB_DEV double a(int o) const { return o == 0 ? a0 : (o == 1 ? a1 : a2); }
+
+    // flux (linear_scalar_advection_2d.jl:221-225)
+    TB_DEV void flux(const double (&u)[1], int o, double (&f)[1]) const { f[0] = a(o) * u[0]; }
+
+    TB_DEV void numflux(int id, const double (&ul)[1], const double (&ur)[1], int o, double (&f)[1]) const {
+        const double an = a(o);
+        switch (id) {
+        case TRIXI_B200_FLUX_CENTRAL:  // numerical_fluxes.jl:17-25
+            f[0] = 0.5 * (an * ul[0] + an * ur[0]);
+            break;
+        case TRIXI_B200_FLUX_LLF:  // max_abs_speed falls back to the naive one (numerical_fluxes.jl:219-225)
+        case TRIXI_B200_FLUX_LLF_NAIVE: {  // linear_scalar_advection_2d.jl:228-231
+            const double lam = fabs(an);
+            f[0] = 0.5 * (an * ul[0] + an * ur[0]) + (-0.5 * lam * (ur[0] - ul[0]));
+            break;
+        }
+        case TRIXI_B200_FLUX_GODUNOV:  // linear_scalar_advection_2d.jl:248-260
+            f[0] = an >= 0 ? an * ul[0] : an * ur[0];
+            break;
+        default:
+            f[0] = nan("");
+        }
+    }
+    // max_abs_speeds(equation) (linear_scalar_advection_2d.jl:292-294)
+    TB_DEV void max_abs_speeds(const double (&u)[1], double (&lam)[ND]) const {
+        lam[0] = fabs(a0);
+        if constexpr (ND > 1) lam[1] = fabs(a1);
+        if constexpr (ND > 2) lam[2] = fabs(a2);
+    }
+    TB_DEV void source_terms(int id, const double (&u)[1], const double (&x)[ND], double t, double (&s)[1]) const {
+        s[0] = 0.0;
+    }
+    TB_DEV void initial_condition(int id, const double (&x)[ND], double t, double (&u)[1]) const {
+        if (id == TRIXI_B200_IC_CONVERGENCE_TEST) {  // linear_scalar_advection_2d.jl:67-80
+            double s = x[0] - a0 * t;
+            if constexpr (ND > 1) s += x[1] - a1 * t;
+            if constexpr (ND > 2) s += x[2] - a2 * t;
+            u[0] = 1 + 0.5 * sin(2 * M_PI * 0.5 * s);
+        } else if (id == TRIXI_B200_IC_CONSTANT) {
+            u[0] = 2.0;
+        } else {
+            u[0] = nan("");
+        }
+    }
+    TB_DEV void slip_wall(const double (&u)[1], int o, int direction, double (&f)[1]) const { f[0] = nan(""); }
+};
+
+// ---- compressible Euler (compressible_euler_2d.jl, compressible_euler_3d.jl) -------------------------
+template <int ND>
+struct Euler {
+    static constexpr int NDIMS = ND, NVARS = ND + 2;
+    static constexpr bool kConstantSpeed = false;
+    double gamma, inv_gm1;
+    __host__ __device__ explicit Euler(const EqParams &q) : gamma(q.p[0]), inv_gm1(q.p[1]) {}
+
+    // cons2prim (compressible_euler_3d.jl:1783-1793)
+    TB_DEV void cons2prim(const double (&u)[NVARS], double &rho, double (&v)[ND], double &p) const {
+        rho = u[0];
+        double kin = 0.0;
+#pragma unroll
+        for (int d = 0; d < ND; ++d) {
+            v[d] = u[1 + d] / u[0];
+            kin += u[1 + d] * v[d];
+        }
+        p = (gamma - 1) * (u[ND + 1] - 0.5 * kin);
+    }
+
+    // flux(u, orientation) (compressible_euler_3d.jl:420-447)
+    TB_DEV void flux(const double (&u)[NVARS], int o, double (&f)[NVARS]) const {
+        double rho, v[ND], p;
+        cons2prim(u, rho, v, p);
+        double mom[ND];
+#pragma unroll
+        for (int d = 0; d < ND; ++d) mom[d] = u[1 + d];
+        const double rv = pick<ND>(mom, o);
+        f[0] = rv;
+#pragma unroll
+        for (int d = 0; d < ND; ++d) f[1 + d] = rv * v[d] + (d == o ? p : 0.0);
+        f[ND + 1] = (u[ND + 1] + p) * pick<ND>(v, o);
+    }
+
+    // flux_ranocha (compressible_euler_3d.jl:746-793), generic form: ln_mean/inv_ln_mean per pair
+    TB_DEV void flux_ranocha(const double (&ul)[NVARS], const double (&ur)[NVARS], int o,
+                             double (&f)[NVARS]) const {
+        double rho_ll, v_ll[ND], p_ll, rho_rr, v_rr[ND], p_rr;
+        cons2prim(ul, rho_ll, v_ll, p_ll);
+        cons2prim(ur, rho_rr, v_rr, p_rr);
+        const double rho_mean = ln_mean(rho_ll, rho_rr);
+        const double inv_rho_p_mean = p_ll * p_rr * inv_ln_mean(rho_ll * p_rr, rho_rr * p_ll);
+        double v_avg[ND], vsq = 0.0;
+#pragma unroll
+        for (int d = 0; d < ND; ++d) {
+            v_avg[d] = 0.5 * (v_ll[d] + v_rr[d]);
+            vsq += v_ll[d] * v_rr[d];
+        }
+        const double p_avg = 0.5 * (p_ll + p_rr);
+        const double velocity_square_avg = 0.5 * vsq;
+        const double f1 = rho_mean * pick<ND>(v_avg, o);
+        f[0] = f1;
+#pragma unroll
+        for (int d = 0; d < ND; ++d) f[1 + d] = f1 * v_avg[d] + (d == o ? p_avg : 0.0);
+        f[ND + 1] = f1 * (velocity_square_avg + inv_rho_p_mean * inv_gm1) +
+                    0.5 * (p_ll * pick<ND>(v_rr, o) + p_rr * pick<ND>(v_ll, o));
+    }
+
+    // flux_shima_etal (compressible_euler_3d.jl:473-510)
+    TB_DEV void flux_shima(const double (&ul)[NVARS], const double (&ur)[NVARS], int o, double (&f)[NVARS]) const {
+        double rho_ll, v_ll[ND], p_ll, rho_rr, v_rr[ND], p_rr;
+        cons2prim(ul, rho_ll, v_ll, p_ll);
+        cons2prim(ur, rho_rr, v_rr, p_rr);
+        const double rho_avg = 0.5 * (rho_ll + rho_rr), p_avg = 0.5 * (p_ll + p_rr);
+        double v_avg[ND], kin = 0.0;
+#pragma unroll
+        for (int d = 0; d < ND; ++d) {
+            v_avg[d] = 0.5 * (v_ll[d] + v_rr[d]);
+            kin += v_ll[d] * v_rr[d];
+        }
+        const double kin_avg = 0.5 * kin;
+        const double pv_avg = 0.5 * (p_ll * pick<ND>(v_rr, o) + p_rr * pick<ND>(v_ll, o));
+        const double vn = pick<ND>(v_avg, o);
+        const double f1 = rho_avg * vn;
+        f[0] = f1;
+#pragma unroll
+        for (int d = 0; d < ND; ++d) f[1 + d] = f1 * v_avg[d] + (d == o ? p_avg : 0.0);
+        f[ND + 1] = p_avg * vn * inv_gm1 + f1 * kin_avg + pv_avg;
+    }
+
+    // flux_kennedy_gruber (compressible_euler_3d.jl:560-600)
+    TB_DEV void flux_kennedy_gruber(const double (&ul)[NVARS], const double (&ur)[NVARS], int o,
+                                    double (&f)[NVARS]) const {
+        double rho_ll, v_ll[ND], p_ll, rho_rr, v_rr[ND], p_rr;
+        cons2prim(ul, rho_ll, v_ll, p_ll);
+        cons2prim(ur, rho_rr, v_rr, p_rr);
+        const double rho_avg = 0.5 * (rho_ll + rho_rr), p_avg = 0.5 * (p_ll + p_rr);
+        double v_avg[ND];
+#pragma unroll
+        for (int d = 0; d < ND; ++d) v_avg[d] = 0.5 * (v_ll[d] + v_rr[d]);
+        const double e_avg = 0.5 * (ul[ND + 1] / rho_ll + ur[ND + 1] / rho_rr);
+        const double vn = pick<ND>(v_avg, o);
+        const double f1 = rho_avg * vn;
+        f[0] = f1;
+#pragma unroll
+        for (int d = 0; d < ND; ++d) f[1 + d] = f1 * v_avg[d] + (d == o ? p_avg : 0.0);
+        f[ND + 1] = (rho_avg * e_avg + p_avg) * vn;
+    }
+
+    // flux_chandrashekar (compressible_euler_3d.jl:639-690)
+    TB_DEV void flux_chandrashekar(const double (&ul)[NVARS], const double (&ur)[NVARS], int o,
+                                   double (&f)[NVARS]) const {
+        double rho_ll, v_ll[ND], p_ll, rho_rr, v_rr[ND], p_rr;
+        cons2prim(ul, rho_ll, v_ll, p_ll);
+        cons2prim(ur, rho_rr, v_rr, p_rr);
+        const double beta_ll = 0.5 * rho_ll / p_ll, beta_rr = 0.5 * rho_rr / p_rr;
+        double kl = 0.0, kr = 0.0, v_avg[ND];
+#pragma unroll
+        for (int d = 0; d < ND; ++d) {
+            kl += v_ll[d] * v_ll[d];
+            kr += v_rr[d] * v_rr[d];
+            v_avg[d] = 0.5 * (v_ll[d] + v_rr[d]);
+        }
+        const double rho_avg = 0.5 * (rho_ll + rho_rr);
+        const double rho_mean = ln_mean(rho_ll, rho_rr);
+        const double beta_mean = ln_mean(beta_ll, beta_rr);
+        const double beta_avg = 0.5 * (beta_ll + beta_rr);
+        const double p_mean = 0.5 * rho_avg / beta_avg;
+        const double velocity_square_avg = 0.5 * kl + 0.5 * kr;
+        const double f1 = rho_mean * pick<ND>(v_avg, o);
+        f[0] = f1;
+        double s = f1 * 0.5 * (1 / (gamma - 1) / beta_mean - velocity_square_avg);
+#pragma unroll
+        for (int d = 0; d < ND; ++d) {
+            f[1 + d] = f1 * v_avg[d] + (d == o ? p_mean : 0.0);
+            s += f[1 + d] * v_avg[d];
+        }
+        f[ND + 1] = s;
+    }
+
+    TB_DEV void numflux(int id, const double (&ul)[NVARS], const double (&ur)[NVARS], int o,
+                        double (&f)[NVARS]) const {
+        switch (id) {
+        case TRIXI_B200_FLUX_CENTRAL: {  // numerical_fluxes.jl:17-25
+            double fl[NVARS], fr[NVARS];
+            flux(ul, o, fl);
+            flux(ur, o, fr);
+#pragma unroll
+            for (int v = 0; v < NVARS; ++v) f[v] = 0.5 * (fl[v] + fr[v]);
+            break;
+        }
+        case TRIXI_B200_FLUX_LLF:
+        case TRIXI_B200_FLUX_LLF_NAIVE: {  // numerical_fluxes.jl:37-45,172-178
+            double rho_ll, v_ll[ND], p_ll, rho_rr, v_rr[ND], p_rr;
+            cons2prim(ul, rho_ll, v_ll, p_ll);
+            cons2prim(ur, rho_rr, v_rr, p_rr);
+            const double c_ll = sqrt(gamma * p_ll / rho_ll), c_rr = sqrt(gamma * p_rr / rho_rr);
+            const double vl = pick<ND>(v_ll, o), vr = pick<ND>(v_rr, o);
+            // max_abs_speed_naive (compressible_euler_3d.jl:1112-1133) / max_abs_speed (:1156-1177)
+            const double lam = id == TRIXI_B200_FLUX_LLF_NAIVE ? fmax(fabs(vl), fabs(vr)) + fmax(c_ll, c_rr)
+                                                               : fmax(fabs(vl) + c_ll, fabs(vr) + c_rr);
+            double fl[NVARS], fr[NVARS];
+            flux(ul, o, fl);
+            flux(ur, o, fr);
+#pragma unroll
+            for (int v = 0; v < NVARS; ++v) f[v] = 0.5 * (fl[v] + fr[v]) + (-0.5 * lam * (ur[v] - ul[v]));
+            break;
+        }
+        case TRIXI_B200_FLUX_HLL_DAVIS:
+        case TRIXI_B200_FLUX_HLL_NAIVE: {  // FluxHLL numerical_fluxes.jl:422-440
+            double rho_ll, v_ll[ND], p_ll, rho_rr, v_rr[ND], p_rr;
+            cons2prim(ul, rho_ll, v_ll, p_ll);
+            cons2prim(ur, rho_rr, v_rr, p_rr);
+            const double c_ll = sqrt(gamma * p_ll / rho_ll), c_rr = sqrt(gamma * p_rr / rho_rr);
+            const double vl = pick<ND>(v_ll, o), vr = pick<ND>(v_rr, o);
+            double lmin, lmax;
+            if (id == TRIXI_B200_FLUX_HLL_NAIVE) {  // compressible_euler_3d.jl:1201-1218
+                lmin = vl - c_ll;
+                lmax = vr + c_rr;
+            } else {  // min_max_speed_davis :1240-1261
+                lmin = fmin(vl - c_ll, vr - c_rr);
+                lmax = fmax(vl + c_ll, vr + c_rr);
+            }
+            if (lmin >= 0 && lmax >= 0) {
+                flux(ul, o, f);
+            } else if (lmax <= 0 && lmin <= 0) {
+                flux(ur, o, f);
+            } else {
+                double fl[NVARS], fr[NVARS];
+                flux(ul, o, fl);
+                flux(ur, o, fr);
+                const double inv = 1.0 / (lmax - lmin);
+                const double factor_ll = lmax * inv, factor_rr = lmin * inv, factor_diss = lmin * lmax * inv;
+#pragma unroll
+                for (int v = 0; v < NVARS; ++v)
+                    f[v] = factor_ll * fl[v] - factor_rr * fr[v] + factor_diss * (ur[v] - ul[v]);
+            }
+            break;
+        }
+        case TRIXI_B200_FLUX_RANOCHA:
+        case TRIXI_B200_FLUX_RANOCHA_TURBO:
+            flux_ranocha(ul, ur, o, f);
+            break;
+        case TRIXI_B200_FLUX_SHIMA_ETAL:
+            flux_shima(ul, ur, o, f);
+            break;
+        case TRIXI_B200_FLUX_KENNEDY_GRUBER:
+            flux_kennedy_gruber(ul, ur, o, f);
+            break;
+        case TRIXI_B200_FLUX_CHANDRASHEKAR:
+            flux_chandrashekar(ul, ur, o, f);
+            break;
+        default:
+#pragma unroll
+            for (int v = 0; v < NVARS; ++v) f[v] = nan("");
+        }
+    }
+
+    // max_abs_speeds (compressible_euler_3d.jl:1770-1775)
+    TB_DEV void max_abs_speeds(const double (&u)[NVARS], double (&lam)[ND]) const {
+        double rho, v[ND], p;
+        cons2prim(u, rho, v, p);
+        const double c = sqrt(gamma * p / rho);
+#pragma unroll
+        for (int d = 0; d < ND; ++d) lam[d] = fabs(v[d]) + c;
+    }
+
+    TB_DEV void source_terms(int id, const double (&u)[NVARS], const double (&x)[ND], double t,
+                             double (&s)[NVARS]) const {
+        double xs = 0.0;
+#pragma unroll
+        for (int d = 0; d < ND; ++d) xs += x[d];
+        if (id == TRIXI_B200_SRC_CONVERGENCE_TEST) {
+            const double omega = 2 * M_PI * 0.5;
+            double si, co;
+            sincos(omega * (xs - t), &si, &co);
+            const double rho = 2 + 0.1 * si;
+            const double rho_x = omega * 0.1 * co;
+            if constexpr (ND == 3) {  // compressible_euler_3d.jl:127-153
+                const double tmp = (2 * rho - 1.5) * (gamma - 1);
+                s[0] = 2 * rho_x;
+                s[1] = s[2] = s[3] = rho_x * (2 + tmp);
+                s[4] = rho_x * (4 * rho + 3 * tmp);
+            } else {  // compressible_euler_2d.jl:120-145
+                const double tmp = (2 * rho - 1) * (gamma - 1);
+                s[0] = rho_x;
+                s[1] = s[2] = rho_x * (1 + tmp);
+                s[3] = 2 * rho_x * (rho + tmp);
+            }
+        } else if (id == TRIXI_B200_SRC_EOC_TEST_EULER) {
+            double si, co;
+            sincospi(xs - t, &si, &co);
+            const double rhox = 0.1 * M_PI * co, rho = 2 + 0.1 * si;
+            if constexpr (ND == 3) {  // compressible_euler_3d.jl:265-284
+                const double C_grav = -4.0 * 1 / (3 * M_PI);
+                s[0] = rhox * 2;
+                s[1] = s[2] = s[3] = rhox * (2 - C_grav * rho);
+                s[4] = rhox * (3 - 5 * C_grav * rho);
+            } else {  // compressible_euler_2d.jl:272-292
+                const double C_grav = -2.0 * 1 / M_PI;
+                s[0] = rhox;
+                s[1] = s[2] = rhox * (1 - C_grav * rho);
+                s[3] = rhox * (1 - 3 * C_grav * rho);
+            }
+        } else {
+#pragma unroll
+            for (int v = 0; v < NVARS; ++v) s[v] = 0.0;
+        }
+    }
+
+    TB_DEV void initial_condition(int id, const double (&x)[ND], double t, double (&u)[NVARS]) const {
+        if (id == TRIXI_B200_IC_CONSTANT) {  // compressible_euler_3d.jl:78-86
+            u[0] = 1.0;
+            u[1] = 0.1;
+            u[2] = -0.2;
+            if constexpr (ND == 3) u[3] = 0.7;
+            u[ND + 1] = 10.0;
+        } else if (id == TRIXI_B200_IC_CONVERGENCE_TEST) {  // compressible_euler_3d.jl:94-111
+            double xs = 0.0;
+#pragma unroll
+            for (int d = 0; d < ND; ++d) xs += x[d];
+            const double ini = 2 + 0.1 * sin(2 * M_PI * 0.5 * (xs - t));
+#pragma unroll
+            for (int v = 0; v <= ND; ++v) u[v] = ini;
+            u[ND + 1] = ini * ini;
+        } else {
+#pragma unroll
+            for (int v = 0; v < NVARS; ++v) u[v] = nan("");
+        }
+    }
+
+    // boundary_condition_slip_wall for TreeMesh (compressible_euler_3d.jl:315-414): unit normal along
+    // `o`, outward sign from `direction` (1-based), pressure from the 1D Riemann problem
+    TB_DEV void slip_wall(const double (&u)[NVARS], int o, int direction, double (&f)[NVARS]) const {
+        const double sgn = (direction % 2 == 1) ? -1.0 : 1.0;  // outward normal = sgn * e_o
+        double rho, v[ND], p_local;
+        cons2prim(u, rho, v, p_local);
+        const double v_normal = sgn * pick<ND>(v, o);
+        double p_star;
+        if (v_normal <= 0) {
+            const double sound_speed = sqrt(gamma * p_local / rho);
+            const double base = 1 + 0.5 * (gamma - 1) * v_normal / sound_speed;
+            p_star = base >= 0 ? p_local * pow(base, 2 * gamma * inv_gm1) : 0.0;
+        } else {
+            const double A = 2 / ((gamma + 1) * rho);
+            const double B = p_local * (gamma - 1) / (gamma + 1);
+            p_star = p_local + 0.5 * v_normal / A * (v_normal + sqrt(v_normal * v_normal + 4 * A * (p_local + B)));
+        }
+        // flux = p_star * n_outward, then negated again on the - side (:398-414): net +p_star e_o
+#pragma unroll
+        for (int v2 = 0; v2 < NVARS; ++v2) f[v2] = 0.0;
+#pragma unroll
+        for (int d = 0; d < ND; ++d)
+            if (d == o) f[1 + d] = p_star;
+    }
+};
+
+// bc(u_inner, orientation, direction, x, t, surface_flux, equations) for TreeMesh (dg_3d.jl:757)
+template <class EQ>
+TB_DEV void boundary_flux(const EQ &eq, int bc, int ic, int surface_flux, const double (&u_inner)[EQ::NVARS],
+                          int o, int direction, const double (&x)[EQ::NDIMS], double t,
+                          double (&f)[EQ::NVARS]) {
+    if (bc == TRIXI_B200_BC_DIRICHLET) {  // equations.jl:164-183
+        double ub[EQ::NVARS];
+        eq.initial_condition(ic, x, t, ub);
+        if (direction % 2 == 0)
+            eq.numflux(surface_flux, u_inner, ub, o, f);
+        else
+            eq.numflux(surface_flux, ub, u_inner, o, f);
+    } else if (bc == TRIXI_B200_BC_SLIP_WALL) {
+        eq.slip_wall(u_inner, o, direction, f);
+    } else {
+#pragma unroll
+        for (int v = 0; v < EQ::NVARS; ++v) f[v] = nan("");
+    }
+}
+
+}  // namespace tb

@@ -1,0 +1,664 @@
+// libtrixi_b200.so -- C ABI (include/trixi_b200.h): handle life cycle, device-resident state, and the
+// launch sequence of one RHS evaluation / 2N Runge-Kutta stage / CFL reduction.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <cfloat>
+#include <cmath>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "launch.cuh"
+
+using namespace tb;
+
+namespace {
+thread_local std::string g_create_error;
+
+enum { KC_SURFACE = 0, KC_ELEMENT = 1, KC_MAXDT = 2, KC_HALO = 3, KC_COUNT = 4 };
+
+struct ProfEntry {
+    cudaEvent_t a, b;
+    int cls;
+};
+}  // namespace
+
+struct trixi_b200_handle {
+    int device = 0;
+    int ndims = 0, nvars = 0, nnodes = 0, mesh_kind = 0, equation = 0;
+    long long nelements = 0, ulen = 0, sfvlen = 0;
+    const Launchers *L = nullptr;
+    KParams P{};
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+    bool have_elapsed = false;
+    std::vector<void *> allocs;
+    double *vec[3] = {nullptr, nullptr, nullptr};  // u, du, u_tmp
+    unsigned long long *d_cfl = nullptr;
+    unsigned long long *h_cfl = nullptr;  // pinned
+    long long launches = 0;
+    bool profiling = false;
+    std::vector<ProfEntry> prof;
+    double prof_ms[KC_COUNT] = {0, 0, 0, 0};
+    long long prof_n[KC_COUNT] = {0, 0, 0, 0};
+    std::string error;
+    int rank = 0, world_size = 1;
+};
+
+namespace {
+
+int fail(trixi_b200_handle *h, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (h)
+        h->error = buf;
+    else
+        g_create_error = buf;
+    return code;
+}
+
+#define CUDA_TRY(h, expr)                                                                              \
+    do {                                                                                               \
+        cudaError_t err__ = (expr);                                                                    \
+        if (err__ != cudaSuccess)                                                                      \
+            return fail(h, err__ == cudaErrorMemoryAllocation ? TRIXI_B200_ENOMEM : TRIXI_B200_ECUDA,  \
+                        "%s failed: %s", #expr, cudaGetErrorString(err__));                            \
+    } while (0)
+
+template <class T>
+int upload_array(trixi_b200_handle *h, const T *host, size_t count, T **dev) {
+    *dev = nullptr;
+    if (count == 0) return 0;
+    if (!host) return fail(h, TRIXI_B200_EINVAL, "descriptor array missing (null pointer, %zu entries expected)", count);
+    void *p = nullptr;
+    CUDA_TRY(h, cudaMalloc(&p, count * sizeof(T)));
+    h->allocs.push_back(p);
+    CUDA_TRY(h, cudaMemcpy(p, host, count * sizeof(T), cudaMemcpyHostToDevice));
+    *dev = static_cast<T *>(p);
+    return 0;
+}
+
+template <class T>
+int alloc_array(trixi_b200_handle *h, size_t count, T **dev) {
+    *dev = nullptr;
+    if (count == 0) return 0;
+    void *p = nullptr;
+    CUDA_TRY(h, cudaMalloc(&p, count * sizeof(T)));
+    h->allocs.push_back(p);
+    *dev = static_cast<T *>(p);
+    return 0;
+}
+
+struct ProfScope {
+    trixi_b200_handle *h;
+    int cls;
+    ProfEntry e{};
+    bool on;
+    ProfScope(trixi_b200_handle *h_, int cls_) : h(h_), cls(cls_), on(h_->profiling) {
+        if (on) {
+            cudaEventCreate(&e.a);
+            cudaEventCreate(&e.b);
+            e.cls = cls;
+            cudaEventRecord(e.a, h->stream);
+        }
+    }
+    ~ProfScope() {
+        if (on) {
+            cudaEventRecord(e.b, h->stream);
+            h->prof.push_back(e);
+        }
+    }
+};
+
+void prof_collect(trixi_b200_handle *h);
+
+void prof_collect(trixi_b200_handle *h) {
+    if (h->prof.empty()) return;
+    cudaStreamSynchronize(h->stream);
+    for (auto &e : h->prof) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e.a, e.b);
+        h->prof_ms[e.cls] += ms;
+        h->prof_n[e.cls] += 1;
+        cudaEventDestroy(e.a);
+        cudaEventDestroy(e.b);
+    }
+    h->prof.clear();
+}
+
+__global__ void k_fp64_peak(double *sink, int iters, double m) {
+    double x0 = threadIdx.x * 1e-9, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6,
+           x7 = x0 + 7;
+    const double c = 1e-9;
+#pragma unroll 16
+    for (int i = 0; i < iters; ++i) {
+        x0 = fma(x0, m, c);
+        x1 = fma(x1, m, c);
+        x2 = fma(x2, m, c);
+        x3 = fma(x3, m, c);
+        x4 = fma(x4, m, c);
+        x5 = fma(x5, m, c);
+        x6 = fma(x6, m, c);
+        x7 = fma(x7, m, c);
+    }
+    const double r = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    if (r == 123.456) sink[threadIdx.x] = r;
+}
+
+__global__ void k_copy(double2 *dst, const double2 *src, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[i];
+}
+
+int check_launch(trixi_b200_handle *h, const char *what) {
+    if (h->prof.size() > 2048) prof_collect(h);  // bound the number of live events
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return fail(h, TRIXI_B200_ECUDA, "%s launch failed: %s", what, cudaGetErrorString(err));
+    return 0;
+}
+
+// surface fluxes of all faces: interfaces (+ boundaries)
+int run_surface_fluxes(trixi_b200_handle *h, double t) {
+    h->P.t = t;
+    {
+        ProfScope ps(h, KC_SURFACE);
+        h->L->interface_flux(h->P, h->stream);
+        if (h->P.ninterfaces) h->launches++;
+        if (h->P.nboundaries) {
+            h->L->boundary_flux(h->P, h->stream);
+            h->launches++;
+        }
+    }
+    return check_launch(h, "surface flux kernel");
+}
+
+int run_element(trixi_b200_handle *h, bool with_surface) {
+    {
+        ProfScope ps(h, KC_ELEMENT);
+        cudaError_t err = h->L->element(h->P, with_surface, h->stream);
+        if (err != cudaSuccess) return fail(h, TRIXI_B200_ECUDA, "element kernel setup failed: %s", cudaGetErrorString(err));
+        h->launches++;
+    }
+    return check_launch(h, "element kernel");
+}
+
+int run_rhs(trixi_b200_handle *h, double t) {
+    int rc = run_surface_fluxes(h, t);
+    if (rc) return rc;
+    h->P.mode = 0;
+    return run_element(h, true);
+}
+
+}  // namespace
+
+extern "C" {
+
+TRIXI_B200_API int trixi_b200_abi_version(void) { return TRIXI_B200_ABI_VERSION; }
+
+TRIXI_B200_API const char *trixi_b200_last_error(const trixi_b200_handle *h) { return h ? h->error.c_str() : g_create_error.c_str(); }
+
+TRIXI_B200_API void trixi_b200_destroy(trixi_b200_handle *h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    for (auto &e : h->prof) {
+        cudaEventDestroy(e.a);
+        cudaEventDestroy(e.b);
+    }
+    for (void *p : h->allocs) cudaFree(p);
+    if (h->h_cfl) cudaFreeHost(h->h_cfl);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->ev_t0) cudaEventDestroy(h->ev_t0);
+    if (h->ev_t1) cudaEventDestroy(h->ev_t1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+TRIXI_B200_API int trixi_b200_create(const trixi_b200_desc *d, trixi_b200_handle **out) {
+    if (!out) return fail(nullptr, TRIXI_B200_EINVAL, "out pointer is null");
+    *out = nullptr;
+    if (!d) return fail(nullptr, TRIXI_B200_EINVAL, "descriptor is null");
+    if (d->abi_version != TRIXI_B200_ABI_VERSION)
+        return fail(nullptr, TRIXI_B200_EINVAL, "descriptor ABI version %d != library %d", d->abi_version,
+                    TRIXI_B200_ABI_VERSION);
+    if (d->mesh_kind != TRIXI_B200_MESH_TREE)
+        return fail(nullptr, TRIXI_B200_EINVAL, "mesh kind %d not supported by this build", d->mesh_kind);
+    if (d->nmortars != 0) return fail(nullptr, TRIXI_B200_EINVAL, "mortars are not supported by this build");
+    if (d->volume_integral != TRIXI_B200_VOLINT_WEAK_FORM && d->volume_integral != TRIXI_B200_VOLINT_FLUX_DIFFERENCING)
+        return fail(nullptr, TRIXI_B200_EINVAL, "unsupported volume integral type %d", d->volume_integral);
+    if (d->nelements < 0 || d->ninterfaces < 0 || d->nboundaries < 0)
+        return fail(nullptr, TRIXI_B200_EINVAL, "negative container size");
+
+    const Launchers *L = nullptr;
+    switch (d->equation) {
+    case TRIXI_B200_EQ_ADVECTION_2D: L = get_launchers_advection2d(d->nnodes); break;
+    case TRIXI_B200_EQ_EULER_2D: L = get_launchers_euler2d(d->nnodes); break;
+    case TRIXI_B200_EQ_EULER_3D: L = get_launchers_euler3d(d->nnodes); break;
+    default: return fail(nullptr, TRIXI_B200_EINVAL, "equation %d not supported by this build", d->equation);
+    }
+    if (!L) return fail(nullptr, TRIXI_B200_EINVAL, "nnodes = %d not supported (2..8)", d->nnodes);
+    if (L->ndims != d->ndims || L->nvars != d->nvars)
+        return fail(nullptr, TRIXI_B200_EINVAL, "ndims/nvars (%d, %d) do not match equation %d", d->ndims, d->nvars,
+                    d->equation);
+
+    int ndev = 0;
+    cudaError_t err = cudaGetDeviceCount(&ndev);
+    if (err != cudaSuccess || ndev == 0)
+        return fail(nullptr, TRIXI_B200_ENODEVICE, "no CUDA device available (%s); libtrixi_b200 has no CPU fallback",
+                    err == cudaSuccess ? "device count is 0" : cudaGetErrorString(err));
+    int dev = d->device;
+    if (dev < 0) {
+        if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+    }
+    if (dev >= ndev) return fail(nullptr, TRIXI_B200_EINVAL, "device ordinal %d out of range (%d devices)", dev, ndev);
+
+    trixi_b200_handle *h = new (std::nothrow) trixi_b200_handle();
+    if (!h) return fail(nullptr, TRIXI_B200_ENOMEM, "out of host memory");
+    h->device = dev;
+#define CREATE_TRY(expr)                                 \
+    do {                                                 \
+        int rc__ = (expr);                               \
+        if (rc__) {                                      \
+            g_create_error = h->error;                   \
+            trixi_b200_destroy(h);                       \
+            return rc__;                                 \
+        }                                                \
+    } while (0)
+#define CREATE_CUDA(expr)                                                                                   \
+    do {                                                                                                    \
+        cudaError_t e__ = (expr);                                                                           \
+        if (e__ != cudaSuccess) {                                                                           \
+            fail(nullptr, TRIXI_B200_ECUDA, "%s failed: %s", #expr, cudaGetErrorString(e__));                \
+            trixi_b200_destroy(h);                                                                          \
+            return TRIXI_B200_ECUDA;                                                                        \
+        }                                                                                                   \
+    } while (0)
+
+    CREATE_CUDA(cudaSetDevice(dev));
+    CREATE_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CREATE_CUDA(cudaEventCreate(&h->ev0));
+    CREATE_CUDA(cudaEventCreate(&h->ev1));
+    CREATE_CUDA(cudaEventCreate(&h->ev_t0));
+    CREATE_CUDA(cudaEventCreate(&h->ev_t1));
+
+    h->L = L;
+    h->ndims = d->ndims;
+    h->nvars = d->nvars;
+    h->nnodes = d->nnodes;
+    h->mesh_kind = d->mesh_kind;
+    h->equation = d->equation;
+    h->nelements = d->nelements;
+    h->rank = d->rank;
+    h->world_size = d->world_size > 0 ? d->world_size : 1;
+    const int n = d->nnodes, nd = d->ndims, nv = d->nvars;
+    const long long nn = ipow(n, nd), nf = ipow(n, nd - 1);
+    h->ulen = (long long)nv * nn * d->nelements;
+    h->sfvlen = (long long)nv * nf * 2 * nd * d->nelements;
+
+    KParams &P = h->P;
+    P.nelements = d->nelements;
+    P.ninterfaces = d->ninterfaces;
+    P.nboundaries = d->nboundaries;
+    for (int i = 0; i < 3; ++i) CREATE_TRY(alloc_array(h, (size_t)h->ulen, &h->vec[i]));
+    P.u = h->vec[0];
+    P.du = h->vec[1];
+    P.u_tmp = h->vec[2];
+    P.u_out = h->vec[0];
+    CREATE_TRY(alloc_array(h, (size_t)h->sfvlen, &P.sfv));
+    if (h->sfvlen) CREATE_CUDA(cudaMemset(P.sfv, 0xff, h->sfvlen * sizeof(double)));  // NaN like the reference's fill
+
+    double *tmp = nullptr;
+    CREATE_TRY(upload_array(h, d->derivative_split, (size_t)n * n, &tmp));
+    P.dsplit = tmp;
+    CREATE_TRY(upload_array(h, d->derivative_hat, (size_t)n * n, &tmp));
+    P.dhat = tmp;
+    if (!d->inverse_weights) {
+        fail(nullptr, TRIXI_B200_EINVAL, "inverse_weights missing");
+        trixi_b200_destroy(h);
+        return TRIXI_B200_EINVAL;
+    }
+    P.inv_weight0 = d->inverse_weights[0];
+    CREATE_TRY(upload_array(h, d->inverse_jacobian, (size_t)d->nelements, &tmp));
+    P.inverse_jacobian = tmp;
+    CREATE_TRY(upload_array(h, d->node_coordinates, (size_t)(nd * nn * d->nelements), &tmp));
+    P.node_coordinates = tmp;
+
+    long long *itmp = nullptr;
+    static_assert(sizeof(long long) == sizeof(int64_t), "int64 layout");
+    CREATE_TRY(upload_array(h, (const long long *)d->interface_neighbor_ids, (size_t)(2 * d->ninterfaces), &itmp));
+    P.if_neighbors = itmp;
+    CREATE_TRY(upload_array(h, (const long long *)d->interface_orientations, (size_t)d->ninterfaces, &itmp));
+    P.if_orient = itmp;
+    CREATE_TRY(upload_array(h, (const long long *)d->boundary_neighbor_ids, (size_t)d->nboundaries, &itmp));
+    P.bd_neighbor = itmp;
+    CREATE_TRY(upload_array(h, (const long long *)d->boundary_orientations, (size_t)d->nboundaries, &itmp));
+    P.bd_orient = itmp;
+    CREATE_TRY(upload_array(h, (const long long *)d->boundary_neighbor_sides, (size_t)d->nboundaries, &itmp));
+    P.bd_side = itmp;
+    CREATE_TRY(upload_array(h, d->boundary_node_coordinates, (size_t)(nd * nf * d->nboundaries), &tmp));
+    P.bd_coords = tmp;
+    {
+        // boundaries are sorted by direction (containers_3d.jl:398-468): expand the counts to a per-face direction
+        std::vector<int> dir((size_t)d->nboundaries);
+        long long pos = 0;
+        for (int k = 0; k < 2 * nd; ++k)
+            for (long long c = 0; c < d->n_boundaries_per_direction[k] && pos < d->nboundaries; ++c) dir[pos++] = k + 1;
+        if (pos != d->nboundaries) {
+            fail(nullptr, TRIXI_B200_EINVAL, "n_boundaries_per_direction does not sum to nboundaries");
+            trixi_b200_destroy(h);
+            return TRIXI_B200_EINVAL;
+        }
+        int *dtmp = nullptr;
+        CREATE_TRY(upload_array(h, dir.data(), dir.size(), &dtmp));
+        P.bd_direction = dtmp;
+        for (int k = 0; k < 2 * nd; ++k)
+            if (d->n_boundaries_per_direction[k] > 0 && d->boundary_conditions[k] == TRIXI_B200_BC_PERIODIC) {
+                fail(nullptr, TRIXI_B200_EINVAL, "direction %d has boundary faces but a periodic boundary condition", k + 1);
+                trixi_b200_destroy(h);
+                return TRIXI_B200_EINVAL;
+            }
+    }
+    for (int k = 0; k < 6; ++k) {
+        P.bc[k] = d->boundary_conditions[k];
+        P.bc_ic[k] = d->boundary_ic[k];
+    }
+    for (int k = 0; k < 8; ++k) P.eq.p[k] = d->eq_params[k];
+    P.volume_integral = d->volume_integral;
+    P.volume_flux = d->volume_flux;
+    P.surface_flux = d->surface_flux;
+    P.source_terms = d->source_terms;
+    P.t = 0.0;
+    P.mode = 0;
+    P.rk_a = 0.0;
+    P.rk_b_dt = 0.0;
+
+    CREATE_TRY(alloc_array(h, 1, &h->d_cfl));
+    P.cfl_key = h->d_cfl;
+    CREATE_CUDA(cudaMallocHost((void **)&h->h_cfl, sizeof(unsigned long long)));
+    CREATE_CUDA(cudaDeviceSynchronize());
+    *out = h;
+    return TRIXI_B200_OK;
+}
+
+static int which_ok(trixi_b200_handle *h, int which) {
+    if (!h) return TRIXI_B200_EINVAL;
+    if (which < 0 || which > 2) return fail(h, TRIXI_B200_EINVAL, "vector selector %d out of range", which);
+    return 0;
+}
+
+TRIXI_B200_API int trixi_b200_upload(trixi_b200_handle *h, int which, const double *host) {
+    int rc = which_ok(h, which);
+    if (rc) return rc;
+    if (!host && h->ulen) return fail(h, TRIXI_B200_EINVAL, "host pointer is null");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    CUDA_TRY(h, cudaMemcpyAsync(h->vec[which], host, h->ulen * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+TRIXI_B200_API int trixi_b200_download(trixi_b200_handle *h, int which, double *host) {
+    int rc = which_ok(h, which);
+    if (rc) return rc;
+    if (!host && h->ulen) return fail(h, TRIXI_B200_EINVAL, "host pointer is null");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    CUDA_TRY(h, cudaMemcpyAsync(host, h->vec[which], h->ulen * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+TRIXI_B200_API void *trixi_b200_device_ptr(trixi_b200_handle *h, int which) {
+    if (!h || which < 0 || which > 2) return nullptr;
+    return h->vec[which];
+}
+
+TRIXI_B200_API int trixi_b200_synchronize(trixi_b200_handle *h) {
+    if (!h) return TRIXI_B200_EINVAL;
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+TRIXI_B200_API void *trixi_b200_stream(trixi_b200_handle *h) { return h ? (void *)h->stream : nullptr; }
+
+TRIXI_B200_API int trixi_b200_rhs(trixi_b200_handle *h, double t) {
+    if (!h) return TRIXI_B200_EINVAL;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
+    int rc = run_rhs(h, t);
+    if (rc) return rc;
+    CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
+    h->have_elapsed = true;
+    return 0;
+}
+
+TRIXI_B200_API int trixi_b200_rhs_host(trixi_b200_handle *h, double *du_host, const double *u_host, double t) {
+    if (!h) return TRIXI_B200_EINVAL;
+    if ((!du_host || !u_host) && h->ulen) return fail(h, TRIXI_B200_EINVAL, "host pointer is null");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const size_t bytes = h->ulen * sizeof(double);
+    CUDA_TRY(h, cudaMemcpyAsync(h->vec[0], u_host, bytes, cudaMemcpyHostToDevice, h->stream));
+    int rc = trixi_b200_rhs(h, t);
+    if (rc) return rc;
+    CUDA_TRY(h, cudaMemcpyAsync(du_host, h->vec[1], bytes, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+TRIXI_B200_API int trixi_b200_calc_volume_integral(trixi_b200_handle *h) {
+    if (!h) return TRIXI_B200_EINVAL;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    h->P.mode = 0;
+    return run_element(h, false);
+}
+
+TRIXI_B200_API int trixi_b200_calc_surface_fluxes(trixi_b200_handle *h, double t) {
+    if (!h) return TRIXI_B200_EINVAL;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    return run_surface_fluxes(h, t);
+}
+
+TRIXI_B200_API int trixi_b200_download_surface_flux_values(trixi_b200_handle *h, double *host) {
+    if (!h) return TRIXI_B200_EINVAL;
+    if (!host && h->sfvlen) return fail(h, TRIXI_B200_EINVAL, "host pointer is null");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    CUDA_TRY(h, cudaMemcpyAsync(host, h->P.sfv, h->sfvlen * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+TRIXI_B200_API int trixi_b200_max_dt(trixi_b200_handle *h, double t, double *dt_out) {
+    (void)t;
+    if (!h || !dt_out) return TRIXI_B200_EINVAL;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    // max_scaled_speed starts at nextfloat(0.0) (stepsize_dg3d.jl:12): bit pattern 1
+    *h->h_cfl = 1ull;
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_cfl, h->h_cfl, sizeof(unsigned long long), cudaMemcpyHostToDevice, h->stream));
+    {
+        ProfScope ps(h, KC_MAXDT);
+        h->L->max_dt(h->P, h->stream);
+        h->launches++;
+    }
+    int rc = check_launch(h, "max_dt kernel");
+    if (rc) return rc;
+    CUDA_TRY(h, cudaMemcpyAsync(h->h_cfl, h->d_cfl, sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    double max_scaled_speed;
+    memcpy(&max_scaled_speed, h->h_cfl, sizeof(double));
+    *dt_out = 2 / (h->nnodes * max_scaled_speed);
+    return 0;
+}
+
+TRIXI_B200_API int trixi_b200_step_2n(trixi_b200_handle *h, double t, double dt, const double *a, const double *b, const double *c,
+                       int nstages) {
+    if (!h || !a || !b || !c || nstages <= 0) return h ? fail(h, TRIXI_B200_EINVAL, "bad Runge-Kutta tableau") : TRIXI_B200_EINVAL;
+    if (a[0] != 0.0) return fail(h, TRIXI_B200_EINVAL, "2N scheme must have a[1] == 0 (u_tmp starts at zero)");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
+    for (int s = 0; s < nstages; ++s) {
+        const double t_stage = t + dt * c[s];
+        int rc = run_surface_fluxes(h, t_stage);
+        if (rc) return rc;
+        h->P.mode = 1;
+        h->P.rk_a = a[s];
+        h->P.rk_b_dt = b[s] * dt;
+        rc = run_element(h, true);
+        h->P.mode = 0;
+        if (rc) return rc;
+    }
+    CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
+    h->have_elapsed = true;
+    return 0;
+}
+
+TRIXI_B200_API int trixi_b200_solve_2n(trixi_b200_handle *h, double t0, double t_end, double cfl, int64_t max_steps, const double *a,
+                        const double *b, const double *c, int nstages, int64_t *steps_out, double *t_out,
+                        double *dt_out) {
+    if (!h) return TRIXI_B200_EINVAL;
+    double t = t0, dt = 0.0;
+    int64_t steps = 0;
+    bool finalstep = false;
+    while (!finalstep && steps < max_steps) {
+        int rc = trixi_b200_max_dt(h, t, &dt);
+        if (rc) return rc;
+        dt *= cfl;
+        if (std::isnan(dt)) return fail(h, TRIXI_B200_EINVAL, "time step size `dt` is NaN");
+        // limit_dt! (time_integration.jl:46-55)
+        const double tn = t + dt;
+        if (tn > t_end || std::fabs(tn - t_end) <= std::sqrt(DBL_EPSILON) * std::fmax(std::fabs(tn), std::fabs(t_end))) {
+            dt = t_end - t;
+            finalstep = true;
+        }
+        rc = trixi_b200_step_2n(h, t, dt, a, b, c, nstages);
+        if (rc) return rc;
+        t += dt;
+        ++steps;
+    }
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    if (steps_out) *steps_out = steps;
+    if (t_out) *t_out = t;
+    if (dt_out) *dt_out = dt;
+    return 0;
+}
+
+TRIXI_B200_API int trixi_b200_set_eq_param(trixi_b200_handle *h, int index, double value) {
+    if (!h) return TRIXI_B200_EINVAL;
+    if (index < 0 || index >= 8) return fail(h, TRIXI_B200_EINVAL, "equation parameter index %d out of range", index);
+    h->P.eq.p[index] = value;
+    return 0;
+}
+
+TRIXI_B200_API int trixi_b200_comm_unique_id(void *id_out_128_bytes) {
+    (void)id_out_128_bytes;
+    return fail(nullptr, TRIXI_B200_ECOMM, "halo exchange is not part of this build");
+}
+
+TRIXI_B200_API int trixi_b200_comm_init(trixi_b200_handle *h, const void *id_128_bytes) {
+    (void)id_128_bytes;
+    return fail(h, TRIXI_B200_ECOMM, "halo exchange is not part of this build");
+}
+
+TRIXI_B200_API int64_t trixi_b200_launch_count(const trixi_b200_handle *h) { return h ? h->launches : 0; }
+
+TRIXI_B200_API int trixi_b200_last_elapsed_ms(trixi_b200_handle *h, float *ms_out) {
+    if (!h || !ms_out) return TRIXI_B200_EINVAL;
+    if (!h->have_elapsed) return fail(h, TRIXI_B200_EINVAL, "no timed call yet");
+    CUDA_TRY(h, cudaEventSynchronize(h->ev1));
+    CUDA_TRY(h, cudaEventElapsedTime(ms_out, h->ev0, h->ev1));
+    return 0;
+}
+
+TRIXI_B200_API TRIXI_B200_API int trixi_b200_timer_start(trixi_b200_handle *h) {
+    if (!h) return TRIXI_B200_EINVAL;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    CUDA_TRY(h, cudaEventRecord(h->ev_t0, h->stream));
+    return 0;
+}
+
+TRIXI_B200_API int trixi_b200_timer_stop(trixi_b200_handle *h, float *ms_out) {
+    if (!h || !ms_out) return TRIXI_B200_EINVAL;
+    CUDA_TRY(h, cudaEventRecord(h->ev_t1, h->stream));
+    CUDA_TRY(h, cudaEventSynchronize(h->ev_t1));
+    CUDA_TRY(h, cudaEventElapsedTime(ms_out, h->ev_t0, h->ev_t1));
+    return 0;
+}
+
+TRIXI_B200_API int trixi_b200_measure_fp64_peak(trixi_b200_handle *h, double *tflops_out) {
+    if (!h || !tflops_out) return TRIXI_B200_EINVAL;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    cudaDeviceProp prop;
+    CUDA_TRY(h, cudaGetDeviceProperties(&prop, h->device));
+    double *sink = nullptr;
+    CUDA_TRY(h, cudaMalloc((void **)&sink, sizeof(double) * 1024));
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 4096;
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(h->ev_t0, h->stream);
+        k_fp64_peak<<<blocks, threads, 0, h->stream>>>(sink, iters, 1.0000001);
+        cudaEventRecord(h->ev_t1, h->stream);
+        cudaEventSynchronize(h->ev_t1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, h->ev_t0, h->ev_t1);
+        // 8 independent chains x 2 flop per DFMA
+        const double flop = (double)blocks * threads * (double)iters * 8 * 2;
+        if (rep > 0) best = fmax(best, flop / (ms * 1e-3) * 1e-12);
+    }
+    cudaFree(sink);
+    int rc = check_launch(h, "fp64 peak kernel");
+    if (rc) return rc;
+    *tflops_out = best;
+    return 0;
+}
+
+TRIXI_B200_API int trixi_b200_measure_copy_bandwidth(trixi_b200_handle *h, double *gbs_out) {
+    if (!h || !gbs_out) return TRIXI_B200_EINVAL;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const size_t n = (size_t)1 << 28;  // 2 GiB per buffer of doubles
+    double *a = nullptr, *b = nullptr;
+    CUDA_TRY(h, cudaMalloc((void **)&a, n * sizeof(double)));
+    if (cudaMalloc((void **)&b, n * sizeof(double)) != cudaSuccess) {
+        cudaFree(a);
+        return fail(h, TRIXI_B200_ENOMEM, "copy benchmark allocation failed");
+    }
+    cudaMemsetAsync(a, 0, n * sizeof(double), h->stream);
+    double best = 0.0;
+    for (int rep = 0; rep < 6; ++rep) {
+        cudaEventRecord(h->ev_t0, h->stream);
+        k_copy<<<(unsigned)(n / 2 / 256), 256, 0, h->stream>>>((double2 *)b, (const double2 *)a, n / 2);
+        cudaEventRecord(h->ev_t1, h->stream);
+        cudaEventSynchronize(h->ev_t1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, h->ev_t0, h->ev_t1);
+        if (rep > 0) best = fmax(best, 2.0 * n * sizeof(double) / (ms * 1e-3) * 1e-9);
+    }
+    cudaFree(a);
+    cudaFree(b);
+    int rc = check_launch(h, "copy kernel");
+    if (rc) return rc;
+    *gbs_out = best;
+    return 0;
+}
+
+int trixi_b200_profile_enable(trixi_b200_handle *h, int on) {
+    if (!h) return TRIXI_B200_EINVAL;
+    prof_collect(h);
+    h->profiling = on != 0;
+    for (int k = 0; k < KC_COUNT; ++k) {
+        h->prof_ms[k] = 0;
+        h->prof_n[k] = 0;
+    }
+    return 0;
+}
+
+TRIXI_B200_API int trixi_b200_profile_read(trixi_b200_handle *h, int kernel_class, double *ms_out, int64_t *launches_out) {
+    if (!h || kernel_class < 0 || kernel_class >= KC_COUNT) return TRIXI_B200_EINVAL;
+    prof_collect(h);
+    if (ms_out) *ms_out = h->prof_ms[kernel_class];
+    if (launches_out) *launches_out = h->prof_n[kernel_class];
+    return 0;
+}
+
+}  // extern "C"

@@ -24,7 +24,8 @@ EXPORTS = [
     "trixi_b200_calc_volume_integral", "trixi_b200_calc_surface_fluxes",
     "trixi_b200_download_surface_flux_values", "trixi_b200_comm_unique_id", "trixi_b200_comm_init",
     "trixi_b200_launch_count", "trixi_b200_last_elapsed_ms", "trixi_b200_profile_enable",
-    "trixi_b200_profile_read",
+    "trixi_b200_profile_read", "trixi_b200_timer_start", "trixi_b200_timer_stop",
+    "trixi_b200_measure_fp64_peak", "trixi_b200_measure_copy_bandwidth",
 ]
 
 _lib = None
@@ -78,6 +79,10 @@ def load_library(path=None):
     lib.trixi_b200_last_elapsed_ms.argtypes = [vp, C.POINTER(C.c_float)]
     lib.trixi_b200_profile_enable.argtypes = [vp, C.c_int]
     lib.trixi_b200_profile_read.argtypes = [vp, C.c_int, dp, i64p]
+    lib.trixi_b200_timer_start.argtypes = [vp]
+    lib.trixi_b200_timer_stop.argtypes = [vp, C.POINTER(C.c_float)]
+    lib.trixi_b200_measure_fp64_peak.argtypes = [vp, dp]
+    lib.trixi_b200_measure_copy_bandwidth.argtypes = [vp, dp]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if fn.restype is C.c_int and name not in ("trixi_b200_abi_version",):
@@ -209,6 +214,24 @@ class B200Backend:
         ms, n = C.c_double(), C.c_int64()
         self._ck(self.lib.trixi_b200_profile_read(self.h, kernel_class, C.byref(ms), C.byref(n)))
         return ms.value, n.value
+
+    def timer_start(self):
+        self._ck(self.lib.trixi_b200_timer_start(self.h))
+
+    def timer_stop(self):
+        out = C.c_float()
+        self._ck(self.lib.trixi_b200_timer_stop(self.h, C.byref(out)))
+        return out.value
+
+    def measure_fp64_peak(self):
+        out = C.c_double()
+        self._ck(self.lib.trixi_b200_measure_fp64_peak(self.h, C.byref(out)))
+        return out.value
+
+    def measure_copy_bandwidth(self):
+        out = C.c_double()
+        self._ck(self.lib.trixi_b200_measure_copy_bandwidth(self.h, C.byref(out)))
+        return out.value
 
     # distributed
     def comm_unique_id(self):
