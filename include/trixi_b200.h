@@ -203,6 +203,11 @@ TRIXI_B200_API int trixi_b200_solve_2n(trixi_b200_handle *h, double t0, double t
                         const double *a, const double *b, const double *c, int nstages,
                         int64_t *steps_out, double *t_out, double *dt_out);
 
+/* Tuning knobs (the analogue of the reference's compile-time Preferences, src/Trixi.jl:18-23).
+ * TRIXI_B200_OPT_KERNEL_PATH: 0 = tuned kernels where one exists (default), 1 = generic kernels only. */
+#define TRIXI_B200_OPT_KERNEL_PATH 0
+TRIXI_B200_API int trixi_b200_set_option(trixi_b200_handle *h, int option, int value);
+
 /* GlmSpeedCallback (glm_speed.jl:85-105) mutates equations.c_h every step */
 TRIXI_B200_API int trixi_b200_set_eq_param(trixi_b200_handle *h, int index, double value);
 

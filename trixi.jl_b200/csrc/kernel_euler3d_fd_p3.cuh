@@ -1,0 +1,350 @@
+// Tuned element kernel: 3D compressible Euler, polydeg 3 (4^3 nodes), flux-differencing volume integral
+// with flux_ranocha, fused with surface integral, Jacobian, source terms and the 2N Runge-Kutta stage.
+// This is the headline configuration (BASELINE.json: 3D Euler EC p=3).
+//
+// Work decomposition.
+//  * One warp = one CTA = two elements; everything is warp-synchronous (no block barriers), ~7 CTAs
+//    resident per SM so one warp's tile I/O latency hides behind the other warps' FP64 work.
+//  * Tile I/O is TMA: three `cp.async.bulk` loads (u, u_tmp, surface_flux_values of the two elements are
+//    contiguous 5/5/7.5 KB records) signalled on an mbarrier, results leave through `cp.async.bulk`
+//    stores -- no per-thread address arithmetic, no register staging, fully coalesced HBM traffic.
+//  * Per element and direction the 64 nodes form 16 lines of 4 nodes with 6 symmetric node pairs each.
+//    A thread owns one line per direction pass and evaluates its 6 two-point fluxes exactly once (288 per
+//    element, like the reference's symmetric loop dg_3d.jl:177-211), accumulating D_split[a,b] f into
+//    both end nodes in registers.  x and y passes meet in a shared-memory du tile; the z pass keeps its
+//    accumulators and finishes surface integral, Jacobian, sources and the RK update in registers.
+//  * flux_ranocha is evaluated in the hoisted form of the reference's own SIMD kernel
+//    (dg_3d_compressible_euler.jl:289-309,360-385): primitive variables and log(rho), log(p) once per
+//    node, so the logarithmic means need no log per pair.
+//  * The prim and du tiles are AoS records at a swizzled node position pos(i,j,k) = 16k + 4(j^k) + (i^k):
+//    in every direction pass the 16 lines of an element hit 16 distinct 8-byte banks (record strides 5
+//    and 7 are odd, so the map stays bijective); the TMA-filled buffers keep the global (natural) order,
+//    which is conflict-free for the per-node passes.
+#pragma once
+#include <cstdint>
+
+#include "launch.cuh"
+
+namespace tb {
+
+TB_DEV int swz_pos(int n) {
+    const int i = n & 3, j = (n >> 2) & 3, k = n >> 4;
+    return (k << 4) | (((j ^ k) & 3) << 2) | ((i ^ k) & 3);
+}
+
+// 1/x to ~1 ulp: MUFU.RCP64H seed (rcp.approx.ftz.f64, ~20 bits) + two Newton steps (4 DFMA)
+TB_DEV double fast_rcp(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    return r;
+}
+// a / b with one residual correction (Markstein): correctly rounded except in rare ties, no slow path
+TB_DEV double fast_div(double a, double b) {
+    const double r = fast_rcp(b);
+    const double q = a * r;
+    return fma(fma(-b, q, a), r, q);
+}
+
+// ---- TMA / mbarrier helpers (PTX ISA: cp.async.bulk, mbarrier) ---------------------------------------
+TB_DEV uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+TB_DEV void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+TB_DEV void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+TB_DEV bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+TB_DEV void tma_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+TB_DEV void tma_store(void *dst, uint32_t src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes)
+                 : "memory");
+}
+TB_DEV void tma_store_commit_and_wait_read() {
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+TB_DEV void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// Node record in the prim tile: rho, v1, v2, v3, p, log(rho), log(p)
+constexpr int kNP = 7;
+
+// flux_ranocha(u_ll, u_rr, orientation D) (compressible_euler_3d.jl:746-793) on hoisted node records.
+template <int D>
+TB_DEV void ranocha_pair(const double (&L)[kNP], const double (&R)[kNP], double inv_gm1, double (&f)[5]) {
+    const double rho_ll = L[0], p_ll = L[4], rho_rr = R[0], p_rr = R[4];
+    const double dlog_rho = R[5] - L[5];  // log(rho_rr / rho_ll)
+    // ln_mean(rho_ll, rho_rr) (math.jl:198-210)
+    double rho_mean;
+    {
+        const double x = rho_ll, y = rho_rr;
+        const double n = fma(x, x - 2 * y, y * y), d = fma(x, x + 2 * y, y * y);
+        const double f2 = n * fast_rcp(d);
+        const bool series = f2 < 1.0e-4;
+        const double poly = fma(f2, fma(f2, fma(f2, 2.0 / 7.0, 2.0 / 5.0), 2.0 / 3.0), 2.0);
+        rho_mean = fast_div(series ? x + y : y - x, series ? poly : dlog_rho);
+    }
+    // inv_ln_mean(rho_ll * p_rr, rho_rr * p_ll) (math.jl:238-250)
+    double inv_rho_p_mean;
+    {
+        const double x = rho_ll * p_rr, y = rho_rr * p_ll;
+        const double n = fma(x, x - 2 * y, y * y), d = fma(x, x + 2 * y, y * y);
+        const double f2 = n * fast_rcp(d);
+        const bool series = f2 < 1.0e-4;
+        const double poly = fma(f2, fma(f2, fma(f2, 2.0 / 7.0, 2.0 / 5.0), 2.0 / 3.0), 2.0);
+        // log(y / x) = log(rho_rr p_ll) - log(rho_ll p_rr)
+        const double m = fast_div(series ? poly : dlog_rho + (L[6] - R[6]), series ? x + y : y - x);
+        inv_rho_p_mean = p_ll * p_rr * m;
+    }
+    const double v1_avg = 0.5 * (L[1] + R[1]), v2_avg = 0.5 * (L[2] + R[2]), v3_avg = 0.5 * (L[3] + R[3]);
+    const double p_avg = 0.5 * (p_ll + p_rr);
+    const double velocity_square_avg = 0.5 * (L[1] * R[1] + L[2] * R[2] + L[3] * R[3]);
+    const double vn_avg = D == 0 ? v1_avg : (D == 1 ? v2_avg : v3_avg);
+    const double f1 = rho_mean * vn_avg;
+    f[0] = f1;
+    f[1] = f1 * v1_avg + (D == 0 ? p_avg : 0.0);
+    f[2] = f1 * v2_avg + (D == 1 ? p_avg : 0.0);
+    f[3] = f1 * v3_avg + (D == 2 ? p_avg : 0.0);
+    f[4] = f1 * (velocity_square_avg + inv_rho_p_mean * inv_gm1) + 0.5 * (p_ll * R[1 + D] + p_rr * L[1 + D]);
+}
+
+struct TunedCfg {
+    static constexpr int EPB = 2, THREADS = 32;  // one warp, two elements
+    static constexpr int CONS = 320, PRIM = 64 * kNP, SFV = 480;  // doubles per element
+    // s_u, s_ut (natural order, TMA), s_sfv (natural, TMA), s_du, s_prim (swizzled), mbarrier
+    static constexpr size_t SMEM = sizeof(double) * EPB * (3 * CONS + SFV + PRIM) + 16;
+};
+
+// six symmetric pair fluxes of one line, accumulated into both ends
+template <int D>
+TB_DEV void line_fluxes(const double *s_prim_e, int l16, const KParams &P, double inv_gm1, int (&pos)[4],
+                        double (&acc)[4][5]) {
+    // line l16 of direction D: the two fixed coordinates are (l16 % 4, l16 / 4)
+    const int a0 = l16 & 3, a1 = l16 >> 2;
+    double q[4][kNP];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+        const int n = D == 0 ? m + 4 * a0 + 16 * a1 : (D == 1 ? a0 + 4 * m + 16 * a1 : a0 + 4 * a1 + 16 * m);
+        pos[m] = swz_pos(n);
+#pragma unroll
+        for (int c = 0; c < kNP; ++c) q[m][c] = s_prim_e[pos[m] * kNP + c];
+    }
+#pragma unroll
+    for (int m = 0; m < 4; ++m)
+#pragma unroll
+        for (int v = 0; v < 5; ++v) acc[m][v] = 0.0;
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = a + 1; b < 4; ++b) {
+            double f[5];
+            ranocha_pair<D>(q[a], q[b], inv_gm1, f);
+            const double wab = P.dsplit_c[a + 4 * b], wba = P.dsplit_c[b + 4 * a];  // Dsplit[a,b], Dsplit[b,a]
+#pragma unroll
+            for (int v = 0; v < 5; ++v) {
+                acc[a][v] = fma(wab, f[v], acc[a][v]);
+                acc[b][v] = fma(wba, f[v], acc[b][v]);
+            }
+        }
+}
+
+template <bool WITH_SURFACE>
+__global__ void __launch_bounds__(TunedCfg::THREADS, 7) k_element_euler3d_ranocha_p3(const KParams P) {
+    using C = TunedCfg;
+    constexpr int EPB = C::EPB, CONS = C::CONS, PRIM = C::PRIM, SFV = C::SFV;
+    extern __shared__ __align__(128) double smem[];
+    double *s_u = smem;                   // [EPB][64][5] natural: u in, updated u out
+    double *s_ut = s_u + EPB * CONS;      // [EPB][64][5] natural: u_tmp in, u_tmp (or du) out
+    double *s_sfv = s_ut + EPB * CONS;    // [EPB][6][16][5] natural
+    double *s_du = s_sfv + EPB * SFV;     // [EPB][64][5] swizzled
+    double *s_prim = s_du + EPB * CONS;   // [EPB][64][7] swizzled
+    const uint32_t bar = smem_u32(s_prim + EPB * PRIM);
+
+    const int lane = threadIdx.x;
+    const long long e0 = (long long)blockIdx.x * EPB;
+    const int nel = (int)min((long long)EPB, P.nelements - e0);
+    const double gamma = P.eq.p[0], inv_gm1 = P.eq.p[1];
+    const bool rk = P.mode != 0;
+    const bool need_ut = rk && P.rk_a != 0.0;
+
+    // 0. TMA loads of the two contiguous element records
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    if (lane == 0) {
+        const uint32_t bu = (uint32_t)(nel * CONS * sizeof(double)), bs = (uint32_t)(nel * SFV * sizeof(double));
+        mbar_expect_tx(bar, bu + (need_ut ? bu : 0u) + (WITH_SURFACE ? bs : 0u));
+        tma_load(smem_u32(s_u), P.u + e0 * CONS, bu, bar);
+        if (need_ut) tma_load(smem_u32(s_ut), P.u_tmp + e0 * CONS, bu, bar);
+        if (WITH_SURFACE) tma_load(smem_u32(s_sfv), P.sfv + e0 * SFV, bs, bar);
+    }
+    const int le = lane >> 4, l16 = lane & 15;
+    const bool active = le < nel;
+    const double *ue = s_u + le * CONS;
+    while (!mbar_try_wait(bar, 0)) {
+    }
+
+    // 1. cons2prim + logs, 4 nodes per thread (node layer k = r); natural-order reads are conflict-free
+    if (active) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int n = l16 + 16 * r;
+            const double *c = ue + n * 5;
+            const double rho = c[0];
+            const double inv_rho = fast_rcp(rho);
+            // v = rho_v / rho with a residual correction (cons2prim, compressible_euler_3d.jl:1783-1793)
+            double v1 = c[1] * inv_rho, v2 = c[2] * inv_rho, v3 = c[3] * inv_rho;
+            v1 = fma(fma(-rho, v1, c[1]), inv_rho, v1);
+            v2 = fma(fma(-rho, v2, c[2]), inv_rho, v2);
+            v3 = fma(fma(-rho, v3, c[3]), inv_rho, v3);
+            const double pr = (gamma - 1) * (c[4] - 0.5 * (c[1] * v1 + c[2] * v2 + c[3] * v3));
+            double *o = s_prim + le * PRIM + swz_pos(n) * kNP;
+            o[0] = rho;
+            o[1] = v1;
+            o[2] = v2;
+            o[3] = v3;
+            o[4] = pr;
+            o[5] = log(rho);
+            o[6] = log(pr);
+        }
+    }
+    __syncwarp();
+
+    // 2. x and y passes meet in the du tile
+    int pos[4];
+    double acc[4][5];
+    double *due = s_du + le * CONS;
+    if (active) {
+        line_fluxes<0>(s_prim + le * PRIM, l16, P, inv_gm1, pos, acc);
+#pragma unroll
+        for (int m = 0; m < 4; ++m)
+#pragma unroll
+            for (int v = 0; v < 5; ++v) due[pos[m] * 5 + v] = acc[m][v];
+    }
+    __syncwarp();
+    if (active) {
+        line_fluxes<1>(s_prim + le * PRIM, l16, P, inv_gm1, pos, acc);
+#pragma unroll
+        for (int m = 0; m < 4; ++m)
+#pragma unroll
+            for (int v = 0; v < 5; ++v) due[pos[m] * 5 + v] += acc[m][v];
+    }
+    __syncwarp();
+
+    // 3. z pass; its thread owns nodes (i, j, 0..3) with (i, j) = l16 and finishes them in registers
+    if (active) {
+        line_fluxes<2>(s_prim + le * PRIM, l16, P, inv_gm1, pos, acc);
+        const int i = l16 & 3, j = l16 >> 2;
+        const double factor = WITH_SURFACE ? -P.inverse_jacobian[e0 + le] : 1.0;
+        const double *sf = s_sfv + le * SFV;
+        const Euler<3> eq(P.eq);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int n = l16 + 16 * k;
+            double val[5];
+#pragma unroll
+            for (int v = 0; v < 5; ++v) val[v] = due[pos[k] * 5 + v] + acc[k][v];
+            if constexpr (WITH_SURFACE) {
+                // calc_surface_integral! (dg_3d.jl:1337-1394): directions 1..6 = -x,+x,-y,+y,-z,+z
+                if (i == 0 || i == 3) {
+                    const double *s = sf + ((i == 0 ? 0 : 1) * 16 + j + 4 * k) * 5;
+                    const double w = i == 0 ? -P.inv_weight0 : P.inv_weight0;
+#pragma unroll
+                    for (int v = 0; v < 5; ++v) val[v] = fma(s[v], w, val[v]);
+                }
+                if (j == 0 || j == 3) {
+                    const double *s = sf + ((j == 0 ? 2 : 3) * 16 + i + 4 * k) * 5;
+                    const double w = j == 0 ? -P.inv_weight0 : P.inv_weight0;
+#pragma unroll
+                    for (int v = 0; v < 5; ++v) val[v] = fma(s[v], w, val[v]);
+                }
+                if (k == 0 || k == 3) {
+                    const double *s = sf + ((k == 0 ? 4 : 5) * 16 + l16) * 5;
+                    const double w = k == 0 ? -P.inv_weight0 : P.inv_weight0;
+#pragma unroll
+                    for (int v = 0; v < 5; ++v) val[v] = fma(s[v], w, val[v]);
+                }
+                // apply_jacobian! (dg_3d.jl:1396-1414)
+#pragma unroll
+                for (int v = 0; v < 5; ++v) val[v] *= factor;
+                // calc_sources! (dg_3d.jl:1417-1437)
+                if (P.source_terms != TRIXI_B200_SRC_NONE) {
+                    double un[5], x[3], s[5];
+#pragma unroll
+                    for (int v = 0; v < 5; ++v) un[v] = ue[n * 5 + v];
+#pragma unroll
+                    for (int d = 0; d < 3; ++d) x[d] = P.node_coordinates[((e0 + le) * 64 + n) * 3 + d];
+                    eq.source_terms(P.source_terms, un, x, P.t, s);
+#pragma unroll
+                    for (int v = 0; v < 5; ++v) val[v] += s[v];
+                }
+            }
+            double *out_t = s_ut + le * CONS + n * 5;
+            if (!rk) {
+#pragma unroll
+                for (int v = 0; v < 5; ++v) out_t[v] = val[v];
+            } else {
+                // 2N stage (methods_2N.jl:152-158): u_tmp = du - u_tmp * a; u += u_tmp * (b * dt)
+                double *out_u = s_u + le * CONS + n * 5;
+#pragma unroll
+                for (int v = 0; v < 5; ++v) {
+                    const double tmp = need_ut ? val[v] - out_t[v] * P.rk_a : val[v];
+                    out_t[v] = tmp;
+                    out_u[v] = out_u[v] + tmp * P.rk_b_dt;
+                }
+            }
+        }
+    }
+    // 4. results leave through the async proxy
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+        const uint32_t bu = (uint32_t)(nel * CONS * sizeof(double));
+        if (!rk) {
+            tma_store(P.du + e0 * CONS, smem_u32(s_ut), bu);
+        } else {
+            tma_store(P.u_tmp + e0 * CONS, smem_u32(s_ut), bu);
+            tma_store(P.u_out + e0 * CONS, smem_u32(s_u), bu);
+        }
+        tma_store_commit_and_wait_read();
+    }
+}
+
+cudaError_t launch_element_euler3d_ranocha_p3(const KParams &P, bool with_surface, cudaStream_t s) {
+    using C = TunedCfg;
+    static PerDeviceFlag configured;
+    if (!configured.test_and_set()) {
+        cudaError_t err = cudaFuncSetAttribute(k_element_euler3d_ranocha_p3<true>,
+                                               cudaFuncAttributePreferredSharedMemoryCarveout,
+                                               cudaSharedmemCarveoutMaxShared);
+        if (err != cudaSuccess) return err;
+        err = cudaFuncSetAttribute(k_element_euler3d_ranocha_p3<false>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                   cudaSharedmemCarveoutMaxShared);
+        if (err != cudaSuccess) return err;
+    }
+    const unsigned blocks = (unsigned)((P.nelements + C::EPB - 1) / C::EPB);
+    if (with_surface)
+        k_element_euler3d_ranocha_p3<true><<<blocks, C::THREADS, C::SMEM, s>>>(P);
+    else
+        k_element_euler3d_ranocha_p3<false><<<blocks, C::THREADS, C::SMEM, s>>>(P);
+    return cudaSuccess;
+}
+
+}  // namespace tb

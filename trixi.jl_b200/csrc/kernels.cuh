@@ -28,6 +28,8 @@ struct KParams {
     double *sfv;    // surface_flux_values [nv, n^(d-1), 2d, nelem]
     // operators (column-major [n, n]) live in constant-like global memory, staged to smem per block
     const double *dsplit, *dhat;
+    double dsplit_c[kMaxNodes * kMaxNodes];  // same matrix in the kernel-parameter constant bank: a DFMA
+                                             // can take it as an operand without a load or a register
     double inv_weight0;
     // geometry
     const double *inverse_jacobian;  // [nelem]
@@ -48,6 +50,7 @@ struct KParams {
     double rk_a, rk_b_dt;
     // CFL fused output: per-block max of invJ * sum_d max_nodes lambda_d, encoded as ordered uint64
     unsigned long long *cfl_key;  // nullptr: skip
+    int kernel_path;              // 0: tuned kernels where available, 1: generic kernels only
 };
 
 __host__ __device__ constexpr int ipow(int b, int e) { return e == 0 ? 1 : b * ipow(b, e - 1); }

@@ -1,5 +1,7 @@
 // Host-side launchers for the templated kernels and the per-equation dispatch tables.
 #pragma once
+#include <type_traits>
+
 #include "kernels.cuh"
 
 namespace tb {
@@ -33,6 +35,22 @@ void launch_boundary_flux(const KParams &P, cudaStream_t s) {
     k_boundary_flux<EQ, N><<<blocks, threads, 0, s>>>(P);
 }
 
+// cudaFuncSetAttribute is per device: remember what was configured where
+struct PerDeviceFlag {
+    bool done[64] = {};
+    bool test_and_set() {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        dev &= 63;
+        const bool was = done[dev];
+        done[dev] = true;
+        return was;
+    }
+};
+
+// tuned_euler3d.cu
+cudaError_t launch_element_euler3d_ranocha_p3(const KParams &P, bool with_surface, cudaStream_t s);
+
 template <class EQ, int N, int VOLINT, bool WS>
 cudaError_t launch_element_variant(const KParams &P, cudaStream_t s) {
     using C = ElemCfg<EQ, N>;
@@ -42,11 +60,10 @@ cudaError_t launch_element_variant(const KParams &P, cudaStream_t s) {
                                                : 0));
     auto kern = k_element<EQ, N, VOLINT, WS>;
     if (smem > 48 * 1024) {
-        static bool configured = false;
-        if (!configured) {
+        static PerDeviceFlag configured;
+        if (!configured.test_and_set()) {
             cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (err != cudaSuccess) return err;
-            configured = true;
         }
     }
     const unsigned blocks = (unsigned)((P.nelements + C::EPB - 1) / C::EPB);
@@ -57,6 +74,11 @@ cudaError_t launch_element_variant(const KParams &P, cudaStream_t s) {
 template <class EQ, int N>
 cudaError_t launch_element(const KParams &P, bool with_surface, cudaStream_t s) {
     if (P.nelements == 0) return cudaSuccess;
+    if constexpr (std::is_same_v<EQ, Euler<3>> && N == 4) {
+        if (P.kernel_path == 0 && P.volume_integral == TRIXI_B200_VOLINT_FLUX_DIFFERENCING &&
+            (P.volume_flux == TRIXI_B200_FLUX_RANOCHA || P.volume_flux == TRIXI_B200_FLUX_RANOCHA_TURBO))
+            return launch_element_euler3d_ranocha_p3(P, with_surface, s);
+    }
     if (P.volume_integral == TRIXI_B200_VOLINT_WEAK_FORM) {
         return with_surface ? launch_element_variant<EQ, N, TRIXI_B200_VOLINT_WEAK_FORM, true>(P, s)
                             : launch_element_variant<EQ, N, TRIXI_B200_VOLINT_WEAK_FORM, false>(P, s);

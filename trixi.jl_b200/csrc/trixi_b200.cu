@@ -323,6 +323,8 @@ TRIXI_B200_API int trixi_b200_create(const trixi_b200_desc *d, trixi_b200_handle
         return TRIXI_B200_EINVAL;
     }
     P.inv_weight0 = d->inverse_weights[0];
+    for (int q = 0; q < n * n; ++q) P.dsplit_c[q] = d->derivative_split[q];
+    P.kernel_path = 0;
     CREATE_TRY(upload_array(h, d->inverse_jacobian, (size_t)d->nelements, &tmp));
     P.inverse_jacobian = tmp;
     CREATE_TRY(upload_array(h, d->node_coordinates, (size_t)(nd * nn * d->nelements), &tmp));
@@ -549,6 +551,18 @@ TRIXI_B200_API int trixi_b200_set_eq_param(trixi_b200_handle *h, int index, doub
     if (index < 0 || index >= 8) return fail(h, TRIXI_B200_EINVAL, "equation parameter index %d out of range", index);
     h->P.eq.p[index] = value;
     return 0;
+}
+
+TRIXI_B200_API int trixi_b200_set_option(trixi_b200_handle *h, int option, int value) {
+    if (!h) return TRIXI_B200_EINVAL;
+    switch (option) {
+    case TRIXI_B200_OPT_KERNEL_PATH:
+        if (value != 0 && value != 1) return fail(h, TRIXI_B200_EINVAL, "kernel path must be 0 (auto) or 1 (generic)");
+        h->P.kernel_path = value;
+        return 0;
+    default:
+        return fail(h, TRIXI_B200_EINVAL, "unknown option %d", option);
+    }
 }
 
 TRIXI_B200_API int trixi_b200_comm_unique_id(void *id_out_128_bytes) {

@@ -25,7 +25,7 @@ EXPORTS = [
     "trixi_b200_download_surface_flux_values", "trixi_b200_comm_unique_id", "trixi_b200_comm_init",
     "trixi_b200_launch_count", "trixi_b200_last_elapsed_ms", "trixi_b200_profile_enable",
     "trixi_b200_profile_read", "trixi_b200_timer_start", "trixi_b200_timer_stop",
-    "trixi_b200_measure_fp64_peak", "trixi_b200_measure_copy_bandwidth",
+    "trixi_b200_measure_fp64_peak", "trixi_b200_measure_copy_bandwidth", "trixi_b200_set_option",
 ]
 
 _lib = None
@@ -80,6 +80,7 @@ def load_library(path=None):
     lib.trixi_b200_profile_enable.argtypes = [vp, C.c_int]
     lib.trixi_b200_profile_read.argtypes = [vp, C.c_int, dp, i64p]
     lib.trixi_b200_timer_start.argtypes = [vp]
+    lib.trixi_b200_set_option.argtypes = [vp, C.c_int, C.c_int]
     lib.trixi_b200_timer_stop.argtypes = [vp, C.POINTER(C.c_float)]
     lib.trixi_b200_measure_fp64_peak.argtypes = [vp, dp]
     lib.trixi_b200_measure_copy_bandwidth.argtypes = [vp, dp]
@@ -214,6 +215,11 @@ class B200Backend:
         ms, n = C.c_double(), C.c_int64()
         self._ck(self.lib.trixi_b200_profile_read(self.h, kernel_class, C.byref(ms), C.byref(n)))
         return ms.value, n.value
+
+    OPT_KERNEL_PATH = 0
+
+    def set_option(self, option, value):
+        self._ck(self.lib.trixi_b200_set_option(self.h, int(option), int(value)))
 
     def timer_start(self):
         self._ck(self.lib.trixi_b200_timer_start(self.h))
