@@ -84,43 +84,50 @@ TB_DEV void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" 
 // Node record in the prim tile: rho, v1, v2, v3, p, log(rho), log(p)
 constexpr int kNP = 7;
 
-// flux_ranocha(u_ll, u_rr, orientation D) (compressible_euler_3d.jl:746-793) on hoisted node records.
-template <int D>
-TB_DEV void ranocha_pair(const double (&L)[kNP], const double (&R)[kNP], double inv_gm1, double (&f)[5]) {
+// 1/x to ~1e-12: MUFU.RCP64H seed + one Newton step; enough for f^2, which only enters the Ismail-Roe
+// series (sensitivity f^2/3 <= 3e-5) and the branch choice
+TB_DEV double rcp_1nr(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    return fma(r, fma(-x, r, 1.0), r);
+}
+
+// flux_ranocha(u_ll, u_rr, orientation) (compressible_euler_3d.jl:746-793) on hoisted node records whose
+// velocity components have been rotated so that slot 1 is the normal one: (rho, vn, vt1, vt2, p, log rho,
+// log p).  The output is rotated the same way: (f_rho, f_n, f_t1, f_t2, f_E).
+TB_DEV void ranocha_pair_rot(const double (&L)[kNP], const double (&R)[kNP], double inv_gm1, double (&f)[5]) {
     const double rho_ll = L[0], p_ll = L[4], rho_rr = R[0], p_rr = R[4];
     const double dlog_rho = R[5] - L[5];  // log(rho_rr / rho_ll)
-    // ln_mean(rho_ll, rho_rr) (math.jl:198-210)
+    // ln_mean(rho_ll, rho_rr) (math.jl:198-210); f^2 = (x-y)^2/(x+y)^2 as in the reference's SIMD kernel
     double rho_mean;
     {
-        const double x = rho_ll, y = rho_rr;
-        const double n = fma(x, x - 2 * y, y * y), d = fma(x, x + 2 * y, y * y);
-        const double f2 = n * fast_rcp(d);
+        const double sum = rho_ll + rho_rr, dif = rho_rr - rho_ll;
+        const double f2 = (dif * dif) * rcp_1nr(sum * sum);
         const bool series = f2 < 1.0e-4;
         const double poly = fma(f2, fma(f2, fma(f2, 2.0 / 7.0, 2.0 / 5.0), 2.0 / 3.0), 2.0);
-        rho_mean = fast_div(series ? x + y : y - x, series ? poly : dlog_rho);
+        rho_mean = fast_div(series ? sum : dif, series ? poly : dlog_rho);
     }
     // inv_ln_mean(rho_ll * p_rr, rho_rr * p_ll) (math.jl:238-250)
     double inv_rho_p_mean;
     {
         const double x = rho_ll * p_rr, y = rho_rr * p_ll;
-        const double n = fma(x, x - 2 * y, y * y), d = fma(x, x + 2 * y, y * y);
-        const double f2 = n * fast_rcp(d);
+        const double sum = x + y, dif = y - x;
+        const double f2 = (dif * dif) * rcp_1nr(sum * sum);
         const bool series = f2 < 1.0e-4;
         const double poly = fma(f2, fma(f2, fma(f2, 2.0 / 7.0, 2.0 / 5.0), 2.0 / 3.0), 2.0);
         // log(y / x) = log(rho_rr p_ll) - log(rho_ll p_rr)
-        const double m = fast_div(series ? poly : dlog_rho + (L[6] - R[6]), series ? x + y : y - x);
+        const double m = fast_div(series ? poly : dlog_rho + (L[6] - R[6]), series ? sum : dif);
         inv_rho_p_mean = p_ll * p_rr * m;
     }
-    const double v1_avg = 0.5 * (L[1] + R[1]), v2_avg = 0.5 * (L[2] + R[2]), v3_avg = 0.5 * (L[3] + R[3]);
+    const double vn_avg = 0.5 * (L[1] + R[1]), vt1_avg = 0.5 * (L[2] + R[2]), vt2_avg = 0.5 * (L[3] + R[3]);
     const double p_avg = 0.5 * (p_ll + p_rr);
     const double velocity_square_avg = 0.5 * (L[1] * R[1] + L[2] * R[2] + L[3] * R[3]);
-    const double vn_avg = D == 0 ? v1_avg : (D == 1 ? v2_avg : v3_avg);
     const double f1 = rho_mean * vn_avg;
     f[0] = f1;
-    f[1] = f1 * v1_avg + (D == 0 ? p_avg : 0.0);
-    f[2] = f1 * v2_avg + (D == 1 ? p_avg : 0.0);
-    f[3] = f1 * v3_avg + (D == 2 ? p_avg : 0.0);
-    f[4] = f1 * (velocity_square_avg + inv_rho_p_mean * inv_gm1) + 0.5 * (p_ll * R[1 + D] + p_rr * L[1 + D]);
+    f[1] = f1 * vn_avg + p_avg;
+    f[2] = f1 * vt1_avg;
+    f[3] = f1 * vt2_avg;
+    f[4] = f1 * (velocity_square_avg + inv_rho_p_mean * inv_gm1) + 0.5 * (p_ll * R[1] + p_rr * L[1]);
 }
 
 struct TunedCfg {
@@ -129,39 +136,6 @@ struct TunedCfg {
     // s_u, s_ut (natural order, TMA), s_sfv (natural, TMA), s_du, s_prim (swizzled), mbarrier
     static constexpr size_t SMEM = sizeof(double) * EPB * (3 * CONS + SFV + PRIM) + 16;
 };
-
-// six symmetric pair fluxes of one line, accumulated into both ends
-template <int D>
-TB_DEV void line_fluxes(const double *s_prim_e, int l16, const KParams &P, double inv_gm1, int (&pos)[4],
-                        double (&acc)[4][5]) {
-    // line l16 of direction D: the two fixed coordinates are (l16 % 4, l16 / 4)
-    const int a0 = l16 & 3, a1 = l16 >> 2;
-    double q[4][kNP];
-#pragma unroll
-    for (int m = 0; m < 4; ++m) {
-        const int n = D == 0 ? m + 4 * a0 + 16 * a1 : (D == 1 ? a0 + 4 * m + 16 * a1 : a0 + 4 * a1 + 16 * m);
-        pos[m] = swz_pos(n);
-#pragma unroll
-        for (int c = 0; c < kNP; ++c) q[m][c] = s_prim_e[pos[m] * kNP + c];
-    }
-#pragma unroll
-    for (int m = 0; m < 4; ++m)
-#pragma unroll
-        for (int v = 0; v < 5; ++v) acc[m][v] = 0.0;
-#pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = a + 1; b < 4; ++b) {
-            double f[5];
-            ranocha_pair<D>(q[a], q[b], inv_gm1, f);
-            const double wab = P.dsplit_c[a + 4 * b], wba = P.dsplit_c[b + 4 * a];  // Dsplit[a,b], Dsplit[b,a]
-#pragma unroll
-            for (int v = 0; v < 5; ++v) {
-                acc[a][v] = fma(wab, f[v], acc[a][v]);
-                acc[b][v] = fma(wba, f[v], acc[b][v]);
-            }
-        }
-}
 
 template <bool WITH_SURFACE>
 __global__ void __launch_bounds__(TunedCfg::THREADS, 7) k_element_euler3d_ranocha_p3(const KParams P) {
@@ -172,7 +146,7 @@ __global__ void __launch_bounds__(TunedCfg::THREADS, 7) k_element_euler3d_ranoch
     double *s_ut = s_u + EPB * CONS;      // [EPB][64][5] natural: u_tmp in, u_tmp (or du) out
     double *s_sfv = s_ut + EPB * CONS;    // [EPB][6][16][5] natural
     double *s_du = s_sfv + EPB * SFV;     // [EPB][64][5] swizzled
-    double *s_prim = s_du + EPB * CONS;   // [EPB][64][7] swizzled
+    double *s_prim = s_du + EPB * CONS;   // [EPB][64][7] swizzled; after the flux passes: source terms
     const uint32_t bar = smem_u32(s_prim + EPB * PRIM);
 
     const int lane = threadIdx.x;
@@ -198,12 +172,14 @@ __global__ void __launch_bounds__(TunedCfg::THREADS, 7) k_element_euler3d_ranoch
     const int le = lane >> 4, l16 = lane & 15;
     const bool active = le < nel;
     const double *ue = s_u + le * CONS;
+    double *prim_e = s_prim + le * PRIM;
+    double *due = s_du + le * CONS;
     while (!mbar_try_wait(bar, 0)) {
     }
 
     // 1. cons2prim + logs, 4 nodes per thread (node layer k = r); natural-order reads are conflict-free
     if (active) {
-#pragma unroll
+#pragma unroll 1
         for (int r = 0; r < 4; ++r) {
             const int n = l16 + 16 * r;
             const double *c = ue + n * 5;
@@ -215,7 +191,7 @@ __global__ void __launch_bounds__(TunedCfg::THREADS, 7) k_element_euler3d_ranoch
             v2 = fma(fma(-rho, v2, c[2]), inv_rho, v2);
             v3 = fma(fma(-rho, v3, c[3]), inv_rho, v3);
             const double pr = (gamma - 1) * (c[4] - 0.5 * (c[1] * v1 + c[2] * v2 + c[3] * v3));
-            double *o = s_prim + le * PRIM + swz_pos(n) * kNP;
+            double *o = prim_e + swz_pos(n) * kNP;
             o[0] = rho;
             o[1] = v1;
             o[2] = v2;
@@ -227,40 +203,109 @@ __global__ void __launch_bounds__(TunedCfg::THREADS, 7) k_element_euler3d_ranoch
     }
     __syncwarp();
 
-    // 2. x and y passes meet in the du tile
+    // 2. direction passes x, y, z: ONE copy of the flux code (the 18 unrolled pair fluxes of a fully
+    // unrolled version overflow the instruction cache).  The direction only enters through shared-memory
+    // offsets: the velocity slots are rotated while loading, the momentum slots while storing.
     int pos[4];
     double acc[4][5];
-    double *due = s_du + le * CONS;
-    if (active) {
-        line_fluxes<0>(s_prim + le * PRIM, l16, P, inv_gm1, pos, acc);
+    const int a0 = l16 & 3, a1 = l16 >> 2;
+#pragma unroll 1
+    for (int d = 0; d < 3; ++d) {
+        // line l16 of direction d holds nodes base + m * stride
+        const int stride = 1 << (2 * d);
+        const int base = d == 0 ? 4 * l16 : (d == 1 ? a0 + 16 * a1 : l16);
+        const int on = 1 + d, ot1 = d == 2 ? 1 : 2 + d, ot2 = d == 0 ? 3 : d;  // 1 + (d + {0,1,2}) % 3
+        if (active) {
+            double q[4][kNP];
 #pragma unroll
-        for (int m = 0; m < 4; ++m)
+            for (int m = 0; m < 4; ++m) {
+                pos[m] = swz_pos(base + m * stride);
+                const double *src = prim_e + pos[m] * kNP;
+                q[m][0] = src[0];
+                q[m][1] = src[on];
+                q[m][2] = src[ot1];
+                q[m][3] = src[ot2];
+                q[m][4] = src[4];
+                q[m][5] = src[5];
+                q[m][6] = src[6];
+            }
 #pragma unroll
-            for (int v = 0; v < 5; ++v) due[pos[m] * 5 + v] = acc[m][v];
+            for (int m = 0; m < 4; ++m)
+#pragma unroll
+                for (int v = 0; v < 5; ++v) acc[m][v] = 0.0;
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = a + 1; b < 4; ++b) {
+                    double f[5];
+                    ranocha_pair_rot(q[a], q[b], inv_gm1, f);
+                    const double wab = P.dsplit_c[a + 4 * b], wba = P.dsplit_c[b + 4 * a];
+#pragma unroll
+                    for (int v = 0; v < 5; ++v) {
+                        acc[a][v] = fma(wab, f[v], acc[a][v]);
+                        acc[b][v] = fma(wba, f[v], acc[b][v]);
+                    }
+                }
+            if (d < 2) {
+#pragma unroll
+                for (int m = 0; m < 4; ++m) {
+                    double *t = due + pos[m] * 5;
+                    if (d == 0) {
+                        t[0] = acc[m][0];
+                        t[on] = acc[m][1];
+                        t[ot1] = acc[m][2];
+                        t[ot2] = acc[m][3];
+                        t[4] = acc[m][4];
+                    } else {
+                        t[0] += acc[m][0];
+                        t[on] += acc[m][1];
+                        t[ot1] += acc[m][2];
+                        t[ot2] += acc[m][3];
+                        t[4] += acc[m][4];
+                    }
+                }
+            }
+        }
+        __syncwarp();
     }
-    __syncwarp();
-    if (active) {
-        line_fluxes<1>(s_prim + le * PRIM, l16, P, inv_gm1, pos, acc);
-#pragma unroll
-        for (int m = 0; m < 4; ++m)
-#pragma unroll
-            for (int v = 0; v < 5; ++v) due[pos[m] * 5 + v] += acc[m][v];
-    }
-    __syncwarp();
 
-    // 3. z pass; its thread owns nodes (i, j, 0..3) with (i, j) = l16 and finishes them in registers
+    // calc_sources! (dg_3d.jl:1417-1437): evaluated into the (now dead) prim tile, natural node order
+    const bool have_src = WITH_SURFACE && P.source_terms != TRIXI_B200_SRC_NONE;
+    if (have_src) {
+        const Euler<3> eq(P.eq);
+        if (active) {
+#pragma unroll 1
+            for (int k = 0; k < 4; ++k) {
+                const int n = l16 + 16 * k;
+                double un[5], x[3], s[5];
+#pragma unroll
+                for (int v = 0; v < 5; ++v) un[v] = ue[n * 5 + v];
+#pragma unroll
+                for (int dd = 0; dd < 3; ++dd) x[dd] = P.node_coordinates[((e0 + le) * 64 + n) * 3 + dd];
+                eq.source_terms(P.source_terms, un, x, P.t, s);
+#pragma unroll
+                for (int v = 0; v < 5; ++v) prim_e[n * 5 + v] = s[v];
+            }
+        }
+        __syncwarp();
+    }
+
+    // 3. the z-pass thread owns nodes (i, j, 0..3) with (i, j) = l16 and finishes them in registers; its
+    // accumulators are rotated: slots (1, 2, 3) hold the (v3, v1, v2) momentum components
     if (active) {
-        line_fluxes<2>(s_prim + le * PRIM, l16, P, inv_gm1, pos, acc);
-        const int i = l16 & 3, j = l16 >> 2;
+        const int i = a0, j = a1;
         const double factor = WITH_SURFACE ? -P.inverse_jacobian[e0 + le] : 1.0;
         const double *sf = s_sfv + le * SFV;
-        const Euler<3> eq(P.eq);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const int n = l16 + 16 * k;
+            const double *t = due + pos[k] * 5;
             double val[5];
-#pragma unroll
-            for (int v = 0; v < 5; ++v) val[v] = due[pos[k] * 5 + v] + acc[k][v];
+            val[0] = t[0] + acc[k][0];
+            val[1] = t[1] + acc[k][2];
+            val[2] = t[2] + acc[k][3];
+            val[3] = t[3] + acc[k][1];
+            val[4] = t[4] + acc[k][4];
             if constexpr (WITH_SURFACE) {
                 // calc_surface_integral! (dg_3d.jl:1337-1394): directions 1..6 = -x,+x,-y,+y,-z,+z
                 if (i == 0 || i == 3) {
@@ -284,16 +329,9 @@ __global__ void __launch_bounds__(TunedCfg::THREADS, 7) k_element_euler3d_ranoch
                 // apply_jacobian! (dg_3d.jl:1396-1414)
 #pragma unroll
                 for (int v = 0; v < 5; ++v) val[v] *= factor;
-                // calc_sources! (dg_3d.jl:1417-1437)
-                if (P.source_terms != TRIXI_B200_SRC_NONE) {
-                    double un[5], x[3], s[5];
+                if (have_src) {
 #pragma unroll
-                    for (int v = 0; v < 5; ++v) un[v] = ue[n * 5 + v];
-#pragma unroll
-                    for (int d = 0; d < 3; ++d) x[d] = P.node_coordinates[((e0 + le) * 64 + n) * 3 + d];
-                    eq.source_terms(P.source_terms, un, x, P.t, s);
-#pragma unroll
-                    for (int v = 0; v < 5; ++v) val[v] += s[v];
+                    for (int v = 0; v < 5; ++v) val[v] += prim_e[n * 5 + v];
                 }
             }
             double *out_t = s_ut + le * CONS + n * 5;
