@@ -16,26 +16,37 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = os.path.join(_HERE, "libtrixi_oracle.so")
+_LIB_NOFMA = os.path.join(_HERE, "libtrixi_oracle_nofma.so")
 _lib = None
+_lib_nofma = None
 
 
 def build(force=False):
     src = os.path.join(_HERE, "trixi_oracle.c")
     hdr = os.path.join(_HERE, "..", "include", "trixi_b200.h")
-    if (not force and os.path.exists(_LIB)
-            and os.path.getmtime(_LIB) >= max(os.path.getmtime(src), os.path.getmtime(hdr))):
+    newest = max(os.path.getmtime(src), os.path.getmtime(hdr))
+    if (not force and all(os.path.exists(p) and os.path.getmtime(p) >= newest for p in (_LIB, _LIB_NOFMA))):
         return _LIB
-    subprocess.run(["make", "-C", _HERE, "-B", "libtrixi_oracle.so"], check=True, capture_output=True)
+    subprocess.run(["make", "-C", _HERE, "-B", "all"], check=True, capture_output=True)
     return _LIB
 
 
-def load():
-    global _lib
+def _open(path):
+    lib = C.CDLL(path)
+    lib.oracle_max_dt.restype = C.c_double
+    lib.oracle_num_threads.restype = C.c_int
+    return lib
+
+
+def load(nofma=False):
+    global _lib, _lib_nofma
+    build()
+    if nofma:
+        if _lib_nofma is None:
+            _lib_nofma = _open(_LIB_NOFMA)
+        return _lib_nofma
     if _lib is None:
-        build()
-        _lib = C.CDLL(_LIB)
-        _lib.oracle_max_dt.restype = C.c_double
-        _lib.oracle_num_threads.restype = C.c_int
+        _lib = _open(_LIB)
     return _lib
 
 
@@ -46,8 +57,8 @@ def _p(a):
 class OracleBackend:
     U, DU, U_TMP = 0, 1, 2
 
-    def __init__(self, semi, num_threads=None):
-        self.lib = load()
+    def __init__(self, semi, num_threads=None, nofma=False):
+        self.lib = load(nofma)
         if num_threads is not None:
             self.lib.oracle_set_num_threads(int(num_threads))
         self.semi = semi

@@ -3,16 +3,17 @@
 // This is the headline configuration (BASELINE.json: 3D Euler EC p=3).
 //
 // Work decomposition.
-//  * One warp = one CTA = two elements; everything is warp-synchronous (no block barriers), ~7 CTAs
-//    resident per SM so one warp's tile I/O latency hides behind the other warps' FP64 work.
+//  * One warp = one CTA = one element; everything is warp-synchronous (no block barriers), 14 CTAs
+//    resident per SM so one warp's tile I/O latency and FP64 dependency chains hide behind the others.
 //  * Tile I/O is TMA: three `cp.async.bulk` loads (u, u_tmp, surface_flux_values of the two elements are
 //    contiguous 5/5/7.5 KB records) signalled on an mbarrier, results leave through `cp.async.bulk`
 //    stores -- no per-thread address arithmetic, no register staging, fully coalesced HBM traffic.
 //  * Per element and direction the 64 nodes form 16 lines of 4 nodes with 6 symmetric node pairs each.
-//    A thread owns one line per direction pass and evaluates its 6 two-point fluxes exactly once (288 per
-//    element, like the reference's symmetric loop dg_3d.jl:177-211), accumulating D_split[a,b] f into
-//    both end nodes in registers.  x and y passes meet in a shared-memory du tile; the z pass keeps its
-//    accumulators and finishes surface integral, Jacobian, sources and the RK update in registers.
+//    Two threads share a line per direction pass, three pair fluxes each, so every two-point flux is
+//    evaluated exactly once (288 per element, like the reference's symmetric loop dg_3d.jl:177-211);
+//    D_split[a,b] f is accumulated into both end nodes, partial sums meet in a shared-memory du tile, and
+//    after the z pass each thread finishes surface integral, Jacobian, sources and the RK update of its
+//    two nodes in registers.
 //  * flux_ranocha is evaluated in the hoisted form of the reference's own SIMD kernel
 //    (dg_3d_compressible_euler.jl:289-309,360-385): primitive variables and log(rho), log(p) once per
 //    node, so the logarithmic means need no log per pair.
@@ -131,140 +132,153 @@ TB_DEV void ranocha_pair_rot(const double (&L)[kNP], const double (&R)[kNP], dou
 }
 
 struct TunedCfg {
-    static constexpr int EPB = 2, THREADS = 32;  // one warp, two elements
+    static constexpr int EPB = 1, THREADS = 32;  // one warp, one element, two threads per line
     static constexpr int CONS = 320, PRIM = 64 * kNP, SFV = 480;  // doubles per element
     // s_u, s_ut (natural order, TMA), s_sfv (natural, TMA), s_du, s_prim (swizzled), mbarrier
     static constexpr size_t SMEM = sizeof(double) * EPB * (3 * CONS + SFV + PRIM) + 16;
+    static constexpr int MIN_BLOCKS = 14;
 };
 
 template <bool WITH_SURFACE>
-__global__ void __launch_bounds__(TunedCfg::THREADS, 7) k_element_euler3d_ranocha_p3(const KParams P) {
+__global__ void __launch_bounds__(TunedCfg::THREADS, TunedCfg::MIN_BLOCKS)
+    k_element_euler3d_ranocha_p3(const KParams P) {
     using C = TunedCfg;
-    constexpr int EPB = C::EPB, CONS = C::CONS, PRIM = C::PRIM, SFV = C::SFV;
+    constexpr int CONS = C::CONS, PRIM = C::PRIM, SFV = C::SFV;
     extern __shared__ __align__(128) double smem[];
-    double *s_u = smem;                   // [EPB][64][5] natural: u in, updated u out
-    double *s_ut = s_u + EPB * CONS;      // [EPB][64][5] natural: u_tmp in, u_tmp (or du) out
-    double *s_sfv = s_ut + EPB * CONS;    // [EPB][6][16][5] natural
-    double *s_du = s_sfv + EPB * SFV;     // [EPB][64][5] swizzled
-    double *s_prim = s_du + EPB * CONS;   // [EPB][64][7] swizzled; after the flux passes: source terms
-    const uint32_t bar = smem_u32(s_prim + EPB * PRIM);
+    double *s_u = smem;            // [64][5] natural: u in, updated u out
+    double *s_ut = s_u + CONS;     // [64][5] natural: u_tmp in, u_tmp (or du) out
+    double *s_sfv = s_ut + CONS;   // [6][16][5] natural
+    double *s_du = s_sfv + SFV;    // [64][5] swizzled
+    double *s_prim = s_du + CONS;  // [64][7] swizzled; after the flux passes: source terms
+    const uint32_t bar = smem_u32(s_prim + PRIM);
 
     const int lane = threadIdx.x;
-    const long long e0 = (long long)blockIdx.x * EPB;
-    const int nel = (int)min((long long)EPB, P.nelements - e0);
+    const long long e = blockIdx.x;
     const double gamma = P.eq.p[0], inv_gm1 = P.eq.p[1];
     const bool rk = P.mode != 0;
     const bool need_ut = rk && P.rk_a != 0.0;
 
-    // 0. TMA loads of the two contiguous element records
+    // 0. TMA loads of the contiguous element records
     if (lane == 0) {
         mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
     if (lane == 0) {
-        const uint32_t bu = (uint32_t)(nel * CONS * sizeof(double)), bs = (uint32_t)(nel * SFV * sizeof(double));
+        constexpr uint32_t bu = CONS * sizeof(double), bs = SFV * sizeof(double);
         mbar_expect_tx(bar, bu + (need_ut ? bu : 0u) + (WITH_SURFACE ? bs : 0u));
-        tma_load(smem_u32(s_u), P.u + e0 * CONS, bu, bar);
-        if (need_ut) tma_load(smem_u32(s_ut), P.u_tmp + e0 * CONS, bu, bar);
-        if (WITH_SURFACE) tma_load(smem_u32(s_sfv), P.sfv + e0 * SFV, bs, bar);
+        tma_load(smem_u32(s_u), P.u + e * CONS, bu, bar);
+        if (need_ut) tma_load(smem_u32(s_ut), P.u_tmp + e * CONS, bu, bar);
+        if (WITH_SURFACE) tma_load(smem_u32(s_sfv), P.sfv + e * SFV, bs, bar);
     }
-    const int le = lane >> 4, l16 = lane & 15;
-    const bool active = le < nel;
-    const double *ue = s_u + le * CONS;
-    double *prim_e = s_prim + le * PRIM;
-    double *due = s_du + le * CONS;
+    // Two threads (h = 0, 1) share line l16 of every direction pass.  In line-local node numbering
+    // thread h owns nodes lm[0], lm[1] and sees lm[2], lm[3] as foreign: h = 0: (0,1 | 2,3), h = 1: (3,2 | 0,1).
+    // Both evaluate the pairs (lm0,lm1), (lm0,lm2), (lm1,lm3): together all 6 pairs of the line, once each.
+    const int h = lane >> 4, l16 = lane & 15;
+    const int a0 = l16 & 3, a1 = l16 >> 2;
+    const int lm[4] = {h ? 3 : 0, h ? 2 : 1, h ? 0 : 2, h ? 1 : 3};
+    // D_split[a, b] for the three pairs in both directions (column-major n x n)
+    const double w01 = P.dsplit_c[lm[0] + 4 * lm[1]], w10 = P.dsplit_c[lm[1] + 4 * lm[0]];
+    const double w02 = P.dsplit_c[lm[0] + 4 * lm[2]], w20 = P.dsplit_c[lm[2] + 4 * lm[0]];
+    const double w13 = P.dsplit_c[lm[1] + 4 * lm[3]], w31 = P.dsplit_c[lm[3] + 4 * lm[1]];
     while (!mbar_try_wait(bar, 0)) {
     }
 
-    // 1. cons2prim + logs, 4 nodes per thread (node layer k = r); natural-order reads are conflict-free
-    if (active) {
+    // 1. cons2prim + logs for the two nodes (i, j, k = lm[0], lm[1]) this thread also finishes in step 3;
+    //    a half-warp reads 16 consecutive node records: conflict-free
 #pragma unroll 1
-        for (int r = 0; r < 4; ++r) {
-            const int n = l16 + 16 * r;
-            const double *c = ue + n * 5;
-            const double rho = c[0];
-            const double inv_rho = fast_rcp(rho);
-            // v = rho_v / rho with a residual correction (cons2prim, compressible_euler_3d.jl:1783-1793)
-            double v1 = c[1] * inv_rho, v2 = c[2] * inv_rho, v3 = c[3] * inv_rho;
-            v1 = fma(fma(-rho, v1, c[1]), inv_rho, v1);
-            v2 = fma(fma(-rho, v2, c[2]), inv_rho, v2);
-            v3 = fma(fma(-rho, v3, c[3]), inv_rho, v3);
-            const double pr = (gamma - 1) * (c[4] - 0.5 * (c[1] * v1 + c[2] * v2 + c[3] * v3));
-            double *o = prim_e + swz_pos(n) * kNP;
-            o[0] = rho;
-            o[1] = v1;
-            o[2] = v2;
-            o[3] = v3;
-            o[4] = pr;
-            o[5] = log(rho);
-            o[6] = log(pr);
-        }
+    for (int r = 0; r < 2; ++r) {
+        const int n = l16 + 16 * (r == 0 ? lm[0] : lm[1]);
+        const double *c = s_u + n * 5;
+        const double rho = c[0];
+        const double inv_rho = fast_rcp(rho);
+        // v = rho_v / rho with a residual correction (cons2prim, compressible_euler_3d.jl:1783-1793)
+        double v1 = c[1] * inv_rho, v2 = c[2] * inv_rho, v3 = c[3] * inv_rho;
+        v1 = fma(fma(-rho, v1, c[1]), inv_rho, v1);
+        v2 = fma(fma(-rho, v2, c[2]), inv_rho, v2);
+        v3 = fma(fma(-rho, v3, c[3]), inv_rho, v3);
+        const double pr = (gamma - 1) * (c[4] - 0.5 * (c[1] * v1 + c[2] * v2 + c[3] * v3));
+        double *o = s_prim + swz_pos(n) * kNP;
+        o[0] = rho;
+        o[1] = v1;
+        o[2] = v2;
+        o[3] = v3;
+        o[4] = pr;
+        o[5] = log(rho);
+        o[6] = log(pr);
     }
     __syncwarp();
 
-    // 2. direction passes x, y, z: ONE copy of the flux code (the 18 unrolled pair fluxes of a fully
-    // unrolled version overflow the instruction cache).  The direction only enters through shared-memory
-    // offsets: the velocity slots are rotated while loading, the momentum slots while storing.
+    // 2. direction passes x, y, z with ONE copy of the flux code; the direction only enters through
+    // shared-memory offsets (velocity slots rotated while loading, momentum slots while storing)
     int pos[4];
-    double acc[4][5];
-    const int a0 = l16 & 3, a1 = l16 >> 2;
+    double own[2][5], frn[2][5];
 #pragma unroll 1
     for (int d = 0; d < 3; ++d) {
-        // line l16 of direction d holds nodes base + m * stride
         const int stride = 1 << (2 * d);
         const int base = d == 0 ? 4 * l16 : (d == 1 ? a0 + 16 * a1 : l16);
         const int on = 1 + d, ot1 = d == 2 ? 1 : 2 + d, ot2 = d == 0 ? 3 : d;  // 1 + (d + {0,1,2}) % 3
-        if (active) {
-            double q[4][kNP];
+        double q[4][kNP];
 #pragma unroll
-            for (int m = 0; m < 4; ++m) {
-                pos[m] = swz_pos(base + m * stride);
-                const double *src = prim_e + pos[m] * kNP;
-                q[m][0] = src[0];
-                q[m][1] = src[on];
-                q[m][2] = src[ot1];
-                q[m][3] = src[ot2];
-                q[m][4] = src[4];
-                q[m][5] = src[5];
-                q[m][6] = src[6];
-            }
+        for (int m = 0; m < 4; ++m) {
+            pos[m] = swz_pos(base + lm[m] * stride);
+            const double *src = s_prim + pos[m] * kNP;
+            q[m][0] = src[0];
+            q[m][1] = src[on];
+            q[m][2] = src[ot1];
+            q[m][3] = src[ot2];
+            q[m][4] = src[4];
+            q[m][5] = src[5];
+            q[m][6] = src[6];
+        }
+        double f[5];
+        ranocha_pair_rot(q[0], q[1], inv_gm1, f);
 #pragma unroll
-            for (int m = 0; m < 4; ++m)
+        for (int v = 0; v < 5; ++v) {
+            own[0][v] = w01 * f[v];
+            own[1][v] = w10 * f[v];
+        }
+        ranocha_pair_rot(q[0], q[2], inv_gm1, f);
 #pragma unroll
-                for (int v = 0; v < 5; ++v) acc[m][v] = 0.0;
+        for (int v = 0; v < 5; ++v) {
+            own[0][v] = fma(w02, f[v], own[0][v]);
+            frn[0][v] = w20 * f[v];
+        }
+        ranocha_pair_rot(q[1], q[3], inv_gm1, f);
 #pragma unroll
-            for (int a = 0; a < 4; ++a)
+        for (int v = 0; v < 5; ++v) {
+            own[1][v] = fma(w13, f[v], own[1][v]);
+            frn[1][v] = w31 * f[v];
+        }
+        // every node receives one own and one foreign partial per pass; they meet in the du tile
+        if (d < 2) {
 #pragma unroll
-                for (int b = a + 1; b < 4; ++b) {
-                    double f[5];
-                    ranocha_pair_rot(q[a], q[b], inv_gm1, f);
-                    const double wab = P.dsplit_c[a + 4 * b], wba = P.dsplit_c[b + 4 * a];
-#pragma unroll
-                    for (int v = 0; v < 5; ++v) {
-                        acc[a][v] = fma(wab, f[v], acc[a][v]);
-                        acc[b][v] = fma(wba, f[v], acc[b][v]);
-                    }
+            for (int m = 0; m < 2; ++m) {
+                double *t = s_du + pos[m] * 5;
+                if (d == 0) {
+                    t[0] = own[m][0];
+                    t[on] = own[m][1];
+                    t[ot1] = own[m][2];
+                    t[ot2] = own[m][3];
+                    t[4] = own[m][4];
+                } else {
+                    t[0] += own[m][0];
+                    t[on] += own[m][1];
+                    t[ot1] += own[m][2];
+                    t[ot2] += own[m][3];
+                    t[4] += own[m][4];
                 }
-            if (d < 2) {
-#pragma unroll
-                for (int m = 0; m < 4; ++m) {
-                    double *t = due + pos[m] * 5;
-                    if (d == 0) {
-                        t[0] = acc[m][0];
-                        t[on] = acc[m][1];
-                        t[ot1] = acc[m][2];
-                        t[ot2] = acc[m][3];
-                        t[4] = acc[m][4];
-                    } else {
-                        t[0] += acc[m][0];
-                        t[on] += acc[m][1];
-                        t[ot1] += acc[m][2];
-                        t[ot2] += acc[m][3];
-                        t[4] += acc[m][4];
-                    }
-                }
             }
+            __syncwarp();
+        }
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+            double *t = s_du + pos[2 + m] * 5;
+            t[0] += frn[m][0];
+            t[on] += frn[m][1];
+            t[ot1] += frn[m][2];
+            t[ot2] += frn[m][3];
+            t[4] += frn[m][4];
         }
         __syncwarp();
     }
@@ -273,74 +287,72 @@ __global__ void __launch_bounds__(TunedCfg::THREADS, 7) k_element_euler3d_ranoch
     const bool have_src = WITH_SURFACE && P.source_terms != TRIXI_B200_SRC_NONE;
     if (have_src) {
         const Euler<3> eq(P.eq);
-        if (active) {
 #pragma unroll 1
-            for (int k = 0; k < 4; ++k) {
-                const int n = l16 + 16 * k;
-                double un[5], x[3], s[5];
+        for (int r = 0; r < 2; ++r) {
+            const int n = l16 + 16 * (r == 0 ? lm[0] : lm[1]);
+            double un[5], x[3], sv[5];
 #pragma unroll
-                for (int v = 0; v < 5; ++v) un[v] = ue[n * 5 + v];
+            for (int v = 0; v < 5; ++v) un[v] = s_u[n * 5 + v];
 #pragma unroll
-                for (int dd = 0; dd < 3; ++dd) x[dd] = P.node_coordinates[((e0 + le) * 64 + n) * 3 + dd];
-                eq.source_terms(P.source_terms, un, x, P.t, s);
+            for (int dd = 0; dd < 3; ++dd) x[dd] = P.node_coordinates[(e * 64 + n) * 3 + dd];
+            eq.source_terms(P.source_terms, un, x, P.t, sv);
 #pragma unroll
-                for (int v = 0; v < 5; ++v) prim_e[n * 5 + v] = s[v];
-            }
+            for (int v = 0; v < 5; ++v) s_prim[n * 5 + v] = sv[v];
         }
         __syncwarp();
     }
 
-    // 3. the z-pass thread owns nodes (i, j, 0..3) with (i, j) = l16 and finishes them in registers; its
+    // 3. finish the two own nodes (i, j, k = lm[0], lm[1]) of the z line in registers; the z-pass
     // accumulators are rotated: slots (1, 2, 3) hold the (v3, v1, v2) momentum components
-    if (active) {
+    {
         const int i = a0, j = a1;
-        const double factor = WITH_SURFACE ? -P.inverse_jacobian[e0 + le] : 1.0;
-        const double *sf = s_sfv + le * SFV;
+        const double factor = WITH_SURFACE ? -P.inverse_jacobian[e] : 1.0;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
+        for (int r = 0; r < 2; ++r) {
+            const int k = lm[r];
             const int n = l16 + 16 * k;
-            const double *t = due + pos[k] * 5;
+            const double *t = s_du + pos[r] * 5;
             double val[5];
-            val[0] = t[0] + acc[k][0];
-            val[1] = t[1] + acc[k][2];
-            val[2] = t[2] + acc[k][3];
-            val[3] = t[3] + acc[k][1];
-            val[4] = t[4] + acc[k][4];
+            val[0] = t[0] + own[r][0];
+            val[1] = t[1] + own[r][2];
+            val[2] = t[2] + own[r][3];
+            val[3] = t[3] + own[r][1];
+            val[4] = t[4] + own[r][4];
             if constexpr (WITH_SURFACE) {
                 // calc_surface_integral! (dg_3d.jl:1337-1394): directions 1..6 = -x,+x,-y,+y,-z,+z
                 if (i == 0 || i == 3) {
-                    const double *s = sf + ((i == 0 ? 0 : 1) * 16 + j + 4 * k) * 5;
+                    const double *sf = s_sfv + ((i == 0 ? 0 : 1) * 16 + j + 4 * k) * 5;
                     const double w = i == 0 ? -P.inv_weight0 : P.inv_weight0;
 #pragma unroll
-                    for (int v = 0; v < 5; ++v) val[v] = fma(s[v], w, val[v]);
+                    for (int v = 0; v < 5; ++v) val[v] = fma(sf[v], w, val[v]);
                 }
                 if (j == 0 || j == 3) {
-                    const double *s = sf + ((j == 0 ? 2 : 3) * 16 + i + 4 * k) * 5;
+                    const double *sf = s_sfv + ((j == 0 ? 2 : 3) * 16 + i + 4 * k) * 5;
                     const double w = j == 0 ? -P.inv_weight0 : P.inv_weight0;
 #pragma unroll
-                    for (int v = 0; v < 5; ++v) val[v] = fma(s[v], w, val[v]);
+                    for (int v = 0; v < 5; ++v) val[v] = fma(sf[v], w, val[v]);
                 }
-                if (k == 0 || k == 3) {
-                    const double *s = sf + ((k == 0 ? 4 : 5) * 16 + l16) * 5;
-                    const double w = k == 0 ? -P.inv_weight0 : P.inv_weight0;
+                if (r == 0) {  // k = lm[0] is 0 (h = 0) or 3 (h = 1): always a z face; lm[1] never is
+                    const double *sf = s_sfv + ((h ? 5 : 4) * 16 + l16) * 5;
+                    const double w = h ? P.inv_weight0 : -P.inv_weight0;
 #pragma unroll
-                    for (int v = 0; v < 5; ++v) val[v] = fma(s[v], w, val[v]);
+                    for (int v = 0; v < 5; ++v) val[v] = fma(sf[v], w, val[v]);
                 }
                 // apply_jacobian! (dg_3d.jl:1396-1414)
 #pragma unroll
                 for (int v = 0; v < 5; ++v) val[v] *= factor;
                 if (have_src) {
 #pragma unroll
-                    for (int v = 0; v < 5; ++v) val[v] += prim_e[n * 5 + v];
+                    for (int v = 0; v < 5; ++v) val[v] += s_prim[n * 5 + v];
                 }
             }
-            double *out_t = s_ut + le * CONS + n * 5;
+            double *out_t = s_ut + n * 5;
             if (!rk) {
 #pragma unroll
                 for (int v = 0; v < 5; ++v) out_t[v] = val[v];
             } else {
                 // 2N stage (methods_2N.jl:152-158): u_tmp = du - u_tmp * a; u += u_tmp * (b * dt)
-                double *out_u = s_u + le * CONS + n * 5;
+                double *out_u = s_u + n * 5;
 #pragma unroll
                 for (int v = 0; v < 5; ++v) {
                     const double tmp = need_ut ? val[v] - out_t[v] * P.rk_a : val[v];
@@ -354,12 +366,12 @@ __global__ void __launch_bounds__(TunedCfg::THREADS, 7) k_element_euler3d_ranoch
     fence_proxy_async();
     __syncwarp();
     if (lane == 0) {
-        const uint32_t bu = (uint32_t)(nel * CONS * sizeof(double));
+        constexpr uint32_t bu = CONS * sizeof(double);
         if (!rk) {
-            tma_store(P.du + e0 * CONS, smem_u32(s_ut), bu);
+            tma_store(P.du + e * CONS, smem_u32(s_ut), bu);
         } else {
-            tma_store(P.u_tmp + e0 * CONS, smem_u32(s_ut), bu);
-            tma_store(P.u_out + e0 * CONS, smem_u32(s_u), bu);
+            tma_store(P.u_tmp + e * CONS, smem_u32(s_ut), bu);
+            tma_store(P.u_out + e * CONS, smem_u32(s_u), bu);
         }
         tma_store_commit_and_wait_read();
     }
