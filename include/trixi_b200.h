@@ -186,8 +186,9 @@ TRIXI_B200_API int trixi_b200_rhs(trixi_b200_handle *h, double t);
 
 /* max_dt(u, t, mesh, constant_speed, equations, dg, cache) (stepsize_dg3d.jl:8-32, stepsize_dg2d.jl):
  * returns 2 / (nnodes * max_e invJ_e * sum_d max_nodes lambda_d) over the device-resident u;
- * the caller multiplies by cfl(t) (stepsize.jl:146-154).  With world_size > 1 the minimum over ranks
- * is taken (stepsize_dg3d.jl:264-279).  Synchronises. */
+ * the caller multiplies by cfl(t) (stepsize.jl:146-154).  With world_size > 1 this is the rank-local
+ * value; the caller takes the minimum over ranks exactly where the reference calls
+ * MPI.Allreduce!(dt, min) (stepsize_dg3d.jl:264-279).  Synchronises. */
 TRIXI_B200_API int trixi_b200_max_dt(trixi_b200_handle *h, double t, double *dt_out);
 
 /* step!(integrator::SimpleIntegrator2N) stage loop (methods_2N.jl:144-159): for every stage
@@ -219,10 +220,16 @@ TRIXI_B200_API int trixi_b200_calc_volume_integral(trixi_b200_handle *h);
 TRIXI_B200_API int trixi_b200_calc_surface_fluxes(trixi_b200_handle *h, double t);
 TRIXI_B200_API int trixi_b200_download_surface_flux_values(trixi_b200_handle *h, double *host);
 
-/* ---- distributed halo exchange (replaces MPI Isend/Irecv of dg_parallel.jl:66-182) --------------
- * The host process group (torch.distributed / MPI) moves the opaque ids; the data path is NCCL. */
-TRIXI_B200_API int trixi_b200_comm_unique_id(void *id_out_128_bytes);
-TRIXI_B200_API int trixi_b200_comm_init(trixi_b200_handle *h, const void *id_128_bytes);
+/* ---- distributed halo exchange (replaces the MPI Isend/Irecv of dg_parallel.jl:66-182) ----------------
+ * One handle per rank/GPU.  Every handle with world_size > 1 owns a receive buffer that its neighbour
+ * ranks map (CUDA IPC across processes, plain pointers inside one process); during an RHS evaluation the
+ * pack kernel of rank A stores A's face states directly into B's buffer over NVLink and raises a
+ * sequence flag, B's MPI-interface kernel waits on it.  The host process group (torch.distributed / MPI)
+ * only moves the opaque connection blobs once: all-gather `comm_info` of every rank, pass the
+ * concatenation (rank order) to `comm_connect`.  All ranks must then evaluate the RHS collectively. */
+TRIXI_B200_API int64_t trixi_b200_comm_info_size(void);
+TRIXI_B200_API int trixi_b200_comm_info(trixi_b200_handle *h, void *blob_out);
+TRIXI_B200_API int trixi_b200_comm_connect(trixi_b200_handle *h, const void *blobs, int world);
 
 /* ---- measurement helpers --------------------------------------------------------------------- */
 /* number of kernel launches issued by this handle since creation */

@@ -72,6 +72,8 @@ class OracleBackend:
         self.interfaces_u = np.zeros(2 * d.nvars * nf * max(d.ninterfaces, 1))
         self.boundaries_u = np.zeros(2 * d.nvars * nf * max(d.nboundaries, 1))
         self.sfv = np.zeros(d.nvars * nf * 2 * d.ndims * d.nelements)
+        self.mpi_u = np.zeros(2 * d.nvars * nf * max(d.nmpiinterfaces, 1))
+        self.halo = None  # set_halo_exchange(callable) for world_size > 1
         self.nrhs = 0
 
     def num_threads(self):
@@ -90,9 +92,24 @@ class OracleBackend:
     def synchronize(self):
         pass
 
+    def set_halo_exchange(self, exchange):
+        """``exchange(mpi_u_flat)`` fills the remote side of mpi_u (tests: gloo isend/irecv)."""
+        self.halo = exchange
+
     def rhs_arrays(self, du, u, t):
-        self.lib.oracle_rhs(self.holder.byref(), _p(du), _p(u), C.c_double(t), _p(self.interfaces_u),
-                            _p(self.boundaries_u), _p(self.sfv))
+        h = self.holder.byref()
+        if self.desc.world_size > 1:
+            # rhs_hyperbolic! for distributed meshes (dg_2d_parallel.jl:453-563): local work, halo
+            # exchange, then the MPI interface fluxes and the element-local tail
+            if self.halo is None:
+                raise RuntimeError("world_size > 1 needs set_halo_exchange()")
+            self.lib.oracle_rhs_parallel_part1(h, _p(du), _p(u), C.c_double(t), _p(self.interfaces_u),
+                                               _p(self.boundaries_u), _p(self.sfv), _p(self.mpi_u))
+            self.halo(self.mpi_u)
+            self.lib.oracle_rhs_parallel_part2(h, _p(du), _p(u), C.c_double(t), _p(self.sfv), _p(self.mpi_u))
+        else:
+            self.lib.oracle_rhs(h, _p(du), _p(u), C.c_double(t), _p(self.interfaces_u),
+                                _p(self.boundaries_u), _p(self.sfv))
         self.nrhs += 1
 
     def rhs_host(self, du_host, u_host, t):
@@ -112,6 +129,15 @@ class OracleBackend:
 
     def step_2n(self, t, dt, a, b, c):
         a, b, c = (np.ascontiguousarray(x, dtype=np.float64) for x in (a, b, c))
+        if self.desc.world_size > 1:
+            # stage loop of methods_2N.jl:144-159 around the distributed RHS
+            u, du, u_tmp = self.vec
+            u_tmp[:] = 0.0
+            for s in range(len(c)):
+                self.rhs_arrays(du, u, t + dt * c[s])
+                u_tmp[:] = du - u_tmp * a[s]
+                u += u_tmp * (b[s] * dt)
+            return
         self.lib.oracle_step_2n(self.holder.byref(), _p(self.vec[0]), _p(self.vec[1]), _p(self.vec[2]),
                                 C.c_double(t), C.c_double(dt), _p(a), _p(b), _p(c), C.c_int(len(c)),
                                 _p(self.interfaces_u), _p(self.boundaries_u), _p(self.sfv))

@@ -653,6 +653,54 @@ void oracle_calc_boundary_flux(const trixi_b200_desc *d, double *sfv, const doub
     }
 }
 
+/* prolong2mpiinterfaces! dgsem_tree/dg_2d_parallel.jl:565-598 (p4est: dg_3d_parallel.jl:119-165):
+ * the local side of mpi_interfaces_u[2, nv, nf, MI] is filled from u; the remote side arrives through
+ * the halo exchange (dg_parallel.jl:66-182) */
+void oracle_prolong2mpiinterfaces(const trixi_b200_desc *d, double *mu, const double *u) {
+    int n = d->nnodes, nd = d->ndims, nv = d->nvars;
+    int nf = ipow(n, nd - 1), nb = nd == 3 ? n : 1;
+    int64_t esz = (int64_t)nv * ipow(n, nd);
+#pragma omp parallel for schedule(static)
+    for (int64_t I = 0; I < d->nmpiinterfaces; ++I) {
+        int64_t element = d->mpi_local_neighbor_ids[I] - 1;
+        int o = (int)d->mpi_orientations[I] - 1;
+        int side = (int)d->mpi_local_sides[I]; /* 1: local element is the left (-) one */
+        for (int b = 0; b < nb; ++b)
+            for (int a = 0; a < n; ++a) {
+                int fn = a + n * b;
+                int vn = face_to_volume_node(nd, n, o, side == 1 ? n - 1 : 0, a, b);
+                for (int v = 0; v < nv; ++v)
+                    mu[(side - 1) + 2 * (v + nv * (fn + (int64_t)nf * I))] = u[element * esz + nv * vn + v];
+            }
+    }
+}
+
+/* calc_mpi_interface_flux! dgsem_tree/dg_2d_parallel.jl:700-740 (p4est: dg_3d_parallel.jl:167-242): the
+ * shared flux is computed redundantly on both ranks, only the local element's storage is written */
+void oracle_calc_mpi_interface_flux(const trixi_b200_desc *d, double *sfv, const double *mu) {
+    eqn_t eq = make_eqn(d);
+    int n = d->nnodes, nd = d->ndims, nv = d->nvars;
+    int nf = ipow(n, nd - 1);
+    int64_t fsz = (int64_t)nv * nf * 2 * nd;
+#pragma omp parallel for schedule(static)
+    for (int64_t I = 0; I < d->nmpiinterfaces; ++I) {
+        int64_t element = d->mpi_local_neighbor_ids[I] - 1;
+        int o = (int)d->mpi_orientations[I] - 1;
+        int side = (int)d->mpi_local_sides[I];
+        /* left element stores in direction 2*orientation, right element in 2*orientation - 1 (1-based) */
+        int direction0 = side == 1 ? 2 * o + 1 : 2 * o;
+        for (int fn = 0; fn < nf; ++fn) {
+            double ul[MAXV], ur[MAXV], f[MAXV];
+            for (int v = 0; v < nv; ++v) {
+                ul[v] = mu[0 + 2 * (v + nv * (fn + (int64_t)nf * I))];
+                ur[v] = mu[1 + 2 * (v + nv * (fn + (int64_t)nf * I))];
+            }
+            numflux(&eq, d->surface_flux, ul, ur, o, f);
+            for (int v = 0; v < nv; ++v) sfv[element * fsz + v + nv * (fn + nf * direction0)] = f[v];
+        }
+    }
+}
+
 /* calc_surface_integral! dg_3d.jl:1337-1394 / dg_2d.jl:1245-1300 */
 void oracle_calc_surface_integral(const trixi_b200_desc *d, double *du, const double *sfv) {
     int n = d->nnodes, nd = d->ndims, nv = d->nvars;
@@ -716,6 +764,29 @@ void oracle_rhs(const trixi_b200_desc *d, double *du, const double *u, double t,
         oracle_calc_boundary_flux(d, sfv, boundaries_u, t);
     }
     /* mortars: none on conforming meshes (dg_3d.jl:770-1007 are no-ops for nmortars == 0) */
+    oracle_calc_surface_integral(d, du, sfv);
+    oracle_apply_jacobian(d, du);
+    oracle_calc_sources(d, du, u, t);
+}
+
+/* distributed rhs_hyperbolic! (dgsem_tree/dg_2d_parallel.jl:453-563, p4est dg_3d_parallel.jl:8-117) in
+ * two halves around the halo exchange the caller performs: part 1 = prolong2mpiinterfaces + all local
+ * work up to the boundary fluxes; part 2 = calc_mpi_interface_flux!, surface integral, Jacobian, sources */
+void oracle_rhs_parallel_part1(const trixi_b200_desc *d, double *du, const double *u, double t,
+                               double *interfaces_u, double *boundaries_u, double *sfv, double *mpi_u) {
+    oracle_prolong2mpiinterfaces(d, mpi_u, u);
+    oracle_set_zero(d, du);
+    oracle_calc_volume_integral(d, du, u);
+    oracle_prolong2interfaces(d, interfaces_u, u);
+    oracle_calc_interface_flux(d, sfv, interfaces_u);
+    if (d->nboundaries > 0) {
+        oracle_prolong2boundaries(d, boundaries_u, u);
+        oracle_calc_boundary_flux(d, sfv, boundaries_u, t);
+    }
+}
+void oracle_rhs_parallel_part2(const trixi_b200_desc *d, double *du, const double *u, double t, double *sfv,
+                               const double *mpi_u) {
+    oracle_calc_mpi_interface_flux(d, sfv, mpi_u);
     oracle_calc_surface_integral(d, du, sfv);
     oracle_apply_jacobian(d, du);
     oracle_calc_sources(d, du, u, t);

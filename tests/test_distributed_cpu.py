@@ -1,0 +1,93 @@
+"""world_size 2 and 3 on CPU (gloo): the element partition, the MPI-interface containers and the halo
+exchange protocol, driven through the oracle's distributed RHS (dg_2d_parallel.jl:453-563).  The
+reference asserts that MPI runs reproduce the serial results (test/test_mpi_p4est_3d.jl:9-12); here the
+gathered distributed du must equal the serial du bit for bit (the same flux is evaluated with the same
+operands on both sides of a shared face)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, name, out_dir):
+    for p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "oracle")):
+        sys.path.insert(0, p)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.set_num_threads(1)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import oracle
+    import trixi_b200 as T
+    from elixirs import ELIXIRS
+    from trixi_b200.parallel import HostHaloExchange, allreduce_min
+    ex = ELIXIRS[name]
+    semi = ex.build()
+    psemi = ex.build()
+    psemi.__init__(semi.mesh, semi.equations, semi.initial_condition, semi.solver, source_terms=semi.source_terms,
+                   boundary_conditions=semi.boundary_conditions, rank=rank, world_size=world)
+    ob = oracle.OracleBackend(psemi, num_threads=1)
+    ob.set_halo_exchange(HostHaloExchange(psemi, dist).exchange)
+    u = T.compute_coefficients(0.0, psemi)
+    du = np.empty_like(u)
+    ob.rhs_host(du, u, 0.3)
+    # one full RK step and the distributed CFL step size
+    ob.upload(0, u)
+    dt_local = ob.max_dt()
+    dt = allreduce_min(dt_local, dist)
+    alg = T.CarpenterKennedy2N54()
+    ob.step_2n(0.0, 0.5 * dt, alg.a, alg.b, alg.c)
+    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), du=du, u1=ob.download(0), dt=dt,
+             first=psemi.cache.first_element, last=psemi.cache.last_element)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("name", ["tree_3d_euler_ec", "tree_2d_euler_source_terms_nonperiodic"])
+def test_distributed_oracle_equals_serial(world, name, tmp_path, oracle_module):
+    import trixi_b200 as T
+    from elixirs import ELIXIRS
+    port = 29500 + (os.getpid() + world * 7 + len(name)) % 2000
+    mp.spawn(_worker, args=(world, port, name, str(tmp_path)), nprocs=world, join=True)
+    semi = ELIXIRS[name].semi()
+    ob = oracle_module.OracleBackend(semi, num_threads=2)
+    u = T.compute_coefficients(0.0, semi)
+    du = np.empty_like(u)
+    ob.rhs_host(du, u, 0.3)
+    ob.upload(0, u)
+    dt = ob.max_dt()
+    alg = T.CarpenterKennedy2N54()
+    ob.step_2n(0.0, 0.5 * dt, alg.a, alg.b, alg.c)
+    u1 = ob.download(0).reshape(u.shape, order="F")
+    covered = 0
+    for r in range(world):
+        z = np.load(os.path.join(str(tmp_path), f"rank{r}.npz"))
+        first, last = int(z["first"]), int(z["last"])
+        covered += last - first
+        assert float(z["dt"]) == dt
+        np.testing.assert_array_equal(z["du"], du[..., first:last])
+        # the stage update of the distributed driver is NumPy (no FMA contraction): 1-ulp differences
+        np.testing.assert_allclose(z["u1"].reshape(du[..., first:last].shape, order="F"), u1[..., first:last],
+                                   rtol=0, atol=1e-14)
+    assert covered == semi.nelements
+
+
+def test_partition_is_contiguous_and_balanced():
+    from trixi_b200.containers import owner_of, partition_cells
+    for n, w in [(512, 8), (100, 3), (7, 7), (1000, 6)]:
+        ranges = [partition_cells(n, r, w) for r in range(w)]
+        assert ranges[0][0] == 0 and ranges[-1][1] == n
+        assert all(ranges[i][1] == ranges[i + 1][0] for i in range(w - 1))
+        sizes = [b - a for a, b in ranges]
+        assert max(sizes) - min(sizes) <= 1
+        owners = owner_of(np.arange(n), n, w)
+        for r, (a, b) in enumerate(ranges):
+            assert np.all(owners[a:b] == r)
+    with pytest.raises(ValueError):
+        partition_cells(3, 0, 4)

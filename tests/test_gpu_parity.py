@@ -194,3 +194,67 @@ def test_conservation_large():
     total = np.einsum("vijke,ijk->v", du, w3) / semi.cache.elements.inverse_jacobian[0] ** 3
     scale = np.einsum("vijke,ijk->v", np.abs(du), w3) / semi.cache.elements.inverse_jacobian[0] ** 3
     assert np.all(np.abs(total) <= 1e-12 * np.maximum(scale, 1.0))
+
+
+# ---- distributed path: several ranks' handles inside one process on one GPU --------------------------
+def _ranked_semis(name, world):
+    ex = ELIXIRS[name]
+    base = ex.semi()
+    semis = []
+    for r in range(world):
+        semis.append(T.SemidiscretizationHyperbolic(base.mesh, base.equations, base.initial_condition, base.solver,
+                                                    source_terms=base.source_terms,
+                                                    boundary_conditions=base.boundary_conditions,
+                                                    rank=r, world_size=world))
+    return base, semis
+
+
+@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("name", ["tree_3d_euler_ec", "tree_2d_euler_source_terms_nonperiodic"])
+def test_halo_exchange_matches_single_rank(name, world, oracle_module):
+    """The element partition with the device-side halo exchange (pack kernels storing into the peers'
+    receive buffers, sequence flags) reproduces the single-rank result; like the reference asserts for its
+    MPI runs (test/test_mpi_p4est_3d.jl:9-12)."""
+    base, semis = _ranked_semis(name, world)
+    u = _random_admissible_state(base, seed=7)
+    alg = T.CarpenterKennedy2N54()
+    single = base.backend()
+    single.upload(0, u)
+    single.rhs(0.3)
+    du_single = single.download(1).reshape(u.shape, order="F")
+    dt = 0.4 * single.max_dt()
+    for k in range(2):
+        single.step_2n(k * dt, dt, alg.a, alg.b, alg.c)
+    u_single = single.download(0).reshape(u.shape, order="F")
+
+    backends = [s.backend() for s in semis]
+    blobs = [b.comm_info() for b in backends]
+    for b in backends:
+        b.comm_connect(blobs)
+    parts = [(s.cache.first_element, s.cache.last_element) for s in semis]
+    for b, (a, z) in zip(backends, parts):
+        b.upload(0, np.asfortranarray(u[..., a:z]))
+    for b in backends:  # asynchronous: every rank enqueues, nobody blocks the host
+        b.rhs(0.3)
+    for b, (a, z) in zip(backends, parts):
+        np.testing.assert_array_equal(b.download(1).reshape(u[..., a:z].shape, order="F"), du_single[..., a:z])
+    dts = [0.4 * b.max_dt() for b in backends]
+    assert min(dts) == dt
+    for k in range(2):
+        for b in backends:
+            b.step_2n(k * dt, dt, alg.a, alg.b, alg.c)
+    for b, (a, z) in zip(backends, parts):
+        np.testing.assert_array_equal(b.download(0).reshape(u[..., a:z].shape, order="F"), u_single[..., a:z])
+    # and against the oracle
+    ref = oracle_module.OracleBackend(base)
+    du_ref = np.empty_like(u)
+    ref.rhs_host(du_ref, u, 0.3)
+    assert _rel_err(du_single, du_ref) <= _rhs_tolerance(oracle_module, base, u, 0.3, du_ref)
+
+
+def test_unconnected_distributed_handle_fails_loudly():
+    _, semis = _ranked_semis("tree_3d_euler_ec", 2)
+    b = semis[0].backend()
+    from trixi_b200.lib import TrixiB200Error
+    with pytest.raises(TrixiB200Error, match="not connected"):
+        b.rhs(0.0)

@@ -11,6 +11,7 @@ from __future__ import annotations
 import numpy as np
 
 from .basis import SolutionAnalyzer
+from .parallel import allreduce_min
 
 
 class _Callback:
@@ -55,6 +56,9 @@ class StepsizeCallback(_Callback):
     def affect(self, integrator):
         # calculate_dt (stepsize.jl:146-154): cfl(t) * max_dt(u, t, mesh, ...)
         dt = self._cfl(integrator.t) * integrator.backend.max_dt(integrator.t)
+        if integrator.semi.world_size > 1:
+            # MPI.Allreduce!(dt, min) (stepsize_dg3d.jl:264-279)
+            dt = allreduce_min(dt, integrator.semi.comm)
         integrator.dt = dt
         integrator.dtcache = dt
 
@@ -62,7 +66,8 @@ class StepsizeCallback(_Callback):
         """``stepsize_callback(ode)`` (stepsize.jl:128-143)."""
         backend = ode.p.backend()
         backend.upload(backend.U, ode.u0)
-        return self._cfl(ode.tspan[0]) * backend.max_dt(ode.tspan[0])
+        dt = self._cfl(ode.tspan[0]) * backend.max_dt(ode.tspan[0])
+        return allreduce_min(dt, ode.p.comm) if ode.p.world_size > 1 else dt
 
 
 def multiply_dimensionwise(matrix, data):
@@ -93,8 +98,18 @@ def calc_error_norms(u, t, semi, analyzer=None):
         wprod = np.multiply.outer(wprod, w)
     volume_jacobian = (1.0 / cache.elements.inverse_jacobian) ** nd  # dgsem_tree/dg.jl:8-10
     weight = wprod[..., None] * volume_jacobian  # [na.., nelem]
-    l2 = np.sqrt((diff**2 * weight[None]).reshape(eq.nvars, -1).sum(axis=1) / mesh.length_level_0**nd)
+    l2sq = (diff**2 * weight[None]).reshape(eq.nvars, -1).sum(axis=1)
     linf = np.abs(diff).reshape(eq.nvars, -1).max(axis=1)
+    if semi.world_size > 1 and semi.comm is not None:
+        # global reductions like the reference's MPI analysis (analysis_dg2d.jl:170-215)
+        import torch
+        t2, tinf = torch.from_numpy(l2sq.copy()), torch.from_numpy(linf.copy())
+        if semi.comm.get_backend() == "nccl":
+            t2, tinf = t2.cuda(), tinf.cuda()
+        semi.comm.all_reduce(t2, op=semi.comm.ReduceOp.SUM)
+        semi.comm.all_reduce(tinf, op=semi.comm.ReduceOp.MAX)
+        l2sq, linf = t2.cpu().numpy(), tinf.cpu().numpy()
+    l2 = np.sqrt(l2sq / mesh.length_level_0**nd)
     return l2, linf
 
 

@@ -24,8 +24,31 @@ class BoundaryContainer:
     pass
 
 
-def init_elements(mesh, basis):
-    """containers_3d.jl:87-133.  Returns inverse_jacobian[nelem], node_coordinates[ndims, n^d, nelem]."""
+class MPIInterfaceContainer:
+    pass
+
+
+def partition_cells(ncells, rank, world_size):
+    """Contiguous chunk of the space-filling-curve element order owned by ``rank``: equal counts, the
+    remainder goes to the first ranks (``partition!`` parallel_tree_mesh.jl:16-28; p4est
+    ``global_first_quadrant`` dg_parallel.jl:290-296).  Returns (first, last) with last exclusive."""
+    if world_size > ncells:
+        raise ValueError("Too many ranks to properly partition the mesh!")
+    base, rem = divmod(ncells, world_size)
+    first = rank * base + min(rank, rem)
+    return first, first + base + (1 if rank < rem else 0)
+
+
+def owner_of(cells, ncells, world_size):
+    base, rem = divmod(ncells, world_size)
+    split = rem * (base + 1)
+    cells = np.asarray(cells)
+    return np.where(cells < split, cells // (base + 1), rem + (cells - split) // max(base, 1))
+
+
+def init_elements(mesh, basis, cells=None):
+    """containers_3d.jl:87-133.  Returns inverse_jacobian[nelem], node_coordinates[ndims, n^d, nelem];
+    ``cells`` restricts to the global cell indices owned by this rank."""
     nodes = basis.nodes
     n = basis.nnodes
     nd = mesh.ndims
@@ -34,12 +57,12 @@ def init_elements(mesh, basis):
     for w in basis.weights:
         reference_length += 1.0 * w
     reference_offset = (nodes[0] + nodes[-1]) / 2
-    dx = mesh.length_at_level(mesh.levels)
+    dx = mesh.length_at_level(mesh.levels if cells is None else mesh.levels[cells])
     jacobian = dx / reference_length
     el = ElementContainer()
     el.inverse_jacobian = 1.0 / jacobian
-    centers = mesh.cell_coordinates()  # [nd, nelem]
-    nelem = mesh.ncells
+    centers = mesh.cell_coordinates(cells)  # [nd, nelem]
+    nelem = centers.shape[1]
     el.nelements = nelem
     xi = nodes - reference_offset  # [n]
     # node_coordinates[d, i, j, k, e] = center[d, e] + jacobian[e] * xi[index along d]
@@ -54,32 +77,62 @@ def init_elements(mesh, basis):
     return el
 
 
-def init_interfaces(mesh):
-    """containers_3d.jl:229-281 (count :195-227)."""
+def init_interfaces(mesh, first=0, last=None, world_size=1):
+    """containers_3d.jl:229-281 (count :195-227) for the elements [first, last) of this rank.  Faces whose
+    other element lives on another rank become MPI interfaces (``init_mpi_interfaces!``
+    containers_2d.jl:913-973; p4est ``local_neighbor_ids``/``local_sides`` dg_3d_parallel.jl:126-162):
+    sorted by (neighbour rank, global interface id) so both sides enumerate a shared face identically.
+    Returns (interfaces, mpi_interfaces)."""
     nd = mesh.ndims
-    nelem = mesh.ncells
-    nb = np.empty((nelem, nd), dtype=np.int64)
+    ncells = mesh.ncells
+    last = ncells if last is None else last
+    cells = None if (first == 0 and last == ncells) else np.arange(first, last, dtype=np.int64)
+    nloc = last - first
+    gid0 = np.arange(first, last, dtype=np.int64)
+    nbp = np.empty((nloc, nd), dtype=np.int64)  # global neighbour in the positive directions
+    nbm = np.empty((nloc, nd), dtype=np.int64)  # ... negative directions
     for d in range(nd):
-        nb[:, d] = mesh._face_neighbors(2 * d + 1, "same")  # positive direction
-    valid = nb >= 0
-    left = np.repeat(np.arange(nelem, dtype=np.int64)[:, None], nd, axis=1)[valid]
-    right = nb[valid]
-    orient = np.repeat(np.arange(1, nd + 1, dtype=np.int64)[None, :], nelem, axis=0)[valid]
+        nbp[:, d] = mesh._face_neighbors(2 * d + 1, "same", cells)
+        nbm[:, d] = mesh._face_neighbors(2 * d, "same", cells)
+    orient_all = np.repeat(np.arange(1, nd + 1, dtype=np.int64)[None, :], nloc, axis=0)
+    left_all = np.repeat(gid0[:, None], nd, axis=1)
+    is_local_p = (nbp >= first) & (nbp < last)
     ic = InterfaceContainer()
-    ic.neighbor_ids = np.asfortranarray(np.stack([left + 1, right + 1]))  # [2, I], 1-based
-    ic.orientations = orient
-    ic.ninterfaces = orient.shape[0]
-    return ic
+    ic.neighbor_ids = np.asfortranarray(np.stack([left_all[is_local_p] - first + 1,
+                                                  nbp[is_local_p] - first + 1]))  # [2, I], 1-based local
+    ic.orientations = orient_all[is_local_p]
+    ic.ninterfaces = ic.orientations.shape[0]
+
+    mi = MPIInterfaceContainer()
+    rem_p = (nbp >= 0) & ~is_local_p  # local element is the left one (local side 1)
+    rem_m = (nbm >= 0) & ~((nbm >= first) & (nbm < last))  # local element is the right one (side 2)
+    loc = np.concatenate([left_all[rem_p], left_all[rem_m]])
+    remote = np.concatenate([nbp[rem_p], nbm[rem_m]])
+    side = np.concatenate([np.ones(rem_p.sum(), dtype=np.int64), np.full(rem_m.sum(), 2, dtype=np.int64)])
+    orient = np.concatenate([orient_all[rem_p], orient_all[rem_m]])
+    # global interface id = (global id of the left element) * ndims + orientation - 1
+    gif = np.where(side == 1, loc, remote) * nd + (orient - 1)
+    peer = owner_of(remote, ncells, world_size) if remote.size else remote
+    order = np.lexsort((gif, peer))
+    mi.local_neighbor_ids = (loc[order] - first + 1).astype(np.int64)
+    mi.local_sides = side[order]
+    mi.orientations = orient[order]
+    mi.neighbor_ranks = peer[order].astype(np.int64)
+    mi.global_interface_ids = gif[order]
+    mi.nmpiinterfaces = int(order.shape[0])
+    return ic, mi
 
 
-def init_boundaries(mesh, elements, basis):
-    """containers_3d.jl:391-471."""
+def init_boundaries(mesh, elements, basis, first=0, last=None):
+    """containers_3d.jl:391-471 (for the elements [first, last) of this rank)."""
     nd = mesh.ndims
     n = basis.nnodes
+    last = mesh.ncells if last is None else last
+    cells = None if (first == 0 and last == mesh.ncells) else np.arange(first, last, dtype=np.int64)
     ids, orients, sides, coords, counts = [], [], [], [], []
     for direction in range(2 * nd):
-        same = mesh._face_neighbors(direction, "same")
-        coarse = mesh._face_neighbors(direction, "coarse")
+        same = mesh._face_neighbors(direction, "same", cells)
+        coarse = mesh._face_neighbors(direction, "coarse", cells)
         isb = (same < 0) & (coarse < 0)
         # a cell with a *refined* same-level neighbour has a non-leaf neighbour cell -> not a boundary
         if hasattr(mesh, "_has_refined_neighbor"):

@@ -51,6 +51,13 @@ struct KParams {
     // CFL fused output: per-block max of invJ * sum_d max_nodes lambda_d, encoded as ordered uint64
     unsigned long long *cfl_key;  // nullptr: skip
     int kernel_path;              // 0: tuned kernels where available, 1: generic kernels only
+    // distributed: faces shared with other ranks (replaces mpi_interfaces, dg_2d_parallel.jl / dg_parallel.jl)
+    long long nmpi;
+    const long long *mpi_local, *mpi_side, *mpi_orient;  // [nmpi] 1-based local element, local side, orientation
+    const int *mpi_peer_slot;                            // [nmpi] index into the peer tables
+    const long long *mpi_remote_index;                   // [nmpi] slot of this face in the peer's receive buffer
+    double *const *peer_recv;                            // [npeers] peer receive buffers (current parity), NVLink-mapped
+    const double *recv;                                  // my receive buffer (current parity) [nv, nf, nmpi]
 };
 
 __host__ __device__ constexpr int ipow(int b, int e) { return e == 0 ? 1 : b * ipow(b, e - 1); }
@@ -126,6 +133,58 @@ __global__ void __launch_bounds__(256) k_boundary_flux(const KParams P) {
     for (int d = 0; d < ND; ++d) x[d] = P.bd_coords[(B * NF + fn) * ND + d];
     boundary_flux(eq, P.bc[direction - 1], P.bc_ic[direction - 1], P.surface_flux, ui, o, direction, x, P.t, f);
     double *s = P.sfv + ((element * (2 * ND) + (direction - 1)) * NF + fn) * NV;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) s[v] = f[v];
+}
+
+// ---- 2b. faces shared with other ranks -------------------------------------------------------------
+// prolong2mpiinterfaces! + start_mpi_send! fused (dg_2d_parallel.jl:565-598, dg_parallel.jl:66-132): the
+// local face state is stored straight into the neighbour rank's receive buffer over NVLink/PCIe peer
+// mapping -- no send staging, no separate copy.
+template <class EQ, int N>
+__global__ void __launch_bounds__(256) k_mpi_pack(const KParams P) {
+    constexpr int ND = EQ::NDIMS, NV = EQ::NVARS, NF = ipow(N, ND - 1), NN = ipow(N, ND);
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long I = gid / NF;
+    const int fn = (int)(gid % NF);
+    if (I >= P.nmpi) return;
+    const long long element = P.mpi_local[I] - 1;
+    const int o = (int)P.mpi_orient[I] - 1;
+    const int side = (int)P.mpi_side[I];
+    const int vn = face_to_volume_node<ND, N>(o, side == 1 ? N - 1 : 0, fn);
+    const double *pu = P.u + (element * NN + vn) * NV;
+    double *dst = P.peer_recv[P.mpi_peer_slot[I]] + (P.mpi_remote_index[I] * NF + fn) * NV;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) dst[v] = pu[v];
+    __threadfence_system();
+}
+
+// calc_mpi_interface_flux! (dg_2d_parallel.jl:700-740, dg_3d_parallel.jl:167-242): the shared flux is
+// computed on both ranks with identical operands; only the local element's storage is written.
+template <class EQ, int N>
+__global__ void __launch_bounds__(256) k_mpi_interface_flux(const KParams P) {
+    constexpr int ND = EQ::NDIMS, NV = EQ::NVARS, NF = ipow(N, ND - 1), NN = ipow(N, ND);
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long I = gid / NF;
+    const int fn = (int)(gid % NF);
+    if (I >= P.nmpi) return;
+    const EQ eq(P.eq);
+    const long long element = P.mpi_local[I] - 1;
+    const int o = (int)P.mpi_orient[I] - 1;
+    const int side = (int)P.mpi_side[I];
+    const int vn = face_to_volume_node<ND, N>(o, side == 1 ? N - 1 : 0, fn);
+    const double *pl = P.u + (element * NN + vn) * NV;
+    const double *pr = P.recv + (I * NF + fn) * NV;
+    double ul[NV], ur[NV], f[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+        const double a = pl[v], b = pr[v];
+        ul[v] = side == 1 ? a : b;
+        ur[v] = side == 1 ? b : a;
+    }
+    eq.numflux(P.surface_flux, ul, ur, o, f);
+    const int direction0 = side == 1 ? 2 * o + 1 : 2 * o;
+    double *s = P.sfv + ((element * (2 * ND) + direction0) * NF + fn) * NV;
 #pragma unroll
     for (int v = 0; v < NV; ++v) s[v] = f[v];
 }

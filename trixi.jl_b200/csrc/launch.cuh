@@ -12,6 +12,8 @@ struct Launchers {
     // with_surface = false: volume terms only (stage-level parity entry point)
     cudaError_t (*element)(const KParams &, bool with_surface, cudaStream_t);
     void (*max_dt)(const KParams &, cudaStream_t);
+    void (*mpi_pack)(const KParams &, cudaStream_t);
+    void (*mpi_interface_flux)(const KParams &, cudaStream_t);
     int ndims, nvars, nnodes;
 };
 
@@ -33,6 +35,22 @@ void launch_boundary_flux(const KParams &P, cudaStream_t s) {
     const int threads = 256;
     const unsigned blocks = (unsigned)((total + threads - 1) / threads);
     k_boundary_flux<EQ, N><<<blocks, threads, 0, s>>>(P);
+}
+
+template <class EQ, int N>
+void launch_mpi_pack(const KParams &P, cudaStream_t s) {
+    constexpr int NF = ipow(N, EQ::NDIMS - 1);
+    const long long total = P.nmpi * NF;
+    if (total == 0) return;
+    k_mpi_pack<EQ, N><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(P);
+}
+
+template <class EQ, int N>
+void launch_mpi_interface_flux(const KParams &P, cudaStream_t s) {
+    constexpr int NF = ipow(N, EQ::NDIMS - 1);
+    const long long total = P.nmpi * NF;
+    if (total == 0) return;
+    k_mpi_interface_flux<EQ, N><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(P);
 }
 
 // cudaFuncSetAttribute is per device: remember what was configured where
@@ -97,9 +115,14 @@ void launch_max_dt(const KParams &P, cudaStream_t s) {
 
 template <class EQ, int N>
 const Launchers *make_launchers() {
-    static const Launchers L = {&launch_interface_flux<EQ, N>, &launch_boundary_flux<EQ, N>,
-                                &launch_element<EQ, N>,        &launch_max_dt<EQ, N>,
-                                EQ::NDIMS,                     EQ::NVARS,
+    static const Launchers L = {&launch_interface_flux<EQ, N>,
+                                &launch_boundary_flux<EQ, N>,
+                                &launch_element<EQ, N>,
+                                &launch_max_dt<EQ, N>,
+                                &launch_mpi_pack<EQ, N>,
+                                &launch_mpi_interface_flux<EQ, N>,
+                                EQ::NDIMS,
+                                EQ::NVARS,
                                 N};
     return &L;
 }

@@ -8,6 +8,7 @@
 #include <new>
 #include <string>
 #include <vector>
+#include <unistd.h>
 
 #include "launch.cuh"
 
@@ -44,6 +45,24 @@ struct trixi_b200_handle {
     long long prof_n[KC_COUNT] = {0, 0, 0, 0};
     std::string error;
     int rank = 0, world_size = 1;
+    // halo exchange state
+    long long nmpi = 0;
+    std::vector<long long> mpi_counts;        // [world] faces shared with each rank
+    std::vector<int> peers;                   // neighbour ranks in ascending order
+    std::vector<long long> peer_offset;       // first face of each peer's segment in my ordering
+    std::vector<int> h_peer_slot;             // [nmpi]
+    char *comm_base = nullptr;                // one allocation: flags | recv parity 0 | recv parity 1
+    size_t flag_bytes = 0, recv_bytes = 0;
+    std::vector<void *> ipc_opened;
+    std::vector<char *> peer_base;            // [npeers] mapped base of each peer's comm allocation
+    std::vector<long long> peer_nmpi;         // [npeers] total faces of that peer (its recv buffer size)
+    std::vector<long long> my_offset_in_peer; // [npeers]
+    double **d_peer_recv[2] = {nullptr, nullptr};        // device pointer tables per parity
+    unsigned long long **d_peer_flag[2] = {nullptr, nullptr};
+    int *d_peer_ranks = nullptr;
+    long long *d_mpi_remote_index = nullptr;
+    bool comm_connected = false;
+    unsigned long long comm_seq = 0;
 };
 
 namespace {
@@ -154,6 +173,28 @@ __global__ void k_copy(double2 *dst, const double2 *src, size_t n) {
     if (i < n) dst[i] = src[i];
 }
 
+// start_mpi_send! completion: after the pack kernel (stream order) every peer's flag for me is raised to
+// the sequence number of this RHS evaluation
+__global__ void k_mpi_signal(unsigned long long *const *peer_flag, int npeers, unsigned long long seq) {
+    const int p = threadIdx.x;
+    if (p < npeers) {
+        __threadfence_system();
+        *reinterpret_cast<volatile unsigned long long *>(peer_flag[p]) = seq;
+        __threadfence_system();
+    }
+}
+// finish_mpi_receive! (dg_parallel.jl:134-182): wait until every neighbour rank has delivered its faces
+__global__ void k_mpi_wait(const unsigned long long *flags, const int *peer_ranks, int npeers,
+                           unsigned long long seq) {
+    const int p = threadIdx.x;
+    if (p < npeers) {
+        const volatile unsigned long long *f = flags + peer_ranks[p];
+        while (*f < seq) {
+        }
+        __threadfence_system();
+    }
+}
+
 int check_launch(trixi_b200_handle *h, const char *what) {
     if (h->prof.size() > 2048) prof_collect(h);  // bound the number of live events
     cudaError_t err = cudaGetLastError();
@@ -186,8 +227,41 @@ int run_element(trixi_b200_handle *h, bool with_surface) {
     return check_launch(h, "element kernel");
 }
 
+// One RHS evaluation's surface part.  Distributed order (dg_3d_parallel.jl:8-117): pack+send, local
+// interfaces and boundaries while the faces travel, wait, MPI interface fluxes.
+int run_all_surface_fluxes(trixi_b200_handle *h, double t) {
+    const bool dist = h->world_size > 1 && h->nmpi > 0;
+    if (h->world_size > 1 && !h->comm_connected)
+        return fail(h, TRIXI_B200_ECOMM, "world_size > 1 but the halo exchange is not connected (trixi_b200_comm_connect)");
+    int parity = 0;
+    const int npeers = (int)h->peers.size();
+    if (dist) {
+        const unsigned long long seq = ++h->comm_seq;
+        parity = (int)(seq & 1);
+        h->P.peer_recv = h->d_peer_recv[parity];
+        h->P.recv = reinterpret_cast<const double *>(h->comm_base + h->flag_bytes + parity * h->recv_bytes);
+        ProfScope ps(h, KC_HALO);
+        h->L->mpi_pack(h->P, h->stream);
+        k_mpi_signal<<<1, 32, 0, h->stream>>>(h->d_peer_flag[parity], npeers, seq);
+        h->launches += 2;
+    }
+    int rc = check_launch(h, "halo pack");
+    if (rc) return rc;
+    rc = run_surface_fluxes(h, t);
+    if (rc) return rc;
+    if (dist) {
+        ProfScope ps(h, KC_HALO);
+        const unsigned long long *flags =
+            reinterpret_cast<const unsigned long long *>(h->comm_base) + (size_t)parity * h->world_size;
+        k_mpi_wait<<<1, 32, 0, h->stream>>>(flags, h->d_peer_ranks, npeers, h->comm_seq);
+        h->L->mpi_interface_flux(h->P, h->stream);
+        h->launches += 2;
+    }
+    return check_launch(h, "mpi interface flux");
+}
+
 int run_rhs(trixi_b200_handle *h, double t) {
-    int rc = run_surface_fluxes(h, t);
+    int rc = run_all_surface_fluxes(h, t);
     if (rc) return rc;
     h->P.mode = 0;
     return run_element(h, true);
@@ -209,6 +283,7 @@ TRIXI_B200_API void trixi_b200_destroy(trixi_b200_handle *h) {
         cudaEventDestroy(e.a);
         cudaEventDestroy(e.b);
     }
+    for (void *p : h->ipc_opened) cudaIpcCloseMemHandle(p);
     for (void *p : h->allocs) cudaFree(p);
     if (h->h_cfl) cudaFreeHost(h->h_cfl);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -379,6 +454,56 @@ TRIXI_B200_API int trixi_b200_create(const trixi_b200_desc *d, trixi_b200_handle
     P.rk_a = 0.0;
     P.rk_b_dt = 0.0;
 
+    // faces shared with other ranks: sorted by (neighbour rank, global interface id) by the caller
+    h->nmpi = d->nmpiinterfaces;
+    P.nmpi = d->nmpiinterfaces;
+    if (d->world_size > 64) {
+        fail(nullptr, TRIXI_B200_EINVAL, "world_size %d > 64 not supported", d->world_size);
+        trixi_b200_destroy(h);
+        return TRIXI_B200_EINVAL;
+    }
+    h->mpi_counts.assign(h->world_size, 0);
+    if (d->nmpiinterfaces > 0) {
+        if (!d->mpi_neighbor_ranks || !d->mpi_local_neighbor_ids || !d->mpi_local_sides || !d->mpi_orientations) {
+            fail(nullptr, TRIXI_B200_EINVAL, "MPI interface arrays missing");
+            trixi_b200_destroy(h);
+            return TRIXI_B200_EINVAL;
+        }
+        h->h_peer_slot.resize((size_t)d->nmpiinterfaces);
+        long long prev = -1;
+        for (long long i = 0; i < d->nmpiinterfaces; ++i) {
+            const long long r = d->mpi_neighbor_ranks[i];
+            if (r < 0 || r >= h->world_size || r == h->rank || r < prev) {
+                fail(nullptr, TRIXI_B200_EINVAL, "mpi_neighbor_ranks must be sorted ranks in [0, world_size) other than my own");
+                trixi_b200_destroy(h);
+                return TRIXI_B200_EINVAL;
+            }
+            if (r != prev) {
+                h->peers.push_back((int)r);
+                h->peer_offset.push_back(i);
+            }
+            prev = r;
+            h->mpi_counts[(size_t)r]++;
+            h->h_peer_slot[(size_t)i] = (int)h->peers.size() - 1;
+        }
+        CREATE_TRY(upload_array(h, (const long long *)d->mpi_local_neighbor_ids, (size_t)d->nmpiinterfaces, &itmp));
+        P.mpi_local = itmp;
+        CREATE_TRY(upload_array(h, (const long long *)d->mpi_local_sides, (size_t)d->nmpiinterfaces, &itmp));
+        P.mpi_side = itmp;
+        CREATE_TRY(upload_array(h, (const long long *)d->mpi_orientations, (size_t)d->nmpiinterfaces, &itmp));
+        P.mpi_orient = itmp;
+        int *stmp = nullptr;
+        CREATE_TRY(upload_array(h, h->h_peer_slot.data(), h->h_peer_slot.size(), &stmp));
+        P.mpi_peer_slot = stmp;
+    }
+    if (h->world_size > 1) {
+        // one allocation other ranks map: [flags 2 x world] [recv parity 0] [recv parity 1]
+        h->flag_bytes = ((size_t)2 * h->world_size * sizeof(unsigned long long) + 255) / 256 * 256;
+        h->recv_bytes = ((size_t)h->nmpi * nf * nv * sizeof(double) + 255) / 256 * 256;
+        CREATE_TRY(alloc_array(h, h->flag_bytes + 2 * h->recv_bytes + 256, &h->comm_base));
+        CREATE_CUDA(cudaMemset(h->comm_base, 0, h->flag_bytes + 2 * h->recv_bytes));
+    }
+
     CREATE_TRY(alloc_array(h, 1, &h->d_cfl));
     P.cfl_key = h->d_cfl;
     CREATE_CUDA(cudaMallocHost((void **)&h->h_cfl, sizeof(unsigned long long)));
@@ -460,7 +585,7 @@ TRIXI_B200_API int trixi_b200_calc_volume_integral(trixi_b200_handle *h) {
 TRIXI_B200_API int trixi_b200_calc_surface_fluxes(trixi_b200_handle *h, double t) {
     if (!h) return TRIXI_B200_EINVAL;
     CUDA_TRY(h, cudaSetDevice(h->device));
-    return run_surface_fluxes(h, t);
+    return run_all_surface_fluxes(h, t);
 }
 
 TRIXI_B200_API int trixi_b200_download_surface_flux_values(trixi_b200_handle *h, double *host) {
@@ -502,7 +627,7 @@ TRIXI_B200_API int trixi_b200_step_2n(trixi_b200_handle *h, double t, double dt,
     CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
     for (int s = 0; s < nstages; ++s) {
         const double t_stage = t + dt * c[s];
-        int rc = run_surface_fluxes(h, t_stage);
+        int rc = run_all_surface_fluxes(h, t_stage);
         if (rc) return rc;
         h->P.mode = 1;
         h->P.rk_a = a[s];
@@ -520,6 +645,8 @@ TRIXI_B200_API int trixi_b200_solve_2n(trixi_b200_handle *h, double t0, double t
                         const double *b, const double *c, int nstages, int64_t *steps_out, double *t_out,
                         double *dt_out) {
     if (!h) return TRIXI_B200_EINVAL;
+    if (h->world_size > 1)
+        return fail(h, TRIXI_B200_EINVAL, "solve_2n is single-rank: distributed runs reduce dt over ranks on the host");
     double t = t0, dt = 0.0;
     int64_t steps = 0;
     bool finalstep = false;
@@ -565,14 +692,115 @@ TRIXI_B200_API int trixi_b200_set_option(trixi_b200_handle *h, int option, int v
     }
 }
 
-TRIXI_B200_API int trixi_b200_comm_unique_id(void *id_out_128_bytes) {
-    (void)id_out_128_bytes;
-    return fail(nullptr, TRIXI_B200_ECOMM, "halo exchange is not part of this build");
+// ---- halo exchange wiring ----------------------------------------------------------------------------
+namespace {
+struct CommBlob {
+    int32_t magic, rank, world, device;
+    int64_t pid;
+    uint64_t raw_ptr;
+    cudaIpcMemHandle_t handle;
+    int64_t nmpi;
+    int64_t counts[64];
+};
+constexpr int32_t kCommMagic = 0x7b200c01;
+}  // namespace
+
+TRIXI_B200_API int64_t trixi_b200_comm_info_size(void) { return (int64_t)sizeof(CommBlob); }
+
+TRIXI_B200_API int trixi_b200_comm_info(trixi_b200_handle *h, void *blob_out) {
+    if (!h || !blob_out) return TRIXI_B200_EINVAL;
+    if (h->world_size <= 1) return fail(h, TRIXI_B200_ECOMM, "world_size is 1: nothing to exchange");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    CommBlob b;
+    memset(&b, 0, sizeof(b));
+    b.magic = kCommMagic;
+    b.rank = h->rank;
+    b.world = h->world_size;
+    b.device = h->device;
+    b.pid = (int64_t)getpid();
+    b.raw_ptr = (uint64_t)(uintptr_t)h->comm_base;
+    CUDA_TRY(h, cudaIpcGetMemHandle(&b.handle, h->comm_base));
+    b.nmpi = h->nmpi;
+    for (int r = 0; r < h->world_size; ++r) b.counts[r] = h->mpi_counts[(size_t)r];
+    memcpy(blob_out, &b, sizeof(b));
+    return 0;
 }
 
-TRIXI_B200_API int trixi_b200_comm_init(trixi_b200_handle *h, const void *id_128_bytes) {
-    (void)id_128_bytes;
-    return fail(h, TRIXI_B200_ECOMM, "halo exchange is not part of this build");
+TRIXI_B200_API int trixi_b200_comm_connect(trixi_b200_handle *h, const void *blobs, int world) {
+    if (!h || !blobs) return TRIXI_B200_EINVAL;
+    if (world != h->world_size) return fail(h, TRIXI_B200_ECOMM, "got %d blobs for world_size %d", world, h->world_size);
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const CommBlob *B = static_cast<const CommBlob *>(blobs);
+    for (int r = 0; r < world; ++r)
+        if (B[r].magic != kCommMagic || B[r].rank != r || B[r].world != world)
+            return fail(h, TRIXI_B200_ECOMM, "malformed comm blob for rank %d", r);
+    const int npeers = (int)h->peers.size();
+    const int n = h->nnodes, nd = h->ndims;
+    const long long nf = ipow(n, nd - 1);
+    h->peer_base.assign((size_t)npeers, nullptr);
+    h->peer_nmpi.assign((size_t)npeers, 0);
+    h->my_offset_in_peer.assign((size_t)npeers, 0);
+    for (int p = 0; p < npeers; ++p) {
+        const CommBlob &pb = B[h->peers[(size_t)p]];
+        if (pb.counts[h->rank] != h->mpi_counts[(size_t)pb.rank])
+            return fail(h, TRIXI_B200_ECOMM, "rank %d shares %lld faces with me, I share %lld with it", pb.rank,
+                        (long long)pb.counts[h->rank], h->mpi_counts[(size_t)pb.rank]);
+        long long off = 0;
+        for (int q = 0; q < h->rank; ++q) off += pb.counts[q];
+        h->my_offset_in_peer[(size_t)p] = off;
+        h->peer_nmpi[(size_t)p] = pb.nmpi;
+        if (pb.pid == (int64_t)getpid()) {
+            // same process (several handles in one process): the pointer is directly usable
+            if (pb.device != h->device) {
+                cudaError_t e = cudaDeviceEnablePeerAccess(pb.device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+                    return fail(h, TRIXI_B200_ECOMM, "cudaDeviceEnablePeerAccess(%d) failed: %s", pb.device,
+                                cudaGetErrorString(e));
+                cudaGetLastError();
+            }
+            h->peer_base[(size_t)p] = reinterpret_cast<char *>((uintptr_t)pb.raw_ptr);
+        } else {
+            void *mapped = nullptr;
+            cudaError_t e = cudaIpcOpenMemHandle(&mapped, pb.handle, cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess)
+                return fail(h, TRIXI_B200_ECOMM, "cudaIpcOpenMemHandle for rank %d failed: %s", pb.rank,
+                            cudaGetErrorString(e));
+            h->ipc_opened.push_back(mapped);
+            h->peer_base[(size_t)p] = static_cast<char *>(mapped);
+        }
+    }
+    // device tables
+    std::vector<long long> remote_index((size_t)h->nmpi);
+    for (long long i = 0; i < h->nmpi; ++i) {
+        const int p = h->h_peer_slot[(size_t)i];
+        remote_index[(size_t)i] = h->my_offset_in_peer[(size_t)p] + (i - h->peer_offset[(size_t)p]);
+    }
+    if (h->nmpi > 0) {
+        int rc = upload_array(h, remote_index.data(), remote_index.size(), &h->d_mpi_remote_index);
+        if (rc) return rc;
+        h->P.mpi_remote_index = h->d_mpi_remote_index;
+        rc = upload_array(h, h->peers.data(), h->peers.size(), &h->d_peer_ranks);
+        if (rc) return rc;
+        for (int parity = 0; parity < 2; ++parity) {
+            std::vector<double *> recv((size_t)npeers);
+            std::vector<unsigned long long *> flag((size_t)npeers);
+            for (int p = 0; p < npeers; ++p) {
+                const size_t peer_flag_bytes = ((size_t)2 * world * sizeof(unsigned long long) + 255) / 256 * 256;
+                const size_t peer_recv_bytes =
+                    ((size_t)h->peer_nmpi[(size_t)p] * nf * h->nvars * sizeof(double) + 255) / 256 * 256;
+                char *base = h->peer_base[(size_t)p];
+                recv[(size_t)p] = reinterpret_cast<double *>(base + peer_flag_bytes + (size_t)parity * peer_recv_bytes);
+                flag[(size_t)p] = reinterpret_cast<unsigned long long *>(base) + (size_t)parity * world + h->rank;
+            }
+            rc = upload_array(h, recv.data(), recv.size(), &h->d_peer_recv[parity]);
+            if (rc) return rc;
+            rc = upload_array(h, flag.data(), flag.size(), &h->d_peer_flag[parity]);
+            if (rc) return rc;
+        }
+    }
+    CUDA_TRY(h, cudaDeviceSynchronize());
+    h->comm_connected = true;
+    return 0;
 }
 
 TRIXI_B200_API int64_t trixi_b200_launch_count(const trixi_b200_handle *h) { return h ? h->launches : 0; }

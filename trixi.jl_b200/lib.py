@@ -22,7 +22,8 @@ EXPORTS = [
     "trixi_b200_stream", "trixi_b200_rhs_host", "trixi_b200_rhs", "trixi_b200_max_dt",
     "trixi_b200_step_2n", "trixi_b200_solve_2n", "trixi_b200_set_eq_param",
     "trixi_b200_calc_volume_integral", "trixi_b200_calc_surface_fluxes",
-    "trixi_b200_download_surface_flux_values", "trixi_b200_comm_unique_id", "trixi_b200_comm_init",
+    "trixi_b200_download_surface_flux_values", "trixi_b200_comm_info_size", "trixi_b200_comm_info",
+    "trixi_b200_comm_connect",
     "trixi_b200_launch_count", "trixi_b200_last_elapsed_ms", "trixi_b200_profile_enable",
     "trixi_b200_profile_read", "trixi_b200_timer_start", "trixi_b200_timer_stop",
     "trixi_b200_measure_fp64_peak", "trixi_b200_measure_copy_bandwidth", "trixi_b200_set_option",
@@ -72,8 +73,10 @@ def load_library(path=None):
     lib.trixi_b200_calc_volume_integral.argtypes = [vp]
     lib.trixi_b200_calc_surface_fluxes.argtypes = [vp, C.c_double]
     lib.trixi_b200_download_surface_flux_values.argtypes = [vp, dp]
-    lib.trixi_b200_comm_unique_id.argtypes = [vp]
-    lib.trixi_b200_comm_init.argtypes = [vp, vp]
+    lib.trixi_b200_comm_info_size.argtypes = []
+    lib.trixi_b200_comm_info_size.restype = C.c_int64
+    lib.trixi_b200_comm_info.argtypes = [vp, vp]
+    lib.trixi_b200_comm_connect.argtypes = [vp, vp, C.c_int]
     lib.trixi_b200_launch_count.argtypes = [vp]
     lib.trixi_b200_launch_count.restype = C.c_int64
     lib.trixi_b200_last_elapsed_ms.argtypes = [vp, C.POINTER(C.c_float)]
@@ -240,11 +243,21 @@ class B200Backend:
         return out.value
 
     # distributed
-    def comm_unique_id(self):
-        buf = C.create_string_buffer(128)
-        self._ck(self.lib.trixi_b200_comm_unique_id(buf))
+    def comm_info(self):
+        """Opaque connection blob of this rank (to be all-gathered by the host process group)."""
+        buf = C.create_string_buffer(int(self.lib.trixi_b200_comm_info_size()))
+        self._ck(self.lib.trixi_b200_comm_info(self.h, buf))
         return buf.raw
 
-    def comm_init(self, unique_id):
-        buf = C.create_string_buffer(bytes(unique_id), 128)
-        self._ck(self.lib.trixi_b200_comm_init(self.h, buf))
+    def comm_connect(self, blobs):
+        """``blobs``: list of every rank's ``comm_info()`` in rank order."""
+        joined = b"".join(blobs)
+        buf = C.create_string_buffer(joined, len(joined))
+        self._ck(self.lib.trixi_b200_comm_connect(self.h, buf, len(blobs)))
+
+    def connect(self, dist):
+        """Wire the halo exchange through a ``torch.distributed`` process group (plumbing only)."""
+        blobs = [None] * dist.get_world_size()
+        dist.all_gather_object(blobs, self.comm_info())
+        self.comm_connect(blobs)
+        dist.barrier()

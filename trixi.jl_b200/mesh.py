@@ -106,15 +106,17 @@ class TreeMesh:
         # abstract_tree.jl:56
         return self.length_level_0 / (1 << np.asarray(level)).astype(np.float64)
 
-    def cell_coordinates(self):
+    def cell_coordinates(self, cells=None):
         """Cell midpoints, accumulated parent->child exactly like ``child_coordinates``
         (abstract_tree.jl:668-674): x_child = x_parent + sign * (parent_length/2) / 2."""
-        x = np.repeat(self.center_level_0[:, None], self.ncells, axis=1).copy()
-        lmax = int(self.levels.max())
+        levels = self.levels if cells is None else self.levels[cells]
+        icoords = self.icoords if cells is None else self.icoords[:, cells]
+        x = np.repeat(self.center_level_0[:, None], levels.shape[0], axis=1).copy()
+        lmax = int(levels.max()) if levels.shape[0] else 0
         for l in range(1, lmax + 1):
-            active = self.levels >= l
+            active = levels >= l
             # bit of the ancestor at level l
-            bit = (self.icoords >> np.maximum(self.levels - l, 0)) & 1
+            bit = (icoords >> np.maximum(levels - l, 0)) & 1
             sign = np.where(bit == 1, 1.0, -1.0)
             child_length = self.length_level_0 / (1 << (l - 1)) / 2
             x = np.where(active[None, :], x + sign * child_length / 2, x)
@@ -164,38 +166,41 @@ class TreeMesh:
         ok = (pos < self.ncells) & (self._keys[pos_c] == key) & (self.levels[pos_c] == level)
         return np.where(ok, pos_c, -1)
 
-    def _shifted(self, direction):
+    def _shifted(self, direction, cells=None):
         d = direction // 2
         step = -1 if direction % 2 == 0 else 1
-        n_at_level = np.int64(1) << self.levels
-        c = self.icoords.copy()
+        levels = self.levels if cells is None else self.levels[cells]
+        n_at_level = np.int64(1) << levels
+        c = self.icoords.copy() if cells is None else self.icoords[:, cells].copy()
         c[d] += step
         outside = (c[d] < 0) | (c[d] >= n_at_level)
         if self.periodicity[d]:
             c[d] = np.mod(c[d], n_at_level)
             outside = np.zeros_like(outside)
-        return c, outside
+        return c, outside, levels
 
-    def _face_neighbors(self, direction, want):
-        c, outside = self._shifted(direction)
+    def _face_neighbors(self, direction, want, cells=None):
+        """Global index of the face neighbour of every cell (or of the subset ``cells``) in
+        ``direction`` (0-based: -x,+x,-y,...), -1 if there is none of the wanted kind."""
+        c, outside, levels = self._shifted(direction, cells)
         c_safe = np.where(outside[None, :], 0, c)
         if want == "same":
-            idx = self._lookup(self.levels, c_safe)
+            idx = self._lookup(levels, c_safe)
             return np.where(outside, -1, idx)
         if want == "coarse":
-            lv = np.maximum(self.levels - 1, 0)
+            lv = np.maximum(levels - 1, 0)
             idx = self._lookup(lv, c_safe >> 1)
-            idx = np.where((self.levels == 0) | outside, -1, idx)
+            idx = np.where((levels == 0) | outside, -1, idx)
             return idx
         if want == "coarse_of_fine":
             # does a leaf two levels finer touch this face?  check the 2^(d-1) level+1 neighbour
             # slots: if such a slot is neither a leaf at level+1 nor covered by a coarser/same leaf,
             # it is refined further -> imbalance.
             d = direction // 2
-            bad = np.zeros(self.ncells, dtype=bool)
-            same = self._lookup(self.levels, c_safe)
-            coarse = self._lookup(np.maximum(self.levels - 1, 0), c_safe >> 1)
-            covered = (same >= 0) | ((coarse >= 0) & (self.levels > 0)) | outside
+            bad = np.zeros(levels.shape[0], dtype=bool)
+            same = self._lookup(levels, c_safe)
+            coarse = self._lookup(np.maximum(levels - 1, 0), c_safe >> 1)
+            covered = (same >= 0) | ((coarse >= 0) & (levels > 0)) | outside
             others = [e for e in range(self.ndims) if e != d]
             for sub in range(1 << (self.ndims - 1)):
                 cc = c_safe * 2
@@ -203,7 +208,7 @@ class TreeMesh:
                 cc[d] += 0 if direction % 2 == 1 else 1
                 for b, e in enumerate(others):
                     cc[e] += (sub >> b) & 1
-                lv1 = self.levels + 1
+                lv1 = levels + 1
                 ok_lv = lv1 <= self._lmax
                 fine = self._lookup(np.minimum(lv1, self._lmax), np.where(ok_lv[None, :], cc, 0))
                 fine = np.where(ok_lv, fine, -1)
@@ -243,16 +248,18 @@ class CartesianBoxMesh(TreeMesh):
     def length_at_level(self, level):
         return np.full(np.shape(level), self.dx)
 
-    def cell_coordinates(self):
-        return self.coordinates_min[:, None] + (self.icoords + 0.5) * self.dx
+    def cell_coordinates(self, cells=None):
+        ic = self.icoords if cells is None else self.icoords[:, cells]
+        return self.coordinates_min[:, None] + (ic + 0.5) * self.dx
 
-    def _face_neighbors(self, direction, want):
+    def _face_neighbors(self, direction, want, cells=None):
+        ncells = self.ncells if cells is None else len(cells)
         if want != "same":
-            return np.full(self.ncells, -1, dtype=np.int64)
+            return np.full(ncells, -1, dtype=np.int64)
         d = direction // 2
         step = -1 if direction % 2 == 0 else 1
         n = self.cells_per_dimension
-        c = self.icoords.copy()
+        c = self.icoords.copy() if cells is None else self.icoords[:, cells].copy()
         c[d] += step
         outside = (c[d] < 0) | (c[d] >= n[d])
         if self.periodicity[d]:

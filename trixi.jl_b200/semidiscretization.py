@@ -14,7 +14,7 @@ import time
 import numpy as np
 
 from . import _abi
-from .containers import init_boundaries, init_elements, init_interfaces
+from .containers import init_boundaries, init_elements, init_interfaces, partition_cells
 from .equations import (BC_DIRICHLET, BC_PERIODIC, BC_SLIP_WALL, IC_NONE, SRC_NONE,
                         BoundaryConditionDirichlet, boundary_condition_periodic, resolve_flux)
 from .mesh import TreeMesh
@@ -46,13 +46,18 @@ class Cache:
     pass
 
 
-def create_cache(mesh, equations, solver):
-    """``create_cache`` for TreeMesh (dgsem_tree/dg_2d.jl:14-37)."""
+def create_cache(mesh, equations, solver, rank=0, world_size=1):
+    """``create_cache`` for TreeMesh (dgsem_tree/dg_2d.jl:14-37; with ``world_size > 1`` the containers
+    of this rank's contiguous chunk of the element order plus its MPI interfaces,
+    dgsem_tree/dg_2d_parallel.jl:245-281)."""
     cache = Cache()
     if isinstance(mesh, TreeMesh):
-        cache.elements = init_elements(mesh, solver.basis)
-        cache.interfaces = init_interfaces(mesh)
-        cache.boundaries = init_boundaries(mesh, cache.elements, solver.basis)
+        first, last = partition_cells(mesh.ncells, rank, world_size)
+        cache.first_element, cache.last_element = first, last
+        cells = None if world_size == 1 else np.arange(first, last, dtype=np.int64)
+        cache.elements = init_elements(mesh, solver.basis, cells)
+        cache.interfaces, cache.mpi_interfaces = init_interfaces(mesh, first, last, world_size)
+        cache.boundaries = init_boundaries(mesh, cache.elements, solver.basis, first, last)
     else:
         raise TypeError(f"unsupported mesh type {type(mesh).__name__}")
     return cache
@@ -97,14 +102,16 @@ class SemidiscretizationHyperbolic:
     boundary_conditions)`` (semidiscretization_hyperbolic.jl:50-76)."""
 
     def __init__(self, mesh, equations, initial_condition, solver, source_terms=None,
-                 boundary_conditions=boundary_condition_periodic, device=-1):
+                 boundary_conditions=boundary_condition_periodic, device=-1, rank=0, world_size=1, comm=None):
         if mesh.ndims != equations.ndims:
             raise ValueError("mesh and equations must have the same number of dimensions")
         self.mesh, self.equations, self.solver = mesh, equations, solver
         self.initial_condition = initial_condition
         self.source_terms = source_terms
         self.boundary_conditions = boundary_conditions
-        self.cache = create_cache(mesh, equations, solver)
+        self.rank, self.world_size = int(rank), int(world_size)
+        self.comm = comm  # torch.distributed (plumbing: connection blobs, dt / error-norm reductions)
+        self.cache = create_cache(mesh, equations, solver, self.rank, self.world_size)
         self.performance_counter = PerformanceCounter()
         self.device = device
         self._bc_tags, self._bc_ics = _digest_boundary_conditions(boundary_conditions, mesh)
@@ -117,8 +124,12 @@ class SemidiscretizationHyperbolic:
         return self.cache.elements.nelements
 
     def ndofs(self):
-        """Number of DOFs = nodes (docs/src/performance.md:201-218, solvers/dg.jl:969-971)."""
+        """Number of DOFs = nodes (docs/src/performance.md:201-218, solvers/dg.jl:969-971); local to
+        this rank."""
         return self.nelements * self.solver.nnodes ** self.mesh.ndims
+
+    def ndofsglobal(self):
+        return self.mesh.ncells * self.solver.nnodes ** self.mesh.ndims
 
     def u_shape(self):
         return (self.equations.nvars,) + (self.solver.nnodes,) * self.mesh.ndims + (self.nelements,)
@@ -166,8 +177,14 @@ class SemidiscretizationHyperbolic:
         for i in range(6):
             d.n_boundaries_per_direction[i] = int(b.n_boundaries_per_direction[i])
         d.nmortars = 0
-        d.rank, d.world_size = 0, 1
-        d.nmpiinterfaces = 0
+        d.rank, d.world_size = self.rank, self.world_size
+        mi = cache.mpi_interfaces
+        d.nmpiinterfaces = mi.nmpiinterfaces
+        if mi.nmpiinterfaces:
+            h.set_i64("mpi_local_neighbor_ids", mi.local_neighbor_ids)
+            h.set_i64("mpi_local_sides", mi.local_sides)
+            h.set_i64("mpi_orientations", mi.orientations)
+            h.set_i64("mpi_neighbor_ranks", mi.neighbor_ranks)
         self._desc = h
         return h
 
@@ -177,6 +194,8 @@ class SemidiscretizationHyperbolic:
         if self._backend is None:
             from .lib import B200Backend
             self._backend = B200Backend(self.descriptor(), self.u_length())
+            if self.world_size > 1 and self.comm is not None:
+                self._backend.connect(self.comm)
         return self._backend
 
     def set_backend(self, backend):
