@@ -33,20 +33,45 @@ UNIT = "DOF-updates/s"
 ALGO_FLOP_PER_DOF_VOLUME = 312.5  # 4.5 pairs x 67 + 11 (p = 3, Euler 3D, flux_ranocha)
 
 
-def make_semi(level, device=-1):
+def box_cells(level, world):
+    """Weak scaling: every rank keeps a (2^level)^3-element block; the global box doubles in x, y, z in turn."""
+    n = [1 << level] * 3
+    k, d = world, 0
+    while k > 1:
+        if k % 2:
+            raise ValueError("--gpus must be a power of two")
+        n[d % 3] *= 2
+        k //= 2
+        d += 1
+    return tuple(n)
+
+
+def make_semi(level, device=-1, rank=0, world=1, comm=None):
     import trixi_b200 as T
     # examples/tree_3d_dgsem/elixir_euler_ec.jl at a larger refinement level
     eq = T.CompressibleEulerEquations3D(1.4)
     solver = T.DGSEM(polydeg=3, surface_flux=T.flux_ranocha,
                      volume_integral=T.VolumeIntegralFluxDifferencing(T.flux_ranocha))
-    mesh = T.TreeMesh((-2.0,) * 3, (2.0,) * 3, initial_refinement_level=level, periodicity=True)
-    return T.SemidiscretizationHyperbolic(mesh, eq, T.initial_condition_weak_blast_wave, solver, device=device)
+    if world == 1:
+        mesh = T.TreeMesh((-2.0,) * 3, (2.0,) * 3, initial_refinement_level=level, periodicity=True)
+    else:
+        # same cells (size 4 / 2^level) and the same Morton element order as the TreeMesh, on a box that
+        # grows with the number of ranks; contiguous chunks of the order are (2^level)^3 blocks
+        mesh = T.CartesianBoxMesh((-2.0,) * 3, 4.0 / (1 << level), box_cells(level, world), periodicity=True)
+    return T.SemidiscretizationHyperbolic(mesh, eq, T.initial_condition_weak_blast_wave, solver, device=device,
+                                          rank=rank, world_size=world, comm=comm)
 
 
-def workload_name(level):
+def workload_name(level, world=1):
     n = 1 << level
-    return (f"tree_3d_dgsem/elixir_euler_ec.jl: 3D Euler EC flux differencing (flux_ranocha), polydeg=3, "
-            f"TreeMesh level {level} ({n}^3 elements, {64 * n**3 / 1e6:.1f} M DOF), periodic, weak blast wave IC")
+    base = ("tree_3d_dgsem/elixir_euler_ec.jl: 3D Euler EC flux differencing (flux_ranocha), polydeg=3, ")
+    if world == 1:
+        return base + (f"TreeMesh level {level} ({n}^3 elements, {64 * n**3 / 1e6:.1f} M DOF), periodic, "
+                       "weak blast wave IC")
+    nx, ny, nz = box_cells(level, world)
+    return base + (f"Cartesian box {nx}x{ny}x{nz} elements in TreeMesh (Morton) order = {n}^3 elements "
+                   f"({64 * n**3 / 1e6:.1f} M DOF) per rank, {64 * nx * ny * nz / 1e6:.1f} M DOF total, periodic, "
+                   "weak blast wave IC")
 
 
 class ClockSampler:
@@ -175,18 +200,25 @@ def run_b200(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    semi = make_semi(args.level, device=local_rank)
+    from trixi_b200.parallel import allreduce_min
+    semi = make_semi(args.level, device=local_rank, rank=rank, world=world, comm=dist if world > 1 else None)
     gpu = semi.backend()
     ndofs = semi.ndofs()
     u0 = T.compute_coefficients(0.0, semi)
     gpu.upload(0, u0)
     alg = T.CarpenterKennedy2N54()
     cfl = 1.3
-    dt = cfl * gpu.max_dt()
+
+    def new_dt():
+        # StepsizeCallback (stepsize.jl:93-126): device max_dt reduction, min over ranks
+        local = cfl * gpu.max_dt()
+        return allreduce_min(local, dist) if world > 1 else local
+
+    dt = new_dt()
 
     def one_step(t):
         gpu.step_2n(t, dt_holder[0], alg.a, alg.b, alg.c)
-        dt_holder[0] = cfl * gpu.max_dt()  # StepsizeCallback after every step (stepsize.jl:93-126)
+        dt_holder[0] = new_dt()
 
     dt_holder = [dt]
     t = 0.0
@@ -213,6 +245,7 @@ def run_b200(args, rank, world, local_rank):
     elem_ms, elem_n = gpu.profile_read(1)
     surf_ms, surf_n = gpu.profile_read(0)
     cfl_ms, cfl_n = gpu.profile_read(2)
+    halo_ms, halo_n = gpu.profile_read(3)
     gpu.profile_enable(False)
     clocks = sampler.stop() if rank == 0 else None
 
@@ -222,7 +255,7 @@ def run_b200(args, rank, world, local_rank):
     ms_max = float(t_ms.item())
     u_final = gpu.download(0)
     finite = bool(np.isfinite(u_final).all())
-    total_dofs = ndofs * world  # weak scaling: every rank owns a level-L mesh partition
+    total_dofs = semi.ndofsglobal()  # weak scaling: every rank owns a (2^level)^3-element block
     value = total_dofs * 5 * args.steps / (ms_max * 1e-3)
 
     # ---- end-to-end through the public API with host buffers ---------------------------------------
@@ -267,10 +300,13 @@ def run_b200(args, rank, world, local_rank):
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "pid_ns_per_dof_rhs": 1e9 / value * world,
-            "config": {"workload": workload_name(args.level), "ndofs_per_gpu": ndofs,
+            "config": {"workload": workload_name(args.level, world), "ndofs_per_gpu": ndofs,
                        "rhs_per_step": 5, "time_integrator": "CarpenterKennedy2N54 (fused stage update)",
                        "l2_hygiene": "inputs larger than L2 (u alone is %.1f GB)" % (n * 8 / 1e9),
-                       "parallelism": "1 rank per GPU" if world == 1 else f"{world} ranks, independent partitions"},
+                       "parallelism": "1 rank per GPU" if world == 1 else
+                       f"{world} ranks: Morton-order element partition, face halo exchange by direct peer "
+                       "stores over NVLink (CUDA IPC) + sequence flags inside libtrixi_b200, dt min-allreduce "
+                       "over NCCL"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * 8, "d2h_bytes_per_step": n * 8,
                     "call": "rhs_hyperbolic(du_host, u_host, semi, t) -> trixi_b200_rhs_host, pinned host buffers",
@@ -286,7 +322,7 @@ def run_b200(args, rank, world, local_rank):
                                   "algorithmic_flop_per_dof": ALGO_FLOP_PER_DOF_VOLUME + 45.0},
                          "copy_gbs_measured_here": copy_gbs},
             "kernel_time_share": {"surface_flux_ms": surf_ms, "element_ms": elem_ms, "max_dt_ms": cfl_ms,
-                                  "timed_region_ms": ms_max},
+                                  "halo_pack_wait_mpiflux_ms": halo_ms, "timed_region_ms": ms_max},
             "wall_s": wall, "finite": finite,
         }
         if cpu:

@@ -109,7 +109,7 @@ def calc_error_norms(u, t, semi, analyzer=None):
         semi.comm.all_reduce(t2, op=semi.comm.ReduceOp.SUM)
         semi.comm.all_reduce(tinf, op=semi.comm.ReduceOp.MAX)
         l2sq, linf = t2.cpu().numpy(), tinf.cpu().numpy()
-    l2 = np.sqrt(l2sq / mesh.length_level_0**nd)
+    l2 = np.sqrt(l2sq / mesh.total_volume())
     return l2, linf
 
 

@@ -377,6 +377,12 @@ __global__ void __launch_bounds__(TunedCfg::THREADS, TunedCfg::MIN_BLOCKS)
     }
 }
 
+cudaError_t preload_tuned_euler3d() {
+    cudaError_t e = preload_kernel(k_element_euler3d_ranocha_p3<true>);
+    if (e != cudaSuccess) return e;
+    return preload_kernel(k_element_euler3d_ranocha_p3<false>);
+}
+
 cudaError_t launch_element_euler3d_ranocha_p3(const KParams &P, bool with_surface, cudaStream_t s) {
     using C = TunedCfg;
     static PerDeviceFlag configured;

@@ -14,6 +14,9 @@ struct Launchers {
     void (*max_dt)(const KParams &, cudaStream_t);
     void (*mpi_pack)(const KParams &, cudaStream_t);
     void (*mpi_interface_flux)(const KParams &, cudaStream_t);
+    // Force-load every kernel of this table (CUDA loads kernels lazily at first launch, and that load can
+    // need a context synchronisation: fatal while a halo wait kernel of another handle is spinning)
+    cudaError_t (*preload)();
     int ndims, nvars, nnodes;
 };
 
@@ -113,6 +116,33 @@ void launch_max_dt(const KParams &P, cudaStream_t s) {
     k_max_dt<EQ, N><<<blocks, C::THREADS, 0, s>>>(P);
 }
 
+template <class K>
+cudaError_t preload_kernel(K kern) {
+    cudaFuncAttributes attr;
+    return cudaFuncGetAttributes(&attr, kern);
+}
+
+cudaError_t preload_tuned_euler3d();  // tuned_euler3d.cu
+
+template <class EQ, int N>
+cudaError_t preload_all() {
+    cudaError_t e;
+#define TB_PRELOAD(k)                      \
+    if ((e = preload_kernel(k)) != cudaSuccess) return e
+    TB_PRELOAD((k_interface_flux<EQ, N>));
+    TB_PRELOAD((k_boundary_flux<EQ, N>));
+    TB_PRELOAD((k_mpi_pack<EQ, N>));
+    TB_PRELOAD((k_mpi_interface_flux<EQ, N>));
+    TB_PRELOAD((k_max_dt<EQ, N>));
+    TB_PRELOAD((k_element<EQ, N, TRIXI_B200_VOLINT_WEAK_FORM, true>));
+    TB_PRELOAD((k_element<EQ, N, TRIXI_B200_VOLINT_WEAK_FORM, false>));
+    TB_PRELOAD((k_element<EQ, N, TRIXI_B200_VOLINT_FLUX_DIFFERENCING, true>));
+    TB_PRELOAD((k_element<EQ, N, TRIXI_B200_VOLINT_FLUX_DIFFERENCING, false>));
+#undef TB_PRELOAD
+    if constexpr (std::is_same_v<EQ, Euler<3>> && N == 4) return preload_tuned_euler3d();
+    return cudaSuccess;
+}
+
 template <class EQ, int N>
 const Launchers *make_launchers() {
     static const Launchers L = {&launch_interface_flux<EQ, N>,
@@ -121,6 +151,7 @@ const Launchers *make_launchers() {
                                 &launch_max_dt<EQ, N>,
                                 &launch_mpi_pack<EQ, N>,
                                 &launch_mpi_interface_flux<EQ, N>,
+                                &preload_all<EQ, N>,
                                 EQ::NDIMS,
                                 EQ::NVARS,
                                 N};

@@ -504,6 +504,10 @@ TRIXI_B200_API int trixi_b200_create(const trixi_b200_desc *d, trixi_b200_handle
         CREATE_CUDA(cudaMemset(h->comm_base, 0, h->flag_bytes + 2 * h->recv_bytes));
     }
 
+    CREATE_CUDA(L->preload());
+    CREATE_CUDA(preload_kernel(k_mpi_signal));
+    CREATE_CUDA(preload_kernel(k_mpi_wait));
+
     CREATE_TRY(alloc_array(h, 1, &h->d_cfl));
     P.cfl_key = h->d_cfl;
     CREATE_CUDA(cudaMallocHost((void **)&h->h_cfl, sizeof(unsigned long long)));

@@ -106,6 +106,10 @@ class TreeMesh:
         # abstract_tree.jl:56
         return self.length_level_0 / (1 << np.asarray(level)).astype(np.float64)
 
+    def total_volume(self):
+        # tree_mesh.jl:311-313
+        return self.length_level_0 ** self.ndims
+
     def cell_coordinates(self, cells=None):
         """Cell midpoints, accumulated parent->child exactly like ``child_coordinates``
         (abstract_tree.jl:668-674): x_child = x_parent + sign * (parent_length/2) / 2."""
@@ -223,27 +227,36 @@ class TreeMesh:
 
 
 class CartesianBoxMesh(TreeMesh):
-    """Synthetic uniform periodic Cartesian connectivity with an arbitrary number of elements per
-    direction (100^3 = 64 M DOF and 200^3 = 512 M DOF are not TreeMesh levels).
-    Elements are ordered x-fastest; everything downstream consumes the same Tree containers."""
+    """Synthetic uniform Cartesian connectivity with an arbitrary number of cubic cells per direction
+    (100^3 = 64 M DOF, 200^3 = 512 M DOF and the weak-scaling boxes 256x128x128, ... are
+    not TreeMesh levels).  Cells are ordered along the same Morton curve as TreeMesh leaves, so a box of
+    2^L cells per direction reproduces the TreeMesh of level L exactly and contiguous chunks of the
+    ordering are compact blocks.  Everything downstream consumes the same Tree containers."""
 
-    def __init__(self, coordinates_min, coordinates_max, cells_per_dimension, periodicity=True):
+    def __init__(self, coordinates_min, cell_length, cells_per_dimension, periodicity=True):
         self.ndims = len(coordinates_min)
         self.cells_per_dimension = tuple(int(c) for c in cells_per_dimension)
+        if len(self.cells_per_dimension) != self.ndims:
+            raise ValueError("cells_per_dimension must have one entry per dimension")
         self.coordinates_min = np.array(coordinates_min, dtype=np.float64)
-        self.coordinates_max = np.array(coordinates_max, dtype=np.float64)
-        self.length_level_0 = float(self.coordinates_max[0] - self.coordinates_min[0])
-        self.center_level_0 = 0.5 * (self.coordinates_min + self.coordinates_max)
+        self.dx = float(cell_length)
+        self.domain_lengths = self.dx * np.array(self.cells_per_dimension, dtype=np.float64)
+        self.length_level_0 = float(self.domain_lengths.max())
+        self.center_level_0 = self.coordinates_min + 0.5 * self.domain_lengths
         if isinstance(periodicity, bool):
             periodicity = (periodicity,) * self.ndims
         self.periodicity = tuple(periodicity)
         n = self.cells_per_dimension
-        if len(set(n)) != 1:
-            raise ValueError("CartesianBoxMesh needs the same number of cells in every direction")
-        grids = np.meshgrid(*[np.arange(m, dtype=np.int64) for m in n[::-1]], indexing="ij")
-        self.icoords = np.stack([g.ravel() for g in grids[::-1]])
+        grids = np.meshgrid(*[np.arange(m, dtype=np.int64) for m in n], indexing="ij")
+        ic = np.stack([g.ravel() for g in grids])
+        key = morton_key(ic, self.ndims)
+        order = np.argsort(key, kind="stable")
+        self.icoords = np.ascontiguousarray(ic[:, order])
+        self._keys = key[order]
         self.levels = np.zeros(self.icoords.shape[1], dtype=np.int64)
-        self.dx = self.length_level_0 / n[0]
+
+    def total_volume(self):
+        return float(np.prod(self.domain_lengths))
 
     def length_at_level(self, level):
         return np.full(np.shape(level), self.dx)
@@ -265,9 +278,7 @@ class CartesianBoxMesh(TreeMesh):
         if self.periodicity[d]:
             c[d] %= n[d]
             outside[:] = False
-        idx = c[0].copy()
-        stride = 1
-        for e in range(1, self.ndims):
-            stride *= n[e - 1]
-            idx = idx + c[e] * stride
-        return np.where(outside, -1, idx)
+        c[d] = np.where(outside, 0, c[d])
+        key = morton_key(c, self.ndims)
+        pos = np.searchsorted(self._keys, key)
+        return np.where(outside, -1, pos)
