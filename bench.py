@@ -83,12 +83,12 @@ class ClockSampler:
         self.lines = []
 
     def start(self):
-        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+        q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
@@ -98,7 +98,13 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
+
+    def mark_begin(self):
+        self.t_begin = time.time()
+
+    def mark_end(self):
+        self.t_end = time.time()
 
     def stop(self):
         if not self.proc:
@@ -110,8 +116,12 @@ class ClockSampler:
             pass
         sm, smax, power, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.lines:
-            parts = [p.strip() for p in line.split(",")]
+        t0, t1 = getattr(self, "t_begin", 0.0), getattr(self, "t_end", float("inf"))
+        window = [l for (ts, l) in self.lines if t0 <= ts <= t1 + 0.06]
+        if not window:  # very short timed region: fall back to the nearest samples
+            window = [l for (_, l) in self.lines[-3:]]
+        for line in window:
+            parts = [p.strip() for p in line.split(",")][1:]
             if len(parts) < 7:
                 continue
             try:
@@ -183,7 +193,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_b200(args, rank, world, local_rank):
@@ -222,17 +232,18 @@ def run_b200(args, rank, world, local_rank):
 
     dt_holder = [dt]
     t = 0.0
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()  # started before the warm-up so samples exist even for a short timed region
     for _ in range(args.warmup):
         one_step(t)
         t += dt_holder[0]
 
     # ---- device-resident timed region --------------------------------------------------------------
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     gpu.profile_enable(True)
     launches0 = gpu.launch_count()
     barrier()
+    sampler.mark_begin()
     gpu.timer_start()
     t_wall0 = time.perf_counter()
     for _ in range(args.steps):
@@ -240,6 +251,7 @@ def run_b200(args, rank, world, local_rank):
         t += dt_holder[0]
     ms = gpu.timer_stop()
     barrier()
+    sampler.mark_end()
     wall = time.perf_counter() - t_wall0
     launches = gpu.launch_count() - launches0
     elem_ms, elem_n = gpu.profile_read(1)
@@ -327,15 +339,33 @@ def run_b200(args, rank, world, local_rank):
         }
         if cpu:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def _protect_stdout():
+    """Libraries (NCCL's version banner, torchrun notices) may print to fd 1; the driver wants exactly one
+    JSON line there.  Everything else goes to stderr."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line):
+    _REAL_STDOUT.write(json.dumps(line) + "\n")
+    _REAL_STDOUT.flush()
+
+
 def main():
+    _protect_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--level", type=int, default=7, help="TreeMesh refinement level per GPU (7 = 134 M DOF)")
     ap.add_argument("--cpu-level", type=int, default=5, help="refinement level of the bounded CPU sample")
