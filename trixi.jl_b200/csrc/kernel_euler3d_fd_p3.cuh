@@ -33,23 +33,6 @@ TB_DEV int swz_pos(int n) {
     return (k << 4) | (((j ^ k) & 3) << 2) | ((i ^ k) & 3);
 }
 
-// 1/x to ~1 ulp: MUFU.RCP64H seed (rcp.approx.ftz.f64, ~20 bits) + two Newton steps (4 DFMA)
-TB_DEV double fast_rcp(double x) {
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-    double e = fma(-x, r, 1.0);
-    r = fma(r, e, r);
-    e = fma(-x, r, 1.0);
-    r = fma(r, e, r);
-    return r;
-}
-// a / b with one residual correction (Markstein): correctly rounded except in rare ties, no slow path
-TB_DEV double fast_div(double a, double b) {
-    const double r = fast_rcp(b);
-    const double q = a * r;
-    return fma(fma(-b, q, a), r, q);
-}
-
 // ---- TMA / mbarrier helpers (PTX ISA: cp.async.bulk, mbarrier) ---------------------------------------
 TB_DEV uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 TB_DEV void mbar_init(uint32_t bar, uint32_t count) {
@@ -84,14 +67,6 @@ TB_DEV void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" 
 
 // Node record in the prim tile: rho, v1, v2, v3, p, log(rho), log(p)
 constexpr int kNP = 7;
-
-// 1/x to ~1e-12: MUFU.RCP64H seed + one Newton step; enough for f^2, which only enters the Ismail-Roe
-// series (sensitivity f^2/3 <= 3e-5) and the branch choice
-TB_DEV double rcp_1nr(double x) {
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-    return fma(r, fma(-x, r, 1.0), r);
-}
 
 // flux_ranocha(u_ll, u_rr, orientation) (compressible_euler_3d.jl:746-793) on hoisted node records whose
 // velocity components have been rotated so that slot 1 is the normal one: (rho, vn, vt1, vt2, p, log rho,

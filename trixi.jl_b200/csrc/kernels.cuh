@@ -82,7 +82,27 @@ TB_DEV unsigned long long cfl_encode(double v) {
 }
 
 // ---- 1. interfaces ------------------------------------------------------------------------------
-template <class EQ, int N>
+template <class EQ>
+struct HasFastRanocha {
+    static constexpr bool value = false;
+};
+template <int ND>
+struct HasFastRanocha<Euler<ND>> {
+    static constexpr bool value = true;
+};
+
+// surface flux of one face node; FAST selects the fast-division flux_ranocha (tuned path)
+template <class EQ, bool FAST>
+TB_DEV void surface_numflux(const EQ &eq, int id, const double (&ul)[EQ::NVARS], const double (&ur)[EQ::NVARS], int o,
+                            double (&f)[EQ::NVARS]) {
+    if constexpr (FAST && HasFastRanocha<EQ>::value) {
+        eq.flux_ranocha_fast(ul, ur, o, f);
+    } else {
+        eq.numflux(id, ul, ur, o, f);
+    }
+}
+
+template <class EQ, int N, bool FAST = false>
 __global__ void __launch_bounds__(256) k_interface_flux(const KParams P) {
     constexpr int ND = EQ::NDIMS, NV = EQ::NVARS, NF = ipow(N, ND - 1), NN = ipow(N, ND);
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -100,7 +120,7 @@ __global__ void __launch_bounds__(256) k_interface_flux(const KParams P) {
         ul[v] = pl[v];
         ur[v] = pr[v];
     }
-    eq.numflux(P.surface_flux, ul, ur, o, f);
+    surface_numflux<EQ, FAST>(eq, P.surface_flux, ul, ur, o, f);
     // left element: direction 2*orientation (1-based) = index 2o+1; right element: 2o (dg_3d.jl:581-597)
     double *sl = P.sfv + ((left * (2 * ND) + (2 * o + 1)) * NF + fn) * NV;
     double *sr = P.sfv + ((right * (2 * ND) + (2 * o)) * NF + fn) * NV;
@@ -161,7 +181,7 @@ __global__ void __launch_bounds__(256) k_mpi_pack(const KParams P) {
 
 // calc_mpi_interface_flux! (dg_2d_parallel.jl:700-740, dg_3d_parallel.jl:167-242): the shared flux is
 // computed on both ranks with identical operands; only the local element's storage is written.
-template <class EQ, int N>
+template <class EQ, int N, bool FAST = false>
 __global__ void __launch_bounds__(256) k_mpi_interface_flux(const KParams P) {
     constexpr int ND = EQ::NDIMS, NV = EQ::NVARS, NF = ipow(N, ND - 1), NN = ipow(N, ND);
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -182,7 +202,7 @@ __global__ void __launch_bounds__(256) k_mpi_interface_flux(const KParams P) {
         ul[v] = side == 1 ? a : b;
         ur[v] = side == 1 ? b : a;
     }
-    eq.numflux(P.surface_flux, ul, ur, o, f);
+    surface_numflux<EQ, FAST>(eq, P.surface_flux, ul, ur, o, f);
     const int direction0 = side == 1 ? 2 * o + 1 : 2 * o;
     double *s = P.sfv + ((element * (2 * ND) + direction0) * NF + fn) * NV;
 #pragma unroll

@@ -27,7 +27,11 @@ void launch_interface_flux(const KParams &P, cudaStream_t s) {
     if (total == 0) return;
     const int threads = 256;
     const unsigned blocks = (unsigned)((total + threads - 1) / threads);
-    k_interface_flux<EQ, N><<<blocks, threads, 0, s>>>(P);
+    if (HasFastRanocha<EQ>::value && P.kernel_path == 0 &&
+        (P.surface_flux == TRIXI_B200_FLUX_RANOCHA || P.surface_flux == TRIXI_B200_FLUX_RANOCHA_TURBO))
+        k_interface_flux<EQ, N, true><<<blocks, threads, 0, s>>>(P);
+    else
+        k_interface_flux<EQ, N><<<blocks, threads, 0, s>>>(P);
 }
 
 template <class EQ, int N>
@@ -53,7 +57,11 @@ void launch_mpi_interface_flux(const KParams &P, cudaStream_t s) {
     constexpr int NF = ipow(N, EQ::NDIMS - 1);
     const long long total = P.nmpi * NF;
     if (total == 0) return;
-    k_mpi_interface_flux<EQ, N><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(P);
+    if (HasFastRanocha<EQ>::value && P.kernel_path == 0 &&
+        (P.surface_flux == TRIXI_B200_FLUX_RANOCHA || P.surface_flux == TRIXI_B200_FLUX_RANOCHA_TURBO))
+        k_mpi_interface_flux<EQ, N, true><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(P);
+    else
+        k_mpi_interface_flux<EQ, N><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(P);
 }
 
 // cudaFuncSetAttribute is per device: remember what was configured where
@@ -130,6 +138,8 @@ cudaError_t preload_all() {
 #define TB_PRELOAD(k)                      \
     if ((e = preload_kernel(k)) != cudaSuccess) return e
     TB_PRELOAD((k_interface_flux<EQ, N>));
+    TB_PRELOAD((k_interface_flux<EQ, N, true>));
+    TB_PRELOAD((k_mpi_interface_flux<EQ, N, true>));
     TB_PRELOAD((k_boundary_flux<EQ, N>));
     TB_PRELOAD((k_mpi_pack<EQ, N>));
     TB_PRELOAD((k_mpi_interface_flux<EQ, N>));

@@ -45,6 +45,45 @@ TB_DEV double inv_ln_mean(double x, double y) {
     return log(y / x) / (y - x);
 }
 
+// ---- fast FP64 reciprocal / division (no IEEE slow path, ~1 ulp) -------------------------------------
+// 1/x: MUFU.RCP64H seed (rcp.approx.ftz.f64, ~20 bits) + two Newton steps (4 DFMA)
+TB_DEV double fast_rcp(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    return r;
+}
+// a / b with one residual correction (Markstein): correctly rounded except in rare ties
+TB_DEV double fast_div(double a, double b) {
+    const double r = fast_rcp(b);
+    const double q = a * r;
+    return fma(fma(-b, q, a), r, q);
+}
+// 1/x to ~1e-12: seed + one Newton step; enough for f^2 of the logarithmic means, which only enters the
+// Ismail-Roe series (sensitivity f^2/3 <= 3e-5) and the branch choice
+TB_DEV double rcp_1nr(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    return fma(r, fma(-x, r, 1.0), r);
+}
+// ln_mean / inv_ln_mean (math.jl:198-250) with fast divisions; the log is only evaluated where the
+// series does not apply
+TB_DEV double ln_mean_fast(double x, double y) {
+    const double sum = x + y, dif = y - x;
+    const double f2 = (dif * dif) * rcp_1nr(sum * sum);
+    if (f2 < 1.0e-4) return fast_div(sum, fma(f2, fma(f2, fma(f2, 2.0 / 7.0, 2.0 / 5.0), 2.0 / 3.0), 2.0));
+    return fast_div(dif, log(fast_div(y, x)));
+}
+TB_DEV double inv_ln_mean_fast(double x, double y) {
+    const double sum = x + y, dif = y - x;
+    const double f2 = (dif * dif) * rcp_1nr(sum * sum);
+    if (f2 < 1.0e-4) return fast_div(fma(f2, fma(f2, fma(f2, 2.0 / 7.0, 2.0 / 5.0), 2.0 / 3.0), 2.0), sum);
+    return fast_div(log(fast_div(y, x)), dif);
+}
+
 // ---- linear scalar advection (linear_scalar_advection_2d.jl / _3d.jl) -------------------------------
 template <int ND>
 struct Advection {
@@ -155,6 +194,41 @@ struct Euler {
 #pragma unroll
         for (int d = 0; d < ND; ++d) f[1 + d] = f1 * v_avg[d] + (d == o ? p_avg : 0.0);
         f[ND + 1] = f1 * (velocity_square_avg + inv_rho_p_mean * inv_gm1) +
+                    0.5 * (p_ll * pick<ND>(v_rr, o) + p_rr * pick<ND>(v_ll, o));
+    }
+
+    // cons2prim / flux_ranocha with the fast divisions above (tuned surface kernel); same formulas
+    TB_DEV void cons2prim_fast(const double (&u)[NVARS], double &rho, double (&v)[ND], double &p) const {
+        rho = u[0];
+        const double inv_rho = fast_rcp(rho);
+        double kin = 0.0;
+#pragma unroll
+        for (int d = 0; d < ND; ++d) {
+            const double q = u[1 + d] * inv_rho;
+            v[d] = fma(fma(-rho, q, u[1 + d]), inv_rho, q);
+            kin += u[1 + d] * v[d];
+        }
+        p = (gamma - 1) * (u[ND + 1] - 0.5 * kin);
+    }
+    TB_DEV void flux_ranocha_fast(const double (&ul)[NVARS], const double (&ur)[NVARS], int o,
+                                  double (&f)[NVARS]) const {
+        double rho_ll, v_ll[ND], p_ll, rho_rr, v_rr[ND], p_rr;
+        cons2prim_fast(ul, rho_ll, v_ll, p_ll);
+        cons2prim_fast(ur, rho_rr, v_rr, p_rr);
+        const double rho_mean = ln_mean_fast(rho_ll, rho_rr);
+        const double inv_rho_p_mean = p_ll * p_rr * inv_ln_mean_fast(rho_ll * p_rr, rho_rr * p_ll);
+        double v_avg[ND], vsq = 0.0;
+#pragma unroll
+        for (int d = 0; d < ND; ++d) {
+            v_avg[d] = 0.5 * (v_ll[d] + v_rr[d]);
+            vsq += v_ll[d] * v_rr[d];
+        }
+        const double p_avg = 0.5 * (p_ll + p_rr);
+        const double f1 = rho_mean * pick<ND>(v_avg, o);
+        f[0] = f1;
+#pragma unroll
+        for (int d = 0; d < ND; ++d) f[1 + d] = f1 * v_avg[d] + (d == o ? p_avg : 0.0);
+        f[ND + 1] = f1 * (0.5 * vsq + inv_rho_p_mean * inv_gm1) +
                     0.5 * (p_ll * pick<ND>(v_rr, o) + p_rr * pick<ND>(v_ll, o));
     }
 
