@@ -69,7 +69,8 @@ class OracleBackend:
         self.vec = [np.zeros(n), np.zeros(n), np.zeros(n)]
         d = self.desc
         nf = d.nnodes ** (d.ndims - 1)
-        self.interfaces_u = np.zeros(2 * d.nvars * nf * max(d.ninterfaces, 1))
+        self.interfaces_u = np.zeros(max(2 * d.nvars * nf * max(d.ninterfaces, 1),
+                                         d.nvars * nf * 2 * d.ndims * d.nelements))
         self.boundaries_u = np.zeros(2 * d.nvars * nf * max(d.nboundaries, 1))
         self.sfv = np.zeros(d.nvars * nf * 2 * d.ndims * d.nelements)
         self.mpi_u = np.zeros(2 * d.nvars * nf * max(d.nmpiinterfaces, 1))

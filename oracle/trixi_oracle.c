@@ -311,6 +311,153 @@ static void numflux(const eqn_t *eq, int flux_id, const double *ul, const double
     }
 }
 
+/* ---- normal-direction versions (curved meshes) -------------------------------------------------- */
+/* flux(u, normal_direction, eq) compressible_euler_3d.jl:449-463 */
+static inline void euler_flux_normal(const eqn_t *eq, const double *u, const double *n, double *f) {
+    int nd = eq->nd;
+    double rho, v[3], p;
+    euler_cons2prim(eq, u, &rho, v, &p);
+    double v_normal = 0.0;
+    for (int d = 0; d < nd; ++d) v_normal += v[d] * n[d];
+    double rho_v_normal = rho * v_normal;
+    f[0] = rho_v_normal;
+    for (int d = 0; d < nd; ++d) f[1 + d] = rho_v_normal * v[d] + p * n[d];
+    f[nd + 1] = (u[nd + 1] + p) * v_normal;
+}
+
+/* flux_ranocha(u_ll, u_rr, normal_direction, eq) compressible_euler_3d.jl:795-828 */
+static inline void euler_flux_ranocha_normal(const eqn_t *eq, const double *ul, const double *ur, const double *n,
+                                             double *f) {
+    int nd = eq->nd;
+    double rho_ll, v_ll[3], p_ll, rho_rr, v_rr[3], p_rr;
+    euler_cons2prim(eq, ul, &rho_ll, v_ll, &p_ll);
+    euler_cons2prim(eq, ur, &rho_rr, v_rr, &p_rr);
+    double v_dot_n_ll = 0.0, v_dot_n_rr = 0.0;
+    for (int d = 0; d < nd; ++d) {
+        v_dot_n_ll += v_ll[d] * n[d];
+        v_dot_n_rr += v_rr[d] * n[d];
+    }
+    double rho_mean = ln_mean(rho_ll, rho_rr);
+    double inv_rho_p_mean = p_ll * p_rr * inv_ln_mean(rho_ll * p_rr, rho_rr * p_ll);
+    double v_avg[3], vsq = 0.0;
+    for (int d = 0; d < nd; ++d) {
+        v_avg[d] = 0.5 * (v_ll[d] + v_rr[d]);
+        vsq += v_ll[d] * v_rr[d];
+    }
+    double p_avg = 0.5 * (p_ll + p_rr);
+    double velocity_square_avg = 0.5 * vsq;
+    double f1 = rho_mean * 0.5 * (v_dot_n_ll + v_dot_n_rr);
+    f[0] = f1;
+    for (int d = 0; d < nd; ++d) f[1 + d] = f1 * v_avg[d] + p_avg * n[d];
+    f[nd + 1] = f1 * (velocity_square_avg + inv_rho_p_mean * eq->inv_gm1) +
+                0.5 * (p_ll * v_dot_n_rr + p_rr * v_dot_n_ll);
+}
+
+static inline double vec_norm(int nd, const double *n) {
+    double s = 0.0;
+    for (int d = 0; d < nd; ++d) s += n[d] * n[d];
+    return sqrt(s);
+}
+
+static inline void phys_flux_normal(const eqn_t *eq, const double *u, const double *n, double *f) {
+    if (is_euler(eq)) {
+        euler_flux_normal(eq, u, n, f);
+    } else { /* linear_scalar_advection_2d.jl:233-238 */
+        double a = 0.0;
+        for (int d = 0; d < eq->nd; ++d) a += eq->a[d] * n[d];
+        f[0] = a * u[0];
+    }
+}
+
+/* two-point numerical flux with a (non-normalised) normal vector */
+static void numflux_normal(const eqn_t *eq, int flux_id, const double *ul, const double *ur, const double *n,
+                           double *f) {
+    int nv = eq->nv, nd = eq->nd;
+    switch (flux_id) {
+    case TRIXI_B200_FLUX_CENTRAL: {
+        double fl[MAXV], fr[MAXV];
+        phys_flux_normal(eq, ul, n, fl);
+        phys_flux_normal(eq, ur, n, fr);
+        for (int v = 0; v < nv; ++v) f[v] = 0.5 * (fl[v] + fr[v]);
+        return;
+    }
+    case TRIXI_B200_FLUX_LLF:
+    case TRIXI_B200_FLUX_LLF_NAIVE: {
+        double fl[MAXV], fr[MAXV], lam;
+        phys_flux_normal(eq, ul, n, fl);
+        phys_flux_normal(eq, ur, n, fr);
+        if (is_euler(eq)) {
+            /* max_abs_speed_naive :1135-1153, max_abs_speed :1180-1199 */
+            double rho_ll, v_ll[3], p_ll, rho_rr, v_rr[3], p_rr;
+            euler_cons2prim(eq, ul, &rho_ll, v_ll, &p_ll);
+            euler_cons2prim(eq, ur, &rho_rr, v_rr, &p_rr);
+            double vl = 0.0, vr = 0.0;
+            for (int d = 0; d < nd; ++d) {
+                vl += v_ll[d] * n[d];
+                vr += v_rr[d] * n[d];
+            }
+            double c_ll = sqrt(eq->gamma * p_ll / rho_ll), c_rr = sqrt(eq->gamma * p_rr / rho_rr);
+            double norm_ = vec_norm(nd, n);
+            lam = flux_id == TRIXI_B200_FLUX_LLF_NAIVE ? fmax(fabs(vl), fabs(vr)) + fmax(c_ll, c_rr) * norm_
+                                                       : fmax(fabs(vl) + c_ll * norm_, fabs(vr) + c_rr * norm_);
+        } else { /* linear_scalar_advection_2d.jl:241-246 */
+            double a = 0.0;
+            for (int d = 0; d < nd; ++d) a += eq->a[d] * n[d];
+            lam = fabs(a);
+        }
+        for (int v = 0; v < nv; ++v) f[v] = 0.5 * (fl[v] + fr[v]) + (-0.5 * lam * (ur[v] - ul[v]));
+        return;
+    }
+    case TRIXI_B200_FLUX_HLL_DAVIS:
+    case TRIXI_B200_FLUX_HLL_NAIVE: { /* compressible_euler_3d.jl:1220-1237, 1263-1285 */
+        double rho_ll, v_ll[3], p_ll, rho_rr, v_rr[3], p_rr;
+        euler_cons2prim(eq, ul, &rho_ll, v_ll, &p_ll);
+        euler_cons2prim(eq, ur, &rho_rr, v_rr, &p_rr);
+        double vl = 0.0, vr = 0.0;
+        for (int d = 0; d < nd; ++d) {
+            vl += v_ll[d] * n[d];
+            vr += v_rr[d] * n[d];
+        }
+        double norm_ = vec_norm(nd, n);
+        double c_ll = sqrt(eq->gamma * p_ll / rho_ll) * norm_, c_rr = sqrt(eq->gamma * p_rr / rho_rr) * norm_;
+        double lmin, lmax;
+        if (flux_id == TRIXI_B200_FLUX_HLL_NAIVE) {
+            lmin = vl - c_ll;
+            lmax = vr + c_rr;
+        } else {
+            lmin = fmin(vl - c_ll, vr - c_rr);
+            lmax = fmax(vl + c_ll, vr + c_rr);
+        }
+        if (lmin >= 0 && lmax >= 0) {
+            phys_flux_normal(eq, ul, n, f);
+        } else if (lmax <= 0 && lmin <= 0) {
+            phys_flux_normal(eq, ur, n, f);
+        } else {
+            double fl[MAXV], fr[MAXV];
+            phys_flux_normal(eq, ul, n, fl);
+            phys_flux_normal(eq, ur, n, fr);
+            double inv = 1.0 / (lmax - lmin);
+            double factor_ll = lmax * inv, factor_rr = lmin * inv, factor_diss = lmin * lmax * inv;
+            for (int v = 0; v < nv; ++v)
+                f[v] = factor_ll * fl[v] - factor_rr * fr[v] + factor_diss * (ur[v] - ul[v]);
+        }
+        return;
+    }
+    case TRIXI_B200_FLUX_RANOCHA:
+    case TRIXI_B200_FLUX_RANOCHA_TURBO:
+        euler_flux_ranocha_normal(eq, ul, ur, n, f);
+        return;
+    case TRIXI_B200_FLUX_GODUNOV: { /* linear_scalar_advection_2d.jl:262-275 */
+        double a = 0.0;
+        for (int d = 0; d < nd; ++d) a += eq->a[d] * n[d];
+        f[0] = a >= 0 ? a * ul[0] : a * ur[0];
+        return;
+    }
+    default:
+        for (int v = 0; v < nv; ++v) f[v] = NAN;
+    }
+}
+
 /* ---- initial conditions used as Dirichlet data ----------------------------------------------------- */
 static void ic_eval(const eqn_t *eq, int ic, const double *x, double t, double *u) {
     int nd = eq->nd;
@@ -403,6 +550,30 @@ static void boundary_flux(const eqn_t *eq, int bc, int ic, int surface_flux, con
             for (int v = 0; v < eq->nv; ++v) f[v] = -f[v];
         } else {
             euler_slip_wall_normal(eq, u_inner, nrm, f);
+        }
+    } else {
+        for (int v = 0; v < eq->nv; ++v) f[v] = NAN;
+    }
+}
+
+/* boundary flux for curved meshes: bc(u_inner, normal, direction, x, t, surface_flux, eq)
+ * (dgsem_structured/dg.jl:124-165) */
+static void boundary_flux_normal(const eqn_t *eq, int bc, int ic, int surface_flux, const double *u_inner,
+                                 const double *n, int direction, const double *x, double t, double *f) {
+    if (bc == TRIXI_B200_BC_DIRICHLET) { /* equations.jl:164-183 */
+        double ub[MAXV];
+        ic_eval(eq, ic, x, t, ub);
+        if (direction % 2 == 0)
+            numflux_normal(eq, surface_flux, u_inner, ub, n, f);
+        else
+            numflux_normal(eq, surface_flux, ub, u_inner, n, f);
+    } else if (bc == TRIXI_B200_BC_SLIP_WALL) { /* compressible_euler_3d.jl:398-414 */
+        if (direction % 2 == 1) {
+            double mn[3] = {-n[0], -n[1], eq->nd == 3 ? -n[2] : 0.0};
+            euler_slip_wall_normal(eq, u_inner, mn, f);
+            for (int v = 0; v < eq->nv; ++v) f[v] = -f[v];
+        } else {
+            euler_slip_wall_normal(eq, u_inner, n, f);
         }
     } else {
         for (int v = 0; v < eq->nv; ++v) f[v] = NAN;
@@ -751,10 +922,248 @@ void oracle_calc_sources(const trixi_b200_desc *d, double *du, const double *u, 
         }
 }
 
+/* ---- curved meshes: src/solvers/dgsem_structured/ ------------------------------------------------ */
+/* contravariant vector Ja^index at a node (dgsem_structured/dg.jl:27-30); storage [dim, index, node, elem] */
+static inline void get_contravariant_vector(const trixi_b200_desc *d, int index, int64_t node, int64_t e,
+                                            double *ja) {
+    int nd = d->ndims;
+    int64_t nn = ipow(d->nnodes, nd);
+    const double *p = d->contravariant_vectors + (int64_t)nd * nd * (node + nn * e) + (int64_t)nd * index;
+    for (int dim = 0; dim < nd; ++dim) ja[dim] = p[dim];
+}
+
+/* weak_form_kernel! dgsem_structured/dg_3d.jl:36-89 / dg_2d.jl:85-124 */
+static void weak_form_kernel_curved(const trixi_b200_desc *d, const eqn_t *eq, double *du, const double *u,
+                                    int64_t e) {
+    int n = d->nnodes, nd = d->ndims, nv = d->nvars;
+    int n3 = nd == 3 ? n : 1;
+    const double *Dhat = d->derivative_hat;
+    int stride[3] = {1, n, n * n};
+    for (int k = 0; k < n3; ++k)
+        for (int j = 0; j < n; ++j)
+            for (int i = 0; i < n; ++i) {
+                int idx[3] = {i, j, k};
+                int64_t node = i + n * (j + n * k);
+                const double *un = u + (int64_t)nv * node;
+                double fl[3][MAXV];
+                for (int o = 0; o < nd; ++o) phys_flux(eq, un, o, fl[o]);
+                for (int a = 0; a < nd; ++a) {
+                    double ja[3], cf[MAXV];
+                    get_contravariant_vector(d, a, node, e, ja);
+                    for (int v = 0; v < nv; ++v) {
+                        double s = ja[0] * fl[0][v] + ja[1] * fl[1][v];
+                        if (nd == 3) s += ja[2] * fl[2][v];
+                        cf[v] = s;
+                    }
+                    for (int ii = 0; ii < n; ++ii) {
+                        double w = Dhat[ii + n * idx[a]];
+                        double *t = du + (int64_t)nv * (node + (ii - idx[a]) * stride[a]);
+                        for (int v = 0; v < nv; ++v) t[v] = t[v] + w * cf[v];
+                    }
+                }
+            }
+}
+
+/* flux_differencing_kernel! dgsem_structured/dg_3d.jl:94-175 / dg_2d.jl:126-190 */
+static void flux_differencing_kernel_curved(const trixi_b200_desc *d, const eqn_t *eq, double *du, const double *u,
+                                            int64_t e) {
+    int n = d->nnodes, nd = d->ndims, nv = d->nvars;
+    int n3 = nd == 3 ? n : 1;
+    const double *Ds = d->derivative_split;
+    int stride[3] = {1, n, n * n};
+    for (int k = 0; k < n3; ++k)
+        for (int j = 0; j < n; ++j)
+            for (int i = 0; i < n; ++i) {
+                int idx[3] = {i, j, k};
+                int64_t node = i + n * (j + n * k);
+                const double *un = u + nv * node;
+                for (int a = 0; a < nd; ++a) {
+                    double ja_node[3];
+                    get_contravariant_vector(d, a, node, e, ja_node);
+                    for (int ii = idx[a] + 1; ii < n; ++ii) {
+                        int64_t node2 = node + (ii - idx[a]) * stride[a];
+                        double ja2[3], ja_avg[3], f[MAXV];
+                        get_contravariant_vector(d, a, node2, e, ja2);
+                        for (int dim = 0; dim < nd; ++dim) ja_avg[dim] = 0.5 * (ja_node[dim] + ja2[dim]);
+                        numflux_normal(eq, d->volume_flux, un, u + nv * node2, ja_avg, f);
+                        double w1 = Ds[idx[a] + n * ii], w2 = Ds[ii + n * idx[a]];
+                        for (int v = 0; v < nv; ++v) du[nv * node + v] = du[nv * node + v] + w1 * f[v];
+                        for (int v = 0; v < nv; ++v) du[nv * node2 + v] = du[nv * node2 + v] + w2 * f[v];
+                    }
+                }
+            }
+}
+
+void oracle_calc_volume_integral_curved(const trixi_b200_desc *d, double *du, const double *u) {
+    eqn_t eq = make_eqn(d);
+    int64_t esz = (int64_t)d->nvars * ipow(d->nnodes, d->ndims);
+#pragma omp parallel for schedule(static)
+    for (int64_t e = 0; e < d->nelements; ++e) {
+        if (d->volume_integral == TRIXI_B200_VOLINT_WEAK_FORM)
+            weak_form_kernel_curved(d, &eq, du + e * esz, u + e * esz, e);
+        else
+            flux_differencing_kernel_curved(d, &eq, du + e * esz, u + e * esz, e);
+    }
+}
+
+/* prolong2interfaces! dgsem_structured/dg_3d.jl:619-655: interfaces_u[nv, nf, 2nd, nelem] */
+void oracle_prolong2interfaces_structured(const trixi_b200_desc *d, double *iu, const double *u) {
+    int n = d->nnodes, nd = d->ndims, nv = d->nvars;
+    int nf = ipow(n, nd - 1), nb = nd == 3 ? n : 1;
+    int64_t esz = (int64_t)nv * ipow(n, nd), fsz = (int64_t)nv * nf * 2 * nd;
+#pragma omp parallel for schedule(static)
+    for (int64_t e = 0; e < d->nelements; ++e)
+        for (int b = 0; b < nb; ++b)
+            for (int a = 0; a < n; ++a)
+                for (int o = 0; o < nd; ++o)
+                    for (int side = 0; side < 2; ++side) {
+                        int vn = face_to_volume_node(nd, n, o, side ? n - 1 : 0, a, b);
+                        for (int v = 0; v < nv; ++v)
+                            iu[e * fsz + v + nv * ((a + n * b) + nf * (2 * o + side))] = u[e * esz + nv * vn + v];
+                    }
+}
+
+/* calc_interface_flux! dgsem_structured/dg_3d.jl:657-753 */
+void oracle_calc_interface_flux_structured(const trixi_b200_desc *d, double *sfv, const double *iu) {
+    eqn_t eq = make_eqn(d);
+    int n = d->nnodes, nd = d->ndims, nv = d->nvars;
+    int nf = ipow(n, nd - 1), nb = nd == 3 ? n : 1;
+    int64_t nn = ipow(n, nd), fsz = (int64_t)nv * nf * 2 * nd;
+#pragma omp parallel for schedule(static)
+    for (int64_t right = 0; right < d->nelements; ++right)
+        for (int o = 0; o < nd; ++o) {
+            int64_t left = d->left_neighbors[o + nd * right] - 1;
+            if (left < 0) continue;
+            int right_direction = 2 * o + 1, left_direction = 2 * o; /* 0-based */
+            for (int b = 0; b < nb; ++b)
+                for (int a = 0; a < n; ++a) {
+                    int fn = a + n * b;
+                    double ul[MAXV], ur[MAXV], f[MAXV], ja[3], nrm[3] = {0, 0, 0};
+                    for (int v = 0; v < nv; ++v) {
+                        ul[v] = iu[left * fsz + v + nv * (fn + nf * right_direction)];
+                        ur[v] = iu[right * fsz + v + nv * (fn + nf * left_direction)];
+                    }
+                    int vn = face_to_volume_node(nd, n, o, 0, a, b); /* first layer of the right element */
+                    double ij = d->inverse_jacobian[vn + nn * right];
+                    double sign_jacobian = (ij > 0) - (ij < 0);
+                    get_contravariant_vector(d, o, vn, right, ja);
+                    for (int dim = 0; dim < nd; ++dim) nrm[dim] = sign_jacobian * ja[dim];
+                    numflux_normal(&eq, d->surface_flux, ul, ur, nrm, f);
+                    for (int v = 0; v < nv; ++v) {
+                        double fv = sign_jacobian * f[v];
+                        sfv[left * fsz + v + nv * (fn + nf * right_direction)] = fv;
+                        sfv[right * fsz + v + nv * (fn + nf * left_direction)] = fv;
+                    }
+                }
+        }
+}
+
+/* calc_boundary_flux! dgsem_structured/dg_3d.jl:755-935 + calc_boundary_flux_by_direction! dg.jl:124-165;
+ * the boundary faces come as the direction-sorted list of the descriptor */
+void oracle_calc_boundary_flux_structured(const trixi_b200_desc *d, double *sfv, const double *iu, double t) {
+    eqn_t eq = make_eqn(d);
+    int n = d->nnodes, nd = d->ndims, nv = d->nvars;
+    int nf = ipow(n, nd - 1), nb = nd == 3 ? n : 1;
+    int64_t nn = ipow(n, nd), fsz = (int64_t)nv * nf * 2 * nd;
+    int64_t first = 0;
+    for (int direction = 1; direction <= 2 * nd; ++direction) {
+        int64_t cnt = d->n_boundaries_per_direction[direction - 1];
+        int bc = d->boundary_conditions[direction - 1], ic = d->boundary_ic[direction - 1];
+        int o = (direction - 1) / 2;
+#pragma omp parallel for schedule(static)
+        for (int64_t B = first; B < first + cnt; ++B) {
+            int64_t e = d->boundary_neighbor_ids[B] - 1;
+            for (int b = 0; b < nb; ++b)
+                for (int a = 0; a < n; ++a) {
+                    int fn = a + n * b;
+                    int vn = face_to_volume_node(nd, n, o, direction % 2 == 1 ? 0 : n - 1, a, b);
+                    double ui[MAXV], f[MAXV], ja[3], nrm[3] = {0, 0, 0};
+                    for (int v = 0; v < nv; ++v) ui[v] = iu[e * fsz + v + nv * (fn + nf * (direction - 1))];
+                    const double *x = d->node_coordinates + (int64_t)nd * (vn + nn * e);
+                    double ij = d->inverse_jacobian[vn + nn * e];
+                    double sign_jacobian = (ij > 0) - (ij < 0);
+                    get_contravariant_vector(d, o, vn, e, ja);
+                    for (int dim = 0; dim < nd; ++dim) nrm[dim] = sign_jacobian * ja[dim];
+                    boundary_flux_normal(&eq, bc, ic, d->surface_flux, ui, nrm, direction, x, t, f);
+                    for (int v = 0; v < nv; ++v) sfv[e * fsz + v + nv * (fn + nf * (direction - 1))] = sign_jacobian * f[v];
+                }
+        }
+        first += cnt;
+    }
+}
+
+/* apply_jacobian! dgsem_structured/dg_3d.jl:937-956 */
+void oracle_apply_jacobian_curved(const trixi_b200_desc *d, double *du) {
+    int nv = d->nvars;
+    int64_t nn = ipow(d->nnodes, d->ndims);
+#pragma omp parallel for schedule(static)
+    for (int64_t e = 0; e < d->nelements; ++e)
+        for (int64_t q = 0; q < nn; ++q) {
+            double factor = -d->inverse_jacobian[q + nn * e];
+            for (int v = 0; v < nv; ++v) du[nv * (q + nn * e) + v] *= factor;
+        }
+}
+
+/* rhs_hyperbolic! dgsem_structured/dg.jl:41-94; interfaces_u doubles as the work array [nv,nf,2nd,nelem] */
+void oracle_rhs_structured(const trixi_b200_desc *d, double *du, const double *u, double t, double *interfaces_u,
+                           double *sfv) {
+    oracle_set_zero(d, du);
+    oracle_calc_volume_integral_curved(d, du, u);
+    oracle_prolong2interfaces_structured(d, interfaces_u, u);
+    oracle_calc_interface_flux_structured(d, sfv, interfaces_u);
+    if (d->nboundaries > 0) oracle_calc_boundary_flux_structured(d, sfv, interfaces_u, t);
+    oracle_calc_surface_integral(d, du, sfv); /* shared with TreeMesh (dg_3d.jl:1337) */
+    oracle_apply_jacobian_curved(d, du);
+    oracle_calc_sources(d, du, u, t);
+}
+
+/* max_dt for curved meshes stepsize_dg3d.jl:79-123 (constant speed: :125-160), stepsize_dg2d.jl */
+double oracle_max_dt_curved(const trixi_b200_desc *d, const double *u) {
+    eqn_t eq = make_eqn(d);
+    int nv = d->nvars, nd = d->ndims;
+    int64_t nn = ipow(d->nnodes, nd);
+    double max_lambda = 0.0;
+    int nanflag = 0;
+#pragma omp parallel for schedule(static) reduction(max : max_lambda) reduction(| : nanflag)
+    for (int64_t e = 0; e < d->nelements; ++e) {
+        double ml[3] = {0, 0, 0};
+        for (int64_t q = 0; q < nn; ++q) {
+            double lam[3] = {0, 0, 0};
+            if (is_euler(&eq)) {
+                double rho, v[3], p;
+                euler_cons2prim(&eq, u + nv * (q + nn * e), &rho, v, &p);
+                double c = sqrt(eq.gamma * p / rho);
+                for (int dd = 0; dd < nd; ++dd) lam[dd] = fabs(v[dd]) + c;
+            } else {
+                for (int dd = 0; dd < nd; ++dd) lam[dd] = fabs(eq.a[dd]);
+            }
+            double inv_jacobian = fabs(d->inverse_jacobian[q + nn * e]);
+            for (int a = 0; a < nd; ++a) {
+                double ja[3], s = 0.0;
+                get_contravariant_vector(d, a, q, e, ja);
+                for (int dim = 0; dim < nd; ++dim) s += ja[dim] * lam[dim];
+                double val = inv_jacobian * fabs(s);
+                if (isnan(val)) nanflag = 1;
+                ml[a] = fmax(ml[a], val);
+            }
+        }
+        double s = 0.0;
+        for (int a = 0; a < nd; ++a) s += ml[a];
+        if (s > max_lambda) max_lambda = s;
+    }
+    if (nanflag) return NAN;
+    double max_scaled_speed = fmax(DBL_TRUE_MIN, max_lambda);
+    return 2 / (d->nnodes * max_scaled_speed);
+}
+
 /* rhs_hyperbolic! dgsem_tree/dg_2d.jl:113-186.  Work arrays: interfaces_u [2,nv,nf,I],
  * boundaries_u [2,nv,nf,B], sfv [nv,nf,2nd,nelem] (owned by the caller = the cache). */
 void oracle_rhs(const trixi_b200_desc *d, double *du, const double *u, double t, double *interfaces_u,
                 double *boundaries_u, double *sfv) {
+    if (d->mesh_kind == TRIXI_B200_MESH_STRUCTURED) {
+        oracle_rhs_structured(d, du, u, t, interfaces_u, sfv);
+        return;
+    }
     oracle_set_zero(d, du);
     oracle_calc_volume_integral(d, du, u);
     oracle_prolong2interfaces(d, interfaces_u, u);
@@ -794,6 +1203,7 @@ void oracle_rhs_parallel_part2(const trixi_b200_desc *d, double *du, const doubl
 
 /* max_dt stepsize_dg3d.jl:8-32 (constant_speed False), stepsize_dg2d.jl:60-75 (True) */
 double oracle_max_dt(const trixi_b200_desc *d, const double *u) {
+    if (d->mesh_kind != TRIXI_B200_MESH_TREE) return oracle_max_dt_curved(d, u);
     eqn_t eq = make_eqn(d);
     int nv = d->nvars, nd = d->ndims;
     int64_t nn = ipow(d->nnodes, nd);

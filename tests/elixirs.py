@@ -205,3 +205,95 @@ ELIXIRS = {e.name: e for e in [
            [0.006614198043413566, 0.0006614198043973507, 0.001322839608837334, 0.000165354951256802],
            "test/test_tree_2d_euler.jl:117-135"),
 ]}
+
+
+# ---- StructuredMesh (curved) -----------------------------------------------------------------------------
+def _warped_mapping_3d(xi_, eta_, zeta_):
+    # examples/structured_3d_dgsem/elixir_euler_free_stream.jl:17-41
+    pi = np.pi
+    xi = 1.5 * xi_ + 1.5
+    eta = 1.5 * eta_ + 1.5
+    zeta = 1.5 * zeta_ + 1.5
+    y = eta + 3 / 8 * (np.cos(1.5 * pi * (2 * xi - 3) / 3) * np.cos(0.5 * pi * (2 * eta - 3) / 3)
+                       * np.cos(0.5 * pi * (2 * zeta - 3) / 3))
+    x = xi + 3 / 8 * (np.cos(0.5 * pi * (2 * xi - 3) / 3) * np.cos(2 * pi * (2 * y - 3) / 3)
+                      * np.cos(0.5 * pi * (2 * zeta - 3) / 3))
+    z = zeta + 3 / 8 * (np.cos(0.5 * pi * (2 * x - 3) / 3) * np.cos(pi * (2 * y - 3) / 3)
+                        * np.cos(0.5 * pi * (2 * zeta - 3) / 3))
+    return x, y, z
+
+
+def _nonperiodic_curved_mapping_3d(xi, eta, zeta):
+    # examples/structured_3d_dgsem/elixir_euler_source_terms_nonperiodic_curved.jl:26-47
+    pi = np.pi
+    y = eta + 1 / 6 * (np.cos(1.5 * pi * (2 * xi - 3) / 3) * np.cos(0.5 * pi * (2 * eta - 3) / 3)
+                       * np.cos(0.5 * pi * (2 * zeta - 3) / 3))
+    x = xi + 1 / 6 * (np.cos(0.5 * pi * (2 * xi - 3) / 3) * np.cos(2 * pi * (2 * y - 3) / 3)
+                      * np.cos(0.5 * pi * (2 * zeta - 3) / 3))
+    z = zeta + 1 / 6 * (np.cos(0.5 * pi * (2 * x - 3) / 3) * np.cos(pi * (2 * y - 3) / 3)
+                        * np.cos(0.5 * pi * (2 * zeta - 3) / 3))
+    return x + 1, y + 1, z + 1
+
+
+def _structured3d_free_stream():
+    eq = T.CompressibleEulerEquations3D(1.4)
+    solver = T.DGSEM(polydeg=3, surface_flux=T.FluxLaxFriedrichs(T.max_abs_speed_naive),
+                     volume_integral=T.VolumeIntegralWeakForm())
+    mesh = T.StructuredMesh((4, 4, 4), _warped_mapping_3d, periodicity=True)
+    return T.SemidiscretizationHyperbolic(mesh, eq, T.initial_condition_constant, solver)
+
+
+def _structured3d_ec():
+    eq = T.CompressibleEulerEquations3D(5 / 3)
+    solver = T.DGSEM(polydeg=5, surface_flux=T.flux_ranocha,
+                     volume_integral=T.VolumeIntegralFluxDifferencing(T.flux_ranocha))
+    mesh = T.StructuredMesh((4, 4, 4), _warped_mapping_3d, periodicity=True)
+    return T.SemidiscretizationHyperbolic(mesh, eq, T.initial_condition_weak_blast_wave, solver)
+
+
+def _structured3d_source_terms():
+    eq = T.CompressibleEulerEquations3D(1.4)
+    solver = T.DGSEM(polydeg=3, surface_flux=T.FluxLaxFriedrichs(T.max_abs_speed_naive),
+                     volume_integral=T.VolumeIntegralWeakForm())
+    faces = (lambda s, t: (0.0 * s, s + 1.0, t + 1.0), lambda s, t: (2.0 + 0.0 * s, s + 1.0, t + 1.0),
+             lambda s, t: (s + 1.0, 0.0 * s, t + 1.0), lambda s, t: (s + 1.0, 2.0 + 0.0 * s, t + 1.0),
+             lambda s, t: (s + 1.0, t + 1.0, 0.0 * s), lambda s, t: (s + 1.0, t + 1.0, 2.0 + 0.0 * s))
+    mesh = T.StructuredMesh((4, 4, 4), faces=faces, periodicity=True)
+    return T.SemidiscretizationHyperbolic(mesh, eq, T.initial_condition_convergence_test, solver,
+                                          source_terms=T.source_terms_convergence_test)
+
+
+def _structured3d_source_terms_nonperiodic_curved():
+    eq = T.CompressibleEulerEquations3D(1.4)
+    solver = T.DGSEM(polydeg=3, surface_flux=T.FluxLaxFriedrichs(T.max_abs_speed_naive),
+                     volume_integral=T.VolumeIntegralWeakForm())
+    mesh = T.StructuredMesh((4, 4, 4), _nonperiodic_curved_mapping_3d, periodicity=False)
+    return T.SemidiscretizationHyperbolic(mesh, eq, T.initial_condition_convergence_test, solver,
+                                          source_terms=T.source_terms_convergence_test,
+                                          boundary_conditions=T.BoundaryConditionDirichlet(
+                                              T.initial_condition_convergence_test))
+
+
+ELIXIRS.update({e.name: e for e in [
+    Elixir("structured_3d_euler_free_stream", _structured3d_free_stream, (0.0, 1.0), 1.3,
+           [2.8815700334367128e-15, 9.361915278236651e-15, 9.95614203619935e-15, 1.6809941842374106e-14,
+            1.4815037041566735e-14],
+           [4.1300296516055823e-14, 2.0444756998472258e-13, 1.0133560657266116e-13, 2.0627943797535409e-13,
+            2.8954616482224083e-13], "test/test_structured_3d.jl:72-98", rtol=0, atol=5e-12),
+    Elixir("structured_3d_euler_ec", _structured3d_ec, (0.0, 0.25), 1.0,
+           [0.011367083018614027, 0.007022020327490176, 0.006759580335962235, 0.006820337637760632,
+            0.02912659127566544],
+           [0.2761764220925329, 0.20286331858055706, 0.18763944865434593, 0.19313636558790004,
+            0.707563913727584], "test/test_structured_3d.jl:200-220"),
+    Elixir("structured_3d_euler_source_terms", _structured3d_source_terms, (0.0, 5.0), 0.6,
+           [0.010385936842224346, 0.009776048833895767, 0.00977604883389591, 0.009776048833895733,
+            0.01506687097416608],
+           [0.03285848350791731, 0.0321792316408982, 0.032179231640894645, 0.032179231640895534,
+            0.0655408023333299], "test/test_structured_3d.jl:50-70"),
+    Elixir("structured_3d_euler_source_terms_nonperiodic_curved", _structured3d_source_terms_nonperiodic_curved,
+           (0.0, 5.0), 0.6,
+           [0.0032940531178824463, 0.003275679548217804, 0.0030020672748714084, 0.00324007343451744,
+            0.005721986362580164],
+           [0.03156756290660656, 0.033597629023726316, 0.02095783702361409, 0.03353574465232212,
+            0.05873635745032857], "test/test_structured_3d.jl:125-148"),
+]})

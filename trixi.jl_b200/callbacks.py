@@ -96,8 +96,17 @@ def calc_error_norms(u, t, semi, analyzer=None):
     wprod = w
     for _ in range(nd - 1):
         wprod = np.multiply.outer(wprod, w)
-    volume_jacobian = (1.0 / cache.elements.inverse_jacobian) ** nd  # dgsem_tree/dg.jl:8-10
-    weight = wprod[..., None] * volume_jacobian  # [na.., nelem]
+    if getattr(semi, "is_curved", False):
+        # analysis_dg3d.jl:163-216: the Jacobian is interpolated to the analysis nodes, |J| weights the
+        # quadrature and the total volume is accumulated the same way
+        jac = 1.0 / cache.elements.inverse_jacobian  # [n.., nelem]
+        jac_local = multiply_dimensionwise(V, jac[None])[0]
+        weight = wprod[..., None] * np.abs(jac_local)
+        total_volume = weight.sum()
+    else:
+        volume_jacobian = (1.0 / cache.elements.inverse_jacobian) ** nd  # dgsem_tree/dg.jl:8-10
+        weight = wprod[..., None] * volume_jacobian  # [na.., nelem]
+        total_volume = None
     l2sq = (diff**2 * weight[None]).reshape(eq.nvars, -1).sum(axis=1)
     linf = np.abs(diff).reshape(eq.nvars, -1).max(axis=1)
     if semi.world_size > 1 and semi.comm is not None:
@@ -109,7 +118,7 @@ def calc_error_norms(u, t, semi, analyzer=None):
         semi.comm.all_reduce(t2, op=semi.comm.ReduceOp.SUM)
         semi.comm.all_reduce(tinf, op=semi.comm.ReduceOp.MAX)
         l2sq, linf = t2.cpu().numpy(), tinf.cpu().numpy()
-    l2 = np.sqrt(l2sq / mesh.total_volume())
+    l2 = np.sqrt(l2sq / (mesh.total_volume() if total_volume is None else total_volume))
     return l2, linf
 
 

@@ -14,10 +14,12 @@ import time
 import numpy as np
 
 from . import _abi
-from .containers import init_boundaries, init_elements, init_interfaces, partition_cells
+from .containers import (BoundaryContainer, InterfaceContainer, MPIInterfaceContainer, init_boundaries,
+                         init_elements, init_interfaces, partition_cells)
 from .equations import (BC_DIRICHLET, BC_PERIODIC, BC_SLIP_WALL, IC_NONE, SRC_NONE,
                         BoundaryConditionDirichlet, boundary_condition_periodic, resolve_flux)
 from .mesh import TreeMesh
+from .structured import StructuredMesh, init_elements_structured
 
 MESH_TREE, MESH_STRUCTURED, MESH_P4EST = 0, 1, 2
 
@@ -58,9 +60,53 @@ def create_cache(mesh, equations, solver, rank=0, world_size=1):
         cache.elements = init_elements(mesh, solver.basis, cells)
         cache.interfaces, cache.mpi_interfaces = init_interfaces(mesh, first, last, world_size)
         cache.boundaries = init_boundaries(mesh, cache.elements, solver.basis, first, last)
+    elif isinstance(mesh, StructuredMesh):
+        if world_size != 1:
+            raise NotImplementedError("StructuredMesh runs on a single rank (the reference has no MPI path for it)")
+        # create_cache dgsem_structured/dg.jl:11-25
+        cache.first_element, cache.last_element = 0, mesh.ncells
+        cache.elements = init_elements_structured(mesh, solver.basis)
+        cache.interfaces = InterfaceContainer()
+        cache.interfaces.ninterfaces = 0  # faces are found through left_neighbors (dg_3d.jl:657-689)
+        cache.interfaces.neighbor_ids = np.zeros((2, 0), dtype=np.int64)
+        cache.interfaces.orientations = np.zeros(0, dtype=np.int64)
+        cache.mpi_interfaces = MPIInterfaceContainer()
+        cache.mpi_interfaces.nmpiinterfaces = 0
+        cache.boundaries = _structured_boundaries(mesh, cache.elements)
     else:
         raise TypeError(f"unsupported mesh type {type(mesh).__name__}")
     return cache
+
+
+def _structured_boundaries(mesh, elements):
+    """Domain-boundary faces of a StructuredMesh as a direction-sorted list (the reference loops over the
+    boundary cells of each direction, dgsem_structured/dg_3d.jl:755-935)."""
+    nd = mesh.ndims
+    cells = mesh.cells_per_dimension
+    lin = np.arange(1, mesh.ncells + 1, dtype=np.int64).reshape(cells, order="F")
+    ids, counts = [], []
+    for direction in range(2 * nd):
+        d = direction // 2
+        if mesh.periodicity[d]:
+            counts.append(0)
+            continue
+        idx = [slice(None)] * nd
+        idx[d] = 0 if direction % 2 == 0 else cells[d] - 1
+        el = lin[tuple(idx)].ravel(order="F")
+        ids.append(el)
+        counts.append(el.shape[0])
+    bc = BoundaryContainer()
+    bc.neighbor_ids = np.concatenate(ids).astype(np.int64) if ids else np.zeros(0, dtype=np.int64)
+    orient, side = [], []
+    for direction, c in enumerate(counts):
+        orient += [direction // 2 + 1] * c
+        side += [2 if direction % 2 == 0 else 1] * c
+    bc.orientations = np.array(orient, dtype=np.int64)
+    bc.neighbor_sides = np.array(side, dtype=np.int64)
+    bc.node_coordinates = np.zeros((nd, 0))
+    bc.n_boundaries_per_direction = np.array(counts + [0] * (6 - len(counts)), dtype=np.int64)
+    bc.nboundaries = int(bc.neighbor_ids.shape[0])
+    return bc
 
 
 def _digest_boundary_conditions(boundary_conditions, mesh):
@@ -131,6 +177,10 @@ class SemidiscretizationHyperbolic:
     def ndofsglobal(self):
         return self.mesh.ncells * self.solver.nnodes ** self.mesh.ndims
 
+    @property
+    def is_curved(self):
+        return isinstance(self.mesh, StructuredMesh)
+
     def u_shape(self):
         return (self.equations.nvars,) + (self.solver.nnodes,) * self.mesh.ndims + (self.nelements,)
 
@@ -147,7 +197,7 @@ class SemidiscretizationHyperbolic:
         d.abi_version = _abi.ABI_VERSION
         d.device = self.device
         d.ndims, d.nvars, d.nnodes = self.mesh.ndims, eq.nvars, dg.nnodes
-        d.mesh_kind = MESH_TREE
+        d.mesh_kind = MESH_STRUCTURED if isinstance(self.mesh, StructuredMesh) else MESH_TREE
         d.nelements = self.nelements
         d.equation = eq.eq_id
         d.volume_integral = dg.volume_integral.kind
@@ -164,6 +214,9 @@ class SemidiscretizationHyperbolic:
         h.set_f64("inverse_weights", dg.basis.inverse_weights)
         h.set_f64("inverse_jacobian", cache.elements.inverse_jacobian)
         h.set_f64("node_coordinates", cache.elements.node_coordinates)
+        if isinstance(self.mesh, StructuredMesh):
+            h.set_f64("contravariant_vectors", cache.elements.contravariant_vectors)
+            h.set_i64("left_neighbors", cache.elements.left_neighbors)
         d.ninterfaces = cache.interfaces.ninterfaces
         h.set_i64("interface_neighbor_ids", cache.interfaces.neighbor_ids)
         h.set_i64("interface_orientations", cache.interfaces.orientations)
@@ -173,7 +226,8 @@ class SemidiscretizationHyperbolic:
             h.set_i64("boundary_neighbor_ids", b.neighbor_ids)
             h.set_i64("boundary_orientations", b.orientations)
             h.set_i64("boundary_neighbor_sides", b.neighbor_sides)
-            h.set_f64("boundary_node_coordinates", b.node_coordinates)
+            if b.node_coordinates.size:
+                h.set_f64("boundary_node_coordinates", b.node_coordinates)
         for i in range(6):
             d.n_boundaries_per_direction[i] = int(b.n_boundaries_per_direction[i])
         d.nmortars = 0
