@@ -147,11 +147,20 @@ class OracleBackend:
     # stage-level ------------------------------------------------------------------------------------
     def calc_volume_integral(self):
         self.lib.oracle_set_zero(self.holder.byref(), _p(self.vec[1]))
+        if self.desc.mesh_kind != 0:
+            self.lib.oracle_calc_volume_integral_curved(self.holder.byref(), _p(self.vec[1]), _p(self.vec[0]))
+            return
         self.lib.oracle_calc_volume_integral(self.holder.byref(), _p(self.vec[1]), _p(self.vec[0]))
 
     def calc_surface_fluxes(self, t):
         h = self.holder.byref()
         self.sfv[:] = np.nan
+        if self.desc.mesh_kind == 1:
+            self.lib.oracle_prolong2interfaces_structured(h, _p(self.interfaces_u), _p(self.vec[0]))
+            self.lib.oracle_calc_interface_flux_structured(h, _p(self.sfv), _p(self.interfaces_u))
+            if self.desc.nboundaries > 0:
+                self.lib.oracle_calc_boundary_flux_structured(h, _p(self.sfv), _p(self.interfaces_u), C.c_double(t))
+            return
         self.lib.oracle_prolong2interfaces(h, _p(self.interfaces_u), _p(self.vec[0]))
         self.lib.oracle_calc_interface_flux(h, _p(self.sfv), _p(self.interfaces_u))
         if self.desc.nboundaries > 0:

@@ -52,7 +52,8 @@ RHS_CASES = ["tree_3d_euler_ec", "tree_3d_euler_source_terms", "tree_3d_euler_so
              "tree_3d_euler_convergence", "tree_3d_euler_taylor_green_vortex", "tree_3d_euler_ec_chandrashekar",
              "tree_3d_euler_ec_kennedy_gruber", "tree_3d_euler_ec_shima_etal", "tree_2d_advection_basic",
              "tree_2d_euler_source_terms", "tree_2d_euler_source_terms_nonperiodic", "tree_2d_euler_ec",
-             "tree_2d_euler_density_wave"]
+             "tree_2d_euler_density_wave", "structured_3d_euler_free_stream", "structured_3d_euler_ec",
+             "structured_3d_euler_source_terms", "structured_3d_euler_source_terms_nonperiodic_curved"]
 
 
 @pytest.mark.parametrize("name", RHS_CASES)
@@ -75,7 +76,8 @@ def test_rhs_matches_oracle(name, state, oracle_module):
     assert _rel_err(du_gpu, du_ref) <= _rhs_tolerance(oracle_module, semi, u, t, du_ref)
 
 
-@pytest.mark.parametrize("name", ["tree_3d_euler_ec", "tree_3d_euler_source_terms", "tree_2d_euler_source_terms_nonperiodic"])
+@pytest.mark.parametrize("name", ["tree_3d_euler_ec", "tree_3d_euler_source_terms", "tree_2d_euler_source_terms_nonperiodic",
+                                  "structured_3d_euler_ec", "structured_3d_euler_source_terms_nonperiodic_curved"])
 def test_stage_level_parity(name, oracle_module):
     """calc_volume_integral! and the surface flux stages separately, like the reference's kernel parity
     tests (test/test_performance_specializations_3d.jl:49-89)."""
@@ -99,7 +101,8 @@ def test_stage_level_parity(name, oracle_module):
     assert _rel_err(sfv_gpu[m], sfv_ref[m]) <= RHS_TOL
 
 
-@pytest.mark.parametrize("name", ["tree_3d_euler_ec", "tree_2d_advection_basic", "tree_2d_euler_density_wave"])
+@pytest.mark.parametrize("name", ["tree_3d_euler_ec", "tree_2d_advection_basic", "tree_2d_euler_density_wave",
+                                  "structured_3d_euler_ec", "structured_3d_euler_source_terms_nonperiodic_curved"])
 def test_max_dt_matches_oracle(name, oracle_module):
     semi = ELIXIRS[name].semi()
     u = _random_admissible_state(semi, seed=4)
@@ -142,7 +145,9 @@ def test_step_2n_matches_oracle(name, oracle_module):
 GOLDEN_GPU = ["tree_3d_euler_ec", "tree_3d_euler_ec_constant", "tree_3d_euler_source_terms",
               "tree_3d_euler_convergence", "tree_3d_euler_taylor_green_vortex", "tree_3d_euler_density_pulse",
               "tree_2d_advection_basic", "tree_2d_euler_source_terms", "tree_2d_euler_source_terms_nonperiodic",
-              "tree_2d_euler_ec", "tree_2d_euler_density_wave"]
+              "tree_2d_euler_ec", "tree_2d_euler_density_wave", "structured_3d_euler_free_stream",
+              "structured_3d_euler_ec", "structured_3d_euler_source_terms",
+              "structured_3d_euler_source_terms_nonperiodic_curved"]
 
 
 @pytest.mark.parametrize("name", GOLDEN_GPU)

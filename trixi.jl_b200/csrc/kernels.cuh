@@ -32,8 +32,10 @@ struct KParams {
                                              // can take it as an operand without a load or a register
     double inv_weight0;
     // geometry
-    const double *inverse_jacobian;  // [nelem]
-    const double *node_coordinates;  // [nd, n^d, nelem]
+    const double *inverse_jacobian;       // Tree: [nelem]; curved: [n^d, nelem]
+    const double *node_coordinates;       // [nd, n^d, nelem]
+    const double *contravariant_vectors;  // curved: [nd (dim), nd (index), n^d, nelem]
+    int curved;                           // 0: Cartesian TreeMesh kernels, 1: curved (Structured/P4est) kernels
     // connectivity (1-based int64 as uploaded)
     const long long *if_neighbors;  // [2, I]
     const long long *if_orient;     // [I]
@@ -410,5 +412,276 @@ __global__ void __launch_bounds__(ElemCfg<EQ, N>::THREADS) k_max_dt(const KParam
     }
 }
 
+
+// =====================================================================================================
+// Curved meshes (StructuredMesh; src/solvers/dgsem_structured/).  Same launch structure; the geometry
+// enters through the contravariant vectors Ja^i[dim] (dg.jl:27-30) and the nodal inverse Jacobian.
+// =====================================================================================================
+template <int ND, int NN>
+TB_DEV void load_ja(const KParams &P, int index, long long node, long long e, double (&ja)[ND]) {
+    const double *p = P.contravariant_vectors + ((e * NN + node) * ND + index) * ND;
+#pragma unroll
+    for (int d = 0; d < ND; ++d) ja[d] = p[d];
+}
+
+// prolong2interfaces! + calc_interface_flux! (dgsem_structured/dg_3d.jl:619-753): the normal is the
+// contravariant vector of the right element's first node layer times sign(inverse_jacobian)
+template <class EQ, int N>
+__global__ void __launch_bounds__(256) k_interface_flux_curved(const KParams P) {
+    constexpr int ND = EQ::NDIMS, NV = EQ::NVARS, NF = ipow(N, ND - 1), NN = ipow(N, ND);
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long I = gid / NF;
+    const int fn = (int)(gid % NF);
+    if (I >= P.ninterfaces) return;
+    const EQ eq(P.eq);
+    const long long left = P.if_neighbors[2 * I] - 1, right = P.if_neighbors[2 * I + 1] - 1;
+    const int o = (int)P.if_orient[I] - 1;
+    const int nl = face_to_volume_node<ND, N>(o, N - 1, fn), nr = face_to_volume_node<ND, N>(o, 0, fn);
+    double ul[NV], ur[NV], f[NV], nrm[ND];
+    const double *pl = P.u + (left * NN + nl) * NV, *pr = P.u + (right * NN + nr) * NV;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+        ul[v] = pl[v];
+        ur[v] = pr[v];
+    }
+    const double ij = P.inverse_jacobian[right * NN + nr];
+    const double sign_jacobian = ij > 0 ? 1.0 : (ij < 0 ? -1.0 : 0.0);
+    load_ja<ND, NN>(P, o, nr, right, nrm);
+#pragma unroll
+    for (int d = 0; d < ND; ++d) nrm[d] *= sign_jacobian;
+    eq.numflux_normal(P.surface_flux, ul, ur, nrm, f);
+    double *sl = P.sfv + ((left * (2 * ND) + (2 * o + 1)) * NF + fn) * NV;
+    double *sr = P.sfv + ((right * (2 * ND) + (2 * o)) * NF + fn) * NV;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+        const double fv = sign_jacobian * f[v];
+        sl[v] = fv;
+        sr[v] = fv;
+    }
+}
+
+// calc_boundary_flux! (dgsem_structured/dg_3d.jl:755-935, dg.jl:124-165)
+template <class EQ, int N>
+__global__ void __launch_bounds__(256) k_boundary_flux_curved(const KParams P) {
+    constexpr int ND = EQ::NDIMS, NV = EQ::NVARS, NF = ipow(N, ND - 1), NN = ipow(N, ND);
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long B = gid / NF;
+    const int fn = (int)(gid % NF);
+    if (B >= P.nboundaries) return;
+    const EQ eq(P.eq);
+    const long long element = P.bd_neighbor[B] - 1;
+    const int direction = P.bd_direction[B];  // 1-based
+    const int o = (direction - 1) / 2;
+    const int vn = face_to_volume_node<ND, N>(o, direction % 2 == 1 ? 0 : N - 1, fn);
+    double ui[NV], f[NV], x[ND], nrm[ND];
+    const double *pu = P.u + (element * NN + vn) * NV;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) ui[v] = pu[v];
+#pragma unroll
+    for (int d = 0; d < ND; ++d) x[d] = P.node_coordinates[(element * NN + vn) * ND + d];
+    const double ij = P.inverse_jacobian[element * NN + vn];
+    const double sign_jacobian = ij > 0 ? 1.0 : (ij < 0 ? -1.0 : 0.0);
+    load_ja<ND, NN>(P, o, vn, element, nrm);
+#pragma unroll
+    for (int d = 0; d < ND; ++d) nrm[d] *= sign_jacobian;
+    boundary_flux_normal(eq, P.bc[direction - 1], P.bc_ic[direction - 1], P.surface_flux, ui, nrm, direction, x, P.t, f);
+    double *s = P.sfv + ((element * (2 * ND) + (direction - 1)) * NF + fn) * NV;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) s[v] = sign_jacobian * f[v];
+}
+
+// element kernel for curved meshes: weak_form_kernel! / flux_differencing_kernel!
+// (dgsem_structured/dg_3d.jl:36-175), calc_surface_integral! (dg_3d.jl:1337-1394, shared with TreeMesh),
+// apply_jacobian! with the nodal inverse Jacobian (dgsem_structured/dg_3d.jl:937-956), sources, 2N stage
+template <class EQ, int N, int VOLINT, bool WITH_SURFACE>
+__global__ void __launch_bounds__(ElemCfg<EQ, N>::THREADS) k_element_curved(const KParams P) {
+    using C = ElemCfg<EQ, N>;
+    constexpr int ND = C::ND, NV = C::NV, NN = C::NN, EPB = C::EPB, US = C::US, NF = ipow(N, ND - 1);
+    extern __shared__ double smem[];
+    double *s_u = smem;                 // [EPB*NN][US]
+    double *s_D = s_u + EPB * NN * US;  // [N*N]
+    double *s_f = s_D + N * N;          // weak form: contravariant fluxes [ND][EPB*NN][US]
+
+    const EQ eq(P.eq);
+    const int tid = threadIdx.x;
+    const long long e0 = (long long)blockIdx.x * EPB;
+    const int nel = (int)min((long long)EPB, P.nelements - e0);
+    const double *Dsrc = VOLINT == TRIXI_B200_VOLINT_WEAK_FORM ? P.dhat : P.dsplit;
+    for (int q = tid; q < N * N; q += C::THREADS) s_D[q] = Dsrc[q];
+    {
+        const double *src = P.u + e0 * NN * NV;
+        const int total = nel * NN * NV;
+        for (int q = tid; q < total; q += C::THREADS) {
+            const int node = q / NV, v = q - node * NV;
+            s_u[node * US + v] = src[q];
+        }
+    }
+    __syncthreads();
+
+    const int le = tid / NN, node = tid - le * NN;
+    const bool active = le < nel;
+    const long long e = e0 + le;
+    int idx[3];
+    idx[0] = node % N;
+    idx[1] = (node / N) % N;
+    idx[2] = ND == 3 ? node / (N * N) : 0;
+    const int stride[3] = {1, N, N * N};
+    const double *ue = s_u + le * NN * US;
+    double un[NV], acc[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+        un[v] = active ? ue[node * US + v] : 0.0;
+        acc[v] = 0.0;
+    }
+
+    if constexpr (VOLINT == TRIXI_B200_VOLINT_WEAK_FORM) {
+        if (active) {
+            double fl[ND][NV];
+#pragma unroll
+            for (int d = 0; d < ND; ++d) eq.flux(un, d, fl[d]);
+#pragma unroll
+            for (int a = 0; a < ND; ++a) {
+                double ja[ND];
+                load_ja<ND, NN>(P, a, node, e, ja);
+#pragma unroll
+                for (int v = 0; v < NV; ++v) {
+                    double sum = ja[0] * fl[0][v];
+#pragma unroll
+                    for (int d = 1; d < ND; ++d) sum += ja[d] * fl[d][v];
+                    s_f[(a * EPB * NN + le * NN + node) * US + v] = sum;
+                }
+            }
+        }
+        __syncthreads();
+        if (active) {
+#pragma unroll
+            for (int d = 0; d < ND; ++d) {
+                const int base = node - idx[d] * stride[d];
+#pragma unroll
+                for (int l = 0; l < N; ++l) {
+                    const double w = s_D[idx[d] + N * l];
+                    const double *f = s_f + (d * EPB * NN + le * NN + base + l * stride[d]) * US;
+#pragma unroll
+                    for (int v = 0; v < NV; ++v) acc[v] = fma(w, f[v], acc[v]);
+                }
+            }
+        }
+    } else {
+        if (active) {
+#pragma unroll
+            for (int d = 0; d < ND; ++d) {
+                const int base = node - idx[d] * stride[d];
+                double ja_node[ND];
+                load_ja<ND, NN>(P, d, node, e, ja_node);
+#pragma unroll 1
+                for (int l = 0; l < N; ++l) {
+                    if (l == idx[d]) continue;
+                    const int node2 = base + l * stride[d];
+                    double up[NV], f[NV], ja2[ND], ja_avg[ND];
+                    const double *pu = ue + node2 * US;
+#pragma unroll
+                    for (int v = 0; v < NV; ++v) up[v] = pu[v];
+                    load_ja<ND, NN>(P, d, node2, e, ja2);
+                    // 0.5 * (Ja_lower + Ja_upper): same operand order on both ends
+#pragma unroll
+                    for (int q = 0; q < ND; ++q) ja_avg[q] = l > idx[d] ? 0.5 * (ja_node[q] + ja2[q]) : 0.5 * (ja2[q] + ja_node[q]);
+                    if (l > idx[d])
+                        eq.numflux_normal(P.volume_flux, un, up, ja_avg, f);
+                    else
+                        eq.numflux_normal(P.volume_flux, up, un, ja_avg, f);
+                    const double w = s_D[idx[d] + N * l];
+#pragma unroll
+                    for (int v = 0; v < NV; ++v) acc[v] = fma(w, f[v], acc[v]);
+                }
+            }
+        }
+    }
+    if (!active) return;
+
+    if constexpr (WITH_SURFACE) {
+        const double *sf = P.sfv + e * (2 * ND) * NF * NV;
+#pragma unroll
+        for (int d = 0; d < ND; ++d) {
+            int fn;
+            if constexpr (ND == 2)
+                fn = d == 0 ? idx[1] : idx[0];
+            else
+                fn = d == 0 ? idx[1] + N * idx[2] : (d == 1 ? idx[0] + N * idx[2] : idx[0] + N * idx[1]);
+            if (idx[d] == 0) {
+                const double *sq = sf + ((2 * d) * NF + fn) * NV;
+#pragma unroll
+                for (int v = 0; v < NV; ++v) acc[v] = acc[v] - sq[v] * P.inv_weight0;
+            }
+            if (idx[d] == N - 1) {
+                const double *sq = sf + ((2 * d + 1) * NF + fn) * NV;
+#pragma unroll
+                for (int v = 0; v < NV; ++v) acc[v] = acc[v] + sq[v] * P.inv_weight0;
+            }
+        }
+        const double factor = -P.inverse_jacobian[e * NN + node];
+#pragma unroll
+        for (int v = 0; v < NV; ++v) acc[v] *= factor;
+        if (P.source_terms != TRIXI_B200_SRC_NONE) {
+            double x[ND], sv[NV];
+#pragma unroll
+            for (int d = 0; d < ND; ++d) x[d] = P.node_coordinates[(e * NN + node) * ND + d];
+            eq.source_terms(P.source_terms, un, x, P.t, sv);
+#pragma unroll
+            for (int v = 0; v < NV; ++v) acc[v] += sv[v];
+        }
+    }
+    const long long off = (e * NN + node) * NV;
+    if (P.mode == 0) {
+#pragma unroll
+        for (int v = 0; v < NV; ++v) P.du[off + v] = acc[v];
+    } else {
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            const double tmp = P.rk_a == 0.0 ? acc[v] : acc[v] - P.u_tmp[off + v] * P.rk_a;
+            P.u_tmp[off + v] = tmp;
+            P.u_out[off + v] = un[v] + tmp * P.rk_b_dt;
+        }
+    }
+}
+
+// max_dt for curved meshes (stepsize_dg3d.jl:79-123): per node inv_jacobian * |Ja^i . lambda|, per-direction
+// maxima over the element's nodes, their sum, global max
+template <class EQ, int N>
+__global__ void __launch_bounds__(ElemCfg<EQ, N>::THREADS) k_max_dt_curved(const KParams P) {
+    using C = ElemCfg<EQ, N>;
+    constexpr int ND = C::ND, NV = C::NV, NN = C::NN, EPB = C::EPB;
+    __shared__ unsigned long long s_lam[ND][EPB];
+    const EQ eq(P.eq);
+    const int tid = threadIdx.x;
+    const long long e0 = (long long)blockIdx.x * EPB;
+    const int le = tid / NN, node = tid - le * NN;
+    const long long e = e0 + le;
+    if (tid < ND * EPB) (&s_lam[0][0])[tid] = 0ull;
+    __syncthreads();
+    if (e < P.nelements) {
+        double un[NV], lam[ND];
+        const double *pu = P.u + (e * NN + node) * NV;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) un[v] = pu[v];
+        eq.max_abs_speeds(un, lam);
+        const double inv_jacobian = fabs(P.inverse_jacobian[e * NN + node]);
+#pragma unroll
+        for (int a = 0; a < ND; ++a) {
+            double ja[ND];
+            load_ja<ND, NN>(P, a, node, e, ja);
+            double sum = ja[0] * lam[0];
+#pragma unroll
+            for (int d = 1; d < ND; ++d) sum += ja[d] * lam[d];
+            atomicMax(&s_lam[a][le], cfl_encode(inv_jacobian * fabs(sum)));
+        }
+    }
+    __syncthreads();
+    if (tid < EPB && e0 + tid < P.nelements) {
+        double sum = 0.0;
+#pragma unroll
+        for (int d = 0; d < ND; ++d) sum += __longlong_as_double((long long)s_lam[d][tid]);
+        atomicMax(P.cfl_key, cfl_encode(sum));
+    }
+}
 
 }  // namespace tb

@@ -27,8 +27,10 @@ void launch_interface_flux(const KParams &P, cudaStream_t s) {
     if (total == 0) return;
     const int threads = 256;
     const unsigned blocks = (unsigned)((total + threads - 1) / threads);
-    if (HasFastRanocha<EQ>::value && P.kernel_path == 0 &&
-        (P.surface_flux == TRIXI_B200_FLUX_RANOCHA || P.surface_flux == TRIXI_B200_FLUX_RANOCHA_TURBO))
+    if (P.curved)
+        k_interface_flux_curved<EQ, N><<<blocks, threads, 0, s>>>(P);
+    else if (HasFastRanocha<EQ>::value && P.kernel_path == 0 &&
+             (P.surface_flux == TRIXI_B200_FLUX_RANOCHA || P.surface_flux == TRIXI_B200_FLUX_RANOCHA_TURBO))
         k_interface_flux<EQ, N, true><<<blocks, threads, 0, s>>>(P);
     else
         k_interface_flux<EQ, N><<<blocks, threads, 0, s>>>(P);
@@ -41,7 +43,10 @@ void launch_boundary_flux(const KParams &P, cudaStream_t s) {
     if (total == 0) return;
     const int threads = 256;
     const unsigned blocks = (unsigned)((total + threads - 1) / threads);
-    k_boundary_flux<EQ, N><<<blocks, threads, 0, s>>>(P);
+    if (P.curved)
+        k_boundary_flux_curved<EQ, N><<<blocks, threads, 0, s>>>(P);
+    else
+        k_boundary_flux<EQ, N><<<blocks, threads, 0, s>>>(P);
 }
 
 template <class EQ, int N>
@@ -87,6 +92,19 @@ cudaError_t launch_element_variant(const KParams &P, cudaStream_t s) {
                                           (VOLINT == TRIXI_B200_VOLINT_WEAK_FORM
                                                ? (size_t)C::ND * C::EPB * C::NN * C::US
                                                : 0));
+    const unsigned blocks = (unsigned)((P.nelements + C::EPB - 1) / C::EPB);
+    if (P.curved) {
+        auto kern = k_element_curved<EQ, N, VOLINT, WS>;
+        if (smem > 48 * 1024) {
+            static PerDeviceFlag configured;
+            if (!configured.test_and_set()) {
+                cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (err != cudaSuccess) return err;
+            }
+        }
+        kern<<<blocks, C::THREADS, smem, s>>>(P);
+        return cudaSuccess;
+    }
     auto kern = k_element<EQ, N, VOLINT, WS>;
     if (smem > 48 * 1024) {
         static PerDeviceFlag configured;
@@ -95,7 +113,6 @@ cudaError_t launch_element_variant(const KParams &P, cudaStream_t s) {
             if (err != cudaSuccess) return err;
         }
     }
-    const unsigned blocks = (unsigned)((P.nelements + C::EPB - 1) / C::EPB);
     kern<<<blocks, C::THREADS, smem, s>>>(P);
     return cudaSuccess;
 }
@@ -104,7 +121,7 @@ template <class EQ, int N>
 cudaError_t launch_element(const KParams &P, bool with_surface, cudaStream_t s) {
     if (P.nelements == 0) return cudaSuccess;
     if constexpr (std::is_same_v<EQ, Euler<3>> && N == 4) {
-        if (P.kernel_path == 0 && P.volume_integral == TRIXI_B200_VOLINT_FLUX_DIFFERENCING &&
+        if (!P.curved && P.kernel_path == 0 && P.volume_integral == TRIXI_B200_VOLINT_FLUX_DIFFERENCING &&
             (P.volume_flux == TRIXI_B200_FLUX_RANOCHA || P.volume_flux == TRIXI_B200_FLUX_RANOCHA_TURBO))
             return launch_element_euler3d_ranocha_p3(P, with_surface, s);
     }
@@ -121,7 +138,10 @@ void launch_max_dt(const KParams &P, cudaStream_t s) {
     using C = ElemCfg<EQ, N>;
     if (P.nelements == 0) return;
     const unsigned blocks = (unsigned)((P.nelements + C::EPB - 1) / C::EPB);
-    k_max_dt<EQ, N><<<blocks, C::THREADS, 0, s>>>(P);
+    if (P.curved)
+        k_max_dt_curved<EQ, N><<<blocks, C::THREADS, 0, s>>>(P);
+    else
+        k_max_dt<EQ, N><<<blocks, C::THREADS, 0, s>>>(P);
 }
 
 template <class K>
@@ -144,6 +164,13 @@ cudaError_t preload_all() {
     TB_PRELOAD((k_mpi_pack<EQ, N>));
     TB_PRELOAD((k_mpi_interface_flux<EQ, N>));
     TB_PRELOAD((k_max_dt<EQ, N>));
+    TB_PRELOAD((k_max_dt_curved<EQ, N>));
+    TB_PRELOAD((k_interface_flux_curved<EQ, N>));
+    TB_PRELOAD((k_boundary_flux_curved<EQ, N>));
+    TB_PRELOAD((k_element_curved<EQ, N, TRIXI_B200_VOLINT_WEAK_FORM, true>));
+    TB_PRELOAD((k_element_curved<EQ, N, TRIXI_B200_VOLINT_WEAK_FORM, false>));
+    TB_PRELOAD((k_element_curved<EQ, N, TRIXI_B200_VOLINT_FLUX_DIFFERENCING, true>));
+    TB_PRELOAD((k_element_curved<EQ, N, TRIXI_B200_VOLINT_FLUX_DIFFERENCING, false>));
     TB_PRELOAD((k_element<EQ, N, TRIXI_B200_VOLINT_WEAK_FORM, true>));
     TB_PRELOAD((k_element<EQ, N, TRIXI_B200_VOLINT_WEAK_FORM, false>));
     TB_PRELOAD((k_element<EQ, N, TRIXI_B200_VOLINT_FLUX_DIFFERENCING, true>));

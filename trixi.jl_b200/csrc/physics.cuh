@@ -115,6 +115,37 @@ struct Advection {
             f[0] = nan("");
         }
     }
+    TB_DEV double a_dot(const double (&n)[ND]) const {
+        double s = a0 * n[0];
+        if constexpr (ND > 1) s += a1 * n[1];
+        if constexpr (ND > 2) s += a2 * n[2];
+        return s;
+    }
+    // flux(u, normal_direction) (linear_scalar_advection_2d.jl:233-238)
+    TB_DEV void flux_normal(const double (&u)[1], const double (&n)[ND], double (&f)[1]) const {
+        f[0] = a_dot(n) * u[0];
+    }
+    TB_DEV void numflux_normal(int id, const double (&ul)[1], const double (&ur)[1], const double (&n)[ND],
+                               double (&f)[1]) const {
+        const double an = a_dot(n);
+        switch (id) {
+        case TRIXI_B200_FLUX_CENTRAL:
+            f[0] = 0.5 * (an * ul[0] + an * ur[0]);
+            break;
+        case TRIXI_B200_FLUX_LLF:
+        case TRIXI_B200_FLUX_LLF_NAIVE:  // linear_scalar_advection_2d.jl:241-246
+            f[0] = 0.5 * (an * ul[0] + an * ur[0]) + (-0.5 * fabs(an) * (ur[0] - ul[0]));
+            break;
+        case TRIXI_B200_FLUX_GODUNOV:  // :262-275
+            f[0] = an >= 0 ? an * ul[0] : an * ur[0];
+            break;
+        default:
+            f[0] = nan("");
+        }
+    }
+    TB_DEV void slip_wall_normal(const double (&u)[1], const double (&n)[ND], int direction, double (&f)[1]) const {
+        f[0] = nan("");
+    }
     // max_abs_speeds(equation) (linear_scalar_advection_2d.jl:292-294)
     TB_DEV void max_abs_speeds(const double (&u)[1], double (&lam)[ND]) const {
         lam[0] = fabs(a0);
@@ -382,6 +413,147 @@ struct Euler {
         }
     }
 
+    // ---- normal-direction versions (curved meshes) ----
+    // flux(u, normal_direction) (compressible_euler_3d.jl:449-463)
+    TB_DEV void flux_normal(const double (&u)[NVARS], const double (&n)[ND], double (&f)[NVARS]) const {
+        double rho, v[ND], p;
+        cons2prim(u, rho, v, p);
+        double v_normal = 0.0;
+#pragma unroll
+        for (int d = 0; d < ND; ++d) v_normal += v[d] * n[d];
+        const double rho_v_normal = rho * v_normal;
+        f[0] = rho_v_normal;
+#pragma unroll
+        for (int d = 0; d < ND; ++d) f[1 + d] = rho_v_normal * v[d] + p * n[d];
+        f[ND + 1] = (u[ND + 1] + p) * v_normal;
+    }
+    // flux_ranocha(u_ll, u_rr, normal_direction) (compressible_euler_3d.jl:795-828)
+    TB_DEV void flux_ranocha_normal(const double (&ul)[NVARS], const double (&ur)[NVARS], const double (&n)[ND],
+                                    double (&f)[NVARS]) const {
+        double rho_ll, v_ll[ND], p_ll, rho_rr, v_rr[ND], p_rr;
+        cons2prim(ul, rho_ll, v_ll, p_ll);
+        cons2prim(ur, rho_rr, v_rr, p_rr);
+        double v_dot_n_ll = 0.0, v_dot_n_rr = 0.0, v_avg[ND], vsq = 0.0;
+#pragma unroll
+        for (int d = 0; d < ND; ++d) {
+            v_dot_n_ll += v_ll[d] * n[d];
+            v_dot_n_rr += v_rr[d] * n[d];
+            v_avg[d] = 0.5 * (v_ll[d] + v_rr[d]);
+            vsq += v_ll[d] * v_rr[d];
+        }
+        const double rho_mean = ln_mean(rho_ll, rho_rr);
+        const double inv_rho_p_mean = p_ll * p_rr * inv_ln_mean(rho_ll * p_rr, rho_rr * p_ll);
+        const double p_avg = 0.5 * (p_ll + p_rr);
+        const double f1 = rho_mean * 0.5 * (v_dot_n_ll + v_dot_n_rr);
+        f[0] = f1;
+#pragma unroll
+        for (int d = 0; d < ND; ++d) f[1 + d] = f1 * v_avg[d] + p_avg * n[d];
+        f[ND + 1] = f1 * (0.5 * vsq + inv_rho_p_mean * inv_gm1) + 0.5 * (p_ll * v_dot_n_rr + p_rr * v_dot_n_ll);
+    }
+    TB_DEV void numflux_normal(int id, const double (&ul)[NVARS], const double (&ur)[NVARS], const double (&n)[ND],
+                               double (&f)[NVARS]) const {
+        switch (id) {
+        case TRIXI_B200_FLUX_CENTRAL: {
+            double fl[NVARS], fr[NVARS];
+            flux_normal(ul, n, fl);
+            flux_normal(ur, n, fr);
+#pragma unroll
+            for (int v = 0; v < NVARS; ++v) f[v] = 0.5 * (fl[v] + fr[v]);
+            break;
+        }
+        case TRIXI_B200_FLUX_LLF:
+        case TRIXI_B200_FLUX_LLF_NAIVE:
+        case TRIXI_B200_FLUX_HLL_DAVIS:
+        case TRIXI_B200_FLUX_HLL_NAIVE: {
+            double rho_ll, v_ll[ND], p_ll, rho_rr, v_rr[ND], p_rr;
+            cons2prim(ul, rho_ll, v_ll, p_ll);
+            cons2prim(ur, rho_rr, v_rr, p_rr);
+            double vl = 0.0, vr = 0.0, nsq = 0.0;
+#pragma unroll
+            for (int d = 0; d < ND; ++d) {
+                vl += v_ll[d] * n[d];
+                vr += v_rr[d] * n[d];
+                nsq += n[d] * n[d];
+            }
+            const double norm_ = sqrt(nsq);
+            const double c_ll = sqrt(gamma * p_ll / rho_ll), c_rr = sqrt(gamma * p_rr / rho_rr);
+            double fl[NVARS], fr[NVARS];
+            if (id == TRIXI_B200_FLUX_LLF || id == TRIXI_B200_FLUX_LLF_NAIVE) {
+                // max_abs_speed_naive (:1135-1153) / max_abs_speed (:1180-1199)
+                const double lam = id == TRIXI_B200_FLUX_LLF_NAIVE
+                                       ? fmax(fabs(vl), fabs(vr)) + fmax(c_ll, c_rr) * norm_
+                                       : fmax(fabs(vl) + c_ll * norm_, fabs(vr) + c_rr * norm_);
+                flux_normal(ul, n, fl);
+                flux_normal(ur, n, fr);
+#pragma unroll
+                for (int v = 0; v < NVARS; ++v) f[v] = 0.5 * (fl[v] + fr[v]) + (-0.5 * lam * (ur[v] - ul[v]));
+            } else {
+                // min_max_speed_naive (:1220-1237) / min_max_speed_davis (:1263-1285)
+                const double cl = c_ll * norm_, cr = c_rr * norm_;
+                double lmin, lmax;
+                if (id == TRIXI_B200_FLUX_HLL_NAIVE) {
+                    lmin = vl - cl;
+                    lmax = vr + cr;
+                } else {
+                    lmin = fmin(vl - cl, vr - cr);
+                    lmax = fmax(vl + cl, vr + cr);
+                }
+                if (lmin >= 0 && lmax >= 0) {
+                    flux_normal(ul, n, f);
+                } else if (lmax <= 0 && lmin <= 0) {
+                    flux_normal(ur, n, f);
+                } else {
+                    flux_normal(ul, n, fl);
+                    flux_normal(ur, n, fr);
+                    const double inv = 1.0 / (lmax - lmin);
+                    const double factor_ll = lmax * inv, factor_rr = lmin * inv, factor_diss = lmin * lmax * inv;
+#pragma unroll
+                    for (int v = 0; v < NVARS; ++v)
+                        f[v] = factor_ll * fl[v] - factor_rr * fr[v] + factor_diss * (ur[v] - ul[v]);
+                }
+            }
+            break;
+        }
+        case TRIXI_B200_FLUX_RANOCHA:
+        case TRIXI_B200_FLUX_RANOCHA_TURBO:
+            flux_ranocha_normal(ul, ur, n, f);
+            break;
+        default:
+#pragma unroll
+            for (int v = 0; v < NVARS; ++v) f[v] = nan("");
+        }
+    }
+    // boundary_condition_slip_wall(u_inner, normal_direction, direction, ...) for StructuredMesh
+    // (compressible_euler_3d.jl:315-366,398-414)
+    TB_DEV void slip_wall_normal(const double (&u)[NVARS], const double (&n)[ND], int direction,
+                                 double (&f)[NVARS]) const {
+        const double sgn = (direction % 2 == 1) ? -1.0 : 1.0;  // outward normal = sgn * n
+        double nsq = 0.0;
+#pragma unroll
+        for (int d = 0; d < ND; ++d) nsq += n[d] * n[d];
+        const double norm_ = sqrt(nsq);
+        double rho, v[ND], p_local;
+        cons2prim(u, rho, v, p_local);
+        double v_normal = 0.0;
+#pragma unroll
+        for (int d = 0; d < ND; ++d) v_normal += v[d] * (sgn * n[d] / norm_);
+        double p_star;
+        if (v_normal <= 0) {
+            const double sound_speed = sqrt(gamma * p_local / rho);
+            const double base = 1 + 0.5 * (gamma - 1) * v_normal / sound_speed;
+            p_star = base >= 0 ? p_local * pow(base, 2 * gamma * inv_gm1) : 0.0;
+        } else {
+            const double A = 2 / ((gamma + 1) * rho);
+            const double B = p_local * (gamma - 1) / (gamma + 1);
+            p_star = p_local + 0.5 * v_normal / A * (v_normal + sqrt(v_normal * v_normal + 4 * A * (p_local + B)));
+        }
+        // p_star * (sgn n / |n|) * |n|, negated again on the - side: net p_star * n
+        f[0] = 0.0;
+#pragma unroll
+        for (int d = 0; d < ND; ++d) f[1 + d] = p_star * (n[d] / norm_) * norm_;
+        f[ND + 1] = 0.0;
+    }
+
     // max_abs_speeds (compressible_euler_3d.jl:1770-1775)
     TB_DEV void max_abs_speeds(const double (&u)[NVARS], double (&lam)[ND]) const {
         double rho, v[ND], p;
@@ -495,6 +667,26 @@ TB_DEV void boundary_flux(const EQ &eq, int bc, int ic, int surface_flux, const 
             eq.numflux(surface_flux, ub, u_inner, o, f);
     } else if (bc == TRIXI_B200_BC_SLIP_WALL) {
         eq.slip_wall(u_inner, o, direction, f);
+    } else {
+#pragma unroll
+        for (int v = 0; v < EQ::NVARS; ++v) f[v] = nan("");
+    }
+}
+
+// bc(u_inner, normal, direction, x, t, surface_flux, equations) for curved meshes (dgsem_structured/dg.jl:124-165)
+template <class EQ>
+TB_DEV void boundary_flux_normal(const EQ &eq, int bc, int ic, int surface_flux, const double (&u_inner)[EQ::NVARS],
+                                 const double (&n)[EQ::NDIMS], int direction, const double (&x)[EQ::NDIMS], double t,
+                                 double (&f)[EQ::NVARS]) {
+    if (bc == TRIXI_B200_BC_DIRICHLET) {
+        double ub[EQ::NVARS];
+        eq.initial_condition(ic, x, t, ub);
+        if (direction % 2 == 0)
+            eq.numflux_normal(surface_flux, u_inner, ub, n, f);
+        else
+            eq.numflux_normal(surface_flux, ub, u_inner, n, f);
+    } else if (bc == TRIXI_B200_BC_SLIP_WALL) {
+        eq.slip_wall_normal(u_inner, n, direction, f);
     } else {
 #pragma unroll
         for (int v = 0; v < EQ::NVARS; ++v) f[v] = nan("");

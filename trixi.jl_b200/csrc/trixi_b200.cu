@@ -301,8 +301,13 @@ TRIXI_B200_API int trixi_b200_create(const trixi_b200_desc *d, trixi_b200_handle
     if (d->abi_version != TRIXI_B200_ABI_VERSION)
         return fail(nullptr, TRIXI_B200_EINVAL, "descriptor ABI version %d != library %d", d->abi_version,
                     TRIXI_B200_ABI_VERSION);
-    if (d->mesh_kind != TRIXI_B200_MESH_TREE)
+    if (d->mesh_kind != TRIXI_B200_MESH_TREE && d->mesh_kind != TRIXI_B200_MESH_STRUCTURED)
         return fail(nullptr, TRIXI_B200_EINVAL, "mesh kind %d not supported by this build", d->mesh_kind);
+    const bool structured = d->mesh_kind == TRIXI_B200_MESH_STRUCTURED;
+    if (structured && (!d->contravariant_vectors || !d->left_neighbors))
+        return fail(nullptr, TRIXI_B200_EINVAL, "StructuredMesh needs contravariant_vectors and left_neighbors");
+    if (structured && d->world_size > 1)
+        return fail(nullptr, TRIXI_B200_EINVAL, "StructuredMesh is single-rank (as in the reference)");
     if (d->nmortars != 0) return fail(nullptr, TRIXI_B200_EINVAL, "mortars are not supported by this build");
     if (d->volume_integral != TRIXI_B200_VOLINT_WEAK_FORM && d->volume_integral != TRIXI_B200_VOLINT_FLUX_DIFFERENCING)
         return fail(nullptr, TRIXI_B200_EINVAL, "unsupported volume integral type %d", d->volume_integral);
@@ -375,9 +380,25 @@ TRIXI_B200_API int trixi_b200_create(const trixi_b200_desc *d, trixi_b200_handle
     h->ulen = (long long)nv * nn * d->nelements;
     h->sfvlen = (long long)nv * nf * 2 * nd * d->nelements;
 
+    // StructuredMesh: faces are given through left_neighbors (dgsem_structured/containers.jl:8-34); build the
+    // (left, right, orientation) list the interface kernel iterates over
+    std::vector<long long> s_if_neighbors, s_if_orient;
+    long long n_if = d->ninterfaces;
+    if (structured) {
+        for (long long e = 0; e < d->nelements; ++e)
+            for (int o = 0; o < nd; ++o) {
+                const long long left = d->left_neighbors[o + (long long)nd * e];
+                if (left > 0) {
+                    s_if_neighbors.push_back(left);
+                    s_if_neighbors.push_back(e + 1);
+                    s_if_orient.push_back(o + 1);
+                }
+            }
+        n_if = (long long)s_if_orient.size();
+    }
     KParams &P = h->P;
     P.nelements = d->nelements;
-    P.ninterfaces = d->ninterfaces;
+    P.ninterfaces = n_if;
     P.nboundaries = d->nboundaries;
     for (int i = 0; i < 3; ++i) CREATE_TRY(alloc_array(h, (size_t)h->ulen, &h->vec[i]));
     P.u = h->vec[0];
@@ -400,25 +421,40 @@ TRIXI_B200_API int trixi_b200_create(const trixi_b200_desc *d, trixi_b200_handle
     P.inv_weight0 = d->inverse_weights[0];
     for (int q = 0; q < n * n; ++q) P.dsplit_c[q] = d->derivative_split[q];
     P.kernel_path = 0;
-    CREATE_TRY(upload_array(h, d->inverse_jacobian, (size_t)d->nelements, &tmp));
+    CREATE_TRY(upload_array(h, d->inverse_jacobian, (size_t)(structured ? nn * d->nelements : d->nelements), &tmp));
     P.inverse_jacobian = tmp;
+    P.curved = structured ? 1 : 0;
+    P.contravariant_vectors = nullptr;
+    if (structured) {
+        CREATE_TRY(upload_array(h, d->contravariant_vectors, (size_t)(nd * nd * nn * d->nelements), &tmp));
+        P.contravariant_vectors = tmp;
+    }
     CREATE_TRY(upload_array(h, d->node_coordinates, (size_t)(nd * nn * d->nelements), &tmp));
     P.node_coordinates = tmp;
 
     long long *itmp = nullptr;
     static_assert(sizeof(long long) == sizeof(int64_t), "int64 layout");
-    CREATE_TRY(upload_array(h, (const long long *)d->interface_neighbor_ids, (size_t)(2 * d->ninterfaces), &itmp));
-    P.if_neighbors = itmp;
-    CREATE_TRY(upload_array(h, (const long long *)d->interface_orientations, (size_t)d->ninterfaces, &itmp));
-    P.if_orient = itmp;
+    if (structured) {
+        CREATE_TRY(upload_array(h, s_if_neighbors.data(), s_if_neighbors.size(), &itmp));
+        P.if_neighbors = itmp;
+        CREATE_TRY(upload_array(h, s_if_orient.data(), s_if_orient.size(), &itmp));
+        P.if_orient = itmp;
+    } else {
+        CREATE_TRY(upload_array(h, (const long long *)d->interface_neighbor_ids, (size_t)(2 * d->ninterfaces), &itmp));
+        P.if_neighbors = itmp;
+        CREATE_TRY(upload_array(h, (const long long *)d->interface_orientations, (size_t)d->ninterfaces, &itmp));
+        P.if_orient = itmp;
+    }
     CREATE_TRY(upload_array(h, (const long long *)d->boundary_neighbor_ids, (size_t)d->nboundaries, &itmp));
     P.bd_neighbor = itmp;
     CREATE_TRY(upload_array(h, (const long long *)d->boundary_orientations, (size_t)d->nboundaries, &itmp));
     P.bd_orient = itmp;
     CREATE_TRY(upload_array(h, (const long long *)d->boundary_neighbor_sides, (size_t)d->nboundaries, &itmp));
     P.bd_side = itmp;
-    CREATE_TRY(upload_array(h, d->boundary_node_coordinates, (size_t)(nd * nf * d->nboundaries), &tmp));
-    P.bd_coords = tmp;
+    if (!structured) {  // curved kernels read the element's own node coordinates
+        CREATE_TRY(upload_array(h, d->boundary_node_coordinates, (size_t)(nd * nf * d->nboundaries), &tmp));
+        P.bd_coords = tmp;
+    }
     {
         // boundaries are sorted by direction (containers_3d.jl:398-468): expand the counts to a per-face direction
         std::vector<int> dir((size_t)d->nboundaries);
