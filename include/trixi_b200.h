@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define TRIXI_B200_ABI_VERSION 1
+#define TRIXI_B200_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define TRIXI_B200_API __attribute__((visibility("default")))
@@ -126,7 +126,9 @@ typedef struct trixi_b200_desc {
     int64_t ninterfaces;
     const int64_t *interface_neighbor_ids;  /* [2, ninterfaces] 1-based, 1 = left/-, 2 = right/+ */
     const int64_t *interface_orientations;  /* [ninterfaces] in 1..ndims */
-    const int64_t *interface_node_indices;  /* P4est only: [2, ninterfaces, ndims] symbols 0..5, else NULL */
+    const int64_t *interface_node_indices;  /* P4est only: [ndims, 2, ninterfaces] node_indices tuples
+                                               (dgsem_p4est/containers.jl:226-252) encoded :begin 0, :end 1,
+                                               :i_forward 2, :i_backward 3, :j_forward 4, :j_backward 5 */
 
     /* boundary container (containers_3d.jl:284-295), sorted by direction */
     int64_t nboundaries;
@@ -155,6 +157,10 @@ typedef struct trixi_b200_desc {
     const int64_t *mpi_orientations;       /* [nmpiinterfaces] */
     const int64_t *mpi_neighbor_ranks;     /* [nmpiinterfaces] peer rank of each face; faces are sorted by
                                               (peer rank, global interface id) on both sides */
+
+    /* P4est boundary container (dgsem_p4est/containers.jl:302-345): node_indices [ndims, nboundaries], same
+     * encoding as interface_node_indices; boundaries sorted by boundary name = direction */
+    const int64_t *boundary_node_indices;
 } trixi_b200_desc;
 
 typedef struct trixi_b200_handle trixi_b200_handle;

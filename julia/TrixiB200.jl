@@ -104,6 +104,7 @@ struct Desc
     mpi_local_sides::Ptr{Int64}
     mpi_orientations::Ptr{Int64}
     mpi_neighbor_ranks::Ptr{Int64}
+    boundary_node_indices::Ptr{Int64}
 end
 
 # ---- the backend object ---------------------------------------------------------------------------------
@@ -142,7 +143,7 @@ function B200(semi::SemidiscretizationHyperbolic; device = -1)
     nbd = ntuple(i -> i <= 2 * ndims(mesh) ? Int64(bd.n_boundaries_per_direction[i]) : Int64(0), 6)
     handle = Ref{Ptr{Cvoid}}(C_NULL)
     GC.@preserve D_split D_hat inv_w el ifc bd begin   # the library copies during `create` only
-        desc = Desc(1, device, ndims(mesh), nvariables(equations), nnodes(dg), MESH_TREE,
+        desc = Desc(2, device, ndims(mesh), nvariables(equations), nnodes(dg), MESH_TREE,
                     nelements(dg, cache), equation_id(equations), volint, volflux,
                     flux_id(dg.surface_integral.surface_flux), source_id(semi.source_terms),
                     bc_tags, bc_ics, 0, equation_params(equations),
@@ -152,7 +153,7 @@ function B200(semi::SemidiscretizationHyperbolic; device = -1)
                     nboundaries(dg, cache), pointer(bd.neighbor_ids), pointer(bd.orientations),
                     pointer(bd.neighbor_sides), pointer(bd.node_coordinates), nbd,
                     0, C_NULL, C_NULL, C_NULL, C_NULL, C_NULL, C_NULL, C_NULL, C_NULL,
-                    0, 1, 0, C_NULL, C_NULL, C_NULL, C_NULL)
+                    0, 1, 0, C_NULL, C_NULL, C_NULL, C_NULL, C_NULL)
         rc = ccall((:trixi_b200_create, libtrixi_b200), Cint, (Ref{Desc}, Ref{Ptr{Cvoid}}), desc, handle)
     end
     check(nothing, rc)

@@ -155,6 +155,12 @@ class OracleBackend:
     def calc_surface_fluxes(self, t):
         h = self.holder.byref()
         self.sfv[:] = np.nan
+        if self.desc.mesh_kind == 2:
+            self.lib.oracle_prolong2interfaces_p4est(h, _p(self.interfaces_u), _p(self.vec[0]))
+            self.lib.oracle_calc_interface_flux_p4est(h, _p(self.sfv), _p(self.interfaces_u))
+            if self.desc.nboundaries > 0:
+                self.lib.oracle_calc_boundary_flux_p4est(h, _p(self.sfv), _p(self.vec[0]), C.c_double(t))
+            return
         if self.desc.mesh_kind == 1:
             self.lib.oracle_prolong2interfaces_structured(h, _p(self.interfaces_u), _p(self.vec[0]))
             self.lib.oracle_calc_interface_flux_structured(h, _p(self.sfv), _p(self.interfaces_u))

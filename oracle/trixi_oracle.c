@@ -447,6 +447,36 @@ static void numflux_normal(const eqn_t *eq, int flux_id, const double *ul, const
     case TRIXI_B200_FLUX_RANOCHA_TURBO:
         euler_flux_ranocha_normal(eq, ul, ur, n, f);
         return;
+    case TRIXI_B200_FLUX_KENNEDY_GRUBER:
+    case TRIXI_B200_FLUX_SHIMA_ETAL: { /* compressible_euler_3d.jl:602-627 / :512-547 */
+        double rho_ll, v_ll[3], p_ll, rho_rr, v_rr[3], p_rr;
+        euler_cons2prim(eq, ul, &rho_ll, v_ll, &p_ll);
+        euler_cons2prim(eq, ur, &rho_rr, v_rr, &p_rr);
+        double rho_avg = 0.5 * (rho_ll + rho_rr), p_avg = 0.5 * (p_ll + p_rr), v_avg[3];
+        for (int d = 0; d < nd; ++d) v_avg[d] = 0.5 * (v_ll[d] + v_rr[d]);
+        if (flux_id == TRIXI_B200_FLUX_KENNEDY_GRUBER) {
+            double e_avg = 0.5 * (ul[nd + 1] / rho_ll + ur[nd + 1] / rho_rr);
+            double v_dot_n_avg = 0.0;
+            for (int d = 0; d < nd; ++d) v_dot_n_avg += v_avg[d] * n[d];
+            double f1 = rho_avg * v_dot_n_avg;
+            f[0] = f1;
+            for (int d = 0; d < nd; ++d) f[1 + d] = f1 * v_avg[d] + p_avg * n[d];
+            f[nd + 1] = f1 * e_avg + p_avg * v_dot_n_avg;
+        } else {
+            double vl = 0.0, vr = 0.0, vsq = 0.0;
+            for (int d = 0; d < nd; ++d) {
+                vl += v_ll[d] * n[d];
+                vr += v_rr[d] * n[d];
+                vsq += v_ll[d] * v_rr[d];
+            }
+            double v_dot_n_avg = 0.5 * (vl + vr), velocity_square_avg = 0.5 * vsq;
+            double f1 = rho_avg * v_dot_n_avg;
+            f[0] = f1;
+            for (int d = 0; d < nd; ++d) f[1 + d] = f1 * v_avg[d] + p_avg * n[d];
+            f[nd + 1] = f1 * velocity_square_avg + p_avg * v_dot_n_avg * eq->inv_gm1 + 0.5 * (p_ll * vr + p_rr * vl);
+        }
+        return;
+    }
     case TRIXI_B200_FLUX_GODUNOV: { /* linear_scalar_advection_2d.jl:262-275 */
         double a = 0.0;
         for (int d = 0; d < nd; ++d) a += eq->a[d] * n[d];
@@ -1156,12 +1186,188 @@ double oracle_max_dt_curved(const trixi_b200_desc *d, const double *u) {
     return 2 / (d->nnodes * max_scaled_speed);
 }
 
+/* ---- P4estMesh: src/solvers/dgsem_p4est/ ------------------------------------------------------------- */
+/* node index along one axis from a symbolic index (index_to_start_step_3d dg_3d.jl:61-80 in closed form);
+ * encoding :begin 0, :end 1, :i_forward 2, :i_backward 3, :j_forward 4, :j_backward 5 */
+static inline int p4_index(int sym, int n, int i, int j) {
+    switch (sym) {
+    case 0: return 0;
+    case 1: return n - 1;
+    case 2: return i;
+    case 3: return n - 1 - i;
+    case 4: return j;
+    default: return n - 1 - j;
+    }
+}
+/* indices2direction dgsem_p4est/containers.jl (direction 1..6 of a face from its index tuple), 0-based here */
+static inline int p4_direction(int nd, const int64_t *idx) {
+    for (int c = 0; c < nd; ++c) {
+        if (idx[c] == 0) return 2 * c;
+        if (idx[c] == 1) return 2 * c + 1;
+    }
+    return -1;
+}
+static inline int64_t p4_volume_node(int nd, int n, const int64_t *idx, int i, int j) {
+    int64_t node = 0, stride = 1;
+    for (int c = 0; c < nd; ++c) {
+        node += stride * p4_index((int)idx[c], n, i, j);
+        stride *= n;
+    }
+    return node;
+}
+/* surface_indices dg_3d.jl:82-92: the two (3D) / one (2D) varying symbols of an index tuple */
+static inline void p4_surface_node(int nd, int n, const int64_t *idx, int i, int j, int *fn) {
+    int s[2] = {0, 0}, k = 0;
+    for (int c = 0; c < nd; ++c)
+        if (idx[c] > 1) s[k++] = p4_index((int)idx[c], n, i, j);
+    *fn = nd == 3 ? s[0] + n * s[1] : s[0];
+}
+
+/* get_normal_direction dgsem_p4est/dg.jl:74-86: outward normal = +-Ja^orientation */
+static inline void p4_normal(const trixi_b200_desc *d, int direction0, int64_t node, int64_t e, double *nrm) {
+    double ja[3] = {0, 0, 0};
+    get_contravariant_vector(d, direction0 / 2, node, e, ja);
+    double sgn = direction0 % 2 == 0 ? -1.0 : 1.0;
+    for (int dim = 0; dim < d->ndims; ++dim) nrm[dim] = sgn * ja[dim];
+}
+
+/* prolong2interfaces! dgsem_p4est/dg_3d.jl:94-183: interfaces_u[2, nv, nf, I], both sides stored at the
+ * primary's face node (i, j) */
+void oracle_prolong2interfaces_p4est(const trixi_b200_desc *d, double *iu, const double *u) {
+    int n = d->nnodes, nd = d->ndims, nv = d->nvars;
+    int nf = ipow(n, nd - 1), nb = nd == 3 ? n : 1;
+    int64_t esz = (int64_t)nv * ipow(n, nd);
+#pragma omp parallel for schedule(static)
+    for (int64_t I = 0; I < d->ninterfaces; ++I)
+        for (int side = 0; side < 2; ++side) {
+            int64_t e = d->interface_neighbor_ids[2 * I + side] - 1;
+            const int64_t *idx = d->interface_node_indices + (int64_t)nd * (side + 2 * I);
+            for (int j = 0; j < nb; ++j)
+                for (int i = 0; i < n; ++i) {
+                    int64_t vn = p4_volume_node(nd, n, idx, i, j);
+                    for (int v = 0; v < nv; ++v)
+                        iu[side + 2 * (v + nv * ((i + n * j) + (int64_t)nf * I))] = u[e * esz + nv * vn + v];
+                }
+        }
+}
+
+/* calc_interface_flux! dgsem_p4est/dg_3d.jl:185-314 */
+void oracle_calc_interface_flux_p4est(const trixi_b200_desc *d, double *sfv, const double *iu) {
+    eqn_t eq = make_eqn(d);
+    int n = d->nnodes, nd = d->ndims, nv = d->nvars;
+    int nf = ipow(n, nd - 1), nb = nd == 3 ? n : 1;
+    int64_t fsz = (int64_t)nv * nf * 2 * nd;
+#pragma omp parallel for schedule(static)
+    for (int64_t I = 0; I < d->ninterfaces; ++I) {
+        int64_t primary = d->interface_neighbor_ids[2 * I] - 1, secondary = d->interface_neighbor_ids[2 * I + 1] - 1;
+        const int64_t *pidx = d->interface_node_indices + (int64_t)nd * (0 + 2 * I);
+        const int64_t *sidx = d->interface_node_indices + (int64_t)nd * (1 + 2 * I);
+        int pdir = p4_direction(nd, pidx), sdir = p4_direction(nd, sidx);
+        for (int j = 0; j < nb; ++j)
+            for (int i = 0; i < n; ++i) {
+                double ul[MAXV], ur[MAXV], f[MAXV], nrm[3] = {0, 0, 0};
+                int fn = i + n * j, fn_sec;
+                for (int v = 0; v < nv; ++v) {
+                    ul[v] = iu[0 + 2 * (v + nv * (fn + (int64_t)nf * I))];
+                    ur[v] = iu[1 + 2 * (v + nv * (fn + (int64_t)nf * I))];
+                }
+                p4_normal(d, pdir, p4_volume_node(nd, n, pidx, i, j), primary, nrm);
+                numflux_normal(&eq, d->surface_flux, ul, ur, nrm, f);
+                p4_surface_node(nd, n, sidx, i, j, &fn_sec);
+                for (int v = 0; v < nv; ++v) {
+                    sfv[primary * fsz + v + nv * (fn + nf * pdir)] = f[v];
+                    sfv[secondary * fsz + v + nv * (fn_sec + nf * sdir)] = -f[v];
+                }
+            }
+    }
+}
+
+/* prolong2boundaries! + calc_boundary_flux! dgsem_p4est/dg_3d.jl:412-548; Dirichlet for unstructured
+ * meshes (equations.jl:206-228): flux(u_inner, u_boundary, outward normal) */
+void oracle_calc_boundary_flux_p4est(const trixi_b200_desc *d, double *sfv, const double *u, double t) {
+    eqn_t eq = make_eqn(d);
+    int n = d->nnodes, nd = d->ndims, nv = d->nvars;
+    int nf = ipow(n, nd - 1), nb = nd == 3 ? n : 1;
+    int64_t nn = ipow(n, nd), esz = nv * nn, fsz = (int64_t)nv * nf * 2 * nd;
+    int64_t first = 0;
+    for (int name = 0; name < 2 * nd; ++name) {
+        int64_t cnt = d->n_boundaries_per_direction[name];
+        int bc = d->boundary_conditions[name], ic = d->boundary_ic[name];
+#pragma omp parallel for schedule(static)
+        for (int64_t B = first; B < first + cnt; ++B) {
+            int64_t e = d->boundary_neighbor_ids[B] - 1;
+            const int64_t *idx = d->boundary_node_indices + (int64_t)nd * B;
+            int dir = p4_direction(nd, idx);
+            for (int j = 0; j < nb; ++j)
+                for (int i = 0; i < n; ++i) {
+                    int64_t vn = p4_volume_node(nd, n, idx, i, j);
+                    double ui[MAXV], f[MAXV], nrm[3] = {0, 0, 0};
+                    for (int v = 0; v < nv; ++v) ui[v] = u[e * esz + nv * vn + v];
+                    p4_normal(d, dir, vn, e, nrm);
+                    const double *x = d->node_coordinates + (int64_t)nd * (vn + nn * e);
+                    if (bc == TRIXI_B200_BC_DIRICHLET) {
+                        double ub[MAXV];
+                        ic_eval(&eq, ic, x, t, ub);
+                        numflux_normal(&eq, d->surface_flux, ui, ub, nrm, f);
+                    } else if (bc == TRIXI_B200_BC_SLIP_WALL) { /* compressible_euler_3d.jl:315-366 */
+                        euler_slip_wall_normal(&eq, ui, nrm, f);
+                    } else {
+                        for (int v = 0; v < nv; ++v) f[v] = NAN;
+                    }
+                    for (int v = 0; v < nv; ++v) sfv[e * fsz + v + nv * ((i + n * j) + nf * dir)] = f[v];
+                }
+        }
+        first += cnt;
+    }
+}
+
+/* calc_surface_integral! dgsem_p4est/dg_3d.jl:976-1034: outward normals everywhere => "+" on all six faces */
+void oracle_calc_surface_integral_p4est(const trixi_b200_desc *d, double *du, const double *sfv) {
+    int n = d->nnodes, nd = d->ndims, nv = d->nvars;
+    int nf = ipow(n, nd - 1), nb = nd == 3 ? n : 1;
+    int64_t esz = (int64_t)nv * ipow(n, nd), fsz = (int64_t)nv * nf * 2 * nd;
+    double factor = d->inverse_weights[0];
+#pragma omp parallel for schedule(static)
+    for (int64_t e = 0; e < d->nelements; ++e) {
+        double *due = du + e * esz;
+        const double *s = sfv + e * fsz;
+        for (int m = 0; m < nb; ++m)
+            for (int l = 0; l < n; ++l) {
+                int fn = l + n * m;
+                for (int v = 0; v < nv; ++v)
+                    for (int o = 0; o < nd; ++o) {
+                        int lo = face_to_volume_node(nd, n, o, 0, l, m);
+                        int hi = face_to_volume_node(nd, n, o, n - 1, l, m);
+                        due[nv * lo + v] = due[nv * lo + v] + s[v + nv * (fn + nf * (2 * o))] * factor;
+                        due[nv * hi + v] = due[nv * hi + v] + s[v + nv * (fn + nf * (2 * o + 1))] * factor;
+                    }
+            }
+    }
+}
+
+/* rhs_hyperbolic! dgsem_tree/dg_2d.jl:113-186 dispatched for P4estMesh (conforming: no mortars) */
+void oracle_rhs_p4est(const trixi_b200_desc *d, double *du, const double *u, double t, double *interfaces_u,
+                      double *sfv) {
+    oracle_set_zero(d, du);
+    oracle_calc_volume_integral_curved(d, du, u); /* shared kernels dgsem_structured/dg_3d.jl:36-175 */
+    oracle_prolong2interfaces_p4est(d, interfaces_u, u);
+    oracle_calc_interface_flux_p4est(d, sfv, interfaces_u);
+    if (d->nboundaries > 0) oracle_calc_boundary_flux_p4est(d, sfv, u, t);
+    oracle_calc_surface_integral_p4est(d, du, sfv);
+    oracle_apply_jacobian_curved(d, du);
+    oracle_calc_sources(d, du, u, t);
+}
+
 /* rhs_hyperbolic! dgsem_tree/dg_2d.jl:113-186.  Work arrays: interfaces_u [2,nv,nf,I],
  * boundaries_u [2,nv,nf,B], sfv [nv,nf,2nd,nelem] (owned by the caller = the cache). */
 void oracle_rhs(const trixi_b200_desc *d, double *du, const double *u, double t, double *interfaces_u,
                 double *boundaries_u, double *sfv) {
     if (d->mesh_kind == TRIXI_B200_MESH_STRUCTURED) {
         oracle_rhs_structured(d, du, u, t, interfaces_u, sfv);
+        return;
+    }
+    if (d->mesh_kind == TRIXI_B200_MESH_P4EST) {
+        oracle_rhs_p4est(d, du, u, t, interfaces_u, sfv);
         return;
     }
     oracle_set_zero(d, du);

@@ -297,3 +297,46 @@ ELIXIRS.update({e.name: e for e in [
            [0.03156756290660656, 0.033597629023726316, 0.02095783702361409, 0.03353574465232212,
             0.05873635745032857], "test/test_structured_3d.jl:125-148"),
 ]})
+
+
+# ---- P4estMesh (programmatic forests) ----------------------------------------------------------------------
+def _p4est3d_source_terms_nonperiodic(volume_integral=None):
+    # examples/p4est_3d_dgsem/elixir_euler_source_terms_nonperiodic.jl
+    eq = T.CompressibleEulerEquations3D(1.4)
+    solver = T.DGSEM(polydeg=3, surface_flux=T.FluxLaxFriedrichs(T.max_abs_speed_naive),
+                     volume_integral=volume_integral or T.VolumeIntegralWeakForm())
+    mesh = T.P4estMesh((2, 2, 2), polydeg=1, coordinates_min=(0.0, 0.0, 0.0), coordinates_max=(2.0, 2.0, 2.0),
+                       periodicity=False, initial_refinement_level=1)
+    return T.SemidiscretizationHyperbolic(mesh, eq, T.initial_condition_convergence_test, solver,
+                                          source_terms=T.source_terms_convergence_test,
+                                          boundary_conditions=T.BoundaryConditionDirichlet(
+                                              T.initial_condition_convergence_test))
+
+
+def _p4est3d_source_terms():
+    # examples/p4est_3d_dgsem/elixir_euler_source_terms.jl (same discretisation as the TreeMesh elixir at
+    # level 3 -> the reference asserts no golden for it; the TreeMesh value at 8^3 elements is used as a
+    # cross-check in tests/test_oracle_golden.py::test_p4est_brick_equals_treemesh)
+    eq = T.CompressibleEulerEquations3D(1.4)
+    solver = T.DGSEM(polydeg=3, surface_flux=T.FluxLaxFriedrichs(T.max_abs_speed_naive),
+                     volume_integral=T.VolumeIntegralWeakForm())
+    mesh = T.P4estMesh((4, 4, 4), polydeg=3, coordinates_min=(0.0, 0.0, 0.0), coordinates_max=(2.0, 2.0, 2.0),
+                       periodicity=True, initial_refinement_level=1)
+    return T.SemidiscretizationHyperbolic(mesh, eq, T.initial_condition_convergence_test, solver,
+                                          source_terms=T.source_terms_convergence_test)
+
+
+ELIXIRS.update({e.name: e for e in [
+    Elixir("p4est_3d_euler_source_terms_nonperiodic", _p4est3d_source_terms_nonperiodic, (0.0, 1.0), 0.6,
+           [0.0015106060984283647, 0.0014733349038567685, 0.00147333490385685, 0.001473334903856929,
+            0.0028149479453087093],
+           [0.008070806335238156, 0.009007245083113125, 0.009007245083121784, 0.009007245083102688,
+            0.01562861968368434], "test/test_p4est_3d.jl:140-161"),
+    Elixir("p4est_3d_euler_source_terms_nonperiodic_kennedy_gruber",
+           lambda: _p4est3d_source_terms_nonperiodic(T.VolumeIntegralFluxDifferencing(T.flux_kennedy_gruber)),
+           (0.0, 5.0), 0.6,
+           [0.0014517629881062517, 0.0014469623017050836, 0.001446962301705153, 0.0014469623017051368,
+            0.002934065359862918],
+           [0.01031578086475382, 0.011300883615913193, 0.011300883615896096, 0.011300883615918522,
+            0.02090696711453477], "test/test_cuda_3d.jl:58-75 (native Float64 run of the reference's GPU test)"),
+]})

@@ -9,6 +9,7 @@ from .callbacks import (AliveCallback, AnalysisCallback, StepsizeCallback, Summa
                         calc_error_norms)
 from .equations import *  # noqa: F401,F403
 from .mesh import CartesianBoxMesh, TreeMesh  # noqa: F401
+from .p4est import P4estMesh  # noqa: F401
 from .structured import StructuredMesh  # noqa: F401
 from .semidiscretization import (ODEProblem, SemidiscretizationHyperbolic, compute_coefficients,  # noqa: F401
                                  rhs_hyperbolic, semidiscretize)

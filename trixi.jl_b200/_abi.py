@@ -8,7 +8,7 @@ import ctypes as C
 
 import numpy as np
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 c_double_p = C.POINTER(C.c_double)
 c_int64_p = C.POINTER(C.c_int64)
@@ -46,6 +46,7 @@ class Desc(C.Structure):
         ("nmpiinterfaces", C.c_int64),
         ("mpi_local_neighbor_ids", c_int64_p), ("mpi_local_sides", c_int64_p),
         ("mpi_orientations", c_int64_p), ("mpi_neighbor_ranks", c_int64_p),
+        ("boundary_node_indices", c_int64_p),
     ]
 
 

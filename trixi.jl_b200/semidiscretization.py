@@ -19,6 +19,7 @@ from .containers import (BoundaryContainer, InterfaceContainer, MPIInterfaceCont
 from .equations import (BC_DIRICHLET, BC_PERIODIC, BC_SLIP_WALL, IC_NONE, SRC_NONE,
                         BoundaryConditionDirichlet, boundary_condition_periodic, resolve_flux)
 from .mesh import TreeMesh
+from .p4est import P4estMesh, init_boundaries_p4est, init_elements_p4est, init_interfaces_p4est
 from .structured import StructuredMesh, init_elements_structured
 
 MESH_TREE, MESH_STRUCTURED, MESH_P4EST = 0, 1, 2
@@ -73,6 +74,16 @@ def create_cache(mesh, equations, solver, rank=0, world_size=1):
         cache.mpi_interfaces = MPIInterfaceContainer()
         cache.mpi_interfaces.nmpiinterfaces = 0
         cache.boundaries = _structured_boundaries(mesh, cache.elements)
+    elif isinstance(mesh, P4estMesh):
+        if world_size != 1:
+            raise NotImplementedError("P4estMesh partitions need libp4est; single rank here")
+        # create_cache dgsem_p4est/dg.jl:13-70
+        cache.first_element, cache.last_element = 0, mesh.ncells
+        cache.elements = init_elements_p4est(mesh, solver.basis)
+        cache.interfaces = init_interfaces_p4est(mesh)
+        cache.mpi_interfaces = MPIInterfaceContainer()
+        cache.mpi_interfaces.nmpiinterfaces = 0
+        cache.boundaries = init_boundaries_p4est(mesh)
     else:
         raise TypeError(f"unsupported mesh type {type(mesh).__name__}")
     return cache
@@ -179,7 +190,7 @@ class SemidiscretizationHyperbolic:
 
     @property
     def is_curved(self):
-        return isinstance(self.mesh, StructuredMesh)
+        return isinstance(self.mesh, (StructuredMesh, P4estMesh))
 
     def u_shape(self):
         return (self.equations.nvars,) + (self.solver.nnodes,) * self.mesh.ndims + (self.nelements,)
@@ -197,7 +208,8 @@ class SemidiscretizationHyperbolic:
         d.abi_version = _abi.ABI_VERSION
         d.device = self.device
         d.ndims, d.nvars, d.nnodes = self.mesh.ndims, eq.nvars, dg.nnodes
-        d.mesh_kind = MESH_STRUCTURED if isinstance(self.mesh, StructuredMesh) else MESH_TREE
+        d.mesh_kind = (MESH_STRUCTURED if isinstance(self.mesh, StructuredMesh)
+                       else MESH_P4EST if isinstance(self.mesh, P4estMesh) else MESH_TREE)
         d.nelements = self.nelements
         d.equation = eq.eq_id
         d.volume_integral = dg.volume_integral.kind
@@ -217,6 +229,11 @@ class SemidiscretizationHyperbolic:
         if isinstance(self.mesh, StructuredMesh):
             h.set_f64("contravariant_vectors", cache.elements.contravariant_vectors)
             h.set_i64("left_neighbors", cache.elements.left_neighbors)
+        if isinstance(self.mesh, P4estMesh):
+            h.set_f64("contravariant_vectors", cache.elements.contravariant_vectors)
+            h.set_i64("interface_node_indices", cache.interfaces.node_indices)
+            if cache.boundaries.nboundaries:
+                h.set_i64("boundary_node_indices", cache.boundaries.node_indices)
         d.ninterfaces = cache.interfaces.ninterfaces
         h.set_i64("interface_neighbor_ids", cache.interfaces.neighbor_ids)
         h.set_i64("interface_orientations", cache.interfaces.orientations)

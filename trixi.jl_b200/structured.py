@@ -100,6 +100,45 @@ class StructuredMesh:
         return f"StructuredMesh{{{self.ndims}}} {self.cells_per_dimension}"
 
 
+def compute_metric_terms(X, D):
+    """jacobian_matrix, contravariant_vectors and inverse_jacobian from nodal coordinates
+    ``X[dim, nodes.., element]`` (containers_3d.jl:63-342 / containers_2d.jl:60-120); shared by the
+    StructuredMesh and P4estMesh element containers (dgsem_p4est/containers_3d.jl:9-27)."""
+    nd = X.shape[0]
+    shape_nodes = X.shape[1:1 + nd]
+    nelem = X.shape[-1]
+    # jacobian_matrix[dim, index, nodes.., element] = d x_dim / d xi_index (containers_3d.jl:63-123)
+    J = np.empty((nd, nd) + tuple(shape_nodes) + (nelem,), order="F")
+    for a in range(nd):
+        J[:, a] = np.moveaxis(np.tensordot(D, X, axes=([1], [1 + a])), 0, 1 + a)
+    if nd == 2:
+        # containers_2d.jl:90-107
+        Ja = np.empty_like(J)
+        Ja[0, 0] = J[1, 1]
+        Ja[1, 0] = -J[0, 1]
+        Ja[0, 1] = -J[1, 0]
+        Ja[1, 1] = J[0, 0]
+        inv_jac = 1.0 / (J[0, 0] * J[1, 1] - J[0, 1] * J[1, 0])
+    else:
+        # curl-invariant form (containers_3d.jl:125-285):
+        # Ja[n, 1] = d/deta (0.5 (x_m dx_l/dzeta - x_l dx_m/dzeta)) - d/dzeta (0.5 (x_m dx_l/deta - x_l dx_m/deta)) ...
+        def ddx(a, field):  # derivative along reference axis a of field[nodes.., elem]
+            return np.moveaxis(np.tensordot(D, field, axes=([1], [a])), 0, a)
+        Ja = np.empty_like(J)
+        for nn in range(3):
+            m = (nn + 1) % 3
+            l = (nn + 2) % 3
+            def term(c):  # 0.5 * (x_m * J[l, c] - x_l * J[m, c])
+                return 0.5 * (X[m] * J[l, c] - X[l] * J[m, c])
+            Ja[nn, 0] = ddx(1, term(2)) - ddx(2, term(1))
+            Ja[nn, 1] = ddx(2, term(0)) - ddx(0, term(2))
+            Ja[nn, 2] = ddx(0, term(1)) - ddx(1, term(0))
+        det = (J[0, 0] * J[1, 1] * J[2, 2] + J[0, 1] * J[1, 2] * J[2, 0] + J[0, 2] * J[1, 0] * J[2, 1]
+               - J[2, 0] * J[1, 1] * J[0, 2] - J[2, 1] * J[1, 2] * J[0, 0] - J[2, 2] * J[1, 0] * J[0, 1])
+        inv_jac = 1.0 / det
+    return J, np.asfortranarray(Ja), np.asfortranarray(inv_jac)
+
+
 class StructuredElementContainer:
     pass
 
@@ -133,39 +172,10 @@ def init_elements_structured(mesh, basis):
     el = StructuredElementContainer()
     el.nelements = nelem
     el.node_coordinates = np.asfortranarray(coords)
-    X = el.node_coordinates
-    # jacobian_matrix[dim, index, nodes.., element] = d x_dim / d xi_index (containers_3d.jl:63-123)
-    J = np.empty((nd, nd) + tuple(shape_nodes) + (nelem,), order="F")
-    for a in range(nd):
-        J[:, a] = np.moveaxis(np.tensordot(D, X, axes=([1], [1 + a])), 0, 1 + a)
-    if nd == 2:
-        # containers_2d.jl:90-107
-        Ja = np.empty_like(J)
-        Ja[0, 0] = J[1, 1]
-        Ja[1, 0] = -J[0, 1]
-        Ja[0, 1] = -J[1, 0]
-        Ja[1, 1] = J[0, 0]
-        inv_jac = 1.0 / (J[0, 0] * J[1, 1] - J[0, 1] * J[1, 0])
-    else:
-        # curl-invariant form (containers_3d.jl:125-285):
-        # Ja[n, 1] = d/deta (0.5 (x_m dx_l/dzeta - x_l dx_m/dzeta)) - d/dzeta (0.5 (x_m dx_l/deta - x_l dx_m/deta)) ...
-        def ddx(a, field):  # derivative along reference axis a of field[nodes.., elem]
-            return np.moveaxis(np.tensordot(D, field, axes=([1], [a])), 0, a)
-        Ja = np.empty_like(J)
-        for nn in range(3):
-            m = (nn + 1) % 3
-            l = (nn + 2) % 3
-            def term(c):  # 0.5 * (x_m * J[l, c] - x_l * J[m, c])
-                return 0.5 * (X[m] * J[l, c] - X[l] * J[m, c])
-            Ja[nn, 0] = ddx(1, term(2)) - ddx(2, term(1))
-            Ja[nn, 1] = ddx(2, term(0)) - ddx(0, term(2))
-            Ja[nn, 2] = ddx(0, term(1)) - ddx(1, term(0))
-        det = (J[0, 0] * J[1, 1] * J[2, 2] + J[0, 1] * J[1, 2] * J[2, 0] + J[0, 2] * J[1, 0] * J[2, 1]
-               - J[2, 0] * J[1, 1] * J[0, 2] - J[2, 1] * J[1, 2] * J[0, 0] - J[2, 2] * J[1, 0] * J[0, 1])
-        inv_jac = 1.0 / det
+    J, Ja, inv_jac = compute_metric_terms(el.node_coordinates, D)
     el.jacobian_matrix = J
-    el.contravariant_vectors = np.asfortranarray(Ja)   # [dim, index, nodes.., element]
-    el.inverse_jacobian = np.asfortranarray(inv_jac)   # [nodes.., element]
+    el.contravariant_vectors = Ja   # [dim, index, nodes.., element]
+    el.inverse_jacobian = inv_jac   # [nodes.., element]
     # left neighbours (containers_3d.jl:344-400): 1-based, 0 at a non-periodic domain boundary
     lin = np.arange(1, nelem + 1, dtype=np.int64).reshape(cells, order="F")
     left = np.empty((nd, nelem), dtype=np.int64, order="F")
