@@ -53,7 +53,8 @@ RHS_CASES = ["tree_3d_euler_ec", "tree_3d_euler_source_terms", "tree_3d_euler_so
              "tree_3d_euler_ec_kennedy_gruber", "tree_3d_euler_ec_shima_etal", "tree_2d_advection_basic",
              "tree_2d_euler_source_terms", "tree_2d_euler_source_terms_nonperiodic", "tree_2d_euler_ec",
              "tree_2d_euler_density_wave", "structured_3d_euler_free_stream", "structured_3d_euler_ec",
-             "structured_3d_euler_source_terms", "structured_3d_euler_source_terms_nonperiodic_curved"]
+             "structured_3d_euler_source_terms", "structured_3d_euler_source_terms_nonperiodic_curved",
+             "p4est_3d_euler_source_terms_nonperiodic", "p4est_3d_euler_source_terms_nonperiodic_kennedy_gruber"]
 
 
 @pytest.mark.parametrize("name", RHS_CASES)
@@ -77,7 +78,8 @@ def test_rhs_matches_oracle(name, state, oracle_module):
 
 
 @pytest.mark.parametrize("name", ["tree_3d_euler_ec", "tree_3d_euler_source_terms", "tree_2d_euler_source_terms_nonperiodic",
-                                  "structured_3d_euler_ec", "structured_3d_euler_source_terms_nonperiodic_curved"])
+                                  "structured_3d_euler_ec", "structured_3d_euler_source_terms_nonperiodic_curved",
+                                  "p4est_3d_euler_source_terms_nonperiodic_kennedy_gruber"])
 def test_stage_level_parity(name, oracle_module):
     """calc_volume_integral! and the surface flux stages separately, like the reference's kernel parity
     tests (test/test_performance_specializations_3d.jl:49-89)."""
@@ -147,7 +149,8 @@ GOLDEN_GPU = ["tree_3d_euler_ec", "tree_3d_euler_ec_constant", "tree_3d_euler_so
               "tree_2d_advection_basic", "tree_2d_euler_source_terms", "tree_2d_euler_source_terms_nonperiodic",
               "tree_2d_euler_ec", "tree_2d_euler_density_wave", "structured_3d_euler_free_stream",
               "structured_3d_euler_ec", "structured_3d_euler_source_terms",
-              "structured_3d_euler_source_terms_nonperiodic_curved"]
+              "structured_3d_euler_source_terms_nonperiodic_curved", "p4est_3d_euler_source_terms_nonperiodic",
+              "p4est_3d_euler_source_terms_nonperiodic_kennedy_gruber"]
 
 
 @pytest.mark.parametrize("name", GOLDEN_GPU)

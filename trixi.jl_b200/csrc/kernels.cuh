@@ -36,6 +36,9 @@ struct KParams {
     const double *node_coordinates;       // [nd, n^d, nelem]
     const double *contravariant_vectors;  // curved: [nd (dim), nd (index), n^d, nelem]
     int curved;                           // 0: Cartesian TreeMesh kernels, 1: curved (Structured/P4est) kernels
+    int p4est;                            // 1: P4est conventions (outward normals, "+" surface integral, node_indices)
+    const long long *if_node_indices;     // P4est: [nd, 2, I] encoded symbols
+    const long long *bd_node_indices;     // P4est: [nd, B]
     // connectivity (1-based int64 as uploaded)
     const long long *if_neighbors;  // [2, I]
     const long long *if_orient;     // [I]
@@ -608,9 +611,12 @@ __global__ void __launch_bounds__(ElemCfg<EQ, N>::THREADS) k_element_curved(cons
             else
                 fn = d == 0 ? idx[1] + N * idx[2] : (d == 1 ? idx[0] + N * idx[2] : idx[0] + N * idx[1]);
             if (idx[d] == 0) {
+                // Structured: "-" on negative faces (dg_3d.jl:1337-1394); P4est: "+" everywhere because the
+                // fluxes are taken along outward normals (dgsem_p4est/dg_3d.jl:976-1034)
                 const double *sq = sf + ((2 * d) * NF + fn) * NV;
+                const double w = P.p4est ? P.inv_weight0 : -P.inv_weight0;
 #pragma unroll
-                for (int v = 0; v < NV; ++v) acc[v] = acc[v] - sq[v] * P.inv_weight0;
+                for (int v = 0; v < NV; ++v) acc[v] = acc[v] + sq[v] * w;
             }
             if (idx[d] == N - 1) {
                 const double *sq = sf + ((2 * d + 1) * NF + fn) * NV;
@@ -682,6 +688,117 @@ __global__ void __launch_bounds__(ElemCfg<EQ, N>::THREADS) k_max_dt_curved(const
         for (int d = 0; d < ND; ++d) sum += __longlong_as_double((long long)s_lam[d][tid]);
         atomicMax(P.cfl_key, cfl_encode(sum));
     }
+}
+
+// =====================================================================================================
+// P4estMesh (src/solvers/dgsem_p4est/): unstructured conforming hexahedra/quadrilaterals.  Volume terms,
+// Jacobian and max_dt are the curved kernels above; faces are addressed through symbolic node_indices.
+// =====================================================================================================
+TB_DEV int p4_index(int sym, int n, int i, int j) {
+    // index_to_start_step_3d (dg_3d.jl:61-80) in closed form; :begin 0 :end 1 :i_forward 2 :i_backward 3
+    // :j_forward 4 :j_backward 5
+    return sym == 0 ? 0 : sym == 1 ? n - 1 : sym == 2 ? i : sym == 3 ? n - 1 - i : sym == 4 ? j : n - 1 - j;
+}
+template <int ND, int N>
+TB_DEV void p4_face(const long long *idx, int i, int j, int &volume_node, int &surface_node, int &direction0) {
+    int node = 0, stride = 1, s0 = 0, s1 = 0, k = 0;
+    direction0 = 0;
+#pragma unroll
+    for (int c = 0; c < ND; ++c) {
+        const int sym = (int)idx[c];
+        const int q = p4_index(sym, N, i, j);
+        node += stride * q;
+        stride *= N;
+        if (sym == 0) direction0 = 2 * c;
+        if (sym == 1) direction0 = 2 * c + 1;
+        if (sym > 1) {
+            if (k == 0)
+                s0 = q;
+            else
+                s1 = q;
+            ++k;
+        }
+    }
+    volume_node = node;
+    surface_node = ND == 3 ? s0 + N * s1 : s0;
+}
+
+// prolong2interfaces! + calc_interface_flux! (dgsem_p4est/dg_3d.jl:94-314): outward normal of the primary
+// element (dg.jl:74-86), +flux to the primary, -flux to the secondary element
+template <class EQ, int N>
+__global__ void __launch_bounds__(256) k_interface_flux_p4est(const KParams P) {
+    constexpr int ND = EQ::NDIMS, NV = EQ::NVARS, NF = ipow(N, ND - 1), NN = ipow(N, ND);
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long I = gid / NF;
+    const int fn = (int)(gid % NF);
+    if (I >= P.ninterfaces) return;
+    const EQ eq(P.eq);
+    const int i = fn % N, j = fn / N;
+    const long long primary = P.if_neighbors[2 * I] - 1, secondary = P.if_neighbors[2 * I + 1] - 1;
+    int pn, pfn, pdir, sn, sfn, sdir;
+    p4_face<ND, N>(P.if_node_indices + (2 * I + 0) * ND, i, j, pn, pfn, pdir);
+    p4_face<ND, N>(P.if_node_indices + (2 * I + 1) * ND, i, j, sn, sfn, sdir);
+    double ul[NV], ur[NV], f[NV], nrm[ND];
+    const double *pl = P.u + (primary * NN + pn) * NV, *pr = P.u + (secondary * NN + sn) * NV;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+        ul[v] = pl[v];
+        ur[v] = pr[v];
+    }
+    load_ja<ND, NN>(P, pdir / 2, pn, primary, nrm);
+    if (pdir % 2 == 0) {
+#pragma unroll
+        for (int d = 0; d < ND; ++d) nrm[d] = -nrm[d];
+    }
+    eq.numflux_normal(P.surface_flux, ul, ur, nrm, f);
+    double *sp = P.sfv + ((primary * (2 * ND) + pdir) * NF + fn) * NV;
+    double *ss = P.sfv + ((secondary * (2 * ND) + sdir) * NF + sfn) * NV;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+        sp[v] = f[v];
+        ss[v] = -f[v];
+    }
+}
+
+// prolong2boundaries! + calc_boundary_flux! (dgsem_p4est/dg_3d.jl:412-548)
+template <class EQ, int N>
+__global__ void __launch_bounds__(256) k_boundary_flux_p4est(const KParams P) {
+    constexpr int ND = EQ::NDIMS, NV = EQ::NVARS, NF = ipow(N, ND - 1), NN = ipow(N, ND);
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long B = gid / NF;
+    const int fn = (int)(gid % NF);
+    if (B >= P.nboundaries) return;
+    const EQ eq(P.eq);
+    const int i = fn % N, j = fn / N;
+    const long long element = P.bd_neighbor[B] - 1;
+    const int name = P.bd_direction[B] - 1;  // boundaries sorted by name = direction
+    int vn, sfn, dir;
+    p4_face<ND, N>(P.bd_node_indices + B * ND, i, j, vn, sfn, dir);
+    double ui[NV], f[NV], x[ND], nrm[ND];
+    const double *pu = P.u + (element * NN + vn) * NV;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) ui[v] = pu[v];
+#pragma unroll
+    for (int d = 0; d < ND; ++d) x[d] = P.node_coordinates[(element * NN + vn) * ND + d];
+    load_ja<ND, NN>(P, dir / 2, vn, element, nrm);
+    if (dir % 2 == 0) {
+#pragma unroll
+        for (int d = 0; d < ND; ++d) nrm[d] = -nrm[d];
+    }
+    const int bc = P.bc[name];
+    if (bc == TRIXI_B200_BC_DIRICHLET) {  // equations.jl:206-228: flux(u_inner, u_boundary, outward normal)
+        double ub[NV];
+        eq.initial_condition(P.bc_ic[name], x, P.t, ub);
+        eq.numflux_normal(P.surface_flux, ui, ub, nrm, f);
+    } else if (bc == TRIXI_B200_BC_SLIP_WALL) {
+        eq.slip_wall_outward(ui, nrm, f);
+    } else {
+#pragma unroll
+        for (int v = 0; v < NV; ++v) f[v] = nan("");
+    }
+    double *s = P.sfv + ((element * (2 * ND) + dir) * NF + fn) * NV;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) s[v] = f[v];
 }
 
 }  // namespace tb

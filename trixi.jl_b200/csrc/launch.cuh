@@ -27,7 +27,9 @@ void launch_interface_flux(const KParams &P, cudaStream_t s) {
     if (total == 0) return;
     const int threads = 256;
     const unsigned blocks = (unsigned)((total + threads - 1) / threads);
-    if (P.curved)
+    if (P.p4est)
+        k_interface_flux_p4est<EQ, N><<<blocks, threads, 0, s>>>(P);
+    else if (P.curved)
         k_interface_flux_curved<EQ, N><<<blocks, threads, 0, s>>>(P);
     else if (HasFastRanocha<EQ>::value && P.kernel_path == 0 &&
              (P.surface_flux == TRIXI_B200_FLUX_RANOCHA || P.surface_flux == TRIXI_B200_FLUX_RANOCHA_TURBO))
@@ -43,7 +45,9 @@ void launch_boundary_flux(const KParams &P, cudaStream_t s) {
     if (total == 0) return;
     const int threads = 256;
     const unsigned blocks = (unsigned)((total + threads - 1) / threads);
-    if (P.curved)
+    if (P.p4est)
+        k_boundary_flux_p4est<EQ, N><<<blocks, threads, 0, s>>>(P);
+    else if (P.curved)
         k_boundary_flux_curved<EQ, N><<<blocks, threads, 0, s>>>(P);
     else
         k_boundary_flux<EQ, N><<<blocks, threads, 0, s>>>(P);
@@ -166,6 +170,8 @@ cudaError_t preload_all() {
     TB_PRELOAD((k_max_dt<EQ, N>));
     TB_PRELOAD((k_max_dt_curved<EQ, N>));
     TB_PRELOAD((k_interface_flux_curved<EQ, N>));
+    TB_PRELOAD((k_interface_flux_p4est<EQ, N>));
+    TB_PRELOAD((k_boundary_flux_p4est<EQ, N>));
     TB_PRELOAD((k_boundary_flux_curved<EQ, N>));
     TB_PRELOAD((k_element_curved<EQ, N, TRIXI_B200_VOLINT_WEAK_FORM, true>));
     TB_PRELOAD((k_element_curved<EQ, N, TRIXI_B200_VOLINT_WEAK_FORM, false>));

@@ -146,6 +146,7 @@ struct Advection {
     TB_DEV void slip_wall_normal(const double (&u)[1], const double (&n)[ND], int direction, double (&f)[1]) const {
         f[0] = nan("");
     }
+    TB_DEV void slip_wall_outward(const double (&u)[1], const double (&n)[ND], double (&f)[1]) const { f[0] = nan(""); }
     // max_abs_speeds(equation) (linear_scalar_advection_2d.jl:292-294)
     TB_DEV void max_abs_speeds(const double (&u)[1], double (&lam)[ND]) const {
         lam[0] = fabs(a0);
@@ -518,6 +519,42 @@ struct Euler {
         case TRIXI_B200_FLUX_RANOCHA_TURBO:
             flux_ranocha_normal(ul, ur, n, f);
             break;
+        case TRIXI_B200_FLUX_KENNEDY_GRUBER:
+        case TRIXI_B200_FLUX_SHIMA_ETAL: {  // compressible_euler_3d.jl:602-627 / :512-547
+            double rho_ll, v_ll[ND], p_ll, rho_rr, v_rr[ND], p_rr;
+            cons2prim(ul, rho_ll, v_ll, p_ll);
+            cons2prim(ur, rho_rr, v_rr, p_rr);
+            const double rho_avg = 0.5 * (rho_ll + rho_rr), p_avg = 0.5 * (p_ll + p_rr);
+            double v_avg[ND];
+#pragma unroll
+            for (int d = 0; d < ND; ++d) v_avg[d] = 0.5 * (v_ll[d] + v_rr[d]);
+            if (id == TRIXI_B200_FLUX_KENNEDY_GRUBER) {
+                const double e_avg = 0.5 * (ul[ND + 1] / rho_ll + ur[ND + 1] / rho_rr);
+                double v_dot_n_avg = 0.0;
+#pragma unroll
+                for (int d = 0; d < ND; ++d) v_dot_n_avg += v_avg[d] * n[d];
+                const double f1 = rho_avg * v_dot_n_avg;
+                f[0] = f1;
+#pragma unroll
+                for (int d = 0; d < ND; ++d) f[1 + d] = f1 * v_avg[d] + p_avg * n[d];
+                f[ND + 1] = f1 * e_avg + p_avg * v_dot_n_avg;
+            } else {
+                double vl = 0.0, vr = 0.0, vsq = 0.0;
+#pragma unroll
+                for (int d = 0; d < ND; ++d) {
+                    vl += v_ll[d] * n[d];
+                    vr += v_rr[d] * n[d];
+                    vsq += v_ll[d] * v_rr[d];
+                }
+                const double v_dot_n_avg = 0.5 * (vl + vr);
+                const double f1 = rho_avg * v_dot_n_avg;
+                f[0] = f1;
+#pragma unroll
+                for (int d = 0; d < ND; ++d) f[1 + d] = f1 * v_avg[d] + p_avg * n[d];
+                f[ND + 1] = f1 * (0.5 * vsq) + p_avg * v_dot_n_avg * inv_gm1 + 0.5 * (p_ll * vr + p_rr * vl);
+            }
+            break;
+        }
         default:
 #pragma unroll
             for (int v = 0; v < NVARS; ++v) f[v] = nan("");
@@ -552,6 +589,11 @@ struct Euler {
 #pragma unroll
         for (int d = 0; d < ND; ++d) f[1 + d] = p_star * (n[d] / norm_) * norm_;
         f[ND + 1] = 0.0;
+    }
+
+    // boundary_condition_slip_wall(u_inner, outward normal, x, t, ...) for P4estMesh (:315-366)
+    TB_DEV void slip_wall_outward(const double (&u)[NVARS], const double (&n)[ND], double (&f)[NVARS]) const {
+        slip_wall_normal(u, n, 2, f);  // even direction: the normal is used as is
     }
 
     // max_abs_speeds (compressible_euler_3d.jl:1770-1775)

@@ -301,9 +301,16 @@ TRIXI_B200_API int trixi_b200_create(const trixi_b200_desc *d, trixi_b200_handle
     if (d->abi_version != TRIXI_B200_ABI_VERSION)
         return fail(nullptr, TRIXI_B200_EINVAL, "descriptor ABI version %d != library %d", d->abi_version,
                     TRIXI_B200_ABI_VERSION);
-    if (d->mesh_kind != TRIXI_B200_MESH_TREE && d->mesh_kind != TRIXI_B200_MESH_STRUCTURED)
+    if (d->mesh_kind != TRIXI_B200_MESH_TREE && d->mesh_kind != TRIXI_B200_MESH_STRUCTURED &&
+        d->mesh_kind != TRIXI_B200_MESH_P4EST)
         return fail(nullptr, TRIXI_B200_EINVAL, "mesh kind %d not supported by this build", d->mesh_kind);
     const bool structured = d->mesh_kind == TRIXI_B200_MESH_STRUCTURED;
+    const bool p4est = d->mesh_kind == TRIXI_B200_MESH_P4EST;
+    if (p4est && (!d->contravariant_vectors || (d->ninterfaces > 0 && !d->interface_node_indices) ||
+                  (d->nboundaries > 0 && !d->boundary_node_indices)))
+        return fail(nullptr, TRIXI_B200_EINVAL, "P4estMesh needs contravariant_vectors and node_indices");
+    if (p4est && d->world_size > 1)
+        return fail(nullptr, TRIXI_B200_EINVAL, "P4estMesh handles are single-rank in this build");
     if (structured && (!d->contravariant_vectors || !d->left_neighbors))
         return fail(nullptr, TRIXI_B200_EINVAL, "StructuredMesh needs contravariant_vectors and left_neighbors");
     if (structured && d->world_size > 1)
@@ -421,11 +428,15 @@ TRIXI_B200_API int trixi_b200_create(const trixi_b200_desc *d, trixi_b200_handle
     P.inv_weight0 = d->inverse_weights[0];
     for (int q = 0; q < n * n; ++q) P.dsplit_c[q] = d->derivative_split[q];
     P.kernel_path = 0;
-    CREATE_TRY(upload_array(h, d->inverse_jacobian, (size_t)(structured ? nn * d->nelements : d->nelements), &tmp));
+    const bool curved = structured || p4est;
+    CREATE_TRY(upload_array(h, d->inverse_jacobian, (size_t)(curved ? nn * d->nelements : d->nelements), &tmp));
     P.inverse_jacobian = tmp;
-    P.curved = structured ? 1 : 0;
+    P.curved = curved ? 1 : 0;
+    P.p4est = p4est ? 1 : 0;
     P.contravariant_vectors = nullptr;
-    if (structured) {
+    P.if_node_indices = nullptr;
+    P.bd_node_indices = nullptr;
+    if (curved) {
         CREATE_TRY(upload_array(h, d->contravariant_vectors, (size_t)(nd * nd * nn * d->nelements), &tmp));
         P.contravariant_vectors = tmp;
     }
@@ -442,16 +453,26 @@ TRIXI_B200_API int trixi_b200_create(const trixi_b200_desc *d, trixi_b200_handle
     } else {
         CREATE_TRY(upload_array(h, (const long long *)d->interface_neighbor_ids, (size_t)(2 * d->ninterfaces), &itmp));
         P.if_neighbors = itmp;
-        CREATE_TRY(upload_array(h, (const long long *)d->interface_orientations, (size_t)d->ninterfaces, &itmp));
-        P.if_orient = itmp;
+        if (!p4est) {
+            CREATE_TRY(upload_array(h, (const long long *)d->interface_orientations, (size_t)d->ninterfaces, &itmp));
+            P.if_orient = itmp;
+        }
     }
     CREATE_TRY(upload_array(h, (const long long *)d->boundary_neighbor_ids, (size_t)d->nboundaries, &itmp));
     P.bd_neighbor = itmp;
-    CREATE_TRY(upload_array(h, (const long long *)d->boundary_orientations, (size_t)d->nboundaries, &itmp));
-    P.bd_orient = itmp;
-    CREATE_TRY(upload_array(h, (const long long *)d->boundary_neighbor_sides, (size_t)d->nboundaries, &itmp));
-    P.bd_side = itmp;
-    if (!structured) {  // curved kernels read the element's own node coordinates
+    if (!p4est) {
+        CREATE_TRY(upload_array(h, (const long long *)d->boundary_orientations, (size_t)d->nboundaries, &itmp));
+        P.bd_orient = itmp;
+        CREATE_TRY(upload_array(h, (const long long *)d->boundary_neighbor_sides, (size_t)d->nboundaries, &itmp));
+        P.bd_side = itmp;
+    }
+    if (p4est) {
+        CREATE_TRY(upload_array(h, (const long long *)d->interface_node_indices, (size_t)(nd * 2 * d->ninterfaces), &itmp));
+        P.if_node_indices = itmp;
+        CREATE_TRY(upload_array(h, (const long long *)d->boundary_node_indices, (size_t)(nd * d->nboundaries), &itmp));
+        P.bd_node_indices = itmp;
+    }
+    if (!curved) {  // curved kernels read the element's own node coordinates
         CREATE_TRY(upload_array(h, d->boundary_node_coordinates, (size_t)(nd * nf * d->nboundaries), &tmp));
         P.bd_coords = tmp;
     }
