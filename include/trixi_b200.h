@@ -68,8 +68,10 @@ enum {
     TRIXI_B200_FLUX_HINDENLANG_GASSNER = 9, /* ideal_glm_mhd_3d.jl:680-855 */
     TRIXI_B200_FLUX_GODUNOV = 10,           /* linear_scalar_advection_2d.jl:248-275 */
     TRIXI_B200_FLUX_RANOCHA_TURBO = 11,     /* dg_3d_compressible_euler.jl:265-617: hoisted logs */
-    TRIXI_B200_FLUX_LLF_MHD_POWELL = 12,
-    TRIXI_B200_FLUX_HINDENLANG_GASSNER_POWELL = 13
+    TRIXI_B200_FLUX_LLF_MHD_POWELL = 12,            /* (flux_lax_friedrichs, flux_nonconservative_powell) */
+    TRIXI_B200_FLUX_HINDENLANG_GASSNER_POWELL = 13, /* (flux_hindenlang_gassner, flux_nonconservative_powell)
+                                                       ideal_glm_mhd_3d.jl:295-340,680-779 */
+    TRIXI_B200_FLUX_LLF_NAIVE_MHD_POWELL = 14       /* (FluxLaxFriedrichs(max_abs_speed_naive), powell) */
 };
 
 /* source terms (calc_sources! dg_3d.jl:1417-1437 calls an arbitrary closure; here: registry) */

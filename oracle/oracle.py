@@ -93,6 +93,9 @@ class OracleBackend:
     def synchronize(self):
         pass
 
+    def set_eq_param(self, index, value):
+        self.desc.eq_params[index] = float(value)
+
     def set_halo_exchange(self, exchange):
         """``exchange(mpi_u_flat)`` fills the remote side of mpi_u (tests: gloo isend/irecv)."""
         self.halo = exchange

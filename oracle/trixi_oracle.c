@@ -230,6 +230,107 @@ static inline void euler_min_max_speed(const eqn_t *eq, const double *ul, const 
     }
 }
 
+/* ---- ideal GLM-MHD 3D (ideal_glm_mhd_3d.jl) ------------------------------------------------------------ */
+/* cons2prim :1231-1243: (rho, v1, v2, v3, p, B1, B2, B3, psi) */
+static inline void mhd_cons2prim(const eqn_t *eq, const double *u, double *prim) {
+    double rho = u[0];
+    double v1 = u[1] / rho, v2 = u[2] / rho, v3 = u[3] / rho;
+    double p = (eq->gamma - 1) *
+               (u[4] - 0.5 * (u[1] * v1 + u[2] * v2 + u[3] * v3 + u[5] * u[5] + u[6] * u[6] + u[7] * u[7] + u[8] * u[8]));
+    prim[0] = rho;
+    prim[1] = v1;
+    prim[2] = v2;
+    prim[3] = v3;
+    prim[4] = p;
+    prim[5] = u[5];
+    prim[6] = u[6];
+    prim[7] = u[7];
+    prim[8] = u[8];
+}
+
+/* flux(u, orientation) :187-234 */
+static inline void mhd_flux(const eqn_t *eq, const double *u, int o, double *f) {
+    double rho = u[0], psi = u[8];
+    double v[3] = {u[1] / rho, u[2] / rho, u[3] / rho};
+    const double *B = u + 5;
+    double kin_en = 0.5 * (u[1] * v[0] + u[2] * v[1] + u[3] * v[2]);
+    double mag_en = 0.5 * (B[0] * B[0] + B[1] * B[1] + B[2] * B[2]);
+    double p_over_gamma_minus_one = (u[4] - kin_en - mag_en - 0.5 * psi * psi);
+    double p = (eq->gamma - 1) * p_over_gamma_minus_one;
+    double rv = u[1 + o];
+    f[0] = rv;
+    for (int d = 0; d < 3; ++d) f[1 + d] = rv * v[d] - B[o] * B[d];
+    f[1 + o] = rv * v[o] + p + mag_en - B[o] * B[o];
+    f[4] = (kin_en + eq->gamma * p_over_gamma_minus_one + 2 * mag_en) * v[o] -
+           B[o] * (v[0] * B[0] + v[1] * B[1] + v[2] * B[2]) + eq->c_h * psi * B[o];
+    for (int d = 0; d < 3; ++d) f[5 + d] = v[o] * B[d] - v[d] * B[o];
+    f[5 + o] = eq->c_h * psi;
+    f[8] = eq->c_h * B[o];
+}
+
+/* flux_nonconservative_powell(u_ll, u_rr, orientation) :295-340 */
+static inline void mhd_noncons_powell(const eqn_t *eq, const double *ul, const double *ur, int o, double *f) {
+    (void)eq;
+    double v_ll[3] = {ul[1] / ul[0], ul[2] / ul[0], ul[3] / ul[0]};
+    const double *B_ll = ul + 5;
+    double psi_ll = ul[8], psi_rr = ur[8];
+    double v_dot_B_ll = v_ll[0] * B_ll[0] + v_ll[1] * B_ll[1] + v_ll[2] * B_ll[2];
+    double Bn_rr = ur[5 + o];
+    f[0] = 0.0;
+    for (int d = 0; d < 3; ++d) f[1 + d] = B_ll[d] * Bn_rr;
+    f[4] = v_dot_B_ll * Bn_rr + v_ll[o] * psi_ll * psi_rr;
+    for (int d = 0; d < 3; ++d) f[5 + d] = v_ll[d] * Bn_rr;
+    f[8] = v_ll[o] * psi_rr;
+}
+
+/* flux_hindenlang_gassner(u_ll, u_rr, orientation) :680-779 */
+static inline void mhd_flux_hindenlang_gassner(const eqn_t *eq, const double *ul, const double *ur, int o,
+                                               double *f) {
+    double L[9], R[9];
+    mhd_cons2prim(eq, ul, L);
+    mhd_cons2prim(eq, ur, R);
+    double rho_ll = L[0], p_ll = L[4], psi_ll = L[8], rho_rr = R[0], p_rr = R[4], psi_rr = R[8];
+    const double *v_ll = L + 1, *v_rr = R + 1, *B_ll = L + 5, *B_rr = R + 5;
+    double rho_mean = ln_mean(rho_ll, rho_rr);
+    double inv_rho_p_mean = p_ll * p_rr * inv_ln_mean(rho_ll * p_rr, rho_rr * p_ll);
+    double v_avg[3];
+    for (int d = 0; d < 3; ++d) v_avg[d] = 0.5 * (v_ll[d] + v_rr[d]);
+    double p_avg = 0.5 * (p_ll + p_rr), psi_avg = 0.5 * (psi_ll + psi_rr);
+    double velocity_square_avg = 0.5 * (v_ll[0] * v_rr[0] + v_ll[1] * v_rr[1] + v_ll[2] * v_rr[2]);
+    double magnetic_square_avg = 0.5 * (B_ll[0] * B_rr[0] + B_ll[1] * B_rr[1] + B_ll[2] * B_rr[2]);
+    double f1 = rho_mean * v_avg[o];
+    f[0] = f1;
+    for (int d = 0; d < 3; ++d) f[1 + d] = f1 * v_avg[d] - 0.5 * (B_ll[o] * B_rr[d] + B_rr[o] * B_ll[d]);
+    f[1 + o] = f1 * v_avg[o] + p_avg + magnetic_square_avg - 0.5 * (B_ll[o] * B_rr[o] + B_rr[o] * B_ll[o]);
+    for (int d = 0; d < 3; ++d)
+        f[5 + d] = 0.5 * (v_ll[o] * B_ll[d] - v_ll[d] * B_ll[o] + v_rr[o] * B_rr[d] - v_rr[d] * B_rr[o]);
+    f[5 + o] = eq->c_h * psi_avg;
+    f[8] = eq->c_h * 0.5 * (B_ll[o] + B_rr[o]);
+    /* energy flux: the reference lists the two transverse directions in ascending order */
+    int t1 = o == 0 ? 1 : 0, t2 = o == 2 ? 1 : 2;
+    f[4] = f1 * (velocity_square_avg + inv_rho_p_mean * eq->inv_gm1) +
+           0.5 * (+p_ll * v_rr[o] + p_rr * v_ll[o] + (v_ll[o] * B_ll[t1] * B_rr[t1] + v_rr[o] * B_rr[t1] * B_ll[t1]) +
+                  (v_ll[o] * B_ll[t2] * B_rr[t2] + v_rr[o] * B_rr[t2] * B_ll[t2]) -
+                  (v_ll[t1] * B_ll[o] * B_rr[t1] + v_rr[t1] * B_rr[o] * B_ll[t1]) -
+                  (v_ll[t2] * B_ll[o] * B_rr[t2] + v_rr[t2] * B_rr[o] * B_ll[t2]) +
+                  eq->c_h * (B_ll[o] * psi_rr + B_rr[o] * psi_ll));
+}
+
+/* calc_fast_wavespeed(cons, orientation) :1350-1376 */
+static inline double mhd_fast_wavespeed(const eqn_t *eq, const double *u, int o) {
+    double rho = u[0], psi = u[8];
+    double v1 = u[1] / rho, v2 = u[2] / rho, v3 = u[3] / rho;
+    double kin_en = 0.5 * (u[1] * v1 + u[2] * v2 + u[3] * v3);
+    double mag_en = 0.5 * (u[5] * u[5] + u[6] * u[6] + u[7] * u[7]);
+    double p = (eq->gamma - 1) * (u[4] - kin_en - mag_en - 0.5 * psi * psi);
+    double a_square = eq->gamma * p / rho;
+    double sqrt_rho = sqrt(rho);
+    double b[3] = {u[5] / sqrt_rho, u[6] / sqrt_rho, u[7] / sqrt_rho};
+    double b_square = b[0] * b[0] + b[1] * b[1] + b[2] * b[2];
+    double s = a_square + b_square;
+    return sqrt(0.5 * s + 0.5 * sqrt(s * s - 4 * a_square * b[o] * b[o]));
+}
+
 /* ---- linear scalar advection (linear_scalar_advection_2d.jl:221-246) ----------------------------- */
 static inline void adv_flux(const eqn_t *eq, const double *u, int o, double *f) { f[0] = eq->a[o] * u[0]; }
 
@@ -238,15 +339,24 @@ static inline int is_euler(const eqn_t *eq) {
     return eq->id == TRIXI_B200_EQ_EULER_2D || eq->id == TRIXI_B200_EQ_EULER_3D;
 }
 
+static inline int is_mhd(const eqn_t *eq) { return eq->id == TRIXI_B200_EQ_MHD_3D; }
+
 static inline void phys_flux(const eqn_t *eq, const double *u, int o, double *f) {
     if (is_euler(eq))
         euler_flux(eq, u, o, f);
+    else if (is_mhd(eq))
+        mhd_flux(eq, u, o, f);
     else
         adv_flux(eq, u, o, f);
 }
 
 static inline double max_abs_speed_disp(const eqn_t *eq, const double *ul, const double *ur, int o, int naive) {
     if (is_euler(eq)) return euler_max_abs_speed(eq, ul, ur, o, naive);
+    if (is_mhd(eq)) { /* ideal_glm_mhd_3d.jl:857-928 */
+        double v_ll = ul[1 + o] / ul[0], v_rr = ur[1 + o] / ur[0];
+        double cf_ll = mhd_fast_wavespeed(eq, ul, o), cf_rr = mhd_fast_wavespeed(eq, ur, o);
+        return naive ? fmax(fabs(v_ll), fabs(v_rr)) + fmax(cf_ll, cf_rr) : fmax(fabs(v_ll) + cf_ll, fabs(v_rr) + cf_rr);
+    }
     /* advection: max_abs_speed falls back to max_abs_speed_naive = |a| (numerical_fluxes.jl:219-225) */
     return fabs(eq->a[o]);
 }
@@ -306,9 +416,24 @@ static void numflux(const eqn_t *eq, int flux_id, const double *ul, const double
     case TRIXI_B200_FLUX_GODUNOV: /* linear_scalar_advection_2d.jl:248-260 */
         f[0] = eq->a[o] >= 0 ? eq->a[o] * ul[0] : eq->a[o] * ur[0];
         return;
+    case TRIXI_B200_FLUX_HINDENLANG_GASSNER:
+    case TRIXI_B200_FLUX_HINDENLANG_GASSNER_POWELL: /* conservative part of the tuple */
+        mhd_flux_hindenlang_gassner(eq, ul, ur, o, f);
+        return;
+    case TRIXI_B200_FLUX_LLF_NAIVE_MHD_POWELL: /* (FluxLaxFriedrichs(max_abs_speed_naive), powell) */
+        numflux(eq, TRIXI_B200_FLUX_LLF_NAIVE, ul, ur, o, f);
+        return;
+    case TRIXI_B200_FLUX_LLF_MHD_POWELL: /* (flux_lax_friedrichs, powell) */
+        numflux(eq, TRIXI_B200_FLUX_LLF, ul, ur, o, f);
+        return;
     default:
         for (int v = 0; v < nv; ++v) f[v] = NAN;
     }
+}
+
+static inline int flux_has_noncons(int flux_id) {
+    return flux_id == TRIXI_B200_FLUX_HINDENLANG_GASSNER_POWELL || flux_id == TRIXI_B200_FLUX_LLF_MHD_POWELL ||
+           flux_id == TRIXI_B200_FLUX_LLF_NAIVE_MHD_POWELL;
 }
 
 /* ---- normal-direction versions (curved meshes) -------------------------------------------------- */
@@ -746,6 +871,30 @@ static void flux_differencing_kernel(const trixi_b200_desc *d, const eqn_t *eq, 
             }
 }
 
+/* flux_differencing_kernel! with nonconservative terms dg_3d.jl:216-266: the nonsymmetric part */
+static void flux_differencing_noncons(const trixi_b200_desc *d, const eqn_t *eq, double *du, const double *u) {
+    int n = d->nnodes, nv = d->nvars;
+    const double *Ds = d->derivative_split;
+    int stride[3] = {1, n, n * n};
+    for (int k = 0; k < n; ++k)
+        for (int j = 0; j < n; ++j)
+            for (int i = 0; i < n; ++i) {
+                int idx[3] = {i, j, k};
+                int64_t node = i + n * (j + n * k);
+                const double *un = u + nv * node;
+                double integral_contribution[MAXV] = {0};
+                for (int a = 0; a < 3; ++a)
+                    for (int ii = 0; ii < n; ++ii) {
+                        int64_t node2 = node + (ii - idx[a]) * stride[a];
+                        double g[MAXV];
+                        mhd_noncons_powell(eq, un, u + nv * node2, a, g);
+                        double w = Ds[idx[a] + n * ii];
+                        for (int v = 0; v < nv; ++v) integral_contribution[v] = integral_contribution[v] + w * g[v];
+                    }
+                for (int v = 0; v < nv; ++v) du[nv * node + v] = du[nv * node + v] + 0.5 * integral_contribution[v];
+            }
+}
+
 /* calc_volume_integral! calc_volume_integral.jl:180-191 (+ dispatch :11-33) */
 void oracle_calc_volume_integral(const trixi_b200_desc *d, double *du, const double *u) {
     eqn_t eq = make_eqn(d);
@@ -754,8 +903,10 @@ void oracle_calc_volume_integral(const trixi_b200_desc *d, double *du, const dou
     for (int64_t e = 0; e < d->nelements; ++e) {
         if (d->volume_integral == TRIXI_B200_VOLINT_WEAK_FORM)
             weak_form_kernel(d, &eq, du + e * esz, u + e * esz);
-        else
+        else {
             flux_differencing_kernel(d, &eq, du + e * esz, u + e * esz);
+            if (flux_has_noncons(d->volume_flux)) flux_differencing_noncons(d, &eq, du + e * esz, u + e * esz);
+        }
     }
 }
 
@@ -799,6 +950,16 @@ void oracle_calc_interface_flux(const trixi_b200_desc *d, double *sfv, const dou
                 ur[v] = iu[1 + 2 * (v + nv * (fn + (int64_t)nf * I))];
             }
             numflux(&eq, d->surface_flux, ul, ur, o, f);
+            if (flux_has_noncons(d->surface_flux)) { /* dg_3d.jl:604-649 */
+                double nl[MAXV], nr[MAXV];
+                mhd_noncons_powell(&eq, ul, ur, o, nl);
+                mhd_noncons_powell(&eq, ur, ul, o, nr);
+                for (int v = 0; v < nv; ++v) {
+                    sfv[left * fsz + v + nv * (fn + nf * left_direction)] = f[v] + 0.5 * nl[v];
+                    sfv[right * fsz + v + nv * (fn + nf * right_direction)] = f[v] + 0.5 * nr[v];
+                }
+                continue;
+            }
             for (int v = 0; v < nv; ++v) {
                 sfv[left * fsz + v + nv * (fn + nf * left_direction)] = f[v];
                 sfv[right * fsz + v + nv * (fn + nf * right_direction)] = f[v];
@@ -1425,6 +1586,15 @@ double oracle_max_dt(const trixi_b200_desc *d, const double *u) {
                 double c = sqrt(eq.gamma * p / rho); /* max_abs_speeds compressible_euler_3d.jl:1770-1775 */
                 for (int dd = 0; dd < nd; ++dd) {
                     double l = fabs(v[dd]) + c;
+                    if (isnan(l)) nanflag = 1;
+                    ml[dd] = fmax(ml[dd], l);
+                }
+            }
+        } else if (is_mhd(&eq)) { /* max_abs_speeds ideal_glm_mhd_3d.jl:1218-1228 */
+            for (int64_t q = 0; q < nn; ++q) {
+                const double *un = u + nv * (q + nn * e);
+                for (int dd = 0; dd < 3; ++dd) {
+                    double l = fabs(un[1 + dd] / un[0]) + mhd_fast_wavespeed(&eq, un, dd);
                     if (isnan(l)) nanflag = 1;
                     ml[dd] = fmax(ml[dd], l);
                 }

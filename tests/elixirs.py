@@ -340,3 +340,53 @@ ELIXIRS.update({e.name: e for e in [
            [0.01031578086475382, 0.011300883615913193, 0.011300883615896096, 0.011300883615918522,
             0.02090696711453477], "test/test_cuda_3d.jl:58-75 (native Float64 run of the reference's GPU test)"),
 ]})
+
+
+# ---- ideal GLM-MHD 3D -----------------------------------------------------------------------------------------
+class MhdElixir(Elixir):
+    def run(self, semi):
+        ode = T.semidiscretize(semi, self.tspan)
+        analysis = T.AnalysisCallback(semi, interval=100)
+        callbacks = T.CallbackSet(T.SummaryCallback(), analysis, T.StepsizeCallback(cfl=self.cfl),
+                                  T.GlmSpeedCallback(glm_scale=0.5, cfl=self.cfl))
+        sol = T.solve(ode, T.CarpenterKennedy2N54(), dt=1.0, callback=callbacks, maxiters=self.maxiters)
+        l2, linf = analysis(sol)
+        return sol, l2, linf
+
+
+def _mhd3d_ec(initial_condition=T.initial_condition_weak_blast_wave):
+    # examples/tree_3d_dgsem/elixir_mhd_ec.jl
+    eq = T.IdealGlmMhdEquations3D(1.4)
+    flux = (T.flux_hindenlang_gassner, T.flux_nonconservative_powell)
+    solver = T.DGSEM(polydeg=3, surface_flux=flux, volume_integral=T.VolumeIntegralFluxDifferencing(flux))
+    mesh = T.TreeMesh((-2.0,) * 3, (2.0,) * 3, initial_refinement_level=2, periodicity=True)
+    return T.SemidiscretizationHyperbolic(mesh, eq, initial_condition, solver)
+
+
+def _mhd3d_alfven_wave():
+    # examples/tree_3d_dgsem/elixir_mhd_alfven_wave.jl
+    eq = T.IdealGlmMhdEquations3D(5 / 3)
+    surface_flux = (T.FluxLaxFriedrichs(T.max_abs_speed_naive), T.flux_nonconservative_powell)
+    volume_flux = (T.flux_hindenlang_gassner, T.flux_nonconservative_powell)
+    solver = T.DGSEM(polydeg=3, surface_flux=surface_flux,
+                     volume_integral=T.VolumeIntegralFluxDifferencing(volume_flux))
+    mesh = T.TreeMesh((-1.0,) * 3, (1.0,) * 3, initial_refinement_level=2, periodicity=True)
+    return T.SemidiscretizationHyperbolic(mesh, eq, T.initial_condition_convergence_test, solver)
+
+
+ELIXIRS.update({e.name: e for e in [
+    MhdElixir("tree_3d_mhd_ec", _mhd3d_ec, (0.0, 0.4), 1.4,
+              [0.017590099293094203, 0.017695875823827714, 0.017695875823827686, 0.017698038279620777,
+               0.07495006099352074, 0.010391801950005755, 0.010391801950005759, 0.010393502246627087,
+               2.524766553484067e-16],
+              [0.28173002819718196, 0.3297583616136297, 0.32975836161363004, 0.356862935505337,
+               1.2893514981209626, 0.10950981489747313, 0.10950981489747136, 0.11517234329681891,
+               2.0816911067714202e-15], "test/test_tree_3d_mhd.jl:5-34"),
+    MhdElixir("tree_3d_mhd_alfven_wave", _mhd3d_alfven_wave, (0.0, 1.0), 1.5,
+              [0.0032217291057246157, 0.009511644936958913, 0.004217358459420256, 0.011591709179125335,
+               0.009456218722393708, 0.00916500047763897, 0.005069863732625444, 0.011503011541926135,
+               0.003988175543749985],
+              [0.01188593784273051, 0.03638015998373141, 0.01568200398945724, 0.04666974730787579,
+               0.031235294705421968, 0.03316343064943483, 0.011539436992528018, 0.04896687646520839,
+               0.018714054039927555], "test/test_tree_3d_mhd.jl:66-92"),
+]})

@@ -5,8 +5,8 @@ C ABI of ``libtrixi_b200.so`` (``include/trixi_b200.h``).  Import it as ``trixi_
 name contains a dot; ``trixi_b200.py`` at the repository root is the loader).
 """
 from .basis import LobattoLegendreBasis, SolutionAnalyzer, gauss_lobatto_nodes_weights  # noqa: F401
-from .callbacks import (AliveCallback, AnalysisCallback, StepsizeCallback, SummaryCallback,  # noqa: F401
-                        calc_error_norms)
+from .callbacks import (AliveCallback, AnalysisCallback, GlmSpeedCallback, StepsizeCallback,  # noqa: F401
+                        SummaryCallback, calc_error_norms)
 from .equations import *  # noqa: F401,F403
 from .mesh import CartesianBoxMesh, TreeMesh  # noqa: F401
 from .p4est import P4estMesh  # noqa: F401

@@ -70,6 +70,32 @@ class StepsizeCallback(_Callback):
         return allreduce_min(dt, ode.p.comm) if ode.p.world_size > 1 else dt
 
 
+class GlmSpeedCallback(_Callback):
+    """``GlmSpeedCallback(; glm_scale, cfl)`` (glm_speed.jl:55-121, glm_speed_dg.jl:8-27): after every step
+    c_h = glm_scale * dt(c_h = 1) / dt; a host-side scalar update pushed to the device with
+    ``trixi_b200_set_eq_param`` (the equations' c_h is mutable per step)."""
+
+    def __init__(self, glm_scale=0.5, cfl=1.0):
+        assert 0 <= glm_scale <= 1, "glm_scale must be between 0 and 1"
+        self.glm_scale, self.cfl = glm_scale, cfl
+
+    def initialize(self, integrator):
+        self.affect(integrator)
+
+    def condition(self, integrator):
+        return True
+
+    def affect(self, integrator):
+        semi = integrator.semi
+        cfl = self.cfl(integrator.t) if callable(self.cfl) else self.cfl
+        max_scaled_speed_for_c_h = float(np.max(semi.cache.elements.inverse_jacobian)) * semi.mesh.ndims
+        if semi.world_size > 1:
+            max_scaled_speed_for_c_h = -allreduce_min(-max_scaled_speed_for_c_h, semi.comm)
+        c_h_deltat = cfl * 2 / (semi.solver.nnodes * max_scaled_speed_for_c_h)
+        semi.equations.c_h = self.glm_scale * c_h_deltat / integrator.dt
+        integrator.backend.set_eq_param(2, semi.equations.c_h)
+
+
 def multiply_dimensionwise(matrix, data):
     """``multiply_dimensionwise`` (basis_lobatto_legendre.jl / interpolation.jl): apply ``matrix`` along
     every spatial axis of ``data[var, i, j, (k)]`` (leading axis untouched, trailing axes batch)."""

@@ -29,6 +29,7 @@ FLUX_GODUNOV = 10
 FLUX_RANOCHA_TURBO = 11
 FLUX_LLF_MHD_POWELL = 12      # (flux_lax_friedrichs, flux_nonconservative_powell)
 FLUX_HINDENLANG_GASSNER_POWELL = 13
+FLUX_LLF_NAIVE_MHD_POWELL = 14  # (FluxLaxFriedrichs(max_abs_speed_naive), flux_nonconservative_powell)
 
 SRC_NONE, SRC_CONVERGENCE_TEST, SRC_EOC_TEST_EULER, SRC_EOC_TEST_COUPLED_EULER_GRAVITY = 0, 1, 2, 3
 
@@ -104,8 +105,10 @@ def resolve_flux(flux):
             raise ValueError("only flux_nonconservative_powell is supported as nonconservative flux")
         if cons.flux_id == FLUX_HINDENLANG_GASSNER:
             return FLUX_HINDENLANG_GASSNER_POWELL
-        if cons.flux_id in (FLUX_LLF, FLUX_LLF_NAIVE):
+        if cons.flux_id == FLUX_LLF:
             return FLUX_LLF_MHD_POWELL
+        if cons.flux_id == FLUX_LLF_NAIVE:
+            return FLUX_LLF_NAIVE_MHD_POWELL
         raise ValueError(f"unsupported conservative flux {cons} with Powell term")
     if not isinstance(flux, _Flux):
         raise TypeError(f"numerical flux {flux!r} is not in the libtrixi_b200 registry")
@@ -249,11 +252,12 @@ class IdealGlmMhdEquations3D(AbstractEquations):
         return [self.gamma, self.inv_gamma_minus_one, self.c_h] + [0.0] * 5
 
     def prim2cons(self, prim):
-        rho, v1, v2, v3, p, B1, B2, B3, psi = prim
+        # ideal_glm_mhd_3d.jl:1273-1284
+        rho, v1, v2, v3, p, B1, B2, B3, psi = np.broadcast_arrays(*prim)
         rv1, rv2, rv3 = rho * v1, rho * v2, rho * v3
         e = (p * self.inv_gamma_minus_one + 0.5 * (rv1 * v1 + rv2 * v2 + rv3 * v3)
-             + 0.5 * (B1 * B1 + B2 * B2 + B3 * B3) + 0.5 * psi * psi)
-        return np.stack([rho, rv1, rv2, rv3, e, B1, B2, B3, psi])
+             + 0.5 * (B1 * B1 + B2 * B2 + B3 * B3) + 0.5 * psi**2)
+        return np.stack([rho, rv1, rv2, rv3, e, B1 + 0 * rho, B2 + 0 * rho, B3 + 0 * rho, psi + 0 * rho])
 
 
 # ---- initial conditions (host, NumPy-vectorised: x has shape [ndims, ...]) ---------------------------
@@ -269,9 +273,8 @@ def initial_condition_constant(x, t, equations):
     elif isinstance(equations, LinearScalarAdvectionEquation2D):
         vals = (2.0,)
     elif isinstance(equations, IdealGlmMhdEquations3D):
-        # ideal_glm_mhd_3d.jl:86-98 (primitive -> conservative)
-        prim = [np.full(shape, v) for v in (1.0, 0.1, -0.2, 0.3, 10.0 * 0 + 1.0, 3.0, -1.2, 0.5, 0.0)]
-        raise NotImplementedError("filled in with the MHD row")
+        # ideal_glm_mhd_3d.jl:101-113 (conservative values)
+        vals = (1.0, 0.1, -0.2, -0.5, 50.0, 3.0, -1.2, 0.5, 0.0)
     else:
         raise NotImplementedError
     return np.stack([np.full(shape, v) for v in vals])
@@ -295,6 +298,21 @@ def initial_condition_convergence_test(x, t, equations):
         omega = 2 * math.pi * 0.5
         ini = 2 + 0.1 * np.sin(omega * (x[0] + x[1] - t))
         return np.stack([ini, ini, ini, ini**2])
+    if isinstance(equations, IdealGlmMhdEquations3D):
+        # Alfven wave, ideal_glm_mhd_3d.jl:124-150
+        p, omega, r, e = 1.0, 2 * math.pi, 2.0, 0.2
+        nx, ny = 1 / math.sqrt(r**2 + 1), r / math.sqrt(r**2 + 1)
+        sqr = 1.0
+        Va = omega / (ny * sqr)
+        phi_alv = omega / ny * (nx * (x[0] - 0.5 * r) + ny * (x[1] - 0.5 * r)) - Va * t
+        rho = np.ones_like(phi_alv)
+        v1 = -e * ny * np.cos(phi_alv) / rho
+        v2 = e * nx * np.cos(phi_alv) / rho
+        v3 = e * np.sin(phi_alv) / rho
+        B1 = nx - rho * v1 * sqr
+        B2 = ny - rho * v2 * sqr
+        B3 = -rho * v3 * sqr
+        return equations.prim2cons((rho, v1, v2, v3, p * rho, B1, B2, B3, 0.0 * rho))
     raise NotImplementedError
 
 
@@ -313,6 +331,20 @@ def initial_condition_weak_blast_wave(x, t, equations):
         v3 = np.where(outside, 0.0, 0.1882 * np.cos(theta))
         p = np.where(outside, 1.0, 1.245)
         return equations.prim2cons((rho, v1, v2, v3, p))
+    if isinstance(equations, IdealGlmMhdEquations3D):
+        # ideal_glm_mhd_3d.jl:160-180
+        r = np.sqrt(x[0]**2 + x[1]**2 + x[2]**2)
+        phi = np.arctan2(x[1], x[0])
+        with np.errstate(invalid="ignore", divide="ignore"):
+            theta = np.where(r == 0, 0.0, np.arccos(np.where(r == 0, 0.0, x[2] / np.where(r == 0, 1.0, r))))
+        outside = r > 0.5
+        rho = np.where(outside, 1.0, 1.1691)
+        v1 = np.where(outside, 0.0, 0.1882 * np.cos(phi) * np.sin(theta))
+        v2 = np.where(outside, 0.0, 0.1882 * np.sin(phi) * np.sin(theta))
+        v3 = np.where(outside, 0.0, 0.1882 * np.cos(theta))
+        p = np.where(outside, 1.0, 1.245)
+        one = np.ones_like(rho)
+        return equations.prim2cons((rho, v1, v2, v3, p, one, one, one, 0.0 * one))
     if isinstance(equations, CompressibleEulerEquations2D):
         # compressible_euler_2d.jl:181-199
         r = np.sqrt(x[0]**2 + x[1]**2)
