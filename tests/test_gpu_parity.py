@@ -41,6 +41,12 @@ def _random_admissible_state(semi, seed=0, perturb=None):
         rho = 1.0 + perturb * rng.uniform(-1.0, 1.0, size=shape)
         v = [0.3 + perturb * rng.uniform(-1.0, 1.0, size=shape) for _ in range(nd)]
         p = 1.0 + perturb * rng.uniform(-1.0, 1.0, size=shape)
+    if isinstance(eq, T.IdealGlmMhdEquations3D):
+        if perturb is None:
+            extra = [rng.uniform(-1.0, 1.0, size=shape) for _ in range(4)]  # B1, B2, B3, psi
+        else:
+            extra = [0.2 + perturb * rng.uniform(-1.0, 1.0, size=shape) for _ in range(4)]
+        return np.asfortranarray(eq.prim2cons((rho, *v, p, *extra)))
     return np.asfortranarray(eq.prim2cons((rho, *v, p)))
 
 
@@ -54,7 +60,8 @@ RHS_CASES = ["tree_3d_euler_ec", "tree_3d_euler_source_terms", "tree_3d_euler_so
              "tree_2d_euler_source_terms", "tree_2d_euler_source_terms_nonperiodic", "tree_2d_euler_ec",
              "tree_2d_euler_density_wave", "structured_3d_euler_free_stream", "structured_3d_euler_ec",
              "structured_3d_euler_source_terms", "structured_3d_euler_source_terms_nonperiodic_curved",
-             "p4est_3d_euler_source_terms_nonperiodic", "p4est_3d_euler_source_terms_nonperiodic_kennedy_gruber"]
+             "p4est_3d_euler_source_terms_nonperiodic", "p4est_3d_euler_source_terms_nonperiodic_kennedy_gruber",
+             "tree_3d_mhd_ec", "tree_3d_mhd_alfven_wave"]
 
 
 @pytest.mark.parametrize("name", RHS_CASES)
@@ -79,7 +86,8 @@ def test_rhs_matches_oracle(name, state, oracle_module):
 
 @pytest.mark.parametrize("name", ["tree_3d_euler_ec", "tree_3d_euler_source_terms", "tree_2d_euler_source_terms_nonperiodic",
                                   "structured_3d_euler_ec", "structured_3d_euler_source_terms_nonperiodic_curved",
-                                  "p4est_3d_euler_source_terms_nonperiodic_kennedy_gruber"])
+                                  "p4est_3d_euler_source_terms_nonperiodic_kennedy_gruber", "tree_3d_mhd_ec",
+                                  "tree_3d_mhd_alfven_wave"])
 def test_stage_level_parity(name, oracle_module):
     """calc_volume_integral! and the surface flux stages separately, like the reference's kernel parity
     tests (test/test_performance_specializations_3d.jl:49-89)."""
@@ -104,7 +112,8 @@ def test_stage_level_parity(name, oracle_module):
 
 
 @pytest.mark.parametrize("name", ["tree_3d_euler_ec", "tree_2d_advection_basic", "tree_2d_euler_density_wave",
-                                  "structured_3d_euler_ec", "structured_3d_euler_source_terms_nonperiodic_curved"])
+                                  "structured_3d_euler_ec", "structured_3d_euler_source_terms_nonperiodic_curved",
+                                  "tree_3d_mhd_ec"])
 def test_max_dt_matches_oracle(name, oracle_module):
     semi = ELIXIRS[name].semi()
     u = _random_admissible_state(semi, seed=4)
@@ -124,7 +133,8 @@ def test_max_dt_propagates_nan(oracle_module):
     assert np.isnan(gpu.max_dt())
 
 
-@pytest.mark.parametrize("name", ["tree_3d_euler_ec", "tree_3d_euler_source_terms", "tree_2d_advection_basic"])
+@pytest.mark.parametrize("name", ["tree_3d_euler_ec", "tree_3d_euler_source_terms", "tree_2d_advection_basic",
+                                  "tree_3d_mhd_alfven_wave"])
 def test_step_2n_matches_oracle(name, oracle_module):
     """Three full CarpenterKennedy2N54 steps (5 RHS + fused stage updates each) against the oracle's
     separate RHS / axpy sweeps (methods_2N.jl:144-159)."""
@@ -150,7 +160,7 @@ GOLDEN_GPU = ["tree_3d_euler_ec", "tree_3d_euler_ec_constant", "tree_3d_euler_so
               "tree_2d_euler_ec", "tree_2d_euler_density_wave", "structured_3d_euler_free_stream",
               "structured_3d_euler_ec", "structured_3d_euler_source_terms",
               "structured_3d_euler_source_terms_nonperiodic_curved", "p4est_3d_euler_source_terms_nonperiodic",
-              "p4est_3d_euler_source_terms_nonperiodic_kennedy_gruber"]
+              "p4est_3d_euler_source_terms_nonperiodic_kennedy_gruber", "tree_3d_mhd_ec", "tree_3d_mhd_alfven_wave"]
 
 
 @pytest.mark.parametrize("name", GOLDEN_GPU)

@@ -129,6 +129,20 @@ __global__ void __launch_bounds__(256) k_interface_flux(const KParams P) {
     // left element: direction 2*orientation (1-based) = index 2o+1; right element: 2o (dg_3d.jl:581-597)
     double *sl = P.sfv + ((left * (2 * ND) + (2 * o + 1)) * NF + fn) * NV;
     double *sr = P.sfv + ((right * (2 * ND) + (2 * o)) * NF + fn) * NV;
+    if constexpr (EQ::kHasNoncons) {
+        // calc_interface_flux! with nonconservative terms (dg_3d.jl:604-649): flux + 0.5 * noncons per side
+        if (EQ::has_noncons(P.surface_flux)) {
+            double gl[NV], gr[NV];
+            eq.noncons(ul, ur, o, gl);
+            eq.noncons(ur, ul, o, gr);
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+                sl[v] = f[v] + 0.5 * gl[v];
+                sr[v] = f[v] + 0.5 * gr[v];
+            }
+            return;
+        }
+    }
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
         sl[v] = f[v];
@@ -210,6 +224,18 @@ __global__ void __launch_bounds__(256) k_mpi_interface_flux(const KParams P) {
     surface_numflux<EQ, FAST>(eq, P.surface_flux, ul, ur, o, f);
     const int direction0 = side == 1 ? 2 * o + 1 : 2 * o;
     double *s = P.sfv + ((element * (2 * ND) + direction0) * NF + fn) * NV;
+    if constexpr (EQ::kHasNoncons) {
+        if (EQ::has_noncons(P.surface_flux)) {
+            double g[NV];
+            if (side == 1)
+                eq.noncons(ul, ur, o, g);
+            else
+                eq.noncons(ur, ul, o, g);
+#pragma unroll
+            for (int v = 0; v < NV; ++v) s[v] = f[v] + 0.5 * g[v];
+            return;
+        }
+    }
 #pragma unroll
     for (int v = 0; v < NV; ++v) s[v] = f[v];
 }
@@ -319,6 +345,31 @@ __global__ void __launch_bounds__(ElemCfg<EQ, N>::THREADS) k_element(const KPara
                     const double w = s_D[idx[d] + N * l];  // Dsplit[idx_d, l]
 #pragma unroll
                     for (int v = 0; v < NV; ++v) acc[v] = fma(w, f[v], acc[v]);
+                }
+            }
+            if constexpr (EQ::kHasNoncons) {
+                // nonconservative volume terms (dg_3d.jl:216-266): 0.5 * sum_l Dsplit[idx_d, l] g(u, u_l, d)
+                if (EQ::has_noncons(P.volume_flux)) {
+                    double ic[NV];
+#pragma unroll
+                    for (int v = 0; v < NV; ++v) ic[v] = 0.0;
+#pragma unroll
+                    for (int d = 0; d < ND; ++d) {
+                        const int base = node - idx[d] * stride[d];
+#pragma unroll 1
+                        for (int l = 0; l < N; ++l) {
+                            double up[NV], g[NV];
+                            const double *pu = ue + (base + l * stride[d]) * US;
+#pragma unroll
+                            for (int v = 0; v < NV; ++v) up[v] = pu[v];
+                            eq.noncons(un, up, d, g);
+                            const double w = s_D[idx[d] + N * l];
+#pragma unroll
+                            for (int v = 0; v < NV; ++v) ic[v] = fma(w, g[v], ic[v]);
+                        }
+                    }
+#pragma unroll
+                    for (int v = 0; v < NV; ++v) acc[v] = fma(0.5, ic[v], acc[v]);
                 }
             }
         }

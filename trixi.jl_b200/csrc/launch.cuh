@@ -219,5 +219,6 @@ const Launchers *launchers_for_nnodes(int n) {
 const Launchers *get_launchers_advection2d(int nnodes);
 const Launchers *get_launchers_euler2d(int nnodes);
 const Launchers *get_launchers_euler3d(int nnodes);
+const Launchers *get_launchers_mhd3d(int nnodes);
 
 }  // namespace tb

@@ -89,6 +89,7 @@ template <int ND>
 struct Advection {
     static constexpr int NDIMS = ND, NVARS = 1;
     static constexpr bool kConstantSpeed = true;  // have_constant_speed (linear_scalar_advection_2d.jl:290)
+    static constexpr bool kHasNoncons = false;
     double a0, a1, a2;
     __host__ __device__ explicit Advection(const EqParams &q) : a0(q.p[0]), a1(q.p[1]), a2(q.p[2]) {}
     TB_DEV double a(int o) const { return o == 0 ? a0 : (o == 1 ? a1 : a2); }
@@ -176,6 +177,7 @@ template <int ND>
 struct Euler {
     static constexpr int NDIMS = ND, NVARS = ND + 2;
     static constexpr bool kConstantSpeed = false;
+    static constexpr bool kHasNoncons = false;
     double gamma, inv_gm1;
     __host__ __device__ explicit Euler(const EqParams &q) : gamma(q.p[0]), inv_gm1(q.p[1]) {}
 
@@ -692,6 +694,190 @@ struct Euler {
 #pragma unroll
         for (int d = 0; d < ND; ++d)
             if (d == o) f[1 + d] = p_star;
+    }
+};
+
+// ---- ideal GLM-MHD 3D (ideal_glm_mhd_3d.jl) ------------------------------------------------------------
+struct Mhd3D {
+    static constexpr int NDIMS = 3, NVARS = 9;
+    static constexpr bool kConstantSpeed = false;
+    static constexpr bool kHasNoncons = true;  // have_nonconservative_terms (ideal_glm_mhd_3d.jl:81)
+    double gamma, inv_gm1, c_h;
+    __host__ __device__ explicit Mhd3D(const EqParams &q) : gamma(q.p[0]), inv_gm1(q.p[1]), c_h(q.p[2]) {}
+
+    TB_DEV static bool has_noncons(int flux_id) {
+        return flux_id == TRIXI_B200_FLUX_HINDENLANG_GASSNER_POWELL || flux_id == TRIXI_B200_FLUX_LLF_MHD_POWELL ||
+               flux_id == TRIXI_B200_FLUX_LLF_NAIVE_MHD_POWELL;
+    }
+    TB_DEV static double sel3(double a, double b, double c, int o) { return o == 0 ? a : (o == 1 ? b : c); }
+
+    // flux(u, orientation) (:187-234)
+    TB_DEV void flux(const double (&u)[9], int o, double (&f)[9]) const {
+        const double rho = u[0], psi = u[8];
+        const double v[3] = {u[1] / rho, u[2] / rho, u[3] / rho};
+        const double B[3] = {u[5], u[6], u[7]};
+        const double kin_en = 0.5 * (u[1] * v[0] + u[2] * v[1] + u[3] * v[2]);
+        const double mag_en = 0.5 * (B[0] * B[0] + B[1] * B[1] + B[2] * B[2]);
+        const double pogm1 = u[4] - kin_en - mag_en - 0.5 * psi * psi;
+        const double p = (gamma - 1) * pogm1;
+        const double rv = sel3(u[1], u[2], u[3], o), vo = sel3(v[0], v[1], v[2], o), Bo = sel3(B[0], B[1], B[2], o);
+        f[0] = rv;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) f[1 + d] = d == o ? rv * vo + p + mag_en - Bo * Bo : rv * v[d] - Bo * B[d];
+        f[4] = (kin_en + gamma * pogm1 + 2 * mag_en) * vo - Bo * (v[0] * B[0] + v[1] * B[1] + v[2] * B[2]) +
+               c_h * psi * Bo;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) f[5 + d] = d == o ? c_h * psi : vo * B[d] - v[d] * Bo;
+        f[8] = c_h * Bo;
+    }
+
+    // flux_nonconservative_powell(u_ll, u_rr, orientation) (:295-340)
+    TB_DEV void noncons(const double (&ul)[9], const double (&ur)[9], int o, double (&f)[9]) const {
+        const double v_ll[3] = {ul[1] / ul[0], ul[2] / ul[0], ul[3] / ul[0]};
+        const double v_dot_B_ll = v_ll[0] * ul[5] + v_ll[1] * ul[6] + v_ll[2] * ul[7];
+        const double Bn_rr = sel3(ur[5], ur[6], ur[7], o), vo = sel3(v_ll[0], v_ll[1], v_ll[2], o);
+        f[0] = 0.0;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) f[1 + d] = ul[5 + d] * Bn_rr;
+        f[4] = v_dot_B_ll * Bn_rr + vo * ul[8] * ur[8];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) f[5 + d] = v_ll[d] * Bn_rr;
+        f[8] = vo * ur[8];
+    }
+
+    // cons2prim (:1231-1243)
+    TB_DEV void cons2prim(const double (&u)[9], double (&q)[9]) const {
+        const double rho = u[0];
+        const double v1 = u[1] / rho, v2 = u[2] / rho, v3 = u[3] / rho;
+        q[0] = rho;
+        q[1] = v1;
+        q[2] = v2;
+        q[3] = v3;
+        q[4] = (gamma - 1) * (u[4] - 0.5 * (u[1] * v1 + u[2] * v2 + u[3] * v3 + u[5] * u[5] + u[6] * u[6] +
+                                            u[7] * u[7] + u[8] * u[8]));
+        q[5] = u[5];
+        q[6] = u[6];
+        q[7] = u[7];
+        q[8] = u[8];
+    }
+
+    // flux_hindenlang_gassner(u_ll, u_rr, orientation) (:680-779)
+    TB_DEV void flux_hindenlang_gassner(const double (&ul)[9], const double (&ur)[9], int o, double (&f)[9]) const {
+        double L[9], R[9];
+        cons2prim(ul, L);
+        cons2prim(ur, R);
+        const double rho_mean = ln_mean(L[0], R[0]);
+        const double inv_rho_p_mean = L[4] * R[4] * inv_ln_mean(L[0] * R[4], R[0] * L[4]);
+        double v_avg[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) v_avg[d] = 0.5 * (L[1 + d] + R[1 + d]);
+        const double p_avg = 0.5 * (L[4] + R[4]), psi_avg = 0.5 * (L[8] + R[8]);
+        const double velocity_square_avg = 0.5 * (L[1] * R[1] + L[2] * R[2] + L[3] * R[3]);
+        const double magnetic_square_avg = 0.5 * (L[5] * R[5] + L[6] * R[6] + L[7] * R[7]);
+        const double vo_l = sel3(L[1], L[2], L[3], o), vo_r = sel3(R[1], R[2], R[3], o);
+        const double Bo_l = sel3(L[5], L[6], L[7], o), Bo_r = sel3(R[5], R[6], R[7], o);
+        const double f1 = rho_mean * sel3(v_avg[0], v_avg[1], v_avg[2], o);
+        f[0] = f1;
+#pragma unroll
+        for (int d = 0; d < 3; ++d)
+            f[1 + d] = d == o ? f1 * v_avg[d] + p_avg + magnetic_square_avg - 0.5 * (Bo_l * Bo_r + Bo_r * Bo_l)
+                              : f1 * v_avg[d] - 0.5 * (Bo_l * R[5 + d] + Bo_r * L[5 + d]);
+#pragma unroll
+        for (int d = 0; d < 3; ++d)
+            f[5 + d] = d == o ? c_h * psi_avg
+                              : 0.5 * (vo_l * L[5 + d] - L[1 + d] * Bo_l + vo_r * R[5 + d] - R[1 + d] * Bo_r);
+        f[8] = c_h * 0.5 * (Bo_l + Bo_r);
+        // transverse directions in ascending order, as the reference writes them out
+        const int t1 = o == 0 ? 1 : 0, t2 = o == 2 ? 1 : 2;
+        const double vt1_l = sel3(L[1], L[2], L[3], t1), vt1_r = sel3(R[1], R[2], R[3], t1);
+        const double vt2_l = sel3(L[1], L[2], L[3], t2), vt2_r = sel3(R[1], R[2], R[3], t2);
+        const double Bt1_l = sel3(L[5], L[6], L[7], t1), Bt1_r = sel3(R[5], R[6], R[7], t1);
+        const double Bt2_l = sel3(L[5], L[6], L[7], t2), Bt2_r = sel3(R[5], R[6], R[7], t2);
+        f[4] = f1 * (velocity_square_avg + inv_rho_p_mean * inv_gm1) +
+               0.5 * (+L[4] * vo_r + R[4] * vo_l + (vo_l * Bt1_l * Bt1_r + vo_r * Bt1_r * Bt1_l) +
+                      (vo_l * Bt2_l * Bt2_r + vo_r * Bt2_r * Bt2_l) - (vt1_l * Bo_l * Bt1_r + vt1_r * Bo_r * Bt1_l) -
+                      (vt2_l * Bo_l * Bt2_r + vt2_r * Bo_r * Bt2_l) + c_h * (Bo_l * R[8] + Bo_r * L[8]));
+    }
+
+    // calc_fast_wavespeed(cons, orientation) (:1350-1376)
+    TB_DEV double fast_wavespeed(const double (&u)[9], int o) const {
+        const double rho = u[0], psi = u[8];
+        const double v1 = u[1] / rho, v2 = u[2] / rho, v3 = u[3] / rho;
+        const double kin_en = 0.5 * (u[1] * v1 + u[2] * v2 + u[3] * v3);
+        const double mag_en = 0.5 * (u[5] * u[5] + u[6] * u[6] + u[7] * u[7]);
+        const double p = (gamma - 1) * (u[4] - kin_en - mag_en - 0.5 * psi * psi);
+        const double a_square = gamma * p / rho;
+        const double sqrt_rho = sqrt(rho);
+        const double b1 = u[5] / sqrt_rho, b2 = u[6] / sqrt_rho, b3 = u[7] / sqrt_rho;
+        const double b_square = b1 * b1 + b2 * b2 + b3 * b3;
+        const double bo = sel3(b1, b2, b3, o), sum = a_square + b_square;
+        return sqrt(0.5 * sum + 0.5 * sqrt(sum * sum - 4 * a_square * bo * bo));
+    }
+
+    // conservative part of the surface/volume flux (tuples are encoded as one id)
+    TB_DEV void numflux(int id, const double (&ul)[9], const double (&ur)[9], int o, double (&f)[9]) const {
+        switch (id) {
+        case TRIXI_B200_FLUX_CENTRAL: {
+            double fl[9], fr[9];
+            flux(ul, o, fl);
+            flux(ur, o, fr);
+#pragma unroll
+            for (int v = 0; v < 9; ++v) f[v] = 0.5 * (fl[v] + fr[v]);
+            break;
+        }
+        case TRIXI_B200_FLUX_LLF:
+        case TRIXI_B200_FLUX_LLF_NAIVE:
+        case TRIXI_B200_FLUX_LLF_MHD_POWELL:
+        case TRIXI_B200_FLUX_LLF_NAIVE_MHD_POWELL: {  // max_abs_speed(_naive) (:857-928)
+            const bool naive = id == TRIXI_B200_FLUX_LLF_NAIVE || id == TRIXI_B200_FLUX_LLF_NAIVE_MHD_POWELL;
+            const double v_ll = sel3(ul[1], ul[2], ul[3], o) / ul[0], v_rr = sel3(ur[1], ur[2], ur[3], o) / ur[0];
+            const double cf_ll = fast_wavespeed(ul, o), cf_rr = fast_wavespeed(ur, o);
+            const double lam = naive ? fmax(fabs(v_ll), fabs(v_rr)) + fmax(cf_ll, cf_rr)
+                                     : fmax(fabs(v_ll) + cf_ll, fabs(v_rr) + cf_rr);
+            double fl[9], fr[9];
+            flux(ul, o, fl);
+            flux(ur, o, fr);
+#pragma unroll
+            for (int v = 0; v < 9; ++v) f[v] = 0.5 * (fl[v] + fr[v]) + (-0.5 * lam * (ur[v] - ul[v]));
+            break;
+        }
+        case TRIXI_B200_FLUX_HINDENLANG_GASSNER:
+        case TRIXI_B200_FLUX_HINDENLANG_GASSNER_POWELL:
+            flux_hindenlang_gassner(ul, ur, o, f);
+            break;
+        default:
+#pragma unroll
+            for (int v = 0; v < 9; ++v) f[v] = nan("");
+        }
+    }
+    // max_abs_speeds (:1218-1228)
+    TB_DEV void max_abs_speeds(const double (&u)[9], double (&lam)[3]) const {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) lam[d] = fabs(u[1 + d] / u[0]) + fast_wavespeed(u, d);
+    }
+    TB_DEV void source_terms(int id, const double (&u)[9], const double (&x)[3], double t, double (&s)[9]) const {
+#pragma unroll
+        for (int v = 0; v < 9; ++v) s[v] = 0.0;
+    }
+    TB_DEV void initial_condition(int id, const double (&x)[3], double t, double (&u)[9]) const {
+        const double c[9] = {1.0, 0.1, -0.2, -0.5, 50.0, 3.0, -1.2, 0.5, 0.0};  // initial_condition_constant (:101-113)
+#pragma unroll
+        for (int v = 0; v < 9; ++v) u[v] = id == TRIXI_B200_IC_CONSTANT ? c[v] : nan("");
+    }
+    // not part of this build: boundary walls and curved-mesh (normal-direction) MHD fluxes
+    TB_DEV void slip_wall(const double (&u)[9], int o, int direction, double (&f)[9]) const { nanfill(f); }
+    TB_DEV void flux_normal(const double (&u)[9], const double (&n)[3], double (&f)[9]) const { nanfill(f); }
+    TB_DEV void numflux_normal(int id, const double (&ul)[9], const double (&ur)[9], const double (&n)[3],
+                               double (&f)[9]) const {
+        nanfill(f);
+    }
+    TB_DEV void slip_wall_normal(const double (&u)[9], const double (&n)[3], int direction, double (&f)[9]) const {
+        nanfill(f);
+    }
+    TB_DEV void slip_wall_outward(const double (&u)[9], const double (&n)[3], double (&f)[9]) const { nanfill(f); }
+    TB_DEV static void nanfill(double (&f)[9]) {
+#pragma unroll
+        for (int v = 0; v < 9; ++v) f[v] = nan("");
     }
 };
 

@@ -326,6 +326,13 @@ TRIXI_B200_API int trixi_b200_create(const trixi_b200_desc *d, trixi_b200_handle
     case TRIXI_B200_EQ_ADVECTION_2D: L = get_launchers_advection2d(d->nnodes); break;
     case TRIXI_B200_EQ_EULER_2D: L = get_launchers_euler2d(d->nnodes); break;
     case TRIXI_B200_EQ_EULER_3D: L = get_launchers_euler3d(d->nnodes); break;
+    case TRIXI_B200_EQ_MHD_3D:
+        if (d->mesh_kind != TRIXI_B200_MESH_TREE)
+            return fail(nullptr, TRIXI_B200_EINVAL, "GLM-MHD is available on TreeMesh only in this build");
+        if (d->nboundaries > 0)
+            return fail(nullptr, TRIXI_B200_EINVAL, "GLM-MHD boundary conditions are not part of this build (periodic only)");
+        L = get_launchers_mhd3d(d->nnodes);
+        break;
     default: return fail(nullptr, TRIXI_B200_EINVAL, "equation %d not supported by this build", d->equation);
     }
     if (!L) return fail(nullptr, TRIXI_B200_EINVAL, "nnodes = %d not supported (2..8)", d->nnodes);
