@@ -1058,6 +1058,14 @@ void oracle_calc_mpi_interface_flux(const trixi_b200_desc *d, double *sfv, const
                 ur[v] = mu[1 + 2 * (v + nv * (fn + (int64_t)nf * I))];
             }
             numflux(&eq, d->surface_flux, ul, ur, o, f);
+            if (flux_has_noncons(d->surface_flux)) { /* dgsem_p4est/dg_3d_parallel.jl:302-337 (TreeMesh MPI is 2D-only upstream) */
+                double g[MAXV];
+                if (side == 1)
+                    mhd_noncons_powell(&eq, ul, ur, o, g);
+                else
+                    mhd_noncons_powell(&eq, ur, ul, o, g);
+                for (int v = 0; v < nv; ++v) f[v] = f[v] + 0.5 * g[v];
+            }
             for (int v = 0; v < nv; ++v) sfv[element * fsz + v + nv * (fn + nf * direction0)] = f[v];
         }
     }

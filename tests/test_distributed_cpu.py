@@ -27,7 +27,7 @@ def _worker(rank, world, port, name, out_dir):
     from elixirs import ELIXIRS
     from trixi_b200.parallel import HostHaloExchange, allreduce_min
     ex = ELIXIRS[name]
-    semi = ex.build()
+    semi = ex.semi()
     psemi = ex.build()
     psemi.__init__(semi.mesh, semi.equations, semi.initial_condition, semi.solver, source_terms=semi.source_terms,
                    boundary_conditions=semi.boundary_conditions, rank=rank, world_size=world)
@@ -49,7 +49,7 @@ def _worker(rank, world, port, name, out_dir):
 
 
 @pytest.mark.parametrize("world", [2, 3])
-@pytest.mark.parametrize("name", ["tree_3d_euler_ec", "tree_2d_euler_source_terms_nonperiodic"])
+@pytest.mark.parametrize("name", ["tree_3d_euler_ec", "tree_2d_euler_source_terms_nonperiodic", "tree_3d_mhd_ec"])
 def test_distributed_oracle_equals_serial(world, name, tmp_path, oracle_module):
     import trixi_b200 as T
     from elixirs import ELIXIRS

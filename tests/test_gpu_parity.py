@@ -228,7 +228,7 @@ def _ranked_semis(name, world):
 
 
 @pytest.mark.parametrize("world", [2, 3])
-@pytest.mark.parametrize("name", ["tree_3d_euler_ec", "tree_2d_euler_source_terms_nonperiodic"])
+@pytest.mark.parametrize("name", ["tree_3d_euler_ec", "tree_2d_euler_source_terms_nonperiodic", "tree_3d_mhd_ec"])
 def test_halo_exchange_matches_single_rank(name, world, oracle_module):
     """The element partition with the device-side halo exchange (pack kernels storing into the peers'
     receive buffers, sequence flags) reproduces the single-rank result; like the reference asserts for its
