@@ -150,6 +150,116 @@ __global__ void __launch_bounds__(256) k_interface_flux(const KParams P) {
     }
 }
 
+// Same stage with the face data staged through shared memory: a warp owns 32 face nodes (32 / NF whole
+// interfaces), gathers both sides' face values with lane-consecutive addresses (u is AoS, so a face is made of
+// contiguous runs of NV, N*NV or N*N*NV doubles), computes one flux per lane and writes the two
+// surface_flux_values faces (contiguous NF*NV doubles each) back fully coalesced. Used when NF divides 32.
+template <class EQ, int N, bool FAST = false>
+__global__ void __launch_bounds__(256) k_interface_flux_staged(const KParams P) {
+    constexpr int ND = EQ::NDIMS, NV = EQ::NVARS, NF = ipow(N, ND - 1), NN = ipow(N, ND);
+    constexpr int G = 32 / NF;   // interfaces per warp
+    constexpr int FV = NF * NV;  // doubles per face
+    constexpr int WPB = 8;       // warps per block
+    static_assert(32 % NF == 0, "staged interface kernel needs NF | 32");
+    __shared__ double s_all[WPB][2 * G * FV];
+    __shared__ long long s_elem[WPB][2 * G];
+    __shared__ int s_orient[WPB][G];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double *s = s_all[warp];
+    const long long I0 = ((long long)blockIdx.x * WPB + warp) * G;
+    if (I0 >= P.ninterfaces) return;  // the whole warp leaves together
+    const int nvalid = (int)min((long long)G, P.ninterfaces - I0);
+    if (lane < 2 * nvalid) s_elem[warp][lane] = P.if_neighbors[2 * I0 + lane] - 1;
+    if (lane < nvalid) s_orient[warp][lane] = (int)P.if_orient[I0 + lane] - 1;
+    __syncwarp();
+    // 1. gather: slot c = 2 * g + side (side 0: left element, its +face; side 1: right element, its -face).
+    // A slot is warp-uniform, so the element, the orientation and the node strides are uniform values and a
+    // lane only adds its own (a, b, v) offset: face node fn = a + N b sits at volume node
+    // idx S + a SA + b SB with (S, SA, SB) = (1, N, N^2), (N, 1, N^2), (N^2, 1, N) for orientation 0, 1, 2.
+    constexpr int PASSES = (FV + 31) / 32;
+    int la[PASSES], lb[PASSES], lv[PASSES];
+#pragma unroll
+    for (int p = 0; p < PASSES; ++p) {
+        const int q = lane + 32 * p;
+        const int fnq = q / NV;
+        lv[p] = q - fnq * NV;
+        lb[p] = fnq / N;
+        la[p] = fnq - lb[p] * N;
+    }
+#pragma unroll
+    for (int c = 0; c < 2 * G; ++c) {
+        if (c < 2 * nvalid) {
+            const int o = s_orient[warp][c >> 1];
+            const int S = o == 0 ? 1 : (o == 1 ? N : N * N);
+            const int SA = o == 0 ? N : 1;
+            const int SB = (ND == 3 && o == 2) ? N : N * N;
+            const double *base = P.u + (s_elem[warp][c] * NN + ((c & 1) ? 0 : (N - 1) * S)) * NV;
+#pragma unroll
+            for (int p = 0; p < PASSES; ++p) {
+                const int q = lane + 32 * p;
+                if (q < FV) s[c * FV + q] = base[(la[p] * SA + lb[p] * SB) * NV + lv[p]];
+            }
+        }
+    }
+    __syncwarp();
+    // 2. one face node per lane
+    const int g = lane / NF, fn = lane - g * NF;
+    double fl[NV], fr[NV];
+    if (g < nvalid) {
+        const EQ eq(P.eq);
+        const int o = s_orient[warp][g];
+        double ul[NV], ur[NV], f[NV];
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            ul[v] = s[(2 * g) * FV + fn * NV + v];
+            ur[v] = s[(2 * g + 1) * FV + fn * NV + v];
+        }
+        surface_numflux<EQ, FAST>(eq, P.surface_flux, ul, ur, o, f);
+        bool done = false;
+        if constexpr (EQ::kHasNoncons) {
+            // calc_interface_flux! with nonconservative terms (dg_3d.jl:604-649): flux + 0.5 * noncons per side
+            if (EQ::has_noncons(P.surface_flux)) {
+                double gl[NV], gr[NV];
+                eq.noncons(ul, ur, o, gl);
+                eq.noncons(ur, ul, o, gr);
+#pragma unroll
+                for (int v = 0; v < NV; ++v) {
+                    fl[v] = f[v] + 0.5 * gl[v];
+                    fr[v] = f[v] + 0.5 * gr[v];
+                }
+                done = true;
+            }
+        }
+        if (!done) {
+#pragma unroll
+            for (int v = 0; v < NV; ++v) fl[v] = fr[v] = f[v];
+        }
+    }
+    __syncwarp();
+    if (g < nvalid) {
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            s[(2 * g) * FV + fn * NV + v] = fl[v];
+            s[(2 * g + 1) * FV + fn * NV + v] = fr[v];
+        }
+    }
+    __syncwarp();
+    // 3. scatter: left element's direction 2o+1, right element's 2o (0-based; dg_3d.jl:581-597)
+#pragma unroll
+    for (int c = 0; c < 2 * G; ++c) {
+        if (c < 2 * nvalid) {
+            const int o = s_orient[warp][c >> 1];
+            const int dir = (c & 1) ? 2 * o : 2 * o + 1;
+            double *dst = P.sfv + ((s_elem[warp][c] * (2 * ND) + dir) * NF) * NV;
+#pragma unroll
+            for (int p = 0; p < PASSES; ++p) {
+                const int q = lane + 32 * p;
+                if (q < FV) dst[q] = s[c * FV + q];
+            }
+        }
+    }
+}
+
 // ---- 2. boundaries ------------------------------------------------------------------------------
 template <class EQ, int N>
 __global__ void __launch_bounds__(256) k_boundary_flux(const KParams P) {

@@ -31,11 +31,24 @@ void launch_interface_flux(const KParams &P, cudaStream_t s) {
         k_interface_flux_p4est<EQ, N><<<blocks, threads, 0, s>>>(P);
     else if (P.curved)
         k_interface_flux_curved<EQ, N><<<blocks, threads, 0, s>>>(P);
-    else if (HasFastRanocha<EQ>::value && P.kernel_path == 0 &&
-             (P.surface_flux == TRIXI_B200_FLUX_RANOCHA || P.surface_flux == TRIXI_B200_FLUX_RANOCHA_TURBO))
-        k_interface_flux<EQ, N, true><<<blocks, threads, 0, s>>>(P);
-    else
-        k_interface_flux<EQ, N><<<blocks, threads, 0, s>>>(P);
+    else {
+        const bool fast = HasFastRanocha<EQ>::value && P.kernel_path == 0 &&
+                          (P.surface_flux == TRIXI_B200_FLUX_RANOCHA || P.surface_flux == TRIXI_B200_FLUX_RANOCHA_TURBO);
+        if constexpr (32 % NF == 0) {
+            // a warp owns 32 / NF whole interfaces, 8 warps per block
+            const long long per_block = 8 * (32 / NF);
+            const unsigned sblocks = (unsigned)((P.ninterfaces + per_block - 1) / per_block);
+            if (fast)
+                k_interface_flux_staged<EQ, N, true><<<sblocks, 256, 0, s>>>(P);
+            else
+                k_interface_flux_staged<EQ, N><<<sblocks, 256, 0, s>>>(P);
+        } else {
+            if (fast)
+                k_interface_flux<EQ, N, true><<<blocks, threads, 0, s>>>(P);
+            else
+                k_interface_flux<EQ, N><<<blocks, threads, 0, s>>>(P);
+        }
+    }
 }
 
 template <class EQ, int N>
@@ -163,6 +176,10 @@ cudaError_t preload_all() {
     if ((e = preload_kernel(k)) != cudaSuccess) return e
     TB_PRELOAD((k_interface_flux<EQ, N>));
     TB_PRELOAD((k_interface_flux<EQ, N, true>));
+    if constexpr (32 % ipow(N, EQ::NDIMS - 1) == 0) {
+        TB_PRELOAD((k_interface_flux_staged<EQ, N>));
+        TB_PRELOAD((k_interface_flux_staged<EQ, N, true>));
+    }
     TB_PRELOAD((k_mpi_interface_flux<EQ, N, true>));
     TB_PRELOAD((k_boundary_flux<EQ, N>));
     TB_PRELOAD((k_mpi_pack<EQ, N>));
