@@ -213,6 +213,8 @@ def run_b200(args, rank, world, local_rank):
     from trixi_b200.parallel import allreduce_min
     semi = make_semi(args.level, device=local_rank, rank=rank, world=world, comm=dist if world > 1 else None)
     gpu = semi.backend()
+    # u is owned by the handle during the run: the last RK stage also reduces the CFL maxima (max_dt fused)
+    gpu.set_option(gpu.OPT_FUSED_CFL, 0 if args.no_fused_cfl else 1)
     ndofs = semi.ndofs()
     u0 = T.compute_coefficients(0.0, semi)
     gpu.upload(0, u0)
@@ -314,6 +316,8 @@ def run_b200(args, rank, world, local_rank):
             "pid_ns_per_dof_rhs": 1e9 / value * world,
             "config": {"workload": workload_name(args.level, world), "ndofs_per_gpu": ndofs,
                        "rhs_per_step": 5, "time_integrator": "CarpenterKennedy2N54 (fused stage update)",
+                       "max_dt": "separate kernel after every step" if args.no_fused_cfl else
+                       "every step (StepsizeCallback interval 1); reduced by the last RK stage kernel",
                        "l2_hygiene": "inputs larger than L2 (u alone is %.1f GB)" % (n * 8 / 1e9),
                        "parallelism": "1 rank per GPU" if world == 1 else
                        f"{world} ranks: Morton-order element partition, face halo exchange by direct peer "
@@ -372,6 +376,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fused-cfl", action="store_true", help="run max_dt as its own kernel after every step")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -213,8 +213,14 @@ TRIXI_B200_API int trixi_b200_solve_2n(trixi_b200_handle *h, double t0, double t
                         int64_t *steps_out, double *t_out, double *dt_out);
 
 /* Tuning knobs (the analogue of the reference's compile-time Preferences, src/Trixi.jl:18-23).
- * TRIXI_B200_OPT_KERNEL_PATH: 0 = tuned kernels where one exists (default), 1 = generic kernels only. */
+ * TRIXI_B200_OPT_KERNEL_PATH: 0 = tuned kernels where one exists (default), 1 = generic kernels only.
+ * TRIXI_B200_OPT_FUSED_CFL: 1 = the last stage of trixi_b200_step_2n also reduces the CFL wave speeds of the
+ *   state it writes, so the trixi_b200_max_dt that follows (StepsizeCallback, stepsize.jl:75-117) costs no pass
+ *   over u.  The cached value is dropped by trixi_b200_upload(0), trixi_b200_rhs_host and
+ *   trixi_b200_device_ptr(0); a caller that keeps a raw pointer to u and writes through it must leave this at
+ *   0 (default). */
 #define TRIXI_B200_OPT_KERNEL_PATH 0
+#define TRIXI_B200_OPT_FUSED_CFL 1
 TRIXI_B200_API int trixi_b200_set_option(trixi_b200_handle *h, int option, int value);
 
 /* GlmSpeedCallback (glm_speed.jl:85-105) mutates equations.c_h every step */

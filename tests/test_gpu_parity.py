@@ -124,6 +124,36 @@ def test_max_dt_matches_oracle(name, oracle_module):
     assert gpu.max_dt() == pytest.approx(ref.max_dt(), rel=1e-14)
 
 
+def test_fused_cfl_equals_standalone_max_dt(oracle_module):
+    """TRIXI_B200_OPT_FUSED_CFL: the maxima reduced by the last RK stage kernel are the ones the max_dt kernel
+    computes from the same u (to the last ulp or two: Newton reciprocals instead of IEEE divisions), and cost
+    no launch."""
+    semi = ELIXIRS["tree_3d_euler_ec"].semi()
+    gpu = semi.backend()
+    gpu.set_option(gpu.OPT_FUSED_CFL, 1)
+    alg = T.CarpenterKennedy2N54()
+    gpu.upload(0, _random_admissible_state(semi, seed=11))
+    dt = 0.5 * gpu.max_dt()
+    for k in range(2):
+        gpu.step_2n(k * dt, dt, alg.a, alg.b, alg.c)
+        n0 = gpu.launch_count()
+        fused = gpu.max_dt()
+        assert gpu.launch_count() == n0
+        gpu.set_option(gpu.OPT_FUSED_CFL, 0)  # drops the cached maxima
+        standalone = gpu.max_dt()
+        assert gpu.launch_count() == n0 + 1
+        assert fused == pytest.approx(standalone, rel=1e-15)
+        ref = oracle_module.OracleBackend(semi)
+        ref.upload(0, gpu.download(0))
+        assert fused == pytest.approx(ref.max_dt(), rel=1e-14)
+        gpu.set_option(gpu.OPT_FUSED_CFL, 1)
+    # an upload invalidates the cache
+    gpu.upload(0, _random_admissible_state(semi, seed=12))
+    n0 = gpu.launch_count()
+    gpu.max_dt()
+    assert gpu.launch_count() == n0 + 1
+
+
 def test_max_dt_propagates_nan(oracle_module):
     semi = ELIXIRS["tree_3d_euler_ec"].semi()
     u = _random_admissible_state(semi, seed=5)

@@ -282,6 +282,7 @@ __global__ void __launch_bounds__(TunedCfg::THREADS, TunedCfg::MIN_BLOCKS)
     {
         const int i = a0, j = a1;
         const double factor = WITH_SURFACE ? -P.inverse_jacobian[e] : 1.0;
+        unsigned long long cfl0 = 0ull, cfl1 = 0ull, cfl2 = 0ull;
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
             const int k = lm[r];
@@ -328,12 +329,48 @@ __global__ void __launch_bounds__(TunedCfg::THREADS, TunedCfg::MIN_BLOCKS)
             } else {
                 // 2N stage (methods_2N.jl:152-158): u_tmp = du - u_tmp * a; u += u_tmp * (b * dt)
                 double *out_u = s_u + n * 5;
+                double un[5];
 #pragma unroll
                 for (int v = 0; v < 5; ++v) {
                     const double tmp = need_ut ? val[v] - out_t[v] * P.rk_a : val[v];
                     out_t[v] = tmp;
-                    out_u[v] = out_u[v] + tmp * P.rk_b_dt;
+                    un[v] = out_u[v] + tmp * P.rk_b_dt;
+                    out_u[v] = un[v];
                 }
+                if (P.want_cfl) {
+                    // max_dt of the updated state (stepsize_dg3d.jl:8-32); max_abs_speeds
+                    // (compressible_euler_3d.jl:1770-1775) with the divisions done as one Newton reciprocal plus
+                    // a residual correction each (within 1 ulp of k_max_dt's IEEE divisions)
+                    const double rho = un[0], inv_rho = fast_rcp(rho);
+                    double v1 = un[1] * inv_rho, v2 = un[2] * inv_rho, v3 = un[3] * inv_rho;
+                    v1 = fma(fma(-rho, v1, un[1]), inv_rho, v1);
+                    v2 = fma(fma(-rho, v2, un[2]), inv_rho, v2);
+                    v3 = fma(fma(-rho, v3, un[3]), inv_rho, v3);
+                    const double pr = (gamma - 1) * (un[4] - 0.5 * (un[1] * v1 + un[2] * v2 + un[3] * v3));
+                    const double gp = gamma * pr;
+                    double c2 = gp * inv_rho;
+                    c2 = fma(fma(-rho, c2, gp), inv_rho, c2);
+                    const double c = sqrt(c2);
+                    const double lam[3] = {fabs(v1) + c, fabs(v2) + c, fabs(v3) + c};
+                    cfl0 = max(cfl0, cfl_encode(lam[0]));
+                    cfl1 = max(cfl1, cfl_encode(lam[1]));
+                    cfl2 = max(cfl2, cfl_encode(lam[2]));
+                }
+            }
+        }
+        if (P.want_cfl) {
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                cfl0 = max(cfl0, __shfl_xor_sync(0xffffffffu, cfl0, off));
+                cfl1 = max(cfl1, __shfl_xor_sync(0xffffffffu, cfl1, off));
+                cfl2 = max(cfl2, __shfl_xor_sync(0xffffffffu, cfl2, off));
+            }
+            if (lane == 0) {
+                double sum = 0.0;
+                sum += __longlong_as_double((long long)cfl0);
+                sum += __longlong_as_double((long long)cfl1);
+                sum += __longlong_as_double((long long)cfl2);
+                atomicMax(P.cfl_key + (blockIdx.x & (kCflSlots - 1)), cfl_encode(P.inverse_jacobian[e] * sum));
             }
         }
     }

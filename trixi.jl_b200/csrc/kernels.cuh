@@ -54,7 +54,8 @@ struct KParams {
     int mode;  // 0: write du, 1: 2N stage update
     double rk_a, rk_b_dt;
     // CFL fused output: per-block max of invJ * sum_d max_nodes lambda_d, encoded as ordered uint64
-    unsigned long long *cfl_key;  // nullptr: skip
+    unsigned long long *cfl_key;  // kCflSlots partial maxima (spread same-address atomics over L2 slices)
+    int want_cfl;                 // RK stage kernels that support it also reduce the CFL speed of the updated u
     int kernel_path;              // 0: tuned kernels where available, 1: generic kernels only
     // distributed: faces shared with other ranks (replaces mpi_interfaces, dg_2d_parallel.jl / dg_parallel.jl)
     long long nmpi;
@@ -78,6 +79,8 @@ TB_DEV int face_to_volume_node(int o, int s, int fn) {
         return o == 0 ? s + N * (a + N * b) : (o == 1 ? a + N * (s + N * b) : a + N * (b + N * s));
     }
 }
+
+constexpr int kCflSlots = 1024;
 
 TB_DEV unsigned long long cfl_encode(double v) {
     // positive doubles order like their bit patterns; NaN must win the max (Base.max propagates NaN,
@@ -572,7 +575,7 @@ __global__ void __launch_bounds__(ElemCfg<EQ, N>::THREADS) k_max_dt(const KParam
 #pragma unroll
         for (int d = 0; d < ND; ++d) s += __longlong_as_double((long long)s_lam[d][tid]);
         const double val = P.inverse_jacobian[e0 + tid] * s;
-        atomicMax(P.cfl_key, cfl_encode(val));
+        atomicMax(P.cfl_key + (blockIdx.x & (kCflSlots - 1)), cfl_encode(val));
     }
 }
 
@@ -847,7 +850,7 @@ __global__ void __launch_bounds__(ElemCfg<EQ, N>::THREADS) k_max_dt_curved(const
         double sum = 0.0;
 #pragma unroll
         for (int d = 0; d < ND; ++d) sum += __longlong_as_double((long long)s_lam[d][tid]);
-        atomicMax(P.cfl_key, cfl_encode(sum));
+        atomicMax(P.cfl_key + (blockIdx.x & (kCflSlots - 1)), cfl_encode(sum));
     }
 }
 

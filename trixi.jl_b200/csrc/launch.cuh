@@ -12,6 +12,8 @@ struct Launchers {
     // with_surface = false: volume terms only (stage-level parity entry point)
     cudaError_t (*element)(const KParams &, bool with_surface, cudaStream_t);
     void (*max_dt)(const KParams &, cudaStream_t);
+    // true when the RK stage kernel `element` selects for P honours P.want_cfl (fused max_dt)
+    bool (*fuses_cfl)(const KParams &);
     void (*mpi_pack)(const KParams &, cudaStream_t);
     void (*mpi_interface_flux)(const KParams &, cudaStream_t);
     // Force-load every kernel of this table (CUDA loads kernels lazily at first launch, and that load can
@@ -135,12 +137,19 @@ cudaError_t launch_element_variant(const KParams &P, cudaStream_t s) {
 }
 
 template <class EQ, int N>
+bool uses_tuned_element(const KParams &P) {
+    if constexpr (std::is_same_v<EQ, Euler<3>> && N == 4) {
+        return !P.curved && P.kernel_path == 0 && P.volume_integral == TRIXI_B200_VOLINT_FLUX_DIFFERENCING &&
+               (P.volume_flux == TRIXI_B200_FLUX_RANOCHA || P.volume_flux == TRIXI_B200_FLUX_RANOCHA_TURBO);
+    }
+    return false;
+}
+
+template <class EQ, int N>
 cudaError_t launch_element(const KParams &P, bool with_surface, cudaStream_t s) {
     if (P.nelements == 0) return cudaSuccess;
     if constexpr (std::is_same_v<EQ, Euler<3>> && N == 4) {
-        if (!P.curved && P.kernel_path == 0 && P.volume_integral == TRIXI_B200_VOLINT_FLUX_DIFFERENCING &&
-            (P.volume_flux == TRIXI_B200_FLUX_RANOCHA || P.volume_flux == TRIXI_B200_FLUX_RANOCHA_TURBO))
-            return launch_element_euler3d_ranocha_p3(P, with_surface, s);
+        if (uses_tuned_element<EQ, N>(P)) return launch_element_euler3d_ranocha_p3(P, with_surface, s);
     }
     if (P.volume_integral == TRIXI_B200_VOLINT_WEAK_FORM) {
         return with_surface ? launch_element_variant<EQ, N, TRIXI_B200_VOLINT_WEAK_FORM, true>(P, s)
@@ -209,6 +218,7 @@ const Launchers *make_launchers() {
                                 &launch_boundary_flux<EQ, N>,
                                 &launch_element<EQ, N>,
                                 &launch_max_dt<EQ, N>,
+                                &uses_tuned_element<EQ, N>,
                                 &launch_mpi_pack<EQ, N>,
                                 &launch_mpi_interface_flux<EQ, N>,
                                 &preload_all<EQ, N>,

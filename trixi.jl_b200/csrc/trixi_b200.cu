@@ -37,7 +37,9 @@ struct trixi_b200_handle {
     std::vector<void *> allocs;
     double *vec[3] = {nullptr, nullptr, nullptr};  // u, du, u_tmp
     unsigned long long *d_cfl = nullptr;
-    unsigned long long *h_cfl = nullptr;  // pinned
+    unsigned long long *h_cfl = nullptr;  // pinned, kCflSlots entries
+    bool opt_fused_cfl = false;           // TRIXI_B200_OPT_FUSED_CFL
+    bool cfl_valid = false;               // d_cfl holds the maxima of the current u (written by the last RK stage)
     long long launches = 0;
     bool profiling = false;
     std::vector<ProfEntry> prof;
@@ -572,9 +574,10 @@ TRIXI_B200_API int trixi_b200_create(const trixi_b200_desc *d, trixi_b200_handle
     CREATE_CUDA(preload_kernel(k_mpi_signal));
     CREATE_CUDA(preload_kernel(k_mpi_wait));
 
-    CREATE_TRY(alloc_array(h, 1, &h->d_cfl));
+    CREATE_TRY(alloc_array(h, kCflSlots, &h->d_cfl));
     P.cfl_key = h->d_cfl;
-    CREATE_CUDA(cudaMallocHost((void **)&h->h_cfl, sizeof(unsigned long long)));
+    P.want_cfl = 0;
+    CREATE_CUDA(cudaMallocHost((void **)&h->h_cfl, kCflSlots * sizeof(unsigned long long)));
     CREATE_CUDA(cudaDeviceSynchronize());
     *out = h;
     return TRIXI_B200_OK;
@@ -591,6 +594,7 @@ TRIXI_B200_API int trixi_b200_upload(trixi_b200_handle *h, int which, const doub
     if (rc) return rc;
     if (!host && h->ulen) return fail(h, TRIXI_B200_EINVAL, "host pointer is null");
     CUDA_TRY(h, cudaSetDevice(h->device));
+    if (which == 0) h->cfl_valid = false;
     CUDA_TRY(h, cudaMemcpyAsync(h->vec[which], host, h->ulen * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     return 0;
@@ -608,6 +612,7 @@ TRIXI_B200_API int trixi_b200_download(trixi_b200_handle *h, int which, double *
 
 TRIXI_B200_API void *trixi_b200_device_ptr(trixi_b200_handle *h, int which) {
     if (!h || which < 0 || which > 2) return nullptr;
+    if (which == 0) h->cfl_valid = false;  // the caller may write u through the pointer
     return h->vec[which];
 }
 
@@ -635,6 +640,7 @@ TRIXI_B200_API int trixi_b200_rhs_host(trixi_b200_handle *h, double *du_host, co
     if ((!du_host || !u_host) && h->ulen) return fail(h, TRIXI_B200_EINVAL, "host pointer is null");
     CUDA_TRY(h, cudaSetDevice(h->device));
     const size_t bytes = h->ulen * sizeof(double);
+    h->cfl_valid = false;
     CUDA_TRY(h, cudaMemcpyAsync(h->vec[0], u_host, bytes, cudaMemcpyHostToDevice, h->stream));
     int rc = trixi_b200_rhs(h, t);
     if (rc) return rc;
@@ -669,20 +675,25 @@ TRIXI_B200_API int trixi_b200_max_dt(trixi_b200_handle *h, double t, double *dt_
     (void)t;
     if (!h || !dt_out) return TRIXI_B200_EINVAL;
     CUDA_TRY(h, cudaSetDevice(h->device));
-    // max_scaled_speed starts at nextfloat(0.0) (stepsize_dg3d.jl:12): bit pattern 1
-    *h->h_cfl = 1ull;
-    CUDA_TRY(h, cudaMemcpyAsync(h->d_cfl, h->h_cfl, sizeof(unsigned long long), cudaMemcpyHostToDevice, h->stream));
-    {
-        ProfScope ps(h, KC_MAXDT);
-        h->L->max_dt(h->P, h->stream);
-        h->launches++;
+    if (!h->cfl_valid) {
+        CUDA_TRY(h, cudaMemsetAsync(h->d_cfl, 0, kCflSlots * sizeof(unsigned long long), h->stream));
+        {
+            ProfScope ps(h, KC_MAXDT);
+            h->L->max_dt(h->P, h->stream);
+            h->launches++;
+        }
+        int rc = check_launch(h, "max_dt kernel");
+        if (rc) return rc;
     }
-    int rc = check_launch(h, "max_dt kernel");
-    if (rc) return rc;
-    CUDA_TRY(h, cudaMemcpyAsync(h->h_cfl, h->d_cfl, sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(h->h_cfl, h->d_cfl, kCflSlots * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                                h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    // max_scaled_speed starts at nextfloat(0.0) (stepsize_dg3d.jl:12): bit pattern 1; the ordered bit patterns
+    // of the partial maxima (NaN encoded above every finite value) reduce with an integer max
+    unsigned long long key = 1ull;
+    for (int i = 0; i < kCflSlots; ++i) key = h->h_cfl[i] > key ? h->h_cfl[i] : key;
     double max_scaled_speed;
-    memcpy(&max_scaled_speed, h->h_cfl, sizeof(double));
+    memcpy(&max_scaled_speed, &key, sizeof(double));
     *dt_out = 2 / (h->nnodes * max_scaled_speed);
     return 0;
 }
@@ -693,6 +704,8 @@ TRIXI_B200_API int trixi_b200_step_2n(trixi_b200_handle *h, double t, double dt,
     if (a[0] != 0.0) return fail(h, TRIXI_B200_EINVAL, "2N scheme must have a[1] == 0 (u_tmp starts at zero)");
     CUDA_TRY(h, cudaSetDevice(h->device));
     CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
+    h->cfl_valid = false;
+    const bool fuse_cfl = h->opt_fused_cfl && h->L->fuses_cfl(h->P);
     for (int s = 0; s < nstages; ++s) {
         const double t_stage = t + dt * c[s];
         int rc = run_all_surface_fluxes(h, t_stage);
@@ -700,10 +713,17 @@ TRIXI_B200_API int trixi_b200_step_2n(trixi_b200_handle *h, double t, double dt,
         h->P.mode = 1;
         h->P.rk_a = a[s];
         h->P.rk_b_dt = b[s] * dt;
+        if (fuse_cfl && s == nstages - 1) {
+            // the last stage also reduces the CFL wave speeds of the state it writes (max_dt without a pass over u)
+            CUDA_TRY(h, cudaMemsetAsync(h->d_cfl, 0, kCflSlots * sizeof(unsigned long long), h->stream));
+            h->P.want_cfl = 1;
+        }
         rc = run_element(h, true);
         h->P.mode = 0;
+        h->P.want_cfl = 0;
         if (rc) return rc;
     }
+    h->cfl_valid = fuse_cfl;
     CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
     h->have_elapsed = true;
     return 0;
@@ -718,6 +738,13 @@ TRIXI_B200_API int trixi_b200_solve_2n(trixi_b200_handle *h, double t0, double t
     double t = t0, dt = 0.0;
     int64_t steps = 0;
     bool finalstep = false;
+    // the loop owns u for its whole duration: always let the last stage produce the next step's CFL maxima
+    struct FusedCflScope {
+        trixi_b200_handle *h;
+        bool saved;
+        explicit FusedCflScope(trixi_b200_handle *hh) : h(hh), saved(hh->opt_fused_cfl) { h->opt_fused_cfl = true; }
+        ~FusedCflScope() { h->opt_fused_cfl = saved; }
+    } fused_scope(h);
     while (!finalstep && steps < max_steps) {
         int rc = trixi_b200_max_dt(h, t, &dt);
         if (rc) return rc;
@@ -754,6 +781,11 @@ TRIXI_B200_API int trixi_b200_set_option(trixi_b200_handle *h, int option, int v
     case TRIXI_B200_OPT_KERNEL_PATH:
         if (value != 0 && value != 1) return fail(h, TRIXI_B200_EINVAL, "kernel path must be 0 (auto) or 1 (generic)");
         h->P.kernel_path = value;
+        return 0;
+    case TRIXI_B200_OPT_FUSED_CFL:
+        if (value != 0 && value != 1) return fail(h, TRIXI_B200_EINVAL, "fused CFL option must be 0 or 1");
+        h->opt_fused_cfl = value != 0;
+        h->cfl_valid = false;
         return 0;
     default:
         return fail(h, TRIXI_B200_EINVAL, "unknown option %d", option);

@@ -220,6 +220,7 @@ class B200Backend:
         return ms.value, n.value
 
     OPT_KERNEL_PATH = 0
+    OPT_FUSED_CFL = 1
 
     def set_option(self, option, value):
         self._ck(self.lib.trixi_b200_set_option(self.h, int(option), int(value)))

@@ -60,6 +60,9 @@ class SimpleIntegrator2N:
     def __init__(self, ode, alg, dt, callback, maxiters=None):
         self.semi = self.p = ode.p
         self.backend = ode.p.backend()
+        if hasattr(self.backend, "OPT_FUSED_CFL"):
+            # the integrator owns u on the device: the last RK stage may also produce the next max_dt
+            self.backend.set_option(self.backend.OPT_FUSED_CFL, 1)
         self.alg = alg
         self.t = float(ode.tspan[0])
         self.tspan = ode.tspan
