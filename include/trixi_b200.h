@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define TRIXI_B200_ABI_VERSION 2
+#define TRIXI_B200_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define TRIXI_B200_API __attribute__((visibility("default")))
@@ -163,6 +163,10 @@ typedef struct trixi_b200_desc {
     /* P4est boundary container (dgsem_p4est/containers.jl:302-345): node_indices [ndims, nboundaries], same
      * encoding as interface_node_indices; boundaries sorted by boundary name = direction */
     const int64_t *boundary_node_indices;
+
+    /* P4est MPI interface container (dgsem_p4est/containers_parallel.jl:8-28): node_indices of the local side
+     * [ndims, nmpiinterfaces], same encoding; the exchanged face states are aligned at the primary element */
+    const int64_t *mpi_node_indices;
 } trixi_b200_desc;
 
 typedef struct trixi_b200_handle trixi_b200_handle;

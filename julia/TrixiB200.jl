@@ -105,6 +105,7 @@ struct Desc
     mpi_orientations::Ptr{Int64}
     mpi_neighbor_ranks::Ptr{Int64}
     boundary_node_indices::Ptr{Int64}
+    mpi_node_indices::Ptr{Int64}
 end
 
 # ---- the backend object ---------------------------------------------------------------------------------

@@ -1556,8 +1556,69 @@ void oracle_rhs(const trixi_b200_desc *d, double *du, const double *u, double t,
 /* distributed rhs_hyperbolic! (dgsem_tree/dg_2d_parallel.jl:453-563, p4est dg_3d_parallel.jl:8-117) in
  * two halves around the halo exchange the caller performs: part 1 = prolong2mpiinterfaces + all local
  * work up to the boundary fluxes; part 2 = calc_mpi_interface_flux!, surface integral, Jacobian, sources */
+/* prolong2mpiinterfaces! dgsem_p4est/dg_3d_parallel.jl:119-165: mpi_u[2, nv, nf, MI], the local side filled
+ * through the local element's node_indices (interface aligned at the primary element) */
+void oracle_prolong2mpiinterfaces_p4est(const trixi_b200_desc *d, double *mu, const double *u) {
+    int n = d->nnodes, nd = d->ndims, nv = d->nvars;
+    int nf = ipow(n, nd - 1), nb = nd == 3 ? n : 1;
+    int64_t esz = (int64_t)nv * ipow(n, nd);
+#pragma omp parallel for schedule(static)
+    for (int64_t I = 0; I < d->nmpiinterfaces; ++I) {
+        int64_t e = d->mpi_local_neighbor_ids[I] - 1;
+        int side = (int)d->mpi_local_sides[I] - 1;
+        const int64_t *idx = d->mpi_node_indices + (int64_t)nd * I;
+        for (int j = 0; j < nb; ++j)
+            for (int i = 0; i < n; ++i) {
+                int64_t vn = p4_volume_node(nd, n, idx, i, j);
+                for (int v = 0; v < nv; ++v)
+                    mu[side + 2 * (v + nv * ((i + n * j) + (int64_t)nf * I))] = u[e * esz + nv * vn + v];
+            }
+    }
+}
+
+/* calc_mpi_interface_flux! dgsem_p4est/dg_3d_parallel.jl:167-273: normal of the LOCAL element; the secondary
+ * side stores -surface_flux(u_ll, u_rr, -normal) (:262-266) at its own surface node */
+void oracle_calc_mpi_interface_flux_p4est(const trixi_b200_desc *d, double *sfv, const double *mu) {
+    eqn_t eq = make_eqn(d);
+    int n = d->nnodes, nd = d->ndims, nv = d->nvars;
+    int nf = ipow(n, nd - 1), nb = nd == 3 ? n : 1;
+    int64_t fsz = (int64_t)nv * nf * 2 * nd;
+#pragma omp parallel for schedule(static)
+    for (int64_t I = 0; I < d->nmpiinterfaces; ++I) {
+        int64_t e = d->mpi_local_neighbor_ids[I] - 1;
+        int side = (int)d->mpi_local_sides[I];
+        const int64_t *idx = d->mpi_node_indices + (int64_t)nd * I;
+        int dir = p4_direction(nd, idx);
+        for (int j = 0; j < nb; ++j)
+            for (int i = 0; i < n; ++i) {
+                double ul[MAXV], ur[MAXV], f[MAXV], nrm[3] = {0, 0, 0};
+                int fn = i + n * j, fn_loc;
+                for (int v = 0; v < nv; ++v) {
+                    ul[v] = mu[0 + 2 * (v + nv * (fn + (int64_t)nf * I))];
+                    ur[v] = mu[1 + 2 * (v + nv * (fn + (int64_t)nf * I))];
+                }
+                p4_normal(d, dir, p4_volume_node(nd, n, idx, i, j), e, nrm);
+                if (side == 2)
+                    for (int dim = 0; dim < nd; ++dim) nrm[dim] = -nrm[dim];
+                numflux_normal(&eq, d->surface_flux, ul, ur, nrm, f);
+                p4_surface_node(nd, n, idx, i, j, &fn_loc);
+                for (int v = 0; v < nv; ++v)
+                    sfv[e * fsz + v + nv * (fn_loc + nf * dir)] = side == 1 ? f[v] : -f[v];
+            }
+    }
+}
+
 void oracle_rhs_parallel_part1(const trixi_b200_desc *d, double *du, const double *u, double t,
                                double *interfaces_u, double *boundaries_u, double *sfv, double *mpi_u) {
+    if (d->mesh_kind == TRIXI_B200_MESH_P4EST) { /* dgsem_p4est/dg_3d_parallel.jl:8-117 */
+        oracle_prolong2mpiinterfaces_p4est(d, mpi_u, u);
+        oracle_set_zero(d, du);
+        oracle_calc_volume_integral_curved(d, du, u);
+        oracle_prolong2interfaces_p4est(d, interfaces_u, u);
+        oracle_calc_interface_flux_p4est(d, sfv, interfaces_u);
+        if (d->nboundaries > 0) oracle_calc_boundary_flux_p4est(d, sfv, u, t);
+        return;
+    }
     oracle_prolong2mpiinterfaces(d, mpi_u, u);
     oracle_set_zero(d, du);
     oracle_calc_volume_integral(d, du, u);
@@ -1570,6 +1631,13 @@ void oracle_rhs_parallel_part1(const trixi_b200_desc *d, double *du, const doubl
 }
 void oracle_rhs_parallel_part2(const trixi_b200_desc *d, double *du, const double *u, double t, double *sfv,
                                const double *mpi_u) {
+    if (d->mesh_kind == TRIXI_B200_MESH_P4EST) {
+        oracle_calc_mpi_interface_flux_p4est(d, sfv, mpi_u);
+        oracle_calc_surface_integral_p4est(d, du, sfv);
+        oracle_apply_jacobian_curved(d, du);
+        oracle_calc_sources(d, du, u, t);
+        return;
+    }
     oracle_calc_mpi_interface_flux(d, sfv, mpi_u);
     oracle_calc_surface_integral(d, du, sfv);
     oracle_apply_jacobian(d, du);

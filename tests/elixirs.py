@@ -397,3 +397,44 @@ ELIXIRS.update({e.name: e for e in [
                0.031235294705421968, 0.03316343064943483, 0.011539436992528018, 0.04896687646520839,
                0.018714054039927555], "test/test_tree_3d_mhd.jl:66-92"),
 ]})
+
+
+# ---- configurations without a reference golden (cross-checks between mesh types, halo tests) ---------------
+def _p4est3d_curved(initial_condition=T.initial_condition_weak_blast_wave, flux=T.flux_ranocha, level=0, trees=(4, 4, 4)):
+    # the warped mapping of examples/structured_3d_dgsem/elixir_euler_free_stream.jl on a conforming P4estMesh
+    # (examples/p4est_3d_dgsem/elixir_euler_free_stream.jl uses the same mapping with nonconforming refinement)
+    eq = T.CompressibleEulerEquations3D(1.4)
+    solver = T.DGSEM(polydeg=3, surface_flux=T.FluxLaxFriedrichs(T.max_abs_speed_naive) if flux is None else flux,
+                     volume_integral=T.VolumeIntegralWeakForm() if flux is None
+                     else T.VolumeIntegralFluxDifferencing(flux))
+    mesh = T.P4estMesh(trees, polydeg=3, mapping=_warped_mapping_3d, periodicity=True,
+                       initial_refinement_level=level)
+    return T.SemidiscretizationHyperbolic(mesh, eq, initial_condition, solver)
+
+
+def _structured3d_like_p4est_curved(initial_condition=T.initial_condition_weak_blast_wave, flux=T.flux_ranocha):
+    eq = T.CompressibleEulerEquations3D(1.4)
+    solver = T.DGSEM(polydeg=3, surface_flux=T.FluxLaxFriedrichs(T.max_abs_speed_naive) if flux is None else flux,
+                     volume_integral=T.VolumeIntegralWeakForm() if flux is None
+                     else T.VolumeIntegralFluxDifferencing(flux))
+    mesh = T.StructuredMesh((4, 4, 4), _warped_mapping_3d, periodicity=True)
+    return T.SemidiscretizationHyperbolic(mesh, eq, initial_condition, solver)
+
+
+class _Extra:
+    """Same interface as Elixir for the tests that only need ``semi()``."""
+
+    def __init__(self, name, build):
+        self.name, self.build = name, build
+
+    def semi(self, **overrides):
+        return self.build(**overrides)
+
+
+EXTRA = {e.name: e for e in [
+    _Extra("p4est_3d_curved_ec", _p4est3d_curved),
+    _Extra("p4est_3d_curved_weak_form", lambda **kw: _p4est3d_curved(flux=None, **kw)),
+    _Extra("p4est_3d_curved_level1", lambda **kw: _p4est3d_curved(level=1, trees=(2, 2, 2), **kw)),
+    _Extra("structured_3d_like_p4est_curved", _structured3d_like_p4est_curved),
+    _Extra("p4est_3d_periodic_source_terms", _p4est3d_source_terms),
+]}

@@ -24,9 +24,9 @@ def _worker(rank, world, port, name, out_dir):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     import oracle
     import trixi_b200 as T
-    from elixirs import ELIXIRS
+    from elixirs import ELIXIRS, EXTRA
     from trixi_b200.parallel import HostHaloExchange, allreduce_min
-    ex = ELIXIRS[name]
+    ex = ELIXIRS.get(name) or EXTRA[name]
     semi = ex.semi()
     psemi = ex.build()
     psemi.__init__(semi.mesh, semi.equations, semi.initial_condition, semi.solver, source_terms=semi.source_terms,
@@ -49,10 +49,12 @@ def _worker(rank, world, port, name, out_dir):
 
 
 @pytest.mark.parametrize("world", [2, 3])
-@pytest.mark.parametrize("name", ["tree_3d_euler_ec", "tree_2d_euler_source_terms_nonperiodic", "tree_3d_mhd_ec"])
+@pytest.mark.parametrize("name", ["tree_3d_euler_ec", "tree_2d_euler_source_terms_nonperiodic", "tree_3d_mhd_ec",
+                                  "p4est_3d_euler_source_terms_nonperiodic", "p4est_3d_curved_level1"])
 def test_distributed_oracle_equals_serial(world, name, tmp_path, oracle_module):
     import trixi_b200 as T
-    from elixirs import ELIXIRS
+    from elixirs import ELIXIRS, EXTRA
+    ELIXIRS = {**ELIXIRS, **EXTRA}
     port = 29500 + (os.getpid() + world * 7 + len(name)) % 2000
     mp.spawn(_worker, args=(world, port, name, str(tmp_path)), nprocs=world, join=True)
     semi = ELIXIRS[name].semi()
@@ -71,7 +73,12 @@ def test_distributed_oracle_equals_serial(world, name, tmp_path, oracle_module):
         first, last = int(z["first"]), int(z["last"])
         covered += last - first
         assert float(z["dt"]) == dt
-        np.testing.assert_array_equal(z["du"], du[..., first:last])
+        if name.startswith("p4est"):
+            # each rank evaluates a shared face with the normal of its own element
+            # (dgsem_p4est/dg_3d_parallel.jl:262-266): equal to rounding of the metric terms, not bit for bit
+            np.testing.assert_allclose(z["du"], du[..., first:last], rtol=0, atol=1e-13 * np.abs(du).max())
+        else:
+            np.testing.assert_array_equal(z["du"], du[..., first:last])
         # the stage update of the distributed driver is NumPy (no FMA contraction): 1-ulp differences
         np.testing.assert_allclose(z["u1"].reshape(du[..., first:last].shape, order="F"), u1[..., first:last],
                                    rtol=0, atol=1e-14)

@@ -5,7 +5,9 @@ import numpy as np
 import pytest
 import trixi_b200 as T
 
-from elixirs import ELIXIRS
+from elixirs import ELIXIRS as _GOLDEN_ELIXIRS, EXTRA
+
+ELIXIRS = {**_GOLDEN_ELIXIRS, **EXTRA}
 
 pytestmark = pytest.mark.gpu
 
@@ -61,7 +63,8 @@ RHS_CASES = ["tree_3d_euler_ec", "tree_3d_euler_source_terms", "tree_3d_euler_so
              "tree_2d_euler_density_wave", "structured_3d_euler_free_stream", "structured_3d_euler_ec",
              "structured_3d_euler_source_terms", "structured_3d_euler_source_terms_nonperiodic_curved",
              "p4est_3d_euler_source_terms_nonperiodic", "p4est_3d_euler_source_terms_nonperiodic_kennedy_gruber",
-             "tree_3d_mhd_ec", "tree_3d_mhd_alfven_wave"]
+             "tree_3d_mhd_ec", "tree_3d_mhd_alfven_wave", "p4est_3d_curved_ec", "p4est_3d_curved_weak_form",
+             "p4est_3d_curved_level1"]
 
 
 @pytest.mark.parametrize("name", RHS_CASES)
@@ -258,7 +261,8 @@ def _ranked_semis(name, world):
 
 
 @pytest.mark.parametrize("world", [2, 3])
-@pytest.mark.parametrize("name", ["tree_3d_euler_ec", "tree_2d_euler_source_terms_nonperiodic", "tree_3d_mhd_ec"])
+@pytest.mark.parametrize("name", ["tree_3d_euler_ec", "tree_2d_euler_source_terms_nonperiodic", "tree_3d_mhd_ec",
+                                  "p4est_3d_euler_source_terms_nonperiodic", "p4est_3d_curved_level1"])
 def test_halo_exchange_matches_single_rank(name, world, oracle_module):
     """The element partition with the device-side halo exchange (pack kernels storing into the peers'
     receive buffers, sequence flags) reproduces the single-rank result; like the reference asserts for its
@@ -284,15 +288,24 @@ def test_halo_exchange_matches_single_rank(name, world, oracle_module):
         b.upload(0, np.asfortranarray(u[..., a:z]))
     for b in backends:  # asynchronous: every rank enqueues, nobody blocks the host
         b.rhs(0.3)
+    # TreeMesh: both ranks evaluate a shared face with identical operands -> bit-identical to one rank.
+    # P4estMesh: each rank uses the normal of its own element (dg_3d_parallel.jl:262-266) -> equal up to the
+    # rounding of the metric terms, like the reference's MPI runs.
+    def same(x, y):
+        if name.startswith("p4est"):
+            np.testing.assert_allclose(x, y, rtol=0, atol=1e-13 * np.abs(y).max())
+        else:
+            np.testing.assert_array_equal(x, y)
+
     for b, (a, z) in zip(backends, parts):
-        np.testing.assert_array_equal(b.download(1).reshape(u[..., a:z].shape, order="F"), du_single[..., a:z])
+        same(b.download(1).reshape(u[..., a:z].shape, order="F"), du_single[..., a:z])
     dts = [0.4 * b.max_dt() for b in backends]
     assert min(dts) == dt
     for k in range(2):
         for b in backends:
             b.step_2n(k * dt, dt, alg.a, alg.b, alg.c)
     for b, (a, z) in zip(backends, parts):
-        np.testing.assert_array_equal(b.download(0).reshape(u[..., a:z].shape, order="F"), u_single[..., a:z])
+        same(b.download(0).reshape(u[..., a:z].shape, order="F"), u_single[..., a:z])
     # and against the oracle
     ref = oracle_module.OracleBackend(base)
     du_ref = np.empty_like(u)

@@ -8,7 +8,7 @@ import ctypes as C
 
 import numpy as np
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 c_double_p = C.POINTER(C.c_double)
 c_int64_p = C.POINTER(C.c_int64)
@@ -47,6 +47,7 @@ class Desc(C.Structure):
         ("mpi_local_neighbor_ids", c_int64_p), ("mpi_local_sides", c_int64_p),
         ("mpi_orientations", c_int64_p), ("mpi_neighbor_ranks", c_int64_p),
         ("boundary_node_indices", c_int64_p),
+        ("mpi_node_indices", c_int64_p),
     ]
 
 

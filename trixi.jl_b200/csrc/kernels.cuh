@@ -60,6 +60,7 @@ struct KParams {
     // distributed: faces shared with other ranks (replaces mpi_interfaces, dg_2d_parallel.jl / dg_parallel.jl)
     long long nmpi;
     const long long *mpi_local, *mpi_side, *mpi_orient;  // [nmpi] 1-based local element, local side, orientation
+    const long long *mpi_node_indices;                   // P4est: [ndims, nmpi] node_indices of the local side
     const int *mpi_peer_slot;                            // [nmpi] index into the peer tables
     const long long *mpi_remote_index;                   // [nmpi] slot of this face in the peer's receive buffer
     double *const *peer_recv;                            // [npeers] peer receive buffers (current parity), NVLink-mapped
@@ -963,6 +964,63 @@ __global__ void __launch_bounds__(256) k_boundary_flux_p4est(const KParams P) {
     double *s = P.sfv + ((element * (2 * ND) + dir) * NF + fn) * NV;
 #pragma unroll
     for (int v = 0; v < NV; ++v) s[v] = f[v];
+}
+
+// prolong2mpiinterfaces! (dgsem_p4est/dg_3d_parallel.jl:119-165) fused with the send: the local face state,
+// aligned at the primary element, goes straight into the neighbour rank's receive buffer
+template <class EQ, int N>
+__global__ void __launch_bounds__(256) k_mpi_pack_p4est(const KParams P) {
+    constexpr int ND = EQ::NDIMS, NV = EQ::NVARS, NF = ipow(N, ND - 1), NN = ipow(N, ND);
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long I = gid / NF;
+    const int fn = (int)(gid % NF);
+    if (I >= P.nmpi) return;
+    const int i = fn % N, j = fn / N;
+    const long long element = P.mpi_local[I] - 1;
+    int vn, sfn, dir;
+    p4_face<ND, N>(P.mpi_node_indices + I * ND, i, j, vn, sfn, dir);
+    const double *pu = P.u + (element * NN + vn) * NV;
+    double *dst = P.peer_recv[P.mpi_peer_slot[I]] + (P.mpi_remote_index[I] * NF + fn) * NV;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) dst[v] = pu[v];
+    __threadfence_system();
+}
+
+// calc_mpi_interface_flux! (dgsem_p4est/dg_3d_parallel.jl:167-273): each rank uses the outward normal of its
+// OWN element; the secondary side evaluates -f(u_ll, u_rr, -n) (so the two ranks' fluxes agree to rounding of
+// the metric terms, not bit for bit -- as in the reference)
+template <class EQ, int N>
+__global__ void __launch_bounds__(256) k_mpi_interface_flux_p4est(const KParams P) {
+    constexpr int ND = EQ::NDIMS, NV = EQ::NVARS, NF = ipow(N, ND - 1), NN = ipow(N, ND);
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long I = gid / NF;
+    const int fn = (int)(gid % NF);
+    if (I >= P.nmpi) return;
+    const int i = fn % N, j = fn / N;
+    const EQ eq(P.eq);
+    const long long element = P.mpi_local[I] - 1;
+    const int side = (int)P.mpi_side[I];
+    int vn, sfn, dir;
+    p4_face<ND, N>(P.mpi_node_indices + I * ND, i, j, vn, sfn, dir);
+    const double *pl = P.u + (element * NN + vn) * NV;
+    const double *pr = P.recv + (I * NF + fn) * NV;
+    double ul[NV], ur[NV], f[NV], nrm[ND];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+        const double a = pl[v], b = pr[v];
+        ul[v] = side == 1 ? a : b;
+        ur[v] = side == 1 ? b : a;
+    }
+    load_ja<ND, NN>(P, dir / 2, vn, element, nrm);
+    // outward normal (dg.jl:74-86), negated once more on the secondary side
+    if ((dir % 2 == 0) != (side == 2)) {
+#pragma unroll
+        for (int d = 0; d < ND; ++d) nrm[d] = -nrm[d];
+    }
+    eq.numflux_normal(P.surface_flux, ul, ur, nrm, f);
+    double *s = P.sfv + ((element * (2 * ND) + dir) * NF + sfn) * NV;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) s[v] = side == 1 ? f[v] : -f[v];
 }
 
 }  // namespace tb

@@ -73,7 +73,10 @@ void launch_mpi_pack(const KParams &P, cudaStream_t s) {
     constexpr int NF = ipow(N, EQ::NDIMS - 1);
     const long long total = P.nmpi * NF;
     if (total == 0) return;
-    k_mpi_pack<EQ, N><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(P);
+    if (P.p4est)
+        k_mpi_pack_p4est<EQ, N><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(P);
+    else
+        k_mpi_pack<EQ, N><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(P);
 }
 
 template <class EQ, int N>
@@ -81,8 +84,10 @@ void launch_mpi_interface_flux(const KParams &P, cudaStream_t s) {
     constexpr int NF = ipow(N, EQ::NDIMS - 1);
     const long long total = P.nmpi * NF;
     if (total == 0) return;
-    if (HasFastRanocha<EQ>::value && P.kernel_path == 0 &&
-        (P.surface_flux == TRIXI_B200_FLUX_RANOCHA || P.surface_flux == TRIXI_B200_FLUX_RANOCHA_TURBO))
+    if (P.p4est)
+        k_mpi_interface_flux_p4est<EQ, N><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(P);
+    else if (HasFastRanocha<EQ>::value && P.kernel_path == 0 &&
+             (P.surface_flux == TRIXI_B200_FLUX_RANOCHA || P.surface_flux == TRIXI_B200_FLUX_RANOCHA_TURBO))
         k_mpi_interface_flux<EQ, N, true><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(P);
     else
         k_mpi_interface_flux<EQ, N><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(P);
@@ -198,6 +203,8 @@ cudaError_t preload_all() {
     TB_PRELOAD((k_interface_flux_curved<EQ, N>));
     TB_PRELOAD((k_interface_flux_p4est<EQ, N>));
     TB_PRELOAD((k_boundary_flux_p4est<EQ, N>));
+    TB_PRELOAD((k_mpi_pack_p4est<EQ, N>));
+    TB_PRELOAD((k_mpi_interface_flux_p4est<EQ, N>));
     TB_PRELOAD((k_boundary_flux_curved<EQ, N>));
     TB_PRELOAD((k_element_curved<EQ, N, TRIXI_B200_VOLINT_WEAK_FORM, true>));
     TB_PRELOAD((k_element_curved<EQ, N, TRIXI_B200_VOLINT_WEAK_FORM, false>));

@@ -311,8 +311,8 @@ TRIXI_B200_API int trixi_b200_create(const trixi_b200_desc *d, trixi_b200_handle
     if (p4est && (!d->contravariant_vectors || (d->ninterfaces > 0 && !d->interface_node_indices) ||
                   (d->nboundaries > 0 && !d->boundary_node_indices)))
         return fail(nullptr, TRIXI_B200_EINVAL, "P4estMesh needs contravariant_vectors and node_indices");
-    if (p4est && d->world_size > 1)
-        return fail(nullptr, TRIXI_B200_EINVAL, "P4estMesh handles are single-rank in this build");
+    if (p4est && d->nmpiinterfaces > 0 && !d->mpi_node_indices)
+        return fail(nullptr, TRIXI_B200_EINVAL, "P4estMesh MPI interfaces need mpi_node_indices");
     if (structured && (!d->contravariant_vectors || !d->left_neighbors))
         return fail(nullptr, TRIXI_B200_EINVAL, "StructuredMesh needs contravariant_vectors and left_neighbors");
     if (structured && d->world_size > 1)
@@ -558,6 +558,10 @@ TRIXI_B200_API int trixi_b200_create(const trixi_b200_desc *d, trixi_b200_handle
         P.mpi_side = itmp;
         CREATE_TRY(upload_array(h, (const long long *)d->mpi_orientations, (size_t)d->nmpiinterfaces, &itmp));
         P.mpi_orient = itmp;
+        if (p4est) {
+            CREATE_TRY(upload_array(h, (const long long *)d->mpi_node_indices, (size_t)(nd * d->nmpiinterfaces), &itmp));
+            P.mpi_node_indices = itmp;
+        }
         int *stmp = nullptr;
         CREATE_TRY(upload_array(h, h->h_peer_slot.data(), h->h_peer_slot.size(), &stmp));
         P.mpi_peer_slot = stmp;

@@ -20,7 +20,7 @@ from __future__ import annotations
 import numpy as np
 
 from .basis import LobattoLegendreBasis, polynomial_interpolation_matrix
-from .containers import BoundaryContainer, InterfaceContainer
+from .containers import BoundaryContainer, InterfaceContainer, MPIInterfaceContainer, owner_of
 from .mesh import morton_key
 from .structured import compute_metric_terms, coordinates2mapping, transfinite_mapping
 
@@ -97,14 +97,17 @@ class P4estElementContainer:
     pass
 
 
-def init_elements_p4est(mesh, basis):
-    """init_elements! dgsem_p4est/containers.jl:58-76 + containers_3d.jl:9-77."""
+def init_elements_p4est(mesh, basis, first=0, last=None):
+    """init_elements! dgsem_p4est/containers.jl:58-76 + containers_3d.jl:9-77 for the elements
+    [first, last) of this rank (p4est partitions the space-filling curve into contiguous chunks,
+    ``global_first_quadrant`` dg_parallel.jl:290-296)."""
     nd, n = mesh.ndims, basis.nnodes
     if n < mesh.nodes.shape[0]:
         raise ValueError("The solver can't have a lower polydeg than the mesh")
     L = mesh.initial_refinement_level
     quad_length = 1.0 / (1 << L)
-    nelem = mesh.ncells
+    last = mesh.ncells if last is None else last
+    nelem = last - first
     X = np.empty((nd,) + (n,) * nd + (nelem,), order="F")
     # interpolation matrices only depend on the quadrant coordinate along one axis
     mats = []
@@ -112,10 +115,10 @@ def init_elements_p4est(mesh, basis):
         nodes_out = 2 * (quad_length * 1 / 2 * (basis.nodes + 1) + c * quad_length) - 1
         mats.append(polynomial_interpolation_matrix(mesh.nodes, nodes_out))
     mats = np.stack(mats)  # [2^L, n, n_mesh]
-    T = mesh.tree_node_coordinates[..., mesh.tree_of_element]  # [nd, nm.., nelem]
+    T = mesh.tree_node_coordinates[..., mesh.tree_of_element[first:last]]  # [nd, nm.., nelem]
     data = T
     for d in range(nd):
-        M = mats[mesh.quad_coords[d]]  # [nelem, n, nm]
+        M = mats[mesh.quad_coords[d, first:last]]  # [nelem, n, nm]
         # contract axis 1+d of data with the last axis of M, per element
         data = np.moveaxis(data, 1 + d, -2)            # [..., nm, nelem]
         data = np.einsum("eij,...je->...ie", M, data)  # [..., n, nelem]
@@ -144,13 +147,18 @@ def _face_indices(nd, d, side):
     return idx
 
 
-def init_interfaces_p4est(mesh):
+def init_interfaces_p4est(mesh, first=0, last=None, world_size=1):
     """init_interfaces! (dgsem_p4est/containers.jl:264-300) for a conforming brick forest: one interface per
-    interior (or periodic) face, primary = the element on the negative side."""
+    interior (or periodic) face, primary = the element on the negative side.  Faces whose other element
+    belongs to another rank become MPI interfaces (init_mpi_interfaces! containers_parallel.jl:85-127,
+    ``local_neighbor_ids``/``local_sides``/``node_indices`` of the local side), sorted by
+    (neighbour rank, global interface id) (init_mpi_neighbor_connectivity dg_parallel.jl:313-390).
+    Returns (interfaces, mpi_interfaces)."""
     nd = mesh.ndims
     cells = mesh.cells_per_dimension
     gc = mesh.global_coords
-    prim, sec, nidx = [], [], []
+    last = mesh.ncells if last is None else last
+    prim, sec, dims = [], [], []
     for d in range(nd):
         nb = gc.copy()
         nb[d] += 1
@@ -165,24 +173,45 @@ def init_interfaces_p4est(mesh):
         el = np.nonzero(valid)[0]
         prim.append(el)
         sec.append(nbid[valid])
-        ni = np.empty((nd, 2, el.shape[0]), dtype=np.int64)
-        ni[:, 0, :] = np.array(_face_indices(nd, d, 1))[:, None]
-        ni[:, 1, :] = np.array(_face_indices(nd, d, 0))[:, None]
-        nidx.append(ni)
+        dims.append(np.full(el.shape[0], d, dtype=np.int64))
+    prim, sec, dims = np.concatenate(prim), np.concatenate(sec), np.concatenate(dims)
+    face_idx = np.array([[_face_indices(nd, d, 1), _face_indices(nd, d, 0)] for d in range(nd)],
+                        dtype=np.int64)  # [d, side (0 primary: :end face, 1 secondary: :begin face), nd]
+    ploc = (prim >= first) & (prim < last)
+    sloc = (sec >= first) & (sec < last)
+    both = ploc & sloc
     ic = InterfaceContainer()
-    ic.neighbor_ids = np.asfortranarray(np.stack([np.concatenate(prim) + 1, np.concatenate(sec) + 1]))
-    ic.node_indices = np.asfortranarray(np.concatenate(nidx, axis=2))  # [nd, 2, I]
+    ic.neighbor_ids = np.asfortranarray(np.stack([prim[both] - first + 1, sec[both] - first + 1]))
+    ic.node_indices = np.asfortranarray(face_idx[dims[both]].transpose(2, 1, 0))  # [nd, 2, I]
     ic.orientations = np.zeros(ic.neighbor_ids.shape[1], dtype=np.int64)
     ic.ninterfaces = ic.neighbor_ids.shape[1]
-    return ic
+
+    mi = MPIInterfaceContainer()
+    only_p, only_s = ploc & ~sloc, sloc & ~ploc
+    loc = np.concatenate([prim[only_p], sec[only_s]])
+    remote = np.concatenate([sec[only_p], prim[only_s]])
+    side = np.concatenate([np.ones(only_p.sum(), dtype=np.int64), np.full(only_s.sum(), 2, dtype=np.int64)])
+    dim = np.concatenate([dims[only_p], dims[only_s]])
+    gif = np.concatenate([prim[only_p], prim[only_s]]) * nd + dim  # global interface id: primary element, dimension
+    peer = owner_of(remote, mesh.ncells, world_size) if remote.size else remote
+    order = np.lexsort((gif, peer))
+    mi.local_neighbor_ids = (loc[order] - first + 1).astype(np.int64)
+    mi.local_sides = side[order]
+    mi.orientations = (dim[order] + 1).astype(np.int64)
+    mi.node_indices = np.asfortranarray(face_idx[dim[order], side[order] - 1].T.reshape(nd, -1))  # [nd, MI]
+    mi.neighbor_ranks = peer[order].astype(np.int64)
+    mi.global_interface_ids = gif[order]
+    mi.nmpiinterfaces = int(order.shape[0])
+    return ic, mi
 
 
-def init_boundaries_p4est(mesh):
+def init_boundaries_p4est(mesh, first=0, last=None):
     """init_boundaries! (dgsem_p4est/containers.jl:302-345), sorted by boundary name
-    :x_neg, :x_pos, :y_neg, ... (structured_boundary_names! p4est_mesh.jl:298-365)."""
+    :x_neg, :x_pos, :y_neg, ... (structured_boundary_names! p4est_mesh.jl:298-365); elements [first, last)."""
     nd = mesh.ndims
     cells = mesh.cells_per_dimension
-    gc = mesh.global_coords
+    last = mesh.ncells if last is None else last
+    gc = mesh.global_coords[:, first:last]
     ids, nidx, counts = [], [], []
     for direction in range(2 * nd):
         d, side = direction // 2, direction % 2

@@ -75,15 +75,12 @@ def create_cache(mesh, equations, solver, rank=0, world_size=1):
         cache.mpi_interfaces.nmpiinterfaces = 0
         cache.boundaries = _structured_boundaries(mesh, cache.elements)
     elif isinstance(mesh, P4estMesh):
-        if world_size != 1:
-            raise NotImplementedError("P4estMesh partitions need libp4est; single rank here")
-        # create_cache dgsem_p4est/dg.jl:13-70
-        cache.first_element, cache.last_element = 0, mesh.ncells
-        cache.elements = init_elements_p4est(mesh, solver.basis)
-        cache.interfaces = init_interfaces_p4est(mesh)
-        cache.mpi_interfaces = MPIInterfaceContainer()
-        cache.mpi_interfaces.nmpiinterfaces = 0
-        cache.boundaries = init_boundaries_p4est(mesh)
+        # create_cache dgsem_p4est/dg.jl:13-70 (+ dg_parallel.jl:267-311 for a partition)
+        first, last = partition_cells(mesh.ncells, rank, world_size)
+        cache.first_element, cache.last_element = first, last
+        cache.elements = init_elements_p4est(mesh, solver.basis, first, last)
+        cache.interfaces, cache.mpi_interfaces = init_interfaces_p4est(mesh, first, last, world_size)
+        cache.boundaries = init_boundaries_p4est(mesh, first, last)
     else:
         raise TypeError(f"unsupported mesh type {type(mesh).__name__}")
     return cache
@@ -256,6 +253,8 @@ class SemidiscretizationHyperbolic:
             h.set_i64("mpi_local_sides", mi.local_sides)
             h.set_i64("mpi_orientations", mi.orientations)
             h.set_i64("mpi_neighbor_ranks", mi.neighbor_ranks)
+            if isinstance(self.mesh, P4estMesh):
+                h.set_i64("mpi_node_indices", mi.node_indices)
         self._desc = h
         return h
 
