@@ -30,7 +30,7 @@ def _worker(rank, world, port, name, out_dir):
     semi = ex.semi()
     psemi = ex.build()
     psemi.__init__(semi.mesh, semi.equations, semi.initial_condition, semi.solver, source_terms=semi.source_terms,
-                   boundary_conditions=semi.boundary_conditions, rank=rank, world_size=world)
+                   boundary_conditions=semi.boundary_conditions, rank=rank, world_size=world, comm=dist)
     ob = oracle.OracleBackend(psemi, num_threads=1)
     ob.set_halo_exchange(HostHaloExchange(psemi, dist).exchange)
     u = T.compute_coefficients(0.0, psemi)
@@ -42,7 +42,8 @@ def _worker(rank, world, port, name, out_dir):
     dt = allreduce_min(dt_local, dist)
     alg = T.CarpenterKennedy2N54()
     ob.step_2n(0.0, 0.5 * dt, alg.a, alg.b, alg.c)
-    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), du=du, u1=ob.download(0), dt=dt,
+    l2, linf = T.calc_error_norms(ob.download(0), 0.5 * dt, psemi)  # reductions over ranks
+    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), du=du, u1=ob.download(0), dt=dt, l2=l2, linf=linf,
              first=psemi.cache.first_element, last=psemi.cache.last_element)
     dist.barrier()
     dist.destroy_process_group()
@@ -67,12 +68,15 @@ def test_distributed_oracle_equals_serial(world, name, tmp_path, oracle_module):
     alg = T.CarpenterKennedy2N54()
     ob.step_2n(0.0, 0.5 * dt, alg.a, alg.b, alg.c)
     u1 = ob.download(0).reshape(u.shape, order="F")
+    l2, linf = T.calc_error_norms(u1, 0.5 * dt, semi)
     covered = 0
     for r in range(world):
         z = np.load(os.path.join(str(tmp_path), f"rank{r}.npz"))
         first, last = int(z["first"]), int(z["last"])
         covered += last - first
         assert float(z["dt"]) == dt
+        np.testing.assert_allclose(z["l2"], l2, rtol=1e-12, atol=1e-15)  # psi of MHD is round-off only
+        np.testing.assert_allclose(z["linf"], linf, rtol=1e-12, atol=1e-15)
         if name.startswith("p4est"):
             # each rank evaluates a shared face with the normal of its own element
             # (dgsem_p4est/dg_3d_parallel.jl:262-266): equal to rounding of the metric terms, not bit for bit

@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, out_dir):
+def _worker(rank, world, port, out_dir, name="tree_3d_euler_ec"):
     for p in (ROOT, os.path.join(ROOT, "tests")):
         sys.path.insert(0, p)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -23,9 +23,11 @@ def _worker(rank, world, port, out_dir):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     import trixi_b200 as T
     from elixirs import ELIXIRS
-    ex = ELIXIRS["tree_3d_euler_ec"]
+    ex = ELIXIRS[name]
     base = ex.semi()
     semi = T.SemidiscretizationHyperbolic(base.mesh, base.equations, base.initial_condition, base.solver,
+                                          source_terms=base.source_terms,
+                                          boundary_conditions=base.boundary_conditions,
                                           rank=rank, world_size=world, comm=dist, device=rank)
     sol, l2, linf = ex.run(semi)  # full elixir run: StepsizeCallback allreduce + AnalysisCallback reductions
     np.savez(os.path.join(out_dir, f"rank{rank}.npz"), l2=l2, linf=linf, steps=sol.integrator.iter)
@@ -33,13 +35,15 @@ def _worker(rank, world, port, out_dir):
     dist.destroy_process_group()
 
 
-def test_two_gpu_run_reproduces_golden(tmp_path):
+@pytest.mark.parametrize("name", ["tree_3d_euler_ec", "p4est_3d_euler_source_terms_nonperiodic", "tree_3d_mhd_ec"])
+def test_two_gpu_run_reproduces_golden(name, tmp_path):
+    """like test/test_mpi_p4est_3d.jl: the distributed run reproduces the serial golden values"""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from elixirs import ELIXIRS
-    mp.spawn(_worker, args=(2, 29733, str(tmp_path)), nprocs=2, join=True)
-    ex = ELIXIRS["tree_3d_euler_ec"]
+    mp.spawn(_worker, args=(2, 29733 + len(name), str(tmp_path), name), nprocs=2, join=True)
+    ex = ELIXIRS[name]
     for r in range(2):
         z = np.load(os.path.join(str(tmp_path), f"rank{r}.npz"))
         ex.check(z["l2"], z["linf"])

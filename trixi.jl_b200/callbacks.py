@@ -138,12 +138,18 @@ def calc_error_norms(u, t, semi, analyzer=None):
     if semi.world_size > 1 and semi.comm is not None:
         # global reductions like the reference's MPI analysis (analysis_dg2d.jl:170-215)
         import torch
-        t2, tinf = torch.from_numpy(l2sq.copy()), torch.from_numpy(linf.copy())
+        # the total volume of a curved mesh is accumulated with the same quadrature and reduced with the
+        # squared errors (analysis_dg3d.jl:218-275)
+        sums = np.concatenate([l2sq, [0.0 if total_volume is None else total_volume]])
+        t2, tinf = torch.from_numpy(sums), torch.from_numpy(linf.copy())
         if semi.comm.get_backend() == "nccl":
             t2, tinf = t2.cuda(), tinf.cuda()
         semi.comm.all_reduce(t2, op=semi.comm.ReduceOp.SUM)
         semi.comm.all_reduce(tinf, op=semi.comm.ReduceOp.MAX)
-        l2sq, linf = t2.cpu().numpy(), tinf.cpu().numpy()
+        sums, linf = t2.cpu().numpy(), tinf.cpu().numpy()
+        l2sq = sums[:-1]
+        if total_volume is not None:
+            total_volume = float(sums[-1])
     l2 = np.sqrt(l2sq / (mesh.total_volume() if total_volume is None else total_volume))
     return l2, linf
 
