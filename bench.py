@@ -46,24 +46,97 @@ def box_cells(level, world):
     return tuple(n)
 
 
-def make_semi(level, device=-1, rank=0, world=1, comm=None):
+def _warped_mapping_3d(xi_, eta_, zeta_):
+    # examples/structured_3d_dgsem/elixir_euler_free_stream.jl:17-41
+    pi = np.pi
+    xi, eta, zeta = 1.5 * xi_ + 1.5, 1.5 * eta_ + 1.5, 1.5 * zeta_ + 1.5
+    y = eta + 3 / 8 * (np.cos(1.5 * pi * (2 * xi - 3) / 3) * np.cos(0.5 * pi * (2 * eta - 3) / 3)
+                       * np.cos(0.5 * pi * (2 * zeta - 3) / 3))
+    x = xi + 3 / 8 * (np.cos(0.5 * pi * (2 * xi - 3) / 3) * np.cos(2 * pi * (2 * y - 3) / 3)
+                      * np.cos(0.5 * pi * (2 * zeta - 3) / 3))
+    z = zeta + 3 / 8 * (np.cos(0.5 * pi * (2 * x - 3) / 3) * np.cos(pi * (2 * y - 3) / 3)
+                        * np.cos(0.5 * pi * (2 * zeta - 3) / 3))
+    return x, y, z
+
+
+# Secondary workloads (SURVEY.md §8d C2/C4 + the MHD row); `euler_ec` is the headline the driver runs.
+# bytes = algorithmic HBM bytes per DOF of the element kernel in RK mode averaged over the 5 CK54 stages
+# (stage 1 does not read u_tmp): u + sfv + 0.8 u_tmp + geometry + sources' x, plus the u, u_tmp writes.
+WORKLOADS = {
+    "euler_ec": {"nvars": 5, "bytes": 212.0, "flop": 312.5 + 45.0,
+                 "kernel": "k_element_euler3d_ranocha_p3 (volume+surface+jacobian+2N stage, TMA tiles)"},
+    "euler_weak": {"nvars": 5, "bytes": 212.0 + 24.0, "flop": 149.0 + 45.0 + 25.0,
+                   "kernel": "k_element<Euler3D,4,weak form> (volume+surface+jacobian+source+2N stage)"},
+    "structured_curved": {"nvars": 5, "bytes": 212.0 + 72.0 + 8.0, "flop": 149.0 + 45.0 + 45.0,
+                          "kernel": "k_element_curved<Euler3D,4,weak form> (contravariant fluxes, nodal Jacobian)"},
+    "p4est_curved": {"nvars": 5, "bytes": 212.0 + 72.0 + 8.0, "flop": 149.0 + 45.0 + 45.0,
+                     "kernel": "k_element_curved<Euler3D,4,weak form> (P4estMesh: + surface integral)"},
+    "mhd_ec": {"nvars": 9, "bytes": 9 * 8 * (1 + 1.5 + 0.8 + 2), "flop": None,
+               "kernel": "k_element<Mhd3D,4,flux differencing> (Hindenlang-Gassner + Powell nonconservative)"},
+}
+
+
+def make_semi(level, device=-1, rank=0, world=1, comm=None, workload="euler_ec"):
     import trixi_b200 as T
-    # examples/tree_3d_dgsem/elixir_euler_ec.jl at a larger refinement level
-    eq = T.CompressibleEulerEquations3D(1.4)
-    solver = T.DGSEM(polydeg=3, surface_flux=T.flux_ranocha,
-                     volume_integral=T.VolumeIntegralFluxDifferencing(T.flux_ranocha))
-    if world == 1:
-        mesh = T.TreeMesh((-2.0,) * 3, (2.0,) * 3, initial_refinement_level=level, periodicity=True)
-    else:
-        # same cells (size 4 / 2^level) and the same Morton element order as the TreeMesh, on a box that
-        # grows with the number of ranks; contiguous chunks of the order are (2^level)^3 blocks
-        mesh = T.CartesianBoxMesh((-2.0,) * 3, 4.0 / (1 << level), box_cells(level, world), periodicity=True)
-    return T.SemidiscretizationHyperbolic(mesh, eq, T.initial_condition_weak_blast_wave, solver, device=device,
-                                          rank=rank, world_size=world, comm=comm)
-
-
-def workload_name(level, world=1):
+    kw = dict(device=device, rank=rank, world_size=world, comm=comm)
     n = 1 << level
+    if workload == "euler_ec":
+        # examples/tree_3d_dgsem/elixir_euler_ec.jl at a larger refinement level
+        eq = T.CompressibleEulerEquations3D(1.4)
+        solver = T.DGSEM(polydeg=3, surface_flux=T.flux_ranocha,
+                         volume_integral=T.VolumeIntegralFluxDifferencing(T.flux_ranocha))
+        if world == 1:
+            mesh = T.TreeMesh((-2.0,) * 3, (2.0,) * 3, initial_refinement_level=level, periodicity=True)
+        else:
+            # same cells (size 4 / 2^level) and the same Morton element order as the TreeMesh, on a box that
+            # grows with the number of ranks; contiguous chunks of the order are (2^level)^3 blocks
+            mesh = T.CartesianBoxMesh((-2.0,) * 3, 4.0 / (1 << level), box_cells(level, world), periodicity=True)
+        return T.SemidiscretizationHyperbolic(mesh, eq, T.initial_condition_weak_blast_wave, solver, **kw)
+    if world != 1 and workload != "p4est_curved":
+        raise ValueError(f"workload {workload} is single-rank")
+    if workload == "euler_weak":
+        # examples/tree_3d_dgsem/elixir_euler_source_terms.jl (C2)
+        eq = T.CompressibleEulerEquations3D(1.4)
+        solver = T.DGSEM(polydeg=3, surface_flux=T.FluxLaxFriedrichs(T.max_abs_speed_naive),
+                         volume_integral=T.VolumeIntegralWeakForm())
+        mesh = T.TreeMesh((0.0,) * 3, (2.0,) * 3, initial_refinement_level=level, periodicity=True)
+        return T.SemidiscretizationHyperbolic(mesh, eq, T.initial_condition_convergence_test, solver,
+                                              source_terms=T.source_terms_convergence_test, **kw)
+    if workload in ("structured_curved", "p4est_curved"):
+        # examples/structured_3d_dgsem/elixir_euler_free_stream.jl on n^3 cells (C4)
+        eq = T.CompressibleEulerEquations3D(1.4)
+        solver = T.DGSEM(polydeg=3, surface_flux=T.FluxLaxFriedrichs(T.max_abs_speed_naive),
+                         volume_integral=T.VolumeIntegralWeakForm())
+        if workload == "structured_curved":
+            mesh = T.StructuredMesh((n, n, n), _warped_mapping_3d, periodicity=True)
+        else:
+            trees = min(n, 4)
+            mesh = T.P4estMesh((trees,) * 3, polydeg=3, mapping=_warped_mapping_3d, periodicity=True,
+                               initial_refinement_level=int(np.log2(n // trees)))
+        return T.SemidiscretizationHyperbolic(mesh, eq, T.initial_condition_constant, solver, **kw)
+    if workload == "mhd_ec":
+        # examples/tree_3d_dgsem/elixir_mhd_ec.jl
+        eq = T.IdealGlmMhdEquations3D(1.4)
+        eq.c_h = 1.0  # GlmSpeedCallback value of a fixed-dt run; any finite value exercises the same code
+        flux = (T.flux_hindenlang_gassner, T.flux_nonconservative_powell)
+        solver = T.DGSEM(polydeg=3, surface_flux=flux, volume_integral=T.VolumeIntegralFluxDifferencing(flux))
+        mesh = T.TreeMesh((-2.0,) * 3, (2.0,) * 3, initial_refinement_level=level, periodicity=True)
+        return T.SemidiscretizationHyperbolic(mesh, eq, T.initial_condition_weak_blast_wave, solver, **kw)
+    raise ValueError(f"unknown workload {workload}")
+
+
+def workload_name(level, world=1, workload="euler_ec"):
+    n = 1 << level
+    if workload != "euler_ec":
+        desc = {"euler_weak": "tree_3d_dgsem/elixir_euler_source_terms.jl: 3D Euler weak form + LLF(naive) + "
+                              "convergence-test sources, TreeMesh",
+                "structured_curved": "structured_3d_dgsem/elixir_euler_free_stream.jl: 3D Euler weak form + "
+                                     "LLF(naive), warped StructuredMesh",
+                "p4est_curved": "the same warped mapping on a conforming P4estMesh (4^3 trees), 3D Euler weak "
+                                "form + LLF(naive)",
+                "mhd_ec": "tree_3d_dgsem/elixir_mhd_ec.jl: ideal GLM-MHD, flux differencing with "
+                          "flux_hindenlang_gassner + flux_nonconservative_powell, TreeMesh"}[workload]
+        return f"{desc}, polydeg=3, {n}^3 elements ({64 * n**3 / 1e6:.1f} M DOF) per rank, periodic"
     base = ("tree_3d_dgsem/elixir_euler_ec.jl: 3D Euler EC flux differencing (flux_ranocha), polydeg=3, ")
     if world == 1:
         return base + (f"TreeMesh level {level} ({n}^3 elements, {64 * n**3 / 1e6:.1f} M DOF), periodic, "
@@ -153,11 +226,11 @@ def oracle_backend(semi, threads=None):
     return oracle.OracleBackend(semi, num_threads=threads)
 
 
-def time_cpu_reference(level, steps, warmup):
+def time_cpu_reference(level, steps, warmup, workload="euler_ec"):
     """The reference's CPU path restated (oracle/trixi_oracle.c, OpenMP over all host cores):
     CarpenterKennedy2N54 steps on a bounded sample (smaller TreeMesh level of the same workload)."""
     import trixi_b200 as T
-    semi = make_semi(level)
+    semi = make_semi(level, workload=workload)
     ob = oracle_backend(semi)
     u0 = T.compute_coefficients(0.0, semi)
     ob.upload(0, u0)
@@ -179,8 +252,8 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     level = args.cpu_level
-    value, wall, threads, ndofs = time_cpu_reference(level, args.steps, args.warmup)
-    sample = (f"{workload_name(level)}; {args.steps} CK54 steps (5 rhs! + stage updates + max_dt each) "
+    value, wall, threads, ndofs = time_cpu_reference(level, args.steps, args.warmup, args.workload)
+    sample = (f"{workload_name(level, 1, args.workload)}; {args.steps} CK54 steps (5 rhs! + stage updates + max_dt each) "
               f"after {args.warmup} warm-up, OpenMP C restatement of the reference's CPU rhs! "
               f"(Julia/Trixi.jl not installable on this box)")
     line = {
@@ -188,7 +261,7 @@ def run_reference(args, rank, world):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "pid_ns_per_dof_rhs": 1e9 / value * threads,
-        "config": {"workload": workload_name(args.level), "sample": sample},
+        "config": {"workload": workload_name(args.level, 1, args.workload), "sample": sample},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -211,7 +284,9 @@ def run_b200(args, rank, world, local_rank):
         torch.cuda.synchronize()
 
     from trixi_b200.parallel import allreduce_min
-    semi = make_semi(args.level, device=local_rank, rank=rank, world=world, comm=dist if world > 1 else None)
+    semi = make_semi(args.level, device=local_rank, rank=rank, world=world, comm=dist if world > 1 else None,
+                     workload=args.workload)
+    wl = WORKLOADS[args.workload]
     gpu = semi.backend()
     # u is owned by the handle during the run: the last RK stage also reduces the CFL maxima (max_dt fused)
     gpu.set_option(gpu.OPT_FUSED_CFL, 0 if args.no_fused_cfl else 1)
@@ -300,25 +375,35 @@ def run_b200(args, rank, world, local_rank):
         # algorithmic bytes/DOF in RK mode: read u 40 + surface_flux_values 60 + u_tmp 40 (stages 2-5),
         # write u_tmp 40 + u 40 -> 220 B (stage 1: 180 B); average over the 5 stages = 212 B
         elem_avg_ms = elem_ms / max(elem_n, 1)
-        algo_bytes = ndofs * 212.0
+        algo_bytes = ndofs * wl["bytes"]
         achieved_gbs = algo_bytes / (elem_avg_ms * 1e-3) * 1e-9
-        algo_flops = ndofs * (ALGO_FLOP_PER_DOF_VOLUME + 5 * 9.0)
+        algo_flops = ndofs * (wl["flop"] or 0.0)
+        # DRAM traffic of the dominant kernel per launch from the committed `ncu --set full` capture
+        # (dram__bytes_read.sum + dram__bytes_write.sum, scaled by DOF count)
+        traffic, traffic_src = None, None
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                tj = json.load(f).get(args.workload)
+            if tj:
+                traffic, traffic_src = tj["dram_bytes_per_dof"] * ndofs, tj["source"]
         cpu = None
         if not args.no_cpu_baseline:
-            cv, cwall, cthreads, cdofs = time_cpu_reference(args.cpu_level, 3, 1)
+            cv, cwall, cthreads, cdofs = time_cpu_reference(args.cpu_level, 3, 1, args.workload)
             cpu = {"value": cv, "unit": UNIT, "cores": cthreads, "kind": "port",
-                   "sample": f"{workload_name(args.cpu_level)}; 3 CK54 steps (15 rhs!) after 1 warm-up; "
+                   "sample": f"{workload_name(args.cpu_level, 1, args.workload)}; 3 CK54 steps (15 rhs!) after 1 warm-up; "
                              "OpenMP C restatement of the reference's CPU rhs! (oracle/trixi_oracle.c)"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "pid_ns_per_dof_rhs": 1e9 / value * world,
-            "config": {"workload": workload_name(args.level, world), "ndofs_per_gpu": ndofs,
+            "config": {"workload": workload_name(args.level, world, args.workload), "ndofs_per_gpu": ndofs,
                        "rhs_per_step": 5, "time_integrator": "CarpenterKennedy2N54 (fused stage update)",
                        "max_dt": "separate kernel after every step" if args.no_fused_cfl else
                        "every step (StepsizeCallback interval 1); reduced by the last RK stage kernel",
-                       "l2_hygiene": "inputs larger than L2 (u alone is %.1f GB)" % (n * 8 / 1e9),
+                       "l2_hygiene": ("inputs larger than L2 (u alone is %.1f GB)" % (n * 8 / 1e9)) if n * 8 > 2.5e8
+                       else "WARNING: working set comparable to the 126 MB L2; use a larger --level",
                        "parallelism": "1 rank per GPU" if world == 1 else
                        f"{world} ranks: Morton-order element partition, face halo exchange by direct peer "
                        "stores over NVLink (CUDA IPC) + sequence flags inside libtrixi_b200, dt min-allreduce "
@@ -328,14 +413,15 @@ def run_b200(args, rank, world, local_rank):
                     "call": "rhs_hyperbolic(du_host, u_host, semi, t) -> trixi_b200_rhs_host, pinned host buffers",
                     "steps": e2e_steps, "finite": e2e_finite},
             "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "kernel": "k_element (volume+surface+jacobian+2N stage)",
+            "roofline": {"bound": "hbm", "kernel": wl["kernel"],
                          "achieved": achieved_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                         "frac": achieved_gbs / peaks["hbm_gbs"], "peak_kind": peak_kind, "traffic": None,
+                         "frac": achieved_gbs / peaks["hbm_gbs"], "peak_kind": peak_kind, "traffic": traffic,
+                         "traffic_source": traffic_src,
                          "avg_launch_ms": elem_avg_ms, "launches": elem_n,
-                         "algorithmic_bytes_per_dof": 212.0,
+                         "algorithmic_bytes_per_dof": wl["bytes"],
                          "fp64": {"achieved_tflops": algo_flops / (elem_avg_ms * 1e-3) * 1e-12,
                                   "peak_tflops_measured_dfma": fp64_peak,
-                                  "algorithmic_flop_per_dof": ALGO_FLOP_PER_DOF_VOLUME + 45.0},
+                                  "algorithmic_flop_per_dof": wl["flop"]},
                          "copy_gbs_measured_here": copy_gbs},
             "kernel_time_share": {"surface_flux_ms": surf_ms, "element_ms": elem_ms, "max_dt_ms": cfl_ms,
                                   "halo_pack_wait_mpiflux_ms": halo_ms, "timed_region_ms": ms_max},
@@ -375,6 +461,8 @@ def main():
     ap.add_argument("--cpu-level", type=int, default=5, help="refinement level of the bounded CPU sample")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="euler_ec", choices=sorted(WORKLOADS),
+                    help="euler_ec is the headline (BASELINE.json); the others are SURVEY.md §8d's secondary configs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fused-cfl", action="store_true", help="run max_dt as its own kernel after every step")
     args = ap.parse_args()
