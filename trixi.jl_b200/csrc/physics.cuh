@@ -713,8 +713,8 @@ struct Mhd3D {
 
     // flux(u, orientation) (:187-234)
     TB_DEV void flux(const double (&u)[9], int o, double (&f)[9]) const {
-        const double rho = u[0], psi = u[8];
-        const double v[3] = {u[1] / rho, u[2] / rho, u[3] / rho};
+        const double psi = u[8], inv_rho = fast_rcp(u[0]);
+        const double v[3] = {u[1] * inv_rho, u[2] * inv_rho, u[3] * inv_rho};
         const double B[3] = {u[5], u[6], u[7]};
         const double kin_en = 0.5 * (u[1] * v[0] + u[2] * v[1] + u[3] * v[2]);
         const double mag_en = 0.5 * (B[0] * B[0] + B[1] * B[1] + B[2] * B[2]);
@@ -733,7 +733,8 @@ struct Mhd3D {
 
     // flux_nonconservative_powell(u_ll, u_rr, orientation) (:295-340)
     TB_DEV void noncons(const double (&ul)[9], const double (&ur)[9], int o, double (&f)[9]) const {
-        const double v_ll[3] = {ul[1] / ul[0], ul[2] / ul[0], ul[3] / ul[0]};
+        const double inv_rho_ll = fast_rcp(ul[0]);
+        const double v_ll[3] = {ul[1] * inv_rho_ll, ul[2] * inv_rho_ll, ul[3] * inv_rho_ll};
         const double v_dot_B_ll = v_ll[0] * ul[5] + v_ll[1] * ul[6] + v_ll[2] * ul[7];
         const double Bn_rr = sel3(ur[5], ur[6], ur[7], o), vo = sel3(v_ll[0], v_ll[1], v_ll[2], o);
         f[0] = 0.0;
@@ -747,8 +748,8 @@ struct Mhd3D {
 
     // cons2prim (:1231-1243)
     TB_DEV void cons2prim(const double (&u)[9], double (&q)[9]) const {
-        const double rho = u[0];
-        const double v1 = u[1] / rho, v2 = u[2] / rho, v3 = u[3] / rho;
+        const double rho = u[0], inv_rho = fast_rcp(rho);
+        const double v1 = u[1] * inv_rho, v2 = u[2] * inv_rho, v3 = u[3] * inv_rho;
         q[0] = rho;
         q[1] = v1;
         q[2] = v2;
@@ -766,8 +767,8 @@ struct Mhd3D {
         double L[9], R[9];
         cons2prim(ul, L);
         cons2prim(ur, R);
-        const double rho_mean = ln_mean(L[0], R[0]);
-        const double inv_rho_p_mean = L[4] * R[4] * inv_ln_mean(L[0] * R[4], R[0] * L[4]);
+        const double rho_mean = ln_mean_fast(L[0], R[0]);
+        const double inv_rho_p_mean = L[4] * R[4] * inv_ln_mean_fast(L[0] * R[4], R[0] * L[4]);
         double v_avg[3];
 #pragma unroll
         for (int d = 0; d < 3; ++d) v_avg[d] = 0.5 * (L[1 + d] + R[1 + d]);
@@ -801,17 +802,16 @@ struct Mhd3D {
 
     // calc_fast_wavespeed(cons, orientation) (:1350-1376)
     TB_DEV double fast_wavespeed(const double (&u)[9], int o) const {
-        const double rho = u[0], psi = u[8];
-        const double v1 = u[1] / rho, v2 = u[2] / rho, v3 = u[3] / rho;
+        // divisions by rho and sqrt(rho) folded into one Newton reciprocal: b_i^2 = B_i^2 / rho
+        const double psi = u[8], inv_rho = fast_rcp(u[0]);
+        const double v1 = u[1] * inv_rho, v2 = u[2] * inv_rho, v3 = u[3] * inv_rho;
         const double kin_en = 0.5 * (u[1] * v1 + u[2] * v2 + u[3] * v3);
         const double mag_en = 0.5 * (u[5] * u[5] + u[6] * u[6] + u[7] * u[7]);
         const double p = (gamma - 1) * (u[4] - kin_en - mag_en - 0.5 * psi * psi);
-        const double a_square = gamma * p / rho;
-        const double sqrt_rho = sqrt(rho);
-        const double b1 = u[5] / sqrt_rho, b2 = u[6] / sqrt_rho, b3 = u[7] / sqrt_rho;
-        const double b_square = b1 * b1 + b2 * b2 + b3 * b3;
-        const double bo = sel3(b1, b2, b3, o), sum = a_square + b_square;
-        return sqrt(0.5 * sum + 0.5 * sqrt(sum * sum - 4 * a_square * bo * bo));
+        const double a_square = gamma * p * inv_rho;
+        const double b_square = 2 * mag_en * inv_rho;
+        const double Bo = sel3(u[5], u[6], u[7], o), sum = a_square + b_square;
+        return sqrt(0.5 * sum + 0.5 * sqrt(sum * sum - 4 * a_square * (Bo * Bo * inv_rho)));
     }
 
     // conservative part of the surface/volume flux (tuples are encoded as one id)
@@ -830,7 +830,8 @@ struct Mhd3D {
         case TRIXI_B200_FLUX_LLF_MHD_POWELL:
         case TRIXI_B200_FLUX_LLF_NAIVE_MHD_POWELL: {  // max_abs_speed(_naive) (:857-928)
             const bool naive = id == TRIXI_B200_FLUX_LLF_NAIVE || id == TRIXI_B200_FLUX_LLF_NAIVE_MHD_POWELL;
-            const double v_ll = sel3(ul[1], ul[2], ul[3], o) / ul[0], v_rr = sel3(ur[1], ur[2], ur[3], o) / ur[0];
+            const double v_ll = sel3(ul[1], ul[2], ul[3], o) * fast_rcp(ul[0]);
+            const double v_rr = sel3(ur[1], ur[2], ur[3], o) * fast_rcp(ur[0]);
             const double cf_ll = fast_wavespeed(ul, o), cf_rr = fast_wavespeed(ur, o);
             const double lam = naive ? fmax(fabs(v_ll), fabs(v_rr)) + fmax(cf_ll, cf_rr)
                                      : fmax(fabs(v_ll) + cf_ll, fabs(v_rr) + cf_rr);
@@ -853,7 +854,7 @@ struct Mhd3D {
     // max_abs_speeds (:1218-1228)
     TB_DEV void max_abs_speeds(const double (&u)[9], double (&lam)[3]) const {
 #pragma unroll
-        for (int d = 0; d < 3; ++d) lam[d] = fabs(u[1 + d] / u[0]) + fast_wavespeed(u, d);
+        for (int d = 0; d < 3; ++d) lam[d] = fabs(u[1 + d] * fast_rcp(u[0])) + fast_wavespeed(u, d);
     }
     TB_DEV void source_terms(int id, const double (&u)[9], const double (&x)[3], double t, double (&s)[9]) const {
 #pragma unroll
