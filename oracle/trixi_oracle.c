@@ -1527,6 +1527,100 @@ void oracle_rhs_p4est(const trixi_b200_desc *d, double *du, const double *u, dou
     oracle_calc_sources(d, du, u, t);
 }
 
+/* ---- L2 mortars on TreeMesh ----------------------------------------------------------------------------
+ * prolong2mortars! (dg_2d.jl:899-996, dg_3d.jl:770-957), calc_mortar_flux! (dg_2d.jl:1000-1036,
+ * dg_3d.jl:959-1010) and mortar_fluxes_to_elements! (dg_2d.jl:1169-1243, dg_3d.jl:1236-1335) for
+ * conservative equations.  Positions p = 0..2^(d-1)-1: bit 0 = upper half along the first face coordinate
+ * ("right" in 3D, "upper" in 2D), bit 1 = upper half along the second ("upper" in 3D). */
+static void mortar_apply_1d(const double *A, int n, int nv, int nb, int dim, const double *in, double *out, int add) {
+    /* multiply_dimensionwise! (interpolation.jl): out[v, i, j] (+)= sum_ii A[i, ii] in[v, ii, j] along dim 0,
+     * or out[v, i, j] (+)= sum_jj A[j, jj] in[v, i, jj] along dim 1; face data [nv, n, nb] */
+    for (int j = 0; j < nb; ++j)
+        for (int i = 0; i < n; ++i)
+            for (int v = 0; v < nv; ++v) {
+                double acc = 0.0;
+                for (int q = 0; q < n; ++q) {
+                    double a = dim == 0 ? A[i + n * q] : A[j + n * q];
+                    double x = dim == 0 ? in[v + nv * (q + n * j)] : in[v + nv * (i + n * q)];
+                    acc += a * x;
+                }
+                if (add)
+                    out[v + nv * (i + n * j)] += acc;
+                else
+                    out[v + nv * (i + n * j)] = acc;
+            }
+}
+
+void oracle_calc_mortar_flux(const trixi_b200_desc *d, double *sfv, const double *u) {
+    if (d->nmortars <= 0) return;
+    eqn_t eq = make_eqn(d);
+    int n = d->nnodes, nd = d->ndims, nv = d->nvars;
+    int nf = ipow(n, nd - 1), nb = nd == 3 ? n : 1, np = 1 << (nd - 1);
+    int64_t esz = (int64_t)nv * ipow(n, nd), fsz = (int64_t)nv * nf * 2 * nd;
+    const double *fwd[2] = {d->mortar_forward_lower, d->mortar_forward_upper};
+    const double *rev[2] = {d->mortar_reverse_lower, d->mortar_reverse_upper};
+#pragma omp parallel for schedule(static)
+    for (int64_t m = 0; m < d->nmortars; ++m) {
+        const int64_t *ids = d->mortar_neighbor_ids + (int64_t)(np + 1) * m;
+        int64_t large = ids[np] - 1;
+        int o = (int)d->mortar_orientations[m] - 1;
+        int large_side = (int)d->mortar_large_sides[m]; /* 1: large element on the negative (left) side */
+        double ularge[MAXV * 64], tmp[MAXV * 64], uproj[MAXV * 64], fstar[4][MAXV * 64], usmall[MAXV * 64];
+        /* face of the large element that touches the mortar: its +face if it sits on the left */
+        int lidx = large_side == 1 ? n - 1 : 0, sidx = large_side == 1 ? 0 : n - 1;
+        for (int b = 0; b < nb; ++b)
+            for (int a = 0; a < n; ++a) {
+                int vn = face_to_volume_node(nd, n, o, lidx, a, b);
+                for (int v = 0; v < nv; ++v) ularge[v + nv * (a + n * b)] = u[large * esz + nv * vn + v];
+            }
+        for (int p = 0; p < np; ++p) {
+            int64_t small = ids[p] - 1;
+            /* element_solutions_to_mortars!: forward interpolation of the large face to sub-face p */
+            if (nd == 2) {
+                mortar_apply_1d(fwd[p & 1], n, nv, 1, 0, ularge, uproj, 0);
+            } else {
+                mortar_apply_1d(fwd[p & 1], n, nv, nb, 0, ularge, tmp, 0);
+                mortar_apply_1d(fwd[(p >> 1) & 1], n, nv, nb, 1, tmp, uproj, 0);
+            }
+            for (int b = 0; b < nb; ++b)
+                for (int a = 0; a < n; ++a) {
+                    int vn = face_to_volume_node(nd, n, o, sidx, a, b);
+                    for (int v = 0; v < nv; ++v) usmall[v + nv * (a + n * b)] = u[small * esz + nv * vn + v];
+                }
+            /* calc_fstar!: left state = the side on the negative side of the mortar */
+            for (int fn = 0; fn < nf; ++fn) {
+                const double *ul = large_side == 1 ? uproj + nv * fn : usmall + nv * fn;
+                const double *ur = large_side == 1 ? usmall + nv * fn : uproj + nv * fn;
+                numflux(&eq, d->surface_flux, ul, ur, o, fstar[p] + nv * fn);
+            }
+            /* small elements take the flux as it is: direction facing the large element */
+            int dir_small = large_side == 1 ? 2 * o : 2 * o + 1;
+            for (int q = 0; q < nv * nf; ++q) sfv[small * fsz + q + (int64_t)nv * nf * dir_small] = fstar[p][q];
+        }
+        /* L2 projection of the small fluxes onto the large face */
+        int dir_large = large_side == 1 ? 2 * o + 1 : 2 * o;
+        double *out = sfv + large * fsz + (int64_t)nv * nf * dir_large;
+        if (nd == 2) {
+            /* multiply_dimensionwise!(out, reverse_upper, f_upper, reverse_lower, f_lower) (dg_2d.jl:1238-1240) */
+            for (int i = 0; i < n; ++i)
+                for (int v = 0; v < nv; ++v) {
+                    double acc = 0.0;
+                    for (int q = 0; q < n; ++q)
+                        acc += rev[1][i + n * q] * fstar[1][v + nv * q] + rev[0][i + n * q] * fstar[0][v + nv * q];
+                    out[v + nv * i] = acc;
+                }
+        } else {
+            /* upper_left, upper_right, lower_left, lower_right in this order (dg_3d.jl:1314-1331) */
+            static const int order[4] = {2, 3, 0, 1};
+            for (int k = 0; k < 4; ++k) {
+                int p = order[k];
+                mortar_apply_1d(rev[p & 1], n, nv, nb, 0, fstar[p], tmp, 0);
+                mortar_apply_1d(rev[(p >> 1) & 1], n, nv, nb, 1, tmp, out, k > 0);
+            }
+        }
+    }
+}
+
 /* rhs_hyperbolic! dgsem_tree/dg_2d.jl:113-186.  Work arrays: interfaces_u [2,nv,nf,I],
  * boundaries_u [2,nv,nf,B], sfv [nv,nf,2nd,nelem] (owned by the caller = the cache). */
 void oracle_rhs(const trixi_b200_desc *d, double *du, const double *u, double t, double *interfaces_u,
@@ -1547,7 +1641,7 @@ void oracle_rhs(const trixi_b200_desc *d, double *du, const double *u, double t,
         oracle_prolong2boundaries(d, boundaries_u, u);
         oracle_calc_boundary_flux(d, sfv, boundaries_u, t);
     }
-    /* mortars: none on conforming meshes (dg_3d.jl:770-1007 are no-ops for nmortars == 0) */
+    oracle_calc_mortar_flux(d, sfv, u); /* prolong2mortars! + calc_mortar_flux! (no-op without mortars) */
     oracle_calc_surface_integral(d, du, sfv);
     oracle_apply_jacobian(d, du);
     oracle_calc_sources(d, du, u, t);

@@ -399,6 +399,39 @@ ELIXIRS.update({e.name: e for e in [
 ]})
 
 
+# ---- TreeMesh with L2 mortars -----------------------------------------------------------------------------
+def _advection2d_mortar():
+    # examples/tree_2d_dgsem/elixir_advection_mortar.jl
+    eq = T.LinearScalarAdvectionEquation2D((0.2, -0.7))
+    solver = T.DGSEM(polydeg=3, surface_flux=T.flux_lax_friedrichs)
+    patches = ({"type": "box", "coordinates_min": (0.0, -1.0), "coordinates_max": (1.0, 1.0)},)
+    mesh = T.TreeMesh((-1.0, -1.0), (1.0, 1.0), initial_refinement_level=2, refinement_patches=patches,
+                      periodicity=True)
+    return T.SemidiscretizationHyperbolic(mesh, eq, T.initial_condition_convergence_test, solver)
+
+
+def _euler3d_mortar(level=2):
+    # examples/tree_3d_dgsem/elixir_euler_mortar.jl
+    eq = T.CompressibleEulerEquations3D(1.4)
+    solver = T.DGSEM(polydeg=3, surface_flux=T.FluxLaxFriedrichs(T.max_abs_speed_naive))
+    patches = ({"type": "box", "coordinates_min": (0.5, 0.5, 0.5), "coordinates_max": (1.5, 1.5, 1.5)},)
+    mesh = T.TreeMesh((0.0, 0.0, 0.0), (2.0, 2.0, 2.0), initial_refinement_level=level,
+                      refinement_patches=patches, periodicity=True)
+    return T.SemidiscretizationHyperbolic(mesh, eq, T.initial_condition_convergence_test, solver,
+                                          source_terms=T.source_terms_convergence_test)
+
+
+ELIXIRS.update({e.name: e for e in [
+    Elixir("tree_2d_advection_mortar", _advection2d_mortar, (0.0, 1.0), 1.6,
+           [0.0015188466707237375], [0.008446655719187679], "test/test_tree_2d_advection.jl:115-126"),
+    Elixir("tree_3d_euler_mortar", _euler3d_mortar, (0.0, 1.0), 0.6,
+           [0.0019428114665068841, 0.0018659907926698422, 0.0018659907926698589, 0.0018659907926698747,
+            0.0034549095578444056],
+           [0.011355360771142298, 0.011526889155693887, 0.011526889155689002, 0.011526889155701436,
+            0.02299726519821288], "test/test_tree_3d_euler.jl:124-141"),
+]})
+
+
 # ---- configurations without a reference golden (cross-checks between mesh types, halo tests) ---------------
 def _p4est3d_curved(initial_condition=T.initial_condition_weak_blast_wave, flux=T.flux_ranocha, level=0, trees=(4, 4, 4)):
     # the warped mapping of examples/structured_3d_dgsem/elixir_euler_free_stream.jl on a conforming P4estMesh

@@ -216,6 +216,34 @@ class LobattoLegendreBasis:
         return self.polydeg + 1
 
 
+class LobattoLegendreMortarL2:
+    """``MortarL2(basis)`` (basis_lobatto_legendre.jl:159-206): interpolation from a large face to its
+    lower/upper half (``calc_forward_*`` l2projection.jl:26-61) and the discrete L2 projection back, evaluated
+    on Gauss nodes (``calc_reverse_*(n, Val(:gauss))`` l2projection.jl:67-115)."""
+
+    def __init__(self, basis):
+        n = basis.nnodes
+        nodes = basis.nodes
+        wbary = barycentric_weights(nodes)
+        self.forward_upper = np.array([lagrange_interpolating_polynomials(0.5 * (x + 1), nodes, wbary) for x in nodes])
+        self.forward_lower = np.array([lagrange_interpolating_polynomials(0.5 * (x - 1), nodes, wbary) for x in nodes])
+        gn, gw = gauss_nodes_weights(n)
+        gbary = barycentric_weights(gn)
+        g2l = polynomial_interpolation_matrix(gn, nodes)
+        l2g = polynomial_interpolation_matrix(nodes, gn)
+
+        def reverse(shift):
+            op = np.zeros((n, n))
+            for j in range(n):
+                poly = lagrange_interpolating_polynomials(0.5 * (gn[j] + shift), gn, gbary)
+                for i in range(n):
+                    op[i, j] = 0.5 * poly[i] * gw[j] / gw[i]
+            return g2l @ op @ l2g
+
+        self.reverse_upper = reverse(+1.0)
+        self.reverse_lower = reverse(-1.0)
+
+
 class SolutionAnalyzer:
     """Mirror of ``SolutionAnalyzer`` (basis_lobatto_legendre.jl:274-290)."""
 

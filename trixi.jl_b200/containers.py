@@ -123,6 +123,46 @@ def init_interfaces(mesh, first=0, last=None, world_size=1):
     return ic, mi
 
 
+class MortarContainer:
+    nmortars = 0
+
+
+def init_mortars(mesh, first=0, last=None):
+    """``init_mortars!`` (containers_2d.jl:706-810, containers_3d.jl:652-790): one L2 mortar per face of a
+    large element whose same-level neighbour cell is refined; ``neighbor_ids[1..2^(d-1), m]`` are the small
+    elements by position (2D: lower, upper; 3D: lower-left, lower-right, upper-left, upper-right), the last
+    row is the large element; ``large_sides`` 1: large element on the negative side; ordered by
+    (large element, direction) like the reference's loop."""
+    nd = mesh.ndims
+    last = mesh.ncells if last is None else last
+    mc = MortarContainer()
+    nsmall = 1 << (nd - 1)
+    if not hasattr(mesh, "_fine_neighbors") or int(mesh.levels.min()) == int(mesh.levels.max()):
+        mc.neighbor_ids = np.zeros((nsmall + 1, 0), dtype=np.int64)
+        mc.large_sides = np.zeros(0, dtype=np.int64)
+        mc.orientations = np.zeros(0, dtype=np.int64)
+        return mc
+    cells = None if (first == 0 and last == mesh.ncells) else np.arange(first, last, dtype=np.int64)
+    large, small, dirs = [], [], []
+    for direction in range(2 * nd):
+        fine = mesh._fine_neighbors(direction, cells)
+        has = (fine >= 0).all(axis=0)
+        el = np.nonzero(has)[0]
+        large.append(el + first)
+        small.append(fine[:, el])
+        dirs.append(np.full(el.shape[0], direction, dtype=np.int64))
+    large, small, dirs = np.concatenate(large), np.concatenate(small, axis=1), np.concatenate(dirs)
+    if ((small < first) | (small >= last)).any():
+        raise NotImplementedError("mortars across ranks (MPI mortars) are not supported")
+    order = np.lexsort((dirs, large))
+    large, small, dirs = large[order], small[:, order], dirs[order]
+    mc.neighbor_ids = np.asfortranarray(np.concatenate([small, large[None, :]]) - first + 1)
+    mc.large_sides = np.where(dirs % 2 == 1, 1, 2).astype(np.int64)
+    mc.orientations = (dirs // 2 + 1).astype(np.int64)
+    mc.nmortars = int(large.shape[0])
+    return mc
+
+
 def init_boundaries(mesh, elements, basis, first=0, last=None):
     """containers_3d.jl:391-471 (for the elements [first, last) of this rank)."""
     nd = mesh.ndims
@@ -136,7 +176,7 @@ def init_boundaries(mesh, elements, basis, first=0, last=None):
         isb = (same < 0) & (coarse < 0)
         # a cell with a *refined* same-level neighbour has a non-leaf neighbour cell -> not a boundary
         if hasattr(mesh, "_has_refined_neighbor"):
-            isb &= ~mesh._has_refined_neighbor(direction)
+            isb &= ~mesh._has_refined_neighbor(direction, cells)
         el = np.nonzero(isb)[0]
         counts.append(el.shape[0])
         ids.append(el + 1)

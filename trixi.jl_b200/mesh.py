@@ -222,6 +222,30 @@ class TreeMesh:
             return bad, None
         raise ValueError(want)
 
+    def _fine_neighbors(self, direction, cells=None):
+        """The 2^(d-1) leaves one level finer that touch the face ``direction`` of every cell, as
+        [2^(d-1), ncells] (position = bits of the tangential coordinates, lowest dimension first: the
+        lower/upper and left/right of containers_3d.jl:686-715), or -1 where the same-level neighbour cell is
+        not refined."""
+        d = direction // 2
+        c, outside, levels = self._shifted(direction, cells)
+        c_safe = np.where(outside[None, :], 0, c)
+        others = [e for e in range(self.ndims) if e != d]
+        out = np.empty((1 << (self.ndims - 1), levels.shape[0]), dtype=np.int64)
+        lv1 = levels + 1
+        ok_lv = (lv1 <= self._lmax) & ~outside
+        for sub in range(1 << (self.ndims - 1)):
+            cc = c_safe * 2
+            cc[d] += 0 if direction % 2 == 1 else 1  # the children of the neighbour that touch this cell
+            for b, e in enumerate(others):
+                cc[e] += (sub >> b) & 1
+            fine = self._lookup(np.minimum(lv1, self._lmax), np.where(ok_lv[None, :], cc, 0))
+            out[sub] = np.where(ok_lv, fine, -1)
+        return out
+
+    def _has_refined_neighbor(self, direction, cells=None):
+        return (self._fine_neighbors(direction, cells) >= 0).all(axis=0)
+
     def __repr__(self):
         return f"TreeMesh{{{self.ndims}}} with {self.ncells} leaf cells"
 

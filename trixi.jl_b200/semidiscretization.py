@@ -15,9 +15,10 @@ import numpy as np
 
 from . import _abi
 from .containers import (BoundaryContainer, InterfaceContainer, MPIInterfaceContainer, init_boundaries,
-                         init_elements, init_interfaces, partition_cells)
+                         init_elements, init_interfaces, init_mortars, partition_cells)
 from .equations import (BC_DIRICHLET, BC_PERIODIC, BC_SLIP_WALL, IC_NONE, SRC_NONE,
                         BoundaryConditionDirichlet, boundary_condition_periodic, resolve_flux)
+from .basis import LobattoLegendreMortarL2
 from .mesh import TreeMesh
 from .p4est import P4estMesh, init_boundaries_p4est, init_elements_p4est, init_interfaces_p4est
 from .structured import StructuredMesh, init_elements_structured
@@ -61,6 +62,9 @@ def create_cache(mesh, equations, solver, rank=0, world_size=1):
         cache.elements = init_elements(mesh, solver.basis, cells)
         cache.interfaces, cache.mpi_interfaces = init_interfaces(mesh, first, last, world_size)
         cache.boundaries = init_boundaries(mesh, cache.elements, solver.basis, first, last)
+        cache.mortars = init_mortars(mesh, first, last)
+        if cache.mortars.nmortars and world_size > 1:
+            raise NotImplementedError("mortars on a partitioned TreeMesh (MPI mortars) are not supported")
     elif isinstance(mesh, StructuredMesh):
         if world_size != 1:
             raise NotImplementedError("StructuredMesh runs on a single rank (the reference has no MPI path for it)")
@@ -244,7 +248,18 @@ class SemidiscretizationHyperbolic:
                 h.set_f64("boundary_node_coordinates", b.node_coordinates)
         for i in range(6):
             d.n_boundaries_per_direction[i] = int(b.n_boundaries_per_direction[i])
-        d.nmortars = 0
+        mortars = getattr(cache, "mortars", None)
+        d.nmortars = 0 if mortars is None else mortars.nmortars
+        if d.nmortars:
+            # L2 mortars (containers_3d.jl:495-510) and their operators (basis_lobatto_legendre.jl:159-206)
+            l2 = LobattoLegendreMortarL2(dg.basis)
+            h.set_i64("mortar_neighbor_ids", mortars.neighbor_ids)
+            h.set_i64("mortar_large_sides", mortars.large_sides)
+            h.set_i64("mortar_orientations", mortars.orientations)
+            h.set_f64("mortar_forward_upper", l2.forward_upper)
+            h.set_f64("mortar_forward_lower", l2.forward_lower)
+            h.set_f64("mortar_reverse_upper", l2.reverse_upper)
+            h.set_f64("mortar_reverse_lower", l2.reverse_lower)
         d.rank, d.world_size = self.rank, self.world_size
         mi = cache.mpi_interfaces
         d.nmpiinterfaces = mi.nmpiinterfaces
