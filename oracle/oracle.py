@@ -175,6 +175,7 @@ class OracleBackend:
         if self.desc.nboundaries > 0:
             self.lib.oracle_prolong2boundaries(h, _p(self.boundaries_u), _p(self.vec[0]))
             self.lib.oracle_calc_boundary_flux(h, _p(self.sfv), _p(self.boundaries_u), C.c_double(t))
+        self.lib.oracle_calc_mortar_flux(h, _p(self.sfv), _p(self.vec[0]))
 
     def download_surface_flux_values(self, host):
         host[:] = self.sfv

@@ -64,7 +64,7 @@ RHS_CASES = ["tree_3d_euler_ec", "tree_3d_euler_source_terms", "tree_3d_euler_so
              "structured_3d_euler_source_terms", "structured_3d_euler_source_terms_nonperiodic_curved",
              "p4est_3d_euler_source_terms_nonperiodic", "p4est_3d_euler_source_terms_nonperiodic_kennedy_gruber",
              "tree_3d_mhd_ec", "tree_3d_mhd_alfven_wave", "p4est_3d_curved_ec", "p4est_3d_curved_weak_form",
-             "p4est_3d_curved_level1"]
+             "p4est_3d_curved_level1", "tree_2d_advection_mortar", "tree_3d_euler_mortar"]
 
 
 @pytest.mark.parametrize("name", RHS_CASES)
@@ -90,7 +90,7 @@ def test_rhs_matches_oracle(name, state, oracle_module):
 @pytest.mark.parametrize("name", ["tree_3d_euler_ec", "tree_3d_euler_source_terms", "tree_2d_euler_source_terms_nonperiodic",
                                   "structured_3d_euler_ec", "structured_3d_euler_source_terms_nonperiodic_curved",
                                   "p4est_3d_euler_source_terms_nonperiodic_kennedy_gruber", "tree_3d_mhd_ec",
-                                  "tree_3d_mhd_alfven_wave"])
+                                  "tree_3d_mhd_alfven_wave", "tree_2d_advection_mortar", "tree_3d_euler_mortar"])
 def test_stage_level_parity(name, oracle_module):
     """calc_volume_integral! and the surface flux stages separately, like the reference's kernel parity
     tests (test/test_performance_specializations_3d.jl:49-89)."""
@@ -193,7 +193,8 @@ GOLDEN_GPU = ["tree_3d_euler_ec", "tree_3d_euler_ec_constant", "tree_3d_euler_so
               "tree_2d_euler_ec", "tree_2d_euler_density_wave", "structured_3d_euler_free_stream",
               "structured_3d_euler_ec", "structured_3d_euler_source_terms",
               "structured_3d_euler_source_terms_nonperiodic_curved", "p4est_3d_euler_source_terms_nonperiodic",
-              "p4est_3d_euler_source_terms_nonperiodic_kennedy_gruber", "tree_3d_mhd_ec", "tree_3d_mhd_alfven_wave"]
+              "p4est_3d_euler_source_terms_nonperiodic_kennedy_gruber", "tree_3d_mhd_ec", "tree_3d_mhd_alfven_wave",
+              "tree_2d_advection_mortar", "tree_3d_euler_mortar"]
 
 
 @pytest.mark.parametrize("name", GOLDEN_GPU)

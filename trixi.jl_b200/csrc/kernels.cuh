@@ -61,6 +61,11 @@ struct KParams {
     long long nmpi;
     const long long *mpi_local, *mpi_side, *mpi_orient;  // [nmpi] 1-based local element, local side, orientation
     const long long *mpi_node_indices;                   // P4est: [ndims, nmpi] node_indices of the local side
+    // L2 mortars (TreeMesh): neighbor_ids [2^(d-1)+1, M] 1-based (small elements by position, then the large
+    // one), large_sides, orientations; forward (interpolation) and reverse (projection) operators [n, n]
+    long long nmortars;
+    const long long *mortar_ids, *mortar_large_sides, *mortar_orient;
+    const double *mortar_fwd[2], *mortar_rev[2];  // [0] lower, [1] upper
     const int *mpi_peer_slot;                            // [nmpi] index into the peer tables
     const long long *mpi_remote_index;                   // [nmpi] slot of this face in the peer's receive buffer
     double *const *peer_recv;                            // [npeers] peer receive buffers (current parity), NVLink-mapped
@@ -288,6 +293,118 @@ __global__ void __launch_bounds__(256) k_boundary_flux(const KParams P) {
     double *s = P.sfv + ((element * (2 * ND) + (direction - 1)) * NF + fn) * NV;
 #pragma unroll
     for (int v = 0; v < NV; ++v) s[v] = f[v];
+}
+
+// ---- 2a. L2 mortars ---------------------------------------------------------------------------------
+// prolong2mortars! + calc_mortar_flux! + mortar_fluxes_to_elements! fused (dg_2d.jl:899-1243,
+// dg_3d.jl:770-1335), conservative equations.  One block per mortar, one thread per (sub-face, face node);
+// the large face, the interpolation temporaries and the 2^(d-1) flux faces live in shared memory.  Position
+// p: bit 0 = upper half along the first face coordinate, bit 1 = upper half along the second.
+template <class EQ, int N>
+__global__ void __launch_bounds__((1 << (EQ::NDIMS - 1)) * ipow(N, EQ::NDIMS - 1)) k_mortar_flux(const KParams P) {
+    constexpr int ND = EQ::NDIMS, NV = EQ::NVARS, NF = ipow(N, ND - 1), NN = ipow(N, ND), NP = 1 << (ND - 1);
+    __shared__ double s_large[NV * NF];
+    __shared__ double s_tmp[NP][NV * NF];
+    __shared__ double s_f[NP][NV * NF];
+    const long long m = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int p = tid / NF, fn = tid - p * NF;
+    const int a = fn % N, b = fn / N;
+    const EQ eq(P.eq);
+    const long long *ids = P.mortar_ids + (NP + 1) * m;
+    const long long large = ids[NP] - 1, small = ids[p] - 1;
+    const int o = (int)P.mortar_orient[m] - 1;
+    const bool large_left = P.mortar_large_sides[m] == 1;  // large element on the negative side
+    const double *fwd1 = P.mortar_fwd[p & 1], *fwd2 = P.mortar_fwd[(p >> 1) & 1];
+    const double *rev1 = P.mortar_rev[p & 1];
+    // face of the large element that touches the mortar
+    for (int q = tid; q < NV * NF; q += NP * NF) {
+        const int f = q / NV, v = q - f * NV;
+        const int vn = face_to_volume_node<ND, N>(o, large_left ? N - 1 : 0, f);
+        s_large[q] = P.u[(large * NN + vn) * NV + v];
+    }
+    __syncthreads();
+    // element_solutions_to_mortars!: interpolate to sub-face p, first face coordinate first
+    double up[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+        double acc = 0.0;
+        for (int q = 0; q < N; ++q) acc += fwd1[a + N * q] * s_large[v + NV * (q + N * b)];
+        up[v] = acc;
+    }
+    if constexpr (ND == 3) {
+#pragma unroll
+        for (int v = 0; v < NV; ++v) s_tmp[p][v + NV * fn] = up[v];
+        __syncthreads();
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            double acc = 0.0;
+            for (int q = 0; q < N; ++q) acc += fwd2[b + N * q] * s_tmp[p][v + NV * (a + N * q)];
+            up[v] = acc;
+        }
+        __syncthreads();  // s_tmp is reused by the projection below
+    }
+    // calc_fstar!: the left state is the side on the negative side of the mortar
+    double us[NV], f[NV];
+    {
+        const int vn = face_to_volume_node<ND, N>(o, large_left ? 0 : N - 1, fn);
+        const double *pu = P.u + (small * NN + vn) * NV;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) us[v] = pu[v];
+    }
+    if (large_left)
+        eq.numflux(P.surface_flux, up, us, o, f);
+    else
+        eq.numflux(P.surface_flux, us, up, o, f);
+    // the small element takes its flux as it is (its face towards the large element)
+    {
+        double *dst = P.sfv + ((small * (2 * ND) + (large_left ? 2 * o : 2 * o + 1)) * NF + fn) * NV;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            dst[v] = f[v];
+            s_f[p][v + NV * fn] = f[v];
+        }
+    }
+    __syncthreads();
+    // L2 projection onto the large face
+    double *out = P.sfv + ((large * (2 * ND) + (large_left ? 2 * o + 1 : 2 * o)) * NF) * NV;
+    if constexpr (ND == 2) {
+        // multiply_dimensionwise!(out, reverse_upper, f_upper, reverse_lower, f_lower) (dg_2d.jl:1238-1240)
+        if (tid < N) {
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+                double acc = 0.0;
+                for (int q = 0; q < N; ++q)
+                    acc += P.mortar_rev[1][tid + N * q] * s_f[1][v + NV * q] + P.mortar_rev[0][tid + N * q] * s_f[0][v + NV * q];
+                out[v + NV * tid] = acc;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            double acc = 0.0;
+            for (int q = 0; q < N; ++q) acc += rev1[a + N * q] * s_f[p][v + NV * (q + N * b)];
+            s_tmp[p][v + NV * fn] = acc;
+        }
+        __syncthreads();
+        if (tid < NF) {
+            // upper_left, upper_right, lower_left, lower_right in this order (dg_3d.jl:1314-1331)
+            const int order[4] = {2, 3, 0, 1};
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+                double res = 0.0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int pp = order[k];
+                    const double *r2 = P.mortar_rev[(pp >> 1) & 1];
+                    double acc = 0.0;
+                    for (int q = 0; q < N; ++q) acc += r2[b + N * q] * s_tmp[pp][v + NV * (a + N * q)];
+                    res = k == 0 ? acc : res + acc;
+                }
+                out[v + NV * fn] = res;
+            }
+        }
+    }
 }
 
 // ---- 2b. faces shared with other ranks -------------------------------------------------------------

@@ -9,6 +9,7 @@ namespace tb {
 struct Launchers {
     void (*interface_flux)(const KParams &, cudaStream_t);
     void (*boundary_flux)(const KParams &, cudaStream_t);
+    void (*mortar_flux)(const KParams &, cudaStream_t);
     // with_surface = false: volume terms only (stage-level parity entry point)
     cudaError_t (*element)(const KParams &, bool with_surface, cudaStream_t);
     void (*max_dt)(const KParams &, cudaStream_t);
@@ -66,6 +67,13 @@ void launch_boundary_flux(const KParams &P, cudaStream_t s) {
         k_boundary_flux_curved<EQ, N><<<blocks, threads, 0, s>>>(P);
     else
         k_boundary_flux<EQ, N><<<blocks, threads, 0, s>>>(P);
+}
+
+template <class EQ, int N>
+void launch_mortar_flux(const KParams &P, cudaStream_t s) {
+    if (P.nmortars == 0) return;
+    constexpr int threads = (1 << (EQ::NDIMS - 1)) * ipow(N, EQ::NDIMS - 1);
+    k_mortar_flux<EQ, N><<<(unsigned)P.nmortars, threads, 0, s>>>(P);
 }
 
 template <class EQ, int N>
@@ -196,6 +204,7 @@ cudaError_t preload_all() {
     }
     TB_PRELOAD((k_mpi_interface_flux<EQ, N, true>));
     TB_PRELOAD((k_boundary_flux<EQ, N>));
+    TB_PRELOAD((k_mortar_flux<EQ, N>));
     TB_PRELOAD((k_mpi_pack<EQ, N>));
     TB_PRELOAD((k_mpi_interface_flux<EQ, N>));
     TB_PRELOAD((k_max_dt<EQ, N>));
@@ -223,6 +232,7 @@ template <class EQ, int N>
 const Launchers *make_launchers() {
     static const Launchers L = {&launch_interface_flux<EQ, N>,
                                 &launch_boundary_flux<EQ, N>,
+                                &launch_mortar_flux<EQ, N>,
                                 &launch_element<EQ, N>,
                                 &launch_max_dt<EQ, N>,
                                 &uses_tuned_element<EQ, N>,

@@ -215,6 +215,10 @@ int run_surface_fluxes(trixi_b200_handle *h, double t) {
             h->L->boundary_flux(h->P, h->stream);
             h->launches++;
         }
+        if (h->P.nmortars) {
+            h->L->mortar_flux(h->P, h->stream);
+            h->launches++;
+        }
     }
     return check_launch(h, "surface flux kernel");
 }
@@ -317,7 +321,17 @@ TRIXI_B200_API int trixi_b200_create(const trixi_b200_desc *d, trixi_b200_handle
         return fail(nullptr, TRIXI_B200_EINVAL, "StructuredMesh needs contravariant_vectors and left_neighbors");
     if (structured && d->world_size > 1)
         return fail(nullptr, TRIXI_B200_EINVAL, "StructuredMesh is single-rank (as in the reference)");
-    if (d->nmortars != 0) return fail(nullptr, TRIXI_B200_EINVAL, "mortars are not supported by this build");
+    if (d->nmortars < 0) return fail(nullptr, TRIXI_B200_EINVAL, "negative container size");
+    if (d->nmortars > 0) {
+        if (d->mesh_kind != TRIXI_B200_MESH_TREE)
+            return fail(nullptr, TRIXI_B200_EINVAL, "mortars are supported on TreeMesh only");
+        if (d->world_size > 1) return fail(nullptr, TRIXI_B200_EINVAL, "MPI mortars are not supported by this build");
+        if (d->equation == TRIXI_B200_EQ_MHD_3D)
+            return fail(nullptr, TRIXI_B200_EINVAL, "mortars with nonconservative terms are not supported by this build");
+        if (!d->mortar_neighbor_ids || !d->mortar_large_sides || !d->mortar_orientations || !d->mortar_forward_upper ||
+            !d->mortar_forward_lower || !d->mortar_reverse_upper || !d->mortar_reverse_lower)
+            return fail(nullptr, TRIXI_B200_EINVAL, "mortar arrays missing");
+    }
     if (d->volume_integral != TRIXI_B200_VOLINT_WEAK_FORM && d->volume_integral != TRIXI_B200_VOLINT_FLUX_DIFFERENCING)
         return fail(nullptr, TRIXI_B200_EINVAL, "unsupported volume integral type %d", d->volume_integral);
     if (d->nelements < 0 || d->ninterfaces < 0 || d->nboundaries < 0)
@@ -425,6 +439,25 @@ TRIXI_B200_API int trixi_b200_create(const trixi_b200_desc *d, trixi_b200_handle
     if (h->sfvlen) CREATE_CUDA(cudaMemset(P.sfv, 0xff, h->sfvlen * sizeof(double)));  // NaN like the reference's fill
 
     double *tmp = nullptr;
+    P.nmortars = d->nmortars;
+    if (d->nmortars > 0) {
+        const size_t np1 = ((size_t)1 << (nd - 1)) + 1;
+        long long *mtmp = nullptr;
+        CREATE_TRY(upload_array(h, (const long long *)d->mortar_neighbor_ids, np1 * (size_t)d->nmortars, &mtmp));
+        P.mortar_ids = mtmp;
+        CREATE_TRY(upload_array(h, (const long long *)d->mortar_large_sides, (size_t)d->nmortars, &mtmp));
+        P.mortar_large_sides = mtmp;
+        CREATE_TRY(upload_array(h, (const long long *)d->mortar_orientations, (size_t)d->nmortars, &mtmp));
+        P.mortar_orient = mtmp;
+        CREATE_TRY(upload_array(h, d->mortar_forward_lower, (size_t)n * n, &tmp));
+        P.mortar_fwd[0] = tmp;
+        CREATE_TRY(upload_array(h, d->mortar_forward_upper, (size_t)n * n, &tmp));
+        P.mortar_fwd[1] = tmp;
+        CREATE_TRY(upload_array(h, d->mortar_reverse_lower, (size_t)n * n, &tmp));
+        P.mortar_rev[0] = tmp;
+        CREATE_TRY(upload_array(h, d->mortar_reverse_upper, (size_t)n * n, &tmp));
+        P.mortar_rev[1] = tmp;
+    }
     CREATE_TRY(upload_array(h, d->derivative_split, (size_t)n * n, &tmp));
     P.dsplit = tmp;
     CREATE_TRY(upload_array(h, d->derivative_hat, (size_t)n * n, &tmp));
