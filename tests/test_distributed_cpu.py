@@ -102,3 +102,21 @@ def test_partition_is_contiguous_and_balanced():
             assert np.all(owners[a:b] == r)
     with pytest.raises(ValueError):
         partition_cells(3, 0, 4)
+
+
+def test_bench_weak_scaling_box_builds_on_every_rank():
+    """bench.py's N > 1 workload: Morton-ordered CartesianBoxMesh blocks; every rank's containers and
+    descriptor assemble (no GPU needed) and the shared faces pair up."""
+    import bench
+    world = 4
+    semis = [bench.make_semi(2, rank=r, world=world) for r in range(world)]
+    assert sum(s.nelements for s in semis) == semis[0].mesh.ncells
+    for s in semis:
+        s.descriptor()
+        assert s.cache.mortars.nmortars == 0 and s.cache.boundaries.nboundaries == 0
+    # every MPI interface appears on exactly two ranks with opposite sides
+    gids = np.concatenate([s.cache.mpi_interfaces.global_interface_ids for s in semis])
+    sides = np.concatenate([s.cache.mpi_interfaces.local_sides for s in semis])
+    order = np.argsort(gids, kind="stable")
+    g, sd = gids[order], sides[order]
+    assert g.size % 2 == 0 and np.array_equal(g[0::2], g[1::2]) and np.all(sd[0::2] + sd[1::2] == 3)

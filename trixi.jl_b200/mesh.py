@@ -244,6 +244,9 @@ class TreeMesh:
         return out
 
     def _has_refined_neighbor(self, direction, cells=None):
+        if int(self.levels.min()) == int(self.levels.max()):  # uniform mesh (also CartesianBoxMesh)
+            n = self.ncells if cells is None else len(cells)
+            return np.zeros(n, dtype=bool)
         return (self._fine_neighbors(direction, cells) >= 0).all(axis=0)
 
     def __repr__(self):
