@@ -18,16 +18,21 @@
 module TrixiB200
 
 using Trixi
-using Trixi: TreeMesh, DG, DGSEM, SemidiscretizationHyperbolic, nvariables, nnodes, ndims,
-             nelements, ninterfaces, nboundaries, mesh_equations_solver_cache
+using Trixi: TreeMesh, StructuredMesh, P4estMesh, DG, DGSEM, SemidiscretizationHyperbolic, nvariables, nnodes,
+             ndims, nelements, ninterfaces, nboundaries, nmortars, mesh_equations_solver_cache
 
 const libtrixi_b200 = get(ENV, "TRIXI_B200_LIBRARY", "libtrixi_b200.so")
 
 # ---- enums of include/trixi_b200.h ------------------------------------------------------------------
-const MESH_TREE = Cint(0)
+const ABI_VERSION = Int32(3)
+mesh_kind(::TreeMesh) = Cint(0)
+mesh_kind(::StructuredMesh) = Cint(1)
+mesh_kind(::P4estMesh) = Cint(2)
 equation_id(::LinearScalarAdvectionEquation2D) = Cint(1)
 equation_id(::CompressibleEulerEquations2D) = Cint(2)
 equation_id(::CompressibleEulerEquations3D) = Cint(3)
+equation_id(::IdealGlmMhdEquations3D) = Cint(4)
+equation_params(eq::IdealGlmMhdEquations3D) = (eq.gamma, eq.inv_gamma_minus_one, eq.c_h, 0.0, 0.0, 0.0, 0.0, 0.0)
 equation_params(eq::LinearScalarAdvectionEquation2D) = (eq.advection_velocity..., 0.0, 0.0, 0.0, 0.0, 0.0, 0.0)
 equation_params(eq::Union{CompressibleEulerEquations2D, CompressibleEulerEquations3D}) = (eq.gamma,
                                                                                           eq.inv_gamma_minus_one,
@@ -43,6 +48,11 @@ flux_id(::typeof(flux_shima_etal)) = Cint(6)
 flux_id(::typeof(flux_kennedy_gruber)) = Cint(7)
 flux_id(::typeof(flux_chandrashekar)) = Cint(8)
 flux_id(::typeof(flux_godunov)) = Cint(10)
+flux_id(::typeof(flux_hindenlang_gassner)) = Cint(11)
+# (conservative, nonconservative) tuples of the GLM-MHD elixirs (elixir_mhd_ec.jl:13-17)
+flux_id(f::Tuple{typeof(flux_hindenlang_gassner), typeof(flux_nonconservative_powell)}) = Cint(13)
+flux_id(f::Tuple{FluxLaxFriedrichs, typeof(flux_nonconservative_powell)}) =
+    f[1].dissipation.max_abs_speed === max_abs_speed_naive ? Cint(14) : Cint(12)
 flux_id(f) = error("numerical flux $f is not in the libtrixi_b200 registry")
 source_id(::Nothing) = Cint(0)
 source_id(::typeof(source_terms_convergence_test)) = Cint(1)
@@ -126,47 +136,107 @@ function check(b, rc)
     error("libtrixi_b200 error $rc: $msg")   # there is no CPU fallback by design
 end
 
-# Called once after `create_cache` (dgsem_tree/dg_2d.jl:14-37); the analogue of
-# `semidiscretize(...; storage_type = CuArray)` adapting all containers (semidiscretization.jl:115-126).
+# node_indices tuples of Symbols (dgsem_p4est/containers.jl:226-252) -> the integer code of the header
+const INDEX_CODE = Dict(:begin => 0, :end => 1, :i_forward => 2, :i_backward => 3, :j_forward => 4,
+                        :j_backward => 5)
+encode(node_indices::AbstractArray{<:NTuple{N, Symbol}}) where {N} =
+    Int64[INDEX_CODE[t[d]] for d in 1:N, t in node_indices]   # [ndims, size(node_indices)...]
+ptr_or_null(a) = isempty(a) ? Ptr{eltype(a)}(C_NULL) : pointer(a)
+
+# Called once after `create_cache` (dgsem_tree/dg_2d.jl:14-37, dgsem_structured/dg.jl:11-25,
+# dgsem_p4est/dg.jl:13-70); the analogue of `semidiscretize(...; storage_type = CuArray)` adapting all
+# containers (semidiscretization.jl:115-126).  Every array is handed over in the reference's own layout.
 function B200(semi::SemidiscretizationHyperbolic; device = -1)
     mesh, equations, dg, cache = mesh_equations_solver_cache(semi)
-    mesh isa TreeMesh || error("this build of libtrixi_b200 accelerates TreeMesh")
-    @assert Trixi.nmortars(dg, cache) == 0
     basis = dg.basis
     volint, volflux = volume_integral_id(dg.volume_integral)
     bcs = semi.boundary_conditions isa NamedTuple ? values(semi.boundary_conditions) :
           ntuple(_ -> semi.boundary_conditions, 2 * ndims(mesh))
     bc_tags = ntuple(i -> i <= length(bcs) ? bc_id(bcs[i])[1] : Cint(0), 6)
     bc_ics = ntuple(i -> i <= length(bcs) ? bc_id(bcs[i])[2] : Cint(0), 6)
-    el, ifc, bd = cache.elements, cache.interfaces, cache.boundaries
+    el = cache.elements
     D_split, D_hat = Matrix(basis.derivative_split), Matrix(basis.derivative_hat)
     inv_w = collect(basis.inverse_weights)
-    nbd = ntuple(i -> i <= 2 * ndims(mesh) ? Int64(bd.n_boundaries_per_direction[i]) : Int64(0), 6)
+    # geometry and connectivity per mesh type
+    contravariant = mesh isa TreeMesh ? Float64[] : el.contravariant_vectors
+    left_neighbors = mesh isa StructuredMesh ? el.left_neighbors : Int64[]
+    if mesh isa StructuredMesh   # faces are found through left_neighbors (dgsem_structured/dg_3d.jl:657-689)
+        if_ids, if_orient, if_idx, n_if = Int64[], Int64[], Int64[], 0
+        # domain-boundary faces as a direction-sorted list (the reference loops over the boundary cells of each
+        # direction, dgsem_structured/dg_3d.jl:755-935)
+        lin = LinearIndices(size(mesh))
+        bd_ids, bd_orient, bd_sides, counts = Int64[], Int64[], Int64[], Int64[]
+        for direction in 1:(2 * ndims(mesh))
+            d = (direction + 1) ÷ 2
+            if Trixi.isperiodic(mesh, d)
+                push!(counts, 0)
+                continue
+            end
+            cells = vec(selectdim(lin, d, isodd(direction) ? 1 : size(mesh, d)))
+            append!(bd_ids, cells)
+            append!(bd_orient, fill(d, length(cells)))
+            append!(bd_sides, fill(isodd(direction) ? 2 : 1, length(cells)))
+            push!(counts, length(cells))
+        end
+        bd_x, bd_idx, n_bd = Float64[], Int64[], length(bd_ids)
+        nbd = ntuple(i -> i <= length(counts) ? counts[i] : Int64(0), 6)
+    else
+        ifc, bd = cache.interfaces, cache.boundaries
+        if_ids, n_if = ifc.neighbor_ids, ninterfaces(dg, cache)
+        bd_ids, n_bd = bd.neighbor_ids, nboundaries(dg, cache)
+        if mesh isa P4estMesh
+            if_orient, if_idx = Int64[], encode(ifc.node_indices)
+            bd_orient, bd_sides, bd_x, bd_idx = Int64[], Int64[], Float64[], encode(bd.node_indices)
+            # boundaries sorted by name = the order of the boundary-condition container
+            # (UnstructuredSortedBoundaryTypes, dgsem_unstructured/sort_boundary_conditions.jl)
+            counts = length.(semi.boundary_conditions.boundary_indices)
+            nbd = ntuple(i -> i <= length(counts) ? Int64(counts[i]) : Int64(0), 6)
+        else
+            if_orient, if_idx = ifc.orientations, Int64[]
+            bd_orient, bd_sides, bd_x, bd_idx = bd.orientations, bd.neighbor_sides, bd.node_coordinates, Int64[]
+            nbd = ntuple(i -> i <= 2 * ndims(mesh) ? Int64(bd.n_boundaries_per_direction[i]) : Int64(0), 6)
+        end
+    end
+    # L2 mortars (TreeMesh; containers_3d.jl:495-510, operators basis_lobatto_legendre.jl:159-206)
+    n_mo = mesh isa TreeMesh ? nmortars(dg, cache) : 0
+    mo_ids = n_mo > 0 ? cache.mortars.neighbor_ids : Int64[]
+    mo_sides = n_mo > 0 ? cache.mortars.large_sides : Int64[]
+    mo_orient = n_mo > 0 ? cache.mortars.orientations : Int64[]
+    fu, fl, ru, rl = n_mo > 0 ? Matrix.((dg.mortar.forward_upper, dg.mortar.forward_lower,
+                                         dg.mortar.reverse_upper, dg.mortar.reverse_lower)) :
+                     ntuple(_ -> zeros(0, 0), 4)
     handle = Ref{Ptr{Cvoid}}(C_NULL)
-    GC.@preserve D_split D_hat inv_w el ifc bd begin   # the library copies during `create` only
-        desc = Desc(2, device, ndims(mesh), nvariables(equations), nnodes(dg), MESH_TREE,
+    # the library copies during `create` only
+    GC.@preserve D_split D_hat inv_w el contravariant left_neighbors if_ids if_orient if_idx bd_ids bd_orient bd_sides bd_x bd_idx mo_ids mo_sides mo_orient fu fl ru rl begin
+        desc = Desc(ABI_VERSION, device, ndims(mesh), nvariables(equations), nnodes(dg), mesh_kind(mesh),
                     nelements(dg, cache), equation_id(equations), volint, volflux,
                     flux_id(dg.surface_integral.surface_flux), source_id(semi.source_terms),
                     bc_tags, bc_ics, 0, equation_params(equations),
                     pointer(D_split), pointer(D_hat), pointer(inv_w),
-                    pointer(el.inverse_jacobian), pointer(el.node_coordinates), C_NULL,
-                    ninterfaces(dg, cache), pointer(ifc.neighbor_ids), pointer(ifc.orientations), C_NULL,
-                    nboundaries(dg, cache), pointer(bd.neighbor_ids), pointer(bd.orientations),
-                    pointer(bd.neighbor_sides), pointer(bd.node_coordinates), nbd,
-                    0, C_NULL, C_NULL, C_NULL, C_NULL, C_NULL, C_NULL, C_NULL, C_NULL,
-                    0, 1, 0, C_NULL, C_NULL, C_NULL, C_NULL, C_NULL)
+                    pointer(el.inverse_jacobian), pointer(el.node_coordinates), ptr_or_null(contravariant),
+                    n_if, ptr_or_null(if_ids), ptr_or_null(if_orient), ptr_or_null(if_idx),
+                    n_bd, ptr_or_null(bd_ids), ptr_or_null(bd_orient), ptr_or_null(bd_sides), ptr_or_null(bd_x), nbd,
+                    n_mo, ptr_or_null(mo_ids), ptr_or_null(mo_sides), ptr_or_null(mo_orient),
+                    ptr_or_null(fu), ptr_or_null(fl), ptr_or_null(ru), ptr_or_null(rl),
+                    ptr_or_null(left_neighbors),
+                    0, 1, 0, C_NULL, C_NULL, C_NULL, C_NULL,   # single rank: no MPI interfaces
+                    ptr_or_null(bd_idx), C_NULL)
         rc = ccall((:trixi_b200_create, libtrixi_b200), Cint, (Ref{Desc}, Ref{Ptr{Cvoid}}), desc, handle)
     end
     check(nothing, rc)
     return B200(handle[], nvariables(equations) * nnodes(dg)^ndims(mesh) * nelements(dg, cache))
 end
 
+# GlmSpeedCallback (glm_speed.jl:85-105) updates equations.c_h every step
+set_c_h!(backend::B200, c_h) = check(backend, ccall((:trixi_b200_set_eq_param, libtrixi_b200), Cint,
+                                                    (Ptr{Cvoid}, Cint, Float64), backend.handle, 2, c_h))
+
 # ---- the methods Trixi dispatches to ---------------------------------------------------------------------
 # rhs_hyperbolic!(backend, du, u, t, mesh, equations, boundary_conditions, source_terms, dg, cache)
 # (dgsem_tree/dg_2d.jl:113-186), reached from rhs_hyperbolic!(du_ode, u_ode, semi, t)
 # (semidiscretization_hyperbolic.jl:578-597) once `trixi_backend(u)` returns a B200.
-function Trixi.rhs_hyperbolic!(backend::B200, du, u, t, mesh::TreeMesh, equations, boundary_conditions,
-                               source_terms, dg::DG, cache)
+function Trixi.rhs_hyperbolic!(backend::B200, du, u, t, mesh::Union{TreeMesh, StructuredMesh, P4estMesh}, equations,
+                               boundary_conditions, source_terms, dg::DG, cache)
     GC.@preserve du u begin
         check(backend, ccall((:trixi_b200_rhs_host, libtrixi_b200), Cint,
                              (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Float64),
