@@ -290,6 +290,8 @@ def run_b200(args, rank, world, local_rank):
     gpu = semi.backend()
     # u is owned by the handle during the run: the last RK stage also reduces the CFL maxima (max_dt fused)
     gpu.set_option(gpu.OPT_FUSED_CFL, 0 if args.no_fused_cfl else 1)
+    if args.prefetch is not None:
+        gpu.set_option(gpu.OPT_PREFETCH_DISTANCE, args.prefetch)
     ndofs = semi.ndofs()
     u0 = T.compute_coefficients(0.0, semi)
     gpu.upload(0, u0)
@@ -464,6 +466,7 @@ def main():
     ap.add_argument("--workload", default="euler_ec", choices=sorted(WORKLOADS),
                     help="euler_ec is the headline (BASELINE.json); the others are SURVEY.md §8d's secondary configs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--prefetch", type=int, default=None, help="L2 prefetch distance of the tuned element kernel")
     ap.add_argument("--no-fused-cfl", action="store_true", help="run max_dt as its own kernel after every step")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -216,6 +216,16 @@ TRIXI_B200_API int trixi_b200_solve_2n(trixi_b200_handle *h, double t0, double t
                         const double *a, const double *b, const double *c, int nstages,
                         int64_t *steps_out, double *t_out, double *dt_out);
 
+/* calc_error_norms (callbacks_step/analysis_dg3d.jl:123-216, analysis_dg2d.jl:133-215) on the device-resident u:
+ * u, x (and the Jacobian of curved meshes) are interpolated to the n_analysis^d analysis nodes with the
+ * [n_analysis, nnodes] column-major Vandermonde matrix (SolutionAnalyzer, basis_lobatto_legendre.jl:274-290);
+ * the exact solution is the registered initial condition at time t.  Returns, per variable, the quadrature sum
+ * of the squared errors (not yet divided by the volume, no square root: distributed callers add these over ranks
+ * like analysis_dg3d.jl:218-275) and the maximum absolute error, plus the quadrature of the volume. */
+TRIXI_B200_API int trixi_b200_calc_error_norms(trixi_b200_handle *h, double t, int initial_condition, int n_analysis,
+                                               const double *vandermonde, const double *weights, double *l2_sums,
+                                               double *linf, double *volume);
+
 /* Tuning knobs (the analogue of the reference's compile-time Preferences, src/Trixi.jl:18-23).
  * TRIXI_B200_OPT_KERNEL_PATH: 0 = tuned kernels where one exists (default), 1 = generic kernels only.
  * TRIXI_B200_OPT_FUSED_CFL: 1 = the last stage of trixi_b200_step_2n also reduces the CFL wave speeds of the
@@ -225,6 +235,7 @@ TRIXI_B200_API int trixi_b200_solve_2n(trixi_b200_handle *h, double t0, double t
  *   0 (default). */
 #define TRIXI_B200_OPT_KERNEL_PATH 0
 #define TRIXI_B200_OPT_FUSED_CFL 1
+#define TRIXI_B200_OPT_PREFETCH_DISTANCE 2 /* tuned element kernel: L2 prefetch distance in elements (0 = off) */
 TRIXI_B200_API int trixi_b200_set_option(trixi_b200_handle *h, int option, int value);
 
 /* GlmSpeedCallback (glm_speed.jl:85-105) mutates equations.c_h every step */

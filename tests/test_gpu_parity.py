@@ -157,6 +157,41 @@ def test_fused_cfl_equals_standalone_max_dt(oracle_module):
     assert gpu.launch_count() == n0 + 1
 
 
+@pytest.mark.parametrize("name", ["tree_3d_euler_source_terms", "tree_3d_euler_ec", "tree_2d_advection_basic",
+                                  "tree_2d_euler_ec", "structured_3d_euler_source_terms_nonperiodic_curved",
+                                  "structured_3d_euler_free_stream", "p4est_3d_euler_source_terms_nonperiodic",
+                                  "tree_3d_euler_mortar", "tree_2d_advection_mortar"])
+def test_device_error_norms_match_host(name):
+    """trixi_b200_calc_error_norms (interpolation to the analysis grid, exact solution and reductions on the
+    device) against the host implementation of calc_error_norms (analysis_dg3d.jl:123-216)."""
+    semi = ELIXIRS[name].semi()
+    u = T.compute_coefficients(0.3, semi)
+    rng = np.random.default_rng(3)
+    u = np.asfortranarray(u * (1 + 1e-3 * rng.uniform(-1, 1, u.shape)))
+    gpu = semi.backend()
+    gpu.upload(0, u)
+    l2_d, linf_d = T.calc_error_norms_device(gpu, 0.3, semi)
+    assert l2_d is not None
+    l2_h, linf_h = T.calc_error_norms(u, 0.3, semi)
+    np.testing.assert_allclose(l2_d, l2_h, rtol=1e-11)
+    np.testing.assert_allclose(linf_d, linf_h, rtol=1e-10)
+
+
+def test_analysis_callback_on_device_reproduces_golden():
+    """The AnalysisCallback's device path at the final step against the reference's golden values."""
+    ex = ELIXIRS["tree_3d_euler_source_terms"]
+    semi = ex.semi()
+    ode = T.semidiscretize(semi, ex.tspan)
+    analysis = T.AnalysisCallback(semi, interval=100)
+    assert analysis.on_device
+    sol = T.solve(ode, T.CarpenterKennedy2N54(), dt=1.0,
+                  callback=T.CallbackSet(analysis, T.StepsizeCallback(cfl=ex.cfl)))
+    _, _, l2, linf = analysis.history[-1]
+    ex.check(l2, linf)
+    l2_h, linf_h = analysis(sol)
+    np.testing.assert_allclose(l2, l2_h, rtol=1e-11)
+
+
 def test_max_dt_propagates_nan(oracle_module):
     semi = ELIXIRS["tree_3d_euler_ec"].semi()
     u = _random_admissible_state(semi, seed=5)

@@ -154,21 +154,64 @@ def calc_error_norms(u, t, semi, analyzer=None):
     return l2, linf
 
 
+_DEVICE_ICS = {
+    "LinearScalarAdvectionEquation2D": (1, 2),
+    "CompressibleEulerEquations2D": (1, 2, 3),
+    "CompressibleEulerEquations3D": (1, 2, 3),
+    "IdealGlmMhdEquations3D": (1,),
+}
+
+
+def calc_error_norms_device(backend, t, semi, analyzer=None):
+    """``calc_error_norms`` with the interpolation to the analysis grid, the exact solution and the reductions
+    done by ``trixi_b200_calc_error_norms`` on the resident ``u``.  Returns (None, None) when the backend or
+    the initial condition cannot do it (the caller then takes the host path)."""
+    if not hasattr(backend, "calc_error_norms") or not hasattr(backend, "lib"):
+        return None, None
+    ic_id = getattr(semi.initial_condition, "ic_id", 0)
+    if ic_id not in _DEVICE_ICS.get(type(semi.equations).__name__, ()):
+        return None, None
+    if analyzer is None:
+        analyzer = SolutionAnalyzer(semi.solver.basis)
+    if analyzer.weights.shape[0] > 16:
+        return None, None
+    l2sq, linf, volume = backend.calc_error_norms(t, ic_id, analyzer.vandermonde, analyzer.weights, semi.equations.nvars)
+    curved = getattr(semi, "is_curved", False)
+    if semi.world_size > 1 and semi.comm is not None:
+        import torch
+        t2 = torch.from_numpy(np.concatenate([l2sq, [volume]]))
+        tinf = torch.from_numpy(linf.copy())
+        if semi.comm.get_backend() == "nccl":
+            t2, tinf = t2.cuda(), tinf.cuda()
+        semi.comm.all_reduce(t2, op=semi.comm.ReduceOp.SUM)
+        semi.comm.all_reduce(tinf, op=semi.comm.ReduceOp.MAX)
+        sums, linf = t2.cpu().numpy(), tinf.cpu().numpy()
+        l2sq, volume = sums[:-1], float(sums[-1])
+    total_volume = volume if curved else semi.mesh.total_volume()
+    return np.sqrt(l2sq / total_volume), linf
+
+
 class AnalysisCallback(_Callback):
     """``AnalysisCallback(semi; interval)`` (analysis.jl:95-158): records L2/Linf errors; the final
     values are what the reference's tests compare (``analysis_callback(sol)``, analysis.jl:640-668)."""
 
-    def __init__(self, semi, interval=0):
+    def __init__(self, semi, interval=0, on_device=True):
         self.semi = semi
         self.interval = interval
         self.analyzer = SolutionAnalyzer(semi.solver.basis)
         self.history = []
+        # reduce the norms on the device when the backend offers it (no download of u, SURVEY.md §8f row 2)
+        self.on_device = on_device
 
     def condition(self, integrator):
         return (self.interval > 0 and integrator.iter % self.interval == 0) or integrator.finalstep
 
     def affect(self, integrator):
-        l2, linf = calc_error_norms(integrator.download_u(), integrator.t, self.semi, self.analyzer)
+        l2, linf = None, None
+        if self.on_device:
+            l2, linf = calc_error_norms_device(integrator.backend, integrator.t, self.semi, self.analyzer)
+        if l2 is None:
+            l2, linf = calc_error_norms(integrator.download_u(), integrator.t, self.semi, self.analyzer)
         self.history.append((integrator.iter, integrator.t, l2, linf))
 
     def __call__(self, sol):

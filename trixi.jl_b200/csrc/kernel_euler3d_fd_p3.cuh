@@ -63,6 +63,9 @@ TB_DEV void tma_store_commit_and_wait_read() {
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
+TB_DEV void tma_prefetch_l2(const void *src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 TB_DEV void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // Node record in the prim tile: rho, v1, v2, v3, p, log(rho), log(p)
@@ -145,6 +148,14 @@ __global__ void __launch_bounds__(TunedCfg::THREADS, TunedCfg::MIN_BLOCKS)
         tma_load(smem_u32(s_u), P.u + e * CONS, bu, bar);
         if (need_ut) tma_load(smem_u32(s_ut), P.u_tmp + e * CONS, bu, bar);
         if (WITH_SURFACE) tma_load(smem_u32(s_sfv), P.sfv + e * SFV, bs, bar);
+        // warm L2 for the element that will occupy this CTA slot next (blocks are scheduled in index order:
+        // one wave further on), so its tile loads see L2 instead of HBM latency
+        const long long en = e + P.prefetch_distance;
+        if (P.prefetch_distance > 0 && en < P.nelements) {
+            tma_prefetch_l2(P.u + en * CONS, bu);
+            if (need_ut) tma_prefetch_l2(P.u_tmp + en * CONS, bu);
+            if (WITH_SURFACE) tma_prefetch_l2(P.sfv + en * SFV, bs);
+        }
     }
     // Two threads (h = 0, 1) share line l16 of every direction pass.  In line-local node numbering
     // thread h owns nodes lm[0], lm[1] and sees lm[2], lm[3] as foreign: h = 0: (0,1 | 2,3), h = 1: (3,2 | 0,1).

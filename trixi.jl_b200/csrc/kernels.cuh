@@ -57,6 +57,7 @@ struct KParams {
     unsigned long long *cfl_key;  // kCflSlots partial maxima (spread same-address atomics over L2 slices)
     int want_cfl;                 // RK stage kernels that support it also reduce the CFL speed of the updated u
     int kernel_path;              // 0: tuned kernels where available, 1: generic kernels only
+    int prefetch_distance;        // tuned element kernel: L2 prefetch this many elements ahead (0: off)
     // distributed: faces shared with other ranks (replaces mpi_interfaces, dg_2d_parallel.jl / dg_parallel.jl)
     long long nmpi;
     const long long *mpi_local, *mpi_side, *mpi_orient;  // [nmpi] 1-based local element, local side, orientation
@@ -697,6 +698,114 @@ __global__ void __launch_bounds__(ElemCfg<EQ, N>::THREADS) k_max_dt(const KParam
     }
 }
 
+
+// ---- analysis: L2 / Linf errors on the device -------------------------------------------------------
+// calc_error_norms (analysis_dg3d.jl:123-216, analysis_dg2d.jl:133-215): u and x (and 1/inverse_jacobian on
+// curved meshes) are interpolated to the analysis nodes with the Vandermonde matrix, the registered initial
+// condition gives the exact solution, and sum_nodes w J diff^2, max |diff| and sum_nodes w J are reduced.
+// One block per element; every thread evaluates analysis nodes by direct tensor-product sums.
+struct NormParams {
+    int na, ic;
+    double t;
+    const double *vandermonde;  // [na, n] column-major
+    const double *weights;      // [na]
+    double *sums;               // [nvars + 1]: squared errors, volume
+    unsigned long long *linf;   // [nvars] ordered bit patterns
+};
+constexpr int kMaxAnalysisNodes = 16;
+
+template <class EQ, int N>
+__global__ void __launch_bounds__(128) k_error_norms(const KParams P, const NormParams Q) {
+    constexpr int ND = EQ::NDIMS, NV = EQ::NVARS, NN = ipow(N, ND);
+    extern __shared__ __align__(16) double s_dyn[];  // (NV + ND + 1) * NN doubles
+    double *s_u = s_dyn, *s_x = s_u + NV * NN, *s_j = s_x + ND * NN;
+    __shared__ double s_V[kMaxAnalysisNodes * N], s_w[kMaxAnalysisNodes];
+    __shared__ double s_red[4][NV + 1];
+    __shared__ unsigned long long s_max[4][NV];
+    const long long e = blockIdx.x;
+    const int tid = threadIdx.x, na = Q.na;
+    for (int q = tid; q < NV * NN; q += 128) s_u[q] = P.u[e * NV * NN + q];
+    for (int q = tid; q < ND * NN; q += 128) s_x[q] = P.node_coordinates[e * ND * NN + q];
+    if (P.curved)
+        for (int q = tid; q < NN; q += 128) s_j[q] = 1.0 / P.inverse_jacobian[e * NN + q];
+    for (int q = tid; q < na * N; q += 128) s_V[q] = Q.vandermonde[q];
+    for (int q = tid; q < na; q += 128) s_w[q] = Q.weights[q];
+    __syncthreads();
+    const EQ eq(P.eq);
+    double volume_jacobian = 1.0;
+    if (!P.curved) {  // volume_jacobian (dgsem_tree/dg.jl:8-10)
+        const double j1 = 1.0 / P.inverse_jacobian[e];
+#pragma unroll
+        for (int d = 0; d < ND; ++d) volume_jacobian *= j1;
+    }
+    double l2[NV], vol = 0.0;
+    unsigned long long mx[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+        l2[v] = 0.0;
+        mx[v] = 0ull;
+    }
+    const int total = ND == 2 ? na * na : na * na * na;
+    for (int a = tid; a < total; a += 128) {
+        const int a0 = a % na, a1 = (a / na) % na, a2 = ND == 3 ? a / (na * na) : 0;
+        double ua[NV], xa[ND], ja = 0.0;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) ua[v] = 0.0;
+#pragma unroll
+        for (int d = 0; d < ND; ++d) xa[d] = 0.0;
+        for (int k = 0; k < (ND == 3 ? N : 1); ++k) {
+            const double ck = ND == 3 ? s_V[a2 + na * k] : 1.0;
+            for (int j = 0; j < N; ++j) {
+                const double cjk = ck * s_V[a1 + na * j];
+                for (int i = 0; i < N; ++i) {
+                    const double c = cjk * s_V[a0 + na * i];
+                    const int node = i + N * (j + N * k);
+#pragma unroll
+                    for (int v = 0; v < NV; ++v) ua[v] = fma(c, s_u[node * NV + v], ua[v]);
+#pragma unroll
+                    for (int d = 0; d < ND; ++d) xa[d] = fma(c, s_x[node * ND + d], xa[d]);
+                    if (P.curved) ja = fma(c, s_j[node], ja);
+                }
+            }
+        }
+        double uex[NV];
+        eq.initial_condition(Q.ic, xa, Q.t, uex);
+        double w = s_w[a0] * s_w[a1] * (ND == 3 ? s_w[a2] : 1.0);
+        w *= P.curved ? fabs(ja) : volume_jacobian;
+        vol += w;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            const double diff = uex[v] - ua[v];
+            l2[v] = fma(diff * diff, w, l2[v]);
+            mx[v] = max(mx[v], cfl_encode(fabs(diff)));
+        }
+    }
+    // block reduction: warp shuffles, then the four warps through shared memory
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            l2[v] += __shfl_xor_sync(0xffffffffu, l2[v], off);
+            mx[v] = max(mx[v], __shfl_xor_sync(0xffffffffu, mx[v], off));
+        }
+        vol += __shfl_xor_sync(0xffffffffu, vol, off);
+    }
+    const int warp = tid >> 5, lane = tid & 31;
+    if (lane == 0) {
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            s_red[warp][v] = l2[v];
+            s_max[warp][v] = mx[v];
+        }
+        s_red[warp][NV] = vol;
+    }
+    __syncthreads();
+    if (tid <= NV) {
+        const double sum = s_red[0][tid] + s_red[1][tid] + s_red[2][tid] + s_red[3][tid];
+        atomicAdd(Q.sums + tid, sum);
+        if (tid < NV) atomicMax(Q.linf + tid, max(max(s_max[0][tid], s_max[1][tid]), max(s_max[2][tid], s_max[3][tid])));
+    }
+}
 
 // =====================================================================================================
 // Curved meshes (StructuredMesh; src/solvers/dgsem_structured/).  Same launch structure; the geometry

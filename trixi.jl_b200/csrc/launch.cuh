@@ -10,6 +10,7 @@ struct Launchers {
     void (*interface_flux)(const KParams &, cudaStream_t);
     void (*boundary_flux)(const KParams &, cudaStream_t);
     void (*mortar_flux)(const KParams &, cudaStream_t);
+    void (*error_norms)(const KParams &, const NormParams &, cudaStream_t);
     // with_surface = false: volume terms only (stage-level parity entry point)
     cudaError_t (*element)(const KParams &, bool with_surface, cudaStream_t);
     void (*max_dt)(const KParams &, cudaStream_t);
@@ -114,6 +115,18 @@ struct PerDeviceFlag {
     }
 };
 
+template <class EQ, int N>
+void launch_error_norms(const KParams &P, const NormParams &Q, cudaStream_t s) {
+    if (P.nelements == 0) return;
+    constexpr size_t smem = sizeof(double) * (EQ::NVARS + EQ::NDIMS + 1) * ipow(N, EQ::NDIMS);
+    if constexpr (smem > 48 * 1024) {
+        static PerDeviceFlag configured;
+        if (!configured.test_and_set())
+            cudaFuncSetAttribute(k_error_norms<EQ, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    }
+    k_error_norms<EQ, N><<<(unsigned)P.nelements, 128, smem, s>>>(P, Q);
+}
+
 // tuned_euler3d.cu
 cudaError_t launch_element_euler3d_ranocha_p3(const KParams &P, bool with_surface, cudaStream_t s);
 
@@ -205,6 +218,7 @@ cudaError_t preload_all() {
     TB_PRELOAD((k_mpi_interface_flux<EQ, N, true>));
     TB_PRELOAD((k_boundary_flux<EQ, N>));
     TB_PRELOAD((k_mortar_flux<EQ, N>));
+    TB_PRELOAD((k_error_norms<EQ, N>));
     TB_PRELOAD((k_mpi_pack<EQ, N>));
     TB_PRELOAD((k_mpi_interface_flux<EQ, N>));
     TB_PRELOAD((k_max_dt<EQ, N>));
@@ -233,6 +247,7 @@ const Launchers *make_launchers() {
     static const Launchers L = {&launch_interface_flux<EQ, N>,
                                 &launch_boundary_flux<EQ, N>,
                                 &launch_mortar_flux<EQ, N>,
+                                &launch_error_norms<EQ, N>,
                                 &launch_element<EQ, N>,
                                 &launch_max_dt<EQ, N>,
                                 &uses_tuned_element<EQ, N>,

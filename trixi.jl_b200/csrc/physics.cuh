@@ -665,6 +665,34 @@ struct Euler {
 #pragma unroll
             for (int v = 0; v <= ND; ++v) u[v] = ini;
             u[ND + 1] = ini * ini;
+        } else if (id == TRIXI_B200_IC_WEAK_BLAST_WAVE) {
+            // compressible_euler_3d.jl:163-184 / compressible_euler_2d.jl:241-263 (only used by the error norms)
+            double r2 = 0.0;
+#pragma unroll
+            for (int d = 0; d < ND; ++d) r2 += x[d] * x[d];
+            const double r = sqrt(r2);
+            const bool outside = r > 0.5;
+            const double phi = atan2(x[1], x[0]);
+            double vel[3] = {0.0, 0.0, 0.0};
+            if constexpr (ND == 3) {
+                const double theta = r == 0 ? 0.0 : acos(x[2] / r);
+                vel[0] = 0.1882 * cos(phi) * sin(theta);
+                vel[1] = 0.1882 * sin(phi) * sin(theta);
+                vel[2] = 0.1882 * cos(theta);
+            } else {
+                vel[0] = 0.1882 * cos(phi);
+                vel[1] = 0.1882 * sin(phi);
+            }
+            const double rho = outside ? 1.0 : 1.1691, p = outside ? 1.0 : 1.245;
+            double ke = 0.0;
+#pragma unroll
+            for (int d = 0; d < ND; ++d) {
+                const double vd = outside ? 0.0 : vel[d];
+                u[1 + d] = rho * vd;
+                ke += rho * vd * vd;
+            }
+            u[0] = rho;
+            u[ND + 1] = p * inv_gm1 + 0.5 * ke;
         } else {
 #pragma unroll
             for (int v = 0; v < NVARS; ++v) u[v] = nan("");

@@ -38,6 +38,9 @@ struct trixi_b200_handle {
     double *vec[3] = {nullptr, nullptr, nullptr};  // u, du, u_tmp
     unsigned long long *d_cfl = nullptr;
     unsigned long long *h_cfl = nullptr;  // pinned, kCflSlots entries
+    double *norm_buf = nullptr;           // calc_error_norms scratch: Vandermonde, weights, sums
+    size_t norm_buf_len = 0;
+    unsigned long long *norm_linf = nullptr;
     bool opt_fused_cfl = false;           // TRIXI_B200_OPT_FUSED_CFL
     bool cfl_valid = false;               // d_cfl holds the maxima of the current u (written by the last RK stage)
     long long launches = 0;
@@ -614,6 +617,12 @@ TRIXI_B200_API int trixi_b200_create(const trixi_b200_desc *d, trixi_b200_handle
     CREATE_TRY(alloc_array(h, kCflSlots, &h->d_cfl));
     P.cfl_key = h->d_cfl;
     P.want_cfl = 0;
+    {
+        // L2 prefetch distance of the tuned element kernel: one wave of resident CTAs (14 per SM)
+        int sms = 0;
+        CREATE_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
+        P.prefetch_distance = 14 * sms;
+    }
     CREATE_CUDA(cudaMallocHost((void **)&h->h_cfl, kCflSlots * sizeof(unsigned long long)));
     CREATE_CUDA(cudaDeviceSynchronize());
     *out = h;
@@ -735,6 +744,62 @@ TRIXI_B200_API int trixi_b200_max_dt(trixi_b200_handle *h, double t, double *dt_
     return 0;
 }
 
+TRIXI_B200_API int trixi_b200_calc_error_norms(trixi_b200_handle *h, double t, int initial_condition, int n_analysis,
+                                               const double *vandermonde, const double *weights, double *l2_sums,
+                                               double *linf, double *volume) {
+    if (!h || !vandermonde || !weights || !l2_sums || !linf || !volume) return h ? fail(h, TRIXI_B200_EINVAL, "null argument") : TRIXI_B200_EINVAL;
+    if (n_analysis < 1 || n_analysis > kMaxAnalysisNodes)
+        return fail(h, TRIXI_B200_EINVAL, "n_analysis must be in 1..%d", kMaxAnalysisNodes);
+    if (initial_condition != TRIXI_B200_IC_CONSTANT && initial_condition != TRIXI_B200_IC_CONVERGENCE_TEST &&
+        !(initial_condition == TRIXI_B200_IC_WEAK_BLAST_WAVE &&
+          (h->equation == TRIXI_B200_EQ_EULER_2D || h->equation == TRIXI_B200_EQ_EULER_3D)))
+        return fail(h, TRIXI_B200_EINVAL, "initial condition %d is not registered on the device for this equation", initial_condition);
+    if (h->equation == TRIXI_B200_EQ_MHD_3D && initial_condition != TRIXI_B200_IC_CONSTANT)
+        return fail(h, TRIXI_B200_EINVAL, "initial condition %d is not registered on the device for this equation", initial_condition);
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const int nv = h->nvars, n = h->nnodes;
+    const size_t nbuf = (size_t)n_analysis * n + n_analysis + nv + 1;
+    if (h->norm_buf_len < nbuf) {
+        double *p = nullptr;
+        int rc = alloc_array(h, nbuf, &p);
+        if (rc) return rc;
+        h->norm_buf = p;
+        h->norm_buf_len = nbuf;
+        unsigned long long *q = nullptr;
+        rc = alloc_array(h, (size_t)16, &q);
+        if (rc) return rc;
+        h->norm_linf = q;
+    }
+    NormParams Q;
+    Q.na = n_analysis;
+    Q.ic = initial_condition;
+    Q.t = t;
+    double *dV = h->norm_buf, *dw = dV + (size_t)n_analysis * n, *dsum = dw + n_analysis;
+    Q.vandermonde = dV;
+    Q.weights = dw;
+    Q.sums = dsum;
+    Q.linf = h->norm_linf;
+    CUDA_TRY(h, cudaMemcpyAsync(dV, vandermonde, sizeof(double) * n_analysis * n, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(dw, weights, sizeof(double) * n_analysis, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaMemsetAsync(dsum, 0, sizeof(double) * (nv + 1), h->stream));
+    CUDA_TRY(h, cudaMemsetAsync(h->norm_linf, 0, sizeof(unsigned long long) * 16, h->stream));
+    h->L->error_norms(h->P, Q, h->stream);
+    h->launches++;
+    int rc = check_launch(h, "error norm kernel");
+    if (rc) return rc;
+    double sums[16];
+    unsigned long long mx[16];
+    CUDA_TRY(h, cudaMemcpyAsync(sums, dsum, sizeof(double) * (nv + 1), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(mx, h->norm_linf, sizeof(unsigned long long) * nv, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    for (int v = 0; v < nv; ++v) {
+        l2_sums[v] = sums[v];
+        memcpy(&linf[v], &mx[v], sizeof(double));
+    }
+    *volume = sums[nv];
+    return 0;
+}
+
 TRIXI_B200_API int trixi_b200_step_2n(trixi_b200_handle *h, double t, double dt, const double *a, const double *b, const double *c,
                        int nstages) {
     if (!h || !a || !b || !c || nstages <= 0) return h ? fail(h, TRIXI_B200_EINVAL, "bad Runge-Kutta tableau") : TRIXI_B200_EINVAL;
@@ -818,6 +883,10 @@ TRIXI_B200_API int trixi_b200_set_option(trixi_b200_handle *h, int option, int v
     case TRIXI_B200_OPT_KERNEL_PATH:
         if (value != 0 && value != 1) return fail(h, TRIXI_B200_EINVAL, "kernel path must be 0 (auto) or 1 (generic)");
         h->P.kernel_path = value;
+        return 0;
+    case TRIXI_B200_OPT_PREFETCH_DISTANCE:
+        if (value < 0) return fail(h, TRIXI_B200_EINVAL, "prefetch distance must be >= 0");
+        h->P.prefetch_distance = value;
         return 0;
     case TRIXI_B200_OPT_FUSED_CFL:
         if (value != 0 && value != 1) return fail(h, TRIXI_B200_EINVAL, "fused CFL option must be 0 or 1");

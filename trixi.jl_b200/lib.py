@@ -20,7 +20,7 @@ EXPORTS = [
     "trixi_b200_create", "trixi_b200_destroy", "trixi_b200_last_error", "trixi_b200_abi_version",
     "trixi_b200_upload", "trixi_b200_download", "trixi_b200_device_ptr", "trixi_b200_synchronize",
     "trixi_b200_stream", "trixi_b200_rhs_host", "trixi_b200_rhs", "trixi_b200_max_dt",
-    "trixi_b200_step_2n", "trixi_b200_solve_2n", "trixi_b200_set_eq_param",
+    "trixi_b200_step_2n", "trixi_b200_solve_2n", "trixi_b200_set_eq_param", "trixi_b200_calc_error_norms",
     "trixi_b200_calc_volume_integral", "trixi_b200_calc_surface_fluxes",
     "trixi_b200_download_surface_flux_values", "trixi_b200_comm_info_size", "trixi_b200_comm_info",
     "trixi_b200_comm_connect",
@@ -70,6 +70,7 @@ def load_library(path=None):
     lib.trixi_b200_solve_2n.argtypes = [vp, C.c_double, C.c_double, C.c_double, C.c_int64, dp, dp, dp,
                                         C.c_int, i64p, dp, dp]
     lib.trixi_b200_set_eq_param.argtypes = [vp, C.c_int, C.c_double]
+    lib.trixi_b200_calc_error_norms.argtypes = [vp, C.c_double, C.c_int, C.c_int, dp, dp, dp, dp, dp]
     lib.trixi_b200_calc_volume_integral.argtypes = [vp]
     lib.trixi_b200_calc_surface_fluxes.argtypes = [vp, C.c_double]
     lib.trixi_b200_download_surface_flux_values.argtypes = [vp, dp]
@@ -188,6 +189,15 @@ class B200Backend:
                                               C.byref(t_out), C.byref(dt_out)))
         return steps.value, t_out.value, dt_out.value
 
+    def calc_error_norms(self, t, ic_id, vandermonde, weights, nvars):
+        """(sum of squared errors per variable, Linf per variable, quadrature volume) of the resident u."""
+        V = np.ascontiguousarray(np.asarray(vandermonde, dtype=np.float64).ravel(order="F"))
+        w = np.ascontiguousarray(np.asarray(weights, dtype=np.float64))
+        l2, linf, vol = np.empty(nvars), np.empty(nvars), np.empty(1)
+        self._ck(self.lib.trixi_b200_calc_error_norms(self.h, float(t), int(ic_id), int(w.shape[0]), _dptr(V), _dptr(w),
+                                                      _dptr(l2), _dptr(linf), _dptr(vol)))
+        return l2, linf, float(vol[0])
+
     def set_eq_param(self, index, value):
         self._ck(self.lib.trixi_b200_set_eq_param(self.h, int(index), float(value)))
 
@@ -221,6 +231,7 @@ class B200Backend:
 
     OPT_KERNEL_PATH = 0
     OPT_FUSED_CFL = 1
+    OPT_PREFETCH_DISTANCE = 2
 
     def set_option(self, option, value):
         self._ck(self.lib.trixi_b200_set_option(self.h, int(option), int(value)))
