@@ -399,6 +399,84 @@ ELIXIRS.update({e.name: e for e in [
 ]})
 
 
+# ---- StructuredMesh / P4estMesh in 2D ---------------------------------------------------------------------
+def _warped_mapping_2d(xi_, eta_):
+    # examples/structured_2d_dgsem/elixir_euler_free_stream.jl:19-33
+    pi = np.pi
+    xi, eta = 1.5 * xi_ + 1.5, 1.5 * eta_ + 1.5
+    y = eta + 3 / 8 * (np.cos(1.5 * pi * (2 * xi - 3) / 3) * np.cos(0.5 * pi * (2 * eta - 3) / 3))
+    x = xi + 3 / 8 * (np.cos(0.5 * pi * (2 * xi - 3) / 3) * np.cos(2 * pi * (2 * y - 3) / 3))
+    return x, y
+
+
+def _structured2d_advection_basic():
+    eq = T.LinearScalarAdvectionEquation2D((0.2, -0.7))
+    solver = T.DGSEM(polydeg=3, surface_flux=T.flux_lax_friedrichs)
+    mesh = T.StructuredMesh((16, 16), (-1.0, -1.0), (1.0, 1.0), periodicity=True)
+    return T.SemidiscretizationHyperbolic(mesh, eq, T.initial_condition_convergence_test, solver)
+
+
+def _structured2d_free_stream():
+    eq = T.CompressibleEulerEquations2D(1.4)
+    solver = T.DGSEM(polydeg=3, surface_flux=T.FluxLaxFriedrichs(T.max_abs_speed_naive))
+    mesh = T.StructuredMesh((16, 16), _warped_mapping_2d, periodicity=True)
+    return T.SemidiscretizationHyperbolic(mesh, eq, T.initial_condition_constant, solver)
+
+
+def _structured2d_ec():
+    eq = T.CompressibleEulerEquations2D(1.4)
+    solver = T.DGSEM(polydeg=4, surface_flux=T.flux_ranocha,
+                     volume_integral=T.VolumeIntegralFluxDifferencing(T.flux_ranocha))
+    mesh = T.StructuredMesh((16, 16), _warped_mapping_2d, periodicity=True)
+    return T.SemidiscretizationHyperbolic(mesh, eq, T.initial_condition_weak_blast_wave, solver)
+
+
+def _structured2d_source_terms_nonperiodic():
+    eq = T.CompressibleEulerEquations2D(1.4)
+    solver = T.DGSEM(polydeg=3, surface_flux=T.FluxLaxFriedrichs(T.max_abs_speed_naive))
+    mesh = T.StructuredMesh((16, 16), (0.0, 0.0), (2.0, 2.0), periodicity=False)
+    return T.SemidiscretizationHyperbolic(mesh, eq, T.initial_condition_convergence_test, solver,
+                                          source_terms=T.source_terms_convergence_test,
+                                          boundary_conditions=T.BoundaryConditionDirichlet(
+                                              T.initial_condition_convergence_test))
+
+
+def _p4est2d_advection_basic():
+    eq = T.LinearScalarAdvectionEquation2D((0.2, -0.7))
+    solver = T.DGSEM(polydeg=3, surface_flux=T.flux_lax_friedrichs)
+    mesh = T.P4estMesh((8, 8), polydeg=3, coordinates_min=(-1.0, -1.0), coordinates_max=(1.0, 1.0),
+                       initial_refinement_level=1, periodicity=True)
+    return T.SemidiscretizationHyperbolic(mesh, eq, T.initial_condition_convergence_test, solver)
+
+
+class _FreeStreamElixir(Elixir):
+    """Free-stream preservation: the reference's values are round-off (1e-14); compare absolutely."""
+
+    def check(self, l2, linf):
+        assert np.all(l2 <= 50 * np.maximum(self.l2, 1e-15)) and np.all(linf <= 50 * np.maximum(self.linf, 1e-14))
+
+
+ELIXIRS.update({e.name: e for e in [
+    Elixir("structured_2d_advection_basic", _structured2d_advection_basic, (0.0, 1.0), 1.6,
+           [8.311947673061856e-6], [6.627000273229378e-5], "test/test_structured_2d.jl:5-13"),
+    _FreeStreamElixir("structured_2d_euler_free_stream", _structured2d_free_stream, (0.0, 2.0), 2.0,
+                      [2.063350241405049e-15, 1.8571016296925367e-14, 3.1769447886391905e-14,
+                       1.4104095258528071e-14],
+                      [1.9539925233402755e-14, 2.9791447087035294e-13, 6.502853810985698e-13,
+                       2.7000623958883807e-13], "test/test_structured_2d.jl:524-545"),
+    Elixir("structured_2d_euler_ec", _structured2d_ec, (0.0, 0.3), 1.0,
+           [0.03774907669925568, 0.02845190575242045, 0.028262802829412605, 0.13785915638851698],
+           [0.3368296929764073, 0.27644083771519773, 0.27990039685141377, 1.1971436487402016],
+           "test/test_structured_2d.jl:644-663"),
+    Elixir("structured_2d_euler_source_terms_nonperiodic", _structured2d_source_terms_nonperiodic, (0.0, 2.0), 1.0,
+           [2.259440511901724e-6, 2.3188881559075347e-6, 2.3188881559568146e-6, 6.332786324137878e-6],
+           [1.4987382622067003e-5, 1.918201192063762e-5, 1.918201192019353e-5, 6.052671713430158e-5],
+           "test/test_structured_2d.jl:575-598"),
+    Elixir("p4est_2d_advection_basic", _p4est2d_advection_basic, (0.0, 1.0), 1.6,
+           [8.311947673061856e-6], [6.627000273229378e-5], "test/test_p4est_2d.jl:5-13"),
+]})
+
+
 # ---- TreeMesh with L2 mortars -----------------------------------------------------------------------------
 def _advection2d_mortar():
     # examples/tree_2d_dgsem/elixir_advection_mortar.jl

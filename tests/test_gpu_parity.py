@@ -64,7 +64,9 @@ RHS_CASES = ["tree_3d_euler_ec", "tree_3d_euler_source_terms", "tree_3d_euler_so
              "structured_3d_euler_source_terms", "structured_3d_euler_source_terms_nonperiodic_curved",
              "p4est_3d_euler_source_terms_nonperiodic", "p4est_3d_euler_source_terms_nonperiodic_kennedy_gruber",
              "tree_3d_mhd_ec", "tree_3d_mhd_alfven_wave", "p4est_3d_curved_ec", "p4est_3d_curved_weak_form",
-             "p4est_3d_curved_level1", "tree_2d_advection_mortar", "tree_3d_euler_mortar"]
+             "p4est_3d_curved_level1", "tree_2d_advection_mortar", "tree_3d_euler_mortar",
+             "structured_2d_advection_basic", "structured_2d_euler_free_stream", "structured_2d_euler_ec",
+             "structured_2d_euler_source_terms_nonperiodic", "p4est_2d_advection_basic"]
 
 
 @pytest.mark.parametrize("name", RHS_CASES)
@@ -229,7 +231,9 @@ GOLDEN_GPU = ["tree_3d_euler_ec", "tree_3d_euler_ec_constant", "tree_3d_euler_so
               "structured_3d_euler_ec", "structured_3d_euler_source_terms",
               "structured_3d_euler_source_terms_nonperiodic_curved", "p4est_3d_euler_source_terms_nonperiodic",
               "p4est_3d_euler_source_terms_nonperiodic_kennedy_gruber", "tree_3d_mhd_ec", "tree_3d_mhd_alfven_wave",
-              "tree_2d_advection_mortar", "tree_3d_euler_mortar"]
+              "tree_2d_advection_mortar", "tree_3d_euler_mortar", "structured_2d_advection_basic",
+              "structured_2d_euler_free_stream", "structured_2d_euler_ec",
+              "structured_2d_euler_source_terms_nonperiodic", "p4est_2d_advection_basic"]
 
 
 @pytest.mark.parametrize("name", GOLDEN_GPU)
