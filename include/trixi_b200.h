@@ -193,6 +193,11 @@ TRIXI_B200_API void *trixi_b200_stream(trixi_b200_handle *h); /* the library-own
  * (dgsem_tree/dg_2d.jl:113-186; structured dgsem_structured/dg.jl:41-94): du <- rhs(u, t), host
  * buffers: copies u host->device, runs the kernels, copies du device->host, synchronises. */
 TRIXI_B200_API int trixi_b200_rhs_host(trixi_b200_handle *h, double *du_host, const double *u_host, double t);
+/* On conforming TreeMeshes without physical boundaries (single rank) the host-buffer calls are pipelined: u is
+ * uploaded in element chunks along a sweep of the last coordinate axis, every interface / element kernel starts as
+ * soon as its neighbours are resident, and finished chunks are downloaded while later ones are still in flight,
+ * so both PCIe directions and the kernels overlap (pinned host buffers required for the overlap, not for
+ * correctness).  Results are bit-identical to the unpipelined path.  See TRIXI_B200_OPT_HOST_PIPELINE_CHUNK. */
 /* same on the device-resident vectors (asynchronous on the handle's stream) */
 TRIXI_B200_API int trixi_b200_rhs(trixi_b200_handle *h, double t);
 
@@ -208,6 +213,11 @@ TRIXI_B200_API int trixi_b200_max_dt(trixi_b200_handle *h, double t, double *dt_
  * fused into the last RHS kernel.  u_tmp is zeroed first.  Asynchronous. */
 TRIXI_B200_API int trixi_b200_step_2n(trixi_b200_handle *h, double t, double dt, const double *a, const double *b,
                        const double *c, int nstages);
+/* The same step on a host-resident u (read and overwritten in place): the integrator's u lives in a Julia Vector
+ * (methods_2N.jl:95-111).  The first stage consumes u chunk-wise as it arrives, the last stage returns it
+ * chunk-wise as it is finished.  Synchronises. */
+TRIXI_B200_API int trixi_b200_step_2n_host(trixi_b200_handle *h, double *u_host, double t, double dt, const double *a,
+                                            const double *b, const double *c, int nstages);
 /* `nsteps` steps with the CFL step size recomputed on the device after every step
  * (StepsizeCallback interval = 1, stepsize.jl:93-126) and the final step clipped to t_end
  * (time_integration.jl:46-55); no host round trip inside.  Returns the number of steps taken, the
@@ -236,6 +246,8 @@ TRIXI_B200_API int trixi_b200_calc_error_norms(trixi_b200_handle *h, double t, i
 #define TRIXI_B200_OPT_KERNEL_PATH 0
 #define TRIXI_B200_OPT_FUSED_CFL 1
 #define TRIXI_B200_OPT_PREFETCH_DISTANCE 2 /* tuned element kernel: L2 prefetch distance in elements (0 = off) */
+#define TRIXI_B200_OPT_HOST_PIPELINE_CHUNK 3 /* host-buffer calls: elements per chunk; -1 = auto (16-32 MiB, only
+                                                for >= 32 chunks), 0 = one copy each way, no overlap */
 TRIXI_B200_API int trixi_b200_set_option(trixi_b200_handle *h, int option, int value);
 
 /* GlmSpeedCallback (glm_speed.jl:85-105) mutates equations.c_h every step */

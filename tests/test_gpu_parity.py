@@ -359,3 +359,39 @@ def test_unconnected_distributed_handle_fails_loudly():
     from trixi_b200.lib import TrixiB200Error
     with pytest.raises(TrixiB200Error, match="not connected"):
         b.rhs(0.0)
+
+
+@pytest.mark.parametrize("name,chunk", [("tree_3d_euler_ec", 8), ("tree_3d_euler_ec", 5), ("tree_3d_euler_source_terms", 16),
+                                        ("tree_2d_euler_ec", 4), ("tree_3d_mhd_ec", 8), ("tree_2d_advection_basic", 3)])
+def test_pipelined_host_path_is_bit_identical(name, chunk):
+    """TRIXI_B200_OPT_HOST_PIPELINE_CHUNK: rhs_host and step_2n_host stream u in and the result out in element
+    chunks (kernels start as soon as their neighbours are resident); same bits as the one-copy path."""
+    semi = ELIXIRS[name].semi()
+    u = _random_admissible_state(semi, seed=21)
+    gpu = semi.backend()
+    alg = T.CarpenterKennedy2N54()
+
+    def run(chunk_opt):
+        gpu.set_option(gpu.OPT_HOST_PIPELINE_CHUNK, chunk_opt)
+        du = np.full_like(u, np.nan)
+        n0 = gpu.launch_count()
+        gpu.rhs_host(du, u, 0.3)
+        launches = gpu.launch_count() - n0
+        gpu.upload(0, u)
+        dt = 0.4 * gpu.max_dt()
+        un = u.copy(order="F")
+        gpu.step_2n_host(un, 0.0, dt, alg.a, alg.b, alg.c)
+        gpu.step_2n_host(un, dt, dt, alg.a, alg.b, alg.c)
+        return du, un, launches
+
+    du0, un0, l0 = run(0)
+    du1, un1, l1 = run(chunk)
+    assert l1 > l0  # really chunked
+    assert np.array_equal(du0, du1)
+    assert np.array_equal(un0, un1)
+    # and the host step equals the device-resident step
+    gpu.upload(0, u)
+    dt = 0.4 * gpu.max_dt()
+    gpu.step_2n(0.0, dt, alg.a, alg.b, alg.c)
+    gpu.step_2n(dt, dt, alg.a, alg.b, alg.c)
+    assert np.array_equal(gpu.download(0), un0.ravel(order="F"))

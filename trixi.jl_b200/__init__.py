@@ -16,4 +16,4 @@ from .semidiscretization import (ODEProblem, SemidiscretizationHyperbolic, compu
 from .solver import (DGSEM, SurfaceIntegralWeakForm, VolumeIntegralFluxDifferencing,  # noqa: F401
                      VolumeIntegralWeakForm)
 from .time_integration import (CallbackSet, CarpenterKennedy2N43, CarpenterKennedy2N54, init,  # noqa: F401
-                               solve, step)
+                               solve, step, step_2n_host)

@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(TunedCfg::THREADS, TunedCfg::MIN_BLOCKS)
     const uint32_t bar = smem_u32(s_prim + PRIM);
 
     const int lane = threadIdx.x;
-    const long long e = blockIdx.x;
+    const long long e = P.elem_begin + blockIdx.x;
     const double gamma = P.eq.p[0], inv_gm1 = P.eq.p[1];
     const bool rk = P.mode != 0;
     const bool need_ut = rk && P.rk_a != 0.0;
@@ -418,7 +418,7 @@ cudaError_t launch_element_euler3d_ranocha_p3(const KParams &P, bool with_surfac
                                    cudaSharedmemCarveoutMaxShared);
         if (err != cudaSuccess) return err;
     }
-    const unsigned blocks = (unsigned)((P.nelements + C::EPB - 1) / C::EPB);
+    const unsigned blocks = (unsigned)((P.elem_end - P.elem_begin + C::EPB - 1) / C::EPB);
     if (with_surface)
         k_element_euler3d_ranocha_p3<true><<<blocks, C::THREADS, C::SMEM, s>>>(P);
     else

@@ -58,6 +58,7 @@ struct KParams {
     int want_cfl;                 // RK stage kernels that support it also reduce the CFL speed of the updated u
     int kernel_path;              // 0: tuned kernels where available, 1: generic kernels only
     int prefetch_distance;        // tuned element kernel: L2 prefetch this many elements ahead (0: off)
+    long long elem_begin, elem_end;  // TreeMesh element kernels work on [elem_begin, elem_end) (pipelined rhs_host)
     // distributed: faces shared with other ranks (replaces mpi_interfaces, dg_2d_parallel.jl / dg_parallel.jl)
     long long nmpi;
     const long long *mpi_local, *mpi_side, *mpi_orient;  // [nmpi] 1-based local element, local side, orientation
@@ -496,8 +497,8 @@ __global__ void __launch_bounds__(ElemCfg<EQ, N>::THREADS) k_element(const KPara
 
     const EQ eq(P.eq);
     const int tid = threadIdx.x;
-    const long long e0 = (long long)blockIdx.x * EPB;
-    const int nel = (int)min((long long)EPB, P.nelements - e0);
+    const long long e0 = P.elem_begin + (long long)blockIdx.x * EPB;
+    const int nel = (int)min((long long)EPB, P.elem_end - e0);
 
     // stage D and the u tile
     const double *Dsrc = VOLINT == TRIXI_B200_VOLINT_WEAK_FORM ? P.dhat : P.dsplit;

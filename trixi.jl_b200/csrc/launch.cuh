@@ -137,7 +137,7 @@ cudaError_t launch_element_variant(const KParams &P, cudaStream_t s) {
                                           (VOLINT == TRIXI_B200_VOLINT_WEAK_FORM
                                                ? (size_t)C::ND * C::EPB * C::NN * C::US
                                                : 0));
-    const unsigned blocks = (unsigned)((P.nelements + C::EPB - 1) / C::EPB);
+    const unsigned blocks = (unsigned)(((P.curved ? P.nelements : P.elem_end - P.elem_begin) + C::EPB - 1) / C::EPB);
     if (P.curved) {
         auto kern = k_element_curved<EQ, N, VOLINT, WS>;
         if (smem > 48 * 1024) {

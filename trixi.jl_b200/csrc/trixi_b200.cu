@@ -8,6 +8,7 @@
 #include <new>
 #include <string>
 #include <vector>
+#include <algorithm>
 #include <unistd.h>
 
 #include "launch.cuh"
@@ -68,6 +69,22 @@ struct trixi_b200_handle {
     long long *d_mpi_remote_index = nullptr;
     bool comm_connected = false;
     unsigned long long comm_seq = 0;
+    // host-buffer calls (rhs_host, step_2n_host) stream u in and the result out in element chunks so the two PCIe
+    // directions and the kernels overlap
+    int opt_pipeline_chunk = -1;  // TRIXI_B200_OPT_HOST_PIPELINE_CHUNK: -1 auto, 0 off, > 0 elements per chunk
+    struct HostPipeline {
+        bool built = false, usable = false;
+        long long chunk = 0;              // elements per chunk
+        int nchunks = 0;
+        std::vector<int> order;           // chunk uploaded at step k (sweep along the last coordinate axis)
+        std::vector<long long> if_start;  // [nchunks + 1] range of the re-sorted interface list computable after step k
+        std::vector<int> ready_start;     // [nchunks + 1] range of ready_chunks whose elements are complete after step k
+        std::vector<int> ready_chunks;
+        long long *d_if_neighbors = nullptr, *d_if_orient = nullptr;  // interfaces sorted by the step they become ready
+        cudaStream_t s_in = nullptr, s_out = nullptr;
+        std::vector<cudaEvent_t> ev_in, ev_out;
+        cudaEvent_t ev_sync = nullptr;
+    } hp;
 };
 
 namespace {
@@ -276,6 +293,220 @@ int run_rhs(trixi_b200_handle *h, double t) {
     return run_element(h, true);
 }
 
+
+void free_host_pipeline(trixi_b200_handle *h) {
+    auto &hp = h->hp;
+    for (cudaEvent_t e : hp.ev_in) cudaEventDestroy(e);
+    for (cudaEvent_t e : hp.ev_out) cudaEventDestroy(e);
+    hp.ev_in.clear();
+    hp.ev_out.clear();
+    if (hp.ev_sync) cudaEventDestroy(hp.ev_sync);
+    if (hp.s_in) cudaStreamDestroy(hp.s_in);
+    if (hp.s_out) cudaStreamDestroy(hp.s_out);
+    if (hp.d_if_neighbors) cudaFree(hp.d_if_neighbors);
+    if (hp.d_if_orient) cudaFree(hp.d_if_orient);
+    hp = trixi_b200_handle::HostPipeline{};
+}
+
+// Plan of the chunked host-buffer path.  Chunks are contiguous element ranges, uploaded in the order of a sweep
+// along the last coordinate axis; an interface can be computed once both neighbours are resident, an element
+// chunk once all its interfaces are.  Everything is derived from the device-resident connectivity, so the plan
+// can be rebuilt when the chunk size option changes.
+int build_host_pipeline(trixi_b200_handle *h) {
+    free_host_pipeline(h);
+    auto &hp = h->hp;
+    hp.built = true;
+    const KParams &P = h->P;
+    if (h->opt_pipeline_chunk == 0 || P.curved || P.nmortars || P.nboundaries || h->world_size > 1 ||
+        P.ninterfaces == 0 || h->nelements == 0)
+        return 0;
+    const int nd = h->ndims;
+    const long long esz = h->ulen / h->nelements;  // doubles per element
+    long long chunk = h->opt_pipeline_chunk;
+    if (chunk < 0) {
+        // 16-32 MiB per copy, a power of two of elements (whole boxes of the Morton order).  Measured at 134 M DOF
+        // (tools/pcie_probe.py): 2.6 MB copies 172 ms per rhs_host, 10 MB 143 ms, 21 MB 138 ms, 84 MB 154 ms; the
+        // simultaneous two-way PCIe ceiling is 120 ms, one copy each way 208 ms
+        chunk = 1;
+        while (2 * chunk * esz * (long long)sizeof(double) <= (32ll << 20)) chunk *= 2;
+        if (h->nelements < 32 * chunk) return 0;  // small problems: one copy each way is as fast
+    }
+    const long long nel = h->nelements;
+    const long long nch = (nel + chunk - 1) / chunk;
+    if (nch < 2 || nch > (1 << 20)) return 0;
+    hp.chunk = chunk;
+    hp.nchunks = (int)nch;
+
+    const long long nif = P.ninterfaces;
+    std::vector<long long> nb((size_t)(2 * nif)), ori((size_t)nif);
+    std::vector<double> key((size_t)nch);
+    CUDA_TRY(h, cudaMemcpy(nb.data(), P.if_neighbors, sizeof(long long) * 2 * nif, cudaMemcpyDeviceToHost));
+    CUDA_TRY(h, cudaMemcpy(ori.data(), P.if_orient, sizeof(long long) * nif, cudaMemcpyDeviceToHost));
+    const long long nn = esz / h->nvars;
+    CUDA_TRY(h, cudaMemcpy2D(key.data(), sizeof(double), P.node_coordinates + (nd - 1),
+                             sizeof(double) * nd * nn * chunk, sizeof(double), (size_t)nch, cudaMemcpyDeviceToHost));
+    hp.order.resize((size_t)nch);
+    for (int c = 0; c < (int)nch; ++c) hp.order[(size_t)c] = c;
+    std::stable_sort(hp.order.begin(), hp.order.end(), [&](int x, int y) { return key[(size_t)x] < key[(size_t)y]; });
+    std::vector<int> pos((size_t)nch);
+    for (int k = 0; k < (int)nch; ++k) pos[(size_t)hp.order[(size_t)k]] = k;
+
+    // step at which every interface / element chunk becomes computable
+    std::vector<int> if_ready((size_t)nif), el_ready(pos);
+    hp.if_start.assign((size_t)nch + 1, 0);
+    for (long long i = 0; i < nif; ++i) {
+        const long long ca = (nb[(size_t)(2 * i)] - 1) / chunk, cb = (nb[(size_t)(2 * i + 1)] - 1) / chunk;
+        const int r = std::max(pos[(size_t)ca], pos[(size_t)cb]);
+        if_ready[(size_t)i] = r;
+        el_ready[(size_t)ca] = std::max(el_ready[(size_t)ca], r);
+        el_ready[(size_t)cb] = std::max(el_ready[(size_t)cb], r);
+        hp.if_start[(size_t)r + 1]++;
+    }
+    for (long long k = 0; k < nch; ++k) hp.if_start[(size_t)k + 1] += hp.if_start[(size_t)k];
+    {
+        std::vector<long long> cursor(hp.if_start.begin(), hp.if_start.end() - 1);
+        std::vector<long long> snb((size_t)(2 * nif)), sori((size_t)nif);
+        for (long long i = 0; i < nif; ++i) {  // counting sort, stable: the reference's interface order within a step
+            const long long j = cursor[(size_t)if_ready[(size_t)i]]++;
+            snb[(size_t)(2 * j)] = nb[(size_t)(2 * i)];
+            snb[(size_t)(2 * j + 1)] = nb[(size_t)(2 * i + 1)];
+            sori[(size_t)j] = ori[(size_t)i];
+        }
+        CUDA_TRY(h, cudaMalloc((void **)&hp.d_if_neighbors, sizeof(long long) * 2 * nif));
+        CUDA_TRY(h, cudaMalloc((void **)&hp.d_if_orient, sizeof(long long) * nif));
+        CUDA_TRY(h, cudaMemcpy(hp.d_if_neighbors, snb.data(), sizeof(long long) * 2 * nif, cudaMemcpyHostToDevice));
+        CUDA_TRY(h, cudaMemcpy(hp.d_if_orient, sori.data(), sizeof(long long) * nif, cudaMemcpyHostToDevice));
+    }
+    hp.ready_start.assign((size_t)nch + 1, 0);
+    for (long long c = 0; c < nch; ++c) hp.ready_start[(size_t)el_ready[(size_t)c] + 1]++;
+    for (long long k = 0; k < nch; ++k) hp.ready_start[(size_t)k + 1] += hp.ready_start[(size_t)k];
+    {
+        std::vector<int> cursor(hp.ready_start.begin(), hp.ready_start.end() - 1);
+        hp.ready_chunks.resize((size_t)nch);
+        for (int c = 0; c < (int)nch; ++c) hp.ready_chunks[(size_t)cursor[(size_t)el_ready[(size_t)c]]++] = c;  // ascending
+    }
+    CUDA_TRY(h, cudaStreamCreateWithFlags(&hp.s_in, cudaStreamNonBlocking));
+    CUDA_TRY(h, cudaStreamCreateWithFlags(&hp.s_out, cudaStreamNonBlocking));
+    CUDA_TRY(h, cudaEventCreateWithFlags(&hp.ev_sync, cudaEventDisableTiming));
+    hp.ev_in.resize((size_t)nch);
+    hp.ev_out.resize((size_t)nch);
+    for (auto &e : hp.ev_in) CUDA_TRY(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto &e : hp.ev_out) CUDA_TRY(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    hp.usable = true;
+    return 0;
+}
+
+bool host_pipeline_usable(trixi_b200_handle *h, int *rc) {
+    *rc = 0;
+    if (!h->hp.built) *rc = build_host_pipeline(h);
+    return *rc == 0 && h->hp.usable;
+}
+
+// Surface fluxes + element kernel (P.mode / rk_* set by the caller) chunk by chunk.  in_host: u arrives from the
+// host chunk-wise and every kernel starts as soon as its inputs are resident; out_host: the finished chunks of
+// vec[out_which] leave for the host while later chunks are still computed.  In-place RK stages stay safe: a chunk
+// is only updated after all interfaces touching it have been evaluated.
+int run_pipelined(trixi_b200_handle *h, double t, const double *in_host, double *out_host, int out_which) {
+    auto &hp = h->hp;
+    const long long nel = h->nelements, esz = h->ulen / nel, chunk = hp.chunk;
+    const size_t dbl = sizeof(double);
+    int n_out = 0;
+    auto element_range = [&](long long c0, long long c1) -> int {  // chunks [c0, c1)
+        h->P.elem_begin = c0 * chunk;
+        h->P.elem_end = std::min(nel, c1 * chunk);
+        int rc = run_element(h, true);
+        if (rc == 0 && out_host) {
+            cudaEvent_t ev = hp.ev_out[(size_t)n_out++];
+            const long long off = h->P.elem_begin * esz, len = (h->P.elem_end - h->P.elem_begin) * esz;
+            cudaError_t err = cudaEventRecord(ev, h->stream);
+            if (err == cudaSuccess) err = cudaStreamWaitEvent(hp.s_out, ev, 0);
+            if (err == cudaSuccess)
+                err = cudaMemcpyAsync(out_host + off, h->vec[out_which] + off, len * dbl, cudaMemcpyDeviceToHost, hp.s_out);
+            if (err != cudaSuccess) rc = fail(h, TRIXI_B200_ECUDA, "chunked download failed: %s", cudaGetErrorString(err));
+        }
+        h->P.elem_begin = 0;
+        h->P.elem_end = nel;
+        return rc;
+    };
+    if (in_host) {
+        h->P.t = t;
+        // u is overwritten: everything queued earlier must have finished reading it
+        CUDA_TRY(h, cudaEventRecord(hp.ev_sync, h->stream));
+        CUDA_TRY(h, cudaStreamWaitEvent(hp.s_in, hp.ev_sync, 0));
+        const long long *nb_all = h->P.if_neighbors, *ori_all = h->P.if_orient;
+        const long long nif_all = h->P.ninterfaces;
+        int rc = 0;
+        for (int k = 0; k < hp.nchunks && rc == 0; ++k) {
+            const long long c = hp.order[(size_t)k];
+            const long long off = c * chunk * esz, len = (std::min(nel, (c + 1) * chunk) - c * chunk) * esz;
+            CUDA_TRY(h, cudaMemcpyAsync(h->vec[0] + off, in_host + off, len * dbl, cudaMemcpyHostToDevice, hp.s_in));
+            CUDA_TRY(h, cudaEventRecord(hp.ev_in[(size_t)k], hp.s_in));
+            CUDA_TRY(h, cudaStreamWaitEvent(h->stream, hp.ev_in[(size_t)k], 0));
+            const long long i0 = hp.if_start[(size_t)k], i1 = hp.if_start[(size_t)k + 1];
+            if (i1 > i0) {
+                h->P.if_neighbors = hp.d_if_neighbors + 2 * i0;
+                h->P.if_orient = hp.d_if_orient + i0;
+                h->P.ninterfaces = i1 - i0;
+                {
+                    ProfScope ps(h, KC_SURFACE);
+                    h->L->interface_flux(h->P, h->stream);
+                    h->launches++;
+                }
+                h->P.if_neighbors = nb_all;
+                h->P.if_orient = ori_all;
+                h->P.ninterfaces = nif_all;
+                rc = check_launch(h, "surface flux kernel");
+            }
+            for (int q = hp.ready_start[(size_t)k]; q < hp.ready_start[(size_t)k + 1] && rc == 0;) {
+                int q1 = q + 1;  // merge runs of consecutive chunks into one launch and one copy
+                while (q1 < hp.ready_start[(size_t)k + 1] && hp.ready_chunks[(size_t)q1] == hp.ready_chunks[(size_t)q1 - 1] + 1) ++q1;
+                rc = element_range(hp.ready_chunks[(size_t)q], hp.ready_chunks[(size_t)q1 - 1] + 1);
+                q = q1;
+            }
+        }
+        if (rc) return rc;
+    } else {
+        int rc = run_all_surface_fluxes(h, t);
+        for (long long c = 0; c < hp.nchunks && rc == 0; ++c) rc = element_range(c, c + 1);
+        if (rc) return rc;
+    }
+    if (out_host) CUDA_TRY(h, cudaStreamSynchronize(hp.s_out));
+    return 0;
+}
+
+// the stage loop of step!(integrator::SimpleIntegrator2N) (methods_2N.jl:144-159); with host pointers the first
+// stage consumes u as it arrives and the last stage returns it as it is finished
+int run_step_2n(trixi_b200_handle *h, double t, double dt, const double *a, const double *b, const double *c, int nstages,
+                const double *u_in_host, double *u_out_host) {
+    h->cfl_valid = false;
+    const bool fuse_cfl = h->opt_fused_cfl && h->L->fuses_cfl(h->P);
+    for (int s = 0; s < nstages; ++s) {
+        const double t_stage = t + dt * c[s];
+        const double *in = s == 0 ? u_in_host : nullptr;
+        double *out = s == nstages - 1 ? u_out_host : nullptr;
+        h->P.mode = 1;
+        h->P.rk_a = a[s];
+        h->P.rk_b_dt = b[s] * dt;
+        if (fuse_cfl && s == nstages - 1) {
+            // the last stage also reduces the CFL wave speeds of the state it writes (max_dt without a pass over u)
+            CUDA_TRY(h, cudaMemsetAsync(h->d_cfl, 0, kCflSlots * sizeof(unsigned long long), h->stream));
+            h->P.want_cfl = 1;
+        }
+        int rc;
+        if (in || out)
+            rc = run_pipelined(h, t_stage, in, out, 0);
+        else {
+            rc = run_all_surface_fluxes(h, t_stage);
+            if (rc == 0) rc = run_element(h, true);
+        }
+        h->P.mode = 0;
+        h->P.want_cfl = 0;
+        if (rc) return rc;
+    }
+    h->cfl_valid = fuse_cfl;
+    return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -292,6 +523,7 @@ TRIXI_B200_API void trixi_b200_destroy(trixi_b200_handle *h) {
         cudaEventDestroy(e.a);
         cudaEventDestroy(e.b);
     }
+    free_host_pipeline(h);
     for (void *p : h->ipc_opened) cudaIpcCloseMemHandle(p);
     for (void *p : h->allocs) cudaFree(p);
     if (h->h_cfl) cudaFreeHost(h->h_cfl);
@@ -431,6 +663,8 @@ TRIXI_B200_API int trixi_b200_create(const trixi_b200_desc *d, trixi_b200_handle
     }
     KParams &P = h->P;
     P.nelements = d->nelements;
+    P.elem_begin = 0;
+    P.elem_end = d->nelements;
     P.ninterfaces = n_if;
     P.nboundaries = d->nboundaries;
     for (int i = 0; i < 3; ++i) CREATE_TRY(alloc_array(h, (size_t)h->ulen, &h->vec[i]));
@@ -687,8 +921,20 @@ TRIXI_B200_API int trixi_b200_rhs_host(trixi_b200_handle *h, double *du_host, co
     CUDA_TRY(h, cudaSetDevice(h->device));
     const size_t bytes = h->ulen * sizeof(double);
     h->cfl_valid = false;
+    int rc = 0;
+    if (host_pipeline_usable(h, &rc)) {
+        CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
+        h->P.mode = 0;
+        rc = run_pipelined(h, t, u_host, du_host, 1);
+        if (rc) return rc;
+        CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
+        h->have_elapsed = true;
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+        return 0;
+    }
+    if (rc) return rc;
     CUDA_TRY(h, cudaMemcpyAsync(h->vec[0], u_host, bytes, cudaMemcpyHostToDevice, h->stream));
-    int rc = trixi_b200_rhs(h, t);
+    rc = trixi_b200_rhs(h, t);
     if (rc) return rc;
     CUDA_TRY(h, cudaMemcpyAsync(du_host, h->vec[1], bytes, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
@@ -806,28 +1052,31 @@ TRIXI_B200_API int trixi_b200_step_2n(trixi_b200_handle *h, double t, double dt,
     if (a[0] != 0.0) return fail(h, TRIXI_B200_EINVAL, "2N scheme must have a[1] == 0 (u_tmp starts at zero)");
     CUDA_TRY(h, cudaSetDevice(h->device));
     CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
-    h->cfl_valid = false;
-    const bool fuse_cfl = h->opt_fused_cfl && h->L->fuses_cfl(h->P);
-    for (int s = 0; s < nstages; ++s) {
-        const double t_stage = t + dt * c[s];
-        int rc = run_all_surface_fluxes(h, t_stage);
-        if (rc) return rc;
-        h->P.mode = 1;
-        h->P.rk_a = a[s];
-        h->P.rk_b_dt = b[s] * dt;
-        if (fuse_cfl && s == nstages - 1) {
-            // the last stage also reduces the CFL wave speeds of the state it writes (max_dt without a pass over u)
-            CUDA_TRY(h, cudaMemsetAsync(h->d_cfl, 0, kCflSlots * sizeof(unsigned long long), h->stream));
-            h->P.want_cfl = 1;
-        }
-        rc = run_element(h, true);
-        h->P.mode = 0;
-        h->P.want_cfl = 0;
-        if (rc) return rc;
-    }
-    h->cfl_valid = fuse_cfl;
+    int rc = run_step_2n(h, t, dt, a, b, c, nstages, nullptr, nullptr);
+    if (rc) return rc;
     CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
     h->have_elapsed = true;
+    return 0;
+}
+
+TRIXI_B200_API int trixi_b200_step_2n_host(trixi_b200_handle *h, double *u_host, double t, double dt, const double *a,
+                                            const double *b, const double *c, int nstages) {
+    if (!h || !a || !b || !c || nstages <= 0) return h ? fail(h, TRIXI_B200_EINVAL, "bad Runge-Kutta tableau") : TRIXI_B200_EINVAL;
+    if (a[0] != 0.0) return fail(h, TRIXI_B200_EINVAL, "2N scheme must have a[1] == 0 (u_tmp starts at zero)");
+    if (!u_host && h->ulen) return fail(h, TRIXI_B200_EINVAL, "host pointer is null");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const size_t bytes = h->ulen * sizeof(double);
+    int rc = 0;
+    const bool piped = host_pipeline_usable(h, &rc);
+    if (rc) return rc;
+    CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
+    if (!piped) CUDA_TRY(h, cudaMemcpyAsync(h->vec[0], u_host, bytes, cudaMemcpyHostToDevice, h->stream));
+    rc = run_step_2n(h, t, dt, a, b, c, nstages, piped ? u_host : nullptr, piped ? u_host : nullptr);
+    if (rc) return rc;
+    if (!piped) CUDA_TRY(h, cudaMemcpyAsync(u_host, h->vec[0], bytes, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
+    h->have_elapsed = true;
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     return 0;
 }
 
@@ -892,6 +1141,13 @@ TRIXI_B200_API int trixi_b200_set_option(trixi_b200_handle *h, int option, int v
         if (value != 0 && value != 1) return fail(h, TRIXI_B200_EINVAL, "fused CFL option must be 0 or 1");
         h->opt_fused_cfl = value != 0;
         h->cfl_valid = false;
+        return 0;
+    case TRIXI_B200_OPT_HOST_PIPELINE_CHUNK:
+        if (value < -1) return fail(h, TRIXI_B200_EINVAL, "host pipeline chunk must be -1 (auto), 0 (off) or an element count");
+        h->opt_pipeline_chunk = value;
+        CUDA_TRY(h, cudaSetDevice(h->device));
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+        free_host_pipeline(h);  // rebuilt lazily by the next host-buffer call
         return 0;
     default:
         return fail(h, TRIXI_B200_EINVAL, "unknown option %d", option);

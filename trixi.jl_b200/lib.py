@@ -20,7 +20,7 @@ EXPORTS = [
     "trixi_b200_create", "trixi_b200_destroy", "trixi_b200_last_error", "trixi_b200_abi_version",
     "trixi_b200_upload", "trixi_b200_download", "trixi_b200_device_ptr", "trixi_b200_synchronize",
     "trixi_b200_stream", "trixi_b200_rhs_host", "trixi_b200_rhs", "trixi_b200_max_dt",
-    "trixi_b200_step_2n", "trixi_b200_solve_2n", "trixi_b200_set_eq_param", "trixi_b200_calc_error_norms",
+    "trixi_b200_step_2n", "trixi_b200_step_2n_host", "trixi_b200_solve_2n", "trixi_b200_set_eq_param", "trixi_b200_calc_error_norms",
     "trixi_b200_calc_volume_integral", "trixi_b200_calc_surface_fluxes",
     "trixi_b200_download_surface_flux_values", "trixi_b200_comm_info_size", "trixi_b200_comm_info",
     "trixi_b200_comm_connect",
@@ -67,6 +67,7 @@ def load_library(path=None):
     lib.trixi_b200_rhs.argtypes = [vp, C.c_double]
     lib.trixi_b200_max_dt.argtypes = [vp, C.c_double, dp]
     lib.trixi_b200_step_2n.argtypes = [vp, C.c_double, C.c_double, dp, dp, dp, C.c_int]
+    lib.trixi_b200_step_2n_host.argtypes = [vp, dp, C.c_double, C.c_double, dp, dp, dp, C.c_int]
     lib.trixi_b200_solve_2n.argtypes = [vp, C.c_double, C.c_double, C.c_double, C.c_int64, dp, dp, dp,
                                         C.c_int, i64p, dp, dp]
     lib.trixi_b200_set_eq_param.argtypes = [vp, C.c_int, C.c_double]
@@ -181,6 +182,12 @@ class B200Backend:
         a, b, c = (np.ascontiguousarray(x, dtype=np.float64) for x in (a, b, c))
         self._ck(self.lib.trixi_b200_step_2n(self.h, float(t), float(dt), _dptr(a), _dptr(b), _dptr(c), len(c)))
 
+    def step_2n_host(self, u_host, t, dt, a, b, c):
+        """One 2N Runge-Kutta step on a host-resident ``u`` (updated in place)."""
+        a, b, c = (np.ascontiguousarray(x, dtype=np.float64) for x in (a, b, c))
+        self._ck(self.lib.trixi_b200_step_2n_host(self.h, _dptr(_check_host(u_host, self.u_length, True)), float(t),
+                                                  float(dt), _dptr(a), _dptr(b), _dptr(c), len(c)))
+
     def solve_2n(self, t0, t_end, cfl, max_steps, a, b, c):
         a, b, c = (np.ascontiguousarray(x, dtype=np.float64) for x in (a, b, c))
         steps, t_out, dt_out = C.c_int64(), C.c_double(), C.c_double()
@@ -232,6 +239,7 @@ class B200Backend:
     OPT_KERNEL_PATH = 0
     OPT_FUSED_CFL = 1
     OPT_PREFETCH_DISTANCE = 2
+    OPT_HOST_PIPELINE_CHUNK = 3
 
     def set_option(self, option, value):
         self._ck(self.lib.trixi_b200_set_option(self.h, int(option), int(value)))

@@ -118,6 +118,14 @@ def step(integrator):
         integrator.terminate()
 
 
+def step_2n_host(u_ode, semi, t, dt, alg):
+    """The stage loop of ``step!(integrator::SimpleIntegrator2N)`` (methods_2N.jl:144-159) on a host-resident
+    ``u_ode`` (updated in place), for callers that keep the integrator's vectors in host memory like the
+    reference does: u travels to the device and back inside the call (trixi_b200_step_2n_host)."""
+    semi.backend().step_2n_host(u_ode, t, dt, alg.a, alg.b, alg.c)
+    return None
+
+
 class TimeIntegratorSolution:
     def __init__(self, t, u, prob, integrator):
         self.t, self.u, self.prob, self.integrator = t, u, prob, integrator
