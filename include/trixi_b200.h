@@ -218,6 +218,17 @@ TRIXI_B200_API int trixi_b200_step_2n(trixi_b200_handle *h, double t, double dt,
  * chunk-wise as it is finished.  Synchronises. */
 TRIXI_B200_API int trixi_b200_step_2n_host(trixi_b200_handle *h, double *u_host, double t, double dt, const double *a,
                                             const double *b, const double *c, int nstages);
+/* step!(integrator::SimpleIntegrator3Sstar) stage loop (methods_3Sstar.jl:186-207; tableaus
+ * ParsaniKetchesonDeconinck3Sstar94/32 :63-133): u_tmp1 <- 0, u_tmp2 <- u, then per stage du <- rhs(u, t + c_s dt),
+ * u_tmp1 += delta_s u, u <- gamma1_s u + gamma2_s u_tmp1 + gamma3_s u_tmp2 + beta_s dt du.  Asynchronous. */
+TRIXI_B200_API int trixi_b200_step_3sstar(trixi_b200_handle *h, double t, double dt, const double *gamma1, const double *gamma2,
+                                           const double *gamma3, const double *beta, const double *delta, const double *c,
+                                           int nstages);
+/* step!(integrator::SimpleIntegratorSSP) stage loop without stage callbacks (methods_SSP.jl:185-202, SimpleSSPRK33
+ * :23-52): u_tmp <- u, then per stage du <- rhs(u, t + c_s dt), u <- u + dt du,
+ * u <- (numerator_a_s u_tmp + numerator_b_s u) / denominator_s.  Asynchronous. */
+TRIXI_B200_API int trixi_b200_step_ssp(trixi_b200_handle *h, double t, double dt, const double *numerator_a,
+                                        const double *numerator_b, const double *denominator, const double *c, int nstages);
 /* `nsteps` steps with the CFL step size recomputed on the device after every step
  * (StepsizeCallback interval = 1, stepsize.jl:93-126) and the final step clipped to t_end
  * (time_integration.jl:46-55); no host round trip inside.  Returns the number of steps taken, the

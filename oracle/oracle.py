@@ -147,6 +147,25 @@ class OracleBackend:
                                 _p(self.interfaces_u), _p(self.boundaries_u), _p(self.sfv))
         self.nrhs += len(c)
 
+    def step_3sstar(self, t, dt, gamma1, gamma2, gamma3, beta, delta, c):
+        """step!(integrator::SimpleIntegrator3Sstar) stage loop (methods_3Sstar.jl:186-207)."""
+        u, du, u_tmp1 = self.vec
+        u_tmp1[:] = 0.0
+        u_tmp2 = u.copy()
+        for s in range(len(c)):
+            self.rhs_arrays(du, u, t + dt * c[s])
+            u_tmp1 += delta[s] * u
+            u[:] = gamma1[s] * u + gamma2[s] * u_tmp1 + gamma3[s] * u_tmp2 + (beta[s] * dt) * du
+
+    def step_ssp(self, t, dt, numerator_a, numerator_b, denominator, c):
+        """step!(integrator::SimpleIntegratorSSP) stage loop without stage callbacks (methods_SSP.jl:185-202)."""
+        u, du, u_tmp = self.vec
+        u_tmp[:] = u
+        for s in range(len(c)):
+            self.rhs_arrays(du, u, t + dt * c[s])
+            u += dt * du
+            u[:] = (numerator_a[s] * u_tmp + numerator_b[s] * u) / denominator[s]
+
     # stage-level ------------------------------------------------------------------------------------
     def calc_volume_integral(self):
         self.lib.oracle_set_zero(self.holder.byref(), _p(self.vec[1]))

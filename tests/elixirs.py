@@ -21,10 +21,11 @@ def initial_condition_density_wave_2d(x, t, equations):
 
 
 class Elixir:
-    def __init__(self, name, build, tspan, cfl, l2, linf, source, maxiters=None, rtol=1e-9, atol=2e-13):
+    def __init__(self, name, build, tspan, cfl, l2, linf, source, maxiters=None, rtol=1e-9, atol=2e-13,
+                 alg=T.CarpenterKennedy2N54):
         self.name, self.build, self.tspan, self.cfl = name, build, tspan, cfl
         self.l2, self.linf, self.source = np.array(l2), np.array(linf), source
-        self.maxiters, self.rtol, self.atol = maxiters, rtol, atol
+        self.maxiters, self.rtol, self.atol, self.alg = maxiters, rtol, atol, alg
 
     def semi(self, **overrides):
         return self.build(**overrides)
@@ -33,7 +34,7 @@ class Elixir:
         ode = T.semidiscretize(semi, self.tspan)
         analysis = T.AnalysisCallback(semi, interval=100)
         callbacks = T.CallbackSet(T.SummaryCallback(), analysis, T.StepsizeCallback(cfl=self.cfl))
-        sol = T.solve(ode, T.CarpenterKennedy2N54(), dt=1.0, callback=callbacks, maxiters=self.maxiters)
+        sol = T.solve(ode, self.alg(), dt=1.0, callback=callbacks, maxiters=self.maxiters)
         l2, linf = analysis(sol)
         return sol, l2, linf
 
@@ -356,7 +357,7 @@ class MhdElixir(Elixir):
         analysis = T.AnalysisCallback(semi, interval=100)
         callbacks = T.CallbackSet(T.SummaryCallback(), analysis, T.StepsizeCallback(cfl=self.cfl),
                                   T.GlmSpeedCallback(glm_scale=0.5, cfl=self.cfl))
-        sol = T.solve(ode, T.CarpenterKennedy2N54(), dt=1.0, callback=callbacks, maxiters=self.maxiters)
+        sol = T.solve(ode, self.alg(), dt=1.0, callback=callbacks, maxiters=self.maxiters)
         l2, linf = analysis(sol)
         return sol, l2, linf
 
@@ -507,6 +508,39 @@ ELIXIRS.update({e.name: e for e in [
             0.0034549095578444056],
            [0.011355360771142298, 0.011526889155693887, 0.011526889155689002, 0.011526889155701436,
             0.02299726519821288], "test/test_tree_3d_euler.jl:124-141"),
+]})
+
+
+def _advection2d_amr_initial():
+    # examples/tree_2d_dgsem/elixir_advection_timeintegration.jl restricted to its first step (maxiters = 1): the
+    # only AMR that happens is the AMRCallback's initial adaptation (amr.jl:143-167, refine only), i.e. the level-4
+    # mesh is refined where ControllerThreeLevel(IndicatorMax(first); base 4, med 5 > 0.1, max 6 > 0.6)
+    # (amr.jl:1116-1153, indicators_2d.jl IndicatorMax = max over the element's nodes) asks for it, the initial
+    # condition is re-evaluated, and this repeats until the mesh stops changing.  Mesh construction is host-side.
+    eq = T.LinearScalarAdvectionEquation2D((0.2, -0.7))
+    solver = T.DGSEM(polydeg=3, surface_flux=T.flux_lax_friedrichs)
+    mesh = T.TreeMesh((-5.0, -5.0), (5.0, 5.0), initial_refinement_level=4, periodicity=True)
+    for _ in range(10):
+        semi = T.SemidiscretizationHyperbolic(mesh, eq, T.initial_condition_gauss, solver)
+        u = T.compute_coefficients(0.0, semi)
+        alpha = u[0].reshape(-1, u.shape[-1], order="F").max(axis=0)
+        target = np.where(alpha > 0.6, 6, np.where(alpha > 0.1, 5, 4))
+        mask = mesh.levels < target
+        if not mask.any():
+            return semi
+        mesh.refine_cells(mask)
+    raise RuntimeError("initial AMR did not settle")
+
+
+ELIXIRS.update({e.name: e for e in [
+    # the other low-storage integrators, pinned on the one-step runs of the reference's
+    # time-integration tests
+    Elixir("tree_2d_advection_timeintegration_2n43_maxiters1", _advection2d_amr_initial, (0.0, 1.0), 1.0,
+           [1.2135350502911197e-5], [9.999985420537649e-5], "test/test_tree_2d_advection.jl:224-241", maxiters=1,
+           alg=T.CarpenterKennedy2N43),
+    Elixir("tree_2d_advection_timeintegration_3sstar32_maxiters1", _advection2d_amr_initial, (0.0, 1.0), 1.0,
+           [1.2198725469737875e-5], [9.977247740793407e-5], "test/test_tree_2d_advection.jl:278-295", maxiters=1,
+           alg=T.ParsaniKetchesonDeconinck3Sstar32),
 ]})
 
 

@@ -224,7 +224,29 @@ def test_step_2n_matches_oracle(name, oracle_module):
     assert _rel_err(gpu.download(2), ref.download(2)) <= 1e-11  # u_tmp
 
 
-GOLDEN_GPU = ["tree_3d_euler_ec", "tree_3d_euler_ec_constant", "tree_3d_euler_source_terms",
+@pytest.mark.parametrize("name", ["tree_3d_euler_ec", "tree_2d_advection_mortar", "structured_3d_euler_source_terms"])
+@pytest.mark.parametrize("alg", ["ParsaniKetchesonDeconinck3Sstar94", "ParsaniKetchesonDeconinck3Sstar32",
+                                 "SimpleSSPRK33", "CarpenterKennedy2N43"])
+def test_other_integrators_match_oracle(name, alg, oracle_module):
+    """Two steps of the 3S* (methods_3Sstar.jl:186-207), SSPRK33 (methods_SSP.jl:185-202) and 2N43 stage loops
+    against the oracle's restatement."""
+    from trixi_b200 import time_integration as ti
+    semi = ELIXIRS[name].semi()
+    u = T.compute_coefficients(0.0, semi)
+    a = getattr(T, alg)()
+    ref = oracle_module.OracleBackend(semi)
+    gpu = semi.backend()
+    ref.upload(0, u)
+    gpu.upload(0, u.ravel(order="F"))
+    dt = 0.5 * ref.max_dt()
+    for k in range(2):
+        ti._stage_loop(ref, a, 0.1 + k * dt, dt)
+        ti._stage_loop(gpu, a, 0.1 + k * dt, dt)
+    assert _rel_err(gpu.download(0), ref.download(0)) <= 1e-13
+
+
+GOLDEN_GPU = ["tree_2d_advection_timeintegration_2n43_maxiters1", "tree_2d_advection_timeintegration_3sstar32_maxiters1",
+              "tree_3d_euler_ec", "tree_3d_euler_ec_constant", "tree_3d_euler_source_terms",
               "tree_3d_euler_convergence", "tree_3d_euler_taylor_green_vortex", "tree_3d_euler_density_pulse",
               "tree_2d_advection_basic", "tree_2d_euler_source_terms", "tree_2d_euler_source_terms_nonperiodic",
               "tree_2d_euler_ec", "tree_2d_euler_density_wave", "structured_3d_euler_free_stream",

@@ -15,5 +15,6 @@ from .semidiscretization import (ODEProblem, SemidiscretizationHyperbolic, compu
                                  rhs_hyperbolic, semidiscretize)
 from .solver import (DGSEM, SurfaceIntegralWeakForm, VolumeIntegralFluxDifferencing,  # noqa: F401
                      VolumeIntegralWeakForm)
-from .time_integration import (CallbackSet, CarpenterKennedy2N43, CarpenterKennedy2N54, init,  # noqa: F401
-                               solve, step, step_2n_host)
+from .time_integration import (CallbackSet, CarpenterKennedy2N43, CarpenterKennedy2N54,  # noqa: F401
+                               ParsaniKetchesonDeconinck3Sstar32, ParsaniKetchesonDeconinck3Sstar94,
+                               SimpleSSPRK33, init, solve, step, step_2n_host)

@@ -37,6 +37,7 @@ struct trixi_b200_handle {
     bool have_elapsed = false;
     std::vector<void *> allocs;
     double *vec[3] = {nullptr, nullptr, nullptr};  // u, du, u_tmp
+    double *vec_tmp2 = nullptr;                     // u_tmp2 of the 3S* integrators (allocated at first use)
     unsigned long long *d_cfl = nullptr;
     unsigned long long *h_cfl = nullptr;  // pinned, kCflSlots entries
     double *norm_buf = nullptr;           // calc_error_norms scratch: Vandermonde, weights, sums
@@ -193,6 +194,28 @@ __global__ void k_fp64_peak(double *sink, int iters, double m) {
 __global__ void k_copy(double2 *dst, const double2 *src, size_t n) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[i] = src[i];
+}
+
+// Stage updates of the other low-storage integrators (pointwise, HBM-bound; not fused into the element kernel).
+// 3S* (methods_3Sstar.jl:199-205): u_tmp1 += delta u;  u = gamma1 u + gamma2 u_tmp1 + gamma3 u_tmp2 + beta dt du
+__global__ void k_stage_3sstar(double *__restrict__ u, double *__restrict__ u1, const double *__restrict__ u2,
+                               const double *__restrict__ du, size_t n, double delta, double g1, double g2, double g3,
+                               double bdt) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double ui = u[i];
+    const double t1 = fma(delta, ui, u1[i]);
+    u1[i] = t1;
+    u[i] = fma(bdt, du[i], fma(g3, u2[i], fma(g2, t1, g1 * ui)));
+}
+// SimpleSSPRK33 (methods_SSP.jl:192-201): forward Euler step, then the convex combination with numerator and
+// denominator kept apart (a true division, like the reference, so that conservation is not eroded by rounding)
+__global__ void k_stage_ssp(double *__restrict__ u, const double *__restrict__ u_tmp, const double *__restrict__ du,
+                            size_t n, double dt, double na, double nb, double den) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double ue = fma(dt, du[i], u[i]);
+    u[i] = fma(na, u_tmp[i], nb * ue) / den;
 }
 
 // start_mpi_send! completion: after the pack kernel (stream order) every peer's flag for me is raised to
@@ -1077,6 +1100,65 @@ TRIXI_B200_API int trixi_b200_step_2n_host(trixi_b200_handle *h, double *u_host,
     CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
     h->have_elapsed = true;
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+TRIXI_B200_API int trixi_b200_step_3sstar(trixi_b200_handle *h, double t, double dt, const double *gamma1, const double *gamma2,
+                                           const double *gamma3, const double *beta, const double *delta, const double *c,
+                                           int nstages) {
+    if (!h || !gamma1 || !gamma2 || !gamma3 || !beta || !delta || !c || nstages <= 0)
+        return h ? fail(h, TRIXI_B200_EINVAL, "bad Runge-Kutta tableau") : TRIXI_B200_EINVAL;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    if (!h->vec_tmp2) {
+        int rc = alloc_array(h, (size_t)h->ulen, &h->vec_tmp2);
+        if (rc) return rc;
+    }
+    const size_t n = (size_t)h->ulen, bytes = n * sizeof(double);
+    CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
+    h->cfl_valid = false;
+    // u_tmp1 .= 0; u_tmp2 .= u (methods_3Sstar.jl:187-188)
+    CUDA_TRY(h, cudaMemsetAsync(h->vec[2], 0, bytes, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(h->vec_tmp2, h->vec[0], bytes, cudaMemcpyDeviceToDevice, h->stream));
+    for (int s = 0; s < nstages; ++s) {
+        int rc = run_rhs(h, t + dt * c[s]);
+        if (rc) return rc;
+        if (n) {
+            k_stage_3sstar<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->vec[0], h->vec[2], h->vec_tmp2, h->vec[1], n,
+                                                                                 delta[s], gamma1[s], gamma2[s], gamma3[s],
+                                                                                 beta[s] * dt);
+            h->launches++;
+        }
+        rc = check_launch(h, "3S* stage kernel");
+        if (rc) return rc;
+    }
+    CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
+    h->have_elapsed = true;
+    return 0;
+}
+
+TRIXI_B200_API int trixi_b200_step_ssp(trixi_b200_handle *h, double t, double dt, const double *numerator_a,
+                                        const double *numerator_b, const double *denominator, const double *c, int nstages) {
+    if (!h || !numerator_a || !numerator_b || !denominator || !c || nstages <= 0)
+        return h ? fail(h, TRIXI_B200_EINVAL, "bad Runge-Kutta tableau") : TRIXI_B200_EINVAL;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const size_t n = (size_t)h->ulen, bytes = n * sizeof(double);
+    CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
+    h->cfl_valid = false;
+    // u_tmp .= u (methods_SSP.jl:185)
+    CUDA_TRY(h, cudaMemcpyAsync(h->vec[2], h->vec[0], bytes, cudaMemcpyDeviceToDevice, h->stream));
+    for (int s = 0; s < nstages; ++s) {
+        int rc = run_rhs(h, t + dt * c[s]);
+        if (rc) return rc;
+        if (n) {
+            k_stage_ssp<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->vec[0], h->vec[2], h->vec[1], n, dt,
+                                                                              numerator_a[s], numerator_b[s], denominator[s]);
+            h->launches++;
+        }
+        rc = check_launch(h, "SSP stage kernel");
+        if (rc) return rc;
+    }
+    CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
+    h->have_elapsed = true;
     return 0;
 }
 

@@ -316,6 +316,20 @@ def initial_condition_convergence_test(x, t, equations):
     raise NotImplementedError
 
 
+def initial_condition_gauss(x, t, equations):
+    """linear_scalar_advection_2d.jl:88-94 with the periodic translation x_trans_periodic_2d (:43-49, domain
+    length 10, centre 0; Julia's % is the remainder with the sign of the dividend).  Host only."""
+    if not isinstance(equations, LinearScalarAdvectionEquation2D):
+        raise NotImplementedError
+    a = equations.advection_velocity
+    xs = []
+    for d in range(2):
+        shifted = np.fmod(x[d] - a[d] * t, 10.0)
+        offset = ((shifted < -5.0).astype(float) - (shifted > 5.0).astype(float)) * 10.0
+        xs.append(shifted + offset)
+    return np.exp(-(xs[0]**2 + xs[1]**2))[None]
+
+
 @_ic(IC_WEAK_BLAST_WAVE)
 def initial_condition_weak_blast_wave(x, t, equations):
     if isinstance(equations, CompressibleEulerEquations3D):

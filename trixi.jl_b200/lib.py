@@ -20,7 +20,8 @@ EXPORTS = [
     "trixi_b200_create", "trixi_b200_destroy", "trixi_b200_last_error", "trixi_b200_abi_version",
     "trixi_b200_upload", "trixi_b200_download", "trixi_b200_device_ptr", "trixi_b200_synchronize",
     "trixi_b200_stream", "trixi_b200_rhs_host", "trixi_b200_rhs", "trixi_b200_max_dt",
-    "trixi_b200_step_2n", "trixi_b200_step_2n_host", "trixi_b200_solve_2n", "trixi_b200_set_eq_param", "trixi_b200_calc_error_norms",
+    "trixi_b200_step_2n", "trixi_b200_step_2n_host", "trixi_b200_step_3sstar", "trixi_b200_step_ssp",
+    "trixi_b200_solve_2n", "trixi_b200_set_eq_param", "trixi_b200_calc_error_norms",
     "trixi_b200_calc_volume_integral", "trixi_b200_calc_surface_fluxes",
     "trixi_b200_download_surface_flux_values", "trixi_b200_comm_info_size", "trixi_b200_comm_info",
     "trixi_b200_comm_connect",
@@ -68,6 +69,8 @@ def load_library(path=None):
     lib.trixi_b200_max_dt.argtypes = [vp, C.c_double, dp]
     lib.trixi_b200_step_2n.argtypes = [vp, C.c_double, C.c_double, dp, dp, dp, C.c_int]
     lib.trixi_b200_step_2n_host.argtypes = [vp, dp, C.c_double, C.c_double, dp, dp, dp, C.c_int]
+    lib.trixi_b200_step_3sstar.argtypes = [vp, C.c_double, C.c_double, dp, dp, dp, dp, dp, dp, C.c_int]
+    lib.trixi_b200_step_ssp.argtypes = [vp, C.c_double, C.c_double, dp, dp, dp, dp, C.c_int]
     lib.trixi_b200_solve_2n.argtypes = [vp, C.c_double, C.c_double, C.c_double, C.c_int64, dp, dp, dp,
                                         C.c_int, i64p, dp, dp]
     lib.trixi_b200_set_eq_param.argtypes = [vp, C.c_int, C.c_double]
@@ -187,6 +190,14 @@ class B200Backend:
         a, b, c = (np.ascontiguousarray(x, dtype=np.float64) for x in (a, b, c))
         self._ck(self.lib.trixi_b200_step_2n_host(self.h, _dptr(_check_host(u_host, self.u_length, True)), float(t),
                                                   float(dt), _dptr(a), _dptr(b), _dptr(c), len(c)))
+
+    def step_3sstar(self, t, dt, gamma1, gamma2, gamma3, beta, delta, c):
+        arrs = [np.ascontiguousarray(x, dtype=np.float64) for x in (gamma1, gamma2, gamma3, beta, delta, c)]
+        self._ck(self.lib.trixi_b200_step_3sstar(self.h, float(t), float(dt), *[_dptr(x) for x in arrs], len(c)))
+
+    def step_ssp(self, t, dt, numerator_a, numerator_b, denominator, c):
+        arrs = [np.ascontiguousarray(x, dtype=np.float64) for x in (numerator_a, numerator_b, denominator, c)]
+        self._ck(self.lib.trixi_b200_step_ssp(self.h, float(t), float(dt), *[_dptr(x) for x in arrs], len(c)))
 
     def solve_2n(self, t0, t_end, cfl, max_steps, a, b, c):
         a, b, c = (np.ascontiguousarray(x, dtype=np.float64) for x in (a, b, c))

@@ -43,6 +43,65 @@ class CarpenterKennedy2N43:
         self.c = np.array([0.0, 8.0 / 141.0, 86.0 / 125.0, 1.0])
 
 
+class ParsaniKetchesonDeconinck3Sstar94:
+    """Nine-stage, fourth-order 3S* scheme; coefficients from methods_3Sstar.jl:63-96 (Parsani, Ketcheson,
+    Deconinck 2013, DOI 10.1137/120885899)."""
+
+    def __init__(self):
+        self.gamma1 = np.array([0.0000000000000000E+00, -4.6556413837561301E+00, -7.7202649689034453E-01,
+                                -4.0244202720632174E+00, -2.1296873883702272E-02, -2.4350219407769953E+00,
+                                1.9856336960249132E-02, -2.8107894116913812E-01, 1.6894354373677900E-01])
+        self.gamma2 = np.array([1.0000000000000000E+00, 2.4992627683300688E+00, 5.8668202764174726E-01,
+                                1.2051419816240785E+00, 3.4747937498564541E-01, 1.3213458736302766E+00,
+                                3.1196363453264964E-01, 4.3514189245414447E-01, 2.3596980658341213E-01])
+        self.gamma3 = np.array([0.0000000000000000E+00, 0.0000000000000000E+00, 0.0000000000000000E+00,
+                                7.6209857891449362E-01, -1.9811817832965520E-01, -6.2289587091629484E-01,
+                                -3.7522475499063573E-01, -3.3554373281046146E-01, -4.5609629702116454E-02])
+        self.beta = np.array([2.8363432481011769E-01, 9.7364980747486463E-01, 3.3823592364196498E-01,
+                              -3.5849518935750763E-01, -4.1139587569859462E-03, 1.4279689871485013E+00,
+                              1.8084680519536503E-02, 1.6057708856060501E-01, 2.9522267863254809E-01])
+        self.delta = np.array([1.0000000000000000E+00, 1.2629238731608268E+00, 7.5749675232391733E-01,
+                               5.1635907196195419E-01, -2.7463346616574083E-02, -4.3826743572318672E-01,
+                               1.2735870231839268E+00, -6.2947382217730230E-01, 0.0000000000000000E+00])
+        self.c = np.array([0.0000000000000000E+00, 2.8363432481011769E-01, 5.4840742446661772E-01,
+                           3.6872298094969475E-01, -6.8061183026103156E-01, 3.5185265855105619E-01,
+                           1.6659419385562171E+00, 9.7152778807463247E-01, 9.0515694340066954E-01])
+
+
+class ParsaniKetchesonDeconinck3Sstar32:
+    """Three-stage, second-order 3S* scheme; coefficients from methods_3Sstar.jl:114-133."""
+
+    def __init__(self):
+        self.gamma1 = np.array([0.0000000000000000E+00, -1.2664395576322218E-01, 1.1426980685848858E+00])
+        self.gamma2 = np.array([1.0000000000000000E+00, 6.5427782599406470E-01, -8.2869287683723744E-02])
+        self.gamma3 = np.array([0.0, 0.0, 0.0])
+        self.beta = np.array([7.2366074728360086E-01, 3.4217876502651023E-01, 3.6640216242653251E-01])
+        self.delta = np.array([1.0000000000000000E+00, 7.2196567116037724E-01, 0.0000000000000000E+00])
+        self.c = np.array([0.0000000000000000E+00, 7.2366074728360086E-01, 5.9236433182015646E-01])
+
+
+class SimpleSSPRK33:
+    """Shu-Osher SSPRK(3,3) with numerators and denominators kept apart (methods_SSP.jl:23-52); stage callbacks
+    (subcell limiters) are outside the hot path and not supported."""
+
+    def __init__(self):
+        self.numerator_a = np.array([0.0, 3.0, 1.0])
+        self.numerator_b = np.array([1.0, 1.0, 2.0])
+        self.denominator = np.array([1.0, 4.0, 3.0])
+        self.c = np.array([0.0, 1.0, 0.5])
+
+
+def _stage_loop(backend, alg, t, dt):
+    """Dispatch on the algorithm type like the reference's step! methods (methods_2N.jl:131, methods_3Sstar.jl:173,
+    methods_SSP.jl:170)."""
+    if isinstance(alg, (ParsaniKetchesonDeconinck3Sstar94, ParsaniKetchesonDeconinck3Sstar32)):
+        backend.step_3sstar(t, dt, alg.gamma1, alg.gamma2, alg.gamma3, alg.beta, alg.delta, alg.c)
+    elif isinstance(alg, SimpleSSPRK33):
+        backend.step_ssp(t, dt, alg.numerator_a, alg.numerator_b, alg.denominator, alg.c)
+    else:
+        backend.step_2n(t, dt, alg.a, alg.b, alg.c)
+
+
 class CallbackSet:
     def __init__(self, *callbacks):
         self.discrete_callbacks = [cb for cb in callbacks if cb is not None]
@@ -55,7 +114,8 @@ class _Stats:
 
 
 class SimpleIntegrator2N:
-    """methods_2N.jl:95-111.  ``u`` lives on the device (handle-owned); ``integrator.u`` downloads."""
+    """methods_2N.jl:95-111 (and SimpleIntegrator3Sstar methods_3Sstar.jl:136-155, SimpleIntegratorSSP
+    methods_SSP.jl:77-102: same facade, the algorithm type selects the stage loop).  ``u`` lives on the device (handle-owned); ``integrator.u`` downloads."""
 
     def __init__(self, ode, alg, dt, callback, maxiters=None):
         self.semi = self.p = ode.p
@@ -105,7 +165,7 @@ def step(integrator):
     if math.isnan(integrator.dt):
         raise RuntimeError("time step size `dt` is NaN")
     limit_dt(integrator, t_end)
-    integrator.backend.step_2n(integrator.t, integrator.dt, alg.a, alg.b, alg.c)
+    _stage_loop(integrator.backend, alg, integrator.t, integrator.dt)
     integrator.stats.nf += len(alg.c)
     integrator.iter += 1
     integrator.stats.naccept += 1
