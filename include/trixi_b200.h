@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define TRIXI_B200_ABI_VERSION 3
+#define TRIXI_B200_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define TRIXI_B200_API __attribute__((visibility("default")))
@@ -52,7 +52,18 @@ enum {
 };
 
 /* volume integral types (src/solvers/dg.jl:105,135-141) */
-enum { TRIXI_B200_VOLINT_WEAK_FORM = 0, TRIXI_B200_VOLINT_FLUX_DIFFERENCING = 1 };
+enum {
+    TRIXI_B200_VOLINT_WEAK_FORM = 0,
+    TRIXI_B200_VOLINT_FLUX_DIFFERENCING = 1,
+    /* VolumeIntegralShockCapturingHG(indicator; volume_flux_dg, volume_flux_fv) (solvers/dg.jl; driver
+     * dgsem/calc_volume_integral.jl:231-272): per element a blend (1 - alpha) flux differencing + alpha first-order
+     * subcell finite volumes (fv_kernel! dg_3d.jl:268-306), alpha from IndicatorHennemannGassner.  TreeMesh,
+     * conservative equations, single rank. */
+    TRIXI_B200_VOLINT_SHOCK_CAPTURING_HG = 2
+};
+
+/* indicator variables of IndicatorHennemannGassner (compressible_euler_3d.jl:1945-1956 and 2D analogues) */
+enum { TRIXI_B200_INDVAR_DENSITY_PRESSURE = 0, TRIXI_B200_INDVAR_DENSITY = 1, TRIXI_B200_INDVAR_PRESSURE = 2 };
 
 /* numerical fluxes (src/equations/numerical_fluxes.jl, compressible_euler_3d.jl) */
 enum {
@@ -167,6 +178,15 @@ typedef struct trixi_b200_desc {
     /* P4est MPI interface container (dgsem_p4est/containers_parallel.jl:8-28): node_indices of the local side
      * [ndims, nmpiinterfaces], same encoding; the exchanged face states are aligned at the primary element */
     const int64_t *mpi_node_indices;
+
+    /* VolumeIntegralShockCapturingHG: volume_flux above is volume_flux_dg; IndicatorHennemannGassner
+     * (dgsem/indicators.jl:48-70,114-148; dgsem_tree/indicators_3d.jl:41-131, indicators_2d.jl:26-98) */
+    int32_t volume_flux_fv;          /* TRIXI_B200_FLUX_* of the subcell finite volume fluxes */
+    int32_t indicator_variable;      /* TRIXI_B200_INDVAR_* */
+    int32_t indicator_alpha_smooth;  /* apply_smoothing! over interfaces and mortars (indicators_3d.jl:133-186) */
+    int32_t reserved1;
+    double indicator_alpha_max, indicator_alpha_min;
+    const double *inverse_vandermonde_legendre; /* [n, n] column-major (basis_lobatto_legendre.jl:711-724) */
 } trixi_b200_desc;
 
 typedef struct trixi_b200_handle trixi_b200_handle;
@@ -271,6 +291,9 @@ TRIXI_B200_API int trixi_b200_calc_volume_integral(trixi_b200_handle *h);
  * (dg_3d.jl:530-602,651-768) -> surface_flux_values[nvars, n^(d-1), 2*ndims, nelements] */
 TRIXI_B200_API int trixi_b200_calc_surface_fluxes(trixi_b200_handle *h, double t);
 TRIXI_B200_API int trixi_b200_download_surface_flux_values(trixi_b200_handle *h, double *host);
+/* the blending factors alpha [nelements] of IndicatorHennemannGassner for the device-resident u (what the
+ * reference exposes as element variable :indicator_shock_capturing, indicators.jl:20-24); runs the indicator */
+TRIXI_B200_API int trixi_b200_calc_indicator(trixi_b200_handle *h, double *alpha_host);
 
 /* ---- distributed halo exchange (replaces the MPI Isend/Irecv of dg_parallel.jl:66-182) ----------------
  * One handle per rank/GPU.  Every handle with world_size > 1 owns a receive buffer that its neighbour

@@ -24,7 +24,7 @@ using Trixi: TreeMesh, StructuredMesh, P4estMesh, DG, DGSEM, SemidiscretizationH
 const libtrixi_b200 = get(ENV, "TRIXI_B200_LIBRARY", "libtrixi_b200.so")
 
 # ---- enums of include/trixi_b200.h ------------------------------------------------------------------
-const ABI_VERSION = Int32(3)
+const ABI_VERSION = Int32(4)
 mesh_kind(::TreeMesh) = Cint(0)
 mesh_kind(::StructuredMesh) = Cint(1)
 mesh_kind(::P4estMesh) = Cint(2)

@@ -166,6 +166,12 @@ class OracleBackend:
             u += dt * du
             u[:] = (numerator_a[s] * u_tmp + numerator_b[s] * u) / denominator[s]
 
+    def calc_indicator(self):
+        """IndicatorHennemannGassner blending factors of the resident u (dgsem/indicators.jl:114-148)."""
+        alpha = np.zeros(self.desc.nelements)
+        self.lib.oracle_calc_indicator_hg(self.holder.byref(), _p(alpha), _p(self.vec[0]))
+        return alpha
+
     # stage-level ------------------------------------------------------------------------------------
     def calc_volume_integral(self):
         self.lib.oracle_set_zero(self.holder.byref(), _p(self.vec[1]))

@@ -835,7 +835,8 @@ static void weak_form_kernel(const trixi_b200_desc *d, const eqn_t *eq, double *
 }
 
 /* flux_differencing_kernel! dg_3d.jl:166-214 / dg_2d.jl:223-259 */
-static void flux_differencing_kernel(const trixi_b200_desc *d, const eqn_t *eq, double *du, const double *u) {
+static void flux_differencing_kernel(const trixi_b200_desc *d, const eqn_t *eq, double *du, const double *u,
+                                     double alpha) {
     int n = d->nnodes, nd = d->ndims, nv = d->nvars;
     int n3 = nd == 3 ? n : 1;
     const double *Ds = d->derivative_split;
@@ -849,14 +850,14 @@ static void flux_differencing_kernel(const trixi_b200_desc *d, const eqn_t *eq, 
                 for (int ii = i + 1; ii < n; ++ii) {
                     int64_t node2 = ii + n * (j + n * k);
                     numflux(eq, vf, un, u + nv * node2, 0, f);
-                    double w1 = Ds[i + n * ii], w2 = Ds[ii + n * i];
+                    double w1 = alpha * Ds[i + n * ii], w2 = alpha * Ds[ii + n * i];
                     for (int v = 0; v < nv; ++v) du[nv * node + v] = du[nv * node + v] + w1 * f[v];
                     for (int v = 0; v < nv; ++v) du[nv * node2 + v] = du[nv * node2 + v] + w2 * f[v];
                 }
                 for (int jj = j + 1; jj < n; ++jj) {
                     int64_t node2 = i + n * (jj + n * k);
                     numflux(eq, vf, un, u + nv * node2, 1, f);
-                    double w1 = Ds[j + n * jj], w2 = Ds[jj + n * j];
+                    double w1 = alpha * Ds[j + n * jj], w2 = alpha * Ds[jj + n * j];
                     for (int v = 0; v < nv; ++v) du[nv * node + v] = du[nv * node + v] + w1 * f[v];
                     for (int v = 0; v < nv; ++v) du[nv * node2 + v] = du[nv * node2 + v] + w2 * f[v];
                 }
@@ -864,7 +865,7 @@ static void flux_differencing_kernel(const trixi_b200_desc *d, const eqn_t *eq, 
                     for (int kk = k + 1; kk < n; ++kk) {
                         int64_t node2 = i + n * (j + n * kk);
                         numflux(eq, vf, un, u + nv * node2, 2, f);
-                        double w1 = Ds[k + n * kk], w2 = Ds[kk + n * k];
+                        double w1 = alpha * Ds[k + n * kk], w2 = alpha * Ds[kk + n * k];
                         for (int v = 0; v < nv; ++v) du[nv * node + v] = du[nv * node + v] + w1 * f[v];
                         for (int v = 0; v < nv; ++v) du[nv * node2 + v] = du[nv * node2 + v] + w2 * f[v];
                     }
@@ -895,16 +896,179 @@ static void flux_differencing_noncons(const trixi_b200_desc *d, const eqn_t *eq,
             }
 }
 
-/* calc_volume_integral! calc_volume_integral.jl:180-191 (+ dispatch :11-33) */
+
+/* ---- VolumeIntegralShockCapturingHG -------------------------------------------------------------- */
+/* density_pressure / density / pressure (compressible_euler_3d.jl:1937-1956, compressible_euler_2d.jl analogues) */
+static inline double indicator_variable(const trixi_b200_desc *d, const eqn_t *eq, const double *u) {
+    int nd = d->ndims;
+    double rho = u[0], rho_e = u[nd + 1], q = 0.0;
+    for (int a = 0; a < nd; ++a) q = q + u[1 + a] * u[1 + a];
+    switch (d->indicator_variable) {
+    case TRIXI_B200_INDVAR_DENSITY: return rho;
+    case TRIXI_B200_INDVAR_PRESSURE: return (eq->gamma - 1) * (rho_e - 0.5 * q / rho);
+    default: return (eq->gamma - 1) * (rho * rho_e - 0.5 * q);
+    }
+}
+
+/* calc_indicator_hennemann_gassner! (dgsem_tree/indicators_3d.jl:41-131, indicators_2d.jl:26-98) for one element */
+static double indicator_hg_element(const trixi_b200_desc *d, const eqn_t *eq, const double *u, double threshold,
+                                   double parameter_s) {
+    int n = d->nnodes, nd = d->ndims, nv = d->nvars;
+    int n3 = nd == 3 ? n : 1, nn = ipow(n, nd);
+    const double *V = d->inverse_vandermonde_legendre; /* [n, n] column-major */
+    double ind[512], tmp1[512], tmp2[512], modal_buf[512];
+    double *modal = modal_buf;
+    for (int q = 0; q < nn; ++q) ind[q] = indicator_variable(d, eq, u + (int64_t)nv * q);
+    /* multiply_scalar_dimensionwise! (interpolation.jl:207-234, 348-389): x, then y, then z */
+    for (int k = 0; k < n3; ++k)
+        for (int j = 0; j < n; ++j)
+            for (int i = 0; i < n; ++i) {
+                double res = 0.0;
+                for (int ii = 0; ii < n; ++ii) res = res + V[i + n * ii] * ind[ii + n * (j + n * k)];
+                tmp1[i + n * (j + n * k)] = res;
+            }
+    for (int k = 0; k < n3; ++k)
+        for (int j = 0; j < n; ++j)
+            for (int i = 0; i < n; ++i) {
+                double res = 0.0;
+                for (int jj = 0; jj < n; ++jj) res = res + V[j + n * jj] * tmp1[i + n * (jj + n * k)];
+                tmp2[i + n * (j + n * k)] = res;
+            }
+    if (nd == 3) {
+        for (int k = 0; k < n; ++k)
+            for (int j = 0; j < n; ++j)
+                for (int i = 0; i < n; ++i) {
+                    double res = 0.0;
+                    for (int kk = 0; kk < n; ++kk) res = res + V[k + n * kk] * tmp2[i + n * (j + n * kk)];
+                    modal[i + n * (j + n * k)] = res;
+                }
+    } else
+        modal = tmp2;
+#define M3(i, j, k) modal[(i) + n * ((j) + n * (k))]
+    double clip2 = 0.0, clip1, total;
+    if (nd == 3) {
+        for (int k = 0; k < n - 2; ++k)
+            for (int j = 0; j < n - 2; ++j)
+                for (int i = 0; i < n - 2; ++i) clip2 += M3(i, j, k) * M3(i, j, k);
+        clip1 = clip2;
+        for (int j = 0; j < n - 1; ++j)
+            for (int i = 0; i < n - 1; ++i) clip1 += M3(i, j, n - 2) * M3(i, j, n - 2);
+        for (int k = 0; k < n - 2; ++k)
+            for (int i = 0; i < n - 1; ++i) clip1 += M3(i, n - 2, k) * M3(i, n - 2, k);
+        for (int k = 0; k < n - 2; ++k)
+            for (int j = 0; j < n - 2; ++j) clip1 += M3(n - 2, j, k) * M3(n - 2, j, k);
+        total = clip1;
+        for (int j = 0; j < n; ++j)
+            for (int i = 0; i < n; ++i) total += M3(i, j, n - 1) * M3(i, j, n - 1);
+        for (int k = 0; k < n - 1; ++k)
+            for (int i = 0; i < n; ++i) total += M3(i, n - 1, k) * M3(i, n - 1, k);
+        for (int k = 0; k < n - 1; ++k)
+            for (int j = 0; j < n - 1; ++j) total += M3(n - 1, j, k) * M3(n - 1, j, k);
+    } else {
+        for (int j = 0; j < n - 2; ++j)
+            for (int i = 0; i < n - 2; ++i) clip2 += M3(i, j, 0) * M3(i, j, 0);
+        clip1 = clip2;
+        for (int i = 0; i < n - 1; ++i) clip1 += M3(i, n - 2, 0) * M3(i, n - 2, 0);
+        for (int j = 0; j < n - 2; ++j) clip1 += M3(n - 2, j, 0) * M3(n - 2, j, 0);
+        total = clip1;
+        for (int i = 0; i < n; ++i) total += M3(i, n - 1, 0) * M3(i, n - 1, 0);
+        for (int j = 0; j < n - 1; ++j) total += M3(n - 1, j, 0) * M3(n - 1, j, 0);
+    }
+#undef M3
+    double frac1 = total != 0.0 ? (total - clip1) / total : 0.0;
+    double frac2 = clip1 != 0.0 ? (clip1 - clip2) / clip1 : 0.0;
+    double energy = frac1 > frac2 ? frac1 : frac2;
+    double alpha = 1 / (1 + exp(-parameter_s / threshold * (energy - threshold)));
+    if (alpha < d->indicator_alpha_min) alpha = 0.0;
+    if (alpha > 1 - d->indicator_alpha_min) alpha = 1.0;
+    return alpha < d->indicator_alpha_max ? alpha : d->indicator_alpha_max;
+}
+
+static inline double max3(double a, double b, double c) {
+    double m = a > b ? a : b;
+    return m > c ? m : c;
+}
+
+/* (indicator_hg::IndicatorHennemannGassner)(u, mesh, equations, dg, cache) (dgsem/indicators.jl:114-148) with
+ * apply_smoothing! (indicators_3d.jl:133-186, indicators_2d.jl:101-138); alpha [nelements] */
+void oracle_calc_indicator_hg(const trixi_b200_desc *d, double *alpha, const double *u) {
+    eqn_t eq = make_eqn(d);
+    int n = d->nnodes, nd = d->ndims;
+    int64_t esz = (int64_t)d->nvars * ipow(n, nd);
+    double threshold = 0.5 * pow(10.0, -1.8 * pow((double)n, 0.25));
+    double parameter_s = log((1 - 0.0001) / 0.0001);
+#pragma omp parallel for schedule(static)
+    for (int64_t e = 0; e < d->nelements; ++e) alpha[e] = indicator_hg_element(d, &eq, u + e * esz, threshold, parameter_s);
+    if (!d->indicator_alpha_smooth) return;
+    double *tmp = (double *)malloc(sizeof(double) * (size_t)(d->nelements > 0 ? d->nelements : 1));
+    memcpy(tmp, alpha, sizeof(double) * (size_t)d->nelements);
+    for (int64_t I = 0; I < d->ninterfaces; ++I) {
+        int64_t l = d->interface_neighbor_ids[2 * I] - 1, r = d->interface_neighbor_ids[2 * I + 1] - 1;
+        alpha[l] = max3(tmp[l], 0.5 * tmp[r], alpha[l]);
+        alpha[r] = max3(tmp[r], 0.5 * tmp[l], alpha[r]);
+    }
+    int ns = 1 << (nd - 1);
+    for (int64_t M = 0; M < d->nmortars; ++M) {
+        const int64_t *ids = d->mortar_neighbor_ids + (int64_t)(ns + 1) * M;
+        int64_t large = ids[ns] - 1;
+        for (int q = 0; q < ns; ++q) {
+            int64_t sm = ids[q] - 1;
+            alpha[sm] = max3(tmp[sm], 0.5 * tmp[large], alpha[sm]);
+        }
+        for (int q = 0; q < ns; ++q) alpha[large] = max3(tmp[large], 0.5 * tmp[ids[q] - 1], alpha[large]);
+    }
+    free(tmp);
+}
+
+/* fv_kernel! + calcflux_fv! (dg_3d.jl:268-306,352-384; dg_2d.jl analogues): first-order subcell finite volumes,
+ * fstar = 0 on the element boundary */
+static void fv_kernel(const trixi_b200_desc *d, const eqn_t *eq, double *du, const double *u, double alpha) {
+    int n = d->nnodes, nd = d->ndims, nv = d->nvars;
+    int n3 = nd == 3 ? n : 1;
+    const double *iw = d->inverse_weights;
+    int stride[3] = {1, n, n * n};
+    for (int k = 0; k < n3; ++k)
+        for (int j = 0; j < n; ++j)
+            for (int i = 0; i < n; ++i) {
+                int idx[3] = {i, j, k};
+                int64_t node = i + n * (j + n * k);
+                double sum[MAXV] = {0};
+                for (int a = 0; a < nd; ++a) {
+                    double fl[MAXV] = {0}, fr[MAXV] = {0}; /* fstar_R[idx], fstar_L[idx + 1] */
+                    if (idx[a] > 0) numflux(eq, d->volume_flux_fv, u + nv * (node - stride[a]), u + nv * node, a, fl);
+                    if (idx[a] < n - 1) numflux(eq, d->volume_flux_fv, u + nv * node, u + nv * (node + stride[a]), a, fr);
+                    for (int v = 0; v < nv; ++v) sum[v] = sum[v] + iw[idx[a]] * (fr[v] - fl[v]);
+                }
+                for (int v = 0; v < nv; ++v) du[nv * node + v] = du[nv * node + v] + alpha * sum[v];
+            }
+}
+
+/* calc_volume_integral! calc_volume_integral.jl:180-191 (+ dispatch :11-33); shock capturing :231-272 */
 void oracle_calc_volume_integral(const trixi_b200_desc *d, double *du, const double *u) {
     eqn_t eq = make_eqn(d);
     int64_t esz = (int64_t)d->nvars * ipow(d->nnodes, d->ndims);
+    if (d->volume_integral == TRIXI_B200_VOLINT_SHOCK_CAPTURING_HG) {
+        double *alpha = (double *)malloc(sizeof(double) * (size_t)(d->nelements > 0 ? d->nelements : 1));
+        oracle_calc_indicator_hg(d, alpha, u);
+        const double atol = 1.8189894035458565e-12; /* max(100 eps, eps^0.75) for Float64 */
+#pragma omp parallel for schedule(static)
+        for (int64_t e = 0; e < d->nelements; ++e) {
+            if (fabs(alpha[e]) <= atol) /* isapprox(alpha, 0, atol): pure DG */
+                flux_differencing_kernel(d, &eq, du + e * esz, u + e * esz, 1.0);
+            else {
+                flux_differencing_kernel(d, &eq, du + e * esz, u + e * esz, 1 - alpha[e]);
+                fv_kernel(d, &eq, du + e * esz, u + e * esz, alpha[e]);
+            }
+        }
+        free(alpha);
+        return;
+    }
 #pragma omp parallel for schedule(static)
     for (int64_t e = 0; e < d->nelements; ++e) {
         if (d->volume_integral == TRIXI_B200_VOLINT_WEAK_FORM)
             weak_form_kernel(d, &eq, du + e * esz, u + e * esz);
         else {
-            flux_differencing_kernel(d, &eq, du + e * esz, u + e * esz);
+            flux_differencing_kernel(d, &eq, du + e * esz, u + e * esz, 1.0);
             if (flux_has_noncons(d->volume_flux)) flux_differencing_noncons(d, &eq, du + e * esz, u + e * esz);
         }
     }

@@ -544,6 +544,60 @@ ELIXIRS.update({e.name: e for e in [
 ]})
 
 
+def _shockcapturing(eq, volume_flux, surface_flux):
+    basis = T.LobattoLegendreBasis(3)
+    indicator_sc = T.IndicatorHennemannGassner(eq, basis, alpha_max=0.5, alpha_min=0.001, alpha_smooth=True,
+                                               variable=T.density_pressure)
+    volume_integral = T.VolumeIntegralShockCapturingHG(indicator_sc, volume_flux_dg=volume_flux,
+                                                       volume_flux_fv=surface_flux)
+    return T.DGSEM(basis=basis, surface_flux=surface_flux, volume_integral=volume_integral)
+
+
+def _euler3d_shockcapturing(level=3):
+    # examples/tree_3d_dgsem/elixir_euler_shockcapturing.jl
+    eq = T.CompressibleEulerEquations3D(1.4)
+    solver = _shockcapturing(eq, T.flux_ranocha, T.flux_ranocha)
+    mesh = T.TreeMesh((-2.0,) * 3, (2.0,) * 3, initial_refinement_level=level, periodicity=True)
+    return T.SemidiscretizationHyperbolic(mesh, eq, T.initial_condition_weak_blast_wave, solver,
+                                          boundary_conditions=T.boundary_condition_periodic)
+
+
+def _euler2d_shockcapturing(level=5):
+    # examples/tree_2d_dgsem/elixir_euler_shockcapturing.jl
+    eq = T.CompressibleEulerEquations2D(1.4)
+    solver = _shockcapturing(eq, T.flux_shima_etal, T.FluxLaxFriedrichs(T.max_abs_speed_naive))
+    mesh = T.TreeMesh((-2.0, -2.0), (2.0, 2.0), initial_refinement_level=level, periodicity=True)
+    return T.SemidiscretizationHyperbolic(mesh, eq, T.initial_condition_weak_blast_wave, solver,
+                                          boundary_conditions=T.boundary_condition_periodic)
+
+
+def _euler2d_blast_wave(level=6):
+    # examples/tree_2d_dgsem/elixir_euler_blast_wave.jl
+    eq = T.CompressibleEulerEquations2D(1.4)
+    solver = _shockcapturing(eq, T.flux_ranocha, T.FluxLaxFriedrichs(T.max_abs_speed_naive))
+    mesh = T.TreeMesh((-2.0, -2.0), (2.0, 2.0), initial_refinement_level=level, periodicity=True)
+    return T.SemidiscretizationHyperbolic(mesh, eq, T.initial_condition_blast_wave, solver,
+                                          boundary_conditions=T.boundary_condition_periodic)
+
+
+ELIXIRS.update({e.name: e for e in [
+    # VolumeIntegralShockCapturingHG
+    Elixir("tree_3d_euler_shockcapturing", _euler3d_shockcapturing, (0.0, 0.4), 1.4,
+           [0.02570137197844877, 0.016179934130642552, 0.01617993413064253, 0.016172648598753545,
+            0.09261669328795467],
+           [0.3954458125573179, 0.26876916180359345, 0.26876916180359345, 0.26933123042178553,
+            1.3724137121660251], "test/test_tree_3d_euler.jl:203-221"),
+    Elixir("tree_2d_euler_shockcapturing", _euler2d_shockcapturing, (0.0, 1.0), 1.0,
+           [0.05380629130119074, 0.04696798008325309, 0.04697067787841479, 0.19687382235494968],
+           [0.18527440131928286, 0.2404798030563736, 0.23269573860381076, 0.6874012187446894],
+           "test/test_tree_2d_euler.jl:359-376"),
+    Elixir("tree_2d_euler_blast_wave", _euler2d_blast_wave, (0.0, 12.5), 0.9,
+           [0.14170569763947993, 0.11647068900798814, 0.11647072556898294, 0.3391989213659599],
+           [1.6544204510794196, 1.35194638484646, 1.3519463848472744, 1.831228461662809],
+           "test/test_tree_2d_euler.jl:449-467", maxiters=30),
+]})
+
+
 # ---- configurations without a reference golden (cross-checks between mesh types, halo tests) ---------------
 def _p4est3d_curved(initial_condition=T.initial_condition_weak_blast_wave, flux=T.flux_ranocha, level=0, trees=(4, 4, 4)):
     # the warped mapping of examples/structured_3d_dgsem/elixir_euler_free_stream.jl on a conforming P4estMesh

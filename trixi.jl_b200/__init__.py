@@ -13,8 +13,8 @@ from .p4est import P4estMesh  # noqa: F401
 from .structured import StructuredMesh  # noqa: F401
 from .semidiscretization import (ODEProblem, SemidiscretizationHyperbolic, compute_coefficients,  # noqa: F401
                                  rhs_hyperbolic, semidiscretize)
-from .solver import (DGSEM, SurfaceIntegralWeakForm, VolumeIntegralFluxDifferencing,  # noqa: F401
-                     VolumeIntegralWeakForm)
+from .solver import (DGSEM, IndicatorHennemannGassner, SurfaceIntegralWeakForm,  # noqa: F401
+                     VolumeIntegralFluxDifferencing, VolumeIntegralShockCapturingHG, VolumeIntegralWeakForm)
 from .time_integration import (CallbackSet, CarpenterKennedy2N43, CarpenterKennedy2N54,  # noqa: F401
                                ParsaniKetchesonDeconinck3Sstar32, ParsaniKetchesonDeconinck3Sstar94,
                                SimpleSSPRK33, init, solve, step, step_2n_host)

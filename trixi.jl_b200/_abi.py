@@ -8,7 +8,7 @@ import ctypes as C
 
 import numpy as np
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 c_double_p = C.POINTER(C.c_double)
 c_int64_p = C.POINTER(C.c_int64)
@@ -48,6 +48,10 @@ class Desc(C.Structure):
         ("mpi_orientations", c_int64_p), ("mpi_neighbor_ranks", c_int64_p),
         ("boundary_node_indices", c_int64_p),
         ("mpi_node_indices", c_int64_p),
+        ("volume_flux_fv", C.c_int32), ("indicator_variable", C.c_int32),
+        ("indicator_alpha_smooth", C.c_int32), ("reserved1", C.c_int32),
+        ("indicator_alpha_max", C.c_double), ("indicator_alpha_min", C.c_double),
+        ("inverse_vandermonde_legendre", c_double_p),
     ]
 
 

@@ -198,6 +198,29 @@ def lagrange_interpolating_polynomials(x, nodes, wbary):
     return poly / poly.sum()
 
 
+def legendre_polynomial(N, x):
+    """Normalised Legendre polynomial of degree N (legendre_polynomial_and_derivative,
+    basis_lobatto_legendre.jl:677-708: three-term recurrence, scaled by sqrt(N + 1/2))."""
+    if N == 0:
+        poly = 1.0
+    elif N == 1:
+        poly = x
+    else:
+        poly_nm2, poly_nm1 = 1.0, x
+        poly = 0.0
+        for i in range(2, N + 1):
+            poly = ((2 * i - 1) * x * poly_nm1 - (i - 1) * poly_nm2) / i
+            poly_nm2, poly_nm1 = poly_nm1, poly
+    return poly * math.sqrt(N + 0.5)
+
+
+def vandermonde_legendre(nodes):
+    """``vandermonde_legendre(nodes)`` (basis_lobatto_legendre.jl:711-727): nodal -> modal is its inverse."""
+    n = len(nodes)
+    V = np.array([[legendre_polynomial(m, float(nodes[i])) for m in range(n)] for i in range(n)])
+    return V, np.linalg.inv(V)
+
+
 class LobattoLegendreBasis:
     """Mirror of ``LobattoLegendreBasis`` (basis_lobatto_legendre.jl:17-86)."""
 
@@ -209,7 +232,7 @@ class LobattoLegendreBasis:
         self.derivative_matrix = polynomial_derivative_matrix(self.nodes)
         self.derivative_split = calc_Dsplit(self.derivative_matrix, self.weights)
         self.derivative_hat = calc_Dhat(self.derivative_matrix, self.weights)
-        self.inverse_vandermonde_legendre = None  # only used by indicators (out of scope)
+        _, self.inverse_vandermonde_legendre = vandermonde_legendre(self.nodes)
 
     @property
     def nnodes(self):

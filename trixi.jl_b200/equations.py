@@ -97,6 +97,22 @@ flux_lax_friedrichs = FluxLaxFriedrichs()
 flux_hll = FluxHLL()
 
 
+class _IndicatorVariable:
+    """Indicator variables of IndicatorHennemannGassner (``density_pressure`` compressible_euler_3d.jl:1951-1956,
+    ``density``/``pressure`` :1937-1949); evaluated inside the indicator kernel, here only a tag."""
+
+    def __init__(self, name, var_id):
+        self.name, self.var_id = name, var_id
+
+    def __repr__(self):
+        return self.name
+
+
+density_pressure = _IndicatorVariable("density_pressure", 0)
+density = _IndicatorVariable("density", 1)
+pressure = _IndicatorVariable("pressure", 2)
+
+
 def resolve_flux(flux):
     """Map a flux object or a (conservative, nonconservative) tuple to its enum id."""
     if isinstance(flux, tuple):
@@ -328,6 +344,21 @@ def initial_condition_gauss(x, t, equations):
         offset = ((shifted < -5.0).astype(float) - (shifted > 5.0).astype(float)) * 10.0
         xs.append(shifted + offset)
     return np.exp(-(xs[0]**2 + xs[1]**2))[None]
+
+
+def initial_condition_blast_wave(x, t, equations):
+    """The "medium blast wave" of examples/tree_2d_dgsem/elixir_euler_blast_wave.jl:7-30 (Hennemann, Gassner 2020,
+    Sec. 6.3).  Host only."""
+    if not isinstance(equations, CompressibleEulerEquations2D):
+        raise NotImplementedError
+    r = np.sqrt(x[0]**2 + x[1]**2)
+    phi = np.arctan2(x[1], x[0])
+    inside = ~(r > 0.5)
+    rho = np.where(inside, 1.1691, 1.0)
+    v1 = np.where(inside, 0.1882 * np.cos(phi), 0.0)
+    v2 = np.where(inside, 0.1882 * np.sin(phi), 0.0)
+    p = np.where(inside, 1.245, 1.0e-3)
+    return equations.prim2cons((rho, v1, v2, p))
 
 
 @_ic(IC_WEAK_BLAST_WAVE)

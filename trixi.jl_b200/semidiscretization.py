@@ -225,6 +225,13 @@ class SemidiscretizationHyperbolic:
         h.set_f64("derivative_split", dg.basis.derivative_split)
         h.set_f64("derivative_hat", dg.basis.derivative_hat)
         h.set_f64("inverse_weights", dg.basis.inverse_weights)
+        if dg.volume_integral.kind == 2:  # VolumeIntegralShockCapturingHG
+            ind = dg.volume_integral.indicator
+            d.volume_flux_fv = resolve_flux(dg.volume_integral.volume_flux_fv)
+            d.indicator_variable = ind.variable.var_id
+            d.indicator_alpha_smooth = int(ind.alpha_smooth)
+            d.indicator_alpha_max, d.indicator_alpha_min = ind.alpha_max, ind.alpha_min
+            h.set_f64("inverse_vandermonde_legendre", dg.basis.inverse_vandermonde_legendre)
         h.set_f64("inverse_jacobian", cache.elements.inverse_jacobian)
         h.set_f64("node_coordinates", cache.elements.node_coordinates)
         if isinstance(self.mesh, StructuredMesh):

@@ -5,7 +5,7 @@ from __future__ import annotations
 from .basis import LobattoLegendreBasis
 from .equations import flux_central, resolve_flux
 
-VOLINT_WEAK_FORM, VOLINT_FLUX_DIFFERENCING = 0, 1
+VOLINT_WEAK_FORM, VOLINT_FLUX_DIFFERENCING, VOLINT_SHOCK_CAPTURING_HG = 0, 1, 2
 
 
 class VolumeIntegralWeakForm:
@@ -29,6 +29,40 @@ class VolumeIntegralFluxDifferencing:
         return f"VolumeIntegralFluxDifferencing({self.volume_flux})"
 
 
+class IndicatorHennemannGassner:
+    """``IndicatorHennemannGassner(equations, basis; alpha_max, alpha_min, alpha_smooth, variable)``
+    (dgsem/indicators.jl:48-70).  The blending factors are computed on the device by the indicator kernels."""
+
+    def __init__(self, equations, basis, alpha_max=0.5, alpha_min=0.001, alpha_smooth=True, variable=None):
+        if variable is None or not hasattr(variable, "var_id"):
+            raise TypeError("variable must be density_pressure, density or pressure")
+        if equations.nvars < 4:
+            raise TypeError("IndicatorHennemannGassner is supported for the compressible Euler equations")
+        self.equations, self.basis = equations, basis
+        self.alpha_max, self.alpha_min = float(alpha_max), float(alpha_min)
+        self.alpha_smooth, self.variable = bool(alpha_smooth), variable
+
+
+class VolumeIntegralShockCapturingHG:
+    """``VolumeIntegralShockCapturingHG(indicator; volume_flux_dg, volume_flux_fv)`` (solvers/dg.jl): blend of the
+    flux-differencing volume integral and first-order subcell finite volumes per element."""
+    kind = VOLINT_SHOCK_CAPTURING_HG
+
+    def __init__(self, indicator, volume_flux_dg=None, volume_flux_fv=None):
+        if not isinstance(indicator, IndicatorHennemannGassner):
+            raise TypeError("indicator must be an IndicatorHennemannGassner")
+        from .equations import FluxLaxFriedrichs, flux_lax_friedrichs  # noqa: F401
+        self.indicator = indicator
+        self.volume_flux_dg = volume_flux_dg if volume_flux_dg is not None else flux_central
+        self.volume_flux_fv = volume_flux_fv if volume_flux_fv is not None else flux_lax_friedrichs
+        resolve_flux(self.volume_flux_dg)
+        resolve_flux(self.volume_flux_fv)
+        self.volume_flux = self.volume_flux_dg
+
+    def __repr__(self):
+        return f"VolumeIntegralShockCapturingHG({self.volume_flux_dg}, {self.volume_flux_fv})"
+
+
 class SurfaceIntegralWeakForm:
     """``SurfaceIntegralWeakForm(surface_flux)`` (solvers/dg.jl:829-838)."""
 
@@ -40,13 +74,17 @@ class SurfaceIntegralWeakForm:
 class DGSEM:
     """``DGSEM(; polydeg, surface_flux, surface_integral, volume_integral)`` (dgsem.jl:65-73)."""
 
-    def __init__(self, polydeg, surface_flux=flux_central, surface_integral=None, volume_integral=None):
-        self.basis = LobattoLegendreBasis(polydeg)
+    def __init__(self, polydeg=None, surface_flux=flux_central, surface_integral=None, volume_integral=None,
+                 basis=None):
+        # DGSEM(basis, surface_flux, volume_integral) (dgsem.jl:41-63) or DGSEM(; polydeg, ...)
+        self.basis = basis if basis is not None else LobattoLegendreBasis(polydeg)
         self.surface_integral = surface_integral or SurfaceIntegralWeakForm(surface_flux)
         self.volume_integral = volume_integral or VolumeIntegralWeakForm()
-        if not isinstance(self.volume_integral, (VolumeIntegralWeakForm, VolumeIntegralFluxDifferencing)):
+        if not isinstance(self.volume_integral, (VolumeIntegralWeakForm, VolumeIntegralFluxDifferencing,
+                                                 VolumeIntegralShockCapturingHG)):
             # SURVEY.md §2 row 15: other volume integral types are rejected at the boundary
-            raise TypeError("libtrixi_b200 supports VolumeIntegralWeakForm and VolumeIntegralFluxDifferencing")
+            raise TypeError("libtrixi_b200 supports VolumeIntegralWeakForm, VolumeIntegralFluxDifferencing and "
+                            "VolumeIntegralShockCapturingHG")
 
     @property
     def polydeg(self):
