@@ -66,7 +66,8 @@ RHS_CASES = ["tree_3d_euler_ec", "tree_3d_euler_source_terms", "tree_3d_euler_so
              "tree_3d_mhd_ec", "tree_3d_mhd_alfven_wave", "p4est_3d_curved_ec", "p4est_3d_curved_weak_form",
              "p4est_3d_curved_level1", "tree_2d_advection_mortar", "tree_3d_euler_mortar",
              "structured_2d_advection_basic", "structured_2d_euler_free_stream", "structured_2d_euler_ec",
-             "structured_2d_euler_source_terms_nonperiodic", "p4est_2d_advection_basic"]
+             "structured_2d_euler_source_terms_nonperiodic", "p4est_2d_advection_basic",
+             "tree_3d_euler_shockcapturing", "tree_2d_euler_shockcapturing", "tree_2d_euler_blast_wave"]
 
 
 @pytest.mark.parametrize("name", RHS_CASES)
@@ -245,7 +246,40 @@ def test_other_integrators_match_oracle(name, alg, oracle_module):
     assert _rel_err(gpu.download(0), ref.download(0)) <= 1e-13
 
 
-GOLDEN_GPU = ["tree_2d_advection_timeintegration_2n43_maxiters1", "tree_2d_advection_timeintegration_3sstar32_maxiters1",
+def _shock_state(semi, seed):
+    """A state with smooth and strongly varying regions so that pure-DG, blended and alpha_max elements all occur."""
+    u = T.compute_coefficients(0.0, semi)
+    rng = np.random.default_rng(seed)
+    x = semi.cache.elements.node_coordinates
+    bump = 1 + 0.3 * rng.uniform(-1, 1, u.shape[1:]) * (x[0] > 0)
+    u = u * bump[None]
+    return np.asfortranarray(u)
+
+
+@pytest.mark.parametrize("name", ["tree_3d_euler_shockcapturing", "tree_2d_euler_shockcapturing",
+                                  "tree_2d_euler_blast_wave"])
+def test_shock_capturing_indicator_and_rhs(name, oracle_module):
+    """IndicatorHennemannGassner blending factors (indicators_3d.jl:41-186) and the blended volume integral
+    (calc_volume_integral.jl:231-272) against the oracle on a state that exercises all three element kinds."""
+    semi = ELIXIRS[name].semi(level=3) if "3d" in name else ELIXIRS[name].semi(level=4)
+    u = _shock_state(semi, 5)
+    ref = oracle_module.OracleBackend(semi)
+    gpu = semi.backend()
+    ref.upload(0, u)
+    gpu.upload(0, u.ravel(order="F"))
+    a_ref, a_gpu = ref.calc_indicator(), gpu.calc_indicator()
+    assert (a_ref == 0).any() and (a_ref == 0.5).any() and ((a_ref > 0) & (a_ref < 0.5)).any()
+    np.testing.assert_allclose(a_gpu, a_ref, rtol=1e-10, atol=1e-13)
+    ref.calc_volume_integral()
+    gpu.calc_volume_integral()
+    assert _rel_err(gpu.download(1), ref.download(1)) <= RHS_TOL
+    du_ref, du_gpu = np.empty_like(u), np.empty_like(u)
+    ref.rhs_host(du_ref, u, 0.1)
+    gpu.rhs_host(du_gpu, u, 0.1)
+    assert _rel_err(du_gpu, du_ref) <= RHS_TOL
+
+
+GOLDEN_GPU = ["tree_3d_euler_shockcapturing", "tree_2d_euler_shockcapturing", "tree_2d_euler_blast_wave","tree_2d_advection_timeintegration_2n43_maxiters1", "tree_2d_advection_timeintegration_3sstar32_maxiters1",
               "tree_3d_euler_ec", "tree_3d_euler_ec_constant", "tree_3d_euler_source_terms",
               "tree_3d_euler_convergence", "tree_3d_euler_taylor_green_vortex", "tree_3d_euler_density_pulse",
               "tree_2d_advection_basic", "tree_2d_euler_source_terms", "tree_2d_euler_source_terms_nonperiodic",

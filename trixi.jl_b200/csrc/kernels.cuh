@@ -59,6 +59,13 @@ struct KParams {
     int kernel_path;              // 0: tuned kernels where available, 1: generic kernels only
     int prefetch_distance;        // tuned element kernel: L2 prefetch this many elements ahead (0: off)
     long long elem_begin, elem_end;  // TreeMesh element kernels work on [elem_begin, elem_end) (pipelined rhs_host)
+    // VolumeIntegralShockCapturingHG: blending factors of IndicatorHennemannGassner
+    double *alpha;       // [nelem] after smoothing (ordered-bits atomicMax target)
+    double *alpha_raw;   // [nelem] before smoothing
+    const double *inv_vdm;  // inverse_vandermonde_legendre [n, n] column-major
+    double inv_weights_c[kMaxNodes];
+    double ind_alpha_max, ind_alpha_min;
+    int volume_flux_fv, ind_var, ind_smooth;
     // distributed: faces shared with other ranks (replaces mpi_interfaces, dg_2d_parallel.jl / dg_parallel.jl)
     long long nmpi;
     const long long *mpi_local, *mpi_side, *mpi_orient;  // [nmpi] 1-based local element, local side, orientation
@@ -561,6 +568,16 @@ __global__ void __launch_bounds__(ElemCfg<EQ, N>::THREADS) k_element(const KPara
         // as volume_flux(u_lower, u_upper); every node here evaluates its own partners with the same
         // argument order, so both ends see the bit-identical flux.
         if (active) {
+            // VolumeIntegralShockCapturingHG (calc_volume_integral.jl:231-272): pure DG where alpha is (almost)
+            // zero, otherwise (1 - alpha) flux differencing + alpha subcell finite volumes
+            double w_dg = 1.0, w_fv = 0.0;
+            if constexpr (VOLINT == TRIXI_B200_VOLINT_SHOCK_CAPTURING_HG) {
+                const double alpha = P.alpha[e];
+                if (!(fabs(alpha) <= 1.8189894035458565e-12)) {  // isapprox(alpha, 0, atol = max(100 eps, eps^0.75))
+                    w_dg = 1 - alpha;
+                    w_fv = alpha;
+                }
+            }
 #pragma unroll
             for (int d = 0; d < ND; ++d) {
                 const int base = node - idx[d] * stride[d];
@@ -575,9 +592,42 @@ __global__ void __launch_bounds__(ElemCfg<EQ, N>::THREADS) k_element(const KPara
                         eq.numflux(P.volume_flux, un, up, d, f);
                     else
                         eq.numflux(P.volume_flux, up, un, d, f);
-                    const double w = s_D[idx[d] + N * l];  // Dsplit[idx_d, l]
+                    double w = s_D[idx[d] + N * l];  // Dsplit[idx_d, l]
+                    if constexpr (VOLINT == TRIXI_B200_VOLINT_SHOCK_CAPTURING_HG) w = w_dg * w;
 #pragma unroll
                     for (int v = 0; v < NV; ++v) acc[v] = fma(w, f[v], acc[v]);
+                }
+            }
+            if constexpr (VOLINT == TRIXI_B200_VOLINT_SHOCK_CAPTURING_HG) {
+                // fv_kernel! (dg_3d.jl:268-306): du += alpha sum_d inverse_weights[idx_d] (fstar_L[idx_d + 1] -
+                // fstar_R[idx_d]), fstar = volume_flux_fv of neighbouring subcells, zero on the element boundary
+                if (w_fv != 0.0) {
+                    double sum[NV];
+#pragma unroll
+                    for (int v = 0; v < NV; ++v) sum[v] = 0.0;
+#pragma unroll 1
+                    for (int d = 0; d < ND; ++d) {
+                        double fl[NV], fr[NV], up[NV];
+#pragma unroll
+                        for (int v = 0; v < NV; ++v) fl[v] = fr[v] = 0.0;
+                        if (idx[d] > 0) {
+                            const double *pu = ue + (node - stride[d]) * US;
+#pragma unroll
+                            for (int v = 0; v < NV; ++v) up[v] = pu[v];
+                            eq.numflux(P.volume_flux_fv, up, un, d, fl);
+                        }
+                        if (idx[d] < N - 1) {
+                            const double *pu = ue + (node + stride[d]) * US;
+#pragma unroll
+                            for (int v = 0; v < NV; ++v) up[v] = pu[v];
+                            eq.numflux(P.volume_flux_fv, un, up, d, fr);
+                        }
+                        const double iw = P.inv_weights_c[idx[d]];
+#pragma unroll
+                        for (int v = 0; v < NV; ++v) sum[v] = fma(iw, fr[v] - fl[v], sum[v]);
+                    }
+#pragma unroll
+                    for (int v = 0; v < NV; ++v) acc[v] = fma(w_fv, sum[v], acc[v]);
                 }
             }
             if constexpr (EQ::kHasNoncons) {
@@ -663,6 +713,128 @@ __global__ void __launch_bounds__(ElemCfg<EQ, N>::THREADS) k_element(const KPara
         }
     }
     (void)s_red;
+}
+
+// ---- IndicatorHennemannGassner ------------------------------------------------------------------------
+// calc_indicator_hennemann_gassner! (dgsem_tree/indicators_3d.jl:41-131, indicators_2d.jl:26-98): one thread
+// per node evaluates the indicator variable and takes part in the dimension-by-dimension nodal -> modal
+// transform in shared memory (multiply_scalar_dimensionwise!, interpolation.jl:207-234,348-389); the first
+// thread of each element sums the modal energies in the reference's order and applies the logistic map.
+template <class EQ, int N>
+__global__ void __launch_bounds__(ElemCfg<EQ, N>::THREADS) k_indicator_hg(const KParams P, double threshold,
+                                                                          double parameter_s) {
+    using C = ElemCfg<EQ, N>;
+    constexpr int ND = C::ND, NV = C::NV, NN = C::NN, EPB = C::EPB;
+    __shared__ double s_a[EPB * NN], s_b[EPB * NN], s_V[N * N];
+    const EQ eq(P.eq);
+    const int tid = threadIdx.x;
+    const long long e0 = (long long)blockIdx.x * EPB;
+    const int le = tid / NN, node = tid - le * NN;
+    const long long e = e0 + le;
+    const bool active = e < P.nelements;
+    for (int q = tid; q < N * N; q += C::THREADS) s_V[q] = P.inv_vdm[q];
+    if (active) {
+        double un[NV];
+        const double *pu = P.u + (e * NN + node) * NV;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) un[v] = pu[v];
+        s_a[tid] = eq.indicator_variable(P.ind_var, un);
+    }
+    __syncthreads();
+    const int i = node % N, j = (node / N) % N, k = ND == 3 ? node / (N * N) : 0;
+    double *a = s_a + le * NN, *b = s_b + le * NN;
+    if (active) {
+        double res = 0.0;
+#pragma unroll
+        for (int ii = 0; ii < N; ++ii) res = fma(s_V[i + N * ii], a[ii + N * (j + N * k)], res);
+        b[node] = res;
+    }
+    __syncthreads();
+    if (active) {
+        double res = 0.0;
+#pragma unroll
+        for (int jj = 0; jj < N; ++jj) res = fma(s_V[j + N * jj], b[i + N * (jj + N * k)], res);
+        a[node] = res;
+    }
+    __syncthreads();
+    const double *modal = a;
+    if constexpr (ND == 3) {
+        if (active) {
+            double res = 0.0;
+#pragma unroll
+            for (int kk = 0; kk < N; ++kk) res = fma(s_V[k + N * kk], a[i + N * (j + N * kk)], res);
+            b[node] = res;
+        }
+        __syncthreads();
+        modal = b;
+    }
+    if (!active || node != 0) return;
+    auto sq = [&](int x, int y, int z) {
+        const double m = modal[x + N * (y + N * z)];
+        return m * m;
+    };
+    double clip2 = 0.0, clip1, total;
+    if constexpr (ND == 3) {
+        for (int z = 0; z < N - 2; ++z)
+            for (int y = 0; y < N - 2; ++y)
+                for (int x = 0; x < N - 2; ++x) clip2 += sq(x, y, z);
+        clip1 = clip2;
+        for (int y = 0; y < N - 1; ++y)
+            for (int x = 0; x < N - 1; ++x) clip1 += sq(x, y, N - 2);
+        for (int z = 0; z < N - 2; ++z)
+            for (int x = 0; x < N - 1; ++x) clip1 += sq(x, N - 2, z);
+        for (int z = 0; z < N - 2; ++z)
+            for (int y = 0; y < N - 2; ++y) clip1 += sq(N - 2, y, z);
+        total = clip1;
+        for (int y = 0; y < N; ++y)
+            for (int x = 0; x < N; ++x) total += sq(x, y, N - 1);
+        for (int z = 0; z < N - 1; ++z)
+            for (int x = 0; x < N; ++x) total += sq(x, N - 1, z);
+        for (int z = 0; z < N - 1; ++z)
+            for (int y = 0; y < N - 1; ++y) total += sq(N - 1, y, z);
+    } else {
+        for (int y = 0; y < N - 2; ++y)
+            for (int x = 0; x < N - 2; ++x) clip2 += sq(x, y, 0);
+        clip1 = clip2;
+        for (int x = 0; x < N - 1; ++x) clip1 += sq(x, N - 2, 0);
+        for (int y = 0; y < N - 2; ++y) clip1 += sq(N - 2, y, 0);
+        total = clip1;
+        for (int x = 0; x < N; ++x) total += sq(x, N - 1, 0);
+        for (int y = 0; y < N - 1; ++y) total += sq(N - 1, y, 0);
+    }
+    const double frac1 = total != 0.0 ? (total - clip1) / total : 0.0;
+    const double frac2 = clip1 != 0.0 ? (clip1 - clip2) / clip1 : 0.0;
+    const double energy = fmax(frac1, frac2);
+    double alpha = 1 / (1 + exp(-parameter_s / threshold * (energy - threshold)));
+    if (alpha < P.ind_alpha_min) alpha = 0.0;
+    if (alpha > 1 - P.ind_alpha_min) alpha = 1.0;
+    alpha = fmin(P.ind_alpha_max, alpha);
+    P.alpha_raw[e] = alpha;
+    P.alpha[e] = alpha;
+}
+
+// apply_smoothing! (indicators_3d.jl:133-186): alpha[e] = max(alpha_raw[e], 0.5 alpha_raw[neighbours]); the
+// reference's sequential loop is a pure max, so the order does not matter; non-negative doubles order like
+// their bit patterns
+template <class EQ, int N>
+__global__ void __launch_bounds__(256) k_indicator_smooth(const KParams P) {
+    constexpr int NS = 1 << (EQ::NDIMS - 1);
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long *key = reinterpret_cast<unsigned long long *>(P.alpha);
+    if (gid < P.ninterfaces) {
+        const long long l = P.if_neighbors[2 * gid] - 1, r = P.if_neighbors[2 * gid + 1] - 1;
+        atomicMax(key + l, (unsigned long long)__double_as_longlong(0.5 * P.alpha_raw[r]));
+        atomicMax(key + r, (unsigned long long)__double_as_longlong(0.5 * P.alpha_raw[l]));
+    } else if (gid - P.ninterfaces < P.nmortars) {
+        const long long *ids = P.mortar_ids + (NS + 1) * (gid - P.ninterfaces);
+        const long long large = ids[NS] - 1;
+#pragma unroll
+        for (int q = 0; q < NS; ++q) {
+            const long long sm = ids[q] - 1;
+            atomicMax(key + sm, (unsigned long long)__double_as_longlong(0.5 * P.alpha_raw[large]));
+            atomicMax(key + large, (unsigned long long)__double_as_longlong(0.5 * P.alpha_raw[sm]));
+        }
+    }
 }
 
 // ---- max_dt ------------------------------------------------------------------------------------------

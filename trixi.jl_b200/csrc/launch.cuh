@@ -13,6 +13,8 @@ struct Launchers {
     void (*error_norms)(const KParams &, const NormParams &, cudaStream_t);
     // with_surface = false: volume terms only (stage-level parity entry point)
     cudaError_t (*element)(const KParams &, bool with_surface, cudaStream_t);
+    // IndicatorHennemannGassner blending factors of P.u into P.alpha (VolumeIntegralShockCapturingHG)
+    void (*indicator)(const KParams &, cudaStream_t);
     void (*max_dt)(const KParams &, cudaStream_t);
     // true when the RK stage kernel `element` selects for P honours P.want_cfl (fused max_dt)
     bool (*fuses_cfl)(const KParams &);
@@ -181,8 +183,28 @@ cudaError_t launch_element(const KParams &P, bool with_surface, cudaStream_t s) 
         return with_surface ? launch_element_variant<EQ, N, TRIXI_B200_VOLINT_WEAK_FORM, true>(P, s)
                             : launch_element_variant<EQ, N, TRIXI_B200_VOLINT_WEAK_FORM, false>(P, s);
     }
+    if constexpr (HasFastRanocha<EQ>::value) {  // the compressible Euler equations
+        if (P.volume_integral == TRIXI_B200_VOLINT_SHOCK_CAPTURING_HG)
+            return with_surface ? launch_element_variant<EQ, N, TRIXI_B200_VOLINT_SHOCK_CAPTURING_HG, true>(P, s)
+                                : launch_element_variant<EQ, N, TRIXI_B200_VOLINT_SHOCK_CAPTURING_HG, false>(P, s);
+    }
     return with_surface ? launch_element_variant<EQ, N, TRIXI_B200_VOLINT_FLUX_DIFFERENCING, true>(P, s)
                         : launch_element_variant<EQ, N, TRIXI_B200_VOLINT_FLUX_DIFFERENCING, false>(P, s);
+}
+
+// (indicator_hg::IndicatorHennemannGassner)(u, mesh, equations, dg, cache) (dgsem/indicators.jl:114-148)
+template <class EQ, int N>
+void launch_indicator(const KParams &P, cudaStream_t s) {
+    if constexpr (HasFastRanocha<EQ>::value) {
+        using C = ElemCfg<EQ, N>;
+        if (P.nelements == 0) return;
+        // magic parameters (indicators.jl:126-130)
+        const double threshold = 0.5 * pow(10.0, -1.8 * pow((double)N, 0.25));
+        const double parameter_s = log((1 - 0.0001) / 0.0001);
+        k_indicator_hg<EQ, N><<<(unsigned)((P.nelements + C::EPB - 1) / C::EPB), C::THREADS, 0, s>>>(P, threshold, parameter_s);
+        const long long faces = P.ninterfaces + P.nmortars;
+        if (P.ind_smooth && faces > 0) k_indicator_smooth<EQ, N><<<(unsigned)((faces + 255) / 256), 256, 0, s>>>(P);
+    }
 }
 
 template <class EQ, int N>
@@ -237,6 +259,12 @@ cudaError_t preload_all() {
     TB_PRELOAD((k_element<EQ, N, TRIXI_B200_VOLINT_WEAK_FORM, false>));
     TB_PRELOAD((k_element<EQ, N, TRIXI_B200_VOLINT_FLUX_DIFFERENCING, true>));
     TB_PRELOAD((k_element<EQ, N, TRIXI_B200_VOLINT_FLUX_DIFFERENCING, false>));
+    if constexpr (HasFastRanocha<EQ>::value) {
+        TB_PRELOAD((k_element<EQ, N, TRIXI_B200_VOLINT_SHOCK_CAPTURING_HG, true>));
+        TB_PRELOAD((k_element<EQ, N, TRIXI_B200_VOLINT_SHOCK_CAPTURING_HG, false>));
+        TB_PRELOAD((k_indicator_hg<EQ, N>));
+        TB_PRELOAD((k_indicator_smooth<EQ, N>));
+    }
 #undef TB_PRELOAD
     if constexpr (std::is_same_v<EQ, Euler<3>> && N == 4) return preload_tuned_euler3d();
     return cudaSuccess;
@@ -249,6 +277,7 @@ const Launchers *make_launchers() {
                                 &launch_mortar_flux<EQ, N>,
                                 &launch_error_norms<EQ, N>,
                                 &launch_element<EQ, N>,
+                                &launch_indicator<EQ, N>,
                                 &launch_max_dt<EQ, N>,
                                 &uses_tuned_element<EQ, N>,
                                 &launch_mpi_pack<EQ, N>,

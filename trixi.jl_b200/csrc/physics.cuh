@@ -193,6 +193,17 @@ struct Euler {
         p = (gamma - 1) * (u[ND + 1] - 0.5 * kin);
     }
 
+    // indicator variables of IndicatorHennemannGassner: density_pressure, density, pressure
+    // (compressible_euler_3d.jl:1937-1956)
+    TB_DEV double indicator_variable(int var, const double (&u)[NVARS]) const {
+        double q = 0.0;
+#pragma unroll
+        for (int d = 0; d < ND; ++d) q = q + u[1 + d] * u[1 + d];
+        if (var == TRIXI_B200_INDVAR_DENSITY) return u[0];
+        if (var == TRIXI_B200_INDVAR_PRESSURE) return (gamma - 1) * (u[ND + 1] - 0.5 * q / u[0]);
+        return (gamma - 1) * (u[0] * u[ND + 1] - 0.5 * q);
+    }
+
     // flux(u, orientation) (compressible_euler_3d.jl:420-447)
     TB_DEV void flux(const double (&u)[NVARS], int o, double (&f)[NVARS]) const {
         double rho, v[ND], p;

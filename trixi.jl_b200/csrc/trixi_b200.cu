@@ -266,7 +266,18 @@ int run_surface_fluxes(trixi_b200_handle *h, double t) {
     return check_launch(h, "surface flux kernel");
 }
 
+int run_indicator(trixi_b200_handle *h) {
+    h->L->indicator(h->P, h->stream);
+    h->launches += 1 + ((h->P.ind_smooth && h->P.ninterfaces + h->P.nmortars > 0) ? 1 : 0);
+    return check_launch(h, "indicator kernel");
+}
+
 int run_element(trixi_b200_handle *h, bool with_surface) {
+    if (h->P.volume_integral == TRIXI_B200_VOLINT_SHOCK_CAPTURING_HG) {
+        // blending factors of the current u, before the element kernel may update u in place
+        int rc = run_indicator(h);
+        if (rc) return rc;
+    }
     {
         ProfScope ps(h, KC_ELEMENT);
         cudaError_t err = h->L->element(h->P, with_surface, h->stream);
@@ -341,8 +352,8 @@ int build_host_pipeline(trixi_b200_handle *h) {
     hp.built = true;
     const KParams &P = h->P;
     if (h->opt_pipeline_chunk == 0 || P.curved || P.nmortars || P.nboundaries || h->world_size > 1 ||
-        P.ninterfaces == 0 || h->nelements == 0)
-        return 0;
+        P.ninterfaces == 0 || h->nelements == 0 || P.volume_integral == TRIXI_B200_VOLINT_SHOCK_CAPTURING_HG)
+        return 0;  // (the indicator's smoothing needs every neighbour's alpha: no chunk-wise readiness)
     const int nd = h->ndims;
     const long long esz = h->ulen / h->nelements;  // doubles per element
     long long chunk = h->opt_pipeline_chunk;
@@ -590,8 +601,22 @@ TRIXI_B200_API int trixi_b200_create(const trixi_b200_desc *d, trixi_b200_handle
             !d->mortar_forward_lower || !d->mortar_reverse_upper || !d->mortar_reverse_lower)
             return fail(nullptr, TRIXI_B200_EINVAL, "mortar arrays missing");
     }
-    if (d->volume_integral != TRIXI_B200_VOLINT_WEAK_FORM && d->volume_integral != TRIXI_B200_VOLINT_FLUX_DIFFERENCING)
+    if (d->volume_integral != TRIXI_B200_VOLINT_WEAK_FORM && d->volume_integral != TRIXI_B200_VOLINT_FLUX_DIFFERENCING &&
+        d->volume_integral != TRIXI_B200_VOLINT_SHOCK_CAPTURING_HG)
         return fail(nullptr, TRIXI_B200_EINVAL, "unsupported volume integral type %d", d->volume_integral);
+    if (d->volume_integral == TRIXI_B200_VOLINT_SHOCK_CAPTURING_HG) {
+        if (d->mesh_kind != TRIXI_B200_MESH_TREE)
+            return fail(nullptr, TRIXI_B200_EINVAL, "VolumeIntegralShockCapturingHG is available on TreeMesh only in this build");
+        if (d->equation != TRIXI_B200_EQ_EULER_2D && d->equation != TRIXI_B200_EQ_EULER_3D)
+            return fail(nullptr, TRIXI_B200_EINVAL, "VolumeIntegralShockCapturingHG needs the compressible Euler equations");
+        if (d->world_size > 1)
+            return fail(nullptr, TRIXI_B200_EINVAL, "VolumeIntegralShockCapturingHG is single-rank in this build (alpha smoothing across ranks)");
+        if (!d->inverse_vandermonde_legendre)
+            return fail(nullptr, TRIXI_B200_EINVAL, "inverse_vandermonde_legendre missing");
+        if (d->indicator_variable < TRIXI_B200_INDVAR_DENSITY_PRESSURE || d->indicator_variable > TRIXI_B200_INDVAR_PRESSURE)
+            return fail(nullptr, TRIXI_B200_EINVAL, "unknown indicator variable %d", d->indicator_variable);
+        if (d->nnodes < 3) return fail(nullptr, TRIXI_B200_EINVAL, "IndicatorHennemannGassner needs nnodes >= 3");
+    }
     if (d->nelements < 0 || d->ninterfaces < 0 || d->nboundaries < 0)
         return fail(nullptr, TRIXI_B200_EINVAL, "negative container size");
 
@@ -805,6 +830,18 @@ TRIXI_B200_API int trixi_b200_create(const trixi_b200_desc *d, trixi_b200_handle
     }
     for (int k = 0; k < 8; ++k) P.eq.p[k] = d->eq_params[k];
     P.volume_integral = d->volume_integral;
+    if (d->volume_integral == TRIXI_B200_VOLINT_SHOCK_CAPTURING_HG) {
+        P.volume_flux_fv = d->volume_flux_fv;
+        P.ind_var = d->indicator_variable;
+        P.ind_smooth = d->indicator_alpha_smooth;
+        P.ind_alpha_max = d->indicator_alpha_max;
+        P.ind_alpha_min = d->indicator_alpha_min;
+        for (int q = 0; q < n; ++q) P.inv_weights_c[q] = d->inverse_weights[q];
+        CREATE_TRY(upload_array(h, d->inverse_vandermonde_legendre, (size_t)n * n, &tmp));
+        P.inv_vdm = tmp;
+        CREATE_TRY(alloc_array(h, (size_t)d->nelements, &P.alpha));
+        CREATE_TRY(alloc_array(h, (size_t)d->nelements, &P.alpha_raw));
+    }
     P.volume_flux = d->volume_flux;
     P.surface_flux = d->surface_flux;
     P.source_terms = d->source_terms;
@@ -975,6 +1012,19 @@ TRIXI_B200_API int trixi_b200_calc_surface_fluxes(trixi_b200_handle *h, double t
     if (!h) return TRIXI_B200_EINVAL;
     CUDA_TRY(h, cudaSetDevice(h->device));
     return run_all_surface_fluxes(h, t);
+}
+
+TRIXI_B200_API int trixi_b200_calc_indicator(trixi_b200_handle *h, double *alpha_host) {
+    if (!h) return TRIXI_B200_EINVAL;
+    if (h->P.volume_integral != TRIXI_B200_VOLINT_SHOCK_CAPTURING_HG)
+        return fail(h, TRIXI_B200_EINVAL, "the volume integral has no indicator (not VolumeIntegralShockCapturingHG)");
+    if (!alpha_host && h->nelements) return fail(h, TRIXI_B200_EINVAL, "host pointer is null");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    int rc = run_indicator(h);
+    if (rc) return rc;
+    CUDA_TRY(h, cudaMemcpyAsync(alpha_host, h->P.alpha, h->nelements * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return 0;
 }
 
 TRIXI_B200_API int trixi_b200_download_surface_flux_values(trixi_b200_handle *h, double *host) {

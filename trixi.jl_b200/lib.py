@@ -23,7 +23,7 @@ EXPORTS = [
     "trixi_b200_step_2n", "trixi_b200_step_2n_host", "trixi_b200_step_3sstar", "trixi_b200_step_ssp",
     "trixi_b200_solve_2n", "trixi_b200_set_eq_param", "trixi_b200_calc_error_norms",
     "trixi_b200_calc_volume_integral", "trixi_b200_calc_surface_fluxes",
-    "trixi_b200_download_surface_flux_values", "trixi_b200_comm_info_size", "trixi_b200_comm_info",
+    "trixi_b200_download_surface_flux_values", "trixi_b200_calc_indicator", "trixi_b200_comm_info_size", "trixi_b200_comm_info",
     "trixi_b200_comm_connect",
     "trixi_b200_launch_count", "trixi_b200_last_elapsed_ms", "trixi_b200_profile_enable",
     "trixi_b200_profile_read", "trixi_b200_timer_start", "trixi_b200_timer_stop",
@@ -78,6 +78,7 @@ def load_library(path=None):
     lib.trixi_b200_calc_volume_integral.argtypes = [vp]
     lib.trixi_b200_calc_surface_fluxes.argtypes = [vp, C.c_double]
     lib.trixi_b200_download_surface_flux_values.argtypes = [vp, dp]
+    lib.trixi_b200_calc_indicator.argtypes = [vp, dp]
     lib.trixi_b200_comm_info_size.argtypes = []
     lib.trixi_b200_comm_info_size.restype = C.c_int64
     lib.trixi_b200_comm_info.argtypes = [vp, vp]
@@ -225,6 +226,12 @@ class B200Backend:
 
     def calc_surface_fluxes(self, t):
         self._ck(self.lib.trixi_b200_calc_surface_fluxes(self.h, float(t)))
+
+    def calc_indicator(self):
+        """IndicatorHennemannGassner blending factors [nelements] of the resident u."""
+        alpha = np.empty(int(self._holder.desc.nelements))
+        self._ck(self.lib.trixi_b200_calc_indicator(self.h, _dptr(alpha)))
+        return alpha
 
     def download_surface_flux_values(self, host):
         self._ck(self.lib.trixi_b200_download_surface_flux_values(self.h, _dptr(host)))
