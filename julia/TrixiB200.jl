@@ -40,6 +40,18 @@ equation_params(eq::Union{CompressibleEulerEquations2D, CompressibleEulerEquatio
                                                                                           0.0)
 volume_integral_id(::VolumeIntegralWeakForm) = (Cint(0), Cint(0))
 volume_integral_id(v::VolumeIntegralFluxDifferencing) = (Cint(1), flux_id(v.volume_flux))
+# VolumeIntegralShockCapturingHG (solvers/dg.jl): volume_flux = volume_flux_dg; the FV flux and the indicator
+# travel in the descriptor's trailing fields
+volume_integral_id(v::VolumeIntegralShockCapturingHG) = (Cint(2), flux_id(v.volume_flux_dg))
+indicator_variable_id(::typeof(density_pressure)) = Cint(0)
+indicator_variable_id(::typeof(density)) = Cint(1)
+indicator_variable_id(::typeof(pressure)) = Cint(2)
+shock_capturing_fields(v, basis) = (Cint(0), Cint(0), Cint(0), 0.0, 0.0, Float64[])
+function shock_capturing_fields(v::VolumeIntegralShockCapturingHG, basis)
+    ind = v.indicator
+    return (flux_id(v.volume_flux_fv), indicator_variable_id(ind.variable), Cint(ind.alpha_smooth),
+            Float64(ind.alpha_max), Float64(ind.alpha_min), Matrix(basis.inverse_vandermonde_legendre))
+end
 flux_id(::typeof(flux_central)) = Cint(0)
 flux_id(::typeof(flux_ranocha)) = Cint(1)
 flux_id(f::FluxLaxFriedrichs) = f.dissipation.max_abs_speed === max_abs_speed_naive ? Cint(3) : Cint(2)
@@ -116,6 +128,13 @@ struct Desc
     mpi_neighbor_ranks::Ptr{Int64}
     boundary_node_indices::Ptr{Int64}
     mpi_node_indices::Ptr{Int64}
+    volume_flux_fv::Int32
+    indicator_variable::Int32
+    indicator_alpha_smooth::Int32
+    reserved1::Int32
+    indicator_alpha_max::Float64
+    indicator_alpha_min::Float64
+    inverse_vandermonde_legendre::Ptr{Float64}
 end
 
 # ---- the backend object ---------------------------------------------------------------------------------
@@ -205,9 +224,10 @@ function B200(semi::SemidiscretizationHyperbolic; device = -1)
     fu, fl, ru, rl = n_mo > 0 ? Matrix.((dg.mortar.forward_upper, dg.mortar.forward_lower,
                                          dg.mortar.reverse_upper, dg.mortar.reverse_lower)) :
                      ntuple(_ -> zeros(0, 0), 4)
+    fv_flux, ind_var, ind_smooth, ind_max, ind_min, inv_vdm = shock_capturing_fields(dg.volume_integral, dg.basis)
     handle = Ref{Ptr{Cvoid}}(C_NULL)
     # the library copies during `create` only
-    GC.@preserve D_split D_hat inv_w el contravariant left_neighbors if_ids if_orient if_idx bd_ids bd_orient bd_sides bd_x bd_idx mo_ids mo_sides mo_orient fu fl ru rl begin
+    GC.@preserve inv_vdm D_split D_hat inv_w el contravariant left_neighbors if_ids if_orient if_idx bd_ids bd_orient bd_sides bd_x bd_idx mo_ids mo_sides mo_orient fu fl ru rl begin
         desc = Desc(ABI_VERSION, device, ndims(mesh), nvariables(equations), nnodes(dg), mesh_kind(mesh),
                     nelements(dg, cache), equation_id(equations), volint, volflux,
                     flux_id(dg.surface_integral.surface_flux), source_id(semi.source_terms),
@@ -220,7 +240,8 @@ function B200(semi::SemidiscretizationHyperbolic; device = -1)
                     ptr_or_null(fu), ptr_or_null(fl), ptr_or_null(ru), ptr_or_null(rl),
                     ptr_or_null(left_neighbors),
                     0, 1, 0, C_NULL, C_NULL, C_NULL, C_NULL,   # single rank: no MPI interfaces
-                    ptr_or_null(bd_idx), C_NULL)
+                    ptr_or_null(bd_idx), C_NULL,
+                    fv_flux, ind_var, ind_smooth, 0, ind_max, ind_min, ptr_or_null(inv_vdm))
         rc = ccall((:trixi_b200_create, libtrixi_b200), Cint, (Ref{Desc}, Ref{Ptr{Cvoid}}), desc, handle)
     end
     check(nothing, rc)
@@ -264,6 +285,50 @@ function step_2n!(backend::B200, t, dt, alg::Trixi.SimpleAlgorithm2N)
                              backend.handle, t, dt, pointer(a), pointer(b), pointer(c), length(c)))
     end
     return nothing
+end
+
+# The same step on the integrator's host-resident u (methods_2N.jl:95-111 keeps u in a Vector): the first stage
+# consumes u chunk-wise as it arrives over PCIe, the last stage returns it chunk-wise (trixi_b200_step_2n_host)
+function step_2n_host!(backend::B200, u::Vector{Float64}, t, dt, alg::Trixi.SimpleAlgorithm2N)
+    a, b, c = collect(alg.a), collect(alg.b), collect(alg.c)
+    GC.@preserve u a b c begin
+        check(backend, ccall((:trixi_b200_step_2n_host, libtrixi_b200), Cint,
+                             (Ptr{Cvoid}, Ptr{Float64}, Float64, Float64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Cint),
+                             backend.handle, pointer(u), t, dt, pointer(a), pointer(b), pointer(c), length(c)))
+    end
+    return nothing
+end
+
+# step!(integrator::SimpleIntegrator3Sstar) stage loop (methods_3Sstar.jl:186-207)
+function step_3sstar!(backend::B200, t, dt, alg::Trixi.SimpleAlgorithm3Sstar)
+    g1, g2, g3, be, de, c = collect.((alg.gamma1, alg.gamma2, alg.gamma3, alg.beta, alg.delta, alg.c))
+    GC.@preserve g1 g2 g3 be de c begin
+        check(backend, ccall((:trixi_b200_step_3sstar, libtrixi_b200), Cint,
+                             (Ptr{Cvoid}, Float64, Float64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+                              Ptr{Float64}, Ptr{Float64}, Cint),
+                             backend.handle, t, dt, pointer(g1), pointer(g2), pointer(g3), pointer(be), pointer(de),
+                             pointer(c), length(c)))
+    end
+    return nothing
+end
+
+# step!(integrator::SimpleIntegratorSSP) stage loop without stage callbacks (methods_SSP.jl:185-202)
+function step_ssp!(backend::B200, t, dt, alg::Trixi.SimpleAlgorithmSSP)
+    na, nb, den, c = collect.((alg.numerator_a, alg.numerator_b, alg.denominator, alg.c))
+    GC.@preserve na nb den c begin
+        check(backend, ccall((:trixi_b200_step_ssp, libtrixi_b200), Cint,
+                             (Ptr{Cvoid}, Float64, Float64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Cint),
+                             backend.handle, t, dt, pointer(na), pointer(nb), pointer(den), pointer(c), length(c)))
+    end
+    return nothing
+end
+
+# indicator.cache.alpha for the SaveSolutionCallback's :indicator_shock_capturing (indicators.jl:20-24)
+function indicator_alpha(backend::B200, nelements)
+    alpha = Vector{Float64}(undef, nelements)
+    GC.@preserve alpha check(backend, ccall((:trixi_b200_calc_indicator, libtrixi_b200), Cint,
+                                            (Ptr{Cvoid}, Ptr{Float64}), backend.handle, pointer(alpha)))
+    return alpha
 end
 
 upload!(backend::B200, which, host::Vector{Float64}) = GC.@preserve host check(backend,
