@@ -112,9 +112,15 @@ TB_DEV void ranocha_pair_rot(const double (&L)[kNP], const double (&R)[kNP], dou
 struct TunedCfg {
     static constexpr int EPB = 1, THREADS = 32;  // one warp, one element, two threads per line
     static constexpr int CONS = 320, PRIM = 64 * kNP, SFV = 480;  // doubles per element
-    // s_u, s_ut (natural order, TMA), s_sfv (natural, TMA), s_du, s_prim (swizzled), mbarrier
-    static constexpr size_t SMEM = sizeof(double) * EPB * (3 * CONS + SFV + PRIM) + 16;
-    static constexpr int MIN_BLOCKS = 14;
+    // s_u (natural order, TMA), s_sfv (natural, TMA), s_du, s_prim (swizzled), mbarrier, [s_ut (natural, TMA)].
+    // Without source terms the u_tmp tile is not resident during the flux passes: it is loaded into the prim
+    // tile's storage once the z pass has read it for the last time, and leaves from there.  12.6 KB instead of
+    // 15.1 KB per element: 17 instead of 14 resident warps per SM (shared memory is the occupancy limiter,
+    // 105 registers per thread would allow 18).
+    static constexpr size_t SMEM_DEFERRED = sizeof(double) * EPB * (2 * CONS + SFV + PRIM) + 16;
+    static constexpr size_t SMEM_RESIDENT = SMEM_DEFERRED + sizeof(double) * EPB * CONS;
+    static constexpr int MIN_BLOCKS = 17;
+    static constexpr int blocks_per_sm(bool deferred) { return deferred ? 17 : 14; }
 };
 
 template <bool WITH_SURFACE>
@@ -123,12 +129,14 @@ __global__ void __launch_bounds__(TunedCfg::THREADS, TunedCfg::MIN_BLOCKS)
     using C = TunedCfg;
     constexpr int CONS = C::CONS, PRIM = C::PRIM, SFV = C::SFV;
     extern __shared__ __align__(128) double smem[];
+    const bool have_src = WITH_SURFACE && P.source_terms != TRIXI_B200_SRC_NONE;
+    const bool deferred = !have_src;  // must match the launch's dynamic shared memory size
     double *s_u = smem;            // [64][5] natural: u in, updated u out
-    double *s_ut = s_u + CONS;     // [64][5] natural: u_tmp in, u_tmp (or du) out
-    double *s_sfv = s_ut + CONS;   // [6][16][5] natural
+    double *s_sfv = s_u + CONS;    // [6][16][5] natural
     double *s_du = s_sfv + SFV;    // [64][5] swizzled
-    double *s_prim = s_du + CONS;  // [64][7] swizzled; after the flux passes: source terms
+    double *s_prim = s_du + CONS;  // [64][7] swizzled; after the flux passes: source terms or the u_tmp tile
     const uint32_t bar = smem_u32(s_prim + PRIM);
+    double *s_ut = deferred ? s_prim : s_prim + PRIM + 2;  // [64][5] natural: u_tmp in, u_tmp (or du) out
 
     const int lane = threadIdx.x;
     const long long e = P.elem_begin + blockIdx.x;
@@ -144,9 +152,10 @@ __global__ void __launch_bounds__(TunedCfg::THREADS, TunedCfg::MIN_BLOCKS)
     __syncwarp();
     if (lane == 0) {
         constexpr uint32_t bu = CONS * sizeof(double), bs = SFV * sizeof(double);
-        mbar_expect_tx(bar, bu + (need_ut ? bu : 0u) + (WITH_SURFACE ? bs : 0u));
+        const bool ut_now = need_ut && !deferred;
+        mbar_expect_tx(bar, bu + (ut_now ? bu : 0u) + (WITH_SURFACE ? bs : 0u));
         tma_load(smem_u32(s_u), P.u + e * CONS, bu, bar);
-        if (need_ut) tma_load(smem_u32(s_ut), P.u_tmp + e * CONS, bu, bar);
+        if (ut_now) tma_load(smem_u32(s_ut), P.u_tmp + e * CONS, bu, bar);
         if (WITH_SURFACE) tma_load(smem_u32(s_sfv), P.sfv + e * SFV, bs, bar);
         // warm L2 for the element that will occupy this CTA slot next (blocks are scheduled in index order:
         // one wave further on), so its tile loads see L2 instead of HBM latency
@@ -269,8 +278,20 @@ __global__ void __launch_bounds__(TunedCfg::THREADS, TunedCfg::MIN_BLOCKS)
         __syncwarp();
     }
 
+    // the prim tile is dead now: fetch the u_tmp tile into its storage (second phase of the mbarrier); the
+    // surface integral and the Jacobian below run while it is in flight
+    const bool ut_late = need_ut && deferred;
+    if (ut_late) {
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+            constexpr uint32_t bu = CONS * sizeof(double);
+            mbar_expect_tx(bar, bu);
+            tma_load(smem_u32(s_ut), P.u_tmp + e * CONS, bu, bar);
+        }
+    }
+
     // calc_sources! (dg_3d.jl:1417-1437): evaluated into the (now dead) prim tile, natural node order
-    const bool have_src = WITH_SURFACE && P.source_terms != TRIXI_B200_SRC_NONE;
     if (have_src) {
         const Euler<3> eq(P.eq);
 #pragma unroll 1
@@ -294,12 +315,13 @@ __global__ void __launch_bounds__(TunedCfg::THREADS, TunedCfg::MIN_BLOCKS)
         const int i = a0, j = a1;
         const double factor = WITH_SURFACE ? -P.inverse_jacobian[e] : 1.0;
         unsigned long long cfl0 = 0ull, cfl1 = 0ull, cfl2 = 0ull;
+        double vals[2][5];
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
             const int k = lm[r];
             const int n = l16 + 16 * k;
             const double *t = s_du + pos[r] * 5;
-            double val[5];
+            double(&val)[5] = vals[r];
             val[0] = t[0] + own[r][0];
             val[1] = t[1] + own[r][2];
             val[2] = t[2] + own[r][3];
@@ -333,6 +355,15 @@ __global__ void __launch_bounds__(TunedCfg::THREADS, TunedCfg::MIN_BLOCKS)
                     for (int v = 0; v < 5; ++v) val[v] += s_prim[n * 5 + v];
                 }
             }
+        }
+        if (ut_late) {
+            while (!mbar_try_wait(bar, 1)) {
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int n = l16 + 16 * lm[r];
+            double(&val)[5] = vals[r];
             double *out_t = s_ut + n * 5;
             if (!rk) {
 #pragma unroll
@@ -419,10 +450,15 @@ cudaError_t launch_element_euler3d_ranocha_p3(const KParams &P, bool with_surfac
         if (err != cudaSuccess) return err;
     }
     const unsigned blocks = (unsigned)((P.elem_end - P.elem_begin + C::EPB - 1) / C::EPB);
+    // (the kernel derives `deferred` from the same condition)
+    const bool deferred = !(with_surface && P.source_terms != TRIXI_B200_SRC_NONE);
+    const size_t smem = deferred ? C::SMEM_DEFERRED : C::SMEM_RESIDENT;
+    KParams Q = P;
+    if (Q.prefetch_distance < 0) Q.prefetch_distance = C::blocks_per_sm(deferred) * Q.sm_count;
     if (with_surface)
-        k_element_euler3d_ranocha_p3<true><<<blocks, C::THREADS, C::SMEM, s>>>(P);
+        k_element_euler3d_ranocha_p3<true><<<blocks, C::THREADS, smem, s>>>(Q);
     else
-        k_element_euler3d_ranocha_p3<false><<<blocks, C::THREADS, C::SMEM, s>>>(P);
+        k_element_euler3d_ranocha_p3<false><<<blocks, C::THREADS, smem, s>>>(Q);
     return cudaSuccess;
 }
 

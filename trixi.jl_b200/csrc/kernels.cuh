@@ -57,7 +57,9 @@ struct KParams {
     unsigned long long *cfl_key;  // kCflSlots partial maxima (spread same-address atomics over L2 slices)
     int want_cfl;                 // RK stage kernels that support it also reduce the CFL speed of the updated u
     int kernel_path;              // 0: tuned kernels where available, 1: generic kernels only
-    int prefetch_distance;        // tuned element kernel: L2 prefetch this many elements ahead (0: off)
+    int prefetch_distance;        // tuned element kernels: L2 prefetch this many elements ahead (0: off, < 0: one
+                                  // wave of resident CTAs, resolved at launch)
+    int sm_count;
     long long elem_begin, elem_end;  // TreeMesh element kernels work on [elem_begin, elem_end) (pipelined rhs_host)
     // VolumeIntegralShockCapturingHG: blending factors of IndicatorHennemannGassner
     double *alpha;       // [nelem] after smoothing (ordered-bits atomicMax target)

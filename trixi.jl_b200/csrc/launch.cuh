@@ -131,6 +131,7 @@ void launch_error_norms(const KParams &P, const NormParams &Q, cudaStream_t s) {
 
 // tuned_euler3d.cu
 cudaError_t launch_element_euler3d_ranocha_p3(const KParams &P, bool with_surface, cudaStream_t s);
+cudaError_t launch_element_euler3d_weak_p3(const KParams &P, bool with_surface, cudaStream_t s);
 
 template <class EQ, int N, int VOLINT, bool WS>
 cudaError_t launch_element_variant(const KParams &P, cudaStream_t s) {
@@ -167,7 +168,9 @@ cudaError_t launch_element_variant(const KParams &P, cudaStream_t s) {
 template <class EQ, int N>
 bool uses_tuned_element(const KParams &P) {
     if constexpr (std::is_same_v<EQ, Euler<3>> && N == 4) {
-        return !P.curved && P.kernel_path == 0 && P.volume_integral == TRIXI_B200_VOLINT_FLUX_DIFFERENCING &&
+        if (P.curved || P.kernel_path != 0) return false;
+        if (P.volume_integral == TRIXI_B200_VOLINT_WEAK_FORM) return true;
+        return P.volume_integral == TRIXI_B200_VOLINT_FLUX_DIFFERENCING &&
                (P.volume_flux == TRIXI_B200_FLUX_RANOCHA || P.volume_flux == TRIXI_B200_FLUX_RANOCHA_TURBO);
     }
     return false;
@@ -177,7 +180,9 @@ template <class EQ, int N>
 cudaError_t launch_element(const KParams &P, bool with_surface, cudaStream_t s) {
     if (P.nelements == 0) return cudaSuccess;
     if constexpr (std::is_same_v<EQ, Euler<3>> && N == 4) {
-        if (uses_tuned_element<EQ, N>(P)) return launch_element_euler3d_ranocha_p3(P, with_surface, s);
+        if (uses_tuned_element<EQ, N>(P))
+            return P.volume_integral == TRIXI_B200_VOLINT_WEAK_FORM ? launch_element_euler3d_weak_p3(P, with_surface, s)
+                                                                   : launch_element_euler3d_ranocha_p3(P, with_surface, s);
     }
     if (P.volume_integral == TRIXI_B200_VOLINT_WEAK_FORM) {
         return with_surface ? launch_element_variant<EQ, N, TRIXI_B200_VOLINT_WEAK_FORM, true>(P, s)
@@ -224,7 +229,8 @@ cudaError_t preload_kernel(K kern) {
     return cudaFuncGetAttributes(&attr, kern);
 }
 
-cudaError_t preload_tuned_euler3d();  // tuned_euler3d.cu
+cudaError_t preload_tuned_euler3d();       // tuned_euler3d.cu
+cudaError_t preload_tuned_euler3d_weak();  // tuned_euler3d.cu
 
 template <class EQ, int N>
 cudaError_t preload_all() {
@@ -266,7 +272,10 @@ cudaError_t preload_all() {
         TB_PRELOAD((k_indicator_smooth<EQ, N>));
     }
 #undef TB_PRELOAD
-    if constexpr (std::is_same_v<EQ, Euler<3>> && N == 4) return preload_tuned_euler3d();
+    if constexpr (std::is_same_v<EQ, Euler<3>> && N == 4) {
+        if ((e = preload_tuned_euler3d()) != cudaSuccess) return e;
+        return preload_tuned_euler3d_weak();
+    }
     return cudaSuccess;
 }
 

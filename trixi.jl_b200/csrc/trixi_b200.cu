@@ -912,10 +912,11 @@ TRIXI_B200_API int trixi_b200_create(const trixi_b200_desc *d, trixi_b200_handle
     P.cfl_key = h->d_cfl;
     P.want_cfl = 0;
     {
-        // L2 prefetch distance of the tuned element kernel: one wave of resident CTAs (14 per SM)
+        // L2 prefetch distance of the tuned element kernels: one wave of resident CTAs, resolved at launch
         int sms = 0;
         CREATE_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
-        P.prefetch_distance = 14 * sms;
+        P.sm_count = sms;
+        P.prefetch_distance = -1;
     }
     CREATE_CUDA(cudaMallocHost((void **)&h->h_cfl, kCflSlots * sizeof(unsigned long long)));
     CREATE_CUDA(cudaDeviceSynchronize());
@@ -1266,7 +1267,7 @@ TRIXI_B200_API int trixi_b200_set_option(trixi_b200_handle *h, int option, int v
         h->P.kernel_path = value;
         return 0;
     case TRIXI_B200_OPT_PREFETCH_DISTANCE:
-        if (value < 0) return fail(h, TRIXI_B200_EINVAL, "prefetch distance must be >= 0");
+        if (value < -1) return fail(h, TRIXI_B200_EINVAL, "prefetch distance must be >= 0, or -1 for one wave of CTAs");
         h->P.prefetch_distance = value;
         return 0;
     case TRIXI_B200_OPT_FUSED_CFL:
