@@ -19,26 +19,35 @@ namespace tb {
 
 struct WeakCfg {
     static constexpr int THREADS = 32;
-    static constexpr int CONS = 320, SFV = 480, XYZ = 192;  // doubles per element
-    // s_u, s_ut (TMA in/out), s_sfv, s_f (one direction's nodal fluxes), mbarrier, [s_x]
-    static constexpr size_t smem(bool with_sources) {
-        return sizeof(double) * (3 * CONS + SFV + (with_sources ? XYZ : 0)) + 16;
+    static constexpr int CONS = 320, SFV = 480, XYZ = 192, JA = 576, IJ = 64;  // doubles per element
+    // s_u, s_ut (TMA in/out), s_sfv, s_f (one direction's nodal fluxes), mbarrier, [s_ja, s_ij], [s_x]
+    static constexpr size_t smem(bool with_sources, bool curved) {
+        return sizeof(double) * (3 * CONS + SFV + (curved ? JA + IJ : 0) + (with_sources ? XYZ : 0)) + 16;
     }
     static constexpr int MIN_BLOCKS = 18;
-    static constexpr int blocks_per_sm(bool with_sources) { return with_sources ? 16 : 18; }
+    static constexpr int blocks_per_sm(bool with_sources, bool curved) {
+        return (int)((227 * 1024 + 1024) / (smem(with_sources, curved) + 1024));  // 1 KB per CTA is reserved
+    }
 };
 
-template <bool WITH_SURFACE>
-__global__ void __launch_bounds__(WeakCfg::THREADS, WeakCfg::MIN_BLOCKS) k_element_euler3d_weak_p3(const KParams P) {
+// CURVED: StructuredMesh / P4estMesh (weak_form_kernel! dgsem_structured/dg_3d.jl:36-89): contravariant fluxes
+// Ja^a . f, nodal inverse Jacobian (apply_jacobian! :937-956), P4est's all-plus surface integral
+// (dgsem_p4est/dg_3d.jl:976-1034); the element's contravariant_vectors [3, 3, 64] and inverse_jacobian [64]
+// records are two more bulk loads.
+template <bool WITH_SURFACE, bool CURVED>
+__global__ void __launch_bounds__(WeakCfg::THREADS, CURVED ? 12 : WeakCfg::MIN_BLOCKS)
+    k_element_euler3d_weak_p3(const KParams P) {
     using C = WeakCfg;
-    constexpr int CONS = C::CONS, SFV = C::SFV, XYZ = C::XYZ;
+    constexpr int CONS = C::CONS, SFV = C::SFV, XYZ = C::XYZ, JA = C::JA, IJ = C::IJ;
     extern __shared__ __align__(128) double smem[];
     double *s_u = smem;           // [64][5] u in, updated u out
     double *s_ut = s_u + CONS;    // [64][5] u_tmp in, u_tmp (or du) out
     double *s_sfv = s_ut + CONS;  // [6][16][5]
     double *s_f = s_sfv + SFV;    // [64][5] nodal fluxes of the current direction
     const uint32_t bar = smem_u32(s_f + CONS);
-    double *s_x = s_f + CONS + 2;  // [64][3] node coordinates (source terms only)
+    double *s_ja = s_f + CONS + 2;               // curved: [64][3 (index)][3 (dim)]
+    double *s_ij = s_ja + JA;                    // curved: [64]
+    double *s_x = CURVED ? s_ij + IJ : s_ja;     // [64][3] node coordinates (source terms only)
 
     const int lane = threadIdx.x;
     const long long e = P.elem_begin + blockIdx.x;
@@ -54,7 +63,13 @@ __global__ void __launch_bounds__(WeakCfg::THREADS, WeakCfg::MIN_BLOCKS) k_eleme
     __syncwarp();
     if (lane == 0) {
         constexpr uint32_t bu = CONS * sizeof(double), bs = SFV * sizeof(double), bx = XYZ * sizeof(double);
-        mbar_expect_tx(bar, bu + (need_ut ? bu : 0u) + (WITH_SURFACE ? bs : 0u) + (have_src ? bx : 0u));
+        constexpr uint32_t bj = JA * sizeof(double), bi = IJ * sizeof(double);
+        mbar_expect_tx(bar, bu + (need_ut ? bu : 0u) + (WITH_SURFACE ? bs : 0u) + (have_src ? bx : 0u) +
+                                (CURVED ? bj + (WITH_SURFACE ? bi : 0u) : 0u));
+        if constexpr (CURVED) {
+            tma_load(smem_u32(s_ja), P.contravariant_vectors + e * JA, bj, bar);
+            if (WITH_SURFACE) tma_load(smem_u32(s_ij), P.inverse_jacobian + e * IJ, bi, bar);
+        }
         tma_load(smem_u32(s_u), P.u + e * CONS, bu, bar);
         if (need_ut) tma_load(smem_u32(s_ut), P.u_tmp + e * CONS, bu, bar);
         if (WITH_SURFACE) tma_load(smem_u32(s_sfv), P.sfv + e * SFV, bs, bar);
@@ -65,6 +80,10 @@ __global__ void __launch_bounds__(WeakCfg::THREADS, WeakCfg::MIN_BLOCKS) k_eleme
             if (need_ut) tma_prefetch_l2(P.u_tmp + en * CONS, bu);
             if (WITH_SURFACE) tma_prefetch_l2(P.sfv + en * SFV, bs);
             if (have_src) tma_prefetch_l2(P.node_coordinates + en * XYZ, bx);
+            if constexpr (CURVED) {
+                tma_prefetch_l2(P.contravariant_vectors + en * JA, bj);
+                if (WITH_SURFACE) tma_prefetch_l2(P.inverse_jacobian + en * IJ, bi);
+            }
         }
     }
     // node n = lane + 32 r: i = lane & 3, j = (lane >> 2) & 3, k = (lane >> 4) + 2 r.  Rows of D_hat
@@ -104,12 +123,30 @@ __global__ void __launch_bounds__(WeakCfg::THREADS, WeakCfg::MIN_BLOCKS) k_eleme
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
             double *f = s_f + (lane + 32 * r) * 5;
-            const double rv = mom[r][d];
-            f[0] = rv;
-            f[1] = rv * vel[r][0] + (d == 0 ? pr[r] : 0.0);
-            f[2] = rv * vel[r][1] + (d == 1 ? pr[r] : 0.0);
-            f[3] = rv * vel[r][2] + (d == 2 ? pr[r] : 0.0);
-            f[4] = ep[r] * vel[r][d];
+            if constexpr (!CURVED) {
+                const double rv = mom[r][d];
+                f[0] = rv;
+                f[1] = rv * vel[r][0] + (d == 0 ? pr[r] : 0.0);
+                f[2] = rv * vel[r][1] + (d == 1 ? pr[r] : 0.0);
+                f[3] = rv * vel[r][2] + (d == 2 ? pr[r] : 0.0);
+                f[4] = ep[r] * vel[r][d];
+            } else {
+                // contravariant flux Ja^d . (f1, f2, f3) (dgsem_structured/dg_3d.jl:52-84), summed in the order
+                // of the dimensions like the generic kernel
+                const double *ja = s_ja + (lane + 32 * r) * 9 + 3 * d;
+                double sum[5];
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    const double rv = mom[r][q];
+                    const double fq[5] = {rv, rv * vel[r][0] + (q == 0 ? pr[r] : 0.0),
+                                          rv * vel[r][1] + (q == 1 ? pr[r] : 0.0),
+                                          rv * vel[r][2] + (q == 2 ? pr[r] : 0.0), ep[r] * vel[r][q]};
+#pragma unroll
+                    for (int v = 0; v < 5; ++v) sum[v] = q == 0 ? ja[0] * fq[v] : sum[v] + ja[q] * fq[v];
+                }
+#pragma unroll
+                for (int v = 0; v < 5; ++v) f[v] = sum[v];
+            }
         }
         __syncwarp();
 #pragma unroll
@@ -129,7 +166,9 @@ __global__ void __launch_bounds__(WeakCfg::THREADS, WeakCfg::MIN_BLOCKS) k_eleme
         __syncwarp();
     }
 
-    const double factor = WITH_SURFACE ? -P.inverse_jacobian[e] : 1.0;
+    const double factor_tree = (WITH_SURFACE && !CURVED) ? -P.inverse_jacobian[e] : 1.0;
+    // Tree/Structured: "-" on the negative faces; P4est: "+" everywhere (fluxes along outward normals)
+    const double w_neg = (CURVED && P.p4est) ? P.inv_weight0 : -P.inv_weight0;
     unsigned long long cfl0 = 0ull, cfl1 = 0ull, cfl2 = 0ull;
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
@@ -140,23 +179,24 @@ __global__ void __launch_bounds__(WeakCfg::THREADS, WeakCfg::MIN_BLOCKS) k_eleme
             // calc_surface_integral! (dg_3d.jl:1337-1394): directions 1..6 = -x,+x,-y,+y,-z,+z
             if (i == 0 || i == 3) {
                 const double *sf = s_sfv + ((i == 0 ? 0 : 1) * 16 + j + 4 * k) * 5;
-                const double w = i == 0 ? -P.inv_weight0 : P.inv_weight0;
+                const double w = i == 0 ? w_neg : P.inv_weight0;
 #pragma unroll
                 for (int v = 0; v < 5; ++v) val[v] = fma(sf[v], w, val[v]);
             }
             if (j == 0 || j == 3) {
                 const double *sf = s_sfv + ((j == 0 ? 2 : 3) * 16 + i + 4 * k) * 5;
-                const double w = j == 0 ? -P.inv_weight0 : P.inv_weight0;
+                const double w = j == 0 ? w_neg : P.inv_weight0;
 #pragma unroll
                 for (int v = 0; v < 5; ++v) val[v] = fma(sf[v], w, val[v]);
             }
             if (k == 0 || k == 3) {
                 const double *sf = s_sfv + ((k == 0 ? 4 : 5) * 16 + i + 4 * j) * 5;
-                const double w = k == 0 ? -P.inv_weight0 : P.inv_weight0;
+                const double w = k == 0 ? w_neg : P.inv_weight0;
 #pragma unroll
                 for (int v = 0; v < 5; ++v) val[v] = fma(sf[v], w, val[v]);
             }
-            // apply_jacobian! (dg_3d.jl:1396-1414)
+            // apply_jacobian! (dg_3d.jl:1396-1414; curved: nodal, dgsem_structured/dg_3d.jl:937-956)
+            const double factor = CURVED ? -s_ij[n] : factor_tree;
 #pragma unroll
             for (int v = 0; v < 5; ++v) val[v] *= factor;
             // calc_sources! (dg_3d.jl:1417-1437)
@@ -187,7 +227,7 @@ __global__ void __launch_bounds__(WeakCfg::THREADS, WeakCfg::MIN_BLOCKS) k_eleme
                 un[v] = out_u[v] + tmp * P.rk_b_dt;
                 out_u[v] = un[v];
             }
-            if (P.want_cfl) {
+            if (!CURVED && P.want_cfl) {
                 // max_dt of the updated state (stepsize_dg3d.jl:8-32), as in the flux-differencing kernel
                 const double rho = un[0], inv_rho = fast_rcp(rho);
                 double v1 = un[1] * inv_rho, v2 = un[2] * inv_rho, v3 = un[3] * inv_rho;
@@ -205,7 +245,7 @@ __global__ void __launch_bounds__(WeakCfg::THREADS, WeakCfg::MIN_BLOCKS) k_eleme
             }
         }
     }
-    if (rk && P.want_cfl) {
+    if (!CURVED && rk && P.want_cfl) {
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) {
             cfl0 = max(cfl0, __shfl_xor_sync(0xffffffffu, cfl0, off));
@@ -235,33 +275,35 @@ __global__ void __launch_bounds__(WeakCfg::THREADS, WeakCfg::MIN_BLOCKS) k_eleme
 }
 
 cudaError_t preload_tuned_euler3d_weak() {
-    cudaError_t e = preload_kernel(k_element_euler3d_weak_p3<true>);
-    if (e != cudaSuccess) return e;
-    return preload_kernel(k_element_euler3d_weak_p3<false>);
+    cudaError_t e;
+    if ((e = preload_kernel(k_element_euler3d_weak_p3<true, false>)) != cudaSuccess) return e;
+    if ((e = preload_kernel(k_element_euler3d_weak_p3<false, false>)) != cudaSuccess) return e;
+    if ((e = preload_kernel(k_element_euler3d_weak_p3<true, true>)) != cudaSuccess) return e;
+    return preload_kernel(k_element_euler3d_weak_p3<false, true>);
 }
 
-cudaError_t launch_element_euler3d_weak_p3(const KParams &P, bool with_surface, cudaStream_t s) {
+template <bool WS, bool CURVED>
+static cudaError_t launch_weak_variant(const KParams &P, cudaStream_t s) {
     using C = WeakCfg;
     static PerDeviceFlag configured;
+    auto kern = k_element_euler3d_weak_p3<WS, CURVED>;
     if (!configured.test_and_set()) {
-        cudaError_t err = cudaFuncSetAttribute(k_element_euler3d_weak_p3<true>,
-                                               cudaFuncAttributePreferredSharedMemoryCarveout,
+        cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
                                                cudaSharedmemCarveoutMaxShared);
-        if (err != cudaSuccess) return err;
-        err = cudaFuncSetAttribute(k_element_euler3d_weak_p3<false>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                   cudaSharedmemCarveoutMaxShared);
         if (err != cudaSuccess) return err;
     }
     const unsigned blocks = (unsigned)(P.elem_end - P.elem_begin);
-    const bool with_sources = with_surface && P.source_terms != TRIXI_B200_SRC_NONE;
-    const size_t smem = C::smem(with_sources);
+    const bool with_sources = WS && P.source_terms != TRIXI_B200_SRC_NONE;
     KParams Q = P;
-    if (Q.prefetch_distance < 0) Q.prefetch_distance = C::blocks_per_sm(with_sources) * Q.sm_count;
-    if (with_surface)
-        k_element_euler3d_weak_p3<true><<<blocks, C::THREADS, smem, s>>>(Q);
-    else
-        k_element_euler3d_weak_p3<false><<<blocks, C::THREADS, smem, s>>>(Q);
+    if (Q.prefetch_distance < 0) Q.prefetch_distance = C::blocks_per_sm(with_sources, CURVED) * Q.sm_count;
+    kern<<<blocks, C::THREADS, C::smem(with_sources, CURVED), s>>>(Q);
     return cudaSuccess;
+}
+
+cudaError_t launch_element_euler3d_weak_p3(const KParams &P, bool with_surface, cudaStream_t s) {
+    if (P.curved)
+        return with_surface ? launch_weak_variant<true, true>(P, s) : launch_weak_variant<false, true>(P, s);
+    return with_surface ? launch_weak_variant<true, false>(P, s) : launch_weak_variant<false, false>(P, s);
 }
 
 }  // namespace tb

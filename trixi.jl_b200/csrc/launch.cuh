@@ -168,12 +168,18 @@ cudaError_t launch_element_variant(const KParams &P, cudaStream_t s) {
 template <class EQ, int N>
 bool uses_tuned_element(const KParams &P) {
     if constexpr (std::is_same_v<EQ, Euler<3>> && N == 4) {
-        if (P.curved || P.kernel_path != 0) return false;
-        if (P.volume_integral == TRIXI_B200_VOLINT_WEAK_FORM) return true;
-        return P.volume_integral == TRIXI_B200_VOLINT_FLUX_DIFFERENCING &&
+        if (P.kernel_path != 0) return false;
+        if (P.volume_integral == TRIXI_B200_VOLINT_WEAK_FORM) return true;  // TreeMesh and curved meshes
+        return !P.curved && P.volume_integral == TRIXI_B200_VOLINT_FLUX_DIFFERENCING &&
                (P.volume_flux == TRIXI_B200_FLUX_RANOCHA || P.volume_flux == TRIXI_B200_FLUX_RANOCHA_TURBO);
     }
     return false;
+}
+
+// true when the RK stage kernel selected for P also reduces the CFL wave speeds (TreeMesh tuned kernels)
+template <class EQ, int N>
+bool fuses_cfl(const KParams &P) {
+    return uses_tuned_element<EQ, N>(P) && !P.curved;
 }
 
 template <class EQ, int N>
@@ -288,7 +294,7 @@ const Launchers *make_launchers() {
                                 &launch_element<EQ, N>,
                                 &launch_indicator<EQ, N>,
                                 &launch_max_dt<EQ, N>,
-                                &uses_tuned_element<EQ, N>,
+                                &fuses_cfl<EQ, N>,
                                 &launch_mpi_pack<EQ, N>,
                                 &launch_mpi_interface_flux<EQ, N>,
                                 &preload_all<EQ, N>,
