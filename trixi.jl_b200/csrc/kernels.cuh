@@ -174,7 +174,9 @@ __global__ void __launch_bounds__(256) k_interface_flux(const KParams P) {
 // interfaces), gathers both sides' face values with lane-consecutive addresses (u is AoS, so a face is made of
 // contiguous runs of NV, N*NV or N*N*NV doubles), computes one flux per lane and writes the two
 // surface_flux_values faces (contiguous NF*NV doubles each) back fully coalesced. Used when NF divides 32.
-template <class EQ, int N, bool FAST = false>
+// CURVED (StructuredMesh, dgsem_structured/dg_3d.jl:619-753): the flux is taken along the contravariant vector of
+// the right element's first node layer times sign(inverse_jacobian), and stored with that sign on both sides.
+template <class EQ, int N, bool FAST = false, bool CURVED = false>
 __global__ void __launch_bounds__(256) k_interface_flux_staged(const KParams P) {
     constexpr int ND = EQ::NDIMS, NV = EQ::NVARS, NF = ipow(N, ND - 1), NN = ipow(N, ND);
     constexpr int G = 32 / NF;   // interfaces per warp
@@ -234,9 +236,26 @@ __global__ void __launch_bounds__(256) k_interface_flux_staged(const KParams P) 
             ul[v] = s[(2 * g) * FV + fn * NV + v];
             ur[v] = s[(2 * g + 1) * FV + fn * NV + v];
         }
-        surface_numflux<EQ, FAST>(eq, P.surface_flux, ul, ur, o, f);
         bool done = false;
-        if constexpr (EQ::kHasNoncons) {
+        if constexpr (CURVED) {
+            const int SA = o == 0 ? N : 1;
+            const int SB = (ND == 3 && o == 2) ? N : N * N;
+            const int b = fn / N, a = fn - b * N;
+            const long long nr = s_elem[warp][2 * g + 1] * NN + (a * SA + b * SB);
+            const double ij = P.inverse_jacobian[nr];
+            const double sign_jacobian = ij > 0 ? 1.0 : (ij < 0 ? -1.0 : 0.0);
+            const double *ja = P.contravariant_vectors + (nr * ND + o) * ND;
+            double nrm[ND];
+#pragma unroll
+            for (int d = 0; d < ND; ++d) nrm[d] = ja[d] * sign_jacobian;
+            eq.numflux_normal(P.surface_flux, ul, ur, nrm, f);
+#pragma unroll
+            for (int v = 0; v < NV; ++v) fl[v] = fr[v] = sign_jacobian * f[v];
+            done = true;
+        } else {
+            surface_numflux<EQ, FAST>(eq, P.surface_flux, ul, ur, o, f);
+        }
+        if constexpr (EQ::kHasNoncons && !CURVED) {
             // calc_interface_flux! with nonconservative terms (dg_3d.jl:604-649): flux + 0.5 * noncons per side
             if (EQ::has_noncons(P.surface_flux)) {
                 double gl[NV], gr[NV];
@@ -1325,6 +1344,10 @@ __global__ void __launch_bounds__(256) k_interface_flux_p4est(const KParams P) {
         ss[v] = -f[v];
     }
 }
+
+// (A shared-memory staged variant like k_interface_flux_staged was measured and dropped: 0.83 ms against 0.795 ms
+// per launch at 16.8 M DOF -- with the LLF flux along a normal the kernel is bound by its FP64 divisions and
+// square roots and the scattered 24-byte normal loads, not by the face gathers.)
 
 // prolong2boundaries! + calc_boundary_flux! (dgsem_p4est/dg_3d.jl:412-548)
 template <class EQ, int N>

@@ -33,11 +33,19 @@ void launch_interface_flux(const KParams &P, cudaStream_t s) {
     if (total == 0) return;
     const int threads = 256;
     const unsigned blocks = (unsigned)((total + threads - 1) / threads);
-    if (P.p4est)
+    if (P.p4est) {
         k_interface_flux_p4est<EQ, N><<<blocks, threads, 0, s>>>(P);
-    else if (P.curved)
+    } else if (P.curved) {
+        if constexpr (32 % NF == 0 && !EQ::kHasNoncons) {
+            if (P.kernel_path == 0) {
+                const long long per_block = 8 * (32 / NF);
+                k_interface_flux_staged<EQ, N, false, true>
+                    <<<(unsigned)((P.ninterfaces + per_block - 1) / per_block), 256, 0, s>>>(P);
+                return;
+            }
+        }
         k_interface_flux_curved<EQ, N><<<blocks, threads, 0, s>>>(P);
-    else {
+    } else {
         const bool fast = HasFastRanocha<EQ>::value && P.kernel_path == 0 &&
                           (P.surface_flux == TRIXI_B200_FLUX_RANOCHA || P.surface_flux == TRIXI_B200_FLUX_RANOCHA_TURBO);
         if constexpr (32 % NF == 0) {
@@ -248,6 +256,7 @@ cudaError_t preload_all() {
     if constexpr (32 % ipow(N, EQ::NDIMS - 1) == 0) {
         TB_PRELOAD((k_interface_flux_staged<EQ, N>));
         TB_PRELOAD((k_interface_flux_staged<EQ, N, true>));
+        if constexpr (!EQ::kHasNoncons) TB_PRELOAD((k_interface_flux_staged<EQ, N, false, true>));
     }
     TB_PRELOAD((k_mpi_interface_flux<EQ, N, true>));
     TB_PRELOAD((k_boundary_flux<EQ, N>));
