@@ -343,6 +343,59 @@ def test_conservation_large():
     assert np.all(np.abs(total) <= 1e-12 * np.maximum(scale, 1.0))
 
 
+def test_full_size_level6_properties():
+    """BASELINE config 2 size (TreeMesh level 6: 262 144 elements, 16.8 M DOF), size-independent properties:
+    the host-buffer call (chunk pipeline in its automatic configuration: 32 chunks of 8192 elements) gives the same
+    bits as the device-resident call, a CK54 step conserves every variable's integral, the device-side
+    entropy rate of the EC discretisation vanishes (flux_ranocha volume and surface fluxes), and a host-resident
+    step equals the device-resident step."""
+    semi = ELIXIRS["tree_3d_euler_ec"].build(level=6)
+    u = T.compute_coefficients(0.0, semi)
+    rng = np.random.default_rng(7)
+    u *= 1 + 0.05 * rng.uniform(-1, 1, (1,) + u.shape[1:])
+    gpu = semi.backend()
+    flat = np.ascontiguousarray(u.ravel(order="F"))
+    du_host = np.empty_like(flat)
+    n0 = gpu.launch_count()
+    gpu.rhs_host(du_host, flat, 0.0)
+    assert gpu.launch_count() - n0 > 2  # pipelined: many chunk launches
+    gpu.upload(0, flat)
+    gpu.rhs(0.0)
+    du_dev = gpu.download(1)
+    assert np.array_equal(du_host, du_dev)
+    # conservation and entropy conservation of the semidiscretisation
+    du = du_dev.reshape(u.shape, order="F")
+    w = semi.solver.basis.weights
+    w3 = w[:, None, None] * w[None, :, None] * w[None, None, :]
+    vol = 1.0 / semi.cache.elements.inverse_jacobian[0] ** 3
+    total = np.einsum("vijke,ijk->v", du, w3) * vol
+    scale = np.einsum("vijke,ijk->v", np.abs(du), w3) * vol
+    assert np.all(np.abs(total) <= 1e-12 * np.maximum(scale, 1.0))
+    rho, rv1, rv2, rv3, rho_e = u
+    v1, v2, v3 = rv1 / rho, rv2 / rho, rv3 / rho
+    p = 0.4 * (rho_e - 0.5 * (rv1 * v1 + rv2 * v2 + rv3 * v3))
+    s = np.log(p) - 1.4 * np.log(rho)
+    rho_p = rho / p
+    # cons2entropy (compressible_euler_3d.jl:1810-1830)
+    wv = np.stack([(1.4 - s) / 0.4 - 0.5 * rho_p * (v1**2 + v2**2 + v3**2), rho_p * v1, rho_p * v2, rho_p * v3, -rho_p])
+    ds_dt = np.einsum("vijke,vijke,ijk->", wv, du, w3) * vol
+    ds_scale = np.einsum("vijke,vijke,ijk->", np.abs(wv), np.abs(du), w3) * vol
+    assert abs(ds_dt) <= 1e-12 * ds_scale
+    # host-resident step == device-resident step
+    alg = T.CarpenterKennedy2N54()
+    gpu.upload(0, flat)
+    dt = 0.5 * gpu.max_dt()
+    gpu.step_2n(0.0, dt, alg.a, alg.b, alg.c)
+    u_dev = gpu.download(0)
+    u_host = flat.copy()
+    gpu.step_2n_host(u_host, 0.0, dt, alg.a, alg.b, alg.c)
+    assert np.array_equal(u_host, u_dev)
+    m0 = np.einsum("vijke,ijk->v", u, w3) * vol
+    m1 = np.einsum("vijke,ijk->v", u_dev.reshape(u.shape, order="F"), w3) * vol
+    # (the two 16.8 M-term sums themselves carry ~sqrt(N) eps = 4e-13 of round-off)
+    assert np.all(np.abs(m1 - m0) <= 2e-12 * np.maximum(np.abs(m0), 1.0))
+
+
 # ---- distributed path: several ranks' handles inside one process on one GPU --------------------------
 def _ranked_semis(name, world):
     ex = ELIXIRS[name]
