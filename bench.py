@@ -72,7 +72,7 @@ WORKLOADS = {
     "p4est_curved": {"nvars": 5, "bytes": 212.0 + 72.0 + 8.0, "flop": 149.0 + 45.0 + 45.0,
                      "kernel": "k_element_euler3d_weak_p3<curved> (P4estMesh: + surface integral, TMA tiles)"},
     "mhd_ec": {"nvars": 9, "bytes": 9 * 8 * (1 + 1.5 + 0.8 + 2), "flop": None,
-               "kernel": "k_element<Mhd3D,4,flux differencing> (Hindenlang-Gassner + Powell nonconservative)"},
+               "kernel": "k_element_fd3d_p3<Mhd3D> (line sweeps, Hindenlang-Gassner + Powell nonconservative, TMA tiles)"},
 }
 
 

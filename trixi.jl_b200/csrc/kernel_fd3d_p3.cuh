@@ -1,0 +1,333 @@
+// Line-sweep element kernel for any 3D equation system at polydeg 3: flux-differencing volume integral with an
+// arbitrary registered two-point flux (and the nonconservative Powell term of GLM-MHD), fused with surface
+// integral, Jacobian, source terms and the 2N Runge-Kutta stage.  Same skeleton as the headline kernel
+// (kernel_euler3d_fd_p3.cuh) without the hoisted-logarithm trick:
+//  * one warp = one CTA = one element, tiles by cp.async.bulk (u, surface_flux_values up front; u_tmp into the
+//    line tile's storage once the z pass is done), results leave by bulk stores;
+//  * per direction two threads share a line of 4 nodes and evaluate three of its six node pairs each, so
+//    every two-point flux is computed once (the generic one-thread-per-node kernel computes each twice:
+//    flux_differencing_kernel! dg_3d.jl:166-214 has the symmetric loop this restores);
+//  * the line tile holds the conservative states at the swizzled node position of the headline kernel
+//    (record strides 5 and 9 are odd), so the x, y and z sweeps are bank-conflict free.
+// Used for Euler 3D with flux_shima_etal / kennedy_gruber / chandrashekar / central and for GLM-MHD with
+// (flux_hindenlang_gassner, flux_nonconservative_powell): dg_3d.jl:216-266 for the nonconservative part.
+#pragma once
+#include "kernel_euler3d_fd_p3.cuh"
+
+namespace tb {
+
+template <class EQ>
+struct LineSweepCfg {
+    static constexpr int NV = EQ::NVARS, THREADS = 32;
+    static constexpr int CONS = 64 * NV, SFV = 96 * NV;  // doubles per element
+    // s_u (natural, TMA), s_sfv (natural, TMA), s_du (swizzled), s_line (swizzled; later the u_tmp tile), mbarrier
+    static constexpr size_t SMEM = sizeof(double) * (3 * CONS + SFV) + 16;
+    static constexpr int BLOCKS_PER_SM = (int)((227 * 1024 + 1024) / (SMEM + 1024));  // 1 KB per CTA is reserved
+    static constexpr int MIN_BLOCKS = BLOCKS_PER_SM < 8 ? BLOCKS_PER_SM : (BLOCKS_PER_SM > 16 ? 16 : BLOCKS_PER_SM);
+};
+
+template <class EQ, bool WITH_SURFACE>
+__global__ void __launch_bounds__(LineSweepCfg<EQ>::THREADS, LineSweepCfg<EQ>::MIN_BLOCKS)
+    k_element_fd3d_p3(const KParams P) {
+    using C = LineSweepCfg<EQ>;
+    constexpr int NV = C::NV, CONS = C::CONS, SFV = C::SFV;
+    extern __shared__ __align__(128) double smem[];
+    double *s_u = smem;             // [64][NV] natural: u in, updated u out
+    double *s_sfv = s_u + CONS;     // [6][16][NV] natural
+    double *s_du = s_sfv + SFV;     // [64][NV] swizzled
+    double *s_line = s_du + CONS;   // [64][NV] swizzled copy of u for the sweeps
+    double *s_ut = s_line;          // afterwards: [64][NV] natural, u_tmp in, u_tmp (or du) out
+    const uint32_t bar = smem_u32(s_line + CONS);
+
+    const EQ eq(P.eq);
+    const int lane = threadIdx.x;
+    const long long e = P.elem_begin + blockIdx.x;
+    const bool rk = P.mode != 0;
+    const bool need_ut = rk && P.rk_a != 0.0;
+
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    constexpr uint32_t bu = CONS * sizeof(double), bs = SFV * sizeof(double);
+    if (lane == 0) {
+        mbar_expect_tx(bar, bu + (WITH_SURFACE ? bs : 0u));
+        tma_load(smem_u32(s_u), P.u + e * CONS, bu, bar);
+        if (WITH_SURFACE) tma_load(smem_u32(s_sfv), P.sfv + e * SFV, bs, bar);
+        const long long en = e + P.prefetch_distance;
+        if (P.prefetch_distance > 0 && en < P.nelements) {
+            tma_prefetch_l2(P.u + en * CONS, bu);
+            if (need_ut) tma_prefetch_l2(P.u_tmp + en * CONS, bu);
+            if (WITH_SURFACE) tma_prefetch_l2(P.sfv + en * SFV, bs);
+        }
+    }
+    // line-local roles as in the headline kernel: thread h of line l16 owns nodes lm[0], lm[1], sees lm[2], lm[3]
+    const int h = lane >> 4, l16 = lane & 15;
+    const int a0 = l16 & 3, a1 = l16 >> 2;
+    const int lm[4] = {h ? 3 : 0, h ? 2 : 1, h ? 0 : 2, h ? 1 : 3};
+    const double w01 = P.dsplit_c[lm[0] + 4 * lm[1]], w10 = P.dsplit_c[lm[1] + 4 * lm[0]];
+    const double w02 = P.dsplit_c[lm[0] + 4 * lm[2]], w20 = P.dsplit_c[lm[2] + 4 * lm[0]];
+    const double w13 = P.dsplit_c[lm[1] + 4 * lm[3]], w31 = P.dsplit_c[lm[3] + 4 * lm[1]];
+    while (!mbar_try_wait(bar, 0)) {
+    }
+
+    // 1. swizzled copy of the element's states
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int n = lane + 32 * r;
+        const double *c = s_u + n * NV;
+        double *o = s_line + swz_pos(n) * NV;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) o[v] = c[v];
+    }
+    __syncwarp();
+
+    // 2. direction sweeps
+    bool noncons = false;
+    if constexpr (EQ::kHasNoncons) noncons = EQ::has_noncons(P.volume_flux);
+    (void)noncons;
+    int pos[4];
+    double own[2][NV], frn[2][NV];
+#pragma unroll 1
+    for (int d = 0; d < 3; ++d) {
+        const int stride = 1 << (2 * d);
+        const int base = d == 0 ? 4 * l16 : (d == 1 ? a0 + 16 * a1 : l16);
+        double q[4][NV];
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+            pos[m] = swz_pos(base + lm[m] * stride);
+            const double *src = s_line + pos[m] * NV;
+#pragma unroll
+            for (int v = 0; v < NV; ++v) q[m][v] = src[v];
+        }
+        double f[NV], lo[NV], hi[NV];
+        // volume_flux(u_lower, u_upper) like the reference's loop (ii > i): thread h = 1 walks its line downwards,
+        // so its operands are swapped -- by value selects, the two half-warps must not diverge around the flux
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            lo[v] = h ? q[1][v] : q[0][v];
+            hi[v] = h ? q[0][v] : q[1][v];
+        }
+        eq.numflux(P.volume_flux, lo, hi, d, f);
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            own[0][v] = w01 * f[v];
+            own[1][v] = w10 * f[v];
+        }
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            lo[v] = h ? q[2][v] : q[0][v];
+            hi[v] = h ? q[0][v] : q[2][v];
+        }
+        eq.numflux(P.volume_flux, lo, hi, d, f);
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            own[0][v] = fma(w02, f[v], own[0][v]);
+            frn[0][v] = w20 * f[v];
+        }
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            lo[v] = h ? q[3][v] : q[1][v];
+            hi[v] = h ? q[1][v] : q[3][v];
+        }
+        eq.numflux(P.volume_flux, lo, hi, d, f);
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            own[1][v] = fma(w13, f[v], own[1][v]);
+            frn[1][v] = w31 * f[v];
+        }
+        if constexpr (EQ::kHasNoncons) {
+            // nonconservative volume terms (dg_3d.jl:216-266): node a gets 0.5 D_split[a, b] g(u_a, u_b) from
+            // every partner b of its line (D_split has a zero diagonal)
+            if (noncons) {
+                double g[NV];
+                eq.noncons(q[0], q[1], d, g);
+#pragma unroll
+                for (int v = 0; v < NV; ++v) own[0][v] = fma(0.5 * w01, g[v], own[0][v]);
+                eq.noncons(q[1], q[0], d, g);
+#pragma unroll
+                for (int v = 0; v < NV; ++v) own[1][v] = fma(0.5 * w10, g[v], own[1][v]);
+                eq.noncons(q[0], q[2], d, g);
+#pragma unroll
+                for (int v = 0; v < NV; ++v) own[0][v] = fma(0.5 * w02, g[v], own[0][v]);
+                eq.noncons(q[2], q[0], d, g);
+#pragma unroll
+                for (int v = 0; v < NV; ++v) frn[0][v] = fma(0.5 * w20, g[v], frn[0][v]);
+                eq.noncons(q[1], q[3], d, g);
+#pragma unroll
+                for (int v = 0; v < NV; ++v) own[1][v] = fma(0.5 * w13, g[v], own[1][v]);
+                eq.noncons(q[3], q[1], d, g);
+#pragma unroll
+                for (int v = 0; v < NV; ++v) frn[1][v] = fma(0.5 * w31, g[v], frn[1][v]);
+            }
+        }
+        if (d < 2) {
+#pragma unroll
+            for (int m = 0; m < 2; ++m) {
+                double *t = s_du + pos[m] * NV;
+#pragma unroll
+                for (int v = 0; v < NV; ++v) t[v] = d == 0 ? own[m][v] : t[v] + own[m][v];
+            }
+            __syncwarp();
+        }
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+            double *t = s_du + pos[2 + m] * NV;
+#pragma unroll
+            for (int v = 0; v < NV; ++v) t[v] += frn[m][v];
+        }
+        __syncwarp();
+    }
+
+    // the line tile is dead: fetch u_tmp into its storage while the surface terms are applied
+    if (need_ut) {
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+            mbar_expect_tx(bar, bu);
+            tma_load(smem_u32(s_ut), P.u_tmp + e * CONS, bu, bar);
+        }
+    }
+
+    // 3. finish the two own nodes (i, j, k) = (a0, a1, lm[0]), (a0, a1, lm[1]) of the z line
+    const int i = a0, j = a1;
+    const double factor = WITH_SURFACE ? -P.inverse_jacobian[e] : 1.0;
+    const bool have_src = WITH_SURFACE && P.source_terms != TRIXI_B200_SRC_NONE;
+    double vals[2][NV];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int k = lm[r];
+        const int n = l16 + 16 * k;
+        const double *t = s_du + pos[r] * NV;
+        double(&val)[NV] = vals[r];
+#pragma unroll
+        for (int v = 0; v < NV; ++v) val[v] = t[v] + own[r][v];
+        if constexpr (WITH_SURFACE) {
+            // calc_surface_integral! (dg_3d.jl:1337-1394): directions 1..6 = -x,+x,-y,+y,-z,+z
+            if (i == 0 || i == 3) {
+                const double *sf = s_sfv + ((i == 0 ? 0 : 1) * 16 + j + 4 * k) * NV;
+                const double w = i == 0 ? -P.inv_weight0 : P.inv_weight0;
+#pragma unroll
+                for (int v = 0; v < NV; ++v) val[v] = fma(sf[v], w, val[v]);
+            }
+            if (j == 0 || j == 3) {
+                const double *sf = s_sfv + ((j == 0 ? 2 : 3) * 16 + i + 4 * k) * NV;
+                const double w = j == 0 ? -P.inv_weight0 : P.inv_weight0;
+#pragma unroll
+                for (int v = 0; v < NV; ++v) val[v] = fma(sf[v], w, val[v]);
+            }
+            if (k == 0 || k == 3) {
+                const double *sf = s_sfv + ((k == 0 ? 4 : 5) * 16 + l16) * NV;
+                const double w = k == 0 ? -P.inv_weight0 : P.inv_weight0;
+#pragma unroll
+                for (int v = 0; v < NV; ++v) val[v] = fma(sf[v], w, val[v]);
+            }
+            // apply_jacobian! (dg_3d.jl:1396-1414)
+#pragma unroll
+            for (int v = 0; v < NV; ++v) val[v] *= factor;
+            // calc_sources! (dg_3d.jl:1417-1437)
+            if (have_src) {
+                double un[NV], x[3], sv[NV];
+#pragma unroll
+                for (int v = 0; v < NV; ++v) un[v] = s_u[n * NV + v];
+#pragma unroll
+                for (int dd = 0; dd < 3; ++dd) x[dd] = P.node_coordinates[(e * 64 + n) * 3 + dd];
+                eq.source_terms(P.source_terms, un, x, P.t, sv);
+#pragma unroll
+                for (int v = 0; v < NV; ++v) val[v] += sv[v];
+            }
+        }
+    }
+    if (!need_ut) __syncwarp();  // every lane is done with the line tile before it becomes the output tile
+    if (need_ut) {
+        while (!mbar_try_wait(bar, 1)) {
+        }
+    }
+    unsigned long long cfl[3] = {0ull, 0ull, 0ull};
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int n = l16 + 16 * lm[r];
+        double(&val)[NV] = vals[r];
+        double *out_t = s_ut + n * NV;
+        if (!rk) {
+#pragma unroll
+            for (int v = 0; v < NV; ++v) out_t[v] = val[v];
+        } else {
+            // 2N stage (methods_2N.jl:152-158): u_tmp = du - u_tmp * a; u += u_tmp * (b * dt)
+            double *out_u = s_u + n * NV;
+            double un[NV];
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+                const double tmp = need_ut ? val[v] - out_t[v] * P.rk_a : val[v];
+                out_t[v] = tmp;
+                un[v] = out_u[v] + tmp * P.rk_b_dt;
+                out_u[v] = un[v];
+            }
+            if (P.want_cfl) {
+                double lam[3];
+                eq.max_abs_speeds(un, lam);
+#pragma unroll
+                for (int dd = 0; dd < 3; ++dd) cfl[dd] = max(cfl[dd], cfl_encode(lam[dd]));
+            }
+        }
+    }
+    if (rk && P.want_cfl) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+#pragma unroll
+            for (int dd = 0; dd < 3; ++dd) cfl[dd] = max(cfl[dd], __shfl_xor_sync(0xffffffffu, cfl[dd], off));
+        }
+        if (lane == 0) {
+            double sum = 0.0;
+#pragma unroll
+            for (int dd = 0; dd < 3; ++dd) sum += __longlong_as_double((long long)cfl[dd]);
+            atomicMax(P.cfl_key + (blockIdx.x & (kCflSlots - 1)), cfl_encode(P.inverse_jacobian[e] * sum));
+        }
+    }
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+        if (!rk) {
+            tma_store(P.du + e * CONS, smem_u32(s_ut), bu);
+        } else {
+            tma_store(P.u_tmp + e * CONS, smem_u32(s_ut), bu);
+            tma_store(P.u_out + e * CONS, smem_u32(s_u), bu);
+        }
+        tma_store_commit_and_wait_read();
+    }
+}
+
+template <class EQ>
+cudaError_t preload_fd3d_p3() {
+    cudaError_t e = preload_kernel(k_element_fd3d_p3<EQ, true>);
+    if (e != cudaSuccess) return e;
+    return preload_kernel(k_element_fd3d_p3<EQ, false>);
+}
+
+template <class EQ, bool WS>
+cudaError_t launch_fd3d_p3_variant(const KParams &P, cudaStream_t s) {
+    using C = LineSweepCfg<EQ>;
+    static PerDeviceFlag configured;
+    auto kern = k_element_fd3d_p3<EQ, WS>;
+    if (!configured.test_and_set()) {
+        cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                               cudaSharedmemCarveoutMaxShared);
+        if (err != cudaSuccess) return err;
+        if (C::SMEM > 48 * 1024) {
+            err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+            if (err != cudaSuccess) return err;
+        }
+    }
+    KParams Q = P;
+    if (Q.prefetch_distance < 0) Q.prefetch_distance = C::BLOCKS_PER_SM * Q.sm_count;
+    kern<<<(unsigned)(P.elem_end - P.elem_begin), C::THREADS, C::SMEM, s>>>(Q);
+    return cudaSuccess;
+}
+
+template <class EQ>
+cudaError_t launch_element_fd3d_p3(const KParams &P, bool with_surface, cudaStream_t s) {
+    return with_surface ? launch_fd3d_p3_variant<EQ, true>(P, s) : launch_fd3d_p3_variant<EQ, false>(P, s);
+}
+
+}  // namespace tb

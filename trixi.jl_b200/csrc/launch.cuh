@@ -140,6 +140,9 @@ void launch_error_norms(const KParams &P, const NormParams &Q, cudaStream_t s) {
 // tuned_euler3d.cu
 cudaError_t launch_element_euler3d_ranocha_p3(const KParams &P, bool with_surface, cudaStream_t s);
 cudaError_t launch_element_euler3d_weak_p3(const KParams &P, bool with_surface, cudaStream_t s);
+cudaError_t launch_element_linesweep_euler3d(const KParams &P, bool with_surface, cudaStream_t s);
+cudaError_t launch_element_linesweep_mhd3d(const KParams &P, bool with_surface, cudaStream_t s);
+cudaError_t preload_linesweep();
 
 template <class EQ, int N, int VOLINT, bool WS>
 cudaError_t launch_element_variant(const KParams &P, cudaStream_t s) {
@@ -178,8 +181,10 @@ bool uses_tuned_element(const KParams &P) {
     if constexpr (std::is_same_v<EQ, Euler<3>> && N == 4) {
         if (P.kernel_path != 0) return false;
         if (P.volume_integral == TRIXI_B200_VOLINT_WEAK_FORM) return true;  // TreeMesh and curved meshes
-        return !P.curved && P.volume_integral == TRIXI_B200_VOLINT_FLUX_DIFFERENCING &&
-               (P.volume_flux == TRIXI_B200_FLUX_RANOCHA || P.volume_flux == TRIXI_B200_FLUX_RANOCHA_TURBO);
+        return !P.curved && P.volume_integral == TRIXI_B200_VOLINT_FLUX_DIFFERENCING;  // headline or line sweep
+    }
+    if constexpr (std::is_same_v<EQ, Mhd3D> && N == 4) {
+        return P.kernel_path == 0 && !P.curved && P.volume_integral == TRIXI_B200_VOLINT_FLUX_DIFFERENCING;
     }
     return false;
 }
@@ -194,9 +199,15 @@ template <class EQ, int N>
 cudaError_t launch_element(const KParams &P, bool with_surface, cudaStream_t s) {
     if (P.nelements == 0) return cudaSuccess;
     if constexpr (std::is_same_v<EQ, Euler<3>> && N == 4) {
-        if (uses_tuned_element<EQ, N>(P))
-            return P.volume_integral == TRIXI_B200_VOLINT_WEAK_FORM ? launch_element_euler3d_weak_p3(P, with_surface, s)
-                                                                   : launch_element_euler3d_ranocha_p3(P, with_surface, s);
+        if (uses_tuned_element<EQ, N>(P)) {
+            if (P.volume_integral == TRIXI_B200_VOLINT_WEAK_FORM) return launch_element_euler3d_weak_p3(P, with_surface, s);
+            if (P.volume_flux == TRIXI_B200_FLUX_RANOCHA || P.volume_flux == TRIXI_B200_FLUX_RANOCHA_TURBO)
+                return launch_element_euler3d_ranocha_p3(P, with_surface, s);
+            return launch_element_linesweep_euler3d(P, with_surface, s);
+        }
+    }
+    if constexpr (std::is_same_v<EQ, Mhd3D> && N == 4) {
+        if (uses_tuned_element<EQ, N>(P)) return launch_element_linesweep_mhd3d(P, with_surface, s);
     }
     if (P.volume_integral == TRIXI_B200_VOLINT_WEAK_FORM) {
         return with_surface ? launch_element_variant<EQ, N, TRIXI_B200_VOLINT_WEAK_FORM, true>(P, s)
@@ -289,8 +300,10 @@ cudaError_t preload_all() {
 #undef TB_PRELOAD
     if constexpr (std::is_same_v<EQ, Euler<3>> && N == 4) {
         if ((e = preload_tuned_euler3d()) != cudaSuccess) return e;
-        return preload_tuned_euler3d_weak();
+        if ((e = preload_tuned_euler3d_weak()) != cudaSuccess) return e;
+        return preload_linesweep();
     }
+    if constexpr (std::is_same_v<EQ, Mhd3D> && N == 4) return preload_linesweep();
     return cudaSuccess;
 }
 
