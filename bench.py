@@ -65,6 +65,8 @@ def _warped_mapping_3d(xi_, eta_, zeta_):
 WORKLOADS = {
     "euler_ec": {"nvars": 5, "bytes": 212.0, "flop": 312.5 + 45.0,
                  "kernel": "k_element_euler3d_ranocha_p3 (volume+surface+jacobian+2N stage, TMA tiles)"},
+    "tgv": {"nvars": 5, "bytes": 212.0, "flop": 312.5 + 45.0,
+            "kernel": "k_element_euler3d_ranocha_p3 (volume+surface+jacobian+2N stage, TMA tiles)"},
     "euler_weak": {"nvars": 5, "bytes": 212.0 + 24.0, "flop": 149.0 + 45.0 + 25.0,
                    "kernel": "k_element_euler3d_weak_p3 (weak form+surface+jacobian+source+2N stage, TMA tiles)"},
     "structured_curved": {"nvars": 5, "bytes": 212.0 + 72.0 + 8.0, "flop": 149.0 + 45.0 + 45.0,
@@ -80,18 +82,24 @@ def make_semi(level, device=-1, rank=0, world=1, comm=None, workload="euler_ec")
     import trixi_b200 as T
     kw = dict(device=device, rank=rank, world_size=world, comm=comm)
     n = 1 << level
-    if workload == "euler_ec":
-        # examples/tree_3d_dgsem/elixir_euler_ec.jl at a larger refinement level
+    if workload in ("euler_ec", "tgv"):
+        # examples/tree_3d_dgsem/elixir_euler_ec.jl at a larger refinement level; "tgv" (BASELINE config 5):
+        # elixir_euler_taylor_green_vortex.jl = the same volume integral with FluxLaxFriedrichs(max_abs_speed_naive)
+        # surface fluxes on [-pi, pi]^3 and the Mach-0.1 vortex as initial condition
         eq = T.CompressibleEulerEquations3D(1.4)
-        solver = T.DGSEM(polydeg=3, surface_flux=T.flux_ranocha,
+        tgv = workload == "tgv"
+        solver = T.DGSEM(polydeg=3,
+                         surface_flux=T.FluxLaxFriedrichs(T.max_abs_speed_naive) if tgv else T.flux_ranocha,
                          volume_integral=T.VolumeIntegralFluxDifferencing(T.flux_ranocha))
+        half = np.pi if tgv else 2.0
         if world == 1:
-            mesh = T.TreeMesh((-2.0,) * 3, (2.0,) * 3, initial_refinement_level=level, periodicity=True)
+            mesh = T.TreeMesh((-half,) * 3, (half,) * 3, initial_refinement_level=level, periodicity=True)
         else:
-            # same cells (size 4 / 2^level) and the same Morton element order as the TreeMesh, on a box that
+            # same cells (size 2 half / 2^level) and the same Morton element order as the TreeMesh, on a box that
             # grows with the number of ranks; contiguous chunks of the order are (2^level)^3 blocks
-            mesh = T.CartesianBoxMesh((-2.0,) * 3, 4.0 / (1 << level), box_cells(level, world), periodicity=True)
-        return T.SemidiscretizationHyperbolic(mesh, eq, T.initial_condition_weak_blast_wave, solver, **kw)
+            mesh = T.CartesianBoxMesh((-half,) * 3, 2 * half / (1 << level), box_cells(level, world), periodicity=True)
+        ic = T.initial_condition_taylor_green_vortex if tgv else T.initial_condition_weak_blast_wave
+        return T.SemidiscretizationHyperbolic(mesh, eq, ic, solver, **kw)
     if world != 1 and workload != "p4est_curved":
         raise ValueError(f"workload {workload} is single-rank")
     if workload == "euler_weak":
@@ -127,6 +135,11 @@ def make_semi(level, device=-1, rank=0, world=1, comm=None, workload="euler_ec")
 
 def workload_name(level, world=1, workload="euler_ec"):
     n = 1 << level
+    if workload == "tgv":
+        cells = f"{n}^3 elements per rank" if world > 1 else f"TreeMesh level {level} ({n}^3 elements)"
+        return ("tree_3d_dgsem/elixir_euler_taylor_green_vortex.jl: 3D Euler flux differencing (flux_ranocha) + "
+                f"LLF(naive) surface flux, polydeg=3, {cells}, {64 * n**3 * world / 1e6:.1f} M DOF total, periodic "
+                "[-pi, pi]^3 (Morton-ordered Cartesian box for more than one rank)")
     if workload != "euler_ec":
         desc = {"euler_weak": "tree_3d_dgsem/elixir_euler_source_terms.jl: 3D Euler weak form + LLF(naive) + "
                               "convergence-test sources, TreeMesh",

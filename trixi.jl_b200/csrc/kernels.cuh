@@ -121,7 +121,11 @@ template <class EQ, bool FAST>
 TB_DEV void surface_numflux(const EQ &eq, int id, const double (&ul)[EQ::NVARS], const double (&ur)[EQ::NVARS], int o,
                             double (&f)[EQ::NVARS]) {
     if constexpr (FAST && HasFastRanocha<EQ>::value) {
-        eq.flux_ranocha_fast(ul, ur, o, f);
+        // (the launcher selects FAST only for the fluxes of has_fast_surface_flux)
+        if (id == TRIXI_B200_FLUX_LLF || id == TRIXI_B200_FLUX_LLF_NAIVE)
+            eq.flux_llf_fast(id, ul, ur, o, f);
+        else
+            eq.flux_ranocha_fast(ul, ur, o, f);
     } else {
         eq.numflux(id, ul, ur, o, f);
     }

@@ -46,8 +46,8 @@ void launch_interface_flux(const KParams &P, cudaStream_t s) {
         }
         k_interface_flux_curved<EQ, N><<<blocks, threads, 0, s>>>(P);
     } else {
-        const bool fast = HasFastRanocha<EQ>::value && P.kernel_path == 0 &&
-                          (P.surface_flux == TRIXI_B200_FLUX_RANOCHA || P.surface_flux == TRIXI_B200_FLUX_RANOCHA_TURBO);
+        bool fast = false;
+        if constexpr (HasFastRanocha<EQ>::value) fast = P.kernel_path == 0 && EQ::has_fast_surface_flux(P.surface_flux);
         if constexpr (32 % NF == 0) {
             // a warp owns 32 / NF whole interfaces, 8 warps per block
             const long long per_block = 8 * (32 / NF);
@@ -105,11 +105,14 @@ void launch_mpi_interface_flux(const KParams &P, cudaStream_t s) {
     if (total == 0) return;
     if (P.p4est)
         k_mpi_interface_flux_p4est<EQ, N><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(P);
-    else if (HasFastRanocha<EQ>::value && P.kernel_path == 0 &&
-             (P.surface_flux == TRIXI_B200_FLUX_RANOCHA || P.surface_flux == TRIXI_B200_FLUX_RANOCHA_TURBO))
-        k_mpi_interface_flux<EQ, N, true><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(P);
-    else
-        k_mpi_interface_flux<EQ, N><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(P);
+    else {
+        bool fast = false;
+        if constexpr (HasFastRanocha<EQ>::value) fast = P.kernel_path == 0 && EQ::has_fast_surface_flux(P.surface_flux);
+        if (fast)
+            k_mpi_interface_flux<EQ, N, true><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(P);
+        else
+            k_mpi_interface_flux<EQ, N><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(P);
+    }
 }
 
 // cudaFuncSetAttribute is per device: remember what was configured where
