@@ -33,9 +33,16 @@ UNIT = "DOF-updates/s"
 ALGO_FLOP_PER_DOF_VOLUME = 312.5  # 4.5 pairs x 67 + 11 (p = 3, Euler 3D, flux_ranocha)
 
 
+CELLS = None  # --cells: elements per direction and rank instead of 2^level (e.g. 100 -> 64 M DOF, BASELINE config 3)
+
+
+def cells_per_direction(level):
+    return CELLS if CELLS else 1 << level
+
+
 def box_cells(level, world):
     """Weak scaling: every rank keeps a (2^level)^3-element block; the global box doubles in x, y, z in turn."""
-    n = [1 << level] * 3
+    n = [cells_per_direction(level)] * 3
     k, d = world, 0
     while k > 1:
         if k % 2:
@@ -67,6 +74,9 @@ WORKLOADS = {
                  "kernel": "k_element_euler3d_ranocha_p3 (volume+surface+jacobian+2N stage, TMA tiles)"},
     "tgv": {"nvars": 5, "bytes": 212.0, "flop": 312.5 + 45.0,
             "kernel": "k_element_euler3d_ranocha_p3 (volume+surface+jacobian+2N stage, TMA tiles)"},
+    "euler_sc": {"nvars": 5, "bytes": 212.0, "flop": None,
+                 "kernel": "k_element_fd3d_p3<Euler3D, SC> (blended flux differencing + subcell FV, line sweeps, TMA "
+                           "tiles); the indicator kernels are counted under max_dt_ms = 0 / not separately"},
     "euler_weak": {"nvars": 5, "bytes": 212.0 + 24.0, "flop": 149.0 + 45.0 + 25.0,
                    "kernel": "k_element_euler3d_weak_p3 (weak form+surface+jacobian+source+2N stage, TMA tiles)"},
     "structured_curved": {"nvars": 5, "bytes": 212.0 + 72.0 + 8.0, "flop": 149.0 + 45.0 + 45.0,
@@ -81,7 +91,7 @@ WORKLOADS = {
 def make_semi(level, device=-1, rank=0, world=1, comm=None, workload="euler_ec"):
     import trixi_b200 as T
     kw = dict(device=device, rank=rank, world_size=world, comm=comm)
-    n = 1 << level
+    n = cells_per_direction(level)
     if workload in ("euler_ec", "tgv"):
         # examples/tree_3d_dgsem/elixir_euler_ec.jl at a larger refinement level; "tgv" (BASELINE config 5):
         # elixir_euler_taylor_green_vortex.jl = the same volume integral with FluxLaxFriedrichs(max_abs_speed_naive)
@@ -92,12 +102,12 @@ def make_semi(level, device=-1, rank=0, world=1, comm=None, workload="euler_ec")
                          surface_flux=T.FluxLaxFriedrichs(T.max_abs_speed_naive) if tgv else T.flux_ranocha,
                          volume_integral=T.VolumeIntegralFluxDifferencing(T.flux_ranocha))
         half = np.pi if tgv else 2.0
-        if world == 1:
+        if world == 1 and not CELLS:
             mesh = T.TreeMesh((-half,) * 3, (half,) * 3, initial_refinement_level=level, periodicity=True)
         else:
             # same cells (size 2 half / 2^level) and the same Morton element order as the TreeMesh, on a box that
             # grows with the number of ranks; contiguous chunks of the order are (2^level)^3 blocks
-            mesh = T.CartesianBoxMesh((-half,) * 3, 2 * half / (1 << level), box_cells(level, world), periodicity=True)
+            mesh = T.CartesianBoxMesh((-half,) * 3, 2 * half / n, box_cells(level, world), periodicity=True)
         ic = T.initial_condition_taylor_green_vortex if tgv else T.initial_condition_weak_blast_wave
         return T.SemidiscretizationHyperbolic(mesh, eq, ic, solver, **kw)
     if world != 1 and workload != "p4est_curved":
@@ -122,6 +132,16 @@ def make_semi(level, device=-1, rank=0, world=1, comm=None, workload="euler_ec")
             mesh = T.P4estMesh((trees,) * 3, polydeg=3, mapping=_warped_mapping_3d, periodicity=True,
                                initial_refinement_level=int(np.log2(n // trees)))
         return T.SemidiscretizationHyperbolic(mesh, eq, T.initial_condition_constant, solver, **kw)
+    if workload == "euler_sc":
+        # examples/tree_3d_dgsem/elixir_euler_shockcapturing.jl
+        eq = T.CompressibleEulerEquations3D(1.4)
+        basis = T.LobattoLegendreBasis(3)
+        indicator = T.IndicatorHennemannGassner(eq, basis, alpha_max=0.5, alpha_min=0.001, alpha_smooth=True,
+                                                variable=T.density_pressure)
+        volint = T.VolumeIntegralShockCapturingHG(indicator, volume_flux_dg=T.flux_ranocha, volume_flux_fv=T.flux_ranocha)
+        solver = T.DGSEM(basis=basis, surface_flux=T.flux_ranocha, volume_integral=volint)
+        mesh = T.TreeMesh((-2.0,) * 3, (2.0,) * 3, initial_refinement_level=level, periodicity=True)
+        return T.SemidiscretizationHyperbolic(mesh, eq, T.initial_condition_weak_blast_wave, solver, **kw)
     if workload == "mhd_ec":
         # examples/tree_3d_dgsem/elixir_mhd_ec.jl
         eq = T.IdealGlmMhdEquations3D(1.4)
@@ -134,14 +154,16 @@ def make_semi(level, device=-1, rank=0, world=1, comm=None, workload="euler_ec")
 
 
 def workload_name(level, world=1, workload="euler_ec"):
-    n = 1 << level
+    n = cells_per_direction(level)
     if workload == "tgv":
         cells = f"{n}^3 elements per rank" if world > 1 else f"TreeMesh level {level} ({n}^3 elements)"
         return ("tree_3d_dgsem/elixir_euler_taylor_green_vortex.jl: 3D Euler flux differencing (flux_ranocha) + "
                 f"LLF(naive) surface flux, polydeg=3, {cells}, {64 * n**3 * world / 1e6:.1f} M DOF total, periodic "
                 "[-pi, pi]^3 (Morton-ordered Cartesian box for more than one rank)")
     if workload != "euler_ec":
-        desc = {"euler_weak": "tree_3d_dgsem/elixir_euler_source_terms.jl: 3D Euler weak form + LLF(naive) + "
+        desc = {"euler_sc": "tree_3d_dgsem/elixir_euler_shockcapturing.jl: 3D Euler VolumeIntegralShockCapturingHG "
+                            "(IndicatorHennemannGassner, flux_ranocha DG/FV/surface), TreeMesh",
+                "euler_weak": "tree_3d_dgsem/elixir_euler_source_terms.jl: 3D Euler weak form + LLF(naive) + "
                               "convergence-test sources, TreeMesh",
                 "structured_curved": "structured_3d_dgsem/elixir_euler_free_stream.jl: 3D Euler weak form + "
                                      "LLF(naive), warped StructuredMesh",
@@ -151,13 +173,23 @@ def workload_name(level, world=1, workload="euler_ec"):
                           "flux_hindenlang_gassner + flux_nonconservative_powell, TreeMesh"}[workload]
         return f"{desc}, polydeg=3, {n}^3 elements ({64 * n**3 / 1e6:.1f} M DOF) per rank, periodic"
     base = ("tree_3d_dgsem/elixir_euler_ec.jl: 3D Euler EC flux differencing (flux_ranocha), polydeg=3, ")
-    if world == 1:
+    if world == 1 and not CELLS:
         return base + (f"TreeMesh level {level} ({n}^3 elements, {64 * n**3 / 1e6:.1f} M DOF), periodic, "
                        "weak blast wave IC")
     nx, ny, nz = box_cells(level, world)
     return base + (f"Cartesian box {nx}x{ny}x{nz} elements in TreeMesh (Morton) order = {n}^3 elements "
                    f"({64 * n**3 / 1e6:.1f} M DOF) per rank, {64 * nx * ny * nz / 1e6:.1f} M DOF total, periodic, "
                    "weak blast wave IC")
+
+
+def sample_name(level, workload):
+    """Name of the bounded CPU sample (always a uniform TreeMesh level, whatever --cells says)."""
+    global CELLS
+    saved, CELLS = CELLS, None
+    try:
+        return workload_name(level, 1, workload)
+    finally:
+        CELLS = saved
 
 
 class ClockSampler:
@@ -243,7 +275,12 @@ def time_cpu_reference(level, steps, warmup, workload="euler_ec"):
     """The reference's CPU path restated (oracle/trixi_oracle.c, OpenMP over all host cores):
     CarpenterKennedy2N54 steps on a bounded sample (smaller TreeMesh level of the same workload)."""
     import trixi_b200 as T
-    semi = make_semi(level, workload=workload)
+    global CELLS
+    saved, CELLS = CELLS, None  # the bounded CPU sample is always a uniform TreeMesh level
+    try:
+        semi = make_semi(level, workload=workload)
+    finally:
+        CELLS = saved
     ob = oracle_backend(semi)
     u0 = T.compute_coefficients(0.0, semi)
     ob.upload(0, u0)
@@ -266,7 +303,7 @@ def run_reference(args, rank, world):
         return
     level = args.cpu_level
     value, wall, threads, ndofs = time_cpu_reference(level, args.steps, args.warmup, args.workload)
-    sample = (f"{workload_name(level, 1, args.workload)}; {args.steps} CK54 steps (5 rhs! + stage updates + max_dt each) "
+    sample = (f"{sample_name(level, args.workload)}; {args.steps} CK54 steps (5 rhs! + stage updates + max_dt each) "
               f"after {args.warmup} warm-up, OpenMP C restatement of the reference's CPU rhs! "
               f"(Julia/Trixi.jl not installable on this box)")
     line = {
@@ -305,6 +342,8 @@ def run_b200(args, rank, world, local_rank):
     gpu.set_option(gpu.OPT_FUSED_CFL, 0 if args.no_fused_cfl else 1)
     if args.prefetch is not None:
         gpu.set_option(gpu.OPT_PREFETCH_DISTANCE, args.prefetch)
+    if args.generic_kernels:
+        gpu.set_option(gpu.OPT_KERNEL_PATH, 1)
     ndofs = semi.ndofs()
     u0 = T.compute_coefficients(0.0, semi)
     gpu.upload(0, u0)
@@ -423,7 +462,7 @@ def run_b200(args, rank, world, local_rank):
         if not args.no_cpu_baseline:
             cv, cwall, cthreads, cdofs = time_cpu_reference(args.cpu_level, 3, 1, args.workload)
             cpu = {"value": cv, "unit": UNIT, "cores": cthreads, "kind": "port",
-                   "sample": f"{workload_name(args.cpu_level, 1, args.workload)}; 3 CK54 steps (15 rhs!) after 1 warm-up; "
+                   "sample": f"{sample_name(args.cpu_level, args.workload)}; 3 CK54 steps (15 rhs!) after 1 warm-up; "
                              "OpenMP C restatement of the reference's CPU rhs! (oracle/trixi_oracle.c)"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -499,6 +538,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--level", type=int, default=7, help="TreeMesh refinement level per GPU (7 = 134 M DOF)")
+    ap.add_argument("--cells", type=int, default=None,
+                    help="elements per direction and rank on a Morton-ordered Cartesian box instead of a uniform "
+                         "TreeMesh level (euler_ec / tgv): 100 -> 64 M DOF per rank")
     ap.add_argument("--cpu-level", type=int, default=5, help="refinement level of the bounded CPU sample")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
@@ -506,8 +548,12 @@ def main():
                     help="euler_ec is the headline (BASELINE.json); the others are SURVEY.md §8d's secondary configs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--prefetch", type=int, default=None, help="L2 prefetch distance of the tuned element kernel")
+    ap.add_argument("--generic-kernels", action="store_true",
+                    help="TRIXI_B200_OPT_KERNEL_PATH = 1: the generic one-thread-per-node kernels (before/after numbers)")
     ap.add_argument("--no-fused-cfl", action="store_true", help="run max_dt as its own kernel after every step")
     args = ap.parse_args()
+    global CELLS
+    CELLS = args.cells
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

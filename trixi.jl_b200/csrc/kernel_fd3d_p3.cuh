@@ -26,7 +26,13 @@ struct LineSweepCfg {
     static constexpr int MIN_BLOCKS = BLOCKS_PER_SM < 8 ? BLOCKS_PER_SM : (BLOCKS_PER_SM > 16 ? 16 : BLOCKS_PER_SM);
 };
 
-template <class EQ, bool WITH_SURFACE>
+// SC: VolumeIntegralShockCapturingHG (calc_volume_integral.jl:231-272).  The blending factor is per element =
+// per warp, so pure-DG elements skip the finite-volume part without divergence.  Blended elements scale the
+// D_split weights by 1 - alpha and add alpha w_i^-1 (f*_{i+1/2} - f*_{i-1/2}) per direction (fv_kernel!
+// dg_3d.jl:268-306) for their own two nodes: thread h = 0 needs the subcell fluxes (0,1) and (1,2) of its line,
+// thread h = 1 needs (2,3) and (1,2); the first is the operand pair of its first two-point flux, (1,2) is
+// evaluated by both threads with identical operands (bitwise equal, so the subcell scheme stays conservative).
+template <class EQ, bool WITH_SURFACE, bool SC = false>
 __global__ void __launch_bounds__(LineSweepCfg<EQ>::THREADS, LineSweepCfg<EQ>::MIN_BLOCKS)
     k_element_fd3d_p3(const KParams P) {
     using C = LineSweepCfg<EQ>;
@@ -66,9 +72,20 @@ __global__ void __launch_bounds__(LineSweepCfg<EQ>::THREADS, LineSweepCfg<EQ>::M
     const int h = lane >> 4, l16 = lane & 15;
     const int a0 = l16 & 3, a1 = l16 >> 2;
     const int lm[4] = {h ? 3 : 0, h ? 2 : 1, h ? 0 : 2, h ? 1 : 3};
-    const double w01 = P.dsplit_c[lm[0] + 4 * lm[1]], w10 = P.dsplit_c[lm[1] + 4 * lm[0]];
-    const double w02 = P.dsplit_c[lm[0] + 4 * lm[2]], w20 = P.dsplit_c[lm[2] + 4 * lm[0]];
-    const double w13 = P.dsplit_c[lm[1] + 4 * lm[3]], w31 = P.dsplit_c[lm[3] + 4 * lm[1]];
+    double w01 = P.dsplit_c[lm[0] + 4 * lm[1]], w10 = P.dsplit_c[lm[1] + 4 * lm[0]];
+    double w02 = P.dsplit_c[lm[0] + 4 * lm[2]], w20 = P.dsplit_c[lm[2] + 4 * lm[0]];
+    double w13 = P.dsplit_c[lm[1] + 4 * lm[3]], w31 = P.dsplit_c[lm[3] + 4 * lm[1]];
+    double fv0 = 0.0, fv1 = 0.0;  // alpha * (+-) inverse_weights of the two own nodes; 0: pure DG element
+    if constexpr (SC) {
+        const double alpha = P.alpha[e];
+        if (!(fabs(alpha) <= 1.8189894035458565e-12)) {  // isapprox(alpha, 0, atol = max(100 eps, eps^0.75))
+            const double w_dg = 1 - alpha;
+            w01 *= w_dg, w10 *= w_dg, w02 *= w_dg, w20 *= w_dg, w13 *= w_dg, w31 *= w_dg;
+            const double sgn = h ? -alpha : alpha;
+            fv0 = sgn * P.inv_weights_c[0];  // nodes 0 and 3 (inverse_weights is symmetric)
+            fv1 = sgn * P.inv_weights_c[1];  // nodes 1 and 2
+        }
+    }
     while (!mbar_try_wait(bar, 0)) {
     }
 
@@ -114,6 +131,24 @@ __global__ void __launch_bounds__(LineSweepCfg<EQ>::THREADS, LineSweepCfg<EQ>::M
         for (int v = 0; v < NV; ++v) {
             own[0][v] = w01 * f[v];
             own[1][v] = w10 * f[v];
+        }
+        if constexpr (SC) {
+            if (fv0 != 0.0) {
+                // subcell fluxes: (lo, hi) is still the pair (0,1) [h = 0] or (2,3) [h = 1]
+                double fa[NV], fb[NV];
+                eq.numflux(P.volume_flux_fv, lo, hi, d, fa);
+#pragma unroll
+                for (int v = 0; v < NV; ++v) {
+                    lo[v] = h ? q[3][v] : q[1][v];  // the pair (1,2)
+                    hi[v] = h ? q[1][v] : q[2][v];
+                }
+                eq.numflux(P.volume_flux_fv, lo, hi, d, fb);
+#pragma unroll
+                for (int v = 0; v < NV; ++v) {
+                    own[0][v] = fma(fv0, fa[v], own[0][v]);          // node 0: +f(0,1); node 3: -f(2,3)
+                    own[1][v] = fma(fv1, fb[v] - fa[v], own[1][v]);  // node 1: f(1,2) - f(0,1); node 2: f(2,3) - f(1,2)
+                }
+            }
         }
 #pragma unroll
         for (int v = 0; v < NV; ++v) {
@@ -298,18 +333,18 @@ __global__ void __launch_bounds__(LineSweepCfg<EQ>::THREADS, LineSweepCfg<EQ>::M
     }
 }
 
-template <class EQ>
+template <class EQ, bool SC = false>
 cudaError_t preload_fd3d_p3() {
-    cudaError_t e = preload_kernel(k_element_fd3d_p3<EQ, true>);
+    cudaError_t e = preload_kernel(k_element_fd3d_p3<EQ, true, SC>);
     if (e != cudaSuccess) return e;
-    return preload_kernel(k_element_fd3d_p3<EQ, false>);
+    return preload_kernel(k_element_fd3d_p3<EQ, false, SC>);
 }
 
-template <class EQ, bool WS>
+template <class EQ, bool WS, bool SC = false>
 cudaError_t launch_fd3d_p3_variant(const KParams &P, cudaStream_t s) {
     using C = LineSweepCfg<EQ>;
     static PerDeviceFlag configured;
-    auto kern = k_element_fd3d_p3<EQ, WS>;
+    auto kern = k_element_fd3d_p3<EQ, WS, SC>;
     if (!configured.test_and_set()) {
         cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
                                                cudaSharedmemCarveoutMaxShared);
@@ -325,9 +360,9 @@ cudaError_t launch_fd3d_p3_variant(const KParams &P, cudaStream_t s) {
     return cudaSuccess;
 }
 
-template <class EQ>
+template <class EQ, bool SC = false>
 cudaError_t launch_element_fd3d_p3(const KParams &P, bool with_surface, cudaStream_t s) {
-    return with_surface ? launch_fd3d_p3_variant<EQ, true>(P, s) : launch_fd3d_p3_variant<EQ, false>(P, s);
+    return with_surface ? launch_fd3d_p3_variant<EQ, true, SC>(P, s) : launch_fd3d_p3_variant<EQ, false, SC>(P, s);
 }
 
 }  // namespace tb

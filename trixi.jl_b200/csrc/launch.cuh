@@ -144,6 +144,7 @@ void launch_error_norms(const KParams &P, const NormParams &Q, cudaStream_t s) {
 cudaError_t launch_element_euler3d_ranocha_p3(const KParams &P, bool with_surface, cudaStream_t s);
 cudaError_t launch_element_euler3d_weak_p3(const KParams &P, bool with_surface, cudaStream_t s);
 cudaError_t launch_element_linesweep_euler3d(const KParams &P, bool with_surface, cudaStream_t s);
+cudaError_t launch_element_linesweep_sc_euler3d(const KParams &P, bool with_surface, cudaStream_t s);
 cudaError_t launch_element_linesweep_mhd3d(const KParams &P, bool with_surface, cudaStream_t s);
 cudaError_t preload_linesweep();
 
@@ -184,7 +185,8 @@ bool uses_tuned_element(const KParams &P) {
     if constexpr (std::is_same_v<EQ, Euler<3>> && N == 4) {
         if (P.kernel_path != 0) return false;
         if (P.volume_integral == TRIXI_B200_VOLINT_WEAK_FORM) return true;  // TreeMesh and curved meshes
-        return !P.curved && P.volume_integral == TRIXI_B200_VOLINT_FLUX_DIFFERENCING;  // headline or line sweep
+        return !P.curved && (P.volume_integral == TRIXI_B200_VOLINT_FLUX_DIFFERENCING ||       // headline or line sweep
+                             P.volume_integral == TRIXI_B200_VOLINT_SHOCK_CAPTURING_HG);  // blended line sweep
     }
     if constexpr (std::is_same_v<EQ, Mhd3D> && N == 4) {
         return P.kernel_path == 0 && !P.curved && P.volume_integral == TRIXI_B200_VOLINT_FLUX_DIFFERENCING;
@@ -204,6 +206,8 @@ cudaError_t launch_element(const KParams &P, bool with_surface, cudaStream_t s) 
     if constexpr (std::is_same_v<EQ, Euler<3>> && N == 4) {
         if (uses_tuned_element<EQ, N>(P)) {
             if (P.volume_integral == TRIXI_B200_VOLINT_WEAK_FORM) return launch_element_euler3d_weak_p3(P, with_surface, s);
+            if (P.volume_integral == TRIXI_B200_VOLINT_SHOCK_CAPTURING_HG)
+                return launch_element_linesweep_sc_euler3d(P, with_surface, s);
             if (P.volume_flux == TRIXI_B200_FLUX_RANOCHA || P.volume_flux == TRIXI_B200_FLUX_RANOCHA_TURBO)
                 return launch_element_euler3d_ranocha_p3(P, with_surface, s);
             return launch_element_linesweep_euler3d(P, with_surface, s);

@@ -8,12 +8,16 @@ namespace tb {
 cudaError_t launch_element_linesweep_euler3d(const KParams &P, bool with_surface, cudaStream_t s) {
     return launch_element_fd3d_p3<Euler<3>>(P, with_surface, s);
 }
+cudaError_t launch_element_linesweep_sc_euler3d(const KParams &P, bool with_surface, cudaStream_t s) {
+    return launch_element_fd3d_p3<Euler<3>, true>(P, with_surface, s);
+}
 cudaError_t launch_element_linesweep_mhd3d(const KParams &P, bool with_surface, cudaStream_t s) {
     return launch_element_fd3d_p3<Mhd3D>(P, with_surface, s);
 }
 cudaError_t preload_linesweep() {
     cudaError_t e = preload_fd3d_p3<Euler<3>>();
     if (e != cudaSuccess) return e;
+    if ((e = preload_fd3d_p3<Euler<3>, true>()) != cudaSuccess) return e;
     return preload_fd3d_p3<Mhd3D>();
 }
 }  // namespace tb
