@@ -117,21 +117,21 @@ struct HasFastRanocha<Euler<ND>> {
 };
 
 // surface flux of one face node; FAST selects the fast-division flux_ranocha (tuned path)
-template <class EQ, bool FAST>
+// FAST: 0 = the registry's generic numflux, 1 = flux_ranocha on fast divisions, 2 = FluxLaxFriedrichs on fast divisions
+// (compile-time: a run-time choice between the two fast fluxes cost the flux_ranocha interface kernel 22%)
+template <class EQ, int FAST>
 TB_DEV void surface_numflux(const EQ &eq, int id, const double (&ul)[EQ::NVARS], const double (&ur)[EQ::NVARS], int o,
                             double (&f)[EQ::NVARS]) {
-    if constexpr (FAST && HasFastRanocha<EQ>::value) {
-        // (the launcher selects FAST only for the fluxes of has_fast_surface_flux)
-        if (id == TRIXI_B200_FLUX_LLF || id == TRIXI_B200_FLUX_LLF_NAIVE)
-            eq.flux_llf_fast(id, ul, ur, o, f);
-        else
-            eq.flux_ranocha_fast(ul, ur, o, f);
+    if constexpr (FAST == 1 && HasFastRanocha<EQ>::value) {
+        eq.flux_ranocha_fast(ul, ur, o, f);
+    } else if constexpr (FAST == 2 && HasFastRanocha<EQ>::value) {
+        eq.flux_llf_fast(id, ul, ur, o, f);
     } else {
         eq.numflux(id, ul, ur, o, f);
     }
 }
 
-template <class EQ, int N, bool FAST = false>
+template <class EQ, int N, int FAST = 0>
 __global__ void __launch_bounds__(256) k_interface_flux(const KParams P) {
     constexpr int ND = EQ::NDIMS, NV = EQ::NVARS, NF = ipow(N, ND - 1), NN = ipow(N, ND);
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(256) k_interface_flux(const KParams P) {
 // surface_flux_values faces (contiguous NF*NV doubles each) back fully coalesced. Used when NF divides 32.
 // CURVED (StructuredMesh, dgsem_structured/dg_3d.jl:619-753): the flux is taken along the contravariant vector of
 // the right element's first node layer times sign(inverse_jacobian), and stored with that sign on both sides.
-template <class EQ, int N, bool FAST = false, bool CURVED = false>
+template <class EQ, int N, int FAST = 0, bool CURVED = false>
 __global__ void __launch_bounds__(256) k_interface_flux_staged(const KParams P) {
     constexpr int ND = EQ::NDIMS, NV = EQ::NVARS, NF = ipow(N, ND - 1), NN = ipow(N, ND);
     constexpr int G = 32 / NF;   // interfaces per warp
@@ -465,7 +465,7 @@ __global__ void __launch_bounds__(256) k_mpi_pack(const KParams P) {
 
 // calc_mpi_interface_flux! (dg_2d_parallel.jl:700-740, dg_3d_parallel.jl:167-242): the shared flux is
 // computed on both ranks with identical operands; only the local element's storage is written.
-template <class EQ, int N, bool FAST = false>
+template <class EQ, int N, int FAST = 0>
 __global__ void __launch_bounds__(256) k_mpi_interface_flux(const KParams P) {
     constexpr int ND = EQ::NDIMS, NV = EQ::NVARS, NF = ipow(N, ND - 1), NN = ipow(N, ND);
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;

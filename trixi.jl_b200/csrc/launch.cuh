@@ -26,6 +26,17 @@ struct Launchers {
     int ndims, nvars, nnodes;
 };
 
+// which compile-time fast surface flux (see surface_numflux) the tuned path may use for P
+template <class EQ>
+int fast_surface_flux_mode(const KParams &P) {
+    if constexpr (HasFastRanocha<EQ>::value) {
+        if (P.kernel_path != 0) return 0;
+        if (P.surface_flux == TRIXI_B200_FLUX_RANOCHA || P.surface_flux == TRIXI_B200_FLUX_RANOCHA_TURBO) return 1;
+        if (P.surface_flux == TRIXI_B200_FLUX_LLF || P.surface_flux == TRIXI_B200_FLUX_LLF_NAIVE) return 2;
+    }
+    return 0;
+}
+
 template <class EQ, int N>
 void launch_interface_flux(const KParams &P, cudaStream_t s) {
     constexpr int NF = ipow(N, EQ::NDIMS - 1);
@@ -39,26 +50,29 @@ void launch_interface_flux(const KParams &P, cudaStream_t s) {
         if constexpr (32 % NF == 0 && !EQ::kHasNoncons) {
             if (P.kernel_path == 0) {
                 const long long per_block = 8 * (32 / NF);
-                k_interface_flux_staged<EQ, N, false, true>
+                k_interface_flux_staged<EQ, N, 0, true>
                     <<<(unsigned)((P.ninterfaces + per_block - 1) / per_block), 256, 0, s>>>(P);
                 return;
             }
         }
         k_interface_flux_curved<EQ, N><<<blocks, threads, 0, s>>>(P);
     } else {
-        bool fast = false;
-        if constexpr (HasFastRanocha<EQ>::value) fast = P.kernel_path == 0 && EQ::has_fast_surface_flux(P.surface_flux);
+        const int fast = fast_surface_flux_mode<EQ>(P);
         if constexpr (32 % NF == 0) {
             // a warp owns 32 / NF whole interfaces, 8 warps per block
             const long long per_block = 8 * (32 / NF);
             const unsigned sblocks = (unsigned)((P.ninterfaces + per_block - 1) / per_block);
-            if (fast)
-                k_interface_flux_staged<EQ, N, true><<<sblocks, 256, 0, s>>>(P);
+            if (fast == 1)
+                k_interface_flux_staged<EQ, N, 1><<<sblocks, 256, 0, s>>>(P);
+            else if (fast == 2)
+                k_interface_flux_staged<EQ, N, 2><<<sblocks, 256, 0, s>>>(P);
             else
                 k_interface_flux_staged<EQ, N><<<sblocks, 256, 0, s>>>(P);
         } else {
-            if (fast)
-                k_interface_flux<EQ, N, true><<<blocks, threads, 0, s>>>(P);
+            if (fast == 1)
+                k_interface_flux<EQ, N, 1><<<blocks, threads, 0, s>>>(P);
+            else if (fast == 2)
+                k_interface_flux<EQ, N, 2><<<blocks, threads, 0, s>>>(P);
             else
                 k_interface_flux<EQ, N><<<blocks, threads, 0, s>>>(P);
         }
@@ -106,10 +120,11 @@ void launch_mpi_interface_flux(const KParams &P, cudaStream_t s) {
     if (P.p4est)
         k_mpi_interface_flux_p4est<EQ, N><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(P);
     else {
-        bool fast = false;
-        if constexpr (HasFastRanocha<EQ>::value) fast = P.kernel_path == 0 && EQ::has_fast_surface_flux(P.surface_flux);
-        if (fast)
-            k_mpi_interface_flux<EQ, N, true><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(P);
+        const int fast = fast_surface_flux_mode<EQ>(P);
+        if (fast == 1)
+            k_mpi_interface_flux<EQ, N, 1><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(P);
+        else if (fast == 2)
+            k_mpi_interface_flux<EQ, N, 2><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(P);
         else
             k_mpi_interface_flux<EQ, N><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(P);
     }
@@ -270,13 +285,16 @@ cudaError_t preload_all() {
 #define TB_PRELOAD(k)                      \
     if ((e = preload_kernel(k)) != cudaSuccess) return e
     TB_PRELOAD((k_interface_flux<EQ, N>));
-    TB_PRELOAD((k_interface_flux<EQ, N, true>));
+    TB_PRELOAD((k_interface_flux<EQ, N, 1>));
+    TB_PRELOAD((k_interface_flux<EQ, N, 2>));
     if constexpr (32 % ipow(N, EQ::NDIMS - 1) == 0) {
         TB_PRELOAD((k_interface_flux_staged<EQ, N>));
-        TB_PRELOAD((k_interface_flux_staged<EQ, N, true>));
-        if constexpr (!EQ::kHasNoncons) TB_PRELOAD((k_interface_flux_staged<EQ, N, false, true>));
+        TB_PRELOAD((k_interface_flux_staged<EQ, N, 1>));
+        TB_PRELOAD((k_interface_flux_staged<EQ, N, 2>));
+        if constexpr (!EQ::kHasNoncons) TB_PRELOAD((k_interface_flux_staged<EQ, N, 0, true>));
     }
-    TB_PRELOAD((k_mpi_interface_flux<EQ, N, true>));
+    TB_PRELOAD((k_mpi_interface_flux<EQ, N, 1>));
+    TB_PRELOAD((k_mpi_interface_flux<EQ, N, 2>));
     TB_PRELOAD((k_boundary_flux<EQ, N>));
     TB_PRELOAD((k_mortar_flux<EQ, N>));
     TB_PRELOAD((k_error_norms<EQ, N>));

@@ -292,10 +292,6 @@ struct Euler {
 #pragma unroll
         for (int v = 0; v < NVARS; ++v) f[v] = 0.5 * (fs[0][v] + fs[1][v]) + (-0.5 * lam * (ur[v] - ul[v]));
     }
-    __host__ __device__ static bool has_fast_surface_flux(int id) {
-        return id == TRIXI_B200_FLUX_RANOCHA || id == TRIXI_B200_FLUX_RANOCHA_TURBO || id == TRIXI_B200_FLUX_LLF ||
-               id == TRIXI_B200_FLUX_LLF_NAIVE;
-    }
     TB_DEV void flux_ranocha_fast(const double (&ul)[NVARS], const double (&ur)[NVARS], int o,
                                   double (&f)[NVARS]) const {
         double rho_ll, v_ll[ND], p_ll, rho_rr, v_rr[ND], p_rr;
