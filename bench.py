@@ -271,7 +271,7 @@ def oracle_backend(semi, threads=None):
     return oracle.OracleBackend(semi, num_threads=threads)
 
 
-def time_cpu_reference(level, steps, warmup, workload="euler_ec"):
+def time_cpu_reference(level, steps, warmup, workload="euler_ec", turbo=False):
     """The reference's CPU path restated (oracle/trixi_oracle.c, OpenMP over all host cores):
     CarpenterKennedy2N54 steps on a bounded sample (smaller TreeMesh level of the same workload)."""
     import trixi_b200 as T
@@ -281,6 +281,11 @@ def time_cpu_reference(level, steps, warmup, workload="euler_ec"):
         semi = make_semi(level, workload=workload)
     finally:
         CELLS = saved
+    if turbo:
+        # the reference's fastest CPU specialization of this volume integral: flux_ranocha_turbo
+        # (dg_3d_compressible_euler.jl:265-617); benchmark_ec.jl itself runs plain flux_ranocha
+        semi.solver.volume_integral = T.VolumeIntegralFluxDifferencing(T.flux_ranocha_turbo)
+        semi._desc = None
     ob = oracle_backend(semi)
     u0 = T.compute_coefficients(0.0, semi)
     ob.upload(0, u0)
@@ -316,6 +321,11 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if args.workload in ("euler_ec", "tgv"):
+        # for the record: the same sample through the reference's SIMD specialization flux_ranocha_turbo (hoisted
+        # logarithms, dg_3d_compressible_euler.jl:265-617); benchmark_ec.jl and this line's value use flux_ranocha
+        line["cpu_baseline"]["flux_ranocha_turbo_value"] = time_cpu_reference(level, args.steps, args.warmup,
+                                                                              args.workload, turbo=True)[0]
     emit(line)
 
 
@@ -461,7 +471,15 @@ def run_b200(args, rank, world, local_rank):
         cpu = None
         if not args.no_cpu_baseline:
             cv, cwall, cthreads, cdofs = time_cpu_reference(args.cpu_level, 3, 1, args.workload)
+            turbo = None
+            if args.workload in ("euler_ec", "tgv"):
+                turbo = time_cpu_reference(args.cpu_level, 3, 1, args.workload, turbo=True)[0]
             cpu = {"value": cv, "unit": UNIT, "cores": cthreads, "kind": "port",
+                   "flux_ranocha_turbo_value": turbo,
+                   "note": "value = the generic flux_differencing_kernel! with flux_ranocha, the configuration "
+                           "benchmark/benchmark_ec.jl times; flux_ranocha_turbo_value = the same sample through the "
+                           "reference's SIMD specialization with hoisted logarithms "
+                           "(dg_3d_compressible_euler.jl:265-617), its fastest CPU path for this volume integral",
                    "sample": f"{sample_name(args.cpu_level, args.workload)}; 3 CK54 steps (15 rhs!) after 1 warm-up; "
                              "OpenMP C restatement of the reference's CPU rhs! (oracle/trixi_oracle.c)"}
         line = {

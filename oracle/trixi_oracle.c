@@ -872,6 +872,88 @@ static void flux_differencing_kernel(const trixi_b200_desc *d, const eqn_t *eq, 
             }
 }
 
+
+/* flux_differencing_kernel! for flux_ranocha_turbo on TreeMesh{3} (dgsem_tree/dg_3d_compressible_euler.jl:265-617):
+ * primitive variables and log(rho), log(p) once per node, the logarithmic means inlined with
+ * z = (y - x)^2 / (x + y)^2 and the branch as a select, SIMD along the 16 lines of a direction.  The reference
+ * permutes its temporaries so that the SIMD index is contiguous; here the temporaries are SoA [7][64] and the
+ * inner loop runs over the n^2 lines with their stride (same arithmetic, same summation order per node: x pairs,
+ * then y pairs, then z pairs, each in the order (i, ii) of the triangular loop). */
+static void flux_differencing_kernel_turbo(const trixi_b200_desc *d, const eqn_t *eq, double *du, const double *u,
+                                           double alpha) {
+    enum { N = 4, NN = 64 };
+    const double *Ds = d->derivative_split;
+    double prim[7][NN], acc[5][NN];
+    for (int q = 0; q < NN; ++q) {
+        double rho = u[5 * q], rv1 = u[5 * q + 1], rv2 = u[5 * q + 2], rv3 = u[5 * q + 3], rho_e = u[5 * q + 4];
+        double v1 = rv1 / rho, v2 = rv2 / rho, v3 = rv3 / rho;
+        double p = (eq->gamma - 1) * (rho_e - 0.5 * (rv1 * v1 + rv2 * v2 + rv3 * v3));
+        prim[0][q] = rho;
+        prim[1][q] = v1;
+        prim[2][q] = v2;
+        prim[3][q] = v3;
+        prim[4][q] = p;
+        prim[5][q] = log(rho);
+        prim[6][q] = log(p);
+        for (int v = 0; v < 5; ++v) acc[v][q] = 0.0;
+    }
+    const int stride[3] = {1, N, N * N};
+    for (int o = 0; o < 3; ++o) {
+        /* the 16 lines of direction o start at the nodes whose o-th index is 0 */
+        int line0[16], nl = 0;
+        for (int q = 0; q < NN; ++q)
+            if ((q / stride[o]) % N == 0) line0[nl++] = q;
+        for (int i = 0; i < N; ++i)
+            for (int ii = i + 1; ii < N; ++ii) {
+                const double factor_i = alpha * Ds[i + N * ii], factor_ii = alpha * Ds[ii + N * i];
+#pragma omp simd
+                for (int l = 0; l < 16; ++l) {
+                    const int a = line0[l] + i * stride[o], b = line0[l] + ii * stride[o];
+                    const double rho_ll = prim[0][a], p_ll = prim[4][a], log_rho_ll = prim[5][a], log_p_ll = prim[6][a];
+                    const double rho_rr = prim[0][b], p_rr = prim[4][b], log_rho_rr = prim[5][b], log_p_rr = prim[6][b];
+                    const double v1_ll = prim[1][a], v2_ll = prim[2][a], v3_ll = prim[3][a];
+                    const double v1_rr = prim[1][b], v2_rr = prim[2][b], v3_rr = prim[3][b];
+                    const double x1_plus_y1 = rho_ll + rho_rr, y1_minus_x1 = rho_rr - rho_ll;
+                    const double z1 = (y1_minus_x1 * y1_minus_x1) / (x1_plus_y1 * x1_plus_y1);
+                    const double special_path1 = x1_plus_y1 / (2 + z1 * (2.0 / 3 + z1 * (2.0 / 5 + 2.0 / 7 * z1)));
+                    const double regular_path1 = y1_minus_x1 / (log_rho_rr - log_rho_ll);
+                    const double rho_mean = z1 < 1.0e-4 ? special_path1 : regular_path1;
+                    const double x2 = rho_ll * p_rr, log_x2 = log_rho_ll + log_p_rr;
+                    const double y2 = rho_rr * p_ll, log_y2 = log_rho_rr + log_p_ll;
+                    const double x2_plus_y2 = x2 + y2, y2_minus_x2 = y2 - x2;
+                    const double z2 = (y2_minus_x2 * y2_minus_x2) / (x2_plus_y2 * x2_plus_y2);
+                    const double special_path2 = (2 + z2 * (2.0 / 3 + z2 * (2.0 / 5 + 2.0 / 7 * z2))) / x2_plus_y2;
+                    const double regular_path2 = (log_y2 - log_x2) / y2_minus_x2;
+                    const double inv_rho_p_mean = p_ll * p_rr * (z2 < 1.0e-4 ? special_path2 : regular_path2);
+                    const double v1_avg = 0.5 * (v1_ll + v1_rr), v2_avg = 0.5 * (v2_ll + v2_rr), v3_avg = 0.5 * (v3_ll + v3_rr);
+                    const double p_avg = 0.5 * (p_ll + p_rr);
+                    const double velocity_square_avg = 0.5 * (v1_ll * v1_rr + v2_ll * v2_rr + v3_ll * v3_rr);
+                    const double vn_avg = o == 0 ? v1_avg : (o == 1 ? v2_avg : v3_avg);
+                    const double vn_ll = o == 0 ? v1_ll : (o == 1 ? v2_ll : v3_ll);
+                    const double vn_rr = o == 0 ? v1_rr : (o == 1 ? v2_rr : v3_rr);
+                    const double f1 = rho_mean * vn_avg;
+                    const double f2 = f1 * v1_avg + (o == 0 ? p_avg : 0.0);
+                    const double f3 = f1 * v2_avg + (o == 1 ? p_avg : 0.0);
+                    const double f4 = f1 * v3_avg + (o == 2 ? p_avg : 0.0);
+                    const double f5 = f1 * (velocity_square_avg + inv_rho_p_mean * eq->inv_gm1) +
+                                      0.5 * (p_ll * vn_rr + p_rr * vn_ll);
+                    acc[0][a] += factor_i * f1;
+                    acc[1][a] += factor_i * f2;
+                    acc[2][a] += factor_i * f3;
+                    acc[3][a] += factor_i * f4;
+                    acc[4][a] += factor_i * f5;
+                    acc[0][b] += factor_ii * f1;
+                    acc[1][b] += factor_ii * f2;
+                    acc[2][b] += factor_ii * f3;
+                    acc[3][b] += factor_ii * f4;
+                    acc[4][b] += factor_ii * f5;
+                }
+            }
+    }
+    for (int q = 0; q < NN; ++q)
+        for (int v = 0; v < 5; ++v) du[5 * q + v] += acc[v][q];
+}
+
 /* flux_differencing_kernel! with nonconservative terms dg_3d.jl:216-266: the nonsymmetric part */
 static void flux_differencing_noncons(const trixi_b200_desc *d, const eqn_t *eq, double *du, const double *u) {
     int n = d->nnodes, nv = d->nvars;
@@ -1067,6 +1149,10 @@ void oracle_calc_volume_integral(const trixi_b200_desc *d, double *du, const dou
     for (int64_t e = 0; e < d->nelements; ++e) {
         if (d->volume_integral == TRIXI_B200_VOLINT_WEAK_FORM)
             weak_form_kernel(d, &eq, du + e * esz, u + e * esz);
+        else if (d->volume_flux == TRIXI_B200_FLUX_RANOCHA_TURBO && d->equation == TRIXI_B200_EQ_EULER_3D &&
+                 d->nnodes == 4 && d->mesh_kind == TRIXI_B200_MESH_TREE)
+            /* the reference's performance specialization (dispatch on typeof(flux_ranocha_turbo)) */
+            flux_differencing_kernel_turbo(d, &eq, du + e * esz, u + e * esz, 1.0);
         else {
             flux_differencing_kernel(d, &eq, du + e * esz, u + e * esz, 1.0);
             if (flux_has_noncons(d->volume_flux)) flux_differencing_noncons(d, &eq, du + e * esz, u + e * esz);

@@ -636,4 +636,7 @@ EXTRA = {e.name: e for e in [
     _Extra("p4est_3d_curved_level1", lambda **kw: _p4est3d_curved(level=1, trees=(2, 2, 2), **kw)),
     _Extra("structured_3d_like_p4est_curved", _structured3d_like_p4est_curved),
     _Extra("p4est_3d_periodic_source_terms", _p4est3d_source_terms),
+    # the reference's SIMD specialization (flux_ranocha_turbo, dg_3d_compressible_euler.jl:265-617) as the oracle side
+    # of the tuned GPU kernel, which evaluates the same hoisted-logarithm form
+    _Extra("tree_3d_euler_ec_turbo", lambda **kw: _euler3d_ec(flux=T.flux_ranocha_turbo, **kw)),
 ]}

@@ -67,7 +67,8 @@ RHS_CASES = ["tree_3d_euler_ec", "tree_3d_euler_source_terms", "tree_3d_euler_so
              "p4est_3d_curved_level1", "tree_2d_advection_mortar", "tree_3d_euler_mortar",
              "structured_2d_advection_basic", "structured_2d_euler_free_stream", "structured_2d_euler_ec",
              "structured_2d_euler_source_terms_nonperiodic", "p4est_2d_advection_basic",
-             "tree_3d_euler_shockcapturing", "tree_2d_euler_shockcapturing", "tree_2d_euler_blast_wave"]
+             "tree_3d_euler_shockcapturing", "tree_2d_euler_shockcapturing", "tree_2d_euler_blast_wave",
+             "tree_3d_euler_ec_turbo"]
 
 
 @pytest.mark.parametrize("name", RHS_CASES)

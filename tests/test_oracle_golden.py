@@ -53,3 +53,26 @@ def test_p4est_brick_equals_treemesh(oracle_module):
     # the forest's metric terms go through the curl-invariant form (containers_3d.jl:125-285): 4e-13 relative
     # round-off on Ja, amplified by inverse_jacobian = 512 and |flux| ~ 10 against the TreeMesh's exact 2/dx
     assert np.abs(da[..., oa] - db[..., ob]).max() <= 1e-9 * np.abs(db).max()
+
+
+def test_turbo_kernel_matches_generic(oracle_module):
+    """The reference's performance specialization for flux_ranocha_turbo (dg_3d_compressible_euler.jl:265-617, hoisted
+    logarithms) against the generic flux_differencing_kernel! -- its own parity test is
+    test/test_performance_specializations_3d.jl:49-89 (isapprox of du)."""
+    import trixi_b200 as T
+
+    def semi(flux):
+        eq = T.CompressibleEulerEquations3D(1.4)
+        solver = T.DGSEM(polydeg=3, surface_flux=T.flux_ranocha, volume_integral=T.VolumeIntegralFluxDifferencing(flux))
+        mesh = T.TreeMesh((-2.0,) * 3, (2.0,) * 3, initial_refinement_level=2, periodicity=True)
+        return T.SemidiscretizationHyperbolic(mesh, eq, T.initial_condition_weak_blast_wave, solver)
+
+    a, b = semi(T.flux_ranocha), semi(T.flux_ranocha_turbo)
+    u = T.compute_coefficients(0.0, a)
+    rng = np.random.default_rng(0)
+    for amplitude in (0.2, 1e-3):  # regular and series branch of the logarithmic means
+        v = np.asfortranarray(u * (1 + amplitude * rng.uniform(-1, 1, (1,) + u.shape[1:])))
+        da, db = np.empty_like(v), np.empty_like(v)
+        oracle_module.OracleBackend(a).rhs_host(da, v, 0.0)
+        oracle_module.OracleBackend(b).rhs_host(db, v, 0.0)
+        assert np.abs(da - db).max() <= 1e-13 * np.abs(da).max()
