@@ -76,3 +76,16 @@ def test_turbo_kernel_matches_generic(oracle_module):
         oracle_module.OracleBackend(a).rhs_host(da, v, 0.0)
         oracle_module.OracleBackend(b).rhs_host(db, v, 0.0)
         assert np.abs(da - db).max() <= 1e-13 * np.abs(da).max()
+
+
+def test_goldens_are_the_reference_test_suite_values():
+    """tests/golden/reference_goldens.json was extracted from the reference's test/*.jl by
+    tests/golden/extract_reference_goldens.py; the values the elixirs are checked against are those, bit for bit."""
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_goldens.json")) as f:
+        golden = json.load(f)
+    assert sorted(golden) == sorted(ELIXIRS)
+    for name, ex in ELIXIRS.items():
+        assert golden[name]["l2"] == list(ex.l2) and golden[name]["linf"] == list(ex.linf), name
+        assert golden[name]["source"] == ex.source
