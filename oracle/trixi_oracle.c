@@ -2056,6 +2056,17 @@ void oracle_numflux(const trixi_b200_desc *d, int flux_id, const double *ul, con
     eqn_t eq = make_eqn(d);
     numflux(&eq, flux_id, ul, ur, orientation - 1, f);
 }
+void oracle_numflux_normal(const trixi_b200_desc *d, int flux_id, const double *ul, const double *ur,
+                           const double *normal_direction, double *f) {
+    eqn_t eq = make_eqn(d);
+    numflux_normal(&eq, flux_id, ul, ur, normal_direction, f);
+}
+void oracle_flux_normal(const trixi_b200_desc *d, const double *u, const double *normal_direction, double *f) {
+    eqn_t eq = make_eqn(d);
+    phys_flux_normal(&eq, u, normal_direction, f);
+}
+double oracle_ln_mean(double x, double y) { return ln_mean(x, y); }
+double oracle_inv_ln_mean(double x, double y) { return inv_ln_mean(x, y); }
 void oracle_flux(const trixi_b200_desc *d, const double *u, int orientation, double *f) {
     eqn_t eq = make_eqn(d);
     phys_flux(&eq, u, orientation - 1, f);
