@@ -280,6 +280,32 @@ def test_shock_capturing_indicator_and_rhs(name, oracle_module):
     assert _rel_err(du_gpu, du_ref) <= RHS_TOL
 
 
+@pytest.mark.parametrize("name", ["tree_3d_euler_ec", "tree_3d_euler_source_terms", "tree_3d_euler_ec_shima_etal",
+                                  "tree_3d_mhd_ec", "tree_3d_euler_shockcapturing", "structured_3d_euler_source_terms",
+                                  "p4est_3d_euler_source_terms_nonperiodic", "tree_3d_euler_taylor_green_vortex"])
+def test_tuned_kernels_match_generic_kernels(name):
+    """The performance specializations (TMA line-sweep / weak-form kernels, staged and fast-division interface
+    kernels) against the generic one-thread-per-node kernels (TRIXI_B200_OPT_KERNEL_PATH = 1), RHS and two CK54
+    steps: the analogue of test/test_performance_specializations_3d.jl:49-89."""
+    semi = ELIXIRS[name].semi()
+    u = _random_admissible_state(semi, seed=31) if "shockcapturing" not in name else _shock_state(semi, 6)
+    gpu = semi.backend()
+    alg = T.CarpenterKennedy2N54()
+    out = []
+    for path in (0, 1):
+        gpu.set_option(gpu.OPT_KERNEL_PATH, path)
+        du = np.empty_like(u)
+        gpu.rhs_host(du, u, 0.2)
+        gpu.upload(0, u)
+        dt = 0.4 * gpu.max_dt()
+        gpu.step_2n(0.0, dt, alg.a, alg.b, alg.c)
+        gpu.step_2n(dt, dt, alg.a, alg.b, alg.c)
+        out.append((du, gpu.download(0), dt))
+    assert _rel_err(out[0][0], out[1][0]) <= RHS_TOL
+    assert out[0][2] == pytest.approx(out[1][2], rel=1e-14)
+    assert _rel_err(out[0][1], out[1][1]) <= 1e-13
+
+
 GOLDEN_GPU = ["tree_3d_euler_shockcapturing", "tree_2d_euler_shockcapturing", "tree_2d_euler_blast_wave","tree_2d_advection_timeintegration_2n43_maxiters1", "tree_2d_advection_timeintegration_3sstar32_maxiters1",
               "tree_3d_euler_ec", "tree_3d_euler_ec_constant", "tree_3d_euler_source_terms",
               "tree_3d_euler_convergence", "tree_3d_euler_taylor_green_vortex", "tree_3d_euler_density_pulse",
