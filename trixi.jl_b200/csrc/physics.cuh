@@ -258,39 +258,36 @@ struct Euler {
     // FluxLaxFriedrichs (numerical_fluxes.jl:37-45,172-178) with max_abs_speed(_naive)
     // (compressible_euler_3d.jl:1112-1177) on Newton reciprocals: two MUFU seeds per face node instead of eight IEEE
     // divisions; every quotient carries a residual correction (within 1 ulp of the generic path)
+    TB_DEV void llf_fast_side(const double (&u)[NVARS], int o, double (&fs)[NVARS], double &lam_v, double &lam_c) const {
+        const double rho = u[0], inv_rho = fast_rcp(rho);
+        double v[ND], mom[ND], kin = 0.0;
+#pragma unroll
+        for (int d = 0; d < ND; ++d) {
+            mom[d] = u[1 + d];
+            const double q = u[1 + d] * inv_rho;
+            v[d] = fma(fma(-rho, q, u[1 + d]), inv_rho, q);
+            kin += u[1 + d] * v[d];
+        }
+        const double p = (gamma - 1) * (u[ND + 1] - 0.5 * kin);
+        const double gp = gamma * p;
+        double c2 = gp * inv_rho;
+        c2 = fma(fma(-rho, c2, gp), inv_rho, c2);
+        lam_c = sqrt(c2);
+        const double rv = pick<ND>(mom, o), vo = pick<ND>(v, o);
+        lam_v = fabs(vo);
+        fs[0] = rv;
+#pragma unroll
+        for (int d = 0; d < ND; ++d) fs[1 + d] = rv * v[d] + (d == o ? p : 0.0);
+        fs[ND + 1] = (u[ND + 1] + p) * vo;
+    }
     TB_DEV void flux_llf_fast(int id, const double (&ul)[NVARS], const double (&ur)[NVARS], int o,
                               double (&f)[NVARS]) const {
-        double lam_v[2], lam_c[2], fs[2][NVARS];
+        double fl[NVARS], fr[NVARS], vl, vr, cl, cr;
+        llf_fast_side(ul, o, fl, vl, cl);
+        llf_fast_side(ur, o, fr, vr, cr);
+        const double lam = id == TRIXI_B200_FLUX_LLF_NAIVE ? fmax(vl, vr) + fmax(cl, cr) : fmax(vl + cl, vr + cr);
 #pragma unroll
-        for (int side = 0; side < 2; ++side) {
-            const double(&u)[NVARS] = side == 0 ? ul : ur;
-            const double rho = u[0], inv_rho = fast_rcp(rho);
-            double v[ND], kin = 0.0;
-#pragma unroll
-            for (int d = 0; d < ND; ++d) {
-                const double q = u[1 + d] * inv_rho;
-                v[d] = fma(fma(-rho, q, u[1 + d]), inv_rho, q);
-                kin += u[1 + d] * v[d];
-            }
-            const double p = (gamma - 1) * (u[ND + 1] - 0.5 * kin);
-            const double gp = gamma * p;
-            double c2 = gp * inv_rho;
-            c2 = fma(fma(-rho, c2, gp), inv_rho, c2);
-            lam_c[side] = sqrt(c2);
-            double mom[ND];
-#pragma unroll
-            for (int d = 0; d < ND; ++d) mom[d] = u[1 + d];
-            const double rv = pick<ND>(mom, o), vo = pick<ND>(v, o);
-            lam_v[side] = fabs(vo);
-            fs[side][0] = rv;
-#pragma unroll
-            for (int d = 0; d < ND; ++d) fs[side][1 + d] = rv * v[d] + (d == o ? p : 0.0);
-            fs[side][ND + 1] = (u[ND + 1] + p) * vo;
-        }
-        const double lam = id == TRIXI_B200_FLUX_LLF_NAIVE ? fmax(lam_v[0], lam_v[1]) + fmax(lam_c[0], lam_c[1])
-                                                           : fmax(lam_v[0] + lam_c[0], lam_v[1] + lam_c[1]);
-#pragma unroll
-        for (int v = 0; v < NVARS; ++v) f[v] = 0.5 * (fs[0][v] + fs[1][v]) + (-0.5 * lam * (ur[v] - ul[v]));
+        for (int v = 0; v < NVARS; ++v) f[v] = 0.5 * (fl[v] + fr[v]) + (-0.5 * lam * (ur[v] - ul[v]));
     }
     TB_DEV void flux_ranocha_fast(const double (&ul)[NVARS], const double (&ur)[NVARS], int o,
                                   double (&f)[NVARS]) const {
