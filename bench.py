@@ -521,6 +521,14 @@ def run_b200(args, rank, world, local_rank):
                                   "peak_tflops_measured_dfma": fp64_peak,
                                   "algorithmic_flop_per_dof": wl["flop"]},
                          "copy_gbs_measured_here": copy_gbs},
+            "roofline_interface_kernel": {
+                # prolong2interfaces! + calc_interface_flux! fused: 3/n face nodes per DOF, each reads both states and
+                # writes the flux to both elements (+ normal and Jacobian sign on curved meshes)
+                "bound": "hbm", "avg_launch_ms": surf_ms / max(surf_n, 1), "launches": surf_n,
+                "algorithmic_bytes_per_dof": 0.75 * (4 * wl["nvars"] * 8 + (32 if "curved" in args.workload else 0)),
+                "achieved": (0.75 * (4 * wl["nvars"] * 8 + (32 if "curved" in args.workload else 0)) * ndofs
+                             / (surf_ms / max(surf_n, 1) * 1e-3) * 1e-9) if surf_n else None,
+                "peak": peaks["hbm_gbs"], "unit": "GB/s"},
             "kernel_time_share": {"surface_flux_ms": surf_ms, "element_ms": elem_ms, "max_dt_ms": cfl_ms,
                                   "halo_pack_wait_mpiflux_ms": halo_ms, "timed_region_ms": ms_max},
             "wall_s": wall, "finite": finite,
