@@ -131,15 +131,19 @@ def test_max_dt_matches_oracle(name, oracle_module):
     assert gpu.max_dt() == pytest.approx(ref.max_dt(), rel=1e-14)
 
 
-def test_fused_cfl_equals_standalone_max_dt(oracle_module):
+@pytest.mark.parametrize("name", ["tree_3d_euler_ec", "tree_3d_euler_source_terms", "tree_3d_euler_ec_shima_etal",
+                                  "tree_3d_mhd_ec", "structured_3d_euler_source_terms",
+                                  "p4est_3d_euler_source_terms_nonperiodic"])
+def test_fused_cfl_equals_standalone_max_dt(name, oracle_module):
     """TRIXI_B200_OPT_FUSED_CFL: the maxima reduced by the last RK stage kernel are the ones the max_dt kernel
     computes from the same u (to the last ulp or two: Newton reciprocals instead of IEEE divisions), and cost
-    no launch."""
-    semi = ELIXIRS["tree_3d_euler_ec"].semi()
+    no launch.  Every tuned element kernel: headline, weak form (tree and curved), line sweep (Euler, MHD)."""
+    semi = ELIXIRS[name].semi()
     gpu = semi.backend()
     gpu.set_option(gpu.OPT_FUSED_CFL, 1)
     alg = T.CarpenterKennedy2N54()
-    gpu.upload(0, _random_admissible_state(semi, seed=11))
+    # (a mildly perturbed state: the weak-form configurations are not robust against node-wise random data)
+    gpu.upload(0, _random_admissible_state(semi, seed=11, perturb=0.05))
     dt = 0.5 * gpu.max_dt()
     for k in range(2):
         gpu.step_2n(k * dt, dt, alg.a, alg.b, alg.c)
@@ -149,7 +153,8 @@ def test_fused_cfl_equals_standalone_max_dt(oracle_module):
         gpu.set_option(gpu.OPT_FUSED_CFL, 0)  # drops the cached maxima
         standalone = gpu.max_dt()
         assert gpu.launch_count() == n0 + 1
-        assert fused == pytest.approx(standalone, rel=1e-15)
+        assert np.isfinite(fused)
+        assert fused == pytest.approx(standalone, rel=4e-15)
         ref = oracle_module.OracleBackend(semi)
         ref.upload(0, gpu.download(0))
         assert fused == pytest.approx(ref.max_dt(), rel=1e-14)

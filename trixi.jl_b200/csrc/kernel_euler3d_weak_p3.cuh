@@ -227,8 +227,8 @@ __global__ void __launch_bounds__(WeakCfg::THREADS, CURVED ? 12 : WeakCfg::MIN_B
                 un[v] = out_u[v] + tmp * P.rk_b_dt;
                 out_u[v] = un[v];
             }
-            if (!CURVED && P.want_cfl) {
-                // max_dt of the updated state (stepsize_dg3d.jl:8-32), as in the flux-differencing kernel
+            if (P.want_cfl) {
+                // max_dt of the updated state (stepsize_dg3d.jl:8-32; curved :94-123), as in the flux-differencing kernel
                 const double rho = un[0], inv_rho = fast_rcp(rho);
                 double v1 = un[1] * inv_rho, v2 = un[2] * inv_rho, v3 = un[3] * inv_rho;
                 v1 = fma(fma(-rho, v1, un[1]), inv_rho, v1);
@@ -239,13 +239,23 @@ __global__ void __launch_bounds__(WeakCfg::THREADS, CURVED ? 12 : WeakCfg::MIN_B
                 double c2 = gp * inv_rho;
                 c2 = fma(fma(-rho, c2, gp), inv_rho, c2);
                 const double c = sqrt(c2);
-                cfl0 = max(cfl0, cfl_encode(fabs(v1) + c));
-                cfl1 = max(cfl1, cfl_encode(fabs(v2) + c));
-                cfl2 = max(cfl2, cfl_encode(fabs(v3) + c));
+                const double lam[3] = {fabs(v1) + c, fabs(v2) + c, fabs(v3) + c};
+                if constexpr (!CURVED) {
+                    cfl0 = max(cfl0, cfl_encode(lam[0]));
+                    cfl1 = max(cfl1, cfl_encode(lam[1]));
+                    cfl2 = max(cfl2, cfl_encode(lam[2]));
+                } else {
+                    // |inverse_jacobian| |Ja^a . lambda| per node and direction a (the nodal Jacobian enters here)
+                    const double *ja = s_ja + n * 9;
+                    const double aij = fabs(s_ij[n]);
+                    cfl0 = max(cfl0, cfl_encode(aij * fabs(ja[0] * lam[0] + ja[1] * lam[1] + ja[2] * lam[2])));
+                    cfl1 = max(cfl1, cfl_encode(aij * fabs(ja[3] * lam[0] + ja[4] * lam[1] + ja[5] * lam[2])));
+                    cfl2 = max(cfl2, cfl_encode(aij * fabs(ja[6] * lam[0] + ja[7] * lam[1] + ja[8] * lam[2])));
+                }
             }
         }
     }
-    if (!CURVED && rk && P.want_cfl) {
+    if (rk && P.want_cfl) {
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) {
             cfl0 = max(cfl0, __shfl_xor_sync(0xffffffffu, cfl0, off));
@@ -257,7 +267,7 @@ __global__ void __launch_bounds__(WeakCfg::THREADS, CURVED ? 12 : WeakCfg::MIN_B
             sum += __longlong_as_double((long long)cfl0);
             sum += __longlong_as_double((long long)cfl1);
             sum += __longlong_as_double((long long)cfl2);
-            atomicMax(P.cfl_key + (blockIdx.x & (kCflSlots - 1)), cfl_encode(P.inverse_jacobian[e] * sum));
+            atomicMax(P.cfl_key + (blockIdx.x & (kCflSlots - 1)), cfl_encode(CURVED ? sum : P.inverse_jacobian[e] * sum));
         }
     }
     fence_proxy_async();

@@ -212,7 +212,7 @@ bool uses_tuned_element(const KParams &P) {
 // true when the RK stage kernel selected for P also reduces the CFL wave speeds (TreeMesh tuned kernels)
 template <class EQ, int N>
 bool fuses_cfl(const KParams &P) {
-    return uses_tuned_element<EQ, N>(P) && !P.curved;
+    return uses_tuned_element<EQ, N>(P);  // (on curved meshes only the weak-form kernel is tuned; it reduces the CFL too)
 }
 
 template <class EQ, int N>
