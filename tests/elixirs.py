@@ -580,6 +580,31 @@ def _euler2d_blast_wave(level=6):
                                           boundary_conditions=T.boundary_condition_periodic)
 
 
+def _euler2d_vortex_shockcapturing(mortar=False):
+    # examples/tree_2d_dgsem/elixir_euler_vortex_shockcapturing.jl / elixir_euler_vortex_mortar_shockcapturing.jl
+    eq = T.CompressibleEulerEquations2D(1.4)
+    solver = _shockcapturing(eq, T.flux_shima_etal, T.FluxLaxFriedrichs(T.max_abs_speed_naive))
+    patches = ({"type": "box", "coordinates_min": (0.0, -10.0), "coordinates_max": (10.0, 10.0)},) if mortar else ()
+    mesh = T.TreeMesh((-10.0, -10.0), (10.0, 10.0), initial_refinement_level=4, refinement_patches=patches,
+                      periodicity=True)
+    return T.SemidiscretizationHyperbolic(mesh, eq, T.initial_condition_isentropic_vortex, solver,
+                                          boundary_conditions=T.boundary_condition_periodic)
+
+
+ELIXIRS.update({e.name: e for e in [
+    # (the MPI run of the first one is asserted against the same values, test/test_mpi_tree.jl:337-356)
+    Elixir("tree_2d_euler_vortex_shockcapturing", _euler2d_vortex_shockcapturing, (0.0, 1.0), 0.7,
+           [0.0017158367642679273, 0.09619888722871434, 0.09616432767924141, 0.17553381166255197],
+           [0.021853862449723982, 0.9878047229255944, 0.9880191167111795, 2.2154030488035588],
+           "test/test_tree_2d_euler.jl:1223-1239"),
+    Elixir("tree_2d_euler_vortex_mortar_shockcapturing", lambda: _euler2d_vortex_shockcapturing(mortar=True),
+           (0.0, 1.0), 0.7,
+           [0.0017203324051381415, 0.09628962899999398, 0.0962124115572114, 0.1758599596626405],
+           [0.021740568112562086, 0.9938841624655501, 1.0041401179009877, 2.2241087041100798],
+           "test/test_tree_2d_euler.jl:1245-1262"),
+]})
+
+
 ELIXIRS.update({e.name: e for e in [
     # VolumeIntegralShockCapturingHG
     Elixir("tree_3d_euler_shockcapturing", _euler3d_shockcapturing, (0.0, 0.4), 1.4,

@@ -35,7 +35,8 @@ def _worker(rank, world, port, out_dir, name="tree_3d_euler_ec"):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("name", ["tree_3d_euler_ec", "p4est_3d_euler_source_terms_nonperiodic", "tree_3d_mhd_ec"])
+@pytest.mark.parametrize("name", ["tree_3d_euler_ec", "p4est_3d_euler_source_terms_nonperiodic", "tree_3d_mhd_ec",
+                                  "tree_2d_euler_vortex_shockcapturing"])  # the last: test/test_mpi_tree.jl:337-356
 def test_two_gpu_run_reproduces_golden(name, tmp_path):
     """like test/test_mpi_p4est_3d.jl: the distributed run reproduces the serial golden values"""
     if torch.cuda.device_count() < 2:

@@ -68,7 +68,7 @@ RHS_CASES = ["tree_3d_euler_ec", "tree_3d_euler_source_terms", "tree_3d_euler_so
              "structured_2d_advection_basic", "structured_2d_euler_free_stream", "structured_2d_euler_ec",
              "structured_2d_euler_source_terms_nonperiodic", "p4est_2d_advection_basic",
              "tree_3d_euler_shockcapturing", "tree_2d_euler_shockcapturing", "tree_2d_euler_blast_wave",
-             "tree_3d_euler_ec_turbo"]
+             "tree_3d_euler_ec_turbo", "tree_2d_euler_vortex_shockcapturing", "tree_2d_euler_vortex_mortar_shockcapturing"]
 
 
 @pytest.mark.parametrize("name", RHS_CASES)
@@ -311,7 +311,8 @@ def test_tuned_kernels_match_generic_kernels(name):
     assert _rel_err(out[0][1], out[1][1]) <= 1e-13
 
 
-GOLDEN_GPU = ["tree_3d_euler_shockcapturing", "tree_2d_euler_shockcapturing", "tree_2d_euler_blast_wave","tree_2d_advection_timeintegration_2n43_maxiters1", "tree_2d_advection_timeintegration_3sstar32_maxiters1",
+GOLDEN_GPU = ["tree_2d_euler_vortex_shockcapturing", "tree_2d_euler_vortex_mortar_shockcapturing",
+              "tree_3d_euler_shockcapturing", "tree_2d_euler_shockcapturing", "tree_2d_euler_blast_wave","tree_2d_advection_timeintegration_2n43_maxiters1", "tree_2d_advection_timeintegration_3sstar32_maxiters1",
               "tree_3d_euler_ec", "tree_3d_euler_ec_constant", "tree_3d_euler_source_terms",
               "tree_3d_euler_convergence", "tree_3d_euler_taylor_green_vortex", "tree_3d_euler_density_pulse",
               "tree_2d_advection_basic", "tree_2d_euler_source_terms", "tree_2d_euler_source_terms_nonperiodic",
@@ -443,13 +444,17 @@ def _ranked_semis(name, world):
 
 @pytest.mark.parametrize("world", [2, 3])
 @pytest.mark.parametrize("name", ["tree_3d_euler_ec", "tree_2d_euler_source_terms_nonperiodic", "tree_3d_mhd_ec",
-                                  "p4est_3d_euler_source_terms_nonperiodic", "p4est_3d_curved_level1"])
+                                  "p4est_3d_euler_source_terms_nonperiodic", "p4est_3d_curved_level1",
+                                  "tree_3d_euler_shockcapturing", "tree_2d_euler_shockcapturing",
+                                  "tree_2d_euler_vortex_shockcapturing"])
 def test_halo_exchange_matches_single_rank(name, world, oracle_module):
     """The element partition with the device-side halo exchange (pack kernels storing into the peers'
     receive buffers, sequence flags) reproduces the single-rank result; like the reference asserts for its
     MPI runs (test/test_mpi_p4est_3d.jl:9-12)."""
     base, semis = _ranked_semis(name, world)
-    u = _random_admissible_state(base, seed=7)
+    # shock capturing: a state with pure-DG, blended and alpha_max elements, so that the smoothing across the
+    # rank boundaries (the neighbour's alpha travels with its face state) matters
+    u = _shock_state(base, 8) if "shockcapturing" in name else _random_admissible_state(base, seed=7)
     alg = T.CarpenterKennedy2N54()
     single = base.backend()
     single.upload(0, u)

@@ -81,6 +81,10 @@ struct KParams {
     const long long *mpi_remote_index;                   // [nmpi] slot of this face in the peer's receive buffer
     double *const *peer_recv;                            // [npeers] peer receive buffers (current parity), NVLink-mapped
     const double *recv;                                  // my receive buffer (current parity) [nv, nf, nmpi]
+    // shock capturing across ranks: the neighbour element's unsmoothed blending factor travels with its face
+    // ([nmpi] doubles behind the face states of every receive buffer)
+    const double *recv_alpha;                            // my receive buffer's alpha part (current parity) [nmpi]
+    const long long *mpi_peer_nmpi;                      // [npeers] faces in that peer's receive buffer
 };
 
 __host__ __device__ constexpr int ipow(int b, int e) { return e == 0 ? 1 : b * ipow(b, e - 1); }
@@ -457,9 +461,12 @@ __global__ void __launch_bounds__(256) k_mpi_pack(const KParams P) {
     const int side = (int)P.mpi_side[I];
     const int vn = face_to_volume_node<ND, N>(o, side == 1 ? N - 1 : 0, fn);
     const double *pu = P.u + (element * NN + vn) * NV;
-    double *dst = P.peer_recv[P.mpi_peer_slot[I]] + (P.mpi_remote_index[I] * NF + fn) * NV;
+    const int slot = P.mpi_peer_slot[I];
+    double *dst = P.peer_recv[slot] + (P.mpi_remote_index[I] * NF + fn) * NV;
 #pragma unroll
     for (int v = 0; v < NV; ++v) dst[v] = pu[v];
+    if (fn == 0 && P.volume_integral == TRIXI_B200_VOLINT_SHOCK_CAPTURING_HG)
+        P.peer_recv[slot][P.mpi_peer_nmpi[slot] * NF * NV + P.mpi_remote_index[I]] = P.alpha_raw[element];
     __threadfence_system();
 }
 
@@ -859,6 +866,11 @@ __global__ void __launch_bounds__(256) k_indicator_smooth(const KParams P) {
             atomicMax(key + sm, (unsigned long long)__double_as_longlong(0.5 * P.alpha_raw[large]));
             atomicMax(key + large, (unsigned long long)__double_as_longlong(0.5 * P.alpha_raw[sm]));
         }
+    } else if (P.recv_alpha && gid - P.ninterfaces - P.nmortars < P.nmpi) {
+        // faces shared with other ranks (apply_smoothing! over mpi_interfaces, indicators_2d.jl:140-185 in the
+        // reference's parallel TreeMesh): the neighbour's alpha arrived with its face state
+        const long long I = gid - P.ninterfaces - P.nmortars;
+        atomicMax(key + (P.mpi_local[I] - 1), (unsigned long long)__double_as_longlong(0.5 * P.recv_alpha[I]));
     }
 }
 

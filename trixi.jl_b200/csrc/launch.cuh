@@ -13,8 +13,9 @@ struct Launchers {
     void (*error_norms)(const KParams &, const NormParams &, cudaStream_t);
     // with_surface = false: volume terms only (stage-level parity entry point)
     cudaError_t (*element)(const KParams &, bool with_surface, cudaStream_t);
-    // IndicatorHennemannGassner blending factors of P.u into P.alpha (VolumeIntegralShockCapturingHG)
-    void (*indicator)(const KParams &, cudaStream_t);
+    // IndicatorHennemannGassner blending factors of P.u into P.alpha (VolumeIntegralShockCapturingHG):
+    // stage 1 = per-element values (alpha_raw, alpha), stage 2 = smoothing over interfaces, mortars and MPI faces
+    void (*indicator)(const KParams &, int stage, cudaStream_t);
     void (*max_dt)(const KParams &, cudaStream_t);
     // true when the RK stage kernel `element` selects for P honours P.want_cfl (fused max_dt)
     bool (*fuses_cfl)(const KParams &);
@@ -246,16 +247,19 @@ cudaError_t launch_element(const KParams &P, bool with_surface, cudaStream_t s) 
 
 // (indicator_hg::IndicatorHennemannGassner)(u, mesh, equations, dg, cache) (dgsem/indicators.jl:114-148)
 template <class EQ, int N>
-void launch_indicator(const KParams &P, cudaStream_t s) {
+void launch_indicator(const KParams &P, int stage, cudaStream_t s) {
     if constexpr (HasFastRanocha<EQ>::value) {
         using C = ElemCfg<EQ, N>;
         if (P.nelements == 0) return;
-        // magic parameters (indicators.jl:126-130)
-        const double threshold = 0.5 * pow(10.0, -1.8 * pow((double)N, 0.25));
-        const double parameter_s = log((1 - 0.0001) / 0.0001);
-        k_indicator_hg<EQ, N><<<(unsigned)((P.nelements + C::EPB - 1) / C::EPB), C::THREADS, 0, s>>>(P, threshold, parameter_s);
-        const long long faces = P.ninterfaces + P.nmortars;
-        if (P.ind_smooth && faces > 0) k_indicator_smooth<EQ, N><<<(unsigned)((faces + 255) / 256), 256, 0, s>>>(P);
+        if (stage == 1) {
+            // magic parameters (indicators.jl:126-130)
+            const double threshold = 0.5 * pow(10.0, -1.8 * pow((double)N, 0.25));
+            const double parameter_s = log((1 - 0.0001) / 0.0001);
+            k_indicator_hg<EQ, N><<<(unsigned)((P.nelements + C::EPB - 1) / C::EPB), C::THREADS, 0, s>>>(P, threshold, parameter_s);
+        } else {
+            const long long faces = P.ninterfaces + P.nmortars + P.nmpi;
+            if (P.ind_smooth && faces > 0) k_indicator_smooth<EQ, N><<<(unsigned)((faces + 255) / 256), 256, 0, s>>>(P);
+        }
     }
 }
 

@@ -70,6 +70,8 @@ struct trixi_b200_handle {
     long long *d_mpi_remote_index = nullptr;
     bool comm_connected = false;
     unsigned long long comm_seq = 0;
+    bool indicator_done = false;  // distributed shock capturing: alpha of this RHS was computed around the halo exchange
+    long long *d_peer_nmpi = nullptr;
     // host-buffer calls (rhs_host, step_2n_host) stream u in and the result out in element chunks so the two PCIe
     // directions and the kernels overlap
     int opt_pipeline_chunk = -1;  // TRIXI_B200_OPT_HOST_PIPELINE_CHUNK: -1 auto, 0 off, > 0 elements per chunk
@@ -266,18 +268,23 @@ int run_surface_fluxes(trixi_b200_handle *h, double t) {
     return check_launch(h, "surface flux kernel");
 }
 
-int run_indicator(trixi_b200_handle *h) {
-    h->L->indicator(h->P, h->stream);
-    h->launches += 1 + ((h->P.ind_smooth && h->P.ninterfaces + h->P.nmortars > 0) ? 1 : 0);
+// stage 1: per-element blending factors of the current u; stage 2: smoothing (needs the neighbours' stage 1,
+// across ranks: after the halo exchange that carries them)
+int run_indicator(trixi_b200_handle *h, int stage) {
+    h->L->indicator(h->P, stage, h->stream);
+    if (stage == 1 || (h->P.ind_smooth && h->P.ninterfaces + h->P.nmortars + h->P.nmpi > 0)) h->launches++;
     return check_launch(h, "indicator kernel");
 }
 
 int run_element(trixi_b200_handle *h, bool with_surface) {
-    if (h->P.volume_integral == TRIXI_B200_VOLINT_SHOCK_CAPTURING_HG) {
+    if (h->P.volume_integral == TRIXI_B200_VOLINT_SHOCK_CAPTURING_HG && !h->indicator_done) {
         // blending factors of the current u, before the element kernel may update u in place
-        int rc = run_indicator(h);
+        h->P.recv_alpha = nullptr;  // no halo exchange around this call: local smoothing only
+        int rc = run_indicator(h, 1);
+        if (rc == 0) rc = run_indicator(h, 2);
         if (rc) return rc;
     }
+    h->indicator_done = false;
     {
         ProfScope ps(h, KC_ELEMENT);
         cudaError_t err = h->L->element(h->P, with_surface, h->stream);
@@ -295,11 +302,18 @@ int run_all_surface_fluxes(trixi_b200_handle *h, double t) {
         return fail(h, TRIXI_B200_ECOMM, "world_size > 1 but the halo exchange is not connected (trixi_b200_comm_connect)");
     int parity = 0;
     const int npeers = (int)h->peers.size();
+    const bool sc = h->P.volume_integral == TRIXI_B200_VOLINT_SHOCK_CAPTURING_HG;
+    if (dist && sc) {
+        // the unsmoothed blending factors travel with the face states
+        int rc = run_indicator(h, 1);
+        if (rc) return rc;
+    }
     if (dist) {
         const unsigned long long seq = ++h->comm_seq;
         parity = (int)(seq & 1);
         h->P.peer_recv = h->d_peer_recv[parity];
         h->P.recv = reinterpret_cast<const double *>(h->comm_base + h->flag_bytes + parity * h->recv_bytes);
+        h->P.recv_alpha = h->P.recv + h->nmpi * (long long)h->nvars * ipow(h->nnodes, h->ndims - 1);
         ProfScope ps(h, KC_HALO);
         h->L->mpi_pack(h->P, h->stream);
         k_mpi_signal<<<1, 32, 0, h->stream>>>(h->d_peer_flag[parity], npeers, seq);
@@ -317,7 +331,12 @@ int run_all_surface_fluxes(trixi_b200_handle *h, double t) {
         h->L->mpi_interface_flux(h->P, h->stream);
         h->launches += 2;
     }
-    return check_launch(h, "mpi interface flux");
+    rc = check_launch(h, "mpi interface flux");
+    if (rc == 0 && dist && sc) {
+        rc = run_indicator(h, 2);
+        h->indicator_done = true;
+    }
+    return rc;
 }
 
 int run_rhs(trixi_b200_handle *h, double t) {
@@ -609,8 +628,6 @@ TRIXI_B200_API int trixi_b200_create(const trixi_b200_desc *d, trixi_b200_handle
             return fail(nullptr, TRIXI_B200_EINVAL, "VolumeIntegralShockCapturingHG is available on TreeMesh only in this build");
         if (d->equation != TRIXI_B200_EQ_EULER_2D && d->equation != TRIXI_B200_EQ_EULER_3D)
             return fail(nullptr, TRIXI_B200_EINVAL, "VolumeIntegralShockCapturingHG needs the compressible Euler equations");
-        if (d->world_size > 1)
-            return fail(nullptr, TRIXI_B200_EINVAL, "VolumeIntegralShockCapturingHG is single-rank in this build (alpha smoothing across ranks)");
         if (!d->inverse_vandermonde_legendre)
             return fail(nullptr, TRIXI_B200_EINVAL, "inverse_vandermonde_legendre missing");
         if (d->indicator_variable < TRIXI_B200_INDVAR_DENSITY_PRESSURE || d->indicator_variable > TRIXI_B200_INDVAR_PRESSURE)
@@ -899,7 +916,7 @@ TRIXI_B200_API int trixi_b200_create(const trixi_b200_desc *d, trixi_b200_handle
     if (h->world_size > 1) {
         // one allocation other ranks map: [flags 2 x world] [recv parity 0] [recv parity 1]
         h->flag_bytes = ((size_t)2 * h->world_size * sizeof(unsigned long long) + 255) / 256 * 256;
-        h->recv_bytes = ((size_t)h->nmpi * nf * nv * sizeof(double) + 255) / 256 * 256;
+        h->recv_bytes = ((size_t)h->nmpi * (nf * nv + 1) * sizeof(double) + 255) / 256 * 256;  // faces + alpha
         CREATE_TRY(alloc_array(h, h->flag_bytes + 2 * h->recv_bytes + 256, &h->comm_base));
         CREATE_CUDA(cudaMemset(h->comm_base, 0, h->flag_bytes + 2 * h->recv_bytes));
     }
@@ -1021,7 +1038,10 @@ TRIXI_B200_API int trixi_b200_calc_indicator(trixi_b200_handle *h, double *alpha
         return fail(h, TRIXI_B200_EINVAL, "the volume integral has no indicator (not VolumeIntegralShockCapturingHG)");
     if (!alpha_host && h->nelements) return fail(h, TRIXI_B200_EINVAL, "host pointer is null");
     CUDA_TRY(h, cudaSetDevice(h->device));
-    int rc = run_indicator(h);
+    if (h->world_size > 1)
+        return fail(h, TRIXI_B200_EINVAL, "calc_indicator is single-rank: across ranks the smoothing is part of the RHS's halo exchange");
+    int rc = run_indicator(h, 1);
+    if (rc == 0) rc = run_indicator(h, 2);
     if (rc) return rc;
     CUDA_TRY(h, cudaMemcpyAsync(alpha_host, h->P.alpha, h->nelements * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
@@ -1376,13 +1396,16 @@ TRIXI_B200_API int trixi_b200_comm_connect(trixi_b200_handle *h, const void *blo
         h->P.mpi_remote_index = h->d_mpi_remote_index;
         rc = upload_array(h, h->peers.data(), h->peers.size(), &h->d_peer_ranks);
         if (rc) return rc;
+        rc = upload_array(h, h->peer_nmpi.data(), h->peer_nmpi.size(), &h->d_peer_nmpi);
+        if (rc) return rc;
+        h->P.mpi_peer_nmpi = h->d_peer_nmpi;
         for (int parity = 0; parity < 2; ++parity) {
             std::vector<double *> recv((size_t)npeers);
             std::vector<unsigned long long *> flag((size_t)npeers);
             for (int p = 0; p < npeers; ++p) {
                 const size_t peer_flag_bytes = ((size_t)2 * world * sizeof(unsigned long long) + 255) / 256 * 256;
                 const size_t peer_recv_bytes =
-                    ((size_t)h->peer_nmpi[(size_t)p] * nf * h->nvars * sizeof(double) + 255) / 256 * 256;
+                    ((size_t)h->peer_nmpi[(size_t)p] * (nf * h->nvars + 1) * sizeof(double) + 255) / 256 * 256;
                 char *base = h->peer_base[(size_t)p];
                 recv[(size_t)p] = reinterpret_cast<double *>(base + peer_flag_bytes + (size_t)parity * peer_recv_bytes);
                 flag[(size_t)p] = reinterpret_cast<unsigned long long *>(base) + (size_t)parity * world + h->rank;

@@ -346,6 +346,23 @@ def initial_condition_gauss(x, t, equations):
     return np.exp(-(xs[0]**2 + xs[1]**2))[None]
 
 
+def initial_condition_isentropic_vortex(x, t, equations):
+    """The isentropic vortex of examples/tree_2d_dgsem/elixir_euler_vortex_shockcapturing.jl:8-44 (Shu 1997), evaluated
+    like the elixir does (t_loc = 0: the centre is not advected).  Host only."""
+    if not isinstance(equations, CompressibleEulerEquations2D):
+        raise NotImplementedError
+    gamma = equations.gamma
+    iniamplitude, rho, v1, v2, p = 5.0, 1.0, 1.0, 1.0, 25.0
+    rt = p / rho
+    cx, cy = -(x[1] - 0.0), x[0] - 0.0  # cross product of the distance to the centre with the z axis
+    r2 = cx**2 + cy**2
+    du = iniamplitude / (2 * math.pi) * np.exp(0.5 * (1 - r2))
+    dtemp = -(gamma - 1) / (2 * gamma * rt) * du**2
+    rho_ = rho * (1 + dtemp) ** (1 / (gamma - 1))
+    p_ = p * (1 + dtemp) ** (gamma / (gamma - 1))
+    return equations.prim2cons((rho_, v1 + du * cx, v2 + du * cy, p_))
+
+
 def initial_condition_blast_wave(x, t, equations):
     """The "medium blast wave" of examples/tree_2d_dgsem/elixir_euler_blast_wave.jl:7-30 (Hennemann, Gassner 2020,
     Sec. 6.3).  Host only."""
