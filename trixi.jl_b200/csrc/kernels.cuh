@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(256) k_interface_flux(const KParams P) {
 // CURVED (StructuredMesh, dgsem_structured/dg_3d.jl:619-753): the flux is taken along the contravariant vector of
 // the right element's first node layer times sign(inverse_jacobian), and stored with that sign on both sides.
 template <class EQ, int N, int FAST = 0, bool CURVED = false>
-__global__ void __launch_bounds__(256) k_interface_flux_staged(const KParams P) {
+__global__ void __launch_bounds__(256, (FAST == 2 && !CURVED) ? 5 : 1) k_interface_flux_staged(const KParams P) {
     constexpr int ND = EQ::NDIMS, NV = EQ::NVARS, NF = ipow(N, ND - 1), NN = ipow(N, ND);
     constexpr int G = 32 / NF;   // interfaces per warp
     constexpr int FV = NF * NV;  // doubles per face
@@ -239,10 +239,13 @@ __global__ void __launch_bounds__(256) k_interface_flux_staged(const KParams P) 
         const EQ eq(P.eq);
         const int o = s_orient[warp][g];
         double ul[NV], ur[NV], f[NV];
+        constexpr bool kFromMemory = FAST == 2 && !CURVED && HasFastRanocha<EQ>::value;
+        if constexpr (!kFromMemory) {
 #pragma unroll
-        for (int v = 0; v < NV; ++v) {
-            ul[v] = s[(2 * g) * FV + fn * NV + v];
-            ur[v] = s[(2 * g + 1) * FV + fn * NV + v];
+            for (int v = 0; v < NV; ++v) {
+                ul[v] = s[(2 * g) * FV + fn * NV + v];
+                ur[v] = s[(2 * g + 1) * FV + fn * NV + v];
+            }
         }
         bool done = false;
         if constexpr (CURVED) {
@@ -260,6 +263,8 @@ __global__ void __launch_bounds__(256) k_interface_flux_staged(const KParams P) 
 #pragma unroll
             for (int v = 0; v < NV; ++v) fl[v] = fr[v] = sign_jacobian * f[v];
             done = true;
+        } else if constexpr (kFromMemory) {
+            eq.flux_llf_fast_mem(P.surface_flux, s + (2 * g) * FV + fn * NV, s + (2 * g + 1) * FV + fn * NV, o, f);
         } else {
             surface_numflux<EQ, FAST>(eq, P.surface_flux, ul, ur, o, f);
         }
