@@ -29,11 +29,13 @@ mesh_kind(::TreeMesh) = Cint(0)
 mesh_kind(::StructuredMesh) = Cint(1)
 mesh_kind(::P4estMesh) = Cint(2)
 equation_id(::LinearScalarAdvectionEquation2D) = Cint(1)
+equation_id(::LinearScalarAdvectionEquation3D) = Cint(5)
 equation_id(::CompressibleEulerEquations2D) = Cint(2)
 equation_id(::CompressibleEulerEquations3D) = Cint(3)
 equation_id(::IdealGlmMhdEquations3D) = Cint(4)
 equation_params(eq::IdealGlmMhdEquations3D) = (eq.gamma, eq.inv_gamma_minus_one, eq.c_h, 0.0, 0.0, 0.0, 0.0, 0.0)
 equation_params(eq::LinearScalarAdvectionEquation2D) = (eq.advection_velocity..., 0.0, 0.0, 0.0, 0.0, 0.0, 0.0)
+equation_params(eq::LinearScalarAdvectionEquation3D) = (eq.advection_velocity..., 0.0, 0.0, 0.0, 0.0, 0.0)
 equation_params(eq::Union{CompressibleEulerEquations2D, CompressibleEulerEquations3D}) = (eq.gamma,
                                                                                           eq.inv_gamma_minus_one,
                                                                                           0.0, 0.0, 0.0, 0.0, 0.0,

@@ -544,6 +544,37 @@ ELIXIRS.update({e.name: e for e in [
 ]})
 
 
+def _advection3d(kind="tree"):
+    # examples/{tree,structured,p4est}_3d_dgsem/elixir_advection_basic.jl, tree_3d_dgsem/elixir_advection_mortar.jl
+    eq = T.LinearScalarAdvectionEquation3D((0.2, -0.7, 0.5))
+    solver = T.DGSEM(polydeg=3, surface_flux=T.flux_lax_friedrichs)
+    lo, hi = (-1.0,) * 3, (1.0,) * 3
+    if kind == "tree":
+        mesh = T.TreeMesh(lo, hi, initial_refinement_level=3, periodicity=True)
+    elif kind == "mortar":
+        patches = ({"type": "box", "coordinates_min": (0.0, -1.0, -1.0), "coordinates_max": (1.0, 1.0, 1.0)},
+                   {"type": "box", "coordinates_min": (0.0, -0.5, -0.5), "coordinates_max": (0.5, 0.5, 0.5)})
+        mesh = T.TreeMesh(lo, hi, initial_refinement_level=2, refinement_patches=patches, periodicity=True)
+    elif kind == "structured":
+        mesh = T.StructuredMesh((8, 8, 8), lo, hi, periodicity=True)
+    else:
+        mesh = T.P4estMesh((4, 4, 4), polydeg=3, coordinates_min=lo, coordinates_max=hi, initial_refinement_level=1,
+                           periodicity=True)
+    return T.SemidiscretizationHyperbolic(mesh, eq, T.initial_condition_convergence_test, solver)
+
+
+ELIXIRS.update({e.name: e for e in [
+    Elixir("tree_3d_advection_basic", lambda: _advection3d("tree"), (0.0, 1.0), 1.2,
+           [0.00016263963870641478], [0.0014537194925779984], "test/test_tree_3d_advection.jl:5-11"),
+    Elixir("tree_3d_advection_mortar", lambda: _advection3d("mortar"), (0.0, 5.0), 1.2,
+           [0.001810141301577316], [0.017848192256602058], "test/test_tree_3d_advection.jl:81-87"),
+    Elixir("structured_3d_advection_basic", lambda: _advection3d("structured"), (0.0, 1.0), 1.2,
+           [0.00016263963870641478], [0.0014537194925779984], "test/test_structured_3d.jl:5-9"),
+    Elixir("p4est_3d_advection_basic", lambda: _advection3d("p4est"), (0.0, 1.0), 1.2,
+           [0.00016263963870641478], [0.0014537194925779984], "test/test_p4est_3d.jl:5-9"),
+]})
+
+
 def _shockcapturing(eq, volume_flux, surface_flux):
     basis = T.LobattoLegendreBasis(3)
     indicator_sc = T.IndicatorHennemannGassner(eq, basis, alpha_max=0.5, alpha_min=0.001, alpha_smooth=True,

@@ -32,7 +32,7 @@ def _random_admissible_state(semi, seed=0, perturb=None):
     rng = np.random.default_rng(seed)
     eq = semi.equations
     shape = semi.u_shape()[1:]
-    if isinstance(eq, T.LinearScalarAdvectionEquation2D):
+    if isinstance(eq, (T.LinearScalarAdvectionEquation2D, T.LinearScalarAdvectionEquation3D)):
         return np.asfortranarray(rng.uniform(0.5, 2.0, size=(1,) + shape))
     nd = eq.ndims
     if perturb is None:
@@ -68,7 +68,9 @@ RHS_CASES = ["tree_3d_euler_ec", "tree_3d_euler_source_terms", "tree_3d_euler_so
              "structured_2d_advection_basic", "structured_2d_euler_free_stream", "structured_2d_euler_ec",
              "structured_2d_euler_source_terms_nonperiodic", "p4est_2d_advection_basic",
              "tree_3d_euler_shockcapturing", "tree_2d_euler_shockcapturing", "tree_2d_euler_blast_wave",
-             "tree_3d_euler_ec_turbo", "tree_2d_euler_vortex_shockcapturing", "tree_2d_euler_vortex_mortar_shockcapturing"]
+             "tree_3d_euler_ec_turbo", "tree_2d_euler_vortex_shockcapturing", "tree_2d_euler_vortex_mortar_shockcapturing",
+             "tree_3d_advection_basic", "tree_3d_advection_mortar", "structured_3d_advection_basic",
+             "p4est_3d_advection_basic"]
 
 
 @pytest.mark.parametrize("name", RHS_CASES)
@@ -311,7 +313,8 @@ def test_tuned_kernels_match_generic_kernels(name):
     assert _rel_err(out[0][1], out[1][1]) <= 1e-13
 
 
-GOLDEN_GPU = ["tree_2d_euler_vortex_shockcapturing", "tree_2d_euler_vortex_mortar_shockcapturing",
+GOLDEN_GPU = ["tree_3d_advection_basic", "tree_3d_advection_mortar", "structured_3d_advection_basic",
+              "p4est_3d_advection_basic", "tree_2d_euler_vortex_shockcapturing", "tree_2d_euler_vortex_mortar_shockcapturing",
               "tree_3d_euler_shockcapturing", "tree_2d_euler_shockcapturing", "tree_2d_euler_blast_wave","tree_2d_advection_timeintegration_2n43_maxiters1", "tree_2d_advection_timeintegration_3sstar32_maxiters1",
               "tree_3d_euler_ec", "tree_3d_euler_ec_constant", "tree_3d_euler_source_terms",
               "tree_3d_euler_convergence", "tree_3d_euler_taylor_green_vortex", "tree_3d_euler_density_pulse",

@@ -156,6 +156,7 @@ def calc_error_norms(u, t, semi, analyzer=None):
 
 _DEVICE_ICS = {
     "LinearScalarAdvectionEquation2D": (1, 2),
+    "LinearScalarAdvectionEquation3D": (1, 2),
     "CompressibleEulerEquations2D": (1, 2, 3),
     "CompressibleEulerEquations3D": (1, 2, 3),
     "IdealGlmMhdEquations3D": (1,),

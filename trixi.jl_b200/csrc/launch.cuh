@@ -371,6 +371,7 @@ const Launchers *launchers_for_nnodes(int n) {
 
 // one translation unit per equation (parallel nvcc)
 const Launchers *get_launchers_advection2d(int nnodes);
+const Launchers *get_launchers_advection3d(int nnodes);
 const Launchers *get_launchers_euler2d(int nnodes);
 const Launchers *get_launchers_euler3d(int nnodes);
 const Launchers *get_launchers_mhd3d(int nnodes);

@@ -640,6 +640,7 @@ TRIXI_B200_API int trixi_b200_create(const trixi_b200_desc *d, trixi_b200_handle
     const Launchers *L = nullptr;
     switch (d->equation) {
     case TRIXI_B200_EQ_ADVECTION_2D: L = get_launchers_advection2d(d->nnodes); break;
+    case TRIXI_B200_EQ_ADVECTION_3D: L = get_launchers_advection3d(d->nnodes); break;
     case TRIXI_B200_EQ_EULER_2D: L = get_launchers_euler2d(d->nnodes); break;
     case TRIXI_B200_EQ_EULER_3D: L = get_launchers_euler3d(d->nnodes); break;
     case TRIXI_B200_EQ_MHD_3D:

@@ -203,6 +203,23 @@ class LinearScalarAdvectionEquation2D(AbstractEquations):
         return u
 
 
+class LinearScalarAdvectionEquation3D(AbstractEquations):
+    """``LinearScalarAdvectionEquation3D`` (linear_scalar_advection_3d.jl:17-27)."""
+    ndims, nvars, eq_id = 3, 1, 5
+    varnames_cons = ("scalar",)
+
+    def __init__(self, a1, a2=None, a3=None):
+        if a2 is None:
+            a1, a2, a3 = a1
+        self.advection_velocity = (float(a1), float(a2), float(a3))
+
+    def params(self):
+        return list(self.advection_velocity) + [0.0] * 5
+
+    def cons2cons(self, u):
+        return u
+
+
 class CompressibleEulerEquations2D(AbstractEquations):
     """``CompressibleEulerEquations2D`` (compressible_euler_2d.jl:44-53)."""
     ndims, nvars, eq_id = 2, 4, EQ_EULER_2D
@@ -286,7 +303,7 @@ def initial_condition_constant(x, t, equations):
     elif isinstance(equations, CompressibleEulerEquations2D):
         # compressible_euler_2d.jl:78-85
         vals = (1.0, 0.1, -0.2, 10.0)
-    elif isinstance(equations, LinearScalarAdvectionEquation2D):
+    elif isinstance(equations, (LinearScalarAdvectionEquation2D, LinearScalarAdvectionEquation3D)):
         vals = (2.0,)
     elif isinstance(equations, IdealGlmMhdEquations3D):
         # ideal_glm_mhd_3d.jl:101-113 (conservative values)
@@ -298,10 +315,12 @@ def initial_condition_constant(x, t, equations):
 
 @_ic(IC_CONVERGENCE_TEST)
 def initial_condition_convergence_test(x, t, equations):
-    if isinstance(equations, LinearScalarAdvectionEquation2D):
-        # linear_scalar_advection_2d.jl:67-80
+    if isinstance(equations, (LinearScalarAdvectionEquation2D, LinearScalarAdvectionEquation3D)):
+        # linear_scalar_advection_2d.jl:67-80, linear_scalar_advection_3d.jl:58-71
         a = equations.advection_velocity
         xs = (x[0] - a[0] * t) + (x[1] - a[1] * t)
+        if equations.ndims == 3:
+            xs = xs + (x[2] - a[2] * t)
         omega = 2 * math.pi * 0.5
         return (1 + 0.5 * np.sin(omega * xs))[None]
     if isinstance(equations, CompressibleEulerEquations3D):

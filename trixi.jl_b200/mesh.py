@@ -202,9 +202,13 @@ class TreeMesh:
             # it is refined further -> imbalance.
             d = direction // 2
             bad = np.zeros(levels.shape[0], dtype=bool)
-            same = self._lookup(levels, c_safe)
-            coarse = self._lookup(np.maximum(levels - 1, 0), c_safe >> 1)
-            covered = (same >= 0) | ((coarse >= 0) & (levels > 0)) | outside
+            # covered: the neighbour slot is a leaf at this level or lies inside a coarser leaf (any number of levels
+            # coarser: with nested refinement patches a cell can temporarily sit next to a leaf two levels coarser;
+            # that imbalance is the coarse leaf's to resolve, not this cell's)
+            covered = (self._lookup(levels, c_safe) >= 0) | outside
+            for k in range(1, int(levels.max()) + 1):
+                anc = self._lookup(np.maximum(levels - k, 0), c_safe >> k)
+                covered |= (anc >= 0) & (levels >= k)
             others = [e for e in range(self.ndims) if e != d]
             for sub in range(1 << (self.ndims - 1)):
                 cc = c_safe * 2
