@@ -135,6 +135,39 @@ TB_DEV void surface_numflux(const EQ &eq, int id, const double (&ul)[EQ::NVARS],
     }
 }
 
+// Equation systems with nonconservative terms (GLM-MHD): one compiled body of the surface flux for every interface
+// kernel.  N ranks must reproduce one rank bit for bit (the MPI interface kernel and the local interface kernels
+// evaluate the same face), which needs the same FMA contraction of these long expressions at every call site;
+// inlined copies in different kernels are not guaranteed to get it.  fl / fr: flux + 0.5 * noncons for the left /
+// right element (calc_interface_flux! with nonconservative terms, dg_3d.jl:604-649).
+template <class EQ>
+__device__ __noinline__ void surface_flux_noncons(const EQ eq, int id, const double *ul, const double *ur, int o,
+                                                  double *fl, double *fr) {
+    constexpr int NV = EQ::NVARS;
+    double a[NV], b[NV], f[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+        a[v] = ul[v];
+        b[v] = ur[v];
+    }
+    eq.numflux(id, a, b, o, f);
+    if constexpr (EQ::kHasNoncons) {
+        if (EQ::has_noncons(id)) {
+            double gl[NV], gr[NV];
+            eq.noncons(a, b, o, gl);
+            eq.noncons(b, a, o, gr);
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+                fl[v] = f[v] + 0.5 * gl[v];
+                fr[v] = f[v] + 0.5 * gr[v];
+            }
+            return;
+        }
+    }
+#pragma unroll
+    for (int v = 0; v < NV; ++v) fl[v] = fr[v] = f[v];
+}
+
 template <class EQ, int N, int FAST = 0>
 __global__ void __launch_bounds__(256) k_interface_flux(const KParams P) {
     constexpr int ND = EQ::NDIMS, NV = EQ::NVARS, NF = ipow(N, ND - 1), NN = ipow(N, ND);
@@ -153,24 +186,20 @@ __global__ void __launch_bounds__(256) k_interface_flux(const KParams P) {
         ul[v] = pl[v];
         ur[v] = pr[v];
     }
-    surface_numflux<EQ, FAST>(eq, P.surface_flux, ul, ur, o, f);
     // left element: direction 2*orientation (1-based) = index 2o+1; right element: 2o (dg_3d.jl:581-597)
     double *sl = P.sfv + ((left * (2 * ND) + (2 * o + 1)) * NF + fn) * NV;
     double *sr = P.sfv + ((right * (2 * ND) + (2 * o)) * NF + fn) * NV;
     if constexpr (EQ::kHasNoncons) {
-        // calc_interface_flux! with nonconservative terms (dg_3d.jl:604-649): flux + 0.5 * noncons per side
-        if (EQ::has_noncons(P.surface_flux)) {
-            double gl[NV], gr[NV];
-            eq.noncons(ul, ur, o, gl);
-            eq.noncons(ur, ul, o, gr);
+        double fl[NV], fr[NV];
+        surface_flux_noncons<EQ>(eq, P.surface_flux, ul, ur, o, fl, fr);
 #pragma unroll
-            for (int v = 0; v < NV; ++v) {
-                sl[v] = f[v] + 0.5 * gl[v];
-                sr[v] = f[v] + 0.5 * gr[v];
-            }
-            return;
+        for (int v = 0; v < NV; ++v) {
+            sl[v] = fl[v];
+            sr[v] = fr[v];
         }
+        return;
     }
+    surface_numflux<EQ, FAST>(eq, P.surface_flux, ul, ur, o, f);
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
         sl[v] = f[v];
@@ -265,22 +294,11 @@ __global__ void __launch_bounds__(256, (FAST == 2 && !CURVED) ? 5 : 1) k_interfa
             done = true;
         } else if constexpr (kFromMemory) {
             eq.flux_llf_fast_mem(P.surface_flux, s + (2 * g) * FV + fn * NV, s + (2 * g + 1) * FV + fn * NV, o, f);
+        } else if constexpr (EQ::kHasNoncons) {
+            surface_flux_noncons<EQ>(eq, P.surface_flux, ul, ur, o, fl, fr);
+            done = true;
         } else {
             surface_numflux<EQ, FAST>(eq, P.surface_flux, ul, ur, o, f);
-        }
-        if constexpr (EQ::kHasNoncons && !CURVED) {
-            // calc_interface_flux! with nonconservative terms (dg_3d.jl:604-649): flux + 0.5 * noncons per side
-            if (EQ::has_noncons(P.surface_flux)) {
-                double gl[NV], gr[NV];
-                eq.noncons(ul, ur, o, gl);
-                eq.noncons(ur, ul, o, gr);
-#pragma unroll
-                for (int v = 0; v < NV; ++v) {
-                    fl[v] = f[v] + 0.5 * gl[v];
-                    fr[v] = f[v] + 0.5 * gr[v];
-                }
-                done = true;
-            }
         }
         if (!done) {
 #pragma unroll
@@ -498,21 +516,16 @@ __global__ void __launch_bounds__(256) k_mpi_interface_flux(const KParams P) {
         ul[v] = side == 1 ? a : b;
         ur[v] = side == 1 ? b : a;
     }
-    surface_numflux<EQ, FAST>(eq, P.surface_flux, ul, ur, o, f);
     const int direction0 = side == 1 ? 2 * o + 1 : 2 * o;
     double *s = P.sfv + ((element * (2 * ND) + direction0) * NF + fn) * NV;
     if constexpr (EQ::kHasNoncons) {
-        if (EQ::has_noncons(P.surface_flux)) {
-            double g[NV];
-            if (side == 1)
-                eq.noncons(ul, ur, o, g);
-            else
-                eq.noncons(ur, ul, o, g);
+        double fl[NV], fr[NV];
+        surface_flux_noncons<EQ>(eq, P.surface_flux, ul, ur, o, fl, fr);
 #pragma unroll
-            for (int v = 0; v < NV; ++v) s[v] = f[v] + 0.5 * g[v];
-            return;
-        }
+        for (int v = 0; v < NV; ++v) s[v] = side == 1 ? fl[v] : fr[v];
+        return;
     }
+    surface_numflux<EQ, FAST>(eq, P.surface_flux, ul, ur, o, f);
 #pragma unroll
     for (int v = 0; v < NV; ++v) s[v] = f[v];
 }

@@ -272,28 +272,6 @@ struct Euler {
     // FluxLaxFriedrichs (numerical_fluxes.jl:37-45,172-178) with max_abs_speed(_naive)
     // (compressible_euler_3d.jl:1112-1177) on Newton reciprocals: two MUFU seeds per face node instead of eight IEEE
     // divisions; every quotient carries a residual correction (within 1 ulp of the generic path)
-    TB_DEV void llf_fast_side(const double (&u)[NVARS], int o, double (&fs)[NVARS], double &lam_v, double &lam_c) const {
-        const double rho = u[0], inv_rho = fast_rcp(rho);
-        double v[ND], mom[ND], kin = 0.0;
-#pragma unroll
-        for (int d = 0; d < ND; ++d) {
-            mom[d] = u[1 + d];
-            const double q = u[1 + d] * inv_rho;
-            v[d] = fma(fma(-rho, q, u[1 + d]), inv_rho, q);
-            kin += u[1 + d] * v[d];
-        }
-        const double p = (gamma - 1) * (u[ND + 1] - 0.5 * kin);
-        const double gp = gamma * p;
-        double c2 = gp * inv_rho;
-        c2 = fma(fma(-rho, c2, gp), inv_rho, c2);
-        lam_c = fast_sqrt(c2);
-        const double rv = pick<ND>(mom, o), vo = pick<ND>(v, o);
-        lam_v = fabs(vo);
-        fs[0] = rv;
-#pragma unroll
-        for (int d = 0; d < ND; ++d) fs[1 + d] = rv * v[d] + (d == o ? p : 0.0);
-        fs[ND + 1] = (u[ND + 1] + p) * vo;
-    }
     // the same flux with both states left in (shared) memory and re-read for the dissipation term: 40 instead of 62
     // registers in the staged interface kernel, i.e. 6 instead of 4 resident blocks per SM
     TB_DEV void llf_fast_prim(const double *pu, double &rho, double (&v)[ND], double &p, double &c) const {
@@ -328,14 +306,11 @@ struct Euler {
                        hl * (pr[1 + d] - pl[1 + d]);
         f[ND + 1] = 0.5 * ((pl[ND + 1] + p_l) * vo_l + (pr[ND + 1] + p_r) * vo_r) + hl * (pr[ND + 1] - pl[ND + 1]);
     }
+    // (one arithmetic for every caller: the staged, the plain and the MPI interface kernels must agree bit for bit,
+    // N ranks reproduce one rank exactly)
     TB_DEV void flux_llf_fast(int id, const double (&ul)[NVARS], const double (&ur)[NVARS], int o,
                               double (&f)[NVARS]) const {
-        double fl[NVARS], fr[NVARS], vl, vr, cl, cr;
-        llf_fast_side(ul, o, fl, vl, cl);
-        llf_fast_side(ur, o, fr, vr, cr);
-        const double lam = id == TRIXI_B200_FLUX_LLF_NAIVE ? fmax(vl, vr) + fmax(cl, cr) : fmax(vl + cl, vr + cr);
-#pragma unroll
-        for (int v = 0; v < NVARS; ++v) f[v] = 0.5 * (fl[v] + fr[v]) + (-0.5 * lam * (ur[v] - ul[v]));
+        flux_llf_fast_mem(id, &ul[0], &ur[0], o, f);
     }
     TB_DEV void flux_ranocha_fast(const double (&ul)[NVARS], const double (&ur)[NVARS], int o,
                                   double (&f)[NVARS]) const {
