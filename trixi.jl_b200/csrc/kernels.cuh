@@ -214,7 +214,8 @@ __global__ void __launch_bounds__(256) k_interface_flux(const KParams P) {
 // CURVED (StructuredMesh, dgsem_structured/dg_3d.jl:619-753): the flux is taken along the contravariant vector of
 // the right element's first node layer times sign(inverse_jacobian), and stored with that sign on both sides.
 template <class EQ, int N, int FAST = 0, bool CURVED = false>
-__global__ void __launch_bounds__(256, (FAST == 2 && !CURVED) ? 5 : 1) k_interface_flux_staged(const KParams P) {
+__global__ void __launch_bounds__(256, (CURVED || EQ::kHasNoncons) ? 3 : (FAST == 1 ? 6 : (FAST == 2 ? 5 : 4)))
+    k_interface_flux_staged(const KParams P) {  // (resident blocks: what ptxas chose unprompted, 5 for the LLF form)
     constexpr int ND = EQ::NDIMS, NV = EQ::NVARS, NF = ipow(N, ND - 1), NN = ipow(N, ND);
     constexpr int G = 32 / NF;   // interfaces per warp
     constexpr int FV = NF * NV;  // doubles per face
