@@ -132,3 +132,14 @@ def test_ln_mean(oracle_module):
         want = x if x == y else (y - x) / math.log(y / x)
         assert got == pytest.approx(want, rel=1e-12)
         assert lib.oracle_inv_ln_mean(C.c_double(x), C.c_double(y)) == pytest.approx(1 / want, rel=1e-12)
+
+
+def test_nested_refinement_patches_balance():
+    """examples/tree_3d_dgsem/elixir_advection_mortar.jl: two nested box patches on a level-2 TreeMesh.  The second
+    patch puts level-4 leaves next to level-2 leaves across x = 0; refine! (abstract_tree.jl:367-403) restores the
+    2:1 balance by refining exactly the four coarse neighbours."""
+    patches = ({"type": "box", "coordinates_min": (0.0, -1.0, -1.0), "coordinates_max": (1.0, 1.0, 1.0)},
+               {"type": "box", "coordinates_min": (0.0, -0.5, -0.5), "coordinates_max": (0.5, 0.5, 0.5)})
+    mesh = T.TreeMesh((-1.0,) * 3, (1.0,) * 3, initial_refinement_level=2, refinement_patches=patches, periodicity=True)
+    assert list(np.bincount(mesh.levels)) == [0, 0, 28, 256, 256]
+    assert not mesh._unbalanced_mask().any()
