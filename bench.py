@@ -354,6 +354,8 @@ def run_b200(args, rank, world, local_rank):
         gpu.set_option(gpu.OPT_PREFETCH_DISTANCE, args.prefetch)
     if args.generic_kernels:
         gpu.set_option(gpu.OPT_KERNEL_PATH, 1)
+    elif args.kernel_path:
+        gpu.set_option(gpu.OPT_KERNEL_PATH, args.kernel_path)
     ndofs = semi.ndofs()
     u0 = T.compute_coefficients(0.0, semi)
     gpu.upload(0, u0)
@@ -576,6 +578,8 @@ def main():
     ap.add_argument("--prefetch", type=int, default=None, help="L2 prefetch distance of the tuned element kernel")
     ap.add_argument("--generic-kernels", action="store_true",
                     help="TRIXI_B200_OPT_KERNEL_PATH = 1: the generic one-thread-per-node kernels (before/after numbers)")
+    ap.add_argument("--kernel-path", type=int, default=0,
+                    help="TRIXI_B200_OPT_KERNEL_PATH: 2 = the previous generation of the tuned headline kernel (A/B runs)")
     ap.add_argument("--no-fused-cfl", action="store_true", help="run max_dt as its own kernel after every step")
     args = ap.parse_args()
     global CELLS

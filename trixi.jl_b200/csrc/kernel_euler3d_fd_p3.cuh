@@ -2,84 +2,72 @@
 // with flux_ranocha, fused with surface integral, Jacobian, source terms and the 2N Runge-Kutta stage.
 // This is the headline configuration (BASELINE.json: 3D Euler EC p=3).
 //
-// Work decomposition.
-//  * One warp = one CTA = one element; everything is warp-synchronous (no block barriers), 14 CTAs
-//    resident per SM so one warp's tile I/O latency and FP64 dependency chains hide behind the others.
-//  * Tile I/O is TMA: three `cp.async.bulk` loads (u, u_tmp, surface_flux_values of the two elements are
-//    contiguous 5/5/7.5 KB records) signalled on an mbarrier, results leave through `cp.async.bulk`
-//    stores -- no per-thread address arithmetic, no register staging, fully coalesced HBM traffic.
-//  * Per element and direction the 64 nodes form 16 lines of 4 nodes with 6 symmetric node pairs each.
-//    Two threads share a line per direction pass, three pair fluxes each, so every two-point flux is
-//    evaluated exactly once (288 per element, like the reference's symmetric loop dg_3d.jl:177-211);
-//    D_split[a,b] f is accumulated into both end nodes, partial sums meet in a shared-memory du tile, and
-//    after the z pass each thread finishes surface integral, Jacobian, sources and the RK update of its
-//    two nodes in registers.
+// Work decomposition, second generation.  The first generation (one warp per element, two
+// threads per line, kernel_euler3d_fd_p3_v7.cuh) was issue-bound: ncu counted 1136 thread instructions per DOF
+// of which 41% were FP64 -- the rest was shared-memory traffic for operands that two threads of a line both
+// needed, read-modify-write of the du tile by both of them, run-time line roles, and libm logarithms.
+//  * One warp = one CTA = TWO elements, 16 threads per element.  In every direction pass a thread owns one
+//    whole line of 4 nodes: it loads the 4 node records once (28 LDS for 6 two-point fluxes instead of 28 for 3),
+//    evaluates all 6 symmetric pairs with compile-time roles (D_split entries are constant-bank operands of the
+//    DFMAs, no weight registers, no selects), and accumulates the 4 x 5 results in registers.  Every two-point
+//    flux is evaluated exactly once (288 per element, like the reference's symmetric loop dg_3d.jl:177-211);
+//    nobody writes into another thread's nodes, so the du tile sees one store (x), one read-modify-write (y)
+//    and one read (z) per node instead of six accesses.
+//  * 8 CTAs = 16 elements resident per SM (shared-memory-limited, as before); each thread carries six
+//    independent flux evaluations per pass, which is where the latency hiding comes from now.
+//  * Tile I/O is TMA: `cp.async.bulk` loads of the two elements' contiguous u / surface_flux_values / u_tmp
+//    records on mbarriers (u is awaited at once, the surface fluxes only before the epilogue), results leave
+//    through `cp.async.bulk` stores.
 //  * flux_ranocha is evaluated in the hoisted form of the reference's own SIMD kernel
-//    (dg_3d_compressible_euler.jl:289-309,360-385): primitive variables and log(rho), log(p) once per
-//    node, so the logarithmic means need no log per pair.
-//  * The prim and du tiles are AoS records at a swizzled node position pos(i,j,k) = 16k + 4(j^k) + (i^k):
-//    in every direction pass the 16 lines of an element hit 16 distinct 8-byte banks (record strides 5
-//    and 7 are odd, so the map stays bijective); the TMA-filled buffers keep the global (natural) order,
-//    which is conflict-free for the per-node passes.
+//    (dg_3d_compressible_euler.jl:289-309,360-385): primitive variables, log(rho) and log(rho) - log(p) once
+//    per node.  The logarithm is an fdlibm-style kernel for positive normal arguments (libm's takes twice the
+//    instructions for its special cases); the factors 1/2 of the arithmetic means are folded into the
+//    D_split weights (powers of two: bit-identical results).
+//  * The prim and du tiles are AoS records at the swizzled node position pos(i,j,k) = 16k + 4(j^k) + (i^k):
+//    in every direction pass the 16 lines of an element hit 16 distinct 8-byte banks (record strides 5 and 7
+//    are odd); the TMA-filled buffers keep the global (natural) order, conflict-free for the per-node passes.
 #pragma once
 #include <cstdint>
 
-#include "launch.cuh"
+#include "tile_io.cuh"
 
 namespace tb {
 
-TB_DEV int swz_pos(int n) {
-    const int i = n & 3, j = (n >> 2) & 3, k = n >> 4;
-    return (k << 4) | (((j ^ k) & 3) << 2) | ((i ^ k) & 3);
-}
-
-// ---- TMA / mbarrier helpers (PTX ISA: cp.async.bulk, mbarrier) ---------------------------------------
-TB_DEV uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-TB_DEV void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-TB_DEV void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-// try_wait with a suspend-time hint: the warp sleeps in hardware until the phase completes (or ~1 us passes)
-// instead of spinning through the issue slots of the other resident warps (the kernels are issue- and power-bound;
-// ncu counted 8% extra warp instructions from the plain polling loop)
-TB_DEV bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity), "r"(1000u)
-        : "memory");
-    return ok != 0;
-}
-TB_DEV void tma_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                 "l"(src), "r"(bytes), "r"(bar)
-                 : "memory");
-}
-TB_DEV void tma_store(void *dst, uint32_t src, uint32_t bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes)
-                 : "memory");
-}
-TB_DEV void tma_store_commit_and_wait_read() {
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-}
-TB_DEV void tma_prefetch_l2(const void *src, uint32_t bytes) {
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
-}
-TB_DEV void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-// Node record in the prim tile: rho, v1, v2, v3, p, log(rho), log(p)
+// Node record in the prim tile: rho, v1, v2, v3, p, log(rho), log(rho) - log(p)
 constexpr int kNP = 7;
 
-// flux_ranocha(u_ll, u_rr, orientation) (compressible_euler_3d.jl:746-793) on hoisted node records whose
+// log(x) for positive, finite, normal x (fdlibm's __ieee754_log kernel: x = 2^k (1 + f), sqrt(1/2) <= 1 + f <
+// sqrt(2), log(1 + f) = f - hfsq + s (hfsq + R(s^2)), s = f / (2 + f); < 1 ulp).  Everything else (zero,
+// negative, subnormal, inf, NaN) takes libm's log out of line, so the special values propagate like the
+// reference's.  The coefficients sit in the constant bank and are consumed as DFMA operands.
+__constant__ double kLogC[9] = {6.666666666666735130e-01, 3.999999999940941908e-01, 2.857142874366239149e-01,
+                                2.222219843214978396e-01, 1.818357216161805012e-01, 1.531383769920937332e-01,
+                                1.479819860511658591e-01, 6.93147180369123816490e-01, 1.90821492927058770002e-10};
+__device__ __noinline__ double log_special(double x) { return log(x); }
+TB_DEV double log_pos(double x) {
+    const int hi = __double2hiint(x);
+    if (__builtin_expect((unsigned)(hi - 0x00100000) >= 0x7fe00000u, 0)) return log_special(x);
+    const int hx = hi + (0x3ff00000 - 0x3fe6a09e);
+    const int k = (hx >> 20) - 0x3ff;
+    const double m = __hiloint2double((hx & 0x000fffff) + 0x3fe6a09e, __double2loint(x));
+    const double f = m - 1.0;
+    const double hfsq = (0.5 * f) * f;
+    const double s = f * fast_rcp(2.0 + f);
+    const double z = s * s, w = z * z;
+    const double t1 = w * fma(w, fma(w, kLogC[5], kLogC[3]), kLogC[1]);
+    const double t2 = z * fma(w, fma(w, fma(w, kLogC[6], kLogC[4]), kLogC[2]), kLogC[0]);
+    const double R = t2 + t1;
+    const double dk = (double)k;
+    return fma(dk, kLogC[7], (fma(s, hfsq + R, dk * kLogC[8]) - hfsq) + f);
+}
+
+// 4 * flux_ranocha(u_ll, u_rr, orientation) (compressible_euler_3d.jl:746-793) on hoisted node records whose
 // velocity components have been rotated so that slot 1 is the normal one: (rho, vn, vt1, vt2, p, log rho,
-// log p).  The output is rotated the same way: (f_rho, f_n, f_t1, f_t2, f_E).
-TB_DEV void ranocha_pair_rot(const double (&L)[kNP], const double (&R)[kNP], double inv_gm1, double (&f)[5]) {
+// log rho - log p).  The output is rotated the same way and scaled by powers of two that the caller's D_split
+// weights undo: g = (2 f_rho, 4 f_n, 4 f_t1, 4 f_t2, 4 f_E) -- the halves of the arithmetic means never get
+// multiplied out (exact: scaling by 2 commutes with rounding).  igm1x2 = 2 / (gamma - 1).
+TB_DEV void ranocha_pair_rot(const double (&L)[kNP], const double (&R)[kNP], double igm1x2, double (&g)[5]) {
     const double rho_ll = L[0], p_ll = L[4], rho_rr = R[0], p_rr = R[4];
-    const double dlog_rho = R[5] - L[5];  // log(rho_rr / rho_ll)
     // ln_mean(rho_ll, rho_rr) (math.jl:198-210); f^2 = (x-y)^2/(x+y)^2 as in the reference's SIMD kernel
     double rho_mean;
     {
@@ -87,7 +75,7 @@ TB_DEV void ranocha_pair_rot(const double (&L)[kNP], const double (&R)[kNP], dou
         const double f2 = (dif * dif) * rcp_1nr(sum * sum);
         const bool series = f2 < 1.0e-4;
         const double poly = fma(f2, fma(f2, fma(f2, 2.0 / 7.0, 2.0 / 5.0), 2.0 / 3.0), 2.0);
-        rho_mean = fast_div(series ? sum : dif, series ? poly : dlog_rho);
+        rho_mean = fast_div(series ? sum : dif, series ? poly : R[5] - L[5]);
     }
     // inv_ln_mean(rho_ll * p_rr, rho_rr * p_ll) (math.jl:238-250)
     double inv_rho_p_mean;
@@ -97,130 +85,134 @@ TB_DEV void ranocha_pair_rot(const double (&L)[kNP], const double (&R)[kNP], dou
         const double f2 = (dif * dif) * rcp_1nr(sum * sum);
         const bool series = f2 < 1.0e-4;
         const double poly = fma(f2, fma(f2, fma(f2, 2.0 / 7.0, 2.0 / 5.0), 2.0 / 3.0), 2.0);
-        // log(y / x) = log(rho_rr p_ll) - log(rho_ll p_rr)
-        const double m = fast_div(series ? poly : dlog_rho + (L[6] - R[6]), series ? sum : dif);
+        // log(y / x) = (log rho_rr - log p_rr) - (log rho_ll - log p_ll)
+        const double m = fast_div(series ? poly : R[6] - L[6], series ? sum : dif);
         inv_rho_p_mean = p_ll * p_rr * m;
     }
-    const double vn_avg = 0.5 * (L[1] + R[1]), vt1_avg = 0.5 * (L[2] + R[2]), vt2_avg = 0.5 * (L[3] + R[3]);
-    const double p_avg = 0.5 * (p_ll + p_rr);
-    const double velocity_square_avg = 0.5 * (L[1] * R[1] + L[2] * R[2] + L[3] * R[3]);
-    const double f1 = rho_mean * vn_avg;
-    f[0] = f1;
-    f[1] = f1 * vn_avg + p_avg;
-    f[2] = f1 * vt1_avg;
-    f[3] = f1 * vt2_avg;
-    f[4] = f1 * (velocity_square_avg + inv_rho_p_mean * inv_gm1) + 0.5 * (p_ll * R[1] + p_rr * L[1]);
+    const double sn = L[1] + R[1], st1 = L[2] + R[2], st2 = L[3] + R[3];  // 2 v_avg
+    const double ps2 = (p_ll + p_rr) + (p_ll + p_rr);                     // 4 p_avg
+    const double vs = L[1] * R[1] + L[2] * R[2] + L[3] * R[3];            // 2 velocity_square_avg
+    const double f1 = rho_mean * sn;                                       // 2 f_rho
+    const double pv = p_ll * R[1] + p_rr * L[1];
+    g[0] = f1;
+    g[1] = fma(f1, sn, ps2);
+    g[2] = f1 * st1;
+    g[3] = f1 * st2;
+    g[4] = fma(f1, fma(inv_rho_p_mean, igm1x2, vs), pv + pv);
 }
 
 struct TunedCfg {
-    static constexpr int EPB = 1, THREADS = 32;  // one warp, one element, two threads per line
+    static constexpr int EPB = 2, THREADS = 32;  // one warp, two elements, one thread per line
     static constexpr int CONS = 320, PRIM = 64 * kNP, SFV = 480;  // doubles per element
-    // s_u (natural order, TMA), s_sfv (natural, TMA), s_du, s_prim (swizzled), mbarrier, [s_ut (natural, TMA)].
+    // s_u (natural order, TMA), s_sfv (natural, TMA), s_du, s_prim (swizzled), mbarriers, [s_ut (natural, TMA)].
     // Without source terms the u_tmp tile is not resident during the flux passes: it is loaded into the prim
-    // tile's storage once the z pass has read it for the last time, and leaves from there.  12.6 KB instead of
-    // 15.1 KB per element: 17 instead of 14 resident warps per SM (shared memory is the occupancy limiter,
-    // 105 registers per thread would allow 18).
-    static constexpr size_t SMEM_DEFERRED = sizeof(double) * EPB * (2 * CONS + SFV + PRIM) + 16;
+    // tile's storage once the z pass has read it for the last time, and leaves from there.
+    static constexpr size_t SMEM_DEFERRED = sizeof(double) * EPB * (2 * CONS + SFV + PRIM) + 32;
     static constexpr size_t SMEM_RESIDENT = SMEM_DEFERRED + sizeof(double) * EPB * CONS;
-    static constexpr int MIN_BLOCKS = 17;
-    static constexpr int blocks_per_sm(bool deferred) { return deferred ? 17 : 14; }
+    static constexpr int MIN_BLOCKS = 8;
+    static constexpr int blocks_per_sm(bool deferred) { return deferred ? 8 : 7; }
 };
 
 template <bool WITH_SURFACE>
 __global__ void __launch_bounds__(TunedCfg::THREADS, TunedCfg::MIN_BLOCKS)
     k_element_euler3d_ranocha_p3(const KParams P) {
     using C = TunedCfg;
-    constexpr int CONS = C::CONS, PRIM = C::PRIM, SFV = C::SFV;
+    constexpr int CONS = C::CONS, PRIM = C::PRIM, SFV = C::SFV, EPB = C::EPB;
     extern __shared__ __align__(128) double smem[];
     const bool have_src = WITH_SURFACE && P.source_terms != TRIXI_B200_SRC_NONE;
     const bool deferred = !have_src;  // must match the launch's dynamic shared memory size
-    double *s_u = smem;            // [64][5] natural: u in, updated u out
-    double *s_sfv = s_u + CONS;    // [6][16][5] natural
-    double *s_du = s_sfv + SFV;    // [64][5] swizzled
-    double *s_prim = s_du + CONS;  // [64][7] swizzled; after the flux passes: source terms or the u_tmp tile
-    const uint32_t bar = smem_u32(s_prim + PRIM);
-    double *s_ut = deferred ? s_prim : s_prim + PRIM + 2;  // [64][5] natural: u_tmp in, u_tmp (or du) out
+    double *s_u = smem;                   // [2][64][5] natural: u in, updated u out
+    double *s_sfv = s_u + EPB * CONS;     // [2][6][16][5] natural
+    double *s_du = s_sfv + EPB * SFV;     // [2][64][5] swizzled
+    double *s_prim = s_du + EPB * CONS;   // [2][64][7] swizzled; after the flux passes: source terms or u_tmp
+    const uint32_t bar_u = smem_u32(s_prim + EPB * PRIM), bar_s = bar_u + 8, bar_t = bar_u + 16;
+    double *s_ut = deferred ? s_prim : s_prim + EPB * PRIM + 4;  // [2][64][5] natural: u_tmp in, u_tmp (or du) out
 
     const int lane = threadIdx.x;
-    const long long e = P.elem_begin + blockIdx.x;
-    const double gamma = P.eq.p[0], inv_gm1 = P.eq.p[1];
+    const int t = lane & 15;
+    const long long e0 = P.elem_begin + (long long)EPB * blockIdx.x;
+    const int nvalid = (int)min((long long)EPB, P.elem_end - e0);
+    // on an odd tail the second half-warp mirrors the first (same tiles, same values; nothing extra is stored)
+    const int eh = (lane >> 4) < nvalid ? (lane >> 4) : 0;
+    const long long e = e0 + eh;
+    const double gamma = P.eq.p[0], igm1x2 = 2.0 * P.eq.p[1];
     const bool rk = P.mode != 0;
     const bool need_ut = rk && P.rk_a != 0.0;
 
     // 0. TMA loads of the contiguous element records
     if (lane == 0) {
-        mbar_init(bar, 1);
+        mbar_init(bar_u, 1);
+        mbar_init(bar_s, 1);
+        mbar_init(bar_t, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
     if (lane == 0) {
-        constexpr uint32_t bu = CONS * sizeof(double), bs = SFV * sizeof(double);
+        const uint32_t bu = nvalid * CONS * sizeof(double), bs = nvalid * SFV * sizeof(double);
         const bool ut_now = need_ut && !deferred;
-        mbar_expect_tx(bar, bu + (ut_now ? bu : 0u) + (WITH_SURFACE ? bs : 0u));
-        tma_load(smem_u32(s_u), P.u + e * CONS, bu, bar);
-        if (ut_now) tma_load(smem_u32(s_ut), P.u_tmp + e * CONS, bu, bar);
-        if (WITH_SURFACE) tma_load(smem_u32(s_sfv), P.sfv + e * SFV, bs, bar);
-        // warm L2 for the element that will occupy this CTA slot next (blocks are scheduled in index order:
-        // one wave further on), so its tile loads see L2 instead of HBM latency
-        const long long en = e + P.prefetch_distance;
-        if (P.prefetch_distance > 0 && en < P.nelements) {
-            tma_prefetch_l2(P.u + en * CONS, bu);
-            if (need_ut) tma_prefetch_l2(P.u_tmp + en * CONS, bu);
-            if (WITH_SURFACE) tma_prefetch_l2(P.sfv + en * SFV, bs);
+        mbar_expect_tx(bar_u, bu);
+        tma_load(smem_u32(s_u), P.u + e0 * CONS, bu, bar_u);
+        if (WITH_SURFACE || ut_now) {
+            mbar_expect_tx(bar_s, (ut_now ? bu : 0u) + (WITH_SURFACE ? bs : 0u));
+            if (ut_now) tma_load(smem_u32(s_ut), P.u_tmp + e0 * CONS, bu, bar_s);
+            if (WITH_SURFACE) tma_load(smem_u32(s_sfv), P.sfv + e0 * SFV, bs, bar_s);
+        }
+        // warm L2 for the elements that will occupy this CTA slot next (blocks are scheduled in index order:
+        // one wave further on), so their tile loads see L2 instead of HBM latency
+        const long long en = e0 + P.prefetch_distance;
+        if (P.prefetch_distance > 0 && en + EPB <= P.nelements) {
+            constexpr uint32_t bu2 = EPB * CONS * sizeof(double), bs2 = EPB * SFV * sizeof(double);
+            tma_prefetch_l2(P.u + en * CONS, bu2);
+            if (need_ut) tma_prefetch_l2(P.u_tmp + en * CONS, bu2);
+            if (WITH_SURFACE) tma_prefetch_l2(P.sfv + en * SFV, bs2);
         }
     }
-    // Two threads (h = 0, 1) share line l16 of every direction pass.  In line-local node numbering
-    // thread h owns nodes lm[0], lm[1] and sees lm[2], lm[3] as foreign: h = 0: (0,1 | 2,3), h = 1: (3,2 | 0,1).
-    // Both evaluate the pairs (lm0,lm1), (lm0,lm2), (lm1,lm3): together all 6 pairs of the line, once each.
-    const int h = lane >> 4, l16 = lane & 15;
-    const int a0 = l16 & 3, a1 = l16 >> 2;
-    const int lm[4] = {h ? 3 : 0, h ? 2 : 1, h ? 0 : 2, h ? 1 : 3};
-    // D_split[a, b] for the three pairs in both directions (column-major n x n)
-    const double w01 = P.dsplit_c[lm[0] + 4 * lm[1]], w10 = P.dsplit_c[lm[1] + 4 * lm[0]];
-    const double w02 = P.dsplit_c[lm[0] + 4 * lm[2]], w20 = P.dsplit_c[lm[2] + 4 * lm[0]];
-    const double w13 = P.dsplit_c[lm[1] + 4 * lm[3]], w31 = P.dsplit_c[lm[3] + 4 * lm[1]];
-    while (!mbar_try_wait(bar, 0)) {
+    double *const su = s_u + eh * CONS, *const sp = s_prim + eh * PRIM, *const sd = s_du + eh * CONS;
+    while (!mbar_try_wait(bar_u, 0)) {
     }
 
-    // 1. cons2prim + logs for the two nodes (i, j, k = lm[0], lm[1]) this thread also finishes in step 3;
+    // 1. cons2prim + logs for nodes t, t + 16, t + 32, t + 48 (the z line this thread also finishes in step 3);
     //    a half-warp reads 16 consecutive node records: conflict-free
-#pragma unroll 1
-    for (int r = 0; r < 2; ++r) {
-        const int n = l16 + 16 * (r == 0 ? lm[0] : lm[1]);
-        const double *c = s_u + n * 5;
-        const double rho = c[0];
+#pragma unroll 2
+    for (int r = 0; r < 4; ++r) {
+        const double *c = su + (t + 16 * r) * 5;
+        const double rho = c[0], m1 = c[1], m2 = c[2], m3 = c[3];
         const double inv_rho = fast_rcp(rho);
         // v = rho_v / rho with a residual correction (cons2prim, compressible_euler_3d.jl:1783-1793)
-        double v1 = c[1] * inv_rho, v2 = c[2] * inv_rho, v3 = c[3] * inv_rho;
-        v1 = fma(fma(-rho, v1, c[1]), inv_rho, v1);
-        v2 = fma(fma(-rho, v2, c[2]), inv_rho, v2);
-        v3 = fma(fma(-rho, v3, c[3]), inv_rho, v3);
-        const double pr = (gamma - 1) * (c[4] - 0.5 * (c[1] * v1 + c[2] * v2 + c[3] * v3));
-        double *o = s_prim + swz_pos(n) * kNP;
+        double v1 = m1 * inv_rho, v2 = m2 * inv_rho, v3 = m3 * inv_rho;
+        v1 = fma(fma(-rho, v1, m1), inv_rho, v1);
+        v2 = fma(fma(-rho, v2, m2), inv_rho, v2);
+        v3 = fma(fma(-rho, v3, m3), inv_rho, v3);
+        const double pr = (gamma - 1) * (c[4] - 0.5 * (m1 * v1 + m2 * v2 + m3 * v3));
+        const double lr = log_pos(rho);
+        double *o = sp + (16 * r + (t ^ (5 * r))) * kNP;  // swz_pos(t + 16 r)
         o[0] = rho;
         o[1] = v1;
         o[2] = v2;
         o[3] = v3;
         o[4] = pr;
-        o[5] = log(rho);
-        o[6] = log(pr);
+        o[5] = lr;
+        o[6] = lr - log_pos(pr);
     }
     __syncwarp();
 
     // 2. direction passes x, y, z with ONE copy of the flux code; the direction only enters through
-    // shared-memory offsets (velocity slots rotated while loading, momentum slots while storing)
+    // shared-memory offsets (velocity slots rotated while loading, momentum slots while storing).
+    // The line of this thread: x: (j, k) = (t & 3, t >> 2), y: (i, k) = (t & 3, t >> 2), z: (i, j) likewise;
+    // its node m sits at swizzled position B ^ (m * M) with M = 1, 4, 21.
+    const int a0 = t & 3, a1 = t >> 2;
+    const int B0 = 16 * a1 + 4 * (a0 ^ a1) + a1, B1 = 20 * a1 + (a0 ^ a1);
+    double acc[4][5];
     int pos[4];
-    double own[2][5], frn[2][5];
 #pragma unroll 1
     for (int d = 0; d < 3; ++d) {
-        const int stride = 1 << (2 * d);
-        const int base = d == 0 ? 4 * l16 : (d == 1 ? a0 + 16 * a1 : l16);
+        const int B = d == 0 ? B0 : (d == 1 ? B1 : t), M = d == 0 ? 1 : (d == 1 ? 4 : 21);
         const int on = 1 + d, ot1 = d == 2 ? 1 : 2 + d, ot2 = d == 0 ? 3 : d;  // 1 + (d + {0,1,2}) % 3
         double q[4][kNP];
 #pragma unroll
         for (int m = 0; m < 4; ++m) {
-            pos[m] = swz_pos(base + lm[m] * stride);
-            const double *src = s_prim + pos[m] * kNP;
+            pos[m] = B ^ (m * M);
+            const double *src = sp + pos[m] * kNP;
             q[m][0] = src[0];
             q[m][1] = src[on];
             q[m][2] = src[ot1];
@@ -229,68 +221,60 @@ __global__ void __launch_bounds__(TunedCfg::THREADS, TunedCfg::MIN_BLOCKS)
             q[m][5] = src[5];
             q[m][6] = src[6];
         }
-        double f[5];
-        ranocha_pair_rot(q[0], q[1], inv_gm1, f);
+        // du[a] += D_split[a, b] f(a, b), du[b] += D_split[b, a] f(a, b) for the 6 pairs a < b of the line;
+        // dsplit_h = D_split / 2 and dsplit_q = D_split / 4 undo the scaling of g
+        double g[5];
+#define TB_PAIR(a, b, FIRST_A, FIRST_B)                                                                        \
+    ranocha_pair_rot(q[a], q[b], igm1x2, g);                                                                   \
+    acc[a][0] = FIRST_A ? P.dsplit_h[a + 4 * b] * g[0] : fma(P.dsplit_h[a + 4 * b], g[0], acc[a][0]);          \
+    acc[b][0] = FIRST_B ? P.dsplit_h[b + 4 * a] * g[0] : fma(P.dsplit_h[b + 4 * a], g[0], acc[b][0]);          \
+    _Pragma("unroll") for (int v = 1; v < 5; ++v) {                                                            \
+        acc[a][v] = FIRST_A ? P.dsplit_q[a + 4 * b] * g[v] : fma(P.dsplit_q[a + 4 * b], g[v], acc[a][v]);      \
+        acc[b][v] = FIRST_B ? P.dsplit_q[b + 4 * a] * g[v] : fma(P.dsplit_q[b + 4 * a], g[v], acc[b][v]);      \
+    }
+        TB_PAIR(0, 1, true, true)
+        TB_PAIR(2, 3, true, true)
+        TB_PAIR(0, 2, false, false)
+        TB_PAIR(1, 3, false, false)
+        TB_PAIR(0, 3, false, false)
+        TB_PAIR(1, 2, false, false)
+#undef TB_PAIR
+        // the x and y sums meet in the du tile; the z sums stay in registers for step 3
+        if (d == 0) {
 #pragma unroll
-        for (int v = 0; v < 5; ++v) {
-            own[0][v] = w01 * f[v];
-            own[1][v] = w10 * f[v];
-        }
-        ranocha_pair_rot(q[0], q[2], inv_gm1, f);
+            for (int m = 0; m < 4; ++m) {
+                double *o = sd + pos[m] * 5;
+                o[0] = acc[m][0];
+                o[1] = acc[m][1];
+                o[2] = acc[m][2];
+                o[3] = acc[m][3];
+                o[4] = acc[m][4];
+            }
+            __syncwarp();
+        } else if (d == 1) {
 #pragma unroll
-        for (int v = 0; v < 5; ++v) {
-            own[0][v] = fma(w02, f[v], own[0][v]);
-            frn[0][v] = w20 * f[v];
-        }
-        ranocha_pair_rot(q[1], q[3], inv_gm1, f);
-#pragma unroll
-        for (int v = 0; v < 5; ++v) {
-            own[1][v] = fma(w13, f[v], own[1][v]);
-            frn[1][v] = w31 * f[v];
-        }
-        // every node receives one own and one foreign partial per pass; they meet in the du tile
-        if (d < 2) {
-#pragma unroll
-            for (int m = 0; m < 2; ++m) {
-                double *t = s_du + pos[m] * 5;
-                if (d == 0) {
-                    t[0] = own[m][0];
-                    t[on] = own[m][1];
-                    t[ot1] = own[m][2];
-                    t[ot2] = own[m][3];
-                    t[4] = own[m][4];
-                } else {
-                    t[0] += own[m][0];
-                    t[on] += own[m][1];
-                    t[ot1] += own[m][2];
-                    t[ot2] += own[m][3];
-                    t[4] += own[m][4];
-                }
+            for (int m = 0; m < 4; ++m) {
+                double *o = sd + pos[m] * 5;  // accumulators (f_rho, f_y, f_z, f_x, f_E)
+                o[0] += acc[m][0];
+                o[2] += acc[m][1];
+                o[3] += acc[m][2];
+                o[1] += acc[m][3];
+                o[4] += acc[m][4];
             }
             __syncwarp();
         }
-#pragma unroll
-        for (int m = 0; m < 2; ++m) {
-            double *t = s_du + pos[2 + m] * 5;
-            t[0] += frn[m][0];
-            t[on] += frn[m][1];
-            t[ot1] += frn[m][2];
-            t[ot2] += frn[m][3];
-            t[4] += frn[m][4];
-        }
-        __syncwarp();
     }
 
-    // the prim tile is dead now: fetch the u_tmp tile into its storage (second phase of the mbarrier); the
-    // surface integral and the Jacobian below run while it is in flight
+    // the prim tile is dead now: fetch the u_tmp tile into its storage; the surface integral and the Jacobian
+    // below run while it is in flight
     const bool ut_late = need_ut && deferred;
     if (ut_late) {
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
-            constexpr uint32_t bu = CONS * sizeof(double);
-            mbar_expect_tx(bar, bu);
-            tma_load(smem_u32(s_ut), P.u_tmp + e * CONS, bu, bar);
+            const uint32_t bu = nvalid * CONS * sizeof(double);
+            mbar_expect_tx(bar_t, bu);
+            tma_load(smem_u32(s_ut), P.u_tmp + e0 * CONS, bu, bar_t);
         }
     }
 
@@ -298,88 +282,102 @@ __global__ void __launch_bounds__(TunedCfg::THREADS, TunedCfg::MIN_BLOCKS)
     if (have_src) {
         const Euler<3> eq(P.eq);
 #pragma unroll 1
-        for (int r = 0; r < 2; ++r) {
-            const int n = l16 + 16 * (r == 0 ? lm[0] : lm[1]);
+        for (int r = 0; r < 4; ++r) {
+            const int n = t + 16 * r;
             double un[5], x[3], sv[5];
 #pragma unroll
-            for (int v = 0; v < 5; ++v) un[v] = s_u[n * 5 + v];
+            for (int v = 0; v < 5; ++v) un[v] = su[n * 5 + v];
 #pragma unroll
             for (int dd = 0; dd < 3; ++dd) x[dd] = P.node_coordinates[(e * 64 + n) * 3 + dd];
             eq.source_terms(P.source_terms, un, x, P.t, sv);
 #pragma unroll
-            for (int v = 0; v < 5; ++v) s_prim[n * 5 + v] = sv[v];
+            for (int v = 0; v < 5; ++v) sp[n * 5 + v] = sv[v];
         }
         __syncwarp();
     }
+    if (WITH_SURFACE || (need_ut && !deferred)) {
+        while (!mbar_try_wait(bar_s, 0)) {
+        }
+    }
 
-    // 3. finish the two own nodes (i, j, k = lm[0], lm[1]) of the z line in registers; the z-pass
-    // accumulators are rotated: slots (1, 2, 3) hold the (v3, v1, v2) momentum components
+    // 3. finish the z line (i, j) = (a0, a1), nodes n = t + 16 k, in registers; the z-pass accumulators are
+    // rotated: slots (1, 2, 3) hold the (v3, v1, v2) momentum components
     {
         const int i = a0, j = a1;
         const double factor = WITH_SURFACE ? -P.inverse_jacobian[e] : 1.0;
-        unsigned long long cfl0 = 0ull, cfl1 = 0ull, cfl2 = 0ull;
-        double vals[2][5];
+        double val[4][5];
 #pragma unroll
-        for (int r = 0; r < 2; ++r) {
-            const int k = lm[r];
-            const int n = l16 + 16 * k;
-            const double *t = s_du + pos[r] * 5;
-            double(&val)[5] = vals[r];
-            val[0] = t[0] + own[r][0];
-            val[1] = t[1] + own[r][2];
-            val[2] = t[2] + own[r][3];
-            val[3] = t[3] + own[r][1];
-            val[4] = t[4] + own[r][4];
-            if constexpr (WITH_SURFACE) {
-                // calc_surface_integral! (dg_3d.jl:1337-1394): directions 1..6 = -x,+x,-y,+y,-z,+z
-                if (i == 0 || i == 3) {
-                    const double *sf = s_sfv + ((i == 0 ? 0 : 1) * 16 + j + 4 * k) * 5;
-                    const double w = i == 0 ? -P.inv_weight0 : P.inv_weight0;
+        for (int k = 0; k < 4; ++k) {
+            const double *o = sd + pos[k] * 5;
+            val[k][0] = o[0] + acc[k][0];
+            val[k][1] = o[1] + acc[k][2];
+            val[k][2] = o[2] + acc[k][3];
+            val[k][3] = o[3] + acc[k][1];
+            val[k][4] = o[4] + acc[k][4];
+        }
+        if constexpr (WITH_SURFACE) {
+            // calc_surface_integral! (dg_3d.jl:1337-1394): directions 1..6 = -x,+x,-y,+y,-z,+z
+            const double *ssf = s_sfv + eh * SFV;
+            if (i == 0 || i == 3) {
+                const double *sf = ssf + ((i == 0 ? 0 : 1) * 16 + j) * 5;
+                const double w = i == 0 ? -P.inv_weight0 : P.inv_weight0;
 #pragma unroll
-                    for (int v = 0; v < 5; ++v) val[v] = fma(sf[v], w, val[v]);
+                for (int k = 0; k < 4; ++k)
+#pragma unroll
+                    for (int v = 0; v < 5; ++v) val[k][v] = fma(sf[20 * k + v], w, val[k][v]);
+            }
+            if (j == 0 || j == 3) {
+                const double *sf = ssf + ((j == 0 ? 2 : 3) * 16 + i) * 5;
+                const double w = j == 0 ? -P.inv_weight0 : P.inv_weight0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+#pragma unroll
+                    for (int v = 0; v < 5; ++v) val[k][v] = fma(sf[20 * k + v], w, val[k][v]);
+            }
+            {
+                const double *sf = ssf + (4 * 16 + t) * 5;
+#pragma unroll
+                for (int v = 0; v < 5; ++v) {
+                    val[0][v] = fma(sf[v], -P.inv_weight0, val[0][v]);
+                    val[3][v] = fma(sf[80 + v], P.inv_weight0, val[3][v]);
                 }
-                if (j == 0 || j == 3) {
-                    const double *sf = s_sfv + ((j == 0 ? 2 : 3) * 16 + i + 4 * k) * 5;
-                    const double w = j == 0 ? -P.inv_weight0 : P.inv_weight0;
+            }
+            // apply_jacobian! (dg_3d.jl:1396-1414)
 #pragma unroll
-                    for (int v = 0; v < 5; ++v) val[v] = fma(sf[v], w, val[v]);
-                }
-                if (r == 0) {  // k = lm[0] is 0 (h = 0) or 3 (h = 1): always a z face; lm[1] never is
-                    const double *sf = s_sfv + ((h ? 5 : 4) * 16 + l16) * 5;
-                    const double w = h ? P.inv_weight0 : -P.inv_weight0;
+            for (int k = 0; k < 4; ++k)
 #pragma unroll
-                    for (int v = 0; v < 5; ++v) val[v] = fma(sf[v], w, val[v]);
-                }
-                // apply_jacobian! (dg_3d.jl:1396-1414)
+                for (int v = 0; v < 5; ++v) val[k][v] *= factor;
+            if (have_src) {
 #pragma unroll
-                for (int v = 0; v < 5; ++v) val[v] *= factor;
-                if (have_src) {
+                for (int k = 0; k < 4; ++k)
 #pragma unroll
-                    for (int v = 0; v < 5; ++v) val[v] += s_prim[n * 5 + v];
-                }
+                    for (int v = 0; v < 5; ++v) val[k][v] += sp[(t + 16 * k) * 5 + v];
             }
         }
         if (ut_late) {
-            while (!mbar_try_wait(bar, 1)) {
+            while (!mbar_try_wait(bar_t, 0)) {
             }
         }
+        double *const sut = s_ut + eh * CONS;
+        unsigned long long cfl0 = 0ull, cfl1 = 0ull, cfl2 = 0ull;
 #pragma unroll
-        for (int r = 0; r < 2; ++r) {
-            const int n = l16 + 16 * lm[r];
-            double(&val)[5] = vals[r];
-            double *out_t = s_ut + n * 5;
+        for (int k = 0; k < 4; ++k) {
+            double *out_t = sut + (t + 16 * k) * 5;
             if (!rk) {
 #pragma unroll
-                for (int v = 0; v < 5; ++v) out_t[v] = val[v];
+                for (int v = 0; v < 5; ++v) out_t[v] = val[k][v];
             } else {
                 // 2N stage (methods_2N.jl:152-158): u_tmp = du - u_tmp * a; u += u_tmp * (b * dt)
-                double *out_u = s_u + n * 5;
+                double *out_u = su + (t + 16 * k) * 5;
                 double un[5];
+                if (need_ut) {  // (warp-uniform)
+#pragma unroll
+                    for (int v = 0; v < 5; ++v) val[k][v] -= out_t[v] * P.rk_a;
+                }
 #pragma unroll
                 for (int v = 0; v < 5; ++v) {
-                    const double tmp = need_ut ? val[v] - out_t[v] * P.rk_a : val[v];
-                    out_t[v] = tmp;
-                    un[v] = out_u[v] + tmp * P.rk_b_dt;
+                    out_t[v] = val[k][v];
+                    un[v] = out_u[v] + val[k][v] * P.rk_b_dt;
                     out_u[v] = un[v];
                 }
                 if (P.want_cfl) {
@@ -396,26 +394,26 @@ __global__ void __launch_bounds__(TunedCfg::THREADS, TunedCfg::MIN_BLOCKS)
                     double c2 = gp * inv_rho;
                     c2 = fma(fma(-rho, c2, gp), inv_rho, c2);
                     const double c = sqrt(c2);
-                    const double lam[3] = {fabs(v1) + c, fabs(v2) + c, fabs(v3) + c};
-                    cfl0 = max(cfl0, cfl_encode(lam[0]));
-                    cfl1 = max(cfl1, cfl_encode(lam[1]));
-                    cfl2 = max(cfl2, cfl_encode(lam[2]));
+                    cfl0 = max(cfl0, cfl_encode(fabs(v1) + c));
+                    cfl1 = max(cfl1, cfl_encode(fabs(v2) + c));
+                    cfl2 = max(cfl2, cfl_encode(fabs(v3) + c));
                 }
             }
         }
-        if (P.want_cfl) {
+        if (P.want_cfl && rk) {
 #pragma unroll
-            for (int off = 16; off > 0; off >>= 1) {
+            for (int off = 8; off > 0; off >>= 1) {  // per element = per half-warp
                 cfl0 = max(cfl0, __shfl_xor_sync(0xffffffffu, cfl0, off));
                 cfl1 = max(cfl1, __shfl_xor_sync(0xffffffffu, cfl1, off));
                 cfl2 = max(cfl2, __shfl_xor_sync(0xffffffffu, cfl2, off));
             }
-            if (lane == 0) {
+            if (t == 0 && (lane >> 4) < nvalid) {
                 double sum = 0.0;
                 sum += __longlong_as_double((long long)cfl0);
                 sum += __longlong_as_double((long long)cfl1);
                 sum += __longlong_as_double((long long)cfl2);
-                atomicMax(P.cfl_key + (blockIdx.x & (kCflSlots - 1)), cfl_encode(P.inverse_jacobian[e] * sum));
+                atomicMax(P.cfl_key + ((blockIdx.x * 2 + (lane >> 4)) & (kCflSlots - 1)),
+                          cfl_encode(P.inverse_jacobian[e] * sum));
             }
         }
     }
@@ -423,12 +421,12 @@ __global__ void __launch_bounds__(TunedCfg::THREADS, TunedCfg::MIN_BLOCKS)
     fence_proxy_async();
     __syncwarp();
     if (lane == 0) {
-        constexpr uint32_t bu = CONS * sizeof(double);
+        const uint32_t bu = nvalid * CONS * sizeof(double);
         if (!rk) {
-            tma_store(P.du + e * CONS, smem_u32(s_ut), bu);
+            tma_store(P.du + e0 * CONS, smem_u32(s_ut), bu);
         } else {
-            tma_store(P.u_tmp + e * CONS, smem_u32(s_ut), bu);
-            tma_store(P.u_out + e * CONS, smem_u32(s_u), bu);
+            tma_store(P.u_tmp + e0 * CONS, smem_u32(s_ut), bu);
+            tma_store(P.u_out + e0 * CONS, smem_u32(s_u), bu);
         }
         tma_store_commit_and_wait_read();
     }
@@ -457,7 +455,7 @@ cudaError_t launch_element_euler3d_ranocha_p3(const KParams &P, bool with_surfac
     const bool deferred = !(with_surface && P.source_terms != TRIXI_B200_SRC_NONE);
     const size_t smem = deferred ? C::SMEM_DEFERRED : C::SMEM_RESIDENT;
     KParams Q = P;
-    if (Q.prefetch_distance < 0) Q.prefetch_distance = C::blocks_per_sm(deferred) * Q.sm_count;
+    if (Q.prefetch_distance < 0) Q.prefetch_distance = C::EPB * C::blocks_per_sm(deferred) * Q.sm_count;
     if (with_surface)
         k_element_euler3d_ranocha_p3<true><<<blocks, C::THREADS, smem, s>>>(Q);
     else

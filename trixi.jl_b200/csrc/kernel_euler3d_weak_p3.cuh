@@ -13,7 +13,7 @@
 //    shared tile [64][5] (natural order, odd record stride), then every node contracts its line with its row of
 //    D_hat held in registers: du[:, node] += sum_l D_hat[idx_d, l] f_d[:, line(l)].
 #pragma once
-#include "kernel_euler3d_fd_p3.cuh"
+#include "tile_io.cuh"
 
 namespace tb {
 

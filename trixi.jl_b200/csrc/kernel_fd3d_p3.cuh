@@ -12,7 +12,7 @@
 // Used for Euler 3D with flux_shima_etal / kennedy_gruber / chandrashekar / central and for GLM-MHD with
 // (flux_hindenlang_gassner, flux_nonconservative_powell): dg_3d.jl:216-266 for the nonconservative part.
 #pragma once
-#include "kernel_euler3d_fd_p3.cuh"
+#include "tile_io.cuh"
 
 namespace tb {
 

@@ -30,6 +30,8 @@ struct KParams {
     const double *dsplit, *dhat;
     double dsplit_c[kMaxNodes * kMaxNodes];  // same matrix in the kernel-parameter constant bank: a DFMA
                                              // can take it as an operand without a load or a register
+    double dsplit_h[16], dsplit_q[16];       // nnodes = 4 only: D_split / 2 and D_split / 4 (exact), for the tuned
+                                             // kernels whose two-point fluxes come scaled by powers of two
     double inv_weight0;
     // geometry
     const double *inverse_jacobian;       // Tree: [nelem]; curved: [n^d, nelem]

@@ -31,7 +31,7 @@ struct Launchers {
 template <class EQ>
 int fast_surface_flux_mode(const KParams &P) {
     if constexpr (HasFastRanocha<EQ>::value) {
-        if (P.kernel_path != 0) return 0;
+        if (P.kernel_path == 1) return 0;
         if (P.surface_flux == TRIXI_B200_FLUX_RANOCHA || P.surface_flux == TRIXI_B200_FLUX_RANOCHA_TURBO) return 1;
         if (P.surface_flux == TRIXI_B200_FLUX_LLF || P.surface_flux == TRIXI_B200_FLUX_LLF_NAIVE) return 2;
     }
@@ -158,6 +158,7 @@ void launch_error_norms(const KParams &P, const NormParams &Q, cudaStream_t s) {
 
 // tuned_euler3d.cu
 cudaError_t launch_element_euler3d_ranocha_p3(const KParams &P, bool with_surface, cudaStream_t s);
+cudaError_t launch_element_euler3d_ranocha_p3_v7(const KParams &P, bool with_surface, cudaStream_t s);
 cudaError_t launch_element_euler3d_weak_p3(const KParams &P, bool with_surface, cudaStream_t s);
 cudaError_t launch_element_linesweep_euler3d(const KParams &P, bool with_surface, cudaStream_t s);
 cudaError_t launch_element_linesweep_sc_euler3d(const KParams &P, bool with_surface, cudaStream_t s);
@@ -199,13 +200,13 @@ cudaError_t launch_element_variant(const KParams &P, cudaStream_t s) {
 template <class EQ, int N>
 bool uses_tuned_element(const KParams &P) {
     if constexpr (std::is_same_v<EQ, Euler<3>> && N == 4) {
-        if (P.kernel_path != 0) return false;
+        if (P.kernel_path == 1) return false;
         if (P.volume_integral == TRIXI_B200_VOLINT_WEAK_FORM) return true;  // TreeMesh and curved meshes
         return !P.curved && (P.volume_integral == TRIXI_B200_VOLINT_FLUX_DIFFERENCING ||       // headline or line sweep
                              P.volume_integral == TRIXI_B200_VOLINT_SHOCK_CAPTURING_HG);  // blended line sweep
     }
     if constexpr (std::is_same_v<EQ, Mhd3D> && N == 4) {
-        return P.kernel_path == 0 && !P.curved && P.volume_integral == TRIXI_B200_VOLINT_FLUX_DIFFERENCING;
+        return P.kernel_path != 1 && !P.curved && P.volume_integral == TRIXI_B200_VOLINT_FLUX_DIFFERENCING;
     }
     return false;
 }
@@ -225,7 +226,8 @@ cudaError_t launch_element(const KParams &P, bool with_surface, cudaStream_t s) 
             if (P.volume_integral == TRIXI_B200_VOLINT_SHOCK_CAPTURING_HG)
                 return launch_element_linesweep_sc_euler3d(P, with_surface, s);
             if (P.volume_flux == TRIXI_B200_FLUX_RANOCHA || P.volume_flux == TRIXI_B200_FLUX_RANOCHA_TURBO)
-                return launch_element_euler3d_ranocha_p3(P, with_surface, s);
+                return P.kernel_path == 2 ? launch_element_euler3d_ranocha_p3_v7(P, with_surface, s)
+                                          : launch_element_euler3d_ranocha_p3(P, with_surface, s);
             return launch_element_linesweep_euler3d(P, with_surface, s);
         }
     }
@@ -281,6 +283,7 @@ cudaError_t preload_kernel(K kern) {
 }
 
 cudaError_t preload_tuned_euler3d();       // tuned_euler3d.cu
+cudaError_t preload_tuned_euler3d_v7();
 cudaError_t preload_tuned_euler3d_weak();  // tuned_euler3d.cu
 
 template <class EQ, int N>
@@ -329,6 +332,7 @@ cudaError_t preload_all() {
 #undef TB_PRELOAD
     if constexpr (std::is_same_v<EQ, Euler<3>> && N == 4) {
         if ((e = preload_tuned_euler3d()) != cudaSuccess) return e;
+        if ((e = preload_tuned_euler3d_v7()) != cudaSuccess) return e;
         if ((e = preload_tuned_euler3d_weak()) != cudaSuccess) return e;
         return preload_linesweep();
     }

@@ -772,6 +772,11 @@ TRIXI_B200_API int trixi_b200_create(const trixi_b200_desc *d, trixi_b200_handle
     }
     P.inv_weight0 = d->inverse_weights[0];
     for (int q = 0; q < n * n; ++q) P.dsplit_c[q] = d->derivative_split[q];
+    if (n == 4)
+        for (int q = 0; q < 16; ++q) {
+            P.dsplit_h[q] = 0.5 * d->derivative_split[q];
+            P.dsplit_q[q] = 0.25 * d->derivative_split[q];
+        }
     P.kernel_path = 0;
     const bool curved = structured || p4est;
     CREATE_TRY(upload_array(h, d->inverse_jacobian, (size_t)(curved ? nn * d->nelements : d->nelements), &tmp));
@@ -1284,7 +1289,7 @@ TRIXI_B200_API int trixi_b200_set_option(trixi_b200_handle *h, int option, int v
     if (!h) return TRIXI_B200_EINVAL;
     switch (option) {
     case TRIXI_B200_OPT_KERNEL_PATH:
-        if (value != 0 && value != 1) return fail(h, TRIXI_B200_EINVAL, "kernel path must be 0 (auto) or 1 (generic)");
+        if (value < 0 || value > 2) return fail(h, TRIXI_B200_EINVAL, "kernel path must be 0 (auto), 1 (generic) or 2 (previous-generation tuned kernels)");
         h->P.kernel_path = value;
         return 0;
     case TRIXI_B200_OPT_PREFETCH_DISTANCE:

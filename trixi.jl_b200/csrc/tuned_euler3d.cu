@@ -1,6 +1,7 @@
 // Translation unit of the tuned 3D kernels at polydeg 3: the headline flux_ranocha kernel, the weak-form kernel
 // and the line-sweep flux-differencing kernel for the other two-point fluxes and GLM-MHD.
 #include "kernel_euler3d_fd_p3.cuh"
+#include "kernel_euler3d_fd_p3_v7.cuh"
 #include "kernel_euler3d_weak_p3.cuh"
 #include "kernel_fd3d_p3.cuh"
 
