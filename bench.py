@@ -265,10 +265,30 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
 
 
+def host_cores():
+    """Cores this process may run on.  Asked for explicitly: torch.distributed.run exports OMP_NUM_THREADS=1, which
+    would silently put the OpenMP reference on one core."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def cpu_model():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
 def oracle_backend(semi, threads=None):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle
-    return oracle.OracleBackend(semi, num_threads=threads)
+    return oracle.OracleBackend(semi, num_threads=threads or host_cores())
 
 
 def time_cpu_reference(level, steps, warmup, workload="euler_ec", turbo=False):
@@ -317,7 +337,8 @@ def run_reference(args, rank, world):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "pid_ns_per_dof_rhs": 1e9 / value * threads,
         "config": {"workload": workload_name(args.level, 1, args.workload), "sample": sample},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "cpu_model": cpu_model(), "kind": "port",
+                         "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -356,6 +377,8 @@ def run_b200(args, rank, world, local_rank):
         gpu.set_option(gpu.OPT_KERNEL_PATH, 1)
     elif args.kernel_path:
         gpu.set_option(gpu.OPT_KERNEL_PATH, args.kernel_path)
+    if args.no_reduce_update:
+        gpu.set_option(gpu.OPT_RK_REDUCE_UPDATE, 0)
     ndofs = semi.ndofs()
     u0 = T.compute_coefficients(0.0, semi)
     gpu.upload(0, u0)
@@ -472,17 +495,17 @@ def run_b200(args, rank, world, local_rank):
                 traffic, traffic_src = tj["dram_bytes_per_dof"] * ndofs, tj["source"]
         cpu = None
         if not args.no_cpu_baseline:
-            cv, cwall, cthreads, cdofs = time_cpu_reference(args.cpu_level, 3, 1, args.workload)
+            cv, cwall, cthreads, cdofs = time_cpu_reference(args.cpu_level, 5, 2, args.workload)
             turbo = None
             if args.workload in ("euler_ec", "tgv"):
-                turbo = time_cpu_reference(args.cpu_level, 3, 1, args.workload, turbo=True)[0]
-            cpu = {"value": cv, "unit": UNIT, "cores": cthreads, "kind": "port",
+                turbo = time_cpu_reference(args.cpu_level, 5, 2, args.workload, turbo=True)[0]
+            cpu = {"value": cv, "unit": UNIT, "cores": cthreads, "cpu_model": cpu_model(), "kind": "port",
                    "flux_ranocha_turbo_value": turbo,
                    "note": "value = the generic flux_differencing_kernel! with flux_ranocha, the configuration "
                            "benchmark/benchmark_ec.jl times; flux_ranocha_turbo_value = the same sample through the "
                            "reference's SIMD specialization with hoisted logarithms "
                            "(dg_3d_compressible_euler.jl:265-617), its fastest CPU path for this volume integral",
-                   "sample": f"{sample_name(args.cpu_level, args.workload)}; 3 CK54 steps (15 rhs!) after 1 warm-up; "
+                   "sample": f"{sample_name(args.cpu_level, args.workload)}; 5 CK54 steps (25 rhs!) after 2 warm-up; "
                              "OpenMP C restatement of the reference's CPU rhs! (oracle/trixi_oracle.c)"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -569,8 +592,9 @@ def main():
     ap.add_argument("--cells", type=int, default=None,
                     help="elements per direction and rank on a Morton-ordered Cartesian box instead of a uniform "
                          "TreeMesh level (euler_ec / tgv): 100 -> 64 M DOF per rank")
-    ap.add_argument("--cpu-level", type=int, default=5, help="refinement level of the bounded CPU sample")
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-level", type=int, default=6,
+                    help="refinement level of the bounded CPU sample (6 = 16.8 M DOF, SURVEY.md §8d)")
+    ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="euler_ec", choices=sorted(WORKLOADS),
                     help="euler_ec is the headline (BASELINE.json); the others are SURVEY.md §8d's secondary configs")
@@ -580,6 +604,8 @@ def main():
                     help="TRIXI_B200_OPT_KERNEL_PATH = 1: the generic one-thread-per-node kernels (before/after numbers)")
     ap.add_argument("--kernel-path", type=int, default=0,
                     help="TRIXI_B200_OPT_KERNEL_PATH: 2 = the previous generation of the tuned headline kernel (A/B runs)")
+    ap.add_argument("--no-reduce-update", action="store_true",
+                    help="TRIXI_B200_OPT_RK_REDUCE_UPDATE = 0: keep a resident u tile instead of the L2 reduce-add")
     ap.add_argument("--no-fused-cfl", action="store_true", help="run max_dt as its own kernel after every step")
     args = ap.parse_args()
     global CELLS

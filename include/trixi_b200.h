@@ -268,7 +268,8 @@ TRIXI_B200_API int trixi_b200_calc_error_norms(trixi_b200_handle *h, double t, i
                                                double *linf, double *volume);
 
 /* Tuning knobs (the analogue of the reference's compile-time Preferences, src/Trixi.jl:18-23).
- * TRIXI_B200_OPT_KERNEL_PATH: 0 = tuned kernels where one exists (default), 1 = generic kernels only.
+ * TRIXI_B200_OPT_KERNEL_PATH: 0 = tuned kernels where one exists (default), 1 = generic kernels only,
+ *   2 = the previous generation of the tuned headline kernel (kept for A/B measurements).
  * TRIXI_B200_OPT_FUSED_CFL: 1 = the last stage of trixi_b200_step_2n also reduces the CFL wave speeds of the
  *   state it writes, so the trixi_b200_max_dt that follows (StepsizeCallback, stepsize.jl:75-117) costs no pass
  *   over u.  The cached value is dropped by trixi_b200_upload(0), trixi_b200_rhs_host and
@@ -279,6 +280,10 @@ TRIXI_B200_API int trixi_b200_calc_error_norms(trixi_b200_handle *h, double t, i
 #define TRIXI_B200_OPT_PREFETCH_DISTANCE 2 /* tuned element kernel: L2 prefetch distance in elements (0 = off) */
 #define TRIXI_B200_OPT_HOST_PIPELINE_CHUNK 3 /* host-buffer calls: elements per chunk; -1 = auto (16-32 MiB, only
                                                 for >= 32 chunks), 0 = one copy each way, no overlap */
+/* TRIXI_B200_OPT_RK_REDUCE_UPDATE (default 1): the tuned 2N stage kernels apply u += (b dt) u_tmp as a bulk
+ * reduce-add onto u in L2 instead of reading u back into the SM; the product is rounded before the addition in
+ * both forms, so the option does not change results. */
+#define TRIXI_B200_OPT_RK_REDUCE_UPDATE 4
 TRIXI_B200_API int trixi_b200_set_option(trixi_b200_handle *h, int option, int value);
 
 /* GlmSpeedCallback (glm_speed.jl:85-105) mutates equations.c_h every step */

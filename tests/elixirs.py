@@ -108,12 +108,14 @@ def _euler2d_source_terms(periodic=True):
                                           source_terms=T.source_terms_convergence_test, boundary_conditions=bcs)
 
 
-def _euler2d_ec(flux=T.flux_ranocha):
-    # examples/tree_2d_dgsem/elixir_euler_ec.jl
+def _euler2d_ec(flux=T.flux_ranocha, boundary_conditions=None):
+    # examples/tree_2d_dgsem/elixir_euler_ec.jl (test/test_tree_2d_euler.jl:1318-1339 runs it with periodicity = false
+    # and boundary_condition_slip_wall on all four sides)
     eq = T.CompressibleEulerEquations2D(1.4)
     solver = T.DGSEM(polydeg=3, surface_flux=flux, volume_integral=T.VolumeIntegralFluxDifferencing(flux))
-    mesh = T.TreeMesh((-2.0, -2.0), (2.0, 2.0), initial_refinement_level=5, periodicity=True)
-    return T.SemidiscretizationHyperbolic(mesh, eq, T.initial_condition_weak_blast_wave, solver)
+    mesh = T.TreeMesh((-2.0, -2.0), (2.0, 2.0), initial_refinement_level=5, periodicity=boundary_conditions is None)
+    return T.SemidiscretizationHyperbolic(mesh, eq, T.initial_condition_weak_blast_wave, solver,
+                                          boundary_conditions=boundary_conditions or T.boundary_condition_periodic)
 
 
 def _euler2d_density_wave():
@@ -193,6 +195,11 @@ ELIXIRS = {e.name: e for e in [
            [0.061751715597716854, 0.05018223615408711, 0.05018989446443463, 0.225871559730513],
            [0.29347582879608825, 0.31081249232844693, 0.3107380389947736, 1.0540358049885143],
            "test/test_tree_2d_euler.jl:290-307"),
+    Elixir("tree_2d_euler_ec_slip_wall", lambda: _euler2d_ec(boundary_conditions=T.boundary_condition_slip_wall),
+           (0.0, 0.1), 0.3,
+           [0.03341239373099515, 0.026673245711492915, 0.026678871434568822, 0.12397486476145089],
+           [0.3290981764688339, 0.3812055782309788, 0.3812041851225023, 1.168251216556933],
+           "test/test_tree_2d_euler.jl:1318-1339"),
     Elixir("tree_2d_euler_ec_kennedy_gruber", lambda: _euler2d_ec(flux=T.flux_kennedy_gruber), (0.0, 0.4), 1.0,
            [0.03481471610306124, 0.027694280613944234, 0.027697905866996532, 0.12932052501462554],
            [0.31052098400669004, 0.3481295959664616, 0.34807152194137336, 1.1044947556170719],
@@ -676,6 +683,73 @@ def _structured3d_like_p4est_curved(initial_condition=T.initial_condition_weak_b
     return T.SemidiscretizationHyperbolic(mesh, eq, initial_condition, solver)
 
 
+def _curved_mapping_2d(xi, eta):
+    # a smooth deformation of [-1, 1]^2 that keeps the four sides straight (nonperiodic curved meshes)
+    pi = np.pi
+    x = xi + 0.1 * np.sin(pi * xi) * np.cos(0.5 * pi * eta)
+    y = eta + 0.1 * np.cos(0.5 * pi * x) * np.sin(pi * eta)
+    return x + 1, y + 1
+
+
+def _parity_case(mesh_kind, ndims, surface_flux, boundary_conditions=None, volume_flux=None):
+    """Registry entries the reference has no fixed-mesh golden for: FluxLaxFriedrichs(max_abs_speed),
+    FluxHLL along normals, slip walls.  Convergence-test state with its source terms (smooth, subsonic, velocity
+    (1, 1[, 1]): the slip wall sees inflow on one side and outflow on the other, i.e. both branches of its pressure
+    Riemann solution, compressible_euler_3d.jl:338-356)."""
+    eq = T.CompressibleEulerEquations3D(1.4) if ndims == 3 else T.CompressibleEulerEquations2D(1.4)
+    volint = T.VolumeIntegralFluxDifferencing(volume_flux) if volume_flux else T.VolumeIntegralWeakForm()
+    solver = T.DGSEM(polydeg=3, surface_flux=surface_flux, volume_integral=volint)
+    periodic = boundary_conditions is None
+    if mesh_kind == "tree":
+        mesh = T.TreeMesh((0.0,) * ndims, (2.0,) * ndims, initial_refinement_level=3 if ndims == 2 else 2,
+                          periodicity=periodic)
+    elif mesh_kind == "structured":
+        cells = (8, 8) if ndims == 2 else (4, 4, 4)
+        if periodic:
+            mesh = T.StructuredMesh(cells, _warped_mapping_2d if ndims == 2 else _warped_mapping_3d, periodicity=True)
+        else:
+            mesh = T.StructuredMesh(cells, _curved_mapping_2d if ndims == 2 else _nonperiodic_curved_mapping_3d,
+                                    periodicity=False)
+    else:
+        trees = (4, 4) if ndims == 2 else (2, 2, 2)
+        if periodic:
+            mesh = T.P4estMesh(trees, polydeg=3, mapping=_warped_mapping_2d if ndims == 2 else _warped_mapping_3d,
+                               periodicity=True, initial_refinement_level=1)
+        else:
+            mesh = T.P4estMesh(trees, polydeg=3,
+                               mapping=_curved_mapping_2d if ndims == 2 else _nonperiodic_curved_mapping_3d,
+                               periodicity=False, initial_refinement_level=1)
+    return T.SemidiscretizationHyperbolic(mesh, eq, T.initial_condition_convergence_test, solver,
+                                          source_terms=T.source_terms_convergence_test,
+                                          boundary_conditions=boundary_conditions or T.boundary_condition_periodic)
+
+
+def _slip_wall_mixed(ndims):
+    # slip walls in the first direction, Dirichlet in the others (like structured_2d_dgsem/
+    # elixir_euler_rayleigh_taylor_instability.jl:71-76): per-direction boundary condition dispatch
+    dirichlet = T.BoundaryConditionDirichlet(T.initial_condition_convergence_test)
+    return (T.boundary_condition_slip_wall,) * 2 + (dirichlet,) * (2 * ndims - 2)
+
+
+PARITY_EXTRA = {}
+for _mesh in ("tree", "structured", "p4est"):
+    for _nd in (2, 3):
+        _tag = f"{_mesh}_{_nd}d_euler"
+        PARITY_EXTRA[f"{_tag}_llf_max_abs_speed"] = (
+            lambda m=_mesh, n=_nd: _parity_case(m, n, T.FluxLaxFriedrichs(T.max_abs_speed)))
+        PARITY_EXTRA[f"{_tag}_llf_max_abs_speed_nonperiodic"] = (
+            lambda m=_mesh, n=_nd: _parity_case(m, n, T.flux_lax_friedrichs, T.BoundaryConditionDirichlet(
+                T.initial_condition_convergence_test)))
+        PARITY_EXTRA[f"{_tag}_hll"] = lambda m=_mesh, n=_nd: _parity_case(m, n, T.flux_hll)
+        PARITY_EXTRA[f"{_tag}_hll_naive"] = (
+            lambda m=_mesh, n=_nd: _parity_case(m, n, T.FluxHLL(T.min_max_speed_naive), volume_flux=T.flux_ranocha))
+        PARITY_EXTRA[f"{_tag}_slip_wall"] = (
+            lambda m=_mesh, n=_nd: _parity_case(m, n, T.flux_lax_friedrichs, T.boundary_condition_slip_wall))
+        PARITY_EXTRA[f"{_tag}_slip_wall_mixed"] = (
+            lambda m=_mesh, n=_nd: _parity_case(m, n, T.FluxLaxFriedrichs(T.max_abs_speed_naive), _slip_wall_mixed(n),
+                                                volume_flux=T.flux_ranocha))
+
+
 class _Extra:
     """Same interface as Elixir for the tests that only need ``semi()``."""
 
@@ -696,3 +770,4 @@ EXTRA = {e.name: e for e in [
     # of the tuned GPU kernel, which evaluates the same hoisted-logarithm form
     _Extra("tree_3d_euler_ec_turbo", lambda **kw: _euler3d_ec(flux=T.flux_ranocha_turbo, **kw)),
 ]}
+EXTRA.update({name: _Extra(name, build) for name, build in PARITY_EXTRA.items()})

@@ -5,7 +5,10 @@ import numpy as np
 import pytest
 import trixi_b200 as T
 
-from elixirs import ELIXIRS as _GOLDEN_ELIXIRS, EXTRA
+import json
+import os
+
+from elixirs import ELIXIRS as _GOLDEN_ELIXIRS, EXTRA, PARITY_EXTRA
 
 ELIXIRS = {**_GOLDEN_ELIXIRS, **EXTRA}
 
@@ -14,16 +17,43 @@ pytestmark = pytest.mark.gpu
 RHS_TOL = 1e-12
 
 
-def _rhs_tolerance(oracle_module, semi, u, t, du_ref):
-    """1e-12 relative (BASELINE.json), but never below twice the reference algorithm's own rounding
-    noise on this input: the same C restatement built with and without FMA contraction -- both legal
-    evaluations of the reference's `@muladd` code -- differs by 1.3e-12 on the Mach-0.1 Taylor-Green
-    state, where the energy flux terms cancel to 1/1000 of their size."""
+# The one configuration whose reference arithmetic is itself noisier than 1e-12: on the Mach-0.1 Taylor-Green state
+# the energy flux terms cancel to 1/1000 of their size, and the same C restatement built with and without FMA
+# contraction -- both legal evaluations of the reference's `@muladd` code -- differs by 1.3e-12.
+# Only there the tolerance is max(1e-12, 2 x that measured noise); every other case is held to a flat 1e-12.
+NOISE_LIMITED = {"tree_3d_euler_taylor_green_vortex"}
+
+
+def _oracle_noise(oracle_module, semi, u, t, du_ref):
     alt = oracle_module.OracleBackend(semi, nofma=True)
     du_alt = np.empty_like(u)
     alt.rhs_host(du_alt, u, t)
-    noise = _rel_err(du_alt, du_ref)
-    return max(RHS_TOL, 2.0 * noise)
+    return _rel_err(du_alt, du_ref)
+
+
+def _rhs_tolerance(name, noise):
+    return max(RHS_TOL, 2.0 * noise) if name in NOISE_LIMITED else RHS_TOL
+
+
+_PARITY_TABLE = []
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _write_parity_table():
+    """Every per-RHS comparison of this module, with the observed error and the tolerance it was held to, goes to
+    gpurun_out/parity_errors.json (copied to profiles/ by hand after a GPU run)."""
+    yield
+    if not _PARITY_TABLE:
+        return
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    try:
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "parity_errors.json"), "w") as f:
+            json.dump({"criterion": "max|du_gpu - du_ref| / max|du_ref| per RHS evaluation",
+                       "oracle_noise": "same comparison between the oracle built with and without FMA contraction",
+                       "cases": sorted(_PARITY_TABLE, key=lambda r: (r["case"], r["state"]))}, f, indent=1)
+    except OSError:
+        pass
 
 
 def _random_admissible_state(semi, seed=0, perturb=None):
@@ -70,7 +100,7 @@ RHS_CASES = ["tree_3d_euler_ec", "tree_3d_euler_source_terms", "tree_3d_euler_so
              "tree_3d_euler_shockcapturing", "tree_2d_euler_shockcapturing", "tree_2d_euler_blast_wave",
              "tree_3d_euler_ec_turbo", "tree_2d_euler_vortex_shockcapturing", "tree_2d_euler_vortex_mortar_shockcapturing",
              "tree_3d_advection_basic", "tree_3d_advection_mortar", "structured_3d_advection_basic",
-             "p4est_3d_advection_basic"]
+             "p4est_3d_advection_basic"] + sorted(PARITY_EXTRA)
 
 
 @pytest.mark.parametrize("name", RHS_CASES)
@@ -90,7 +120,12 @@ def test_rhs_matches_oracle(name, state, oracle_module):
     du_gpu = np.full_like(u, np.nan)
     T.rhs_hyperbolic(du_gpu, u, semi, t)  # the public call: host buffers in and out through the C ABI
     assert np.all(np.isfinite(du_gpu))
-    assert _rel_err(du_gpu, du_ref) <= _rhs_tolerance(oracle_module, semi, u, t, du_ref)
+    err = _rel_err(du_gpu, du_ref)
+    noise = _oracle_noise(oracle_module, semi, u, t, du_ref)
+    tol = _rhs_tolerance(name, noise)
+    _PARITY_TABLE.append({"case": name, "state": state, "rel_err": float(err), "tolerance": float(tol),
+                          "oracle_noise": float(noise), "ndofs": int(semi.ndofs())})
+    assert err <= tol
 
 
 @pytest.mark.parametrize("name", ["tree_3d_euler_ec", "tree_3d_euler_source_terms", "tree_2d_euler_source_terms_nonperiodic",
@@ -319,7 +354,8 @@ GOLDEN_GPU = ["tree_3d_advection_basic", "tree_3d_advection_mortar", "structured
               "tree_3d_euler_ec", "tree_3d_euler_ec_constant", "tree_3d_euler_source_terms",
               "tree_3d_euler_convergence", "tree_3d_euler_taylor_green_vortex", "tree_3d_euler_density_pulse",
               "tree_2d_advection_basic", "tree_2d_euler_source_terms", "tree_2d_euler_source_terms_nonperiodic",
-              "tree_2d_euler_ec", "tree_2d_euler_density_wave", "structured_3d_euler_free_stream",
+              "tree_2d_euler_ec", "tree_2d_euler_ec_slip_wall", "tree_2d_euler_density_wave",
+              "structured_3d_euler_free_stream",
               "structured_3d_euler_ec", "structured_3d_euler_source_terms",
               "structured_3d_euler_source_terms_nonperiodic_curved", "p4est_3d_euler_source_terms_nonperiodic",
               "p4est_3d_euler_source_terms_nonperiodic_kennedy_gruber", "tree_3d_mhd_ec", "tree_3d_mhd_alfven_wave",
@@ -499,7 +535,7 @@ def test_halo_exchange_matches_single_rank(name, world, oracle_module):
     ref = oracle_module.OracleBackend(base)
     du_ref = np.empty_like(u)
     ref.rhs_host(du_ref, u, 0.3)
-    assert _rel_err(du_single, du_ref) <= _rhs_tolerance(oracle_module, base, u, 0.3, du_ref)
+    assert _rel_err(du_single, du_ref) <= RHS_TOL
 
 
 def test_unconnected_distributed_handle_fails_loudly():

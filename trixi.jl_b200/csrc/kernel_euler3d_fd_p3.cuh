@@ -104,14 +104,28 @@ TB_DEV void ranocha_pair_rot(const double (&L)[kNP], const double (&R)[kNP], dou
 struct TunedCfg {
     static constexpr int EPB = 2, THREADS = 32;  // one warp, two elements, one thread per line
     static constexpr int CONS = 320, PRIM = 64 * kNP, SFV = 480;  // doubles per element
-    // s_u (natural order, TMA), s_sfv (natural, TMA), s_du, s_prim (swizzled), mbarriers, [s_ut (natural, TMA)].
-    // Without source terms the u_tmp tile is not resident during the flux passes: it is loaded into the prim
-    // tile's storage once the z pass has read it for the last time, and leaves from there.
-    static constexpr size_t SMEM_DEFERRED = sizeof(double) * EPB * (2 * CONS + SFV + PRIM) + 32;
-    static constexpr size_t SMEM_RESIDENT = SMEM_DEFERRED + sizeof(double) * EPB * CONS;
-    static constexpr int MIN_BLOCKS = 8;
-    static constexpr int blocks_per_sm(bool deferred) { return deferred ? 8 : 7; }
+    // Shared memory is what limits the resident warps, so the tiles take turns in one region per element:
+    //   flux passes:  [prim tile 448 | du tile 320 | pad 32]   (u arrives in the du tile's storage and is consumed
+    //                                                           by the primitive-variable pass before the x pass)
+    //   epilogue:     [surface_flux_values 480 | u_tmp 320]    (fetched once the z pass has read the prim tile)
+    // 6400 B per element: 16 CTAs = 32 elements per SM.  The updated u leaves as a bulk reduce-add of b dt u_tmp onto
+    // u in L2 (cp.reduce.async.bulk .add.f64), so u is not needed in the epilogue at all.  Launches that do need it
+    // there (source terms, the CFL reduction of the last stage, out-of-place updates) keep a resident u tile:
+    // 8960 B per element, 12 CTAs per SM.
+    static constexpr int REGION = PRIM + CONS + 32;
+    static_assert(REGION >= SFV + CONS, "epilogue tiles must fit the flux-pass region");
+    static constexpr size_t SMEM_STREAM = sizeof(double) * EPB * REGION + 32;
+    static constexpr size_t SMEM_RESIDENT = SMEM_STREAM + sizeof(double) * EPB * CONS;
+    static constexpr int MIN_BLOCKS = 16;
+    static constexpr int blocks_per_sm(bool resident) { return resident ? 12 : 16; }
 };
+
+// u_resident(P): must match between the launcher (shared memory size) and the kernel
+TB_DEV_HOST bool tuned_u_resident(const KParams &P, bool with_surface) {
+    const bool have_src = with_surface && P.source_terms != TRIXI_B200_SRC_NONE;
+    const bool rk = P.mode != 0;
+    return have_src || (rk && (P.want_cfl || !P.rk_reduce_update || P.u_out != P.u));
+}
 
 template <bool WITH_SURFACE>
 __global__ void __launch_bounds__(TunedCfg::THREADS, TunedCfg::MIN_BLOCKS)
@@ -120,13 +134,13 @@ __global__ void __launch_bounds__(TunedCfg::THREADS, TunedCfg::MIN_BLOCKS)
     constexpr int CONS = C::CONS, PRIM = C::PRIM, SFV = C::SFV, EPB = C::EPB;
     extern __shared__ __align__(128) double smem[];
     const bool have_src = WITH_SURFACE && P.source_terms != TRIXI_B200_SRC_NONE;
-    const bool deferred = !have_src;  // must match the launch's dynamic shared memory size
-    double *s_u = smem;                   // [2][64][5] natural: u in, updated u out
-    double *s_sfv = s_u + EPB * CONS;     // [2][6][16][5] natural
-    double *s_du = s_sfv + EPB * SFV;     // [2][64][5] swizzled
-    double *s_prim = s_du + EPB * CONS;   // [2][64][7] swizzled; after the flux passes: source terms or u_tmp
-    const uint32_t bar_u = smem_u32(s_prim + EPB * PRIM), bar_s = bar_u + 8, bar_t = bar_u + 16;
-    double *s_ut = deferred ? s_prim : s_prim + EPB * PRIM + 4;  // [2][64][5] natural: u_tmp in, u_tmp (or du) out
+    const bool resident = tuned_u_resident(P, WITH_SURFACE);
+    double *s_prim = smem;                 // [2][64][7] swizzled
+    double *s_du = s_prim + EPB * PRIM;    // [2][64][5] swizzled; before the x pass: u, natural order (not resident)
+    double *s_sfv = smem;                  // epilogue: [2][6][16][5] natural; then b dt u_tmp [2][64][5] (not resident)
+    double *s_ut = smem + EPB * SFV;       // epilogue: [2][64][5] natural: u_tmp in, u_tmp (or du) out
+    const uint32_t bar_u = smem_u32(smem + EPB * C::REGION), bar_s = bar_u + 8;
+    double *s_u = smem + EPB * C::REGION + 4;  // resident only: [2][64][5] natural: u in, updated u out
 
     const int lane = threadIdx.x;
     const int t = lane & 15;
@@ -138,36 +152,29 @@ __global__ void __launch_bounds__(TunedCfg::THREADS, TunedCfg::MIN_BLOCKS)
     const double gamma = P.eq.p[0], igm1x2 = 2.0 * P.eq.p[1];
     const bool rk = P.mode != 0;
     const bool need_ut = rk && P.rk_a != 0.0;
+    const uint32_t bu = nvalid * CONS * sizeof(double), bs = nvalid * SFV * sizeof(double);
 
-    // 0. TMA loads of the contiguous element records
+    // 0. TMA load of the two contiguous u records; the records the epilogue will want are pulled into L2 meanwhile
     if (lane == 0) {
         mbar_init(bar_u, 1);
         mbar_init(bar_s, 1);
-        mbar_init(bar_t, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
+    double *const s_uin = resident ? s_u : s_du;
     if (lane == 0) {
-        const uint32_t bu = nvalid * CONS * sizeof(double), bs = nvalid * SFV * sizeof(double);
-        const bool ut_now = need_ut && !deferred;
         mbar_expect_tx(bar_u, bu);
-        tma_load(smem_u32(s_u), P.u + e0 * CONS, bu, bar_u);
-        if (WITH_SURFACE || ut_now) {
-            mbar_expect_tx(bar_s, (ut_now ? bu : 0u) + (WITH_SURFACE ? bs : 0u));
-            if (ut_now) tma_load(smem_u32(s_ut), P.u_tmp + e0 * CONS, bu, bar_s);
-            if (WITH_SURFACE) tma_load(smem_u32(s_sfv), P.sfv + e0 * SFV, bs, bar_s);
-        }
+        tma_load(smem_u32(s_uin), P.u + e0 * CONS, bu, bar_u);
+        if (WITH_SURFACE) tma_prefetch_l2(P.sfv + e0 * SFV, bs);
+        if (need_ut) tma_prefetch_l2(P.u_tmp + e0 * CONS, bu);
         // warm L2 for the elements that will occupy this CTA slot next (blocks are scheduled in index order:
-        // one wave further on), so their tile loads see L2 instead of HBM latency
+        // one wave further on), so their u tile sees L2 instead of HBM latency
         const long long en = e0 + P.prefetch_distance;
-        if (P.prefetch_distance > 0 && en + EPB <= P.nelements) {
-            constexpr uint32_t bu2 = EPB * CONS * sizeof(double), bs2 = EPB * SFV * sizeof(double);
-            tma_prefetch_l2(P.u + en * CONS, bu2);
-            if (need_ut) tma_prefetch_l2(P.u_tmp + en * CONS, bu2);
-            if (WITH_SURFACE) tma_prefetch_l2(P.sfv + en * SFV, bs2);
-        }
+        if (P.prefetch_distance > 0 && en + EPB <= P.nelements)
+            tma_prefetch_l2(P.u + en * CONS, EPB * CONS * sizeof(double));
     }
-    double *const su = s_u + eh * CONS, *const sp = s_prim + eh * PRIM, *const sd = s_du + eh * CONS;
+    const double *const su = s_uin + eh * CONS;
+    double *const sp = s_prim + eh * PRIM, *const sd = s_du + eh * CONS;
     while (!mbar_try_wait(bar_u, 0)) {
     }
 
@@ -194,7 +201,7 @@ __global__ void __launch_bounds__(TunedCfg::THREADS, TunedCfg::MIN_BLOCKS)
         o[5] = lr;
         o[6] = lr - log_pos(pr);
     }
-    __syncwarp();
+    __syncwarp();  // (also: every thread has read u before the x pass overwrites the du tile)
 
     // 2. direction passes x, y, z with ONE copy of the flux code; the direction only enters through
     // shared-memory offsets (velocity slots rotated while loading, momentum slots while storing).
@@ -265,56 +272,33 @@ __global__ void __launch_bounds__(TunedCfg::THREADS, TunedCfg::MIN_BLOCKS)
         }
     }
 
-    // the prim tile is dead now: fetch the u_tmp tile into its storage; the surface integral and the Jacobian
-    // below run while it is in flight
-    const bool ut_late = need_ut && deferred;
-    if (ut_late) {
-        fence_proxy_async();
-        __syncwarp();
+    // 3. finish the z line (i, j) = (a0, a1), nodes n = t + 16 k, in registers; the z-pass accumulators are
+    // rotated: slots (1, 2, 3) hold the (v3, v1, v2) momentum components
+    double val[4][5];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const double *o = sd + pos[k] * 5;
+        val[k][0] = o[0] + acc[k][0];
+        val[k][1] = o[1] + acc[k][2];
+        val[k][2] = o[2] + acc[k][3];
+        val[k][3] = o[3] + acc[k][1];
+        val[k][4] = o[4] + acc[k][4];
+    }
+    // the prim and du tiles are dead now: fetch surface_flux_values and u_tmp into their storage
+    const bool late = WITH_SURFACE || need_ut;
+    fence_proxy_async();
+    __syncwarp();
+    if (late) {
         if (lane == 0) {
-            const uint32_t bu = nvalid * CONS * sizeof(double);
-            mbar_expect_tx(bar_t, bu);
-            tma_load(smem_u32(s_ut), P.u_tmp + e0 * CONS, bu, bar_t);
+            mbar_expect_tx(bar_s, (WITH_SURFACE ? bs : 0u) + (need_ut ? bu : 0u));
+            if (WITH_SURFACE) tma_load(smem_u32(s_sfv), P.sfv + e0 * SFV, bs, bar_s);
+            if (need_ut) tma_load(smem_u32(s_ut), P.u_tmp + e0 * CONS, bu, bar_s);
         }
-    }
-
-    // calc_sources! (dg_3d.jl:1417-1437): evaluated into the (now dead) prim tile, natural node order
-    if (have_src) {
-        const Euler<3> eq(P.eq);
-#pragma unroll 1
-        for (int r = 0; r < 4; ++r) {
-            const int n = t + 16 * r;
-            double un[5], x[3], sv[5];
-#pragma unroll
-            for (int v = 0; v < 5; ++v) un[v] = su[n * 5 + v];
-#pragma unroll
-            for (int dd = 0; dd < 3; ++dd) x[dd] = P.node_coordinates[(e * 64 + n) * 3 + dd];
-            eq.source_terms(P.source_terms, un, x, P.t, sv);
-#pragma unroll
-            for (int v = 0; v < 5; ++v) sp[n * 5 + v] = sv[v];
-        }
-        __syncwarp();
-    }
-    if (WITH_SURFACE || (need_ut && !deferred)) {
         while (!mbar_try_wait(bar_s, 0)) {
         }
     }
-
-    // 3. finish the z line (i, j) = (a0, a1), nodes n = t + 16 k, in registers; the z-pass accumulators are
-    // rotated: slots (1, 2, 3) hold the (v3, v1, v2) momentum components
     {
         const int i = a0, j = a1;
-        const double factor = WITH_SURFACE ? -P.inverse_jacobian[e] : 1.0;
-        double val[4][5];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const double *o = sd + pos[k] * 5;
-            val[k][0] = o[0] + acc[k][0];
-            val[k][1] = o[1] + acc[k][2];
-            val[k][2] = o[2] + acc[k][3];
-            val[k][3] = o[3] + acc[k][1];
-            val[k][4] = o[4] + acc[k][4];
-        }
         if constexpr (WITH_SURFACE) {
             // calc_surface_integral! (dg_3d.jl:1337-1394): directions 1..6 = -x,+x,-y,+y,-z,+z
             const double *ssf = s_sfv + eh * SFV;
@@ -343,77 +327,107 @@ __global__ void __launch_bounds__(TunedCfg::THREADS, TunedCfg::MIN_BLOCKS)
                 }
             }
             // apply_jacobian! (dg_3d.jl:1396-1414)
+            const double factor = -P.inverse_jacobian[e];
 #pragma unroll
             for (int k = 0; k < 4; ++k)
 #pragma unroll
                 for (int v = 0; v < 5; ++v) val[k][v] *= factor;
+            // calc_sources! (dg_3d.jl:1417-1437)
             if (have_src) {
+                const Euler<3> eq(P.eq);
+#pragma unroll 1
+                for (int k = 0; k < 4; ++k) {
+                    const int n = t + 16 * k;
+                    double un[5], x[3], sv[5];
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
+                    for (int v = 0; v < 5; ++v) un[v] = su[n * 5 + v];
 #pragma unroll
-                    for (int v = 0; v < 5; ++v) val[k][v] += sp[(t + 16 * k) * 5 + v];
-            }
-        }
-        if (ut_late) {
-            while (!mbar_try_wait(bar_t, 0)) {
+                    for (int dd = 0; dd < 3; ++dd) x[dd] = P.node_coordinates[(e * 64 + n) * 3 + dd];
+                    eq.source_terms(P.source_terms, un, x, P.t, sv);
+#pragma unroll
+                    for (int v = 0; v < 5; ++v) {
+                        // (k is a run-time index here: select instead of indexing the register array)
+                        val[0][v] += k == 0 ? sv[v] : 0.0;
+                        val[1][v] += k == 1 ? sv[v] : 0.0;
+                        val[2][v] += k == 2 ? sv[v] : 0.0;
+                        val[3][v] += k == 3 ? sv[v] : 0.0;
+                    }
+                }
             }
         }
         double *const sut = s_ut + eh * CONS;
-        unsigned long long cfl0 = 0ull, cfl1 = 0ull, cfl2 = 0ull;
+        if (!rk) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            double *out_t = sut + (t + 16 * k) * 5;
-            if (!rk) {
+            for (int k = 0; k < 4; ++k)
 #pragma unroll
-                for (int v = 0; v < 5; ++v) out_t[v] = val[k][v];
+                for (int v = 0; v < 5; ++v) sut[(t + 16 * k) * 5 + v] = val[k][v];
+        } else {
+            // 2N stage (methods_2N.jl:152-158): u_tmp = du - u_tmp * a; u += u_tmp * (b * dt).  The product is
+            // rounded before it is added, here and in the bulk reduce-add, so both forms give the same bits.
+            if (need_ut) {  // (warp-uniform)
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+#pragma unroll
+                    for (int v = 0; v < 5; ++v) val[k][v] -= sut[(t + 16 * k) * 5 + v] * P.rk_a;
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+#pragma unroll
+                for (int v = 0; v < 5; ++v) sut[(t + 16 * k) * 5 + v] = val[k][v];
+            if (!resident) {
+                __syncwarp();  // every thread is done with surface_flux_values: b dt u_tmp takes its place
+                double *const sinc = s_sfv + eh * CONS;
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+#pragma unroll
+                    for (int v = 0; v < 5; ++v) sinc[(t + 16 * k) * 5 + v] = __dmul_rn(val[k][v], P.rk_b_dt);
             } else {
-                // 2N stage (methods_2N.jl:152-158): u_tmp = du - u_tmp * a; u += u_tmp * (b * dt)
-                double *out_u = su + (t + 16 * k) * 5;
-                double un[5];
-                if (need_ut) {  // (warp-uniform)
+                double *const suo = s_u + eh * CONS;
+                unsigned long long cfl0 = 0ull, cfl1 = 0ull, cfl2 = 0ull;
 #pragma unroll
-                    for (int v = 0; v < 5; ++v) val[k][v] -= out_t[v] * P.rk_a;
-                }
+                for (int k = 0; k < 4; ++k) {
+                    double *out_u = suo + (t + 16 * k) * 5;
+                    double un[5];
 #pragma unroll
-                for (int v = 0; v < 5; ++v) {
-                    out_t[v] = val[k][v];
-                    un[v] = out_u[v] + val[k][v] * P.rk_b_dt;
-                    out_u[v] = un[v];
+                    for (int v = 0; v < 5; ++v) {
+                        un[v] = __dadd_rn(out_u[v], __dmul_rn(val[k][v], P.rk_b_dt));
+                        out_u[v] = un[v];
+                    }
+                    if (P.want_cfl) {
+                        // max_dt of the updated state (stepsize_dg3d.jl:8-32); max_abs_speeds
+                        // (compressible_euler_3d.jl:1770-1775) with the divisions done as one Newton reciprocal plus
+                        // a residual correction each (within 1 ulp of k_max_dt's IEEE divisions)
+                        const double rho = un[0], inv_rho = fast_rcp(rho);
+                        double v1 = un[1] * inv_rho, v2 = un[2] * inv_rho, v3 = un[3] * inv_rho;
+                        v1 = fma(fma(-rho, v1, un[1]), inv_rho, v1);
+                        v2 = fma(fma(-rho, v2, un[2]), inv_rho, v2);
+                        v3 = fma(fma(-rho, v3, un[3]), inv_rho, v3);
+                        const double pr = (gamma - 1) * (un[4] - 0.5 * (un[1] * v1 + un[2] * v2 + un[3] * v3));
+                        const double gp = gamma * pr;
+                        double c2 = gp * inv_rho;
+                        c2 = fma(fma(-rho, c2, gp), inv_rho, c2);
+                        const double c = sqrt(c2);
+                        cfl0 = max(cfl0, cfl_encode(fabs(v1) + c));
+                        cfl1 = max(cfl1, cfl_encode(fabs(v2) + c));
+                        cfl2 = max(cfl2, cfl_encode(fabs(v3) + c));
+                    }
                 }
                 if (P.want_cfl) {
-                    // max_dt of the updated state (stepsize_dg3d.jl:8-32); max_abs_speeds
-                    // (compressible_euler_3d.jl:1770-1775) with the divisions done as one Newton reciprocal plus
-                    // a residual correction each (within 1 ulp of k_max_dt's IEEE divisions)
-                    const double rho = un[0], inv_rho = fast_rcp(rho);
-                    double v1 = un[1] * inv_rho, v2 = un[2] * inv_rho, v3 = un[3] * inv_rho;
-                    v1 = fma(fma(-rho, v1, un[1]), inv_rho, v1);
-                    v2 = fma(fma(-rho, v2, un[2]), inv_rho, v2);
-                    v3 = fma(fma(-rho, v3, un[3]), inv_rho, v3);
-                    const double pr = (gamma - 1) * (un[4] - 0.5 * (un[1] * v1 + un[2] * v2 + un[3] * v3));
-                    const double gp = gamma * pr;
-                    double c2 = gp * inv_rho;
-                    c2 = fma(fma(-rho, c2, gp), inv_rho, c2);
-                    const double c = sqrt(c2);
-                    cfl0 = max(cfl0, cfl_encode(fabs(v1) + c));
-                    cfl1 = max(cfl1, cfl_encode(fabs(v2) + c));
-                    cfl2 = max(cfl2, cfl_encode(fabs(v3) + c));
-                }
-            }
-        }
-        if (P.want_cfl && rk) {
 #pragma unroll
-            for (int off = 8; off > 0; off >>= 1) {  // per element = per half-warp
-                cfl0 = max(cfl0, __shfl_xor_sync(0xffffffffu, cfl0, off));
-                cfl1 = max(cfl1, __shfl_xor_sync(0xffffffffu, cfl1, off));
-                cfl2 = max(cfl2, __shfl_xor_sync(0xffffffffu, cfl2, off));
-            }
-            if (t == 0 && (lane >> 4) < nvalid) {
-                double sum = 0.0;
-                sum += __longlong_as_double((long long)cfl0);
-                sum += __longlong_as_double((long long)cfl1);
-                sum += __longlong_as_double((long long)cfl2);
-                atomicMax(P.cfl_key + ((blockIdx.x * 2 + (lane >> 4)) & (kCflSlots - 1)),
-                          cfl_encode(P.inverse_jacobian[e] * sum));
+                    for (int off = 8; off > 0; off >>= 1) {  // per element = per half-warp
+                        cfl0 = max(cfl0, __shfl_xor_sync(0xffffffffu, cfl0, off));
+                        cfl1 = max(cfl1, __shfl_xor_sync(0xffffffffu, cfl1, off));
+                        cfl2 = max(cfl2, __shfl_xor_sync(0xffffffffu, cfl2, off));
+                    }
+                    if (t == 0 && (lane >> 4) < nvalid) {
+                        double sum = 0.0;
+                        sum += __longlong_as_double((long long)cfl0);
+                        sum += __longlong_as_double((long long)cfl1);
+                        sum += __longlong_as_double((long long)cfl2);
+                        atomicMax(P.cfl_key + ((blockIdx.x * 2 + (lane >> 4)) & (kCflSlots - 1)),
+                                  cfl_encode(P.inverse_jacobian[e] * sum));
+                    }
+                }
             }
         }
     }
@@ -421,12 +435,14 @@ __global__ void __launch_bounds__(TunedCfg::THREADS, TunedCfg::MIN_BLOCKS)
     fence_proxy_async();
     __syncwarp();
     if (lane == 0) {
-        const uint32_t bu = nvalid * CONS * sizeof(double);
         if (!rk) {
             tma_store(P.du + e0 * CONS, smem_u32(s_ut), bu);
         } else {
             tma_store(P.u_tmp + e0 * CONS, smem_u32(s_ut), bu);
-            tma_store(P.u_out + e0 * CONS, smem_u32(s_u), bu);
+            if (resident)
+                tma_store(P.u_out + e0 * CONS, smem_u32(s_u), bu);
+            else
+                tma_reduce_add_f64(P.u_out + e0 * CONS, smem_u32(s_sfv), bu);
         }
         tma_store_commit_and_wait_read();
     }
@@ -451,11 +467,10 @@ cudaError_t launch_element_euler3d_ranocha_p3(const KParams &P, bool with_surfac
         if (err != cudaSuccess) return err;
     }
     const unsigned blocks = (unsigned)((P.elem_end - P.elem_begin + C::EPB - 1) / C::EPB);
-    // (the kernel derives `deferred` from the same condition)
-    const bool deferred = !(with_surface && P.source_terms != TRIXI_B200_SRC_NONE);
-    const size_t smem = deferred ? C::SMEM_DEFERRED : C::SMEM_RESIDENT;
+    const bool resident = tuned_u_resident(P, with_surface);  // (the kernel evaluates the same condition)
+    const size_t smem = resident ? C::SMEM_RESIDENT : C::SMEM_STREAM;
     KParams Q = P;
-    if (Q.prefetch_distance < 0) Q.prefetch_distance = C::EPB * C::blocks_per_sm(deferred) * Q.sm_count;
+    if (Q.prefetch_distance < 0) Q.prefetch_distance = C::EPB * C::blocks_per_sm(resident) * Q.sm_count;
     if (with_surface)
         k_element_euler3d_ranocha_p3<true><<<blocks, C::THREADS, smem, s>>>(Q);
     else

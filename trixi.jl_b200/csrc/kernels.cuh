@@ -62,6 +62,7 @@ struct KParams {
     int prefetch_distance;        // tuned element kernels: L2 prefetch this many elements ahead (0: off, < 0: one
                                   // wave of resident CTAs, resolved at launch)
     int sm_count;
+    int rk_reduce_update;         // tuned kernels: u += b dt u_tmp as a bulk reduce-add in L2 (TRIXI_B200_OPT_RK_REDUCE_UPDATE)
     long long elem_begin, elem_end;  // TreeMesh element kernels work on [elem_begin, elem_end) (pipelined rhs_host)
     // VolumeIntegralShockCapturingHG: blending factors of IndicatorHennemannGassner
     double *alpha;       // [nelem] after smoothing (ordered-bits atomicMax target)

@@ -17,6 +17,7 @@ struct EqParams {
 };
 
 #define TB_DEV __device__ __forceinline__
+#define TB_DEV_HOST __host__ __device__ __forceinline__
 
 template <int ND>
 TB_DEV double pick(const double (&v)[ND], int o) {

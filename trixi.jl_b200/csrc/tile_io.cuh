@@ -41,6 +41,12 @@ TB_DEV void tma_store(void *dst, uint32_t src, uint32_t bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes)
                  : "memory");
 }
+// global[i] += shared[i] (FP64, round to nearest) performed by the L2's reduction units: UBLKRED.ADD.F64 in SASS
+TB_DEV void tma_reduce_add_f64(void *dst, uint32_t src, uint32_t bytes) {
+    asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], %2;" ::"l"(dst), "r"(src),
+                 "r"(bytes)
+                 : "memory");
+}
 TB_DEV void tma_store_commit_and_wait_read() {
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");

@@ -778,6 +778,7 @@ TRIXI_B200_API int trixi_b200_create(const trixi_b200_desc *d, trixi_b200_handle
             P.dsplit_q[q] = 0.25 * d->derivative_split[q];
         }
     P.kernel_path = 0;
+    P.rk_reduce_update = 1;
     const bool curved = structured || p4est;
     CREATE_TRY(upload_array(h, d->inverse_jacobian, (size_t)(curved ? nn * d->nelements : d->nelements), &tmp));
     P.inverse_jacobian = tmp;
@@ -1300,6 +1301,10 @@ TRIXI_B200_API int trixi_b200_set_option(trixi_b200_handle *h, int option, int v
         if (value != 0 && value != 1) return fail(h, TRIXI_B200_EINVAL, "fused CFL option must be 0 or 1");
         h->opt_fused_cfl = value != 0;
         h->cfl_valid = false;
+        return 0;
+    case TRIXI_B200_OPT_RK_REDUCE_UPDATE:
+        if (value != 0 && value != 1) return fail(h, TRIXI_B200_EINVAL, "reduce-update option must be 0 or 1");
+        h->P.rk_reduce_update = value;
         return 0;
     case TRIXI_B200_OPT_HOST_PIPELINE_CHUNK:
         if (value < -1) return fail(h, TRIXI_B200_EINVAL, "host pipeline chunk must be -1 (auto), 0 (off) or an element count");

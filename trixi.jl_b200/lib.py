@@ -258,6 +258,7 @@ class B200Backend:
     OPT_FUSED_CFL = 1
     OPT_PREFETCH_DISTANCE = 2
     OPT_HOST_PIPELINE_CHUNK = 3
+    OPT_RK_REDUCE_UPDATE = 4
 
     def set_option(self, option, value):
         self._ck(self.lib.trixi_b200_set_option(self.h, int(option), int(value)))
