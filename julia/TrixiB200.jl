@@ -6,20 +6,27 @@
 # the C ABI of include/trixi_b200.h -- the same mechanism as ext/TrixiCUDACoreExt.jl uses to plug in
 # CUDA.jl, but without KernelAbstractions.  Julia is not installed in the build container or on the GPU
 # box, so this file is exercised only by inspection; its Python twin (trixi.jl_b200/lib.py) binds the
-# identical entry points and is what the test-suite drives.
+# identical entry points and is what the test-suite drives (tests/c_abi_smoke.c drives them from plain C).
 #
-# Usage (the only change to an elixir):
+# Usage (the only change to an elixir is the `offload` line):
 #
 #     using Trixi, TrixiB200
 #     semi = SemidiscretizationHyperbolic(mesh, equations, initial_condition, solver; ...)
-#     semi = TrixiB200.offload(semi)            # uploads the cache once (create_cache -> trixi_b200_create)
 #     ode  = semidiscretize(semi, tspan)
+#     ode  = TrixiB200.offload(ode)             # create_cache -> trixi_b200_create; u0 becomes a B200Vector
 #     sol  = Trixi.solve(ode, Trixi.CarpenterKennedy2N54(); dt = 1.0, callback = callbacks)
+#
+# From there on everything dispatches on the array type of the solution vector, exactly like `CuArray` does for
+# the reference's KernelAbstractions path: `trixi_backend(u)` returns the `B200` object, `rhs_hyperbolic!`,
+# `max_dt` and `step!` below take over, and the callbacks keep seeing a host array.
 module TrixiB200
 
 using Trixi
 using Trixi: TreeMesh, StructuredMesh, P4estMesh, DG, DGSEM, SemidiscretizationHyperbolic, nvariables, nnodes,
-             ndims, nelements, ninterfaces, nboundaries, nmortars, mesh_equations_solver_cache
+             ndims, nelements, ninterfaces, nboundaries, nmortars, mesh_equations_solver_cache, True, False
+import KernelAbstractions
+import LoopVectorization
+import SciMLBase
 
 const libtrixi_b200 = get(ENV, "TRIXI_B200_LIBRARY", "libtrixi_b200.so")
 
@@ -71,9 +78,13 @@ flux_id(f) = error("numerical flux $f is not in the libtrixi_b200 registry")
 source_id(::Nothing) = Cint(0)
 source_id(::typeof(source_terms_convergence_test)) = Cint(1)
 source_id(::typeof(Trixi.source_terms_eoc_test_euler)) = Cint(2)
+source_id(::typeof(Trixi.source_terms_eoc_test_coupled_euler_gravity)) = Cint(3)
 source_id(f) = error("source term $f is not in the libtrixi_b200 registry")
 ic_id(::typeof(initial_condition_constant)) = Cint(1)
 ic_id(::typeof(initial_condition_convergence_test)) = Cint(2)
+ic_id(::typeof(initial_condition_weak_blast_wave)) = Cint(3)
+ic_id(::typeof(Trixi.initial_condition_eoc_test_coupled_euler_gravity)) = Cint(4)
+ic_id(f) = error("initial condition $f is not in the libtrixi_b200 registry of Dirichlet boundary states")
 bc_id(::Trixi.BoundaryConditionPeriodic) = (Cint(0), Cint(0))
 bc_id(bc::BoundaryConditionDirichlet) = (Cint(1), ic_id(bc.boundary_value_function))
 bc_id(::typeof(boundary_condition_slip_wall)) = (Cint(2), Cint(0))
@@ -140,11 +151,14 @@ struct Desc
 end
 
 # ---- the backend object ---------------------------------------------------------------------------------
+# (deliberately NOT a subtype of KernelAbstractions.Backend: the reference's `rhs_hyperbolic!(backend::Backend, ...)`
+# methods for P4estMesh, dgsem_p4est/dg_2d_gpu.jl:8-73, would be ambiguous with the one below)
 mutable struct B200
     handle::Ptr{Cvoid}
     ulength::Int
+    device_u_valid::Bool   # the handle's device-resident u equals the integrator's host u
     function B200(handle, ulength)
-        b = new(handle, ulength)
+        b = new(handle, ulength, false)
         finalizer(x -> ccall((:trixi_b200_destroy, libtrixi_b200), Cvoid, (Ptr{Cvoid},), x.handle), b)
         return b
     end
@@ -260,6 +274,8 @@ set_c_h!(backend::B200, c_h) = check(backend, ccall((:trixi_b200_set_eq_param, l
 # (semidiscretization_hyperbolic.jl:578-597) once `trixi_backend(u)` returns a B200.
 function Trixi.rhs_hyperbolic!(backend::B200, du, u, t, mesh::Union{TreeMesh, StructuredMesh, P4estMesh}, equations,
                                boundary_conditions, source_terms, dg::DG, cache)
+    sync_equation_params!(backend, equations)
+    backend.device_u_valid = false   # rhs_host leaves the caller's `u` argument on the device, not the integrator's
     GC.@preserve du u begin
         check(backend, ccall((:trixi_b200_rhs_host, libtrixi_b200), Cint,
                              (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Float64),
@@ -340,5 +356,118 @@ upload!(backend::B200, which, host::Vector{Float64}) = GC.@preserve host check(b
 download!(host::Vector{Float64}, backend::B200, which) = GC.@preserve host check(backend,
     ccall((:trixi_b200_download, libtrixi_b200), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}), backend.handle, which,
           pointer(host)))
+
+# ---- the array type that carries the backend ----------------------------------------------------------------
+# The reference selects its accelerator path through the array type of the solution vector: `storage_type`
+# (src/auxiliary/containers.jl:250-268, ext/TrixiCUDACoreExt.jl:9-11) and `trixi_backend(u) = get_backend(u)`
+# (containers.jl:278-285).  `B200Array` is a host-resident `Array` tagged with the `B200` handle: callbacks, I/O and
+# `Array(u)` (analysis_dg3d.jl:172-177) see ordinary host memory; the hot-path methods below see the tag.
+struct B200Array{T, N} <: DenseArray{T, N}
+    data::Array{T, N}
+    backend::B200
+end
+const B200Vector{T} = B200Array{T, 1}
+Base.size(a::B200Array) = size(a.data)
+Base.IndexStyle(::Type{<:B200Array}) = IndexLinear()
+Base.@propagate_inbounds Base.getindex(a::B200Array, i::Int) = a.data[i]
+Base.@propagate_inbounds function Base.setindex!(a::B200Array, v, i::Int)
+    a.backend.device_u_valid = false   # a host-side write (callback, limiter, restart) invalidates the device copy
+    a.data[i] = v
+    return a
+end
+Base.similar(a::B200Array, ::Type{T}, dims::Dims{N}) where {T, N} = B200Array{T, N}(Array{T, N}(undef, dims), a.backend)
+Base.copy(a::B200Array{T, N}) where {T, N} = B200Array{T, N}(copy(a.data), a.backend)
+Base.pointer(a::B200Array) = pointer(a.data)
+Base.unsafe_convert(::Type{Ptr{T}}, a::B200Array{T}) where {T} = pointer(a.data)
+Base.strides(a::B200Array) = strides(a.data)
+Base.Array(a::B200Array) = a.data
+Base.resize!(::B200Array, n) = error("libtrixi_b200: a change of the element count (AMR) needs a new handle")
+
+Trixi.storage_type(::Type{<:B200Array}) = B200Array
+KernelAbstractions.get_backend(a::B200Array) = a.backend
+# `@trixi_timeit_ext backend ...` (auxiliary.jl:94-103) synchronises the backend when debug timings are on
+KernelAbstractions.synchronize(b::B200) = check(b, ccall((:trixi_b200_synchronize, libtrixi_b200), Cint, (Ptr{Cvoid},),
+                                                         b.handle))
+# keep the tagged vector off the Polyester/PtrArray path (dg.jl:1189-1204) ...
+LoopVectorization.check_args(::B200Array) = false
+# ... and carry the tag through `wrap_array` (dg.jl:1205-1211 would `unsafe_wrap(ArrayType{...}, ptr, dims)`,
+# which cannot know the handle)
+@inline function Trixi.wrap_array(u_ode::B200Array{T, 1}, mesh::Trixi.AbstractMesh, equations, dg::DGSEM,
+                                  cache) where {T}
+    dims = (nvariables(equations), ntuple(_ -> nnodes(dg), ndims(mesh))..., nelements(dg, cache))
+    return B200Array{T, ndims(mesh) + 2}(unsafe_wrap(Array{T, ndims(mesh) + 2}, pointer(u_ode.data), dims),
+                                         u_ode.backend)
+end
+Trixi.wrap_array_native(u_ode::B200Array{T, 1}, mesh::Trixi.AbstractMesh, equations, dg::DG, cache) where {T} =
+    Trixi.wrap_array_native(u_ode.data, mesh, equations, dg, cache)
+
+"""
+    offload(ode::ODEProblem; device = -1)
+
+Create the `libtrixi_b200` handle for `ode.p` (a `SemidiscretizationHyperbolic`) and return the same problem with
+`u0` wrapped in a [`B200Array`](@ref).  `Trixi.solve`/`init` (methods_2N.jl:113-129) then build `u`, `du` and
+`u_tmp` with `copy`/`similar`, so the integrator's vectors all carry the backend.
+"""
+function offload(ode::SciMLBase.ODEProblem; device = -1)
+    backend = B200(ode.p; device = device)
+    return SciMLBase.remake(ode; u0 = B200Array{Float64, 1}(copy(ode.u0), backend))
+end
+offload(semi::SemidiscretizationHyperbolic, tspan; kwargs...) = offload(Trixi.semidiscretize(semi, tspan); kwargs...)
+
+# GlmSpeedCallback (glm_speed.jl:85-105) mutates equations.c_h between steps
+sync_equation_params!(backend::B200, equations) = nothing
+sync_equation_params!(backend::B200, equations::IdealGlmMhdEquations3D) = set_c_h!(backend, equations.c_h)
+
+function ensure_device_u!(u::B200Array)
+    if !u.backend.device_u_valid
+        GC.@preserve u check(u.backend, ccall((:trixi_b200_upload, libtrixi_b200), Cint,
+                                               (Ptr{Cvoid}, Cint, Ptr{Float64}), u.backend.handle, 0, pointer(u.data)))
+        u.backend.device_u_valid = true
+    end
+    return nothing
+end
+
+# max_dt(u, t, mesh, constant_speed, equations, dg, cache) (stepsize_dg2d.jl:8-75, stepsize_dg3d.jl:8-123), called by
+# calculate_dt (stepsize.jl:146-154) with the wrapped u.  One method per reference method so that the argument
+# lists stay comparable (more specific in `u` only): no ambiguities.  After a `step!` below the device copy is
+# current and the CFL maxima were already reduced by the last Runge-Kutta stage (TRIXI_B200_OPT_FUSED_CFL).
+for (M, C) in ((:(TreeMesh{2}), :False), (:(TreeMesh{2}), :True), (:(TreeMesh{3}), :False), (:(TreeMesh{3}), :True),
+               (:(StructuredMesh{2}), :Any), (:(StructuredMesh{3}), :Any), (:(P4estMesh{2}), :Any),
+               (:(P4estMesh{3}), :Any))
+    @eval function Trixi.max_dt(u::B200Array, t, mesh::$M, constant_speed::$C, equations, dg::DG, cache)
+        sync_equation_params!(u.backend, equations)
+        ensure_device_u!(u)
+        return max_dt_device(u.backend, t)
+    end
+end
+
+# step!(integrator::SimpleIntegrator2N) (methods_2N.jl:131-168) for integrators whose vectors are B200Arrays: the
+# bookkeeping is the reference's, the stage loop :144-159 is one call (u travels in chunks that overlap the first
+# and the last stage; afterwards the host and the device copies of u agree).
+function Trixi.step!(integrator::Trixi.SimpleIntegrator2N{<:Real, <:B200Array})
+    prob = integrator.sol.prob
+    alg = integrator.alg
+    t_end = last(prob.tspan)
+    callbacks = integrator.opts.callback
+
+    @assert !integrator.finalstep
+    if isnan(integrator.dt)
+        error("time step size `dt` is NaN")
+    end
+    Trixi.limit_dt!(integrator, t_end)
+
+    backend = integrator.u.backend
+    _, equations, _, _ = mesh_equations_solver_cache(prob.p)
+    sync_equation_params!(backend, equations)
+    check(backend, ccall((:trixi_b200_set_option, libtrixi_b200), Cint, (Ptr{Cvoid}, Cint, Cint), backend.handle, 1, 1))
+    step_2n_host!(backend, integrator.u.data, integrator.t, integrator.dt, alg)
+    backend.device_u_valid = true
+
+    integrator.iter += 1
+    integrator.t += integrator.dt
+    Trixi.@trixi_timeit Trixi.timer() "Step-Callbacks" Trixi.handle_callbacks!(callbacks, integrator)
+    Trixi.check_max_iter!(integrator)
+    return nothing
+end
 
 end # module

@@ -634,6 +634,16 @@ static void ic_eval(const eqn_t *eq, int ic, const double *x, double t, double *
             u[nd + 1] = ini * ini;
             return;
         }
+        case TRIXI_B200_IC_EOC_TEST_COUPLED_EULER_GRAVITY: { /* compressible_euler_3d.jl:196-215, _2d.jl:212-230 */
+            double s = 0.0;
+            for (int d = 0; d < nd; ++d) s += x[d];
+            double ini = 2 + 0.1 * sin(M_PI * fmod(s - t, 2.0));
+            double p = nd == 3 ? ini * ini * 1 * 2 / (3 * M_PI) : ini * ini * 1 / M_PI;
+            u[0] = ini;
+            for (int d = 0; d < nd; ++d) u[1 + d] = ini * 1.0;
+            u[nd + 1] = p * eq->inv_gm1 + 0.5 * (nd * (ini * 1.0) * 1.0);
+            return;
+        }
         default:
             break;
         }
@@ -775,6 +785,21 @@ static void source_terms(const eqn_t *eq, int src, const double *u, const double
             du[0] = rhox;
             du[1] = du[2] = rhox * (1 - C_grav * rho);
             du[3] = rhox * (1 - 3 * C_grav * rho);
+        }
+        return;
+    }
+    case TRIXI_B200_SRC_EOC_TEST_COUPLED_EULER_GRAVITY: {
+        double r = fmod(s - t, 2.0);
+        double si = sin(M_PI * r), co = cos(M_PI * r);
+        double rhox = 0.1 * M_PI * co, rho = 2 + 0.1 * si;
+        if (nd == 3) { /* compressible_euler_3d.jl:228-249 */
+            double C_grav = -4.0 * 1 / (3 * M_PI);
+            du[0] = du[1] = du[2] = du[3] = 2 * rhox;
+            du[4] = 2 * rhox * (1.5 - C_grav * rho);
+        } else { /* compressible_euler_2d.jl:241-261 */
+            double C_grav = -2.0 * 1 / M_PI;
+            du[0] = du[1] = du[2] = rhox;
+            du[3] = (1 - C_grav * rho) * rhox;
         }
         return;
     }

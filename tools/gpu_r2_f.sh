@@ -1,0 +1,20 @@
+#!/bin/bash
+set -x
+mkdir -p gpurun_out
+timeout 2400 python -m pytest tests -q -m gpu > gpurun_out/f_pytest.log 2>&1
+echo "pytest exit $?" >> gpurun_out/f_pytest.log
+tail -6 gpurun_out/f_pytest.log
+B="python bench.py --steps 10 --warmup 3 --no-cpu-baseline --e2e-steps 1"
+timeout 600 $B > gpurun_out/f_bench_v11.json 2> gpurun_out/f_bench_v11.err
+timeout 600 $B --kernel-path 2 > gpurun_out/f_bench_v7.json 2> gpurun_out/f_bench_v7.err
+timeout 600 $B > gpurun_out/f_bench_v11b.json 2> gpurun_out/f_bench_v11b.err
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_element_euler3d_ranocha_p3 -s 6 -c 2 -o gpurun_out/f_prof_v11 python bench.py --level 6 --steps 2 --warmup 1 --no-cpu-baseline --e2e-steps 1 > gpurun_out/f_ncu.log 2>&1
+python - <<'PY'
+import json
+for n in ("v11","v7","v11b"):
+    try:
+        d=json.load(open(f"gpurun_out/f_bench_{n}.json"))
+        print(n, d["value"]/1e9, d["ms_per_step"], d["roofline"]["avg_launch_ms"], d["roofline"]["frac"], d["roofline_interface_kernel"]["avg_launch_ms"], d["clocks"]["sm_mhz"], d["e2e"]["value"]/1e9, d["finite"])
+    except Exception as e:
+        print(n, "failed", e)
+PY

@@ -204,8 +204,14 @@ class AnalysisCallback(_Callback):
         # reduce the norms on the device when the backend offers it (no download of u)
         self.on_device = on_device
 
+    def initialize(self, integrator):
+        # analysis.jl:160-231: the callback also fires once at initialization (iter 0)
+        if self.interval > 0:
+            self.affect(integrator)
+
     def condition(self, integrator):
-        return (self.interval > 0 and integrator.iter % self.interval == 0) or integrator.finalstep
+        # analysis.jl:123-127: interval > 0 && (iter % interval == 0 || isfinished(integrator))
+        return self.interval > 0 and (integrator.iter % self.interval == 0 or integrator.finalstep)
 
     def affect(self, integrator):
         l2, linf = None, None

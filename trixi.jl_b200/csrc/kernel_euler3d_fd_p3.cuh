@@ -33,7 +33,7 @@
 
 namespace tb {
 
-// Node record in the prim tile: rho, v1, v2, v3, p, log(rho), log(rho) - log(p)
+// Node record in the prim tile: rho, v1, v2, v3, 2 p, log(rho), log(rho) - log(p)
 constexpr int kNP = 7;
 
 // log(x) for positive, finite, normal x (fdlibm's __ieee754_log kernel: x = 2^k (1 + f), sqrt(1/2) <= 1 + f <
@@ -62,59 +62,65 @@ TB_DEV double log_pos(double x) {
 }
 
 // 4 * flux_ranocha(u_ll, u_rr, orientation) (compressible_euler_3d.jl:746-793) on hoisted node records whose
-// velocity components have been rotated so that slot 1 is the normal one: (rho, vn, vt1, vt2, p, log rho,
+// velocity components have been rotated so that slot 1 is the normal one: (rho, vn, vt1, vt2, 2 p, log rho,
 // log rho - log p).  The output is rotated the same way and scaled by powers of two that the caller's D_split
 // weights undo: g = (2 f_rho, 4 f_n, 4 f_t1, 4 f_t2, 4 f_E) -- the halves of the arithmetic means never get
-// multiplied out (exact: scaling by 2 commutes with rounding).  igm1x2 = 2 / (gamma - 1).
-TB_DEV void ranocha_pair_rot(const double (&L)[kNP], const double (&R)[kNP], double igm1x2, double (&g)[5]) {
-    const double rho_ll = L[0], p_ll = L[4], rho_rr = R[0], p_rr = R[4];
-    // ln_mean(rho_ll, rho_rr) (math.jl:198-210); f^2 = (x-y)^2/(x+y)^2 as in the reference's SIMD kernel
+// multiplied out, and the record carries 2 p so that the doubled pressure terms need no doubling either (exact:
+// scaling by 2 commutes with rounding).  igm1 = 1 / (gamma - 1).
+TB_DEV void ranocha_pair_rot(const double (&L)[kNP], const double (&R)[kNP], double igm1, double (&g)[5]) {
+    const double rho_ll = L[0], p2_ll = L[4], rho_rr = R[0], p2_rr = R[4];
+    // ln_mean(rho_ll, rho_rr) (math.jl:198-210); f^2 = ((x - y) / (x + y))^2
     double rho_mean;
     {
         const double sum = rho_ll + rho_rr, dif = rho_rr - rho_ll;
-        const double f2 = (dif * dif) * rcp_1nr(sum * sum);
+        const double f = dif * rcp_1nr(sum), f2 = f * f;
         const bool series = f2 < 1.0e-4;
         const double poly = fma(f2, fma(f2, fma(f2, 2.0 / 7.0, 2.0 / 5.0), 2.0 / 3.0), 2.0);
         rho_mean = fast_div(series ? sum : dif, series ? poly : R[5] - L[5]);
     }
-    // inv_ln_mean(rho_ll * p_rr, rho_rr * p_ll) (math.jl:238-250)
-    double inv_rho_p_mean;
+    // 2 p_ll p_rr inv_ln_mean(rho_ll p_rr, rho_rr p_ll) (math.jl:238-250) from the doubled pressures:
+    // x = 2 rho_ll p_rr, y = 2 rho_rr p_ll, p2_ll p2_rr inv_ln_mean(x, y) = 2 p_ll p_rr inv_ln_mean(x / 2, y / 2)
+    double inv_rho_p_mean2;
     {
-        const double x = rho_ll * p_rr, y = rho_rr * p_ll;
+        const double x = rho_ll * p2_rr, y = rho_rr * p2_ll;
         const double sum = x + y, dif = y - x;
-        const double f2 = (dif * dif) * rcp_1nr(sum * sum);
+        const double f = dif * rcp_1nr(sum), f2 = f * f;
         const bool series = f2 < 1.0e-4;
         const double poly = fma(f2, fma(f2, fma(f2, 2.0 / 7.0, 2.0 / 5.0), 2.0 / 3.0), 2.0);
         // log(y / x) = (log rho_rr - log p_rr) - (log rho_ll - log p_ll)
         const double m = fast_div(series ? poly : R[6] - L[6], series ? sum : dif);
-        inv_rho_p_mean = p_ll * p_rr * m;
+        inv_rho_p_mean2 = p2_ll * p2_rr * m;
     }
     const double sn = L[1] + R[1], st1 = L[2] + R[2], st2 = L[3] + R[3];  // 2 v_avg
-    const double ps2 = (p_ll + p_rr) + (p_ll + p_rr);                     // 4 p_avg
     const double vs = L[1] * R[1] + L[2] * R[2] + L[3] * R[3];            // 2 velocity_square_avg
     const double f1 = rho_mean * sn;                                       // 2 f_rho
-    const double pv = p_ll * R[1] + p_rr * L[1];
     g[0] = f1;
-    g[1] = fma(f1, sn, ps2);
+    g[1] = fma(f1, sn, p2_ll + p2_rr);                                      // 4 (f_rho v_avg + p_avg)
     g[2] = f1 * st1;
     g[3] = f1 * st2;
-    g[4] = fma(f1, fma(inv_rho_p_mean, igm1x2, vs), pv + pv);
+    g[4] = fma(f1, fma(inv_rho_p_mean2, igm1, vs), p2_ll * R[1] + p2_rr * L[1]);
 }
 
 struct TunedCfg {
     static constexpr int EPB = 2, THREADS = 32;  // one warp, two elements, one thread per line
     static constexpr int CONS = 320, PRIM = 64 * kNP, SFV = 480;  // doubles per element
-    // Shared memory is what limits the resident warps, so the tiles take turns in one region per element:
-    //   flux passes:  [prim tile 448 | du tile 320 | pad 32]   (u arrives in the du tile's storage and is consumed
-    //                                                           by the primitive-variable pass before the x pass)
-    //   epilogue:     [surface_flux_values 480 | u_tmp 320]    (fetched once the z pass has read the prim tile)
-    // 6400 B per element: 16 CTAs = 32 elements per SM.  The updated u leaves as a bulk reduce-add of b dt u_tmp onto
+    // Shared memory is what limits the resident warps, so the tiles take turns in one region per CTA (doubles):
+    //   flux passes:  [prim tiles 0..896 | pad | du tiles 976..1616]   (u arrives in the du tiles' storage and is
+    //                                           consumed by the primitive-variable pass before the x pass)
+    //   epilogue:     [surface_flux_values 0..968 | u_tmp 976..1616]   (the faces are fetched while the z pass
+    //                                           computes -- it has read the prim tile by then -- and u_tmp once
+    //                                           the du tile has been read; b dt u_tmp finally goes to 0..640)
+    // 6.4 KB per element: 16 CTAs = 32 elements per SM.  The updated u leaves as a bulk reduce-add of b dt u_tmp onto
     // u in L2 (cp.reduce.async.bulk .add.f64), so u is not needed in the epilogue at all.  Launches that do need it
     // there (source terms, the CFL reduction of the last stage, out-of-place updates) keep a resident u tile:
-    // 8960 B per element, 12 CTAs per SM.
-    static constexpr int REGION = PRIM + CONS + 32;
-    static_assert(REGION >= SFV + CONS, "epilogue tiles must fit the flux-pass region");
-    static constexpr size_t SMEM_STREAM = sizeof(double) * EPB * REGION + 32;
+    // 8.9 KB per element, 12 CTAs per SM.
+    // The second element's faces sit at 488 instead of 480 doubles: in the surface integral the lanes of the two
+    // elements then hit different banks (offset 8 against a lane stride of 5).  The two faces of a direction
+    // still share banks (2-way conflict on 40 of ~800 shared-memory instructions per warp): separating them
+    // too needs one bulk copy per face, and issuing twelve copies cost more issue slots than the conflicts.
+    static constexpr int OFF_DU = 976, REGION = OFF_DU + EPB * CONS, SFV_H = 488;
+    static_assert(SFV_H + SFV <= OFF_DU, "face tiles must stay clear of the du tile");
+    static constexpr size_t SMEM_STREAM = sizeof(double) * REGION + 32;
     static constexpr size_t SMEM_RESIDENT = SMEM_STREAM + sizeof(double) * EPB * CONS;
     static constexpr int MIN_BLOCKS = 16;
     static constexpr int blocks_per_sm(bool resident) { return resident ? 12 : 16; }
@@ -136,11 +142,12 @@ __global__ void __launch_bounds__(TunedCfg::THREADS, TunedCfg::MIN_BLOCKS)
     const bool have_src = WITH_SURFACE && P.source_terms != TRIXI_B200_SRC_NONE;
     const bool resident = tuned_u_resident(P, WITH_SURFACE);
     double *s_prim = smem;                 // [2][64][7] swizzled
-    double *s_du = s_prim + EPB * PRIM;    // [2][64][5] swizzled; before the x pass: u, natural order (not resident)
-    double *s_sfv = smem;                  // epilogue: [2][6][16][5] natural; then b dt u_tmp [2][64][5] (not resident)
-    double *s_ut = smem + EPB * SFV;       // epilogue: [2][64][5] natural: u_tmp in, u_tmp (or du) out
-    const uint32_t bar_u = smem_u32(smem + EPB * C::REGION), bar_s = bar_u + 8;
-    double *s_u = smem + EPB * C::REGION + 4;  // resident only: [2][64][5] natural: u in, updated u out
+    double *s_du = smem + C::OFF_DU;       // [2][64][5] swizzled; before the x pass: u, natural order (not resident)
+    double *s_sfv = smem;                  // epilogue: [6][16][5] natural order per element, element h at h * 488
+    double *s_inc = smem;                  // then b dt u_tmp [2][64][5] natural (not resident)
+    double *s_ut = smem + C::OFF_DU;       // epilogue: [2][64][5] natural: u_tmp in, u_tmp (or du) out
+    const uint32_t bar_u = smem_u32(smem + C::REGION), bar_s = bar_u + 8, bar_t = bar_u + 16;
+    double *s_u = smem + C::REGION + 4;    // resident only: [2][64][5] natural: u in, updated u out
 
     const int lane = threadIdx.x;
     const int t = lane & 15;
@@ -149,7 +156,7 @@ __global__ void __launch_bounds__(TunedCfg::THREADS, TunedCfg::MIN_BLOCKS)
     // on an odd tail the second half-warp mirrors the first (same tiles, same values; nothing extra is stored)
     const int eh = (lane >> 4) < nvalid ? (lane >> 4) : 0;
     const long long e = e0 + eh;
-    const double gamma = P.eq.p[0], igm1x2 = 2.0 * P.eq.p[1];
+    const double gamma = P.eq.p[0], igm1 = P.eq.p[1];
     const bool rk = P.mode != 0;
     const bool need_ut = rk && P.rk_a != 0.0;
     const uint32_t bu = nvalid * CONS * sizeof(double), bs = nvalid * SFV * sizeof(double);
@@ -158,6 +165,7 @@ __global__ void __launch_bounds__(TunedCfg::THREADS, TunedCfg::MIN_BLOCKS)
     if (lane == 0) {
         mbar_init(bar_u, 1);
         mbar_init(bar_s, 1);
+        mbar_init(bar_t, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
@@ -165,7 +173,7 @@ __global__ void __launch_bounds__(TunedCfg::THREADS, TunedCfg::MIN_BLOCKS)
     if (lane == 0) {
         mbar_expect_tx(bar_u, bu);
         tma_load(smem_u32(s_uin), P.u + e0 * CONS, bu, bar_u);
-        if (WITH_SURFACE) tma_prefetch_l2(P.sfv + e0 * SFV, bs);
+        if (WITH_SURFACE) tma_prefetch_l2(P.sfv + e0 * SFV, bs);  // (bs: both elements' faces)
         if (need_ut) tma_prefetch_l2(P.u_tmp + e0 * CONS, bu);
         // warm L2 for the elements that will occupy this CTA slot next (blocks are scheduled in index order:
         // one wave further on), so their u tile sees L2 instead of HBM latency
@@ -197,7 +205,7 @@ __global__ void __launch_bounds__(TunedCfg::THREADS, TunedCfg::MIN_BLOCKS)
         o[1] = v1;
         o[2] = v2;
         o[3] = v3;
-        o[4] = pr;
+        o[4] = pr + pr;
         o[5] = lr;
         o[6] = lr - log_pos(pr);
     }
@@ -228,11 +236,23 @@ __global__ void __launch_bounds__(TunedCfg::THREADS, TunedCfg::MIN_BLOCKS)
             q[m][5] = src[5];
             q[m][6] = src[6];
         }
+        if (WITH_SURFACE && d == 2) {
+            // the prim tile has been read for the last time: the surface fluxes land in its storage while the z
+            // pass computes
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+                constexpr uint32_t bs1 = SFV * sizeof(double);
+                mbar_expect_tx(bar_s, bs);
+                tma_load(smem_u32(s_sfv), P.sfv + e0 * SFV, bs1, bar_s);
+                if (nvalid == EPB) tma_load(smem_u32(s_sfv + C::SFV_H), P.sfv + (e0 + 1) * SFV, bs1, bar_s);
+            }
+        }
         // du[a] += D_split[a, b] f(a, b), du[b] += D_split[b, a] f(a, b) for the 6 pairs a < b of the line;
         // dsplit_h = D_split / 2 and dsplit_q = D_split / 4 undo the scaling of g
         double g[5];
 #define TB_PAIR(a, b, FIRST_A, FIRST_B)                                                                        \
-    ranocha_pair_rot(q[a], q[b], igm1x2, g);                                                                   \
+    ranocha_pair_rot(q[a], q[b], igm1, g);                                                                   \
     acc[a][0] = FIRST_A ? P.dsplit_h[a + 4 * b] * g[0] : fma(P.dsplit_h[a + 4 * b], g[0], acc[a][0]);          \
     acc[b][0] = FIRST_B ? P.dsplit_h[b + 4 * a] * g[0] : fma(P.dsplit_h[b + 4 * a], g[0], acc[b][0]);          \
     _Pragma("unroll") for (int v = 1; v < 5; ++v) {                                                            \
@@ -284,16 +304,14 @@ __global__ void __launch_bounds__(TunedCfg::THREADS, TunedCfg::MIN_BLOCKS)
         val[k][3] = o[3] + acc[k][1];
         val[k][4] = o[4] + acc[k][4];
     }
-    // the prim and du tiles are dead now: fetch surface_flux_values and u_tmp into their storage
-    const bool late = WITH_SURFACE || need_ut;
+    // the du tile is dead now: u_tmp takes its place
     fence_proxy_async();
     __syncwarp();
-    if (late) {
-        if (lane == 0) {
-            mbar_expect_tx(bar_s, (WITH_SURFACE ? bs : 0u) + (need_ut ? bu : 0u));
-            if (WITH_SURFACE) tma_load(smem_u32(s_sfv), P.sfv + e0 * SFV, bs, bar_s);
-            if (need_ut) tma_load(smem_u32(s_ut), P.u_tmp + e0 * CONS, bu, bar_s);
-        }
+    if (need_ut && lane == 0) {
+        mbar_expect_tx(bar_t, bu);
+        tma_load(smem_u32(s_ut), P.u_tmp + e0 * CONS, bu, bar_t);
+    }
+    if (WITH_SURFACE) {
         while (!mbar_try_wait(bar_s, 0)) {
         }
     }
@@ -301,9 +319,9 @@ __global__ void __launch_bounds__(TunedCfg::THREADS, TunedCfg::MIN_BLOCKS)
         const int i = a0, j = a1;
         if constexpr (WITH_SURFACE) {
             // calc_surface_integral! (dg_3d.jl:1337-1394): directions 1..6 = -x,+x,-y,+y,-z,+z
-            const double *ssf = s_sfv + eh * SFV;
+            const double *ssf = s_sfv + eh * C::SFV_H;
             if (i == 0 || i == 3) {
-                const double *sf = ssf + ((i == 0 ? 0 : 1) * 16 + j) * 5;
+                const double *sf = ssf + (i == 0 ? 0 : 80) + j * 5;
                 const double w = i == 0 ? -P.inv_weight0 : P.inv_weight0;
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
@@ -311,7 +329,7 @@ __global__ void __launch_bounds__(TunedCfg::THREADS, TunedCfg::MIN_BLOCKS)
                     for (int v = 0; v < 5; ++v) val[k][v] = fma(sf[20 * k + v], w, val[k][v]);
             }
             if (j == 0 || j == 3) {
-                const double *sf = ssf + ((j == 0 ? 2 : 3) * 16 + i) * 5;
+                const double *sf = ssf + (j == 0 ? 160 : 240) + i * 5;
                 const double w = j == 0 ? -P.inv_weight0 : P.inv_weight0;
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
@@ -319,7 +337,7 @@ __global__ void __launch_bounds__(TunedCfg::THREADS, TunedCfg::MIN_BLOCKS)
                     for (int v = 0; v < 5; ++v) val[k][v] = fma(sf[20 * k + v], w, val[k][v]);
             }
             {
-                const double *sf = ssf + (4 * 16 + t) * 5;
+                const double *sf = ssf + 320 + t * 5;
 #pragma unroll
                 for (int v = 0; v < 5; ++v) {
                     val[0][v] = fma(sf[v], -P.inv_weight0, val[0][v]);
@@ -356,6 +374,10 @@ __global__ void __launch_bounds__(TunedCfg::THREADS, TunedCfg::MIN_BLOCKS)
             }
         }
         double *const sut = s_ut + eh * CONS;
+        if (need_ut) {
+            while (!mbar_try_wait(bar_t, 0)) {
+            }
+        }
         if (!rk) {
 #pragma unroll
             for (int k = 0; k < 4; ++k)
@@ -376,7 +398,7 @@ __global__ void __launch_bounds__(TunedCfg::THREADS, TunedCfg::MIN_BLOCKS)
                 for (int v = 0; v < 5; ++v) sut[(t + 16 * k) * 5 + v] = val[k][v];
             if (!resident) {
                 __syncwarp();  // every thread is done with surface_flux_values: b dt u_tmp takes its place
-                double *const sinc = s_sfv + eh * CONS;
+                double *const sinc = s_inc + eh * CONS;
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
 #pragma unroll
@@ -442,7 +464,7 @@ __global__ void __launch_bounds__(TunedCfg::THREADS, TunedCfg::MIN_BLOCKS)
             if (resident)
                 tma_store(P.u_out + e0 * CONS, smem_u32(s_u), bu);
             else
-                tma_reduce_add_f64(P.u_out + e0 * CONS, smem_u32(s_sfv), bu);
+                tma_reduce_add_f64(P.u_out + e0 * CONS, smem_u32(s_inc), bu);
         }
         tma_store_commit_and_wait_read();
     }

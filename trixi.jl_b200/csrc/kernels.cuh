@@ -494,7 +494,8 @@ __global__ void __launch_bounds__(256) k_mpi_pack(const KParams P) {
     for (int v = 0; v < NV; ++v) dst[v] = pu[v];
     if (fn == 0 && P.volume_integral == TRIXI_B200_VOLINT_SHOCK_CAPTURING_HG)
         P.peer_recv[slot][P.mpi_peer_nmpi[slot] * NF * NV + P.mpi_remote_index[I]] = P.alpha_raw[element];
-    __threadfence_system();
+    // (no fence here: the signal kernel that follows in stream order issues one system-scope fence per peer before
+    // it raises the flag, and fences are cumulative over everything that happened before the kernel started)
 }
 
 // calc_mpi_interface_flux! (dg_2d_parallel.jl:700-740, dg_3d_parallel.jl:167-242): the shared flux is
@@ -532,6 +533,103 @@ __global__ void __launch_bounds__(256) k_mpi_interface_flux(const KParams P) {
     surface_numflux<EQ, FAST>(eq, P.surface_flux, ul, ur, o, f);
 #pragma unroll
     for (int v = 0; v < NV; ++v) s[v] = f[v];
+}
+
+// The same stage in the form of k_interface_flux_staged: a warp owns 32 / NF shared faces, gathers the local side
+// from u with lane-consecutive addresses, copies the neighbour rank's side from the receive buffer (already one
+// contiguous [NV, NF] record per face), computes one flux per lane with exactly the arithmetic of the local
+// interface kernel (N ranks must reproduce one rank bit for bit) and writes the local element's face coalesced.
+template <class EQ, int N, int FAST = 0>
+__global__ void __launch_bounds__(256, EQ::kHasNoncons ? 3 : (FAST == 1 ? 6 : (FAST == 2 ? 5 : 4)))
+    k_mpi_interface_flux_staged(const KParams P) {
+    constexpr int ND = EQ::NDIMS, NV = EQ::NVARS, NF = ipow(N, ND - 1), NN = ipow(N, ND);
+    constexpr int G = 32 / NF, FV = NF * NV, WPB = 8;
+    static_assert(32 % NF == 0, "staged interface kernel needs NF | 32");
+    __shared__ double s_all[WPB][2 * G * FV];
+    __shared__ long long s_elem[WPB][G];
+    __shared__ int s_orient[WPB][G], s_side[WPB][G];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double *s = s_all[warp];
+    const long long I0 = ((long long)blockIdx.x * WPB + warp) * G;
+    if (I0 >= P.nmpi) return;  // the whole warp leaves together
+    const int nvalid = (int)min((long long)G, P.nmpi - I0);
+    if (lane < nvalid) {
+        s_elem[warp][lane] = P.mpi_local[I0 + lane] - 1;
+        s_orient[warp][lane] = (int)P.mpi_orient[I0 + lane] - 1;
+        s_side[warp][lane] = (int)P.mpi_side[I0 + lane];
+    }
+    __syncwarp();
+    constexpr int PASSES = (FV + 31) / 32;
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+        if (g < nvalid) {
+            const int o = s_orient[warp][g], side = s_side[warp][g];
+            const int S = o == 0 ? 1 : (o == 1 ? N : N * N);
+            const int SA = o == 0 ? N : 1;
+            const int SB = (ND == 3 && o == 2) ? N : N * N;
+            // local element on the left/- side (side 1): its +face; on the right/+ side: its -face
+            const double *base = P.u + (s_elem[warp][g] * NN + (side == 1 ? (N - 1) * S : 0)) * NV;
+            const double *remote = P.recv + (I0 + g) * FV;
+            double *sl = s + (2 * g + (side == 1 ? 0 : 1)) * FV, *sr = s + (2 * g + (side == 1 ? 1 : 0)) * FV;
+#pragma unroll
+            for (int p = 0; p < PASSES; ++p) {
+                const int q = lane + 32 * p;
+                if (q < FV) {
+                    const int fnq = q / NV, v = q - fnq * NV, b = fnq / N, a = fnq - b * N;
+                    sl[q] = base[(a * SA + b * SB) * NV + v];
+                    sr[q] = remote[q];
+                }
+            }
+        }
+    }
+    __syncwarp();
+    const int g = lane / NF, fn = lane - g * NF;
+    double fl[NV], fr[NV];
+    if (g < nvalid) {
+        const EQ eq(P.eq);
+        const int o = s_orient[warp][g];
+        double f[NV];
+        constexpr bool kFromMemory = FAST == 2 && HasFastRanocha<EQ>::value;
+        if constexpr (kFromMemory) {
+            eq.flux_llf_fast_mem(P.surface_flux, s + (2 * g) * FV + fn * NV, s + (2 * g + 1) * FV + fn * NV, o, f);
+#pragma unroll
+            for (int v = 0; v < NV; ++v) fl[v] = fr[v] = f[v];
+        } else {
+            double ul[NV], ur[NV];
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+                ul[v] = s[(2 * g) * FV + fn * NV + v];
+                ur[v] = s[(2 * g + 1) * FV + fn * NV + v];
+            }
+            if constexpr (EQ::kHasNoncons) {
+                surface_flux_noncons<EQ>(eq, P.surface_flux, ul, ur, o, fl, fr);
+            } else {
+                surface_numflux<EQ, FAST>(eq, P.surface_flux, ul, ur, o, f);
+#pragma unroll
+                for (int v = 0; v < NV; ++v) fl[v] = fr[v] = f[v];
+            }
+        }
+    }
+    __syncwarp();
+    if (g < nvalid) {
+        const bool left = s_side[warp][g] == 1;  // the local element takes the flux of its own side
+#pragma unroll
+        for (int v = 0; v < NV; ++v) s[g * FV + fn * NV + v] = left ? fl[v] : fr[v];
+    }
+    __syncwarp();
+#pragma unroll
+    for (int g2 = 0; g2 < G; ++g2) {
+        if (g2 < nvalid) {
+            const int o = s_orient[warp][g2];
+            const int dir = s_side[warp][g2] == 1 ? 2 * o + 1 : 2 * o;
+            double *dst = P.sfv + ((s_elem[warp][g2] * (2 * ND) + dir) * NF) * NV;
+#pragma unroll
+            for (int p = 0; p < PASSES; ++p) {
+                const int q = lane + 32 * p;
+                if (q < FV) dst[q] = s[g2 * FV + q];
+            }
+        }
+    }
 }
 
 // ---- 3. element kernel ----------------------------------------------------------------------------
@@ -1445,7 +1543,6 @@ __global__ void __launch_bounds__(256) k_mpi_pack_p4est(const KParams P) {
     double *dst = P.peer_recv[P.mpi_peer_slot[I]] + (P.mpi_remote_index[I] * NF + fn) * NV;
 #pragma unroll
     for (int v = 0; v < NV; ++v) dst[v] = pu[v];
-    __threadfence_system();
 }
 
 // calc_mpi_interface_flux! (dgsem_p4est/dg_3d_parallel.jl:167-273): each rank uses the outward normal of its

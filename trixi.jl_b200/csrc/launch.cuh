@@ -122,6 +122,19 @@ void launch_mpi_interface_flux(const KParams &P, cudaStream_t s) {
         k_mpi_interface_flux_p4est<EQ, N><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(P);
     else {
         const int fast = fast_surface_flux_mode<EQ>(P);
+        if constexpr (32 % NF == 0) {
+            if (P.kernel_path != 1) {
+                const long long per_block = 8 * (32 / NF);
+                const unsigned sblocks = (unsigned)((P.nmpi + per_block - 1) / per_block);
+                if (fast == 1)
+                    k_mpi_interface_flux_staged<EQ, N, 1><<<sblocks, 256, 0, s>>>(P);
+                else if (fast == 2)
+                    k_mpi_interface_flux_staged<EQ, N, 2><<<sblocks, 256, 0, s>>>(P);
+                else
+                    k_mpi_interface_flux_staged<EQ, N><<<sblocks, 256, 0, s>>>(P);
+                return;
+            }
+        }
         if (fast == 1)
             k_mpi_interface_flux<EQ, N, 1><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(P);
         else if (fast == 2)
@@ -299,6 +312,9 @@ cudaError_t preload_all() {
         TB_PRELOAD((k_interface_flux_staged<EQ, N, 1>));
         TB_PRELOAD((k_interface_flux_staged<EQ, N, 2>));
         if constexpr (!EQ::kHasNoncons) TB_PRELOAD((k_interface_flux_staged<EQ, N, 0, true>));
+        TB_PRELOAD((k_mpi_interface_flux_staged<EQ, N>));
+        TB_PRELOAD((k_mpi_interface_flux_staged<EQ, N, 1>));
+        TB_PRELOAD((k_mpi_interface_flux_staged<EQ, N, 2>));
     }
     TB_PRELOAD((k_mpi_interface_flux<EQ, N, 1>));
     TB_PRELOAD((k_mpi_interface_flux<EQ, N, 2>));

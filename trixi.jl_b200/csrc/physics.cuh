@@ -57,9 +57,13 @@ TB_DEV double fast_rcp(double x) {
     r = fma(r, e, r);
     return r;
 }
-// a / b with one residual correction (Markstein): correctly rounded except in rare ties
+// a / b: seed, ONE Newton step (relative error e1 ~ 2^-40) and a residual correction of the quotient (Markstein):
+// q' = q + r (a - b q) has relative error e1^2 before its final rounding, so the second Newton step of fast_rcp
+// would buy nothing here.  Correctly rounded except in rare ties.
 TB_DEV double fast_div(double a, double b) {
-    const double r = fast_rcp(b);
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+    r = fma(r, fma(-b, r, 1.0), r);
     const double q = a * r;
     return fma(fma(-b, q, a), r, q);
 }
@@ -713,6 +717,19 @@ struct Euler {
                 s[1] = s[2] = rhox * (1 - C_grav * rho);
                 s[3] = rhox * (1 - 3 * C_grav * rho);
             }
+        } else if (id == TRIXI_B200_SRC_EOC_TEST_COUPLED_EULER_GRAVITY) {
+            double si, co;
+            sincospi(xs - t, &si, &co);
+            const double rhox = 0.1 * M_PI * co, rho = 2 + 0.1 * si;
+            if constexpr (ND == 3) {  // compressible_euler_3d.jl:228-249
+                const double C_grav = -4.0 * 1 / (3 * M_PI);
+                s[0] = s[1] = s[2] = s[3] = 2 * rhox;
+                s[4] = 2 * rhox * (1.5 - C_grav * rho);
+            } else {  // compressible_euler_2d.jl:241-261
+                const double C_grav = -2.0 * 1 / M_PI;
+                s[0] = s[1] = s[2] = rhox;
+                s[3] = (1 - C_grav * rho) * rhox;
+            }
         } else {
 #pragma unroll
             for (int v = 0; v < NVARS; ++v) s[v] = 0.0;
@@ -720,7 +737,18 @@ struct Euler {
     }
 
     TB_DEV void initial_condition(int id, const double (&x)[ND], double t, double (&u)[NVARS]) const {
-        if (id == TRIXI_B200_IC_CONSTANT) {  // compressible_euler_3d.jl:78-86
+        if (id == TRIXI_B200_IC_EOC_TEST_COUPLED_EULER_GRAVITY) {
+            // compressible_euler_3d.jl:196-215 / compressible_euler_2d.jl:212-230 (gamma = 2 is the caller's business)
+            double xs = 0.0;
+#pragma unroll
+            for (int d = 0; d < ND; ++d) xs += x[d];
+            const double ini = 2 + 0.1 * sinpi(xs - t);
+            const double p = ND == 3 ? ini * ini * 1 * 2 / (3 * M_PI) : ini * ini * 1 / M_PI;
+            u[0] = ini;
+#pragma unroll
+            for (int d = 0; d < ND; ++d) u[1 + d] = ini * 1.0;
+            u[ND + 1] = p * inv_gm1 + 0.5 * (ND * (ini * 1.0) * 1.0);
+        } else if (id == TRIXI_B200_IC_CONSTANT) {  // compressible_euler_3d.jl:78-86
             u[0] = 1.0;
             u[1] = 0.1;
             u[2] = -0.2;

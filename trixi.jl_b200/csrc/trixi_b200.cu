@@ -223,8 +223,7 @@ __global__ void k_stage_ssp(double *__restrict__ u, const double *__restrict__ u
 // start_mpi_send! completion: after the pack kernel (stream order) every peer's flag for me is raised to
 // the sequence number of this RHS evaluation
 __global__ void k_mpi_signal(unsigned long long *const *peer_flag, int npeers, unsigned long long seq) {
-    const int p = threadIdx.x;
-    if (p < npeers) {
+    for (int p = threadIdx.x; p < npeers; p += blockDim.x) {  // (world_size <= 64: up to 63 peers)
         __threadfence_system();
         *reinterpret_cast<volatile unsigned long long *>(peer_flag[p]) = seq;
         __threadfence_system();
@@ -233,8 +232,7 @@ __global__ void k_mpi_signal(unsigned long long *const *peer_flag, int npeers, u
 // finish_mpi_receive! (dg_parallel.jl:134-182): wait until every neighbour rank has delivered its faces
 __global__ void k_mpi_wait(const unsigned long long *flags, const int *peer_ranks, int npeers,
                            unsigned long long seq) {
-    const int p = threadIdx.x;
-    if (p < npeers) {
+    for (int p = threadIdx.x; p < npeers; p += blockDim.x) {
         const volatile unsigned long long *f = flags + peer_ranks[p];
         while (*f < seq) {
         }
@@ -636,6 +634,35 @@ TRIXI_B200_API int trixi_b200_create(const trixi_b200_desc *d, trixi_b200_handle
     }
     if (d->nelements < 0 || d->ninterfaces < 0 || d->nboundaries < 0)
         return fail(nullptr, TRIXI_B200_EINVAL, "negative container size");
+
+    // registry entries the device implements (physics.cuh): anything else would run with zero sources / NaN
+    // boundary states without an error, so it is refused here
+    {
+        const bool euler = d->equation == TRIXI_B200_EQ_EULER_2D || d->equation == TRIXI_B200_EQ_EULER_3D;
+        const bool advection = d->equation == TRIXI_B200_EQ_ADVECTION_2D || d->equation == TRIXI_B200_EQ_ADVECTION_3D;
+        const int src = d->source_terms;
+        const bool src_ok = src == TRIXI_B200_SRC_NONE ||
+                            (euler && (src == TRIXI_B200_SRC_CONVERGENCE_TEST || src == TRIXI_B200_SRC_EOC_TEST_EULER ||
+                                       src == TRIXI_B200_SRC_EOC_TEST_COUPLED_EULER_GRAVITY));
+        if (!src_ok)
+            return fail(nullptr, TRIXI_B200_EINVAL, "source terms %d are not implemented on the device for equation %d", src,
+                        d->equation);
+        for (int k = 0; k < 2 * d->ndims && k < 6; ++k) {
+            const int bc = d->boundary_conditions[k], ic = d->boundary_ic[k];
+            if (bc != TRIXI_B200_BC_PERIODIC && bc != TRIXI_B200_BC_DIRICHLET && bc != TRIXI_B200_BC_SLIP_WALL)
+                return fail(nullptr, TRIXI_B200_EINVAL, "unknown boundary condition %d in direction %d", bc, k + 1);
+            if (bc == TRIXI_B200_BC_SLIP_WALL && !euler)
+                return fail(nullptr, TRIXI_B200_EINVAL, "boundary_condition_slip_wall needs the compressible Euler equations");
+            if (bc != TRIXI_B200_BC_DIRICHLET) continue;
+            const bool ic_ok = ic == TRIXI_B200_IC_CONSTANT || ((euler || advection) && ic == TRIXI_B200_IC_CONVERGENCE_TEST) ||
+                               (euler && (ic == TRIXI_B200_IC_WEAK_BLAST_WAVE ||
+                                          ic == TRIXI_B200_IC_EOC_TEST_COUPLED_EULER_GRAVITY));
+            if (!ic_ok)
+                return fail(nullptr, TRIXI_B200_EINVAL,
+                            "Dirichlet boundary state %d (direction %d) is not implemented on the device for equation %d", ic,
+                            k + 1, d->equation);
+        }
+    }
 
     const Launchers *L = nullptr;
     switch (d->equation) {
@@ -1283,6 +1310,7 @@ TRIXI_B200_API int trixi_b200_set_eq_param(trixi_b200_handle *h, int index, doub
     if (!h) return TRIXI_B200_EINVAL;
     if (index < 0 || index >= 8) return fail(h, TRIXI_B200_EINVAL, "equation parameter index %d out of range", index);
     h->P.eq.p[index] = value;
+    h->cfl_valid = false;  // wave speeds reduced by the last RK stage used the old parameter (c_h of GlmSpeedCallback)
     return 0;
 }
 

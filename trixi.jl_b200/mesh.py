@@ -153,11 +153,13 @@ class TreeMesh:
         return mask
 
     def refine_box(self, coordinates_min, coordinates_max):
-        # refine_box! abstract_tree.jl:405-419: cells whose midpoint lies inside the box
+        # refine_box! abstract_tree.jl:405-419: cells whose midpoint lies strictly inside the box
+        if any(lo > hi for lo, hi in zip(coordinates_min, coordinates_max)):
+            raise ValueError("coordinates_min must not exceed coordinates_max")  # coordinates_min_max_check
         x = self.cell_coordinates()
         inside = np.ones(self.ncells, dtype=bool)
         for d in range(self.ndims):
-            inside &= (x[d] >= coordinates_min[d]) & (x[d] <= coordinates_max[d])
+            inside &= (x[d] > coordinates_min[d]) & (x[d] < coordinates_max[d])
         self.refine_cells(inside)
 
     # ---- neighbour search -----------------------------------------------------------------------

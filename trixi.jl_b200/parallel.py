@@ -56,10 +56,16 @@ class HostHaloExchange:
 
 
 def allreduce_min(value, dist):
+    """min over ranks that propagates NaN like the reference's `min` (a NaN dt must abort every rank, not just the
+    one that produced it: the others would otherwise wait in the halo exchange forever)."""
+    import math
+
     import torch
-    t = torch.tensor([value], dtype=torch.float64)
+    v = float(value)
+    t = torch.tensor([-math.inf if math.isnan(v) else v], dtype=torch.float64)
     if dist is not None and dist.is_initialized() and dist.get_world_size() > 1:
         if dist.get_backend() == "nccl":
             t = t.cuda()
         dist.all_reduce(t, op=dist.ReduceOp.MIN)
-    return float(t.item())
+    out = float(t.item())
+    return math.nan if out == -math.inf else out
