@@ -83,6 +83,17 @@ WORKLOADS = {
                           "kernel": "k_element_euler3d_weak_p3<curved> (contravariant fluxes, nodal Jacobian, TMA tiles)"},
     "p4est_curved": {"nvars": 5, "bytes": 212.0 + 72.0 + 8.0, "flop": 149.0 + 45.0 + 45.0,
                      "kernel": "k_element_euler3d_weak_p3<curved> (P4estMesh: + surface integral, TMA tiles)"},
+    # curved flux differencing: u + sfv + 0.8 u_tmp + contravariant vectors (72) + nodal
+    # Jacobian (8) read, u_tmp + u written
+    "structured_ec": {"nvars": 5, "bytes": 212.0 + 72.0 + 8.0, "flop": None,
+                      "kernel": "k_element_euler3d_ranocha_curved_p3 (flux_ranocha along averaged contravariant vectors, "
+                                "line per thread, TMA tiles)"},
+    "p4est_ec": {"nvars": 5, "bytes": 212.0 + 72.0 + 8.0, "flop": None,
+                 "kernel": "k_element_euler3d_ranocha_curved_p3 (P4estMesh: + surface integral)"},
+    # the reference's own GPU benchmark (benchmark/CUDA/elixir_euler_taylor_green_vortex.jl + run.jl): P4estMesh
+    # 4^3 trees, polydeg 5, flux_ranocha volume + flux_lax_friedrichs surface, CarpenterKennedy2N54
+    "p4est_tgv_p5": {"nvars": 5, "bytes": 212.0 + 72.0 + 8.0, "flop": None,
+                     "kernel": "k_element_curved<Euler3D, 6> (generic one-thread-per-node flux differencing, polydeg 5)"},
     "mhd_ec": {"nvars": 9, "bytes": 9 * 8 * (1 + 1.5 + 0.8 + 2), "flop": None,
                "kernel": "k_element_fd3d_p3<Mhd3D> (line sweeps, Hindenlang-Gassner + Powell nonconservative, TMA tiles)"},
 }
@@ -132,6 +143,30 @@ def make_semi(level, device=-1, rank=0, world=1, comm=None, workload="euler_ec")
             mesh = T.P4estMesh((trees,) * 3, polydeg=3, mapping=_warped_mapping_3d, periodicity=True,
                                initial_refinement_level=int(np.log2(n // trees)))
         return T.SemidiscretizationHyperbolic(mesh, eq, T.initial_condition_constant, solver, **kw)
+    if workload in ("structured_ec", "p4est_ec"):
+        # examples/structured_3d_dgsem/elixir_euler_ec.jl / p4est_3d_dgsem/elixir_euler_ec.jl at polydeg 3: entropy
+        # conservative flux differencing on the warped mapping (the P4estMesh elixir reads a mesh file; here the same
+        # mapping on a programmatic forest)
+        eq = T.CompressibleEulerEquations3D(5 / 3)
+        solver = T.DGSEM(polydeg=3, surface_flux=T.flux_ranocha,
+                         volume_integral=T.VolumeIntegralFluxDifferencing(T.flux_ranocha))
+        if workload == "structured_ec":
+            mesh = T.StructuredMesh((n, n, n), _warped_mapping_3d, periodicity=True)
+        else:
+            trees = min(n, 4)
+            mesh = T.P4estMesh((trees,) * 3, polydeg=3, mapping=_warped_mapping_3d, periodicity=True,
+                               initial_refinement_level=int(np.log2(n // trees)))
+        return T.SemidiscretizationHyperbolic(mesh, eq, T.initial_condition_weak_blast_wave, solver, **kw)
+    if workload == "p4est_tgv_p5":
+        # benchmark/CUDA/elixir_euler_taylor_green_vortex.jl:29-44 (run.jl: initial_refinement_level = 3 -> 32^3
+        # elements = 7.1 M DOF, which is --level 5 here)
+        eq = T.CompressibleEulerEquations3D(1.4)
+        solver = T.DGSEM(polydeg=5, surface_flux=T.flux_lax_friedrichs,
+                         volume_integral=T.VolumeIntegralFluxDifferencing(T.flux_ranocha))
+        trees = min(n, 4)
+        mesh = T.P4estMesh((trees,) * 3, polydeg=1, coordinates_min=(-np.pi,) * 3, coordinates_max=(np.pi,) * 3,
+                           periodicity=True, initial_refinement_level=int(np.log2(n // trees)))
+        return T.SemidiscretizationHyperbolic(mesh, eq, T.initial_condition_taylor_green_vortex, solver, **kw)
     if workload == "euler_sc":
         # examples/tree_3d_dgsem/elixir_euler_shockcapturing.jl
         eq = T.CompressibleEulerEquations3D(1.4)
@@ -170,8 +205,15 @@ def workload_name(level, world=1, workload="euler_ec"):
                 "p4est_curved": "the same warped mapping on a conforming P4estMesh (4^3 trees), 3D Euler weak "
                                 "form + LLF(naive)",
                 "mhd_ec": "tree_3d_dgsem/elixir_mhd_ec.jl: ideal GLM-MHD, flux differencing with "
-                          "flux_hindenlang_gassner + flux_nonconservative_powell, TreeMesh"}[workload]
-        return f"{desc}, polydeg=3, {n}^3 elements ({64 * n**3 / 1e6:.1f} M DOF) per rank, periodic"
+                          "flux_hindenlang_gassner + flux_nonconservative_powell, TreeMesh",
+                "structured_ec": "structured_3d_dgsem/elixir_euler_ec.jl at polydeg 3: 3D Euler EC flux differencing "
+                                 "(flux_ranocha) on the warped StructuredMesh",
+                "p4est_ec": "p4est_3d_dgsem/elixir_euler_ec.jl at polydeg 3 on a programmatic warped forest (4^3 "
+                            "trees): 3D Euler EC flux differencing (flux_ranocha), P4estMesh",
+                "p4est_tgv_p5": "benchmark/CUDA/elixir_euler_taylor_green_vortex.jl (the reference's GPU benchmark): "
+                                "P4estMesh 4^3 trees, flux_ranocha volume + flux_lax_friedrichs surface"}[workload]
+        pd = 5 if workload == "p4est_tgv_p5" else 3
+        return (f"{desc}, polydeg={pd}, {n}^3 elements ({(pd + 1)**3 * n**3 / 1e6:.1f} M DOF) per rank, periodic")
     base = ("tree_3d_dgsem/elixir_euler_ec.jl: 3D Euler EC flux differencing (flux_ranocha), polydeg=3, ")
     if world == 1 and not CELLS:
         return base + (f"TreeMesh level {level} ({n}^3 elements, {64 * n**3 / 1e6:.1f} M DOF), periodic, "
@@ -424,6 +466,7 @@ def run_b200(args, rank, world, local_rank):
     surf_ms, surf_n = gpu.profile_read(0)
     cfl_ms, cfl_n = gpu.profile_read(2)
     halo_ms, halo_n = gpu.profile_read(3)
+    wait_ms, wait_n = gpu.profile_read(4)
     gpu.profile_enable(False)
     clocks = sampler.stop() if rank == 0 else None
 
@@ -555,7 +598,8 @@ def run_b200(args, rank, world, local_rank):
                              / (surf_ms / max(surf_n, 1) * 1e-3) * 1e-9) if surf_n else None,
                 "peak": peaks["hbm_gbs"], "unit": "GB/s"},
             "kernel_time_share": {"surface_flux_ms": surf_ms, "element_ms": elem_ms, "max_dt_ms": cfl_ms,
-                                  "halo_pack_wait_mpiflux_ms": halo_ms, "timed_region_ms": ms_max},
+                                  "halo_pack_wait_mpiflux_ms": halo_ms + wait_ms, "halo_wait_ms": wait_ms,
+                                  "timed_region_ms": ms_max},
             "wall_s": wall, "finite": finite,
         }
         if cpu:

@@ -326,7 +326,8 @@ TRIXI_B200_API int trixi_b200_measure_fp64_peak(trixi_b200_handle *h, double *tf
 TRIXI_B200_API int trixi_b200_measure_copy_bandwidth(trixi_b200_handle *h, double *gbs_out);
 /* per-kernel-class accumulated device time (ms) and launch counts since the last reset; classes:
  * 0 = surface-flux kernel, 1 = element kernel (volume+surface+jacobian+source+RK), 2 = max_dt,
- * 3 = halo pack/unpack.  Enabling costs two event records per launch. */
+ * 3 = halo pack + signal + MPI interface flux, 4 = halo wait (spinning on the neighbours' flags: skew between
+ * ranks shows up here).  Enabling costs two event records per launch. */
 TRIXI_B200_API int trixi_b200_profile_enable(trixi_b200_handle *h, int on);
 TRIXI_B200_API int trixi_b200_profile_read(trixi_b200_handle *h, int kernel_class, double *ms_out, int64_t *launches_out);
 

@@ -61,16 +61,11 @@ TB_DEV double log_pos(double x) {
     return fma(dk, kLogC[7], (fma(s, hfsq + R, dk * kLogC[8]) - hfsq) + f);
 }
 
-// 4 * flux_ranocha(u_ll, u_rr, orientation) (compressible_euler_3d.jl:746-793) on hoisted node records whose
-// velocity components have been rotated so that slot 1 is the normal one: (rho, vn, vt1, vt2, 2 p, log rho,
-// log rho - log p).  The output is rotated the same way and scaled by powers of two that the caller's D_split
-// weights undo: g = (2 f_rho, 4 f_n, 4 f_t1, 4 f_t2, 4 f_E) -- the halves of the arithmetic means never get
-// multiplied out, and the record carries 2 p so that the doubled pressure terms need no doubling either (exact:
-// scaling by 2 commutes with rounding).  igm1 = 1 / (gamma - 1).
-TB_DEV void ranocha_pair_rot(const double (&L)[kNP], const double (&R)[kNP], double igm1, double (&g)[5]) {
+// ln_mean(rho_ll, rho_rr) and 2 p_ll p_rr inv_ln_mean(rho_ll p_rr, rho_rr p_ll) (math.jl:198-250) from node records
+// (rho, ., ., ., 2 p, log rho, log rho - log p): f^2 = ((x - y) / (x + y))^2 decides between the Ismail-Roe series
+// and the hoisted logarithms, and the chosen operands go through ONE division each.
+TB_DEV void ranocha_means(const double *L, const double *R, double &rho_mean, double &inv_rho_p_mean2) {
     const double rho_ll = L[0], p2_ll = L[4], rho_rr = R[0], p2_rr = R[4];
-    // ln_mean(rho_ll, rho_rr) (math.jl:198-210); f^2 = ((x - y) / (x + y))^2
-    double rho_mean;
     {
         const double sum = rho_ll + rho_rr, dif = rho_rr - rho_ll;
         const double f = dif * rcp_1nr(sum), f2 = f * f;
@@ -78,10 +73,8 @@ TB_DEV void ranocha_pair_rot(const double (&L)[kNP], const double (&R)[kNP], dou
         const double poly = fma(f2, fma(f2, fma(f2, 2.0 / 7.0, 2.0 / 5.0), 2.0 / 3.0), 2.0);
         rho_mean = fast_div(series ? sum : dif, series ? poly : R[5] - L[5]);
     }
-    // 2 p_ll p_rr inv_ln_mean(rho_ll p_rr, rho_rr p_ll) (math.jl:238-250) from the doubled pressures:
-    // x = 2 rho_ll p_rr, y = 2 rho_rr p_ll, p2_ll p2_rr inv_ln_mean(x, y) = 2 p_ll p_rr inv_ln_mean(x / 2, y / 2)
-    double inv_rho_p_mean2;
     {
+        // x = 2 rho_ll p_rr, y = 2 rho_rr p_ll: p2_ll p2_rr inv_ln_mean(x, y) = 2 p_ll p_rr inv_ln_mean(x / 2, y / 2)
         const double x = rho_ll * p2_rr, y = rho_rr * p2_ll;
         const double sum = x + y, dif = y - x;
         const double f = dif * rcp_1nr(sum), f2 = f * f;
@@ -91,6 +84,18 @@ TB_DEV void ranocha_pair_rot(const double (&L)[kNP], const double (&R)[kNP], dou
         const double m = fast_div(series ? poly : R[6] - L[6], series ? sum : dif);
         inv_rho_p_mean2 = p2_ll * p2_rr * m;
     }
+}
+
+// 4 * flux_ranocha(u_ll, u_rr, orientation) (compressible_euler_3d.jl:746-793) on hoisted node records whose
+// velocity components have been rotated so that slot 1 is the normal one: (rho, vn, vt1, vt2, 2 p, log rho,
+// log rho - log p).  The output is rotated the same way and scaled by powers of two that the caller's D_split
+// weights undo: g = (2 f_rho, 4 f_n, 4 f_t1, 4 f_t2, 4 f_E) -- the halves of the arithmetic means never get
+// multiplied out, and the record carries 2 p so that the doubled pressure terms need no doubling either (exact:
+// scaling by 2 commutes with rounding).  igm1 = 1 / (gamma - 1).
+TB_DEV void ranocha_pair_rot(const double (&L)[kNP], const double (&R)[kNP], double igm1, double (&g)[5]) {
+    const double p2_ll = L[4], p2_rr = R[4];
+    double rho_mean, inv_rho_p_mean2;
+    ranocha_means(L, R, rho_mean, inv_rho_p_mean2);
     const double sn = L[1] + R[1], st1 = L[2] + R[2], st2 = L[3] + R[3];  // 2 v_avg
     const double vs = L[1] * R[1] + L[2] * R[2] + L[3] * R[3];            // 2 velocity_square_avg
     const double f1 = rho_mean * sn;                                       // 2 f_rho

@@ -107,10 +107,18 @@ void launch_mpi_pack(const KParams &P, cudaStream_t s) {
     constexpr int NF = ipow(N, EQ::NDIMS - 1);
     const long long total = P.nmpi * NF;
     if (total == 0) return;
-    if (P.p4est)
+    if (P.p4est) {
         k_mpi_pack_p4est<EQ, N><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(P);
-    else
-        k_mpi_pack<EQ, N><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(P);
+        return;
+    }
+    if constexpr (32 % NF == 0 && (NF * EQ::NVARS) % 2 == 0) {
+        if (P.kernel_path != 1) {
+            const long long per_block = 8 * (32 / NF);
+            k_mpi_pack_staged<EQ, N><<<(unsigned)((P.nmpi + per_block - 1) / per_block), 256, 0, s>>>(P);
+            return;
+        }
+    }
+    k_mpi_pack<EQ, N><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(P);
 }
 
 template <class EQ, int N>
@@ -172,6 +180,7 @@ void launch_error_norms(const KParams &P, const NormParams &Q, cudaStream_t s) {
 // tuned_euler3d.cu
 cudaError_t launch_element_euler3d_ranocha_p3(const KParams &P, bool with_surface, cudaStream_t s);
 cudaError_t launch_element_euler3d_ranocha_p3_v7(const KParams &P, bool with_surface, cudaStream_t s);
+cudaError_t launch_element_euler3d_ranocha_curved_p3(const KParams &P, bool with_surface, cudaStream_t s);
 cudaError_t launch_element_euler3d_weak_p3(const KParams &P, bool with_surface, cudaStream_t s);
 cudaError_t launch_element_linesweep_euler3d(const KParams &P, bool with_surface, cudaStream_t s);
 cudaError_t launch_element_linesweep_sc_euler3d(const KParams &P, bool with_surface, cudaStream_t s);
@@ -215,8 +224,11 @@ bool uses_tuned_element(const KParams &P) {
     if constexpr (std::is_same_v<EQ, Euler<3>> && N == 4) {
         if (P.kernel_path == 1) return false;
         if (P.volume_integral == TRIXI_B200_VOLINT_WEAK_FORM) return true;  // TreeMesh and curved meshes
-        return !P.curved && (P.volume_integral == TRIXI_B200_VOLINT_FLUX_DIFFERENCING ||       // headline or line sweep
-                             P.volume_integral == TRIXI_B200_VOLINT_SHOCK_CAPTURING_HG);  // blended line sweep
+        if (P.curved)  // flux differencing with flux_ranocha along averaged contravariant vectors
+            return P.volume_integral == TRIXI_B200_VOLINT_FLUX_DIFFERENCING &&
+                   (P.volume_flux == TRIXI_B200_FLUX_RANOCHA || P.volume_flux == TRIXI_B200_FLUX_RANOCHA_TURBO);
+        return P.volume_integral == TRIXI_B200_VOLINT_FLUX_DIFFERENCING ||       // headline or line sweep
+               P.volume_integral == TRIXI_B200_VOLINT_SHOCK_CAPTURING_HG;        // blended line sweep
     }
     if constexpr (std::is_same_v<EQ, Mhd3D> && N == 4) {
         return P.kernel_path != 1 && !P.curved && P.volume_integral == TRIXI_B200_VOLINT_FLUX_DIFFERENCING;
@@ -227,7 +239,9 @@ bool uses_tuned_element(const KParams &P) {
 // true when the RK stage kernel selected for P also reduces the CFL wave speeds (TreeMesh tuned kernels)
 template <class EQ, int N>
 bool fuses_cfl(const KParams &P) {
-    return uses_tuned_element<EQ, N>(P);  // (on curved meshes only the weak-form kernel is tuned; it reduces the CFL too)
+    // (on curved meshes only the weak-form kernel reduces the CFL too; the curved flux-differencing kernel leaves it
+    // to k_max_dt_curved)
+    return uses_tuned_element<EQ, N>(P) && !(P.curved && P.volume_integral != TRIXI_B200_VOLINT_WEAK_FORM);
 }
 
 template <class EQ, int N>
@@ -236,6 +250,7 @@ cudaError_t launch_element(const KParams &P, bool with_surface, cudaStream_t s) 
     if constexpr (std::is_same_v<EQ, Euler<3>> && N == 4) {
         if (uses_tuned_element<EQ, N>(P)) {
             if (P.volume_integral == TRIXI_B200_VOLINT_WEAK_FORM) return launch_element_euler3d_weak_p3(P, with_surface, s);
+            if (P.curved) return launch_element_euler3d_ranocha_curved_p3(P, with_surface, s);
             if (P.volume_integral == TRIXI_B200_VOLINT_SHOCK_CAPTURING_HG)
                 return launch_element_linesweep_sc_euler3d(P, with_surface, s);
             if (P.volume_flux == TRIXI_B200_FLUX_RANOCHA || P.volume_flux == TRIXI_B200_FLUX_RANOCHA_TURBO)
@@ -297,6 +312,7 @@ cudaError_t preload_kernel(K kern) {
 
 cudaError_t preload_tuned_euler3d();       // tuned_euler3d.cu
 cudaError_t preload_tuned_euler3d_v7();
+cudaError_t preload_tuned_euler3d_curved();
 cudaError_t preload_tuned_euler3d_weak();  // tuned_euler3d.cu
 
 template <class EQ, int N>
@@ -312,6 +328,7 @@ cudaError_t preload_all() {
         TB_PRELOAD((k_interface_flux_staged<EQ, N, 1>));
         TB_PRELOAD((k_interface_flux_staged<EQ, N, 2>));
         if constexpr (!EQ::kHasNoncons) TB_PRELOAD((k_interface_flux_staged<EQ, N, 0, true>));
+        if constexpr ((ipow(N, EQ::NDIMS - 1) * EQ::NVARS) % 2 == 0) TB_PRELOAD((k_mpi_pack_staged<EQ, N>));
         TB_PRELOAD((k_mpi_interface_flux_staged<EQ, N>));
         TB_PRELOAD((k_mpi_interface_flux_staged<EQ, N, 1>));
         TB_PRELOAD((k_mpi_interface_flux_staged<EQ, N, 2>));
@@ -349,6 +366,7 @@ cudaError_t preload_all() {
     if constexpr (std::is_same_v<EQ, Euler<3>> && N == 4) {
         if ((e = preload_tuned_euler3d()) != cudaSuccess) return e;
         if ((e = preload_tuned_euler3d_v7()) != cudaSuccess) return e;
+        if ((e = preload_tuned_euler3d_curved()) != cudaSuccess) return e;
         if ((e = preload_tuned_euler3d_weak()) != cudaSuccess) return e;
         return preload_linesweep();
     }

@@ -18,7 +18,7 @@ using namespace tb;
 namespace {
 thread_local std::string g_create_error;
 
-enum { KC_SURFACE = 0, KC_ELEMENT = 1, KC_MAXDT = 2, KC_HALO = 3, KC_COUNT = 4 };
+enum { KC_SURFACE = 0, KC_ELEMENT = 1, KC_MAXDT = 2, KC_HALO = 3, KC_HALO_WAIT = 4, KC_COUNT = 5 };
 
 struct ProfEntry {
     cudaEvent_t a, b;
@@ -48,8 +48,8 @@ struct trixi_b200_handle {
     long long launches = 0;
     bool profiling = false;
     std::vector<ProfEntry> prof;
-    double prof_ms[KC_COUNT] = {0, 0, 0, 0};
-    long long prof_n[KC_COUNT] = {0, 0, 0, 0};
+    double prof_ms[KC_COUNT] = {0, 0, 0, 0, 0};
+    long long prof_n[KC_COUNT] = {0, 0, 0, 0, 0};
     std::string error;
     int rank = 0, world_size = 1;
     // halo exchange state
@@ -322,10 +322,13 @@ int run_all_surface_fluxes(trixi_b200_handle *h, double t) {
     rc = run_surface_fluxes(h, t);
     if (rc) return rc;
     if (dist) {
+        {
+            ProfScope ps(h, KC_HALO_WAIT);
+            const unsigned long long *flags =
+                reinterpret_cast<const unsigned long long *>(h->comm_base) + (size_t)parity * h->world_size;
+            k_mpi_wait<<<1, 32, 0, h->stream>>>(flags, h->d_peer_ranks, npeers, h->comm_seq);
+        }
         ProfScope ps(h, KC_HALO);
-        const unsigned long long *flags =
-            reinterpret_cast<const unsigned long long *>(h->comm_base) + (size_t)parity * h->world_size;
-        k_mpi_wait<<<1, 32, 0, h->stream>>>(flags, h->d_peer_ranks, npeers, h->comm_seq);
         h->L->mpi_interface_flux(h->P, h->stream);
         h->launches += 2;
     }
@@ -803,6 +806,7 @@ TRIXI_B200_API int trixi_b200_create(const trixi_b200_desc *d, trixi_b200_handle
         for (int q = 0; q < 16; ++q) {
             P.dsplit_h[q] = 0.5 * d->derivative_split[q];
             P.dsplit_q[q] = 0.25 * d->derivative_split[q];
+            P.dsplit_e[q] = 0.125 * d->derivative_split[q];
         }
     P.kernel_path = 0;
     P.rk_reduce_update = 1;

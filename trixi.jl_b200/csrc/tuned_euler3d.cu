@@ -2,6 +2,7 @@
 // and the line-sweep flux-differencing kernel for the other two-point fluxes and GLM-MHD.
 #include "kernel_euler3d_fd_p3.cuh"
 #include "kernel_euler3d_fd_p3_v7.cuh"
+#include "kernel_euler3d_fd_curved_p3.cuh"
 #include "kernel_euler3d_weak_p3.cuh"
 #include "kernel_fd3d_p3.cuh"
 
