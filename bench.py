@@ -327,6 +327,43 @@ def cpu_model():
     return "unknown"
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Run this rank on the host cores next to its GPU, so that the pinned host buffers it allocates afterwards are
+    first-touched on that NUMA node and its H2D/D2H copies do not cross the socket interconnect (the end-to-end path
+    is PCIe- and host-memory-bound; with 8 ranks on one socket's memory it collapses).  Returns a short description."""
+    try:
+        import torch
+        props = torch.cuda.get_device_properties(local_rank)
+        bus = getattr(props, "pci_bus_id", None)
+        dom = getattr(props, "pci_domain_id", 0)
+        dev = getattr(props, "pci_device_id", 0)
+        if bus is None:
+            return "pci bus id unknown: affinity unchanged"
+        base = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0"
+        with open(os.path.join(base, "local_cpulist")) as f:
+            cpulist = f.read().strip()
+        node = "?"
+        try:
+            with open(os.path.join(base, "numa_node")) as f:
+                node = f.read().strip()
+        except OSError:
+            pass
+        cpus = set()
+        for part in cpulist.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return f"numa node {node}, {len(allowed)} cores"
+        return f"numa node {node}: no allowed cores, affinity unchanged"
+    except Exception as exc:  # noqa: BLE001 (best effort: the bench must run without sysfs)
+        return f"affinity unchanged ({type(exc).__name__})"
+
+
 def oracle_backend(semi, threads=None):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle
@@ -398,6 +435,8 @@ def run_b200(args, rank, world, local_rank):
     import trixi_b200 as T
 
     torch.cuda.set_device(local_rank)
+    all_cores = os.sched_getaffinity(0)
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else "single rank: affinity unchanged"
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -425,7 +464,7 @@ def run_b200(args, rank, world, local_rank):
     u0 = T.compute_coefficients(0.0, semi)
     gpu.upload(0, u0)
     alg = T.CarpenterKennedy2N54()
-    cfl = 1.3
+    cfl = 0.1 if args.workload == "p4est_tgv_p5" else 1.3  # (the benchmark elixir's own StepsizeCallback(cfl = 0.1))
 
     def new_dt():
         # StepsizeCallback (stepsize.jl:93-126): device max_dt reduction, min over ranks
@@ -516,6 +555,49 @@ def run_b200(args, rank, world, local_rank):
     e2e_rhs_value = total_dofs * e2e_steps / rhs_wall
     e2e_finite = e2e_finite and bool(np.isfinite(du_host).all())
 
+    # ---- BASELINE config 5 beside the headline: Taylor-Green vortex, 100^3 elements (64 M DOF) per rank; on 8 GPUs this
+    # is the 200^3-element / 512 M DOF problem of the config as written (same metric, own timed region) ----------
+    config5 = None
+    if args.workload == "euler_ec" and not args.no_config5:
+        global CELLS
+        saved_cells, CELLS = CELLS, 100
+        try:
+            semi5 = make_semi(args.level, device=local_rank, rank=rank, world=world, comm=dist if world > 1 else None,
+                              workload="tgv")
+            gpu5 = semi5.backend()
+            gpu5.set_option(gpu5.OPT_FUSED_CFL, 1)
+            gpu5.upload(0, T.compute_coefficients(0.0, semi5))
+            dt5 = [cfl * gpu5.max_dt()]
+            if world > 1:
+                dt5[0] = allreduce_min(dt5[0], dist)
+
+            def step5():
+                gpu5.step_2n(0.0, dt5[0], alg.a, alg.b, alg.c)
+                local = cfl * gpu5.max_dt()
+                dt5[0] = allreduce_min(local, dist) if world > 1 else local
+
+            for _ in range(args.warmup):
+                step5()
+            steps5 = min(args.steps, 10)
+            barrier()
+            gpu5.timer_start()
+            for _ in range(steps5):
+                step5()
+            ms5 = gpu5.timer_stop()
+            barrier()
+            t5 = torch.tensor([ms5], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(t5, op=dist.ReduceOp.MAX)
+            ms5 = float(t5.item())
+            config5 = {"workload": workload_name(args.level, world, "tgv"), "total_dofs": semi5.ndofsglobal(),
+                       "value": semi5.ndofsglobal() * 5 * steps5 / (ms5 * 1e-3), "unit": UNIT, "steps": steps5,
+                       "ms_per_step": ms5 / steps5,
+                       "note": "weak scaling at 64 M DOF per GPU: the 8-GPU line is BASELINE config 5 as written "
+                               "(512 M DOF); its 1-GPU line is the per-GPU share to compare with"}
+            del gpu5, semi5
+        finally:
+            CELLS = saved_cells
+
     if rank == 0:
         peaks, peak_kind = measured_peaks()
         fp64_peak = gpu.measure_fp64_peak()
@@ -537,6 +619,7 @@ def run_b200(args, rank, world, local_rank):
             if tj:
                 traffic, traffic_src = tj["dram_bytes_per_dof"] * ndofs, tj["source"]
         cpu = None
+        os.sched_setaffinity(0, all_cores)  # the CPU reference below uses every host core again
         if not args.no_cpu_baseline:
             cv, cwall, cthreads, cdofs = time_cpu_reference(args.cpu_level, 5, 2, args.workload)
             turbo = None
@@ -571,6 +654,7 @@ def run_b200(args, rank, world, local_rank):
                             "trixi_b200_max_dt, pinned host u updated in place; chunked copies overlap the first and "
                             "last stage",
                     "steps": e2e_steps, "ms_per_step": e2e_wall / e2e_steps * 1e3, "finite": e2e_finite,
+                    "host_affinity_rank0": numa,
                     "rhs_call": {"value": e2e_rhs_value, "unit": UNIT, "ms_per_call": rhs_wall / e2e_steps * 1e3,
                                  "call": "rhs_hyperbolic(du_host, u_host, semi, t) -> trixi_b200_rhs_host: H2D u, "
                                          "1 RHS, D2H du per call, chunked so both PCIe directions overlap",
@@ -604,6 +688,8 @@ def run_b200(args, rank, world, local_rank):
         }
         if cpu:
             line["cpu_baseline"] = cpu
+        if config5:
+            line["config5_tgv"] = config5
         emit(line)
     if world > 1:
         dist.destroy_process_group()
@@ -643,6 +729,8 @@ def main():
     ap.add_argument("--workload", default="euler_ec", choices=sorted(WORKLOADS),
                     help="euler_ec is the headline (BASELINE.json); the others are SURVEY.md §8d's secondary configs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-config5", action="store_true",
+                    help="skip the secondary timed region on BASELINE config 5 (TGV, 64 M DOF per GPU)")
     ap.add_argument("--prefetch", type=int, default=None, help="L2 prefetch distance of the tuned element kernel")
     ap.add_argument("--generic-kernels", action="store_true",
                     help="TRIXI_B200_OPT_KERNEL_PATH = 1: the generic one-thread-per-node kernels (before/after numbers)")

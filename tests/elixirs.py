@@ -750,6 +750,25 @@ for _mesh in ("tree", "structured", "p4est"):
                                                 volume_flux=T.flux_ranocha))
 
 
+def _p4est3d_tgv_p5():
+    # benchmark/CUDA/elixir_euler_taylor_green_vortex.jl:29-44 (the reference's GPU benchmark) on 2^3 trees, level 1
+    eq = T.CompressibleEulerEquations3D(1.4)
+    solver = T.DGSEM(polydeg=5, surface_flux=T.flux_lax_friedrichs,
+                     volume_integral=T.VolumeIntegralFluxDifferencing(T.flux_ranocha))
+    mesh = T.P4estMesh((2, 2, 2), polydeg=1, coordinates_min=(-np.pi,) * 3, coordinates_max=(np.pi,) * 3,
+                       periodicity=True, initial_refinement_level=1)
+    return T.SemidiscretizationHyperbolic(mesh, eq, T.initial_condition_taylor_green_vortex, solver)
+
+
+def _p4est3d_curved_p5():
+    # the warped mapping at polydeg 5 (flux_ranocha volume and surface fluxes): curved p = 5 flux differencing
+    eq = T.CompressibleEulerEquations3D(1.4)
+    solver = T.DGSEM(polydeg=5, surface_flux=T.flux_ranocha,
+                     volume_integral=T.VolumeIntegralFluxDifferencing(T.flux_ranocha))
+    mesh = T.P4estMesh((3, 3, 3), polydeg=5, mapping=_warped_mapping_3d, periodicity=True, initial_refinement_level=0)
+    return T.SemidiscretizationHyperbolic(mesh, eq, T.initial_condition_weak_blast_wave, solver)
+
+
 class _Extra:
     """Same interface as Elixir for the tests that only need ``semi()``."""
 
@@ -769,5 +788,7 @@ EXTRA = {e.name: e for e in [
     # the reference's SIMD specialization (flux_ranocha_turbo, dg_3d_compressible_euler.jl:265-617) as the oracle side
     # of the tuned GPU kernel, which evaluates the same hoisted-logarithm form
     _Extra("tree_3d_euler_ec_turbo", lambda **kw: _euler3d_ec(flux=T.flux_ranocha_turbo, **kw)),
+    _Extra("p4est_3d_tgv_p5", _p4est3d_tgv_p5),
+    _Extra("p4est_3d_curved_p5", _p4est3d_curved_p5),
 ]}
 EXTRA.update({name: _Extra(name, build) for name, build in PARITY_EXTRA.items()})

@@ -26,7 +26,7 @@ RHS_TOL = 1e-12
 # elixir_advection_basic.jl in 3D: the advection velocity (0.2, -0.7, 0.5) sums to zero and the initial condition only
 # depends on x + y + z, so du = -a . grad u cancels analytically and du_ref is what rounding leaves of it (the
 # oracle's own FMA/no-FMA difference is 5e-12 there).
-NOISE_LIMITED = {"tree_3d_euler_taylor_green_vortex", "structured_3d_euler_free_stream",
+NOISE_LIMITED = {"tree_3d_euler_taylor_green_vortex", "p4est_3d_tgv_p5", "structured_3d_euler_free_stream",
                  "structured_2d_euler_free_stream", "tree_3d_advection_basic", "structured_3d_advection_basic",
                  "p4est_3d_advection_basic"}
 
@@ -107,7 +107,7 @@ RHS_CASES = ["tree_3d_euler_ec", "tree_3d_euler_source_terms", "tree_3d_euler_so
              "tree_3d_euler_shockcapturing", "tree_2d_euler_shockcapturing", "tree_2d_euler_blast_wave",
              "tree_3d_euler_ec_turbo", "tree_2d_euler_vortex_shockcapturing", "tree_2d_euler_vortex_mortar_shockcapturing",
              "tree_3d_advection_basic", "tree_3d_advection_mortar", "structured_3d_advection_basic",
-             "p4est_3d_advection_basic"] + sorted(PARITY_EXTRA)
+             "p4est_3d_advection_basic", "p4est_3d_tgv_p5", "p4est_3d_curved_p5"] + sorted(PARITY_EXTRA)
 
 
 @pytest.mark.parametrize("name", RHS_CASES)
@@ -331,7 +331,9 @@ def test_shock_capturing_indicator_and_rhs(name, oracle_module):
 
 @pytest.mark.parametrize("name", ["tree_3d_euler_ec", "tree_3d_euler_source_terms", "tree_3d_euler_ec_shima_etal",
                                   "tree_3d_mhd_ec", "tree_3d_euler_shockcapturing", "structured_3d_euler_source_terms",
-                                  "p4est_3d_euler_source_terms_nonperiodic", "tree_3d_euler_taylor_green_vortex"])
+                                  "p4est_3d_euler_source_terms_nonperiodic", "tree_3d_euler_taylor_green_vortex",
+                                  "structured_3d_euler_ec", "p4est_3d_curved_ec", "p4est_3d_curved_level1",
+                                  "p4est_3d_tgv_p5", "p4est_3d_curved_p5"])
 def test_tuned_kernels_match_generic_kernels(name):
     """The performance specializations (TMA line-sweep / weak-form kernels, staged and fast-division interface
     kernels) against the generic one-thread-per-node kernels (TRIXI_B200_OPT_KERNEL_PATH = 1), RHS and two CK54

@@ -22,27 +22,6 @@
 
 namespace tb {
 
-constexpr int kNPC = 16, kNPC_STRIDE = 17;  // rho, v1, v2, v3, 2 p, log rho, log rho - log p, Ja^1, Ja^2, Ja^3
-
-// 8 * flux_ranocha(u_ll, u_rr, 0.5 (ja_ll + ja_rr)) except for the density flux, which comes as 4 f_rho:
-// n = ja_ll + ja_rr, f1 = rho_mean (v_ll . n + v_rr . n) = 4 f_rho, g_m = f1 (v_ll + v_rr) + (2 p_ll + 2 p_rr) n,
-// g_E = f1 (2 velocity_square_avg + 2 inv_rho_p_mean / (gamma - 1)) + (2 p_ll v_rr . n + 2 p_rr v_ll . n)
-TB_DEV void ranocha_pair_normal(const double *L, const double *R, int d, double igm1, double (&g)[5]) {
-    double rho_mean, inv_rho_p_mean2;
-    ranocha_means(L, R, rho_mean, inv_rho_p_mean2);
-    const double *jl = L + 7 + 3 * d, *jr = R + 7 + 3 * d;
-    const double n1 = jl[0] + jr[0], n2 = jl[1] + jr[1], n3 = jl[2] + jr[2];
-    const double vn_ll = L[1] * n1 + L[2] * n2 + L[3] * n3, vn_rr = R[1] * n1 + R[2] * n2 + R[3] * n3;
-    const double p2s = L[4] + R[4];
-    const double vs = L[1] * R[1] + L[2] * R[2] + L[3] * R[3];
-    const double f1 = rho_mean * (vn_ll + vn_rr);
-    g[0] = f1;
-    g[1] = fma(f1, L[1] + R[1], p2s * n1);
-    g[2] = fma(f1, L[2] + R[2], p2s * n2);
-    g[3] = fma(f1, L[3] + R[3], p2s * n3);
-    g[4] = fma(f1, fma(inv_rho_p_mean2, igm1, vs), L[4] * vn_rr + R[4] * vn_ll);
-}
-
 struct CurvedCfg {
     static constexpr int EPB = 2, THREADS = 32;
     static constexpr int CONS = 320, REC = 64 * kNPC_STRIDE, SFV = 480;  // doubles per element

@@ -181,6 +181,8 @@ void launch_error_norms(const KParams &P, const NormParams &Q, cudaStream_t s) {
 cudaError_t launch_element_euler3d_ranocha_p3(const KParams &P, bool with_surface, cudaStream_t s);
 cudaError_t launch_element_euler3d_ranocha_p3_v7(const KParams &P, bool with_surface, cudaStream_t s);
 cudaError_t launch_element_euler3d_ranocha_curved_p3(const KParams &P, bool with_surface, cudaStream_t s);
+cudaError_t launch_element_euler3d_ranocha_curved_p5(const KParams &P, bool with_surface, cudaStream_t s);  // tuned_euler3d_p5.cu
+cudaError_t preload_tuned_euler3d_curved_p5();
 cudaError_t launch_element_euler3d_weak_p3(const KParams &P, bool with_surface, cudaStream_t s);
 cudaError_t launch_element_linesweep_euler3d(const KParams &P, bool with_surface, cudaStream_t s);
 cudaError_t launch_element_linesweep_sc_euler3d(const KParams &P, bool with_surface, cudaStream_t s);
@@ -233,6 +235,11 @@ bool uses_tuned_element(const KParams &P) {
     if constexpr (std::is_same_v<EQ, Mhd3D> && N == 4) {
         return P.kernel_path != 1 && !P.curved && P.volume_integral == TRIXI_B200_VOLINT_FLUX_DIFFERENCING;
     }
+    if constexpr (std::is_same_v<EQ, Euler<3>> && N == 6) {  // curved flux differencing with flux_ranocha at polydeg 5
+        return P.kernel_path != 1 && P.curved && P.volume_integral == TRIXI_B200_VOLINT_FLUX_DIFFERENCING &&
+               (P.volume_flux == TRIXI_B200_FLUX_RANOCHA || P.volume_flux == TRIXI_B200_FLUX_RANOCHA_TURBO) &&
+               P.source_terms == TRIXI_B200_SRC_NONE;
+    }
     return false;
 }
 
@@ -261,6 +268,9 @@ cudaError_t launch_element(const KParams &P, bool with_surface, cudaStream_t s) 
     }
     if constexpr (std::is_same_v<EQ, Mhd3D> && N == 4) {
         if (uses_tuned_element<EQ, N>(P)) return launch_element_linesweep_mhd3d(P, with_surface, s);
+    }
+    if constexpr (std::is_same_v<EQ, Euler<3>> && N == 6) {
+        if (uses_tuned_element<EQ, N>(P)) return launch_element_euler3d_ranocha_curved_p5(P, with_surface, s);
     }
     if (P.volume_integral == TRIXI_B200_VOLINT_WEAK_FORM) {
         return with_surface ? launch_element_variant<EQ, N, TRIXI_B200_VOLINT_WEAK_FORM, true>(P, s)
@@ -371,6 +381,7 @@ cudaError_t preload_all() {
         return preload_linesweep();
     }
     if constexpr (std::is_same_v<EQ, Mhd3D> && N == 4) return preload_linesweep();
+    if constexpr (std::is_same_v<EQ, Euler<3>> && N == 6) return preload_tuned_euler3d_curved_p5();
     return cudaSuccess;
 }
 
