@@ -460,6 +460,8 @@ def run_b200(args, rank, world, local_rank):
         gpu.set_option(gpu.OPT_KERNEL_PATH, args.kernel_path)
     if args.no_reduce_update:
         gpu.set_option(gpu.OPT_RK_REDUCE_UPDATE, 0)
+    if args.two_copy_face_flux:
+        gpu.set_option(gpu.OPT_SINGLE_FACE_FLUX, 0)
     ndofs = semi.ndofs()
     u0 = T.compute_coefficients(0.0, semi)
     gpu.upload(0, u0)
@@ -633,6 +635,11 @@ def run_b200(args, rank, world, local_rank):
                            "(dg_3d_compressible_euler.jl:265-617), its fastest CPU path for this volume integral",
                    "sample": f"{sample_name(args.cpu_level, args.workload)}; 5 CK54 steps (25 rhs!) after 2 warm-up; "
                              "OpenMP C restatement of the reference's CPU rhs! (oracle/trixi_oracle.c)"}
+        single_copy = args.workload in ("euler_ec", "tgv") and not args.two_copy_face_flux and not args.generic_kernels \
+            and args.kernel_path == 0
+        curved_wl = "curved" in args.workload or args.workload in ("structured_ec", "p4est_ec", "p4est_tgv_p5")
+        nn1 = 6 if args.workload == "p4est_tgv_p5" else 4  # 3 / n face nodes per DOF
+        if_bytes = 3.0 / nn1 * ((3 if single_copy else 4) * wl["nvars"] * 8 + (32 if curved_wl else 0))
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
@@ -677,9 +684,9 @@ def run_b200(args, rank, world, local_rank):
                 # prolong2interfaces! + calc_interface_flux! fused: 3/n face nodes per DOF, each reads both states and
                 # writes the flux to both elements (+ normal and Jacobian sign on curved meshes)
                 "bound": "hbm", "avg_launch_ms": surf_ms / max(surf_n, 1), "launches": surf_n,
-                "algorithmic_bytes_per_dof": 0.75 * (4 * wl["nvars"] * 8 + (32 if "curved" in args.workload else 0)),
-                "achieved": (0.75 * (4 * wl["nvars"] * 8 + (32 if "curved" in args.workload else 0)) * ndofs
-                             / (surf_ms / max(surf_n, 1) * 1e-3) * 1e-9) if surf_n else None,
+                # (euler_ec / tgv: one copy of the flux per interface unless --two-copy-face-flux: 3 instead of 4 records)
+                "algorithmic_bytes_per_dof": if_bytes,
+                "achieved": (if_bytes * ndofs / (surf_ms / max(surf_n, 1) * 1e-3) * 1e-9) if surf_n else None,
                 "peak": peaks["hbm_gbs"], "unit": "GB/s"},
             "kernel_time_share": {"surface_flux_ms": surf_ms, "element_ms": elem_ms, "max_dt_ms": cfl_ms,
                                   "halo_pack_wait_mpiflux_ms": halo_ms + wait_ms, "halo_wait_ms": wait_ms,
@@ -738,6 +745,8 @@ def main():
                     help="TRIXI_B200_OPT_KERNEL_PATH: 2 = the previous generation of the tuned headline kernel (A/B runs)")
     ap.add_argument("--no-reduce-update", action="store_true",
                     help="TRIXI_B200_OPT_RK_REDUCE_UPDATE = 0: keep a resident u tile instead of the L2 reduce-add")
+    ap.add_argument("--two-copy-face-flux", action="store_true",
+                    help="TRIXI_B200_OPT_SINGLE_FACE_FLUX = 0: the interface kernel writes both neighbours' copies")
     ap.add_argument("--no-fused-cfl", action="store_true", help="run max_dt as its own kernel after every step")
     args = ap.parse_args()
     global CELLS

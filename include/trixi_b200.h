@@ -284,6 +284,11 @@ TRIXI_B200_API int trixi_b200_calc_error_norms(trixi_b200_handle *h, double t, i
  * reduce-add onto u in L2 instead of reading u back into the SM; the product is rounded before the addition in
  * both forms, so the option does not change results. */
 #define TRIXI_B200_OPT_RK_REDUCE_UPDATE 4
+/* TRIXI_B200_OPT_SINGLE_FACE_FLUX (default 1): on TreeMeshes with conservative equations both neighbours of a
+ * conforming interface receive the same flux (dg_3d.jl:581-597); where the tuned element kernel supports it the
+ * interface kernel writes it once (the left element's + face) and the right element fetches it from there.  Does not
+ * change results; trixi_b200_download_surface_flux_values always returns the reference's two-copy layout. */
+#define TRIXI_B200_OPT_SINGLE_FACE_FLUX 5
 TRIXI_B200_API int trixi_b200_set_option(trixi_b200_handle *h, int option, int value);
 
 /* GlmSpeedCallback (glm_speed.jl:85-105) mutates equations.c_h every step */

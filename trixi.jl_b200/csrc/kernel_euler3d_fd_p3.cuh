@@ -52,7 +52,7 @@ struct TunedCfg {
     // too needs one bulk copy per face, and issuing twelve copies cost more issue slots than the conflicts.
     static constexpr int OFF_DU = 976, REGION = OFF_DU + EPB * CONS, SFV_H = 488;
     static_assert(SFV_H + SFV <= OFF_DU, "face tiles must stay clear of the du tile");
-    static constexpr size_t SMEM_STREAM = sizeof(double) * REGION + 32;
+    static constexpr size_t SMEM_STREAM = sizeof(double) * REGION + 64;  // + 3 mbarriers + 6 neighbour ids
     static constexpr size_t SMEM_RESIDENT = SMEM_STREAM + sizeof(double) * EPB * CONS;
     static constexpr int MIN_BLOCKS = 16;
     static constexpr int blocks_per_sm(bool resident) { return resident ? 12 : 16; }
@@ -72,7 +72,8 @@ __global__ void __launch_bounds__(TunedCfg::THREADS, TunedCfg::MIN_BLOCKS)
     double *s_inc = smem;                  // then b dt u_tmp [2][64][5] natural (not resident)
     double *s_ut = smem + C::OFF_DU;       // epilogue: [2][64][5] natural: u_tmp in, u_tmp (or du) out
     const uint32_t bar_u = smem_u32(smem + C::REGION), bar_s = bar_u + 8, bar_t = bar_u + 16;
-    double *s_u = smem + C::REGION + 4;    // resident only: [2][64][5] natural: u in, updated u out
+    int *s_nb = reinterpret_cast<int *>(smem + C::REGION + 4);  // [2][3] left neighbours (single-copy face fluxes)
+    double *s_u = smem + C::REGION + 8;    // resident only: [2][64][5] natural: u in, updated u out
 
     const int lane = threadIdx.x;
     const int t = lane & 15;
@@ -98,7 +99,9 @@ __global__ void __launch_bounds__(TunedCfg::THREADS, TunedCfg::MIN_BLOCKS)
     if (lane == 0) {
         mbar_expect_tx(bar_u, bu);
         tma_load(smem_u32(s_uin), P.u + e0 * CONS, bu, bar_u);
-        if (WITH_SURFACE) tma_prefetch_l2(P.sfv + e0 * SFV, bs);  // (bs: both elements' faces)
+        // (single-copy face fluxes: half of the own block is never read and the rest is fetched a whole z pass before
+        // it is needed, so nothing is prefetched)
+        if (WITH_SURFACE && !P.sfv_single) tma_prefetch_l2(P.sfv + e0 * SFV, bs);
         if (need_ut) tma_prefetch_l2(P.u_tmp + e0 * CONS, bu);
         // warm L2 for the elements that will occupy this CTA slot next (blocks are scheduled in index order:
         // one wave further on), so their u tile sees L2 instead of HBM latency
@@ -106,6 +109,7 @@ __global__ void __launch_bounds__(TunedCfg::THREADS, TunedCfg::MIN_BLOCKS)
         if (P.prefetch_distance > 0 && en + EPB <= P.nelements)
             tma_prefetch_l2(P.u + en * CONS, EPB * CONS * sizeof(double));
     }
+    if (WITH_SURFACE && P.sfv_single && lane < 3 * nvalid) s_nb[lane] = P.minus_nb[e0 * 3 + lane];
     const double *const su = s_uin + eh * CONS;
     double *const sp = s_prim + eh * PRIM, *const sd = s_du + eh * CONS;
     while (!mbar_try_wait(bar_u, 0)) {
@@ -167,10 +171,26 @@ __global__ void __launch_bounds__(TunedCfg::THREADS, TunedCfg::MIN_BLOCKS)
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) {
-                constexpr uint32_t bs1 = SFV * sizeof(double);
+                constexpr uint32_t bs1 = SFV * sizeof(double), bf = 80 * sizeof(double);
                 mbar_expect_tx(bar_s, bs);
-                tma_load(smem_u32(s_sfv), P.sfv + e0 * SFV, bs1, bar_s);
-                if (nvalid == EPB) tma_load(smem_u32(s_sfv + C::SFV_H), P.sfv + (e0 + 1) * SFV, bs1, bar_s);
+                if (!P.sfv_single) {
+                    tma_load(smem_u32(s_sfv), P.sfv + e0 * SFV, bs1, bar_s);
+                    if (nvalid == EPB) tma_load(smem_u32(s_sfv + C::SFV_H), P.sfv + (e0 + 1) * SFV, bs1, bar_s);
+                } else {
+                    // + faces from the element's own block; - faces from the left neighbour's + face, or from the
+                    // own block where the face is a boundary, a mortar or shared with another rank
+                    for (int q = 0; q < nvalid; ++q) {
+                        const double *own = P.sfv + (e0 + q) * SFV;
+                        const uint32_t dst = smem_u32(s_sfv + q * C::SFV_H);
+#pragma unroll
+                        for (int o = 0; o < 3; ++o) {
+                            const int nb = s_nb[3 * q + o];
+                            const double *minus = nb >= 0 ? P.sfv + (long long)nb * SFV + (2 * o + 1) * 80 : own + 2 * o * 80;
+                            tma_load(dst + (2 * o + 1) * bf, own + (2 * o + 1) * 80, bf, bar_s);
+                            tma_load(dst + 2 * o * bf, minus, bf, bar_s);
+                        }
+                    }
+                }
             }
         }
         // du[a] += D_split[a, b] f(a, b), du[b] += D_split[b, a] f(a, b) for the 6 pairs a < b of the line;

@@ -63,6 +63,13 @@ struct KParams {
                                   // wave of resident CTAs, resolved at launch)
     int sm_count;
     int rk_reduce_update;         // tuned kernels: u += b dt u_tmp as a bulk reduce-add in L2 (TRIXI_B200_OPT_RK_REDUCE_UPDATE)
+    // Single-copy interface fluxes (TreeMesh, conservative equations: both neighbours of a conforming interface get
+    // the same flux, dg_3d.jl:581-597): the interface kernel only writes the left element's + face, and the element
+    // kernel fetches its - faces from its left neighbours' + faces.  minus_nb[ndims, nelements]: 0-based element
+    // across the - face in each direction, or -1 where that face is a boundary, a mortar or shared with another
+    // rank (those kernels keep writing the element's own slot).  sfv_single is decided per RHS evaluation.
+    const int *minus_nb;
+    int sfv_single;
     long long elem_begin, elem_end;  // TreeMesh element kernels work on [elem_begin, elem_end) (pipelined rhs_host)
     // VolumeIntegralShockCapturingHG: blending factors of IndicatorHennemannGassner
     double *alpha;       // [nelem] after smoothing (ordered-bits atomicMax target)
@@ -204,9 +211,10 @@ __global__ void __launch_bounds__(256) k_interface_flux(const KParams P) {
     }
     surface_numflux<EQ, FAST>(eq, P.surface_flux, ul, ur, o, f);
 #pragma unroll
-    for (int v = 0; v < NV; ++v) {
-        sl[v] = f[v];
-        sr[v] = f[v];
+    for (int v = 0; v < NV; ++v) sl[v] = f[v];
+    if (!P.sfv_single) {
+#pragma unroll
+        for (int v = 0; v < NV; ++v) sr[v] = f[v];
     }
 }
 
@@ -321,7 +329,7 @@ __global__ void __launch_bounds__(256, (CURVED || EQ::kHasNoncons) ? 3 : (FAST =
     // 3. scatter: left element's direction 2o+1, right element's 2o (0-based; dg_3d.jl:581-597)
 #pragma unroll
     for (int c = 0; c < 2 * G; ++c) {
-        if (c < 2 * nvalid) {
+        if (c < 2 * nvalid && !((c & 1) && !CURVED && P.sfv_single)) {  // (single copy: the left element's + face only)
             const int o = s_orient[warp][c >> 1];
             const int dir = (c & 1) ? 2 * o : 2 * o + 1;
             double *dst = P.sfv + ((s_elem[warp][c] * (2 * ND) + dir) * NF) * NV;
@@ -332,6 +340,20 @@ __global__ void __launch_bounds__(256, (CURVED || EQ::kHasNoncons) ? 3 : (FAST =
             }
         }
     }
+}
+
+// surface_flux_values in the reference's layout after a single-copy evaluation: the right element's - face gets
+// the left element's + face (only the stage-level download needs it)
+template <class EQ, int N>
+__global__ void __launch_bounds__(256) k_sfv_fill_right(const KParams P) {
+    constexpr int ND = EQ::NDIMS, NV = EQ::NVARS, NF = ipow(N, ND - 1), FV = NF * NV;
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long I = gid / FV;
+    const int q = (int)(gid - I * FV);
+    if (I >= P.ninterfaces) return;
+    const long long left = P.if_neighbors[2 * I] - 1, right = P.if_neighbors[2 * I + 1] - 1;
+    const int o = (int)P.if_orient[I] - 1;
+    P.sfv[(right * (2 * ND) + 2 * o) * FV + q] = P.sfv[(left * (2 * ND) + 2 * o + 1) * FV + q];
 }
 
 // ---- 2. boundaries ------------------------------------------------------------------------------

@@ -19,6 +19,9 @@ struct Launchers {
     void (*max_dt)(const KParams &, cudaStream_t);
     // true when the RK stage kernel `element` selects for P honours P.want_cfl (fused max_dt)
     bool (*fuses_cfl)(const KParams &);
+    // true when the element kernel selected for P can fetch its - faces from the left neighbours (P.minus_nb)
+    bool (*single_face_flux)(const KParams &);
+    void (*sfv_fill_right)(const KParams &, cudaStream_t);
     void (*mpi_pack)(const KParams &, cudaStream_t);
     void (*mpi_interface_flux)(const KParams &, cudaStream_t);
     // Force-load every kernel of this table (CUDA loads kernels lazily at first launch, and that load can
@@ -251,6 +254,24 @@ bool fuses_cfl(const KParams &P) {
     return uses_tuned_element<EQ, N>(P) && !(P.curved && P.volume_integral != TRIXI_B200_VOLINT_WEAK_FORM);
 }
 
+// the TreeMesh headline kernel is the one element kernel that reads its - faces through P.minus_nb
+template <class EQ, int N>
+bool single_face_flux(const KParams &P) {
+    if constexpr (std::is_same_v<EQ, Euler<3>> && N == 4) {
+        return P.kernel_path == 0 && !P.curved && P.minus_nb != nullptr &&
+               P.volume_integral == TRIXI_B200_VOLINT_FLUX_DIFFERENCING &&
+               (P.volume_flux == TRIXI_B200_FLUX_RANOCHA || P.volume_flux == TRIXI_B200_FLUX_RANOCHA_TURBO);
+    }
+    return false;
+}
+
+template <class EQ, int N>
+void launch_sfv_fill_right(const KParams &P, cudaStream_t s) {
+    const long long total = P.ninterfaces * ipow(N, EQ::NDIMS - 1) * EQ::NVARS;
+    if (total == 0 || P.curved) return;
+    k_sfv_fill_right<EQ, N><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(P);
+}
+
 template <class EQ, int N>
 cudaError_t launch_element(const KParams &P, bool with_surface, cudaStream_t s) {
     if (P.nelements == 0) return cudaSuccess;
@@ -346,6 +367,7 @@ cudaError_t preload_all() {
     TB_PRELOAD((k_mpi_interface_flux<EQ, N, 1>));
     TB_PRELOAD((k_mpi_interface_flux<EQ, N, 2>));
     TB_PRELOAD((k_boundary_flux<EQ, N>));
+    TB_PRELOAD((k_sfv_fill_right<EQ, N>));
     TB_PRELOAD((k_mortar_flux<EQ, N>));
     TB_PRELOAD((k_error_norms<EQ, N>));
     TB_PRELOAD((k_mpi_pack<EQ, N>));
@@ -395,6 +417,8 @@ const Launchers *make_launchers() {
                                 &launch_indicator<EQ, N>,
                                 &launch_max_dt<EQ, N>,
                                 &fuses_cfl<EQ, N>,
+                                &single_face_flux<EQ, N>,
+                                &launch_sfv_fill_right<EQ, N>,
                                 &launch_mpi_pack<EQ, N>,
                                 &launch_mpi_interface_flux<EQ, N>,
                                 &preload_all<EQ, N>,

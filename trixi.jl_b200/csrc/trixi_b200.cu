@@ -44,6 +44,7 @@ struct trixi_b200_handle {
     size_t norm_buf_len = 0;
     unsigned long long *norm_linf = nullptr;
     bool opt_fused_cfl = false;           // TRIXI_B200_OPT_FUSED_CFL
+    bool opt_single_face_flux = true;     // TRIXI_B200_OPT_SINGLE_FACE_FLUX
     bool cfl_valid = false;               // d_cfl holds the maxima of the current u (written by the last RK stage)
     long long launches = 0;
     bool profiling = false;
@@ -247,6 +248,12 @@ int check_launch(trixi_b200_handle *h, const char *what) {
     return 0;
 }
 
+// one copy of every conforming interface flux where the element kernel of this configuration can fetch it from
+// the left neighbour (decided per evaluation: the kernel selection can change through set_option)
+void choose_face_flux_layout(trixi_b200_handle *h) {
+    h->P.sfv_single = h->opt_single_face_flux && h->P.minus_nb && h->L->single_face_flux(h->P) ? 1 : 0;
+}
+
 // surface fluxes of all faces: interfaces (+ boundaries)
 int run_surface_fluxes(trixi_b200_handle *h, double t) {
     h->P.t = t;
@@ -295,6 +302,7 @@ int run_element(trixi_b200_handle *h, bool with_surface) {
 // One RHS evaluation's surface part.  Distributed order (dg_3d_parallel.jl:8-117): pack+send, local
 // interfaces and boundaries while the faces travel, wait, MPI interface fluxes.
 int run_all_surface_fluxes(trixi_b200_handle *h, double t) {
+    choose_face_flux_layout(h);
     const bool dist = h->world_size > 1 && h->nmpi > 0;
     if (h->world_size > 1 && !h->comm_connected)
         return fail(h, TRIXI_B200_ECOMM, "world_size > 1 but the halo exchange is not connected (trixi_b200_comm_connect)");
@@ -484,6 +492,7 @@ int run_pipelined(trixi_b200_handle *h, double t, const double *in_host, double 
     };
     if (in_host) {
         h->P.t = t;
+        choose_face_flux_layout(h);
         // u is overwritten: everything queued earlier must have finished reading it
         CUDA_TRY(h, cudaEventRecord(hp.ev_sync, h->stream));
         CUDA_TRY(h, cudaStreamWaitEvent(hp.s_in, hp.ev_sync, 0));
@@ -840,6 +849,25 @@ TRIXI_B200_API int trixi_b200_create(const trixi_b200_desc *d, trixi_b200_handle
             P.if_orient = itmp;
         }
     }
+    P.minus_nb = nullptr;
+    P.sfv_single = 0;
+    if (!curved && d->equation != TRIXI_B200_EQ_MHD_3D && d->ninterfaces > 0 && d->nelements < (1ll << 31)) {
+        // left neighbour across the - face of every element (conforming interior interfaces only)
+        std::vector<int> mnb((size_t)nd * (size_t)d->nelements, -1);
+        for (long long I = 0; I < d->ninterfaces; ++I) {
+            const long long left = d->interface_neighbor_ids[2 * I] - 1, right = d->interface_neighbor_ids[2 * I + 1] - 1;
+            const long long o = d->interface_orientations[I] - 1;
+            if (left < 0 || right < 0 || left >= d->nelements || right >= d->nelements || o < 0 || o >= nd) {
+                fail(nullptr, TRIXI_B200_EINVAL, "interface %lld has invalid neighbor ids or orientation", I + 1);
+                trixi_b200_destroy(h);
+                return TRIXI_B200_EINVAL;
+            }
+            mnb[(size_t)(o + nd * right)] = (int)left;
+        }
+        int *mtmp = nullptr;
+        CREATE_TRY(upload_array(h, mnb.data(), mnb.size(), &mtmp));
+        P.minus_nb = mtmp;
+    }
     CREATE_TRY(upload_array(h, (const long long *)d->boundary_neighbor_ids, (size_t)d->nboundaries, &itmp));
     P.bd_neighbor = itmp;
     if (!p4est) {
@@ -1090,6 +1118,12 @@ TRIXI_B200_API int trixi_b200_download_surface_flux_values(trixi_b200_handle *h,
     if (!h) return TRIXI_B200_EINVAL;
     if (!host && h->sfvlen) return fail(h, TRIXI_B200_EINVAL, "host pointer is null");
     CUDA_TRY(h, cudaSetDevice(h->device));
+    if (h->P.sfv_single) {  // the reference's layout holds the flux on both sides of an interface
+        h->L->sfv_fill_right(h->P, h->stream);
+        h->launches++;
+        int rc = check_launch(h, "surface flux fill kernel");
+        if (rc) return rc;
+    }
     CUDA_TRY(h, cudaMemcpyAsync(host, h->P.sfv, h->sfvlen * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     return 0;
@@ -1333,6 +1367,10 @@ TRIXI_B200_API int trixi_b200_set_option(trixi_b200_handle *h, int option, int v
         if (value != 0 && value != 1) return fail(h, TRIXI_B200_EINVAL, "fused CFL option must be 0 or 1");
         h->opt_fused_cfl = value != 0;
         h->cfl_valid = false;
+        return 0;
+    case TRIXI_B200_OPT_SINGLE_FACE_FLUX:
+        if (value != 0 && value != 1) return fail(h, TRIXI_B200_EINVAL, "single-face-flux option must be 0 or 1");
+        h->opt_single_face_flux = value != 0;
         return 0;
     case TRIXI_B200_OPT_RK_REDUCE_UPDATE:
         if (value != 0 && value != 1) return fail(h, TRIXI_B200_EINVAL, "reduce-update option must be 0 or 1");
