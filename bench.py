@@ -462,6 +462,8 @@ def run_b200(args, rank, world, local_rank):
         gpu.set_option(gpu.OPT_RK_REDUCE_UPDATE, 0)
     if args.two_copy_face_flux:
         gpu.set_option(gpu.OPT_SINGLE_FACE_FLUX, 0)
+    if args.l2_hints is not None:
+        gpu.set_option(gpu.OPT_L2_HINTS, args.l2_hints)
     ndofs = semi.ndofs()
     u0 = T.compute_coefficients(0.0, semi)
     gpu.upload(0, u0)
@@ -745,6 +747,7 @@ def main():
                     help="TRIXI_B200_OPT_KERNEL_PATH: 2 = the previous generation of the tuned headline kernel (A/B runs)")
     ap.add_argument("--no-reduce-update", action="store_true",
                     help="TRIXI_B200_OPT_RK_REDUCE_UPDATE = 0: keep a resident u tile instead of the L2 reduce-add")
+    ap.add_argument("--l2-hints", type=int, default=None, help="TRIXI_B200_OPT_L2_HINTS (0/1)")
     ap.add_argument("--two-copy-face-flux", action="store_true",
                     help="TRIXI_B200_OPT_SINGLE_FACE_FLUX = 0: the interface kernel writes both neighbours' copies")
     ap.add_argument("--no-fused-cfl", action="store_true", help="run max_dt as its own kernel after every step")

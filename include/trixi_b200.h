@@ -289,6 +289,9 @@ TRIXI_B200_API int trixi_b200_calc_error_norms(trixi_b200_handle *h, double t, i
  * interface kernel writes it once (the left element's + face) and the right element fetches it from there.  Does not
  * change results; trixi_b200_download_surface_flux_values always returns the reference's two-copy layout. */
 #define TRIXI_B200_OPT_SINGLE_FACE_FLUX 5
+/* TRIXI_B200_OPT_L2_HINTS: L2 eviction priorities on the bulk copies of the tuned headline kernel (u evict_last until
+ * its reduce-add, everything else evict_first).  Performance only. */
+#define TRIXI_B200_OPT_L2_HINTS 6
 TRIXI_B200_API int trixi_b200_set_option(trixi_b200_handle *h, int option, int value);
 
 /* GlmSpeedCallback (glm_speed.jl:85-105) mutates equations.c_h every step */

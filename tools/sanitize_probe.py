@@ -9,9 +9,14 @@ sys.path.insert(0, "tests")
 import trixi_b200 as T  # noqa: E402
 from elixirs import ELIXIRS, EXTRA  # noqa: E402
 
+# round 2 adds: the rebuilt headline kernel in its streamed (reduce-add, single-copy face fluxes) and resident forms
+# (tree_3d_euler_ec runs both: the fused-CFL last stage keeps a resident u tile), with boundary faces
+# (tree_3d_euler_slip_wall_mixed), the curved flux-differencing kernels at p = 3 and p = 5, and the staged halo kernels
+# (two in-process ranks)
 CASES = ["tree_3d_euler_ec", "tree_3d_euler_source_terms", "tree_3d_euler_ec_shima_etal", "tree_3d_mhd_ec",
          "tree_3d_euler_shockcapturing", "structured_3d_euler_source_terms", "p4est_3d_euler_source_terms_nonperiodic",
-         "tree_3d_euler_mortar", "tree_2d_euler_ec"]
+         "tree_3d_euler_mortar", "tree_2d_euler_ec", "tree_3d_euler_slip_wall_mixed", "p4est_3d_curved_ec",
+         "structured_3d_euler_ec", "p4est_3d_curved_p5"]
 
 
 def main():
@@ -32,6 +37,29 @@ def main():
         ok = bool(np.isfinite(gpu.download(0)).all() and np.isfinite(du).all())
         print(name, "finite" if ok else "NOT FINITE", flush=True)
         gpu.close()
+    if "--halo" in sys.argv:  # (not under compute-sanitizer: it serialises kernels, and a wait kernel spinning for a
+        halo_probe()          # pack kernel that cannot start would hang)
+
+
+def halo_probe():
+    """Two ranks in one process: staged pack, signal / wait, staged MPI interface flux."""
+    from test_gpu_parity import _ranked_semis
+    alg = T.CarpenterKennedy2N54()
+    base, semis = _ranked_semis("tree_3d_euler_ec", 2)
+    backends = [s.backend() for s in semis]
+    blobs = [b.comm_info() for b in backends]
+    for b in backends:
+        b.comm_connect(blobs)
+    u = T.compute_coefficients(0.0, base)
+    for b, s in zip(backends, semis):
+        a, z = s.cache.first_element, s.cache.last_element
+        b.upload(0, np.asfortranarray(u[..., a:z]))
+    dt = 0.4 * min(b.max_dt() for b in backends)
+    for k in range(2):
+        for b in backends:
+            b.step_2n(k * dt, dt, alg.a, alg.b, alg.c)
+    ok = all(bool(np.isfinite(b.download(0)).all()) for b in backends)
+    print("halo (2 in-process ranks)", "finite" if ok else "NOT FINITE", flush=True)
 
 
 if __name__ == "__main__":

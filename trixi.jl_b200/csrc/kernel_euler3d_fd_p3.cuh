@@ -37,21 +37,22 @@ struct TunedCfg {
     static constexpr int EPB = 2, THREADS = 32;  // one warp, two elements, one thread per line
     static constexpr int CONS = 320, PRIM = 64 * kNP, SFV = 480;  // doubles per element
     // Shared memory is what limits the resident warps, so the tiles take turns in one region per CTA (doubles):
-    //   flux passes:  [prim tiles 0..896 | pad | du tiles 976..1616]   (u arrives in the du tiles' storage and is
+    //   flux passes:  [prim tiles 0..896 | pad | du tiles 1004..1644]  (u arrives in the du tiles' storage and is
     //                                           consumed by the primitive-variable pass before the x pass)
-    //   epilogue:     [surface_flux_values 0..968 | u_tmp 976..1616]   (the faces are fetched while the z pass
+    //   epilogue:     [surface_flux_values 0..1004 | u_tmp 1004..1644] (the faces are fetched while the z pass
     //                                           computes -- it has read the prim tile by then -- and u_tmp once
     //                                           the du tile has been read; b dt u_tmp finally goes to 0..640)
     // 6.4 KB per element: 16 CTAs = 32 elements per SM.  The updated u leaves as a bulk reduce-add of b dt u_tmp onto
     // u in L2 (cp.reduce.async.bulk .add.f64), so u is not needed in the epilogue at all.  Launches that do need it
     // there (source terms, the CFL reduction of the last stage, out-of-place updates) keep a resident u tile:
     // 8.9 KB per element, 12 CTAs per SM.
-    // The second element's faces sit at 488 instead of 480 doubles: in the surface integral the lanes of the two
-    // elements then hit different banks (offset 8 against a lane stride of 5).  The two faces of a direction
-    // still share banks (2-way conflict on 40 of ~800 shared-memory instructions per warp): separating them
-    // too needs one bulk copy per face, and issuing twelve copies cost more issue slots than the conflicts.
-    static constexpr int OFF_DU = 976, REGION = OFF_DU + EPB * CONS, SFV_H = 488;
-    static_assert(SFV_H + SFV <= OFF_DU, "face tiles must stay clear of the du tile");
+    // Face tiles: element h at h * 504; with single-copy face fluxes every face arrives by its own 640-byte bulk
+    // copy anyway and sits at q * 84, so that in the surface integral the lanes of the two faces of a direction
+    // (and of the two elements) hit different banks (offsets 0, 4, 8, 12 against a lane stride of 5:
+    // conflict-free); with two-copy face fluxes an element's six faces arrive as one block (stride 80: the two
+    // faces of a direction share banks).
+    static constexpr int OFF_DU = 1004, REGION = OFF_DU + EPB * CONS, SFV_H = 504, SFV_PAD = 84;
+    static_assert(SFV_H + 5 * SFV_PAD + 80 <= OFF_DU, "face tiles must stay clear of the du tile");
     static constexpr size_t SMEM_STREAM = sizeof(double) * REGION + 64;  // + 3 mbarriers + 6 neighbour ids
     static constexpr size_t SMEM_RESIDENT = SMEM_STREAM + sizeof(double) * EPB * CONS;
     static constexpr int MIN_BLOCKS = 16;
@@ -68,7 +69,7 @@ __global__ void __launch_bounds__(TunedCfg::THREADS, TunedCfg::MIN_BLOCKS)
     const bool resident = tuned_u_resident(P, WITH_SURFACE);
     double *s_prim = smem;                 // [2][64][7] swizzled
     double *s_du = smem + C::OFF_DU;       // [2][64][5] swizzled; before the x pass: u, natural order (not resident)
-    double *s_sfv = smem;                  // epilogue: [6][16][5] natural order per element, element h at h * 488
+    double *s_sfv = smem;                  // epilogue: six [16][5] faces per element at stride fs, element h at h * 504
     double *s_inc = smem;                  // then b dt u_tmp [2][64][5] natural (not resident)
     double *s_ut = smem + C::OFF_DU;       // epilogue: [2][64][5] natural: u_tmp in, u_tmp (or du) out
     const uint32_t bar_u = smem_u32(smem + C::REGION), bar_s = bar_u + 8, bar_t = bar_u + 16;
@@ -87,6 +88,9 @@ __global__ void __launch_bounds__(TunedCfg::THREADS, TunedCfg::MIN_BLOCKS)
     const bool need_ut = rk && P.rk_a != 0.0;
     const uint32_t bu = nvalid * CONS * sizeof(double), bs = nvalid * SFV * sizeof(double);
 
+    // L2 priorities: u is touched again by this CTA's reduce-add ~10 us later (evict_last); everything else streams
+    const bool hints = P.l2_hints != 0;
+    const uint64_t pol_keep = hints ? l2_policy_evict_last() : 0ull, pol_stream = hints ? l2_policy_evict_first() : 0ull;
     // 0. TMA load of the two contiguous u records; the records the epilogue will want are pulled into L2 meanwhile
     if (lane == 0) {
         mbar_init(bar_u, 1);
@@ -98,7 +102,10 @@ __global__ void __launch_bounds__(TunedCfg::THREADS, TunedCfg::MIN_BLOCKS)
     double *const s_uin = resident ? s_u : s_du;
     if (lane == 0) {
         mbar_expect_tx(bar_u, bu);
-        tma_load(smem_u32(s_uin), P.u + e0 * CONS, bu, bar_u);
+        if (hints && !resident)
+            tma_load_hint(smem_u32(s_uin), P.u + e0 * CONS, bu, bar_u, pol_keep);
+        else
+            tma_load(smem_u32(s_uin), P.u + e0 * CONS, bu, bar_u);
         // (single-copy face fluxes: half of the own block is never read and the rest is fetched a whole z pass before
         // it is needed, so nothing is prefetched)
         if (WITH_SURFACE && !P.sfv_single) tma_prefetch_l2(P.sfv + e0 * SFV, bs);
@@ -170,27 +177,25 @@ __global__ void __launch_bounds__(TunedCfg::THREADS, TunedCfg::MIN_BLOCKS)
             // pass computes
             fence_proxy_async();
             __syncwarp();
-            if (lane == 0) {
-                constexpr uint32_t bs1 = SFV * sizeof(double), bf = 80 * sizeof(double);
-                mbar_expect_tx(bar_s, bs);
-                if (!P.sfv_single) {
+            constexpr uint32_t bs1 = SFV * sizeof(double), bf = 80 * sizeof(double);
+            if (lane == 0) mbar_expect_tx(bar_s, bs);
+            if (!P.sfv_single) {
+                if (lane == 0) {
                     tma_load(smem_u32(s_sfv), P.sfv + e0 * SFV, bs1, bar_s);
                     if (nvalid == EPB) tma_load(smem_u32(s_sfv + C::SFV_H), P.sfv + (e0 + 1) * SFV, bs1, bar_s);
-                } else {
-                    // + faces from the element's own block; - faces from the left neighbour's + face, or from the
-                    // own block where the face is a boundary, a mortar or shared with another rank
-                    for (int q = 0; q < nvalid; ++q) {
-                        const double *own = P.sfv + (e0 + q) * SFV;
-                        const uint32_t dst = smem_u32(s_sfv + q * C::SFV_H);
-#pragma unroll
-                        for (int o = 0; o < 3; ++o) {
-                            const int nb = s_nb[3 * q + o];
-                            const double *minus = nb >= 0 ? P.sfv + (long long)nb * SFV + (2 * o + 1) * 80 : own + 2 * o * 80;
-                            tma_load(dst + (2 * o + 1) * bf, own + (2 * o + 1) * 80, bf, bar_s);
-                            tma_load(dst + 2 * o * bf, minus, bf, bar_s);
-                        }
-                    }
                 }
+            } else if (lane < 6 * nvalid) {
+                // one 640-byte copy per face, addresses computed by twelve lanes in parallel: + faces from the
+                // element's own block; - faces from the left neighbour's + face, or from the own block where the
+                // face is a boundary, a mortar or shared with another rank
+                const int q = lane >= 6 ? 1 : 0, f = lane - 6 * q, o = f >> 1;
+                const int nb = (f & 1) ? -1 : s_nb[3 * q + o];
+                const double *src = nb >= 0 ? P.sfv + (long long)nb * SFV + (2 * o + 1) * 80 : P.sfv + (e0 + q) * SFV + f * 80;
+                const uint32_t dst = smem_u32(s_sfv + q * C::SFV_H + f * C::SFV_PAD);
+                if (hints)
+                    tma_load_hint(dst, src, bf, bar_s, pol_stream);
+                else
+                    tma_load(dst, src, bf, bar_s);
             }
         }
         // du[a] += D_split[a, b] f(a, b), du[b] += D_split[b, a] f(a, b) for the 6 pairs a < b of the line;
@@ -254,7 +259,10 @@ __global__ void __launch_bounds__(TunedCfg::THREADS, TunedCfg::MIN_BLOCKS)
     __syncwarp();
     if (need_ut && lane == 0) {
         mbar_expect_tx(bar_t, bu);
-        tma_load(smem_u32(s_ut), P.u_tmp + e0 * CONS, bu, bar_t);
+        if (hints)
+            tma_load_hint(smem_u32(s_ut), P.u_tmp + e0 * CONS, bu, bar_t, pol_stream);
+        else
+            tma_load(smem_u32(s_ut), P.u_tmp + e0 * CONS, bu, bar_t);
     }
     if (WITH_SURFACE) {
         while (!mbar_try_wait(bar_s, 0)) {
@@ -265,8 +273,9 @@ __global__ void __launch_bounds__(TunedCfg::THREADS, TunedCfg::MIN_BLOCKS)
         if constexpr (WITH_SURFACE) {
             // calc_surface_integral! (dg_3d.jl:1337-1394): directions 1..6 = -x,+x,-y,+y,-z,+z
             const double *ssf = s_sfv + eh * C::SFV_H;
+            const int fs = P.sfv_single ? C::SFV_PAD : 80;  // face stride in the tile
             if (i == 0 || i == 3) {
-                const double *sf = ssf + (i == 0 ? 0 : 80) + j * 5;
+                const double *sf = ssf + (i == 0 ? 0 : fs) + j * 5;
                 const double w = i == 0 ? -P.inv_weight0 : P.inv_weight0;
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
@@ -274,7 +283,7 @@ __global__ void __launch_bounds__(TunedCfg::THREADS, TunedCfg::MIN_BLOCKS)
                     for (int v = 0; v < 5; ++v) val[k][v] = fma(sf[20 * k + v], w, val[k][v]);
             }
             if (j == 0 || j == 3) {
-                const double *sf = ssf + (j == 0 ? 160 : 240) + i * 5;
+                const double *sf = ssf + (j == 0 ? 2 * fs : 3 * fs) + i * 5;
                 const double w = j == 0 ? -P.inv_weight0 : P.inv_weight0;
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
@@ -282,11 +291,11 @@ __global__ void __launch_bounds__(TunedCfg::THREADS, TunedCfg::MIN_BLOCKS)
                     for (int v = 0; v < 5; ++v) val[k][v] = fma(sf[20 * k + v], w, val[k][v]);
             }
             {
-                const double *sf = ssf + 320 + t * 5;
+                const double *sf = ssf + 4 * fs + t * 5;
 #pragma unroll
                 for (int v = 0; v < 5; ++v) {
                     val[0][v] = fma(sf[v], -P.inv_weight0, val[0][v]);
-                    val[3][v] = fma(sf[80 + v], P.inv_weight0, val[3][v]);
+                    val[3][v] = fma(sf[fs + v], P.inv_weight0, val[3][v]);
                 }
             }
             // apply_jacobian! (dg_3d.jl:1396-1414)
@@ -404,6 +413,9 @@ __global__ void __launch_bounds__(TunedCfg::THREADS, TunedCfg::MIN_BLOCKS)
     if (lane == 0) {
         if (!rk) {
             tma_store(P.du + e0 * CONS, smem_u32(s_ut), bu);
+        } else if (hints && !resident) {
+            tma_store_hint(P.u_tmp + e0 * CONS, smem_u32(s_ut), bu, pol_stream);
+            tma_reduce_add_f64_hint(P.u_out + e0 * CONS, smem_u32(s_inc), bu, pol_stream);
         } else {
             tma_store(P.u_tmp + e0 * CONS, smem_u32(s_ut), bu);
             if (resident)

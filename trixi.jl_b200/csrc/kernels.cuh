@@ -70,6 +70,7 @@ struct KParams {
     // rank (those kernels keep writing the element's own slot).  sfv_single is decided per RHS evaluation.
     const int *minus_nb;
     int sfv_single;
+    int l2_hints;                 // tuned headline kernel: L2 eviction priorities on its bulk copies (TRIXI_B200_OPT_L2_HINTS)
     long long elem_begin, elem_end;  // TreeMesh element kernels work on [elem_begin, elem_end) (pipelined rhs_host)
     // VolumeIntegralShockCapturingHG: blending factors of IndicatorHennemannGassner
     double *alpha;       // [nelem] after smoothing (ordered-bits atomicMax target)

@@ -37,6 +37,34 @@ TB_DEV void tma_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar
                  "l"(src), "r"(bytes), "r"(bar)
                  : "memory");
 }
+// L2 eviction priorities for streaming tiles (createpolicy + .L2::cache_hint): data that is read once should leave
+// L2 first, data that the same CTA touches again a few microseconds later should stay
+TB_DEV uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+TB_DEV uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+TB_DEV void tma_load_hint(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+        "l"(src), "r"(bytes), "r"(bar), "l"(policy)
+        : "memory");
+}
+TB_DEV void tma_store_hint(void *dst, uint32_t src, uint32_t bytes, uint64_t policy) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst), "r"(src),
+                 "r"(bytes), "l"(policy)
+                 : "memory");
+}
+TB_DEV void tma_reduce_add_f64_hint(void *dst, uint32_t src, uint32_t bytes, uint64_t policy) {
+    asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.L2::cache_hint.add.f64 [%0], [%1], %2, %3;" ::"l"(dst),
+                 "r"(src), "r"(bytes), "l"(policy)
+                 : "memory");
+}
 TB_DEV void tma_store(void *dst, uint32_t src, uint32_t bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes)
                  : "memory");

@@ -819,6 +819,7 @@ TRIXI_B200_API int trixi_b200_create(const trixi_b200_desc *d, trixi_b200_handle
         }
     P.kernel_path = 0;
     P.rk_reduce_update = 1;
+    P.l2_hints = 0;
     const bool curved = structured || p4est;
     CREATE_TRY(upload_array(h, d->inverse_jacobian, (size_t)(curved ? nn * d->nelements : d->nelements), &tmp));
     P.inverse_jacobian = tmp;
@@ -1367,6 +1368,10 @@ TRIXI_B200_API int trixi_b200_set_option(trixi_b200_handle *h, int option, int v
         if (value != 0 && value != 1) return fail(h, TRIXI_B200_EINVAL, "fused CFL option must be 0 or 1");
         h->opt_fused_cfl = value != 0;
         h->cfl_valid = false;
+        return 0;
+    case TRIXI_B200_OPT_L2_HINTS:
+        if (value != 0 && value != 1) return fail(h, TRIXI_B200_EINVAL, "L2 hint option must be 0 or 1");
+        h->P.l2_hints = value;
         return 0;
     case TRIXI_B200_OPT_SINGLE_FACE_FLUX:
         if (value != 0 && value != 1) return fail(h, TRIXI_B200_EINVAL, "single-face-flux option must be 0 or 1");

@@ -260,6 +260,7 @@ class B200Backend:
     OPT_HOST_PIPELINE_CHUNK = 3
     OPT_RK_REDUCE_UPDATE = 4
     OPT_SINGLE_FACE_FLUX = 5
+    OPT_L2_HINTS = 6
 
     def set_option(self, option, value):
         self._ck(self.lib.trixi_b200_set_option(self.h, int(option), int(value)))
