@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define TRIXI_B200_ABI_VERSION 4
+#define TRIXI_B200_ABI_VERSION 5
 
 #if defined(__GNUC__)
 #define TRIXI_B200_API __attribute__((visibility("default")))
@@ -187,6 +187,11 @@ typedef struct trixi_b200_desc {
     int32_t reserved1;
     double indicator_alpha_max, indicator_alpha_min;
     const double *inverse_vandermonde_legendre; /* [n, n] column-major (basis_lobatto_legendre.jl:711-724) */
+
+    /* P4est L2 mortar container (dgsem_p4est/containers.jl:563-613): node_indices [ndims, 2, nmortars], 1: the small
+     * side, 2: the large side, same encoding as interface_node_indices; mortar_neighbor_ids holds the small elements
+     * by position and the large element last; mortar_large_sides / mortar_orientations are TreeMesh-only */
+    const int64_t *mortar_node_indices;
 } trixi_b200_desc;
 
 typedef struct trixi_b200_handle trixi_b200_handle;

@@ -31,7 +31,7 @@ import SciMLBase
 const libtrixi_b200 = get(ENV, "TRIXI_B200_LIBRARY", "libtrixi_b200.so")
 
 # ---- enums of include/trixi_b200.h ------------------------------------------------------------------
-const ABI_VERSION = Int32(4)
+const ABI_VERSION = Int32(5)
 mesh_kind(::TreeMesh) = Cint(0)
 mesh_kind(::StructuredMesh) = Cint(1)
 mesh_kind(::P4estMesh) = Cint(2)
@@ -148,6 +148,7 @@ struct Desc
     indicator_alpha_max::Float64
     indicator_alpha_min::Float64
     inverse_vandermonde_legendre::Ptr{Float64}
+    mortar_node_indices::Ptr{Int64}
 end
 
 # ---- the backend object ---------------------------------------------------------------------------------
@@ -232,18 +233,20 @@ function B200(semi::SemidiscretizationHyperbolic; device = -1)
             nbd = ntuple(i -> i <= 2 * ndims(mesh) ? Int64(bd.n_boundaries_per_direction[i]) : Int64(0), 6)
         end
     end
-    # L2 mortars (TreeMesh; containers_3d.jl:495-510, operators basis_lobatto_legendre.jl:159-206)
-    n_mo = mesh isa TreeMesh ? nmortars(dg, cache) : 0
+    # L2 mortars (TreeMesh containers_3d.jl:495-510; P4estMesh dgsem_p4est/containers.jl:563-613; operators
+    # basis_lobatto_legendre.jl:159-206)
+    n_mo = mesh isa StructuredMesh ? 0 : nmortars(dg, cache)
     mo_ids = n_mo > 0 ? cache.mortars.neighbor_ids : Int64[]
-    mo_sides = n_mo > 0 ? cache.mortars.large_sides : Int64[]
-    mo_orient = n_mo > 0 ? cache.mortars.orientations : Int64[]
+    mo_sides = n_mo > 0 && mesh isa TreeMesh ? cache.mortars.large_sides : Int64[]
+    mo_orient = n_mo > 0 && mesh isa TreeMesh ? cache.mortars.orientations : Int64[]
+    mo_idx = n_mo > 0 && mesh isa P4estMesh ? encode(cache.mortars.node_indices) : Int64[]
     fu, fl, ru, rl = n_mo > 0 ? Matrix.((dg.mortar.forward_upper, dg.mortar.forward_lower,
                                          dg.mortar.reverse_upper, dg.mortar.reverse_lower)) :
                      ntuple(_ -> zeros(0, 0), 4)
     fv_flux, ind_var, ind_smooth, ind_max, ind_min, inv_vdm = shock_capturing_fields(dg.volume_integral, dg.basis)
     handle = Ref{Ptr{Cvoid}}(C_NULL)
     # the library copies during `create` only
-    GC.@preserve inv_vdm D_split D_hat inv_w el contravariant left_neighbors if_ids if_orient if_idx bd_ids bd_orient bd_sides bd_x bd_idx mo_ids mo_sides mo_orient fu fl ru rl begin
+    GC.@preserve inv_vdm D_split D_hat inv_w el contravariant left_neighbors if_ids if_orient if_idx bd_ids bd_orient bd_sides bd_x bd_idx mo_ids mo_sides mo_orient mo_idx fu fl ru rl begin
         desc = Desc(ABI_VERSION, device, ndims(mesh), nvariables(equations), nnodes(dg), mesh_kind(mesh),
                     nelements(dg, cache), equation_id(equations), volint, volflux,
                     flux_id(dg.surface_integral.surface_flux), source_id(semi.source_terms),
@@ -257,7 +260,8 @@ function B200(semi::SemidiscretizationHyperbolic; device = -1)
                     ptr_or_null(left_neighbors),
                     0, 1, 0, C_NULL, C_NULL, C_NULL, C_NULL,   # single rank: no MPI interfaces
                     ptr_or_null(bd_idx), C_NULL,
-                    fv_flux, ind_var, ind_smooth, 0, ind_max, ind_min, ptr_or_null(inv_vdm))
+                    fv_flux, ind_var, ind_smooth, 0, ind_max, ind_min, ptr_or_null(inv_vdm),
+                    ptr_or_null(mo_idx))
         rc = ccall((:trixi_b200_create, libtrixi_b200), Cint, (Ref{Desc}, Ref{Ptr{Cvoid}}), desc, handle)
     end
     check(nothing, rc)

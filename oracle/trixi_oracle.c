@@ -1789,7 +1789,8 @@ void oracle_calc_surface_integral_p4est(const trixi_b200_desc *d, double *du, co
     }
 }
 
-/* rhs_hyperbolic! dgsem_tree/dg_2d.jl:113-186 dispatched for P4estMesh (conforming: no mortars) */
+/* rhs_hyperbolic! dgsem_tree/dg_2d.jl:113-186 dispatched for P4estMesh */
+void oracle_calc_mortar_flux_p4est(const trixi_b200_desc *d, double *sfv, const double *u);
 void oracle_rhs_p4est(const trixi_b200_desc *d, double *du, const double *u, double t, double *interfaces_u,
                       double *sfv) {
     oracle_set_zero(d, du);
@@ -1797,6 +1798,7 @@ void oracle_rhs_p4est(const trixi_b200_desc *d, double *du, const double *u, dou
     oracle_prolong2interfaces_p4est(d, interfaces_u, u);
     oracle_calc_interface_flux_p4est(d, sfv, interfaces_u);
     if (d->nboundaries > 0) oracle_calc_boundary_flux_p4est(d, sfv, u, t);
+    oracle_calc_mortar_flux_p4est(d, sfv, u); /* prolong2mortars! + calc_mortar_flux! (no-op without mortars) */
     oracle_calc_surface_integral_p4est(d, du, sfv);
     oracle_apply_jacobian_curved(d, du);
     oracle_calc_sources(d, du, u, t);
@@ -1893,6 +1895,87 @@ void oracle_calc_mortar_flux(const trixi_b200_desc *d, double *sfv, const double
                 mortar_apply_1d(rev[(p >> 1) & 1], n, nv, nb, 1, tmp, out, k > 0);
             }
         }
+    }
+}
+
+/* ---- L2 mortars on P4estMesh -----------------------------------------------------------------------------
+ * prolong2mortars! (dgsem_p4est/dg_2d.jl:802-868, dg_3d.jl:651-748), calc_mortar_flux! (dg_2d.jl:870-961,
+ * dg_3d.jl:750-858, conservative equations) and mortar_fluxes_to_elements! (dg_2d.jl:997-1055, dg_3d.jl:890-974).
+ * neighbor_ids [2^(d-1)+1, M]: small elements by position, then the large element; node_indices [nd, 2, M]:
+ * 1 = small side (always forward), 2 = large side.  The flux uses the outward normal of the small element and
+ * goes to the large element projected, with the sign switched and scaled by 2^(d-1). */
+void oracle_calc_mortar_flux_p4est(const trixi_b200_desc *d, double *sfv, const double *u) {
+    if (d->nmortars <= 0) return;
+    eqn_t eq = make_eqn(d);
+    int n = d->nnodes, nd = d->ndims, nv = d->nvars;
+    int nf = ipow(n, nd - 1), nb = nd == 3 ? n : 1, np = 1 << (nd - 1);
+    int64_t esz = (int64_t)nv * ipow(n, nd), fsz = (int64_t)nv * nf * 2 * nd;
+    const double *fwd[2] = {d->mortar_forward_lower, d->mortar_forward_upper};
+    const double *rev[2] = {d->mortar_reverse_lower, d->mortar_reverse_upper};
+#pragma omp parallel for schedule(static)
+    for (int64_t m = 0; m < d->nmortars; ++m) {
+        const int64_t *ids = d->mortar_neighbor_ids + (int64_t)(np + 1) * m;
+        const int64_t *small_idx = d->mortar_node_indices + (int64_t)nd * (0 + 2 * m);
+        const int64_t *large_idx = d->mortar_node_indices + (int64_t)nd * (1 + 2 * m);
+        int64_t large = ids[np] - 1;
+        int small_dir = p4_direction(nd, small_idx), large_dir = p4_direction(nd, large_idx);
+        double u_buffer[MAXV * 64], tmp[MAXV * 64], u_large[4][MAXV * 64], fstar[4][MAXV * 64];
+        /* prolong2mortars!: the large face in the orientation of the small side ... */
+        for (int j = 0; j < nb; ++j)
+            for (int i = 0; i < n; ++i) {
+                int64_t vn = p4_volume_node(nd, n, large_idx, i, j);
+                for (int v = 0; v < nv; ++v) u_buffer[v + nv * (i + n * j)] = u[large * esz + nv * vn + v];
+            }
+        /* ... interpolated to the 2^(d-1) small faces */
+        for (int p = 0; p < np; ++p) {
+            if (nd == 2) {
+                mortar_apply_1d(fwd[p & 1], n, nv, 1, 0, u_buffer, u_large[p], 0);
+            } else {
+                mortar_apply_1d(fwd[p & 1], n, nv, nb, 0, u_buffer, tmp, 0);
+                mortar_apply_1d(fwd[(p >> 1) & 1], n, nv, nb, 1, tmp, u_large[p], 0);
+            }
+        }
+        /* calc_mortar_flux!: u_ll = small element, u_rr = interpolated large element, normal of the small element */
+        for (int p = 0; p < np; ++p) {
+            int64_t small = ids[p] - 1;
+            for (int j = 0; j < nb; ++j)
+                for (int i = 0; i < n; ++i) {
+                    int64_t vn = p4_volume_node(nd, n, small_idx, i, j);
+                    double nrm[3] = {0, 0, 0};
+                    p4_normal(d, small_dir, vn, small, nrm);
+                    numflux_normal(&eq, d->surface_flux, u + small * esz + nv * vn, u_large[p] + nv * (i + n * j), nrm,
+                                   fstar[p] + nv * (i + n * j));
+                }
+            /* mortar_fluxes_to_elements!: small to small */
+            for (int q = 0; q < nv * nf; ++q) sfv[small * fsz + q + (int64_t)nv * nf * small_dir] = fstar[p][q];
+        }
+        /* project the small fluxes to the large element */
+        if (nd == 2) {
+            /* multiply_dimensionwise!(u_buffer, reverse_upper, fstar[2], reverse_lower, fstar[1]) (dg_2d.jl:1020-1022) */
+            for (int i = 0; i < n; ++i)
+                for (int v = 0; v < nv; ++v) {
+                    double acc = 0.0;
+                    for (int q = 0; q < n; ++q)
+                        acc += rev[1][i + n * q] * fstar[1][v + nv * q] + rev[0][i + n * q] * fstar[0][v + nv * q];
+                    u_buffer[v + nv * i] = acc;
+                }
+        } else {
+            /* positions 1..4 in this order (dg_3d.jl:914-929) */
+            for (int p = 0; p < 4; ++p) {
+                mortar_apply_1d(rev[p & 1], n, nv, nb, 0, fstar[p], tmp, 0);
+                mortar_apply_1d(rev[(p >> 1) & 1], n, nv, nb, 1, tmp, u_buffer, p > 0);
+            }
+        }
+        /* sign switch and scaling by the area ratio (dg_2d.jl:1024-1031, dg_3d.jl:931-939), then the copy in the
+         * orientation of the large face (surface_indices of the large side) */
+        double scale = nd == 2 ? -2.0 : -4.0;
+        for (int j = 0; j < nb; ++j)
+            for (int i = 0; i < n; ++i) {
+                int fn_large;
+                p4_surface_node(nd, n, large_idx, i, j, &fn_large);
+                for (int v = 0; v < nv; ++v)
+                    sfv[large * fsz + v + nv * (fn_large + nf * large_dir)] = u_buffer[v + nv * (i + n * j)] * scale;
+            }
     }
 }
 

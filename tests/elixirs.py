@@ -661,6 +661,44 @@ ELIXIRS.update({e.name: e for e in [
 ]})
 
 
+# ---- P4estMesh with hanging faces (L2 mortars) ---------------------------------------------------------------
+def _refine_origin_quadrant(max_level):
+    # refine_fn of the nonconforming elixirs: the quadrant at the origin of every tree, recursively
+    def refine_fn(which_tree, *xyz_level):
+        *xyz, level = xyz_level
+        return all(c == 0 for c in xyz) and level < max_level
+    return refine_fn
+
+
+def _p4est3d_advection_nonconforming():
+    # examples/p4est_3d_dgsem/elixir_advection_nonconforming.jl
+    eq = T.LinearScalarAdvectionEquation3D((0.2, -0.7, 0.5))
+    solver = T.DGSEM(polydeg=3, surface_flux=T.flux_lax_friedrichs)
+    mesh = T.P4estMesh((1, 1, 1), polydeg=3, coordinates_min=(-1.0,) * 3, coordinates_max=(1.0,) * 3,
+                       initial_refinement_level=2, periodicity=True)
+    mesh.refine(_refine_origin_quadrant(3), recursive=True)
+    return T.SemidiscretizationHyperbolic(mesh, eq, T.initial_condition_convergence_test, solver)
+
+
+def _p4est2d_advection_nonconforming_flag():
+    # examples/p4est_2d_dgsem/elixir_advection_nonconforming_flag.jl
+    eq = T.LinearScalarAdvectionEquation2D((0.2, -0.7))
+    solver = T.DGSEM(polydeg=4, surface_flux=T.flux_lax_friedrichs)
+    faces = (lambda s: (-1.0 + 0 * s, s - 1.0), lambda s: (1.0 + 0 * s, s + 1.0),
+             lambda s: (s, -1.0 + np.sin(0.5 * np.pi * s)), lambda s: (s, 1.0 + np.sin(0.5 * np.pi * s)))
+    mesh = T.P4estMesh((3, 2), polydeg=3, faces=faces, periodicity=True, initial_refinement_level=1)
+    mesh.refine(_refine_origin_quadrant(4), recursive=True)
+    return T.SemidiscretizationHyperbolic(mesh, eq, T.initial_condition_convergence_test, solver)
+
+
+ELIXIRS.update({e.name: e for e in [
+    Elixir("p4est_3d_advection_nonconforming", _p4est3d_advection_nonconforming, (0.0, 1.0), 1.6,
+           [0.00253595715323843], [0.016486952252155795], "test/test_p4est_3d.jl:43-50"),
+    Elixir("p4est_2d_advection_nonconforming_flag", _p4est2d_advection_nonconforming_flag, (0.0, 0.2), 1.6,
+           [3.198940059144588e-5], [0.00030636069494005547], "test/test_p4est_2d.jl:58-66"),
+]})
+
+
 # ---- configurations without a reference golden (cross-checks between mesh types, halo tests) ---------------
 def _p4est3d_curved(initial_condition=T.initial_condition_weak_blast_wave, flux=T.flux_ranocha, level=0, trees=(4, 4, 4)):
     # the warped mapping of examples/structured_3d_dgsem/elixir_euler_free_stream.jl on a conforming P4estMesh
@@ -792,3 +830,77 @@ EXTRA = {e.name: e for e in [
     _Extra("p4est_3d_curved_p5", _p4est3d_curved_p5),
 ]}
 EXTRA.update({name: _Extra(name, build) for name, build in PARITY_EXTRA.items()})
+
+
+def _free_stream_mapping_3d(xi_, eta_, zeta_):
+    # examples/p4est_3d_dgsem/elixir_euler_free_stream.jl:34-56 (the structured mapping "with less warping")
+    pi = np.pi
+    xi, eta, zeta = 1.5 * xi_ + 1.5, 1.5 * eta_ + 1.5, 1.5 * zeta_ + 1.5
+    y = eta + 1 / 6 * (np.cos(1.5 * pi * (2 * xi - 3) / 3) * np.cos(0.5 * pi * (2 * eta - 3) / 3)
+                       * np.cos(0.5 * pi * (2 * zeta - 3) / 3))
+    x = xi + 1 / 6 * (np.cos(0.5 * pi * (2 * xi - 3) / 3) * np.cos(2 * pi * (2 * y - 3) / 3)
+                      * np.cos(0.5 * pi * (2 * zeta - 3) / 3))
+    z = zeta + 1 / 6 * (np.cos(0.5 * pi * (2 * x - 3) / 3) * np.cos(pi * (2 * y - 3) / 3)
+                        * np.cos(0.5 * pi * (2 * zeta - 3) / 3))
+    return x, y, z
+
+
+def _refine_origin_quadrant_of_even_trees(max_level):
+    def refine_fn(which_tree, *xyz_level):
+        *xyz, level = xyz_level
+        return which_tree % 2 == 0 and all(c == 0 for c in xyz) and level < max_level
+    return refine_fn
+
+
+def _p4est3d_free_stream_nonconforming():
+    # examples/p4est_3d_dgsem/elixir_euler_free_stream.jl on a programmatic 2^3-tree forest instead of the downloaded
+    # cube_unstructured_1.inp: same mapping, mesh polydeg 2 = half the solver polydeg 4 (free-stream preservation on
+    # non-conforming meshes), Dirichlet boundaries, the origin quadrant of every second tree refined to level 2
+    eq = T.CompressibleEulerEquations3D(1.4)
+    solver = T.DGSEM(polydeg=4, surface_flux=T.FluxLaxFriedrichs(T.max_abs_speed_naive),
+                     volume_integral=T.VolumeIntegralWeakForm())
+    mesh = T.P4estMesh((2, 2, 2), polydeg=2, mapping=_free_stream_mapping_3d, periodicity=False,
+                       initial_refinement_level=0)
+    mesh.refine(_refine_origin_quadrant_of_even_trees(2), recursive=True)
+    return T.SemidiscretizationHyperbolic(mesh, eq, T.initial_condition_constant, solver,
+                                          boundary_conditions=T.BoundaryConditionDirichlet(T.initial_condition_constant))
+
+
+def _p4est3d_nonconforming_curved(flux=T.flux_ranocha, polydeg=3, periodic=True):
+    # the warped mapping with hanging faces: curved mortars (normals of the small elements), tuned curved kernels
+    eq = T.CompressibleEulerEquations3D(1.4)
+    solver = T.DGSEM(polydeg=polydeg, surface_flux=T.flux_lax_friedrichs if flux is None else flux,
+                     volume_integral=T.VolumeIntegralWeakForm() if flux is None
+                     else T.VolumeIntegralFluxDifferencing(flux))
+    mesh = T.P4estMesh((2, 2, 2), polydeg=polydeg, periodicity=periodic, initial_refinement_level=1,
+                       mapping=_warped_mapping_3d if periodic else _nonperiodic_curved_mapping_3d)
+    mesh.refine(_refine_origin_quadrant_of_even_trees(3), recursive=True)
+    if periodic:
+        return T.SemidiscretizationHyperbolic(mesh, eq, T.initial_condition_weak_blast_wave, solver)
+    return T.SemidiscretizationHyperbolic(mesh, eq, T.initial_condition_convergence_test, solver,
+                                          source_terms=T.source_terms_convergence_test,
+                                          boundary_conditions=T.BoundaryConditionDirichlet(
+                                              T.initial_condition_convergence_test))
+
+
+def _p4est2d_nonconforming_curved(surface_flux, periodic=True):
+    eq = T.CompressibleEulerEquations2D(1.4)
+    solver = T.DGSEM(polydeg=3, surface_flux=surface_flux)
+    mesh = T.P4estMesh((3, 2), polydeg=3, periodicity=periodic, initial_refinement_level=1,
+                       mapping=_warped_mapping_2d if periodic else _curved_mapping_2d)
+    mesh.refine(_refine_origin_quadrant(3), recursive=True)
+    bcs = None if periodic else _slip_wall_mixed(2)
+    return T.SemidiscretizationHyperbolic(mesh, eq, T.initial_condition_convergence_test, solver,
+                                          source_terms=T.source_terms_convergence_test,
+                                          boundary_conditions=bcs or T.boundary_condition_periodic)
+
+
+NONCONFORMING_EXTRA = {
+    "p4est_3d_free_stream_nonconforming": _p4est3d_free_stream_nonconforming,
+    "p4est_3d_nonconforming_curved_ec": _p4est3d_nonconforming_curved,
+    "p4est_3d_nonconforming_curved_weak_form_nonperiodic": lambda: _p4est3d_nonconforming_curved(None, periodic=False),
+    "p4est_3d_nonconforming_curved_ec_p5": lambda: _p4est3d_nonconforming_curved(polydeg=5),
+    "p4est_2d_nonconforming_curved_hll": lambda: _p4est2d_nonconforming_curved(T.flux_hll),
+    "p4est_2d_nonconforming_curved_slip_wall": lambda: _p4est2d_nonconforming_curved(T.flux_lax_friedrichs, periodic=False),
+}
+EXTRA.update({name: _Extra(name, build) for name, build in NONCONFORMING_EXTRA.items()})

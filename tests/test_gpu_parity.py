@@ -8,7 +8,7 @@ import trixi_b200 as T
 import json
 import os
 
-from elixirs import ELIXIRS as _GOLDEN_ELIXIRS, EXTRA, PARITY_EXTRA
+from elixirs import ELIXIRS as _GOLDEN_ELIXIRS, EXTRA, NONCONFORMING_EXTRA, PARITY_EXTRA
 
 ELIXIRS = {**_GOLDEN_ELIXIRS, **EXTRA}
 
@@ -28,7 +28,7 @@ RHS_TOL = 1e-12
 # oracle's own FMA/no-FMA difference is 5e-12 there).
 NOISE_LIMITED = {"tree_3d_euler_taylor_green_vortex", "p4est_3d_tgv_p5", "structured_3d_euler_free_stream",
                  "structured_2d_euler_free_stream", "tree_3d_advection_basic", "structured_3d_advection_basic",
-                 "p4est_3d_advection_basic"}
+                 "p4est_3d_advection_basic", "p4est_3d_advection_nonconforming", "p4est_3d_free_stream_nonconforming"}
 
 
 def _oracle_noise(oracle_module, semi, u, t, du_ref):
@@ -107,7 +107,8 @@ RHS_CASES = ["tree_3d_euler_ec", "tree_3d_euler_source_terms", "tree_3d_euler_so
              "tree_3d_euler_shockcapturing", "tree_2d_euler_shockcapturing", "tree_2d_euler_blast_wave",
              "tree_3d_euler_ec_turbo", "tree_2d_euler_vortex_shockcapturing", "tree_2d_euler_vortex_mortar_shockcapturing",
              "tree_3d_advection_basic", "tree_3d_advection_mortar", "structured_3d_advection_basic",
-             "p4est_3d_advection_basic", "p4est_3d_tgv_p5", "p4est_3d_curved_p5"] + sorted(PARITY_EXTRA)
+             "p4est_3d_advection_basic", "p4est_3d_tgv_p5", "p4est_3d_curved_p5", "p4est_3d_advection_nonconforming",
+             "p4est_2d_advection_nonconforming_flag"] + sorted(PARITY_EXTRA) + sorted(NONCONFORMING_EXTRA)
 
 
 @pytest.mark.parametrize("name", RHS_CASES)

@@ -78,6 +78,49 @@ def test_turbo_kernel_matches_generic(oracle_module):
         assert np.abs(da - db).max() <= 1e-13 * np.abs(da).max()
 
 
+def test_p4est_nonconforming_free_stream(oracle_module):
+    """examples/p4est_3d_dgsem/elixir_euler_free_stream.jl (test/test_p4est_3d.jl:164-184) on a programmatic forest:
+    with a mesh polydeg of half the solver polydeg a constant state stays constant across curved hanging faces
+    (mortar normals taken from the small elements, the large side scaled by 4) -- and does not with a full-degree
+    mesh, which is what the reference's comment in that elixir says."""
+    import trixi_b200 as T
+    from elixirs import EXTRA
+    ex = EXTRA["p4est_3d_free_stream_nonconforming"]
+    semi = ex.semi()
+    assert semi.cache.mortars.nmortars > 0 and semi.cache.boundaries.nboundaries > 0
+    u = T.compute_coefficients(0.0, semi)
+    du = np.empty_like(u)
+    oracle_module.OracleBackend(semi).rhs_host(du, u, 0.0)
+    assert np.abs(du).max() < 5e-10
+    # the reference's run: t = 0.03, errors of 1e-14 .. 1e-11
+    semi.set_backend(oracle_module.OracleBackend(semi))
+    ode = T.semidiscretize(semi, (0.0, 0.03))
+    analysis = T.AnalysisCallback(semi, interval=100)
+    sol = T.solve(ode, T.CarpenterKennedy2N54(), dt=1.0,
+                  callback=T.CallbackSet(analysis, T.StepsizeCallback(cfl=1.2)))
+    l2, linf = analysis(sol)
+    assert np.all(l2 < 1e-12) and np.all(linf < 5e-11)
+
+
+def test_p4est_refine_and_balance():
+    """refine_p4est! + balance! on a periodic 3 x 2 forest (elixir_advection_nonconforming_flag.jl): the corner
+    quadrant of every tree goes from level 1 to 4, the 2:1 face balance ripples outwards and across the periodic
+    boundary; leaves tile the forest exactly and stay in Morton order per tree."""
+    from elixirs import ELIXIRS
+    semi = ELIXIRS["p4est_2d_advection_nonconforming_flag"].semi()
+    mesh = semi.mesh
+    assert mesh.ncells == 168 and int(mesh.levels.max()) == 4 and int(mesh.levels.min()) >= 1
+    area = np.sum(0.25 ** mesh.levels.astype(float))
+    assert abs(area - 6.0) < 1e-14
+    assert np.all(np.diff(mesh.tree_of_element) >= 0)
+    # every hanging face has exactly one level of difference
+    mo = semi.cache.mortars
+    lv = mesh.levels
+    assert np.all(lv[mo.neighbor_ids[:-1] - 1] == lv[mo.neighbor_ids[-1] - 1][None, :] + 1)
+    # faces are counted once: 4 per element = 2 interfaces + (1 + 2) mortar sides
+    assert 2 * semi.cache.interfaces.ninterfaces + 3 * mo.nmortars == 4 * mesh.ncells
+
+
 def test_goldens_are_the_reference_test_suite_values():
     """tests/golden/reference_goldens.json was extracted from the reference's test/*.jl by
     tests/golden/extract_reference_goldens.py; the values the elixirs are checked against are those, bit for bit."""

@@ -8,7 +8,7 @@ import ctypes as C
 
 import numpy as np
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 c_double_p = C.POINTER(C.c_double)
 c_int64_p = C.POINTER(C.c_int64)
@@ -52,6 +52,7 @@ class Desc(C.Structure):
         ("indicator_alpha_smooth", C.c_int32), ("reserved1", C.c_int32),
         ("indicator_alpha_max", C.c_double), ("indicator_alpha_min", C.c_double),
         ("inverse_vandermonde_legendre", c_double_p),
+        ("mortar_node_indices", c_int64_p),
     ]
 
 

@@ -87,6 +87,7 @@ struct KParams {
     // one), large_sides, orientations; forward (interpolation) and reverse (projection) operators [n, n]
     long long nmortars;
     const long long *mortar_ids, *mortar_large_sides, *mortar_orient;
+    const long long *mortar_node_indices;         // P4est: [nd, 2, M], 1 = small side, 2 = large side
     const double *mortar_fwd[2], *mortar_rev[2];  // [0] lower, [1] upper
     const int *mpi_peer_slot;                            // [nmpi] index into the peer tables
     const long long *mpi_remote_index;                   // [nmpi] slot of this face in the peer's receive buffer
@@ -1552,6 +1553,119 @@ __global__ void __launch_bounds__(256) k_interface_flux_p4est(const KParams P) {
     for (int v = 0; v < NV; ++v) {
         sp[v] = f[v];
         ss[v] = -f[v];
+    }
+}
+
+// prolong2mortars! + calc_mortar_flux! + mortar_fluxes_to_elements! (dgsem_p4est/dg_2d.jl:802-1055,
+// dg_3d.jl:651-974), conservative equations, fused like k_mortar_flux: one block per mortar, one thread per
+// (position, face node).  The mortar is aligned at the small side (its node_indices always run forward); the
+// large face is read and written through its own node_indices.  The flux is taken along the outward normal of
+// the small element; the large element receives the L2 projection with the sign switched and scaled by the
+// ratio of the face areas, 2^(d-1).
+template <class EQ, int N>
+__global__ void __launch_bounds__((1 << (EQ::NDIMS - 1)) * ipow(N, EQ::NDIMS - 1)) k_mortar_flux_p4est(const KParams P) {
+    constexpr int ND = EQ::NDIMS, NV = EQ::NVARS, NF = ipow(N, ND - 1), NN = ipow(N, ND), NP = 1 << (ND - 1);
+    __shared__ double s_large[NV * NF];
+    __shared__ double s_tmp[NP][NV * NF];
+    __shared__ double s_f[NP][NV * NF];
+    const long long m = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int p = tid / NF, fn = tid - p * NF;
+    const int a = fn % N, b = fn / N;
+    const EQ eq(P.eq);
+    const long long *ids = P.mortar_ids + (NP + 1) * m;
+    const long long *sidx = P.mortar_node_indices + (2 * m + 0) * ND, *lidx = P.mortar_node_indices + (2 * m + 1) * ND;
+    const long long large = ids[NP] - 1, small = ids[p] - 1;
+    const double *fwd1 = P.mortar_fwd[p & 1], *fwd2 = P.mortar_fwd[(p >> 1) & 1];
+    const double *rev1 = P.mortar_rev[p & 1];
+    // the large face in the orientation of the mortar
+    for (int q = tid; q < NV * NF; q += NP * NF) {
+        const int f = q / NV, v = q - f * NV;
+        int vn, sfn, dir;
+        p4_face<ND, N>(lidx, f % N, f / N, vn, sfn, dir);
+        s_large[q] = P.u[(large * NN + vn) * NV + v];
+    }
+    __syncthreads();
+    // interpolation to position p, first face coordinate first (multiply_dimensionwise! interpolation.jl:237-264)
+    double up[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+        double acc = 0.0;
+        for (int q = 0; q < N; ++q) acc += fwd1[a + N * q] * s_large[v + NV * (q + N * b)];
+        up[v] = acc;
+    }
+    if constexpr (ND == 3) {
+#pragma unroll
+        for (int v = 0; v < NV; ++v) s_tmp[p][v + NV * fn] = up[v];
+        __syncthreads();
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            double acc = 0.0;
+            for (int q = 0; q < N; ++q) acc += fwd2[b + N * q] * s_tmp[p][v + NV * (a + N * q)];
+            up[v] = acc;
+        }
+        __syncthreads();  // s_tmp is reused by the projection below
+    }
+    // flux(u_small, u_large interpolated, outward normal of the small element)
+    double us[NV], f[NV], nrm[ND];
+    int svn, ssfn, sdir;
+    p4_face<ND, N>(sidx, a, b, svn, ssfn, sdir);
+    {
+        const double *pu = P.u + (small * NN + svn) * NV;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) us[v] = pu[v];
+    }
+    load_ja<ND, NN>(P, sdir / 2, svn, small, nrm);
+    if (sdir % 2 == 0) {
+#pragma unroll
+        for (int d = 0; d < ND; ++d) nrm[d] = -nrm[d];
+    }
+    eq.numflux_normal(P.surface_flux, us, up, nrm, f);
+    {
+        double *dst = P.sfv + ((small * (2 * ND) + sdir) * NF + fn) * NV;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            dst[v] = f[v];
+            s_f[p][v + NV * fn] = f[v];
+        }
+    }
+    __syncthreads();
+    // L2 projection onto the large face
+    int lvn, lsfn, ldir;
+    p4_face<ND, N>(lidx, a, b, lvn, lsfn, ldir);
+    double *out = P.sfv + ((large * (2 * ND) + ldir) * NF + lsfn) * NV;
+    if constexpr (ND == 2) {
+        if (tid < N) {
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+                double acc = 0.0;
+                for (int q = 0; q < N; ++q)
+                    acc += P.mortar_rev[1][tid + N * q] * s_f[1][v + NV * q] + P.mortar_rev[0][tid + N * q] * s_f[0][v + NV * q];
+                out[v] = acc * -2.0;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            double acc = 0.0;
+            for (int q = 0; q < N; ++q) acc += rev1[a + N * q] * s_f[p][v + NV * (q + N * b)];
+            s_tmp[p][v + NV * fn] = acc;
+        }
+        __syncthreads();
+        if (tid < NF) {
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+                double res = 0.0;
+#pragma unroll
+                for (int pp = 0; pp < 4; ++pp) {  // positions 1..4 in this order (dg_3d.jl:914-929)
+                    const double *r2 = P.mortar_rev[(pp >> 1) & 1];
+                    double acc = 0.0;
+                    for (int q = 0; q < N; ++q) acc += r2[b + N * q] * s_tmp[pp][v + NV * (a + N * q)];
+                    res = pp == 0 ? acc : res + acc;
+                }
+                out[v] = res * -4.0;
+            }
+        }
     }
 }
 

@@ -102,7 +102,10 @@ template <class EQ, int N>
 void launch_mortar_flux(const KParams &P, cudaStream_t s) {
     if (P.nmortars == 0) return;
     constexpr int threads = (1 << (EQ::NDIMS - 1)) * ipow(N, EQ::NDIMS - 1);
-    k_mortar_flux<EQ, N><<<(unsigned)P.nmortars, threads, 0, s>>>(P);
+    if (P.p4est)
+        k_mortar_flux_p4est<EQ, N><<<(unsigned)P.nmortars, threads, 0, s>>>(P);
+    else
+        k_mortar_flux<EQ, N><<<(unsigned)P.nmortars, threads, 0, s>>>(P);
 }
 
 template <class EQ, int N>
@@ -369,6 +372,7 @@ cudaError_t preload_all() {
     TB_PRELOAD((k_boundary_flux<EQ, N>));
     TB_PRELOAD((k_sfv_fill_right<EQ, N>));
     TB_PRELOAD((k_mortar_flux<EQ, N>));
+    TB_PRELOAD((k_mortar_flux_p4est<EQ, N>));
     TB_PRELOAD((k_error_norms<EQ, N>));
     TB_PRELOAD((k_mpi_pack<EQ, N>));
     TB_PRELOAD((k_mpi_interface_flux<EQ, N>));

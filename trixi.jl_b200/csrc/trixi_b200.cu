@@ -621,13 +621,12 @@ TRIXI_B200_API int trixi_b200_create(const trixi_b200_desc *d, trixi_b200_handle
         return fail(nullptr, TRIXI_B200_EINVAL, "StructuredMesh is single-rank (as in the reference)");
     if (d->nmortars < 0) return fail(nullptr, TRIXI_B200_EINVAL, "negative container size");
     if (d->nmortars > 0) {
-        if (d->mesh_kind != TRIXI_B200_MESH_TREE)
-            return fail(nullptr, TRIXI_B200_EINVAL, "mortars are supported on TreeMesh only");
+        if (structured) return fail(nullptr, TRIXI_B200_EINVAL, "a StructuredMesh has no mortars");
         if (d->world_size > 1) return fail(nullptr, TRIXI_B200_EINVAL, "MPI mortars are not supported by this build");
         if (d->equation == TRIXI_B200_EQ_MHD_3D)
             return fail(nullptr, TRIXI_B200_EINVAL, "mortars with nonconservative terms are not supported by this build");
-        if (!d->mortar_neighbor_ids || !d->mortar_large_sides || !d->mortar_orientations || !d->mortar_forward_upper ||
-            !d->mortar_forward_lower || !d->mortar_reverse_upper || !d->mortar_reverse_lower)
+        if (!d->mortar_neighbor_ids || !d->mortar_forward_upper || !d->mortar_forward_lower || !d->mortar_reverse_upper ||
+            !d->mortar_reverse_lower || (p4est ? !d->mortar_node_indices : !d->mortar_large_sides || !d->mortar_orientations))
             return fail(nullptr, TRIXI_B200_EINVAL, "mortar arrays missing");
     }
     if (d->volume_integral != TRIXI_B200_VOLINT_WEAK_FORM && d->volume_integral != TRIXI_B200_VOLINT_FLUX_DIFFERENCING &&
@@ -787,10 +786,15 @@ TRIXI_B200_API int trixi_b200_create(const trixi_b200_desc *d, trixi_b200_handle
         long long *mtmp = nullptr;
         CREATE_TRY(upload_array(h, (const long long *)d->mortar_neighbor_ids, np1 * (size_t)d->nmortars, &mtmp));
         P.mortar_ids = mtmp;
-        CREATE_TRY(upload_array(h, (const long long *)d->mortar_large_sides, (size_t)d->nmortars, &mtmp));
-        P.mortar_large_sides = mtmp;
-        CREATE_TRY(upload_array(h, (const long long *)d->mortar_orientations, (size_t)d->nmortars, &mtmp));
-        P.mortar_orient = mtmp;
+        if (p4est) {
+            CREATE_TRY(upload_array(h, (const long long *)d->mortar_node_indices, 2 * (size_t)nd * (size_t)d->nmortars, &mtmp));
+            P.mortar_node_indices = mtmp;
+        } else {
+            CREATE_TRY(upload_array(h, (const long long *)d->mortar_large_sides, (size_t)d->nmortars, &mtmp));
+            P.mortar_large_sides = mtmp;
+            CREATE_TRY(upload_array(h, (const long long *)d->mortar_orientations, (size_t)d->nmortars, &mtmp));
+            P.mortar_orient = mtmp;
+        }
         CREATE_TRY(upload_array(h, d->mortar_forward_lower, (size_t)n * n, &tmp));
         P.mortar_fwd[0] = tmp;
         CREATE_TRY(upload_array(h, d->mortar_forward_upper, (size_t)n * n, &tmp));

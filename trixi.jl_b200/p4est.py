@@ -13,6 +13,11 @@ initial_refinement_level, periodicity)`` (p4est_mesh.jl:189-247):
   * interface / boundary containers with symbolic ``node_indices`` (dgsem_p4est/containers.jl:226-262,
     init_interface_node_indices! containers_3d.jl:86-143), encoded as integers for the C ABI:
     :begin 0, :end 1, :i_forward 2, :i_backward 3, :j_forward 4, :j_backward 5.
+A forest may be refined non-uniformly before the semidiscretization is built -- ``refine(refine_fn)`` is
+``refine_p4est!(mesh.p4est, recursive, refine_fn_c, C_NULL)`` with the callback's (which_tree, quadrant.x/.y/.z,
+quadrant.level) (p4est_mesh.jl:2457-2482), ``balance()`` the 2:1 face balance ``create_cache`` applies
+(``balance!`` p4est_mesh.jl:2484-2493, dgsem_p4est/dg.jl:13-16).  Hanging faces become L2 mortars
+(``init_mortars!`` dgsem_p4est/containers.jl:686-689,902-948, node indices containers_3d.jl:159-201).
 Mesh files (``P4estMesh{NDIMS}(meshfile)``) and AMR need libp4est and stay with the reference.
 """
 from __future__ import annotations
@@ -63,7 +68,121 @@ class P4estMesh:
         lut = np.full(self.cells_per_dimension, -1, dtype=np.int64)
         lut[tuple(self.global_coords)] = np.arange(self.ncells, dtype=np.int64)
         self._lut = lut
+        self.levels = np.full(self.ncells, L, dtype=np.int64)
+        self.is_uniform = True
         self.tree_node_coordinates = self._calc_tree_node_coordinates()
+
+    # P4EST_MAXLEVEL = 30, P8EST_MAXLEVEL = 19: quadrant.x/.y/.z are multiples of root_len / 2^level
+    @property
+    def root_len(self):
+        return 1 << (30 if self.ndims == 2 else 19)
+
+    def _set_leaves(self, tree, level, coords):
+        """Store the leaves sorted tree by tree, Morton order inside a tree (p4est's quadrant order)."""
+        nd = self.ndims
+        lmax = int(level.max()) if level.size else 0
+        fine = coords << (lmax - level)[None, :]
+        order = np.lexsort((morton_key(fine, nd), tree))
+        self.tree_of_element = tree[order]
+        self.levels = level[order]
+        self.quad_coords = coords[:, order]
+        self.is_uniform = bool(np.all(self.levels == self.levels[0]))
+        if self.is_uniform:
+            L = int(self.levels[0])
+            self.initial_refinement_level = L
+            q = 1 << L
+            tcoord = np.stack(np.unravel_index(self.tree_of_element, self.trees_per_dimension, order="F"))
+            self.global_coords = tcoord * q + self.quad_coords
+            self.cells_per_dimension = tuple(t * q for t in self.trees_per_dimension)
+            lut = np.full(self.cells_per_dimension, -1, dtype=np.int64)
+            lut[tuple(self.global_coords)] = np.arange(self.ncells, dtype=np.int64)
+            self._lut = lut
+        else:
+            self._lut = self.global_coords = self.cells_per_dimension = None
+        self._leaf_index = None
+        self._surfaces = None
+
+    def refine(self, refine_fn, recursive=True):
+        """``refine_p4est!``: ``refine_fn(which_tree, x, y[, z], level) -> bool`` with p4est's integer quadrant
+        coordinates; ``recursive`` re-offers the children.  Call ``balance()`` (or build a semidiscretization,
+        which balances like the reference's ``create_cache``) afterwards."""
+        nd = self.ndims
+        todo = [(int(t), int(l), tuple(int(c) for c in self.quad_coords[:, e]))
+                for e, (t, l) in enumerate(zip(self.tree_of_element, self.levels))]
+        done = []
+        while todo:
+            nxt = []
+            for t, l, c in todo:
+                h = self.root_len >> l
+                if refine_fn(t, *[ci * h for ci in c], l):
+                    children = [(t, l + 1, tuple(2 * c[d] + ((child >> d) & 1) for d in range(nd)))
+                                for child in range(1 << nd)]
+                    (nxt if recursive else done).extend(children)
+                else:
+                    done.append((t, l, c))
+            todo = nxt
+        self._set_leaves(np.array([x[0] for x in done], dtype=np.int64), np.array([x[1] for x in done], dtype=np.int64),
+                         np.array([x[2] for x in done], dtype=np.int64).T.reshape(nd, -1))
+        return self
+
+    def leaf_index(self):
+        if getattr(self, "_leaf_index", None) is None:
+            self._leaf_index = {(int(t), int(l)) + tuple(int(c) for c in self.quad_coords[:, e]): e
+                                for e, (t, l) in enumerate(zip(self.tree_of_element, self.levels))}
+        return self._leaf_index
+
+    def neighbor_cell(self, tree, level, coords, d, side):
+        """(tree, coords) of the same-size cell across face (d, side) of a quadrant, or None at a domain boundary."""
+        tp = self.trees_per_dimension
+        tc = list(np.unravel_index(tree, tp, order="F"))
+        c = list(coords)
+        c[d] += 1 if side else -1
+        q = 1 << level
+        if c[d] < 0 or c[d] >= q:
+            tc[d] += 1 if side else -1
+            c[d] %= q
+            if tc[d] < 0 or tc[d] >= tp[d]:
+                if not self.periodicity[d]:
+                    return None
+                tc[d] %= tp[d]
+        return int(np.ravel_multi_index(tuple(int(x) for x in tc), tp, order="F")), tuple(c)
+
+    def find_leaf(self, tree, level, coords):
+        """The leaf covering cell (tree, level, coords): (element, its level), or None if the cell is subdivided."""
+        idx = self.leaf_index()
+        for k in range(level + 1):
+            e = idx.get((tree, level - k) + tuple(ci >> k for ci in coords))
+            if e is not None:
+                return e, level - k
+        return None
+
+    def balance(self):
+        """2:1 balance across faces (P4EST_CONNECT_FACE): a leaf whose face neighbour is more than one level finer is
+        split, until nothing changes."""
+        nd = self.ndims
+        while True:
+            split = set()
+            for e in range(self.ncells):
+                t, l = int(self.tree_of_element[e]), int(self.levels[e])
+                c = tuple(int(x) for x in self.quad_coords[:, e])
+                for d in range(nd):
+                    for side in (0, 1):
+                        nb = self.neighbor_cell(t, l, c, d, side)
+                        if nb is None:
+                            continue
+                        found = self.find_leaf(nb[0], l, nb[1])
+                        if found is not None and found[1] < l - 1:
+                            split.add(found[0])
+            if not split:
+                return self
+            keep = np.array([e not in split for e in range(self.ncells)])
+            tree, level, coords = [self.tree_of_element[keep]], [self.levels[keep]], [self.quad_coords[:, keep]]
+            for e in sorted(split):
+                for child in range(1 << nd):
+                    tree.append(self.tree_of_element[e:e + 1])
+                    level.append(self.levels[e:e + 1] + 1)
+                    coords.append((2 * self.quad_coords[:, e] + np.array([(child >> d) & 1 for d in range(nd)]))[:, None])
+            self._set_leaves(np.concatenate(tree), np.concatenate(level), np.concatenate(coords, axis=1))
 
     @property
     def ncells(self):
@@ -104,26 +223,28 @@ def init_elements_p4est(mesh, basis, first=0, last=None):
     nd, n = mesh.ndims, basis.nnodes
     if n < mesh.nodes.shape[0]:
         raise ValueError("The solver can't have a lower polydeg than the mesh")
-    L = mesh.initial_refinement_level
-    quad_length = 1.0 / (1 << L)
     last = mesh.ncells if last is None else last
     nelem = last - first
     X = np.empty((nd,) + (n,) * nd + (nelem,), order="F")
-    # interpolation matrices only depend on the quadrant coordinate along one axis
-    mats = []
-    for c in range(1 << L):
-        nodes_out = 2 * (quad_length * 1 / 2 * (basis.nodes + 1) + c * quad_length) - 1
-        mats.append(polynomial_interpolation_matrix(mesh.nodes, nodes_out))
-    mats = np.stack(mats)  # [2^L, n, n_mesh]
-    T = mesh.tree_node_coordinates[..., mesh.tree_of_element[first:last]]  # [nd, nm.., nelem]
-    data = T
-    for d in range(nd):
-        M = mats[mesh.quad_coords[d, first:last]]  # [nelem, n, nm]
-        # contract axis 1+d of data with the last axis of M, per element
-        data = np.moveaxis(data, 1 + d, -2)            # [..., nm, nelem]
-        data = np.einsum("eij,...je->...ie", M, data)  # [..., n, nelem]
-        data = np.moveaxis(data, -2, 1 + d)
-    X[...] = data
+    levels = mesh.levels[first:last]
+    for L in np.unique(levels):
+        sel = np.nonzero(levels == L)[0]
+        quad_length = 1.0 / (1 << int(L))
+        # interpolation matrices only depend on the quadrant coordinate along one axis
+        # (quad_length = p4est_quadrant_len(level) / p4est_root_len, anchor = quad.x / p4est_root_len)
+        used = np.unique(mesh.quad_coords[:, first:last][:, sel])
+        mats = np.zeros((1 << int(L), n, mesh.nodes.shape[0]))
+        for c in used:
+            nodes_out = 2 * (quad_length * 1 / 2 * (basis.nodes + 1) + c * quad_length) - 1
+            mats[c] = polynomial_interpolation_matrix(mesh.nodes, nodes_out)
+        data = mesh.tree_node_coordinates[..., mesh.tree_of_element[first:last][sel]]  # [nd, nm.., nsel]
+        for d in range(nd):
+            M = mats[mesh.quad_coords[d, first:last][sel]]  # [nsel, n, nm]
+            # contract axis 1+d of data with the last axis of M, per element
+            data = np.moveaxis(data, 1 + d, -2)            # [..., nm, nsel]
+            data = np.einsum("eij,...je->...ie", M, data)  # [..., n, nsel]
+            data = np.moveaxis(data, -2, 1 + d)
+        X[..., sel] = data
     el = P4estElementContainer()
     el.nelements = nelem
     el.node_coordinates = X
@@ -147,6 +268,108 @@ def _face_indices(nd, d, side):
     return idx
 
 
+class P4estMortarContainer:
+    """P4estMortarContainer (dgsem_p4est/containers.jl:563-613): ``neighbor_ids [2^(d-1)+1, M]`` (small elements by
+    position, the large element last), ``node_indices [ndims, 2, M]`` (1: small side, 2: large side)."""
+    pass
+
+
+def _init_surfaces_general(mesh):
+    """init_surfaces! (dgsem_p4est/containers.jl:786-838) for a forest with hanging faces: p4est's face iteration is
+    replaced by a walk over the leaves and their 2*ndims faces.  A face whose same-size neighbour cell is a leaf of the
+    same level is an interface (taken from the negative side: primary = the element whose + face it is), a subdivided
+    neighbour cell makes a mortar with this leaf as the large element, a coarser neighbour is handled from its side.
+    Trees of a brick share their axes (orientation code 0, opposite faces), so both sides index forward
+    (orientation_to_indices_p4est containers_3d.jl:206-300 with flipped = false, code 0)."""
+    if getattr(mesh, "_surfaces", None) is not None:
+        return mesh._surfaces
+    nd = mesh.ndims
+    npos = 1 << (nd - 1)
+    surf_dims = [[c for c in range(nd) if c != d] for d in range(nd)]
+    prim, sec, idim = [], [], []
+    m_ids, m_idx = [], []
+    bnd = [[] for _ in range(2 * nd)]
+    for e in range(mesh.ncells):
+        t, l = int(mesh.tree_of_element[e]), int(mesh.levels[e])
+        c = tuple(int(x) for x in mesh.quad_coords[:, e])
+        for d in range(nd):
+            for side in (0, 1):
+                nb = mesh.neighbor_cell(t, l, c, d, side)
+                if nb is None:
+                    bnd[2 * d + side].append(e)
+                    continue
+                found = mesh.find_leaf(nb[0], l, nb[1])
+                if found is not None:
+                    if found[1] == l and side == 1:
+                        prim.append(e)
+                        sec.append(found[0])
+                        idim.append(d)
+                    elif found[1] < l - 1:
+                        raise ValueError("the forest is not 2:1 balanced; call mesh.balance()")
+                    continue
+                # hanging face: the 2^(d-1) small elements in the z-order of the face coordinates
+                small = []
+                for pos in range(npos):
+                    cc = [2 * x for x in nb[1]]
+                    cc[d] += 0 if side == 1 else 1
+                    for k, sd in enumerate(surf_dims[d]):
+                        cc[sd] += (pos >> k) & 1
+                    f2 = mesh.find_leaf(nb[0], l + 1, tuple(cc))
+                    if f2 is None or f2[1] != l + 1:
+                        raise ValueError("the forest is not 2:1 balanced; call mesh.balance()")
+                    small.append(f2[0])
+                m_ids.append(small + [e])
+                m_idx.append([_face_indices(nd, d, 1 - side), _face_indices(nd, d, side)])
+    face_idx = np.array([[_face_indices(nd, d, 1), _face_indices(nd, d, 0)] for d in range(nd)], dtype=np.int64)
+    ic = InterfaceContainer()
+    prim, sec, idim = (np.array(x, dtype=np.int64) for x in (prim, sec, idim))
+    ic.neighbor_ids = np.asfortranarray(np.stack([prim + 1, sec + 1])) if prim.size else np.zeros((2, 0), dtype=np.int64)
+    ic.node_indices = (np.asfortranarray(face_idx[idim].transpose(2, 1, 0)) if prim.size
+                       else np.zeros((nd, 2, 0), dtype=np.int64))
+    ic.orientations = np.zeros(prim.shape[0], dtype=np.int64)
+    ic.ninterfaces = int(prim.shape[0])
+    mc = P4estMortarContainer()
+    mc.nmortars = len(m_ids)
+    mc.neighbor_ids = (np.asfortranarray(np.array(m_ids, dtype=np.int64).T + 1) if m_ids
+                       else np.zeros((npos + 1, 0), dtype=np.int64))
+    mc.node_indices = (np.asfortranarray(np.array(m_idx, dtype=np.int64).transpose(2, 1, 0)) if m_ids
+                       else np.zeros((nd, 2, 0), dtype=np.int64))
+    bc = BoundaryContainer()
+    counts = [len(b) for b in bnd]
+    bc.neighbor_ids = np.array([e + 1 for b in bnd for e in b], dtype=np.int64)
+    bc.node_indices = (np.asfortranarray(np.array([_face_indices(nd, dr // 2, dr % 2) for dr, b in enumerate(bnd) for _ in b],
+                                                  dtype=np.int64).T.reshape(nd, -1)))
+    bc.orientations = np.array([dr // 2 + 1 for dr, b in enumerate(bnd) for _ in b], dtype=np.int64)
+    bc.neighbor_sides = np.array([2 if dr % 2 == 0 else 1 for dr, b in enumerate(bnd) for _ in b], dtype=np.int64)
+    bc.node_coordinates = np.zeros((nd, 0))
+    bc.n_boundaries_per_direction = np.array(counts + [0] * (6 - len(counts)), dtype=np.int64)
+    bc.nboundaries = int(bc.neighbor_ids.shape[0])
+    mesh._surfaces = (ic, mc, bc)
+    return mesh._surfaces
+
+
+def _empty_mpi_interfaces(nd):
+    mi = MPIInterfaceContainer()
+    mi.local_neighbor_ids = mi.local_sides = mi.orientations = mi.neighbor_ranks = np.zeros(0, dtype=np.int64)
+    mi.global_interface_ids = np.zeros(0, dtype=np.int64)
+    mi.node_indices = np.zeros((nd, 0), dtype=np.int64)
+    mi.nmpiinterfaces = 0
+    return mi
+
+
+def init_mortars_p4est(mesh, first=0, last=None, world_size=1):
+    """init_mortars! (dgsem_p4est/containers.jl:646-689).  Conforming forests have none."""
+    if mesh.is_uniform:
+        mc = P4estMortarContainer()
+        mc.nmortars = 0
+        mc.neighbor_ids = np.zeros(((1 << (mesh.ndims - 1)) + 1, 0), dtype=np.int64)
+        mc.node_indices = np.zeros((mesh.ndims, 2, 0), dtype=np.int64)
+        return mc
+    if world_size != 1:
+        raise NotImplementedError("non-conforming P4estMesh across ranks (MPI mortars) is not supported")
+    return _init_surfaces_general(mesh)[1]
+
+
 def init_interfaces_p4est(mesh, first=0, last=None, world_size=1):
     """init_interfaces! (dgsem_p4est/containers.jl:264-300) for a conforming brick forest: one interface per
     interior (or periodic) face, primary = the element on the negative side.  Faces whose other element
@@ -155,6 +378,10 @@ def init_interfaces_p4est(mesh, first=0, last=None, world_size=1):
     (neighbour rank, global interface id) (init_mpi_neighbor_connectivity dg_parallel.jl:313-390).
     Returns (interfaces, mpi_interfaces)."""
     nd = mesh.ndims
+    if not mesh.is_uniform:
+        if world_size != 1:
+            raise NotImplementedError("non-conforming P4estMesh across ranks (MPI mortars) is not supported")
+        return _init_surfaces_general(mesh)[0], _empty_mpi_interfaces(nd)
     cells = mesh.cells_per_dimension
     gc = mesh.global_coords
     last = mesh.ncells if last is None else last
@@ -209,6 +436,8 @@ def init_boundaries_p4est(mesh, first=0, last=None):
     """init_boundaries! (dgsem_p4est/containers.jl:302-345), sorted by boundary name
     :x_neg, :x_pos, :y_neg, ... (structured_boundary_names! p4est_mesh.jl:298-365); elements [first, last)."""
     nd = mesh.ndims
+    if not mesh.is_uniform:
+        return _init_surfaces_general(mesh)[2]
     cells = mesh.cells_per_dimension
     last = mesh.ncells if last is None else last
     gc = mesh.global_coords[:, first:last]

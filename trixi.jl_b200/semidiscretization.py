@@ -20,7 +20,8 @@ from .equations import (BC_DIRICHLET, BC_PERIODIC, BC_SLIP_WALL, IC_NONE, SRC_NO
                         BoundaryConditionDirichlet, boundary_condition_periodic, resolve_flux)
 from .basis import LobattoLegendreMortarL2
 from .mesh import TreeMesh
-from .p4est import P4estMesh, init_boundaries_p4est, init_elements_p4est, init_interfaces_p4est
+from .p4est import (P4estMesh, init_boundaries_p4est, init_elements_p4est, init_interfaces_p4est,
+                    init_mortars_p4est)
 from .structured import StructuredMesh, init_elements_structured
 
 MESH_TREE, MESH_STRUCTURED, MESH_P4EST = 0, 1, 2
@@ -79,12 +80,16 @@ def create_cache(mesh, equations, solver, rank=0, world_size=1):
         cache.mpi_interfaces.nmpiinterfaces = 0
         cache.boundaries = _structured_boundaries(mesh, cache.elements)
     elif isinstance(mesh, P4estMesh):
-        # create_cache dgsem_p4est/dg.jl:13-70 (+ dg_parallel.jl:267-311 for a partition)
+        # create_cache dgsem_p4est/dg.jl:13-70 (+ dg_parallel.jl:267-311 for a partition); the forest is balanced
+        # first "in case someone has tampered with the p4est after creating the mesh" (dg.jl:13-16)
+        if not mesh.is_uniform:
+            mesh.balance()
         first, last = partition_cells(mesh.ncells, rank, world_size)
         cache.first_element, cache.last_element = first, last
         cache.elements = init_elements_p4est(mesh, solver.basis, first, last)
         cache.interfaces, cache.mpi_interfaces = init_interfaces_p4est(mesh, first, last, world_size)
         cache.boundaries = init_boundaries_p4est(mesh, first, last)
+        cache.mortars = init_mortars_p4est(mesh, first, last, world_size)
     else:
         raise TypeError(f"unsupported mesh type {type(mesh).__name__}")
     return cache
@@ -261,8 +266,11 @@ class SemidiscretizationHyperbolic:
             # L2 mortars (containers_3d.jl:495-510) and their operators (basis_lobatto_legendre.jl:159-206)
             l2 = LobattoLegendreMortarL2(dg.basis)
             h.set_i64("mortar_neighbor_ids", mortars.neighbor_ids)
-            h.set_i64("mortar_large_sides", mortars.large_sides)
-            h.set_i64("mortar_orientations", mortars.orientations)
+            if isinstance(self.mesh, P4estMesh):
+                h.set_i64("mortar_node_indices", mortars.node_indices)
+            else:
+                h.set_i64("mortar_large_sides", mortars.large_sides)
+                h.set_i64("mortar_orientations", mortars.orientations)
             h.set_f64("mortar_forward_upper", l2.forward_upper)
             h.set_f64("mortar_forward_lower", l2.forward_lower)
             h.set_f64("mortar_reverse_upper", l2.reverse_upper)
