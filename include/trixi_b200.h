@@ -82,7 +82,10 @@ enum {
     TRIXI_B200_FLUX_LLF_MHD_POWELL = 12,            /* (flux_lax_friedrichs, flux_nonconservative_powell) */
     TRIXI_B200_FLUX_HINDENLANG_GASSNER_POWELL = 13, /* (flux_hindenlang_gassner, flux_nonconservative_powell)
                                                        ideal_glm_mhd_3d.jl:295-340,680-779 */
-    TRIXI_B200_FLUX_LLF_NAIVE_MHD_POWELL = 14       /* (FluxLaxFriedrichs(max_abs_speed_naive), powell) */
+    TRIXI_B200_FLUX_LLF_NAIVE_MHD_POWELL = 14,      /* (FluxLaxFriedrichs(max_abs_speed_naive), powell) */
+    TRIXI_B200_FLUX_HLLE_MHD_POWELL = 15            /* (flux_hlle, powell): FluxHLL(min_max_speed_einfeldt)
+                                                       numerical_fluxes.jl:422-457, ideal_glm_mhd_3d.jl:1094-1130,
+                                                       Roe averages :1415-1491 */
 };
 
 /* source terms (calc_sources! dg_3d.jl:1417-1437 calls an arbitrary closure; here: registry) */
@@ -192,6 +195,26 @@ typedef struct trixi_b200_desc {
      * side, 2: the large side, same encoding as interface_node_indices; mortar_neighbor_ids holds the small elements
      * by position and the large element last; mortar_large_sides / mortar_orientations are TreeMesh-only */
     const int64_t *mortar_node_indices;
+
+    /* MPI mortars (MPIL2MortarContainer dgsem_tree/containers_2d.jl:1003-1070, P4estMPIMortarContainer
+     * dgsem_p4est/containers_parallel.jl:130-210): mortars whose elements live on more than one rank.
+     * mpi_mortar_neighbor_ids [2^(d-1)+1, nmpimortars], small elements by position, the large element last:
+     *   > 0  element of this rank (1-based);
+     *   < 0  minus the 1-based position of the MPI-interface entry through which that element's face state arrives
+     *        (its remote side); those entries have mpi_is_mortar_piece = 1: both ranks send the face of their own
+     *        element there as for a conforming shared face, but no interface flux is evaluated;
+     *   = 0  a small element this rank neither owns nor needs (it does not own the large element).
+     * Every rank evaluates the mortar fluxes of the positions it has both sides of and stores them for its own
+     * elements only (calc_mpi_mortar_flux! + mpi_mortar_fluxes_to_elements!, dg_2d_parallel.jl:742-860,
+     * dgsem_p4est/dg_3d_parallel.jl:382-560). */
+    int64_t nmpimortars;
+    const int64_t *mpi_mortar_neighbor_ids;
+    const int64_t *mpi_mortar_large_sides;        /* TreeMesh: [nmpimortars] */
+    const int64_t *mpi_mortar_orientations;       /* TreeMesh: [nmpimortars] */
+    const int64_t *mpi_mortar_node_indices;       /* P4est: [ndims, 2, nmpimortars], 1: small side, 2: large side */
+    const double *mpi_mortar_normal_directions;   /* P4est: [ndims, n^(d-1), 2^(d-1), nmpimortars] outward normals of
+                                                     the small elements (they may be remote) */
+    const int64_t *mpi_is_mortar_piece;           /* [nmpiinterfaces], NULL = all zero */
 } trixi_b200_desc;
 
 typedef struct trixi_b200_handle trixi_b200_handle;

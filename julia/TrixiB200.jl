@@ -149,6 +149,13 @@ struct Desc
     indicator_alpha_min::Float64
     inverse_vandermonde_legendre::Ptr{Float64}
     mortar_node_indices::Ptr{Int64}
+    nmpimortars::Int64
+    mpi_mortar_neighbor_ids::Ptr{Int64}
+    mpi_mortar_large_sides::Ptr{Int64}
+    mpi_mortar_orientations::Ptr{Int64}
+    mpi_mortar_node_indices::Ptr{Int64}
+    mpi_mortar_normal_directions::Ptr{Float64}
+    mpi_is_mortar_piece::Ptr{Int64}
 end
 
 # ---- the backend object ---------------------------------------------------------------------------------
@@ -261,7 +268,8 @@ function B200(semi::SemidiscretizationHyperbolic; device = -1)
                     0, 1, 0, C_NULL, C_NULL, C_NULL, C_NULL,   # single rank: no MPI interfaces
                     ptr_or_null(bd_idx), C_NULL,
                     fv_flux, ind_var, ind_smooth, 0, ind_max, ind_min, ptr_or_null(inv_vdm),
-                    ptr_or_null(mo_idx))
+                    ptr_or_null(mo_idx),
+                    0, C_NULL, C_NULL, C_NULL, C_NULL, C_NULL, C_NULL)   # single rank: no MPI mortars
         rc = ccall((:trixi_b200_create, libtrixi_b200), Cint, (Ref{Desc}, Ref{Ptr{Cvoid}}), desc, handle)
     end
     check(nothing, rc)

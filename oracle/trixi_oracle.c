@@ -331,6 +331,43 @@ static inline double mhd_fast_wavespeed(const eqn_t *eq, const double *u, int o)
     return sqrt(0.5 * s + 0.5 * sqrt(s * s - 4 * a_square * b[o] * b[o]));
 }
 
+/* calc_fast_wavespeed_roe(u_ll, u_rr, orientation) :1415-1491 (Cargo & Gallice Roe averages) */
+static inline void mhd_fast_wavespeed_roe(const eqn_t *eq, const double *ul, const double *ur, int o, double *vel_out,
+                                          double *c_f) {
+    double rho_ll = ul[0], rho_rr = ur[0];
+    double v_ll[3] = {ul[1] / rho_ll, ul[2] / rho_ll, ul[3] / rho_ll};
+    double v_rr[3] = {ur[1] / rho_rr, ur[2] / rho_rr, ur[3] / rho_rr};
+    const double *B_ll = ul + 5, *B_rr = ur + 5;
+    double kin_en_ll = 0.5 * (ul[1] * v_ll[0] + ul[2] * v_ll[1] + ul[3] * v_ll[2]);
+    double mag_norm_ll = B_ll[0] * B_ll[0] + B_ll[1] * B_ll[1] + B_ll[2] * B_ll[2];
+    double p_ll = (eq->gamma - 1) * (ul[4] - kin_en_ll - 0.5 * mag_norm_ll - 0.5 * ul[8] * ul[8]);
+    double kin_en_rr = 0.5 * (ur[1] * v_rr[0] + ur[2] * v_rr[1] + ur[3] * v_rr[2]);
+    double mag_norm_rr = B_rr[0] * B_rr[0] + B_rr[1] * B_rr[1] + B_rr[2] * B_rr[2];
+    double p_rr = (eq->gamma - 1) * (ur[4] - kin_en_rr - 0.5 * mag_norm_rr - 0.5 * ur[8] * ur[8]);
+    double p_total_ll = p_ll + 0.5 * mag_norm_ll, p_total_rr = p_rr + 0.5 * mag_norm_rr;
+    double sqrt_rho_ll = sqrt(rho_ll), sqrt_rho_rr = sqrt(rho_rr);
+    double inv_sqrt_rho_add = 1 / (sqrt_rho_ll + sqrt_rho_rr), inv_sqrt_rho_prod = 1 / (sqrt_rho_ll * sqrt_rho_rr);
+    double rho_ll_roe = sqrt_rho_ll * inv_sqrt_rho_add, rho_rr_roe = sqrt_rho_rr * inv_sqrt_rho_add;
+    double v_roe[3], B_roe[3];
+    for (int d = 0; d < 3; ++d) {
+        v_roe[d] = v_ll[d] * rho_ll_roe + v_rr[d] * rho_rr_roe;
+        B_roe[d] = B_ll[d] * rho_ll_roe + B_rr[d] * rho_rr_roe;
+    }
+    double H_ll = (ul[4] + p_total_ll) / rho_ll, H_rr = (ur[4] + p_total_rr) / rho_rr;
+    double H_roe = H_ll * rho_ll_roe + H_rr * rho_rr_roe;
+    double dB0 = B_ll[0] - B_rr[0], dB1 = B_ll[1] - B_rr[1], dB2 = B_ll[2] - B_rr[2];
+    double X = 0.5 * (dB0 * dB0 + dB1 * dB1 + dB2 * dB2) * (inv_sqrt_rho_add * inv_sqrt_rho_add);
+    double b_square_roe = (B_roe[0] * B_roe[0] + B_roe[1] * B_roe[1] + B_roe[2] * B_roe[2]) * inv_sqrt_rho_prod;
+    double a_square_roe = ((2 - eq->gamma) * X +
+                           (eq->gamma - 1) * (H_roe - 0.5 * (v_roe[0] * v_roe[0] + v_roe[1] * v_roe[1] + v_roe[2] * v_roe[2]) -
+                                              b_square_roe));
+    double c_a_roe = B_roe[o] * B_roe[o] * inv_sqrt_rho_prod;
+    double s = a_square_roe + b_square_roe;
+    double a_star_roe = sqrt(s * s - 4 * a_square_roe * c_a_roe);
+    *c_f = sqrt(0.5 * (a_square_roe + b_square_roe + a_star_roe));
+    *vel_out = v_roe[o];
+}
+
 /* ---- linear scalar advection (linear_scalar_advection_2d.jl:221-246) ----------------------------- */
 static inline void adv_flux(const eqn_t *eq, const double *u, int o, double *f) { f[0] = eq->a[o] * u[0]; }
 
@@ -423,6 +460,26 @@ static void numflux(const eqn_t *eq, int flux_id, const double *ul, const double
     case TRIXI_B200_FLUX_LLF_NAIVE_MHD_POWELL: /* (FluxLaxFriedrichs(max_abs_speed_naive), powell) */
         numflux(eq, TRIXI_B200_FLUX_LLF_NAIVE, ul, ur, o, f);
         return;
+    case TRIXI_B200_FLUX_HLLE_MHD_POWELL: { /* FluxHLL numerical_fluxes.jl:422-449 with min_max_speed_einfeldt
+                                              ideal_glm_mhd_3d.jl:1094-1130 */
+        double c_f_ll = mhd_fast_wavespeed(eq, ul, o), c_f_rr = mhd_fast_wavespeed(eq, ur, o), vel_roe, c_f_roe;
+        mhd_fast_wavespeed_roe(eq, ul, ur, o, &vel_roe, &c_f_roe);
+        double lmin = fmin(ul[1 + o] / ul[0] - c_f_ll, vel_roe - c_f_roe);
+        double lmax = fmax(ur[1 + o] / ur[0] + c_f_rr, vel_roe + c_f_roe);
+        if (lmin >= 0 && lmax >= 0) {
+            mhd_flux(eq, ul, o, f);
+        } else if (lmax <= 0 && lmin <= 0) {
+            mhd_flux(eq, ur, o, f);
+        } else {
+            double fl[MAXV], fr[MAXV];
+            mhd_flux(eq, ul, o, fl);
+            mhd_flux(eq, ur, o, fr);
+            double inv = 1 / (lmax - lmin);
+            double factor_ll = lmax * inv, factor_rr = lmin * inv, factor_diss = lmin * lmax * inv;
+            for (int v = 0; v < nv; ++v) f[v] = factor_ll * fl[v] - factor_rr * fr[v] + factor_diss * (ur[v] - ul[v]);
+        }
+        return;
+    }
     case TRIXI_B200_FLUX_LLF_MHD_POWELL: /* (flux_lax_friedrichs, powell) */
         numflux(eq, TRIXI_B200_FLUX_LLF, ul, ur, o, f);
         return;
@@ -433,7 +490,7 @@ static void numflux(const eqn_t *eq, int flux_id, const double *ul, const double
 
 static inline int flux_has_noncons(int flux_id) {
     return flux_id == TRIXI_B200_FLUX_HINDENLANG_GASSNER_POWELL || flux_id == TRIXI_B200_FLUX_LLF_MHD_POWELL ||
-           flux_id == TRIXI_B200_FLUX_LLF_NAIVE_MHD_POWELL;
+           flux_id == TRIXI_B200_FLUX_LLF_NAIVE_MHD_POWELL || flux_id == TRIXI_B200_FLUX_HLLE_MHD_POWELL;
 }
 
 /* ---- normal-direction versions (curved meshes) -------------------------------------------------- */
@@ -1321,6 +1378,7 @@ void oracle_calc_mpi_interface_flux(const trixi_b200_desc *d, double *sfv, const
     int64_t fsz = (int64_t)nv * nf * 2 * nd;
 #pragma omp parallel for schedule(static)
     for (int64_t I = 0; I < d->nmpiinterfaces; ++I) {
+        if (d->mpi_is_mortar_piece && d->mpi_is_mortar_piece[I]) continue; /* exchange only: see MPI mortars */
         int64_t element = d->mpi_local_neighbor_ids[I] - 1;
         int o = (int)d->mpi_orientations[I] - 1;
         int side = (int)d->mpi_local_sides[I];
@@ -1791,6 +1849,7 @@ void oracle_calc_surface_integral_p4est(const trixi_b200_desc *d, double *du, co
 
 /* rhs_hyperbolic! dgsem_tree/dg_2d.jl:113-186 dispatched for P4estMesh */
 void oracle_calc_mortar_flux_p4est(const trixi_b200_desc *d, double *sfv, const double *u);
+void oracle_calc_mpi_mortar_flux(const trixi_b200_desc *d, double *sfv, const double *u, const double *mpi_u);
 void oracle_rhs_p4est(const trixi_b200_desc *d, double *du, const double *u, double t, double *interfaces_u,
                       double *sfv) {
     oracle_set_zero(d, du);
@@ -1843,6 +1902,7 @@ void oracle_calc_mortar_flux(const trixi_b200_desc *d, double *sfv, const double
         int o = (int)d->mortar_orientations[m] - 1;
         int large_side = (int)d->mortar_large_sides[m]; /* 1: large element on the negative (left) side */
         double ularge[MAXV * 64], tmp[MAXV * 64], uproj[MAXV * 64], fstar[4][MAXV * 64], usmall[MAXV * 64];
+        double fprim[4][MAXV * 64];
         /* face of the large element that touches the mortar: its +face if it sits on the left */
         int lidx = large_side == 1 ? n - 1 : 0, sidx = large_side == 1 ? 0 : n - 1;
         for (int b = 0; b < nb; ++b)
@@ -1869,10 +1929,24 @@ void oracle_calc_mortar_flux(const trixi_b200_desc *d, double *sfv, const double
                 const double *ul = large_side == 1 ? uproj + nv * fn : usmall + nv * fn;
                 const double *ur = large_side == 1 ? usmall + nv * fn : uproj + nv * fn;
                 numflux(&eq, d->surface_flux, ul, ur, o, fstar[p] + nv * fn);
+                for (int v = 0; v < nv; ++v) fprim[p][v + nv * fn] = fstar[p][v + nv * fn];
+                if (flux_has_noncons(d->surface_flux)) {
+                    /* dg_3d.jl:1012-1233: fstar_primary (kept by the small elements) takes
+                     * nonconservative_flux(u_large, u_small), fstar_secondary (projected to the large element)
+                     * nonconservative_flux(u_small, u_large), each weighted 0.5 -- for either large side */
+                    const double *ularge_p = uproj + nv * fn, *usmall_p = usmall + nv * fn;
+                    double np_[MAXV], ns_[MAXV];
+                    mhd_noncons_powell(&eq, ularge_p, usmall_p, o, np_);
+                    mhd_noncons_powell(&eq, usmall_p, ularge_p, o, ns_);
+                    for (int v = 0; v < nv; ++v) {
+                        fprim[p][v + nv * fn] += 0.5 * np_[v];
+                        fstar[p][v + nv * fn] += 0.5 * ns_[v];
+                    }
+                }
             }
-            /* small elements take the flux as it is: direction facing the large element */
+            /* small elements take the (primary) flux as it is: direction facing the large element */
             int dir_small = large_side == 1 ? 2 * o : 2 * o + 1;
-            for (int q = 0; q < nv * nf; ++q) sfv[small * fsz + q + (int64_t)nv * nf * dir_small] = fstar[p][q];
+            for (int q = 0; q < nv * nf; ++q) sfv[small * fsz + q + (int64_t)nv * nf * dir_small] = fprim[p][q];
         }
         /* L2 projection of the small fluxes onto the large face */
         int dir_large = large_side == 1 ? 2 * o + 1 : 2 * o;
@@ -1979,6 +2053,136 @@ void oracle_calc_mortar_flux_p4est(const trixi_b200_desc *d, double *sfv, const 
     }
 }
 
+/* ---- MPI mortars ---------------------------------------------------------------------------------------------
+ * calc_mpi_mortar_flux! + mpi_mortar_fluxes_to_elements! (dgsem_tree/dg_2d_parallel.jl:742-860, dgsem_p4est/
+ * dg_2d_parallel.jl:270-420, dg_3d_parallel.jl:382-560): the arithmetic of the serial mortars above, with the faces
+ * of remote elements taken from the exchanged buffer (the remote side of the MPI-interface entry a negative
+ * neighbor id points to) and fluxes stored for local elements only.  The reference ships all faces of a mortar in
+ * one buffer; here every (large, small) pair of different ranks is one exchange-only MPI-interface entry. */
+static void mm_fetch_face(const trixi_b200_desc *d, int64_t id, const double *u, const double *mpi_u, int o, int fidx,
+                          const int64_t *idx, double *out) {
+    int n = d->nnodes, nd = d->ndims, nv = d->nvars;
+    int nf = ipow(n, nd - 1), nb = nd == 3 ? n : 1;
+    int64_t esz = (int64_t)nv * ipow(n, nd);
+    if (id > 0) {
+        for (int b = 0; b < nb; ++b)
+            for (int a = 0; a < n; ++a) {
+                int64_t vn = idx ? p4_volume_node(nd, n, idx, a, b) : face_to_volume_node(nd, n, o, fidx, a, b);
+                for (int v = 0; v < nv; ++v) out[v + nv * (a + n * b)] = u[(id - 1) * esz + nv * vn + v];
+            }
+    } else {
+        int64_t I = -id - 1;
+        int remote = 1 - ((int)d->mpi_local_sides[I] - 1);
+        for (int fn = 0; fn < nf; ++fn)
+            for (int v = 0; v < nv; ++v) out[v + nv * fn] = mpi_u[remote + 2 * (v + nv * (fn + (int64_t)nf * I))];
+    }
+}
+
+void oracle_calc_mpi_mortar_flux(const trixi_b200_desc *d, double *sfv, const double *u, const double *mpi_u) {
+    if (d->nmpimortars <= 0) return;
+    eqn_t eq = make_eqn(d);
+    int n = d->nnodes, nd = d->ndims, nv = d->nvars;
+    int nf = ipow(n, nd - 1), nb = nd == 3 ? n : 1, np = 1 << (nd - 1);
+    int64_t fsz = (int64_t)nv * nf * 2 * nd;
+    int p4 = d->mesh_kind == TRIXI_B200_MESH_P4EST;
+    const double *fwd[2] = {d->mortar_forward_lower, d->mortar_forward_upper};
+    const double *rev[2] = {d->mortar_reverse_lower, d->mortar_reverse_upper};
+#pragma omp parallel for schedule(static)
+    for (int64_t m = 0; m < d->nmpimortars; ++m) {
+        const int64_t *ids = d->mpi_mortar_neighbor_ids + (int64_t)(np + 1) * m;
+        const int64_t *small_idx = p4 ? d->mpi_mortar_node_indices + (int64_t)nd * (0 + 2 * m) : NULL;
+        const int64_t *large_idx = p4 ? d->mpi_mortar_node_indices + (int64_t)nd * (1 + 2 * m) : NULL;
+        int o = p4 ? 0 : (int)d->mpi_mortar_orientations[m] - 1;
+        int large_side = p4 ? 0 : (int)d->mpi_mortar_large_sides[m];
+        int lidx = large_side == 1 ? n - 1 : 0, sidx = large_side == 1 ? 0 : n - 1;
+        int small_dir = p4 ? p4_direction(nd, small_idx) : (large_side == 1 ? 2 * o : 2 * o + 1);
+        int large_dir = p4 ? p4_direction(nd, large_idx) : (large_side == 1 ? 2 * o + 1 : 2 * o);
+        double ularge[MAXV * 64], tmp[MAXV * 64], uproj[MAXV * 64], usmall[MAXV * 64], fstar[4][MAXV * 64],
+            fprim[MAXV * 64], out[MAXV * 64];
+        if (ids[np] == 0) continue; /* cannot happen: a rank with a small element receives the large face */
+        mm_fetch_face(d, ids[np], u, mpi_u, o, lidx, large_idx, ularge);
+        for (int p = 0; p < np; ++p) {
+            if (ids[p] == 0) continue; /* neither local nor needed */
+            if (nd == 2) {
+                mortar_apply_1d(fwd[p & 1], n, nv, 1, 0, ularge, uproj, 0);
+            } else {
+                mortar_apply_1d(fwd[p & 1], n, nv, nb, 0, ularge, tmp, 0);
+                mortar_apply_1d(fwd[(p >> 1) & 1], n, nv, nb, 1, tmp, uproj, 0);
+            }
+            mm_fetch_face(d, ids[p], u, mpi_u, o, sidx, small_idx, usmall);
+            for (int fn = 0; fn < nf; ++fn) {
+                double *f = fstar[p] + nv * fn;
+                if (p4) {
+                    const double *nrm = d->mpi_mortar_normal_directions + (int64_t)nd * (fn + (int64_t)nf * (p + (int64_t)np * m));
+                    double nn[3] = {0, 0, 0};
+                    for (int k = 0; k < nd; ++k) nn[k] = nrm[k];
+                    numflux_normal(&eq, d->surface_flux, usmall + nv * fn, uproj + nv * fn, nn, f);
+                } else {
+                    const double *ul = large_side == 1 ? uproj + nv * fn : usmall + nv * fn;
+                    const double *ur = large_side == 1 ? usmall + nv * fn : uproj + nv * fn;
+                    numflux(&eq, d->surface_flux, ul, ur, o, f);
+                }
+                for (int v = 0; v < nv; ++v) fprim[v + nv * fn] = f[v];
+                if (!p4 && flux_has_noncons(d->surface_flux)) {
+                    double np_[MAXV], ns_[MAXV];
+                    mhd_noncons_powell(&eq, uproj + nv * fn, usmall + nv * fn, o, np_);
+                    mhd_noncons_powell(&eq, usmall + nv * fn, uproj + nv * fn, o, ns_);
+                    for (int v = 0; v < nv; ++v) {
+                        fprim[v + nv * fn] += 0.5 * np_[v];
+                        f[v] += 0.5 * ns_[v];
+                    }
+                }
+            }
+            if (ids[p] > 0)
+                for (int q = 0; q < nv * nf; ++q) sfv[(ids[p] - 1) * fsz + q + (int64_t)nv * nf * small_dir] = fprim[q];
+        }
+        if (ids[np] < 0) continue; /* the large element belongs to another rank */
+        int64_t large = ids[np] - 1;
+        if (p4) {
+            if (nd == 2) {
+                for (int i = 0; i < n; ++i)
+                    for (int v = 0; v < nv; ++v) {
+                        double acc = 0.0;
+                        for (int q = 0; q < n; ++q)
+                            acc += rev[1][i + n * q] * fstar[1][v + nv * q] + rev[0][i + n * q] * fstar[0][v + nv * q];
+                        out[v + nv * i] = acc;
+                    }
+            } else {
+                for (int p = 0; p < 4; ++p) {
+                    mortar_apply_1d(rev[p & 1], n, nv, nb, 0, fstar[p], tmp, 0);
+                    mortar_apply_1d(rev[(p >> 1) & 1], n, nv, nb, 1, tmp, out, p > 0);
+                }
+            }
+            double scale = nd == 2 ? -2.0 : -4.0;
+            for (int j = 0; j < nb; ++j)
+                for (int i = 0; i < n; ++i) {
+                    int fn_large;
+                    p4_surface_node(nd, n, large_idx, i, j, &fn_large);
+                    for (int v = 0; v < nv; ++v)
+                        sfv[large * fsz + v + nv * (fn_large + nf * large_dir)] = out[v + nv * (i + n * j)] * scale;
+                }
+        } else {
+            double *dst = sfv + large * fsz + (int64_t)nv * nf * large_dir;
+            if (nd == 2) {
+                for (int i = 0; i < n; ++i)
+                    for (int v = 0; v < nv; ++v) {
+                        double acc = 0.0;
+                        for (int q = 0; q < n; ++q)
+                            acc += rev[1][i + n * q] * fstar[1][v + nv * q] + rev[0][i + n * q] * fstar[0][v + nv * q];
+                        dst[v + nv * i] = acc;
+                    }
+            } else {
+                static const int order[4] = {2, 3, 0, 1};
+                for (int k = 0; k < 4; ++k) {
+                    int p = order[k];
+                    mortar_apply_1d(rev[p & 1], n, nv, nb, 0, fstar[p], tmp, 0);
+                    mortar_apply_1d(rev[(p >> 1) & 1], n, nv, nb, 1, tmp, dst, k > 0);
+                }
+            }
+        }
+    }
+}
+
 /* rhs_hyperbolic! dgsem_tree/dg_2d.jl:113-186.  Work arrays: interfaces_u [2,nv,nf,I],
  * boundaries_u [2,nv,nf,B], sfv [nv,nf,2nd,nelem] (owned by the caller = the cache). */
 void oracle_rhs(const trixi_b200_desc *d, double *du, const double *u, double t, double *interfaces_u,
@@ -2037,6 +2241,7 @@ void oracle_calc_mpi_interface_flux_p4est(const trixi_b200_desc *d, double *sfv,
     int64_t fsz = (int64_t)nv * nf * 2 * nd;
 #pragma omp parallel for schedule(static)
     for (int64_t I = 0; I < d->nmpiinterfaces; ++I) {
+        if (d->mpi_is_mortar_piece && d->mpi_is_mortar_piece[I]) continue; /* exchange only: see MPI mortars */
         int64_t e = d->mpi_local_neighbor_ids[I] - 1;
         int side = (int)d->mpi_local_sides[I];
         const int64_t *idx = d->mpi_node_indices + (int64_t)nd * I;
@@ -2069,6 +2274,7 @@ void oracle_rhs_parallel_part1(const trixi_b200_desc *d, double *du, const doubl
         oracle_prolong2interfaces_p4est(d, interfaces_u, u);
         oracle_calc_interface_flux_p4est(d, sfv, interfaces_u);
         if (d->nboundaries > 0) oracle_calc_boundary_flux_p4est(d, sfv, u, t);
+        oracle_calc_mortar_flux_p4est(d, sfv, u);
         return;
     }
     oracle_prolong2mpiinterfaces(d, mpi_u, u);
@@ -2080,17 +2286,20 @@ void oracle_rhs_parallel_part1(const trixi_b200_desc *d, double *du, const doubl
         oracle_prolong2boundaries(d, boundaries_u, u);
         oracle_calc_boundary_flux(d, sfv, boundaries_u, t);
     }
+    oracle_calc_mortar_flux(d, sfv, u);
 }
 void oracle_rhs_parallel_part2(const trixi_b200_desc *d, double *du, const double *u, double t, double *sfv,
                                const double *mpi_u) {
     if (d->mesh_kind == TRIXI_B200_MESH_P4EST) {
         oracle_calc_mpi_interface_flux_p4est(d, sfv, mpi_u);
+        oracle_calc_mpi_mortar_flux(d, sfv, u, mpi_u);
         oracle_calc_surface_integral_p4est(d, du, sfv);
         oracle_apply_jacobian_curved(d, du);
         oracle_calc_sources(d, du, u, t);
         return;
     }
     oracle_calc_mpi_interface_flux(d, sfv, mpi_u);
+    oracle_calc_mpi_mortar_flux(d, sfv, u, mpi_u);
     oracle_calc_surface_integral(d, du, sfv);
     oracle_apply_jacobian(d, du);
     oracle_calc_sources(d, du, u, t);

@@ -389,7 +389,26 @@ def _mhd3d_alfven_wave():
     return T.SemidiscretizationHyperbolic(mesh, eq, T.initial_condition_convergence_test, solver)
 
 
+def _mhd3d_alfven_wave_mortar():
+    # examples/tree_3d_dgsem/elixir_mhd_alfven_wave_mortar.jl: L2 mortars with nonconservative terms, flux_hlle
+    eq = T.IdealGlmMhdEquations3D(5 / 3)
+    volume_flux = (T.flux_hindenlang_gassner, T.flux_nonconservative_powell)
+    solver = T.DGSEM(polydeg=3, surface_flux=(T.flux_hlle, T.flux_nonconservative_powell),
+                     volume_integral=T.VolumeIntegralFluxDifferencing(volume_flux))
+    patches = ({"type": "box", "coordinates_min": (-0.5, -0.5, -0.5), "coordinates_max": (0.5, 0.5, 0.5)},)
+    mesh = T.TreeMesh((-1.0,) * 3, (1.0,) * 3, initial_refinement_level=2, refinement_patches=patches,
+                      periodicity=True)
+    return T.SemidiscretizationHyperbolic(mesh, eq, T.initial_condition_convergence_test, solver)
+
+
 ELIXIRS.update({e.name: e for e in [
+    MhdElixir("tree_3d_mhd_alfven_wave_mortar", _mhd3d_alfven_wave_mortar, (0.0, 0.25), 1.0,
+              [0.002117092205724962, 0.0082287162318041, 0.0034356818644221947, 0.009802676239657889,
+               0.008065655848544878, 0.00822223011240085, 0.0033142782650662905, 0.009782724705061424,
+               0.003818346240751859],
+              [0.01498490966057986, 0.1168609357063561, 0.024026660552548984, 0.09909160811731985,
+               0.06507407924731945, 0.09999894905805326, 0.029292103110423517, 0.09399116188535625,
+               0.031263077562076205], "test/test_tree_3d_mhd.jl:130-158"),
     MhdElixir("tree_3d_mhd_ec", _mhd3d_ec, (0.0, 0.4), 1.4,
               [0.017590099293094203, 0.017695875823827714, 0.017695875823827686, 0.017698038279620777,
                0.07495006099352074, 0.010391801950005755, 0.010391801950005759, 0.010393502246627087,

@@ -31,6 +31,9 @@ NOISE_LIMITED = {"tree_3d_euler_taylor_green_vortex", "p4est_3d_tgv_p5", "struct
                  "p4est_3d_advection_basic", "p4est_3d_advection_nonconforming", "p4est_3d_free_stream_nonconforming"}
 
 
+NAN_PROPAGATION = {("p4est_3d_nonconforming_curved_ec_p5", "random")}
+
+
 def _oracle_noise(oracle_module, semi, u, t, du_ref):
     alt = oracle_module.OracleBackend(semi, nofma=True)
     du_alt = np.empty_like(u)
@@ -100,7 +103,7 @@ RHS_CASES = ["tree_3d_euler_ec", "tree_3d_euler_source_terms", "tree_3d_euler_so
              "tree_2d_euler_density_wave", "structured_3d_euler_free_stream", "structured_3d_euler_ec",
              "structured_3d_euler_source_terms", "structured_3d_euler_source_terms_nonperiodic_curved",
              "p4est_3d_euler_source_terms_nonperiodic", "p4est_3d_euler_source_terms_nonperiodic_kennedy_gruber",
-             "tree_3d_mhd_ec", "tree_3d_mhd_alfven_wave", "p4est_3d_curved_ec", "p4est_3d_curved_weak_form",
+             "tree_3d_mhd_ec", "tree_3d_mhd_alfven_wave", "tree_3d_mhd_alfven_wave_mortar", "p4est_3d_curved_ec", "p4est_3d_curved_weak_form",
              "p4est_3d_curved_level1", "tree_2d_advection_mortar", "tree_3d_euler_mortar",
              "structured_2d_advection_basic", "structured_2d_euler_free_stream", "structured_2d_euler_ec",
              "structured_2d_euler_source_terms_nonperiodic", "p4est_2d_advection_basic",
@@ -127,9 +130,17 @@ def test_rhs_matches_oracle(name, state, oracle_module):
     ref.rhs_host(du_ref, u, t)
     du_gpu = np.full_like(u, np.nan)
     T.rhs_hyperbolic(du_gpu, u, semi, t)  # the public call: host buffers in and out through the C ABI
-    assert np.all(np.isfinite(du_gpu))
+    finite = np.isfinite(du_ref)
+    if (name, state) in NAN_PROPAGATION:
+        # the degree-5 interpolation of the random state to the small faces leaves the admissible set (negative
+        # pressure): the reference's NaN-propagating sqrt/log (math.jl:89-97,137-146) poison those mortars' elements;
+        # the CUDA path must poison exactly the same entries and agree everywhere else
+        assert not finite.all() and np.array_equal(np.isfinite(du_gpu), finite)
+        du_gpu, du_ref = np.where(finite, du_gpu, 0.0), np.where(finite, du_ref, 0.0)
+    else:
+        assert finite.all() and np.all(np.isfinite(du_gpu))
     err = _rel_err(du_gpu, du_ref)
-    noise = _oracle_noise(oracle_module, semi, u, t, du_ref)
+    noise = 0.0 if not finite.all() else _oracle_noise(oracle_module, semi, u, t, du_ref)
     tol = _rhs_tolerance(name, noise)
     _PARITY_TABLE.append({"case": name, "state": state, "rel_err": float(err), "tolerance": float(tol),
                           "oracle_noise": float(noise), "ndofs": int(semi.ndofs())})

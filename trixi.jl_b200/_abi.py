@@ -53,6 +53,10 @@ class Desc(C.Structure):
         ("indicator_alpha_max", C.c_double), ("indicator_alpha_min", C.c_double),
         ("inverse_vandermonde_legendre", c_double_p),
         ("mortar_node_indices", c_int64_p),
+        ("nmpimortars", C.c_int64),
+        ("mpi_mortar_neighbor_ids", c_int64_p), ("mpi_mortar_large_sides", c_int64_p),
+        ("mpi_mortar_orientations", c_int64_p), ("mpi_mortar_node_indices", c_int64_p),
+        ("mpi_mortar_normal_directions", c_double_p), ("mpi_is_mortar_piece", c_int64_p),
     ]
 
 

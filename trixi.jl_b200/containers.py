@@ -152,8 +152,9 @@ def init_mortars(mesh, first=0, last=None):
         small.append(fine[:, el])
         dirs.append(np.full(el.shape[0], direction, dtype=np.int64))
     large, small, dirs = np.concatenate(large), np.concatenate(small, axis=1), np.concatenate(dirs)
-    if ((small < first) | (small >= last)).any():
-        raise NotImplementedError("mortars across ranks (MPI mortars) are not supported")
+    # mortars with an element on another rank are MPI mortars (init_mpi_mortars below)
+    all_local = ((small >= first) & (small < last)).all(axis=0)
+    large, small, dirs = large[all_local], small[:, all_local], dirs[all_local]
     order = np.lexsort((dirs, large))
     large, small, dirs = large[order], small[:, order], dirs[order]
     mc.neighbor_ids = np.asfortranarray(np.concatenate([small, large[None, :]]) - first + 1)
@@ -194,3 +195,102 @@ def init_boundaries(mesh, elements, basis, first=0, last=None):
     bc.n_boundaries_per_direction = np.array(counts + [0] * (6 - len(counts)), dtype=np.int64)
     bc.nboundaries = int(bc.neighbor_ids.shape[0])
     return bc
+
+
+class MPIMortarContainer:
+    nmpimortars = 0
+
+
+def merge_mpi_mortar_pieces(mi, pieces, nd):
+    """Appends the (large element, small element) pairs of mortars that straddle ranks to the MPI interface list as
+    exchange-only entries (``is_mortar_piece``): each side sends the face of its own element like for a conforming
+    shared face (prolong2mpimortars! + start_mpi_send!, dg_2d_parallel.jl:600-698, dgsem_p4est/dg_3d_parallel.jl:275-380
+    send the same faces inside one mortar buffer), but no interface flux is evaluated there.  ``pieces`` rows:
+    (local element 0-based local id, local side, orientation, peer rank, key, node_indices or None).  Returns the
+    position of every piece in the merged, (peer, key)-sorted list."""
+    npc = len(pieces)
+    old = mi.nmpiinterfaces
+    has_idx = getattr(mi, "node_indices", None) is not None and (old > 0 or (npc and pieces[0][5] is not None))
+    loc = np.concatenate([mi.local_neighbor_ids, np.array([q[0] + 1 for q in pieces], dtype=np.int64)])
+    side = np.concatenate([mi.local_sides, np.array([q[1] for q in pieces], dtype=np.int64)])
+    orient = np.concatenate([mi.orientations, np.array([q[2] for q in pieces], dtype=np.int64)])
+    peer = np.concatenate([mi.neighbor_ranks, np.array([q[3] for q in pieces], dtype=np.int64)])
+    key = np.concatenate([mi.global_interface_ids, np.array([q[4] for q in pieces], dtype=np.int64)])
+    piece = np.concatenate([np.zeros(old, dtype=np.int64), np.ones(npc, dtype=np.int64)])
+    if has_idx:
+        idx_old = mi.node_indices if old else np.zeros((nd, 0), dtype=np.int64)
+        idx_new = np.array([q[5] for q in pieces], dtype=np.int64).reshape(npc, nd).T
+        node_indices = np.concatenate([idx_old, idx_new], axis=1)
+    order = np.lexsort((key, peer))
+    mi.local_neighbor_ids, mi.local_sides, mi.orientations = loc[order], side[order], orient[order]
+    mi.neighbor_ranks, mi.global_interface_ids, mi.is_mortar_piece = peer[order], key[order], piece[order]
+    if has_idx:
+        mi.node_indices = np.asfortranarray(node_indices[:, order])
+    mi.nmpiinterfaces = int(order.shape[0])
+    where = np.empty(order.shape[0], dtype=np.int64)
+    where[order] = np.arange(order.shape[0])
+    return where[old:]
+
+
+def init_mpi_mortars(mesh, mi, first, last, world_size):
+    """``init_mpi_mortars!`` (containers_2d.jl:1131-1258; the reference has TreeMesh MPI in 2D only, here any
+    dimension): mortars with elements on more than one rank.  ``neighbor_ids[p, m]`` > 0: local element (1-based),
+    < 0: minus the 1-based position in the MPI interface list of the exchange entry that brings that element's face,
+    0: a small element this rank neither owns nor needs (it does not own the large element).  Appends the exchange
+    entries to ``mi``."""
+    nd = mesh.ndims
+    nsmall = 1 << (nd - 1)
+    mm = MPIMortarContainer()
+    mm.neighbor_ids = np.zeros((nsmall + 1, 0), dtype=np.int64)
+    mm.large_sides = np.zeros(0, dtype=np.int64)
+    mm.orientations = np.zeros(0, dtype=np.int64)
+    if not hasattr(mi, "is_mortar_piece"):
+        mi.is_mortar_piece = np.zeros(mi.nmpiinterfaces, dtype=np.int64)
+    if world_size == 1 or not hasattr(mesh, "_fine_neighbors") or int(mesh.levels.min()) == int(mesh.levels.max()):
+        return mm
+    large, small, dirs = [], [], []
+    for direction in range(2 * nd):
+        fine = mesh._fine_neighbors(direction, None)
+        el = np.nonzero((fine >= 0).all(axis=0))[0]
+        large.append(el)
+        small.append(fine[:, el])
+        dirs.append(np.full(el.shape[0], direction, dtype=np.int64))
+    large, small, dirs = np.concatenate(large), np.concatenate(small, axis=1), np.concatenate(dirs)
+    order = np.lexsort((dirs, large))
+    large, small, dirs = large[order], small[:, order], dirs[order]
+    local = lambda e: (e >= first) & (e < last)  # noqa: E731
+    ids_all = np.concatenate([small, large[None, :]])
+    mixed = local(ids_all).any(axis=0) & ~local(ids_all).all(axis=0)
+    base_key = mesh.ncells * nd  # above every conforming interface id
+    pieces, slots, records = [], [], []
+    for m in np.nonzero(mixed)[0]:
+        L, direction = int(large[m]), int(dirs[m])
+        o, large_side = direction // 2 + 1, 1 if direction % 2 == 1 else 2
+        owner_L = int(owner_of(np.array([L]), mesh.ncells, world_size)[0])
+        rec = [0] * (nsmall + 1)
+        rec[nsmall] = L - first + 1 if local(L) else 0
+        for p in range(nsmall):
+            s = int(small[p, m])
+            owner_s = int(owner_of(np.array([s]), mesh.ncells, world_size)[0])
+            key = base_key + (int(m) * nsmall + p)
+            if local(s):
+                rec[p] = s - first + 1
+            if owner_s == owner_L:
+                continue
+            if local(L):    # send the large face, receive the small face
+                pieces.append((L - first, large_side, o, owner_s, key, None))
+                slots.append((len(records), p))
+            elif local(s):  # send the small face, receive the large face
+                pieces.append((s - first, 3 - large_side, o, owner_L, key, None))
+                slots.append((len(records), nsmall))
+        records.append((rec, large_side, o))
+    where = merge_mpi_mortar_pieces(mi, pieces, nd)
+    for (r, p), w in zip(slots, where):
+        if records[r][0][p] == 0:
+            records[r][0][p] = -(int(w) + 1)
+    if records:
+        mm.neighbor_ids = np.asfortranarray(np.array([r[0] for r in records], dtype=np.int64).T)
+        mm.large_sides = np.array([r[1] for r in records], dtype=np.int64)
+        mm.orientations = np.array([r[2] for r in records], dtype=np.int64)
+    mm.nmpimortars = len(records)
+    return mm

@@ -448,10 +448,31 @@ __global__ void __launch_bounds__((1 << (EQ::NDIMS - 1)) * ipow(N, EQ::NDIMS - 1
     // the small element takes its flux as it is (its face towards the large element)
     {
         double *dst = P.sfv + ((small * (2 * ND) + (large_left ? 2 * o : 2 * o + 1)) * NF + fn) * NV;
+        if constexpr (EQ::kHasNoncons) {
+            // dg_3d.jl:1012-1233: the primary flux (small elements) adds 0.5 nonconservative_flux(u_large, u_small), the
+            // secondary flux (projected to the large element) 0.5 nonconservative_flux(u_small, u_large)
+            if (EQ::has_noncons(P.surface_flux)) {
+                double np_[NV], ns_[NV];
+                eq.noncons(up, us, o, np_);
+                eq.noncons(us, up, o, ns_);
 #pragma unroll
-        for (int v = 0; v < NV; ++v) {
-            dst[v] = f[v];
-            s_f[p][v + NV * fn] = f[v];
+                for (int v = 0; v < NV; ++v) {
+                    dst[v] = f[v] + 0.5 * np_[v];
+                    s_f[p][v + NV * fn] = f[v] + 0.5 * ns_[v];
+                }
+            } else {
+#pragma unroll
+                for (int v = 0; v < NV; ++v) {
+                    dst[v] = f[v];
+                    s_f[p][v + NV * fn] = f[v];
+                }
+            }
+        } else {
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+                dst[v] = f[v];
+                s_f[p][v + NV * fn] = f[v];
+            }
         }
     }
     __syncthreads();

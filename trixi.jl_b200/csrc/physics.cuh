@@ -832,7 +832,7 @@ struct Mhd3D {
 
     TB_DEV static bool has_noncons(int flux_id) {
         return flux_id == TRIXI_B200_FLUX_HINDENLANG_GASSNER_POWELL || flux_id == TRIXI_B200_FLUX_LLF_MHD_POWELL ||
-               flux_id == TRIXI_B200_FLUX_LLF_NAIVE_MHD_POWELL;
+               flux_id == TRIXI_B200_FLUX_LLF_NAIVE_MHD_POWELL || flux_id == TRIXI_B200_FLUX_HLLE_MHD_POWELL;
     }
     TB_DEV static double sel3(double a, double b, double c, int o) { return o == 0 ? a : (o == 1 ? b : c); }
 
@@ -939,9 +939,66 @@ struct Mhd3D {
         return sqrt(0.5 * sum + 0.5 * sqrt(sum * sum - 4 * a_square * (Bo * Bo * inv_rho)));
     }
 
+    // calc_fast_wavespeed_roe(u_ll, u_rr, orientation) (:1415-1491): Roe averages of Cargo & Gallice
+    TB_DEV void fast_wavespeed_roe(const double (&ul)[9], const double (&ur)[9], int o, double &vel_out, double &c_f) const {
+        const double inv_rho_ll = 1.0 / ul[0], inv_rho_rr = 1.0 / ur[0];
+        const double v_ll[3] = {ul[1] * inv_rho_ll, ul[2] * inv_rho_ll, ul[3] * inv_rho_ll};
+        const double v_rr[3] = {ur[1] * inv_rho_rr, ur[2] * inv_rho_rr, ur[3] * inv_rho_rr};
+        const double kin_en_ll = 0.5 * (ul[1] * v_ll[0] + ul[2] * v_ll[1] + ul[3] * v_ll[2]);
+        const double mag_norm_ll = ul[5] * ul[5] + ul[6] * ul[6] + ul[7] * ul[7];
+        const double p_ll = (gamma - 1) * (ul[4] - kin_en_ll - 0.5 * mag_norm_ll - 0.5 * ul[8] * ul[8]);
+        const double kin_en_rr = 0.5 * (ur[1] * v_rr[0] + ur[2] * v_rr[1] + ur[3] * v_rr[2]);
+        const double mag_norm_rr = ur[5] * ur[5] + ur[6] * ur[6] + ur[7] * ur[7];
+        const double p_rr = (gamma - 1) * (ur[4] - kin_en_rr - 0.5 * mag_norm_rr - 0.5 * ur[8] * ur[8]);
+        const double p_total_ll = p_ll + 0.5 * mag_norm_ll, p_total_rr = p_rr + 0.5 * mag_norm_rr;
+        const double sqrt_rho_ll = sqrt(ul[0]), sqrt_rho_rr = sqrt(ur[0]);
+        const double inv_sqrt_rho_add = 1.0 / (sqrt_rho_ll + sqrt_rho_rr), inv_sqrt_rho_prod = 1.0 / (sqrt_rho_ll * sqrt_rho_rr);
+        const double rho_ll_roe = sqrt_rho_ll * inv_sqrt_rho_add, rho_rr_roe = sqrt_rho_rr * inv_sqrt_rho_add;
+        double v_roe[3], B_roe[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            v_roe[d] = v_ll[d] * rho_ll_roe + v_rr[d] * rho_rr_roe;
+            B_roe[d] = ul[5 + d] * rho_ll_roe + ur[5 + d] * rho_rr_roe;
+        }
+        const double H_ll = (ul[4] + p_total_ll) * inv_rho_ll, H_rr = (ur[4] + p_total_rr) * inv_rho_rr;
+        const double H_roe = H_ll * rho_ll_roe + H_rr * rho_rr_roe;
+        const double dB0 = ul[5] - ur[5], dB1 = ul[6] - ur[6], dB2 = ul[7] - ur[7];
+        const double X = 0.5 * (dB0 * dB0 + dB1 * dB1 + dB2 * dB2) * (inv_sqrt_rho_add * inv_sqrt_rho_add);
+        const double b_square_roe = (B_roe[0] * B_roe[0] + B_roe[1] * B_roe[1] + B_roe[2] * B_roe[2]) * inv_sqrt_rho_prod;
+        const double a_square_roe =
+            (2 - gamma) * X + (gamma - 1) * (H_roe - 0.5 * (v_roe[0] * v_roe[0] + v_roe[1] * v_roe[1] + v_roe[2] * v_roe[2]) -
+                                             b_square_roe);
+        const double Bo = sel3(B_roe[0], B_roe[1], B_roe[2], o);
+        const double c_a_roe = Bo * Bo * inv_sqrt_rho_prod, sum = a_square_roe + b_square_roe;
+        const double a_star_roe = sqrt(sum * sum - 4 * a_square_roe * c_a_roe);
+        c_f = sqrt(0.5 * (a_square_roe + b_square_roe + a_star_roe));
+        vel_out = sel3(v_roe[0], v_roe[1], v_roe[2], o);
+    }
+
     // conservative part of the surface/volume flux (tuples are encoded as one id)
     TB_DEV void numflux(int id, const double (&ul)[9], const double (&ur)[9], int o, double (&f)[9]) const {
         switch (id) {
+        case TRIXI_B200_FLUX_HLLE_MHD_POWELL: {  // FluxHLL (numerical_fluxes.jl:422-449), min_max_speed_einfeldt (:1094-1130)
+            const double cf_ll = fast_wavespeed(ul, o), cf_rr = fast_wavespeed(ur, o);
+            double vel_roe, cf_roe;
+            fast_wavespeed_roe(ul, ur, o, vel_roe, cf_roe);
+            const double lmin = fmin(sel3(ul[1], ul[2], ul[3], o) / ul[0] - cf_ll, vel_roe - cf_roe);
+            const double lmax = fmax(sel3(ur[1], ur[2], ur[3], o) / ur[0] + cf_rr, vel_roe + cf_roe);
+            if (lmin >= 0 && lmax >= 0) {
+                flux(ul, o, f);
+            } else if (lmax <= 0 && lmin <= 0) {
+                flux(ur, o, f);
+            } else {
+                double fl[9], fr[9];
+                flux(ul, o, fl);
+                flux(ur, o, fr);
+                const double inv = 1.0 / (lmax - lmin);
+                const double factor_ll = lmax * inv, factor_rr = lmin * inv, factor_diss = lmin * lmax * inv;
+#pragma unroll
+                for (int v = 0; v < 9; ++v) f[v] = factor_ll * fl[v] - factor_rr * fr[v] + factor_diss * (ur[v] - ul[v]);
+            }
+            break;
+        }
         case TRIXI_B200_FLUX_CENTRAL: {
             double fl[9], fr[9];
             flux(ul, o, fl);

@@ -623,8 +623,6 @@ TRIXI_B200_API int trixi_b200_create(const trixi_b200_desc *d, trixi_b200_handle
     if (d->nmortars > 0) {
         if (structured) return fail(nullptr, TRIXI_B200_EINVAL, "a StructuredMesh has no mortars");
         if (d->world_size > 1) return fail(nullptr, TRIXI_B200_EINVAL, "MPI mortars are not supported by this build");
-        if (d->equation == TRIXI_B200_EQ_MHD_3D)
-            return fail(nullptr, TRIXI_B200_EINVAL, "mortars with nonconservative terms are not supported by this build");
         if (!d->mortar_neighbor_ids || !d->mortar_forward_upper || !d->mortar_forward_lower || !d->mortar_reverse_upper ||
             !d->mortar_reverse_lower || (p4est ? !d->mortar_node_indices : !d->mortar_large_sides || !d->mortar_orientations))
             return fail(nullptr, TRIXI_B200_EINVAL, "mortar arrays missing");

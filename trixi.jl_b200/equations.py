@@ -30,6 +30,8 @@ FLUX_RANOCHA_TURBO = 11
 FLUX_LLF_MHD_POWELL = 12      # (flux_lax_friedrichs, flux_nonconservative_powell)
 FLUX_HINDENLANG_GASSNER_POWELL = 13
 FLUX_LLF_NAIVE_MHD_POWELL = 14  # (FluxLaxFriedrichs(max_abs_speed_naive), flux_nonconservative_powell)
+FLUX_HLLE_MHD_POWELL = 15  # (flux_hlle, flux_nonconservative_powell)
+FLUX_HLLE = -2  # FluxHLL(min_max_speed_einfeldt): only inside the MHD tuple above
 
 SRC_NONE, SRC_CONVERGENCE_TEST, SRC_EOC_TEST_EULER, SRC_EOC_TEST_COUPLED_EULER_GRAVITY = 0, 1, 2, 3
 
@@ -64,6 +66,10 @@ def min_max_speed_naive():
     pass
 
 
+def min_max_speed_einfeldt():
+    pass
+
+
 flux_central = _Flux("flux_central", FLUX_CENTRAL)
 flux_ranocha = _Flux("flux_ranocha", FLUX_RANOCHA)
 flux_ranocha_turbo = _Flux("flux_ranocha_turbo", FLUX_RANOCHA_TURBO)
@@ -90,11 +96,14 @@ def FluxHLL(speed=min_max_speed_davis):
         return _Flux("FluxHLL(min_max_speed_davis)", FLUX_HLL_DAVIS)
     if speed is min_max_speed_naive:
         return _Flux("FluxHLL(min_max_speed_naive)", FLUX_HLL_NAIVE)
+    if speed is min_max_speed_einfeldt:
+        return _Flux("FluxHLL(min_max_speed_einfeldt)", FLUX_HLLE)
     raise ValueError("unsupported wave speed estimate for FluxHLL")
 
 
 flux_lax_friedrichs = FluxLaxFriedrichs()
 flux_hll = FluxHLL()
+flux_hlle = FluxHLL(min_max_speed_einfeldt)  # numerical_fluxes.jl:457
 
 
 class _IndicatorVariable:
@@ -125,9 +134,13 @@ def resolve_flux(flux):
             return FLUX_LLF_MHD_POWELL
         if cons.flux_id == FLUX_LLF_NAIVE:
             return FLUX_LLF_NAIVE_MHD_POWELL
+        if cons.flux_id == FLUX_HLLE:
+            return FLUX_HLLE_MHD_POWELL
         raise ValueError(f"unsupported conservative flux {cons} with Powell term")
     if not isinstance(flux, _Flux):
         raise TypeError(f"numerical flux {flux!r} is not in the libtrixi_b200 registry")
+    if flux.flux_id == FLUX_HLLE:
+        raise ValueError("flux_hlle is available for IdealGlmMhdEquations3D with flux_nonconservative_powell only")
     return flux.flux_id
 
 

@@ -274,21 +274,32 @@ class P4estMortarContainer:
     pass
 
 
-def _init_surfaces_general(mesh):
-    """init_surfaces! (dgsem_p4est/containers.jl:786-838) for a forest with hanging faces: p4est's face iteration is
-    replaced by a walk over the leaves and their 2*ndims faces.  A face whose same-size neighbour cell is a leaf of the
-    same level is an interface (taken from the negative side: primary = the element whose + face it is), a subdivided
-    neighbour cell makes a mortar with this leaf as the large element, a coarser neighbour is handled from its side.
-    Trees of a brick share their axes (orientation code 0, opposite faces), so both sides index forward
-    (orientation_to_indices_p4est containers_3d.jl:206-300 with flipped = false, code 0)."""
-    if getattr(mesh, "_surfaces", None) is not None:
-        return mesh._surfaces
+def _init_surfaces_general(mesh, first=0, last=None, world_size=1, basis=None):
+    """init_surfaces! (dgsem_p4est/containers.jl:786-838; with ranks init_surfaces_iter_face_parallel
+    containers_parallel.jl:380-520) for a forest with hanging faces: p4est's face iteration is replaced by a walk over
+    the leaves and their 2*ndims faces.  A face whose same-size neighbour cell is a leaf of the same level is an
+    interface (taken from the negative side: primary = the element whose + face it is), a subdivided neighbour cell
+    makes a mortar with this leaf as the large element, a coarser neighbour is handled from its side.  Trees of a
+    brick share their axes (orientation code 0, opposite faces), so both sides index forward
+    (orientation_to_indices_p4est containers_3d.jl:206-300 with flipped = false, code 0).
+    Elements [first, last) belong to this rank: surfaces with elements of two ranks become MPI interfaces / MPI
+    mortars.  Returns (interfaces, mortars, boundaries, mpi_interfaces, mpi_mortars)."""
+    last = mesh.ncells if last is None else last
+    cache_key = (first, last, world_size)
+    if getattr(mesh, "_surfaces", None) is not None and mesh._surfaces[0] == cache_key:
+        return mesh._surfaces[1]
+    from .containers import MPIMortarContainer, merge_mpi_mortar_pieces
     nd = mesh.ndims
     npos = 1 << (nd - 1)
     surf_dims = [[c for c in range(nd) if c != d] for d in range(nd)]
+    local = lambda e: first <= e < last  # noqa: E731
+    owner = lambda e: int(owner_of(np.array([e]), mesh.ncells, world_size)[0])  # noqa: E731
     prim, sec, idim = [], [], []
     m_ids, m_idx = [], []
     bnd = [[] for _ in range(2 * nd)]
+    mpi_rows = []          # conforming faces shared with another rank
+    mm_records, pieces, slots = [], [], []
+    base_key = mesh.ncells * nd
     for e in range(mesh.ncells):
         t, l = int(mesh.tree_of_element[e]), int(mesh.levels[e])
         c = tuple(int(x) for x in mesh.quad_coords[:, e])
@@ -296,14 +307,21 @@ def _init_surfaces_general(mesh):
             for side in (0, 1):
                 nb = mesh.neighbor_cell(t, l, c, d, side)
                 if nb is None:
-                    bnd[2 * d + side].append(e)
+                    if local(e):
+                        bnd[2 * d + side].append(e - first)
                     continue
                 found = mesh.find_leaf(nb[0], l, nb[1])
                 if found is not None:
                     if found[1] == l and side == 1:
-                        prim.append(e)
-                        sec.append(found[0])
-                        idim.append(d)
+                        o = found[0]
+                        if local(e) and local(o):
+                            prim.append(e - first)
+                            sec.append(o - first)
+                            idim.append(d)
+                        elif local(e):  # local element is the primary one
+                            mpi_rows.append((e - first, 1, d + 1, owner(o), e * nd + d, _face_indices(nd, d, 1)))
+                        elif local(o):
+                            mpi_rows.append((o - first, 2, d + 1, owner(e), e * nd + d, _face_indices(nd, d, 0)))
                     elif found[1] < l - 1:
                         raise ValueError("the forest is not 2:1 balanced; call mesh.balance()")
                     continue
@@ -318,8 +336,30 @@ def _init_surfaces_general(mesh):
                     if f2 is None or f2[1] != l + 1:
                         raise ValueError("the forest is not 2:1 balanced; call mesh.balance()")
                     small.append(f2[0])
-                m_ids.append(small + [e])
-                m_idx.append([_face_indices(nd, d, 1 - side), _face_indices(nd, d, side)])
+                idx = [_face_indices(nd, d, 1 - side), _face_indices(nd, d, side)]
+                members = small + [e]
+                nloc = sum(local(x) for x in members)
+                if nloc == len(members):
+                    m_ids.append([x - first for x in members])
+                    m_idx.append(idx)
+                elif nloc > 0:
+                    # MPI mortar (init_mpi_mortars! containers_parallel.jl:130-210): local elements by id, the others
+                    # through exchange-only entries of the MPI interface list (see merge_mpi_mortar_pieces)
+                    rec = [(x - first + 1) if local(x) else 0 for x in members]
+                    owner_l = owner(e)
+                    mortar_key = e * 2 * nd + 2 * d + side
+                    for pos, sm in enumerate(small):
+                        owner_s = owner(sm)
+                        if owner_s == owner_l:
+                            continue
+                        key = base_key + mortar_key * npos + pos
+                        if local(e):
+                            pieces.append((e - first, 2, d + 1, owner_s, key, idx[1]))
+                            slots.append((len(mm_records), pos))
+                        elif local(sm):
+                            pieces.append((sm - first, 1, d + 1, owner_l, key, idx[0]))
+                            slots.append((len(mm_records), npos))
+                    mm_records.append((rec, idx, small))
     face_idx = np.array([[_face_indices(nd, d, 1), _face_indices(nd, d, 0)] for d in range(nd)], dtype=np.int64)
     ic = InterfaceContainer()
     prim, sec, idim = (np.array(x, dtype=np.int64) for x in (prim, sec, idim))
@@ -344,8 +384,61 @@ def _init_surfaces_general(mesh):
     bc.node_coordinates = np.zeros((nd, 0))
     bc.n_boundaries_per_direction = np.array(counts + [0] * (6 - len(counts)), dtype=np.int64)
     bc.nboundaries = int(bc.neighbor_ids.shape[0])
-    mesh._surfaces = (ic, mc, bc)
-    return mesh._surfaces
+    # MPI interfaces sorted by (neighbour rank, global interface id), then the mortar pieces merged in
+    mi = _empty_mpi_interfaces(nd)
+    if mpi_rows:
+        rows = sorted(mpi_rows, key=lambda r: (r[3], r[4]))
+        mi.local_neighbor_ids = np.array([r[0] + 1 for r in rows], dtype=np.int64)
+        mi.local_sides = np.array([r[1] for r in rows], dtype=np.int64)
+        mi.orientations = np.array([r[2] for r in rows], dtype=np.int64)
+        mi.neighbor_ranks = np.array([r[3] for r in rows], dtype=np.int64)
+        mi.global_interface_ids = np.array([r[4] for r in rows], dtype=np.int64)
+        mi.node_indices = np.asfortranarray(np.array([r[5] for r in rows], dtype=np.int64).T.reshape(nd, -1))
+        mi.nmpiinterfaces = len(rows)
+    mi.is_mortar_piece = np.zeros(mi.nmpiinterfaces, dtype=np.int64)
+    mm = MPIMortarContainer()
+    mm.neighbor_ids = np.zeros((npos + 1, 0), dtype=np.int64)
+    mm.node_indices = np.zeros((nd, 2, 0), dtype=np.int64)
+    mm.small_elements_global = np.zeros((npos, 0), dtype=np.int64)
+    if mm_records:
+        where = merge_mpi_mortar_pieces(mi, pieces, nd)
+        for (r, p), w in zip(slots, where):
+            if mm_records[r][0][p] == 0:
+                mm_records[r][0][p] = -(int(w) + 1)
+        mm.neighbor_ids = np.asfortranarray(np.array([r[0] for r in mm_records], dtype=np.int64).T)
+        mm.node_indices = np.asfortranarray(np.array([r[1] for r in mm_records], dtype=np.int64).transpose(2, 1, 0))
+        mm.small_elements_global = np.array([r[2] for r in mm_records], dtype=np.int64).T
+    mm.nmpimortars = len(mm_records)
+    mesh._surfaces = (cache_key, (ic, mc, bc, mi, mm))
+    return mesh._surfaces[1]
+
+
+def init_mpi_mortar_normals_p4est(mesh, basis, mm):
+    """``normal_directions`` of the MPI mortar container (dgsem_p4est/containers_parallel.jl:130-155,
+    init_normal_directions! :557-620): the outward normals of the small elements at the mortar's face nodes,
+    [ndims, n^(d-1), 2^(d-1), MM] -- the small elements may live on another rank, so the normals cannot be read from
+    the local contravariant vectors."""
+    nd, n = mesh.ndims, basis.nnodes
+    nf, npos = n ** (nd - 1), 1 << (nd - 1)
+    out = np.zeros((nd, nf, npos, mm.nmpimortars), order="F")
+    if mm.nmpimortars == 0:
+        return out
+    elements = np.unique(mm.small_elements_global)
+    pos_of = {int(e): k for k, e in enumerate(elements)}
+    ja = {}
+    for e in elements:  # one element at a time: exactly the arithmetic of the owner's init_elements_p4est
+        el = init_elements_p4est(mesh, basis, int(e), int(e) + 1)
+        ja[int(e)] = el.contravariant_vectors[..., 0].reshape((nd, nd) + (n,) * nd, order="F")
+    del pos_of
+    for m in range(mm.nmpimortars):
+        sidx = mm.node_indices[:, 0, m]
+        direction = [k for k in range(nd) if sidx[k] in (IDX_BEGIN, IDX_END)][0]
+        sign = 1.0 if sidx[direction] == IDX_END else -1.0
+        for p in range(npos):
+            J = ja[int(mm.small_elements_global[p, m])]  # [nd (component), nd (which vector), n, n(, n)]
+            face = np.take(J[:, direction], n - 1 if sidx[direction] == IDX_END else 0, axis=1 + direction)
+            out[:, :, p, m] = sign * face.reshape(nd, nf, order="F")
+    return out
 
 
 def _empty_mpi_interfaces(nd):
@@ -365,9 +458,21 @@ def init_mortars_p4est(mesh, first=0, last=None, world_size=1):
         mc.neighbor_ids = np.zeros(((1 << (mesh.ndims - 1)) + 1, 0), dtype=np.int64)
         mc.node_indices = np.zeros((mesh.ndims, 2, 0), dtype=np.int64)
         return mc
-    if world_size != 1:
-        raise NotImplementedError("non-conforming P4estMesh across ranks (MPI mortars) is not supported")
-    return _init_surfaces_general(mesh)[1]
+    return _init_surfaces_general(mesh, first, last, world_size)[1]
+
+
+def init_mpi_mortars_p4est(mesh, basis, first=0, last=None, world_size=1):
+    """init_mpi_mortars! (dgsem_p4est/containers_parallel.jl:130-210) incl. the small elements' normals."""
+    from .containers import MPIMortarContainer
+    if mesh.is_uniform:
+        mm = MPIMortarContainer()
+        mm.neighbor_ids = np.zeros(((1 << (mesh.ndims - 1)) + 1, 0), dtype=np.int64)
+        mm.node_indices = np.zeros((mesh.ndims, 2, 0), dtype=np.int64)
+        mm.normal_directions = np.zeros((mesh.ndims, 0))
+        return mm
+    mm = _init_surfaces_general(mesh, first, last, world_size)[4]
+    mm.normal_directions = init_mpi_mortar_normals_p4est(mesh, basis, mm)
+    return mm
 
 
 def init_interfaces_p4est(mesh, first=0, last=None, world_size=1):
@@ -379,9 +484,8 @@ def init_interfaces_p4est(mesh, first=0, last=None, world_size=1):
     Returns (interfaces, mpi_interfaces)."""
     nd = mesh.ndims
     if not mesh.is_uniform:
-        if world_size != 1:
-            raise NotImplementedError("non-conforming P4estMesh across ranks (MPI mortars) is not supported")
-        return _init_surfaces_general(mesh)[0], _empty_mpi_interfaces(nd)
+        surf = _init_surfaces_general(mesh, first, last, world_size)
+        return surf[0], surf[3]
     cells = mesh.cells_per_dimension
     gc = mesh.global_coords
     last = mesh.ncells if last is None else last
@@ -432,12 +536,12 @@ def init_interfaces_p4est(mesh, first=0, last=None, world_size=1):
     return ic, mi
 
 
-def init_boundaries_p4est(mesh, first=0, last=None):
+def init_boundaries_p4est(mesh, first=0, last=None, world_size=1):
     """init_boundaries! (dgsem_p4est/containers.jl:302-345), sorted by boundary name
     :x_neg, :x_pos, :y_neg, ... (structured_boundary_names! p4est_mesh.jl:298-365); elements [first, last)."""
     nd = mesh.ndims
     if not mesh.is_uniform:
-        return _init_surfaces_general(mesh)[2]
+        return _init_surfaces_general(mesh, first, last, world_size)[2]
     cells = mesh.cells_per_dimension
     last = mesh.ncells if last is None else last
     gc = mesh.global_coords[:, first:last]

@@ -15,13 +15,13 @@ import numpy as np
 
 from . import _abi
 from .containers import (BoundaryContainer, InterfaceContainer, MPIInterfaceContainer, init_boundaries,
-                         init_elements, init_interfaces, init_mortars, partition_cells)
+                         init_elements, init_interfaces, init_mortars, init_mpi_mortars, partition_cells)
 from .equations import (BC_DIRICHLET, BC_PERIODIC, BC_SLIP_WALL, IC_NONE, SRC_NONE,
                         BoundaryConditionDirichlet, boundary_condition_periodic, resolve_flux)
 from .basis import LobattoLegendreMortarL2
 from .mesh import TreeMesh
 from .p4est import (P4estMesh, init_boundaries_p4est, init_elements_p4est, init_interfaces_p4est,
-                    init_mortars_p4est)
+                    init_mortars_p4est, init_mpi_mortars_p4est)
 from .structured import StructuredMesh, init_elements_structured
 
 MESH_TREE, MESH_STRUCTURED, MESH_P4EST = 0, 1, 2
@@ -64,8 +64,7 @@ def create_cache(mesh, equations, solver, rank=0, world_size=1):
         cache.interfaces, cache.mpi_interfaces = init_interfaces(mesh, first, last, world_size)
         cache.boundaries = init_boundaries(mesh, cache.elements, solver.basis, first, last)
         cache.mortars = init_mortars(mesh, first, last)
-        if cache.mortars.nmortars and world_size > 1:
-            raise NotImplementedError("mortars on a partitioned TreeMesh (MPI mortars) are not supported")
+        cache.mpi_mortars = init_mpi_mortars(mesh, cache.mpi_interfaces, first, last, world_size)
     elif isinstance(mesh, StructuredMesh):
         if world_size != 1:
             raise NotImplementedError("StructuredMesh runs on a single rank (the reference has no MPI path for it)")
@@ -88,8 +87,9 @@ def create_cache(mesh, equations, solver, rank=0, world_size=1):
         cache.first_element, cache.last_element = first, last
         cache.elements = init_elements_p4est(mesh, solver.basis, first, last)
         cache.interfaces, cache.mpi_interfaces = init_interfaces_p4est(mesh, first, last, world_size)
-        cache.boundaries = init_boundaries_p4est(mesh, first, last)
+        cache.boundaries = init_boundaries_p4est(mesh, first, last, world_size)
         cache.mortars = init_mortars_p4est(mesh, first, last, world_size)
+        cache.mpi_mortars = init_mpi_mortars_p4est(mesh, solver.basis, first, last, world_size)
     else:
         raise TypeError(f"unsupported mesh type {type(mesh).__name__}")
     return cache
@@ -285,6 +285,24 @@ class SemidiscretizationHyperbolic:
             h.set_i64("mpi_neighbor_ranks", mi.neighbor_ranks)
             if isinstance(self.mesh, P4estMesh):
                 h.set_i64("mpi_node_indices", mi.node_indices)
+            if getattr(mi, "is_mortar_piece", None) is not None and np.any(mi.is_mortar_piece):
+                h.set_i64("mpi_is_mortar_piece", mi.is_mortar_piece)
+        mm = getattr(cache, "mpi_mortars", None)
+        d.nmpimortars = 0 if mm is None else mm.nmpimortars
+        if d.nmpimortars:
+            l2 = LobattoLegendreMortarL2(dg.basis)
+            h.set_i64("mpi_mortar_neighbor_ids", mm.neighbor_ids)
+            if isinstance(self.mesh, P4estMesh):
+                h.set_i64("mpi_mortar_node_indices", mm.node_indices)
+                h.set_f64("mpi_mortar_normal_directions", mm.normal_directions)
+            else:
+                h.set_i64("mpi_mortar_large_sides", mm.large_sides)
+                h.set_i64("mpi_mortar_orientations", mm.orientations)
+            if not d.nmortars:  # the operators travel with the local mortar fields
+                h.set_f64("mortar_forward_upper", l2.forward_upper)
+                h.set_f64("mortar_forward_lower", l2.forward_lower)
+                h.set_f64("mortar_reverse_upper", l2.reverse_upper)
+                h.set_f64("mortar_reverse_lower", l2.reverse_lower)
         self._desc = h
         return h
 
