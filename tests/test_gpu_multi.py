@@ -36,7 +36,10 @@ def _worker(rank, world, port, out_dir, name="tree_3d_euler_ec"):
 
 
 @pytest.mark.parametrize("name", ["tree_3d_euler_ec", "p4est_3d_euler_source_terms_nonperiodic", "tree_3d_mhd_ec",
-                                  "tree_2d_euler_vortex_shockcapturing"])  # the last: test/test_mpi_tree.jl:337-356
+                                  "tree_2d_euler_vortex_shockcapturing",  # test/test_mpi_tree.jl:337-356
+                                  # MPI mortars: test/test_mpi_tree.jl (elixir_advection_mortar.jl) and
+                                  # test/test_mpi_p4est_2d.jl:33-45 assert the serial values for the MPI runs
+                                  "tree_2d_advection_mortar", "p4est_2d_advection_nonconforming_flag"])
 def test_two_gpu_run_reproduces_golden(name, tmp_path):
     """like test/test_mpi_p4est_3d.jl: the distributed run reproduces the serial golden values"""
     if torch.cuda.device_count() < 2:

@@ -382,7 +382,9 @@ GOLDEN_GPU = ["tree_3d_advection_basic", "tree_3d_advection_mortar", "structured
               "p4est_3d_euler_source_terms_nonperiodic_kennedy_gruber", "tree_3d_mhd_ec", "tree_3d_mhd_alfven_wave",
               "tree_2d_advection_mortar", "tree_3d_euler_mortar", "structured_2d_advection_basic",
               "structured_2d_euler_free_stream", "structured_2d_euler_ec",
-              "structured_2d_euler_source_terms_nonperiodic", "p4est_2d_advection_basic"]
+              "structured_2d_euler_source_terms_nonperiodic", "p4est_2d_advection_basic",
+              "p4est_3d_advection_nonconforming", "p4est_2d_advection_nonconforming_flag",
+              "tree_3d_mhd_alfven_wave_mortar"]
 
 
 @pytest.mark.parametrize("name", GOLDEN_GPU)
@@ -506,7 +508,13 @@ def _ranked_semis(name, world):
 @pytest.mark.parametrize("name", ["tree_3d_euler_ec", "tree_2d_euler_source_terms_nonperiodic", "tree_3d_mhd_ec",
                                   "p4est_3d_euler_source_terms_nonperiodic", "p4est_3d_curved_level1",
                                   "tree_3d_euler_shockcapturing", "tree_2d_euler_shockcapturing",
-                                  "tree_2d_euler_vortex_shockcapturing"])
+                                  "tree_2d_euler_vortex_shockcapturing",
+                                  # mortars that straddle ranks (MPI mortars), also with nonconservative terms and with
+                                  # the blending factor smoothed across them
+                                  "tree_2d_advection_mortar", "tree_3d_euler_mortar", "tree_3d_mhd_alfven_wave_mortar",
+                                  "tree_2d_euler_vortex_mortar_shockcapturing", "p4est_2d_advection_nonconforming_flag",
+                                  "p4est_3d_nonconforming_curved_ec",
+                                  "p4est_3d_nonconforming_curved_weak_form_nonperiodic"])
 def test_halo_exchange_matches_single_rank(name, world, oracle_module):
     """The element partition with the device-side halo exchange (pack kernels storing into the peers'
     receive buffers, sequence flags) reproduces the single-rank result; like the reference asserts for its
@@ -514,7 +522,13 @@ def test_halo_exchange_matches_single_rank(name, world, oracle_module):
     base, semis = _ranked_semis(name, world)
     # shock capturing: a state with pure-DG, blended and alpha_max elements, so that the smoothing across the
     # rank boundaries (the neighbour's alpha travels with its face state) matters
-    u = _shock_state(base, 8) if "shockcapturing" in name else _random_admissible_state(base, seed=7)
+    if "shockcapturing" in name:
+        u = _shock_state(base, 8)
+    elif "nonconforming" in name:
+        # bounded fluctuations: the interpolation of a wild random state to the small faces leaves the admissible set
+        u = _random_admissible_state(base, seed=7, perturb=0.1)
+    else:
+        u = _random_admissible_state(base, seed=7)
     alg = T.CarpenterKennedy2N54()
     single = base.backend()
     single.upload(0, u)
@@ -539,7 +553,9 @@ def test_halo_exchange_matches_single_rank(name, world, oracle_module):
     # rounding of the metric terms, like the reference's MPI runs.
     def same(x, y):
         if name.startswith("p4est"):
-            np.testing.assert_allclose(x, y, rtol=0, atol=1e-13 * np.abs(y).max())
+            # (refined forests amplify the metric rounding by inverse_jacobian * inverse_weights, see
+            # tests/test_distributed_cpu.py; the MPI mortars themselves are bit-identical)
+            np.testing.assert_allclose(x, y, rtol=0, atol=(2e-11 if "nonconforming" in name else 1e-13) * np.abs(y).max())
         else:
             np.testing.assert_array_equal(x, y)
 

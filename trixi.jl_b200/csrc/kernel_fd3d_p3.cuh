@@ -12,16 +12,110 @@
 // Used for Euler 3D with flux_shima_etal / kennedy_gruber / chandrashekar / central and for GLM-MHD with
 // (flux_hindenlang_gassner, flux_nonconservative_powell): dg_3d.jl:216-266 for the nonconservative part.
 #pragma once
+#include "ranocha_common.cuh"
 #include "tile_io.cuh"
 
 namespace tb {
+
+// Hoisted node records for the sweeps (what the reference's flux_ranocha_turbo / flux_shima_etal_turbo specializations
+// do for Euler, dg_3d_compressible_euler.jl:289-309): an equation may keep primitive variables and logarithms per node in
+// the line tile instead of the conservative state, so that the two-point flux of a pair needs neither cons2prim nor a
+// logarithm.  Default: no record, the line tile holds the conservative variables.
+template <class EQ>
+struct NodeRecord {
+    static constexpr bool kHas = false;
+    static constexpr int N = EQ::NVARS;
+};
+
+// GLM-MHD: (rho, v1, v2, v3, p, B1, B2, B3, psi, log rho, log rho - log p).  flux_hindenlang_gassner
+// (ideal_glm_mhd_3d.jl:680-779) needs ln_mean(rho_ll, rho_rr) and inv_ln_mean(rho_ll p_rr, rho_rr p_ll): with the two
+// logarithms per NODE both come out of one division each (log(rho_rr p_ll / (rho_ll p_rr)) is the difference of the
+// second logarithm entries); flux_nonconservative_powell (:295-340) reads velocities and fields directly.
+template <>
+struct NodeRecord<Mhd3D> {
+    static constexpr bool kHas = true;
+    static constexpr int N = 11;
+    TB_DEV_HOST static bool applies(int volume_flux) {
+        return volume_flux == TRIXI_B200_FLUX_HINDENLANG_GASSNER || volume_flux == TRIXI_B200_FLUX_HINDENLANG_GASSNER_POWELL;
+    }
+    TB_DEV static void make(const Mhd3D &eq, const double *u, double *r) {
+        const double rho = u[0], inv_rho = fast_rcp(rho);
+        const double v1 = u[1] * inv_rho, v2 = u[2] * inv_rho, v3 = u[3] * inv_rho;
+        const double p = (eq.gamma - 1) * (u[4] - 0.5 * (u[1] * v1 + u[2] * v2 + u[3] * v3 + u[5] * u[5] + u[6] * u[6] +
+                                                         u[7] * u[7] + u[8] * u[8]));
+        const double lrho = log_pos(rho);
+        r[0] = rho, r[1] = v1, r[2] = v2, r[3] = v3, r[4] = p;
+        r[5] = u[5], r[6] = u[6], r[7] = u[7], r[8] = u[8];
+        r[9] = lrho, r[10] = lrho - log_pos(p);
+    }
+    TB_DEV static void flux(const Mhd3D &eq, int /*id*/, const double *L, const double *R, int o, double (&f)[9]) {
+        double rho_mean, inv_rho_p_mean;
+        {
+            const double sum = L[0] + R[0], dif = R[0] - L[0];
+            const double q = dif * rcp_1nr(sum), f2 = q * q;
+            const bool series = f2 < 1.0e-4;
+            const double poly = fma(f2, fma(f2, fma(f2, 2.0 / 7.0, 2.0 / 5.0), 2.0 / 3.0), 2.0);
+            rho_mean = fast_div(series ? sum : dif, series ? poly : R[9] - L[9]);
+        }
+        {
+            const double x = L[0] * R[4], y = R[0] * L[4];
+            const double sum = x + y, dif = y - x;
+            const double q = dif * rcp_1nr(sum), f2 = q * q;
+            const bool series = f2 < 1.0e-4;
+            const double poly = fma(f2, fma(f2, fma(f2, 2.0 / 7.0, 2.0 / 5.0), 2.0 / 3.0), 2.0);
+            inv_rho_p_mean = L[4] * R[4] * fast_div(series ? poly : R[10] - L[10], series ? sum : dif);
+        }
+        const double c_h = eq.c_h;
+        double v_avg[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) v_avg[d] = 0.5 * (L[1 + d] + R[1 + d]);
+        const double p_avg = 0.5 * (L[4] + R[4]), psi_avg = 0.5 * (L[8] + R[8]);
+        const double velocity_square_avg = 0.5 * (L[1] * R[1] + L[2] * R[2] + L[3] * R[3]);
+        const double magnetic_square_avg = 0.5 * (L[5] * R[5] + L[6] * R[6] + L[7] * R[7]);
+        const double vo_l = Mhd3D::sel3(L[1], L[2], L[3], o), vo_r = Mhd3D::sel3(R[1], R[2], R[3], o);
+        const double Bo_l = Mhd3D::sel3(L[5], L[6], L[7], o), Bo_r = Mhd3D::sel3(R[5], R[6], R[7], o);
+        const double f1 = rho_mean * Mhd3D::sel3(v_avg[0], v_avg[1], v_avg[2], o);
+        f[0] = f1;
+#pragma unroll
+        for (int d = 0; d < 3; ++d)
+            f[1 + d] = d == o ? f1 * v_avg[d] + p_avg + magnetic_square_avg - 0.5 * (Bo_l * Bo_r + Bo_r * Bo_l)
+                              : f1 * v_avg[d] - 0.5 * (Bo_l * R[5 + d] + Bo_r * L[5 + d]);
+#pragma unroll
+        for (int d = 0; d < 3; ++d)
+            f[5 + d] = d == o ? c_h * psi_avg
+                              : 0.5 * (vo_l * L[5 + d] - L[1 + d] * Bo_l + vo_r * R[5 + d] - R[1 + d] * Bo_r);
+        f[8] = c_h * 0.5 * (Bo_l + Bo_r);
+        const int t1 = o == 0 ? 1 : 0, t2 = o == 2 ? 1 : 2;
+        const double vt1_l = Mhd3D::sel3(L[1], L[2], L[3], t1), vt1_r = Mhd3D::sel3(R[1], R[2], R[3], t1);
+        const double vt2_l = Mhd3D::sel3(L[1], L[2], L[3], t2), vt2_r = Mhd3D::sel3(R[1], R[2], R[3], t2);
+        const double Bt1_l = Mhd3D::sel3(L[5], L[6], L[7], t1), Bt1_r = Mhd3D::sel3(R[5], R[6], R[7], t1);
+        const double Bt2_l = Mhd3D::sel3(L[5], L[6], L[7], t2), Bt2_r = Mhd3D::sel3(R[5], R[6], R[7], t2);
+        f[4] = f1 * (velocity_square_avg + inv_rho_p_mean * eq.inv_gm1) +
+               0.5 * (+L[4] * vo_r + R[4] * vo_l + (vo_l * Bt1_l * Bt1_r + vo_r * Bt1_r * Bt1_l) +
+                      (vo_l * Bt2_l * Bt2_r + vo_r * Bt2_r * Bt2_l) - (vt1_l * Bo_l * Bt1_r + vt1_r * Bo_r * Bt1_l) -
+                      (vt2_l * Bo_l * Bt2_r + vt2_r * Bo_r * Bt2_l) + c_h * (Bo_l * R[8] + Bo_r * L[8]));
+    }
+    // flux_nonconservative_powell(u_ll, u_rr, orientation) on records
+    TB_DEV static void noncons(const double *L, const double *R, int o, double (&g)[9]) {
+        const double v_dot_B_ll = L[1] * L[5] + L[2] * L[6] + L[3] * L[7];
+        const double Bn_rr = Mhd3D::sel3(R[5], R[6], R[7], o), vo = Mhd3D::sel3(L[1], L[2], L[3], o);
+        g[0] = 0.0;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) g[1 + d] = L[5 + d] * Bn_rr;
+        g[4] = v_dot_B_ll * Bn_rr + vo * L[8] * R[8];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) g[5 + d] = L[1 + d] * Bn_rr;
+        g[8] = vo * R[8];
+    }
+};
 
 template <class EQ>
 struct LineSweepCfg {
     static constexpr int NV = EQ::NVARS, THREADS = 32;
     static constexpr int CONS = 64 * NV, SFV = 96 * NV;  // doubles per element
+    static constexpr int LINE = 64 * NodeRecord<EQ>::N;  // the line tile: states or hoisted node records
     // s_u (natural, TMA), s_sfv (natural, TMA), s_du (swizzled), s_line (swizzled; later the u_tmp tile), mbarrier
-    static constexpr size_t SMEM = sizeof(double) * (3 * CONS + SFV) + 16;
+    static constexpr size_t SMEM = sizeof(double) * (2 * CONS + SFV + LINE) + 16;
     static constexpr int BLOCKS_PER_SM = (int)((227 * 1024 + 1024) / (SMEM + 1024));  // 1 KB per CTA is reserved
     static constexpr int MIN_BLOCKS = BLOCKS_PER_SM < 8 ? BLOCKS_PER_SM : (BLOCKS_PER_SM > 16 ? 16 : BLOCKS_PER_SM);
 };
@@ -32,18 +126,21 @@ struct LineSweepCfg {
 // dg_3d.jl:268-306) for their own two nodes: thread h = 0 needs the subcell fluxes (0,1) and (1,2) of its line,
 // thread h = 1 needs (2,3) and (1,2); the first is the operand pair of its first two-point flux, (1,2) is
 // evaluated by both threads with identical operands (bitwise equal, so the subcell scheme stays conservative).
-template <class EQ, bool WITH_SURFACE, bool SC = false>
+template <class EQ, bool WITH_SURFACE, bool SC = false, bool REC = false>
 __global__ void __launch_bounds__(LineSweepCfg<EQ>::THREADS, LineSweepCfg<EQ>::MIN_BLOCKS)
     k_element_fd3d_p3(const KParams P) {
     using C = LineSweepCfg<EQ>;
+    using Rec = NodeRecord<EQ>;
+    static_assert(!REC || (Rec::kHas && !SC), "node records: equation support, no shock capturing");
     constexpr int NV = C::NV, CONS = C::CONS, SFV = C::SFV;
+    constexpr int NR = REC ? Rec::N : NV;  // doubles per node in the line tile
     extern __shared__ __align__(128) double smem[];
     double *s_u = smem;             // [64][NV] natural: u in, updated u out
     double *s_sfv = s_u + CONS;     // [6][16][NV] natural
     double *s_du = s_sfv + SFV;     // [64][NV] swizzled
     double *s_line = s_du + CONS;   // [64][NV] swizzled copy of u for the sweeps
     double *s_ut = s_line;          // afterwards: [64][NV] natural, u_tmp in, u_tmp (or du) out
-    const uint32_t bar = smem_u32(s_line + CONS);
+    const uint32_t bar = smem_u32(s_line + C::LINE);
 
     const EQ eq(P.eq);
     const int lane = threadIdx.x;
@@ -94,9 +191,13 @@ __global__ void __launch_bounds__(LineSweepCfg<EQ>::THREADS, LineSweepCfg<EQ>::M
     for (int r = 0; r < 2; ++r) {
         const int n = lane + 32 * r;
         const double *c = s_u + n * NV;
-        double *o = s_line + swz_pos(n) * NV;
+        double *o = s_line + swz_pos(n) * NR;
+        if constexpr (REC) {
+            Rec::make(eq, c, o);
+        } else {
 #pragma unroll
-        for (int v = 0; v < NV; ++v) o[v] = c[v];
+            for (int v = 0; v < NV; ++v) o[v] = c[v];
+        }
     }
     __syncwarp();
 
@@ -110,23 +211,35 @@ __global__ void __launch_bounds__(LineSweepCfg<EQ>::THREADS, LineSweepCfg<EQ>::M
     for (int d = 0; d < 3; ++d) {
         const int stride = 1 << (2 * d);
         const int base = d == 0 ? 4 * l16 : (d == 1 ? a0 + 16 * a1 : l16);
-        double q[4][NV];
+        double q[4][NR];
 #pragma unroll
         for (int m = 0; m < 4; ++m) {
             pos[m] = swz_pos(base + lm[m] * stride);
-            const double *src = s_line + pos[m] * NV;
+            const double *src = s_line + pos[m] * NR;
 #pragma unroll
-            for (int v = 0; v < NV; ++v) q[m][v] = src[v];
+            for (int v = 0; v < NR; ++v) q[m][v] = src[v];
         }
-        double f[NV], lo[NV], hi[NV];
+        double f[NV], lo[NR], hi[NR];
+        auto two_point = [&](const double(&a)[NR], const double(&b)[NR], double(&out)[NV]) {
+            if constexpr (REC)
+                Rec::flux(eq, P.volume_flux, a, b, d, out);
+            else
+                eq.numflux(P.volume_flux, a, b, d, out);
+        };
+        auto noncons_term = [&](const double(&a)[NR], const double(&b)[NR], double(&out)[NV]) {
+            if constexpr (REC)
+                Rec::noncons(a, b, d, out);
+            else if constexpr (EQ::kHasNoncons)
+                eq.noncons(a, b, d, out);
+        };
         // volume_flux(u_lower, u_upper) like the reference's loop (ii > i): thread h = 1 walks its line downwards,
         // so its operands are swapped -- by value selects, the two half-warps must not diverge around the flux
 #pragma unroll
-        for (int v = 0; v < NV; ++v) {
+        for (int v = 0; v < NR; ++v) {
             lo[v] = h ? q[1][v] : q[0][v];
             hi[v] = h ? q[0][v] : q[1][v];
         }
-        eq.numflux(P.volume_flux, lo, hi, d, f);
+        two_point(lo, hi, f);
 #pragma unroll
         for (int v = 0; v < NV; ++v) {
             own[0][v] = w01 * f[v];
@@ -151,22 +264,22 @@ __global__ void __launch_bounds__(LineSweepCfg<EQ>::THREADS, LineSweepCfg<EQ>::M
             }
         }
 #pragma unroll
-        for (int v = 0; v < NV; ++v) {
+        for (int v = 0; v < NR; ++v) {
             lo[v] = h ? q[2][v] : q[0][v];
             hi[v] = h ? q[0][v] : q[2][v];
         }
-        eq.numflux(P.volume_flux, lo, hi, d, f);
+        two_point(lo, hi, f);
 #pragma unroll
         for (int v = 0; v < NV; ++v) {
             own[0][v] = fma(w02, f[v], own[0][v]);
             frn[0][v] = w20 * f[v];
         }
 #pragma unroll
-        for (int v = 0; v < NV; ++v) {
+        for (int v = 0; v < NR; ++v) {
             lo[v] = h ? q[3][v] : q[1][v];
             hi[v] = h ? q[1][v] : q[3][v];
         }
-        eq.numflux(P.volume_flux, lo, hi, d, f);
+        two_point(lo, hi, f);
 #pragma unroll
         for (int v = 0; v < NV; ++v) {
             own[1][v] = fma(w13, f[v], own[1][v]);
@@ -177,22 +290,22 @@ __global__ void __launch_bounds__(LineSweepCfg<EQ>::THREADS, LineSweepCfg<EQ>::M
             // every partner b of its line (D_split has a zero diagonal)
             if (noncons) {
                 double g[NV];
-                eq.noncons(q[0], q[1], d, g);
+                noncons_term(q[0], q[1], g);
 #pragma unroll
                 for (int v = 0; v < NV; ++v) own[0][v] = fma(0.5 * w01, g[v], own[0][v]);
-                eq.noncons(q[1], q[0], d, g);
+                noncons_term(q[1], q[0], g);
 #pragma unroll
                 for (int v = 0; v < NV; ++v) own[1][v] = fma(0.5 * w10, g[v], own[1][v]);
-                eq.noncons(q[0], q[2], d, g);
+                noncons_term(q[0], q[2], g);
 #pragma unroll
                 for (int v = 0; v < NV; ++v) own[0][v] = fma(0.5 * w02, g[v], own[0][v]);
-                eq.noncons(q[2], q[0], d, g);
+                noncons_term(q[2], q[0], g);
 #pragma unroll
                 for (int v = 0; v < NV; ++v) frn[0][v] = fma(0.5 * w20, g[v], frn[0][v]);
-                eq.noncons(q[1], q[3], d, g);
+                noncons_term(q[1], q[3], g);
 #pragma unroll
                 for (int v = 0; v < NV; ++v) own[1][v] = fma(0.5 * w13, g[v], own[1][v]);
-                eq.noncons(q[3], q[1], d, g);
+                noncons_term(q[3], q[1], g);
 #pragma unroll
                 for (int v = 0; v < NV; ++v) frn[1][v] = fma(0.5 * w31, g[v], frn[1][v]);
             }
@@ -337,14 +450,18 @@ template <class EQ, bool SC = false>
 cudaError_t preload_fd3d_p3() {
     cudaError_t e = preload_kernel(k_element_fd3d_p3<EQ, true, SC>);
     if (e != cudaSuccess) return e;
+    if constexpr (NodeRecord<EQ>::kHas && !SC) {
+        if ((e = preload_kernel(k_element_fd3d_p3<EQ, true, false, true>)) != cudaSuccess) return e;
+        if ((e = preload_kernel(k_element_fd3d_p3<EQ, false, false, true>)) != cudaSuccess) return e;
+    }
     return preload_kernel(k_element_fd3d_p3<EQ, false, SC>);
 }
 
-template <class EQ, bool WS, bool SC = false>
+template <class EQ, bool WS, bool SC = false, bool REC = false>
 cudaError_t launch_fd3d_p3_variant(const KParams &P, cudaStream_t s) {
     using C = LineSweepCfg<EQ>;
     static PerDeviceFlag configured;
-    auto kern = k_element_fd3d_p3<EQ, WS, SC>;
+    auto kern = k_element_fd3d_p3<EQ, WS, SC, REC>;
     if (!configured.test_and_set()) {
         cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
                                                cudaSharedmemCarveoutMaxShared);
@@ -362,6 +479,12 @@ cudaError_t launch_fd3d_p3_variant(const KParams &P, cudaStream_t s) {
 
 template <class EQ, bool SC = false>
 cudaError_t launch_element_fd3d_p3(const KParams &P, bool with_surface, cudaStream_t s) {
+    if constexpr (NodeRecord<EQ>::kHas && !SC) {
+        // hoisted node records where the volume flux has a record form (kernel_path 2 = the plain form, for A/B runs)
+        if (NodeRecord<EQ>::applies(P.volume_flux) && P.kernel_path != 2)
+            return with_surface ? launch_fd3d_p3_variant<EQ, true, false, true>(P, s)
+                                : launch_fd3d_p3_variant<EQ, false, false, true>(P, s);
+    }
     return with_surface ? launch_fd3d_p3_variant<EQ, true, SC>(P, s) : launch_fd3d_p3_variant<EQ, false, SC>(P, s);
 }
 

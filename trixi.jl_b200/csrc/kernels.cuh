@@ -88,6 +88,12 @@ struct KParams {
     long long nmortars;
     const long long *mortar_ids, *mortar_large_sides, *mortar_orient;
     const long long *mortar_node_indices;         // P4est: [nd, 2, M], 1 = small side, 2 = large side
+    // MPI mortars: ids > 0 local element, < 0 minus the 1-based MPI-interface entry whose received face is that
+    // element's, 0 not available (include/trixi_b200.h); the exchange-only entries are flagged in mpi_is_piece
+    long long nmpimortars;
+    const long long *mpi_mortar_ids, *mpi_mortar_large_sides, *mpi_mortar_orient, *mpi_mortar_node_indices;
+    const double *mpi_mortar_normals;             // P4est: [nd, NF, 2^(d-1), MM]
+    const long long *mpi_is_piece;                // [nmpi] or nullptr
     const double *mortar_fwd[2], *mortar_rev[2];  // [0] lower, [1] upper
     const int *mpi_peer_slot;                            // [nmpi] index into the peer tables
     const long long *mpi_remote_index;                   // [nmpi] slot of this face in the peer's receive buffer
@@ -384,6 +390,40 @@ __global__ void __launch_bounds__(256) k_boundary_flux(const KParams P) {
     for (int v = 0; v < NV; ++v) s[v] = f[v];
 }
 
+// The point flux of a TreeMesh mortar, shared (out of line) by the local and the MPI mortar kernel so that N ranks
+// evaluate exactly the arithmetic of one rank (inlined copies may contract to different FMAs).  fprim goes to the
+// small element, fsec is projected to the large one; they differ by the nonconservative terms only
+// (dg_3d.jl:1012-1233: 0.5 nonconservative_flux(u_large, u_small) and 0.5 nonconservative_flux(u_small, u_large)).
+template <class EQ>
+__device__ __noinline__ void mortar_point_flux(const EQ &eq, int flux_id, const double *ularge, const double *usmall, int o,
+                                               bool large_left, double *fprim, double *fsec) {
+    constexpr int NV = EQ::NVARS;
+    double up[NV], us[NV], f[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+        up[v] = ularge[v];
+        us[v] = usmall[v];
+    }
+    if (large_left)
+        eq.numflux(flux_id, up, us, o, f);
+    else
+        eq.numflux(flux_id, us, up, o, f);
+#pragma unroll
+    for (int v = 0; v < NV; ++v) fprim[v] = fsec[v] = f[v];
+    if constexpr (EQ::kHasNoncons) {
+        if (EQ::has_noncons(flux_id)) {
+            double np_[NV], ns_[NV];
+            eq.noncons(up, us, o, np_);
+            eq.noncons(us, up, o, ns_);
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+                fprim[v] = f[v] + 0.5 * np_[v];
+                fsec[v] = f[v] + 0.5 * ns_[v];
+            }
+        }
+    }
+}
+
 // ---- 2a. L2 mortars ---------------------------------------------------------------------------------
 // prolong2mortars! + calc_mortar_flux! + mortar_fluxes_to_elements! fused (dg_2d.jl:899-1243,
 // dg_3d.jl:770-1335), conservative equations.  One block per mortar, one thread per (sub-face, face node);
@@ -441,38 +481,15 @@ __global__ void __launch_bounds__((1 << (EQ::NDIMS - 1)) * ipow(N, EQ::NDIMS - 1
 #pragma unroll
         for (int v = 0; v < NV; ++v) us[v] = pu[v];
     }
-    if (large_left)
-        eq.numflux(P.surface_flux, up, us, o, f);
-    else
-        eq.numflux(P.surface_flux, us, up, o, f);
-    // the small element takes its flux as it is (its face towards the large element)
+    // the small element takes its (primary) flux as it is (its face towards the large element)
     {
+        double fsec[NV];
+        mortar_point_flux<EQ>(eq, P.surface_flux, up, us, o, large_left, f, fsec);
         double *dst = P.sfv + ((small * (2 * ND) + (large_left ? 2 * o : 2 * o + 1)) * NF + fn) * NV;
-        if constexpr (EQ::kHasNoncons) {
-            // dg_3d.jl:1012-1233: the primary flux (small elements) adds 0.5 nonconservative_flux(u_large, u_small), the
-            // secondary flux (projected to the large element) 0.5 nonconservative_flux(u_small, u_large)
-            if (EQ::has_noncons(P.surface_flux)) {
-                double np_[NV], ns_[NV];
-                eq.noncons(up, us, o, np_);
-                eq.noncons(us, up, o, ns_);
 #pragma unroll
-                for (int v = 0; v < NV; ++v) {
-                    dst[v] = f[v] + 0.5 * np_[v];
-                    s_f[p][v + NV * fn] = f[v] + 0.5 * ns_[v];
-                }
-            } else {
-#pragma unroll
-                for (int v = 0; v < NV; ++v) {
-                    dst[v] = f[v];
-                    s_f[p][v + NV * fn] = f[v];
-                }
-            }
-        } else {
-#pragma unroll
-            for (int v = 0; v < NV; ++v) {
-                dst[v] = f[v];
-                s_f[p][v + NV * fn] = f[v];
-            }
+        for (int v = 0; v < NV; ++v) {
+            dst[v] = f[v];
+            s_f[p][v + NV * fn] = fsec[v];
         }
     }
     __syncthreads();
@@ -603,6 +620,7 @@ __global__ void __launch_bounds__(256) k_mpi_interface_flux(const KParams P) {
     const long long I = gid / NF;
     const int fn = (int)(gid % NF);
     if (I >= P.nmpi) return;
+    if (P.mpi_is_piece && P.mpi_is_piece[I]) return;  // exchange-only entry of an MPI mortar
     const EQ eq(P.eq);
     const long long element = P.mpi_local[I] - 1;
     const int o = (int)P.mpi_orient[I] - 1;
@@ -715,7 +733,7 @@ __global__ void __launch_bounds__(256, EQ::kHasNoncons ? 3 : (FAST == 1 ? 6 : (F
     __syncwarp();
 #pragma unroll
     for (int g2 = 0; g2 < G; ++g2) {
-        if (g2 < nvalid) {
+        if (g2 < nvalid && !(P.mpi_is_piece && P.mpi_is_piece[I0 + g2])) {  // (exchange-only entries of MPI mortars)
             const int o = s_orient[warp][g2];
             const int dir = s_side[warp][g2] == 1 ? 2 * o + 1 : 2 * o;
             double *dst = P.sfv + ((s_elem[warp][g2] * (2 * ND) + dir) * NF) * NV;
@@ -1764,6 +1782,7 @@ __global__ void __launch_bounds__(256) k_mpi_interface_flux_p4est(const KParams 
     const long long I = gid / NF;
     const int fn = (int)(gid % NF);
     if (I >= P.nmpi) return;
+    if (P.mpi_is_piece && P.mpi_is_piece[I]) return;  // exchange-only entry of an MPI mortar
     const int i = fn % N, j = fn / N;
     const EQ eq(P.eq);
     const long long element = P.mpi_local[I] - 1;
@@ -1789,6 +1808,148 @@ __global__ void __launch_bounds__(256) k_mpi_interface_flux_p4est(const KParams 
     double *s = P.sfv + ((element * (2 * ND) + dir) * NF + sfn) * NV;
 #pragma unroll
     for (int v = 0; v < NV; ++v) s[v] = side == 1 ? f[v] : -f[v];
+}
+
+// calc_mpi_mortar_flux! + mpi_mortar_fluxes_to_elements! (dgsem_tree/dg_2d_parallel.jl:742-860, dgsem_p4est/
+// dg_3d_parallel.jl:382-560) for both mesh kinds: k_mortar_flux / k_mortar_flux_p4est with the faces of remote
+// elements read from the receive buffer of the halo exchange (already in the mortar's alignment) and results stored
+// for local elements only.  A rank that does not own the large element evaluates just the positions of its own small
+// elements.  P4est: the small elements' outward normals come precomputed (they may be remote).
+template <class EQ, int N>
+__global__ void __launch_bounds__((1 << (EQ::NDIMS - 1)) * ipow(N, EQ::NDIMS - 1)) k_mpi_mortar_flux(const KParams P) {
+    constexpr int ND = EQ::NDIMS, NV = EQ::NVARS, NF = ipow(N, ND - 1), NN = ipow(N, ND), NP = 1 << (ND - 1);
+    __shared__ double s_large[NV * NF];
+    __shared__ double s_tmp[NP][NV * NF];
+    __shared__ double s_f[NP][NV * NF];
+    const long long m = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int p = tid / NF, fn = tid - p * NF;
+    const int a = fn % N, b = fn / N;
+    const EQ eq(P.eq);
+    const bool p4 = P.p4est != 0;
+    const long long *ids = P.mpi_mortar_ids + (NP + 1) * m;
+    const long long *sidx = p4 ? P.mpi_mortar_node_indices + (2 * m + 0) * ND : nullptr;
+    const long long *lidx = p4 ? P.mpi_mortar_node_indices + (2 * m + 1) * ND : nullptr;
+    const long long large_id = ids[NP], small_id = ids[p];
+    const int o = p4 ? 0 : (int)P.mpi_mortar_orient[m] - 1;
+    const bool large_left = !p4 && P.mpi_mortar_large_sides[m] == 1;
+    const double *fwd1 = P.mortar_fwd[p & 1], *fwd2 = P.mortar_fwd[(p >> 1) & 1];
+    const double *rev1 = P.mortar_rev[p & 1];
+    for (int q = tid; q < NV * NF; q += NP * NF) {
+        const int f = q / NV, v = q - f * NV;
+        double val;
+        if (large_id > 0) {
+            int vn, sfn, dir;
+            if (p4)
+                p4_face<ND, N>(lidx, f % N, f / N, vn, sfn, dir);
+            else
+                vn = face_to_volume_node<ND, N>(o, large_left ? N - 1 : 0, f);
+            val = P.u[((large_id - 1) * NN + vn) * NV + v];
+        } else {
+            val = P.recv[((-large_id - 1) * NF + f) * NV + v];
+        }
+        s_large[q] = val;
+    }
+    __syncthreads();
+    double up[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+        double acc = 0.0;
+        for (int q = 0; q < N; ++q) acc += fwd1[a + N * q] * s_large[v + NV * (q + N * b)];
+        up[v] = acc;
+    }
+    if constexpr (ND == 3) {
+#pragma unroll
+        for (int v = 0; v < NV; ++v) s_tmp[p][v + NV * fn] = up[v];
+        __syncthreads();
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            double acc = 0.0;
+            for (int q = 0; q < N; ++q) acc += fwd2[b + N * q] * s_tmp[p][v + NV * (a + N * q)];
+            up[v] = acc;
+        }
+        __syncthreads();
+    }
+    double us[NV], f[NV], fs[NV];
+    int sdir = large_left ? 2 * o : 2 * o + 1;
+    if (small_id != 0) {
+        if (small_id > 0) {
+            int svn, ssfn;
+            if (p4)
+                p4_face<ND, N>(sidx, a, b, svn, ssfn, sdir);
+            else
+                svn = face_to_volume_node<ND, N>(o, large_left ? 0 : N - 1, fn);
+            const double *pu = P.u + ((small_id - 1) * NN + svn) * NV;
+#pragma unroll
+            for (int v = 0; v < NV; ++v) us[v] = pu[v];
+        } else {
+            const double *pu = P.recv + ((-small_id - 1) * NF + fn) * NV;
+#pragma unroll
+            for (int v = 0; v < NV; ++v) us[v] = pu[v];
+        }
+        if (p4) {
+            double nrm[ND];
+            const double *pn = P.mpi_mortar_normals + ((m * NP + p) * NF + fn) * ND;
+#pragma unroll
+            for (int d = 0; d < ND; ++d) nrm[d] = pn[d];
+            eq.numflux_normal(P.surface_flux, us, up, nrm, f);
+#pragma unroll
+            for (int v = 0; v < NV; ++v) fs[v] = f[v];
+        } else {
+            mortar_point_flux<EQ>(eq, P.surface_flux, up, us, o, large_left, f, fs);
+        }
+        if (small_id > 0) {
+            double *dst = P.sfv + (((small_id - 1) * (2 * ND) + sdir) * NF + fn) * NV;
+#pragma unroll
+            for (int v = 0; v < NV; ++v) dst[v] = f[v];
+        }
+#pragma unroll
+        for (int v = 0; v < NV; ++v) s_f[p][v + NV * fn] = fs[v];
+    }
+    if (large_id < 0) return;  // (uniform over the block) the large element belongs to another rank
+    __syncthreads();
+    int lsfn = fn, ldir = large_left ? 2 * o + 1 : 2 * o;
+    if (p4) {
+        int lvn;
+        p4_face<ND, N>(lidx, a, b, lvn, lsfn, ldir);
+    }
+    double *out = P.sfv + (((large_id - 1) * (2 * ND) + ldir) * NF + lsfn) * NV;
+    const double scale = p4 ? (ND == 2 ? -2.0 : -4.0) : 1.0;
+    if constexpr (ND == 2) {
+        if (tid < N) {
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+                double acc = 0.0;
+                for (int q = 0; q < N; ++q)
+                    acc += P.mortar_rev[1][tid + N * q] * s_f[1][v + NV * q] + P.mortar_rev[0][tid + N * q] * s_f[0][v + NV * q];
+                out[v] = p4 ? acc * scale : acc;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            double acc = 0.0;
+            for (int q = 0; q < N; ++q) acc += rev1[a + N * q] * s_f[p][v + NV * (q + N * b)];
+            s_tmp[p][v + NV * fn] = acc;
+        }
+        __syncthreads();
+        if (tid < NF) {
+            // TreeMesh: upper_left, upper_right, lower_left, lower_right (dg_3d.jl:1314-1331); P4est: positions 1..4
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+                double res = 0.0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int pp = p4 ? k : (k + 2) & 3;
+                    const double *r2 = P.mortar_rev[(pp >> 1) & 1];
+                    double acc = 0.0;
+                    for (int q = 0; q < N; ++q) acc += r2[b + N * q] * s_tmp[pp][v + NV * (a + N * q)];
+                    res = k == 0 ? acc : res + acc;
+                }
+                out[v] = p4 ? res * scale : res;
+            }
+        }
+    }
 }
 
 }  // namespace tb

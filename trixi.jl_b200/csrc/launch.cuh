@@ -128,7 +128,7 @@ void launch_mpi_pack(const KParams &P, cudaStream_t s) {
 }
 
 template <class EQ, int N>
-void launch_mpi_interface_flux(const KParams &P, cudaStream_t s) {
+void launch_mpi_conforming_flux(const KParams &P, cudaStream_t s) {
     constexpr int NF = ipow(N, EQ::NDIMS - 1);
     const long long total = P.nmpi * NF;
     if (total == 0) return;
@@ -155,6 +155,16 @@ void launch_mpi_interface_flux(const KParams &P, cudaStream_t s) {
             k_mpi_interface_flux<EQ, N, 2><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(P);
         else
             k_mpi_interface_flux<EQ, N><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(P);
+    }
+}
+
+// shared conforming faces, then the mortars that straddle ranks (both read the same receive buffer)
+template <class EQ, int N>
+void launch_mpi_interface_flux(const KParams &P, cudaStream_t s) {
+    launch_mpi_conforming_flux<EQ, N>(P, s);
+    if (P.nmpimortars > 0) {
+        constexpr int threads = (1 << (EQ::NDIMS - 1)) * ipow(N, EQ::NDIMS - 1);
+        k_mpi_mortar_flux<EQ, N><<<(unsigned)P.nmpimortars, threads, 0, s>>>(P);
     }
 }
 
@@ -373,6 +383,7 @@ cudaError_t preload_all() {
     TB_PRELOAD((k_sfv_fill_right<EQ, N>));
     TB_PRELOAD((k_mortar_flux<EQ, N>));
     TB_PRELOAD((k_mortar_flux_p4est<EQ, N>));
+    TB_PRELOAD((k_mpi_mortar_flux<EQ, N>));
     TB_PRELOAD((k_error_norms<EQ, N>));
     TB_PRELOAD((k_mpi_pack<EQ, N>));
     TB_PRELOAD((k_mpi_interface_flux<EQ, N>));

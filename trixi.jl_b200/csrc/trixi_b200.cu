@@ -622,10 +622,26 @@ TRIXI_B200_API int trixi_b200_create(const trixi_b200_desc *d, trixi_b200_handle
     if (d->nmortars < 0) return fail(nullptr, TRIXI_B200_EINVAL, "negative container size");
     if (d->nmortars > 0) {
         if (structured) return fail(nullptr, TRIXI_B200_EINVAL, "a StructuredMesh has no mortars");
-        if (d->world_size > 1) return fail(nullptr, TRIXI_B200_EINVAL, "MPI mortars are not supported by this build");
         if (!d->mortar_neighbor_ids || !d->mortar_forward_upper || !d->mortar_forward_lower || !d->mortar_reverse_upper ||
             !d->mortar_reverse_lower || (p4est ? !d->mortar_node_indices : !d->mortar_large_sides || !d->mortar_orientations))
             return fail(nullptr, TRIXI_B200_EINVAL, "mortar arrays missing");
+    }
+    if (d->nmpimortars < 0) return fail(nullptr, TRIXI_B200_EINVAL, "negative container size");
+    if (d->nmpimortars > 0) {
+        if (structured || d->world_size < 2 || d->nmpiinterfaces <= 0 || !d->mpi_is_mortar_piece)
+            return fail(nullptr, TRIXI_B200_EINVAL, "MPI mortars need world_size > 1 and their exchange entries in the MPI interface list");
+        if (!d->mpi_mortar_neighbor_ids || !d->mortar_forward_upper || !d->mortar_forward_lower || !d->mortar_reverse_upper ||
+            !d->mortar_reverse_lower ||
+            (p4est ? !d->mpi_mortar_node_indices || !d->mpi_mortar_normal_directions
+                   : !d->mpi_mortar_large_sides || !d->mpi_mortar_orientations))
+            return fail(nullptr, TRIXI_B200_EINVAL, "MPI mortar arrays missing");
+        const int64_t np1 = ((int64_t)1 << (d->ndims - 1)) + 1;
+        for (int64_t q = 0; q < np1 * d->nmpimortars; ++q) {
+            const int64_t id = d->mpi_mortar_neighbor_ids[q];
+            if (id > d->nelements || -id > d->nmpiinterfaces || (id < 0 && !d->mpi_is_mortar_piece[-id - 1]))
+                return fail(nullptr, TRIXI_B200_EINVAL, "mpi_mortar_neighbor_ids[%lld] = %lld is out of range", (long long)q,
+                            (long long)id);
+        }
     }
     if (d->volume_integral != TRIXI_B200_VOLINT_WEAK_FORM && d->volume_integral != TRIXI_B200_VOLINT_FLUX_DIFFERENCING &&
         d->volume_integral != TRIXI_B200_VOLINT_SHOCK_CAPTURING_HG)
@@ -778,7 +794,41 @@ TRIXI_B200_API int trixi_b200_create(const trixi_b200_desc *d, trixi_b200_handle
     if (h->sfvlen) CREATE_CUDA(cudaMemset(P.sfv, 0xff, h->sfvlen * sizeof(double)));  // NaN like the reference's fill
 
     double *tmp = nullptr;
+    P.nmpimortars = d->nmpimortars;
+    if (d->nmpimortars > 0) {
+        const size_t np = (size_t)1 << (nd - 1);
+        long long *mtmp = nullptr;
+        CREATE_TRY(upload_array(h, (const long long *)d->mpi_mortar_neighbor_ids, (np + 1) * (size_t)d->nmpimortars, &mtmp));
+        P.mpi_mortar_ids = mtmp;
+        if (p4est) {
+            CREATE_TRY(upload_array(h, (const long long *)d->mpi_mortar_node_indices, 2 * (size_t)nd * (size_t)d->nmpimortars, &mtmp));
+            P.mpi_mortar_node_indices = mtmp;
+            CREATE_TRY(upload_array(h, d->mpi_mortar_normal_directions,
+                                    (size_t)nd * (size_t)ipow(n, nd - 1) * np * (size_t)d->nmpimortars, &tmp));
+            P.mpi_mortar_normals = tmp;
+        } else {
+            CREATE_TRY(upload_array(h, (const long long *)d->mpi_mortar_large_sides, (size_t)d->nmpimortars, &mtmp));
+            P.mpi_mortar_large_sides = mtmp;
+            CREATE_TRY(upload_array(h, (const long long *)d->mpi_mortar_orientations, (size_t)d->nmpimortars, &mtmp));
+            P.mpi_mortar_orient = mtmp;
+        }
+    }
+    if (d->nmpiinterfaces > 0 && d->mpi_is_mortar_piece) {
+        long long *mtmp = nullptr;
+        CREATE_TRY(upload_array(h, (const long long *)d->mpi_is_mortar_piece, (size_t)d->nmpiinterfaces, &mtmp));
+        P.mpi_is_piece = mtmp;
+    }
     P.nmortars = d->nmortars;
+    if (d->nmortars > 0 || d->nmpimortars > 0) {
+        CREATE_TRY(upload_array(h, d->mortar_forward_lower, (size_t)n * n, &tmp));
+        P.mortar_fwd[0] = tmp;
+        CREATE_TRY(upload_array(h, d->mortar_forward_upper, (size_t)n * n, &tmp));
+        P.mortar_fwd[1] = tmp;
+        CREATE_TRY(upload_array(h, d->mortar_reverse_lower, (size_t)n * n, &tmp));
+        P.mortar_rev[0] = tmp;
+        CREATE_TRY(upload_array(h, d->mortar_reverse_upper, (size_t)n * n, &tmp));
+        P.mortar_rev[1] = tmp;
+    }
     if (d->nmortars > 0) {
         const size_t np1 = ((size_t)1 << (nd - 1)) + 1;
         long long *mtmp = nullptr;
@@ -793,14 +843,6 @@ TRIXI_B200_API int trixi_b200_create(const trixi_b200_desc *d, trixi_b200_handle
             CREATE_TRY(upload_array(h, (const long long *)d->mortar_orientations, (size_t)d->nmortars, &mtmp));
             P.mortar_orient = mtmp;
         }
-        CREATE_TRY(upload_array(h, d->mortar_forward_lower, (size_t)n * n, &tmp));
-        P.mortar_fwd[0] = tmp;
-        CREATE_TRY(upload_array(h, d->mortar_forward_upper, (size_t)n * n, &tmp));
-        P.mortar_fwd[1] = tmp;
-        CREATE_TRY(upload_array(h, d->mortar_reverse_lower, (size_t)n * n, &tmp));
-        P.mortar_rev[0] = tmp;
-        CREATE_TRY(upload_array(h, d->mortar_reverse_upper, (size_t)n * n, &tmp));
-        P.mortar_rev[1] = tmp;
     }
     CREATE_TRY(upload_array(h, d->derivative_split, (size_t)n * n, &tmp));
     P.dsplit = tmp;
