@@ -48,7 +48,12 @@ struct NodeRecord<Mhd3D> {
         r[5] = u[5], r[6] = u[6], r[7] = u[7], r[8] = u[8];
         r[9] = lrho, r[10] = lrho - log_pos(p);
     }
-    TB_DEV static void flux(const Mhd3D &eq, int /*id*/, const double *L, const double *R, int o, double (&f)[9]) {
+    // The sweeps hand over records whose velocity and field components have been rotated cyclically so that slot 1 / 5 is
+    // the sweep direction (kRotated): the flux below is the orientation-1 form with compile-time component indices -- no
+    // selects on the direction, no arm of a conditional evaluated in vain.  Its momentum and field components come out in
+    // the same rotated order.  (The transverse sums then run in rotated order: last-bit differences to the reference.)
+    static constexpr bool kRotated = true;
+    TB_DEV static void flux(const Mhd3D &eq, int /*id*/, const double *L, const double *R, double (&f)[9]) {
         double rho_mean, inv_rho_p_mean;
         {
             const double sum = L[0] + R[0], dif = R[0] - L[0];
@@ -66,45 +71,32 @@ struct NodeRecord<Mhd3D> {
             inv_rho_p_mean = L[4] * R[4] * fast_div(series ? poly : R[10] - L[10], series ? sum : dif);
         }
         const double c_h = eq.c_h;
-        double v_avg[3];
-#pragma unroll
-        for (int d = 0; d < 3; ++d) v_avg[d] = 0.5 * (L[1 + d] + R[1 + d]);
+        const double vn_avg = 0.5 * (L[1] + R[1]), vt1_avg = 0.5 * (L[2] + R[2]), vt2_avg = 0.5 * (L[3] + R[3]);
         const double p_avg = 0.5 * (L[4] + R[4]), psi_avg = 0.5 * (L[8] + R[8]);
         const double velocity_square_avg = 0.5 * (L[1] * R[1] + L[2] * R[2] + L[3] * R[3]);
         const double magnetic_square_avg = 0.5 * (L[5] * R[5] + L[6] * R[6] + L[7] * R[7]);
-        const double vo_l = Mhd3D::sel3(L[1], L[2], L[3], o), vo_r = Mhd3D::sel3(R[1], R[2], R[3], o);
-        const double Bo_l = Mhd3D::sel3(L[5], L[6], L[7], o), Bo_r = Mhd3D::sel3(R[5], R[6], R[7], o);
-        const double f1 = rho_mean * Mhd3D::sel3(v_avg[0], v_avg[1], v_avg[2], o);
+        const double f1 = rho_mean * vn_avg;
         f[0] = f1;
-#pragma unroll
-        for (int d = 0; d < 3; ++d)
-            f[1 + d] = d == o ? f1 * v_avg[d] + p_avg + magnetic_square_avg - 0.5 * (Bo_l * Bo_r + Bo_r * Bo_l)
-                              : f1 * v_avg[d] - 0.5 * (Bo_l * R[5 + d] + Bo_r * L[5 + d]);
-#pragma unroll
-        for (int d = 0; d < 3; ++d)
-            f[5 + d] = d == o ? c_h * psi_avg
-                              : 0.5 * (vo_l * L[5 + d] - L[1 + d] * Bo_l + vo_r * R[5 + d] - R[1 + d] * Bo_r);
-        f[8] = c_h * 0.5 * (Bo_l + Bo_r);
-        const int t1 = o == 0 ? 1 : 0, t2 = o == 2 ? 1 : 2;
-        const double vt1_l = Mhd3D::sel3(L[1], L[2], L[3], t1), vt1_r = Mhd3D::sel3(R[1], R[2], R[3], t1);
-        const double vt2_l = Mhd3D::sel3(L[1], L[2], L[3], t2), vt2_r = Mhd3D::sel3(R[1], R[2], R[3], t2);
-        const double Bt1_l = Mhd3D::sel3(L[5], L[6], L[7], t1), Bt1_r = Mhd3D::sel3(R[5], R[6], R[7], t1);
-        const double Bt2_l = Mhd3D::sel3(L[5], L[6], L[7], t2), Bt2_r = Mhd3D::sel3(R[5], R[6], R[7], t2);
+        f[1] = f1 * vn_avg + p_avg + magnetic_square_avg - 0.5 * (L[5] * R[5] + R[5] * L[5]);
+        f[2] = f1 * vt1_avg - 0.5 * (L[5] * R[6] + R[5] * L[6]);
+        f[3] = f1 * vt2_avg - 0.5 * (L[5] * R[7] + R[5] * L[7]);
+        f[5] = c_h * psi_avg;
+        f[6] = 0.5 * (L[1] * L[6] - L[2] * L[5] + R[1] * R[6] - R[2] * R[5]);
+        f[7] = 0.5 * (L[1] * L[7] - L[3] * L[5] + R[1] * R[7] - R[3] * R[5]);
+        f[8] = c_h * 0.5 * (L[5] + R[5]);
         f[4] = f1 * (velocity_square_avg + inv_rho_p_mean * eq.inv_gm1) +
-               0.5 * (+L[4] * vo_r + R[4] * vo_l + (vo_l * Bt1_l * Bt1_r + vo_r * Bt1_r * Bt1_l) +
-                      (vo_l * Bt2_l * Bt2_r + vo_r * Bt2_r * Bt2_l) - (vt1_l * Bo_l * Bt1_r + vt1_r * Bo_r * Bt1_l) -
-                      (vt2_l * Bo_l * Bt2_r + vt2_r * Bo_r * Bt2_l) + c_h * (Bo_l * R[8] + Bo_r * L[8]));
+               0.5 * (+L[4] * R[1] + R[4] * L[1] + (L[1] * L[6] * R[6] + R[1] * R[6] * L[6]) +
+                      (L[1] * L[7] * R[7] + R[1] * R[7] * L[7]) - (L[2] * L[5] * R[6] + R[2] * R[5] * L[6]) -
+                      (L[3] * L[5] * R[7] + R[3] * R[5] * L[7]) + c_h * (L[5] * R[8] + R[5] * L[8]));
     }
-    // flux_nonconservative_powell(u_ll, u_rr, orientation) on records
-    TB_DEV static void noncons(const double *L, const double *R, int o, double (&g)[9]) {
+    // flux_nonconservative_powell(u_ll, u_rr, orientation) on rotated records
+    TB_DEV static void noncons(const double *L, const double *R, double (&g)[9]) {
         const double v_dot_B_ll = L[1] * L[5] + L[2] * L[6] + L[3] * L[7];
-        const double Bn_rr = Mhd3D::sel3(R[5], R[6], R[7], o), vo = Mhd3D::sel3(L[1], L[2], L[3], o);
+        const double Bn_rr = R[5], vo = L[1];
         g[0] = 0.0;
-#pragma unroll
-        for (int d = 0; d < 3; ++d) g[1 + d] = L[5 + d] * Bn_rr;
+        g[1] = L[5] * Bn_rr, g[2] = L[6] * Bn_rr, g[3] = L[7] * Bn_rr;
         g[4] = v_dot_B_ll * Bn_rr + vo * L[8] * R[8];
-#pragma unroll
-        for (int d = 0; d < 3; ++d) g[5 + d] = L[1 + d] * Bn_rr;
+        g[5] = L[1] * Bn_rr, g[6] = L[2] * Bn_rr, g[7] = L[3] * Bn_rr;
         g[8] = vo * R[8];
     }
 };
@@ -216,30 +208,43 @@ __global__ void __launch_bounds__(LineSweepCfg<EQ>::THREADS, LineSweepCfg<EQ>::M
         for (int m = 0; m < 4; ++m) {
             pos[m] = swz_pos(base + lm[m] * stride);
             const double *src = s_line + pos[m] * NR;
+            if constexpr (REC) {
+                // cyclic rotation: slot k of the velocity / field triples holds component (d + k) mod 3
+                const int c1 = d == 2 ? 0 : d + 1, c2 = d == 0 ? 2 : d - 1;
+                q[m][0] = src[0], q[m][4] = src[4], q[m][8] = src[8], q[m][9] = src[9], q[m][10] = src[10];
+                q[m][1] = src[1 + d], q[m][2] = src[1 + c1], q[m][3] = src[1 + c2];
+                q[m][5] = src[5 + d], q[m][6] = src[5 + c1], q[m][7] = src[5 + c2];
+            } else {
 #pragma unroll
-            for (int v = 0; v < NR; ++v) q[m][v] = src[v];
+                for (int v = 0; v < NR; ++v) q[m][v] = src[v];
+            }
         }
         double f[NV], lo[NR], hi[NR];
         auto two_point = [&](const double(&a)[NR], const double(&b)[NR], double(&out)[NV]) {
             if constexpr (REC)
-                Rec::flux(eq, P.volume_flux, a, b, d, out);
+                Rec::flux(eq, P.volume_flux, a, b, out);
             else
                 eq.numflux(P.volume_flux, a, b, d, out);
         };
         auto noncons_term = [&](const double(&a)[NR], const double(&b)[NR], double(&out)[NV]) {
             if constexpr (REC)
-                Rec::noncons(a, b, d, out);
+                Rec::noncons(a, b, out);
             else if constexpr (EQ::kHasNoncons)
                 eq.noncons(a, b, d, out);
         };
         // volume_flux(u_lower, u_upper) like the reference's loop (ii > i): thread h = 1 walks its line downwards,
         // so its operands are swapped -- by value selects, the two half-warps must not diverge around the flux
+        if constexpr (REC) {
+            // (record fluxes are symmetric up to rounding: no operand swap for the downward half-warp)
+            two_point(q[0], q[1], f);
+        } else {
 #pragma unroll
-        for (int v = 0; v < NR; ++v) {
-            lo[v] = h ? q[1][v] : q[0][v];
-            hi[v] = h ? q[0][v] : q[1][v];
+            for (int v = 0; v < NR; ++v) {
+                lo[v] = h ? q[1][v] : q[0][v];
+                hi[v] = h ? q[0][v] : q[1][v];
+            }
+            two_point(lo, hi, f);
         }
-        two_point(lo, hi, f);
 #pragma unroll
         for (int v = 0; v < NV; ++v) {
             own[0][v] = w01 * f[v];
@@ -263,23 +268,33 @@ __global__ void __launch_bounds__(LineSweepCfg<EQ>::THREADS, LineSweepCfg<EQ>::M
                 }
             }
         }
+        if constexpr (REC) {
+            // (record fluxes are symmetric up to rounding: no operand swap for the downward half-warp)
+            two_point(q[0], q[2], f);
+        } else {
 #pragma unroll
-        for (int v = 0; v < NR; ++v) {
-            lo[v] = h ? q[2][v] : q[0][v];
-            hi[v] = h ? q[0][v] : q[2][v];
+            for (int v = 0; v < NR; ++v) {
+                lo[v] = h ? q[2][v] : q[0][v];
+                hi[v] = h ? q[0][v] : q[2][v];
+            }
+            two_point(lo, hi, f);
         }
-        two_point(lo, hi, f);
 #pragma unroll
         for (int v = 0; v < NV; ++v) {
             own[0][v] = fma(w02, f[v], own[0][v]);
             frn[0][v] = w20 * f[v];
         }
+        if constexpr (REC) {
+            // (record fluxes are symmetric up to rounding: no operand swap for the downward half-warp)
+            two_point(q[1], q[3], f);
+        } else {
 #pragma unroll
-        for (int v = 0; v < NR; ++v) {
-            lo[v] = h ? q[3][v] : q[1][v];
-            hi[v] = h ? q[1][v] : q[3][v];
+            for (int v = 0; v < NR; ++v) {
+                lo[v] = h ? q[3][v] : q[1][v];
+                hi[v] = h ? q[1][v] : q[3][v];
+            }
+            two_point(lo, hi, f);
         }
-        two_point(lo, hi, f);
 #pragma unroll
         for (int v = 0; v < NV; ++v) {
             own[1][v] = fma(w13, f[v], own[1][v]);
@@ -310,12 +325,21 @@ __global__ void __launch_bounds__(LineSweepCfg<EQ>::THREADS, LineSweepCfg<EQ>::M
                 for (int v = 0; v < NV; ++v) frn[1][v] = fma(0.5 * w31, g[v], frn[1][v]);
             }
         }
+        // (records: the triples of own/frn are in the rotated order of this direction; component of slot k)
+        int comp[NV];
+#pragma unroll
+        for (int v = 0; v < NV; ++v) comp[v] = v;
+        if constexpr (REC) {
+            const int c1 = d == 2 ? 0 : d + 1, c2 = d == 0 ? 2 : d - 1;
+            comp[1] = 1 + d, comp[2] = 1 + c1, comp[3] = 1 + c2;
+            comp[5] = 5 + d, comp[6] = 5 + c1, comp[7] = 5 + c2;
+        }
         if (d < 2) {
 #pragma unroll
             for (int m = 0; m < 2; ++m) {
                 double *t = s_du + pos[m] * NV;
 #pragma unroll
-                for (int v = 0; v < NV; ++v) t[v] = d == 0 ? own[m][v] : t[v] + own[m][v];
+                for (int v = 0; v < NV; ++v) t[comp[v]] = d == 0 ? own[m][v] : t[comp[v]] + own[m][v];
             }
             __syncwarp();
         }
@@ -323,7 +347,7 @@ __global__ void __launch_bounds__(LineSweepCfg<EQ>::THREADS, LineSweepCfg<EQ>::M
         for (int m = 0; m < 2; ++m) {
             double *t = s_du + pos[2 + m] * NV;
 #pragma unroll
-            for (int v = 0; v < NV; ++v) t[v] += frn[m][v];
+            for (int v = 0; v < NV; ++v) t[comp[v]] += frn[m][v];
         }
         __syncwarp();
     }
@@ -349,8 +373,15 @@ __global__ void __launch_bounds__(LineSweepCfg<EQ>::THREADS, LineSweepCfg<EQ>::M
         const int n = l16 + 16 * k;
         const double *t = s_du + pos[r] * NV;
         double(&val)[NV] = vals[r];
+        if constexpr (REC) {
+            // the z sweep left own[] in its rotated order: slot k of a triple holds component (2 + k) mod 3
+            constexpr int slot_of[9] = {0, 2, 3, 1, 4, 6, 7, 5, 8};
 #pragma unroll
-        for (int v = 0; v < NV; ++v) val[v] = t[v] + own[r][v];
+            for (int v = 0; v < NV; ++v) val[v] = t[v] + own[r][slot_of[v]];
+        } else {
+#pragma unroll
+            for (int v = 0; v < NV; ++v) val[v] = t[v] + own[r][v];
+        }
         if constexpr (WITH_SURFACE) {
             // calc_surface_integral! (dg_3d.jl:1337-1394): directions 1..6 = -x,+x,-y,+y,-z,+z
             if (i == 0 || i == 3) {
