@@ -57,8 +57,9 @@ enum {
     TRIXI_B200_VOLINT_FLUX_DIFFERENCING = 1,
     /* VolumeIntegralShockCapturingHG(indicator; volume_flux_dg, volume_flux_fv) (solvers/dg.jl; driver
      * dgsem/calc_volume_integral.jl:231-272): per element a blend (1 - alpha) flux differencing + alpha first-order
-     * subcell finite volumes (fv_kernel! dg_3d.jl:268-306), alpha from IndicatorHennemannGassner.  TreeMesh,
-     * compressible Euler; across ranks the neighbour's alpha travels with the halo exchange. */
+     * subcell finite volumes (fv_kernel! dg_3d.jl:268-306), alpha from IndicatorHennemannGassner.  Compressible
+     * Euler on TreeMesh (across ranks the neighbour's alpha travels with the halo exchange) and, single rank, on
+     * StructuredMesh / P4estMesh (subcell_normal_vectors below). */
     TRIXI_B200_VOLINT_SHOCK_CAPTURING_HG = 2
 };
 
@@ -215,6 +216,11 @@ typedef struct trixi_b200_desc {
     const double *mpi_mortar_normal_directions;   /* P4est: [ndims, n^(d-1), 2^(d-1), nmpimortars] outward normals of
                                                      the small elements (they may be remote) */
     const int64_t *mpi_is_mortar_piece;           /* [nmpiinterfaces], NULL = all zero */
+
+    /* VolumeIntegralShockCapturingHG on curved meshes: NormalVectorContainer (dgsem_structured/containers_3d.jl:488-541),
+     * the free-stream preserving normals of the subcell interfaces used by calcflux_fv! (dgsem_structured/
+     * dg_3d.jl:377-436): direction a -> [ndims, n .. (n - 1 along a) .., nelements]; NULL otherwise */
+    const double *subcell_normal_vectors[3];
 } trixi_b200_desc;
 
 typedef struct trixi_b200_handle trixi_b200_handle;

@@ -156,6 +156,7 @@ struct Desc
     mpi_mortar_node_indices::Ptr{Int64}
     mpi_mortar_normal_directions::Ptr{Float64}
     mpi_is_mortar_piece::Ptr{Int64}
+    subcell_normal_vectors::NTuple{3, Ptr{Float64}}
 end
 
 # ---- the backend object ---------------------------------------------------------------------------------
@@ -251,9 +252,14 @@ function B200(semi::SemidiscretizationHyperbolic; device = -1)
                                          dg.mortar.reverse_upper, dg.mortar.reverse_lower)) :
                      ntuple(_ -> zeros(0, 0), 4)
     fv_flux, ind_var, ind_smooth, ind_max, ind_min, inv_vdm = shock_capturing_fields(dg.volume_integral, dg.basis)
+    # shock capturing on curved meshes: cache.normal_vectors (NormalVectorContainer, dgsem_structured/containers_3d.jl:488-541)
+    nvc = haskey(cache, :normal_vectors) ? cache.normal_vectors : nothing
+    subcell_normals = nvc === nothing ? ntuple(_ -> Ptr{Float64}(C_NULL), 3) :
+                      (pointer(nvc.normal_vectors_1), pointer(nvc.normal_vectors_2),
+                       ndims(mesh) == 3 ? pointer(nvc.normal_vectors_3) : Ptr{Float64}(C_NULL))
     handle = Ref{Ptr{Cvoid}}(C_NULL)
     # the library copies during `create` only
-    GC.@preserve inv_vdm D_split D_hat inv_w el contravariant left_neighbors if_ids if_orient if_idx bd_ids bd_orient bd_sides bd_x bd_idx mo_ids mo_sides mo_orient mo_idx fu fl ru rl begin
+    GC.@preserve nvc inv_vdm D_split D_hat inv_w el contravariant left_neighbors if_ids if_orient if_idx bd_ids bd_orient bd_sides bd_x bd_idx mo_ids mo_sides mo_orient mo_idx fu fl ru rl begin
         desc = Desc(ABI_VERSION, device, ndims(mesh), nvariables(equations), nnodes(dg), mesh_kind(mesh),
                     nelements(dg, cache), equation_id(equations), volint, volflux,
                     flux_id(dg.surface_integral.surface_flux), source_id(semi.source_terms),
@@ -269,7 +275,8 @@ function B200(semi::SemidiscretizationHyperbolic; device = -1)
                     ptr_or_null(bd_idx), C_NULL,
                     fv_flux, ind_var, ind_smooth, 0, ind_max, ind_min, ptr_or_null(inv_vdm),
                     ptr_or_null(mo_idx),
-                    0, C_NULL, C_NULL, C_NULL, C_NULL, C_NULL, C_NULL)   # single rank: no MPI mortars
+                    0, C_NULL, C_NULL, C_NULL, C_NULL, C_NULL, C_NULL,   # single rank: no MPI mortars
+                    subcell_normals)
         rc = ccall((:trixi_b200_create, libtrixi_b200), Cint, (Ref{Desc}, Ref{Ptr{Cvoid}}), desc, handle)
     end
     check(nothing, rc)

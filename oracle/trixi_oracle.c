@@ -1166,6 +1166,17 @@ void oracle_calc_indicator_hg(const trixi_b200_desc *d, double *alpha, const dou
     if (!d->indicator_alpha_smooth) return;
     double *tmp = (double *)malloc(sizeof(double) * (size_t)(d->nelements > 0 ? d->nelements : 1));
     memcpy(tmp, alpha, sizeof(double) * (size_t)d->nelements);
+    if (d->mesh_kind == TRIXI_B200_MESH_STRUCTURED) {
+        /* apply_smoothing! dgsem_structured/indicators_2d.jl:8-37, indicators_3d.jl:8-40: over the elements and
+         * their left neighbours (periodic meshes only, as the reference asserts) */
+        for (int64_t e = 0; e < d->nelements; ++e)
+            for (int a = 0; a < nd; ++a) {
+                int64_t l = d->left_neighbors[a + (int64_t)nd * e] - 1;
+                if (l < 0) continue;
+                alpha[l] = max3(tmp[l], 0.5 * tmp[e], alpha[l]);
+                alpha[e] = max3(tmp[e], 0.5 * tmp[l], alpha[e]);
+            }
+    }
     for (int64_t I = 0; I < d->ninterfaces; ++I) {
         int64_t l = d->interface_neighbor_ids[2 * I] - 1, r = d->interface_neighbor_ids[2 * I + 1] - 1;
         alpha[l] = max3(tmp[l], 0.5 * tmp[r], alpha[l]);
@@ -1498,7 +1509,7 @@ static void weak_form_kernel_curved(const trixi_b200_desc *d, const eqn_t *eq, d
 
 /* flux_differencing_kernel! dgsem_structured/dg_3d.jl:94-175 / dg_2d.jl:126-190 */
 static void flux_differencing_kernel_curved(const trixi_b200_desc *d, const eqn_t *eq, double *du, const double *u,
-                                            int64_t e) {
+                                            int64_t e, double alpha) {
     int n = d->nnodes, nd = d->ndims, nv = d->nvars;
     int n3 = nd == 3 ? n : 1;
     const double *Ds = d->derivative_split;
@@ -1518,7 +1529,7 @@ static void flux_differencing_kernel_curved(const trixi_b200_desc *d, const eqn_
                         get_contravariant_vector(d, a, node2, e, ja2);
                         for (int dim = 0; dim < nd; ++dim) ja_avg[dim] = 0.5 * (ja_node[dim] + ja2[dim]);
                         numflux_normal(eq, d->volume_flux, un, u + nv * node2, ja_avg, f);
-                        double w1 = Ds[idx[a] + n * ii], w2 = Ds[ii + n * idx[a]];
+                        double w1 = alpha * Ds[idx[a] + n * ii], w2 = alpha * Ds[ii + n * idx[a]];
                         for (int v = 0; v < nv; ++v) du[nv * node + v] = du[nv * node + v] + w1 * f[v];
                         for (int v = 0; v < nv; ++v) du[nv * node2 + v] = du[nv * node2 + v] + w2 * f[v];
                     }
@@ -1526,15 +1537,75 @@ static void flux_differencing_kernel_curved(const trixi_b200_desc *d, const eqn_
             }
 }
 
+/* fv_kernel! (dg_3d.jl:268-306, shared by all meshes) with calcflux_fv! for curved meshes (dgsem_structured/
+ * dg_2d.jl, dg_3d.jl:377-436): first-order subcell finite volumes along the precomputed free-stream preserving
+ * normal vectors (NormalVectorContainer, containers_3d.jl:352-541); fstar = 0 on the element boundary */
+static void fv_kernel_curved(const trixi_b200_desc *d, const eqn_t *eq, double *du, const double *u, int64_t e,
+                             double alpha) {
+    int n = d->nnodes, nd = d->ndims, nv = d->nvars;
+    int n3 = nd == 3 ? n : 1;
+    const double *iw = d->inverse_weights;
+    int stride[3] = {1, n, n * n};
+    for (int k = 0; k < n3; ++k)
+        for (int j = 0; j < n; ++j)
+            for (int i = 0; i < n; ++i) {
+                int idx[3] = {i, j, k};
+                int64_t node = i + n * (j + n * k);
+                double sum[MAXV] = {0};
+                for (int a = 0; a < nd; ++a) {
+                    /* normal_vectors_a [nd, dims.., nelements] with n - 1 entries along direction a */
+                    int dims[3] = {n, n, n3};
+                    dims[a] = n - 1;
+                    int64_t per_elem = (int64_t)dims[0] * dims[1] * (nd == 3 ? dims[2] : 1);
+                    const double *nvec = d->subcell_normal_vectors[a] + (int64_t)nd * per_elem * e;
+                    double fl[MAXV] = {0}, fr[MAXV] = {0}; /* fstar_R[idx], fstar_L[idx + 1] */
+                    for (int side = 0; side < 2; ++side) {
+                        int pos[3] = {i, j, k};
+                        if (side == 0) {
+                            if (idx[a] == 0) continue;
+                            pos[a] = idx[a] - 1;
+                        } else if (idx[a] == n - 1)
+                            continue;
+                        int64_t q = pos[0] + (int64_t)dims[0] * (pos[1] + (int64_t)dims[1] * pos[2]);
+                        double nrm[3] = {0, 0, 0};
+                        for (int c = 0; c < nd; ++c) nrm[c] = nvec[c + nd * q];
+                        if (side == 0)
+                            numflux_normal(eq, d->volume_flux_fv, u + nv * (node - stride[a]), u + nv * node, nrm, fl);
+                        else
+                            numflux_normal(eq, d->volume_flux_fv, u + nv * node, u + nv * (node + stride[a]), nrm, fr);
+                    }
+                    for (int v = 0; v < nv; ++v) sum[v] = sum[v] + iw[idx[a]] * (fr[v] - fl[v]);
+                }
+                for (int v = 0; v < nv; ++v) du[nv * node + v] = du[nv * node + v] + alpha * sum[v];
+            }
+}
+
+void oracle_calc_indicator_hg(const trixi_b200_desc *d, double *alpha, const double *u);
 void oracle_calc_volume_integral_curved(const trixi_b200_desc *d, double *du, const double *u) {
     eqn_t eq = make_eqn(d);
     int64_t esz = (int64_t)d->nvars * ipow(d->nnodes, d->ndims);
+    if (d->volume_integral == TRIXI_B200_VOLINT_SHOCK_CAPTURING_HG) { /* calc_volume_integral.jl:231-272 */
+        double *alpha = (double *)malloc(sizeof(double) * (size_t)(d->nelements > 0 ? d->nelements : 1));
+        oracle_calc_indicator_hg(d, alpha, u);
+        const double atol = 1.8189894035458565e-12; /* max(100 eps, eps^0.75) for Float64 */
+#pragma omp parallel for schedule(static)
+        for (int64_t e = 0; e < d->nelements; ++e) {
+            if (fabs(alpha[e]) <= atol)
+                flux_differencing_kernel_curved(d, &eq, du + e * esz, u + e * esz, e, 1.0);
+            else {
+                flux_differencing_kernel_curved(d, &eq, du + e * esz, u + e * esz, e, 1 - alpha[e]);
+                fv_kernel_curved(d, &eq, du + e * esz, u + e * esz, e, alpha[e]);
+            }
+        }
+        free(alpha);
+        return;
+    }
 #pragma omp parallel for schedule(static)
     for (int64_t e = 0; e < d->nelements; ++e) {
         if (d->volume_integral == TRIXI_B200_VOLINT_WEAK_FORM)
             weak_form_kernel_curved(d, &eq, du + e * esz, u + e * esz, e);
         else
-            flux_differencing_kernel_curved(d, &eq, du + e * esz, u + e * esz, e);
+            flux_differencing_kernel_curved(d, &eq, du + e * esz, u + e * esz, e, 1.0);
     }
 }
 

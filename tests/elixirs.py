@@ -718,6 +718,93 @@ ELIXIRS.update({e.name: e for e in [
 ]})
 
 
+# ---- shock capturing on curved meshes (VolumeIntegralShockCapturingHG with subcell normal vectors) -------------
+def _sedov_ic(ndims, p0_outer):
+    # initial_condition_(medium_)sedov_blast_wave of the elixir_euler_sedov.jl files
+    def ic(x, t, equations):
+        r = np.sqrt(sum(x[d] ** 2 for d in range(ndims)))
+        r0, E = 0.21875, 1.0
+        p0_inner = 3 * (equations.gamma - 1) * E / ((3 if ndims == 2 else 4) * np.pi * r0 ** 2)
+        p = np.where(r > r0, p0_outer, p0_inner)
+        rho = np.ones_like(r)
+        zero = np.zeros_like(r)
+        return equations.prim2cons((rho,) + (zero,) * ndims + (p,))
+    return ic
+
+
+def _sedov_solver(eq, polydeg):
+    basis = T.LobattoLegendreBasis(polydeg)
+    surface_flux = T.FluxLaxFriedrichs(T.max_abs_speed_naive)
+    indicator_sc = T.IndicatorHennemannGassner(eq, basis, alpha_max=1.0, alpha_min=0.001, alpha_smooth=True,
+                                               variable=T.density_pressure)
+    volume_integral = T.VolumeIntegralShockCapturingHG(indicator_sc, volume_flux_dg=T.flux_ranocha,
+                                                       volume_flux_fv=surface_flux)
+    return T.DGSEM(basis=basis, surface_flux=surface_flux, volume_integral=volume_integral)
+
+
+def _structured3d_sedov():
+    # examples/structured_3d_dgsem/elixir_euler_sedov.jl
+    eq = T.CompressibleEulerEquations3D(1.4)
+
+    def mapping(xi, eta, zeta):
+        pi = np.pi
+        y = eta + 0.125 * (np.cos(1.5 * pi * xi) * np.cos(0.5 * pi * eta) * np.cos(0.5 * pi * zeta))
+        x = xi + 0.125 * (np.cos(0.5 * pi * xi) * np.cos(2 * pi * y) * np.cos(0.5 * pi * zeta))
+        z = zeta + 0.125 * (np.cos(0.5 * pi * x) * np.cos(pi * y) * np.cos(0.5 * pi * zeta))
+        return x, y, z
+    mesh = T.StructuredMesh((4, 4, 4), mapping, periodicity=True)
+    return T.SemidiscretizationHyperbolic(mesh, eq, _sedov_ic(3, 1.0e-3), _sedov_solver(eq, 3))
+
+
+def _structured2d_sedov():
+    # examples/structured_2d_dgsem/elixir_euler_sedov.jl
+    eq = T.CompressibleEulerEquations2D(1.4)
+
+    def mapping(xi, eta):
+        pi = np.pi
+        y = eta + 0.125 * (np.cos(1.5 * pi * xi) * np.cos(0.5 * pi * eta))
+        x = xi + 0.125 * (np.cos(0.5 * pi * xi) * np.cos(2 * pi * y))
+        return x, y
+    mesh = T.StructuredMesh((16, 16), mapping, periodicity=True)
+    return T.SemidiscretizationHyperbolic(mesh, eq, _sedov_ic(2, 1.0e-5), _sedov_solver(eq, 4))
+
+
+def _p4est2d_sedov():
+    # examples/p4est_2d_dgsem/elixir_euler_sedov.jl
+    eq = T.CompressibleEulerEquations2D(1.4)
+    mesh = T.P4estMesh((4, 4), polydeg=4, initial_refinement_level=2, coordinates_min=(-1.0, -1.0),
+                       coordinates_max=(1.0, 1.0), periodicity=True)
+    return T.SemidiscretizationHyperbolic(mesh, eq, _sedov_ic(2, 1.0e-5), _sedov_solver(eq, 4))
+
+
+def _p4est3d_sedov():
+    # examples/p4est_3d_dgsem/elixir_euler_sedov.jl
+    eq = T.CompressibleEulerEquations3D(1.4)
+    mesh = T.P4estMesh((4, 4, 4), polydeg=4, coordinates_min=(-1.0,) * 3, coordinates_max=(1.0,) * 3, periodicity=True)
+    return T.SemidiscretizationHyperbolic(mesh, eq, _sedov_ic(3, 1.0e-3), _sedov_solver(eq, 5))
+
+
+# (the reference prints these goldens with nine significant digits)
+ELIXIRS.update({e.name: e for e in [
+    Elixir("structured_3d_euler_sedov", _structured3d_sedov, (0.0, 0.3), 0.5,
+           [5.30310390e-02, 2.53167260e-02, 2.64276438e-02, 2.52195992e-02, 3.56830295e-01],
+           [6.16356950e-01, 2.50600049e-01, 2.74796377e-01, 2.46448217e-01, 4.77888479e+00],
+           "test/test_structured_3d.jl:222-241", rtol=2e-8),
+    Elixir("structured_2d_euler_sedov", _structured2d_sedov, (0.0, 0.3), 0.5,
+           [3.69856202e-01, 2.35242180e-01, 2.41444928e-01, 1.28807120e+00],
+           [1.82786223e+00, 1.30452904e+00, 1.40347257e+00, 6.21791658e+00],
+           "test/test_structured_2d.jl:664-682", rtol=2e-8),
+    Elixir("p4est_2d_euler_sedov", _p4est2d_sedov, (0.0, 0.3), 0.5,
+           [3.76149952e-01, 2.46970327e-01, 2.46970327e-01, 1.28889042e+00],
+           [1.22139001e+00, 1.17742626e+00, 1.17742626e+00, 6.20638482e+00],
+           "test/test_p4est_2d.jl:370-388", rtol=2e-8),
+    Elixir("p4est_3d_euler_sedov", _p4est3d_sedov, (0.0, 0.3), 0.5,
+           [7.82070951e-02, 4.33260474e-02, 4.33260474e-02, 4.33260474e-02, 3.75260911e-01],
+           [7.45329845e-01, 3.21754792e-01, 3.21754792e-01, 3.21754792e-01, 4.76151527e+00],
+           "test/test_p4est_3d.jl:376-396", rtol=2e-8),
+]})
+
+
 # ---- configurations without a reference golden (cross-checks between mesh types, halo tests) ---------------
 def _p4est3d_curved(initial_condition=T.initial_condition_weak_blast_wave, flux=T.flux_ranocha, level=0, trees=(4, 4, 4)):
     # the warped mapping of examples/structured_3d_dgsem/elixir_euler_free_stream.jl on a conforming P4estMesh

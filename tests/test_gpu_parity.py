@@ -111,7 +111,8 @@ RHS_CASES = ["tree_3d_euler_ec", "tree_3d_euler_source_terms", "tree_3d_euler_so
              "tree_3d_euler_ec_turbo", "tree_2d_euler_vortex_shockcapturing", "tree_2d_euler_vortex_mortar_shockcapturing",
              "tree_3d_advection_basic", "tree_3d_advection_mortar", "structured_3d_advection_basic",
              "p4est_3d_advection_basic", "p4est_3d_tgv_p5", "p4est_3d_curved_p5", "p4est_3d_advection_nonconforming",
-             "p4est_2d_advection_nonconforming_flag"] + sorted(PARITY_EXTRA) + sorted(NONCONFORMING_EXTRA)
+             "p4est_2d_advection_nonconforming_flag", "structured_3d_euler_sedov", "structured_2d_euler_sedov",
+             "p4est_2d_euler_sedov", "p4est_3d_euler_sedov"] + sorted(PARITY_EXTRA) + sorted(NONCONFORMING_EXTRA)
 
 
 @pytest.mark.parametrize("name", RHS_CASES)
@@ -384,7 +385,8 @@ GOLDEN_GPU = ["tree_3d_advection_basic", "tree_3d_advection_mortar", "structured
               "structured_2d_euler_free_stream", "structured_2d_euler_ec",
               "structured_2d_euler_source_terms_nonperiodic", "p4est_2d_advection_basic",
               "p4est_3d_advection_nonconforming", "p4est_2d_advection_nonconforming_flag",
-              "tree_3d_mhd_alfven_wave_mortar"]
+              "tree_3d_mhd_alfven_wave_mortar", "structured_3d_euler_sedov", "structured_2d_euler_sedov",
+              "p4est_2d_euler_sedov", "p4est_3d_euler_sedov"]
 
 
 @pytest.mark.parametrize("name", GOLDEN_GPU)

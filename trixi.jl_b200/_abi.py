@@ -57,6 +57,7 @@ class Desc(C.Structure):
         ("mpi_mortar_neighbor_ids", c_int64_p), ("mpi_mortar_large_sides", c_int64_p),
         ("mpi_mortar_orientations", c_int64_p), ("mpi_mortar_node_indices", c_int64_p),
         ("mpi_mortar_normal_directions", c_double_p), ("mpi_is_mortar_piece", c_int64_p),
+        ("subcell_normal_vectors", c_double_p * 3),
     ]
 
 
@@ -90,6 +91,11 @@ class DescHolder:
         a = _i64(arr)
         self._keep.append(a)
         setattr(self.desc, name, a.ctypes.data_as(c_int64_p))
+
+    def set_f64_item(self, name, index, arr):
+        a = _f64(arr)
+        self._keep.append(a)
+        getattr(self.desc, name)[index] = a.ctypes.data_as(c_double_p)
 
     def byref(self):
         return C.byref(self.desc)

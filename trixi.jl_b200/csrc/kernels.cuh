@@ -76,6 +76,7 @@ struct KParams {
     double *alpha;       // [nelem] after smoothing (ordered-bits atomicMax target)
     double *alpha_raw;   // [nelem] before smoothing
     const double *inv_vdm;  // inverse_vandermonde_legendre [n, n] column-major
+    const double *subcell_normals[3];  // curved meshes: normal vectors of the subcell interfaces per direction
     double inv_weights_c[kMaxNodes];
     double ind_alpha_max, ind_alpha_min;
     int volume_flux_fv, ind_var, ind_smooth;
@@ -1406,6 +1407,15 @@ __global__ void __launch_bounds__(ElemCfg<EQ, N>::THREADS) k_element_curved(cons
         }
     } else {
         if (active) {
+            // VolumeIntegralShockCapturingHG (calc_volume_integral.jl:231-272) as in k_element
+            double w_dg = 1.0, w_fv = 0.0;
+            if constexpr (VOLINT == TRIXI_B200_VOLINT_SHOCK_CAPTURING_HG) {
+                const double alpha = P.alpha[e];
+                if (!(fabs(alpha) <= 1.8189894035458565e-12)) {
+                    w_dg = 1 - alpha;
+                    w_fv = alpha;
+                }
+            }
 #pragma unroll
             for (int d = 0; d < ND; ++d) {
                 const int base = node - idx[d] * stride[d];
@@ -1427,9 +1437,56 @@ __global__ void __launch_bounds__(ElemCfg<EQ, N>::THREADS) k_element_curved(cons
                         eq.numflux_normal(P.volume_flux, un, up, ja_avg, f);
                     else
                         eq.numflux_normal(P.volume_flux, up, un, ja_avg, f);
-                    const double w = s_D[idx[d] + N * l];
+                    double w = s_D[idx[d] + N * l];
+                    if constexpr (VOLINT == TRIXI_B200_VOLINT_SHOCK_CAPTURING_HG) w = w_dg * w;
 #pragma unroll
                     for (int v = 0; v < NV; ++v) acc[v] = fma(w, f[v], acc[v]);
+                }
+            }
+            if constexpr (VOLINT == TRIXI_B200_VOLINT_SHOCK_CAPTURING_HG) {
+                // fv_kernel! (dg_3d.jl:268-306) with calcflux_fv! for curved meshes (dgsem_structured/dg_3d.jl:377-436):
+                // subcell fluxes along the precomputed free-stream preserving normal vectors, zero on the element boundary
+                if (w_fv != 0.0) {
+                    double sum[NV];
+#pragma unroll
+                    for (int v = 0; v < NV; ++v) sum[v] = 0.0;
+#pragma unroll 1
+                    for (int d = 0; d < ND; ++d) {
+                        // normal_vectors_d [ND, dims.., nelements] with N - 1 entries along direction d
+                        int dims[3] = {N, N, ND == 3 ? N : 1};
+                        dims[d] = N - 1;
+                        const long long per_elem = (long long)dims[0] * dims[1] * dims[2];
+                        const double *nvec = P.subcell_normals[d] + ND * per_elem * e;
+                        double fl[NV], fr[NV], up[NV], nrm[ND];
+#pragma unroll
+                        for (int v = 0; v < NV; ++v) fl[v] = fr[v] = 0.0;
+                        int pos[3] = {idx[0], idx[1], idx[2]};
+                        if (idx[d] > 0) {
+                            pos[d] = idx[d] - 1;
+                            const long long q = pos[0] + (long long)dims[0] * (pos[1] + (long long)dims[1] * pos[2]);
+#pragma unroll
+                            for (int c = 0; c < ND; ++c) nrm[c] = nvec[c + ND * q];
+                            const double *pu = ue + (node - stride[d]) * US;
+#pragma unroll
+                            for (int v = 0; v < NV; ++v) up[v] = pu[v];
+                            eq.numflux_normal(P.volume_flux_fv, up, un, nrm, fl);
+                        }
+                        if (idx[d] < N - 1) {
+                            pos[d] = idx[d];
+                            const long long q = pos[0] + (long long)dims[0] * (pos[1] + (long long)dims[1] * pos[2]);
+#pragma unroll
+                            for (int c = 0; c < ND; ++c) nrm[c] = nvec[c + ND * q];
+                            const double *pu = ue + (node + stride[d]) * US;
+#pragma unroll
+                            for (int v = 0; v < NV; ++v) up[v] = pu[v];
+                            eq.numflux_normal(P.volume_flux_fv, un, up, nrm, fr);
+                        }
+                        const double iw = P.inv_weights_c[idx[d]];
+#pragma unroll
+                        for (int v = 0; v < NV; ++v) sum[v] = fma(iw, fr[v] - fl[v], sum[v]);
+                    }
+#pragma unroll
+                    for (int v = 0; v < NV; ++v) acc[v] = fma(w_fv, sum[v], acc[v]);
                 }
             }
         }

@@ -406,6 +406,8 @@ cudaError_t preload_all() {
     if constexpr (HasFastRanocha<EQ>::value) {
         TB_PRELOAD((k_element<EQ, N, TRIXI_B200_VOLINT_SHOCK_CAPTURING_HG, true>));
         TB_PRELOAD((k_element<EQ, N, TRIXI_B200_VOLINT_SHOCK_CAPTURING_HG, false>));
+        TB_PRELOAD((k_element_curved<EQ, N, TRIXI_B200_VOLINT_SHOCK_CAPTURING_HG, true>));
+        TB_PRELOAD((k_element_curved<EQ, N, TRIXI_B200_VOLINT_SHOCK_CAPTURING_HG, false>));
         TB_PRELOAD((k_indicator_hg<EQ, N>));
         TB_PRELOAD((k_indicator_smooth<EQ, N>));
     }

@@ -647,8 +647,14 @@ TRIXI_B200_API int trixi_b200_create(const trixi_b200_desc *d, trixi_b200_handle
         d->volume_integral != TRIXI_B200_VOLINT_SHOCK_CAPTURING_HG)
         return fail(nullptr, TRIXI_B200_EINVAL, "unsupported volume integral type %d", d->volume_integral);
     if (d->volume_integral == TRIXI_B200_VOLINT_SHOCK_CAPTURING_HG) {
-        if (d->mesh_kind != TRIXI_B200_MESH_TREE)
-            return fail(nullptr, TRIXI_B200_EINVAL, "VolumeIntegralShockCapturingHG is available on TreeMesh only in this build");
+        if (d->mesh_kind != TRIXI_B200_MESH_TREE) {
+            if (d->world_size > 1)
+                return fail(nullptr, TRIXI_B200_EINVAL, "VolumeIntegralShockCapturingHG on curved meshes is single-rank in this build");
+            for (int a = 0; a < d->ndims; ++a)
+                if (!d->subcell_normal_vectors[a])
+                    return fail(nullptr, TRIXI_B200_EINVAL,
+                                "VolumeIntegralShockCapturingHG on a curved mesh needs subcell_normal_vectors (NormalVectorContainer)");
+        }
         if (d->equation != TRIXI_B200_EQ_EULER_2D && d->equation != TRIXI_B200_EQ_EULER_3D)
             return fail(nullptr, TRIXI_B200_EINVAL, "VolumeIntegralShockCapturingHG needs the compressible Euler equations");
         if (!d->inverse_vandermonde_legendre)
@@ -969,6 +975,14 @@ TRIXI_B200_API int trixi_b200_create(const trixi_b200_desc *d, trixi_b200_handle
         P.inv_vdm = tmp;
         CREATE_TRY(alloc_array(h, (size_t)d->nelements, &P.alpha));
         CREATE_TRY(alloc_array(h, (size_t)d->nelements, &P.alpha_raw));
+        if (d->mesh_kind != TRIXI_B200_MESH_TREE) {
+            for (int a = 0; a < nd; ++a) {
+                size_t per_elem = (size_t)nd;
+                for (int b = 0; b < nd; ++b) per_elem *= (size_t)(b == a ? n - 1 : n);
+                CREATE_TRY(upload_array(h, d->subcell_normal_vectors[a], per_elem * (size_t)d->nelements, &tmp));
+                P.subcell_normals[a] = tmp;
+            }
+        }
     }
     P.volume_flux = d->volume_flux;
     P.surface_flux = d->surface_flux;

@@ -237,6 +237,14 @@ class SemidiscretizationHyperbolic:
             d.indicator_alpha_smooth = int(ind.alpha_smooth)
             d.indicator_alpha_max, d.indicator_alpha_min = ind.alpha_max, ind.alpha_min
             h.set_f64("inverse_vandermonde_legendre", dg.basis.inverse_vandermonde_legendre)
+            if self.is_curved:
+                # cache.normal_vectors (create_cache for VolumeIntegralShockCapturingHG on curved meshes,
+                # dgsem_structured/dg.jl: NormalVectorContainer)
+                from .structured import calc_normalvectors_subcell_fv
+                if getattr(cache, "normal_vectors", None) is None:
+                    cache.normal_vectors = calc_normalvectors_subcell_fv(cache.elements.contravariant_vectors, dg.basis)
+                for a, nv in enumerate(cache.normal_vectors):
+                    h.set_f64_item("subcell_normal_vectors", a, nv)
         h.set_f64("inverse_jacobian", cache.elements.inverse_jacobian)
         h.set_f64("node_coordinates", cache.elements.node_coordinates)
         if isinstance(self.mesh, StructuredMesh):

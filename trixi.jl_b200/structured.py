@@ -188,3 +188,27 @@ def init_elements_structured(mesh, basis):
         left[d] = ln.ravel(order="F")
     el.left_neighbors = left
     return el
+
+
+def calc_normalvectors_subcell_fv(contravariant_vectors, basis):
+    """``calc_normalvectors_subcell_fv!`` (dgsem_structured/containers_2d.jl / containers_3d.jl:352-486, container
+    ``NormalVectorContainer{2,3}D`` :488-541): the free-stream preserving normal vectors of the subcell finite-volume
+    interfaces inside every element, used by ``calcflux_fv!`` on curved meshes (dgsem_structured/dg_3d.jl:377-436).
+    For direction a, interface i (between nodes i and i + 1 along a):
+    n_i = Ja^a(node 1) + sum_{l <= i} sum_m w_l D[l, m] Ja^a(node m).
+    Returns one array per direction, [ndims, n.. (n - 1 along a) .., nelements], Fortran-ordered."""
+    Ja = np.asarray(contravariant_vectors)  # [component, index, nodes.., element]
+    nd = Ja.shape[0]
+    n = basis.nnodes
+    w, D = basis.weights, basis.derivative_matrix
+    out = []
+    for a in range(nd):
+        J = np.moveaxis(Ja[:, a], 1 + a, 1)  # [component, node along a, others.., element]
+        nv = np.empty((nd, n - 1) + J.shape[2:])
+        cur = J[:, 0].copy()
+        for i in range(n - 1):
+            for m in range(n):
+                cur = cur + (w[i] * D[i, m]) * J[:, m]
+            nv[:, i] = cur
+        out.append(np.asfortranarray(np.moveaxis(nv, 1, 1 + a)))
+    return out
