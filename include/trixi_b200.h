@@ -84,9 +84,10 @@ enum {
     TRIXI_B200_FLUX_HINDENLANG_GASSNER_POWELL = 13, /* (flux_hindenlang_gassner, flux_nonconservative_powell)
                                                        ideal_glm_mhd_3d.jl:295-340,680-779 */
     TRIXI_B200_FLUX_LLF_NAIVE_MHD_POWELL = 14,      /* (FluxLaxFriedrichs(max_abs_speed_naive), powell) */
-    TRIXI_B200_FLUX_HLLE_MHD_POWELL = 15            /* (flux_hlle, powell): FluxHLL(min_max_speed_einfeldt)
+    TRIXI_B200_FLUX_HLLE_MHD_POWELL = 15,           /* (flux_hlle, powell): FluxHLL(min_max_speed_einfeldt)
                                                        numerical_fluxes.jl:422-457, ideal_glm_mhd_3d.jl:1094-1130,
                                                        Roe averages :1415-1491 */
+    TRIXI_B200_FLUX_CENTRAL_MHD_POWELL = 16         /* (flux_central, flux_nonconservative_powell) */
 };
 
 /* source terms (calc_sources! dg_3d.jl:1417-1437 calls an arbitrary closure; here: registry) */

@@ -368,6 +368,205 @@ static inline void mhd_fast_wavespeed_roe(const eqn_t *eq, const double *ul, con
     *vel_out = v_roe[o];
 }
 
+/* flux(u, normal_direction) :236-275 */
+static inline void mhd_flux_normal(const eqn_t *eq, const double *u, const double *n, double *f) {
+    double rho = u[0], psi = u[8];
+    double v1 = u[1] / rho, v2 = u[2] / rho, v3 = u[3] / rho;
+    double B1 = u[5], B2 = u[6], B3 = u[7];
+    double kin_en = 0.5 * (u[1] * v1 + u[2] * v2 + u[3] * v3);
+    double mag_en = 0.5 * (B1 * B1 + B2 * B2 + B3 * B3);
+    double p_over_gamma_minus_one = (u[4] - kin_en - mag_en - 0.5 * psi * psi);
+    double p = (eq->gamma - 1) * p_over_gamma_minus_one;
+    double v_normal = v1 * n[0] + v2 * n[1] + v3 * n[2];
+    double B_normal = B1 * n[0] + B2 * n[1] + B3 * n[2];
+    double rho_v_normal = rho * v_normal;
+    f[0] = rho_v_normal;
+    f[1] = rho_v_normal * v1 - B1 * B_normal + (p + mag_en) * n[0];
+    f[2] = rho_v_normal * v2 - B2 * B_normal + (p + mag_en) * n[1];
+    f[3] = rho_v_normal * v3 - B3 * B_normal + (p + mag_en) * n[2];
+    f[4] = ((kin_en + eq->gamma * p_over_gamma_minus_one + 2 * mag_en) * v_normal - B_normal * (v1 * B1 + v2 * B2 + v3 * B3) +
+            eq->c_h * psi * B_normal);
+    f[5] = (eq->c_h * psi * n[0] + (v2 * B1 - v1 * B2) * n[1] + (v3 * B1 - v1 * B3) * n[2]);
+    f[6] = ((v1 * B2 - v2 * B1) * n[0] + eq->c_h * psi * n[1] + (v3 * B2 - v2 * B3) * n[2]);
+    f[7] = ((v1 * B3 - v3 * B1) * n[0] + (v2 * B3 - v3 * B2) * n[1] + eq->c_h * psi * n[2]);
+    f[8] = eq->c_h * B_normal;
+}
+
+/* flux_nonconservative_powell(u_ll, u_rr, normal_direction) :342-374 */
+static inline void mhd_noncons_powell_normal(const eqn_t *eq, const double *ul, const double *ur, const double *n,
+                                             double *f) {
+    (void)eq;
+    double v1_ll = ul[1] / ul[0], v2_ll = ul[2] / ul[0], v3_ll = ul[3] / ul[0];
+    double B1_ll = ul[5], B2_ll = ul[6], B3_ll = ul[7], psi_ll = ul[8], psi_rr = ur[8];
+    double v_dot_B_ll = v1_ll * B1_ll + v2_ll * B2_ll + v3_ll * B3_ll;
+    double v_dot_n_ll = v1_ll * n[0] + v2_ll * n[1] + v3_ll * n[2];
+    double B_dot_n_rr = ur[5] * n[0] + ur[6] * n[1] + ur[7] * n[2];
+    f[0] = 0.0;
+    f[1] = B1_ll * B_dot_n_rr;
+    f[2] = B2_ll * B_dot_n_rr;
+    f[3] = B3_ll * B_dot_n_rr;
+    f[4] = v_dot_B_ll * B_dot_n_rr + v_dot_n_ll * psi_ll * psi_rr;
+    f[5] = v1_ll * B_dot_n_rr;
+    f[6] = v2_ll * B_dot_n_rr;
+    f[7] = v3_ll * B_dot_n_rr;
+    f[8] = v_dot_n_ll * psi_rr;
+}
+
+/* flux_hindenlang_gassner(u_ll, u_rr, normal_direction) :781-855 */
+static inline void mhd_flux_hindenlang_gassner_normal(const eqn_t *eq, const double *ul, const double *ur, const double *n,
+                                                      double *f) {
+    double L[9], R[9];
+    mhd_cons2prim(eq, ul, L);
+    mhd_cons2prim(eq, ur, R);
+    double rho_ll = L[0], v1_ll = L[1], v2_ll = L[2], v3_ll = L[3], p_ll = L[4], B1_ll = L[5], B2_ll = L[6], B3_ll = L[7],
+           psi_ll = L[8];
+    double rho_rr = R[0], v1_rr = R[1], v2_rr = R[2], v3_rr = R[3], p_rr = R[4], B1_rr = R[5], B2_rr = R[6], B3_rr = R[7],
+           psi_rr = R[8];
+    double v_dot_n_ll = v1_ll * n[0] + v2_ll * n[1] + v3_ll * n[2];
+    double v_dot_n_rr = v1_rr * n[0] + v2_rr * n[1] + v3_rr * n[2];
+    double B_dot_n_ll = B1_ll * n[0] + B2_ll * n[1] + B3_ll * n[2];
+    double B_dot_n_rr = B1_rr * n[0] + B2_rr * n[1] + B3_rr * n[2];
+    double rho_mean = ln_mean(rho_ll, rho_rr);
+    double inv_rho_p_mean = p_ll * p_rr * inv_ln_mean(rho_ll * p_rr, rho_rr * p_ll);
+    double v1_avg = 0.5 * (v1_ll + v1_rr), v2_avg = 0.5 * (v2_ll + v2_rr), v3_avg = 0.5 * (v3_ll + v3_rr);
+    double p_avg = 0.5 * (p_ll + p_rr), psi_avg = 0.5 * (psi_ll + psi_rr);
+    double velocity_square_avg = 0.5 * (v1_ll * v1_rr + v2_ll * v2_rr + v3_ll * v3_rr);
+    double magnetic_square_avg = 0.5 * (B1_ll * B1_rr + B2_ll * B2_rr + B3_ll * B3_rr);
+    double f1 = rho_mean * 0.5 * (v_dot_n_ll + v_dot_n_rr);
+    f[0] = f1;
+    f[1] = (f1 * v1_avg + (p_avg + magnetic_square_avg) * n[0] - 0.5 * (B_dot_n_ll * B1_rr + B_dot_n_rr * B1_ll));
+    f[2] = (f1 * v2_avg + (p_avg + magnetic_square_avg) * n[1] - 0.5 * (B_dot_n_ll * B2_rr + B_dot_n_rr * B2_ll));
+    f[3] = (f1 * v3_avg + (p_avg + magnetic_square_avg) * n[2] - 0.5 * (B_dot_n_ll * B3_rr + B_dot_n_rr * B3_ll));
+    f[5] = (eq->c_h * psi_avg * n[0] +
+            0.5 * (v_dot_n_ll * B1_ll - v1_ll * B_dot_n_ll + v_dot_n_rr * B1_rr - v1_rr * B_dot_n_rr));
+    f[6] = (eq->c_h * psi_avg * n[1] +
+            0.5 * (v_dot_n_ll * B2_ll - v2_ll * B_dot_n_ll + v_dot_n_rr * B2_rr - v2_rr * B_dot_n_rr));
+    f[7] = (eq->c_h * psi_avg * n[2] +
+            0.5 * (v_dot_n_ll * B3_ll - v3_ll * B_dot_n_ll + v_dot_n_rr * B3_rr - v3_rr * B_dot_n_rr));
+    f[8] = eq->c_h * 0.5 * (B_dot_n_ll + B_dot_n_rr);
+    f[4] = (f1 * (velocity_square_avg + inv_rho_p_mean * eq->inv_gm1) +
+            0.5 * (+p_ll * v_dot_n_rr + p_rr * v_dot_n_ll + (v_dot_n_ll * B1_ll * B1_rr + v_dot_n_rr * B1_rr * B1_ll) +
+                   (v_dot_n_ll * B2_ll * B2_rr + v_dot_n_rr * B2_rr * B2_ll) +
+                   (v_dot_n_ll * B3_ll * B3_rr + v_dot_n_rr * B3_rr * B3_ll) -
+                   (v1_ll * B_dot_n_ll * B1_rr + v1_rr * B_dot_n_rr * B1_ll) -
+                   (v2_ll * B_dot_n_ll * B2_rr + v2_rr * B_dot_n_rr * B2_ll) -
+                   (v3_ll * B_dot_n_ll * B3_rr + v3_rr * B_dot_n_rr * B3_ll) +
+                   eq->c_h * (B_dot_n_ll * psi_rr + B_dot_n_rr * psi_ll)));
+}
+
+/* calc_fast_wavespeed(cons, normal_direction) :1378-1404 */
+static inline double mhd_fast_wavespeed_normal(const eqn_t *eq, const double *u, const double *n) {
+    double rho = u[0], psi = u[8];
+    double v1 = u[1] / rho, v2 = u[2] / rho, v3 = u[3] / rho;
+    double kin_en = 0.5 * (u[1] * v1 + u[2] * v2 + u[3] * v3);
+    double mag_en = 0.5 * (u[5] * u[5] + u[6] * u[6] + u[7] * u[7]);
+    double p = (eq->gamma - 1) * (u[4] - kin_en - mag_en - 0.5 * psi * psi);
+    double a_square = eq->gamma * p / rho;
+    double sqrt_rho = sqrt(rho);
+    double b1 = u[5] / sqrt_rho, b2 = u[6] / sqrt_rho, b3 = u[7] / sqrt_rho;
+    double b_square = b1 * b1 + b2 * b2 + b3 * b3;
+    double norm_squared = (n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+    double bn = (b1 * n[0] + b2 * n[1] + b3 * n[2]);
+    double b_dot_n_squared = bn * bn / norm_squared;
+    double s = a_square + b_square;
+    return sqrt((0.5 * s + 0.5 * sqrt(s * s - 4 * a_square * b_dot_n_squared)) * norm_squared);
+}
+
+/* calc_fast_wavespeed_roe(u_ll, u_rr, normal_direction) :1493-1565 */
+static inline void mhd_fast_wavespeed_roe_normal(const eqn_t *eq, const double *ul, const double *ur, const double *n,
+                                                 double *vel_out, double *c_f) {
+    double rho_ll = ul[0], rho_rr = ur[0];
+    double v_ll[3] = {ul[1] / rho_ll, ul[2] / rho_ll, ul[3] / rho_ll};
+    double v_rr[3] = {ur[1] / rho_rr, ur[2] / rho_rr, ur[3] / rho_rr};
+    const double *B_ll = ul + 5, *B_rr = ur + 5;
+    double kin_en_ll = 0.5 * (ul[1] * v_ll[0] + ul[2] * v_ll[1] + ul[3] * v_ll[2]);
+    double mag_norm_ll = B_ll[0] * B_ll[0] + B_ll[1] * B_ll[1] + B_ll[2] * B_ll[2];
+    double p_ll = (eq->gamma - 1) * (ul[4] - kin_en_ll - 0.5 * mag_norm_ll - 0.5 * ul[8] * ul[8]);
+    double kin_en_rr = 0.5 * (ur[1] * v_rr[0] + ur[2] * v_rr[1] + ur[3] * v_rr[2]);
+    double mag_norm_rr = B_rr[0] * B_rr[0] + B_rr[1] * B_rr[1] + B_rr[2] * B_rr[2];
+    double p_rr = (eq->gamma - 1) * (ur[4] - kin_en_rr - 0.5 * mag_norm_rr - 0.5 * ur[8] * ur[8]);
+    double p_total_ll = p_ll + 0.5 * mag_norm_ll, p_total_rr = p_rr + 0.5 * mag_norm_rr;
+    double sqrt_rho_ll = sqrt(rho_ll), sqrt_rho_rr = sqrt(rho_rr);
+    double inv_sqrt_rho_add = 1 / (sqrt_rho_ll + sqrt_rho_rr), inv_sqrt_rho_prod = 1 / (sqrt_rho_ll * sqrt_rho_rr);
+    double rho_ll_roe = sqrt_rho_ll * inv_sqrt_rho_add, rho_rr_roe = sqrt_rho_rr * inv_sqrt_rho_add;
+    double v_roe[3], B_roe[3];
+    for (int d = 0; d < 3; ++d) {
+        v_roe[d] = v_ll[d] * rho_ll_roe + v_rr[d] * rho_rr_roe;
+        B_roe[d] = B_ll[d] * rho_ll_roe + B_rr[d] * rho_rr_roe;
+    }
+    double H_ll = (ul[4] + p_total_ll) / rho_ll, H_rr = (ur[4] + p_total_rr) / rho_rr;
+    double H_roe = H_ll * rho_ll_roe + H_rr * rho_rr_roe;
+    double dB0 = B_ll[0] - B_rr[0], dB1 = B_ll[1] - B_rr[1], dB2 = B_ll[2] - B_rr[2];
+    double X = 0.5 * (dB0 * dB0 + dB1 * dB1 + dB2 * dB2) * (inv_sqrt_rho_add * inv_sqrt_rho_add);
+    double b_square_roe = (B_roe[0] * B_roe[0] + B_roe[1] * B_roe[1] + B_roe[2] * B_roe[2]) * inv_sqrt_rho_prod;
+    double a_square_roe = ((2 - eq->gamma) * X +
+                           (eq->gamma - 1) * (H_roe - 0.5 * (v_roe[0] * v_roe[0] + v_roe[1] * v_roe[1] + v_roe[2] * v_roe[2]) -
+                                              b_square_roe));
+    double norm_squared = (n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+    double Bn = (B_roe[0] * n[0] + B_roe[1] * n[1] + B_roe[2] * n[2]);
+    double B_roe_dot_n_squared = Bn * Bn / norm_squared;
+    double c_a_roe = B_roe_dot_n_squared * inv_sqrt_rho_prod;
+    double s = a_square_roe + b_square_roe;
+    double a_star_roe = sqrt(s * s - 4 * a_square_roe * c_a_roe);
+    *c_f = sqrt(0.5 * (a_square_roe + b_square_roe + a_star_roe) * norm_squared);
+    *vel_out = (v_roe[0] * n[0] + v_roe[1] * n[1] + v_roe[2] * n[2]);
+}
+
+/* conservative part of the MHD surface / volume fluxes along a normal vector (tuples are encoded as one id) */
+static void mhd_numflux_normal(const eqn_t *eq, int flux_id, const double *ul, const double *ur, const double *n, double *f) {
+    switch (flux_id) {
+    case TRIXI_B200_FLUX_CENTRAL:
+    case TRIXI_B200_FLUX_CENTRAL_MHD_POWELL: {
+        double fl[9], fr[9];
+        mhd_flux_normal(eq, ul, n, fl);
+        mhd_flux_normal(eq, ur, n, fr);
+        for (int v = 0; v < 9; ++v) f[v] = 0.5 * (fl[v] + fr[v]);
+        return;
+    }
+    case TRIXI_B200_FLUX_LLF:
+    case TRIXI_B200_FLUX_LLF_NAIVE:
+    case TRIXI_B200_FLUX_LLF_MHD_POWELL:
+    case TRIXI_B200_FLUX_LLF_NAIVE_MHD_POWELL: { /* max_abs_speed(_naive) :879-956 */
+        int naive = flux_id == TRIXI_B200_FLUX_LLF_NAIVE || flux_id == TRIXI_B200_FLUX_LLF_NAIVE_MHD_POWELL;
+        double v_ll = (ul[1] / ul[0] * n[0] + ul[2] / ul[0] * n[1] + ul[3] / ul[0] * n[2]);
+        double v_rr = (ur[1] / ur[0] * n[0] + ur[2] / ur[0] * n[1] + ur[3] / ur[0] * n[2]);
+        double cf_ll = mhd_fast_wavespeed_normal(eq, ul, n), cf_rr = mhd_fast_wavespeed_normal(eq, ur, n);
+        double lam = naive ? fmax(fabs(v_ll), fabs(v_rr)) + fmax(cf_ll, cf_rr) : fmax(fabs(v_ll) + cf_ll, fabs(v_rr) + cf_rr);
+        double fl[9], fr[9];
+        mhd_flux_normal(eq, ul, n, fl);
+        mhd_flux_normal(eq, ur, n, fr);
+        for (int v = 0; v < 9; ++v) f[v] = 0.5 * (fl[v] + fr[v]) + (-0.5 * lam * (ur[v] - ul[v]));
+        return;
+    }
+    case TRIXI_B200_FLUX_HINDENLANG_GASSNER:
+    case TRIXI_B200_FLUX_HINDENLANG_GASSNER_POWELL:
+        mhd_flux_hindenlang_gassner_normal(eq, ul, ur, n, f);
+        return;
+    case TRIXI_B200_FLUX_HLLE_MHD_POWELL: { /* min_max_speed_einfeldt :1132-1166 */
+        double v_normal_ll = (ul[1] / ul[0] * n[0] + ul[2] / ul[0] * n[1] + ul[3] / ul[0] * n[2]);
+        double v_normal_rr = (ur[1] / ur[0] * n[0] + ur[2] / ur[0] * n[1] + ur[3] / ur[0] * n[2]);
+        double c_f_ll = mhd_fast_wavespeed_normal(eq, ul, n), c_f_rr = mhd_fast_wavespeed_normal(eq, ur, n), v_roe, c_f_roe;
+        mhd_fast_wavespeed_roe_normal(eq, ul, ur, n, &v_roe, &c_f_roe);
+        double lmin = fmin(v_normal_ll - c_f_ll, v_roe - c_f_roe), lmax = fmax(v_normal_rr + c_f_rr, v_roe + c_f_roe);
+        if (lmin >= 0 && lmax >= 0) {
+            mhd_flux_normal(eq, ul, n, f);
+        } else if (lmax <= 0 && lmin <= 0) {
+            mhd_flux_normal(eq, ur, n, f);
+        } else {
+            double fl[9], fr[9];
+            mhd_flux_normal(eq, ul, n, fl);
+            mhd_flux_normal(eq, ur, n, fr);
+            double inv = 1 / (lmax - lmin);
+            double factor_ll = lmax * inv, factor_rr = lmin * inv, factor_diss = lmin * lmax * inv;
+            for (int v = 0; v < 9; ++v) f[v] = factor_ll * fl[v] - factor_rr * fr[v] + factor_diss * (ur[v] - ul[v]);
+        }
+        return;
+    }
+    default:
+        for (int v = 0; v < 9; ++v) f[v] = NAN;
+    }
+}
+
 /* ---- linear scalar advection (linear_scalar_advection_2d.jl:221-246) ----------------------------- */
 static inline void adv_flux(const eqn_t *eq, const double *u, int o, double *f) { f[0] = eq->a[o] * u[0]; }
 
@@ -402,6 +601,7 @@ static inline double max_abs_speed_disp(const eqn_t *eq, const double *ul, const
 static void numflux(const eqn_t *eq, int flux_id, const double *ul, const double *ur, int o, double *f) {
     int nv = eq->nv;
     switch (flux_id) {
+    case TRIXI_B200_FLUX_CENTRAL_MHD_POWELL:
     case TRIXI_B200_FLUX_CENTRAL: { /* numerical_fluxes.jl:17-25 */
         double fl[MAXV], fr[MAXV];
         phys_flux(eq, ul, o, fl);
@@ -490,7 +690,8 @@ static void numflux(const eqn_t *eq, int flux_id, const double *ul, const double
 
 static inline int flux_has_noncons(int flux_id) {
     return flux_id == TRIXI_B200_FLUX_HINDENLANG_GASSNER_POWELL || flux_id == TRIXI_B200_FLUX_LLF_MHD_POWELL ||
-           flux_id == TRIXI_B200_FLUX_LLF_NAIVE_MHD_POWELL || flux_id == TRIXI_B200_FLUX_HLLE_MHD_POWELL;
+           flux_id == TRIXI_B200_FLUX_LLF_NAIVE_MHD_POWELL || flux_id == TRIXI_B200_FLUX_HLLE_MHD_POWELL ||
+           flux_id == TRIXI_B200_FLUX_CENTRAL_MHD_POWELL;
 }
 
 /* ---- normal-direction versions (curved meshes) -------------------------------------------------- */
@@ -544,6 +745,8 @@ static inline double vec_norm(int nd, const double *n) {
 static inline void phys_flux_normal(const eqn_t *eq, const double *u, const double *n, double *f) {
     if (is_euler(eq)) {
         euler_flux_normal(eq, u, n, f);
+    } else if (is_mhd(eq)) {
+        mhd_flux_normal(eq, u, n, f);
     } else { /* linear_scalar_advection_2d.jl:233-238 */
         double a = 0.0;
         for (int d = 0; d < eq->nd; ++d) a += eq->a[d] * n[d];
@@ -555,6 +758,10 @@ static inline void phys_flux_normal(const eqn_t *eq, const double *u, const doub
 static void numflux_normal(const eqn_t *eq, int flux_id, const double *ul, const double *ur, const double *n,
                            double *f) {
     int nv = eq->nv, nd = eq->nd;
+    if (is_mhd(eq)) {
+        mhd_numflux_normal(eq, flux_id, ul, ur, n, f);
+        return;
+    }
     switch (flux_id) {
     case TRIXI_B200_FLUX_CENTRAL: {
         double fl[MAXV], fr[MAXV];
@@ -703,6 +910,38 @@ static void ic_eval(const eqn_t *eq, int ic, const double *x, double t, double *
         }
         default:
             break;
+        }
+    } else if (is_mhd(eq)) {
+        double prim[9];
+        if (ic == TRIXI_B200_IC_CONSTANT) { /* ideal_glm_mhd_3d.jl:101-113 */
+            static const double c[9] = {1.0, 0.1, -0.2, -0.5, 50.0, 3.0, -1.2, 0.5, 0.0};
+            for (int v = 0; v < 9; ++v) u[v] = c[v];
+            return;
+        }
+        if (ic == TRIXI_B200_IC_CONVERGENCE_TEST) { /* :124-151: Alfven wave, gamma = 5/3 */
+            double p = 1, omega = 2 * M_PI, r = 2, e = 0.2;
+            double nx = 1 / sqrt(r * r + 1), ny = r / sqrt(r * r + 1), sqr = 1;
+            double Va = omega / (ny * sqr);
+            double phi_alv = omega / ny * (nx * (x[0] - 0.5 * r) + ny * (x[1] - 0.5 * r)) - Va * t;
+            double rho = 1;
+            prim[0] = rho;
+            prim[1] = -e * ny * cos(phi_alv) / rho;
+            prim[2] = e * nx * cos(phi_alv) / rho;
+            prim[3] = e * sin(phi_alv) / rho;
+            prim[4] = p;
+            prim[5] = nx - rho * prim[1] * sqr;
+            prim[6] = ny - rho * prim[2] * sqr;
+            prim[7] = -rho * prim[3] * sqr;
+            prim[8] = 0;
+            /* prim2cons :1273-1284 */
+            u[0] = prim[0];
+            u[1] = prim[0] * prim[1];
+            u[2] = prim[0] * prim[2];
+            u[3] = prim[0] * prim[3];
+            u[4] = prim[4] * eq->inv_gm1 + 0.5 * (u[1] * prim[1] + u[2] * prim[2] + u[3] * prim[3]) +
+                   0.5 * (prim[5] * prim[5] + prim[6] * prim[6] + prim[7] * prim[7]) + 0.5 * prim[8] * prim[8];
+            for (int v = 5; v < 9; ++v) u[v] = prim[v];
+            return;
         }
     } else if (ic == TRIXI_B200_IC_CONVERGENCE_TEST) { /* linear_scalar_advection_2d.jl:67-80 */
         double s = 0.0;
@@ -1537,6 +1776,37 @@ static void flux_differencing_kernel_curved(const trixi_b200_desc *d, const eqn_
             }
 }
 
+/* nonconservative volume terms on curved meshes (dgsem_structured/dg_3d.jl:177-283): for every node
+ * 0.5 sum_d sum_ii D_split[i, ii] g(u_node, u_ii, 0.5 (Ja^d_node + Ja^d_ii)) */
+static void flux_differencing_noncons_curved(const trixi_b200_desc *d, const eqn_t *eq, double *du, const double *u,
+                                             int64_t e) {
+    int n = d->nnodes, nv = d->nvars;
+    const double *Ds = d->derivative_split;
+    int stride[3] = {1, n, n * n};
+    for (int k = 0; k < n; ++k)
+        for (int j = 0; j < n; ++j)
+            for (int i = 0; i < n; ++i) {
+                int idx[3] = {i, j, k};
+                int64_t node = i + n * (j + n * k);
+                const double *un = u + nv * node;
+                double integral_contribution[MAXV] = {0};
+                for (int a = 0; a < 3; ++a) {
+                    double ja_node[3];
+                    get_contravariant_vector(d, a, node, e, ja_node);
+                    for (int ii = 0; ii < n; ++ii) {
+                        int64_t node2 = node + (ii - idx[a]) * stride[a];
+                        double ja2[3], ja_avg[3], g[MAXV];
+                        get_contravariant_vector(d, a, node2, e, ja2);
+                        for (int dim = 0; dim < 3; ++dim) ja_avg[dim] = 0.5 * (ja_node[dim] + ja2[dim]);
+                        mhd_noncons_powell_normal(eq, un, u + nv * node2, ja_avg, g);
+                        double w = Ds[idx[a] + n * ii];
+                        for (int v = 0; v < nv; ++v) integral_contribution[v] = integral_contribution[v] + w * g[v];
+                    }
+                }
+                for (int v = 0; v < nv; ++v) du[nv * node + v] = du[nv * node + v] + 0.5 * integral_contribution[v];
+            }
+}
+
 /* fv_kernel! (dg_3d.jl:268-306, shared by all meshes) with calcflux_fv! for curved meshes (dgsem_structured/
  * dg_2d.jl, dg_3d.jl:377-436): first-order subcell finite volumes along the precomputed free-stream preserving
  * normal vectors (NormalVectorContainer, containers_3d.jl:352-541); fstar = 0 on the element boundary */
@@ -1604,8 +1874,10 @@ void oracle_calc_volume_integral_curved(const trixi_b200_desc *d, double *du, co
     for (int64_t e = 0; e < d->nelements; ++e) {
         if (d->volume_integral == TRIXI_B200_VOLINT_WEAK_FORM)
             weak_form_kernel_curved(d, &eq, du + e * esz, u + e * esz, e);
-        else
+        else {
             flux_differencing_kernel_curved(d, &eq, du + e * esz, u + e * esz, e, 1.0);
+            if (flux_has_noncons(d->volume_flux)) flux_differencing_noncons_curved(d, &eq, du + e * esz, u + e * esz, e);
+        }
     }
 }
 
@@ -1652,6 +1924,17 @@ void oracle_calc_interface_flux_structured(const trixi_b200_desc *d, double *sfv
                     get_contravariant_vector(d, o, vn, right, ja);
                     for (int dim = 0; dim < nd; ++dim) nrm[dim] = sign_jacobian * ja[dim];
                     numflux_normal(&eq, d->surface_flux, ul, ur, nrm, f);
+                    if (flux_has_noncons(d->surface_flux)) { /* dgsem_structured/dg_3d.jl:755-828 */
+                        double gl[MAXV], gr[MAXV];
+                        mhd_noncons_powell_normal(&eq, ul, ur, nrm, gl);
+                        mhd_noncons_powell_normal(&eq, ur, ul, nrm, gr);
+                        for (int v = 0; v < nv; ++v) {
+                            double fv = sign_jacobian * f[v];
+                            sfv[left * fsz + v + nv * (fn + nf * right_direction)] = fv + 0.5 * (sign_jacobian * gl[v]);
+                            sfv[right * fsz + v + nv * (fn + nf * left_direction)] = fv + 0.5 * (sign_jacobian * gr[v]);
+                        }
+                        continue;
+                    }
                     for (int v = 0; v < nv; ++v) {
                         double fv = sign_jacobian * f[v];
                         sfv[left * fsz + v + nv * (fn + nf * right_direction)] = fv;
@@ -1737,6 +2020,9 @@ double oracle_max_dt_curved(const trixi_b200_desc *d, const double *u) {
                 euler_cons2prim(&eq, u + nv * (q + nn * e), &rho, v, &p);
                 double c = sqrt(eq.gamma * p / rho);
                 for (int dd = 0; dd < nd; ++dd) lam[dd] = fabs(v[dd]) + c;
+            } else if (is_mhd(&eq)) { /* max_abs_speeds ideal_glm_mhd_3d.jl:1218-1228 */
+                const double *un = u + nv * (q + nn * e);
+                for (int dd = 0; dd < 3; ++dd) lam[dd] = fabs(un[1 + dd] / un[0]) + mhd_fast_wavespeed(&eq, un, dd);
             } else {
                 for (int dd = 0; dd < nd; ++dd) lam[dd] = fabs(eq.a[dd]);
             }
@@ -1847,6 +2133,16 @@ void oracle_calc_interface_flux_p4est(const trixi_b200_desc *d, double *sfv, con
                 p4_normal(d, pdir, p4_volume_node(nd, n, pidx, i, j), primary, nrm);
                 numflux_normal(&eq, d->surface_flux, ul, ur, nrm, f);
                 p4_surface_node(nd, n, sidx, i, j, &fn_sec);
+                if (flux_has_noncons(d->surface_flux)) { /* dgsem_p4est/dg_3d.jl:340-375 */
+                    double gp[MAXV], gs[MAXV];
+                    mhd_noncons_powell_normal(&eq, ul, ur, nrm, gp);
+                    mhd_noncons_powell_normal(&eq, ur, ul, nrm, gs);
+                    for (int v = 0; v < nv; ++v) {
+                        sfv[primary * fsz + v + nv * (fn + nf * pdir)] = f[v] + 0.5 * gp[v];
+                        sfv[secondary * fsz + v + nv * (fn_sec + nf * sdir)] = -(f[v] + 0.5 * gs[v]);
+                    }
+                    continue;
+                }
                 for (int v = 0; v < nv; ++v) {
                     sfv[primary * fsz + v + nv * (fn + nf * pdir)] = f[v];
                     sfv[secondary * fsz + v + nv * (fn_sec + nf * sdir)] = -f[v];
@@ -1882,6 +2178,11 @@ void oracle_calc_boundary_flux_p4est(const trixi_b200_desc *d, double *sfv, cons
                         double ub[MAXV];
                         ic_eval(&eq, ic, x, t, ub);
                         numflux_normal(&eq, d->surface_flux, ui, ub, nrm, f);
+                        if (flux_has_noncons(d->surface_flux)) { /* equations.jl:232-247, dgsem_p4est/dg_3d.jl:550-590 */
+                            double g[MAXV];
+                            mhd_noncons_powell_normal(&eq, ui, ub, nrm, g);
+                            for (int v = 0; v < nv; ++v) f[v] = f[v] + 0.5 * g[v];
+                        }
                     } else if (bc == TRIXI_B200_BC_SLIP_WALL) { /* compressible_euler_3d.jl:315-366 */
                         euler_slip_wall_normal(&eq, ui, nrm, f);
                     } else {
@@ -2064,7 +2365,7 @@ void oracle_calc_mortar_flux_p4est(const trixi_b200_desc *d, double *sfv, const 
         const int64_t *large_idx = d->mortar_node_indices + (int64_t)nd * (1 + 2 * m);
         int64_t large = ids[np] - 1;
         int small_dir = p4_direction(nd, small_idx), large_dir = p4_direction(nd, large_idx);
-        double u_buffer[MAXV * 64], tmp[MAXV * 64], u_large[4][MAXV * 64], fstar[4][MAXV * 64];
+        double u_buffer[MAXV * 64], tmp[MAXV * 64], u_large[4][MAXV * 64], fstar[4][MAXV * 64], fprim[4][MAXV * 64];
         /* prolong2mortars!: the large face in the orientation of the small side ... */
         for (int j = 0; j < nb; ++j)
             for (int i = 0; i < n; ++i) {
@@ -2088,11 +2389,22 @@ void oracle_calc_mortar_flux_p4est(const trixi_b200_desc *d, double *sfv, const 
                     int64_t vn = p4_volume_node(nd, n, small_idx, i, j);
                     double nrm[3] = {0, 0, 0};
                     p4_normal(d, small_dir, vn, small, nrm);
-                    numflux_normal(&eq, d->surface_flux, u + small * esz + nv * vn, u_large[p] + nv * (i + n * j), nrm,
-                                   fstar[p] + nv * (i + n * j));
+                    const double *us = u + small * esz + nv * vn, *ul_ = u_large[p] + nv * (i + n * j);
+                    double *fsec = fstar[p] + nv * (i + n * j), *fpri = fprim[p] + nv * (i + n * j);
+                    numflux_normal(&eq, d->surface_flux, us, ul_, nrm, fsec);
+                    for (int v = 0; v < nv; ++v) fpri[v] = fsec[v];
+                    if (flux_has_noncons(d->surface_flux)) { /* dg_3d.jl:860-888: 0.5 g(u_ll, u_rr) / 0.5 g(u_rr, u_ll) */
+                        double gp[MAXV], gs[MAXV];
+                        mhd_noncons_powell_normal(&eq, us, ul_, nrm, gp);
+                        mhd_noncons_powell_normal(&eq, ul_, us, nrm, gs);
+                        for (int v = 0; v < nv; ++v) {
+                            fpri[v] = fsec[v] + 0.5 * gp[v];
+                            fsec[v] = fsec[v] + 0.5 * gs[v];
+                        }
+                    }
                 }
             /* mortar_fluxes_to_elements!: small to small */
-            for (int q = 0; q < nv * nf; ++q) sfv[small * fsz + q + (int64_t)nv * nf * small_dir] = fstar[p][q];
+            for (int q = 0; q < nv * nf; ++q) sfv[small * fsz + q + (int64_t)nv * nf * small_dir] = fprim[p][q];
         }
         /* project the small fluxes to the large element */
         if (nd == 2) {
@@ -2188,6 +2500,14 @@ void oracle_calc_mpi_mortar_flux(const trixi_b200_desc *d, double *sfv, const do
                     double nn[3] = {0, 0, 0};
                     for (int k = 0; k < nd; ++k) nn[k] = nrm[k];
                     numflux_normal(&eq, d->surface_flux, usmall + nv * fn, uproj + nv * fn, nn, f);
+                    if (flux_has_noncons(d->surface_flux)) {
+                        double gp[MAXV], gs[MAXV];
+                        mhd_noncons_powell_normal(&eq, usmall + nv * fn, uproj + nv * fn, nn, gp);
+                        mhd_noncons_powell_normal(&eq, uproj + nv * fn, usmall + nv * fn, nn, gs);
+                        for (int v = 0; v < nv; ++v) fprim[v + nv * fn] = f[v] + 0.5 * gp[v];
+                        for (int v = 0; v < nv; ++v) f[v] = f[v] + 0.5 * gs[v];
+                        continue;
+                    }
                 } else {
                     const double *ul = large_side == 1 ? uproj + nv * fn : usmall + nv * fn;
                     const double *ur = large_side == 1 ? usmall + nv * fn : uproj + nv * fn;
@@ -2330,6 +2650,16 @@ void oracle_calc_mpi_interface_flux_p4est(const trixi_b200_desc *d, double *sfv,
                     for (int dim = 0; dim < nd; ++dim) nrm[dim] = -nrm[dim];
                 numflux_normal(&eq, d->surface_flux, ul, ur, nrm, f);
                 p4_surface_node(nd, n, idx, i, j, &fn_loc);
+                if (flux_has_noncons(d->surface_flux)) { /* dg_3d_parallel.jl:302-337 */
+                    double g[MAXV];
+                    if (side == 1)
+                        mhd_noncons_powell_normal(&eq, ul, ur, nrm, g);
+                    else
+                        mhd_noncons_powell_normal(&eq, ur, ul, nrm, g);
+                    for (int v = 0; v < nv; ++v)
+                        sfv[e * fsz + v + nv * (fn_loc + nf * dir)] = side == 1 ? f[v] + 0.5 * g[v] : -f[v] + 0.5 * (-g[v]);
+                    continue;
+                }
                 for (int v = 0; v < nv; ++v)
                     sfv[e * fsz + v + nv * (fn_loc + nf * dir)] = side == 1 ? f[v] : -f[v];
             }

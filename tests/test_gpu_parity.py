@@ -112,7 +112,8 @@ RHS_CASES = ["tree_3d_euler_ec", "tree_3d_euler_source_terms", "tree_3d_euler_so
              "tree_3d_advection_basic", "tree_3d_advection_mortar", "structured_3d_advection_basic",
              "p4est_3d_advection_basic", "p4est_3d_tgv_p5", "p4est_3d_curved_p5", "p4est_3d_advection_nonconforming",
              "p4est_2d_advection_nonconforming_flag", "structured_3d_euler_sedov", "structured_2d_euler_sedov",
-             "p4est_2d_euler_sedov", "p4est_3d_euler_sedov"] + sorted(PARITY_EXTRA) + sorted(NONCONFORMING_EXTRA)
+             "p4est_2d_euler_sedov", "p4est_3d_euler_sedov", "structured_3d_mhd_ec", "structured_3d_mhd_alfven_wave",
+             "p4est_3d_mhd_alfven_wave_nonconforming", "p4est_3d_mhd_alfven_wave_nonperiodic"] + sorted(PARITY_EXTRA) + sorted(NONCONFORMING_EXTRA)
 
 
 @pytest.mark.parametrize("name", RHS_CASES)
@@ -386,7 +387,8 @@ GOLDEN_GPU = ["tree_3d_advection_basic", "tree_3d_advection_mortar", "structured
               "structured_2d_euler_source_terms_nonperiodic", "p4est_2d_advection_basic",
               "p4est_3d_advection_nonconforming", "p4est_2d_advection_nonconforming_flag",
               "tree_3d_mhd_alfven_wave_mortar", "structured_3d_euler_sedov", "structured_2d_euler_sedov",
-              "p4est_2d_euler_sedov", "p4est_3d_euler_sedov"]
+              "p4est_2d_euler_sedov", "p4est_3d_euler_sedov", "structured_3d_mhd_ec", "structured_3d_mhd_alfven_wave",
+              "p4est_3d_mhd_alfven_wave_nonconforming", "p4est_3d_mhd_alfven_wave_nonperiodic"]
 
 
 @pytest.mark.parametrize("name", GOLDEN_GPU)
@@ -516,7 +518,8 @@ def _ranked_semis(name, world):
                                   "tree_2d_advection_mortar", "tree_3d_euler_mortar", "tree_3d_mhd_alfven_wave_mortar",
                                   "tree_2d_euler_vortex_mortar_shockcapturing", "p4est_2d_advection_nonconforming_flag",
                                   "p4est_3d_nonconforming_curved_ec",
-                                  "p4est_3d_nonconforming_curved_weak_form_nonperiodic"])
+                                  "p4est_3d_nonconforming_curved_weak_form_nonperiodic",
+                                  "p4est_3d_mhd_alfven_wave_nonconforming", "p4est_3d_mhd_alfven_wave_nonperiodic"])
 def test_halo_exchange_matches_single_rank(name, world, oracle_module):
     """The element partition with the device-side halo exchange (pack kernels storing into the peers'
     receive buffers, sequence flags) reproduces the single-rank result; like the reference asserts for its
@@ -557,7 +560,7 @@ def test_halo_exchange_matches_single_rank(name, world, oracle_module):
         if name.startswith("p4est"):
             # (refined forests amplify the metric rounding by inverse_jacobian * inverse_weights, see
             # tests/test_distributed_cpu.py; the MPI mortars themselves are bit-identical)
-            np.testing.assert_allclose(x, y, rtol=0, atol=(2e-11 if "nonconforming" in name else 1e-13) * np.abs(y).max())
+            np.testing.assert_allclose(x, y, rtol=0, atol=(2e-10 if "nonconforming" in name else 1e-13) * np.abs(y).max())
         else:
             np.testing.assert_array_equal(x, y)
 

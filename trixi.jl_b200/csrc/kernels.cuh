@@ -1291,6 +1291,20 @@ __global__ void __launch_bounds__(256) k_interface_flux_curved(const KParams P) 
     eq.numflux_normal(P.surface_flux, ul, ur, nrm, f);
     double *sl = P.sfv + ((left * (2 * ND) + (2 * o + 1)) * NF + fn) * NV;
     double *sr = P.sfv + ((right * (2 * ND) + (2 * o)) * NF + fn) * NV;
+    if constexpr (EQ::kHasNoncons) {
+        if (EQ::has_noncons(P.surface_flux)) {  // dgsem_structured/dg_3d.jl:755-828
+            double gl[NV], gr[NV];
+            eq.noncons_normal(ul, ur, nrm, gl);
+            eq.noncons_normal(ur, ul, nrm, gr);
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+                const double fv = sign_jacobian * f[v];
+                sl[v] = fv + 0.5 * (sign_jacobian * gl[v]);
+                sr[v] = fv + 0.5 * (sign_jacobian * gr[v]);
+            }
+            return;
+        }
+    }
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
         const double fv = sign_jacobian * f[v];
@@ -1441,6 +1455,38 @@ __global__ void __launch_bounds__(ElemCfg<EQ, N>::THREADS) k_element_curved(cons
                     if constexpr (VOLINT == TRIXI_B200_VOLINT_SHOCK_CAPTURING_HG) w = w_dg * w;
 #pragma unroll
                     for (int v = 0; v < NV; ++v) acc[v] = fma(w, f[v], acc[v]);
+                }
+            }
+            if constexpr (EQ::kHasNoncons) {
+                // nonconservative volume terms on curved meshes (dgsem_structured/dg_3d.jl:177-283):
+                // 0.5 sum_d sum_l Dsplit[idx_d, l] g(u, u_l, 0.5 (Ja^d + Ja^d_l))
+                if (EQ::has_noncons(P.volume_flux)) {
+                    double ic[NV];
+#pragma unroll
+                    for (int v = 0; v < NV; ++v) ic[v] = 0.0;
+#pragma unroll
+                    for (int d = 0; d < ND; ++d) {
+                        const int base = node - idx[d] * stride[d];
+                        double ja_node[ND];
+                        load_ja<ND, NN>(P, d, node, e, ja_node);
+#pragma unroll 1
+                        for (int l = 0; l < N; ++l) {
+                            const int node2 = base + l * stride[d];
+                            double up[NV], g[NV], ja2[ND], ja_avg[ND];
+                            const double *pu = ue + node2 * US;
+#pragma unroll
+                            for (int v = 0; v < NV; ++v) up[v] = pu[v];
+                            load_ja<ND, NN>(P, d, node2, e, ja2);
+#pragma unroll
+                            for (int q = 0; q < ND; ++q) ja_avg[q] = 0.5 * (ja_node[q] + ja2[q]);
+                            eq.noncons_normal(un, up, ja_avg, g);
+                            const double w = s_D[idx[d] + N * l];
+#pragma unroll
+                            for (int v = 0; v < NV; ++v) ic[v] = fma(w, g[v], ic[v]);
+                        }
+                    }
+#pragma unroll
+                    for (int v = 0; v < NV; ++v) acc[v] = fma(0.5, ic[v], acc[v]);
                 }
             }
             if constexpr (VOLINT == TRIXI_B200_VOLINT_SHOCK_CAPTURING_HG) {
@@ -1645,6 +1691,19 @@ __global__ void __launch_bounds__(256) k_interface_flux_p4est(const KParams P) {
     eq.numflux_normal(P.surface_flux, ul, ur, nrm, f);
     double *sp = P.sfv + ((primary * (2 * ND) + pdir) * NF + fn) * NV;
     double *ss = P.sfv + ((secondary * (2 * ND) + sdir) * NF + sfn) * NV;
+    if constexpr (EQ::kHasNoncons) {
+        if (EQ::has_noncons(P.surface_flux)) {  // dgsem_p4est/dg_3d.jl:340-375
+            double gp[NV], gs[NV];
+            eq.noncons_normal(ul, ur, nrm, gp);
+            eq.noncons_normal(ur, ul, nrm, gs);
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+                sp[v] = f[v] + 0.5 * gp[v];
+                ss[v] = -(f[v] + 0.5 * gs[v]);
+            }
+            return;
+        }
+    }
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
         sp[v] = f[v];
@@ -1719,10 +1778,26 @@ __global__ void __launch_bounds__((1 << (EQ::NDIMS - 1)) * ipow(N, EQ::NDIMS - 1
     eq.numflux_normal(P.surface_flux, us, up, nrm, f);
     {
         double *dst = P.sfv + ((small * (2 * ND) + sdir) * NF + fn) * NV;
+        bool done = false;
+        if constexpr (EQ::kHasNoncons) {
+            if (EQ::has_noncons(P.surface_flux)) {  // dg_3d.jl:860-888: 0.5 g(u_ll, u_rr) primary, 0.5 g(u_rr, u_ll) secondary
+                double gp[NV], gs[NV];
+                eq.noncons_normal(us, up, nrm, gp);
+                eq.noncons_normal(up, us, nrm, gs);
 #pragma unroll
-        for (int v = 0; v < NV; ++v) {
-            dst[v] = f[v];
-            s_f[p][v + NV * fn] = f[v];
+                for (int v = 0; v < NV; ++v) {
+                    dst[v] = f[v] + 0.5 * gp[v];
+                    s_f[p][v + NV * fn] = f[v] + 0.5 * gs[v];
+                }
+                done = true;
+            }
+        }
+        if (!done) {
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+                dst[v] = f[v];
+                s_f[p][v + NV * fn] = f[v];
+            }
         }
     }
     __syncthreads();
@@ -1799,6 +1874,14 @@ __global__ void __launch_bounds__(256) k_boundary_flux_p4est(const KParams P) {
         double ub[NV];
         eq.initial_condition(P.bc_ic[name], x, P.t, ub);
         eq.numflux_normal(P.surface_flux, ui, ub, nrm, f);
+        if constexpr (EQ::kHasNoncons) {
+            if (EQ::has_noncons(P.surface_flux)) {  // equations.jl:232-247: flux + 0.5 g(u_inner, u_boundary, n)
+                double g[NV];
+                eq.noncons_normal(ui, ub, nrm, g);
+#pragma unroll
+                for (int v = 0; v < NV; ++v) f[v] = f[v] + 0.5 * g[v];
+            }
+        }
     } else if (bc == TRIXI_B200_BC_SLIP_WALL) {
         eq.slip_wall_outward(ui, nrm, f);
     } else {
@@ -1863,6 +1946,18 @@ __global__ void __launch_bounds__(256) k_mpi_interface_flux_p4est(const KParams 
     }
     eq.numflux_normal(P.surface_flux, ul, ur, nrm, f);
     double *s = P.sfv + ((element * (2 * ND) + dir) * NF + sfn) * NV;
+    if constexpr (EQ::kHasNoncons) {
+        if (EQ::has_noncons(P.surface_flux)) {  // dg_3d_parallel.jl:302-337
+            double g[NV];
+            if (side == 1)
+                eq.noncons_normal(ul, ur, nrm, g);
+            else
+                eq.noncons_normal(ur, ul, nrm, g);
+#pragma unroll
+            for (int v = 0; v < NV; ++v) s[v] = side == 1 ? f[v] + 0.5 * g[v] : -f[v] + 0.5 * (-g[v]);
+            return;
+        }
+    }
 #pragma unroll
     for (int v = 0; v < NV; ++v) s[v] = side == 1 ? f[v] : -f[v];
 }
@@ -1952,6 +2047,18 @@ __global__ void __launch_bounds__((1 << (EQ::NDIMS - 1)) * ipow(N, EQ::NDIMS - 1
             eq.numflux_normal(P.surface_flux, us, up, nrm, f);
 #pragma unroll
             for (int v = 0; v < NV; ++v) fs[v] = f[v];
+            if constexpr (EQ::kHasNoncons) {
+                if (EQ::has_noncons(P.surface_flux)) {
+                    double gp[NV], gs[NV];
+                    eq.noncons_normal(us, up, nrm, gp);
+                    eq.noncons_normal(up, us, nrm, gs);
+#pragma unroll
+                    for (int v = 0; v < NV; ++v) {
+                        fs[v] = f[v] + 0.5 * gs[v];
+                        f[v] = f[v] + 0.5 * gp[v];
+                    }
+                }
+            }
         } else {
             mortar_point_flux<EQ>(eq, P.surface_flux, up, us, o, large_left, f, fs);
         }

@@ -832,7 +832,8 @@ struct Mhd3D {
 
     TB_DEV static bool has_noncons(int flux_id) {
         return flux_id == TRIXI_B200_FLUX_HINDENLANG_GASSNER_POWELL || flux_id == TRIXI_B200_FLUX_LLF_MHD_POWELL ||
-               flux_id == TRIXI_B200_FLUX_LLF_NAIVE_MHD_POWELL || flux_id == TRIXI_B200_FLUX_HLLE_MHD_POWELL;
+               flux_id == TRIXI_B200_FLUX_LLF_NAIVE_MHD_POWELL || flux_id == TRIXI_B200_FLUX_HLLE_MHD_POWELL ||
+               flux_id == TRIXI_B200_FLUX_CENTRAL_MHD_POWELL;
     }
     TB_DEV static double sel3(double a, double b, double c, int o) { return o == 0 ? a : (o == 1 ? b : c); }
 
@@ -999,7 +1000,8 @@ struct Mhd3D {
             }
             break;
         }
-        case TRIXI_B200_FLUX_CENTRAL: {
+        case TRIXI_B200_FLUX_CENTRAL:
+        case TRIXI_B200_FLUX_CENTRAL_MHD_POWELL: {
             double fl[9], fr[9];
             flux(ul, o, fl);
             flux(ur, o, fr);
@@ -1043,17 +1045,203 @@ struct Mhd3D {
         for (int v = 0; v < 9; ++v) s[v] = 0.0;
     }
     TB_DEV void initial_condition(int id, const double (&x)[3], double t, double (&u)[9]) const {
+        if (id == TRIXI_B200_IC_CONVERGENCE_TEST) {  // Alfven wave (:124-151) + prim2cons (:1273-1284)
+            const double p = 1, omega = 2 * 3.141592653589793, r = 2, e = 0.2;
+            const double nx = 1 / sqrt(r * r + 1), ny = r / sqrt(r * r + 1), sqr = 1;
+            const double Va = omega / (ny * sqr);
+            const double phi_alv = omega / ny * (nx * (x[0] - 0.5 * r) + ny * (x[1] - 0.5 * r)) - Va * t;
+            double sn, cs;
+            sincos(phi_alv, &sn, &cs);
+            const double rho = 1;
+            const double v1 = -e * ny * cs / rho, v2 = e * nx * cs / rho, v3 = e * sn / rho;
+            const double B1 = nx - rho * v1 * sqr, B2 = ny - rho * v2 * sqr, B3 = -rho * v3 * sqr, psi = 0;
+            u[0] = rho, u[1] = rho * v1, u[2] = rho * v2, u[3] = rho * v3;
+            u[4] = p * inv_gm1 + 0.5 * (u[1] * v1 + u[2] * v2 + u[3] * v3) + 0.5 * (B1 * B1 + B2 * B2 + B3 * B3) + 0.5 * psi * psi;
+            u[5] = B1, u[6] = B2, u[7] = B3, u[8] = psi;
+            return;
+        }
         const double c[9] = {1.0, 0.1, -0.2, -0.5, 50.0, 3.0, -1.2, 0.5, 0.0};  // initial_condition_constant (:101-113)
 #pragma unroll
         for (int v = 0; v < 9; ++v) u[v] = id == TRIXI_B200_IC_CONSTANT ? c[v] : nan("");
     }
-    // not part of this build: boundary walls and curved-mesh (normal-direction) MHD fluxes
-    TB_DEV void slip_wall(const double (&u)[9], int o, int direction, double (&f)[9]) const { nanfill(f); }
-    TB_DEV void flux_normal(const double (&u)[9], const double (&n)[3], double (&f)[9]) const { nanfill(f); }
+    // ---- curved meshes: fluxes along a (non-normalised) normal vector -----------------------------------------
+    // flux(u, normal_direction) (:236-275)
+    TB_DEV void flux_normal(const double (&u)[9], const double (&n)[3], double (&f)[9]) const {
+        const double rho = u[0], psi = u[8], inv_rho = 1.0 / rho;
+        const double v1 = u[1] * inv_rho, v2 = u[2] * inv_rho, v3 = u[3] * inv_rho;
+        const double B1 = u[5], B2 = u[6], B3 = u[7];
+        const double kin_en = 0.5 * (u[1] * v1 + u[2] * v2 + u[3] * v3);
+        const double mag_en = 0.5 * (B1 * B1 + B2 * B2 + B3 * B3);
+        const double pogm1 = u[4] - kin_en - mag_en - 0.5 * psi * psi;
+        const double p = (gamma - 1) * pogm1;
+        const double v_normal = v1 * n[0] + v2 * n[1] + v3 * n[2];
+        const double B_normal = B1 * n[0] + B2 * n[1] + B3 * n[2];
+        const double rho_v_normal = rho * v_normal;
+        f[0] = rho_v_normal;
+        f[1] = rho_v_normal * v1 - B1 * B_normal + (p + mag_en) * n[0];
+        f[2] = rho_v_normal * v2 - B2 * B_normal + (p + mag_en) * n[1];
+        f[3] = rho_v_normal * v3 - B3 * B_normal + (p + mag_en) * n[2];
+        f[4] = (kin_en + gamma * pogm1 + 2 * mag_en) * v_normal - B_normal * (v1 * B1 + v2 * B2 + v3 * B3) + c_h * psi * B_normal;
+        f[5] = c_h * psi * n[0] + (v2 * B1 - v1 * B2) * n[1] + (v3 * B1 - v1 * B3) * n[2];
+        f[6] = (v1 * B2 - v2 * B1) * n[0] + c_h * psi * n[1] + (v3 * B2 - v2 * B3) * n[2];
+        f[7] = (v1 * B3 - v3 * B1) * n[0] + (v2 * B3 - v3 * B2) * n[1] + c_h * psi * n[2];
+        f[8] = c_h * B_normal;
+    }
+    // flux_nonconservative_powell(u_ll, u_rr, normal_direction) (:342-374)
+    TB_DEV void noncons_normal(const double (&ul)[9], const double (&ur)[9], const double (&n)[3], double (&f)[9]) const {
+        const double inv_rho_ll = 1.0 / ul[0];
+        const double v1 = ul[1] * inv_rho_ll, v2 = ul[2] * inv_rho_ll, v3 = ul[3] * inv_rho_ll;
+        const double v_dot_B_ll = v1 * ul[5] + v2 * ul[6] + v3 * ul[7];
+        const double v_dot_n_ll = v1 * n[0] + v2 * n[1] + v3 * n[2];
+        const double B_dot_n_rr = ur[5] * n[0] + ur[6] * n[1] + ur[7] * n[2];
+        f[0] = 0.0;
+        f[1] = ul[5] * B_dot_n_rr, f[2] = ul[6] * B_dot_n_rr, f[3] = ul[7] * B_dot_n_rr;
+        f[4] = v_dot_B_ll * B_dot_n_rr + v_dot_n_ll * ul[8] * ur[8];
+        f[5] = v1 * B_dot_n_rr, f[6] = v2 * B_dot_n_rr, f[7] = v3 * B_dot_n_rr;
+        f[8] = v_dot_n_ll * ur[8];
+    }
+    // flux_hindenlang_gassner(u_ll, u_rr, normal_direction) (:781-855)
+    TB_DEV void flux_hindenlang_gassner_normal(const double (&ul)[9], const double (&ur)[9], const double (&n)[3],
+                                               double (&f)[9]) const {
+        double L[9], R[9];
+        cons2prim(ul, L);
+        cons2prim(ur, R);
+        const double v_dot_n_ll = L[1] * n[0] + L[2] * n[1] + L[3] * n[2], v_dot_n_rr = R[1] * n[0] + R[2] * n[1] + R[3] * n[2];
+        const double B_dot_n_ll = L[5] * n[0] + L[6] * n[1] + L[7] * n[2], B_dot_n_rr = R[5] * n[0] + R[6] * n[1] + R[7] * n[2];
+        const double rho_mean = ln_mean_fast(L[0], R[0]);
+        const double inv_rho_p_mean = L[4] * R[4] * inv_ln_mean_fast(L[0] * R[4], R[0] * L[4]);
+        const double p_avg = 0.5 * (L[4] + R[4]), psi_avg = 0.5 * (L[8] + R[8]);
+        const double velocity_square_avg = 0.5 * (L[1] * R[1] + L[2] * R[2] + L[3] * R[3]);
+        const double magnetic_square_avg = 0.5 * (L[5] * R[5] + L[6] * R[6] + L[7] * R[7]);
+        const double f1 = rho_mean * 0.5 * (v_dot_n_ll + v_dot_n_rr);
+        f[0] = f1;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            f[1 + d] = f1 * (0.5 * (L[1 + d] + R[1 + d])) + (p_avg + magnetic_square_avg) * n[d] -
+                       0.5 * (B_dot_n_ll * R[5 + d] + B_dot_n_rr * L[5 + d]);
+            f[5 + d] = c_h * psi_avg * n[d] + 0.5 * (v_dot_n_ll * L[5 + d] - L[1 + d] * B_dot_n_ll + v_dot_n_rr * R[5 + d] -
+                                                     R[1 + d] * B_dot_n_rr);
+        }
+        f[8] = c_h * 0.5 * (B_dot_n_ll + B_dot_n_rr);
+        f[4] = f1 * (velocity_square_avg + inv_rho_p_mean * inv_gm1) +
+               0.5 * (+L[4] * v_dot_n_rr + R[4] * v_dot_n_ll + (v_dot_n_ll * L[5] * R[5] + v_dot_n_rr * R[5] * L[5]) +
+                      (v_dot_n_ll * L[6] * R[6] + v_dot_n_rr * R[6] * L[6]) + (v_dot_n_ll * L[7] * R[7] + v_dot_n_rr * R[7] * L[7]) -
+                      (L[1] * B_dot_n_ll * R[5] + R[1] * B_dot_n_rr * L[5]) - (L[2] * B_dot_n_ll * R[6] + R[2] * B_dot_n_rr * L[6]) -
+                      (L[3] * B_dot_n_ll * R[7] + R[3] * B_dot_n_rr * L[7]) + c_h * (B_dot_n_ll * R[8] + B_dot_n_rr * L[8]));
+    }
+    // calc_fast_wavespeed(cons, normal_direction) (:1378-1404)
+    TB_DEV double fast_wavespeed_normal(const double (&u)[9], const double (&n)[3]) const {
+        const double psi = u[8], inv_rho = 1.0 / u[0];
+        const double v1 = u[1] * inv_rho, v2 = u[2] * inv_rho, v3 = u[3] * inv_rho;
+        const double kin_en = 0.5 * (u[1] * v1 + u[2] * v2 + u[3] * v3);
+        const double mag_en = 0.5 * (u[5] * u[5] + u[6] * u[6] + u[7] * u[7]);
+        const double p = (gamma - 1) * (u[4] - kin_en - mag_en - 0.5 * psi * psi);
+        const double a_square = gamma * p * inv_rho;
+        const double inv_sqrt_rho = 1.0 / sqrt(u[0]);
+        const double b1 = u[5] * inv_sqrt_rho, b2 = u[6] * inv_sqrt_rho, b3 = u[7] * inv_sqrt_rho;
+        const double b_square = b1 * b1 + b2 * b2 + b3 * b3;
+        const double norm_squared = n[0] * n[0] + n[1] * n[1] + n[2] * n[2];
+        const double bn = b1 * n[0] + b2 * n[1] + b3 * n[2];
+        const double b_dot_n_squared = bn * bn / norm_squared, sum = a_square + b_square;
+        return sqrt((0.5 * sum + 0.5 * sqrt(sum * sum - 4 * a_square * b_dot_n_squared)) * norm_squared);
+    }
+    // calc_fast_wavespeed_roe(u_ll, u_rr, normal_direction) (:1493-1565)
+    TB_DEV void fast_wavespeed_roe_normal(const double (&ul)[9], const double (&ur)[9], const double (&n)[3], double &vel_out,
+                                          double &c_f) const {
+        const double inv_rho_ll = 1.0 / ul[0], inv_rho_rr = 1.0 / ur[0];
+        const double v_ll[3] = {ul[1] * inv_rho_ll, ul[2] * inv_rho_ll, ul[3] * inv_rho_ll};
+        const double v_rr[3] = {ur[1] * inv_rho_rr, ur[2] * inv_rho_rr, ur[3] * inv_rho_rr};
+        const double kin_en_ll = 0.5 * (ul[1] * v_ll[0] + ul[2] * v_ll[1] + ul[3] * v_ll[2]);
+        const double mag_norm_ll = ul[5] * ul[5] + ul[6] * ul[6] + ul[7] * ul[7];
+        const double p_ll = (gamma - 1) * (ul[4] - kin_en_ll - 0.5 * mag_norm_ll - 0.5 * ul[8] * ul[8]);
+        const double kin_en_rr = 0.5 * (ur[1] * v_rr[0] + ur[2] * v_rr[1] + ur[3] * v_rr[2]);
+        const double mag_norm_rr = ur[5] * ur[5] + ur[6] * ur[6] + ur[7] * ur[7];
+        const double p_rr = (gamma - 1) * (ur[4] - kin_en_rr - 0.5 * mag_norm_rr - 0.5 * ur[8] * ur[8]);
+        const double p_total_ll = p_ll + 0.5 * mag_norm_ll, p_total_rr = p_rr + 0.5 * mag_norm_rr;
+        const double sqrt_rho_ll = sqrt(ul[0]), sqrt_rho_rr = sqrt(ur[0]);
+        const double inv_sqrt_rho_add = 1.0 / (sqrt_rho_ll + sqrt_rho_rr), inv_sqrt_rho_prod = 1.0 / (sqrt_rho_ll * sqrt_rho_rr);
+        const double rho_ll_roe = sqrt_rho_ll * inv_sqrt_rho_add, rho_rr_roe = sqrt_rho_rr * inv_sqrt_rho_add;
+        double v_roe[3], B_roe[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            v_roe[d] = v_ll[d] * rho_ll_roe + v_rr[d] * rho_rr_roe;
+            B_roe[d] = ul[5 + d] * rho_ll_roe + ur[5 + d] * rho_rr_roe;
+        }
+        const double H_ll = (ul[4] + p_total_ll) * inv_rho_ll, H_rr = (ur[4] + p_total_rr) * inv_rho_rr;
+        const double H_roe = H_ll * rho_ll_roe + H_rr * rho_rr_roe;
+        const double dB0 = ul[5] - ur[5], dB1 = ul[6] - ur[6], dB2 = ul[7] - ur[7];
+        const double X = 0.5 * (dB0 * dB0 + dB1 * dB1 + dB2 * dB2) * (inv_sqrt_rho_add * inv_sqrt_rho_add);
+        const double b_square_roe = (B_roe[0] * B_roe[0] + B_roe[1] * B_roe[1] + B_roe[2] * B_roe[2]) * inv_sqrt_rho_prod;
+        const double a_square_roe =
+            (2 - gamma) * X + (gamma - 1) * (H_roe - 0.5 * (v_roe[0] * v_roe[0] + v_roe[1] * v_roe[1] + v_roe[2] * v_roe[2]) -
+                                             b_square_roe);
+        const double norm_squared = n[0] * n[0] + n[1] * n[1] + n[2] * n[2];
+        const double Bn = B_roe[0] * n[0] + B_roe[1] * n[1] + B_roe[2] * n[2];
+        const double c_a_roe = Bn * Bn / norm_squared * inv_sqrt_rho_prod, sum = a_square_roe + b_square_roe;
+        const double a_star_roe = sqrt(sum * sum - 4 * a_square_roe * c_a_roe);
+        c_f = sqrt(0.5 * (a_square_roe + b_square_roe + a_star_roe) * norm_squared);
+        vel_out = v_roe[0] * n[0] + v_roe[1] * n[1] + v_roe[2] * n[2];
+    }
     TB_DEV void numflux_normal(int id, const double (&ul)[9], const double (&ur)[9], const double (&n)[3],
                                double (&f)[9]) const {
-        nanfill(f);
+        switch (id) {
+        case TRIXI_B200_FLUX_CENTRAL:
+        case TRIXI_B200_FLUX_CENTRAL_MHD_POWELL: {
+            double fl[9], fr[9];
+            flux_normal(ul, n, fl);
+            flux_normal(ur, n, fr);
+#pragma unroll
+            for (int v = 0; v < 9; ++v) f[v] = 0.5 * (fl[v] + fr[v]);
+            break;
+        }
+        case TRIXI_B200_FLUX_LLF:
+        case TRIXI_B200_FLUX_LLF_NAIVE:
+        case TRIXI_B200_FLUX_LLF_MHD_POWELL:
+        case TRIXI_B200_FLUX_LLF_NAIVE_MHD_POWELL: {  // max_abs_speed(_naive) (:879-956)
+            const bool naive = id == TRIXI_B200_FLUX_LLF_NAIVE || id == TRIXI_B200_FLUX_LLF_NAIVE_MHD_POWELL;
+            const double v_ll = (ul[1] * n[0] + ul[2] * n[1] + ul[3] * n[2]) / ul[0];
+            const double v_rr = (ur[1] * n[0] + ur[2] * n[1] + ur[3] * n[2]) / ur[0];
+            const double cf_ll = fast_wavespeed_normal(ul, n), cf_rr = fast_wavespeed_normal(ur, n);
+            const double lam = naive ? fmax(fabs(v_ll), fabs(v_rr)) + fmax(cf_ll, cf_rr)
+                                     : fmax(fabs(v_ll) + cf_ll, fabs(v_rr) + cf_rr);
+            double fl[9], fr[9];
+            flux_normal(ul, n, fl);
+            flux_normal(ur, n, fr);
+#pragma unroll
+            for (int v = 0; v < 9; ++v) f[v] = 0.5 * (fl[v] + fr[v]) + (-0.5 * lam * (ur[v] - ul[v]));
+            break;
+        }
+        case TRIXI_B200_FLUX_HINDENLANG_GASSNER:
+        case TRIXI_B200_FLUX_HINDENLANG_GASSNER_POWELL:
+            flux_hindenlang_gassner_normal(ul, ur, n, f);
+            break;
+        case TRIXI_B200_FLUX_HLLE_MHD_POWELL: {  // min_max_speed_einfeldt (:1132-1166)
+            const double vn_ll = (ul[1] * n[0] + ul[2] * n[1] + ul[3] * n[2]) / ul[0];
+            const double vn_rr = (ur[1] * n[0] + ur[2] * n[1] + ur[3] * n[2]) / ur[0];
+            const double cf_ll = fast_wavespeed_normal(ul, n), cf_rr = fast_wavespeed_normal(ur, n);
+            double v_roe, cf_roe;
+            fast_wavespeed_roe_normal(ul, ur, n, v_roe, cf_roe);
+            const double lmin = fmin(vn_ll - cf_ll, v_roe - cf_roe), lmax = fmax(vn_rr + cf_rr, v_roe + cf_roe);
+            if (lmin >= 0 && lmax >= 0) {
+                flux_normal(ul, n, f);
+            } else if (lmax <= 0 && lmin <= 0) {
+                flux_normal(ur, n, f);
+            } else {
+                double fl[9], fr[9];
+                flux_normal(ul, n, fl);
+                flux_normal(ur, n, fr);
+                const double inv = 1.0 / (lmax - lmin);
+                const double factor_ll = lmax * inv, factor_rr = lmin * inv, factor_diss = lmin * lmax * inv;
+#pragma unroll
+                for (int v = 0; v < 9; ++v) f[v] = factor_ll * fl[v] - factor_rr * fr[v] + factor_diss * (ur[v] - ul[v]);
+            }
+            break;
+        }
+        default: nanfill(f);
+        }
     }
+    // not part of this build: boundary walls
+    TB_DEV void slip_wall(const double (&u)[9], int o, int direction, double (&f)[9]) const { nanfill(f); }
     TB_DEV void slip_wall_normal(const double (&u)[9], const double (&n)[3], int direction, double (&f)[9]) const {
         nanfill(f);
     }

@@ -685,7 +685,7 @@ TRIXI_B200_API int trixi_b200_create(const trixi_b200_desc *d, trixi_b200_handle
             if (bc == TRIXI_B200_BC_SLIP_WALL && !euler)
                 return fail(nullptr, TRIXI_B200_EINVAL, "boundary_condition_slip_wall needs the compressible Euler equations");
             if (bc != TRIXI_B200_BC_DIRICHLET) continue;
-            const bool ic_ok = ic == TRIXI_B200_IC_CONSTANT || ((euler || advection) && ic == TRIXI_B200_IC_CONVERGENCE_TEST) ||
+            const bool ic_ok = ic == TRIXI_B200_IC_CONSTANT || ic == TRIXI_B200_IC_CONVERGENCE_TEST ||
                                (euler && (ic == TRIXI_B200_IC_WEAK_BLAST_WAVE ||
                                           ic == TRIXI_B200_IC_EOC_TEST_COUPLED_EULER_GRAVITY));
             if (!ic_ok)
@@ -702,10 +702,9 @@ TRIXI_B200_API int trixi_b200_create(const trixi_b200_desc *d, trixi_b200_handle
     case TRIXI_B200_EQ_EULER_2D: L = get_launchers_euler2d(d->nnodes); break;
     case TRIXI_B200_EQ_EULER_3D: L = get_launchers_euler3d(d->nnodes); break;
     case TRIXI_B200_EQ_MHD_3D:
-        if (d->mesh_kind != TRIXI_B200_MESH_TREE)
-            return fail(nullptr, TRIXI_B200_EINVAL, "GLM-MHD is available on TreeMesh only in this build");
-        if (d->nboundaries > 0)
-            return fail(nullptr, TRIXI_B200_EINVAL, "GLM-MHD boundary conditions are not part of this build (periodic only)");
+        if (d->nboundaries > 0 && d->mesh_kind != TRIXI_B200_MESH_P4EST)
+            return fail(nullptr, TRIXI_B200_EINVAL,
+                        "GLM-MHD boundary conditions are available on P4estMesh only in this build (Dirichlet)");
         L = get_launchers_mhd3d(d->nnodes);
         break;
     default: return fail(nullptr, TRIXI_B200_EINVAL, "equation %d not supported by this build", d->equation);
@@ -1225,7 +1224,8 @@ TRIXI_B200_API int trixi_b200_calc_error_norms(trixi_b200_handle *h, double t, i
         !(initial_condition == TRIXI_B200_IC_WEAK_BLAST_WAVE &&
           (h->equation == TRIXI_B200_EQ_EULER_2D || h->equation == TRIXI_B200_EQ_EULER_3D)))
         return fail(h, TRIXI_B200_EINVAL, "initial condition %d is not registered on the device for this equation", initial_condition);
-    if (h->equation == TRIXI_B200_EQ_MHD_3D && initial_condition != TRIXI_B200_IC_CONSTANT)
+    if (h->equation == TRIXI_B200_EQ_MHD_3D && initial_condition != TRIXI_B200_IC_CONSTANT &&
+        initial_condition != TRIXI_B200_IC_CONVERGENCE_TEST)
         return fail(h, TRIXI_B200_EINVAL, "initial condition %d is not registered on the device for this equation", initial_condition);
     CUDA_TRY(h, cudaSetDevice(h->device));
     const int nv = h->nvars, n = h->nnodes;

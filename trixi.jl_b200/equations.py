@@ -31,6 +31,7 @@ FLUX_LLF_MHD_POWELL = 12      # (flux_lax_friedrichs, flux_nonconservative_powel
 FLUX_HINDENLANG_GASSNER_POWELL = 13
 FLUX_LLF_NAIVE_MHD_POWELL = 14  # (FluxLaxFriedrichs(max_abs_speed_naive), flux_nonconservative_powell)
 FLUX_HLLE_MHD_POWELL = 15  # (flux_hlle, flux_nonconservative_powell)
+FLUX_CENTRAL_MHD_POWELL = 16  # (flux_central, flux_nonconservative_powell)
 FLUX_HLLE = -2  # FluxHLL(min_max_speed_einfeldt): only inside the MHD tuple above
 
 SRC_NONE, SRC_CONVERGENCE_TEST, SRC_EOC_TEST_EULER, SRC_EOC_TEST_COUPLED_EULER_GRAVITY = 0, 1, 2, 3
@@ -136,6 +137,8 @@ def resolve_flux(flux):
             return FLUX_LLF_NAIVE_MHD_POWELL
         if cons.flux_id == FLUX_HLLE:
             return FLUX_HLLE_MHD_POWELL
+        if cons.flux_id == FLUX_CENTRAL:
+            return FLUX_CENTRAL_MHD_POWELL
         raise ValueError(f"unsupported conservative flux {cons} with Powell term")
     if not isinstance(flux, _Flux):
         raise TypeError(f"numerical flux {flux!r} is not in the libtrixi_b200 registry")
