@@ -16,7 +16,12 @@ from elixirs import ELIXIRS, EXTRA  # noqa: E402
 CASES = ["tree_3d_euler_ec", "tree_3d_euler_source_terms", "tree_3d_euler_ec_shima_etal", "tree_3d_mhd_ec",
          "tree_3d_euler_shockcapturing", "structured_3d_euler_source_terms", "p4est_3d_euler_source_terms_nonperiodic",
          "tree_3d_euler_mortar", "tree_2d_euler_ec", "tree_3d_euler_slip_wall_mixed", "p4est_3d_curved_ec",
-         "structured_3d_euler_ec", "p4est_3d_curved_p5"]
+         "structured_3d_euler_ec", "p4est_3d_curved_p5",
+         # round 2, second half: P4est mortars (2D curved + 3D), mortars with nonconservative terms, GLM-MHD node records,
+         # shock capturing and GLM-MHD on curved meshes
+         "p4est_2d_advection_nonconforming_flag", "p4est_3d_nonconforming_curved_ec", "tree_3d_mhd_alfven_wave_mortar",
+         "structured_3d_euler_sedov", "p4est_2d_euler_sedov", "structured_3d_mhd_ec",
+         "p4est_3d_mhd_alfven_wave_nonperiodic"]
 
 
 def main():

@@ -53,6 +53,25 @@ struct NodeRecord<Mhd3D> {
     // selects on the direction, no arm of a conditional evaluated in vain.  Its momentum and field components come out in
     // the same rotated order.  (The transverse sums then run in rotated order: last-bit differences to the reference.)
     static constexpr bool kRotated = true;
+    // record of a node with the triples rotated for sweep direction d: slot k holds component (d + k) mod 3
+    TB_DEV static void load(const double *src, int d, double *q) {
+        const int c1 = d == 2 ? 0 : d + 1, c2 = d == 0 ? 2 : d - 1;
+        q[0] = src[0], q[4] = src[4], q[8] = src[8], q[9] = src[9], q[10] = src[10];
+        q[1] = src[1 + d], q[2] = src[1 + c1], q[3] = src[1 + c2];
+        q[5] = src[5 + d], q[6] = src[5 + c1], q[7] = src[5 + c2];
+    }
+    // conservative component held by result slot v in direction d
+    TB_DEV static void comps(int d, int (&comp)[9]) {
+        const int c1 = d == 2 ? 0 : d + 1, c2 = d == 0 ? 2 : d - 1;
+        comp[0] = 0, comp[4] = 4, comp[8] = 8;
+        comp[1] = 1 + d, comp[2] = 1 + c1, comp[3] = 1 + c2;
+        comp[5] = 5 + d, comp[6] = 5 + c1, comp[7] = 5 + c2;
+    }
+    // slot that holds component v after the z sweep (d = 2)
+    TB_DEV static constexpr int slot_of(int v) {
+        constexpr int t[9] = {0, 2, 3, 1, 4, 6, 7, 5, 8};
+        return t[v];
+    }
     TB_DEV static void flux(const Mhd3D &eq, int /*id*/, const double *L, const double *R, double (&f)[9]) {
         double rho_mean, inv_rho_p_mean;
         {
@@ -101,6 +120,72 @@ struct NodeRecord<Mhd3D> {
     }
 };
 
+// Compressible Euler with flux_ranocha (the volume flux of the shock-capturing elixirs): (rho, v1, v2, v3, p, log rho,
+// log rho - log p) as in the reference's flux_ranocha_turbo specialization (dg_3d_compressible_euler.jl:289-309), same
+// rotated-frame convention as above.
+template <>
+struct NodeRecord<Euler<3>> {
+    static constexpr bool kHas = true;
+    static constexpr int N = 7;
+    static constexpr bool kRotated = true;
+    TB_DEV_HOST static bool applies(int volume_flux) {
+        return volume_flux == TRIXI_B200_FLUX_RANOCHA || volume_flux == TRIXI_B200_FLUX_RANOCHA_TURBO;
+    }
+    TB_DEV static void make(const Euler<3> &eq, const double *u, double *r) {
+        const double rho = u[0], inv_rho = fast_rcp(rho);
+        double v1 = u[1] * inv_rho, v2 = u[2] * inv_rho, v3 = u[3] * inv_rho;
+        v1 = fma(fma(-rho, v1, u[1]), inv_rho, v1);
+        v2 = fma(fma(-rho, v2, u[2]), inv_rho, v2);
+        v3 = fma(fma(-rho, v3, u[3]), inv_rho, v3);
+        const double p = (eq.gamma - 1) * (u[4] - 0.5 * (u[1] * v1 + u[2] * v2 + u[3] * v3));
+        const double lrho = log_pos(rho);
+        r[0] = rho, r[1] = v1, r[2] = v2, r[3] = v3, r[4] = p, r[5] = lrho, r[6] = lrho - log_pos(p);
+    }
+    TB_DEV static void load(const double *src, int d, double *q) {
+        const int c1 = d == 2 ? 0 : d + 1, c2 = d == 0 ? 2 : d - 1;
+        q[0] = src[0], q[4] = src[4], q[5] = src[5], q[6] = src[6];
+        q[1] = src[1 + d], q[2] = src[1 + c1], q[3] = src[1 + c2];
+    }
+    TB_DEV static void comps(int d, int (&comp)[5]) {
+        const int c1 = d == 2 ? 0 : d + 1, c2 = d == 0 ? 2 : d - 1;
+        comp[0] = 0, comp[4] = 4;
+        comp[1] = 1 + d, comp[2] = 1 + c1, comp[3] = 1 + c2;
+    }
+    TB_DEV static constexpr int slot_of(int v) {
+        constexpr int t[5] = {0, 2, 3, 1, 4};
+        return t[v];
+    }
+    // flux_ranocha (compressible_euler_3d.jl:746-793) in the rotated frame: slot 1 is the normal velocity
+    TB_DEV static void flux(const Euler<3> &eq, int /*id*/, const double *L, const double *R, double (&f)[5]) {
+        double rho_mean, inv_rho_p_mean;
+        {
+            const double sum = L[0] + R[0], dif = R[0] - L[0];
+            const double q = dif * rcp_1nr(sum), f2 = q * q;
+            const bool series = f2 < 1.0e-4;
+            const double poly = fma(f2, fma(f2, fma(f2, 2.0 / 7.0, 2.0 / 5.0), 2.0 / 3.0), 2.0);
+            rho_mean = fast_div(series ? sum : dif, series ? poly : R[5] - L[5]);
+        }
+        {
+            const double x = L[0] * R[4], y = R[0] * L[4];
+            const double sum = x + y, dif = y - x;
+            const double q = dif * rcp_1nr(sum), f2 = q * q;
+            const bool series = f2 < 1.0e-4;
+            const double poly = fma(f2, fma(f2, fma(f2, 2.0 / 7.0, 2.0 / 5.0), 2.0 / 3.0), 2.0);
+            inv_rho_p_mean = L[4] * R[4] * fast_div(series ? poly : R[6] - L[6], series ? sum : dif);
+        }
+        const double vn_avg = 0.5 * (L[1] + R[1]), vt1_avg = 0.5 * (L[2] + R[2]), vt2_avg = 0.5 * (L[3] + R[3]);
+        const double p_avg = 0.5 * (L[4] + R[4]);
+        const double velocity_square_avg = 0.5 * (L[1] * R[1] + L[2] * R[2] + L[3] * R[3]);
+        const double f1 = rho_mean * vn_avg;
+        f[0] = f1;
+        f[1] = f1 * vn_avg + p_avg;
+        f[2] = f1 * vt1_avg;
+        f[3] = f1 * vt2_avg;
+        f[4] = f1 * (velocity_square_avg + inv_rho_p_mean * eq.inv_gm1) + 0.5 * (L[4] * R[1] + R[4] * L[1]);
+    }
+    TB_DEV static void noncons(const double *, const double *, double (&)[5]) {}
+};
+
 template <class EQ>
 struct LineSweepCfg {
     static constexpr int NV = EQ::NVARS, THREADS = 32;
@@ -123,7 +208,7 @@ __global__ void __launch_bounds__(LineSweepCfg<EQ>::THREADS, LineSweepCfg<EQ>::M
     k_element_fd3d_p3(const KParams P) {
     using C = LineSweepCfg<EQ>;
     using Rec = NodeRecord<EQ>;
-    static_assert(!REC || (Rec::kHas && !SC), "node records: equation support, no shock capturing");
+    static_assert(!REC || Rec::kHas, "node records need equation support");
     constexpr int NV = C::NV, CONS = C::CONS, SFV = C::SFV;
     constexpr int NR = REC ? Rec::N : NV;  // doubles per node in the line tile
     extern __shared__ __align__(128) double smem[];
@@ -209,16 +294,17 @@ __global__ void __launch_bounds__(LineSweepCfg<EQ>::THREADS, LineSweepCfg<EQ>::M
             pos[m] = swz_pos(base + lm[m] * stride);
             const double *src = s_line + pos[m] * NR;
             if constexpr (REC) {
-                // cyclic rotation: slot k of the velocity / field triples holds component (d + k) mod 3
-                const int c1 = d == 2 ? 0 : d + 1, c2 = d == 0 ? 2 : d - 1;
-                q[m][0] = src[0], q[m][4] = src[4], q[m][8] = src[8], q[m][9] = src[9], q[m][10] = src[10];
-                q[m][1] = src[1 + d], q[m][2] = src[1 + c1], q[m][3] = src[1 + c2];
-                q[m][5] = src[5 + d], q[m][6] = src[5 + c1], q[m][7] = src[5 + c2];
+                Rec::load(src, d, q[m]);  // cyclic rotation: slot k of a triple holds component (d + k) mod 3
             } else {
 #pragma unroll
                 for (int v = 0; v < NR; ++v) q[m][v] = src[v];
             }
         }
+        // (records: the triples of own/frn are in the rotated order of this direction; component of slot v)
+        int comp[NV];
+#pragma unroll
+        for (int v = 0; v < NV; ++v) comp[v] = v;
+        if constexpr (REC) Rec::comps(d, comp);
         double f[NV], lo[NR], hi[NR];
         auto two_point = [&](const double(&a)[NR], const double(&b)[NR], double(&out)[NV]) {
             if constexpr (REC)
@@ -252,15 +338,47 @@ __global__ void __launch_bounds__(LineSweepCfg<EQ>::THREADS, LineSweepCfg<EQ>::M
         }
         if constexpr (SC) {
             if (fv0 != 0.0) {
-                // subcell fluxes: (lo, hi) is still the pair (0,1) [h = 0] or (2,3) [h = 1]
                 double fa[NV], fb[NV];
-                eq.numflux(P.volume_flux_fv, lo, hi, d, fa);
+                if constexpr (REC) {
+                    // the subcell fluxes want conservative states: the natural-order u tile still holds them (blended
+                    // elements only, the branch is uniform over the warp); results go to the slots of this direction
+                    const double *c0 = s_u + (base + lm[0] * stride) * NV, *c1 = s_u + (base + lm[1] * stride) * NV;
+                    const double *c2 = s_u + (base + lm[2] * stride) * NV, *c3 = s_u + (base + lm[3] * stride) * NV;
+                    double ca[NV], cb[NV], ga[NV], gb[NV];
 #pragma unroll
-                for (int v = 0; v < NV; ++v) {
-                    lo[v] = h ? q[3][v] : q[1][v];  // the pair (1,2)
-                    hi[v] = h ? q[1][v] : q[2][v];
+                    for (int v = 0; v < NV; ++v) {
+                        ca[v] = h ? c1[v] : c0[v];  // the pair (0,1) [h = 0] or (2,3) [h = 1], lower node first
+                        cb[v] = h ? c0[v] : c1[v];
+                    }
+                    eq.numflux(P.volume_flux_fv, ca, cb, d, ga);
+#pragma unroll
+                    for (int v = 0; v < NV; ++v) {
+                        ca[v] = h ? c3[v] : c1[v];  // the pair (1,2)
+                        cb[v] = h ? c1[v] : c2[v];
+                    }
+                    eq.numflux(P.volume_flux_fv, ca, cb, d, gb);
+#pragma unroll
+                    for (int v = 0; v < NV; ++v) {
+                        // slot v holds component comp[v]: a select over the (at most three) candidates
+                        const int cv = comp[v];
+                        if (v >= 1 && v <= 3) {
+                            fa[v] = cv == 1 ? ga[1] : (cv == 2 ? ga[2] : ga[3]);
+                            fb[v] = cv == 1 ? gb[1] : (cv == 2 ? gb[2] : gb[3]);
+                        } else {
+                            fa[v] = ga[v];
+                            fb[v] = gb[v];
+                        }
+                    }
+                } else {
+                    // subcell fluxes: (lo, hi) is still the pair (0,1) [h = 0] or (2,3) [h = 1]
+                    eq.numflux(P.volume_flux_fv, lo, hi, d, fa);
+#pragma unroll
+                    for (int v = 0; v < NV; ++v) {
+                        lo[v] = h ? q[3][v] : q[1][v];  // the pair (1,2)
+                        hi[v] = h ? q[1][v] : q[2][v];
+                    }
+                    eq.numflux(P.volume_flux_fv, lo, hi, d, fb);
                 }
-                eq.numflux(P.volume_flux_fv, lo, hi, d, fb);
 #pragma unroll
                 for (int v = 0; v < NV; ++v) {
                     own[0][v] = fma(fv0, fa[v], own[0][v]);          // node 0: +f(0,1); node 3: -f(2,3)
@@ -325,15 +443,6 @@ __global__ void __launch_bounds__(LineSweepCfg<EQ>::THREADS, LineSweepCfg<EQ>::M
                 for (int v = 0; v < NV; ++v) frn[1][v] = fma(0.5 * w31, g[v], frn[1][v]);
             }
         }
-        // (records: the triples of own/frn are in the rotated order of this direction; component of slot k)
-        int comp[NV];
-#pragma unroll
-        for (int v = 0; v < NV; ++v) comp[v] = v;
-        if constexpr (REC) {
-            const int c1 = d == 2 ? 0 : d + 1, c2 = d == 0 ? 2 : d - 1;
-            comp[1] = 1 + d, comp[2] = 1 + c1, comp[3] = 1 + c2;
-            comp[5] = 5 + d, comp[6] = 5 + c1, comp[7] = 5 + c2;
-        }
         if (d < 2) {
 #pragma unroll
             for (int m = 0; m < 2; ++m) {
@@ -375,9 +484,8 @@ __global__ void __launch_bounds__(LineSweepCfg<EQ>::THREADS, LineSweepCfg<EQ>::M
         double(&val)[NV] = vals[r];
         if constexpr (REC) {
             // the z sweep left own[] in its rotated order: slot k of a triple holds component (2 + k) mod 3
-            constexpr int slot_of[9] = {0, 2, 3, 1, 4, 6, 7, 5, 8};
 #pragma unroll
-            for (int v = 0; v < NV; ++v) val[v] = t[v] + own[r][slot_of[v]];
+            for (int v = 0; v < NV; ++v) val[v] = t[v] + own[r][Rec::slot_of(v)];
         } else {
 #pragma unroll
             for (int v = 0; v < NV; ++v) val[v] = t[v] + own[r][v];
@@ -481,9 +589,9 @@ template <class EQ, bool SC = false>
 cudaError_t preload_fd3d_p3() {
     cudaError_t e = preload_kernel(k_element_fd3d_p3<EQ, true, SC>);
     if (e != cudaSuccess) return e;
-    if constexpr (NodeRecord<EQ>::kHas && !SC) {
-        if ((e = preload_kernel(k_element_fd3d_p3<EQ, true, false, true>)) != cudaSuccess) return e;
-        if ((e = preload_kernel(k_element_fd3d_p3<EQ, false, false, true>)) != cudaSuccess) return e;
+    if constexpr (NodeRecord<EQ>::kHas) {
+        if ((e = preload_kernel(k_element_fd3d_p3<EQ, true, SC, true>)) != cudaSuccess) return e;
+        if ((e = preload_kernel(k_element_fd3d_p3<EQ, false, SC, true>)) != cudaSuccess) return e;
     }
     return preload_kernel(k_element_fd3d_p3<EQ, false, SC>);
 }
@@ -510,11 +618,11 @@ cudaError_t launch_fd3d_p3_variant(const KParams &P, cudaStream_t s) {
 
 template <class EQ, bool SC = false>
 cudaError_t launch_element_fd3d_p3(const KParams &P, bool with_surface, cudaStream_t s) {
-    if constexpr (NodeRecord<EQ>::kHas && !SC) {
+    if constexpr (NodeRecord<EQ>::kHas) {
         // hoisted node records where the volume flux has a record form (kernel_path 2 = the plain form, for A/B runs)
         if (NodeRecord<EQ>::applies(P.volume_flux) && P.kernel_path != 2)
-            return with_surface ? launch_fd3d_p3_variant<EQ, true, false, true>(P, s)
-                                : launch_fd3d_p3_variant<EQ, false, false, true>(P, s);
+            return with_surface ? launch_fd3d_p3_variant<EQ, true, SC, true>(P, s)
+                                : launch_fd3d_p3_variant<EQ, false, SC, true>(P, s);
     }
     return with_surface ? launch_fd3d_p3_variant<EQ, true, SC>(P, s) : launch_fd3d_p3_variant<EQ, false, SC>(P, s);
 }
