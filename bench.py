@@ -77,6 +77,8 @@ WORKLOADS = {
     "euler_sc": {"nvars": 5, "bytes": 212.0, "flop": None,
                  "kernel": "k_element_fd3d_p3<Euler3D, SC> (blended flux differencing + subcell FV, line sweeps, TMA "
                            "tiles); the indicator kernels are counted under max_dt_ms = 0 / not separately"},
+    "euler_shima": {"nvars": 5, "bytes": 212.0, "flop": None,
+                    "kernel": "k_element_fd3d_p3<Euler3D> (flux_shima_etal on hoisted node records, line sweeps, TMA tiles)"},
     "euler_weak": {"nvars": 5, "bytes": 212.0 + 24.0, "flop": 149.0 + 45.0 + 25.0,
                    "kernel": "k_element_euler3d_weak_p3 (weak form+surface+jacobian+source+2N stage, TMA tiles)"},
     "structured_curved": {"nvars": 5, "bytes": 212.0 + 72.0 + 8.0, "flop": 149.0 + 45.0 + 45.0,
@@ -93,7 +95,8 @@ WORKLOADS = {
     # the reference's own GPU benchmark (benchmark/CUDA/elixir_euler_taylor_green_vortex.jl + run.jl): P4estMesh
     # 4^3 trees, polydeg 5, flux_ranocha volume + flux_lax_friedrichs surface, CarpenterKennedy2N54
     "p4est_tgv_p5": {"nvars": 5, "bytes": 212.0 + 72.0 + 8.0, "flop": None,
-                     "kernel": "k_element_curved<Euler3D, 6> (generic one-thread-per-node flux differencing, polydeg 5)"},
+                     "kernel": "k_element_euler3d_ranocha_curved_pn<6> (flux_ranocha along averaged contravariant vectors at "
+                               "polydeg 5, line per thread, TMA / cp.async tiles)"},
     "mhd_ec": {"nvars": 9, "bytes": 9 * 8 * (1 + 1.5 + 0.8 + 2), "flop": None,
                "kernel": "k_element_fd3d_p3<Mhd3D> (line sweeps, Hindenlang-Gassner + Powell nonconservative, TMA tiles)"},
 }
@@ -123,6 +126,14 @@ def make_semi(level, device=-1, rank=0, world=1, comm=None, workload="euler_ec")
         return T.SemidiscretizationHyperbolic(mesh, eq, ic, solver, **kw)
     if world != 1 and workload != "p4est_curved":
         raise ValueError(f"workload {workload} is single-rank")
+    if workload == "euler_shima":
+        # examples/tree_3d_dgsem/elixir_euler_ec.jl with the kinetic-energy preserving flux_shima_etal (the reference's
+        # other SIMD specialization, flux_shima_etal_turbo) as volume flux and LLF surface fluxes
+        eq = T.CompressibleEulerEquations3D(1.4)
+        solver = T.DGSEM(polydeg=3, surface_flux=T.flux_lax_friedrichs,
+                         volume_integral=T.VolumeIntegralFluxDifferencing(T.flux_shima_etal))
+        mesh = T.TreeMesh((-2.0,) * 3, (2.0,) * 3, initial_refinement_level=level, periodicity=True)
+        return T.SemidiscretizationHyperbolic(mesh, eq, T.initial_condition_weak_blast_wave, solver, **kw)
     if workload == "euler_weak":
         # examples/tree_3d_dgsem/elixir_euler_source_terms.jl (C2)
         eq = T.CompressibleEulerEquations3D(1.4)
@@ -198,6 +209,8 @@ def workload_name(level, world=1, workload="euler_ec"):
     if workload != "euler_ec":
         desc = {"euler_sc": "tree_3d_dgsem/elixir_euler_shockcapturing.jl: 3D Euler VolumeIntegralShockCapturingHG "
                             "(IndicatorHennemannGassner, flux_ranocha DG/FV/surface), TreeMesh",
+                "euler_shima": "tree_3d_dgsem/elixir_euler_ec.jl with flux_shima_etal as volume flux and "
+                               "flux_lax_friedrichs surface fluxes, TreeMesh",
                 "euler_weak": "tree_3d_dgsem/elixir_euler_source_terms.jl: 3D Euler weak form + LLF(naive) + "
                               "convergence-test sources, TreeMesh",
                 "structured_curved": "structured_3d_dgsem/elixir_euler_free_stream.jl: 3D Euler weak form + "

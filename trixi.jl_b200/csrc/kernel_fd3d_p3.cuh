@@ -38,7 +38,7 @@ struct NodeRecord<Mhd3D> {
     TB_DEV_HOST static bool applies(int volume_flux) {
         return volume_flux == TRIXI_B200_FLUX_HINDENLANG_GASSNER || volume_flux == TRIXI_B200_FLUX_HINDENLANG_GASSNER_POWELL;
     }
-    TB_DEV static void make(const Mhd3D &eq, const double *u, double *r) {
+    TB_DEV static void make(const Mhd3D &eq, int /*id*/, const double *u, double *r) {
         const double rho = u[0], inv_rho = fast_rcp(rho);
         const double v1 = u[1] * inv_rho, v2 = u[2] * inv_rho, v3 = u[3] * inv_rho;
         const double p = (eq.gamma - 1) * (u[4] - 0.5 * (u[1] * v1 + u[2] * v2 + u[3] * v3 + u[5] * u[5] + u[6] * u[6] +
@@ -128,18 +128,29 @@ struct NodeRecord<Euler<3>> {
     static constexpr bool kHas = true;
     static constexpr int N = 7;
     static constexpr bool kRotated = true;
+    TB_DEV_HOST static bool is_ranocha(int id) { return id == TRIXI_B200_FLUX_RANOCHA || id == TRIXI_B200_FLUX_RANOCHA_TURBO; }
+    // flux_shima_etal and flux_kennedy_gruber use the primitive part only (the reference's second turbo
+    // specialization is flux_shima_etal_turbo, dg_3d_compressible_euler.jl:8-263); Kennedy-Gruber keeps the specific
+    // total energy in slot 5
     TB_DEV_HOST static bool applies(int volume_flux) {
-        return volume_flux == TRIXI_B200_FLUX_RANOCHA || volume_flux == TRIXI_B200_FLUX_RANOCHA_TURBO;
+        return is_ranocha(volume_flux) || volume_flux == TRIXI_B200_FLUX_SHIMA_ETAL ||
+               volume_flux == TRIXI_B200_FLUX_KENNEDY_GRUBER;
     }
-    TB_DEV static void make(const Euler<3> &eq, const double *u, double *r) {
+    TB_DEV static void make(const Euler<3> &eq, int id, const double *u, double *r) {
         const double rho = u[0], inv_rho = fast_rcp(rho);
         double v1 = u[1] * inv_rho, v2 = u[2] * inv_rho, v3 = u[3] * inv_rho;
         v1 = fma(fma(-rho, v1, u[1]), inv_rho, v1);
         v2 = fma(fma(-rho, v2, u[2]), inv_rho, v2);
         v3 = fma(fma(-rho, v3, u[3]), inv_rho, v3);
         const double p = (eq.gamma - 1) * (u[4] - 0.5 * (u[1] * v1 + u[2] * v2 + u[3] * v3));
-        const double lrho = log_pos(rho);
-        r[0] = rho, r[1] = v1, r[2] = v2, r[3] = v3, r[4] = p, r[5] = lrho, r[6] = lrho - log_pos(p);
+        r[0] = rho, r[1] = v1, r[2] = v2, r[3] = v3, r[4] = p;
+        if (is_ranocha(id)) {
+            const double lrho = log_pos(rho);
+            r[5] = lrho, r[6] = lrho - log_pos(p);
+        } else {
+            const double e = u[4] * inv_rho;
+            r[5] = fma(fma(-rho, e, u[4]), inv_rho, e), r[6] = 0.0;
+        }
     }
     TB_DEV static void load(const double *src, int d, double *q) {
         const int c1 = d == 2 ? 0 : d + 1, c2 = d == 0 ? 2 : d - 1;
@@ -156,7 +167,26 @@ struct NodeRecord<Euler<3>> {
         return t[v];
     }
     // flux_ranocha (compressible_euler_3d.jl:746-793) in the rotated frame: slot 1 is the normal velocity
-    TB_DEV static void flux(const Euler<3> &eq, int /*id*/, const double *L, const double *R, double (&f)[5]) {
+    TB_DEV static void flux(const Euler<3> &eq, int id, const double *L, const double *R, double (&f)[5]) {
+        if (!is_ranocha(id)) {
+            // flux_shima_etal (compressible_euler_3d.jl:473-510) / flux_kennedy_gruber (:560-600), rotated frame
+            const double rho_avg = 0.5 * (L[0] + R[0]), p_avg = 0.5 * (L[4] + R[4]);
+            const double vn_avg = 0.5 * (L[1] + R[1]), vt1_avg = 0.5 * (L[2] + R[2]), vt2_avg = 0.5 * (L[3] + R[3]);
+            const double f1 = rho_avg * vn_avg;
+            f[0] = f1;
+            f[1] = f1 * vn_avg + p_avg;
+            f[2] = f1 * vt1_avg;
+            f[3] = f1 * vt2_avg;
+            if (id == TRIXI_B200_FLUX_SHIMA_ETAL) {
+                const double kin_avg = 0.5 * (L[1] * R[1] + L[2] * R[2] + L[3] * R[3]);
+                const double pv_avg = 0.5 * (L[4] * R[1] + R[4] * L[1]);
+                f[4] = p_avg * vn_avg * eq.inv_gm1 + f1 * kin_avg + pv_avg;
+            } else {
+                const double e_avg = 0.5 * (L[5] + R[5]);
+                f[4] = (rho_avg * e_avg + p_avg) * vn_avg;
+            }
+            return;
+        }
         double rho_mean, inv_rho_p_mean;
         {
             const double sum = L[0] + R[0], dif = R[0] - L[0];
@@ -270,7 +300,7 @@ __global__ void __launch_bounds__(LineSweepCfg<EQ>::THREADS, LineSweepCfg<EQ>::M
         const double *c = s_u + n * NV;
         double *o = s_line + swz_pos(n) * NR;
         if constexpr (REC) {
-            Rec::make(eq, c, o);
+            Rec::make(eq, P.volume_flux, c, o);
         } else {
 #pragma unroll
             for (int v = 0; v < NV; ++v) o[v] = c[v];
