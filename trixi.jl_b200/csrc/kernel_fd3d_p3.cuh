@@ -366,56 +366,6 @@ __global__ void __launch_bounds__(LineSweepCfg<EQ>::THREADS, LineSweepCfg<EQ>::M
             own[0][v] = w01 * f[v];
             own[1][v] = w10 * f[v];
         }
-        if constexpr (SC) {
-            if (fv0 != 0.0) {
-                double fa[NV], fb[NV];
-                if constexpr (REC) {
-                    // the subcell fluxes want conservative states: the natural-order u tile still holds them (blended
-                    // elements only, the branch is uniform over the warp); results go to the slots of this direction
-                    const double *c0 = s_u + (base + lm[0] * stride) * NV, *c1 = s_u + (base + lm[1] * stride) * NV;
-                    const double *c2 = s_u + (base + lm[2] * stride) * NV, *c3 = s_u + (base + lm[3] * stride) * NV;
-                    double ca[NV], cb[NV], ga[NV], gb[NV];
-#pragma unroll
-                    for (int v = 0; v < NV; ++v) {
-                        ca[v] = h ? c1[v] : c0[v];  // the pair (0,1) [h = 0] or (2,3) [h = 1], lower node first
-                        cb[v] = h ? c0[v] : c1[v];
-                    }
-                    eq.numflux(P.volume_flux_fv, ca, cb, d, ga);
-#pragma unroll
-                    for (int v = 0; v < NV; ++v) {
-                        ca[v] = h ? c3[v] : c1[v];  // the pair (1,2)
-                        cb[v] = h ? c1[v] : c2[v];
-                    }
-                    eq.numflux(P.volume_flux_fv, ca, cb, d, gb);
-#pragma unroll
-                    for (int v = 0; v < NV; ++v) {
-                        // slot v holds component comp[v]: a select over the (at most three) candidates
-                        const int cv = comp[v];
-                        if (v >= 1 && v <= 3) {
-                            fa[v] = cv == 1 ? ga[1] : (cv == 2 ? ga[2] : ga[3]);
-                            fb[v] = cv == 1 ? gb[1] : (cv == 2 ? gb[2] : gb[3]);
-                        } else {
-                            fa[v] = ga[v];
-                            fb[v] = gb[v];
-                        }
-                    }
-                } else {
-                    // subcell fluxes: (lo, hi) is still the pair (0,1) [h = 0] or (2,3) [h = 1]
-                    eq.numflux(P.volume_flux_fv, lo, hi, d, fa);
-#pragma unroll
-                    for (int v = 0; v < NV; ++v) {
-                        lo[v] = h ? q[3][v] : q[1][v];  // the pair (1,2)
-                        hi[v] = h ? q[1][v] : q[2][v];
-                    }
-                    eq.numflux(P.volume_flux_fv, lo, hi, d, fb);
-                }
-#pragma unroll
-                for (int v = 0; v < NV; ++v) {
-                    own[0][v] = fma(fv0, fa[v], own[0][v]);          // node 0: +f(0,1); node 3: -f(2,3)
-                    own[1][v] = fma(fv1, fb[v] - fa[v], own[1][v]);  // node 1: f(1,2) - f(0,1); node 2: f(2,3) - f(1,2)
-                }
-            }
-        }
         if constexpr (REC) {
             // (record fluxes are symmetric up to rounding: no operand swap for the downward half-warp)
             two_point(q[0], q[2], f);
@@ -489,6 +439,44 @@ __global__ void __launch_bounds__(LineSweepCfg<EQ>::THREADS, LineSweepCfg<EQ>::M
             for (int v = 0; v < NV; ++v) t[comp[v]] += frn[m][v];
         }
         __syncwarp();
+    }
+
+    // VolumeIntegralShockCapturingHG, blended elements only (the branch is uniform over the warp): the subcell
+    // finite-volume part alpha w_i^-1 (f*_{i+1/2} - f*_{i-1/2}) (fv_kernel! dg_3d.jl:268-306) as its own pass over the
+    // three directions, after the sweeps -- inside them its registers cost every pure-DG element a quarter of its
+    // speed.  Thread h = 0 of a line needs the subcell fluxes (0,1) and (1,2), thread h = 1 needs (2,3) and (1,2);
+    // (1,2) is evaluated by both with identical operands (bitwise equal, so the subcell scheme stays conservative).
+    // The conservative states come from the natural-order u tile, the results go to the du tile.
+    if constexpr (SC) {
+        if (fv0 != 0.0) {
+#pragma unroll 1
+            for (int d = 0; d < 3; ++d) {
+                const int stride = 1 << (2 * d);
+                const int base = d == 0 ? 4 * l16 : (d == 1 ? a0 + 16 * a1 : l16);
+                const double *c0 = s_u + (base + lm[0] * stride) * NV, *c1 = s_u + (base + lm[1] * stride) * NV;
+                const double *c2 = s_u + (base + lm[2] * stride) * NV, *c3 = s_u + (base + lm[3] * stride) * NV;
+                double ca[NV], cb[NV], fa[NV], fb[NV];
+#pragma unroll
+                for (int v = 0; v < NV; ++v) {
+                    ca[v] = h ? c1[v] : c0[v];  // the pair (0,1) [h = 0] or (2,3) [h = 1], lower node first
+                    cb[v] = h ? c0[v] : c1[v];
+                }
+                eq.numflux(P.volume_flux_fv, ca, cb, d, fa);
+#pragma unroll
+                for (int v = 0; v < NV; ++v) {
+                    ca[v] = h ? c3[v] : c1[v];  // the pair (1,2)
+                    cb[v] = h ? c1[v] : c2[v];
+                }
+                eq.numflux(P.volume_flux_fv, ca, cb, d, fb);
+                double *t0 = s_du + swz_pos(base + lm[0] * stride) * NV, *t1 = s_du + swz_pos(base + lm[1] * stride) * NV;
+#pragma unroll
+                for (int v = 0; v < NV; ++v) {
+                    t0[v] = fma(fv0, fa[v], t0[v]);          // node 0: +f(0,1); node 3: -f(2,3)
+                    t1[v] = fma(fv1, fb[v] - fa[v], t1[v]);  // node 1: f(1,2) - f(0,1); node 2: f(2,3) - f(1,2)
+                }
+                __syncwarp();
+            }
+        }
     }
 
     // the line tile is dead: fetch u_tmp into its storage while the surface terms are applied
