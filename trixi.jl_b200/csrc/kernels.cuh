@@ -1080,6 +1080,80 @@ __global__ void __launch_bounds__(ElemCfg<EQ, N>::THREADS) k_indicator_hg(const 
     P.alpha[e] = alpha;
 }
 
+// The same indicator for 3D, polydeg 3 with a warp per element (8 elements per block): lanes read the element record
+// coalesced (two nodes each), the modal transform runs along x, y, z in two 64-entry shared tiles with the inverse
+// Vandermonde matrix in registers-by-broadcast, and the three energies are warp reductions (the one-thread-per-node
+// kernel above leaves the 64 + 37 + 8 squared coefficients to one thread).  Summation order differs from the
+// reference's sequential sums in the last bits.
+template <class EQ>
+__global__ void __launch_bounds__(256) k_indicator_hg_3d_p3(const KParams P, double threshold, double parameter_s) {
+    constexpr int NV = EQ::NVARS;
+    __shared__ double s_a[8][64], s_b[8][64], s_V[16];
+    const EQ eq(P.eq);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long e = (long long)blockIdx.x * 8 + warp;
+    if (threadIdx.x < 16) s_V[threadIdx.x] = P.inv_vdm[threadIdx.x];
+    __syncthreads();
+    if (e >= P.nelements) return;  // (whole warps leave; no block barrier below)
+    double *sa = s_a[warp], *sb = s_b[warp];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int n = lane + 32 * r;
+        double un[NV];
+        const double *pu = P.u + (e * 64 + n) * NV;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) un[v] = pu[v];
+        sa[n] = eq.indicator_variable(P.ind_var, un);
+    }
+    __syncwarp();
+    double m2[2] = {0.0, 0.0};
+#pragma unroll
+    for (int pass = 0; pass < 3; ++pass) {
+        const double *src = pass == 1 ? sb : sa;
+        double *dst = pass == 1 ? sa : sb;
+        const int st = pass == 0 ? 1 : (pass == 1 ? 4 : 16);
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int n = lane + 32 * r;
+            const int c = (n / st) & 3, b0 = n - c * st;
+            double res = 0.0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) res = fma(s_V[c + 4 * q], src[b0 + q * st], res);
+            if (pass < 2)
+                dst[n] = res;
+            else
+                m2[r] = res * res;
+        }
+        if (pass < 2) __syncwarp();
+    }
+    double total = 0.0, clip1 = 0.0, clip2 = 0.0;
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int n = lane + 32 * r;
+        const int mx = max(n & 3, max((n >> 2) & 3, n >> 4));  // highest mode index of this coefficient
+        total += m2[r];
+        if (mx <= 2) clip1 += m2[r];
+        if (mx <= 1) clip2 += m2[r];
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        total += __shfl_xor_sync(0xffffffffu, total, off);
+        clip1 += __shfl_xor_sync(0xffffffffu, clip1, off);
+        clip2 += __shfl_xor_sync(0xffffffffu, clip2, off);
+    }
+    if (lane == 0) {
+        const double frac1 = total != 0.0 ? (total - clip1) / total : 0.0;
+        const double frac2 = clip1 != 0.0 ? (clip1 - clip2) / clip1 : 0.0;
+        const double energy = fmax(frac1, frac2);
+        double alpha = 1 / (1 + exp(-parameter_s / threshold * (energy - threshold)));
+        if (alpha < P.ind_alpha_min) alpha = 0.0;
+        if (alpha > 1 - P.ind_alpha_min) alpha = 1.0;
+        alpha = fmin(P.ind_alpha_max, alpha);
+        P.alpha_raw[e] = alpha;
+        P.alpha[e] = alpha;
+    }
+}
+
 // apply_smoothing! (indicators_3d.jl:133-186): alpha[e] = max(alpha_raw[e], 0.5 alpha_raw[neighbours]); the
 // reference's sequential loop is a pure max, so the order does not matter; non-negative doubles order like
 // their bit patterns

@@ -329,6 +329,12 @@ void launch_indicator(const KParams &P, int stage, cudaStream_t s) {
             // magic parameters (indicators.jl:126-130)
             const double threshold = 0.5 * pow(10.0, -1.8 * pow((double)N, 0.25));
             const double parameter_s = log((1 - 0.0001) / 0.0001);
+            if constexpr (EQ::NDIMS == 3 && N == 4) {
+                if (P.kernel_path != 1) {  // warp per element
+                    k_indicator_hg_3d_p3<EQ><<<(unsigned)((P.nelements + 7) / 8), 256, 0, s>>>(P, threshold, parameter_s);
+                    return;
+                }
+            }
             k_indicator_hg<EQ, N><<<(unsigned)((P.nelements + C::EPB - 1) / C::EPB), C::THREADS, 0, s>>>(P, threshold, parameter_s);
         } else {
             const long long faces = P.ninterfaces + P.nmortars + P.nmpi;
@@ -409,6 +415,7 @@ cudaError_t preload_all() {
         TB_PRELOAD((k_element_curved<EQ, N, TRIXI_B200_VOLINT_SHOCK_CAPTURING_HG, true>));
         TB_PRELOAD((k_element_curved<EQ, N, TRIXI_B200_VOLINT_SHOCK_CAPTURING_HG, false>));
         TB_PRELOAD((k_indicator_hg<EQ, N>));
+        if constexpr (EQ::NDIMS == 3 && N == 4) TB_PRELOAD((k_indicator_hg_3d_p3<EQ>));
         TB_PRELOAD((k_indicator_smooth<EQ, N>));
     }
 #undef TB_PRELOAD
