@@ -1084,3 +1084,23 @@ NONCONFORMING_EXTRA = {
     "p4est_2d_nonconforming_curved_slip_wall": lambda: _p4est2d_nonconforming_curved(T.flux_lax_friedrichs, periodic=False),
 }
 EXTRA.update({name: _Extra(name, build) for name, build in NONCONFORMING_EXTRA.items()})
+
+
+def _p4est_nonconforming_sc(ndims):
+    # shock capturing across hanging faces of a curved forest: blending factors smoothed over interfaces AND mortars
+    # (apply_smoothing! indicators_2d.jl:104-138, indicators_3d.jl:125-186 for P4estMesh), subcell normal vectors on
+    # elements of two sizes
+    eq = T.CompressibleEulerEquations3D(1.4) if ndims == 3 else T.CompressibleEulerEquations2D(1.4)
+    if ndims == 3:
+        mesh = T.P4estMesh((2, 2, 2), polydeg=3, periodicity=True, initial_refinement_level=1, mapping=_warped_mapping_3d)
+        mesh.refine(_refine_origin_quadrant_of_even_trees(3), recursive=True)
+    else:
+        mesh = T.P4estMesh((3, 2), polydeg=3, periodicity=True, initial_refinement_level=1, mapping=_warped_mapping_2d)
+        mesh.refine(_refine_origin_quadrant(3), recursive=True)
+    return T.SemidiscretizationHyperbolic(mesh, eq, _sedov_ic(ndims, 1.0e-3), _sedov_solver(eq, 3))
+
+
+NONCONFORMING_EXTRA["p4est_3d_nonconforming_shock_capturing"] = lambda: _p4est_nonconforming_sc(3)
+NONCONFORMING_EXTRA["p4est_2d_nonconforming_shock_capturing"] = lambda: _p4est_nonconforming_sc(2)
+EXTRA.update({name: _Extra(name, NONCONFORMING_EXTRA[name]) for name in
+              ("p4est_3d_nonconforming_shock_capturing", "p4est_2d_nonconforming_shock_capturing")})

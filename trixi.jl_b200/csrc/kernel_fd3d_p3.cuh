@@ -134,7 +134,7 @@ struct NodeRecord<Euler<3>> {
     // total energy in slot 5
     TB_DEV_HOST static bool applies(int volume_flux) {
         return is_ranocha(volume_flux) || volume_flux == TRIXI_B200_FLUX_SHIMA_ETAL ||
-               volume_flux == TRIXI_B200_FLUX_KENNEDY_GRUBER;
+               volume_flux == TRIXI_B200_FLUX_KENNEDY_GRUBER || volume_flux == TRIXI_B200_FLUX_CHANDRASHEKAR;
     }
     TB_DEV static void make(const Euler<3> &eq, int id, const double *u, double *r) {
         const double rho = u[0], inv_rho = fast_rcp(rho);
@@ -147,6 +147,10 @@ struct NodeRecord<Euler<3>> {
         if (is_ranocha(id)) {
             const double lrho = log_pos(rho);
             r[5] = lrho, r[6] = lrho - log_pos(p);
+        } else if (id == TRIXI_B200_FLUX_CHANDRASHEKAR) {
+            // flux_chandrashekar works with beta = rho / (2 p): slot 4 holds beta, slot 6 log(rho / p) (= log beta + log 2)
+            const double lrho = log_pos(rho);
+            r[4] = 0.5 * fast_div(rho, p), r[5] = lrho, r[6] = lrho - log_pos(p);
         } else {
             const double e = u[4] * inv_rho;
             r[5] = fma(fma(-rho, e, u[4]), inv_rho, e), r[6] = 0.0;
@@ -168,6 +172,37 @@ struct NodeRecord<Euler<3>> {
     }
     // flux_ranocha (compressible_euler_3d.jl:746-793) in the rotated frame: slot 1 is the normal velocity
     TB_DEV static void flux(const Euler<3> &eq, int id, const double *L, const double *R, double (&f)[5]) {
+        if (id == TRIXI_B200_FLUX_CHANDRASHEKAR) {
+            // flux_chandrashekar (compressible_euler_3d.jl:639-690), rotated frame; both logarithmic means from the
+            // hoisted logarithms
+            double rho_mean, inv_beta_mean;
+            {
+                const double sum = L[0] + R[0], dif = R[0] - L[0];
+                const double q = dif * rcp_1nr(sum), f2 = q * q;
+                const bool series = f2 < 1.0e-4;
+                const double poly = fma(f2, fma(f2, fma(f2, 2.0 / 7.0, 2.0 / 5.0), 2.0 / 3.0), 2.0);
+                rho_mean = fast_div(series ? sum : dif, series ? poly : R[5] - L[5]);
+            }
+            {
+                const double sum = L[4] + R[4], dif = R[4] - L[4];
+                const double q = dif * rcp_1nr(sum), f2 = q * q;
+                const bool series = f2 < 1.0e-4;
+                const double poly = fma(f2, fma(f2, fma(f2, 2.0 / 7.0, 2.0 / 5.0), 2.0 / 3.0), 2.0);
+                inv_beta_mean = fast_div(series ? poly : R[6] - L[6], series ? sum : dif);
+            }
+            const double rho_avg = 0.5 * (L[0] + R[0]), beta_avg = 0.5 * (L[4] + R[4]);
+            const double vn_avg = 0.5 * (L[1] + R[1]), vt1_avg = 0.5 * (L[2] + R[2]), vt2_avg = 0.5 * (L[3] + R[3]);
+            const double p_mean = 0.5 * fast_div(rho_avg, beta_avg);
+            const double velocity_square_avg = 0.5 * (L[1] * L[1] + L[2] * L[2] + L[3] * L[3]) +
+                                               0.5 * (R[1] * R[1] + R[2] * R[2] + R[3] * R[3]);
+            const double f1 = rho_mean * vn_avg;
+            f[0] = f1;
+            f[1] = f1 * vn_avg + p_mean;
+            f[2] = f1 * vt1_avg;
+            f[3] = f1 * vt2_avg;
+            f[4] = f1 * 0.5 * (eq.inv_gm1 * inv_beta_mean - velocity_square_avg) + f[1] * vn_avg + f[2] * vt1_avg + f[3] * vt2_avg;
+            return;
+        }
         if (!is_ranocha(id)) {
             // flux_shima_etal (compressible_euler_3d.jl:473-510) / flux_kennedy_gruber (:560-600), rotated frame
             const double rho_avg = 0.5 * (L[0] + R[0]), p_avg = 0.5 * (L[4] + R[4]);
