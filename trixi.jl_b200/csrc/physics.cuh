@@ -507,8 +507,8 @@ struct Euler {
     TB_DEV void flux_ranocha_normal(const double (&ul)[NVARS], const double (&ur)[NVARS], const double (&n)[ND],
                                     double (&f)[NVARS]) const {
         double rho_ll, v_ll[ND], p_ll, rho_rr, v_rr[ND], p_rr;
-        cons2prim(ul, rho_ll, v_ll, p_ll);
-        cons2prim(ur, rho_rr, v_rr, p_rr);
+        cons2prim_fast(ul, rho_ll, v_ll, p_ll);  // (fast divisions as in flux_ranocha_fast: within 1 ulp)
+        cons2prim_fast(ur, rho_rr, v_rr, p_rr);
         double v_dot_n_ll = 0.0, v_dot_n_rr = 0.0, v_avg[ND], vsq = 0.0;
 #pragma unroll
         for (int d = 0; d < ND; ++d) {
@@ -541,9 +541,13 @@ struct Euler {
         case TRIXI_B200_FLUX_LLF_NAIVE:
         case TRIXI_B200_FLUX_HLL_DAVIS:
         case TRIXI_B200_FLUX_HLL_NAIVE: {
-            double rho_ll, v_ll[ND], p_ll, rho_rr, v_rr[ND], p_rr;
-            cons2prim(ul, rho_ll, v_ll, p_ll);
-            cons2prim(ur, rho_rr, v_rr, p_rr);
+            // primitives, sound speeds and |n| on Newton reciprocals / square roots with residual corrections (within
+            // 1 ulp of the IEEE forms; the generic path spent most of the curved interface kernels' time in eight
+            // IEEE divisions and three square roots per face node: every flux(u, n) repeated cons2prim), and both
+            // physical fluxes from those primitives
+            double rho_ll, v_ll[ND], p_ll, c_ll, rho_rr, v_rr[ND], p_rr, c_rr;
+            llf_fast_prim(&ul[0], rho_ll, v_ll, p_ll, c_ll);
+            llf_fast_prim(&ur[0], rho_rr, v_rr, p_rr, c_rr);
             double vl = 0.0, vr = 0.0, nsq = 0.0;
 #pragma unroll
             for (int d = 0; d < ND; ++d) {
@@ -551,16 +555,23 @@ struct Euler {
                 vr += v_rr[d] * n[d];
                 nsq += n[d] * n[d];
             }
-            const double norm_ = sqrt(nsq);
-            const double c_ll = sqrt(gamma * p_ll / rho_ll), c_rr = sqrt(gamma * p_rr / rho_rr);
+            const double norm_ = fast_sqrt(nsq);
             double fl[NVARS], fr[NVARS];
+            // flux(u, normal_direction) (:449-463) from the primitives at hand
+            auto flux_prim = [&](double rho, const double(&v)[ND], double pp, double vn, double rho_e, double(&g)[NVARS]) {
+                const double rvn = rho * vn;
+                g[0] = rvn;
+#pragma unroll
+                for (int d = 0; d < ND; ++d) g[1 + d] = rvn * v[d] + pp * n[d];
+                g[ND + 1] = (rho_e + pp) * vn;
+            };
             if (id == TRIXI_B200_FLUX_LLF || id == TRIXI_B200_FLUX_LLF_NAIVE) {
                 // max_abs_speed_naive (:1135-1153) / max_abs_speed (:1180-1199)
                 const double lam = id == TRIXI_B200_FLUX_LLF_NAIVE
                                        ? fmax(fabs(vl), fabs(vr)) + fmax(c_ll, c_rr) * norm_
                                        : fmax(fabs(vl) + c_ll * norm_, fabs(vr) + c_rr * norm_);
-                flux_normal(ul, n, fl);
-                flux_normal(ur, n, fr);
+                flux_prim(rho_ll, v_ll, p_ll, vl, ul[ND + 1], fl);
+                flux_prim(rho_rr, v_rr, p_rr, vr, ur[ND + 1], fr);
 #pragma unroll
                 for (int v = 0; v < NVARS; ++v) f[v] = 0.5 * (fl[v] + fr[v]) + (-0.5 * lam * (ur[v] - ul[v]));
             } else {
@@ -575,12 +586,12 @@ struct Euler {
                     lmax = fmax(vl + cl, vr + cr);
                 }
                 if (lmin >= 0 && lmax >= 0) {
-                    flux_normal(ul, n, f);
+                    flux_prim(rho_ll, v_ll, p_ll, vl, ul[ND + 1], f);
                 } else if (lmax <= 0 && lmin <= 0) {
-                    flux_normal(ur, n, f);
+                    flux_prim(rho_rr, v_rr, p_rr, vr, ur[ND + 1], f);
                 } else {
-                    flux_normal(ul, n, fl);
-                    flux_normal(ur, n, fr);
+                    flux_prim(rho_ll, v_ll, p_ll, vl, ul[ND + 1], fl);
+                    flux_prim(rho_rr, v_rr, p_rr, vr, ur[ND + 1], fr);
                     const double inv = 1.0 / (lmax - lmin);
                     const double factor_ll = lmax * inv, factor_rr = lmin * inv, factor_diss = lmin * lmax * inv;
 #pragma unroll
