@@ -302,6 +302,23 @@ TRIXI_B200_API int trixi_b200_calc_error_norms(trixi_b200_handle *h, double t, i
                                                const double *vandermonde, const double *weights, double *l2_sums,
                                                double *linf, double *volume);
 
+/* integrate_via_indices (callbacks_step/analysis_dg3d.jl:364-473, analysis_dg2d.jl analogues; the reference has a
+ * device form of it, :405-458) for the integrands of the AnalysisCallback's `analysis_integrals` (analysis.jl:680-760)
+ * on the device-resident u: the quadrature sum over this rank's elements, NOT normalised (distributed callers add the
+ * sums and the volumes over ranks, then divide), plus the quadrature of the volume.  `integral` has nvars entries for
+ * TRIXI_B200_INTEGRAL_CONS, one entry otherwise.  TRIXI_B200_INTEGRAL_ENTROPY_TIMEDERIVATIVE is
+ * analyze(entropy_timederivative, du, u, ...) (analysis_dg3d.jl:506-517): sum of cons2entropy(u) . du with the
+ * device-resident du (e.g. of the last trixi_b200_rhs).  Entropy and energies: compressible Euler. */
+enum {
+    TRIXI_B200_INTEGRAL_CONS = 0,                   /* integrate(u): conservation (cons2cons) */
+    TRIXI_B200_INTEGRAL_ENTROPY = 1,                /* entropy = entropy_math (compressible_euler_3d.jl:1970-2009) */
+    TRIXI_B200_INTEGRAL_ENERGY_TOTAL = 2,           /* :2012 */
+    TRIXI_B200_INTEGRAL_ENERGY_KINETIC = 3,         /* :2015-2018 */
+    TRIXI_B200_INTEGRAL_ENERGY_INTERNAL = 4,        /* :2021-2023 */
+    TRIXI_B200_INTEGRAL_ENTROPY_TIMEDERIVATIVE = 5  /* cons2entropy :1796-1817 */
+};
+TRIXI_B200_API int trixi_b200_integrate(trixi_b200_handle *h, int quantity, double *integral, double *volume);
+
 /* Tuning knobs (the analogue of the reference's compile-time Preferences, src/Trixi.jl:18-23).
  * TRIXI_B200_OPT_KERNEL_PATH: 0 = tuned kernels where one exists (default), 1 = generic kernels only,
  *   2 = the previous generation of the tuned headline kernel (kept for A/B measurements).

@@ -96,6 +96,13 @@ class OracleBackend:
     def set_eq_param(self, index, value):
         self.desc.eq_params[index] = float(value)
 
+    def integrate(self, quantity, nvars):
+        """same surface as B200Backend.integrate: (sums, volume) of vec[0] (and vec[1] for the entropy time derivative)"""
+        out, vol = np.zeros(nvars), C.c_double(0.0)
+        self.lib.oracle_integrate(self.holder.byref(), C.c_int(int(quantity)), _p(self.vec[0]), _p(self.vec[1]), _p(out),
+                                  C.byref(vol))
+        return (out if quantity == 0 else out[:1]), float(vol.value)
+
     def set_halo_exchange(self, exchange):
         """``exchange(mpi_u_flat)`` fills the remote side of mpi_u (tests: gloo isend/irecv)."""
         self.halo = exchange

@@ -2706,6 +2706,70 @@ void oracle_rhs_parallel_part2(const trixi_b200_desc *d, double *du, const doubl
     oracle_calc_sources(d, du, u, t);
 }
 
+/* integrate_via_indices (callbacks_step/analysis_dg3d.jl:364-425, analysis_dg2d.jl analogues) with the integrands of
+ * analysis_integrals: integrate(u) (cons2cons), entropy (compressible_euler_3d.jl:1959-2009), energy_total/kinetic/
+ * internal (:2012-2023), entropy_timederivative = cons2entropy(u) . du (:1796-1817, analysis_dg3d.jl:506-517).
+ * out: [nvars] for TRIXI_B200_INTEGRAL_CONS, [1] otherwise; NOT normalised; *volume = quadrature of the volume. */
+void oracle_integrate(const trixi_b200_desc *d, int quantity, const double *u, const double *du, double *out,
+                      double *volume) {
+    eqn_t eq = make_eqn(d);
+    int n = d->nnodes, nd = d->ndims, nv = d->nvars;
+    int n3 = nd == 3 ? n : 1;
+    int64_t nn = ipow(n, nd);
+    int curved = d->mesh_kind != TRIXI_B200_MESH_TREE;
+    double sums[MAXV] = {0}, vol = 0.0;
+    for (int64_t e = 0; e < d->nelements; ++e)
+        for (int k = 0; k < n3; ++k)
+            for (int j = 0; j < n; ++j)
+                for (int i = 0; i < n; ++i) {
+                    int64_t node = i + n * (j + n * k);
+                    double w = (1 / d->inverse_weights[i]) * (1 / d->inverse_weights[j]) * (nd == 3 ? 1 / d->inverse_weights[k] : 1.0);
+                    if (curved)
+                        w *= fabs(1 / d->inverse_jacobian[node + nn * e]);
+                    else
+                        for (int a = 0; a < nd; ++a) w *= 1 / d->inverse_jacobian[e];
+                    const double *un = u + nv * (node + nn * e);
+                    vol += w;
+                    if (quantity == TRIXI_B200_INTEGRAL_CONS) {
+                        for (int v = 0; v < nv; ++v) sums[v] += w * un[v];
+                        continue;
+                    }
+                    double val = NAN;
+                    if (is_euler(&eq)) {
+                        double rho = un[0], msq = 0.0;
+                        for (int a = 0; a < nd; ++a) msq += un[1 + a] * un[1 + a];
+                        if (quantity == TRIXI_B200_INTEGRAL_ENERGY_TOTAL)
+                            val = un[nd + 1];
+                        else if (quantity == TRIXI_B200_INTEGRAL_ENERGY_KINETIC)
+                            val = 0.5 * msq / rho;
+                        else if (quantity == TRIXI_B200_INTEGRAL_ENERGY_INTERNAL)
+                            val = un[nd + 1] - 0.5 * msq / rho;
+                        else if (quantity == TRIXI_B200_INTEGRAL_ENTROPY) {
+                            double p = (eq.gamma - 1) * (un[nd + 1] - 0.5 * msq / rho);
+                            double s_ = log(p) - eq.gamma * log(rho);
+                            val = -s_ * rho * eq.inv_gm1;
+                        } else if (quantity == TRIXI_B200_INTEGRAL_ENTROPY_TIMEDERIVATIVE) {
+                            const double *dn = du + nv * (node + nn * e);
+                            double v[3] = {0, 0, 0}, v_square = 0.0;
+                            for (int a = 0; a < nd; ++a) {
+                                v[a] = un[1 + a] / rho;
+                                v_square += v[a] * v[a];
+                            }
+                            double p = (eq.gamma - 1) * (un[nd + 1] - 0.5 * rho * v_square);
+                            double s_ = log(p) - eq.gamma * log(rho);
+                            double rho_p = rho / p;
+                            val = ((eq.gamma - s_) * eq.inv_gm1 - 0.5 * rho_p * v_square) * dn[0];
+                            for (int a = 0; a < nd; ++a) val += rho_p * v[a] * dn[1 + a];
+                            val += -rho_p * dn[nd + 1];
+                        }
+                    }
+                    sums[0] += w * val;
+                }
+    int nvals = quantity == TRIXI_B200_INTEGRAL_CONS ? nv : 1;
+    for (int v = 0; v < nvals; ++v) out[v] = sums[v];
+    *volume = vol;
+}
+
 /* max_dt stepsize_dg3d.jl:8-32 (constant_speed False), stepsize_dg2d.jl:60-75 (True) */
 double oracle_max_dt(const trixi_b200_desc *d, const double *u) {
     if (d->mesh_kind != TRIXI_B200_MESH_TREE) return oracle_max_dt_curved(d, u);

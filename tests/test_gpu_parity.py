@@ -622,3 +622,51 @@ def test_pipelined_host_path_is_bit_identical(name, chunk):
     gpu.step_2n(0.0, dt, alg.a, alg.b, alg.c)
     gpu.step_2n(dt, dt, alg.a, alg.b, alg.c)
     assert np.array_equal(gpu.download(0), un0.ravel(order="F"))
+
+
+@pytest.mark.parametrize("name", ["tree_3d_euler_ec", "tree_2d_euler_source_terms", "structured_3d_euler_ec",
+                                  "p4est_3d_nonconforming_curved_ec", "tree_2d_advection_basic", "tree_3d_mhd_ec"])
+def test_device_integrals_match_oracle(name, oracle_module):
+    """integrate_via_indices with the AnalysisCallback's integrands (analysis_dg3d.jl:364-517) on the device against the
+    oracle's restatement and against the definition in NumPy: conservation for every equation, entropy, energies and
+    the entropy time derivative for the compressible Euler equations; the EC scheme's entropy production is zero."""
+    semi = ELIXIRS[name].semi()
+    u = _random_admissible_state(semi, seed=11, perturb=0.2)
+    gpu, ref = semi.backend(), oracle_module.OracleBackend(semi)
+    gpu.upload(0, u)
+    ref.upload(0, u)
+    gpu.rhs(0.0)
+    du = np.empty_like(u)
+    ref.rhs_host(du, u, 0.0)
+    ref.upload(1, du)
+    nv = semi.equations.nvars
+    euler = isinstance(semi.equations, (T.CompressibleEulerEquations2D, T.CompressibleEulerEquations3D))
+    for quantity in range(6 if euler else 1):
+        a, va = gpu.integrate(quantity, nv)
+        b, vb = ref.integrate(quantity, nv)
+        assert abs(va - vb) <= 1e-12 * abs(vb)
+        scale = np.maximum(np.abs(b), 1e-300)
+        if quantity == 5:
+            # the sum of cons2entropy(u) . du cancels to round-off for entropy-conservative fluxes: compare absolutely
+            # against the size of the summands
+            absdu = np.abs(du).max() * vb
+            assert np.all(np.abs(a - b) <= 1e-11 * absdu)
+        else:
+            assert np.all(np.abs(a - b) <= 1e-12 * scale), (quantity, a, b)
+    # the definition: conservation = sum of w |J| u
+    w = semi.solver.basis.weights
+    nd = semi.mesh.ndims
+    wprod = w
+    for _ in range(nd - 1):
+        wprod = np.multiply.outer(wprod, w)
+    inv_jac = semi.cache.elements.inverse_jacobian
+    jac = np.abs(1.0 / inv_jac) if semi.is_curved else (1.0 / inv_jac) ** nd
+    weight = wprod[..., None] * jac
+    cons = (u * weight[None]).reshape(nv, -1).sum(axis=1)
+    a, va = gpu.integrate(0, nv)
+    np.testing.assert_allclose(a, cons, rtol=1e-11, atol=1e-13 * np.abs(cons).max())
+    np.testing.assert_allclose(va, weight.sum(), rtol=1e-12)
+    if name == "tree_3d_euler_ec":
+        # entropy conservation of the EC scheme (flux_ranocha both): |dS/dt| is round-off
+        dsdt = T.integrate_device(gpu, semi, "entropy_timederivative")
+        assert abs(dsdt[0]) < 1e-12 * np.abs(du).max()

@@ -6,7 +6,7 @@ name contains a dot; ``trixi_b200.py`` at the repository root is the loader).
 """
 from .basis import LobattoLegendreBasis, SolutionAnalyzer, gauss_lobatto_nodes_weights  # noqa: F401
 from .callbacks import (AliveCallback, AnalysisCallback, GlmSpeedCallback, StepsizeCallback,  # noqa: F401
-                        SummaryCallback, calc_error_norms, calc_error_norms_device)
+                        SummaryCallback, calc_error_norms, calc_error_norms_device, integrate_device)
 from .equations import *  # noqa: F401,F403
 from .mesh import CartesianBoxMesh, TreeMesh  # noqa: F401
 from .p4est import P4estMesh  # noqa: F401

@@ -192,13 +192,41 @@ def calc_error_norms_device(backend, t, semi, analyzer=None):
     return np.sqrt(l2sq / total_volume), linf
 
 
+# analysis_integrals of the AnalysisCallback (analysis.jl:680-760): name -> integrand id of the C ABI
+ANALYSIS_INTEGRALS = {"conservation": 0, "entropy": 1, "energy_total": 2, "energy_kinetic": 3, "energy_internal": 4,
+                      "entropy_timederivative": 5}
+
+
+def integrate_device(backend, semi, name, normalize=True):
+    """``integrate(func, u, mesh, equations, dg, cache; normalize)`` / ``analyze(entropy_timederivative, du, u, ...)``
+    (analysis_dg3d.jl:364-517) on the resident u (and du): quadrature on the device, sums over ranks here, division by
+    the total volume last -- exactly where the reference's MPI analysis reduces (analysis_dg2d.jl:170-215)."""
+    sums, volume = backend.integrate(ANALYSIS_INTEGRALS[name], semi.equations.nvars)
+    if semi.world_size > 1 and semi.comm is not None:
+        import torch
+        t = torch.from_numpy(np.concatenate([sums, [volume]]))
+        if semi.comm.get_backend() == "nccl":
+            t = t.cuda()
+        semi.comm.all_reduce(t, op=semi.comm.ReduceOp.SUM)
+        r = t.cpu().numpy()
+        sums, volume = r[:-1], float(r[-1])
+    if not normalize:
+        return sums
+    total = volume if getattr(semi, "is_curved", False) else semi.mesh.total_volume()
+    return sums / total
+
+
 class AnalysisCallback(_Callback):
     """``AnalysisCallback(semi; interval)`` (analysis.jl:95-158): records L2/Linf errors; the final
     values are what the reference's tests compare (``analysis_callback(sol)``, analysis.jl:640-668)."""
 
-    def __init__(self, semi, interval=0, on_device=True):
+    def __init__(self, semi, interval=0, on_device=True, analysis_integrals=()):
         self.semi = semi
         self.interval = interval
+        # analysis_integrals (analysis.jl:95-158; the reference's default is (entropy_timederivative,)): evaluated on
+        # the device by trixi_b200_integrate; ``integrals`` collects (iter, t, {name: value})
+        self.analysis_integrals = tuple(analysis_integrals)
+        self.integrals = []
         self.analyzer = SolutionAnalyzer(semi.solver.basis)
         self.history = []
         # reduce the norms on the device when the backend offers it (no download of u, SURVEY.md §8f row 2)
@@ -220,6 +248,13 @@ class AnalysisCallback(_Callback):
         if l2 is None:
             l2, linf = calc_error_norms(integrator.download_u(), integrator.t, self.semi, self.analyzer)
         self.history.append((integrator.iter, integrator.t, l2, linf))
+        if self.analysis_integrals and hasattr(integrator.backend, "integrate"):
+            vals = {}
+            for name in self.analysis_integrals:
+                if name == "entropy_timederivative":
+                    integrator.backend.rhs(integrator.t)  # du of the current state (analysis.jl:349-350)
+                vals[name] = integrate_device(integrator.backend, self.semi, name)
+            self.integrals.append((integrator.iter, integrator.t, vals))
 
     def __call__(self, sol):
         l2, linf = calc_error_norms(sol.u[-1], sol.t[-1], self.semi, self.analyzer)

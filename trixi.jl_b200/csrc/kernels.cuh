@@ -78,6 +78,7 @@ struct KParams {
     const double *inv_vdm;  // inverse_vandermonde_legendre [n, n] column-major
     const double *subcell_normals[3];  // curved meshes: normal vectors of the subcell interfaces per direction
     double inv_weights_c[kMaxNodes];
+    double weights_c[kMaxNodes];  // quadrature weights (1 / inverse_weights), for integrate_via_indices
     double ind_alpha_max, ind_alpha_min;
     int volume_flux_fv, ind_var, ind_smooth;
     // distributed: faces shared with other ranks (replaces mpi_interfaces, dg_2d_parallel.jl / dg_parallel.jl)
@@ -1323,6 +1324,71 @@ __global__ void __launch_bounds__(128) k_error_norms(const KParams P, const Norm
         const double sum = s_red[0][tid] + s_red[1][tid] + s_red[2][tid] + s_red[3][tid];
         atomicAdd(Q.sums + tid, sum);
         if (tid < NV) atomicMax(Q.linf + tid, max(max(s_max[0][tid], s_max[1][tid]), max(s_max[2][tid], s_max[3][tid])));
+    }
+}
+
+// integrate_via_indices (analysis_dg3d.jl:364-473): sum over nodes of w_i w_j (w_k) |J| func(u, node), one thread per
+// node; the integrands are the AnalysisCallback's analysis_integrals.  sums: [nvals + 1] (values, volume).
+template <class EQ, int N>
+__global__ void __launch_bounds__(256) k_integrate(const KParams P, int quantity, double *sums) {
+    constexpr int ND = EQ::NDIMS, NV = EQ::NVARS, NN = ipow(N, ND);
+    __shared__ double s_red[8][NV + 1];
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long e = gid / NN;
+    const int node = (int)(gid - e * NN);
+    double val[NV], w = 0.0;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) val[v] = 0.0;
+    if (e < P.nelements) {
+        const EQ eq(P.eq);
+        const int i = node % N, j = (node / N) % N, k = ND == 3 ? node / (N * N) : 0;
+        w = P.weights_c[i] * P.weights_c[j] * (ND == 3 ? P.weights_c[k] : 1.0);
+        if (P.curved) {
+            w *= fabs(1.0 / P.inverse_jacobian[e * NN + node]);
+        } else {  // volume_jacobian (dgsem_tree/dg.jl:8-10)
+            const double j1 = 1.0 / P.inverse_jacobian[e];
+            double vj = 1.0;
+#pragma unroll
+            for (int d = 0; d < ND; ++d) vj *= j1;
+            w *= vj;
+        }
+        double un[NV];
+        const double *pu = P.u + (e * NN + node) * NV;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) un[v] = pu[v];
+        if (quantity == TRIXI_B200_INTEGRAL_CONS) {
+#pragma unroll
+            for (int v = 0; v < NV; ++v) val[v] = w * un[v];
+        } else {
+            double dun[NV];
+#pragma unroll
+            for (int v = 0; v < NV; ++v) dun[v] = 0.0;
+            if (quantity == TRIXI_B200_INTEGRAL_ENTROPY_TIMEDERIVATIVE) {
+                const double *pd = P.du + (e * NN + node) * NV;
+#pragma unroll
+                for (int v = 0; v < NV; ++v) dun[v] = pd[v];
+            }
+            val[0] = w * eq.analysis_integrand(quantity, un, dun);
+        }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+#pragma unroll
+        for (int v = 0; v < NV; ++v) val[v] += __shfl_xor_sync(0xffffffffu, val[v], off);
+        w += __shfl_xor_sync(0xffffffffu, w, off);
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) {
+#pragma unroll
+        for (int v = 0; v < NV; ++v) s_red[warp][v] = val[v];
+        s_red[warp][NV] = w;
+    }
+    __syncthreads();
+    if (threadIdx.x <= NV) {
+        double sum = 0.0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) sum += s_red[q][threadIdx.x];
+        atomicAdd(sums + threadIdx.x, sum);
     }
 }
 

@@ -11,6 +11,7 @@ struct Launchers {
     void (*boundary_flux)(const KParams &, cudaStream_t);
     void (*mortar_flux)(const KParams &, cudaStream_t);
     void (*error_norms)(const KParams &, const NormParams &, cudaStream_t);
+    void (*integrate)(const KParams &, int quantity, double *sums, cudaStream_t);
     // with_surface = false: volume terms only (stage-level parity entry point)
     cudaError_t (*element)(const KParams &, bool with_surface, cudaStream_t);
     // IndicatorHennemannGassner blending factors of P.u into P.alpha (VolumeIntegralShockCapturingHG):
@@ -191,6 +192,13 @@ void launch_error_norms(const KParams &P, const NormParams &Q, cudaStream_t s) {
             cudaFuncSetAttribute(k_error_norms<EQ, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     }
     k_error_norms<EQ, N><<<(unsigned)P.nelements, 128, smem, s>>>(P, Q);
+}
+
+template <class EQ, int N>
+void launch_integrate(const KParams &P, int quantity, double *sums, cudaStream_t s) {
+    const long long total = P.nelements * ipow(N, EQ::NDIMS);
+    if (total == 0) return;
+    k_integrate<EQ, N><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(P, quantity, sums);
 }
 
 // tuned_euler3d.cu
@@ -388,6 +396,7 @@ cudaError_t preload_all() {
     TB_PRELOAD((k_boundary_flux<EQ, N>));
     TB_PRELOAD((k_sfv_fill_right<EQ, N>));
     TB_PRELOAD((k_mortar_flux<EQ, N>));
+    TB_PRELOAD((k_integrate<EQ, N>));
     TB_PRELOAD((k_mortar_flux_p4est<EQ, N>));
     TB_PRELOAD((k_mpi_mortar_flux<EQ, N>));
     TB_PRELOAD((k_error_norms<EQ, N>));
@@ -437,6 +446,7 @@ const Launchers *make_launchers() {
                                 &launch_boundary_flux<EQ, N>,
                                 &launch_mortar_flux<EQ, N>,
                                 &launch_error_norms<EQ, N>,
+                                &launch_integrate<EQ, N>,
                                 &launch_element<EQ, N>,
                                 &launch_indicator<EQ, N>,
                                 &launch_max_dt<EQ, N>,

@@ -142,6 +142,7 @@ struct Advection {
         return s;
     }
     // flux(u, normal_direction) (linear_scalar_advection_2d.jl:233-238)
+    TB_DEV double analysis_integrand(int, const double (&)[1], const double (&)[1]) const { return nan(""); }
     TB_DEV void flux_normal(const double (&u)[1], const double (&n)[ND], double (&f)[1]) const {
         f[0] = a_dot(n) * u[0];
     }
@@ -235,6 +236,41 @@ struct Euler {
 #pragma unroll
         for (int d = 0; d < ND; ++d) f[1 + d] = rv * v[d] + (d == o ? p : 0.0);
         f[ND + 1] = (u[ND + 1] + p) * pick<ND>(v, o);
+    }
+
+    // integrands of the AnalysisCallback's analysis_integrals: entropy = entropy_math (:1959-2009), energies
+    // (:2012-2023), cons2entropy(u) . du (:1796-1817, analysis_dg3d.jl:506-517); NaN for an unknown id
+    TB_DEV double analysis_integrand(int quantity, const double (&u)[NVARS], const double (&du)[NVARS]) const {
+        const double rho = u[0];
+        double msq = 0.0;
+#pragma unroll
+        for (int d = 0; d < ND; ++d) msq += u[1 + d] * u[1 + d];
+        switch (quantity) {
+        case TRIXI_B200_INTEGRAL_ENERGY_TOTAL: return u[ND + 1];
+        case TRIXI_B200_INTEGRAL_ENERGY_KINETIC: return 0.5 * msq / rho;
+        case TRIXI_B200_INTEGRAL_ENERGY_INTERNAL: return u[ND + 1] - 0.5 * msq / rho;
+        case TRIXI_B200_INTEGRAL_ENTROPY: {
+            const double p = (gamma - 1) * (u[ND + 1] - 0.5 * msq / rho);
+            const double s = log(p) - gamma * log(rho);
+            return -s * rho * inv_gm1;
+        }
+        case TRIXI_B200_INTEGRAL_ENTROPY_TIMEDERIVATIVE: {
+            double v[ND], v_square = 0.0;
+#pragma unroll
+            for (int d = 0; d < ND; ++d) {
+                v[d] = u[1 + d] / rho;
+                v_square += v[d] * v[d];
+            }
+            const double p = (gamma - 1) * (u[ND + 1] - 0.5 * rho * v_square);
+            const double s = log(p) - gamma * log(rho);
+            const double rho_p = rho / p;
+            double dot = ((gamma - s) * inv_gm1 - 0.5 * rho_p * v_square) * du[0];
+#pragma unroll
+            for (int d = 0; d < ND; ++d) dot += rho_p * v[d] * du[1 + d];
+            return dot + (-rho_p) * du[ND + 1];
+        }
+        default: return nan("");
+        }
     }
 
     // flux_ranocha (compressible_euler_3d.jl:746-793), generic form: ln_mean/inv_ln_mean per pair
@@ -951,6 +987,7 @@ struct Mhd3D {
         return sqrt(0.5 * sum + 0.5 * sqrt(sum * sum - 4 * a_square * (Bo * Bo * inv_rho)));
     }
 
+    TB_DEV double analysis_integrand(int, const double (&)[9], const double (&)[9]) const { return nan(""); }
     // calc_fast_wavespeed_roe(u_ll, u_rr, orientation) (:1415-1491): Roe averages of Cargo & Gallice
     TB_DEV void fast_wavespeed_roe(const double (&ul)[9], const double (&ur)[9], int o, double &vel_out, double &c_f) const {
         const double inv_rho_ll = 1.0 / ul[0], inv_rho_rr = 1.0 / ur[0];

@@ -45,6 +45,7 @@ struct trixi_b200_handle {
     unsigned long long *norm_linf = nullptr;
     bool opt_fused_cfl = false;           // TRIXI_B200_OPT_FUSED_CFL
     bool opt_single_face_flux = true;     // TRIXI_B200_OPT_SINGLE_FACE_FLUX
+    double *integral_buf = nullptr;       // trixi_b200_integrate: [nvars + 1] sums
     bool cfl_valid = false;               // d_cfl holds the maxima of the current u (written by the last RK stage)
     long long launches = 0;
     bool profiling = false;
@@ -859,6 +860,7 @@ TRIXI_B200_API int trixi_b200_create(const trixi_b200_desc *d, trixi_b200_handle
         return TRIXI_B200_EINVAL;
     }
     P.inv_weight0 = d->inverse_weights[0];
+    for (int q = 0; q < n; ++q) P.weights_c[q] = 1.0 / d->inverse_weights[q];
     for (int q = 0; q < n * n; ++q) P.dsplit_c[q] = d->derivative_split[q];
     if (n == 4)
         for (int q = 0; q < 16; ++q) {
@@ -1267,6 +1269,33 @@ TRIXI_B200_API int trixi_b200_calc_error_norms(trixi_b200_handle *h, double t, i
         l2_sums[v] = sums[v];
         memcpy(&linf[v], &mx[v], sizeof(double));
     }
+    *volume = sums[nv];
+    return 0;
+}
+
+TRIXI_B200_API int trixi_b200_integrate(trixi_b200_handle *h, int quantity, double *integral, double *volume) {
+    if (!h || !integral || !volume) return h ? fail(h, TRIXI_B200_EINVAL, "null argument") : TRIXI_B200_EINVAL;
+    if (quantity < TRIXI_B200_INTEGRAL_CONS || quantity > TRIXI_B200_INTEGRAL_ENTROPY_TIMEDERIVATIVE)
+        return fail(h, TRIXI_B200_EINVAL, "unknown integrand %d", quantity);
+    const bool euler = h->equation == TRIXI_B200_EQ_EULER_2D || h->equation == TRIXI_B200_EQ_EULER_3D;
+    if (quantity != TRIXI_B200_INTEGRAL_CONS && !euler)
+        return fail(h, TRIXI_B200_EINVAL, "integrand %d is registered for the compressible Euler equations only", quantity);
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const int nv = h->nvars;
+    if (!h->integral_buf) {
+        int rc = alloc_array(h, (size_t)16, &h->integral_buf);
+        if (rc) return rc;
+    }
+    CUDA_TRY(h, cudaMemsetAsync(h->integral_buf, 0, sizeof(double) * 16, h->stream));
+    h->L->integrate(h->P, quantity, h->integral_buf, h->stream);
+    h->launches++;
+    int rc = check_launch(h, "integrate kernel");
+    if (rc) return rc;
+    double sums[16];
+    CUDA_TRY(h, cudaMemcpyAsync(sums, h->integral_buf, sizeof(double) * (nv + 1), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    const int nvals = quantity == TRIXI_B200_INTEGRAL_CONS ? nv : 1;
+    for (int v = 0; v < nvals; ++v) integral[v] = sums[v];
     *volume = sums[nv];
     return 0;
 }

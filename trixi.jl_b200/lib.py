@@ -21,7 +21,7 @@ EXPORTS = [
     "trixi_b200_upload", "trixi_b200_download", "trixi_b200_device_ptr", "trixi_b200_synchronize",
     "trixi_b200_stream", "trixi_b200_rhs_host", "trixi_b200_rhs", "trixi_b200_max_dt",
     "trixi_b200_step_2n", "trixi_b200_step_2n_host", "trixi_b200_step_3sstar", "trixi_b200_step_ssp",
-    "trixi_b200_solve_2n", "trixi_b200_set_eq_param", "trixi_b200_calc_error_norms",
+    "trixi_b200_solve_2n", "trixi_b200_set_eq_param", "trixi_b200_calc_error_norms", "trixi_b200_integrate",
     "trixi_b200_calc_volume_integral", "trixi_b200_calc_surface_fluxes",
     "trixi_b200_download_surface_flux_values", "trixi_b200_calc_indicator", "trixi_b200_comm_info_size", "trixi_b200_comm_info",
     "trixi_b200_comm_connect",
@@ -75,6 +75,7 @@ def load_library(path=None):
                                         C.c_int, i64p, dp, dp]
     lib.trixi_b200_set_eq_param.argtypes = [vp, C.c_int, C.c_double]
     lib.trixi_b200_calc_error_norms.argtypes = [vp, C.c_double, C.c_int, C.c_int, dp, dp, dp, dp, dp]
+    lib.trixi_b200_integrate.argtypes = [vp, C.c_int, dp, dp]
     lib.trixi_b200_calc_volume_integral.argtypes = [vp]
     lib.trixi_b200_calc_surface_fluxes.argtypes = [vp, C.c_double]
     lib.trixi_b200_download_surface_flux_values.argtypes = [vp, dp]
@@ -216,6 +217,13 @@ class B200Backend:
         self._ck(self.lib.trixi_b200_calc_error_norms(self.h, float(t), int(ic_id), int(w.shape[0]), _dptr(V), _dptr(w),
                                                       _dptr(l2), _dptr(linf), _dptr(vol)))
         return l2, linf, float(vol[0])
+
+    def integrate(self, quantity, nvars):
+        """integrate_via_indices of one of the registered integrands over the resident u (and du): (quadrature sums,
+        quadrature volume) of this rank, not normalised."""
+        out, vol = np.zeros(nvars), np.empty(1)
+        self._ck(self.lib.trixi_b200_integrate(self.h, int(quantity), _dptr(out), _dptr(vol)))
+        return (out if quantity == 0 else out[:1]), float(vol[0])
 
     def set_eq_param(self, index, value):
         self._ck(self.lib.trixi_b200_set_eq_param(self.h, int(index), float(value)))
