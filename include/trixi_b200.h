@@ -344,6 +344,10 @@ TRIXI_B200_API int trixi_b200_integrate(trixi_b200_handle *h, int quantity, doub
 /* TRIXI_B200_OPT_L2_HINTS: L2 eviction priorities on the bulk copies of the tuned headline kernel (u evict_last until
  * its reduce-add, everything else evict_first).  Performance only. */
 #define TRIXI_B200_OPT_L2_HINTS 6
+/* TRIXI_B200_OPT_FUSED_STAGE (default 1): trixi_b200_step_3sstar / trixi_b200_step_ssp apply their stage updates
+ * (methods_3Sstar.jl:195-205, methods_SSP.jl:192-201) in the epilogue of the element kernel, as trixi_b200_step_2n
+ * always does; 0 = rhs! into du followed by a pointwise stage kernel.  Same operations, bit-identical results. */
+#define TRIXI_B200_OPT_FUSED_STAGE 7
 TRIXI_B200_API int trixi_b200_set_option(trixi_b200_handle *h, int option, int value);
 
 /* GlmSpeedCallback (glm_speed.jl:85-105) mutates equations.c_h every step */

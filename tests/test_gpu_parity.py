@@ -310,6 +310,52 @@ def test_other_integrators_match_oracle(name, alg, oracle_module):
     assert _rel_err(gpu.download(0), ref.download(0)) <= 1e-13
 
 
+_FUSED_STAGE_CASES = ["tree_3d_euler_ec",                    # headline kernel (resident form)
+                      "tree_3d_euler_source_terms",          # weak form, source terms
+                      "tree_3d_euler_ec_shima_etal",         # line-sweep kernel
+                      "tree_3d_euler_shockcapturing",        # blended line-sweep kernel
+                      "tree_3d_mhd_alfven_wave",             # GLM-MHD line-sweep kernel
+                      "structured_3d_euler_ec",              # curved flux differencing, p = 3
+                      "structured_3d_euler_source_terms",    # curved weak form
+                      "p4est_3d_nonconforming_curved_ec_p5",  # curved flux differencing, p = 5, mortars
+                      "tree_2d_euler_ec", "tree_2d_advection_mortar", "p4est_2d_advection_basic",  # generic kernels
+                      "tree_3d_euler_ec:generic"]
+
+
+@pytest.mark.parametrize("name", _FUSED_STAGE_CASES)
+@pytest.mark.parametrize("alg", ["ParsaniKetchesonDeconinck3Sstar94", "ParsaniKetchesonDeconinck3Sstar32",
+                                 "SimpleSSPRK33"])
+def test_fused_3sstar_ssp_stages(name, alg, oracle_module):
+    """The 3S* (methods_3Sstar.jl:186-207) and SSPRK33 (methods_SSP.jl:185-202) stage updates applied in the element
+    kernels' epilogues (every kernel family) against the unfused rhs! + pointwise stage kernel -- bit for bit, the
+    operations are the same -- and against the oracle; the CFL reduction fused into the last stage against max_dt."""
+    from trixi_b200 import time_integration as ti
+    generic = name.endswith(":generic")
+    semi = ELIXIRS[name.split(":")[0]].semi()
+    u = T.compute_coefficients(0.0, semi)
+    a = getattr(T, alg)()
+    ref = oracle_module.OracleBackend(semi)
+    from trixi_b200.lib import B200Backend
+    fused, plain = semi.backend(), B200Backend(semi.descriptor(), semi.u_length())
+    for b in (fused, plain):
+        if generic:
+            b.set_option(b.OPT_KERNEL_PATH, 1)
+        b.upload(0, u.ravel(order="F"))
+    plain.set_option(plain.OPT_FUSED_STAGE, 0)
+    fused.set_option(fused.OPT_FUSED_CFL, 1)
+    ref.upload(0, u)
+    dt = 0.5 * ref.max_dt()
+    for k in range(2):
+        for b in (ref, fused, plain):
+            ti._stage_loop(b, a, 0.1 + k * dt, dt)
+    assert fused.launch_count() < plain.launch_count()
+    assert np.array_equal(fused.download(0), plain.download(0))
+    assert _rel_err(fused.download(0), ref.download(0)) <= 1e-13
+    # max_dt right after the step: reduced by the last fused stage where the kernel can, else k_max_dt
+    dt_f, dt_p = fused.max_dt(), plain.max_dt()
+    assert abs(dt_f - dt_p) <= 1e-14 * dt_p
+
+
 def _shock_state(semi, seed):
     """A state with smooth and strongly varying regions so that pure-DG, blended and alpha_max elements all occur."""
     u = T.compute_coefficients(0.0, semi)

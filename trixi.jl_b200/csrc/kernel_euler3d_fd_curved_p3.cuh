@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(CurvedCfg::THREADS, CurvedCfg::MIN_BLOCKS)
     const long long e = e0 + eh;
     const double gamma = P.eq.p[0], igm1 = P.eq.p[1];
     const bool rk = P.mode != 0;
-    const bool need_ut = rk && P.rk_a != 0.0;
+    const bool need_ut = rk && P.rk_read_tmp;
     const uint32_t bu = nvalid * CONS * sizeof(double), bs = nvalid * SFV * sizeof(double);
 
     if (lane == 0) {
@@ -267,16 +267,19 @@ __global__ void __launch_bounds__(CurvedCfg::THREADS, CurvedCfg::MIN_BLOCKS)
                 for (int v = 0; v < 5; ++v) sut[(t + 16 * k) * 5 + v] = val[k][v];
         } else {
             // 2N stage (methods_2N.jl:152-158), arithmetic as in the TreeMesh kernel
-            if (need_ut) {
+            const bool rk2n = P.mode == 1;  // (modes 2 and 3, the 3S* and SSP stages, always run resident)
+            if (need_ut && rk2n) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
 #pragma unroll
                     for (int v = 0; v < 5; ++v) val[k][v] -= sut[(t + 16 * k) * 5 + v] * P.rk_a;
             }
+            if (rk2n) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
+                for (int k = 0; k < 4; ++k)
 #pragma unroll
-                for (int v = 0; v < 5; ++v) sut[(t + 16 * k) * 5 + v] = val[k][v];
+                    for (int v = 0; v < 5; ++v) sut[(t + 16 * k) * 5 + v] = val[k][v];
+            }
             if (!resident) {
                 double *const sinc = s_inc + eh * CONS;  // (behind the face tiles: no wait for their readers)
 #pragma unroll
@@ -290,7 +293,15 @@ __global__ void __launch_bounds__(CurvedCfg::THREADS, CurvedCfg::MIN_BLOCKS)
 #pragma unroll
                     for (int v = 0; v < 5; ++v) {
                         double *out_u = suo + (t + 16 * k) * 5 + v;
-                        *out_u = __dadd_rn(*out_u, __dmul_rn(val[k][v], P.rk_b_dt));
+                        if (rk2n) {
+                            *out_u = __dadd_rn(*out_u, __dmul_rn(val[k][v], P.rk_b_dt));
+                        } else {  // 3S* / SSP stage (KParams::mode 2, 3): u_tmp2 straight from global memory
+                            double *out_t = sut + (t + 16 * k) * 5 + v;
+                            double xn;
+                            *out_u = rk_stage_3s_ssp(P, val[k][v], need_ut ? *out_t : 0.0, *out_u,
+                                                     P.mode == 2 ? P.u_tmp2[e * CONS + (t + 16 * k) * 5 + v] : 0.0, xn);
+                            *out_t = xn;
+                        }
                     }
             }
         }
@@ -301,7 +312,7 @@ __global__ void __launch_bounds__(CurvedCfg::THREADS, CurvedCfg::MIN_BLOCKS)
         if (!rk) {
             tma_store(P.du + e0 * CONS, smem_u32(s_ut), bu);
         } else {
-            tma_store(P.u_tmp + e0 * CONS, smem_u32(s_ut), bu);
+            if (P.rk_write_tmp) tma_store(P.u_tmp + e0 * CONS, smem_u32(s_ut), bu);
             if (resident)
                 tma_store(P.u_out + e0 * CONS, smem_u32(s_u), bu);
             else

@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(CurvedNCfg<N, EPB_>::THREADS, 2) k_element_eul
     const long long e = e0 + le;
     const double gamma = P.eq.p[0], igm1 = P.eq.p[1];
     const bool rk = P.mode != 0;
-    const bool need_ut = rk && P.rk_a != 0.0;
+    const bool need_ut = rk && P.rk_read_tmp;
     constexpr uint32_t bu1 = CONS * sizeof(double), bs1 = SFV * sizeof(double);
 
     if (tid == 0) {
@@ -264,17 +264,20 @@ __global__ void __launch_bounds__(CurvedNCfg<N, EPB_>::THREADS, 2) k_element_eul
         }
     }
     double *const sut = s_ut + le * DU;
+    const bool rk2n = P.mode == 1;  // (modes 2 and 3, the 3S* and SSP stages, always run resident)
     if (active) {
-        if (rk && need_ut) {
+        if (rk2n && need_ut) {
 #pragma unroll
             for (int k = 0; k < N; ++k)
 #pragma unroll
                 for (int v = 0; v < 5; ++v) val[k][v] -= sut[(l + NL * k) * 5 + v] * P.rk_a;
         }
+        if (!rk || rk2n) {
 #pragma unroll
-        for (int k = 0; k < N; ++k)
+            for (int k = 0; k < N; ++k)
 #pragma unroll
-            for (int v = 0; v < 5; ++v) sut[(l + NL * k) * 5 + v] = val[k][v];  // du (mode 0) or the new u_tmp
+                for (int v = 0; v < 5; ++v) sut[(l + NL * k) * 5 + v] = val[k][v];  // du (mode 0) or the new u_tmp
+        }
     }
     if (rk) {
         if (!resident) {
@@ -293,7 +296,15 @@ __global__ void __launch_bounds__(CurvedNCfg<N, EPB_>::THREADS, 2) k_element_eul
 #pragma unroll
                 for (int v = 0; v < 5; ++v) {
                     double *out_u = suo + (l + NL * k) * 5 + v;
-                    *out_u = __dadd_rn(*out_u, __dmul_rn(val[k][v], P.rk_b_dt));
+                    if (rk2n) {
+                        *out_u = __dadd_rn(*out_u, __dmul_rn(val[k][v], P.rk_b_dt));
+                    } else {  // 3S* / SSP stage (KParams::mode 2, 3): u_tmp2 straight from global memory
+                        double *out_t = sut + (l + NL * k) * 5 + v;
+                        double xn;
+                        *out_u = rk_stage_3s_ssp(P, val[k][v], need_ut ? *out_t : 0.0, *out_u,
+                                                 P.mode == 2 ? P.u_tmp2[e * CONS + (l + NL * k) * 5 + v] : 0.0, xn);
+                        *out_t = xn;
+                    }
                 }
         }
     }
@@ -304,7 +315,7 @@ __global__ void __launch_bounds__(CurvedNCfg<N, EPB_>::THREADS, 2) k_element_eul
             if (!rk) {
                 tma_store(P.du + (e0 + qq) * CONS, smem_u32(s_ut + qq * DU), bu1);
             } else {
-                tma_store(P.u_tmp + (e0 + qq) * CONS, smem_u32(s_ut + qq * DU), bu1);
+                if (P.rk_write_tmp) tma_store(P.u_tmp + (e0 + qq) * CONS, smem_u32(s_ut + qq * DU), bu1);
                 if (resident)
                     tma_store(P.u_out + (e0 + qq) * CONS, smem_u32(s_u + qq * CONS), bu1);
                 else

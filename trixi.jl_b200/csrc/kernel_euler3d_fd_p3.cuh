@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(TunedCfg::THREADS, TunedCfg::MIN_BLOCKS)
     const long long e = e0 + eh;
     const double gamma = P.eq.p[0], igm1 = P.eq.p[1];
     const bool rk = P.mode != 0;
-    const bool need_ut = rk && P.rk_a != 0.0;
+    const bool need_ut = rk && P.rk_read_tmp;
     const uint32_t bu = nvalid * CONS * sizeof(double), bs = nvalid * SFV * sizeof(double);
 
     // L2 priorities: u is touched again by this CTA's reduce-add ~10 us later (evict_last); everything else streams
@@ -340,16 +340,19 @@ __global__ void __launch_bounds__(TunedCfg::THREADS, TunedCfg::MIN_BLOCKS)
         } else {
             // 2N stage (methods_2N.jl:152-158): u_tmp = du - u_tmp * a; u += u_tmp * (b * dt).  The product is
             // rounded before it is added, here and in the bulk reduce-add, so both forms give the same bits.
-            if (need_ut) {  // (warp-uniform)
+            const bool rk2n = P.mode == 1;  // (modes 2 and 3, the 3S* and SSP stages, always run resident)
+            if (need_ut && rk2n) {  // (warp-uniform)
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
 #pragma unroll
                     for (int v = 0; v < 5; ++v) val[k][v] -= sut[(t + 16 * k) * 5 + v] * P.rk_a;
             }
+            if (rk2n) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
+                for (int k = 0; k < 4; ++k)
 #pragma unroll
-                for (int v = 0; v < 5; ++v) sut[(t + 16 * k) * 5 + v] = val[k][v];
+                    for (int v = 0; v < 5; ++v) sut[(t + 16 * k) * 5 + v] = val[k][v];
+            }
             if (!resident) {
                 __syncwarp();  // every thread is done with surface_flux_values: b dt u_tmp takes its place
                 double *const sinc = s_inc + eh * CONS;
@@ -364,10 +367,25 @@ __global__ void __launch_bounds__(TunedCfg::THREADS, TunedCfg::MIN_BLOCKS)
                 for (int k = 0; k < 4; ++k) {
                     double *out_u = suo + (t + 16 * k) * 5;
                     double un[5];
+                    if (rk2n) {
 #pragma unroll
-                    for (int v = 0; v < 5; ++v) {
-                        un[v] = __dadd_rn(out_u[v], __dmul_rn(val[k][v], P.rk_b_dt));
-                        out_u[v] = un[v];
+                        for (int v = 0; v < 5; ++v) {
+                            un[v] = __dadd_rn(out_u[v], __dmul_rn(val[k][v], P.rk_b_dt));
+                            out_u[v] = un[v];
+                        }
+                    } else {
+                        // 3S* / SSP stage (KParams::mode 2, 3): u_tmp2 comes straight from global memory (40-byte
+                        // node records, consecutive lanes = consecutive records)
+                        const double *u2 = P.u_tmp2 + e * CONS + (t + 16 * k) * 5;
+                        double *out_t = sut + (t + 16 * k) * 5;
+#pragma unroll
+                        for (int v = 0; v < 5; ++v) {
+                            double xn;
+                            un[v] = rk_stage_3s_ssp(P, val[k][v], need_ut ? out_t[v] : 0.0, out_u[v],
+                                                    P.mode == 2 ? u2[v] : 0.0, xn);
+                            out_t[v] = xn;
+                            out_u[v] = un[v];
+                        }
                     }
                     if (P.want_cfl) {
                         // max_dt of the updated state (stepsize_dg3d.jl:8-32); max_abs_speeds
@@ -417,7 +435,7 @@ __global__ void __launch_bounds__(TunedCfg::THREADS, TunedCfg::MIN_BLOCKS)
             tma_store_hint(P.u_tmp + e0 * CONS, smem_u32(s_ut), bu, pol_stream);
             tma_reduce_add_f64_hint(P.u_out + e0 * CONS, smem_u32(s_inc), bu, pol_stream);
         } else {
-            tma_store(P.u_tmp + e0 * CONS, smem_u32(s_ut), bu);
+            if (P.rk_write_tmp) tma_store(P.u_tmp + e0 * CONS, smem_u32(s_ut), bu);
             if (resident)
                 tma_store(P.u_out + e0 * CONS, smem_u32(s_u), bu);
             else

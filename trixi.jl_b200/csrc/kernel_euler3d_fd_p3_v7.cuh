@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(TunedCfgV7::THREADS, TunedCfgV7::MIN_BLOCKS)
     const long long e = P.elem_begin + blockIdx.x;
     const double gamma = P.eq.p[0], inv_gm1 = P.eq.p[1];
     const bool rk = P.mode != 0;
-    const bool need_ut = rk && P.rk_a != 0.0;
+    const bool need_ut = rk && P.rk_read_tmp;
 
     // 0. TMA loads of the contiguous element records
     if (lane == 0) {

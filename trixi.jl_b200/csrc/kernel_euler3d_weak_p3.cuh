@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(WeakCfg::THREADS, CURVED ? 12 : WeakCfg::MIN_B
     const long long e = P.elem_begin + blockIdx.x;
     const double gamma = P.eq.p[0];
     const bool rk = P.mode != 0;
-    const bool need_ut = rk && P.rk_a != 0.0;
+    const bool need_ut = rk && P.rk_read_tmp;
     const bool have_src = WITH_SURFACE && P.source_terms != TRIXI_B200_SRC_NONE;
 
     if (lane == 0) {
@@ -220,12 +220,25 @@ __global__ void __launch_bounds__(WeakCfg::THREADS, CURVED ? 12 : WeakCfg::MIN_B
             // 2N stage (methods_2N.jl:152-158): u_tmp = du - u_tmp * a; u += u_tmp * (b * dt)
             double *out_u = s_u + n * 5;
             double un[5];
+            if (P.mode == 1) {
 #pragma unroll
-            for (int v = 0; v < 5; ++v) {
-                const double tmp = need_ut ? val[v] - out_t[v] * P.rk_a : val[v];
-                out_t[v] = tmp;
-                un[v] = out_u[v] + tmp * P.rk_b_dt;
-                out_u[v] = un[v];
+                for (int v = 0; v < 5; ++v) {
+                    const double tmp = need_ut ? val[v] - out_t[v] * P.rk_a : val[v];
+                    out_t[v] = tmp;
+                    un[v] = out_u[v] + tmp * P.rk_b_dt;
+                    out_u[v] = un[v];
+                }
+            } else {
+                // 3S* / SSP stage (KParams::mode 2, 3): u_tmp2 comes straight from global memory (40-byte node
+                // records, consecutive lanes = consecutive records)
+                const double *u2 = P.u_tmp2 + (e * 64 + n) * 5;
+#pragma unroll
+                for (int v = 0; v < 5; ++v) {
+                    double xn;
+                    un[v] = rk_stage_3s_ssp(P, val[v], need_ut ? out_t[v] : 0.0, out_u[v], P.mode == 2 ? u2[v] : 0.0, xn);
+                    out_t[v] = xn;
+                    out_u[v] = un[v];
+                }
             }
             if (P.want_cfl) {
                 // max_dt of the updated state (stepsize_dg3d.jl:8-32; curved :94-123), as in the flux-differencing kernel
@@ -277,7 +290,7 @@ __global__ void __launch_bounds__(WeakCfg::THREADS, CURVED ? 12 : WeakCfg::MIN_B
         if (!rk) {
             tma_store(P.du + e * CONS, smem_u32(s_ut), bu);
         } else {
-            tma_store(P.u_tmp + e * CONS, smem_u32(s_ut), bu);
+            if (P.rk_write_tmp) tma_store(P.u_tmp + e * CONS, smem_u32(s_ut), bu);
             tma_store(P.u_out + e * CONS, smem_u32(s_u), bu);
         }
         tma_store_commit_and_wait_read();

@@ -288,7 +288,7 @@ __global__ void __launch_bounds__(LineSweepCfg<EQ>::THREADS, LineSweepCfg<EQ>::M
     const int lane = threadIdx.x;
     const long long e = P.elem_begin + blockIdx.x;
     const bool rk = P.mode != 0;
-    const bool need_ut = rk && P.rk_a != 0.0;
+    const bool need_ut = rk && P.rk_read_tmp;
 
     if (lane == 0) {
         mbar_init(bar, 1);
@@ -597,12 +597,24 @@ __global__ void __launch_bounds__(LineSweepCfg<EQ>::THREADS, LineSweepCfg<EQ>::M
             // 2N stage (methods_2N.jl:152-158): u_tmp = du - u_tmp * a; u += u_tmp * (b * dt)
             double *out_u = s_u + n * NV;
             double un[NV];
+            if (P.mode == 1) {
 #pragma unroll
-            for (int v = 0; v < NV; ++v) {
-                const double tmp = need_ut ? val[v] - out_t[v] * P.rk_a : val[v];
-                out_t[v] = tmp;
-                un[v] = out_u[v] + tmp * P.rk_b_dt;
-                out_u[v] = un[v];
+                for (int v = 0; v < NV; ++v) {
+                    const double tmp = need_ut ? val[v] - out_t[v] * P.rk_a : val[v];
+                    out_t[v] = tmp;
+                    un[v] = out_u[v] + tmp * P.rk_b_dt;
+                    out_u[v] = un[v];
+                }
+            } else {
+                // 3S* / SSP stage (KParams::mode 2, 3): u_tmp2 comes straight from global memory
+                const double *u2 = P.u_tmp2 + (e * 64 + n) * NV;
+#pragma unroll
+                for (int v = 0; v < NV; ++v) {
+                    double xn;
+                    un[v] = rk_stage_3s_ssp(P, val[v], need_ut ? out_t[v] : 0.0, out_u[v], P.mode == 2 ? u2[v] : 0.0, xn);
+                    out_t[v] = xn;
+                    out_u[v] = un[v];
+                }
             }
             if (P.want_cfl) {
                 double lam[3];
@@ -631,7 +643,7 @@ __global__ void __launch_bounds__(LineSweepCfg<EQ>::THREADS, LineSweepCfg<EQ>::M
         if (!rk) {
             tma_store(P.du + e * CONS, smem_u32(s_ut), bu);
         } else {
-            tma_store(P.u_tmp + e * CONS, smem_u32(s_ut), bu);
+            if (P.rk_write_tmp) tma_store(P.u_tmp + e * CONS, smem_u32(s_ut), bu);
             tma_store(P.u_out + e * CONS, smem_u32(s_u), bu);
         }
         tma_store_commit_and_wait_read();

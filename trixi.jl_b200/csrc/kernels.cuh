@@ -52,9 +52,20 @@ struct KParams {
     EqParams eq;
     int volume_integral, volume_flux, surface_flux, source_terms;
     double t;
-    // RK stage (mode 1): u_tmp = du - u_tmp * a; u = u + u_tmp * b_dt
-    int mode;  // 0: write du, 1: 2N stage update
-    double rk_a, rk_b_dt;
+    // RK stage fused into the element kernels.  mode 0: write du.
+    // mode 1, 2N (methods_2N.jl:152-158): u_tmp = du - u_tmp * a; u = u + u_tmp * b_dt
+    // mode 2, 3S* (methods_3Sstar.jl:195-205): u_tmp (= u_tmp1) += delta * u;
+    //         u = gamma1 * u + gamma2 * u_tmp + gamma3 * u_tmp2 + (beta dt) * du;  rk_k = {delta, gamma1, gamma2, gamma3},
+    //         rk_b_dt = beta dt
+    // mode 3, SSP (methods_SSP.jl:192-201): u = (numerator_a * u_tmp + numerator_b * (u + dt du)) / denominator;
+    //         rk_k = {numerator_a, numerator_b, denominator}, rk_b_dt = dt
+    // rk_read_tmp = 0: the kernel takes the known value of u_tmp instead of reading it (2N: first stage, a = 0; 3S*:
+    // first stage, u_tmp1 = 0; SSP: first stage, u_tmp = u, which the kernel then also writes: no copy pass).
+    // rk_write_tmp = 0: u_tmp is left alone (SSP after the first stage).
+    int mode;
+    int rk_read_tmp, rk_write_tmp;
+    double rk_a, rk_b_dt, rk_k[4];
+    const double *u_tmp2;  // 3S*: the third register (read only)
     // CFL fused output: per-block max of invJ * sum_d max_nodes lambda_d, encoded as ordered uint64
     unsigned long long *cfl_key;  // kCflSlots partial maxima (spread same-address atomics over L2 slices)
     int want_cfl;                 // RK stage kernels that support it also reduce the CFL speed of the updated u
@@ -128,6 +139,23 @@ TB_DEV unsigned long long cfl_encode(double v) {
     // stepsize_dg3d.jl:24-28)
     if (isnan(v)) return 0x7ff8000000000000ull;
     return (unsigned long long)__double_as_longlong(v);
+}
+
+// Fused stage updates of the 3S* and SSP integrators for one value (P.mode 2 and 3; see KParams): d = du, x = u_tmp
+// (not looked at when !P.rk_read_tmp), u, u2 = u_tmp2 (3S* only).  Returns the new u; x_new is what u_tmp receives when
+// P.rk_write_tmp.  The operations are those of the unfused k_stage_3sstar / k_stage_ssp, so both paths give the same bits.
+TB_DEV double rk_stage_3s_ssp(const KParams &P, double d, double x, double u, double u2, double &x_new) {
+    if (P.mode == 2) {
+        // u_tmp1 += delta * u; u = gamma1 u + gamma2 u_tmp1 + gamma3 u_tmp2 + beta dt du (methods_3Sstar.jl:195-205)
+        const double t1 = P.rk_read_tmp ? fma(P.rk_k[0], u, x) : P.rk_k[0] * u;
+        x_new = t1;
+        return fma(P.rk_b_dt, d, fma(P.rk_k[3], u2, fma(P.rk_k[2], t1, P.rk_k[1] * u)));
+    }
+    // u = (numerator_a u_tmp + numerator_b (u + dt du)) / denominator (methods_SSP.jl:192-201); u_tmp = u in stage 1
+    const double xx = P.rk_read_tmp ? x : u;
+    x_new = xx;
+    const double ue = fma(P.rk_b_dt, d, u);
+    return fma(P.rk_k[0], xx, P.rk_k[1] * ue) / P.rk_k[2];
 }
 
 // ---- 1. interfaces ------------------------------------------------------------------------------
@@ -968,15 +996,25 @@ __global__ void __launch_bounds__(ElemCfg<EQ, N>::THREADS) k_element(const KPara
     if (P.mode == 0) {
 #pragma unroll
         for (int v = 0; v < NV; ++v) P.du[off + v] = acc[v];
-    } else {
+    } else if (P.mode == 1) {
         // 2N stage (methods_2N.jl:152-158): u_tmp = du - u_tmp * a; u += u_tmp * (b * dt)
 #pragma unroll
         for (int v = 0; v < NV; ++v) {
             // first stage: a = 0 and u_tmp = 0 (methods_2N.jl:144), so du - 0 * 0 == du exactly; skipping
             // the read also removes the `u_tmp .= 0` sweep
-            const double tmp = P.rk_a == 0.0 ? acc[v] : acc[v] - P.u_tmp[off + v] * P.rk_a;
+            const double tmp = P.rk_read_tmp ? acc[v] - P.u_tmp[off + v] * P.rk_a : acc[v];
             P.u_tmp[off + v] = tmp;
             un[v] = un[v] + tmp * P.rk_b_dt;
+            P.u_out[off + v] = un[v];
+        }
+    } else {
+        // 3S* / SSP stage
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            double xn;
+            un[v] = rk_stage_3s_ssp(P, acc[v], P.rk_read_tmp ? P.u_tmp[off + v] : 0.0, un[v],
+                                    P.mode == 2 ? P.u_tmp2[off + v] : 0.0, xn);
+            if (P.rk_write_tmp) P.u_tmp[off + v] = xn;
             P.u_out[off + v] = un[v];
         }
     }
@@ -1718,12 +1756,22 @@ __global__ void __launch_bounds__(ElemCfg<EQ, N>::THREADS) k_element_curved(cons
     if (P.mode == 0) {
 #pragma unroll
         for (int v = 0; v < NV; ++v) P.du[off + v] = acc[v];
-    } else {
+    } else if (P.mode == 1) {
 #pragma unroll
         for (int v = 0; v < NV; ++v) {
-            const double tmp = P.rk_a == 0.0 ? acc[v] : acc[v] - P.u_tmp[off + v] * P.rk_a;
+            const double tmp = P.rk_read_tmp ? acc[v] - P.u_tmp[off + v] * P.rk_a : acc[v];
             P.u_tmp[off + v] = tmp;
             P.u_out[off + v] = un[v] + tmp * P.rk_b_dt;
+        }
+    } else {
+        // 3S* / SSP stage
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            double xn;
+            const double unew = rk_stage_3s_ssp(P, acc[v], P.rk_read_tmp ? P.u_tmp[off + v] : 0.0, un[v],
+                                                P.mode == 2 ? P.u_tmp2[off + v] : 0.0, xn);
+            if (P.rk_write_tmp) P.u_tmp[off + v] = xn;
+            P.u_out[off + v] = unew;
         }
     }
 }

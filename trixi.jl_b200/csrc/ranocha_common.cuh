@@ -107,7 +107,8 @@ TB_DEV void ranocha_pair_normal(const double *L, const double *R, int d, double 
 TB_DEV_HOST bool tuned_u_resident(const KParams &P, bool with_surface) {
     const bool have_src = with_surface && P.source_terms != TRIXI_B200_SRC_NONE;
     const bool rk = P.mode != 0;
-    return have_src || (rk && (P.want_cfl || !P.rk_reduce_update || P.u_out != P.u));
+    // (the 3S* and SSP stage updates, modes 2 and 3, are not u += increment: they need u in the epilogue)
+    return have_src || (rk && (P.mode != 1 || P.want_cfl || !P.rk_reduce_update || P.u_out != P.u));
 }
 
 }  // namespace tb

@@ -45,6 +45,7 @@ struct trixi_b200_handle {
     unsigned long long *norm_linf = nullptr;
     bool opt_fused_cfl = false;           // TRIXI_B200_OPT_FUSED_CFL
     bool opt_single_face_flux = true;     // TRIXI_B200_OPT_SINGLE_FACE_FLUX
+    bool opt_fused_stage = true;          // TRIXI_B200_OPT_FUSED_STAGE
     double *integral_buf = nullptr;       // trixi_b200_integrate: [nvars + 1] sums
     bool cfl_valid = false;               // d_cfl holds the maxima of the current u (written by the last RK stage)
     long long launches = 0;
@@ -551,6 +552,8 @@ int run_step_2n(trixi_b200_handle *h, double t, double dt, const double *a, cons
         h->P.mode = 1;
         h->P.rk_a = a[s];
         h->P.rk_b_dt = b[s] * dt;
+        h->P.rk_read_tmp = a[s] != 0.0;  // a = 0: du - 0 * u_tmp = du, u_tmp is not read (first stage: no zero fill)
+        h->P.rk_write_tmp = 1;
         if (fuse_cfl && s == nstages - 1) {
             // the last stage also reduces the CFL wave speeds of the state it writes (max_dt without a pass over u)
             CUDA_TRY(h, cudaMemsetAsync(h->d_cfl, 0, kCflSlots * sizeof(unsigned long long), h->stream));
@@ -570,6 +573,24 @@ int run_step_2n(trixi_b200_handle *h, double t, double dt, const double *a, cons
     h->cfl_valid = fuse_cfl;
     return 0;
 }
+
+// One stage of a 3S* or SSP scheme with the update fused into the element kernel (KParams::mode 2 / 3, set up by the
+// caller): surface fluxes of u, then the element kernel writes u (and u_tmp) instead of du.  The last stage also
+// reduces the CFL wave speeds where the kernel can.
+int run_fused_stage(trixi_b200_handle *h, double t_stage, bool cfl) {
+    if (cfl) {
+        CUDA_TRY(h, cudaMemsetAsync(h->d_cfl, 0, kCflSlots * sizeof(unsigned long long), h->stream));
+        h->P.want_cfl = 1;
+    }
+    int rc = run_all_surface_fluxes(h, t_stage);
+    if (rc == 0) rc = run_element(h, true);
+    h->P.mode = 0;
+    h->P.want_cfl = 0;
+    return rc;
+}
+
+// every element kernel but the previous-generation headline kernel (TRIXI_B200_OPT_KERNEL_PATH 2) knows modes 2 and 3
+bool stage_fusable(const trixi_b200_handle *h) { return h->opt_fused_stage && h->P.kernel_path != 2; }
 
 }  // namespace
 
@@ -992,6 +1013,10 @@ TRIXI_B200_API int trixi_b200_create(const trixi_b200_desc *d, trixi_b200_handle
     P.mode = 0;
     P.rk_a = 0.0;
     P.rk_b_dt = 0.0;
+    P.rk_read_tmp = 0;
+    P.rk_write_tmp = 0;
+    P.u_tmp2 = nullptr;
+    for (double &k : P.rk_k) k = 0.0;
 
     // faces shared with other ranks: sorted by (neighbour rank, global interface id) by the caller
     h->nmpi = d->nmpiinterfaces;
@@ -1347,9 +1372,32 @@ TRIXI_B200_API int trixi_b200_step_3sstar(trixi_b200_handle *h, double t, double
     const size_t n = (size_t)h->ulen, bytes = n * sizeof(double);
     CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
     h->cfl_valid = false;
-    // u_tmp1 .= 0; u_tmp2 .= u (methods_3Sstar.jl:187-188)
-    CUDA_TRY(h, cudaMemsetAsync(h->vec[2], 0, bytes, h->stream));
+    // u_tmp2 .= u (methods_3Sstar.jl:188)
     CUDA_TRY(h, cudaMemcpyAsync(h->vec_tmp2, h->vec[0], bytes, cudaMemcpyDeviceToDevice, h->stream));
+    if (stage_fusable(h)) {
+        // The stage update (methods_3Sstar.jl:195-205) runs in the element kernel's epilogue: du never reaches memory
+        // and u is read once.  u_tmp1 .= 0 (:187) is not swept either: the first stage takes it as zero.
+        const bool fuse_cfl = h->opt_fused_cfl && h->L->fuses_cfl(h->P);
+        h->P.u_tmp2 = h->vec_tmp2;
+        for (int s = 0; s < nstages; ++s) {
+            h->P.mode = 2;
+            h->P.rk_k[0] = delta[s];
+            h->P.rk_k[1] = gamma1[s];
+            h->P.rk_k[2] = gamma2[s];
+            h->P.rk_k[3] = gamma3[s];
+            h->P.rk_b_dt = beta[s] * dt;
+            h->P.rk_read_tmp = s > 0;
+            h->P.rk_write_tmp = 1;
+            int rc = run_fused_stage(h, t + dt * c[s], fuse_cfl && s == nstages - 1);
+            if (rc) return rc;
+        }
+        h->cfl_valid = fuse_cfl;
+        CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
+        h->have_elapsed = true;
+        return 0;
+    }
+    // u_tmp1 .= 0 (:187)
+    CUDA_TRY(h, cudaMemsetAsync(h->vec[2], 0, bytes, h->stream));
     for (int s = 0; s < nstages; ++s) {
         int rc = run_rhs(h, t + dt * c[s]);
         if (rc) return rc;
@@ -1375,6 +1423,27 @@ TRIXI_B200_API int trixi_b200_step_ssp(trixi_b200_handle *h, double t, double dt
     const size_t n = (size_t)h->ulen, bytes = n * sizeof(double);
     CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
     h->cfl_valid = false;
+    if (stage_fusable(h)) {
+        // The stage update (methods_SSP.jl:192-201) runs in the element kernel's epilogue.  u_tmp .= u (:185) is not a
+        // copy pass: the first stage takes u for u_tmp and writes it out beside the new u; later stages only read it.
+        const bool fuse_cfl = h->opt_fused_cfl && h->L->fuses_cfl(h->P);
+        for (int s = 0; s < nstages; ++s) {
+            h->P.mode = 3;
+            h->P.rk_k[0] = numerator_a[s];
+            h->P.rk_k[1] = numerator_b[s];
+            h->P.rk_k[2] = denominator[s];
+            h->P.rk_k[3] = 0.0;
+            h->P.rk_b_dt = dt;
+            h->P.rk_read_tmp = s > 0;
+            h->P.rk_write_tmp = s == 0;
+            int rc = run_fused_stage(h, t + dt * c[s], fuse_cfl && s == nstages - 1);
+            if (rc) return rc;
+        }
+        h->cfl_valid = fuse_cfl;
+        CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
+        h->have_elapsed = true;
+        return 0;
+    }
     // u_tmp .= u (methods_SSP.jl:185)
     CUDA_TRY(h, cudaMemcpyAsync(h->vec[2], h->vec[0], bytes, cudaMemcpyDeviceToDevice, h->stream));
     for (int s = 0; s < nstages; ++s) {
@@ -1463,6 +1532,10 @@ TRIXI_B200_API int trixi_b200_set_option(trixi_b200_handle *h, int option, int v
     case TRIXI_B200_OPT_SINGLE_FACE_FLUX:
         if (value != 0 && value != 1) return fail(h, TRIXI_B200_EINVAL, "single-face-flux option must be 0 or 1");
         h->opt_single_face_flux = value != 0;
+        return 0;
+    case TRIXI_B200_OPT_FUSED_STAGE:
+        if (value != 0 && value != 1) return fail(h, TRIXI_B200_EINVAL, "fused-stage option must be 0 or 1");
+        h->opt_fused_stage = value != 0;
         return 0;
     case TRIXI_B200_OPT_RK_REDUCE_UPDATE:
         if (value != 0 && value != 1) return fail(h, TRIXI_B200_EINVAL, "reduce-update option must be 0 or 1");

@@ -269,6 +269,7 @@ class B200Backend:
     OPT_RK_REDUCE_UPDATE = 4
     OPT_SINGLE_FACE_FLUX = 5
     OPT_L2_HINTS = 6
+    OPT_FUSED_STAGE = 7
 
     def set_option(self, option, value):
         self._ck(self.lib.trixi_b200_set_option(self.h, int(option), int(value)))
