@@ -559,6 +559,8 @@ def _ranked_semis(name, world):
                                   "p4est_3d_euler_source_terms_nonperiodic", "p4est_3d_curved_level1",
                                   "tree_3d_euler_shockcapturing", "tree_2d_euler_shockcapturing",
                                   "tree_2d_euler_vortex_shockcapturing",
+                                  # shock capturing on curved forests across ranks
+                                  "p4est_2d_euler_sedov", "p4est_3d_euler_sedov",
                                   # mortars that straddle ranks (MPI mortars), also with nonconservative terms and with
                                   # the blending factor smoothed across them
                                   "tree_2d_advection_mortar", "tree_3d_euler_mortar", "tree_3d_mhd_alfven_wave_mortar",
@@ -573,7 +575,7 @@ def test_halo_exchange_matches_single_rank(name, world, oracle_module):
     base, semis = _ranked_semis(name, world)
     # shock capturing: a state with pure-DG, blended and alpha_max elements, so that the smoothing across the
     # rank boundaries (the neighbour's alpha travels with its face state) matters
-    if "shockcapturing" in name:
+    if "shockcapturing" in name or "sedov" in name:
         u = _shock_state(base, 8)
     elif "nonconforming" in name:
         # bounded fluctuations: the interpolation of a wild random state to the small faces leaves the admissible set

@@ -2095,9 +2095,13 @@ __global__ void __launch_bounds__(256) k_mpi_pack_p4est(const KParams P) {
     int vn, sfn, dir;
     p4_face<ND, N>(P.mpi_node_indices + I * ND, i, j, vn, sfn, dir);
     const double *pu = P.u + (element * NN + vn) * NV;
-    double *dst = P.peer_recv[P.mpi_peer_slot[I]] + (P.mpi_remote_index[I] * NF + fn) * NV;
+    const int slot = P.mpi_peer_slot[I];
+    double *dst = P.peer_recv[slot] + (P.mpi_remote_index[I] * NF + fn) * NV;
 #pragma unroll
     for (int v = 0; v < NV; ++v) dst[v] = pu[v];
+    // shock capturing: the unsmoothed blending factor of the local element travels with its face (as on TreeMeshes)
+    if (fn == 0 && P.volume_integral == TRIXI_B200_VOLINT_SHOCK_CAPTURING_HG)
+        P.peer_recv[slot][P.mpi_peer_nmpi[slot] * NF * NV + P.mpi_remote_index[I]] = P.alpha_raw[element];
 }
 
 // calc_mpi_interface_flux! (dgsem_p4est/dg_3d_parallel.jl:167-273): each rank uses the outward normal of its

@@ -670,8 +670,6 @@ TRIXI_B200_API int trixi_b200_create(const trixi_b200_desc *d, trixi_b200_handle
         return fail(nullptr, TRIXI_B200_EINVAL, "unsupported volume integral type %d", d->volume_integral);
     if (d->volume_integral == TRIXI_B200_VOLINT_SHOCK_CAPTURING_HG) {
         if (d->mesh_kind != TRIXI_B200_MESH_TREE) {
-            if (d->world_size > 1)
-                return fail(nullptr, TRIXI_B200_EINVAL, "VolumeIntegralShockCapturingHG on curved meshes is single-rank in this build");
             for (int a = 0; a < d->ndims; ++a)
                 if (!d->subcell_normal_vectors[a])
                     return fail(nullptr, TRIXI_B200_EINVAL,
