@@ -58,8 +58,9 @@ enum {
     /* VolumeIntegralShockCapturingHG(indicator; volume_flux_dg, volume_flux_fv) (solvers/dg.jl; driver
      * dgsem/calc_volume_integral.jl:231-272): per element a blend (1 - alpha) flux differencing + alpha first-order
      * subcell finite volumes (fv_kernel! dg_3d.jl:268-306), alpha from IndicatorHennemannGassner.  Compressible
-     * Euler on TreeMesh, P4estMesh (across ranks the neighbour's alpha travels with the halo exchange) and
-     * StructuredMesh; curved meshes need subcell_normal_vectors below. */
+     * Euler and ideal GLM-MHD (calcflux_fv! with nonconservative terms, dg_3d.jl:391-452) on TreeMesh, P4estMesh
+     * (across ranks the neighbour's alpha travels with the halo exchange) and StructuredMesh; curved meshes need
+     * subcell_normal_vectors below. */
     TRIXI_B200_VOLINT_SHOCK_CAPTURING_HG = 2
 };
 

@@ -1276,7 +1276,8 @@ static void flux_differencing_kernel_turbo(const trixi_b200_desc *d, const eqn_t
 }
 
 /* flux_differencing_kernel! with nonconservative terms dg_3d.jl:216-266: the nonsymmetric part */
-static void flux_differencing_noncons(const trixi_b200_desc *d, const eqn_t *eq, double *du, const double *u) {
+static void flux_differencing_noncons(const trixi_b200_desc *d, const eqn_t *eq, double *du, const double *u,
+                                      double alpha) {
     int n = d->nnodes, nv = d->nvars;
     const double *Ds = d->derivative_split;
     int stride[3] = {1, n, n * n};
@@ -1295,7 +1296,9 @@ static void flux_differencing_noncons(const trixi_b200_desc *d, const eqn_t *eq,
                         double w = Ds[idx[a] + n * ii];
                         for (int v = 0; v < nv; ++v) integral_contribution[v] = integral_contribution[v] + w * g[v];
                     }
-                for (int v = 0; v < nv; ++v) du[nv * node + v] = du[nv * node + v] + 0.5 * integral_contribution[v];
+                /* multiply_add_to_node_vars!(du, alpha * 0.5, integral_contribution, ...) (dg_3d.jl:259-262) */
+                for (int v = 0; v < nv; ++v)
+                    du[nv * node + v] = du[nv * node + v] + (alpha * 0.5) * integral_contribution[v];
             }
 }
 
@@ -1304,6 +1307,16 @@ static void flux_differencing_noncons(const trixi_b200_desc *d, const eqn_t *eq,
 /* density_pressure / density / pressure (compressible_euler_3d.jl:1937-1956, compressible_euler_2d.jl analogues) */
 static inline double indicator_variable(const trixi_b200_desc *d, const eqn_t *eq, const double *u) {
     int nd = d->ndims;
+    if (d->equation == TRIXI_B200_EQ_MHD_3D) {
+        /* density, pressure, density_pressure of the ideal GLM-MHD equations (ideal_glm_mhd_3d.jl:1318-1347) */
+        double rho = u[0], mom2 = u[1] * u[1] + u[2] * u[2] + u[3] * u[3];
+        double mag = u[5] * u[5] + u[6] * u[6] + u[7] * u[7], psi2 = u[8] * u[8];
+        switch (d->indicator_variable) {
+        case TRIXI_B200_INDVAR_DENSITY: return rho;
+        case TRIXI_B200_INDVAR_PRESSURE: return (eq->gamma - 1) * (u[4] - 0.5 * (mom2 / rho + mag + psi2));
+        default: return (eq->gamma - 1) * (rho * u[4] - 0.5 * (mom2 + rho * (mag + psi2)));
+        }
+    }
     double rho = u[0], rho_e = u[nd + 1], q = 0.0;
     for (int a = 0; a < nd; ++a) q = q + u[1 + a] * u[1 + a];
     switch (d->indicator_variable) {
@@ -1451,6 +1464,19 @@ static void fv_kernel(const trixi_b200_desc *d, const eqn_t *eq, double *du, con
                     double fl[MAXV] = {0}, fr[MAXV] = {0}; /* fstar_R[idx], fstar_L[idx + 1] */
                     if (idx[a] > 0) numflux(eq, d->volume_flux_fv, u + nv * (node - stride[a]), u + nv * node, a, fl);
                     if (idx[a] < n - 1) numflux(eq, d->volume_flux_fv, u + nv * node, u + nv * (node + stride[a]), a, fr);
+                    if (flux_has_noncons(d->volume_flux_fv)) {
+                        /* calcflux_fv! with nonconservative terms (dg_3d.jl:391-452): fstar_R[idx] = flux + 0.5
+                         * g(u_rr, u_ll), fstar_L[idx + 1] = flux + 0.5 g(u_ll, u_rr): the node's own state comes first */
+                        double g[MAXV];
+                        if (idx[a] > 0) {
+                            mhd_noncons_powell(eq, u + nv * node, u + nv * (node - stride[a]), a, g);
+                            for (int v = 0; v < nv; ++v) fl[v] = fl[v] + 0.5 * g[v];
+                        }
+                        if (idx[a] < n - 1) {
+                            mhd_noncons_powell(eq, u + nv * node, u + nv * (node + stride[a]), a, g);
+                            for (int v = 0; v < nv; ++v) fr[v] = fr[v] + 0.5 * g[v];
+                        }
+                    }
                     for (int v = 0; v < nv; ++v) sum[v] = sum[v] + iw[idx[a]] * (fr[v] - fl[v]);
                 }
                 for (int v = 0; v < nv; ++v) du[nv * node + v] = du[nv * node + v] + alpha * sum[v];
@@ -1467,10 +1493,13 @@ void oracle_calc_volume_integral(const trixi_b200_desc *d, double *du, const dou
         const double atol = 1.8189894035458565e-12; /* max(100 eps, eps^0.75) for Float64 */
 #pragma omp parallel for schedule(static)
         for (int64_t e = 0; e < d->nelements; ++e) {
-            if (fabs(alpha[e]) <= atol) /* isapprox(alpha, 0, atol): pure DG */
+            const int noncons = flux_has_noncons(d->volume_flux);
+            if (fabs(alpha[e]) <= atol) { /* isapprox(alpha, 0, atol): pure DG */
                 flux_differencing_kernel(d, &eq, du + e * esz, u + e * esz, 1.0);
-            else {
+                if (noncons) flux_differencing_noncons(d, &eq, du + e * esz, u + e * esz, 1.0);
+            } else {
                 flux_differencing_kernel(d, &eq, du + e * esz, u + e * esz, 1 - alpha[e]);
+                if (noncons) flux_differencing_noncons(d, &eq, du + e * esz, u + e * esz, 1 - alpha[e]);
                 fv_kernel(d, &eq, du + e * esz, u + e * esz, alpha[e]);
             }
         }
@@ -1487,7 +1516,7 @@ void oracle_calc_volume_integral(const trixi_b200_desc *d, double *du, const dou
             flux_differencing_kernel_turbo(d, &eq, du + e * esz, u + e * esz, 1.0);
         else {
             flux_differencing_kernel(d, &eq, du + e * esz, u + e * esz, 1.0);
-            if (flux_has_noncons(d->volume_flux)) flux_differencing_noncons(d, &eq, du + e * esz, u + e * esz);
+            if (flux_has_noncons(d->volume_flux)) flux_differencing_noncons(d, &eq, du + e * esz, u + e * esz, 1.0);
         }
     }
 }
@@ -1779,7 +1808,7 @@ static void flux_differencing_kernel_curved(const trixi_b200_desc *d, const eqn_
 /* nonconservative volume terms on curved meshes (dgsem_structured/dg_3d.jl:177-283): for every node
  * 0.5 sum_d sum_ii D_split[i, ii] g(u_node, u_ii, 0.5 (Ja^d_node + Ja^d_ii)) */
 static void flux_differencing_noncons_curved(const trixi_b200_desc *d, const eqn_t *eq, double *du, const double *u,
-                                             int64_t e) {
+                                             int64_t e, double alpha) {
     int n = d->nnodes, nv = d->nvars;
     const double *Ds = d->derivative_split;
     int stride[3] = {1, n, n * n};
@@ -1803,7 +1832,8 @@ static void flux_differencing_noncons_curved(const trixi_b200_desc *d, const eqn
                         for (int v = 0; v < nv; ++v) integral_contribution[v] = integral_contribution[v] + w * g[v];
                     }
                 }
-                for (int v = 0; v < nv; ++v) du[nv * node + v] = du[nv * node + v] + 0.5 * integral_contribution[v];
+                for (int v = 0; v < nv; ++v)
+                    du[nv * node + v] = du[nv * node + v] + (alpha * 0.5) * integral_contribution[v];
             }
 }
 
@@ -1843,6 +1873,15 @@ static void fv_kernel_curved(const trixi_b200_desc *d, const eqn_t *eq, double *
                             numflux_normal(eq, d->volume_flux_fv, u + nv * (node - stride[a]), u + nv * node, nrm, fl);
                         else
                             numflux_normal(eq, d->volume_flux_fv, u + nv * node, u + nv * (node + stride[a]), nrm, fr);
+                        if (flux_has_noncons(d->volume_flux_fv)) {
+                            /* calcflux_fv! with nonconservative terms (dgsem_structured/dg_3d.jl:438-530): ftilde_R =
+                             * ftilde + 0.5 g(u_rr, u_ll, n), ftilde_L = ftilde + 0.5 g(u_ll, u_rr, n) */
+                            double g[MAXV];
+                            double *f = side == 0 ? fl : fr;
+                            mhd_noncons_powell_normal(eq, u + nv * node,
+                                                      u + nv * (side == 0 ? node - stride[a] : node + stride[a]), nrm, g);
+                            for (int v = 0; v < nv; ++v) f[v] = f[v] + 0.5 * g[v];
+                        }
                     }
                     for (int v = 0; v < nv; ++v) sum[v] = sum[v] + iw[idx[a]] * (fr[v] - fl[v]);
                 }
@@ -1860,10 +1899,13 @@ void oracle_calc_volume_integral_curved(const trixi_b200_desc *d, double *du, co
         const double atol = 1.8189894035458565e-12; /* max(100 eps, eps^0.75) for Float64 */
 #pragma omp parallel for schedule(static)
         for (int64_t e = 0; e < d->nelements; ++e) {
-            if (fabs(alpha[e]) <= atol)
+            const int noncons = flux_has_noncons(d->volume_flux);
+            if (fabs(alpha[e]) <= atol) {
                 flux_differencing_kernel_curved(d, &eq, du + e * esz, u + e * esz, e, 1.0);
-            else {
+                if (noncons) flux_differencing_noncons_curved(d, &eq, du + e * esz, u + e * esz, e, 1.0);
+            } else {
                 flux_differencing_kernel_curved(d, &eq, du + e * esz, u + e * esz, e, 1 - alpha[e]);
+                if (noncons) flux_differencing_noncons_curved(d, &eq, du + e * esz, u + e * esz, e, 1 - alpha[e]);
                 fv_kernel_curved(d, &eq, du + e * esz, u + e * esz, e, alpha[e]);
             }
         }
@@ -1876,7 +1918,8 @@ void oracle_calc_volume_integral_curved(const trixi_b200_desc *d, double *du, co
             weak_form_kernel_curved(d, &eq, du + e * esz, u + e * esz, e);
         else {
             flux_differencing_kernel_curved(d, &eq, du + e * esz, u + e * esz, e, 1.0);
-            if (flux_has_noncons(d->volume_flux)) flux_differencing_noncons_curved(d, &eq, du + e * esz, u + e * esz, e);
+            if (flux_has_noncons(d->volume_flux))
+                flux_differencing_noncons_curved(d, &eq, du + e * esz, u + e * esz, e, 1.0);
         }
     }
 }

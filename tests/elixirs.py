@@ -879,6 +879,48 @@ ELIXIRS.update({e.name: e for e in [
 ]})
 
 
+# ---- shock capturing for GLM-MHD (VolumeIntegralShockCapturingHG with nonconservative terms) -----------------------
+def _mhd_sc_solver(eq):
+    flux = (T.flux_hindenlang_gassner, T.flux_nonconservative_powell)
+    basis = T.LobattoLegendreBasis(4)
+    indicator_sc = T.IndicatorHennemannGassner(eq, basis, alpha_max=0.5, alpha_min=0.001, alpha_smooth=True,
+                                               variable=T.density_pressure)
+    volume_integral = T.VolumeIntegralShockCapturingHG(indicator_sc, volume_flux_dg=flux, volume_flux_fv=flux)
+    return T.DGSEM(basis=basis, surface_flux=flux, volume_integral=volume_integral)
+
+
+def _mhd3d_ec_shockcapturing(level=3):
+    # examples/tree_3d_dgsem/elixir_mhd_ec_shockcapturing.jl
+    eq = T.IdealGlmMhdEquations3D(1.4)
+    mesh = T.TreeMesh((-2.0,) * 3, (2.0,) * 3, initial_refinement_level=level, periodicity=True)
+    return T.SemidiscretizationHyperbolic(mesh, eq, T.initial_condition_weak_blast_wave, _mhd_sc_solver(eq))
+
+
+def _structured3d_mhd_ec_shockcapturing(cells=(8, 8, 8)):
+    # examples/structured_3d_dgsem/elixir_mhd_ec_shockcapturing.jl
+    eq = T.IdealGlmMhdEquations3D(1.4)
+    mesh = T.StructuredMesh(cells, _warped_mapping_3d, periodicity=True)
+    return T.SemidiscretizationHyperbolic(mesh, eq, T.initial_condition_weak_blast_wave, _mhd_sc_solver(eq))
+
+
+ELIXIRS.update({e.name: e for e in [
+    MhdElixir("tree_3d_mhd_ec_shockcapturing", _mhd3d_ec_shockcapturing, (0.0, 1.0), 1.4,
+              [0.0186712969755079, 0.01620736832264799, 0.01620736832264803, 0.016207474382769683,
+               0.07306422729650594, 0.007355137041002365, 0.0073551370410023425, 0.00735520932001833,
+               0.000506140942330923],
+              [0.28040713666979633, 0.27212885844703694, 0.2721288584470349, 0.2837380205051839,
+               0.7915852408267114, 0.08770240288089526, 0.08770240288089792, 0.08773409387876674,
+               0.050221095224119834], "test/test_tree_3d_mhd.jl:254-282"),
+    MhdElixir("structured_3d_mhd_ec_shockcapturing", _structured3d_mhd_ec_shockcapturing, (0.0, 0.25), 1.4,
+              [0.009352631216098996, 0.008058649096024162, 0.00802704129788766, 0.008071417834885589,
+               0.03490914976431044, 0.003930194255268652, 0.003921907459117296, 0.003906321239858786,
+               4.1971260184918575e-5],
+              [0.307491045404509, 0.26790087991041506, 0.2712430701672931, 0.2654540237991884,
+               0.9620943261873176, 0.181632512204141, 0.15995711137712265, 0.1791807940466812,
+               0.015138421396338456], "test/test_structured_3d.jl:309-329"),
+]})
+
+
 # ---- configurations without a reference golden (cross-checks between mesh types, halo tests) ---------------
 def _p4est3d_curved(initial_condition=T.initial_condition_weak_blast_wave, flux=T.flux_ranocha, level=0, trees=(4, 4, 4)):
     # the warped mapping of examples/structured_3d_dgsem/elixir_euler_free_stream.jl on a conforming P4estMesh

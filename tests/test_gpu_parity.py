@@ -113,7 +113,8 @@ RHS_CASES = ["tree_3d_euler_ec", "tree_3d_euler_source_terms", "tree_3d_euler_so
              "p4est_3d_advection_basic", "p4est_3d_tgv_p5", "p4est_3d_curved_p5", "p4est_3d_advection_nonconforming",
              "p4est_2d_advection_nonconforming_flag", "structured_3d_euler_sedov", "structured_2d_euler_sedov",
              "p4est_2d_euler_sedov", "p4est_3d_euler_sedov", "structured_3d_mhd_ec", "structured_3d_mhd_alfven_wave",
-             "p4est_3d_mhd_alfven_wave_nonconforming", "p4est_3d_mhd_alfven_wave_nonperiodic"] + sorted(PARITY_EXTRA) + sorted(NONCONFORMING_EXTRA)
+             "p4est_3d_mhd_alfven_wave_nonconforming", "p4est_3d_mhd_alfven_wave_nonperiodic",
+             "tree_3d_mhd_ec_shockcapturing", "structured_3d_mhd_ec_shockcapturing"] + sorted(PARITY_EXTRA) + sorted(NONCONFORMING_EXTRA)
 
 
 @pytest.mark.parametrize("name", RHS_CASES)
@@ -367,7 +368,7 @@ def _shock_state(semi, seed):
 
 
 @pytest.mark.parametrize("name", ["tree_3d_euler_shockcapturing", "tree_2d_euler_shockcapturing",
-                                  "tree_2d_euler_blast_wave"])
+                                  "tree_2d_euler_blast_wave", "tree_3d_mhd_ec_shockcapturing"])
 def test_shock_capturing_indicator_and_rhs(name, oracle_module):
     """IndicatorHennemannGassner blending factors (indicators_3d.jl:41-186) and the blended volume integral
     (calc_volume_integral.jl:231-272) against the oracle on a state that exercises all three element kinds."""
@@ -434,7 +435,8 @@ GOLDEN_GPU = ["tree_3d_advection_basic", "tree_3d_advection_mortar", "structured
               "p4est_3d_advection_nonconforming", "p4est_2d_advection_nonconforming_flag",
               "tree_3d_mhd_alfven_wave_mortar", "structured_3d_euler_sedov", "structured_2d_euler_sedov",
               "p4est_2d_euler_sedov", "p4est_3d_euler_sedov", "structured_3d_mhd_ec", "structured_3d_mhd_alfven_wave",
-              "p4est_3d_mhd_alfven_wave_nonconforming", "p4est_3d_mhd_alfven_wave_nonperiodic"]
+              "p4est_3d_mhd_alfven_wave_nonconforming", "p4est_3d_mhd_alfven_wave_nonperiodic",
+              "tree_3d_mhd_ec_shockcapturing", "structured_3d_mhd_ec_shockcapturing"]
 
 
 @pytest.mark.parametrize("name", GOLDEN_GPU)
@@ -558,7 +560,7 @@ def _ranked_semis(name, world):
 @pytest.mark.parametrize("name", ["tree_3d_euler_ec", "tree_2d_euler_source_terms_nonperiodic", "tree_3d_mhd_ec",
                                   "p4est_3d_euler_source_terms_nonperiodic", "p4est_3d_curved_level1",
                                   "tree_3d_euler_shockcapturing", "tree_2d_euler_shockcapturing",
-                                  "tree_2d_euler_vortex_shockcapturing",
+                                  "tree_2d_euler_vortex_shockcapturing", "tree_3d_mhd_ec_shockcapturing",
                                   # shock capturing on curved forests across ranks
                                   "p4est_2d_euler_sedov", "p4est_3d_euler_sedov",
                                   # mortars that straddle ranks (MPI mortars), also with nonconservative terms and with

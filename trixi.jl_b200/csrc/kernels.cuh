@@ -911,12 +911,30 @@ __global__ void __launch_bounds__(ElemCfg<EQ, N>::THREADS) k_element(const KPara
 #pragma unroll
                             for (int v = 0; v < NV; ++v) up[v] = pu[v];
                             eq.numflux(P.volume_flux_fv, up, un, d, fl);
+                            if constexpr (EQ::kHasNoncons) {
+                                // calcflux_fv! with nonconservative terms (dg_3d.jl:391-452): fstar_R = flux + 0.5
+                                // g(u_rr, u_ll), fstar_L = flux + 0.5 g(u_ll, u_rr) -- the node's own state first
+                                if (EQ::has_noncons(P.volume_flux_fv)) {
+                                    double g[NV];
+                                    eq.noncons(un, up, d, g);
+#pragma unroll
+                                    for (int v = 0; v < NV; ++v) fl[v] = fl[v] + 0.5 * g[v];
+                                }
+                            }
                         }
                         if (idx[d] < N - 1) {
                             const double *pu = ue + (node + stride[d]) * US;
 #pragma unroll
                             for (int v = 0; v < NV; ++v) up[v] = pu[v];
                             eq.numflux(P.volume_flux_fv, un, up, d, fr);
+                            if constexpr (EQ::kHasNoncons) {
+                                if (EQ::has_noncons(P.volume_flux_fv)) {
+                                    double g[NV];
+                                    eq.noncons(un, up, d, g);
+#pragma unroll
+                                    for (int v = 0; v < NV; ++v) fr[v] = fr[v] + 0.5 * g[v];
+                                }
+                            }
                         }
                         const double iw = P.inv_weights_c[idx[d]];
 #pragma unroll
@@ -947,8 +965,11 @@ __global__ void __launch_bounds__(ElemCfg<EQ, N>::THREADS) k_element(const KPara
                             for (int v = 0; v < NV; ++v) ic[v] = fma(w, g[v], ic[v]);
                         }
                     }
+                    // multiply_add_to_node_vars!(du, alpha * 0.5, integral_contribution, ...) (dg_3d.jl:259-262; alpha =
+                    // 1 - blending factor under shock capturing, else 1)
+                    const double half = VOLINT == TRIXI_B200_VOLINT_SHOCK_CAPTURING_HG ? w_dg * 0.5 : 0.5;
 #pragma unroll
-                    for (int v = 0; v < NV; ++v) acc[v] = fma(0.5, ic[v], acc[v]);
+                    for (int v = 0; v < NV; ++v) acc[v] = fma(half, ic[v], acc[v]);
                 }
             }
         }
@@ -1663,8 +1684,9 @@ __global__ void __launch_bounds__(ElemCfg<EQ, N>::THREADS) k_element_curved(cons
                             for (int v = 0; v < NV; ++v) ic[v] = fma(w, g[v], ic[v]);
                         }
                     }
+                    const double half = VOLINT == TRIXI_B200_VOLINT_SHOCK_CAPTURING_HG ? w_dg * 0.5 : 0.5;
 #pragma unroll
-                    for (int v = 0; v < NV; ++v) acc[v] = fma(0.5, ic[v], acc[v]);
+                    for (int v = 0; v < NV; ++v) acc[v] = fma(half, ic[v], acc[v]);
                 }
             }
             if constexpr (VOLINT == TRIXI_B200_VOLINT_SHOCK_CAPTURING_HG) {
@@ -1694,6 +1716,16 @@ __global__ void __launch_bounds__(ElemCfg<EQ, N>::THREADS) k_element_curved(cons
 #pragma unroll
                             for (int v = 0; v < NV; ++v) up[v] = pu[v];
                             eq.numflux_normal(P.volume_flux_fv, up, un, nrm, fl);
+                            if constexpr (EQ::kHasNoncons) {
+                                // calcflux_fv! with nonconservative terms (dgsem_structured/dg_3d.jl:438-530): ftilde_R =
+                                // ftilde + 0.5 g(u_rr, u_ll, n), ftilde_L = ftilde + 0.5 g(u_ll, u_rr, n)
+                                if (EQ::has_noncons(P.volume_flux_fv)) {
+                                    double g[NV];
+                                    eq.noncons_normal(un, up, nrm, g);
+#pragma unroll
+                                    for (int v = 0; v < NV; ++v) fl[v] = fl[v] + 0.5 * g[v];
+                                }
+                            }
                         }
                         if (idx[d] < N - 1) {
                             pos[d] = idx[d];
@@ -1704,6 +1736,14 @@ __global__ void __launch_bounds__(ElemCfg<EQ, N>::THREADS) k_element_curved(cons
 #pragma unroll
                             for (int v = 0; v < NV; ++v) up[v] = pu[v];
                             eq.numflux_normal(P.volume_flux_fv, un, up, nrm, fr);
+                            if constexpr (EQ::kHasNoncons) {
+                                if (EQ::has_noncons(P.volume_flux_fv)) {
+                                    double g[NV];
+                                    eq.noncons_normal(un, up, nrm, g);
+#pragma unroll
+                                    for (int v = 0; v < NV; ++v) fr[v] = fr[v] + 0.5 * g[v];
+                                }
+                            }
                         }
                         const double iw = P.inv_weights_c[idx[d]];
 #pragma unroll

@@ -318,7 +318,7 @@ cudaError_t launch_element(const KParams &P, bool with_surface, cudaStream_t s) 
         return with_surface ? launch_element_variant<EQ, N, TRIXI_B200_VOLINT_WEAK_FORM, true>(P, s)
                             : launch_element_variant<EQ, N, TRIXI_B200_VOLINT_WEAK_FORM, false>(P, s);
     }
-    if constexpr (HasFastRanocha<EQ>::value) {  // the compressible Euler equations
+    if constexpr (HasFastRanocha<EQ>::value || EQ::kHasNoncons) {  // compressible Euler, ideal GLM-MHD
         if (P.volume_integral == TRIXI_B200_VOLINT_SHOCK_CAPTURING_HG)
             return with_surface ? launch_element_variant<EQ, N, TRIXI_B200_VOLINT_SHOCK_CAPTURING_HG, true>(P, s)
                                 : launch_element_variant<EQ, N, TRIXI_B200_VOLINT_SHOCK_CAPTURING_HG, false>(P, s);
@@ -330,7 +330,7 @@ cudaError_t launch_element(const KParams &P, bool with_surface, cudaStream_t s) 
 // (indicator_hg::IndicatorHennemannGassner)(u, mesh, equations, dg, cache) (dgsem/indicators.jl:114-148)
 template <class EQ, int N>
 void launch_indicator(const KParams &P, int stage, cudaStream_t s) {
-    if constexpr (HasFastRanocha<EQ>::value) {
+    if constexpr (HasFastRanocha<EQ>::value || EQ::kHasNoncons) {  // compressible Euler, ideal GLM-MHD
         using C = ElemCfg<EQ, N>;
         if (P.nelements == 0) return;
         if (stage == 1) {
@@ -418,7 +418,7 @@ cudaError_t preload_all() {
     TB_PRELOAD((k_element<EQ, N, TRIXI_B200_VOLINT_WEAK_FORM, false>));
     TB_PRELOAD((k_element<EQ, N, TRIXI_B200_VOLINT_FLUX_DIFFERENCING, true>));
     TB_PRELOAD((k_element<EQ, N, TRIXI_B200_VOLINT_FLUX_DIFFERENCING, false>));
-    if constexpr (HasFastRanocha<EQ>::value) {
+    if constexpr (HasFastRanocha<EQ>::value || EQ::kHasNoncons) {
         TB_PRELOAD((k_element<EQ, N, TRIXI_B200_VOLINT_SHOCK_CAPTURING_HG, true>));
         TB_PRELOAD((k_element<EQ, N, TRIXI_B200_VOLINT_SHOCK_CAPTURING_HG, false>));
         TB_PRELOAD((k_element_curved<EQ, N, TRIXI_B200_VOLINT_SHOCK_CAPTURING_HG, true>));

@@ -884,6 +884,15 @@ struct Mhd3D {
     }
     TB_DEV static double sel3(double a, double b, double c, int o) { return o == 0 ? a : (o == 1 ? b : c); }
 
+    // indicator variables of IndicatorHennemannGassner: density_pressure, density, pressure (:1318-1347)
+    TB_DEV double indicator_variable(int var, const double (&u)[9]) const {
+        const double mom2 = u[1] * u[1] + u[2] * u[2] + u[3] * u[3];
+        const double mag = u[5] * u[5] + u[6] * u[6] + u[7] * u[7], psi2 = u[8] * u[8];
+        if (var == TRIXI_B200_INDVAR_DENSITY) return u[0];
+        if (var == TRIXI_B200_INDVAR_PRESSURE) return (gamma - 1) * (u[4] - 0.5 * (mom2 / u[0] + mag + psi2));
+        return (gamma - 1) * (u[0] * u[4] - 0.5 * (mom2 + u[0] * (mag + psi2)));
+    }
+
     // flux(u, orientation) (:187-234)
     TB_DEV void flux(const double (&u)[9], int o, double (&f)[9]) const {
         const double psi = u[8], inv_rho = fast_rcp(u[0]);

@@ -675,8 +675,10 @@ TRIXI_B200_API int trixi_b200_create(const trixi_b200_desc *d, trixi_b200_handle
                     return fail(nullptr, TRIXI_B200_EINVAL,
                                 "VolumeIntegralShockCapturingHG on a curved mesh needs subcell_normal_vectors (NormalVectorContainer)");
         }
-        if (d->equation != TRIXI_B200_EQ_EULER_2D && d->equation != TRIXI_B200_EQ_EULER_3D)
-            return fail(nullptr, TRIXI_B200_EINVAL, "VolumeIntegralShockCapturingHG needs the compressible Euler equations");
+        if (d->equation != TRIXI_B200_EQ_EULER_2D && d->equation != TRIXI_B200_EQ_EULER_3D &&
+            d->equation != TRIXI_B200_EQ_MHD_3D)
+            return fail(nullptr, TRIXI_B200_EINVAL,
+                        "VolumeIntegralShockCapturingHG needs the compressible Euler or the ideal GLM-MHD equations");
         if (!d->inverse_vandermonde_legendre)
             return fail(nullptr, TRIXI_B200_EINVAL, "inverse_vandermonde_legendre missing");
         if (d->indicator_variable < TRIXI_B200_INDVAR_DENSITY_PRESSURE || d->indicator_variable > TRIXI_B200_INDVAR_PRESSURE)
