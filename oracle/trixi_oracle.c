@@ -230,6 +230,54 @@ static inline void euler_min_max_speed(const eqn_t *eq, const double *ul, const 
     }
 }
 
+static inline double vec_norm(int nd, const double *n);
+/* min_max_speed_einfeldt (compressible_euler_3d.jl:1662-1707 with an orientation, :1723-1771 along a normal direction;
+ * compressible_euler_2d.jl:1925-1966, :1982-2025): Roe averages with the positivity-preserving bound of Einfeldt et al.
+ * n == NULL: orientation o (0-based) */
+static inline void euler_min_max_speed_einfeldt(const eqn_t *eq, const double *ul, const double *ur, int o, const double *n,
+                                                double *lmin, double *lmax) {
+    int nd = eq->nd;
+    double rho_ll, v_ll[3] = {0, 0, 0}, p_ll, rho_rr, v_rr[3] = {0, 0, 0}, p_rr;
+    euler_cons2prim(eq, ul, &rho_ll, v_ll, &p_ll);
+    euler_cons2prim(eq, ur, &rho_rr, v_rr, &p_rr);
+    double vn_ll, vn_rr, norm_ = 1.0;
+    if (n) {
+        vn_ll = 0.0;
+        vn_rr = 0.0;
+        for (int d = 0; d < nd; ++d) {
+            vn_ll += v_ll[d] * n[d];
+            vn_rr += v_rr[d] * n[d];
+        }
+        norm_ = vec_norm(nd, n);
+    } else {
+        vn_ll = v_ll[o];
+        vn_rr = v_rr[o];
+    }
+    double H_ll = (ul[nd + 1] + p_ll) / rho_ll, H_rr = (ur[nd + 1] + p_rr) / rho_rr;
+    double c_ll = sqrt(eq->gamma * p_ll / rho_ll), c_rr = sqrt(eq->gamma * p_rr / rho_rr);
+    if (n) {
+        c_ll = c_ll * norm_;
+        c_rr = c_rr * norm_;
+    }
+    double sqrt_rho_ll = sqrt(rho_ll), sqrt_rho_rr = sqrt(rho_rr);
+    double inv_sum_sqrt_rho = 1.0 / (sqrt_rho_ll + sqrt_rho_rr);
+    double v_roe[3] = {0, 0, 0}, v_roe_mag = 0.0, vn_roe = 0.0;
+    for (int d = 0; d < nd; ++d) {
+        v_roe[d] = (sqrt_rho_ll * v_ll[d] + sqrt_rho_rr * v_rr[d]) * inv_sum_sqrt_rho;
+        v_roe_mag += v_roe[d] * v_roe[d];
+    }
+    if (n)
+        for (int d = 0; d < nd; ++d) vn_roe += v_roe[d] * n[d];
+    else
+        vn_roe = v_roe[o];
+    double H_roe = (sqrt_rho_ll * H_ll + sqrt_rho_rr * H_rr) * inv_sum_sqrt_rho;
+    double c_roe = sqrt((eq->gamma - 1) * (H_roe - 0.5 * v_roe_mag));
+    if (n) c_roe = c_roe * norm_;
+    double beta = sqrt(0.5 * (eq->gamma - 1) / eq->gamma);
+    *lmin = fmin(fmin(vn_roe - c_roe, vn_ll - beta * c_ll), 0.0);
+    *lmax = fmax(fmax(vn_roe + c_roe, vn_rr + beta * c_rr), 0.0);
+}
+
 /* ---- ideal GLM-MHD 3D (ideal_glm_mhd_3d.jl) ------------------------------------------------------------ */
 /* cons2prim :1231-1243: (rho, v1, v2, v3, p, B1, B2, B3, psi) */
 static inline void mhd_cons2prim(const eqn_t *eq, const double *u, double *prim) {
@@ -618,10 +666,14 @@ static void numflux(const eqn_t *eq, int flux_id, const double *ul, const double
         for (int v = 0; v < nv; ++v) f[v] = 0.5 * (fl[v] + fr[v]) + (-0.5 * lam * (ur[v] - ul[v]));
         return;
     }
+    case TRIXI_B200_FLUX_HLLE:
     case TRIXI_B200_FLUX_HLL_DAVIS:
     case TRIXI_B200_FLUX_HLL_NAIVE: { /* FluxHLL numerical_fluxes.jl:422-440 */
         double lmin, lmax;
-        euler_min_max_speed(eq, ul, ur, o, flux_id == TRIXI_B200_FLUX_HLL_NAIVE, &lmin, &lmax);
+        if (flux_id == TRIXI_B200_FLUX_HLLE)
+            euler_min_max_speed_einfeldt(eq, ul, ur, o, NULL, &lmin, &lmax);
+        else
+            euler_min_max_speed(eq, ul, ur, o, flux_id == TRIXI_B200_FLUX_HLL_NAIVE, &lmin, &lmax);
         if (lmin >= 0 && lmax >= 0) {
             phys_flux(eq, ul, o, f);
         } else if (lmax <= 0 && lmin <= 0) {
@@ -797,8 +849,9 @@ static void numflux_normal(const eqn_t *eq, int flux_id, const double *ul, const
         for (int v = 0; v < nv; ++v) f[v] = 0.5 * (fl[v] + fr[v]) + (-0.5 * lam * (ur[v] - ul[v]));
         return;
     }
+    case TRIXI_B200_FLUX_HLLE:
     case TRIXI_B200_FLUX_HLL_DAVIS:
-    case TRIXI_B200_FLUX_HLL_NAIVE: { /* compressible_euler_3d.jl:1220-1237, 1263-1285 */
+    case TRIXI_B200_FLUX_HLL_NAIVE: { /* compressible_euler_3d.jl:1220-1237, 1263-1285, 1723-1771 */
         double rho_ll, v_ll[3], p_ll, rho_rr, v_rr[3], p_rr;
         euler_cons2prim(eq, ul, &rho_ll, v_ll, &p_ll);
         euler_cons2prim(eq, ur, &rho_rr, v_rr, &p_rr);
@@ -810,7 +863,9 @@ static void numflux_normal(const eqn_t *eq, int flux_id, const double *ul, const
         double norm_ = vec_norm(nd, n);
         double c_ll = sqrt(eq->gamma * p_ll / rho_ll) * norm_, c_rr = sqrt(eq->gamma * p_rr / rho_rr) * norm_;
         double lmin, lmax;
-        if (flux_id == TRIXI_B200_FLUX_HLL_NAIVE) {
+        if (flux_id == TRIXI_B200_FLUX_HLLE) {
+            euler_min_max_speed_einfeldt(eq, ul, ur, 0, n, &lmin, &lmax);
+        } else if (flux_id == TRIXI_B200_FLUX_HLL_NAIVE) {
             lmin = vl - c_ll;
             lmax = vr + c_rr;
         } else {

@@ -732,9 +732,9 @@ def _sedov_ic(ndims, p0_outer):
     return ic
 
 
-def _sedov_solver(eq, polydeg):
+def _sedov_solver(eq, polydeg, surface_flux=None):
     basis = T.LobattoLegendreBasis(polydeg)
-    surface_flux = T.FluxLaxFriedrichs(T.max_abs_speed_naive)
+    surface_flux = surface_flux or T.FluxLaxFriedrichs(T.max_abs_speed_naive)
     indicator_sc = T.IndicatorHennemannGassner(eq, basis, alpha_max=1.0, alpha_min=0.001, alpha_smooth=True,
                                                variable=T.density_pressure)
     volume_integral = T.VolumeIntegralShockCapturingHG(indicator_sc, volume_flux_dg=T.flux_ranocha,
@@ -769,19 +769,34 @@ def _structured2d_sedov():
     return T.SemidiscretizationHyperbolic(mesh, eq, _sedov_ic(2, 1.0e-5), _sedov_solver(eq, 4))
 
 
-def _p4est2d_sedov():
+def _p4est2d_sedov(surface_flux=None):
     # examples/p4est_2d_dgsem/elixir_euler_sedov.jl
     eq = T.CompressibleEulerEquations2D(1.4)
     mesh = T.P4estMesh((4, 4), polydeg=4, initial_refinement_level=2, coordinates_min=(-1.0, -1.0),
                        coordinates_max=(1.0, 1.0), periodicity=True)
-    return T.SemidiscretizationHyperbolic(mesh, eq, _sedov_ic(2, 1.0e-5), _sedov_solver(eq, 4))
+    return T.SemidiscretizationHyperbolic(mesh, eq, _sedov_ic(2, 1.0e-5), _sedov_solver(eq, 4, surface_flux))
 
 
-def _p4est3d_sedov():
+def _p4est3d_sedov(surface_flux=None):
     # examples/p4est_3d_dgsem/elixir_euler_sedov.jl
     eq = T.CompressibleEulerEquations3D(1.4)
     mesh = T.P4estMesh((4, 4, 4), polydeg=4, coordinates_min=(-1.0,) * 3, coordinates_max=(1.0,) * 3, periodicity=True)
-    return T.SemidiscretizationHyperbolic(mesh, eq, _sedov_ic(3, 1.0e-3), _sedov_solver(eq, 5))
+    return T.SemidiscretizationHyperbolic(mesh, eq, _sedov_ic(3, 1.0e-3), _sedov_solver(eq, 5, surface_flux))
+
+
+def _tree2d_sedov_blast_wave(surface_flux=None, level=6):
+    # examples/tree_2d_dgsem/elixir_euler_sedov_blast_wave.jl without its AMRCallback (the reference's HLLE test passes
+    # callbacks = CallbackSet(summary, analysis, alive, stepsize), test/test_tree_2d_euler.jl:757-760)
+    eq = T.CompressibleEulerEquations2D(1.4)
+    basis = T.LobattoLegendreBasis(3)
+    surface_flux = surface_flux or T.FluxLaxFriedrichs(T.max_abs_speed_naive)
+    indicator_sc = T.IndicatorHennemannGassner(eq, basis, alpha_max=0.5, alpha_min=0.001, alpha_smooth=True,
+                                               variable=T.density_pressure)
+    volume_integral = T.VolumeIntegralShockCapturingHG(indicator_sc, volume_flux_dg=T.flux_chandrashekar,
+                                                       volume_flux_fv=surface_flux)
+    solver = T.DGSEM(basis=basis, surface_flux=surface_flux, volume_integral=volume_integral)
+    mesh = T.TreeMesh((-2.0, -2.0), (2.0, 2.0), initial_refinement_level=level, periodicity=True)
+    return T.SemidiscretizationHyperbolic(mesh, eq, _sedov_ic(2, 1.0e-5), solver)
 
 
 # (the reference prints these goldens with nine significant digits)
@@ -802,6 +817,20 @@ ELIXIRS.update({e.name: e for e in [
            [7.82070951e-02, 4.33260474e-02, 4.33260474e-02, 4.33260474e-02, 3.75260911e-01],
            [7.45329845e-01, 3.21754792e-01, 3.21754792e-01, 3.21754792e-01, 4.76151527e+00],
            "test/test_p4est_3d.jl:376-396", rtol=2e-8),
+    # flux_hlle = FluxHLL(min_max_speed_einfeldt) of the compressible Euler equations, as surface flux and as the
+    # subcell finite-volume flux
+    Elixir("p4est_2d_euler_sedov_hlle", lambda: _p4est2d_sedov(T.flux_hlle), (0.0, 0.3), 0.5,
+           [0.40853279043747015, 0.25356771650524296, 0.2535677165052422, 1.2984601729572691],
+           [1.3840909333784284, 1.3077772519086124, 1.3077772519086157, 6.298798630968632],
+           "test/test_p4est_2d.jl:471-490"),
+    Elixir("p4est_3d_euler_sedov_hlle", lambda: _p4est3d_sedov(T.flux_hlle), (0.0, 0.3), 0.5,
+           [0.09946224487902565, 0.04863386374672001, 0.048633863746720116, 0.04863386374672032, 0.3751015774232693],
+           [0.789241521871487, 0.42046970270100276, 0.42046970270100276, 0.4204697027010028, 4.730877375538398],
+           "test/test_p4est_3d.jl:510-531"),
+    Elixir("tree_2d_euler_sedov_blast_wave_hlle", lambda **kw: _tree2d_sedov_blast_wave(T.flux_hlle, **kw), (0.0, 0.5), 0.8,
+           [0.352405949321075, 0.17207721487429464, 0.17207721487433883, 0.6263024434020885],
+           [2.760997358628186, 1.8279186132509326, 1.8279186132502805, 6.251573757093399],
+           "test/test_tree_2d_euler.jl:740-766"),
 ]})
 
 
@@ -921,6 +950,54 @@ ELIXIRS.update({e.name: e for e in [
 ]})
 
 
+# ---- further variants of the MHD elixirs asserted by the reference's test-suite -------------------------------------
+def initial_condition_orszag_tang_3d(x, t, equations):
+    # test/test_tree_3d_mhd.jl:190-211: the Orszag-Tang vortex adapted to 3D (Bohm et al. 2020, table 4)
+    pi = math.pi
+    rho = 25.0 / (36.0 * pi) + 0 * x[0]
+    v1, v2, v3 = -np.sin(2.0 * pi * x[2]), np.sin(2.0 * pi * x[0]), np.sin(2.0 * pi * x[1])
+    p = 5.0 / (12.0 * pi)
+    B1 = -np.sin(2.0 * pi * x[2]) / (4.0 * pi)
+    B2 = np.sin(4.0 * pi * x[0]) / (4.0 * pi)
+    B3 = np.sin(4.0 * pi * x[1]) / (4.0 * pi)
+    return equations.prim2cons((rho, v1, v2, v3, p, B1, B2, B3, 0.0))
+
+
+def _mhd3d_orszag_tang_hlle():
+    # examples/tree_3d_dgsem/elixir_mhd_alfven_wave.jl with the overrides of test/test_tree_3d_mhd.jl:160-223
+    eq = T.IdealGlmMhdEquations3D(5 / 3)
+    solver = T.DGSEM(polydeg=3, surface_flux=(T.flux_hlle, T.flux_nonconservative_powell),
+                     volume_integral=T.VolumeIntegralFluxDifferencing((T.flux_central, T.flux_nonconservative_powell)))
+    mesh = T.TreeMesh((0.0,) * 3, (1.0,) * 3, initial_refinement_level=3, periodicity=True)
+    return T.SemidiscretizationHyperbolic(mesh, eq, initial_condition_orszag_tang_3d, solver)
+
+
+ELIXIRS.update({e.name: e for e in [
+    MhdElixir("tree_3d_mhd_ec_constant", lambda: _mhd3d_ec(initial_condition=T.initial_condition_constant), (0.0, 0.4), 1.4,
+              [4.270231310667203e-16, 2.4381208042014784e-15, 5.345107673575357e-15, 3.00313882171883e-15,
+               1.7772703118758417e-14, 1.0340110783830874e-15, 1.1779095371939702e-15, 9.961878521814573e-16,
+               8.1201730630719145e-16],
+              [2.4424906541753444e-15, 2.881028748902281e-14, 2.4646951146678475e-14, 2.3092638912203256e-14,
+               2.3447910280083306e-13, 1.7763568394002505e-14, 1.0436096431476471e-14, 2.042810365310288e-14,
+               7.057203733035201e-15], "test/test_tree_3d_mhd.jl:34-66", rtol=0, atol=1000 * 2.220446049250313e-16),
+    MhdElixir("tree_3d_mhd_orszag_tang_hlle", _mhd3d_orszag_tang_hlle, (0.0, 0.06), 1.1,
+              [0.004391143689111404, 0.04144737547475548, 0.041501307637678286, 0.04150353006408862,
+               0.03693135855995625, 0.021125605214031118, 0.03295607553556973, 0.03296235755245784,
+               7.16035229384135e-6],
+              [0.017894703320895378, 0.08486850681397005, 0.0891044523165206, 0.08492024792056754,
+               0.10448301878352373, 0.05381260695579509, 0.0884774018719996, 0.07784546966765199,
+               7.71609149516089e-5], "test/test_tree_3d_mhd.jl:160-223"),
+    MhdElixir("structured_3d_mhd_alfven_wave_llf_naive",
+              lambda: _structured3d_mhd_alfven_wave(surface_flux=T.FluxLaxFriedrichs(T.max_abs_speed_naive)), (0.0, 1.0), 1.2,
+              [0.0030477691235949685, 0.00145609137038748, 0.0009092809766088607, 0.0017949926915475929,
+               0.0012981612165627713, 0.0014525841626158234, 0.0013275465154956557, 0.0016728767532610933,
+               0.0013751925705271012],
+              [0.02778552932540901, 0.027511633996169835, 0.012637649797178449, 0.03920805095546112,
+               0.02126543791857216, 0.031563506812970266, 0.02116105422516923, 0.03419432640106229,
+               0.020324891223351533], "test/test_structured_3d.jl:287-307"),
+]})
+
+
 # ---- configurations without a reference golden (cross-checks between mesh types, halo tests) ---------------
 def _p4est3d_curved(initial_condition=T.initial_condition_weak_blast_wave, flux=T.flux_ranocha, level=0, trees=(4, 4, 4)):
     # the warped mapping of examples/structured_3d_dgsem/elixir_euler_free_stream.jl on a conforming P4estMesh
@@ -1001,6 +1078,7 @@ for _mesh in ("tree", "structured", "p4est"):
             lambda m=_mesh, n=_nd: _parity_case(m, n, T.flux_lax_friedrichs, T.BoundaryConditionDirichlet(
                 T.initial_condition_convergence_test)))
         PARITY_EXTRA[f"{_tag}_hll"] = lambda m=_mesh, n=_nd: _parity_case(m, n, T.flux_hll)
+        PARITY_EXTRA[f"{_tag}_hlle"] = lambda m=_mesh, n=_nd: _parity_case(m, n, T.flux_hlle)
         PARITY_EXTRA[f"{_tag}_hll_naive"] = (
             lambda m=_mesh, n=_nd: _parity_case(m, n, T.FluxHLL(T.min_max_speed_naive), volume_flux=T.flux_ranocha))
         PARITY_EXTRA[f"{_tag}_slip_wall"] = (

@@ -114,7 +114,9 @@ RHS_CASES = ["tree_3d_euler_ec", "tree_3d_euler_source_terms", "tree_3d_euler_so
              "p4est_2d_advection_nonconforming_flag", "structured_3d_euler_sedov", "structured_2d_euler_sedov",
              "p4est_2d_euler_sedov", "p4est_3d_euler_sedov", "structured_3d_mhd_ec", "structured_3d_mhd_alfven_wave",
              "p4est_3d_mhd_alfven_wave_nonconforming", "p4est_3d_mhd_alfven_wave_nonperiodic",
-             "tree_3d_mhd_ec_shockcapturing", "structured_3d_mhd_ec_shockcapturing"] + sorted(PARITY_EXTRA) + sorted(NONCONFORMING_EXTRA)
+             "tree_3d_mhd_ec_shockcapturing", "structured_3d_mhd_ec_shockcapturing", "tree_3d_mhd_orszag_tang_hlle",
+             "structured_3d_mhd_alfven_wave_llf_naive", "p4est_2d_euler_sedov_hlle", "p4est_3d_euler_sedov_hlle",
+             "tree_2d_euler_sedov_blast_wave_hlle"] + sorted(PARITY_EXTRA) + sorted(NONCONFORMING_EXTRA)
 
 
 @pytest.mark.parametrize("name", RHS_CASES)
@@ -436,7 +438,9 @@ GOLDEN_GPU = ["tree_3d_advection_basic", "tree_3d_advection_mortar", "structured
               "tree_3d_mhd_alfven_wave_mortar", "structured_3d_euler_sedov", "structured_2d_euler_sedov",
               "p4est_2d_euler_sedov", "p4est_3d_euler_sedov", "structured_3d_mhd_ec", "structured_3d_mhd_alfven_wave",
               "p4est_3d_mhd_alfven_wave_nonconforming", "p4est_3d_mhd_alfven_wave_nonperiodic",
-              "tree_3d_mhd_ec_shockcapturing", "structured_3d_mhd_ec_shockcapturing"]
+              "tree_3d_mhd_ec_shockcapturing", "structured_3d_mhd_ec_shockcapturing", "tree_3d_mhd_ec_constant",
+              "tree_3d_mhd_orszag_tang_hlle", "structured_3d_mhd_alfven_wave_llf_naive", "p4est_2d_euler_sedov_hlle",
+              "p4est_3d_euler_sedov_hlle", "tree_2d_euler_sedov_blast_wave_hlle"]
 
 
 @pytest.mark.parametrize("name", GOLDEN_GPU)

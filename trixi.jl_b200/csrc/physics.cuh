@@ -213,6 +213,23 @@ struct Euler {
         p = (gamma - 1) * (u[ND + 1] - 0.5 * kin);
     }
 
+    // Roe averages of min_max_speed_einfeldt (compressible_euler_3d.jl:1675-1686): velocity and sound speed
+    TB_DEV void roe_average(const double (&ul)[NVARS], const double (&ur)[NVARS], double rho_ll, const double (&v_ll)[ND],
+                            double p_ll, double rho_rr, const double (&v_rr)[ND], double p_rr, double (&v_roe)[ND],
+                            double &c_roe) const {
+        const double H_ll = (ul[ND + 1] + p_ll) / rho_ll, H_rr = (ur[ND + 1] + p_rr) / rho_rr;
+        const double sqrt_rho_ll = sqrt(rho_ll), sqrt_rho_rr = sqrt(rho_rr);
+        const double inv_sum_sqrt_rho = 1.0 / (sqrt_rho_ll + sqrt_rho_rr);
+        double v_roe_mag = 0.0;
+#pragma unroll
+        for (int d = 0; d < ND; ++d) {
+            v_roe[d] = (sqrt_rho_ll * v_ll[d] + sqrt_rho_rr * v_rr[d]) * inv_sum_sqrt_rho;
+            v_roe_mag += v_roe[d] * v_roe[d];
+        }
+        const double H_roe = (sqrt_rho_ll * H_ll + sqrt_rho_rr * H_rr) * inv_sum_sqrt_rho;
+        c_roe = sqrt((gamma - 1) * (H_roe - 0.5 * v_roe_mag));
+    }
+
     // indicator variables of IndicatorHennemannGassner: density_pressure, density, pressure
     // (compressible_euler_3d.jl:1937-1956)
     TB_DEV double indicator_variable(int var, const double (&u)[NVARS]) const {
@@ -475,6 +492,7 @@ struct Euler {
             for (int v = 0; v < NVARS; ++v) f[v] = 0.5 * (fl[v] + fr[v]) + (-0.5 * lam * (ur[v] - ul[v]));
             break;
         }
+        case TRIXI_B200_FLUX_HLLE:
         case TRIXI_B200_FLUX_HLL_DAVIS:
         case TRIXI_B200_FLUX_HLL_NAIVE: {  // FluxHLL numerical_fluxes.jl:422-440
             double rho_ll, v_ll[ND], p_ll, rho_rr, v_rr[ND], p_rr;
@@ -483,7 +501,14 @@ struct Euler {
             const double c_ll = sqrt(gamma * p_ll / rho_ll), c_rr = sqrt(gamma * p_rr / rho_rr);
             const double vl = pick<ND>(v_ll, o), vr = pick<ND>(v_rr, o);
             double lmin, lmax;
-            if (id == TRIXI_B200_FLUX_HLL_NAIVE) {  // compressible_euler_3d.jl:1201-1218
+            if (id == TRIXI_B200_FLUX_HLLE) {  // min_max_speed_einfeldt :1662-1707
+                double v_roe[ND];
+                double c_roe;
+                roe_average(ul, ur, rho_ll, v_ll, p_ll, rho_rr, v_rr, p_rr, v_roe, c_roe);
+                const double beta = sqrt(0.5 * (gamma - 1) / gamma), vroe = pick<ND>(v_roe, o);
+                lmin = fmin(fmin(vroe - c_roe, vl - beta * c_ll), 0.0);
+                lmax = fmax(fmax(vroe + c_roe, vr + beta * c_rr), 0.0);
+            } else if (id == TRIXI_B200_FLUX_HLL_NAIVE) {  // compressible_euler_3d.jl:1201-1218
                 lmin = vl - c_ll;
                 lmax = vr + c_rr;
             } else {  // min_max_speed_davis :1240-1261
@@ -571,6 +596,44 @@ struct Euler {
             flux_normal(ur, n, fr);
 #pragma unroll
             for (int v = 0; v < NVARS; ++v) f[v] = 0.5 * (fl[v] + fr[v]);
+            break;
+        }
+        case TRIXI_B200_FLUX_HLLE: {  // FluxHLL with min_max_speed_einfeldt along a normal direction (:1723-1771)
+            double rho_ll, v_ll[ND], p_ll, rho_rr, v_rr[ND], p_rr;
+            cons2prim(ul, rho_ll, v_ll, p_ll);
+            cons2prim(ur, rho_rr, v_rr, p_rr);
+            double vl = 0.0, vr = 0.0, nsq = 0.0;
+#pragma unroll
+            for (int d = 0; d < ND; ++d) {
+                vl += v_ll[d] * n[d];
+                vr += v_rr[d] * n[d];
+                nsq += n[d] * n[d];
+            }
+            const double norm_ = sqrt(nsq);
+            const double c_ll = sqrt(gamma * p_ll / rho_ll) * norm_, c_rr = sqrt(gamma * p_rr / rho_rr) * norm_;
+            double v_roe[ND], c_roe;
+            roe_average(ul, ur, rho_ll, v_ll, p_ll, rho_rr, v_rr, p_rr, v_roe, c_roe);
+            c_roe = c_roe * norm_;
+            double vroe = 0.0;
+#pragma unroll
+            for (int d = 0; d < ND; ++d) vroe += v_roe[d] * n[d];
+            const double beta = sqrt(0.5 * (gamma - 1) / gamma);
+            const double lmin = fmin(fmin(vroe - c_roe, vl - beta * c_ll), 0.0);
+            const double lmax = fmax(fmax(vroe + c_roe, vr + beta * c_rr), 0.0);
+            if (lmin >= 0 && lmax >= 0) {
+                flux_normal(ul, n, f);
+            } else if (lmax <= 0 && lmin <= 0) {
+                flux_normal(ur, n, f);
+            } else {
+                double fl[NVARS], fr[NVARS];
+                flux_normal(ul, n, fl);
+                flux_normal(ur, n, fr);
+                const double inv = 1.0 / (lmax - lmin);
+                const double factor_ll = lmax * inv, factor_rr = lmin * inv, factor_diss = lmin * lmax * inv;
+#pragma unroll
+                for (int v = 0; v < NVARS; ++v)
+                    f[v] = factor_ll * fl[v] - factor_rr * fr[v] + factor_diss * (ur[v] - ul[v]);
+            }
             break;
         }
         case TRIXI_B200_FLUX_LLF:

@@ -693,6 +693,11 @@ TRIXI_B200_API int trixi_b200_create(const trixi_b200_desc *d, trixi_b200_handle
     {
         const bool euler = d->equation == TRIXI_B200_EQ_EULER_2D || d->equation == TRIXI_B200_EQ_EULER_3D;
         const bool advection = d->equation == TRIXI_B200_EQ_ADVECTION_2D || d->equation == TRIXI_B200_EQ_ADVECTION_3D;
+        // flux_hlle without the Powell term is the compressible Euler one (min_max_speed_einfeldt of those equations)
+        if (!euler && (d->surface_flux == TRIXI_B200_FLUX_HLLE || d->volume_flux == TRIXI_B200_FLUX_HLLE ||
+                       d->volume_flux_fv == TRIXI_B200_FLUX_HLLE))
+            return fail(nullptr, TRIXI_B200_EINVAL, "flux_hlle (FluxHLL(min_max_speed_einfeldt)) is implemented for the "
+                                                    "compressible Euler equations and, with the Powell term, for GLM-MHD");
         const int src = d->source_terms;
         const bool src_ok = src == TRIXI_B200_SRC_NONE ||
                             (euler && (src == TRIXI_B200_SRC_CONVERGENCE_TEST || src == TRIXI_B200_SRC_EOC_TEST_EULER ||

@@ -32,7 +32,7 @@ FLUX_HINDENLANG_GASSNER_POWELL = 13
 FLUX_LLF_NAIVE_MHD_POWELL = 14  # (FluxLaxFriedrichs(max_abs_speed_naive), flux_nonconservative_powell)
 FLUX_HLLE_MHD_POWELL = 15  # (flux_hlle, flux_nonconservative_powell)
 FLUX_CENTRAL_MHD_POWELL = 16  # (flux_central, flux_nonconservative_powell)
-FLUX_HLLE = -2  # FluxHLL(min_max_speed_einfeldt): only inside the MHD tuple above
+FLUX_HLLE = 17  # flux_hlle = FluxHLL(min_max_speed_einfeldt): compressible Euler; with the Powell term -> 15
 
 SRC_NONE, SRC_CONVERGENCE_TEST, SRC_EOC_TEST_EULER, SRC_EOC_TEST_COUPLED_EULER_GRAVITY = 0, 1, 2, 3
 
@@ -142,8 +142,6 @@ def resolve_flux(flux):
         raise ValueError(f"unsupported conservative flux {cons} with Powell term")
     if not isinstance(flux, _Flux):
         raise TypeError(f"numerical flux {flux!r} is not in the libtrixi_b200 registry")
-    if flux.flux_id == FLUX_HLLE:
-        raise ValueError("flux_hlle is available for IdealGlmMhdEquations3D with flux_nonconservative_powell only")
     return flux.flux_id
 
 
