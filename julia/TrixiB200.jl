@@ -64,16 +64,23 @@ end
 flux_id(::typeof(flux_central)) = Cint(0)
 flux_id(::typeof(flux_ranocha)) = Cint(1)
 flux_id(f::FluxLaxFriedrichs) = f.dissipation.max_abs_speed === max_abs_speed_naive ? Cint(3) : Cint(2)
-flux_id(f::FluxHLL) = f.min_max_speed === min_max_speed_naive ? Cint(5) : Cint(4)
+# FluxHLL(min_max_speed_davis) = flux_hll, FluxHLL(min_max_speed_naive), FluxHLL(min_max_speed_einfeldt) = flux_hlle
+flux_id(f::FluxHLL) = f.min_max_speed === min_max_speed_naive ? Cint(5) :
+                      (f.min_max_speed === Trixi.min_max_speed_einfeldt ? Cint(17) : Cint(4))
 flux_id(::typeof(flux_shima_etal)) = Cint(6)
 flux_id(::typeof(flux_kennedy_gruber)) = Cint(7)
 flux_id(::typeof(flux_chandrashekar)) = Cint(8)
 flux_id(::typeof(flux_godunov)) = Cint(10)
-flux_id(::typeof(flux_hindenlang_gassner)) = Cint(11)
+flux_id(::typeof(flux_hindenlang_gassner)) = Cint(9)
+flux_id(::typeof(Trixi.flux_ranocha_turbo)) = Cint(11)
 # (conservative, nonconservative) tuples of the GLM-MHD elixirs (elixir_mhd_ec.jl:13-17)
 flux_id(f::Tuple{typeof(flux_hindenlang_gassner), typeof(flux_nonconservative_powell)}) = Cint(13)
 flux_id(f::Tuple{FluxLaxFriedrichs, typeof(flux_nonconservative_powell)}) =
     f[1].dissipation.max_abs_speed === max_abs_speed_naive ? Cint(14) : Cint(12)
+flux_id(f::Tuple{FluxHLL, typeof(flux_nonconservative_powell)}) =
+    f[1].min_max_speed === Trixi.min_max_speed_einfeldt ? Cint(15) :
+    error("FluxHLL with the Powell term: only min_max_speed_einfeldt (flux_hlle) is in the libtrixi_b200 registry")
+flux_id(f::Tuple{typeof(flux_central), typeof(flux_nonconservative_powell)}) = Cint(16)
 flux_id(f) = error("numerical flux $f is not in the libtrixi_b200 registry")
 source_id(::Nothing) = Cint(0)
 source_id(::typeof(source_terms_convergence_test)) = Cint(1)

@@ -21,7 +21,12 @@ CASES = ["tree_3d_euler_ec", "tree_3d_euler_source_terms", "tree_3d_euler_ec_shi
          # shock capturing and GLM-MHD on curved meshes
          "p4est_2d_advection_nonconforming_flag", "p4est_3d_nonconforming_curved_ec", "tree_3d_mhd_alfven_wave_mortar",
          "structured_3d_euler_sedov", "p4est_2d_euler_sedov", "structured_3d_mhd_ec",
-         "p4est_3d_mhd_alfven_wave_nonperiodic"]
+         "p4est_3d_mhd_alfven_wave_nonperiodic",
+         # round 2, last part: shock capturing for GLM-MHD (TreeMesh and curved), flux_hlle of the Euler equations
+         "tree_3d_mhd_ec_shockcapturing", "structured_3d_mhd_ec_shockcapturing", "p4est_3d_euler_sedov_hlle"]
+# the 3S* and SSP stage updates fused into the element kernels (modes 2, 3): one case per kernel family
+STAGE_CASES = ["tree_3d_euler_ec", "tree_3d_euler_source_terms", "tree_3d_euler_ec_shima_etal", "tree_3d_mhd_ec",
+               "tree_3d_euler_shockcapturing", "structured_3d_euler_ec", "p4est_3d_curved_p5", "tree_2d_euler_ec"]
 
 
 def main():
@@ -41,6 +46,20 @@ def main():
             dt = 0.5 * gpu.max_dt()
         ok = bool(np.isfinite(gpu.download(0)).all() and np.isfinite(du).all())
         print(name, "finite" if ok else "NOT FINITE", flush=True)
+        gpu.close()
+    from trixi_b200 import time_integration as ti
+    for name in STAGE_CASES:
+        ex = (ELIXIRS.get(name) or EXTRA[name])
+        semi = ex.semi()
+        gpu = semi.backend()
+        gpu.set_option(gpu.OPT_FUSED_CFL, 1)
+        gpu.upload(0, T.compute_coefficients(0.0, semi))
+        dt = 0.5 * gpu.max_dt()
+        for alg_name in ("ParsaniKetchesonDeconinck3Sstar32", "SimpleSSPRK33"):
+            ti._stage_loop(gpu, getattr(T, alg_name)(), 0.0, dt)
+            dt = 0.5 * gpu.max_dt()
+        ok = bool(np.isfinite(gpu.download(0)).all())
+        print(name, "fused 3S*/SSP stages", "finite" if ok else "NOT FINITE", flush=True)
         gpu.close()
     if "--halo" in sys.argv:  # (not under compute-sanitizer: it serialises kernels, and a wait kernel spinning for a
         halo_probe()          # pack kernel that cannot start would hang)
