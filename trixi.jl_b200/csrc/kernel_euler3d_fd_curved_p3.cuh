@@ -34,7 +34,8 @@ struct CurvedCfg {
     static constexpr int blocks_per_sm(bool resident) { return resident ? 8 : 9; }
 };
 
-template <bool WITH_SURFACE>
+// GEN: also the 3S* / SSP stage updates (KParams::mode 2, 3); see kernel_euler3d_fd_p3.cuh
+template <bool WITH_SURFACE, bool GEN = false>
 __global__ void __launch_bounds__(CurvedCfg::THREADS, CurvedCfg::MIN_BLOCKS)
     k_element_euler3d_ranocha_curved_p3(const KParams P) {
     using C = CurvedCfg;
@@ -267,7 +268,7 @@ __global__ void __launch_bounds__(CurvedCfg::THREADS, CurvedCfg::MIN_BLOCKS)
                 for (int v = 0; v < 5; ++v) sut[(t + 16 * k) * 5 + v] = val[k][v];
         } else {
             // 2N stage (methods_2N.jl:152-158), arithmetic as in the TreeMesh kernel
-            const bool rk2n = P.mode == 1;  // (modes 2 and 3, the 3S* and SSP stages, always run resident)
+            const bool rk2n = !GEN || P.mode == 1;  // (modes 2 and 3, the 3S* and SSP stages, always run resident)
             if (need_ut && rk2n) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
@@ -312,7 +313,7 @@ __global__ void __launch_bounds__(CurvedCfg::THREADS, CurvedCfg::MIN_BLOCKS)
         if (!rk) {
             tma_store(P.du + e0 * CONS, smem_u32(s_ut), bu);
         } else {
-            if (P.rk_write_tmp) tma_store(P.u_tmp + e0 * CONS, smem_u32(s_ut), bu);
+            if (!GEN || P.rk_write_tmp) tma_store(P.u_tmp + e0 * CONS, smem_u32(s_ut), bu);
             if (resident)
                 tma_store(P.u_out + e0 * CONS, smem_u32(s_u), bu);
             else
@@ -325,6 +326,7 @@ __global__ void __launch_bounds__(CurvedCfg::THREADS, CurvedCfg::MIN_BLOCKS)
 cudaError_t preload_tuned_euler3d_curved() {
     cudaError_t e = preload_kernel(k_element_euler3d_ranocha_curved_p3<true>);
     if (e != cudaSuccess) return e;
+    if ((e = preload_kernel(k_element_euler3d_ranocha_curved_p3<true, true>)) != cudaSuccess) return e;
     return preload_kernel(k_element_euler3d_ranocha_curved_p3<false>);
 }
 
@@ -339,6 +341,9 @@ cudaError_t launch_element_euler3d_ranocha_curved_p3(const KParams &P, bool with
         err = cudaFuncSetAttribute(k_element_euler3d_ranocha_curved_p3<false>,
                                    cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         if (err != cudaSuccess) return err;
+        err = cudaFuncSetAttribute(k_element_euler3d_ranocha_curved_p3<true, true>,
+                                   cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (err != cudaSuccess) return err;
     }
     const unsigned blocks = (unsigned)((P.nelements + C::EPB - 1) / C::EPB);
     KParams Q = P;
@@ -346,7 +351,9 @@ cudaError_t launch_element_euler3d_ranocha_curved_p3(const KParams &P, bool with
     const bool resident = tuned_u_resident(Q, with_surface);
     const size_t smem = resident ? C::SMEM_RESIDENT : C::SMEM_STREAM;
     if (Q.prefetch_distance < 0) Q.prefetch_distance = C::EPB * C::blocks_per_sm(resident) * Q.sm_count;
-    if (with_surface)
+    if (Q.mode > 1)  // 3S* / SSP stage (always with the surface terms)
+        k_element_euler3d_ranocha_curved_p3<true, true><<<blocks, C::THREADS, smem, s>>>(Q);
+    else if (with_surface)
         k_element_euler3d_ranocha_curved_p3<true><<<blocks, C::THREADS, smem, s>>>(Q);
     else
         k_element_euler3d_ranocha_curved_p3<false><<<blocks, C::THREADS, smem, s>>>(Q);

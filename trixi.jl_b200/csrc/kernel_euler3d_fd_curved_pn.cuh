@@ -44,7 +44,8 @@ struct CurvedNCfg {
 
 // (two resident blocks per SM: a 5-warp block puts two warps on one scheduler, whose register file holds three warps
 // of 168 registers; a 4-warp block leaves each scheduler two warps of up to 255)
-template <int N, int EPB_, bool WITH_SURFACE>
+// GEN: also the 3S* / SSP stage updates (KParams::mode 2, 3); see kernel_euler3d_fd_p3.cuh
+template <int N, int EPB_, bool WITH_SURFACE, bool GEN = false>
 __global__ void __launch_bounds__(CurvedNCfg<N, EPB_>::THREADS, 2) k_element_euler3d_ranocha_curved_pn(const KParams P) {
     using C = CurvedNCfg<N, EPB_>;
     constexpr int NN = C::NN, NL = C::NL, NF = C::NF, EPB = C::EPB, CONS = C::CONS, SFV = C::SFV;
@@ -264,7 +265,7 @@ __global__ void __launch_bounds__(CurvedNCfg<N, EPB_>::THREADS, 2) k_element_eul
         }
     }
     double *const sut = s_ut + le * DU;
-    const bool rk2n = P.mode == 1;  // (modes 2 and 3, the 3S* and SSP stages, always run resident)
+    const bool rk2n = !GEN || P.mode == 1;  // (modes 2 and 3, the 3S* and SSP stages, always run resident)
     if (active) {
         if (rk2n && need_ut) {
 #pragma unroll
@@ -315,7 +316,7 @@ __global__ void __launch_bounds__(CurvedNCfg<N, EPB_>::THREADS, 2) k_element_eul
             if (!rk) {
                 tma_store(P.du + (e0 + qq) * CONS, smem_u32(s_ut + qq * DU), bu1);
             } else {
-                if (P.rk_write_tmp) tma_store(P.u_tmp + (e0 + qq) * CONS, smem_u32(s_ut + qq * DU), bu1);
+                if (!GEN || P.rk_write_tmp) tma_store(P.u_tmp + (e0 + qq) * CONS, smem_u32(s_ut + qq * DU), bu1);
                 if (resident)
                     tma_store(P.u_out + (e0 + qq) * CONS, smem_u32(s_u + qq * CONS), bu1);
                 else
@@ -330,6 +331,7 @@ template <int N, int EPB>
 cudaError_t preload_tuned_euler3d_curved_pn() {
     cudaError_t e = preload_kernel(k_element_euler3d_ranocha_curved_pn<N, EPB, true>);
     if (e != cudaSuccess) return e;
+    if ((e = preload_kernel(k_element_euler3d_ranocha_curved_pn<N, EPB, true, true>)) != cudaSuccess) return e;
     return preload_kernel(k_element_euler3d_ranocha_curved_pn<N, EPB, false>);
 }
 
@@ -346,6 +348,11 @@ cudaError_t launch_element_euler3d_ranocha_curved_pn(const KParams &P, bool with
         if (err != cudaSuccess) return err;
         cudaFuncSetAttribute(k_element_euler3d_ranocha_curved_pn<N, EPB, true>,
                              cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        err = cudaFuncSetAttribute(k_element_euler3d_ranocha_curved_pn<N, EPB, true, true>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_RESIDENT);
+        if (err != cudaSuccess) return err;
+        cudaFuncSetAttribute(k_element_euler3d_ranocha_curved_pn<N, EPB, true, true>,
+                             cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         cudaFuncSetAttribute(k_element_euler3d_ranocha_curved_pn<N, EPB, false>,
                              cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     }
@@ -354,7 +361,9 @@ cudaError_t launch_element_euler3d_ranocha_curved_pn(const KParams &P, bool with
     Q.want_cfl = 0;  // (k_max_dt_curved reduces the CFL speeds of curved meshes)
     const bool resident = tuned_u_resident(Q, with_surface);
     const size_t smem = resident ? C::SMEM_RESIDENT : C::SMEM_STREAM;
-    if (with_surface)
+    if (Q.mode > 1)  // 3S* / SSP stage (always with the surface terms)
+        k_element_euler3d_ranocha_curved_pn<N, EPB, true, true><<<blocks, C::THREADS, smem, s>>>(Q);
+    else if (with_surface)
         k_element_euler3d_ranocha_curved_pn<N, EPB, true><<<blocks, C::THREADS, smem, s>>>(Q);
     else
         k_element_euler3d_ranocha_curved_pn<N, EPB, false><<<blocks, C::THREADS, smem, s>>>(Q);

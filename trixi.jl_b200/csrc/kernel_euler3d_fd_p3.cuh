@@ -59,7 +59,9 @@ struct TunedCfg {
     static constexpr int blocks_per_sm(bool resident) { return resident ? 12 : 16; }
 };
 
-template <bool WITH_SURFACE>
+// GEN: the instantiation that also knows the 3S* and SSP stage updates (KParams::mode 2, 3); write-du and 2N launches
+// use GEN = false, whose code is exactly the 2N kernel (the extra epilogue code costs 2% when it is merely present)
+template <bool WITH_SURFACE, bool GEN = false>
 __global__ void __launch_bounds__(TunedCfg::THREADS, TunedCfg::MIN_BLOCKS)
     k_element_euler3d_ranocha_p3(const KParams P) {
     using C = TunedCfg;
@@ -340,7 +342,7 @@ __global__ void __launch_bounds__(TunedCfg::THREADS, TunedCfg::MIN_BLOCKS)
         } else {
             // 2N stage (methods_2N.jl:152-158): u_tmp = du - u_tmp * a; u += u_tmp * (b * dt).  The product is
             // rounded before it is added, here and in the bulk reduce-add, so both forms give the same bits.
-            const bool rk2n = P.mode == 1;  // (modes 2 and 3, the 3S* and SSP stages, always run resident)
+            const bool rk2n = !GEN || P.mode == 1;  // (modes 2 and 3, the 3S* and SSP stages, always run resident)
             if (need_ut && rk2n) {  // (warp-uniform)
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
@@ -435,7 +437,7 @@ __global__ void __launch_bounds__(TunedCfg::THREADS, TunedCfg::MIN_BLOCKS)
             tma_store_hint(P.u_tmp + e0 * CONS, smem_u32(s_ut), bu, pol_stream);
             tma_reduce_add_f64_hint(P.u_out + e0 * CONS, smem_u32(s_inc), bu, pol_stream);
         } else {
-            if (P.rk_write_tmp) tma_store(P.u_tmp + e0 * CONS, smem_u32(s_ut), bu);
+            if (!GEN || P.rk_write_tmp) tma_store(P.u_tmp + e0 * CONS, smem_u32(s_ut), bu);
             if (resident)
                 tma_store(P.u_out + e0 * CONS, smem_u32(s_u), bu);
             else
@@ -448,6 +450,7 @@ __global__ void __launch_bounds__(TunedCfg::THREADS, TunedCfg::MIN_BLOCKS)
 cudaError_t preload_tuned_euler3d() {
     cudaError_t e = preload_kernel(k_element_euler3d_ranocha_p3<true>);
     if (e != cudaSuccess) return e;
+    if ((e = preload_kernel(k_element_euler3d_ranocha_p3<true, true>)) != cudaSuccess) return e;
     return preload_kernel(k_element_euler3d_ranocha_p3<false>);
 }
 
@@ -462,13 +465,18 @@ cudaError_t launch_element_euler3d_ranocha_p3(const KParams &P, bool with_surfac
         err = cudaFuncSetAttribute(k_element_euler3d_ranocha_p3<false>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                    cudaSharedmemCarveoutMaxShared);
         if (err != cudaSuccess) return err;
+        err = cudaFuncSetAttribute(k_element_euler3d_ranocha_p3<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                   cudaSharedmemCarveoutMaxShared);
+        if (err != cudaSuccess) return err;
     }
     const unsigned blocks = (unsigned)((P.elem_end - P.elem_begin + C::EPB - 1) / C::EPB);
     const bool resident = tuned_u_resident(P, with_surface);  // (the kernel evaluates the same condition)
     const size_t smem = resident ? C::SMEM_RESIDENT : C::SMEM_STREAM;
     KParams Q = P;
     if (Q.prefetch_distance < 0) Q.prefetch_distance = C::EPB * C::blocks_per_sm(resident) * Q.sm_count;
-    if (with_surface)
+    if (Q.mode > 1)  // 3S* / SSP stage (always with the surface terms)
+        k_element_euler3d_ranocha_p3<true, true><<<blocks, C::THREADS, smem, s>>>(Q);
+    else if (with_surface)
         k_element_euler3d_ranocha_p3<true><<<blocks, C::THREADS, smem, s>>>(Q);
     else
         k_element_euler3d_ranocha_p3<false><<<blocks, C::THREADS, smem, s>>>(Q);

@@ -34,7 +34,8 @@ struct WeakCfg {
 // Ja^a . f, nodal inverse Jacobian (apply_jacobian! :937-956), P4est's all-plus surface integral
 // (dgsem_p4est/dg_3d.jl:976-1034); the element's contravariant_vectors [3, 3, 64] and inverse_jacobian [64]
 // records are two more bulk loads.
-template <bool WITH_SURFACE, bool CURVED>
+// GEN: also the 3S* / SSP stage updates (KParams::mode 2, 3); see kernel_euler3d_fd_p3.cuh
+template <bool WITH_SURFACE, bool CURVED, bool GEN = false>
 __global__ void __launch_bounds__(WeakCfg::THREADS, CURVED ? 12 : WeakCfg::MIN_BLOCKS)
     k_element_euler3d_weak_p3(const KParams P) {
     using C = WeakCfg;
@@ -220,7 +221,7 @@ __global__ void __launch_bounds__(WeakCfg::THREADS, CURVED ? 12 : WeakCfg::MIN_B
             // 2N stage (methods_2N.jl:152-158): u_tmp = du - u_tmp * a; u += u_tmp * (b * dt)
             double *out_u = s_u + n * 5;
             double un[5];
-            if (P.mode == 1) {
+            if (!GEN || P.mode == 1) {
 #pragma unroll
                 for (int v = 0; v < 5; ++v) {
                     const double tmp = need_ut ? val[v] - out_t[v] * P.rk_a : val[v];
@@ -290,7 +291,7 @@ __global__ void __launch_bounds__(WeakCfg::THREADS, CURVED ? 12 : WeakCfg::MIN_B
         if (!rk) {
             tma_store(P.du + e * CONS, smem_u32(s_ut), bu);
         } else {
-            if (P.rk_write_tmp) tma_store(P.u_tmp + e * CONS, smem_u32(s_ut), bu);
+            if (!GEN || P.rk_write_tmp) tma_store(P.u_tmp + e * CONS, smem_u32(s_ut), bu);
             tma_store(P.u_out + e * CONS, smem_u32(s_u), bu);
         }
         tma_store_commit_and_wait_read();
@@ -302,14 +303,16 @@ cudaError_t preload_tuned_euler3d_weak() {
     if ((e = preload_kernel(k_element_euler3d_weak_p3<true, false>)) != cudaSuccess) return e;
     if ((e = preload_kernel(k_element_euler3d_weak_p3<false, false>)) != cudaSuccess) return e;
     if ((e = preload_kernel(k_element_euler3d_weak_p3<true, true>)) != cudaSuccess) return e;
+    if ((e = preload_kernel(k_element_euler3d_weak_p3<true, false, true>)) != cudaSuccess) return e;
+    if ((e = preload_kernel(k_element_euler3d_weak_p3<true, true, true>)) != cudaSuccess) return e;
     return preload_kernel(k_element_euler3d_weak_p3<false, true>);
 }
 
-template <bool WS, bool CURVED>
+template <bool WS, bool CURVED, bool GEN = false>
 static cudaError_t launch_weak_variant(const KParams &P, cudaStream_t s) {
     using C = WeakCfg;
     static PerDeviceFlag configured;
-    auto kern = k_element_euler3d_weak_p3<WS, CURVED>;
+    auto kern = k_element_euler3d_weak_p3<WS, CURVED, GEN>;
     if (!configured.test_and_set()) {
         cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
                                                cudaSharedmemCarveoutMaxShared);
@@ -324,6 +327,8 @@ static cudaError_t launch_weak_variant(const KParams &P, cudaStream_t s) {
 }
 
 cudaError_t launch_element_euler3d_weak_p3(const KParams &P, bool with_surface, cudaStream_t s) {
+    if (P.mode > 1)  // 3S* / SSP stage (always with the surface terms)
+        return P.curved ? launch_weak_variant<true, true, true>(P, s) : launch_weak_variant<true, false, true>(P, s);
     if (P.curved)
         return with_surface ? launch_weak_variant<true, true>(P, s) : launch_weak_variant<false, true>(P, s);
     return with_surface ? launch_weak_variant<true, false>(P, s) : launch_weak_variant<false, false>(P, s);

@@ -268,7 +268,8 @@ struct LineSweepCfg {
 // dg_3d.jl:268-306) for their own two nodes: thread h = 0 needs the subcell fluxes (0,1) and (1,2) of its line,
 // thread h = 1 needs (2,3) and (1,2); the first is the operand pair of its first two-point flux, (1,2) is
 // evaluated by both threads with identical operands (bitwise equal, so the subcell scheme stays conservative).
-template <class EQ, bool WITH_SURFACE, bool SC = false, bool REC = false>
+// GEN: also the 3S* / SSP stage updates (KParams::mode 2, 3); see kernel_euler3d_fd_p3.cuh
+template <class EQ, bool WITH_SURFACE, bool SC = false, bool REC = false, bool GEN = false>
 __global__ void __launch_bounds__(LineSweepCfg<EQ>::THREADS, LineSweepCfg<EQ>::MIN_BLOCKS)
     k_element_fd3d_p3(const KParams P) {
     using C = LineSweepCfg<EQ>;
@@ -597,7 +598,7 @@ __global__ void __launch_bounds__(LineSweepCfg<EQ>::THREADS, LineSweepCfg<EQ>::M
             // 2N stage (methods_2N.jl:152-158): u_tmp = du - u_tmp * a; u += u_tmp * (b * dt)
             double *out_u = s_u + n * NV;
             double un[NV];
-            if (P.mode == 1) {
+            if (!GEN || P.mode == 1) {
 #pragma unroll
                 for (int v = 0; v < NV; ++v) {
                     const double tmp = need_ut ? val[v] - out_t[v] * P.rk_a : val[v];
@@ -643,7 +644,7 @@ __global__ void __launch_bounds__(LineSweepCfg<EQ>::THREADS, LineSweepCfg<EQ>::M
         if (!rk) {
             tma_store(P.du + e * CONS, smem_u32(s_ut), bu);
         } else {
-            if (P.rk_write_tmp) tma_store(P.u_tmp + e * CONS, smem_u32(s_ut), bu);
+            if (!GEN || P.rk_write_tmp) tma_store(P.u_tmp + e * CONS, smem_u32(s_ut), bu);
             tma_store(P.u_out + e * CONS, smem_u32(s_u), bu);
         }
         tma_store_commit_and_wait_read();
@@ -654,18 +655,20 @@ template <class EQ, bool SC = false>
 cudaError_t preload_fd3d_p3() {
     cudaError_t e = preload_kernel(k_element_fd3d_p3<EQ, true, SC>);
     if (e != cudaSuccess) return e;
+    if ((e = preload_kernel(k_element_fd3d_p3<EQ, true, SC, false, true>)) != cudaSuccess) return e;
     if constexpr (NodeRecord<EQ>::kHas) {
         if ((e = preload_kernel(k_element_fd3d_p3<EQ, true, SC, true>)) != cudaSuccess) return e;
+        if ((e = preload_kernel(k_element_fd3d_p3<EQ, true, SC, true, true>)) != cudaSuccess) return e;
         if ((e = preload_kernel(k_element_fd3d_p3<EQ, false, SC, true>)) != cudaSuccess) return e;
     }
     return preload_kernel(k_element_fd3d_p3<EQ, false, SC>);
 }
 
-template <class EQ, bool WS, bool SC = false, bool REC = false>
+template <class EQ, bool WS, bool SC = false, bool REC = false, bool GEN = false>
 cudaError_t launch_fd3d_p3_variant(const KParams &P, cudaStream_t s) {
     using C = LineSweepCfg<EQ>;
     static PerDeviceFlag configured;
-    auto kern = k_element_fd3d_p3<EQ, WS, SC, REC>;
+    auto kern = k_element_fd3d_p3<EQ, WS, SC, REC, GEN>;
     if (!configured.test_and_set()) {
         cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
                                                cudaSharedmemCarveoutMaxShared);
@@ -685,10 +688,13 @@ template <class EQ, bool SC = false>
 cudaError_t launch_element_fd3d_p3(const KParams &P, bool with_surface, cudaStream_t s) {
     if constexpr (NodeRecord<EQ>::kHas) {
         // hoisted node records where the volume flux has a record form (kernel_path 2 = the plain form, for A/B runs)
-        if (NodeRecord<EQ>::applies(P.volume_flux) && P.kernel_path != 2)
+        if (NodeRecord<EQ>::applies(P.volume_flux) && P.kernel_path != 2) {
+            if (P.mode > 1) return launch_fd3d_p3_variant<EQ, true, SC, true, true>(P, s);  // 3S* / SSP stage
             return with_surface ? launch_fd3d_p3_variant<EQ, true, SC, true>(P, s)
                                 : launch_fd3d_p3_variant<EQ, false, SC, true>(P, s);
+        }
     }
+    if (P.mode > 1) return launch_fd3d_p3_variant<EQ, true, SC, false, true>(P, s);  // 3S* / SSP stage
     return with_surface ? launch_fd3d_p3_variant<EQ, true, SC>(P, s) : launch_fd3d_p3_variant<EQ, false, SC>(P, s);
 }
 
