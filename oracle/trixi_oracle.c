@@ -202,6 +202,40 @@ static inline void euler_flux_chandrashekar(const eqn_t *eq, const double *ul, c
     f[nd + 1] = s;
 }
 
+/* flux_chandrashekar(u_ll, u_rr, normal_direction) compressible_euler_3d.jl:693-733, compressible_euler_2d.jl:639-670 */
+static inline void euler_flux_chandrashekar_normal(const eqn_t *eq, const double *ul, const double *ur, const double *n,
+                                                   double *f) {
+    int nd = eq->nd;
+    double rho_ll, v_ll[3], p_ll, rho_rr, v_rr[3], p_rr;
+    euler_cons2prim(eq, ul, &rho_ll, v_ll, &p_ll);
+    euler_cons2prim(eq, ur, &rho_rr, v_rr, &p_rr);
+    double v_dot_n_ll = 0.0, v_dot_n_rr = 0.0;
+    for (int d = 0; d < nd; ++d) {
+        v_dot_n_ll += v_ll[d] * n[d];
+        v_dot_n_rr += v_rr[d] * n[d];
+    }
+    double beta_ll = 0.5 * rho_ll / p_ll, beta_rr = 0.5 * rho_rr / p_rr;
+    double kl = 0.0, kr = 0.0, v_avg[3];
+    for (int d = 0; d < nd; ++d) {
+        kl += v_ll[d] * v_ll[d];
+        kr += v_rr[d] * v_rr[d];
+        v_avg[d] = 0.5 * (v_ll[d] + v_rr[d]);
+    }
+    double specific_kin_ll = 0.5 * kl, specific_kin_rr = 0.5 * kr;
+    double rho_avg = 0.5 * (rho_ll + rho_rr);
+    double rho_mean = ln_mean(rho_ll, rho_rr);
+    double beta_mean = ln_mean(beta_ll, beta_rr);
+    double beta_avg = 0.5 * (beta_ll + beta_rr);
+    double p_mean = 0.5 * rho_avg / beta_avg;
+    double velocity_square_avg = specific_kin_ll + specific_kin_rr;
+    double f1 = rho_mean * 0.5 * (v_dot_n_ll + v_dot_n_rr);
+    f[0] = f1;
+    for (int d = 0; d < nd; ++d) f[1 + d] = f1 * v_avg[d] + p_mean * n[d];
+    double s = f1 * 0.5 * (1 / (eq->gamma - 1) / beta_mean - velocity_square_avg);
+    for (int d = 0; d < nd; ++d) s += f[1 + d] * v_avg[d];
+    f[nd + 1] = s;
+}
+
 /* max_abs_speed_naive compressible_euler_3d.jl:1112-1133; max_abs_speed :1156-1177 */
 static inline double euler_max_abs_speed(const eqn_t *eq, const double *ul, const double *ur, int o, int naive) {
     double rho_ll, v_ll[3], p_ll, rho_rr, v_rr[3], p_rr;
@@ -927,6 +961,9 @@ static void numflux_normal(const eqn_t *eq, int flux_id, const double *ul, const
         f[0] = a >= 0 ? a * ul[0] : a * ur[0];
         return;
     }
+    case TRIXI_B200_FLUX_CHANDRASHEKAR:
+        euler_flux_chandrashekar_normal(eq, ul, ur, n, f);
+        return;
     default:
         for (int v = 0; v < nv; ++v) f[v] = NAN;
     }

@@ -476,6 +476,52 @@ def _p4est2d_advection_basic():
     return T.SemidiscretizationHyperbolic(mesh, eq, T.initial_condition_convergence_test, solver)
 
 
+def _parallelogram_mapping(xi, eta):
+    # examples/structured_2d_dgsem/elixir_advection_parallelogram.jl:37-39, elixir_euler_source_terms_parallelogram.jl
+    return xi + eta, eta
+
+
+def _waving_flag_faces():
+    # examples/structured_2d_dgsem/elixir_advection_waving_flag.jl:16-20: transfinite mapping of four boundary curves
+    return (lambda s: (-1.0 + 0 * s, s - 1.0), lambda s: (1.0 + 0 * s, s + 1.0),
+            lambda s: (s, -1.0 + np.sin(0.5 * np.pi * s)), lambda s: (s, 1.0 + np.sin(0.5 * np.pi * s)))
+
+
+def initial_condition_parallelogram(x, t, equations):
+    # examples/structured_2d_dgsem/elixir_advection_parallelogram.jl:10-29
+    a = equations.advection_velocity
+    xt = (x[0] - x[1]) - (a[0] - a[1]) * t + (x[1] - a[1] * t)
+    return (1.0 + 0.5 * np.sin(2 * np.pi * 0.5 * xt))[None]
+
+
+def _structured2d_advection(kind):
+    solver = T.DGSEM(polydeg=3, surface_flux=T.flux_lax_friedrichs)
+    if kind == "parallelogram":
+        eq = T.LinearScalarAdvectionEquation2D((-0.5, -0.7))
+        mesh = T.StructuredMesh((16, 16), _parallelogram_mapping, periodicity=True)
+        return T.SemidiscretizationHyperbolic(mesh, eq, initial_condition_parallelogram, solver)
+    eq = T.LinearScalarAdvectionEquation2D((0.2, -0.7))
+    if kind == "waving_flag":
+        mesh = T.StructuredMesh((16, 16), faces=_waving_flag_faces(), periodicity=True)
+        return T.SemidiscretizationHyperbolic(mesh, eq, T.initial_condition_convergence_test, solver)
+    mesh = T.StructuredMesh((16, 16), _warped_mapping_2d, periodicity=True)  # free stream
+    return T.SemidiscretizationHyperbolic(mesh, eq, T.initial_condition_constant, solver)
+
+
+def _structured2d_source_terms(kind):
+    # examples/structured_2d_dgsem/elixir_euler_source_terms.jl, ..._parallelogram.jl, ..._waving_flag.jl
+    eq = T.CompressibleEulerEquations2D(1.4)
+    solver = T.DGSEM(polydeg=3, surface_flux=T.FluxLaxFriedrichs(T.max_abs_speed_naive))
+    if kind == "box":
+        mesh = T.StructuredMesh((16, 16), (0.0, 0.0), (2.0, 2.0), periodicity=True)
+    elif kind == "parallelogram":
+        mesh = T.StructuredMesh((16, 16), _parallelogram_mapping, periodicity=True)
+    else:
+        mesh = T.StructuredMesh((16, 16), faces=_waving_flag_faces(), periodicity=True)
+    return T.SemidiscretizationHyperbolic(mesh, eq, T.initial_condition_convergence_test, solver,
+                                          source_terms=T.source_terms_convergence_test)
+
+
 class _FreeStreamElixir(Elixir):
     """Free-stream preservation: the reference's values are round-off (1e-14); compare absolutely."""
 
@@ -491,6 +537,30 @@ ELIXIRS.update({e.name: e for e in [
                        1.4104095258528071e-14],
                       [1.9539925233402755e-14, 2.9791447087035294e-13, 6.502853810985698e-13,
                        2.7000623958883807e-13], "test/test_structured_2d.jl:524-545"),
+    Elixir("structured_2d_advection_parallelogram", lambda: _structured2d_advection("parallelogram"), (0.0, 1.0), 1.6,
+           [8.311947673061856e-6], [6.627000273229378e-5], "test/test_structured_2d.jl:172-183"),
+    Elixir("structured_2d_advection_waving_flag", lambda: _structured2d_advection("waving_flag"), (0.0, 1.0), 1.4,
+           [0.00018553859900545866], [0.0016167719118129753], "test/test_structured_2d.jl:185-195",
+           # (the Linf error 1.6e-3 agrees to 4.9e-12 absolute = 3e-9 relative on the oracle and 1.1e-11 = 7e-9 on the
+           # GPU: the sine-curved mesh itself is only reproduced to the rounding of libm's sin against Julia's; the
+           # reference's own test tolerance is sqrt(eps) = 1.5e-8 relative)
+           rtol=1.5e-8),
+    _FreeStreamElixir("structured_2d_advection_free_stream", lambda: _structured2d_advection("free_stream"), (0.0, 1.0),
+                      2.0, [6.8925194184204476e-15], [9.903189379656396e-14], "test/test_structured_2d.jl:197-207"),
+    Elixir("structured_2d_euler_source_terms", lambda: _structured2d_source_terms("box"), (0.0, 2.0), 1.0,
+           [9.321181253186009e-7, 1.4181210743438511e-6, 1.4181210743487851e-6, 4.824553091276693e-6],
+           [9.577246529612893e-6, 1.1707525976012434e-5, 1.1707525976456523e-5, 4.8869615580926506e-5],
+           "test/test_structured_2d.jl:358-376"),
+    Elixir("structured_2d_euler_source_terms_parallelogram", lambda: _structured2d_source_terms("parallelogram"),
+           (0.0, 2.0), 0.5,
+           [1.1167802955144833e-5, 1.0805775514153104e-5, 1.953188337010932e-5, 5.5033856574857146e-5],
+           [8.297006495561199e-5, 8.663281475951301e-5, 0.00012264160606778596, 0.00041818802502024965],
+           "test/test_structured_2d.jl:478-499"),
+    Elixir("structured_2d_euler_source_terms_waving_flag", lambda: _structured2d_source_terms("waving_flag"),
+           (0.0, 2.0), 0.8,
+           [2.991891317562739e-5, 3.6063177168283174e-5, 2.7082941743640572e-5, 0.00011414695350996946],
+           [0.0002437454930492855, 0.0003438936171968887, 0.00024217622945688078, 0.001266380414757684],
+           "test/test_structured_2d.jl:501-522"),
     Elixir("structured_2d_euler_ec", _structured2d_ec, (0.0, 0.3), 1.0,
            [0.03774907669925568, 0.02845190575242045, 0.028262802829412605, 0.13785915638851698],
            [0.3368296929764073, 0.27644083771519773, 0.27990039685141377, 1.1971436487402016],
@@ -648,7 +718,62 @@ def _euler2d_vortex_shockcapturing(mortar=False):
                                           boundary_conditions=T.boundary_condition_periodic)
 
 
+def initial_condition_kelvin_helmholtz_instability(x, t, equations):
+    # examples/tree_2d_dgsem/elixir_euler_kelvin_helmholtz_instability.jl:17-28 (Rueda-Ramirez, Gassner 2021)
+    slope = 15
+    B = np.tanh(slope * x[1] + 7.5) - np.tanh(slope * x[1] - 7.5)
+    rho = 0.5 + 0.75 * B
+    v1 = 0.5 * (B - 1)
+    v2 = 0.1 * np.sin(math.pi * (2 * x[0]))
+    return equations.prim2cons((rho, v1, v2, np.ones_like(rho)))
+
+
+def _euler2d_kelvin_helmholtz(level=5):
+    # examples/tree_2d_dgsem/elixir_euler_kelvin_helmholtz_instability.jl
+    eq = T.CompressibleEulerEquations2D(1.4)
+    basis = T.LobattoLegendreBasis(3)
+    surface_flux = T.FluxLaxFriedrichs(T.max_abs_speed_naive)
+    indicator_sc = T.IndicatorHennemannGassner(eq, basis, alpha_max=0.002, alpha_min=0.0001, alpha_smooth=True,
+                                               variable=T.density_pressure)
+    volume_integral = T.VolumeIntegralShockCapturingHG(indicator_sc, volume_flux_dg=T.flux_ranocha,
+                                                       volume_flux_fv=surface_flux)
+    solver = T.DGSEM(basis=basis, surface_flux=surface_flux, volume_integral=volume_integral)
+    mesh = T.TreeMesh((-1.0, -1.0), (1.0, 1.0), initial_refinement_level=level, periodicity=True)
+    return T.SemidiscretizationHyperbolic(mesh, eq, initial_condition_kelvin_helmholtz_instability, solver,
+                                          boundary_conditions=T.boundary_condition_periodic)
+
+
+def _euler2d_vortex(split_mortar=False):
+    # examples/tree_2d_dgsem/elixir_euler_vortex.jl (weak form) / elixir_euler_vortex_mortar_split.jl (flux_shima_etal
+    # flux differencing across L2 mortars)
+    eq = T.CompressibleEulerEquations2D(1.4)
+    surface_flux = T.FluxLaxFriedrichs(T.max_abs_speed_naive)
+    if split_mortar:
+        solver = T.DGSEM(polydeg=3, surface_flux=surface_flux,
+                         volume_integral=T.VolumeIntegralFluxDifferencing(T.flux_shima_etal))
+        patches = ({"type": "box", "coordinates_min": (0.0, -10.0), "coordinates_max": (10.0, 10.0)},)
+    else:
+        solver = T.DGSEM(polydeg=3, surface_flux=surface_flux)
+        patches = ()
+    mesh = T.TreeMesh((-10.0, -10.0), (10.0, 10.0), initial_refinement_level=4, refinement_patches=patches,
+                      periodicity=True)
+    return T.SemidiscretizationHyperbolic(mesh, eq, T.initial_condition_isentropic_vortex, solver,
+                                          boundary_conditions=T.boundary_condition_periodic)
+
+
 ELIXIRS.update({e.name: e for e in [
+    Elixir("tree_2d_euler_kelvin_helmholtz_instability", _euler2d_kelvin_helmholtz, (0.0, 0.2), 1.3,
+           [0.055691508271624536, 0.032986009333751655, 0.05224390923711999, 0.08009536362771563],
+           [0.24043622527087494, 0.1660878796929941, 0.12355946691711608, 0.2694290787257758],
+           "test/test_tree_2d_euler.jl:909-931"),
+    Elixir("tree_2d_euler_vortex", _euler2d_vortex, (0.0, 20.0), 1.1,
+           [0.00013492249515826863, 0.006615696236378061, 0.006782108219800376, 0.016393831451740604],
+           [0.0020782600954247776, 0.08150078921935999, 0.08663621974991986, 0.2829930622010579],
+           "test/test_tree_2d_euler.jl:1162-1179"),
+    Elixir("tree_2d_euler_vortex_mortar_split", lambda: _euler2d_vortex(split_mortar=True), (0.0, 1.0), 1.4,
+           [0.0017203323613648241, 0.09628962878682261, 0.09621241164155782, 0.17585995600340926],
+           [0.021740570456931674, 0.9938841665880938, 1.004140123355135, 2.224108857746245],
+           "test/test_tree_2d_euler.jl:1201-1221"),
     # (the MPI run of the first one is asserted against the same values, test/test_mpi_tree.jl:337-356)
     Elixir("tree_2d_euler_vortex_shockcapturing", _euler2d_vortex_shockcapturing, (0.0, 1.0), 0.7,
            [0.0017158367642679273, 0.09619888722871434, 0.09616432767924141, 0.17553381166255197],
@@ -784,6 +909,20 @@ def _p4est3d_sedov(surface_flux=None):
     return T.SemidiscretizationHyperbolic(mesh, eq, _sedov_ic(3, 1.0e-3), _sedov_solver(eq, 5, surface_flux))
 
 
+def _p4est2d_shockcapturing_ec(volume_flux=None):
+    # examples/p4est_2d_dgsem/elixir_euler_shockcapturing_ec.jl
+    eq = T.CompressibleEulerEquations2D(1.4)
+    basis = T.LobattoLegendreBasis(4)
+    indicator_sc = T.IndicatorHennemannGassner(eq, basis, alpha_max=1.0, alpha_min=0.001, alpha_smooth=True,
+                                               variable=T.density_pressure)
+    volume_integral = T.VolumeIntegralShockCapturingHG(indicator_sc, volume_flux_dg=volume_flux or T.flux_ranocha,
+                                                       volume_flux_fv=T.flux_ranocha)
+    solver = T.DGSEM(basis=basis, surface_flux=T.flux_ranocha, volume_integral=volume_integral)
+    mesh = T.P4estMesh((4, 4), polydeg=4, initial_refinement_level=2, coordinates_min=(-1.0, -1.0),
+                       coordinates_max=(1.0, 1.0), periodicity=True)
+    return T.SemidiscretizationHyperbolic(mesh, eq, T.initial_condition_weak_blast_wave, solver)
+
+
 def _tree2d_sedov_blast_wave(surface_flux=None, level=6):
     # examples/tree_2d_dgsem/elixir_euler_sedov_blast_wave.jl without its AMRCallback (the reference's HLLE test passes
     # callbacks = CallbackSet(summary, analysis, alive, stepsize), test/test_tree_2d_euler.jl:757-760)
@@ -817,6 +956,15 @@ ELIXIRS.update({e.name: e for e in [
            [7.82070951e-02, 4.33260474e-02, 4.33260474e-02, 4.33260474e-02, 3.75260911e-01],
            [7.45329845e-01, 3.21754792e-01, 3.21754792e-01, 3.21754792e-01, 4.76151527e+00],
            "test/test_p4est_3d.jl:376-396", rtol=2e-8),
+    Elixir("p4est_2d_euler_shockcapturing_ec", _p4est2d_shockcapturing_ec, (0.0, 1.0), 1.0,
+           [9.53984675e-02, 1.05633455e-01, 1.05636158e-01, 3.50747237e-01],
+           [2.94357464e-01, 4.07893014e-01, 3.97334516e-01, 1.08142520e+00],
+           "test/test_p4est_2d.jl:300-318", rtol=2e-8),
+    Elixir("p4est_2d_euler_shockcapturing_ec_chandrashekar", lambda: _p4est2d_shockcapturing_ec(T.flux_chandrashekar),
+           (0.0, 1.0), 1.0,
+           [0.09527896382082567, 0.10557894830184737, 0.10559379376154387, 0.3503791205165925],
+           [0.2733486454092644, 0.3877283966722886, 0.38650482703821426, 1.0053712251056308],
+           "test/test_p4est_2d.jl:320-342"),
     # flux_hlle = FluxHLL(min_max_speed_einfeldt) of the compressible Euler equations, as surface flux and as the
     # subcell finite-volume flux
     Elixir("p4est_2d_euler_sedov_hlle", lambda: _p4est2d_sedov(T.flux_hlle), (0.0, 0.3), 0.5,

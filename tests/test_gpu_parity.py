@@ -116,7 +116,11 @@ RHS_CASES = ["tree_3d_euler_ec", "tree_3d_euler_source_terms", "tree_3d_euler_so
              "p4est_3d_mhd_alfven_wave_nonconforming", "p4est_3d_mhd_alfven_wave_nonperiodic",
              "tree_3d_mhd_ec_shockcapturing", "structured_3d_mhd_ec_shockcapturing", "tree_3d_mhd_orszag_tang_hlle",
              "structured_3d_mhd_alfven_wave_llf_naive", "p4est_2d_euler_sedov_hlle", "p4est_3d_euler_sedov_hlle",
-             "tree_2d_euler_sedov_blast_wave_hlle"] + sorted(PARITY_EXTRA) + sorted(NONCONFORMING_EXTRA)
+             "tree_2d_euler_sedov_blast_wave_hlle",
+             "tree_2d_euler_vortex", "tree_2d_euler_vortex_mortar_split", "tree_2d_euler_kelvin_helmholtz_instability",
+             "structured_2d_advection_parallelogram", "structured_2d_advection_waving_flag", "structured_2d_euler_source_terms",
+             "structured_2d_euler_source_terms_parallelogram", "structured_2d_euler_source_terms_waving_flag", "p4est_2d_euler_shockcapturing_ec",
+             "p4est_2d_euler_shockcapturing_ec_chandrashekar"] + sorted(PARITY_EXTRA) + sorted(NONCONFORMING_EXTRA)
 
 
 @pytest.mark.parametrize("name", RHS_CASES)
@@ -440,7 +444,11 @@ GOLDEN_GPU = ["tree_3d_advection_basic", "tree_3d_advection_mortar", "structured
               "p4est_3d_mhd_alfven_wave_nonconforming", "p4est_3d_mhd_alfven_wave_nonperiodic",
               "tree_3d_mhd_ec_shockcapturing", "structured_3d_mhd_ec_shockcapturing", "tree_3d_mhd_ec_constant",
               "tree_3d_mhd_orszag_tang_hlle", "structured_3d_mhd_alfven_wave_llf_naive", "p4est_2d_euler_sedov_hlle",
-              "p4est_3d_euler_sedov_hlle", "tree_2d_euler_sedov_blast_wave_hlle"]
+              "p4est_3d_euler_sedov_hlle", "tree_2d_euler_sedov_blast_wave_hlle",
+             "tree_2d_euler_vortex", "tree_2d_euler_vortex_mortar_split", "tree_2d_euler_kelvin_helmholtz_instability",
+             "structured_2d_advection_parallelogram", "structured_2d_advection_waving_flag", "structured_2d_advection_free_stream",
+             "structured_2d_euler_source_terms", "structured_2d_euler_source_terms_parallelogram", "structured_2d_euler_source_terms_waving_flag",
+             "p4est_2d_euler_shockcapturing_ec", "p4est_2d_euler_shockcapturing_ec_chandrashekar"]
 
 
 @pytest.mark.parametrize("name", GOLDEN_GPU)

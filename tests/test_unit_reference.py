@@ -106,8 +106,6 @@ def test_rotated_fluxes_3d(oracle_module):
         for ul in u_values:
             for ur in u_values:
                 for d in range(3):
-                    if flux == "chandrashekar":
-                        break  # orientation form only, as in the reference (compressible_euler_3d.jl:639-733)
                     n = [0.0, 0.0, 0.0]
                     n[d] = 1.0
                     np.testing.assert_allclose(o.numflux_normal(flux, ul, ur, n), o.numflux(flux, ul, ur, d + 1),

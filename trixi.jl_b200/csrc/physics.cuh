@@ -464,6 +464,39 @@ struct Euler {
         f[ND + 1] = s;
     }
 
+    // flux_chandrashekar(u_ll, u_rr, normal_direction) (compressible_euler_3d.jl:693-733, compressible_euler_2d.jl:639-670)
+    TB_DEV void flux_chandrashekar_normal(const double (&ul)[NVARS], const double (&ur)[NVARS], const double (&n)[ND],
+                                          double (&f)[NVARS]) const {
+        double rho_ll, v_ll[ND], p_ll, rho_rr, v_rr[ND], p_rr;
+        cons2prim(ul, rho_ll, v_ll, p_ll);
+        cons2prim(ur, rho_rr, v_rr, p_rr);
+        const double beta_ll = 0.5 * rho_ll / p_ll, beta_rr = 0.5 * rho_rr / p_rr;
+        double kl = 0.0, kr = 0.0, v_avg[ND], vn_ll = 0.0, vn_rr = 0.0;
+#pragma unroll
+        for (int d = 0; d < ND; ++d) {
+            kl += v_ll[d] * v_ll[d];
+            kr += v_rr[d] * v_rr[d];
+            v_avg[d] = 0.5 * (v_ll[d] + v_rr[d]);
+            vn_ll += v_ll[d] * n[d];
+            vn_rr += v_rr[d] * n[d];
+        }
+        const double rho_avg = 0.5 * (rho_ll + rho_rr);
+        const double rho_mean = ln_mean(rho_ll, rho_rr);
+        const double beta_mean = ln_mean(beta_ll, beta_rr);
+        const double beta_avg = 0.5 * (beta_ll + beta_rr);
+        const double p_mean = 0.5 * rho_avg / beta_avg;
+        const double velocity_square_avg = 0.5 * kl + 0.5 * kr;
+        const double f1 = rho_mean * 0.5 * (vn_ll + vn_rr);
+        f[0] = f1;
+        double s = f1 * 0.5 * (1 / (gamma - 1) / beta_mean - velocity_square_avg);
+#pragma unroll
+        for (int d = 0; d < ND; ++d) {
+            f[1 + d] = f1 * v_avg[d] + p_mean * n[d];
+            s += f[1 + d] * v_avg[d];
+        }
+        f[ND + 1] = s;
+    }
+
     TB_DEV void numflux(int id, const double (&ul)[NVARS], const double (&ur)[NVARS], int o,
                         double (&f)[NVARS]) const {
         switch (id) {
@@ -740,6 +773,9 @@ struct Euler {
             }
             break;
         }
+        case TRIXI_B200_FLUX_CHANDRASHEKAR:
+            flux_chandrashekar_normal(ul, ur, n, f);
+            break;
         default:
 #pragma unroll
             for (int v = 0; v < NVARS; ++v) f[v] = nan("");
