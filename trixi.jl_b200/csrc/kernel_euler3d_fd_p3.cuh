@@ -61,14 +61,19 @@ struct TunedCfg {
 
 // GEN: the instantiation that also knows the 3S* and SSP stage updates (KParams::mode 2, 3); write-du and 2N launches
 // use GEN = false, whose code is exactly the 2N kernel (the extra epilogue code costs 2% when it is merely present)
-template <bool WITH_SURFACE, bool GEN = false>
+// LEAN: the instantiation for the launches that make up four of the five stages of a 2N step on a TreeMesh: 2N stage,
+// streamed u (reduce-add), single-copy face fluxes, no source terms, no L2 hints.  The run-time branches for everything
+// else fold away (2920 -> fewer SASS instructions; the kernel is sensitive to its code size).
+template <bool WITH_SURFACE, bool GEN = false, bool LEAN = false>
 __global__ void __launch_bounds__(TunedCfg::THREADS, TunedCfg::MIN_BLOCKS)
     k_element_euler3d_ranocha_p3(const KParams P) {
     using C = TunedCfg;
     constexpr int CONS = C::CONS, PRIM = C::PRIM, SFV = C::SFV, EPB = C::EPB;
     extern __shared__ __align__(128) double smem[];
-    const bool have_src = WITH_SURFACE && P.source_terms != TRIXI_B200_SRC_NONE;
-    const bool resident = tuned_u_resident(P, WITH_SURFACE);
+    static_assert(!LEAN || (WITH_SURFACE && !GEN), "the lean instantiation is a 2N stage with surface terms");
+    const bool have_src = LEAN ? false : WITH_SURFACE && P.source_terms != TRIXI_B200_SRC_NONE;
+    const bool resident = LEAN ? false : tuned_u_resident(P, WITH_SURFACE);
+    const bool sfv_single = LEAN ? true : P.sfv_single != 0;
     double *s_prim = smem;                 // [2][64][7] swizzled
     double *s_du = smem + C::OFF_DU;       // [2][64][5] swizzled; before the x pass: u, natural order (not resident)
     double *s_sfv = smem;                  // epilogue: six [16][5] faces per element at stride fs, element h at h * 504
@@ -86,12 +91,12 @@ __global__ void __launch_bounds__(TunedCfg::THREADS, TunedCfg::MIN_BLOCKS)
     const int eh = (lane >> 4) < nvalid ? (lane >> 4) : 0;
     const long long e = e0 + eh;
     const double gamma = P.eq.p[0], igm1 = P.eq.p[1];
-    const bool rk = P.mode != 0;
+    const bool rk = LEAN ? true : P.mode != 0;
     const bool need_ut = rk && P.rk_read_tmp;
     const uint32_t bu = nvalid * CONS * sizeof(double), bs = nvalid * SFV * sizeof(double);
 
     // L2 priorities: u is touched again by this CTA's reduce-add ~10 us later (evict_last); everything else streams
-    const bool hints = P.l2_hints != 0;
+    const bool hints = LEAN ? false : P.l2_hints != 0;
     const uint64_t pol_keep = hints ? l2_policy_evict_last() : 0ull, pol_stream = hints ? l2_policy_evict_first() : 0ull;
     // 0. TMA load of the two contiguous u records; the records the epilogue will want are pulled into L2 meanwhile
     if (lane == 0) {
@@ -110,7 +115,7 @@ __global__ void __launch_bounds__(TunedCfg::THREADS, TunedCfg::MIN_BLOCKS)
             tma_load(smem_u32(s_uin), P.u + e0 * CONS, bu, bar_u);
         // (single-copy face fluxes: half of the own block is never read and the rest is fetched a whole z pass before
         // it is needed, so nothing is prefetched)
-        if (WITH_SURFACE && !P.sfv_single) tma_prefetch_l2(P.sfv + e0 * SFV, bs);
+        if (WITH_SURFACE && !sfv_single) tma_prefetch_l2(P.sfv + e0 * SFV, bs);
         if (need_ut) tma_prefetch_l2(P.u_tmp + e0 * CONS, bu);
         // warm L2 for the elements that will occupy this CTA slot next (blocks are scheduled in index order:
         // one wave further on), so their u tile sees L2 instead of HBM latency
@@ -118,7 +123,7 @@ __global__ void __launch_bounds__(TunedCfg::THREADS, TunedCfg::MIN_BLOCKS)
         if (P.prefetch_distance > 0 && en + EPB <= P.nelements)
             tma_prefetch_l2(P.u + en * CONS, EPB * CONS * sizeof(double));
     }
-    if (WITH_SURFACE && P.sfv_single && lane < 3 * nvalid) s_nb[lane] = P.minus_nb[e0 * 3 + lane];
+    if (WITH_SURFACE && sfv_single && lane < 3 * nvalid) s_nb[lane] = P.minus_nb[e0 * 3 + lane];
     const double *const su = s_uin + eh * CONS;
     double *const sp = s_prim + eh * PRIM, *const sd = s_du + eh * CONS;
     while (!mbar_try_wait(bar_u, 0)) {
@@ -181,7 +186,7 @@ __global__ void __launch_bounds__(TunedCfg::THREADS, TunedCfg::MIN_BLOCKS)
             __syncwarp();
             constexpr uint32_t bs1 = SFV * sizeof(double), bf = 80 * sizeof(double);
             if (lane == 0) mbar_expect_tx(bar_s, bs);
-            if (!P.sfv_single) {
+            if (!sfv_single) {
                 if (lane == 0) {
                     tma_load(smem_u32(s_sfv), P.sfv + e0 * SFV, bs1, bar_s);
                     if (nvalid == EPB) tma_load(smem_u32(s_sfv + C::SFV_H), P.sfv + (e0 + 1) * SFV, bs1, bar_s);
@@ -275,7 +280,7 @@ __global__ void __launch_bounds__(TunedCfg::THREADS, TunedCfg::MIN_BLOCKS)
         if constexpr (WITH_SURFACE) {
             // calc_surface_integral! (dg_3d.jl:1337-1394): directions 1..6 = -x,+x,-y,+y,-z,+z
             const double *ssf = s_sfv + eh * C::SFV_H;
-            const int fs = P.sfv_single ? C::SFV_PAD : 80;  // face stride in the tile
+            const int fs = sfv_single ? C::SFV_PAD : 80;  // face stride in the tile
             if (i == 0 || i == 3) {
                 const double *sf = ssf + (i == 0 ? 0 : fs) + j * 5;
                 const double w = i == 0 ? -P.inv_weight0 : P.inv_weight0;
@@ -451,6 +456,7 @@ cudaError_t preload_tuned_euler3d() {
     cudaError_t e = preload_kernel(k_element_euler3d_ranocha_p3<true>);
     if (e != cudaSuccess) return e;
     if ((e = preload_kernel(k_element_euler3d_ranocha_p3<true, true>)) != cudaSuccess) return e;
+    if ((e = preload_kernel(k_element_euler3d_ranocha_p3<true, false, true>)) != cudaSuccess) return e;
     return preload_kernel(k_element_euler3d_ranocha_p3<false>);
 }
 
@@ -468,6 +474,9 @@ cudaError_t launch_element_euler3d_ranocha_p3(const KParams &P, bool with_surfac
         err = cudaFuncSetAttribute(k_element_euler3d_ranocha_p3<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                    cudaSharedmemCarveoutMaxShared);
         if (err != cudaSuccess) return err;
+        err = cudaFuncSetAttribute(k_element_euler3d_ranocha_p3<true, false, true>,
+                                   cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (err != cudaSuccess) return err;
     }
     const unsigned blocks = (unsigned)((P.elem_end - P.elem_begin + C::EPB - 1) / C::EPB);
     const bool resident = tuned_u_resident(P, with_surface);  // (the kernel evaluates the same condition)
@@ -476,6 +485,8 @@ cudaError_t launch_element_euler3d_ranocha_p3(const KParams &P, bool with_surfac
     if (Q.prefetch_distance < 0) Q.prefetch_distance = C::EPB * C::blocks_per_sm(resident) * Q.sm_count;
     if (Q.mode > 1)  // 3S* / SSP stage (always with the surface terms)
         k_element_euler3d_ranocha_p3<true, true><<<blocks, C::THREADS, smem, s>>>(Q);
+    else if (with_surface && Q.mode == 1 && !resident && Q.sfv_single && !Q.l2_hints)
+        k_element_euler3d_ranocha_p3<true, false, true><<<blocks, C::THREADS, smem, s>>>(Q);
     else if (with_surface)
         k_element_euler3d_ranocha_p3<true><<<blocks, C::THREADS, smem, s>>>(Q);
     else
