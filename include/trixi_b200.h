@@ -89,8 +89,9 @@ enum {
                                                        numerical_fluxes.jl:422-457, ideal_glm_mhd_3d.jl:1094-1130,
                                                        Roe averages :1415-1491 */
     TRIXI_B200_FLUX_CENTRAL_MHD_POWELL = 16,        /* (flux_central, flux_nonconservative_powell) */
-    TRIXI_B200_FLUX_HLLE = 17               /* flux_hlle = FluxHLL(min_max_speed_einfeldt) numerical_fluxes.jl:457, compressible
+    TRIXI_B200_FLUX_HLLE = 17,              /* flux_hlle = FluxHLL(min_max_speed_einfeldt) numerical_fluxes.jl:457, compressible
                                              * Euler: compressible_euler_3d.jl:1662-1771, compressible_euler_2d.jl:1925-2025 */
+    TRIXI_B200_FLUX_HLLC = 18               /* flux_hllc compressible_euler_3d.jl:1423-1665, compressible_euler_2d.jl:1720-1925 */
 };
 
 /* source terms (calc_sources! dg_3d.jl:1417-1437 calls an arbitrary closure; here: registry) */

@@ -71,6 +71,7 @@ flux_id(::typeof(flux_shima_etal)) = Cint(6)
 flux_id(::typeof(flux_kennedy_gruber)) = Cint(7)
 flux_id(::typeof(flux_chandrashekar)) = Cint(8)
 flux_id(::typeof(flux_godunov)) = Cint(10)
+flux_id(::typeof(flux_hllc)) = Cint(18)
 flux_id(::typeof(flux_hindenlang_gassner)) = Cint(9)
 flux_id(::typeof(Trixi.flux_ranocha_turbo)) = Cint(11)
 # (conservative, nonconservative) tuples of the GLM-MHD elixirs (elixir_mhd_ec.jl:13-17)

@@ -312,6 +312,113 @@ static inline void euler_min_max_speed_einfeldt(const eqn_t *eq, const double *u
     *lmax = fmax(fmax(vn_roe + c_roe, vn_rr + beta * c_rr), 0.0);
 }
 
+static inline void euler_flux(const eqn_t *eq, const double *u, int o, double *f);
+static inline void euler_flux_normal(const eqn_t *eq, const double *u, const double *n, double *f);
+/* flux_hllc (compressible_euler_3d.jl:1423-1541 with an orientation, :1543-1665 along a normal direction;
+ * compressible_euler_2d.jl:1720-1925).  n == NULL: orientation o (0-based) */
+static inline void euler_flux_hllc(const eqn_t *eq, const double *ul, const double *ur, int o, const double *n,
+                                   double *f) {
+    int nd = eq->nd, nv = eq->nv;
+    double rho_ll = ul[0], rho_rr = ur[0], v_ll[3] = {0, 0, 0}, v_rr[3] = {0, 0, 0};
+    double vsq_ll = 0.0, vsq_rr = 0.0;
+    for (int d = 0; d < nd; ++d) {
+        v_ll[d] = ul[1 + d] / rho_ll;
+        v_rr[d] = ur[1 + d] / rho_rr;
+        vsq_ll += v_ll[d] * v_ll[d];
+        vsq_rr += v_rr[d] * v_rr[d];
+    }
+    double e_ll = ul[nd + 1] / rho_ll, e_rr = ur[nd + 1] / rho_rr;
+    double p_ll, p_rr;
+    if (n) { /* cons2prim */
+        double rl, vl3[3], rr_, vr3[3];
+        euler_cons2prim(eq, ul, &rl, vl3, &p_ll);
+        euler_cons2prim(eq, ur, &rr_, vr3, &p_rr);
+    } else {
+        p_ll = (eq->gamma - 1) * (ul[nd + 1] - 0.5 * rho_ll * vsq_ll);
+        p_rr = (eq->gamma - 1) * (ur[nd + 1] - 0.5 * rho_rr * vsq_rr);
+    }
+    double norm_ = 1.0, norm_sq = 1.0, inv_norm_sq = 1.0, vel_L, vel_R;
+    if (n) {
+        vel_L = 0.0;
+        vel_R = 0.0;
+        for (int d = 0; d < nd; ++d) {
+            vel_L += v_ll[d] * n[d];
+            vel_R += v_rr[d] * n[d];
+        }
+        norm_ = vec_norm(nd, n);
+        norm_sq = norm_ * norm_;
+        inv_norm_sq = 1.0 / norm_sq;
+    } else {
+        vel_L = v_ll[o];
+        vel_R = v_rr[o];
+    }
+    double c_ll = sqrt(eq->gamma * p_ll / rho_ll), c_rr = sqrt(eq->gamma * p_rr / rho_rr);
+    if (n) {
+        c_ll = c_ll * norm_;
+        c_rr = c_rr * norm_;
+    }
+    double f_ll[MAXV], f_rr[MAXV];
+    if (n) {
+        euler_flux_normal(eq, ul, n, f_ll);
+        euler_flux_normal(eq, ur, n, f_rr);
+    } else {
+        euler_flux(eq, ul, o, f_ll);
+        euler_flux(eq, ur, o, f_rr);
+    }
+    double sqrt_rho_ll = sqrt(rho_ll), sqrt_rho_rr = sqrt(rho_rr), sum_sqrt_rho = sqrt_rho_ll + sqrt_rho_rr;
+    double vel_roe, vel_roe_mag = 0.0;
+    if (n) {
+        double v_roe[3];
+        vel_roe = 0.0;
+        for (int d = 0; d < nd; ++d) {
+            v_roe[d] = (sqrt_rho_ll * v_ll[d] + sqrt_rho_rr * v_rr[d]) / sum_sqrt_rho;
+            vel_roe += v_roe[d] * n[d];
+            vel_roe_mag += v_roe[d] * v_roe[d];
+        }
+    } else {
+        vel_roe = (sqrt_rho_ll * vel_L + sqrt_rho_rr * vel_R) / sum_sqrt_rho;
+        for (int d = 0; d < nd; ++d) {
+            double w = sqrt_rho_ll * v_ll[d] + sqrt_rho_rr * v_rr[d];
+            vel_roe_mag += w * w;
+        }
+        vel_roe_mag = vel_roe_mag / (sum_sqrt_rho * sum_sqrt_rho);
+    }
+    double H_ll = (ul[nd + 1] + p_ll) / rho_ll, H_rr = (ur[nd + 1] + p_rr) / rho_rr;
+    double H_roe = (sqrt_rho_ll * H_ll + sqrt_rho_rr * H_rr) / sum_sqrt_rho;
+    double c_roe = sqrt((eq->gamma - 1) * (H_roe - 0.5 * vel_roe_mag));
+    if (n) c_roe = c_roe * norm_;
+    double Ssl = fmin(vel_L - c_ll, vel_roe - c_roe), Ssr = fmax(vel_R + c_rr, vel_roe + c_roe);
+    double sMu_L = Ssl - vel_L, sMu_R = Ssr - vel_R;
+    if (Ssl >= 0) {
+        for (int v = 0; v < nv; ++v) f[v] = f_ll[v];
+        return;
+    }
+    if (Ssr <= 0) {
+        for (int v = 0; v < nv; ++v) f[v] = f_rr[v];
+        return;
+    }
+    double SStar = n ? (rho_ll * vel_L * sMu_L - rho_rr * vel_R * sMu_R + (p_rr - p_ll) * norm_sq) /
+                           (rho_ll * sMu_L - rho_rr * sMu_R)
+                     : (p_rr - p_ll + rho_ll * vel_L * sMu_L - rho_rr * vel_R * sMu_R) / (rho_ll * sMu_L - rho_rr * sMu_R);
+    int left = Ssl <= 0 && 0 <= SStar;
+    const double *us = left ? ul : ur, *fs = left ? f_ll : f_rr, *vs = left ? v_ll : v_rr;
+    double rho_s = left ? rho_ll : rho_rr, sMu = left ? sMu_L : sMu_R, Ss = left ? Ssl : Ssr;
+    double vel_s = left ? vel_L : vel_R, e_s = left ? e_ll : e_rr, p_s = left ? p_ll : p_rr;
+    double densStar = rho_s * sMu / (Ss - SStar);
+    double UStar[MAXV];
+    UStar[0] = densStar;
+    if (n) {
+        double enerStar = e_s + (SStar - vel_s) * (SStar * inv_norm_sq + p_s / (rho_s * sMu));
+        for (int d = 0; d < nd; ++d) UStar[1 + d] = densStar * (vs[d] + (SStar - vel_s) * n[d] * inv_norm_sq);
+        UStar[nd + 1] = densStar * enerStar;
+    } else {
+        double enerStar = e_s + (SStar - vel_s) * (SStar + p_s / (rho_s * sMu));
+        for (int d = 0; d < nd; ++d) UStar[1 + d] = densStar * (d == o ? SStar : vs[d]);
+        UStar[nd + 1] = densStar * enerStar;
+    }
+    for (int v = 0; v < nv; ++v) f[v] = fs[v] + Ss * (UStar[v] - us[v]);
+}
+
 /* ---- ideal GLM-MHD 3D (ideal_glm_mhd_3d.jl) ------------------------------------------------------------ */
 /* cons2prim :1231-1243: (rho, v1, v2, v3, p, B1, B2, B3, psi) */
 static inline void mhd_cons2prim(const eqn_t *eq, const double *u, double *prim) {
@@ -700,6 +807,9 @@ static void numflux(const eqn_t *eq, int flux_id, const double *ul, const double
         for (int v = 0; v < nv; ++v) f[v] = 0.5 * (fl[v] + fr[v]) + (-0.5 * lam * (ur[v] - ul[v]));
         return;
     }
+    case TRIXI_B200_FLUX_HLLC:
+        euler_flux_hllc(eq, ul, ur, o, NULL, f);
+        return;
     case TRIXI_B200_FLUX_HLLE:
     case TRIXI_B200_FLUX_HLL_DAVIS:
     case TRIXI_B200_FLUX_HLL_NAIVE: { /* FluxHLL numerical_fluxes.jl:422-440 */
@@ -963,6 +1073,9 @@ static void numflux_normal(const eqn_t *eq, int flux_id, const double *ul, const
     }
     case TRIXI_B200_FLUX_CHANDRASHEKAR:
         euler_flux_chandrashekar_normal(eq, ul, ur, n, f);
+        return;
+    case TRIXI_B200_FLUX_HLLC:
+        euler_flux_hllc(eq, ul, ur, 0, n, f);
         return;
     default:
         for (int v = 0; v < nv; ++v) f[v] = NAN;

@@ -743,6 +743,35 @@ def _euler2d_kelvin_helmholtz(level=5):
                                           boundary_conditions=T.boundary_condition_periodic)
 
 
+def initial_condition_isentropic_vortex_advected(x, t, equations):
+    # examples/tree_2d_dgsem/elixir_euler_vortex_mortar.jl:18-62: the vortex centre moves with the base flow and is
+    # wrapped to its nearest periodic image (the shock-capturing / split-form elixirs keep it at t_loc = 0)
+    gamma = equations.gamma
+    amplitude, rho, v1, v2, p = 5.0, 1.0, 1.0, 1.0, 25.0
+    rt = p / rho
+    dx, dy = x[0] - (0.0 + v1 * t), x[1] - (0.0 + v2 * t)
+    dx = dx - 20.0 * np.round(dx / 20.0)
+    dy = dy - 20.0 * np.round(dy / 20.0)
+    cx, cy = -dy, dx
+    r2 = cx**2 + cy**2
+    du = amplitude / (2 * math.pi) * np.exp(0.5 * (1 - r2))
+    dtemp = -(gamma - 1) / (2 * gamma * rt) * du**2
+    rho_ = rho * (1 + dtemp) ** (1 / (gamma - 1))
+    p_ = p * (1 + dtemp) ** (gamma / (gamma - 1))
+    return equations.prim2cons((rho_, v1 + du * cx, v2 + du * cy, p_))
+
+
+def _euler2d_vortex_mortar_hllc():
+    # examples/tree_2d_dgsem/elixir_euler_vortex_mortar.jl: weak form, flux_hllc across L2 mortars
+    eq = T.CompressibleEulerEquations2D(1.4)
+    solver = T.DGSEM(polydeg=3, surface_flux=T.flux_hllc)
+    patches = ({"type": "box", "coordinates_min": (0.0, -10.0), "coordinates_max": (10.0, 10.0)},)
+    mesh = T.TreeMesh((-10.0, -10.0), (10.0, 10.0), initial_refinement_level=4, refinement_patches=patches,
+                      periodicity=True)
+    return T.SemidiscretizationHyperbolic(mesh, eq, initial_condition_isentropic_vortex_advected, solver,
+                                          boundary_conditions=T.boundary_condition_periodic)
+
+
 def _euler2d_vortex(split_mortar=False):
     # examples/tree_2d_dgsem/elixir_euler_vortex.jl (weak form) / elixir_euler_vortex_mortar_split.jl (flux_shima_etal
     # flux differencing across L2 mortars)
@@ -770,6 +799,10 @@ ELIXIRS.update({e.name: e for e in [
            [0.00013492249515826863, 0.006615696236378061, 0.006782108219800376, 0.016393831451740604],
            [0.0020782600954247776, 0.08150078921935999, 0.08663621974991986, 0.2829930622010579],
            "test/test_tree_2d_euler.jl:1162-1179"),
+    Elixir("tree_2d_euler_vortex_mortar", _euler2d_vortex_mortar_hllc, (0.0, 1.0), 1.4,
+           [3.1363505551305216e-5, 0.0006614564510650079, 0.0006466955139840528, 0.002661217863027477],
+           [0.0010628052760547346, 0.028186424944457555, 0.01130123802781463, 0.07516351234122709],
+           "test/test_tree_2d_euler.jl:1181-1199"),
     Elixir("tree_2d_euler_vortex_mortar_split", lambda: _euler2d_vortex(split_mortar=True), (0.0, 1.0), 1.4,
            [0.0017203323613648241, 0.09628962878682261, 0.09621241164155782, 0.17585995600340926],
            [0.021740570456931674, 0.9938841665880938, 1.004140123355135, 2.224108857746245],
@@ -971,6 +1004,10 @@ ELIXIRS.update({e.name: e for e in [
            [0.40853279043747015, 0.25356771650524296, 0.2535677165052422, 1.2984601729572691],
            [1.3840909333784284, 1.3077772519086124, 1.3077772519086157, 6.298798630968632],
            "test/test_p4est_2d.jl:471-490"),
+    Elixir("p4est_2d_euler_sedov_hllc", lambda: _p4est2d_sedov(T.flux_hllc), (0.0, 0.3), 0.5,
+           [0.4229948321239887, 0.2559038337457483, 0.2559038337457484, 1.2990046683564136],
+           [1.4989357969730492, 1.325456585141623, 1.3254565851416251, 6.331283015053501],
+           "test/test_p4est_2d.jl:450-469"),
     Elixir("p4est_3d_euler_sedov_hlle", lambda: _p4est3d_sedov(T.flux_hlle), (0.0, 0.3), 0.5,
            [0.09946224487902565, 0.04863386374672001, 0.048633863746720116, 0.04863386374672032, 0.3751015774232693],
            [0.789241521871487, 0.42046970270100276, 0.42046970270100276, 0.4204697027010028, 4.730877375538398],
@@ -1227,6 +1264,7 @@ for _mesh in ("tree", "structured", "p4est"):
                 T.initial_condition_convergence_test)))
         PARITY_EXTRA[f"{_tag}_hll"] = lambda m=_mesh, n=_nd: _parity_case(m, n, T.flux_hll)
         PARITY_EXTRA[f"{_tag}_hlle"] = lambda m=_mesh, n=_nd: _parity_case(m, n, T.flux_hlle)
+        PARITY_EXTRA[f"{_tag}_hllc"] = lambda m=_mesh, n=_nd: _parity_case(m, n, T.flux_hllc)
         PARITY_EXTRA[f"{_tag}_hll_naive"] = (
             lambda m=_mesh, n=_nd: _parity_case(m, n, T.FluxHLL(T.min_max_speed_naive), volume_flux=T.flux_ranocha))
         PARITY_EXTRA[f"{_tag}_slip_wall"] = (

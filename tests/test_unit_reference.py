@@ -9,7 +9,7 @@ import trixi_b200 as T
 from trixi_b200 import basis as B
 
 FLUX = {"central": 0, "ranocha": 1, "llf": 2, "llf_naive": 3, "hll_davis": 4, "hll_naive": 5, "shima_etal": 6,
-        "kennedy_gruber": 7, "chandrashekar": 8, "hlle": 17}
+        "kennedy_gruber": 7, "chandrashekar": 8, "hlle": 17, "hllc": 18}
 
 
 def _semi(ndims):
@@ -89,6 +89,11 @@ def test_hll_consistency(ndims, oracle_module):
                [(1.0, 0.0, 0.0), (0.0, 1.0, 0.0), (0.0, 0.0, 1.0), (0.5, -0.5, 0.2), (-1.2, 0.3, 1.4)])
     for n in normals:
         np.testing.assert_allclose(o.numflux_normal("hll_davis", u, u, n), o.flux_normal(u, n), rtol=1e-13)
+    # test/test_unit.jl (Consistency check for HLLC flux: CEE): the same for flux_hllc
+    for orientation in range(1, ndims + 1):
+        np.testing.assert_allclose(o.numflux("hllc", u, u, orientation), o.flux(u, orientation), rtol=1e-14)
+    for n in normals:
+        np.testing.assert_allclose(o.numflux_normal("hllc", u, u, n), o.flux_normal(u, n), rtol=1e-13)
     # test/test_unit.jl:1803-1849 (Consistency check for HLLE flux: CEE): the same for flux_hlle
     for orientation in range(1, ndims + 1):
         np.testing.assert_allclose(o.numflux("hlle", u, u, orientation), o.flux(u, orientation), rtol=1e-14)
@@ -101,7 +106,7 @@ def test_rotated_fluxes_3d(oracle_module):
     flux equals its orientation form."""
     o = _Oracle(oracle_module, 3)
     u_values = [(1.0, 0.5, -0.7, 0.1, 1.0), (1.5, -0.2, 0.1, 0.2, 5.0)]
-    for flux in ["central", "ranocha", "shima_etal", "kennedy_gruber", "hll_davis", "hlle", "chandrashekar", "llf",
+    for flux in ["central", "ranocha", "shima_etal", "kennedy_gruber", "hll_davis", "hlle", "hllc", "chandrashekar", "llf",
                  "llf_naive"]:
         for ul in u_values:
             for ur in u_values:

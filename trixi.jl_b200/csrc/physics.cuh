@@ -497,9 +497,122 @@ struct Euler {
         f[ND + 1] = s;
     }
 
+    // flux_hllc (compressible_euler_3d.jl:1423-1541 with an orientation, :1543-1665 along a normal direction;
+    // compressible_euler_2d.jl:1720-1925).  NORMAL = false: orientation o, n is not looked at
+    template <bool NORMAL>
+    TB_DEV void flux_hllc(const double (&ul)[NVARS], const double (&ur)[NVARS], int o, const double (&n)[ND],
+                          double (&f)[NVARS]) const {
+        const double rho_ll = ul[0], rho_rr = ur[0];
+        double v_ll[ND], v_rr[ND], vsq_ll = 0.0, vsq_rr = 0.0;
+#pragma unroll
+        for (int d = 0; d < ND; ++d) {
+            v_ll[d] = ul[1 + d] / rho_ll;
+            v_rr[d] = ur[1 + d] / rho_rr;
+            vsq_ll += v_ll[d] * v_ll[d];
+            vsq_rr += v_rr[d] * v_rr[d];
+        }
+        const double e_ll = ul[ND + 1] / rho_ll, e_rr = ur[ND + 1] / rho_rr;
+        double p_ll, p_rr, vel_L, vel_R, norm_ = 1.0, norm_sq = 1.0, inv_norm_sq = 1.0;
+        double f_ll[NVARS], f_rr[NVARS];
+        if constexpr (NORMAL) {
+            double r, vv[ND];
+            cons2prim(ul, r, vv, p_ll);
+            cons2prim(ur, r, vv, p_rr);
+            vel_L = 0.0;
+            vel_R = 0.0;
+            double nsq = 0.0;
+#pragma unroll
+            for (int d = 0; d < ND; ++d) {
+                vel_L += v_ll[d] * n[d];
+                vel_R += v_rr[d] * n[d];
+                nsq += n[d] * n[d];
+            }
+            norm_ = sqrt(nsq);
+            norm_sq = norm_ * norm_;
+            inv_norm_sq = 1.0 / norm_sq;
+            flux_normal(ul, n, f_ll);
+            flux_normal(ur, n, f_rr);
+        } else {
+            p_ll = (gamma - 1) * (ul[ND + 1] - 0.5 * rho_ll * vsq_ll);
+            p_rr = (gamma - 1) * (ur[ND + 1] - 0.5 * rho_rr * vsq_rr);
+            vel_L = pick<ND>(v_ll, o);
+            vel_R = pick<ND>(v_rr, o);
+            flux(ul, o, f_ll);
+            flux(ur, o, f_rr);
+        }
+        double c_ll = sqrt(gamma * p_ll / rho_ll), c_rr = sqrt(gamma * p_rr / rho_rr);
+        if constexpr (NORMAL) {
+            c_ll = c_ll * norm_;
+            c_rr = c_rr * norm_;
+        }
+        const double sqrt_rho_ll = sqrt(rho_ll), sqrt_rho_rr = sqrt(rho_rr), sum_sqrt_rho = sqrt_rho_ll + sqrt_rho_rr;
+        double vel_roe, vel_roe_mag = 0.0;
+        if constexpr (NORMAL) {
+            vel_roe = 0.0;
+#pragma unroll
+            for (int d = 0; d < ND; ++d) {
+                const double vr = (sqrt_rho_ll * v_ll[d] + sqrt_rho_rr * v_rr[d]) / sum_sqrt_rho;
+                vel_roe += vr * n[d];
+                vel_roe_mag += vr * vr;
+            }
+        } else {
+            vel_roe = (sqrt_rho_ll * vel_L + sqrt_rho_rr * vel_R) / sum_sqrt_rho;
+#pragma unroll
+            for (int d = 0; d < ND; ++d) {
+                const double w = sqrt_rho_ll * v_ll[d] + sqrt_rho_rr * v_rr[d];
+                vel_roe_mag += w * w;
+            }
+            vel_roe_mag = vel_roe_mag / (sum_sqrt_rho * sum_sqrt_rho);
+        }
+        const double H_ll = (ul[ND + 1] + p_ll) / rho_ll, H_rr = (ur[ND + 1] + p_rr) / rho_rr;
+        const double H_roe = (sqrt_rho_ll * H_ll + sqrt_rho_rr * H_rr) / sum_sqrt_rho;
+        double c_roe = sqrt((gamma - 1) * (H_roe - 0.5 * vel_roe_mag));
+        if constexpr (NORMAL) c_roe = c_roe * norm_;
+        const double Ssl = fmin(vel_L - c_ll, vel_roe - c_roe), Ssr = fmax(vel_R + c_rr, vel_roe + c_roe);
+        const double sMu_L = Ssl - vel_L, sMu_R = Ssr - vel_R;
+        if (Ssl >= 0) {
+#pragma unroll
+            for (int v = 0; v < NVARS; ++v) f[v] = f_ll[v];
+            return;
+        }
+        if (Ssr <= 0) {
+#pragma unroll
+            for (int v = 0; v < NVARS; ++v) f[v] = f_rr[v];
+            return;
+        }
+        const double SStar =
+            NORMAL ? (rho_ll * vel_L * sMu_L - rho_rr * vel_R * sMu_R + (p_rr - p_ll) * norm_sq) / (rho_ll * sMu_L - rho_rr * sMu_R)
+                   : (p_rr - p_ll + rho_ll * vel_L * sMu_L - rho_rr * vel_R * sMu_R) / (rho_ll * sMu_L - rho_rr * sMu_R);
+        const bool left = Ssl <= 0 && 0 <= SStar;
+        const double rho_s = left ? rho_ll : rho_rr, sMu = left ? sMu_L : sMu_R, Ss = left ? Ssl : Ssr;
+        const double vel_s = left ? vel_L : vel_R, e_s = left ? e_ll : e_rr, p_s = left ? p_ll : p_rr;
+        const double densStar = rho_s * sMu / (Ss - SStar);
+        double UStar[NVARS];
+        UStar[0] = densStar;
+        if constexpr (NORMAL) {
+            const double enerStar = e_s + (SStar - vel_s) * (SStar * inv_norm_sq + p_s / (rho_s * sMu));
+#pragma unroll
+            for (int d = 0; d < ND; ++d)
+                UStar[1 + d] = densStar * ((left ? v_ll[d] : v_rr[d]) + (SStar - vel_s) * n[d] * inv_norm_sq);
+            UStar[ND + 1] = densStar * enerStar;
+        } else {
+            const double enerStar = e_s + (SStar - vel_s) * (SStar + p_s / (rho_s * sMu));
+#pragma unroll
+            for (int d = 0; d < ND; ++d) UStar[1 + d] = densStar * (d == o ? SStar : (left ? v_ll[d] : v_rr[d]));
+            UStar[ND + 1] = densStar * enerStar;
+        }
+#pragma unroll
+        for (int v = 0; v < NVARS; ++v) f[v] = (left ? f_ll[v] : f_rr[v]) + Ss * (UStar[v] - (left ? ul[v] : ur[v]));
+    }
+
     TB_DEV void numflux(int id, const double (&ul)[NVARS], const double (&ur)[NVARS], int o,
                         double (&f)[NVARS]) const {
         switch (id) {
+        case TRIXI_B200_FLUX_HLLC: {
+            const double nn[ND] = {};
+            flux_hllc<false>(ul, ur, o, nn, f);
+            break;
+        }
         case TRIXI_B200_FLUX_CENTRAL: {  // numerical_fluxes.jl:17-25
             double fl[NVARS], fr[NVARS];
             flux(ul, o, fl);
@@ -775,6 +888,9 @@ struct Euler {
         }
         case TRIXI_B200_FLUX_CHANDRASHEKAR:
             flux_chandrashekar_normal(ul, ur, n, f);
+            break;
+        case TRIXI_B200_FLUX_HLLC:
+            flux_hllc<true>(ul, ur, 0, n, f);
             break;
         default:
 #pragma unroll

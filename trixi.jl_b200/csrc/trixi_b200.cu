@@ -698,6 +698,9 @@ TRIXI_B200_API int trixi_b200_create(const trixi_b200_desc *d, trixi_b200_handle
                        d->volume_flux_fv == TRIXI_B200_FLUX_HLLE))
             return fail(nullptr, TRIXI_B200_EINVAL, "flux_hlle (FluxHLL(min_max_speed_einfeldt)) is implemented for the "
                                                     "compressible Euler equations and, with the Powell term, for GLM-MHD");
+        if (!euler && (d->surface_flux == TRIXI_B200_FLUX_HLLC || d->volume_flux == TRIXI_B200_FLUX_HLLC ||
+                       d->volume_flux_fv == TRIXI_B200_FLUX_HLLC))
+            return fail(nullptr, TRIXI_B200_EINVAL, "flux_hllc is implemented for the compressible Euler equations");
         const int src = d->source_terms;
         const bool src_ok = src == TRIXI_B200_SRC_NONE ||
                             (euler && (src == TRIXI_B200_SRC_CONVERGENCE_TEST || src == TRIXI_B200_SRC_EOC_TEST_EULER ||

@@ -32,6 +32,7 @@ FLUX_HINDENLANG_GASSNER_POWELL = 13
 FLUX_LLF_NAIVE_MHD_POWELL = 14  # (FluxLaxFriedrichs(max_abs_speed_naive), flux_nonconservative_powell)
 FLUX_HLLE_MHD_POWELL = 15  # (flux_hlle, flux_nonconservative_powell)
 FLUX_CENTRAL_MHD_POWELL = 16  # (flux_central, flux_nonconservative_powell)
+FLUX_HLLC = 18  # flux_hllc (compressible Euler)
 FLUX_HLLE = 17  # flux_hlle = FluxHLL(min_max_speed_einfeldt): compressible Euler; with the Powell term -> 15
 
 SRC_NONE, SRC_CONVERGENCE_TEST, SRC_EOC_TEST_EULER, SRC_EOC_TEST_COUPLED_EULER_GRAVITY = 0, 1, 2, 3
@@ -105,6 +106,7 @@ def FluxHLL(speed=min_max_speed_davis):
 flux_lax_friedrichs = FluxLaxFriedrichs()
 flux_hll = FluxHLL()
 flux_hlle = FluxHLL(min_max_speed_einfeldt)  # numerical_fluxes.jl:457
+flux_hllc = _Flux("flux_hllc", FLUX_HLLC)  # compressible_euler_3d.jl:1423-1665, compressible_euler_2d.jl:1720-1925
 
 
 class _IndicatorVariable:
