@@ -61,7 +61,10 @@ enum {
      * Euler and ideal GLM-MHD (calcflux_fv! with nonconservative terms, dg_3d.jl:391-452) on TreeMesh, P4estMesh
      * (across ranks the neighbour's alpha travels with the halo exchange) and StructuredMesh; curved meshes need
      * subcell_normal_vectors below. */
-    TRIXI_B200_VOLINT_SHOCK_CAPTURING_HG = 2
+    TRIXI_B200_VOLINT_SHOCK_CAPTURING_HG = 2,
+    /* VolumeIntegralPureLGLFiniteVolume(volume_flux_fv) (solvers/dg.jl:559-583; calc_volume_integral.jl: fv_kernel! on
+     * every element with alpha = true): first-order finite volumes on the LGL subcells, flux `volume_flux_fv` */
+    TRIXI_B200_VOLINT_PURE_LGL_FV = 3
 };
 
 /* indicator variables of IndicatorHennemannGassner (compressible_euler_3d.jl:1945-1956 and 2D analogues) */

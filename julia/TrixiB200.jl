@@ -52,10 +52,14 @@ volume_integral_id(v::VolumeIntegralFluxDifferencing) = (Cint(1), flux_id(v.volu
 # VolumeIntegralShockCapturingHG (solvers/dg.jl): volume_flux = volume_flux_dg; the FV flux and the indicator
 # travel in the descriptor's trailing fields
 volume_integral_id(v::VolumeIntegralShockCapturingHG) = (Cint(2), flux_id(v.volume_flux_dg))
+volume_integral_id(v::VolumeIntegralPureLGLFiniteVolume) = (Cint(3), flux_id(v.volume_flux_fv))
 indicator_variable_id(::typeof(density_pressure)) = Cint(0)
 indicator_variable_id(::typeof(density)) = Cint(1)
 indicator_variable_id(::typeof(pressure)) = Cint(2)
 shock_capturing_fields(v, basis) = (Cint(0), Cint(0), Cint(0), 0.0, 0.0, Float64[])
+# VolumeIntegralPureLGLFiniteVolume (solvers/dg.jl:559-583): only the subcell finite-volume flux
+shock_capturing_fields(v::VolumeIntegralPureLGLFiniteVolume, basis) = (flux_id(v.volume_flux_fv), Cint(0), Cint(0), 0.0, 0.0,
+                                                                       Float64[])
 function shock_capturing_fields(v::VolumeIntegralShockCapturingHG, basis)
     ind = v.indicator
     return (flux_id(v.volume_flux_fv), indicator_variable_id(ind.variable), Cint(ind.alpha_smooth),

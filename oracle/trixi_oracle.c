@@ -1711,6 +1711,11 @@ void oracle_calc_volume_integral(const trixi_b200_desc *d, double *du, const dou
         free(alpha);
         return;
     }
+    if (d->volume_integral == TRIXI_B200_VOLINT_PURE_LGL_FV) { /* fv_kernel! with alpha = true on every element */
+#pragma omp parallel for schedule(static)
+        for (int64_t e = 0; e < d->nelements; ++e) fv_kernel(d, &eq, du + e * esz, u + e * esz, 1.0);
+        return;
+    }
 #pragma omp parallel for schedule(static)
     for (int64_t e = 0; e < d->nelements; ++e) {
         if (d->volume_integral == TRIXI_B200_VOLINT_WEAK_FORM)
@@ -2115,6 +2120,11 @@ void oracle_calc_volume_integral_curved(const trixi_b200_desc *d, double *du, co
             }
         }
         free(alpha);
+        return;
+    }
+    if (d->volume_integral == TRIXI_B200_VOLINT_PURE_LGL_FV) {
+#pragma omp parallel for schedule(static)
+        for (int64_t e = 0; e < d->nelements; ++e) fv_kernel_curved(d, &eq, du + e * esz, u + e * esz, e, 1.0);
         return;
     }
 #pragma omp parallel for schedule(static)

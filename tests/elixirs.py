@@ -761,6 +761,22 @@ def initial_condition_isentropic_vortex_advected(x, t, equations):
     return equations.prim2cons((rho_, v1 + du * cx, v2 + du * cy, p_))
 
 
+def _euler_pure_fv(kind):
+    # examples/tree_3d_dgsem/elixir_euler_convergence_pure_fv.jl, tree_2d_dgsem/elixir_euler_convergence_pure_fv.jl,
+    # tree_2d_dgsem/elixir_euler_blast_wave_pure_fv.jl: VolumeIntegralPureLGLFiniteVolume(flux_hllc)
+    solver = T.DGSEM(basis=T.LobattoLegendreBasis(3), surface_flux=T.flux_hllc,
+                     volume_integral=T.VolumeIntegralPureLGLFiniteVolume(T.flux_hllc))
+    if kind == "blast_wave_2d":
+        eq = T.CompressibleEulerEquations2D(1.4)
+        mesh = T.TreeMesh((-2.0, -2.0), (2.0, 2.0), initial_refinement_level=6, periodicity=True)
+        return T.SemidiscretizationHyperbolic(mesh, eq, T.initial_condition_blast_wave, solver)
+    nd = 3 if kind == "convergence_3d" else 2
+    eq = T.CompressibleEulerEquations3D(1.4) if nd == 3 else T.CompressibleEulerEquations2D(1.4)
+    mesh = T.TreeMesh((0.0,) * nd, (2.0,) * nd, initial_refinement_level=2 if nd == 3 else 4, periodicity=True)
+    return T.SemidiscretizationHyperbolic(mesh, eq, T.initial_condition_convergence_test, solver,
+                                          source_terms=T.source_terms_convergence_test)
+
+
 def _euler2d_vortex_mortar_hllc():
     # examples/tree_2d_dgsem/elixir_euler_vortex_mortar.jl: weak form, flux_hllc across L2 mortars
     eq = T.CompressibleEulerEquations2D(1.4)
@@ -799,6 +815,18 @@ ELIXIRS.update({e.name: e for e in [
            [0.00013492249515826863, 0.006615696236378061, 0.006782108219800376, 0.016393831451740604],
            [0.0020782600954247776, 0.08150078921935999, 0.08663621974991986, 0.2829930622010579],
            "test/test_tree_2d_euler.jl:1162-1179"),
+    Elixir("tree_3d_euler_convergence_pure_fv", lambda: _euler_pure_fv("convergence_3d"), (0.0, 5.0), 0.6,
+           [0.037182410351406, 0.032062252638283974, 0.032062252638283974, 0.03206225263828395, 0.12228177813586687],
+           [0.0693648413632646, 0.0622101894740843, 0.06221018947408474, 0.062210189474084965, 0.24196451799555962],
+           "test/test_tree_3d_euler.jl:58-80"),
+    Elixir("tree_2d_euler_convergence_pure_fv", lambda: _euler_pure_fv("convergence_2d"), (0.0, 2.0), 0.5,
+           [0.026440292358506527, 0.013245905852168414, 0.013245905852168479, 0.03912520302609374],
+           [0.042130817806361964, 0.022685499230187034, 0.022685499230187922, 0.06999771202145322],
+           "test/test_tree_2d_euler.jl:24-44"),
+    Elixir("tree_2d_euler_blast_wave_pure_fv", lambda: _euler_pure_fv("blast_wave_2d"), (0.0, 0.5), 0.9,
+           [0.39957047631960346, 0.21006912294983154, 0.21006903549932, 0.6280328163981136],
+           [2.20417889887697, 1.5487238480003327, 1.5486788679247812, 2.4656795949035857],
+           "test/test_tree_2d_euler.jl:496-517"),
     Elixir("tree_2d_euler_vortex_mortar", _euler2d_vortex_mortar_hllc, (0.0, 1.0), 1.4,
            [3.1363505551305216e-5, 0.0006614564510650079, 0.0006466955139840528, 0.002661217863027477],
            [0.0010628052760547346, 0.028186424944457555, 0.01130123802781463, 0.07516351234122709],
@@ -1213,13 +1241,15 @@ def _curved_mapping_2d(xi, eta):
     return x + 1, y + 1
 
 
-def _parity_case(mesh_kind, ndims, surface_flux, boundary_conditions=None, volume_flux=None):
+def _parity_case(mesh_kind, ndims, surface_flux, boundary_conditions=None, volume_flux=None, pure_fv=False):
     """Registry entries the reference has no fixed-mesh golden for: FluxLaxFriedrichs(max_abs_speed),
     FluxHLL along normals, slip walls.  Convergence-test state with its source terms (smooth, subsonic, velocity
     (1, 1[, 1]): the slip wall sees inflow on one side and outflow on the other, i.e. both branches of its pressure
     Riemann solution, compressible_euler_3d.jl:338-356)."""
     eq = T.CompressibleEulerEquations3D(1.4) if ndims == 3 else T.CompressibleEulerEquations2D(1.4)
     volint = T.VolumeIntegralFluxDifferencing(volume_flux) if volume_flux else T.VolumeIntegralWeakForm()
+    if pure_fv:  # VolumeIntegralPureLGLFiniteVolume, on curved meshes along the subcell normal vectors
+        volint = T.VolumeIntegralPureLGLFiniteVolume(surface_flux)
     solver = T.DGSEM(polydeg=3, surface_flux=surface_flux, volume_integral=volint)
     periodic = boundary_conditions is None
     if mesh_kind == "tree":
@@ -1265,6 +1295,7 @@ for _mesh in ("tree", "structured", "p4est"):
         PARITY_EXTRA[f"{_tag}_hll"] = lambda m=_mesh, n=_nd: _parity_case(m, n, T.flux_hll)
         PARITY_EXTRA[f"{_tag}_hlle"] = lambda m=_mesh, n=_nd: _parity_case(m, n, T.flux_hlle)
         PARITY_EXTRA[f"{_tag}_hllc"] = lambda m=_mesh, n=_nd: _parity_case(m, n, T.flux_hllc)
+        PARITY_EXTRA[f"{_tag}_pure_fv"] = lambda m=_mesh, n=_nd: _parity_case(m, n, T.flux_hllc, pure_fv=True)
         PARITY_EXTRA[f"{_tag}_hll_naive"] = (
             lambda m=_mesh, n=_nd: _parity_case(m, n, T.FluxHLL(T.min_max_speed_naive), volume_flux=T.flux_ranocha))
         PARITY_EXTRA[f"{_tag}_slip_wall"] = (

@@ -14,7 +14,7 @@ from .structured import StructuredMesh  # noqa: F401
 from .semidiscretization import (ODEProblem, SemidiscretizationHyperbolic, compute_coefficients,  # noqa: F401
                                  rhs_hyperbolic, semidiscretize)
 from .solver import (DGSEM, IndicatorHennemannGassner, SurfaceIntegralWeakForm,  # noqa: F401
-                     VolumeIntegralFluxDifferencing, VolumeIntegralShockCapturingHG, VolumeIntegralWeakForm)
+                     VolumeIntegralFluxDifferencing, VolumeIntegralPureLGLFiniteVolume, VolumeIntegralShockCapturingHG, VolumeIntegralWeakForm)
 from .time_integration import (CallbackSet, CarpenterKennedy2N43, CarpenterKennedy2N54,  # noqa: F401
                                ParsaniKetchesonDeconinck3Sstar32, ParsaniKetchesonDeconinck3Sstar94,
                                SimpleSSPRK33, init, solve, step, step_2n_host)

@@ -867,6 +867,8 @@ __global__ void __launch_bounds__(ElemCfg<EQ, N>::THREADS) k_element(const KPara
             // VolumeIntegralShockCapturingHG (calc_volume_integral.jl:231-272): pure DG where alpha is (almost)
             // zero, otherwise (1 - alpha) flux differencing + alpha subcell finite volumes
             double w_dg = 1.0, w_fv = 0.0;
+            constexpr bool kPureFv = VOLINT == TRIXI_B200_VOLINT_PURE_LGL_FV;  // fv_kernel! alone, alpha = true
+            constexpr bool kHasFv = kPureFv || VOLINT == TRIXI_B200_VOLINT_SHOCK_CAPTURING_HG;
             if constexpr (VOLINT == TRIXI_B200_VOLINT_SHOCK_CAPTURING_HG) {
                 const double alpha = P.alpha[e];
                 if (!(fabs(alpha) <= 1.8189894035458565e-12)) {  // isapprox(alpha, 0, atol = max(100 eps, eps^0.75))
@@ -874,8 +876,9 @@ __global__ void __launch_bounds__(ElemCfg<EQ, N>::THREADS) k_element(const KPara
                     w_fv = alpha;
                 }
             }
+            if constexpr (kPureFv) w_fv = 1.0;
 #pragma unroll
-            for (int d = 0; d < ND; ++d) {
+            for (int d = 0; d < (kPureFv ? 0 : ND); ++d) {
                 const int base = node - idx[d] * stride[d];
 #pragma unroll 1
                 for (int l = 0; l < N; ++l) {
@@ -894,7 +897,7 @@ __global__ void __launch_bounds__(ElemCfg<EQ, N>::THREADS) k_element(const KPara
                     for (int v = 0; v < NV; ++v) acc[v] = fma(w, f[v], acc[v]);
                 }
             }
-            if constexpr (VOLINT == TRIXI_B200_VOLINT_SHOCK_CAPTURING_HG) {
+            if constexpr (kHasFv) {
                 // fv_kernel! (dg_3d.jl:268-306): du += alpha sum_d inverse_weights[idx_d] (fstar_L[idx_d + 1] -
                 // fstar_R[idx_d]), fstar = volume_flux_fv of neighbouring subcells, zero on the element boundary
                 if (w_fv != 0.0) {
@@ -944,7 +947,7 @@ __global__ void __launch_bounds__(ElemCfg<EQ, N>::THREADS) k_element(const KPara
                     for (int v = 0; v < NV; ++v) acc[v] = fma(w_fv, sum[v], acc[v]);
                 }
             }
-            if constexpr (EQ::kHasNoncons) {
+            if constexpr (EQ::kHasNoncons && !kPureFv) {
                 // nonconservative volume terms (dg_3d.jl:216-266): 0.5 * sum_l Dsplit[idx_d, l] g(u, u_l, d)
                 if (EQ::has_noncons(P.volume_flux)) {
                     double ic[NV];
@@ -1622,6 +1625,8 @@ __global__ void __launch_bounds__(ElemCfg<EQ, N>::THREADS) k_element_curved(cons
         if (active) {
             // VolumeIntegralShockCapturingHG (calc_volume_integral.jl:231-272) as in k_element
             double w_dg = 1.0, w_fv = 0.0;
+            constexpr bool kPureFv = VOLINT == TRIXI_B200_VOLINT_PURE_LGL_FV;  // fv_kernel! alone, alpha = true
+            constexpr bool kHasFv = kPureFv || VOLINT == TRIXI_B200_VOLINT_SHOCK_CAPTURING_HG;
             if constexpr (VOLINT == TRIXI_B200_VOLINT_SHOCK_CAPTURING_HG) {
                 const double alpha = P.alpha[e];
                 if (!(fabs(alpha) <= 1.8189894035458565e-12)) {
@@ -1629,8 +1634,9 @@ __global__ void __launch_bounds__(ElemCfg<EQ, N>::THREADS) k_element_curved(cons
                     w_fv = alpha;
                 }
             }
+            if constexpr (kPureFv) w_fv = 1.0;
 #pragma unroll
-            for (int d = 0; d < ND; ++d) {
+            for (int d = 0; d < (kPureFv ? 0 : ND); ++d) {
                 const int base = node - idx[d] * stride[d];
                 double ja_node[ND];
                 load_ja<ND, NN>(P, d, node, e, ja_node);
@@ -1656,7 +1662,7 @@ __global__ void __launch_bounds__(ElemCfg<EQ, N>::THREADS) k_element_curved(cons
                     for (int v = 0; v < NV; ++v) acc[v] = fma(w, f[v], acc[v]);
                 }
             }
-            if constexpr (EQ::kHasNoncons) {
+            if constexpr (EQ::kHasNoncons && !kPureFv) {
                 // nonconservative volume terms on curved meshes (dgsem_structured/dg_3d.jl:177-283):
                 // 0.5 sum_d sum_l Dsplit[idx_d, l] g(u, u_l, 0.5 (Ja^d + Ja^d_l))
                 if (EQ::has_noncons(P.volume_flux)) {
@@ -1689,7 +1695,7 @@ __global__ void __launch_bounds__(ElemCfg<EQ, N>::THREADS) k_element_curved(cons
                     for (int v = 0; v < NV; ++v) acc[v] = fma(half, ic[v], acc[v]);
                 }
             }
-            if constexpr (VOLINT == TRIXI_B200_VOLINT_SHOCK_CAPTURING_HG) {
+            if constexpr (kHasFv) {
                 // fv_kernel! (dg_3d.jl:268-306) with calcflux_fv! for curved meshes (dgsem_structured/dg_3d.jl:377-436):
                 // subcell fluxes along the precomputed free-stream preserving normal vectors, zero on the element boundary
                 if (w_fv != 0.0) {

@@ -318,6 +318,9 @@ cudaError_t launch_element(const KParams &P, bool with_surface, cudaStream_t s) 
         return with_surface ? launch_element_variant<EQ, N, TRIXI_B200_VOLINT_WEAK_FORM, true>(P, s)
                             : launch_element_variant<EQ, N, TRIXI_B200_VOLINT_WEAK_FORM, false>(P, s);
     }
+    if (P.volume_integral == TRIXI_B200_VOLINT_PURE_LGL_FV)
+        return with_surface ? launch_element_variant<EQ, N, TRIXI_B200_VOLINT_PURE_LGL_FV, true>(P, s)
+                            : launch_element_variant<EQ, N, TRIXI_B200_VOLINT_PURE_LGL_FV, false>(P, s);
     if constexpr (HasFastRanocha<EQ>::value || EQ::kHasNoncons) {  // compressible Euler, ideal GLM-MHD
         if (P.volume_integral == TRIXI_B200_VOLINT_SHOCK_CAPTURING_HG)
             return with_surface ? launch_element_variant<EQ, N, TRIXI_B200_VOLINT_SHOCK_CAPTURING_HG, true>(P, s)
@@ -418,6 +421,10 @@ cudaError_t preload_all() {
     TB_PRELOAD((k_element<EQ, N, TRIXI_B200_VOLINT_WEAK_FORM, false>));
     TB_PRELOAD((k_element<EQ, N, TRIXI_B200_VOLINT_FLUX_DIFFERENCING, true>));
     TB_PRELOAD((k_element<EQ, N, TRIXI_B200_VOLINT_FLUX_DIFFERENCING, false>));
+    TB_PRELOAD((k_element<EQ, N, TRIXI_B200_VOLINT_PURE_LGL_FV, true>));
+    TB_PRELOAD((k_element<EQ, N, TRIXI_B200_VOLINT_PURE_LGL_FV, false>));
+    TB_PRELOAD((k_element_curved<EQ, N, TRIXI_B200_VOLINT_PURE_LGL_FV, true>));
+    TB_PRELOAD((k_element_curved<EQ, N, TRIXI_B200_VOLINT_PURE_LGL_FV, false>));
     if constexpr (HasFastRanocha<EQ>::value || EQ::kHasNoncons) {
         TB_PRELOAD((k_element<EQ, N, TRIXI_B200_VOLINT_SHOCK_CAPTURING_HG, true>));
         TB_PRELOAD((k_element<EQ, N, TRIXI_B200_VOLINT_SHOCK_CAPTURING_HG, false>));

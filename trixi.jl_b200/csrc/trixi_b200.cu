@@ -666,8 +666,13 @@ TRIXI_B200_API int trixi_b200_create(const trixi_b200_desc *d, trixi_b200_handle
         }
     }
     if (d->volume_integral != TRIXI_B200_VOLINT_WEAK_FORM && d->volume_integral != TRIXI_B200_VOLINT_FLUX_DIFFERENCING &&
-        d->volume_integral != TRIXI_B200_VOLINT_SHOCK_CAPTURING_HG)
+        d->volume_integral != TRIXI_B200_VOLINT_SHOCK_CAPTURING_HG && d->volume_integral != TRIXI_B200_VOLINT_PURE_LGL_FV)
         return fail(nullptr, TRIXI_B200_EINVAL, "unsupported volume integral type %d", d->volume_integral);
+    if (d->volume_integral == TRIXI_B200_VOLINT_PURE_LGL_FV && d->mesh_kind != TRIXI_B200_MESH_TREE)
+        for (int a = 0; a < d->ndims; ++a)
+            if (!d->subcell_normal_vectors[a])
+                return fail(nullptr, TRIXI_B200_EINVAL,
+                            "VolumeIntegralPureLGLFiniteVolume on a curved mesh needs subcell_normal_vectors (NormalVectorContainer)");
     if (d->volume_integral == TRIXI_B200_VOLINT_SHOCK_CAPTURING_HG) {
         if (d->mesh_kind != TRIXI_B200_MESH_TREE) {
             for (int a = 0; a < d->ndims; ++a)
@@ -994,17 +999,21 @@ TRIXI_B200_API int trixi_b200_create(const trixi_b200_desc *d, trixi_b200_handle
     }
     for (int k = 0; k < 8; ++k) P.eq.p[k] = d->eq_params[k];
     P.volume_integral = d->volume_integral;
-    if (d->volume_integral == TRIXI_B200_VOLINT_SHOCK_CAPTURING_HG) {
+    const bool sc_hg = d->volume_integral == TRIXI_B200_VOLINT_SHOCK_CAPTURING_HG;
+    if (sc_hg || d->volume_integral == TRIXI_B200_VOLINT_PURE_LGL_FV) {
+        // the subcell finite-volume part (fv_kernel!): its flux, the inverse weights, the normal vectors on curved meshes
         P.volume_flux_fv = d->volume_flux_fv;
-        P.ind_var = d->indicator_variable;
-        P.ind_smooth = d->indicator_alpha_smooth;
-        P.ind_alpha_max = d->indicator_alpha_max;
-        P.ind_alpha_min = d->indicator_alpha_min;
         for (int q = 0; q < n; ++q) P.inv_weights_c[q] = d->inverse_weights[q];
-        CREATE_TRY(upload_array(h, d->inverse_vandermonde_legendre, (size_t)n * n, &tmp));
-        P.inv_vdm = tmp;
-        CREATE_TRY(alloc_array(h, (size_t)d->nelements, &P.alpha));
-        CREATE_TRY(alloc_array(h, (size_t)d->nelements, &P.alpha_raw));
+        if (sc_hg) {
+            P.ind_var = d->indicator_variable;
+            P.ind_smooth = d->indicator_alpha_smooth;
+            P.ind_alpha_max = d->indicator_alpha_max;
+            P.ind_alpha_min = d->indicator_alpha_min;
+            CREATE_TRY(upload_array(h, d->inverse_vandermonde_legendre, (size_t)n * n, &tmp));
+            P.inv_vdm = tmp;
+            CREATE_TRY(alloc_array(h, (size_t)d->nelements, &P.alpha));
+            CREATE_TRY(alloc_array(h, (size_t)d->nelements, &P.alpha_raw));
+        }
         if (d->mesh_kind != TRIXI_B200_MESH_TREE) {
             for (int a = 0; a < nd; ++a) {
                 size_t per_elem = (size_t)nd;

@@ -230,6 +230,14 @@ class SemidiscretizationHyperbolic:
         h.set_f64("derivative_split", dg.basis.derivative_split)
         h.set_f64("derivative_hat", dg.basis.derivative_hat)
         h.set_f64("inverse_weights", dg.basis.inverse_weights)
+        if dg.volume_integral.kind == 3:  # VolumeIntegralPureLGLFiniteVolume
+            d.volume_flux_fv = resolve_flux(dg.volume_integral.volume_flux_fv)
+            if self.is_curved:
+                from .structured import calc_normalvectors_subcell_fv
+                if getattr(cache, "normal_vectors", None) is None:
+                    cache.normal_vectors = calc_normalvectors_subcell_fv(cache.elements.contravariant_vectors, dg.basis)
+                for a, nv in enumerate(cache.normal_vectors):
+                    h.set_f64_item("subcell_normal_vectors", a, nv)
         if dg.volume_integral.kind == 2:  # VolumeIntegralShockCapturingHG
             ind = dg.volume_integral.indicator
             d.volume_flux_fv = resolve_flux(dg.volume_integral.volume_flux_fv)

@@ -5,7 +5,7 @@ from __future__ import annotations
 from .basis import LobattoLegendreBasis
 from .equations import flux_central, resolve_flux
 
-VOLINT_WEAK_FORM, VOLINT_FLUX_DIFFERENCING, VOLINT_SHOCK_CAPTURING_HG = 0, 1, 2
+VOLINT_WEAK_FORM, VOLINT_FLUX_DIFFERENCING, VOLINT_SHOCK_CAPTURING_HG, VOLINT_PURE_LGL_FV = 0, 1, 2, 3
 
 
 class VolumeIntegralWeakForm:
@@ -63,6 +63,21 @@ class VolumeIntegralShockCapturingHG:
         return f"VolumeIntegralShockCapturingHG({self.volume_flux_dg}, {self.volume_flux_fv})"
 
 
+class VolumeIntegralPureLGLFiniteVolume:
+    """``VolumeIntegralPureLGLFiniteVolume(volume_flux_fv)`` (solvers/dg.jl:559-583): first-order finite volumes on the
+    LGL subcells of every element."""
+    kind = VOLINT_PURE_LGL_FV
+
+    def __init__(self, volume_flux_fv=None):
+        from .equations import flux_lax_friedrichs
+        self.volume_flux_fv = volume_flux_fv if volume_flux_fv is not None else flux_lax_friedrichs
+        resolve_flux(self.volume_flux_fv)
+        self.volume_flux = self.volume_flux_fv
+
+    def __repr__(self):
+        return f"VolumeIntegralPureLGLFiniteVolume({self.volume_flux_fv})"
+
+
 class SurfaceIntegralWeakForm:
     """``SurfaceIntegralWeakForm(surface_flux)`` (solvers/dg.jl:829-838)."""
 
@@ -81,7 +96,7 @@ class DGSEM:
         self.surface_integral = surface_integral or SurfaceIntegralWeakForm(surface_flux)
         self.volume_integral = volume_integral or VolumeIntegralWeakForm()
         if not isinstance(self.volume_integral, (VolumeIntegralWeakForm, VolumeIntegralFluxDifferencing,
-                                                 VolumeIntegralShockCapturingHG)):
+                                                 VolumeIntegralShockCapturingHG, VolumeIntegralPureLGLFiniteVolume)):
             # other volume integral types are rejected at the boundary
             raise TypeError("libtrixi_b200 supports VolumeIntegralWeakForm, VolumeIntegralFluxDifferencing and "
                             "VolumeIntegralShockCapturingHG")
