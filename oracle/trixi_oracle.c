@@ -2270,7 +2270,8 @@ double oracle_max_dt_curved(const trixi_b200_desc *d, const double *u) {
     int nanflag = 0;
 #pragma omp parallel for schedule(static) reduction(max : max_lambda) reduction(| : nanflag)
     for (int64_t e = 0; e < d->nelements; ++e) {
-        double ml[3] = {0, 0, 0};
+        double ml[3] = {0, 0, 0}, ml_const = 0.0;
+        const int constant_speed = !is_euler(&eq) && !is_mhd(&eq); /* have_constant_speed: linear advection */
         for (int64_t q = 0; q < nn; ++q) {
             double lam[3] = {0, 0, 0};
             if (is_euler(&eq)) {
@@ -2285,6 +2286,7 @@ double oracle_max_dt_curved(const trixi_b200_desc *d, const double *u) {
                 for (int dd = 0; dd < nd; ++dd) lam[dd] = fabs(eq.a[dd]);
             }
             double inv_jacobian = fabs(d->inverse_jacobian[q + nn * e]);
+            double node_sum = 0.0;
             for (int a = 0; a < nd; ++a) {
                 double ja[3], s = 0.0;
                 get_contravariant_vector(d, a, q, e, ja);
@@ -2292,7 +2294,16 @@ double oracle_max_dt_curved(const trixi_b200_desc *d, const double *u) {
                 double val = inv_jacobian * fabs(s);
                 if (isnan(val)) nanflag = 1;
                 ml[a] = fmax(ml[a], val);
+                node_sum += fabs(s);
             }
+            /* constant_speed::True (max_scaled_speed_per_element, stepsize_dg3d.jl:176-210, stepsize_dg2d.jl:207-235):
+             * the maximum over the nodes of inv_jacobian * (sum of the transformed speeds), not the sum of the
+             * per-direction maxima */
+            if (constant_speed) ml_const = fmax(ml_const, inv_jacobian * node_sum);
+        }
+        if (constant_speed) {
+            ml[0] = ml_const;
+            ml[1] = ml[2] = 0.0;
         }
         double s = 0.0;
         for (int a = 0; a < nd; ++a) s += ml[a];

@@ -640,6 +640,23 @@ ELIXIRS.update({e.name: e for e in [
 ]})
 
 
+def _structured3d_advection(kind):
+    # examples/structured_3d_dgsem/elixir_advection_free_stream.jl, elixir_advection_nonperiodic_curved.jl
+    eq = T.LinearScalarAdvectionEquation3D((0.2, -0.7, 0.5))
+    solver = T.DGSEM(polydeg=3, surface_flux=T.flux_lax_friedrichs)
+    if kind == "free_stream":
+        mesh = T.StructuredMesh((8, 8, 8), _warped_mapping_3d, periodicity=True)
+        return T.SemidiscretizationHyperbolic(mesh, eq, T.initial_condition_constant, solver)
+
+    def mapping(xi, eta, zeta):  # elixir_advection_nonperiodic_curved.jl:19-40
+        x, y, z = _nonperiodic_curved_mapping_3d(xi, eta, zeta)
+        return x - 1, y - 1, z - 1
+    mesh = T.StructuredMesh((8, 8, 8), mapping, periodicity=False)
+    return T.SemidiscretizationHyperbolic(mesh, eq, T.initial_condition_convergence_test, solver,
+                                          boundary_conditions=T.BoundaryConditionDirichlet(
+                                              T.initial_condition_convergence_test))
+
+
 def _advection3d(kind="tree"):
     # examples/{tree,structured,p4est}_3d_dgsem/elixir_advection_basic.jl, tree_3d_dgsem/elixir_advection_mortar.jl
     eq = T.LinearScalarAdvectionEquation3D((0.2, -0.7, 0.5))
@@ -668,7 +685,12 @@ ELIXIRS.update({e.name: e for e in [
            [0.00016263963870641478], [0.0014537194925779984], "test/test_structured_3d.jl:5-9"),
     Elixir("p4est_3d_advection_basic", lambda: _advection3d("p4est"), (0.0, 1.0), 1.2,
            [0.00016263963870641478], [0.0014537194925779984], "test/test_p4est_3d.jl:5-9"),
+    Elixir("structured_3d_advection_nonperiodic_curved", lambda: _structured3d_advection("nonperiodic_curved"),
+           (0.0, 1.0), 1.2, [0.0004483892474201268], [0.009201820593762955], "test/test_structured_3d.jl:28-39"),
 ]})
+ELIXIRS["structured_3d_advection_free_stream"] = Elixir(
+    "structured_3d_advection_free_stream", lambda: _structured3d_advection("free_stream"), (0.0, 1.0), 2.0,
+    [1.2908196366970896e-14], [1.0262901639634947e-12], "test/test_structured_3d.jl:15-26", rtol=0, atol=8e-13)
 
 
 def _shockcapturing(eq, volume_flux, surface_flux):

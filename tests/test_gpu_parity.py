@@ -122,7 +122,8 @@ RHS_CASES = ["tree_3d_euler_ec", "tree_3d_euler_source_terms", "tree_3d_euler_so
              "structured_2d_euler_source_terms_parallelogram", "structured_2d_euler_source_terms_waving_flag", "p4est_2d_euler_shockcapturing_ec",
              "p4est_2d_euler_shockcapturing_ec_chandrashekar",
              "tree_2d_euler_vortex_mortar", "p4est_2d_euler_sedov_hllc", "tree_3d_euler_convergence_pure_fv",
-             "tree_2d_euler_convergence_pure_fv", "tree_2d_euler_blast_wave_pure_fv"] + sorted(PARITY_EXTRA) + sorted(NONCONFORMING_EXTRA)
+             "tree_2d_euler_convergence_pure_fv", "tree_2d_euler_blast_wave_pure_fv",
+             "structured_3d_advection_nonperiodic_curved"] + sorted(PARITY_EXTRA) + sorted(NONCONFORMING_EXTRA)
 
 
 @pytest.mark.parametrize("name", RHS_CASES)
@@ -452,7 +453,8 @@ GOLDEN_GPU = ["tree_3d_advection_basic", "tree_3d_advection_mortar", "structured
              "structured_2d_euler_source_terms", "structured_2d_euler_source_terms_parallelogram", "structured_2d_euler_source_terms_waving_flag",
              "p4est_2d_euler_shockcapturing_ec", "p4est_2d_euler_shockcapturing_ec_chandrashekar",
              "tree_2d_euler_vortex_mortar", "p4est_2d_euler_sedov_hllc", "tree_3d_euler_convergence_pure_fv",
-             "tree_2d_euler_convergence_pure_fv", "tree_2d_euler_blast_wave_pure_fv"]
+             "tree_2d_euler_convergence_pure_fv", "tree_2d_euler_blast_wave_pure_fv",
+             "structured_3d_advection_nonperiodic_curved", "structured_3d_advection_free_stream"]
 
 
 @pytest.mark.parametrize("name", GOLDEN_GPU)

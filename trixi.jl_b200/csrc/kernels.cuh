@@ -1843,6 +1843,7 @@ __global__ void __launch_bounds__(ElemCfg<EQ, N>::THREADS) k_max_dt_curved(const
         for (int v = 0; v < NV; ++v) un[v] = pu[v];
         eq.max_abs_speeds(un, lam);
         const double inv_jacobian = fabs(P.inverse_jacobian[e * NN + node]);
+        double node_sum = 0.0;
 #pragma unroll
         for (int a = 0; a < ND; ++a) {
             double ja[ND];
@@ -1850,8 +1851,14 @@ __global__ void __launch_bounds__(ElemCfg<EQ, N>::THREADS) k_max_dt_curved(const
             double sum = ja[0] * lam[0];
 #pragma unroll
             for (int d = 1; d < ND; ++d) sum += ja[d] * lam[d];
-            atomicMax(&s_lam[a][le], cfl_encode(inv_jacobian * fabs(sum)));
+            if constexpr (EQ::kConstantSpeed)
+                node_sum += fabs(sum);
+            else
+                atomicMax(&s_lam[a][le], cfl_encode(inv_jacobian * fabs(sum)));
         }
+        // constant_speed::True (max_scaled_speed_per_element, stepsize_dg3d.jl:176-210, stepsize_dg2d.jl:207-235): the
+        // maximum over the nodes of inv_jacobian * (sum of the transformed speeds), not the sum of per-direction maxima
+        if constexpr (EQ::kConstantSpeed) atomicMax(&s_lam[0][le], cfl_encode(inv_jacobian * node_sum));
     }
     __syncthreads();
     if (tid < EPB && e0 + tid < P.nelements) {
