@@ -640,6 +640,21 @@ ELIXIRS.update({e.name: e for e in [
 ]})
 
 
+def initial_condition_sin_3d(x, t, equations):
+    # linear_scalar_advection_3d.jl:91-98
+    a = equations.advection_velocity
+    return (np.sin(2 * np.pi * (x[0] - a[0] * t)) * np.sin(2 * np.pi * (x[1] - a[1] * t))
+            * np.sin(2 * np.pi * (x[2] - a[2] * t)))[None]
+
+
+def _advection3d_extended(initial_condition):
+    # examples/tree_3d_dgsem/elixir_advection_extended.jl with the initial conditions of test_tree_3d_advection.jl:40-64
+    eq = T.LinearScalarAdvectionEquation3D((0.2, -0.7, 0.5))
+    solver = T.DGSEM(polydeg=3, surface_flux=T.flux_lax_friedrichs)
+    mesh = T.TreeMesh((-1.0,) * 3, (1.0,) * 3, initial_refinement_level=3, periodicity=True)
+    return T.SemidiscretizationHyperbolic(mesh, eq, initial_condition, solver)
+
+
 def _structured3d_advection(kind):
     # examples/structured_3d_dgsem/elixir_advection_free_stream.jl, elixir_advection_nonperiodic_curved.jl
     eq = T.LinearScalarAdvectionEquation3D((0.2, -0.7, 0.5))
@@ -688,6 +703,12 @@ ELIXIRS.update({e.name: e for e in [
     Elixir("structured_3d_advection_nonperiodic_curved", lambda: _structured3d_advection("nonperiodic_curved"),
            (0.0, 1.0), 1.2, [0.0004483892474201268], [0.009201820593762955], "test/test_structured_3d.jl:28-39"),
 ]})
+ELIXIRS["tree_3d_advection_extended_sin"] = Elixir(
+    "tree_3d_advection_extended_sin", lambda: _advection3d_extended(initial_condition_sin_3d), (0.0, 1.0), 1.2,
+    [0.002647730309275237], [0.02114324070353557], "test/test_tree_3d_advection.jl:40-48")
+ELIXIRS["tree_3d_advection_extended_constant"] = Elixir(
+    "tree_3d_advection_extended_constant", lambda: _advection3d_extended(T.initial_condition_constant), (0.0, 1.0), 1.2,
+    [7.728011630010656e-16], [3.9968028886505635e-15], "test/test_tree_3d_advection.jl:53-61", rtol=0, atol=5e-14)
 ELIXIRS["structured_3d_advection_free_stream"] = Elixir(
     "structured_3d_advection_free_stream", lambda: _structured3d_advection("free_stream"), (0.0, 1.0), 2.0,
     [1.2908196366970896e-14], [1.0262901639634947e-12], "test/test_structured_3d.jl:15-26", rtol=0, atol=8e-13)

@@ -454,7 +454,8 @@ GOLDEN_GPU = ["tree_3d_advection_basic", "tree_3d_advection_mortar", "structured
              "p4est_2d_euler_shockcapturing_ec", "p4est_2d_euler_shockcapturing_ec_chandrashekar",
              "tree_2d_euler_vortex_mortar", "p4est_2d_euler_sedov_hllc", "tree_3d_euler_convergence_pure_fv",
              "tree_2d_euler_convergence_pure_fv", "tree_2d_euler_blast_wave_pure_fv",
-             "structured_3d_advection_nonperiodic_curved", "structured_3d_advection_free_stream"]
+             "structured_3d_advection_nonperiodic_curved", "structured_3d_advection_free_stream",
+             "tree_3d_advection_extended_sin", "tree_3d_advection_extended_constant"]
 
 
 @pytest.mark.parametrize("name", GOLDEN_GPU)
