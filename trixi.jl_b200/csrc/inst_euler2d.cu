@@ -1,5 +1,7 @@
 // Explicit instantiation of the generic kernels for one equation system (parallel compilation unit).
 #include "launch.cuh"
 namespace tb {
-const Launchers *get_launchers_euler2d(int nnodes) { return launchers_for_nnodes<Euler<2>>(nnodes); }
+const Launchers *get_launchers_euler2d(int nnodes) {
+    return nnodes >= 6 ? get_launchers_euler2d_hi(nnodes) : launchers_among<Euler<2>, 2, 3, 4, 5>(nnodes);
+}
 }  // namespace tb

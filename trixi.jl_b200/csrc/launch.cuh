@@ -469,6 +469,15 @@ const Launchers *make_launchers() {
     return &L;
 }
 
+// the launcher table for nnodes = n if n is one of NS..., else nullptr: a translation unit instantiates the kernels of the
+// listed node counts only (the per-equation tables are split over several units so that they compile in parallel)
+template <class EQ, int... NS>
+const Launchers *launchers_among(int n) {
+    const Launchers *r = nullptr;
+    ((n == NS ? (void)(r = make_launchers<EQ, NS>()) : (void)0), ...);
+    return r;
+}
+
 template <class EQ>
 const Launchers *launchers_for_nnodes(int n) {
     switch (n) {
@@ -489,5 +498,15 @@ const Launchers *get_launchers_advection3d(int nnodes);
 const Launchers *get_launchers_euler2d(int nnodes);
 const Launchers *get_launchers_euler3d(int nnodes);
 const Launchers *get_launchers_mhd3d(int nnodes);
+// (parts of the tables above, one translation unit each)
+const Launchers *get_launchers_euler2d_hi(int nnodes);
+const Launchers *get_launchers_euler3d_n5(int nnodes);
+const Launchers *get_launchers_euler3d_n6(int nnodes);
+const Launchers *get_launchers_euler3d_n7(int nnodes);
+const Launchers *get_launchers_euler3d_n8(int nnodes);
+const Launchers *get_launchers_mhd3d_n5(int nnodes);
+const Launchers *get_launchers_mhd3d_n6(int nnodes);
+const Launchers *get_launchers_mhd3d_n7(int nnodes);
+const Launchers *get_launchers_mhd3d_n8(int nnodes);
 
 }  // namespace tb
