@@ -251,6 +251,16 @@ struct NodeRecord<Euler<3>> {
     TB_DEV static void noncons(const double *, const double *, double (&)[5]) {}
 };
 
+// run-time two-point flux of the line sweeps: the compressible Euler equations take their core switch (see
+// Euler::numflux_core; launch.cuh sends set-ups with flux_hllc / flux_hlle as volume fluxes to the generic kernels)
+template <class EQ, int NVV>
+TB_DEV void numflux_tuned(const EQ &eq, int id, const double (&ul)[NVV], const double (&ur)[NVV], int o, double (&f)[NVV]) {
+    if constexpr (HasFastRanocha<EQ>::value)
+        eq.numflux_core(id, ul, ur, o, f);
+    else
+        eq.numflux(id, ul, ur, o, f);
+}
+
 template <class EQ>
 struct LineSweepCfg {
     static constexpr int NV = EQ::NVARS, THREADS = 32;
@@ -376,7 +386,7 @@ __global__ void __launch_bounds__(LineSweepCfg<EQ>::THREADS, LineSweepCfg<EQ>::M
             if constexpr (REC)
                 Rec::flux(eq, P.volume_flux, a, b, out);
             else
-                eq.numflux(P.volume_flux, a, b, d, out);
+                numflux_tuned(eq, P.volume_flux, a, b, d, out);
         };
         auto noncons_term = [&](const double(&a)[NR], const double(&b)[NR], double(&out)[NV]) {
             if constexpr (REC)
@@ -497,13 +507,13 @@ __global__ void __launch_bounds__(LineSweepCfg<EQ>::THREADS, LineSweepCfg<EQ>::M
                     ca[v] = h ? c1[v] : c0[v];  // the pair (0,1) [h = 0] or (2,3) [h = 1], lower node first
                     cb[v] = h ? c0[v] : c1[v];
                 }
-                eq.numflux(P.volume_flux_fv, ca, cb, d, fa);
+                numflux_tuned(eq, P.volume_flux_fv, ca, cb, d, fa);
 #pragma unroll
                 for (int v = 0; v < NV; ++v) {
                     ca[v] = h ? c3[v] : c1[v];  // the pair (1,2)
                     cb[v] = h ? c1[v] : c2[v];
                 }
-                eq.numflux(P.volume_flux_fv, ca, cb, d, fb);
+                numflux_tuned(eq, P.volume_flux_fv, ca, cb, d, fb);
                 double *t0 = s_du + swz_pos(base + lm[0] * stride) * NV, *t1 = s_du + swz_pos(base + lm[1] * stride) * NV;
 #pragma unroll
                 for (int v = 0; v < NV; ++v) {

@@ -253,8 +253,11 @@ bool uses_tuned_element(const KParams &P) {
         if (P.curved)  // flux differencing with flux_ranocha along averaged contravariant vectors
             return P.volume_integral == TRIXI_B200_VOLINT_FLUX_DIFFERENCING &&
                    (P.volume_flux == TRIXI_B200_FLUX_RANOCHA || P.volume_flux == TRIXI_B200_FLUX_RANOCHA_TURBO);
-        return P.volume_integral == TRIXI_B200_VOLINT_FLUX_DIFFERENCING ||       // headline or line sweep
-               P.volume_integral == TRIXI_B200_VOLINT_SHOCK_CAPTURING_HG;        // blended line sweep
+        // (the line-sweep kernels inline Euler::numflux_core: flux_hllc / flux_hlle as volume or subcell fluxes take
+        // the generic kernels)
+        if (P.volume_integral == TRIXI_B200_VOLINT_FLUX_DIFFERENCING) return Euler<3>::in_core_switch(P.volume_flux);
+        return P.volume_integral == TRIXI_B200_VOLINT_SHOCK_CAPTURING_HG && Euler<3>::in_core_switch(P.volume_flux) &&
+               Euler<3>::in_core_switch(P.volume_flux_fv);  // blended line sweep
     }
     if constexpr (std::is_same_v<EQ, Mhd3D> && N == 4) {
         return P.kernel_path != 1 && !P.curved && P.volume_integral == TRIXI_B200_VOLINT_FLUX_DIFFERENCING;
