@@ -167,6 +167,10 @@ template <int ND>
 struct HasFastRanocha<Euler<ND>> {
     static constexpr bool value = true;
 };
+template <int ND>
+struct HasFastRanocha<EulerAllFluxes<ND>> {
+    static constexpr bool value = true;
+};
 
 // surface flux of one face node; FAST selects the fast-division flux_ranocha (tuned path)
 // FAST: 0 = the registry's generic numflux, 1 = flux_ranocha on fast divisions, 2 = FluxLaxFriedrichs on fast divisions

@@ -501,6 +501,14 @@ const Launchers *get_launchers_advection3d(int nnodes);
 const Launchers *get_launchers_euler2d(int nnodes);
 const Launchers *get_launchers_euler3d(int nnodes);
 const Launchers *get_launchers_mhd3d(int nnodes);
+// second tables of the compressible Euler equations: every registered flux in the run-time switches (EulerAllFluxes)
+const Launchers *get_launchers_euler2d_all(int nnodes);
+const Launchers *get_launchers_euler3d_all(int nnodes);
+const Launchers *get_launchers_euler2d_all_hi(int nnodes);
+const Launchers *get_launchers_euler3d_all_n5(int nnodes);
+const Launchers *get_launchers_euler3d_all_n6(int nnodes);
+const Launchers *get_launchers_euler3d_all_n7(int nnodes);
+const Launchers *get_launchers_euler3d_all_n8(int nnodes);
 // (parts of the tables above, one translation unit each)
 const Launchers *get_launchers_euler2d_hi(int nnodes);
 const Launchers *get_launchers_euler3d_n5(int nnodes);

@@ -605,9 +605,14 @@ struct Euler {
         for (int v = 0; v < NVARS; ++v) f[v] = (left ? f_ll[v] : f_rr[v]) + Ss * (UStar[v] - (left ? ul[v] : ur[v]));
     }
 
+    // Euler<ND>::numflux / numflux_normal hold the core switch; EulerAllFluxes<ND> below holds the full one.  nvcc sizes
+    // a kernel's registers for the longest body of an inlined run-time switch whether or not a run selects it: with
+    // flux_hllc, flux_hlle and flux_chandrashekar along normals in the default switch the curved interface kernels grew
+    // from 70-76 to 120 registers (2-4% on the curved workloads).  `create` picks the launcher table of the second type
+    // when a descriptor names one of those fluxes.
     TB_DEV void numflux(int id, const double (&ul)[NVARS], const double (&ur)[NVARS], int o,
                         double (&f)[NVARS]) const {
-        numflux_impl<true>(id, ul, ur, o, f);
+        numflux_impl<false>(id, ul, ur, o, f);
     }
     // The same switch without flux_hllc and flux_hlle: what the tuned line-sweep kernels inline for their run-time
     // volume / subcell fluxes.  Their register budget is tuned (with the two long bodies inlined the shock-capturing
@@ -761,6 +766,22 @@ struct Euler {
     }
     TB_DEV void numflux_normal(int id, const double (&ul)[NVARS], const double (&ur)[NVARS], const double (&n)[ND],
                                double (&f)[NVARS]) const {
+        numflux_normal_impl<false>(id, ul, ur, n, f);
+    }
+    // (flux_chandrashekar along normals is long as well: with the rare fluxes only)
+    TB_DEV_HOST static bool in_core_switch_normal(int id) {
+        return in_core_switch(id) && id != TRIXI_B200_FLUX_CHANDRASHEKAR;
+    }
+    template <bool FULL>
+    TB_DEV void numflux_normal_impl(int id, const double (&ul)[NVARS], const double (&ur)[NVARS], const double (&n)[ND],
+                                    double (&f)[NVARS]) const {
+        if constexpr (!FULL) {
+            if (!in_core_switch_normal(id)) {
+#pragma unroll
+                for (int v = 0; v < NVARS; ++v) f[v] = nan("");
+                return;
+            }
+        }
         switch (id) {
         case TRIXI_B200_FLUX_CENTRAL: {
             double fl[NVARS], fr[NVARS];
@@ -771,6 +792,7 @@ struct Euler {
             break;
         }
         case TRIXI_B200_FLUX_HLLE: {  // FluxHLL with min_max_speed_einfeldt along a normal direction (:1723-1771)
+          if constexpr (FULL) {
             double rho_ll, v_ll[ND], p_ll, rho_rr, v_rr[ND], p_rr;
             cons2prim(ul, rho_ll, v_ll, p_ll);
             cons2prim(ur, rho_rr, v_rr, p_rr);
@@ -806,6 +828,7 @@ struct Euler {
                 for (int v = 0; v < NVARS; ++v)
                     f[v] = factor_ll * fl[v] - factor_rr * fr[v] + factor_diss * (ur[v] - ul[v]);
             }
+          }
             break;
         }
         case TRIXI_B200_FLUX_LLF:
@@ -913,10 +936,10 @@ struct Euler {
             break;
         }
         case TRIXI_B200_FLUX_CHANDRASHEKAR:
-            flux_chandrashekar_normal(ul, ur, n, f);
+            if constexpr (FULL) flux_chandrashekar_normal(ul, ur, n, f);
             break;
         case TRIXI_B200_FLUX_HLLC:
-            flux_hllc<true>(ul, ur, 0, n, f);
+            if constexpr (FULL) flux_hllc<true>(ul, ur, 0, n, f);
             break;
         default:
 #pragma unroll
@@ -1107,6 +1130,23 @@ struct Euler {
 #pragma unroll
         for (int d = 0; d < ND; ++d)
             if (d == o) f[1 + d] = p_star;
+    }
+};
+
+// The compressible Euler equations with every registered flux in the run-time switches (see Euler::numflux): the
+// equation type of the second launcher table, used when a descriptor names flux_hllc, flux_hlle or, on curved meshes,
+// flux_chandrashekar.  Always on the generic kernels (the tuned ones are tied to Euler<3>).
+template <int ND>
+struct EulerAllFluxes : Euler<ND> {
+    using Base = Euler<ND>;
+    static constexpr int NVARS = Base::NVARS;
+    __host__ __device__ explicit EulerAllFluxes(const EqParams &q) : Base(q) {}
+    TB_DEV void numflux(int id, const double (&ul)[NVARS], const double (&ur)[NVARS], int o, double (&f)[NVARS]) const {
+        this->template numflux_impl<true>(id, ul, ur, o, f);
+    }
+    TB_DEV void numflux_normal(int id, const double (&ul)[NVARS], const double (&ur)[NVARS], const double (&n)[ND],
+                               double (&f)[NVARS]) const {
+        this->template numflux_normal_impl<true>(id, ul, ur, n, f);
     }
 };
 

@@ -734,8 +734,26 @@ TRIXI_B200_API int trixi_b200_create(const trixi_b200_desc *d, trixi_b200_handle
     switch (d->equation) {
     case TRIXI_B200_EQ_ADVECTION_2D: L = get_launchers_advection2d(d->nnodes); break;
     case TRIXI_B200_EQ_ADVECTION_3D: L = get_launchers_advection3d(d->nnodes); break;
-    case TRIXI_B200_EQ_EULER_2D: L = get_launchers_euler2d(d->nnodes); break;
-    case TRIXI_B200_EQ_EULER_3D: L = get_launchers_euler3d(d->nnodes); break;
+    case TRIXI_B200_EQ_EULER_2D:
+    case TRIXI_B200_EQ_EULER_3D: {
+        // flux_hllc, flux_hlle and (along normals) flux_chandrashekar live in the run-time switches of a second launcher
+        // table (EulerAllFluxes, physics.cuh): the default table's kernels are not sized for bodies they never run
+        const bool curved_mesh = d->mesh_kind != TRIXI_B200_MESH_TREE;
+        auto rare = [&](int id) {
+            return id == TRIXI_B200_FLUX_HLLC || id == TRIXI_B200_FLUX_HLLE ||
+                   (curved_mesh && id == TRIXI_B200_FLUX_CHANDRASHEKAR);
+        };
+        const bool fv = d->volume_integral == TRIXI_B200_VOLINT_SHOCK_CAPTURING_HG ||
+                        d->volume_integral == TRIXI_B200_VOLINT_PURE_LGL_FV;
+        const bool all = rare(d->surface_flux) ||
+                         (d->volume_integral != TRIXI_B200_VOLINT_WEAK_FORM && rare(d->volume_flux)) ||
+                         (fv && rare(d->volume_flux_fv));
+        if (d->equation == TRIXI_B200_EQ_EULER_2D)
+            L = all ? get_launchers_euler2d_all(d->nnodes) : get_launchers_euler2d(d->nnodes);
+        else
+            L = all ? get_launchers_euler3d_all(d->nnodes) : get_launchers_euler3d(d->nnodes);
+        break;
+    }
     case TRIXI_B200_EQ_MHD_3D:
         if (d->nboundaries > 0 && d->mesh_kind != TRIXI_B200_MESH_P4EST)
             return fail(nullptr, TRIXI_B200_EINVAL,
