@@ -1,6 +1,6 @@
 """Builds ``libtrixi_b200.so`` in-tree with nvcc for sm_100a (no torch involved: the product is a
 plain C-ABI shared library).  The generic kernels are instantiated in one translation unit per equation system and,
-for the heavy systems, per node count (csrc/inst_*.cu); all units compile in parallel (a full build takes 3-4 minutes on
+for the heavy systems, per node count (csrc/inst_*.cu); all units compile in parallel (a full build takes about 5 minutes on
 8 cores; as five units it took 9)."""
 from __future__ import annotations
 
